@@ -1,0 +1,341 @@
+"""Test-side helpers: ctypes binding of the CPU oracle (oracle/unipeak_oracle.c), runners for the
+compiled reference (oracle/_ref, when present), and the regions-table text format.
+
+Nothing here is imported by the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import struct
+import subprocess
+import sys
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+REF_DIR = os.path.join(ORACLE_DIR, "_ref")
+ORACLE_SO = os.path.join(ORACLE_DIR, "_build", "libupb_oracle.so")
+
+from unipeak_b200.synth import TagData  # noqa: E402
+
+
+def have_ref() -> bool:
+    return all(os.access(os.path.join(REF_DIR, b), os.X_OK) for b in ("regions", "strand_shift", "tags_in_regions", "ref_replay"))
+
+
+# ------------------------------------------------------------------------------------------------
+# oracle binding
+# ------------------------------------------------------------------------------------------------
+class UpoInput(C.Structure):
+    _fields_ = [("n_contigs", C.c_uint32), ("contig_sizes", C.POINTER(C.c_uint32)), ("n_samples", C.c_uint32),
+                ("off", C.POINTER(C.c_uint64)), ("pos", C.POINTER(C.c_uint32)), ("cnt", C.POINTER(C.c_uint32))]
+
+
+class UpoParams(C.Structure):
+    _fields_ = [("bandwidth", C.c_uint32), ("region_threshold", C.c_double), ("kurtosis_threshold", C.c_double),
+                ("corr_threshold", C.c_double), ("hit_threshold", C.c_double), ("directional", C.c_int),
+                ("control", C.POINTER(C.c_uint8)), ("n_coeffs", C.c_uint32), ("coeffs", C.POINTER(C.c_double)),
+                ("background", C.c_double), ("want_profile", C.c_int)]
+
+
+class UpoRegion(C.Structure):
+    _fields_ = [("forward_label", C.c_uint8), ("buffer", C.c_uint8), ("contig", C.c_uint32), ("left", C.c_uint32),
+                ("len", C.c_uint32), ("peak_pos", C.c_uint32), ("peak_score", C.c_double), ("kurtosis", C.c_double),
+                ("corr", C.c_double)]
+
+
+class UpoProfilePoint(C.Structure):
+    _fields_ = [("buffer", C.c_uint8), ("contig", C.c_uint32), ("pos", C.c_uint32), ("score", C.c_double)]
+
+
+class UpoRegionsResult(C.Structure):
+    _fields_ = [("n_rows", C.c_size_t), ("rows", C.POINTER(UpoRegion)), ("counts", C.POINTER(C.c_uint32)),
+                ("n_dropped", C.c_size_t), ("dropped", C.POINTER(UpoRegion)), ("dropped_counts", C.POINTER(C.c_uint32)),
+                ("n_passed", C.c_uint64), ("n_rejected", C.c_uint64), ("tags_in_regions", C.POINTER(C.c_uint64)),
+                ("n_profile", C.c_size_t), ("profile", C.POINTER(UpoProfilePoint)), ("status", C.c_int)]
+
+
+class UpoShiftParams(C.Structure):
+    _fields_ = [("bandwidth", C.c_uint32), ("region_threshold", C.c_double), ("kurtosis_threshold", C.c_double),
+                ("corr_threshold", C.c_double), ("hit_threshold", C.c_uint32), ("min_shift", C.c_uint32),
+                ("max_shift", C.c_uint32), ("n_regions_to_test", C.c_uint32), ("background", C.c_double)]
+
+
+class UpoShiftResult(C.Structure):
+    _fields_ = [("n_regions_found", C.c_uint64), ("n_regions_tested", C.c_uint32), ("n_tags_in_regions", C.c_uint64),
+                ("shift_freq", C.POINTER(C.c_uint64)), ("best_shift", C.c_uint32), ("n_tested_rows", C.c_size_t),
+                ("tested_contig", C.POINTER(C.c_uint32)), ("tested_left", C.POINTER(C.c_uint32)),
+                ("tested_len", C.POINTER(C.c_uint32)), ("tested_best_shift", C.POINTER(C.c_uint32)),
+                ("tested_best_corr", C.POINTER(C.c_double)), ("status", C.c_int)]
+
+
+class UpoRegionKey(C.Structure):
+    _fields_ = [("contig", C.c_uint32), ("start", C.c_uint32), ("end", C.c_uint32)]
+
+
+_oracle = None
+
+
+def build_oracle() -> None:
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "port"])
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(os.path.join(ORACLE_DIR, "unipeak_oracle.c")):
+            build_oracle()
+        lib = C.CDLL(ORACLE_SO)
+        lib.upo_kernel.argtypes = [C.c_uint32, C.c_double, C.POINTER(C.c_double)]
+        lib.upo_kernel.restype = None
+        lib.upo_regions.argtypes = [C.POINTER(UpoInput), C.POINTER(UpoParams), C.POINTER(UpoRegionsResult)]
+        lib.upo_regions_free.argtypes = [C.POINTER(UpoRegionsResult)]
+        lib.upo_strand_shift.argtypes = [C.POINTER(UpoInput), C.POINTER(UpoShiftParams), C.POINTER(UpoShiftResult)]
+        lib.upo_shift_free.argtypes = [C.POINTER(UpoShiftResult)]
+        lib.upo_tags_in_regions.argtypes = [C.POINTER(UpoInput), C.c_int, C.c_uint32, C.c_size_t, C.POINTER(UpoRegionKey), C.POINTER(C.c_uint32)]
+        lib.upo_sort_by_sum_desc.argtypes = [C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        lib.upo_sort_by_sum_desc.restype = None
+        lib.upo_strerror.restype = C.c_char_p
+        _oracle = lib
+    return _oracle
+
+
+def _as_input(data: TagData):
+    sizes = np.ascontiguousarray(data.contig_sizes, dtype=np.uint32)
+    off = np.ascontiguousarray(data.off, dtype=np.uint64)
+    pos = np.ascontiguousarray(data.pos, dtype=np.uint32)
+    cnt = np.ascontiguousarray(data.cnt, dtype=np.uint32)
+    inp = UpoInput(data.n_contigs, sizes.ctypes.data_as(C.POINTER(C.c_uint32)), data.n_samples,
+                   off.ctypes.data_as(C.POINTER(C.c_uint64)), pos.ctypes.data_as(C.POINTER(C.c_uint32)),
+                   cnt.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return inp, (sizes, off, pos, cnt)
+
+
+def region_settings(data: TagData, *, directional=True, bandwidth=50, region_threshold=25.0, kurtosis_threshold=50.0,
+                    corr_threshold=0.3, hit_threshold=10.0, control: Sequence[int] = (), coeffs: Optional[Sequence[float]] = None,
+                    mappable: int = 0, proportional=False) -> Dict:
+    """Derive what src/regions.cpp:104-232 derives from the flags: scaled hit threshold, corr threshold,
+    background, normalised coefficients.  `control` holds 0-based sample indices."""
+    n = data.n_samples
+    ctrl = np.zeros(n, dtype=np.uint8)
+    for i in control:
+        ctrl[i] = 1
+    n_control = int(ctrl.sum())
+    tags = [data.tags(s) for s in range(n)]
+    n_noncontrol = sum(t for t, c in zip(tags, ctrl) if not c)
+    mappable = mappable or data.genome_size()
+    background = float(n_noncontrol) / float(mappable)
+    if directional:
+        background /= 2
+    cf: List[float] = []
+    if proportional:
+        cf = [float(n_noncontrol) / (float(t) * float(n - n_control)) for t, c in zip(tags, ctrl) if not c]
+    elif coeffs:
+        cf = [float(x) for x in coeffs]
+        scaled = 0.0
+        nc_tags = [t for t, c in zip(tags, ctrl) if not c]
+        for x, t in zip(cf, nc_tags):
+            scaled += x * float(t)
+        cf = [x * (n_noncontrol / scaled) for x in cf]   # regions.cpp:228: Counter / double
+    return dict(bandwidth=bandwidth, region_threshold=float(region_threshold), kurtosis_threshold=float(kurtosis_threshold),
+                corr_threshold=(-1.0 if directional else float(corr_threshold)),
+                hit_threshold=float(hit_threshold) * (n - n_control), directional=bool(directional), control=ctrl,
+                coeffs=cf, background=background, tags=tags, n_noncontrol=n_noncontrol, mappable=mappable)
+
+
+def _rows_to_dicts(rows, counts, n_rows, n) -> List[Dict]:
+    out = []
+    for k in range(n_rows):
+        r = rows[k]
+        out.append(dict(forward_label=int(r.forward_label), buffer=int(r.buffer), contig=int(r.contig), left=int(r.left),
+                        len=int(r.len), peak=int(r.peak_pos), peak_score=float(r.peak_score), kurtosis=float(r.kurtosis),
+                        corr=float(r.corr), counts=[int(counts[k * n + e]) for e in range(n)]))
+    return out
+
+
+def oracle_regions(data: TagData, st: Dict, want_profile=False) -> Dict:
+    lib = oracle()
+    inp, keep = _as_input(data)
+    ctrl = np.ascontiguousarray(st["control"], dtype=np.uint8)
+    cf = np.ascontiguousarray(st["coeffs"], dtype=np.float64)
+    p = UpoParams(st["bandwidth"], st["region_threshold"], st["kurtosis_threshold"], st["corr_threshold"], st["hit_threshold"],
+                  1 if st["directional"] else 0, ctrl.ctypes.data_as(C.POINTER(C.c_uint8)), cf.shape[0],
+                  cf.ctypes.data_as(C.POINTER(C.c_double)), st["background"], 1 if want_profile else 0)
+    res = UpoRegionsResult()
+    status = lib.upo_regions(C.byref(inp), C.byref(p), C.byref(res))
+    n = data.n_samples
+    out = dict(status=status, rows=_rows_to_dicts(res.rows, res.counts, res.n_rows, n),
+               dropped=_rows_to_dicts(res.dropped, res.dropped_counts, res.n_dropped, n),
+               n_passed=int(res.n_passed), n_rejected=int(res.n_rejected),
+               tags_in_regions=[int(res.tags_in_regions[e]) for e in range(n)] if res.tags_in_regions else [])
+    if want_profile:
+        m = res.n_profile
+        out["profile"] = [(int(res.profile[i].buffer), int(res.profile[i].contig), int(res.profile[i].pos), float(res.profile[i].score)) for i in range(m)]
+    lib.upo_regions_free(C.byref(res))
+    del keep
+    return out
+
+
+def oracle_strand_shift(data: TagData, *, bandwidth=50, region_threshold=25.0, kurtosis_threshold=50.0, corr_threshold=0.3,
+                        hit_threshold=10, min_shift=25, max_shift=150, n_regions_to_test=1000, mappable=0) -> Dict:
+    lib = oracle()
+    inp, keep = _as_input(data)
+    total = sum(data.tags(s) for s in range(data.n_samples))
+    background = float(total) / float(mappable or data.genome_size())
+    p = UpoShiftParams(bandwidth, region_threshold, kurtosis_threshold, corr_threshold, hit_threshold, min_shift, max_shift,
+                       n_regions_to_test, background)
+    res = UpoShiftResult()
+    status = lib.upo_strand_shift(C.byref(inp), C.byref(p), C.byref(res))
+    out = dict(status=status, n_regions_found=int(res.n_regions_found), n_regions_tested=int(res.n_regions_tested),
+               n_tags_in_regions=int(res.n_tags_in_regions), best_shift=int(res.best_shift), background=background, total_tags=total,
+               shift_freq=[int(res.shift_freq[i]) for i in range(max_shift + 1)] if res.shift_freq else [],
+               tested=[dict(contig=int(res.tested_contig[i]), left=int(res.tested_left[i]), len=int(res.tested_len[i]),
+                            best_shift=int(res.tested_best_shift[i]), best_corr=float(res.tested_best_corr[i]))
+                       for i in range(res.n_tested_rows)])
+    lib.upo_shift_free(C.byref(res))
+    del keep
+    return out
+
+
+def oracle_tags_in_regions(data: TagData, keys: Sequence[Sequence[int]], *, directional=True, extension=0):
+    lib = oracle()
+    inp, keep = _as_input(data)
+    arr = (UpoRegionKey * max(1, len(keys)))()
+    for i, (c, s, e) in enumerate(keys):
+        arr[i] = UpoRegionKey(c, s, e)
+    out = np.zeros(max(1, len(keys) * data.n_samples), dtype=np.uint32)
+    status = lib.upo_tags_in_regions(C.byref(inp), 1 if directional else 0, extension, len(keys), arr,
+                                     out.ctypes.data_as(C.POINTER(C.c_uint32)))
+    del keep
+    return status, out[:len(keys) * data.n_samples].reshape(len(keys), data.n_samples)
+
+
+# ------------------------------------------------------------------------------------------------
+# regions-table text (misc/format.cpp:1141-1162) — the drop-in output contract
+# ------------------------------------------------------------------------------------------------
+def _fmt_g(x: float) -> str:
+    if math.isnan(x):
+        return "-nan" if math.copysign(1.0, x) < 0 else "nan"
+    return "%g" % x
+
+
+def _fmt_2f(x: float) -> str:
+    if math.isnan(x):
+        return "-nan" if math.copysign(1.0, x) < 0 else "nan"
+    return "%.2f" % x
+
+
+def format_region_row(row: Dict, names: Sequence[str], peaks=False, corrs=False) -> str:
+    right = row["left"] + row["len"] - 1
+    coord = "%d-%d" % (row["left"], right) if row["forward_label"] else "%d-%d" % (right, row["left"])
+    s = "%s:%s" % (names[row["contig"]], coord)
+    if peaks:
+        s += "\t%d" % row["peak"]
+    if corrs:
+        s += "\t" + _fmt_g(row["corr"])
+    s += "\t" + _fmt_2f(row["kurtosis"])
+    for c in row["counts"]:
+        s += "\t%d" % c
+    return s
+
+
+def read_table_rows(path: str) -> List[str]:
+    rows = []
+    with open(path) as f:
+        for line in f:
+            line = line.rstrip("\n")
+            if not line or line[0] == "#" or line[0] == "\t":
+                continue
+            rows.append(line)
+    return rows
+
+
+# ------------------------------------------------------------------------------------------------
+# compiled reference runners (only where oracle/_ref exists)
+# ------------------------------------------------------------------------------------------------
+def write_inputs(data: TagData, workdir: str, prefix="s") -> Dict:
+    os.makedirs(workdir, exist_ok=True)
+    ctab = os.path.join(workdir, "contigs.txt")
+    data.write_contig_table(ctab)
+    wigs = []
+    for s in range(data.n_samples):
+        p = os.path.join(workdir, "%s%d.wig" % (prefix, s))
+        data.write_wig(p, s, "%s%d" % (prefix, s))
+        wigs.append(p)
+    return dict(contigs=ctab, wigs=wigs)
+
+
+def run_ref_cli(binary: str, args: Sequence[str], check=True):
+    proc = subprocess.run([os.path.join(REF_DIR, binary)] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    if check and proc.returncode != 0:
+        raise RuntimeError("%s failed (%d): %s" % (binary, proc.returncode, proc.stderr[-2000:]))
+    return proc
+
+
+def _hex(x: float) -> str:
+    return float(x).hex()
+
+
+def run_ref_replay_regions(data: TagData, st: Dict, workdir: str, reps=1) -> Dict:
+    os.makedirs(workdir, exist_ok=True)
+    inp = os.path.join(workdir, "in.upbi")
+    outp = os.path.join(workdir, "out.bin")
+    data.write_upbi(inp)
+    args = ["regions", inp, outp, "bw=%d" % st["bandwidth"], "r=" + _hex(st["region_threshold"]), "k=" + _hex(st["kurtosis_threshold"]),
+            "u=" + _hex(st["corr_threshold"]), "t=" + _hex(st["hit_threshold"]), "background=" + _hex(st["background"]),
+            "directional=%d" % (1 if st["directional"] else 0), "reps=%d" % reps]
+    ctrl = [str(i) for i, c in enumerate(st["control"]) if c]
+    if ctrl:
+        args.append("control=" + ",".join(ctrl))
+    if len(st["coeffs"]):
+        args.append("coeffs=" + ",".join(_hex(x) for x in st["coeffs"]))
+    proc = run_ref_cli("ref_replay", args)
+    seconds = float(proc.stdout.strip().split("=")[1])
+    n = data.n_samples
+    with open(outp, "rb") as f:
+        buf = f.read()
+    o = 0
+    n_rows, n_dropped, n_passed, n_rejected = struct.unpack_from("<QQQQ", buf, o); o += 32
+    tags = list(struct.unpack_from("<%dQ" % n, buf, o)); o += 8 * n
+
+    def rd(k):
+        nonlocal o
+        rows = []
+        for _ in range(k):
+            fwd, contig, left, ln, peak, pscore, kurt, corr = struct.unpack_from("<BIIIIddd", buf, o); o += 1 + 16 + 24
+            counts = list(struct.unpack_from("<%dI" % n, buf, o)); o += 4 * n
+            rows.append(dict(forward_label=fwd, contig=contig, left=left, len=ln, peak=peak, peak_score=pscore, kurtosis=kurt, corr=corr, counts=counts))
+        return rows
+    rows = rd(n_rows)
+    dropped = rd(n_dropped)
+    return dict(rows=rows, dropped=dropped, n_passed=n_passed, n_rejected=n_rejected, tags_in_regions=tags, seconds=seconds)
+
+
+def run_ref_replay_shift(data: TagData, workdir: str, *, bandwidth=50, region_threshold=25.0, kurtosis_threshold=50.0,
+                         corr_threshold=0.3, hit_threshold=10, min_shift=25, max_shift=150, n_regions_to_test=1000, mappable=0) -> Dict:
+    os.makedirs(workdir, exist_ok=True)
+    inp = os.path.join(workdir, "in.upbi")
+    outp = os.path.join(workdir, "shift.bin")
+    data.write_upbi(inp)
+    total = sum(data.tags(s) for s in range(data.n_samples))
+    background = float(total) / float(mappable or data.genome_size())
+    args = ["shift", inp, outp, "bw=%d" % bandwidth, "r=" + _hex(region_threshold), "k=" + _hex(kurtosis_threshold), "u=" + _hex(corr_threshold),
+            "t=%d" % hit_threshold, "background=" + _hex(background), "min_shift=%d" % min_shift, "max_shift=%d" % max_shift, "g=%d" % n_regions_to_test]
+    proc = run_ref_cli("ref_replay", args)
+    with open(outp, "rb") as f:
+        buf = f.read()
+    o = 0
+    n_found, n_tested, n_tags, best = struct.unpack_from("<QIQI", buf, o); o += 24
+    (m,) = struct.unpack_from("<I", buf, o); o += 4
+    freq = list(struct.unpack_from("<%dQ" % m, buf, o)); o += 8 * m
+    tested = []
+    for _ in range(n_tested):
+        c, l, ln, b, corr = struct.unpack_from("<IIIId", buf, o); o += 24
+        tested.append(dict(contig=c, left=l, len=ln, best_shift=b, best_corr=corr))
+    return dict(n_regions_found=n_found, n_regions_tested=n_tested, n_tags_in_regions=n_tags, best_shift=best, shift_freq=freq,
+                tested=tested, seconds=float(proc.stdout.strip().split("=")[1]))
