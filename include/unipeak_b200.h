@@ -1,0 +1,202 @@
+/*
+ * unipeak_b200.h — C-ABI of the B200-native UniPeak region-calling hot path.
+ *
+ * The reference (jwfoley/UniPeak) has no plugin or FFI layer: its hot path is the C++ class surface
+ * Kernel / ProfileBuffer / Region, driven one tag position at a time from the three main()s.  A
+ * streaming add() cannot be a device call, so this boundary is batch-shaped: the caller hands over
+ * what the reference's wiggle front end would have streamed (sorted, unique per-strand tag positions
+ * with counts) and gets back what the reference's drivers would have written.
+ * Every entry point names the reference interface it replaces (paths relative to the reference root).
+ *
+ * Conventions: plain C types only; every function returns UPB_OK (0) or a negative error code and
+ * never throws, exits or aborts; upb_last_error() gives the message; one context per host thread;
+ * all host buffers are the caller's unless a upb_*_free function is named; no CPU fallback exists —
+ * without a CUDA device upb_create fails.
+ */
+#ifndef UNIPEAK_B200_H
+#define UNIPEAK_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UPB_VERSION 1
+
+enum {
+  UPB_OK = 0,
+  UPB_ERR_CUDA = -1,            /* a CUDA runtime call failed (message has the cudaError string) */
+  UPB_ERR_BAD_ARG = -2,
+  UPB_ERR_NO_DEVICE = -3,       /* no CUDA device: there is deliberately no CPU path */
+  UPB_ERR_NOT_LOADED = -4,      /* contigs / tags not set before a call that needs them */
+  UPB_ERR_UNSORTED = -5,        /* reference would assert: misc/peakcall.cpp:171 */
+  UPB_ERR_LEFT_EDGE = -6,       /* a tag lies within `bandwidth` of a contig start: the reference's left-edge
+                                   path (misc/peakcall.cpp:176-184) is not emulated yet */
+  UPB_ERR_REFERENCE_ABORTS = -7,/* the reference's merge loop would trip its own assert on this input
+                                   (several directional samples whose '-' track is read in pass 1) */
+  UPB_ERR_NO_REGIONS = -8,      /* src/strand_shift.cpp:228-230 "no regions qualified" */
+  UPB_ERR_REVERSE_NONDIR = -9,  /* src/tags_in_regions.cpp:167-170 */
+  UPB_ERR_NOMEM = -10,
+  UPB_ERR_UNSUPPORTED = -11
+};
+
+typedef struct upb_ctx upb_ctx;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int upb_create (int device, upb_ctx** out);
+void upb_destroy (upb_ctx* ctx);
+const char* upb_last_error (const upb_ctx* ctx);   /* ctx may be NULL: last error of upb_create on this thread */
+int upb_device_count (void);
+
+/* pinned host memory for the arrays handed to upb_load_tags (optional; any host memory works) */
+int upb_host_alloc (void** out, size_t bytes);
+void upb_host_free (void* p);
+
+/* ---- inputs -------------------------------------------------------------------------------- */
+/* Replaces ContigTable (misc/data.hpp:75-100, filled by parseContigTable, misc/format.cpp:27-57):
+ * sizes in table order; contig index = row. */
+int upb_set_contigs (upb_ctx* ctx, uint32_t n_contigs, const uint32_t* sizes);
+
+/* Replaces the per-sample tag streams ParseAlignStream / NondirParseAlignStream deliver
+ * (misc/format.cpp:503-565, :798-915; consumed at src/regions.cpp:335-354).  For sample s, strand d
+ * (0 '+', 1 '-') and contig c the entries are pos[off[(s*2+d)*(n_contigs+1)+c] .. off[..+c+1]):
+ * strictly ascending 1-based positions (the -s offset already applied, out-of-bounds tags dropped, as
+ * misc/format.cpp:654-678 does) with non-zero counts.  `off` has n_samples*2*(n_contigs+1) entries.
+ * Copies to the device and builds the per-tile search index; the arrays may be freed afterwards.
+ * A rank of a multi-GPU job loads only the contigs it owns (empty segments elsewhere). */
+int upb_load_tags (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt);
+
+/* ---- bin/regions --------------------------------------------------------------------------- */
+/* What src/regions.cpp:104-232 derives from its flags before the hot loop. */
+typedef struct {
+  uint32_t bandwidth;           /* -b; Kernel(bandwidth, 1/background), misc/kernel.cpp:16-35 */
+  double region_threshold;      /* -r (must be > 0) */
+  double kurtosis_threshold;    /* -k (0 disables) */
+  double corr_threshold;        /* -u; callers pass -1 when directional (src/regions.cpp:104-109) */
+  double hit_threshold;         /* -t ALREADY multiplied by the number of non-control samples (src/regions.cpp:155) */
+  int directional;              /* 1: forwardBuffer + reverseBuffer; 0: -D, one buffer sees both strands */
+  const uint8_t* control;       /* [n_samples], 1 = negative control (-e); NULL = none */
+  uint32_t n_coeffs;            /* 0, or the number of non-control samples (-z) */
+  const double* coeffs;         /* already normalised as src/regions.cpp:216-229 */
+  double background;            /* tags per mappable position, halved if directional (src/regions.cpp:209-210) */
+  int reference_order;          /* 1: rows come back in the reference's emission order with its labels and its
+                                   dropped tail; needs every contig loaded in this context.
+                                   0: canonical order (buffer, contig, left), nothing dropped. */
+} upb_region_params;
+
+/* One row per accepted region == one Region the reference pushes into regionsOut (misc/peakcall.cpp:45)
+ * and FormatOutStream::write(Region) prints (misc/format.cpp:1141-1162).  Library-allocated. */
+typedef struct {
+  uint64_t n_rows;
+  uint32_t n_samples;
+  uint8_t* buffer;              /* 0 forwardBuffer, 1 reverseBuffer */
+  uint8_t* forward_label;       /* Region::forward as the reference prints it (differs from buffer only for Q5) */
+  uint8_t* dropped;             /* 1: the reference finalises this region in its last flush and never writes it (Q6) */
+  uint32_t* contig;
+  uint32_t* left;               /* Region::left */
+  uint32_t* len;                /* Region::counts->size() */
+  uint32_t* peak;               /* Region::peakPos */
+  uint64_t* cand_index;         /* ordinal of this region among ALL candidate regions of its (buffer, contig) */
+  double* peak_score;           /* Region::peakScore */
+  double* kurtosis;             /* Region::posKurtosis() */
+  double* corr;                 /* Region::strandCorr(0); NaN where the reference would not have computed it */
+  uint32_t* counts;             /* [n_rows * n_samples] Region::exptSums() — the regions x experiments matrix */
+  uint64_t n_passed;            /* ProfileBuffer::nRegions() summed over buffers (includes dropped rows) */
+  uint64_t n_rejected;          /* ProfileBuffer::nRegionRejects() */
+  uint64_t* tags_in_regions;    /* [n_samples] ProfileBuffer::nTagsInRegions() */
+  uint64_t* unit_candidates;    /* [2 * n_contigs] candidate regions per (buffer, contig) */
+  uint32_t* unit_last_tag;      /* [2 * n_contigs] last add() position per (buffer, contig), 0 if none */
+} upb_region_table;
+
+int upb_call_regions (upb_ctx* ctx, const upb_region_params* params, upb_region_table* out);
+void upb_free_region_table (upb_region_table* t);
+
+/* Host-only: put canonical rows (reference_order == 0), e.g. gathered from several ranks, into the
+ * reference's emission order and set forward_label / dropped (src/regions.cpp:311-391).  `first_pos`
+ * and `last_pos` are [n_samples*2*n_contigs] first/last tag position per (sample, strand, contig),
+ * 0 where empty.  perm_out receives n_rows row indices. */
+int upb_reference_order (uint32_t n_contigs, uint32_t n_samples, int directional, uint32_t bandwidth,
+                         const uint32_t* first_pos, const uint32_t* last_pos,
+                         upb_region_table* t, uint64_t* perm_out);
+
+/* ---- bin/regions -w (profile) -------------------------------------------------------------- */
+/* Replaces the FormatOutStream::write(PosScore) calls of ProfileBuffer::processPosition
+ * (misc/peakcall.cpp:81-84): every position with score != 0 of one (buffer, contig), ascending.
+ * Library-allocated arrays; free with upb_free_profile. */
+typedef struct {
+  uint64_t n;
+  uint32_t* pos;
+  double* score;
+} upb_profile;
+int upb_profile_contig (upb_ctx* ctx, const upb_region_params* params, int buffer, uint32_t contig, upb_profile* out);
+void upb_free_profile (upb_profile* p);
+
+/* ---- bin/strand_shift ---------------------------------------------------------------------- */
+/* What src/strand_shift.cpp:52-137 derives from its flags. */
+typedef struct {
+  uint32_t bandwidth;
+  double region_threshold;
+  double kurtosis_threshold;
+  double corr_threshold;
+  uint32_t hit_threshold;       /* unscaled integer (src/strand_shift.cpp:46,142) */
+  uint32_t min_shift;           /* -n */
+  uint32_t max_shift;           /* -x */
+  uint32_t n_regions_to_test;   /* -g (UShort in the reference) */
+  double background;            /* total tags / mappable (src/strand_shift.cpp:133) */
+} upb_shift_params;
+
+/* What src/strand_shift.cpp:196-300 reports. */
+typedef struct {
+  uint64_t n_regions_found;
+  uint32_t n_regions_tested;
+  uint64_t n_tags_in_regions;
+  uint32_t best_shift;
+  uint32_t n_freq;              /* max_shift + 1 */
+  uint64_t* shift_freq;         /* shiftFreq */
+  /* per tested region, in test order */
+  uint32_t* tested_contig;
+  uint32_t* tested_left;
+  uint32_t* tested_len;
+  uint32_t* tested_best_shift;
+  double* tested_best_corr;
+} upb_shift_report;
+
+int upb_strand_shift (upb_ctx* ctx, const upb_shift_params* params, upb_shift_report* out);
+void upb_free_shift_report (upb_shift_report* r);
+
+/* ---- bin/tags_in_regions ------------------------------------------------------------------- */
+typedef struct {
+  uint32_t contig;
+  uint32_t start;               /* as written in the table; start > end marks a reverse-strand row */
+  uint32_t end;
+} upb_region_key;
+
+/* Replaces the per-row counting loop of src/tags_in_regions.cpp:131-199 over the loaded samples,
+ * including its stream-order semantics.  counts_out is [n_regions * n_samples]. */
+int upb_count_tags_in_regions (upb_ctx* ctx, int directional, uint32_t extension, uint64_t n_regions,
+                               const upb_region_key* regions, uint32_t* counts_out);
+
+/* ---- Kernel -------------------------------------------------------------------------------- */
+/* Replaces Kernel::Kernel (misc/kernel.cpp:16-35): 2*bandwidth+1 Epanechnikov taps scaled to `sum`.
+ * Host arithmetic, identical expression order; the device uses exactly this table. */
+int upb_kernel_taps (uint32_t bandwidth, double sum, double* taps_out);
+
+/* ---- instrumentation ----------------------------------------------------------------------- */
+/* Device-side timings (CUDA events on the context's stream) and launch counts of the last call. */
+typedef struct {
+  float ms_total;               /* first kernel start -> last kernel end */
+  float ms_kde;                 /* the fused pool + KDE + threshold + run-extraction kernel */
+  uint32_t launches;            /* kernels launched by the last call */
+  uint64_t kde_tiles;           /* tiles the KDE kernel visited */
+  uint64_t kde_hot_tiles;       /* tiles that needed exact evaluation */
+  uint64_t n_candidates;
+  uint64_t n_entries;           /* tag entries resident */
+} upb_stats;
+int upb_last_stats (const upb_ctx* ctx, upb_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,174 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle on identical seeded inputs.
+
+Bar (BASELINE.json north_star): region coordinates, peak positions, labels, counts and filter decisions
+bit-exact; here the FP64 statistics (peak score, kurtosis, strand correlation) are ALSO required to be
+bit-identical (tolerance 0), which is stricter than the stated 1e-9 relative.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from refutil import oracle_regions, oracle_strand_shift, region_settings
+from unipeak_b200.synth import TagData, make_synthetic
+
+pytestmark = pytest.mark.gpu
+
+INT_KEYS = ("forward_label", "buffer", "contig", "left", "len", "peak", "counts")
+FP_KEYS = ("peak_score", "kurtosis", "corr")
+
+
+def same_fp(a, b):
+    return a == b or (math.isnan(a) and math.isnan(b))
+
+
+def assert_rows_equal(got, want, what):
+    assert len(got) == len(want), "%s: %d rows, oracle has %d" % (what, len(got), len(want))
+    for i, (g, w) in enumerate(zip(got, want)):
+        for k in INT_KEYS:
+            assert g[k] == w[k], "%s row %d field %s: got %r, oracle %r (%r)" % (what, i, k, g[k], w[k], w)
+        for k in FP_KEYS:
+            assert same_fp(g[k], w[k]), "%s row %d field %s: got %r, oracle %r" % (what, i, k, g[k], w[k])
+
+
+def check_regions(ctx, data, **kw):
+    st = region_settings(data, **kw)
+    want = oracle_regions(data, st)
+    assert want["status"] == 0
+    ctx.load(data)
+    got = ctx.call_regions(**st)
+    assert_rows_equal(got["rows"], want["rows"], "written")
+    assert_rows_equal(got["dropped"], want["dropped"], "dropped")
+    assert got["n_passed"] == want["n_passed"]
+    assert got["n_rejected"] == want["n_rejected"]
+    assert got["tags_in_regions"] == want["tags_in_regions"]
+    return got, want
+
+
+def test_directional_three_samples(gpu_ctx):
+    d = make_synthetic([200000, 100000, 50000], 3, 20000, directional=True, seed=1, peak_spacing=5000)
+    got, _ = check_regions(gpu_ctx, d)
+    assert len(got["rows"]) > 10
+
+
+def test_nondirectional_two_samples_with_corr(gpu_ctx):
+    d = make_synthetic([200000, 100000, 50000], 2, 30000, directional=False, seed=2, peak_spacing=5000)
+    got, _ = check_regions(gpu_ctx, d, directional=False)
+    assert len(got["rows"]) > 0
+
+
+def test_single_contig_low_depth_c1_shape(gpu_ctx):
+    # config 1 shape: one sample, one contig, -m far larger than the contig => every tag is a candidate
+    d = make_synthetic([2000000], 1, 60000, directional=True, seed=3, peak_spacing=10000)
+    got, want = check_regions(gpu_ctx, d, mappable=300000000)
+    assert want["n_rejected"] > 1000
+
+
+def test_controls_and_q4(gpu_ctx):
+    d = make_synthetic([300000, 150000], 4, 25000, directional=True, seed=5, peak_spacing=5000)
+    check_regions(gpu_ctx, d, control=[1, 3])
+
+
+def test_controls_nondirectional(gpu_ctx):
+    d = make_synthetic([300000, 150000], 3, 30000, directional=False, seed=6, peak_spacing=5000)
+    check_regions(gpu_ctx, d, directional=False, control=[2])
+
+
+@pytest.mark.parametrize("bw", [10, 20, 100, 150, 200])
+def test_bandwidth_sweep(gpu_ctx, bw):
+    d = make_synthetic([400000, 100000], 2, 40000, directional=True, seed=7, peak_spacing=8000, bandwidth=200)
+    check_regions(gpu_ctx, d, bandwidth=bw)
+
+
+def test_thresholds_disabled_and_tight(gpu_ctx):
+    d = make_synthetic([300000, 100000], 2, 30000, directional=False, seed=8, peak_spacing=6000)
+    check_regions(gpu_ctx, d, directional=False, kurtosis_threshold=0.0, corr_threshold=-1.0, hit_threshold=1.0, region_threshold=5.0)
+    check_regions(gpu_ctx, d, directional=False, kurtosis_threshold=2.5, corr_threshold=0.8, hit_threshold=30.0, region_threshold=40.0)
+
+
+def dense_data(sizes, n_samples, seed, fill=0.8, max_count=4, bandwidth=50):
+    rng = np.random.default_rng(seed)
+    segs = []
+    for s in range(n_samples):
+        per = [[None] * len(sizes) for _ in range(2)]
+        for d in range(2):
+            for c, size in enumerate(sizes):
+                pos = np.arange(bandwidth + 1, size - bandwidth + 1, dtype=np.uint32)
+                keep = rng.random(pos.shape[0]) < fill
+                pos = pos[keep]
+                per[d][c] = (pos, rng.integers(1, max_count + 1, size=pos.shape[0]).astype(np.uint32))
+        segs.append(per)
+    return TagData.from_segments(sizes, segs)
+
+
+def test_dense_contig_long_regions(gpu_ctx):
+    # near-saturated coverage with a large -m: whole contigs are single regions that span many tiles
+    # (run stitching), every window holds ~2*bw tags, and the last contig's region is finalised by the
+    # final flush, i.e. dropped by the reference (Q6)
+    d = dense_data([30000, 16571], 2, seed=9)
+    got, _ = check_regions(gpu_ctx, d, mappable=100 * d.genome_size())
+    assert max(r["len"] for r in got["rows"] + got["dropped"]) > 16000
+    assert len(got["dropped"]) == 1
+
+
+def test_region_longer_than_65535_wraps_like_the_reference(gpu_ctx):
+    # Q8: the kurtosis offset counter is a 16-bit integer and count/sum are 32-bit: a 99 900-bp region wraps both
+    d = dense_data([100000, 5000], 1, seed=13, fill=0.9, max_count=3)
+    got, _ = check_regions(gpu_ctx, d, mappable=100 * d.genome_size())
+    assert max(r["len"] for r in got["rows"] + got["dropped"]) > 65536
+    check_regions(gpu_ctx, d, mappable=100 * d.genome_size(), directional=False)
+    got, _ = check_regions(gpu_ctx, d, mappable=100 * d.genome_size(), directional=False, corr_threshold=-0.5)
+    assert len(got["rows"]) == 1 and not math.isnan(got["rows"][0]["corr"])
+
+
+def test_empty_and_ragged(gpu_ctx):
+    sizes = [100000, 50000, 70000]
+    full = make_synthetic(sizes, 3, 15000, directional=True, seed=10, peak_spacing=4000)
+    segs = [[[full.seg(s, d, c) for c in range(3)] for d in range(2)] for s in range(3)]
+    e = (np.zeros(0, np.uint32), np.zeros(0, np.uint32))
+    segs[0][1][0] = e          # sample 0 has no '-' tags on contig 0
+    segs[1][0][1] = e
+    segs[1][1][1] = e          # sample 1 has nothing on contig 1
+    segs[2][1] = [e, e, e]     # sample 2 has no '-' tags at all
+    d = TagData.from_segments(sizes, segs)
+    check_regions(gpu_ctx, d)
+
+
+def test_reference_abort_is_reported(gpu_ctx):
+    # several directional samples on a single-contig table: the reference's merge loop reads the '-' tracks
+    # during the '+' pass and trips its own assert (misc/peakcall.cpp:171); the oracle reports that as status 1
+    import unipeak_b200
+    d = make_synthetic([500000], 3, 20000, directional=True, seed=3, peak_spacing=5000)
+    st = region_settings(d)
+    assert oracle_regions(d, st)["status"] == 1
+    gpu_ctx.load(d)
+    with pytest.raises(unipeak_b200.UpbError) as ei:
+        gpu_ctx.call_regions(**st)
+    assert ei.value.code == -7
+    # the canonical (order-free) table is still available
+    got = gpu_ctx.call_regions(**dict(st, reference_order=False))
+    assert len(got["rows"]) > 0
+
+
+def test_strand_shift(gpu_ctx):
+    d = make_synthetic([3000000], 1, 300000, directional=False, seed=11, peak_spacing=10000)
+    want = oracle_strand_shift(d, n_regions_to_test=30, region_threshold=8.0, corr_threshold=0.1)
+    gpu_ctx.load(d)
+    got = gpu_ctx.strand_shift(n_regions_to_test=30, region_threshold=8.0, corr_threshold=0.1, background=want["background"])
+    assert want["status"] == 0 and got["status"] == 0
+    assert want["n_regions_tested"] == 30
+    for k in ("n_regions_found", "n_regions_tested", "n_tags_in_regions", "best_shift", "shift_freq"):
+        assert got[k] == want[k], k
+    assert len(got["tested"]) == len(want["tested"])
+    for g, w in zip(got["tested"], want["tested"]):
+        assert (g["contig"], g["left"], g["len"], g["best_shift"]) == (w["contig"], w["left"], w["len"], w["best_shift"])
+        assert g["best_corr"] == w["best_corr"]
+    assert abs(got["best_shift"] - 90) <= 10   # the planted half-fragment shift
+
+
+def test_strand_shift_no_regions(gpu_ctx):
+    d = make_synthetic([200000], 1, 2000, directional=False, seed=12, peak_spacing=10000)
+    want = oracle_strand_shift(d)
+    gpu_ctx.load(d)
+    got = gpu_ctx.strand_shift(background=want["background"])
+    assert want["status"] == 3 and got["status"] == -8

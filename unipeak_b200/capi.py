@@ -1,0 +1,255 @@
+"""ctypes binding of the C-ABI in include/unipeak_b200.h (the CUDA library built in-tree as
+unipeak_b200/libunipeak_b200.so).  There is no fallback: if the library is missing, or no CUDA device is
+present, every call fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libunipeak_b200.so")
+
+UPB_OK = 0
+ERRORS = {
+    -1: "UPB_ERR_CUDA", -2: "UPB_ERR_BAD_ARG", -3: "UPB_ERR_NO_DEVICE", -4: "UPB_ERR_NOT_LOADED", -5: "UPB_ERR_UNSORTED",
+    -6: "UPB_ERR_LEFT_EDGE", -7: "UPB_ERR_REFERENCE_ABORTS", -8: "UPB_ERR_NO_REGIONS", -9: "UPB_ERR_REVERSE_NONDIR",
+    -10: "UPB_ERR_NOMEM", -11: "UPB_ERR_UNSUPPORTED",
+}
+
+
+class UpbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("%s (%d): %s" % (ERRORS.get(code, "UPB_ERR"), code, msg))
+        self.code = code
+
+
+class RegionParams(C.Structure):
+    _fields_ = [("bandwidth", C.c_uint32), ("region_threshold", C.c_double), ("kurtosis_threshold", C.c_double),
+                ("corr_threshold", C.c_double), ("hit_threshold", C.c_double), ("directional", C.c_int),
+                ("control", C.POINTER(C.c_uint8)), ("n_coeffs", C.c_uint32), ("coeffs", C.POINTER(C.c_double)),
+                ("background", C.c_double), ("reference_order", C.c_int)]
+
+
+class RegionTable(C.Structure):
+    _fields_ = [("n_rows", C.c_uint64), ("n_samples", C.c_uint32), ("buffer", C.POINTER(C.c_uint8)),
+                ("forward_label", C.POINTER(C.c_uint8)), ("dropped", C.POINTER(C.c_uint8)), ("contig", C.POINTER(C.c_uint32)),
+                ("left", C.POINTER(C.c_uint32)), ("len", C.POINTER(C.c_uint32)), ("peak", C.POINTER(C.c_uint32)),
+                ("cand_index", C.POINTER(C.c_uint64)), ("peak_score", C.POINTER(C.c_double)), ("kurtosis", C.POINTER(C.c_double)),
+                ("corr", C.POINTER(C.c_double)), ("counts", C.POINTER(C.c_uint32)), ("n_passed", C.c_uint64),
+                ("n_rejected", C.c_uint64), ("tags_in_regions", C.POINTER(C.c_uint64)), ("unit_candidates", C.POINTER(C.c_uint64)),
+                ("unit_last_tag", C.POINTER(C.c_uint32))]
+
+
+class Profile(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("pos", C.POINTER(C.c_uint32)), ("score", C.POINTER(C.c_double))]
+
+
+class ShiftParams(C.Structure):
+    _fields_ = [("bandwidth", C.c_uint32), ("region_threshold", C.c_double), ("kurtosis_threshold", C.c_double),
+                ("corr_threshold", C.c_double), ("hit_threshold", C.c_uint32), ("min_shift", C.c_uint32),
+                ("max_shift", C.c_uint32), ("n_regions_to_test", C.c_uint32), ("background", C.c_double)]
+
+
+class ShiftReport(C.Structure):
+    _fields_ = [("n_regions_found", C.c_uint64), ("n_regions_tested", C.c_uint32), ("n_tags_in_regions", C.c_uint64),
+                ("best_shift", C.c_uint32), ("n_freq", C.c_uint32), ("shift_freq", C.POINTER(C.c_uint64)),
+                ("tested_contig", C.POINTER(C.c_uint32)), ("tested_left", C.POINTER(C.c_uint32)), ("tested_len", C.POINTER(C.c_uint32)),
+                ("tested_best_shift", C.POINTER(C.c_uint32)), ("tested_best_corr", C.POINTER(C.c_double))]
+
+
+class RegionKey(C.Structure):
+    _fields_ = [("contig", C.c_uint32), ("start", C.c_uint32), ("end", C.c_uint32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("ms_total", C.c_float), ("ms_kde", C.c_float), ("launches", C.c_uint32), ("kde_tiles", C.c_uint64),
+                ("kde_hot_tiles", C.c_uint64), ("n_candidates", C.c_uint64), ("n_entries", C.c_uint64)]
+
+
+EXPORTS = [
+    "upb_create", "upb_destroy", "upb_last_error", "upb_device_count", "upb_host_alloc", "upb_host_free", "upb_set_contigs",
+    "upb_load_tags", "upb_call_regions", "upb_free_region_table", "upb_reference_order", "upb_profile_contig", "upb_free_profile",
+    "upb_strand_shift", "upb_free_shift_report", "upb_count_tags_in_regions", "upb_kernel_taps", "upb_last_stats",
+]
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library; raise if it has not been built (python __graft_entry__.py / unipeak_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s is missing: build it with `python -m unipeak_b200.build` (nvcc, sm_100a). "
+                              "There is no CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.upb_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.upb_destroy.argtypes = [C.c_void_p]
+        L.upb_destroy.restype = None
+        L.upb_last_error.argtypes = [C.c_void_p]
+        L.upb_last_error.restype = C.c_char_p
+        L.upb_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+        L.upb_host_free.argtypes = [C.c_void_p]
+        L.upb_host_free.restype = None
+        L.upb_set_contigs.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        L.upb_load_tags.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.upb_call_regions.argtypes = [C.c_void_p, C.POINTER(RegionParams), C.POINTER(RegionTable)]
+        L.upb_free_region_table.argtypes = [C.POINTER(RegionTable)]
+        L.upb_free_region_table.restype = None
+        L.upb_profile_contig.argtypes = [C.c_void_p, C.POINTER(RegionParams), C.c_int, C.c_uint32, C.POINTER(Profile)]
+        L.upb_free_profile.argtypes = [C.POINTER(Profile)]
+        L.upb_free_profile.restype = None
+        L.upb_strand_shift.argtypes = [C.c_void_p, C.POINTER(ShiftParams), C.POINTER(ShiftReport)]
+        L.upb_free_shift_report.argtypes = [C.POINTER(ShiftReport)]
+        L.upb_free_shift_report.restype = None
+        L.upb_count_tags_in_regions.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint64, C.POINTER(RegionKey), C.c_void_p]
+        L.upb_kernel_taps.argtypes = [C.c_uint32, C.c_double, C.POINTER(C.c_double)]
+        L.upb_last_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.upb_reference_order.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(RegionTable), C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def kernel_taps(bandwidth: int, total: float = 1.0) -> np.ndarray:
+    """Kernel(bandwidth, sum) of the reference (misc/kernel.cpp:16-35)."""
+    out = np.zeros(2 * bandwidth + 1, dtype=np.float64)
+    rc = lib().upb_kernel_taps(bandwidth, total, out.ctypes.data_as(C.POINTER(C.c_double)))
+    if rc:
+        raise UpbError(rc, "upb_kernel_taps")
+    return out
+
+
+def _np(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+
+
+class Context:
+    """One device context (one per host thread / rank)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = lib()
+        self._h = C.c_void_p()
+        rc = self._lib.upb_create(device, C.byref(self._h))
+        if rc:
+            raise UpbError(rc, self._lib.upb_last_error(None).decode())
+        self.n_contigs = 0
+        self.n_samples = 0
+
+    def close(self):
+        if self._h:
+            self._lib.upb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc:
+            raise UpbError(rc, self._lib.upb_last_error(self._h).decode())
+
+    def set_contigs(self, sizes: Sequence[int]):
+        arr = np.ascontiguousarray(sizes, dtype=np.uint32)
+        self._check(self._lib.upb_set_contigs(self._h, arr.shape[0], arr.ctypes.data))
+        self.n_contigs = int(arr.shape[0])
+
+    def load_tags(self, n_samples: int, off: np.ndarray, pos: np.ndarray, cnt: np.ndarray):
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        pos = np.ascontiguousarray(pos, dtype=np.uint32)
+        cnt = np.ascontiguousarray(cnt, dtype=np.uint32)
+        self._check(self._lib.upb_load_tags(self._h, n_samples, off.ctypes.data, pos.ctypes.data, cnt.ctypes.data))
+        self.n_samples = n_samples
+
+    def load_tags_ptr(self, n_samples: int, off_ptr: int, pos_ptr: int, cnt_ptr: int):
+        """Same, from raw host addresses (e.g. pinned buffers owned by the caller)."""
+        self._check(self._lib.upb_load_tags(self._h, n_samples, C.c_void_p(off_ptr), C.c_void_p(pos_ptr), C.c_void_p(cnt_ptr)))
+        self.n_samples = n_samples
+
+    def load(self, data) -> None:
+        """Load a unipeak_b200.synth.TagData."""
+        self.set_contigs(data.contig_sizes)
+        self.load_tags(data.n_samples, data.off, data.pos, data.cnt)
+
+    def call_regions(self, *, bandwidth=50, region_threshold=25.0, kurtosis_threshold=50.0, corr_threshold=-1.0,
+                     hit_threshold=10.0, directional=True, control: Optional[Sequence[int]] = None,
+                     coeffs: Optional[Sequence[float]] = None, background: float, reference_order=True, **_ignored) -> Dict:
+        ctrl = np.ascontiguousarray(control if control is not None else np.zeros(self.n_samples, np.uint8), dtype=np.uint8)
+        cf = np.ascontiguousarray(coeffs if coeffs is not None else [], dtype=np.float64)
+        p = RegionParams(bandwidth, region_threshold, kurtosis_threshold, corr_threshold, hit_threshold, 1 if directional else 0,
+                         ctrl.ctypes.data_as(C.POINTER(C.c_uint8)), cf.shape[0], cf.ctypes.data_as(C.POINTER(C.c_double)),
+                         background, 1 if reference_order else 0)
+        t = RegionTable()
+        self._check(self._lib.upb_call_regions(self._h, C.byref(p), C.byref(t)))
+        try:
+            R, n = int(t.n_rows), int(t.n_samples)
+            cols = dict(buffer=_np(t.buffer, R, np.uint8), forward_label=_np(t.forward_label, R, np.uint8), dropped=_np(t.dropped, R, np.uint8),
+                        contig=_np(t.contig, R, np.uint32), left=_np(t.left, R, np.uint32), len=_np(t.len, R, np.uint32),
+                        peak=_np(t.peak, R, np.uint32), cand_index=_np(t.cand_index, R, np.uint64), peak_score=_np(t.peak_score, R, np.float64),
+                        kurtosis=_np(t.kurtosis, R, np.float64), corr=_np(t.corr, R, np.float64),
+                        counts=_np(t.counts, R * n, np.uint32).reshape(R, n))
+            rows, dropped = [], []
+            for i in range(R):
+                row = dict(forward_label=int(cols["forward_label"][i]), buffer=int(cols["buffer"][i]), contig=int(cols["contig"][i]),
+                           left=int(cols["left"][i]), len=int(cols["len"][i]), peak=int(cols["peak"][i]),
+                           peak_score=float(cols["peak_score"][i]), kurtosis=float(cols["kurtosis"][i]), corr=float(cols["corr"][i]),
+                           counts=[int(x) for x in cols["counts"][i]])
+                (dropped if cols["dropped"][i] else rows).append(row)
+            return dict(rows=rows, dropped=dropped, n_passed=int(t.n_passed), n_rejected=int(t.n_rejected),
+                        tags_in_regions=[int(t.tags_in_regions[s]) for s in range(n)], columns=cols,
+                        unit_candidates=_np(t.unit_candidates, 2 * self.n_contigs, np.uint64),
+                        unit_last_tag=_np(t.unit_last_tag, 2 * self.n_contigs, np.uint32))
+        finally:
+            self._lib.upb_free_region_table(C.byref(t))
+
+    def profile_contig(self, buffer: int, contig: int, *, bandwidth=50, region_threshold=25.0, directional=True,
+                       control: Optional[Sequence[int]] = None, background: float, **_ignored):
+        ctrl = np.ascontiguousarray(control if control is not None else np.zeros(self.n_samples, np.uint8), dtype=np.uint8)
+        p = RegionParams(bandwidth, region_threshold, 0.0, -1.0, 0.0, 1 if directional else 0, ctrl.ctypes.data_as(C.POINTER(C.c_uint8)),
+                         0, None, background, 0)
+        pr = Profile()
+        self._check(self._lib.upb_profile_contig(self._h, C.byref(p), buffer, contig, C.byref(pr)))
+        try:
+            return _np(pr.pos, int(pr.n), np.uint32), _np(pr.score, int(pr.n), np.float64)
+        finally:
+            self._lib.upb_free_profile(C.byref(pr))
+
+    def strand_shift(self, *, bandwidth=50, region_threshold=25.0, kurtosis_threshold=50.0, corr_threshold=0.3, hit_threshold=10,
+                     min_shift=25, max_shift=150, n_regions_to_test=1000, background: float) -> Dict:
+        p = ShiftParams(bandwidth, region_threshold, kurtosis_threshold, corr_threshold, hit_threshold, min_shift, max_shift,
+                        n_regions_to_test, background)
+        r = ShiftReport()
+        rc = self._lib.upb_strand_shift(self._h, C.byref(p), C.byref(r))
+        try:
+            out = dict(status=rc, n_regions_found=int(r.n_regions_found), n_regions_tested=int(r.n_regions_tested),
+                       n_tags_in_regions=int(r.n_tags_in_regions), best_shift=int(r.best_shift),
+                       shift_freq=[int(r.shift_freq[i]) for i in range(int(r.n_freq))] if r.shift_freq else [],
+                       tested=[dict(contig=int(r.tested_contig[i]), left=int(r.tested_left[i]), len=int(r.tested_len[i]),
+                                    best_shift=int(r.tested_best_shift[i]), best_corr=float(r.tested_best_corr[i]))
+                               for i in range(int(r.n_regions_tested))])
+        finally:
+            self._lib.upb_free_shift_report(C.byref(r))
+        if rc and rc != -8:
+            self._check(rc)
+        return out
+
+    def count_tags_in_regions(self, keys: Sequence[Sequence[int]], *, directional=True, extension=0) -> np.ndarray:
+        arr = (RegionKey * max(1, len(keys)))()
+        for i, (c, s, e) in enumerate(keys):
+            arr[i] = RegionKey(c, s, e)
+        out = np.zeros(max(1, len(keys) * self.n_samples), dtype=np.uint32)
+        self._check(self._lib.upb_count_tags_in_regions(self._h, 1 if directional else 0, extension, len(keys), arr, out.ctypes.data))
+        return out[:len(keys) * self.n_samples].reshape(len(keys), self.n_samples)
+
+    def stats(self) -> Dict:
+        s = Stats()
+        self._check(self._lib.upb_last_stats(self._h, C.byref(s)))
+        return dict(ms_total=float(s.ms_total), ms_kde=float(s.ms_kde), launches=int(s.launches), kde_tiles=int(s.kde_tiles),
+                    kde_hot_tiles=int(s.kde_hot_tiles), n_candidates=int(s.n_candidates), n_entries=int(s.n_entries))
