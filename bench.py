@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — genome bp/s of pooled KDE + region calling + count matrix (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c1|tiny]
+
+A step is one pass of the hot path over the resident synthetic input: upb_call_regions() — pooled
+Epanechnikov KDE, thresholding, region extraction, hit/kurtosis(/correlation) filters, regions x samples
+count matrix — ending with the region table in host memory in the reference's emission order.
+N > 1 (torchrun, one process per GPU): contigs are sharded over the ranks (strong scaling: the genome is
+fixed); NCCL carries only the per-sample tag totals (background), the tags-in-regions totals and the
+gather of the region rows to rank 0.
+
+`value`  : genome bp / step time, inputs already resident in HBM (wall clock bracketed by barrier +
+           synchronize, max over ranks).
+`e2e`    : the same through the C-ABI from pinned HOST arrays: H2D copy + index build + call + table D2H.
+`roofline`: the fused KDE kernel, algorithmic bytes (8 B per tag entry read once + 24 B per run written)
+           over its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
+`cpu_baseline` / --impl reference: the reference's own Kernel/ProfileBuffer/Region objects
+           (oracle/_ref/ref_replay, kind "reference") — or the C restatement (kind "port") when the
+           compiled reference is absent — single-threaded like the reference, on a bounded sample
+           (one contig of the same workload, same thresholds).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from unipeak_b200.synth import HG19_NAMES, HG19_SIZES, TagData  # noqa: E402
+
+WORKLOADS = {
+    # name: (description, n_samples, tags_per_sample, directional, contig sizes, names, mappable)
+    "c3": ("3SEQ pooled region calling, 16 samples x 30M tags, full hg19, with regions x experiments count matrix", 16, 30_000_000, True, HG19_SIZES, HG19_NAMES, 0),
+    "c2": ("regions -D on 2 non-directional ChIP-seq samples, full hg19, 20M tags each", 2, 20_000_000, False, HG19_SIZES, HG19_NAMES, 0),
+    "c1": ("regions on one directional 3SEQ sample, chr21 only, 1M tags, -m whole-genome", 1, 1_000_000, True, [48129895], ["chr21"], 3095693983),
+    "tiny": ("smoke-sized: 4 samples x 200k tags on 3 contigs", 4, 200_000, True, [5_000_000, 3_000_000, 1_000_000], ["cA", "cB", "cC"], 0),
+}
+# bounded CPU sample: chr21 + chr22 for the hg19 workloads.  Two contigs, not one: several directional samples on
+# a single-contig table make the reference's own merge loop assert.
+CPU_SAMPLE_CONTIGS = {"c3": [20, 21], "c2": [20, 21], "c1": [0], "tiny": [1, 2]}
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def shard_contigs(sizes, world):
+    """Longest-processing-time assignment of whole contigs to ranks (tag density is uniform in the workload)."""
+    order = sorted(range(len(sizes)), key=lambda c: -sizes[c])
+    load = [0] * world
+    owner = [0] * len(sizes)
+    for c in order:
+        r = min(range(world), key=lambda k: load[k])
+        owner[c] = r
+        load[r] += sizes[c]
+    return owner
+
+
+class ClockSampler:
+    QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx = max(mx, float(s[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def settings_from_totals(tags, n_samples, directional, mappable, genome):
+    """What src/regions.cpp:152-232 derives with default flags (no controls, no coefficients)."""
+    total = int(sum(tags))
+    background = float(total) / float(mappable or genome)
+    if directional:
+        background /= 2
+    return dict(bandwidth=50, region_threshold=25.0, kurtosis_threshold=50.0, corr_threshold=(-1.0 if directional else 0.3),
+                hit_threshold=10.0 * n_samples, directional=directional, control=np.zeros(n_samples, np.uint8), coeffs=[],
+                background=background)
+
+
+def cpu_sample(data: TagData, contigs):
+    """Bounded CPU sample: a few contigs of the same workload (all samples, both strands)."""
+    return data.subset_contigs(list(contigs))
+
+
+def run_cpu_reference(sample: TagData, st: dict, steps: int, workdir: str):
+    """Time the reference's hot path (or the C port) on the bounded sample; returns (seconds per step, kind, rows)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import refutil
+    if refutil.have_ref():
+        best, rows = None, None
+        for _ in range(max(1, steps)):
+            r = refutil.run_ref_replay_regions(sample, st, workdir)
+            best = r["seconds"] if best is None else min(best, r["seconds"])
+            rows = r
+        return best, "reference", rows
+    best, rows = None, None
+    for _ in range(max(1, steps)):
+        t0 = time.perf_counter()
+        r = refutil.oracle_regions(sample, st)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        rows = r
+    return best, "port", rows
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--samples", type=int, default=0)
+    ap.add_argument("--tags", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--seed", type=int, default=20261018)
+    args = ap.parse_args()
+
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    desc, n_samples, tags_per_sample, directional, sizes, names, mappable = WORKLOADS[args.workload]
+    n_samples = args.samples or n_samples
+    tags_per_sample = args.tags or tags_per_sample
+    genome = int(sum(sizes))
+    metric = "genome bp/s for pooled KDE+region calling"
+    config = {"workload": desc if not (args.samples or args.tags) else "%s [overridden: %d samples x %d tags]" % (desc, n_samples, tags_per_sample),
+              "samples": n_samples, "tags_per_sample": tags_per_sample, "genome_bp": genome, "bandwidth": 50,
+              "l2": "inputs (GBs of tag entries) are far larger than the 126 MB L2; no explicit flush",
+              "parallelism": "contig-sharded x%d" % world if world > 1 else "single GPU"}
+
+    import torch
+    if args.impl == "reference":
+        # the reference's own CPU implementation of the path, rank 0 only
+        if rank != 0:
+            return
+        cs = CPU_SAMPLE_CONTIGS[args.workload]
+        if torch.cuda.is_available():
+            from unipeak_b200.synth_gpu import make_synthetic_gpu
+            data = make_synthetic_gpu(sizes, n_samples, tags_per_sample, directional=directional, seed=args.seed, device="cuda:%d" % local_rank)
+        else:
+            from unipeak_b200.synth import make_synthetic
+            data = make_synthetic(sizes, n_samples, tags_per_sample, directional=directional, seed=args.seed)
+        # thresholds come from the whole workload's tag totals, exactly as in our arm
+        st = settings_from_totals([data.tags(s) for s in range(n_samples)], n_samples, directional, mappable, genome)
+        sample = cpu_sample(data, cs)
+        del data
+        with tempfile.TemporaryDirectory() as wd:
+            if args.warmup:
+                run_cpu_reference(sample, st, 1, wd)
+            secs, kind, _rows = run_cpu_reference(sample, st, args.steps, wd)
+        bp = int(sum(sizes[c] for c in cs))
+        val = bp / secs
+        line = {"impl": "reference", "metric": metric, "value": val, "unit": "bp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": val, "unit": "bp/s", "cores": 1, "kind": kind,
+                                 "sample": "contigs %s (%d bp, %d tag entries) of the workload, all samples, workload-wide thresholds; best of %d runs"
+                                           % ("+".join(names[c] for c in cs), bp, int(sample.pos.shape[0]), max(1, args.steps))},
+                "e2e": {"value": val, "unit": "bp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------------------------------------
+    # our arm
+    # ------------------------------------------------------------------------------------------------
+    import torch.distributed as dist
+    import unipeak_b200
+    from unipeak_b200.synth_gpu import make_synthetic_gpu
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    owner = shard_contigs(sizes, world)
+    mine = [c for c in range(len(sizes)) if owner[c] == rank]
+    data = make_synthetic_gpu(sizes, n_samples, tags_per_sample, directional=directional, seed=args.seed, contigs=mine, device=str(dev))
+
+    # pinned host copies (the e2e leg copies from these every step)
+    h_off = torch.from_numpy(data.off.view(np.int64)).pin_memory()
+    h_pos = torch.from_numpy(data.pos.view(np.int32)).pin_memory()
+    h_cnt = torch.from_numpy(data.cnt.view(np.int32)).pin_memory()
+    E = int(data.pos.shape[0])
+
+    # genome-wide tag totals -> background (src/regions.cpp:190-210): the one NCCL all-reduce the path needs up front
+    tags = torch.tensor([data.tags(s) for s in range(n_samples)], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(tags)
+    st = settings_from_totals(tags.cpu().tolist(), n_samples, directional, mappable, genome)
+
+    ctx = unipeak_b200.Context(local_rank)
+    ctx.set_contigs(sizes)
+
+    def load():
+        ctx.load_tags_ptr(n_samples, h_off.data_ptr(), h_pos.data_ptr(), h_cnt.data_ptr())
+
+    C = len(sizes)
+    first_last = None
+
+    def step():
+        res = ctx.call_regions(**dict(st, reference_order=(world == 1), rows=False))
+        if world == 1:
+            return res
+        # gather the canonical rows on rank 0 (NCCL), total the per-sample tags-in-regions (NCCL)
+        cols = res["columns"]
+        R = int(cols["left"].shape[0])
+        tir = torch.tensor(res["tags_in_regions"], dtype=torch.int64, device=dev)
+        dist.all_reduce(tir)
+        nrows = torch.tensor([R], dtype=torch.int64, device=dev)
+        allrows = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(allrows, nrows)
+        counts = [int(x.item()) for x in allrows]
+        rmax = max(counts + [1])
+        # one packed int64 matrix per rank: buffer, contig, left, len, peak, cand_index, kurtosis bits, corr bits, score bits, counts...
+        width = 9 + n_samples
+        pack = np.zeros((rmax, width), dtype=np.int64)
+        if R:
+            pack[:R, 0] = cols["buffer"]; pack[:R, 1] = cols["contig"]; pack[:R, 2] = cols["left"]; pack[:R, 3] = cols["len"]
+            pack[:R, 4] = cols["peak"]; pack[:R, 5] = cols["cand_index"].astype(np.int64)
+            pack[:R, 6] = cols["kurtosis"].view(np.int64); pack[:R, 7] = cols["corr"].view(np.int64); pack[:R, 8] = cols["peak_score"].view(np.int64)
+            pack[:R, 9:] = cols["counts"]
+        t = torch.from_numpy(pack).to(dev)
+        gathered = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+        dist.gather(t, gathered, dst=0)
+        uc = torch.from_numpy(res["unit_candidates"].astype(np.int64)).to(dev)
+        dist.all_reduce(uc)
+        if rank != 0:
+            return None
+        rows = np.concatenate([g.cpu().numpy()[:k] for g, k in zip(gathered, counts)], axis=0)
+        order = np.lexsort((rows[:, 2], rows[:, 1], rows[:, 0]))       # canonical: buffer, contig, left
+        return {"n_rows": int(rows.shape[0]), "rows_packed": rows[order], "tags_in_regions": tir.cpu().tolist(), "unit_candidates": uc.cpu().numpy()}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    load()
+    for _ in range(args.warmup):
+        last = step()
+    kde_ms, launches = [], 0
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            last = step()
+            s = ctx.stats()
+            kde_ms.append(s["ms_kde"]); launches += s["launches"]
+        barrier()
+        dt = time.perf_counter() - t0
+    stats = ctx.stats()
+    tmax = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dt = float(tmax.item())
+    ms_per_step = dt / args.steps * 1e3
+
+    # e2e: pinned host arrays -> device every step
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        load()
+        last = step()
+    barrier()
+    e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e.item()) / e2e_steps * 1e3
+    n_rows = int(last["columns"]["left"].shape[0]) if (world == 1 and last is not None) else (last["n_rows"] if last else 0)
+    d2h = n_rows * (41 + 4 * n_samples)
+
+    # roofline of the fused KDE kernel (rank-local numbers; every rank runs the same kernel on its shard)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
+    kde_avg_ms = float(np.mean(kde_ms)) if kde_ms else float("nan")
+    n_runs_bytes = 24 * stats["n_candidates"]
+    alg_bytes = 8 * E + n_runs_bytes
+    achieved = alg_bytes / (kde_avg_ms * 1e-3) / 1e9 if kde_avg_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "kde_kernel<directional>" if directional else "kde_kernel<nondirectional>", "achieved": achieved, "peak": peak_gbs,
+                "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kde_avg_ms, "kernel_share_of_step": kde_avg_ms / ms_per_step}
+
+    if rank == 0:
+        line = {"metric": metric, "value": genome / (ms_per_step * 1e-3), "unit": "bp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config, "clocks": clocks.summary(),
+                "e2e": {"value": genome / (e2e_ms * 1e-3), "unit": "bp/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": 8 * E + 8 * int(data.off.shape[0]), "d2h_bytes_per_step": d2h},
+                "gpu_launches": launches, "roofline": roofline,
+                "result": {"regions": n_rows, "candidates": stats["n_candidates"], "tag_entries_rank0": E, "kde_tiles": stats["kde_tiles"], "kde_hot_tiles": stats["kde_hot_tiles"],
+                           "device_ms_per_step_rank0": stats["ms_total"]}}
+        if world == 1 and not args.no_cpu:
+            cs = CPU_SAMPLE_CONTIGS[args.workload]
+            sample = cpu_sample(data, cs)
+            with tempfile.TemporaryDirectory() as wd:
+                secs, kind, ref = run_cpu_reference(sample, st, 1, wd)
+            bp = int(sum(sizes[c] for c in cs))
+            # parity spot-check on the sample: every region the CPU side finds on these contigs must equal ours
+            full = ctx.call_regions(**dict(st, reference_order=True, rows=True))
+            ours = [r for r in full["rows"] + full["dropped"] if r["contig"] in cs]
+            theirs = ref["rows"] + ref["dropped"]
+            key_o = lambda r: (cs.index(r["contig"]), r["left"], r["len"], r["peak"], tuple(r["counts"]), r["kurtosis"])
+            key_t = lambda r: (r["contig"], r["left"], r["len"], r["peak"], tuple(r["counts"]), r["kurtosis"])
+            same = sorted(key_o(r) for r in ours) == sorted(key_t(r) for r in theirs)
+            line["cpu_baseline"] = {"value": bp / secs, "unit": "bp/s", "cores": 1, "kind": kind, "seconds": secs,
+                                    "sample": "contigs %s (%d bp, %d tag entries) of the workload, all samples, workload-wide thresholds"
+                                              % ("+".join(names[c] for c in cs), bp, int(sample.pos.shape[0])),
+                                    "host_cores_available": os.cpu_count(), "rows_match_gpu": bool(same), "rows": len(theirs)}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

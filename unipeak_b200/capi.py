@@ -180,7 +180,7 @@ class Context:
 
     def call_regions(self, *, bandwidth=50, region_threshold=25.0, kurtosis_threshold=50.0, corr_threshold=-1.0,
                      hit_threshold=10.0, directional=True, control: Optional[Sequence[int]] = None,
-                     coeffs: Optional[Sequence[float]] = None, background: float, reference_order=True, **_ignored) -> Dict:
+                     coeffs: Optional[Sequence[float]] = None, background: float, reference_order=True, rows=True, **_ignored) -> Dict:
         ctrl = np.ascontiguousarray(control if control is not None else np.zeros(self.n_samples, np.uint8), dtype=np.uint8)
         cf = np.ascontiguousarray(coeffs if coeffs is not None else [], dtype=np.float64)
         p = RegionParams(bandwidth, region_threshold, kurtosis_threshold, corr_threshold, hit_threshold, 1 if directional else 0,
@@ -195,8 +195,9 @@ class Context:
                         peak=_np(t.peak, R, np.uint32), cand_index=_np(t.cand_index, R, np.uint64), peak_score=_np(t.peak_score, R, np.float64),
                         kurtosis=_np(t.kurtosis, R, np.float64), corr=_np(t.corr, R, np.float64),
                         counts=_np(t.counts, R * n, np.uint32).reshape(R, n))
+            want_rows = rows
             rows, dropped = [], []
-            for i in range(R):
+            for i in range(R if want_rows else 0):
                 row = dict(forward_label=int(cols["forward_label"][i]), buffer=int(cols["buffer"][i]), contig=int(cols["contig"][i]),
                            left=int(cols["left"][i]), len=int(cols["len"][i]), peak=int(cols["peak"][i]),
                            peak_score=float(cols["peak_score"][i]), kurtosis=float(cols["kurtosis"][i]), corr=float(cols["corr"][i]),
