@@ -339,3 +339,68 @@ def run_ref_replay_shift(data: TagData, workdir: str, *, bandwidth=50, region_th
         tested.append(dict(contig=c, left=l, len=ln, best_shift=b, best_corr=corr))
     return dict(n_regions_found=n_found, n_regions_tested=n_tested, n_tags_in_regions=n_tags, best_shift=best, shift_freq=freq,
                 tested=tested, seconds=float(proc.stdout.strip().split("=")[1]))
+
+
+# ------------------------------------------------------------------------------------------------
+# golden fixtures (tests/golden/*.npz, written by tests/golden/make_golden.py from the reference itself)
+# ------------------------------------------------------------------------------------------------
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def golden_names(kind: str) -> List[str]:
+    out = []
+    for f in sorted(os.listdir(GOLDEN_DIR)):
+        if f.endswith(".npz") and f.startswith(kind + "_"):
+            out.append(f[:-4])
+    return out
+
+
+def _f(a) -> float:
+    return float(np.asarray(a, dtype=np.uint64).view(np.float64).reshape(-1)[0])
+
+
+def load_golden(name: str):
+    """Returns (TagData, settings dict, expected dict) with doubles restored from their bit patterns."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    data = TagData(z["contig_sizes"].astype(np.uint32), int(z["n_samples"]), z["off"].astype(np.uint64), z["pos"].astype(np.uint32), z["cnt"].astype(np.uint32))
+    kind = str(z["kind"])
+    if kind == "regions":
+        st = dict(bandwidth=int(z["bandwidth"]), region_threshold=_f(z["region_threshold"]), kurtosis_threshold=_f(z["kurtosis_threshold"]),
+                  corr_threshold=_f(z["corr_threshold"]), hit_threshold=_f(z["hit_threshold"]), directional=bool(int(z["directional"])),
+                  control=z["control"].astype(np.uint8), coeffs=[float(x) for x in z["coeffs"].view(np.float64)], background=_f(z["background"]))
+
+        def rows(prefix):
+            k = z[prefix + "left"].shape[0]
+            return [dict(forward_label=int(z[prefix + "forward_label"][i]), contig=int(z[prefix + "contig"][i]), left=int(z[prefix + "left"][i]),
+                         len=int(z[prefix + "len"][i]), peak=int(z[prefix + "peak"][i]), peak_score=float(z[prefix + "peak_score"].view(np.float64)[i]),
+                         kurtosis=float(z[prefix + "kurtosis"].view(np.float64)[i]), corr=float(z[prefix + "corr"].view(np.float64)[i]),
+                         counts=[int(x) for x in z[prefix + "counts"][i]]) for i in range(k)]
+        want = dict(rows=rows("row_"), dropped=rows("drop_"), n_passed=int(z["n_passed"]), n_rejected=int(z["n_rejected"]),
+                    tags_in_regions=[int(x) for x in z["tags_in_regions"]])
+        return data, st, want
+    p = {}
+    for k in z.files:
+        if k.startswith("p_"):
+            v = z[k]
+            p[k[2:]] = _f(v) if v.dtype == np.uint64 else int(v)
+    want = dict(n_regions_found=int(z["n_regions_found"]), n_regions_tested=int(z["n_regions_tested"]), n_tags_in_regions=int(z["n_tags_in_regions"]),
+                best_shift=int(z["best_shift"]), shift_freq=[int(x) for x in z["shift_freq"]], background=_f(z["background"]),
+                tested=[dict(contig=int(z["tested_contig"][i]), left=int(z["tested_left"][i]), len=int(z["tested_len"][i]),
+                             best_shift=int(z["tested_best_shift"][i]), best_corr=float(z["tested_best_corr"].view(np.float64)[i]))
+                        for i in range(z["tested_contig"].shape[0])])
+    return data, p, want
+
+
+def same_fp(a: float, b: float) -> bool:
+    return a == b or (math.isnan(a) and math.isnan(b))
+
+
+def assert_rows_equal(got, want, what, fp_keys=("peak_score", "kurtosis", "corr")):
+    """Bit-exact comparison of region rows (tolerance 0 on the FP64 fields too).  The reference computes
+    strandCorr only when asked; rows whose expected corr is NaN are compared on the other fields."""
+    assert len(got) == len(want), "%s: %d rows, expected %d" % (what, len(got), len(want))
+    for i, (g, w) in enumerate(zip(got, want)):
+        for k in ("forward_label", "contig", "left", "len", "peak", "counts"):
+            assert g[k] == w[k], "%s row %d field %s: got %r, expected %r (%r)" % (what, i, k, g[k], w[k], w)
+        for k in fp_keys:
+            assert same_fp(g[k], w[k]), "%s row %d field %s: got %r, expected %r" % (what, i, k, g[k], w[k])
