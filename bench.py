@@ -13,7 +13,7 @@ gather of the region rows to rank 0.
 `value`  : genome bp / step time, inputs already resident in HBM (wall clock bracketed by barrier +
            synchronize, max over ranks).
 `e2e`    : the same through the C-ABI from pinned HOST arrays: H2D copy + index build + call + table D2H.
-`roofline`: the fused KDE kernel, algorithmic bytes (8 B per tag entry read once + 24 B per run written)
+`roofline`: the fused span kernel, algorithmic bytes (8 B per tag entry read once + 40+4n B per candidate written)
            over its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
 `cpu_baseline` / --impl reference: the reference's own Kernel/ProfileBuffer/Region objects
            (oracle/_ref/ref_replay, kind "reference") — or the C restatement (kind "port") when the
@@ -243,13 +243,13 @@ def main():
     first_last = None
 
     def step():
-        res = ctx.call_regions(**dict(st, reference_order=(world == 1), rows=False))
+        res = ctx.call_regions_view(**dict(st, reference_order=(world == 1)))
         if world == 1:
             return res
         # gather the canonical rows on rank 0 (NCCL), total the per-sample tags-in-regions (NCCL)
-        cols = res["columns"]
-        R = int(cols["left"].shape[0])
-        tir = torch.tensor(res["tags_in_regions"], dtype=torch.int64, device=dev)
+        cols = res
+        R = int(res["n_rows"])
+        tir = torch.from_numpy(res["tags_in_regions"].astype(np.int64)).to(dev)
         dist.all_reduce(tir)
         nrows = torch.tensor([R], dtype=torch.int64, device=dev)
         allrows = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
@@ -312,7 +312,7 @@ def main():
     if world > 1:
         dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e.item()) / e2e_steps * 1e3
-    n_rows = int(last["columns"]["left"].shape[0]) if (world == 1 and last is not None) else (last["n_rows"] if last else 0)
+    n_rows = int(last["n_rows"]) if last else 0
     d2h = n_rows * (41 + 4 * n_samples)
 
     # roofline of the fused KDE kernel (rank-local numbers; every rank runs the same kernel on its shard)
@@ -323,10 +323,10 @@ def main():
         pass
     peak_gbs, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
     kde_avg_ms = float(np.mean(kde_ms)) if kde_ms else float("nan")
-    n_runs_bytes = 24 * stats["n_candidates"]
+    n_runs_bytes = (40 + 4 * n_samples) * stats["n_candidates"]     # run record + kurtosis + per-sample hits
     alg_bytes = 8 * E + n_runs_bytes
     achieved = alg_bytes / (kde_avg_ms * 1e-3) / 1e9 if kde_avg_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "kde_kernel<directional>" if directional else "kde_kernel<nondirectional>", "achieved": achieved, "peak": peak_gbs,
+    roofline = {"bound": "hbm", "kernel": "span_kernel<directional>" if directional else "span_kernel<nondirectional>", "achieved": achieved, "peak": peak_gbs,
                 "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kde_avg_ms, "kernel_share_of_step": kde_avg_ms / ms_per_step}
 
@@ -336,7 +336,8 @@ def main():
                 "config": config, "clocks": clocks.summary(),
                 "e2e": {"value": genome / (e2e_ms * 1e-3), "unit": "bp/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": 8 * E + 8 * int(data.off.shape[0]), "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "roofline": roofline,
-                "result": {"regions": n_rows, "candidates": stats["n_candidates"], "tag_entries_rank0": E, "kde_tiles": stats["kde_tiles"], "kde_hot_tiles": stats["kde_hot_tiles"],
+                "result": {"regions": n_rows, "candidates": stats["n_candidates"], "tag_entries_rank0": E, "spans": stats["kde_tiles"], "pieces": stats["kde_hot_tiles"],
+                           "hot_blocks": stats["hot_blocks"], "exact_evals": stats["exact_evals"], "stitched": stats["n_stitched"],
                            "device_ms_per_step_rank0": stats["ms_total"]}}
         if world == 1 and not args.no_cpu:
             cs = CPU_SAMPLE_CONTIGS[args.workload]
@@ -345,6 +346,7 @@ def main():
                 secs, kind, ref = run_cpu_reference(sample, st, 1, wd)
             bp = int(sum(sizes[c] for c in cs))
             # parity spot-check on the sample: every region the CPU side finds on these contigs must equal ours
+            ctx.release_view()
             full = ctx.call_regions(**dict(st, reference_order=True, rows=True))
             ours = [r for r in full["rows"] + full["dropped"] if r["contig"] in cs]
             theirs = ref["rows"] + ref["dropped"]

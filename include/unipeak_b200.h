@@ -87,7 +87,9 @@ typedef struct {
 } upb_region_params;
 
 /* One row per accepted region == one Region the reference pushes into regionsOut (misc/peakcall.cpp:45)
- * and FormatOutStream::write(Region) prints (misc/format.cpp:1141-1162).  Library-allocated. */
+ * and FormatOutStream::write(Region) prints (misc/format.cpp:1141-1162).  Library-allocated: every array
+ * points into one pinned host slab the device wrote directly; upb_free_region_table hands the slab back to
+ * the context's pool, so free the table before destroying the context. */
 typedef struct {
   uint64_t n_rows;
   uint32_t n_samples;
@@ -98,6 +100,7 @@ typedef struct {
   uint32_t* left;               /* Region::left */
   uint32_t* len;                /* Region::counts->size() */
   uint32_t* peak;               /* Region::peakPos */
+  uint32_t* hit_sum;            /* nonControlSum of misc/peakcall.cpp:36-40 (== Region::sum() when there are no controls) */
   uint64_t* cand_index;         /* ordinal of this region among ALL candidate regions of its (buffer, contig) */
   double* peak_score;           /* Region::peakScore */
   double* kurtosis;             /* Region::posKurtosis() */
@@ -108,6 +111,9 @@ typedef struct {
   uint64_t* tags_in_regions;    /* [n_samples] ProfileBuffer::nTagsInRegions() */
   uint64_t* unit_candidates;    /* [2 * n_contigs] candidate regions per (buffer, contig) */
   uint32_t* unit_last_tag;      /* [2 * n_contigs] last add() position per (buffer, contig), 0 if none */
+  void* _slab;                  /* private: the slab, its size and its owner */
+  uint64_t _slab_bytes;
+  void* _ctx;
 } upb_region_table;
 
 int upb_call_regions (upb_ctx* ctx, const upb_region_params* params, upb_region_table* out);
@@ -187,12 +193,16 @@ int upb_kernel_taps (uint32_t bandwidth, double sum, double* taps_out);
 /* Device-side timings (CUDA events on the context's stream) and launch counts of the last call. */
 typedef struct {
   float ms_total;               /* first kernel start -> last kernel end */
-  float ms_kde;                 /* the fused pool + KDE + threshold + run-extraction kernel */
+  float ms_kde;                 /* the fused pool + KDE + threshold + region-statistics kernel (span_kernel) */
   uint32_t launches;            /* kernels launched by the last call */
-  uint64_t kde_tiles;           /* tiles the KDE kernel visited */
-  uint64_t kde_hot_tiles;       /* tiles that needed exact evaluation */
-  uint64_t n_candidates;
+  uint64_t kde_tiles;           /* spans (16384 positions of one buffer x contig) the kernel visited */
+  uint64_t kde_hot_tiles;       /* pieces (groups of <= 16 hot 32-position blocks) evaluated position by position */
+  uint64_t n_candidates;        /* candidate regions == Region objects the reference would have built */
   uint64_t n_entries;           /* tag entries resident */
+  uint64_t hot_blocks;          /* 32-position blocks that could reach the threshold */
+  uint64_t exact_evals;         /* positions evaluated in the reference's own summation order */
+  uint64_t spans_with_tags;
+  uint64_t n_stitched;          /* candidates cut by a piece / span boundary (statistics by the generic kernels) */
 } upb_stats;
 int upb_last_stats (const upb_ctx* ctx, upb_stats* out);
 

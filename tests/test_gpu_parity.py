@@ -172,3 +172,60 @@ def test_strand_shift_no_regions(gpu_ctx):
     gpu_ctx.load(d)
     got = gpu_ctx.strand_shift(background=want["background"])
     assert want["status"] == 3 and got["status"] == -8
+
+
+# ---- golden fixtures: outputs of the unmodified reference itself (tests/golden/make_golden.py) -------------------
+from refutil import golden_names, load_golden  # noqa: E402
+
+NOT_YET = {"regions_coeffs_q3": -11, "regions_left_edge_q2": -6}   # fixtures the CUDA path still refuses (error code asserted)
+
+
+@pytest.mark.parametrize("name", golden_names("regions"))
+def test_golden_regions(gpu_ctx, name):
+    import unipeak_b200
+    data, st, want = load_golden(name)
+    gpu_ctx.load(data)
+    if name in NOT_YET:
+        with pytest.raises(unipeak_b200.UpbError) as ei:
+            gpu_ctx.call_regions(**st)
+        assert ei.value.code == NOT_YET[name]
+        return
+    got = gpu_ctx.call_regions(**st)
+    # ref_replay evaluates strandCorr() for every row it writes; the library only where the reference's driver would
+    fp = ("peak_score", "kurtosis", "corr") if not st["directional"] else ("peak_score", "kurtosis")
+    for g, w, what in ((got["rows"], want["rows"], "written"), (got["dropped"], want["dropped"], "dropped")):
+        assert len(g) == len(w), "%s %s: %d rows, reference %d" % (name, what, len(g), len(w))
+        for i, (a, b) in enumerate(zip(g, w)):
+            for k in INT_KEYS:
+                if k == "buffer":
+                    continue
+                assert a[k] == b[k], "%s %s row %d %s: got %r, reference %r" % (name, what, i, k, a[k], b[k])
+            for k in fp:
+                assert same_fp(a[k], b[k]), "%s %s row %d %s: got %r, reference %r" % (name, what, i, k, a[k], b[k])
+    assert got["n_passed"] == want["n_passed"] and got["n_rejected"] == want["n_rejected"]
+    assert got["tags_in_regions"] == want["tags_in_regions"]
+
+
+@pytest.mark.parametrize("name", golden_names("shift"))
+def test_golden_shift(gpu_ctx, name):
+    data, p, want = load_golden(name)
+    gpu_ctx.load(data)
+    got = gpu_ctx.strand_shift(background=want["background"], **p)
+    assert got["status"] == 0
+    for k in ("n_regions_found", "n_regions_tested", "n_tags_in_regions", "best_shift", "shift_freq"):
+        assert got[k] == want[k], k
+    assert got["tested"] == want["tested"]
+
+
+def test_fast_classification_is_what_runs(gpu_ctx):
+    # the moment form decides almost every position; the reference-order sum runs only near the threshold and at peaks
+    d = make_synthetic([2000000, 500000], 4, 150000, directional=True, seed=17, peak_spacing=8000)
+    st = region_settings(d)
+    gpu_ctx.load(d)
+    got = gpu_ctx.call_regions(**st)
+    s = gpu_ctx.stats()
+    assert len(got["rows"]) > 50
+    assert s["hot_blocks"] > 0 and s["kde_hot_tiles"] > 0
+    assert s["exact_evals"] < 32 * s["hot_blocks"] / 4, s
+    want = oracle_regions(d, st)
+    assert_rows_equal(got["rows"], want["rows"], "written")

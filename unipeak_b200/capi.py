@@ -38,10 +38,10 @@ class RegionTable(C.Structure):
     _fields_ = [("n_rows", C.c_uint64), ("n_samples", C.c_uint32), ("buffer", C.POINTER(C.c_uint8)),
                 ("forward_label", C.POINTER(C.c_uint8)), ("dropped", C.POINTER(C.c_uint8)), ("contig", C.POINTER(C.c_uint32)),
                 ("left", C.POINTER(C.c_uint32)), ("len", C.POINTER(C.c_uint32)), ("peak", C.POINTER(C.c_uint32)),
-                ("cand_index", C.POINTER(C.c_uint64)), ("peak_score", C.POINTER(C.c_double)), ("kurtosis", C.POINTER(C.c_double)),
+                ("hit_sum", C.POINTER(C.c_uint32)), ("cand_index", C.POINTER(C.c_uint64)), ("peak_score", C.POINTER(C.c_double)), ("kurtosis", C.POINTER(C.c_double)),
                 ("corr", C.POINTER(C.c_double)), ("counts", C.POINTER(C.c_uint32)), ("n_passed", C.c_uint64),
                 ("n_rejected", C.c_uint64), ("tags_in_regions", C.POINTER(C.c_uint64)), ("unit_candidates", C.POINTER(C.c_uint64)),
-                ("unit_last_tag", C.POINTER(C.c_uint32))]
+                ("unit_last_tag", C.POINTER(C.c_uint32)), ("_slab", C.c_void_p), ("_slab_bytes", C.c_uint64), ("_ctx", C.c_void_p)]
 
 
 class Profile(C.Structure):
@@ -67,7 +67,8 @@ class RegionKey(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("ms_total", C.c_float), ("ms_kde", C.c_float), ("launches", C.c_uint32), ("kde_tiles", C.c_uint64),
-                ("kde_hot_tiles", C.c_uint64), ("n_candidates", C.c_uint64), ("n_entries", C.c_uint64)]
+                ("kde_hot_tiles", C.c_uint64), ("n_candidates", C.c_uint64), ("n_entries", C.c_uint64), ("hot_blocks", C.c_uint64),
+                ("exact_evals", C.c_uint64), ("spans_with_tags", C.c_uint64), ("n_stitched", C.c_uint64)]
 
 
 EXPORTS = [
@@ -143,6 +144,7 @@ class Context:
 
     def close(self):
         if self._h:
+            self.release_view()
             self._lib.upb_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -178,23 +180,62 @@ class Context:
         self.set_contigs(data.contig_sizes)
         self.load_tags(data.n_samples, data.off, data.pos, data.cnt)
 
-    def call_regions(self, *, bandwidth=50, region_threshold=25.0, kurtosis_threshold=50.0, corr_threshold=-1.0,
-                     hit_threshold=10.0, directional=True, control: Optional[Sequence[int]] = None,
-                     coeffs: Optional[Sequence[float]] = None, background: float, reference_order=True, rows=True, **_ignored) -> Dict:
+    def _region_params(self, bandwidth, region_threshold, kurtosis_threshold, corr_threshold, hit_threshold, directional, control, coeffs,
+                       background, reference_order):
         ctrl = np.ascontiguousarray(control if control is not None else np.zeros(self.n_samples, np.uint8), dtype=np.uint8)
         cf = np.ascontiguousarray(coeffs if coeffs is not None else [], dtype=np.float64)
         p = RegionParams(bandwidth, region_threshold, kurtosis_threshold, corr_threshold, hit_threshold, 1 if directional else 0,
                          ctrl.ctypes.data_as(C.POINTER(C.c_uint8)), cf.shape[0], cf.ctypes.data_as(C.POINTER(C.c_double)),
                          background, 1 if reference_order else 0)
+        return p, (ctrl, cf)
+
+    @staticmethod
+    def _views(t, n_contigs):
+        """numpy views (no copies) of the table's columns; valid until the table is freed."""
+        R, n = int(t.n_rows), int(t.n_samples)
+
+        def v(ptr, count, dtype):
+            if count == 0:
+                return np.zeros(0, dtype=dtype)
+            return np.ctypeslib.as_array(ptr, shape=(count,)).view(dtype)
+        return dict(buffer=v(t.buffer, R, np.uint8), forward_label=v(t.forward_label, R, np.uint8), dropped=v(t.dropped, R, np.uint8),
+                    contig=v(t.contig, R, np.uint32), left=v(t.left, R, np.uint32), len=v(t.len, R, np.uint32), peak=v(t.peak, R, np.uint32),
+                    hit_sum=v(t.hit_sum, R, np.uint32), cand_index=v(t.cand_index, R, np.uint64), peak_score=v(t.peak_score, R, np.float64),
+                    kurtosis=v(t.kurtosis, R, np.float64), corr=v(t.corr, R, np.float64), counts=v(t.counts, R * n, np.uint32).reshape(R, n),
+                    tags_in_regions=v(t.tags_in_regions, n, np.uint64), unit_candidates=v(t.unit_candidates, 2 * n_contigs, np.uint64),
+                    unit_last_tag=v(t.unit_last_tag, 2 * n_contigs, np.uint32))
+
+    def call_regions_view(self, *, bandwidth=50, region_threshold=25.0, kurtosis_threshold=50.0, corr_threshold=-1.0, hit_threshold=10.0,
+                          directional=True, control: Optional[Sequence[int]] = None, coeffs: Optional[Sequence[float]] = None,
+                          background: float, reference_order=True, **_ignored) -> Dict:
+        """upb_call_regions without any Python-side copy: the returned arrays are views of the library's pinned
+        result slab and stay valid until the next call_regions_view / close on this context."""
+        self.release_view()
+        p, keep = self._region_params(bandwidth, region_threshold, kurtosis_threshold, corr_threshold, hit_threshold, directional, control,
+                                      coeffs, background, reference_order)
+        t = RegionTable()
+        self._check(self._lib.upb_call_regions(self._h, C.byref(p), C.byref(t)))
+        self._view_table = t
+        out = self._views(t, self.n_contigs)
+        out.update(n_rows=int(t.n_rows), n_passed=int(t.n_passed), n_rejected=int(t.n_rejected))
+        return out
+
+    def release_view(self):
+        t = getattr(self, "_view_table", None)
+        if t is not None:
+            self._lib.upb_free_region_table(C.byref(t))
+            self._view_table = None
+
+    def call_regions(self, *, bandwidth=50, region_threshold=25.0, kurtosis_threshold=50.0, corr_threshold=-1.0,
+                     hit_threshold=10.0, directional=True, control: Optional[Sequence[int]] = None,
+                     coeffs: Optional[Sequence[float]] = None, background: float, reference_order=True, rows=True, **_ignored) -> Dict:
+        p, keep = self._region_params(bandwidth, region_threshold, kurtosis_threshold, corr_threshold, hit_threshold, directional, control,
+                                      coeffs, background, reference_order)
         t = RegionTable()
         self._check(self._lib.upb_call_regions(self._h, C.byref(p), C.byref(t)))
         try:
             R, n = int(t.n_rows), int(t.n_samples)
-            cols = dict(buffer=_np(t.buffer, R, np.uint8), forward_label=_np(t.forward_label, R, np.uint8), dropped=_np(t.dropped, R, np.uint8),
-                        contig=_np(t.contig, R, np.uint32), left=_np(t.left, R, np.uint32), len=_np(t.len, R, np.uint32),
-                        peak=_np(t.peak, R, np.uint32), cand_index=_np(t.cand_index, R, np.uint64), peak_score=_np(t.peak_score, R, np.float64),
-                        kurtosis=_np(t.kurtosis, R, np.float64), corr=_np(t.corr, R, np.float64),
-                        counts=_np(t.counts, R * n, np.uint32).reshape(R, n))
+            cols = {k: np.array(v, copy=True) for k, v in self._views(t, self.n_contigs).items()}
             want_rows = rows
             rows, dropped = [], []
             for i in range(R if want_rows else 0):
@@ -204,9 +245,8 @@ class Context:
                            counts=[int(x) for x in cols["counts"][i]])
                 (dropped if cols["dropped"][i] else rows).append(row)
             return dict(rows=rows, dropped=dropped, n_passed=int(t.n_passed), n_rejected=int(t.n_rejected),
-                        tags_in_regions=[int(t.tags_in_regions[s]) for s in range(n)], columns=cols,
-                        unit_candidates=_np(t.unit_candidates, 2 * self.n_contigs, np.uint64),
-                        unit_last_tag=_np(t.unit_last_tag, 2 * self.n_contigs, np.uint32))
+                        tags_in_regions=[int(x) for x in cols["tags_in_regions"]], columns=cols,
+                        unit_candidates=cols["unit_candidates"], unit_last_tag=cols["unit_last_tag"])
         finally:
             self._lib.upb_free_region_table(C.byref(t))
 
@@ -253,4 +293,6 @@ class Context:
         s = Stats()
         self._check(self._lib.upb_last_stats(self._h, C.byref(s)))
         return dict(ms_total=float(s.ms_total), ms_kde=float(s.ms_kde), launches=int(s.launches), kde_tiles=int(s.kde_tiles),
-                    kde_hot_tiles=int(s.kde_hot_tiles), n_candidates=int(s.n_candidates), n_entries=int(s.n_entries))
+                    kde_hot_tiles=int(s.kde_hot_tiles), n_candidates=int(s.n_candidates), n_entries=int(s.n_entries),
+                    hot_blocks=int(s.hot_blocks), exact_evals=int(s.exact_evals), spans_with_tags=int(s.spans_with_tags),
+                    n_stitched=int(s.n_stitched))

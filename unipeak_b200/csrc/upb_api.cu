@@ -5,12 +5,14 @@
 // result tables (src/regions.cpp, src/strand_shift.cpp, src/tags_in_regions.cpp drivers).
 #include "../../include/unipeak_b200.h"
 #include "upb_device.cuh"
+#include "upb_span.cuh"
 
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -24,6 +26,8 @@ struct DevBuf {
   size_t cap = 0;
   template <class T> T* as () const { return (T*)p; }
 };
+
+struct HostSlab { void* p = nullptr; size_t cap = 0; };
 
 struct upb_ctx {
   int device = 0;
@@ -41,12 +45,10 @@ struct upb_ctx {
   bool loaded = false;
   std::vector<uint64_t> off;            // host copy
   std::vector<uint32_t> firstPos, lastPos;   // [(s*2+d)*C + c], 0 if empty
-  DevBuf d_pos, d_cnt, d_cntEff, d_off, d_segStart, d_tidx, d_tidxBase, d_sizes, d_nTilesIdx;
-  // scratch (grow-only)
-  DevBuf d_units, d_taps, d_src, d_control, d_small, d_runs, d_tileBase, d_tileCount, d_tileOrd, d_scanPartial,
-         d_ordRuns, d_ordUnit, d_head, d_headScan, d_cand, d_pass, d_passScan, d_list1, d_counts, d_offsum, d_kurt,
-         d_pass2, d_dUnit, d_dLeft, d_dLen, d_dChunks, d_dOff, d_dChunkStart, d_F, d_R, d_corr, d_candOut, d_bestShift, d_bestCorr,
-         d_pass2Scan, d_list2;
+  DevBuf d_pos, d_cnt, d_cntEff, d_off, d_segStart, d_tidx, d_tidxBase, d_sizes, d_nTilesIdx, d_small;
+  std::map<std::string, DevBuf> scratch;     // grow-only device scratch, by name
+  unsigned char* h_small = nullptr;          // 4 KB of pinned host memory for small read-backs
+  std::vector<HostSlab> slabPool;            // pinned host slabs of freed region tables, reused by the next call
   upb_stats stats;
   std::vector<uint8_t> lastControl;     // control set cntEff was built for
   bool cntEffValid = false;
@@ -82,6 +84,8 @@ extern "C" int upb_device_count (void) {
   return n;
 }
 
+extern "C" void upb_destroy (upb_ctx* ctx);
+
 extern "C" int upb_create (int device, upb_ctx** out) {
   if (!out) return fail(nullptr, UPB_ERR_BAD_ARG, "upb_create: out is NULL");
   *out = nullptr;
@@ -97,6 +101,7 @@ extern "C" int upb_create (int device, upb_ctx** out) {
   ctx->smCount = prop.multiProcessorCount;
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return fail(nullptr, UPB_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
   for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
+  if ((e = cudaMallocHost((void**)&ctx->h_small, 4096)) != cudaSuccess) { upb_destroy(ctx); return fail(nullptr, UPB_ERR_NOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e)); }
   memset(&ctx->stats, 0, sizeof ctx->stats);
   *out = ctx;
   return UPB_OK;
@@ -106,12 +111,11 @@ extern "C" void upb_destroy (upb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   DevBuf* all[] = {&ctx->d_pos, &ctx->d_cnt, &ctx->d_cntEff, &ctx->d_off, &ctx->d_segStart, &ctx->d_tidx, &ctx->d_tidxBase, &ctx->d_sizes,
-    &ctx->d_nTilesIdx, &ctx->d_units, &ctx->d_taps, &ctx->d_src, &ctx->d_control, &ctx->d_small, &ctx->d_runs, &ctx->d_tileBase, &ctx->d_tileCount,
-    &ctx->d_tileOrd, &ctx->d_scanPartial, &ctx->d_ordRuns, &ctx->d_ordUnit, &ctx->d_head, &ctx->d_headScan, &ctx->d_cand, &ctx->d_pass,
-    &ctx->d_passScan, &ctx->d_list1, &ctx->d_counts, &ctx->d_offsum, &ctx->d_kurt, &ctx->d_pass2, &ctx->d_dUnit, &ctx->d_dLeft, &ctx->d_dLen,
-    &ctx->d_dChunks, &ctx->d_dOff, &ctx->d_dChunkStart, &ctx->d_F, &ctx->d_R, &ctx->d_corr, &ctx->d_candOut, &ctx->d_bestShift, &ctx->d_bestCorr,
-    &ctx->d_pass2Scan, &ctx->d_list2};
+    &ctx->d_nTilesIdx, &ctx->d_small};
   for (DevBuf* b : all) release(*b);
+  for (auto& kv : ctx->scratch) release(kv.second);
+  for (HostSlab& h : ctx->slabPool) if (h.p) cudaFreeHost(h.p);
+  if (ctx->h_small) cudaFreeHost(ctx->h_small);
   for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -277,10 +281,11 @@ extern "C" int upb_load_tags (upb_ctx* ctx, uint32_t n_samples, const uint64_t* 
 // ------------------------------------------------------------------------------------------------
 // device-wide exclusive scan (uint32 in, uint64 out); total -> *d_total
 // ------------------------------------------------------------------------------------------------
+#define SCR(name, T, count) ({ DevBuf& b__ = ctx->scratch[name]; int r__ = ensure(ctx, b__, (size_t)(count) * sizeof(T) + 16); if (r__) return r__; (T*)b__.p; })
+
 static int scan_u32 (upb_ctx* ctx, const uint32_t* d_in, uint64_t n, unsigned long long* d_out, unsigned long long* d_total, uint32_t* launches) {
   const uint32_t nBlocks = (uint32_t)((n + SCAN_BLOCK - 1) / SCAN_BLOCK);
-  ENSURE(ctx->d_scanPartial, ((size_t)nBlocks + 1) * 8);
-  unsigned long long* part = ctx->d_scanPartial.as<unsigned long long>();
+  unsigned long long* part = SCR("scanPartial", unsigned long long, (size_t)nBlocks + 1);
   if (nBlocks == 0) { CU(cudaMemsetAsync(d_total, 0, 8, ctx->stream)); return UPB_OK; }
   scan_partial_kernel<<<nBlocks, SCAN_THREADS, 0, ctx->stream>>>(d_in, n, part);
   scan_top_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(part, nBlocks, d_total);
@@ -293,13 +298,6 @@ static int scan_u32 (upb_ctx* ctx, const uint32_t* d_in, uint64_t n, unsigned lo
 // ------------------------------------------------------------------------------------------------
 // the region pipeline shared by bin/regions and bin/strand_shift
 // ------------------------------------------------------------------------------------------------
-struct HostRegion {
-  uint32_t unit, buffer, contig, left, len, peak, wsum;
-  uint64_t candIndex;
-  double score, kurt, corr;
-  std::vector<uint32_t> counts;
-};
-
 struct PipeCfg {
   uint32_t bw;
   double thr, kurtThr, corrThr, hitThr, background;
@@ -308,12 +306,61 @@ struct PipeCfg {
   const uint8_t* control;            // may be NULL
 };
 
+// column layout of one result slab (device copy and pinned host copy share it)
+struct SlabLayout {
+  size_t oContig, oLeft, oLen, oPeak, oWsum, oCandIndex, oPeakScore, oKurt, oCorr, oCounts, oBuffer, devBytes;
+  size_t oLabel, oDropped, oTags, oUnitCand, oUnitLast, totalBytes;   // host-only tail
+};
+
+static SlabLayout slab_layout (size_t R, uint32_t n, uint32_t C) {
+  SlabLayout L;
+  const size_t Rp = (R + 7) & ~(size_t)7;                            // keeps every column 8-byte aligned
+  size_t o = 0;
+  L.oCandIndex = o; o += Rp * 8;
+  L.oPeakScore = o; o += Rp * 8;
+  L.oKurt = o;      o += Rp * 8;
+  L.oCorr = o;      o += Rp * 8;
+  L.oContig = o;    o += Rp * 4;
+  L.oLeft = o;      o += Rp * 4;
+  L.oLen = o;       o += Rp * 4;
+  L.oPeak = o;      o += Rp * 4;
+  L.oWsum = o;      o += Rp * 4;
+  L.oCounts = o;    o += ((R * n + 7) & ~(size_t)7) * 4;
+  L.oBuffer = o;    o += Rp;
+  L.devBytes = o;
+  L.oLabel = o;     o += Rp;
+  L.oDropped = o;   o += Rp;
+  L.oTags = o;      o += (size_t)n * 8;
+  L.oUnitCand = o;  o += 2 * (size_t)C * 8;
+  L.oUnitLast = o;  o += ((2 * (size_t)C + 1) & ~(size_t)1) * 4;
+  L.totalBytes = o + 64;
+  return L;
+}
+
 struct PipeOut {
   std::vector<Unit> units;
-  std::vector<HostRegion> regions;   // accepted, canonical order
   std::vector<uint64_t> unitCand;    // [nUnits]
   uint64_t nCand = 0;
+  uint64_t R = 0;                    // accepted regions, canonical order (buffer, contig, left)
+  HostSlab slab;                     // pinned; columns per `layout`
+  SlabLayout layout;
+  template <class T> T* col (size_t off) const { return (T*)((unsigned char*)slab.p + off); }
 };
+
+static int acquire_slab (upb_ctx* ctx, size_t bytes, HostSlab& out) {
+  size_t best = (size_t)-1;
+  for (size_t i = 0; i < ctx->slabPool.size(); ++i)
+    if (ctx->slabPool[i].cap >= bytes && (best == (size_t)-1 || ctx->slabPool[i].cap < ctx->slabPool[best].cap)) best = i;
+  if (best != (size_t)-1) { out = ctx->slabPool[best]; ctx->slabPool.erase(ctx->slabPool.begin() + best); return UPB_OK; }
+  // drop the smaller ones: a pool that only ever grows would pin memory for ever
+  for (HostSlab& h : ctx->slabPool) if (h.p) cudaFreeHost(h.p);
+  ctx->slabPool.clear();
+  const size_t want = bytes + bytes / 4 + 4096;
+  cudaError_t e = cudaMallocHost(&out.p, want);
+  if (e != cudaSuccess) { out.p = nullptr; out.cap = 0; return fail(ctx, UPB_ERR_NOMEM, std::string("cudaMallocHost(") + std::to_string(want) + "): " + cudaGetErrorString(e)); }
+  out.cap = want;
+  return UPB_OK;
+}
 
 static int check_left_edge (upb_ctx* ctx, uint32_t bw) {
   // every add() call moves the window, control samples included (src/regions.cpp:356-359)
@@ -324,82 +371,22 @@ static int check_left_edge (upb_ctx* ctx, uint32_t bw) {
   return UPB_OK;
 }
 
-static int launch_kde (upb_ctx* ctx, KdeArgs& ka, bool nondir, bool dump, uint32_t totalWork, uint32_t* launches) {
-  const KdeSmem L = kde_smem_layout(ka.bw, ka.nSrc * (nondir ? 2u : 1u), nondir);
-  const size_t smem = L.total;
-  if (smem > 227 * 1024) return fail(ctx, UPB_ERR_UNSUPPORTED, "bandwidth / sample count need more shared memory than one SM has");
-  void (*kern)(const KdeArgs) = nullptr;
-  if (nondir) kern = dump ? kde_kernel<true, true> : kde_kernel<true, false>;
-  else kern = dump ? kde_kernel<false, true> : kde_kernel<false, false>;
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int perSm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, KDE_THREADS, smem));
-  if (perSm < 1) perSm = 1;
-  uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)ctx->smCount * perSm, std::max<uint32_t>(totalWork, 1u));
-  kern<<<grid, KDE_THREADS, smem, ctx->stream>>>(ka);
-  CU(cudaGetLastError());
-  *launches += 1;
-  return UPB_OK;
-}
-
-// dump exact F/R densities for `n` position ranges (device descriptor arrays already filled) and, if asked,
-// strandCorr(shift) for shifts 0..nShifts-1
-static int dump_and_corr (upb_ctx* ctx, KdeArgs base, bool nondir, uint32_t n, uint32_t nShifts, uint32_t* launches,
-                          std::vector<double>* corrOut /* n*nShifts */) {
-  // chunk prefix and scratch offsets
-  ENSURE(ctx->d_dOff, ((size_t)n + 1) * 8);
-  ENSURE(ctx->d_dChunkStart, ((size_t)n + 1) * 8);
-  unsigned long long* d_tot = ctx->d_small.as<unsigned long long>() + 8;
-  int r;
-  if ((r = scan_u32(ctx, ctx->d_dLen.as<uint32_t>(), n, ctx->d_dOff.as<unsigned long long>(), d_tot, launches))) return r;
-  if ((r = scan_u32(ctx, ctx->d_dChunks.as<uint32_t>(), n, ctx->d_dChunkStart.as<unsigned long long>(), d_tot + 1, launches))) return r;
-  unsigned long long tot[2];
-  CU(cudaMemcpyAsync(tot, d_tot, 16, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
-  // append the grand totals as entry n of the two prefix arrays
-  CU(cudaMemcpyAsync(ctx->d_dOff.as<unsigned long long>() + n, &tot[0], 8, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->d_dChunkStart.as<unsigned long long>() + n, &tot[1], 8, cudaMemcpyHostToDevice, ctx->stream));
-  if (tot[1] > 0xFFFFFFF0ull) return fail(ctx, UPB_ERR_UNSUPPORTED, "too many positions to dump in one batch");
-  ENSURE(ctx->d_F, (size_t)(tot[0] + 1) * 8);
-  ENSURE(ctx->d_R, (size_t)(tot[0] + 1) * 8);
-  KdeArgs ka = base;
-  ka.dumpUnit = ctx->d_dUnit.as<uint32_t>(); ka.dumpLeft = ctx->d_dLeft.as<uint32_t>(); ka.dumpLen = ctx->d_dLen.as<uint32_t>();
-  ka.dumpOff = (const uint64_t*)ctx->d_dOff.p; ka.dumpChunkStart = (const uint64_t*)ctx->d_dChunkStart.p; ka.nDump = n;
-  ka.dumpF = ctx->d_F.as<double>(); ka.dumpR = ctx->d_R.as<double>(); ka.dumpNonzero = nullptr;
-  CU(cudaMemsetAsync(ka.ticket, 0, 4, ctx->stream));
-  if ((r = launch_kde(ctx, ka, nondir, true, (uint32_t)tot[1], launches))) return r;
-  if (nShifts) {
-    ENSURE(ctx->d_corr, (size_t)n * nShifts * 8);
-    CorrArgs ca;
-    ca.F = ctx->d_F.as<double>(); ca.R = ctx->d_R.as<double>(); ca.off = (const uint64_t*)ctx->d_dOff.p; ca.len = ctx->d_dLen.as<uint32_t>();
-    ca.n = n; ca.nShifts = nShifts; ca.corr = ctx->d_corr.as<double>();
-    const uint64_t warps = (uint64_t)n * nShifts;
-    const uint64_t blocks = (warps * 32 + 255) / 256;
-    strand_corr_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(ca);
-    CU(cudaGetLastError());
-    *launches += 1;
-    if (corrOut) {
-      corrOut->resize((size_t)n * nShifts);
-      CU(cudaMemcpyAsync(corrOut->data(), ctx->d_corr.p, (size_t)n * nShifts * 8, cudaMemcpyDeviceToHost, ctx->stream));
-      CU(cudaStreamSynchronize(ctx->stream));
-    }
-  }
-  return UPB_OK;
-}
-
-struct KdeBase {
-  KdeArgs ka;
+struct Prep {
   std::vector<Unit> units;
-  uint32_t totalTiles;
-  bool haveControl;
+  std::vector<double> taps;
+  uint32_t totalSpans = 0;
+  uint32_t nSrc = 0;
+  bool haveControl = false;
+  Tags T;
+  DensArgs dens;                     // template for the density kernel
 };
 
 // common set-up: units, taps, source list, control filter
-static int prepare_kde (upb_ctx* ctx, const PipeCfg& cfg, KdeBase& kb, uint32_t* launches) {
+static int prepare (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, uint32_t* launches) {
   const uint32_t C = (uint32_t)ctx->sizes.size();
   const uint32_t n = ctx->nSamples;
   if (!ctx->loaded) return fail(ctx, UPB_ERR_NOT_LOADED, "no tags loaded (upb_set_contigs + upb_load_tags first)");
-  if (cfg.bw == 0 || cfg.bw > (uint32_t)MAX_BW) return fail(ctx, UPB_ERR_UNSUPPORTED, "bandwidth must be in 1..1024");
+  if (cfg.bw == 0 || cfg.bw > (uint32_t)MAX_BW_FAST) return fail(ctx, UPB_ERR_UNSUPPORTED, "bandwidth must be in 1..448");
   if (!(cfg.thr > 0)) return fail(ctx, UPB_ERR_BAD_ARG, "region threshold must be > 0 (the reference's leap handling relies on it, SURVEY Q10)");
   if (!(cfg.background > 0)) return fail(ctx, UPB_ERR_BAD_ARG, "background must be > 0");
   int r;
@@ -409,11 +396,12 @@ static int prepare_kde (upb_ctx* ctx, const PipeCfg& cfg, KdeBase& kb, uint32_t*
   std::vector<uint8_t> control(n, 0);
   bool haveControl = false;
   for (uint32_t s = 0; s < n; ++s) { if (cfg.control && cfg.control[s]) { control[s] = 1; haveControl = true; } else src.push_back(s); }
-  kb.haveControl = haveControl;
+  pr.haveControl = haveControl;
+  pr.nSrc = (uint32_t)src.size();
 
   // units: one per (buffer, contig) that holds at least one non-control tag
-  kb.units.clear();
-  uint32_t tileStart = 0;
+  pr.units.clear();
+  uint64_t spanStart = 0;
   const uint32_t nBuf = cfg.nondir ? 1u : 2u;
   for (uint32_t b = 0; b < nBuf; ++b)
     for (uint32_t c = 0; c < C; ++c) {
@@ -425,25 +413,25 @@ static int prepare_kde (upb_ctx* ctx, const PipeCfg& cfg, KdeBase& kb, uint32_t*
       if (!any) continue;
       Unit u;
       u.contig = c; u.buffer = b; u.size = ctx->sizes[c];
-      u.nTiles = (uint32_t)(((uint64_t)ctx->sizes[c] + cfg.bw + TILE - 1) / TILE);
-      u.tileStart = tileStart;
-      if ((uint64_t)tileStart + u.nTiles > 0xFFFFFFF0ull) return fail(ctx, UPB_ERR_UNSUPPORTED, "too many tiles");
-      tileStart += u.nTiles;
-      kb.units.push_back(u);
+      u.nSpans = (uint32_t)(((uint64_t)ctx->sizes[c] + cfg.bw + SPAN_LEN - 1) / SPAN_LEN);
+      u.spanStart = (uint32_t)spanStart;
+      spanStart += u.nSpans;
+      if (spanStart > 0xFFFFFFF0ull) return fail(ctx, UPB_ERR_UNSUPPORTED, "too many spans");
+      pr.units.push_back(u);
     }
-  kb.totalTiles = tileStart;
+  pr.totalSpans = (uint32_t)spanStart;
 
-  std::vector<double> taps(2 * (size_t)cfg.bw + 1);
-  upb_kernel_taps(cfg.bw, 1 / cfg.background, taps.data());          // src/regions.cpp:232
-  ENSURE(ctx->d_taps, taps.size() * 8);
-  ENSURE(ctx->d_src, (src.size() + 1) * 4);
-  ENSURE(ctx->d_units, (kb.units.size() + 1) * sizeof(Unit));
-  ENSURE(ctx->d_control, n + 1);
+  pr.taps.assign(2 * (size_t)cfg.bw + 1, 0.0);
+  upb_kernel_taps(cfg.bw, 1 / cfg.background, pr.taps.data());      // src/regions.cpp:232
+  double* d_taps = SCR("taps", double, pr.taps.size());
+  uint32_t* d_src = SCR("src", uint32_t, src.size() + 1);
+  Unit* d_units = SCR("units", Unit, pr.units.size() + 1);
+  uint8_t* d_control = SCR("control", uint8_t, n + 1);
   ENSURE(ctx->d_small, 4096);
-  CU(cudaMemcpyAsync(ctx->d_taps.p, taps.data(), taps.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-  if (!src.empty()) CU(cudaMemcpyAsync(ctx->d_src.p, src.data(), src.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-  if (!kb.units.empty()) CU(cudaMemcpyAsync(ctx->d_units.p, kb.units.data(), kb.units.size() * sizeof(Unit), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->d_control.p, control.data(), n, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_taps, pr.taps.data(), pr.taps.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (!src.empty()) CU(cudaMemcpyAsync(d_src, src.data(), src.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (!pr.units.empty()) CU(cudaMemcpyAsync(d_units, pr.units.data(), pr.units.size() * sizeof(Unit), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_control, control.data(), n, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemsetAsync(ctx->d_small.p, 0, 4096, ctx->stream));
 
   // Q4: zero the control tags the reference forgets
@@ -453,7 +441,7 @@ static int prepare_kde (upb_ctx* ctx, const PipeCfg& cfg, KdeBase& kb, uint32_t*
       ControlArgs ca;
       ca.T = make_tags(ctx, false);
       ca.nTilesIdx = ctx->d_nTilesIdx.as<uint32_t>(); ca.segStart = ctx->d_segStart.as<uint64_t>();
-      ca.control = ctx->d_control.as<uint8_t>(); ca.srcSample = ctx->d_src.as<uint32_t>(); ca.nSrc = (uint32_t)src.size();
+      ca.control = d_control; ca.srcSample = d_src; ca.nSrc = (uint32_t)src.size();
       ca.cntEff = ctx->d_cntEff.as<uint32_t>(); ca.nSeg = n * 2 * C; ca.nEntries = ctx->nEntries;
       const uint64_t blocks = (ctx->nEntries + 255) / 256;
       control_filter_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(ca);
@@ -463,232 +451,291 @@ static int prepare_kde (upb_ctx* ctx, const PipeCfg& cfg, KdeBase& kb, uint32_t*
     ctx->lastControl = control;
     ctx->cntEffValid = true;
   }
+  pr.T = make_tags(ctx, haveControl);
 
-  KdeArgs& ka = kb.ka;
-  memset(&ka, 0, sizeof ka);
-  ka.T = make_tags(ctx, haveControl);
-  ka.units = ctx->d_units.as<Unit>();
-  ka.nTilesIdx = ctx->d_nTilesIdx.as<uint32_t>();
-  ka.nUnits = (uint32_t)kb.units.size();
-  ka.totalTiles = kb.totalTiles;
-  ka.srcSample = ctx->d_src.as<uint32_t>();
-  ka.nSrc = (uint32_t)src.size();
-  ka.bw = cfg.bw;
-  ka.taps = ctx->d_taps.as<double>();
-  ka.thr = cfg.thr;
-  ka.kmaxBound = taps[cfg.bw] * (1.0 + 1e-9);
-  ka.nondir = cfg.nondir ? 1 : 0;
-  // d_small layout (4 KB): [0] flags u32, [1] ticket u32, [2] runCount u32, [4..5] hot tiles u64, [8..] scan totals u64
-  ka.flags = ctx->d_small.as<uint32_t>();
-  ka.ticket = ctx->d_small.as<uint32_t>() + 1;
-  ka.runCount = ctx->d_small.as<uint32_t>() + 2;
-  ka.statHotTiles = (unsigned long long*)(ctx->d_small.as<uint32_t>() + 4);
+  DensArgs& da = pr.dens;
+  memset(&da, 0, sizeof da);
+  da.T = pr.T;
+  da.units = d_units;
+  da.nTilesIdx = ctx->d_nTilesIdx.as<uint32_t>();
+  da.srcSample = d_src;
+  da.nSrc = (uint32_t)src.size();
+  da.bw = cfg.bw;
+  da.taps = d_taps;
+  // d_small layout (4 KB): [0] flags u32, [1] ticket u32, [2] runCount u32, [3] multiCount u32, [4..11] span stats u64 x4, [16..] scan totals u64
+  da.ticket = ctx->d_small.as<uint32_t>() + 1;
   return UPB_OK;
 }
 
-static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, PipeOut& out) {
+static int launch_density (upb_ctx* ctx, DensArgs& da, bool nondir, uint32_t totalWork, uint32_t* launches) {
+  const DensSmem L = dens_smem_layout(da.bw, da.nSrc * (nondir ? 2u : 1u), nondir);
+  const size_t smem = L.total;
+  if (smem > 227 * 1024) return fail(ctx, UPB_ERR_UNSUPPORTED, "bandwidth / sample count need more shared memory than one SM has");
+  void (*kern)(const DensArgs) = nondir ? density_kernel<true> : density_kernel<false>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int perSm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, KDE_THREADS, smem));
+  if (perSm < 1) perSm = 1;
+  const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)ctx->smCount * perSm, std::max<uint32_t>(totalWork, 1u));
+  kern<<<grid, KDE_THREADS, smem, ctx->stream>>>(da);
+  CU(cudaGetLastError());
+  *launches += 1;
+  return UPB_OK;
+}
+
+// exact F/R densities for `n` position ranges (descriptor arrays dUnit/dLeft/dLen/dChunks already filled on the
+// device) and, if asked, strandCorr(shift) for shifts 0..nShifts-1 into scratch "corr"
+static int dump_and_corr (upb_ctx* ctx, const DensArgs& base, bool nondir, uint32_t n, uint32_t nShifts, uint32_t* launches) {
+  unsigned long long* dOff = SCR("dOff", unsigned long long, (size_t)n + 1);
+  unsigned long long* dChunkStart = SCR("dChunkStart", unsigned long long, (size_t)n + 1);
+  uint32_t* dUnit = ctx->scratch["dUnit"].as<uint32_t>(); uint32_t* dLeft = ctx->scratch["dLeft"].as<uint32_t>();
+  uint32_t* dLen = ctx->scratch["dLen"].as<uint32_t>(); uint32_t* dChunks = ctx->scratch["dChunks"].as<uint32_t>();
+  unsigned long long* d_tot = ctx->d_small.as<unsigned long long>() + 16;
+  int r;
+  if ((r = scan_u32(ctx, dLen, n, dOff, d_tot, launches))) return r;
+  if ((r = scan_u32(ctx, dChunks, n, dChunkStart, d_tot + 1, launches))) return r;
+  unsigned long long* tot = (unsigned long long*)ctx->h_small;
+  CU(cudaMemcpyAsync(tot, d_tot, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  const unsigned long long totLen = tot[0], totChunks = tot[1];
+  // append the grand totals as entry n of the two prefix arrays
+  CU(cudaMemcpyAsync(dOff + n, d_tot, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dChunkStart + n, d_tot + 1, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (totChunks > 0xFFFFFFF0ull) return fail(ctx, UPB_ERR_UNSUPPORTED, "too many positions to evaluate in one batch");
+  double* F = SCR("F", double, (size_t)totLen + 1);
+  double* R = SCR("R", double, (size_t)totLen + 1);
+  DensArgs da = base;
+  da.dumpUnit = dUnit; da.dumpLeft = dLeft; da.dumpLen = dLen;
+  da.dumpOff = (const uint64_t*)dOff; da.dumpChunkStart = (const uint64_t*)dChunkStart; da.nDump = n;
+  da.dumpF = F; da.dumpR = R;
+  CU(cudaMemsetAsync(da.ticket, 0, 4, ctx->stream));
+  if ((r = launch_density(ctx, da, nondir, (uint32_t)totChunks, launches))) return r;
+  if (nShifts) {
+    double* corr = SCR("corr", double, (size_t)n * nShifts);
+    CorrArgs ca;
+    ca.F = F; ca.R = R; ca.off = (const uint64_t*)dOff; ca.len = dLen; ca.n = n; ca.nShifts = nShifts; ca.corr = corr;
+    const uint64_t warps = (uint64_t)n * nShifts;
+    const uint64_t blocks = (warps * 32 + 255) / 256;
+    strand_corr_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(ca);
+    CU(cudaGetLastError());
+    *launches += 1;
+  }
+  return UPB_OK;
+}
+
+static int launch_span (upb_ctx* ctx, const SpanArgs& sa, bool nondir, uint32_t* launches) {
+  const SpanSmem L = span_smem_layout(sa.bw, sa.nSrc * (nondir ? 2u : 1u), nondir);
+  const size_t smem = L.total;
+  if (smem > 227 * 1024) return fail(ctx, UPB_ERR_UNSUPPORTED, "bandwidth / sample count need more shared memory than one SM has");
+  void (*kern)(const SpanArgs) = nondir ? span_kernel<true> : span_kernel<false>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int perSm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, SP_THREADS, smem));
+  if (perSm < 1) perSm = 1;
+  const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)ctx->smCount * perSm, std::max<uint32_t>(sa.totalSpans, 1u));
+  kern<<<grid, SP_THREADS, smem, ctx->stream>>>(sa);
+  CU(cudaGetLastError());
+  *launches += 1;
+  return UPB_OK;
+}
+
+static void finish_stats (upb_ctx* ctx, uint32_t launches) {
+  cudaEventRecord(ctx->ev[3], ctx->stream);
+  cudaEventSynchronize(ctx->ev[3]);
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]);
+  ctx->stats.ms_total = ms;
+  ctx->stats.launches = launches;
+}
+
+static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& out) {
   CU(cudaSetDevice(ctx->device));
   uint32_t launches = 0;
-  KdeBase kb;
   CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-  int r = prepare_kde(ctx, cfg, kb, &launches);
+  int r = prepare(ctx, cfg, pr, &launches);
   if (r) return r;
-  const uint32_t n = ctx->nSamples;
-  out.units = kb.units;
-  out.unitCand.assign(kb.units.size(), 0);
-  out.regions.clear();
-  out.nCand = 0;
+  const uint32_t n = ctx->nSamples, C = (uint32_t)ctx->sizes.size();
+  const uint32_t nUnits = (uint32_t)pr.units.size();
+  out.units = pr.units;
+  out.unitCand.assign(nUnits, 0);
+  out.nCand = 0; out.R = 0;
   memset(&ctx->stats, 0, sizeof ctx->stats);
   ctx->stats.n_entries = ctx->nEntries;
-  ctx->stats.kde_tiles = kb.totalTiles;
-  if (kb.units.empty() || kb.ka.nSrc == 0) { ctx->stats.launches = launches; return UPB_OK; }
-  KdeArgs ka = kb.ka;
-  const uint32_t totalTiles = kb.totalTiles;
+  ctx->stats.kde_tiles = pr.totalSpans;
+  out.layout = slab_layout(0, n, C);
+  if (nUnits == 0 || pr.nSrc == 0) {
+    if ((r = acquire_slab(ctx, out.layout.totalBytes, out.slab))) return r;
+    memset(out.slab.p, 0, out.layout.totalBytes);
+    finish_stats(ctx, launches);
+    return UPB_OK;
+  }
+  uint32_t* small32 = ctx->d_small.as<uint32_t>();
+  unsigned long long* d_tot = ctx->d_small.as<unsigned long long>() + 16;
+  uint32_t* h32 = (uint32_t*)ctx->h_small;
+  Unit* d_units = ctx->scratch["units"].as<Unit>();
 
-  // ---- K1 -----------------------------------------------------------------------------------------
-  ENSURE(ctx->d_tileBase, (size_t)totalTiles * 4);
-  ENSURE(ctx->d_tileCount, (size_t)totalTiles * 4);
-  size_t runCap = std::max<size_t>(1u << 20, (size_t)(ctx->nEntries / 8));
-  if (ctx->d_runs.cap / sizeof(RunRec) > runCap) runCap = ctx->d_runs.cap / sizeof(RunRec);
+  // ---- K1: the fused span kernel ---------------------------------------------------------------------
+  SpanArgs sa;
+  memset(&sa, 0, sizeof sa);
+  sa.T = pr.T; sa.units = d_units; sa.nTilesIdx = ctx->d_nTilesIdx.as<uint32_t>();
+  sa.srcSample = ctx->scratch["src"].as<uint32_t>(); sa.nSrc = pr.nSrc;
+  sa.nUnits = nUnits; sa.totalSpans = pr.totalSpans; sa.bw = cfg.bw;
+  sa.taps = ctx->scratch["taps"].as<double>();
+  sa.thr = cfg.thr;
+  const double kmax = pr.taps[cfg.bw];                                // K(0) = 0.75 * scale
+  sa.kmaxBound = kmax * (1.0 + 1e-9);
+  sa.cN = kmax / ((double)cfg.bw * (double)cfg.bw);
+  sa.dS = kmax * 1e-11;                                               // >= 100x the worst-case rounding difference between the two forms
+  sa.flags = small32; sa.ticket = small32 + 1; sa.runCount = small32 + 2; sa.stat = (unsigned long long*)(small32 + 4);
+  sa.spanRunCount = SCR("spanRunCount", uint32_t, pr.totalSpans);
+
+  size_t runCap = std::max<size_t>(1u << 18, (size_t)(ctx->nEntries / 64));
+  { const size_t have = ctx->scratch["runs"].cap / sizeof(SpanRun); if (have > runCap) runCap = have; }
   uint32_t nRuns = 0;
-  unsigned long long hotTiles = 0;
   for (int attempt = 0; attempt < 2; ++attempt) {
-    ENSURE(ctx->d_runs, runCap * sizeof(RunRec));
-    ka.runs = ctx->d_runs.as<RunRec>();
-    ka.runCap = (uint32_t)std::min<size_t>(runCap, 0xFFFFFFFFu);
-    ka.tileRunBase = ctx->d_tileBase.as<uint32_t>();
-    ka.tileRunCount = ctx->d_tileCount.as<uint32_t>();
-    CU(cudaMemsetAsync(ctx->d_small.p, 0, 64, ctx->stream));
+    sa.runs = SCR("runs", SpanRun, runCap);
+    sa.runCap = (uint32_t)std::min<size_t>(runCap, 0xFFFFFFF0u);
+    CU(cudaMemsetAsync(ctx->d_small.p, 0, 256, ctx->stream));
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-    if ((r = launch_kde(ctx, ka, cfg.nondir, false, totalTiles, &launches))) return r;
+    if ((r = launch_span(ctx, sa, cfg.nondir, &launches))) return r;
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-    uint32_t small[8];
-    CU(cudaMemcpyAsync(small, ctx->d_small.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(h32, ctx->d_small.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    nRuns = small[2];
-    memcpy(&hotTiles, &small[4], 8);
-    if (!(small[0] & FLAG_RUN_OVERFLOW)) break;
+    nRuns = h32[2];
+    if (!(h32[0] & FLAG_RUN_OVERFLOW)) break;
     if (attempt == 1) return fail(ctx, UPB_ERR_NOMEM, "run buffer overflow after resize");
     runCap = (size_t)nRuns + 1024;                                    // the counter holds the exact need
   }
-  ctx->stats.kde_hot_tiles = hotTiles;
+  { unsigned long long st[4]; memcpy(st, h32 + 4, 32); ctx->stats.kde_hot_tiles = st[1]; ctx->stats.hot_blocks = st[0]; ctx->stats.exact_evals = st[2]; ctx->stats.spans_with_tags = st[3]; }
   { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->stats.ms_kde = ms; }
   if (nRuns == 0) {
-    CU(cudaEventRecord(ctx->ev[3], ctx->stream)); CU(cudaEventSynchronize(ctx->ev[3]));
-    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]); ctx->stats.ms_total = ms; ctx->stats.launches = launches;
+    if ((r = acquire_slab(ctx, out.layout.totalBytes, out.slab))) return r;
+    memset(out.slab.p, 0, out.layout.totalBytes);
+    finish_stats(ctx, launches);
     return UPB_OK;
   }
 
-  // ---- K2: order by tile, stitch runs into candidate regions ---------------------------------------
-  unsigned long long* d_tot = ctx->d_small.as<unsigned long long>() + 8;
-  ENSURE(ctx->d_tileOrd, (size_t)totalTiles * 8);
-  if ((r = scan_u32(ctx, ctx->d_tileCount.as<uint32_t>(), totalTiles, ctx->d_tileOrd.as<unsigned long long>(), d_tot, &launches))) return r;
-  ENSURE(ctx->d_ordRuns, (size_t)nRuns * sizeof(RunRec));
-  ENSURE(ctx->d_ordUnit, (size_t)nRuns * 4);
-  ENSURE(ctx->d_head, (size_t)nRuns * 4);
-  ENSURE(ctx->d_headScan, (size_t)nRuns * 8);
-  order_runs_kernel<<<(totalTiles + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_runs.as<RunRec>(), ctx->d_tileBase.as<uint32_t>(), ctx->d_tileCount.as<uint32_t>(),
-      ctx->d_tileOrd.as<unsigned long long>(), ctx->d_units.as<Unit>(), (uint32_t)kb.units.size(), totalTiles, ctx->d_ordRuns.as<RunRec>(), ctx->d_ordUnit.as<uint32_t>());
-  run_heads_kernel<<<(nRuns + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_ordRuns.as<RunRec>(), ctx->d_ordUnit.as<uint32_t>(), nRuns, ctx->d_head.as<uint32_t>());
+  // ---- K2: (span, rank) order, stitch runs cut by piece / span boundaries ------------------------------
+  unsigned long long* spanOrd = SCR("spanOrd", unsigned long long, pr.totalSpans);
+  if ((r = scan_u32(ctx, sa.spanRunCount, pr.totalSpans, spanOrd, d_tot, &launches))) return r;
+  uint32_t* ordIdx = SCR("ordIdx", uint32_t, nRuns);
+  uint32_t* head = SCR("head", uint32_t, nRuns);
+  unsigned long long* headScan = SCR("headScan", unsigned long long, nRuns);
+  const unsigned gRuns = (nRuns + 255) / 256;
+  run_order_kernel<<<gRuns, 256, 0, ctx->stream>>>(sa.runs, nRuns, spanOrd, ordIdx);
+  run_heads2_kernel<<<gRuns, 256, 0, ctx->stream>>>(sa.runs, ordIdx, nRuns, d_units, nUnits, head);
   CU(cudaGetLastError());
   launches += 2;
-  if ((r = scan_u32(ctx, ctx->d_head.as<uint32_t>(), nRuns, ctx->d_headScan.as<unsigned long long>(), d_tot, &launches))) return r;
-  ENSURE(ctx->d_cand, (size_t)nRuns * sizeof(Cand));                // nCand <= nRuns
-  ENSURE(ctx->d_candOut, (kb.units.size() + 1) * 8);
-  CU(cudaMemsetAsync(ctx->d_candOut.p, 0, (kb.units.size() + 1) * 8, ctx->stream));
-  merge_runs_kernel<<<(nRuns + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_ordRuns.as<RunRec>(), ctx->d_ordUnit.as<uint32_t>(), ctx->d_head.as<uint32_t>(),
-      ctx->d_headScan.as<unsigned long long>(), nRuns, ctx->d_cand.as<Cand>(), ctx->d_candOut.as<unsigned long long>());
+  if ((r = scan_u32(ctx, head, nRuns, headScan, d_tot, &launches))) return r;
+  Cand2* cand = SCR("cand", Cand2, nRuns);                            // nCand <= nRuns
+  unsigned long long* unitCand = SCR("unitCand", unsigned long long, 2 * (size_t)nUnits + 2);
+  unsigned long long* unitFirst = unitCand + nUnits + 1;
+  CU(cudaMemsetAsync(unitCand, 0, (2 * (size_t)nUnits + 2) * 8, ctx->stream));
+  merge_runs2_kernel<<<gRuns, 256, 0, ctx->stream>>>(sa.runs, ordIdx, head, headScan, nRuns, d_units, nUnits, cand, unitCand);
+  unit_first_kernel<<<1, 32, 0, ctx->stream>>>(unitCand, nUnits, unitFirst);
   CU(cudaGetLastError());
-  launches += 1;
-  unsigned long long nCand64 = 0;
-  CU(cudaMemcpyAsync(&nCand64, d_tot, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaMemcpyAsync(out.unitCand.data(), ctx->d_candOut.p, kb.units.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  launches += 2;
+  unsigned long long* h64 = (unsigned long long*)ctx->h_small;
+  CU(cudaMemcpyAsync(h64, d_tot, 8, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  const uint32_t nCand = (uint32_t)nCand64;
+  const uint32_t nCand = (uint32_t)h64[0];
   out.nCand = nCand;
   ctx->stats.n_candidates = nCand;
+  ctx->stats.n_stitched = nRuns - nCand;
+  const unsigned gCand = (nCand + 255) / 256;
 
-  // ---- K3: hit filter -> survivors --------------------------------------------------------------------
-  ENSURE(ctx->d_pass, (size_t)nCand * 4);
-  ENSURE(ctx->d_passScan, (size_t)nCand * 8);
-  ENSURE(ctx->d_list1, (size_t)nCand * 4);
-  hit_filter_kernel<<<(nCand + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_cand.as<Cand>(), nCand, cfg.hitThr, ctx->d_pass.as<uint32_t>());
+  // ---- K3: hit filter (misc/peakcall.cpp:41), then per-region statistics for the survivors ------------------
+  uint32_t* pass = SCR("pass", uint32_t, nCand);
+  unsigned long long* passScan = SCR("passScan", unsigned long long, nCand);
+  uint32_t* list1 = SCR("list1", uint32_t, nCand);
+  cand_hit_kernel<<<gCand, 256, 0, ctx->stream>>>(cand, nCand, cfg.hitThr, pass);
   launches += 1;
-  if ((r = scan_u32(ctx, ctx->d_pass.as<uint32_t>(), nCand, ctx->d_passScan.as<unsigned long long>(), d_tot, &launches))) return r;
-  compact_index_kernel<<<(nCand + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_pass.as<uint32_t>(), ctx->d_passScan.as<unsigned long long>(), nCand, ctx->d_list1.as<uint32_t>());
+  if ((r = scan_u32(ctx, pass, nCand, passScan, d_tot, &launches))) return r;
+  compact_index_kernel<<<gCand, 256, 0, ctx->stream>>>(pass, passScan, nCand, list1);
   CU(cudaGetLastError());
   launches += 1;
-  unsigned long long n1_64 = 0;
-  CU(cudaMemcpyAsync(&n1_64, d_tot, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(h64, d_tot, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(h64 + 8, unitCand, std::min<size_t>((size_t)nUnits, 400) * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  const uint32_t n1 = (uint32_t)n1_64;
+  const uint32_t n1 = (uint32_t)h64[0];
+  if (nUnits <= 400) for (uint32_t u = 0; u < nUnits; ++u) out.unitCand[u] = h64[8 + u];
+  else { CU(cudaMemcpy(out.unitCand.data(), unitCand, (size_t)nUnits * 8, cudaMemcpyDeviceToHost)); }
 
-  std::vector<uint32_t> list1(n1), pass2(n1), counts((size_t)n1 * n);
-  std::vector<double> kurt(n1), corr;
-  std::vector<Cand> cand1(n1);
+  uint64_t R = 0;
+  uint32_t* statCounts = nullptr; double* statKurt = nullptr; uint32_t* pass2 = nullptr; unsigned long long* pass2Scan = nullptr; double* rowCorr = nullptr;
   if (n1) {
-    // ---- per-sample counts, kurtosis ------------------------------------------------------------------
-    ENSURE(ctx->d_counts, (size_t)n1 * n * 4);
-    ENSURE(ctx->d_offsum, (size_t)n1 * n * 4);
-    ENSURE(ctx->d_kurt, (size_t)n1 * 8);
-    ENSURE(ctx->d_pass2, (size_t)n1 * 4);
-    CountArgs ca;
-    ca.T = ka.T; ca.units = ka.units; ca.nTilesIdx = ka.nTilesIdx; ca.cand = ctx->d_cand.as<Cand>(); ca.list = ctx->d_list1.as<uint32_t>();
-    ca.nList = n1; ca.nondir = cfg.nondir ? 1 : 0; ca.counts = ctx->d_counts.as<uint32_t>(); ca.offsum = ctx->d_offsum.as<uint32_t>();
-    const uint64_t cthreads = (uint64_t)n1 * n;
-    region_counts_kernel<<<(unsigned)((cthreads + 255) / 256), 256, 0, ctx->stream>>>(ca);
-    KurtArgs kg;
-    kg.T = ka.T; kg.units = ka.units; kg.nTilesIdx = ka.nTilesIdx; kg.cand = ctx->d_cand.as<Cand>(); kg.list = ctx->d_list1.as<uint32_t>();
-    kg.nList = n1; kg.nondir = cfg.nondir ? 1 : 0; kg.counts = ctx->d_counts.as<uint32_t>(); kg.offsum = ctx->d_offsum.as<uint32_t>();
-    kg.kurtThr = cfg.kurtThr; kg.kurt = ctx->d_kurt.as<double>(); kg.pass = ctx->d_pass2.as<uint32_t>();
-    region_kurtosis_kernel<<<(n1 + KURT_WARPS - 1) / KURT_WARPS, KURT_WARPS * 32, 0, ctx->stream>>>(kg);
+    const unsigned g1 = (n1 + 255) / 256;
+    statCounts = SCR("statCounts", uint32_t, (size_t)n1 * n);
+    statKurt = SCR("statKurt", double, n1);
+    pass2 = SCR("pass2", uint32_t, n1);
+    pass2Scan = SCR("pass2Scan", unsigned long long, n1);
+    StatArgs st;
+    st.T = pr.T; st.units = d_units; st.nTilesIdx = ctx->d_nTilesIdx.as<uint32_t>(); st.cand = cand; st.list = list1; st.nList = n1;
+    st.nondir = cfg.nondir ? 1 : 0; st.kurtThr = cfg.kurtThr; st.counts = statCounts; st.kurt = statKurt; st.pass = pass2;
+    region_stats_kernel<<<(n1 + KURT_WARPS - 1) / KURT_WARPS, KURT_WARPS * 32, 0, ctx->stream>>>(st);
     CU(cudaGetLastError());
-    launches += 2;
+    launches += 1;
 
-    // ---- strand correlation for the regions that got this far (misc/peakcall.cpp:41 evaluates it last) ----
-    std::vector<uint32_t> sel;                                       // indices into list1 space
+    // strand correlation for the regions that got this far (misc/peakcall.cpp:41 evaluates it last)
     if (cfg.needCorr) {
-      ENSURE(ctx->d_pass2Scan, (size_t)n1 * 8);
-      ENSURE(ctx->d_list2, (size_t)n1 * 4);
-      if ((r = scan_u32(ctx, ctx->d_pass2.as<uint32_t>(), n1, ctx->d_pass2Scan.as<unsigned long long>(), d_tot, &launches))) return r;
-      compact_index_kernel<<<(n1 + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_pass2.as<uint32_t>(), ctx->d_pass2Scan.as<unsigned long long>(), n1, ctx->d_list2.as<uint32_t>());
+      if ((r = scan_u32(ctx, pass2, n1, pass2Scan, d_tot, &launches))) return r;
+      uint32_t* list2 = SCR("list2", uint32_t, n1);
+      compact_index_kernel<<<g1, 256, 0, ctx->stream>>>(pass2, pass2Scan, n1, list2);
       launches += 1;
-      unsigned long long n2_64 = 0;
-      CU(cudaMemcpyAsync(&n2_64, d_tot, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaMemcpyAsync(h64, d_tot, 8, cudaMemcpyDeviceToHost, ctx->stream));
       CU(cudaStreamSynchronize(ctx->stream));
-      const uint32_t n2 = (uint32_t)n2_64;
-      sel.resize(n2);
-      corr.assign(n1, std::nan(""));
+      const uint32_t n2 = (uint32_t)h64[0];
+      rowCorr = SCR("rowCorr", double, n1);
+      CU(cudaMemsetAsync(rowCorr, 0xFF, (size_t)n1 * 8, ctx->stream));   // NaN where not computed
       if (n2) {
-        CU(cudaMemcpyAsync(sel.data(), ctx->d_list2.p, (size_t)n2 * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        // list2 holds indices into list1; the dump descriptors need candidate indices
-        ENSURE(ctx->d_dUnit, (size_t)n2 * 4); ENSURE(ctx->d_dLeft, (size_t)n2 * 4); ENSURE(ctx->d_dLen, (size_t)n2 * 4); ENSURE(ctx->d_dChunks, (size_t)n2 * 4);
-        ENSURE(ctx->d_bestShift, (size_t)n2 * 4);
-        gather_u32_kernel<<<(n2 + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_list1.as<uint32_t>(), ctx->d_list2.as<uint32_t>(), n2, ctx->d_bestShift.as<uint32_t>());
-        dump_desc_kernel<<<(n2 + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_cand.as<Cand>(), ctx->d_bestShift.as<uint32_t>(), n2,
-            ctx->d_dUnit.as<uint32_t>(), ctx->d_dLeft.as<uint32_t>(), ctx->d_dLen.as<uint32_t>(), ctx->d_dChunks.as<uint32_t>());
+        uint32_t* dUnit = SCR("dUnit", uint32_t, n2); uint32_t* dLeft = SCR("dLeft", uint32_t, n2);
+        uint32_t* dLen = SCR("dLen", uint32_t, n2); uint32_t* dChunks = SCR("dChunks", uint32_t, n2);
+        dump_desc2_kernel<<<(n2 + 255) / 256, 256, 0, ctx->stream>>>(cand, list1, list2, n2, dUnit, dLeft, dLen, dChunks);
         CU(cudaGetLastError());
-        launches += 2;
-        std::vector<double> c2;
-        if ((r = dump_and_corr(ctx, ka, cfg.nondir, n2, 1, &launches, &c2))) return r;
-        for (uint32_t k = 0; k < n2; ++k) corr[sel[k]] = c2[k];
+        launches += 1;
+        if ((r = dump_and_corr(ctx, pr.dens, cfg.nondir, n2, 1, &launches))) return r;
+        cand_corr_kernel<<<(n2 + 255) / 256, 256, 0, ctx->stream>>>(list2, n2, ctx->scratch["corr"].as<double>(), cfg.corrThr, pass2, rowCorr);
+        CU(cudaGetLastError());
+        launches += 1;
       }
     }
-
-    // ---- bring the survivors back and assemble rows ---------------------------------------------------
-    ENSURE(ctx->d_ordRuns, (size_t)n1 * sizeof(Cand));               // reuse as gather target
-    CU(cudaMemcpyAsync(list1.data(), ctx->d_list1.p, (size_t)n1 * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(pass2.data(), ctx->d_pass2.p, (size_t)n1 * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(kurt.data(), ctx->d_kurt.p, (size_t)n1 * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(counts.data(), ctx->d_counts.p, (size_t)n1 * n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if ((r = scan_u32(ctx, pass2, n1, pass2Scan, d_tot, &launches))) return r;
+    CU(cudaMemcpyAsync(h64, d_tot, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    // candidates of the survivors: copy the whole candidate array only if small, else gather row by row on host
-    std::vector<Cand> allCand;
-    allCand.resize(nCand);
-    CU(cudaMemcpyAsync(allCand.data(), ctx->d_cand.p, (size_t)nCand * sizeof(Cand), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    for (uint32_t i = 0; i < n1; ++i) cand1[i] = allCand[list1[i]];
+    R = h64[0];
   }
-  CU(cudaEventRecord(ctx->ev[3], ctx->stream));
-  CU(cudaEventSynchronize(ctx->ev[3]));
-  { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]); ctx->stats.ms_total = ms; }
-  ctx->stats.launches = launches;
 
-  // first candidate ordinal of each unit
-  std::vector<uint64_t> unitFirst(kb.units.size() + 1, 0);
-  for (size_t u = 0; u < kb.units.size(); ++u) unitFirst[u + 1] = unitFirst[u] + out.unitCand[u];
-  for (uint32_t i = 0; i < n1; ++i) {
-    if (!pass2[i]) continue;
-    double cr = std::nan("");
-    if (cfg.needCorr) {
-      cr = corr[i];
-      if (cfg.corrThr > -1 && !(cr >= cfg.corrThr)) continue;        // misc/peakcall.cpp:41 third clause
-    }
-    HostRegion hr;
-    const Cand& c = cand1[i];
-    hr.unit = c.unit; hr.buffer = kb.units[c.unit].buffer; hr.contig = kb.units[c.unit].contig;
-    hr.left = c.left; hr.len = c.len; hr.peak = c.peak; hr.wsum = c.wsum; hr.score = c.score;
-    hr.kurt = kurt[i]; hr.corr = cr;
-    hr.candIndex = (uint64_t)list1[i] - unitFirst[c.unit];
-    hr.counts.assign(counts.begin() + (size_t)i * n, counts.begin() + (size_t)(i + 1) * n);
-    out.regions.push_back(std::move(hr));
+  // ---- accepted rows -> result slab -------------------------------------------------------------------------
+  out.R = R;
+  out.layout = slab_layout(R, n, C);
+  const SlabLayout& SL = out.layout;
+  if ((r = acquire_slab(ctx, SL.totalBytes, out.slab))) return r;
+  unsigned char* hs = (unsigned char*)out.slab.p;
+  memset(hs + SL.devBytes, 0, SL.totalBytes - SL.devBytes);
+  if (R) {
+    unsigned char* ds = SCR("slab", unsigned char, SL.devBytes);
+    unsigned long long* d_tir = SCR("tir", unsigned long long, n);
+    CU(cudaMemsetAsync(d_tir, 0, (size_t)n * 8, ctx->stream));
+    EmitArgs ea;
+    ea.cand = cand; ea.list = list1; ea.pass = pass2; ea.passScan = pass2Scan; ea.nList = n1; ea.units = d_units; ea.unitFirst = unitFirst;
+    ea.statCounts = statCounts; ea.statKurt = statKurt; ea.rowCorr = rowCorr; ea.nSamples = n;
+    ea.buffer = ds + SL.oBuffer; ea.contig = (uint32_t*)(ds + SL.oContig); ea.left = (uint32_t*)(ds + SL.oLeft); ea.len = (uint32_t*)(ds + SL.oLen);
+    ea.peak = (uint32_t*)(ds + SL.oPeak); ea.wsum = (uint32_t*)(ds + SL.oWsum); ea.candIndex = (unsigned long long*)(ds + SL.oCandIndex);
+    ea.peakScore = (double*)(ds + SL.oPeakScore); ea.kurt = (double*)(ds + SL.oKurt); ea.corr = (double*)(ds + SL.oCorr);
+    ea.counts = (uint32_t*)(ds + SL.oCounts);
+    emit_rows_kernel<<<(n1 + 255) / 256, 256, 0, ctx->stream>>>(ea);
+    tags_in_regions_kernel<<<std::min<unsigned>(ctx->smCount * 4, (unsigned)((R * n + 255) / 256)), 256, (size_t)n * 8, ctx->stream>>>(ea.counts, R, n, d_tir);
+    CU(cudaGetLastError());
+    launches += 2;
+    CU(cudaMemcpyAsync(hs, ds, SL.devBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(hs + SL.oTags, d_tir, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
   }
+  finish_stats(ctx, launches);
   return UPB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
 // reference emission order, labels and dropped tail (src/regions.cpp:311-391)
 // ------------------------------------------------------------------------------------------------
-template <class T> static T* alloc_arr (size_t n) { return (T*)calloc(n ? n : 1, sizeof(T)); }
-
-extern "C" void upb_free_region_table (upb_region_table* t) {
-  if (!t) return;
-  free(t->buffer); free(t->forward_label); free(t->dropped); free(t->contig); free(t->left); free(t->len); free(t->peak);
-  free(t->cand_index); free(t->peak_score); free(t->kurtosis); free(t->corr); free(t->counts); free(t->tags_in_regions);
-  free(t->unit_candidates); free(t->unit_last_tag);
-  memset(t, 0, sizeof *t);
-}
-
 // For one sample: is its '-' track consumed during pass 1 of the directional merge loop?  The stream is
 // '+' contigs in table order, then '-' contigs.  Pass 1 visits contigs in order and consumes whatever
 // sits at the head of the stream for that contig regardless of strand (src/regions.cpp:341), so the
@@ -776,31 +823,35 @@ extern "C" int upb_reference_order (uint32_t C, uint32_t n, int directional, uin
   return UPB_OK;
 }
 
-static int fill_table (upb_ctx* ctx, const PipeOut& po, upb_region_table* t) {
-  const uint32_t n = ctx->nSamples, C = (uint32_t)ctx->sizes.size();
-  const size_t R = po.regions.size();
+// ------------------------------------------------------------------------------------------------
+// result table: columns point into one pinned slab that goes back to the context's pool when freed
+// ------------------------------------------------------------------------------------------------
+extern "C" void upb_free_region_table (upb_region_table* t) {
+  if (!t) return;
+  if (t->_slab) {
+    upb_ctx* ctx = (upb_ctx*)t->_ctx;
+    HostSlab h; h.p = t->_slab; h.cap = (size_t)t->_slab_bytes;
+    if (ctx) ctx->slabPool.push_back(h); else cudaFreeHost(h.p);
+  }
   memset(t, 0, sizeof *t);
-  t->n_rows = R; t->n_samples = n;
-  t->buffer = alloc_arr<uint8_t>(R); t->forward_label = alloc_arr<uint8_t>(R); t->dropped = alloc_arr<uint8_t>(R);
-  t->contig = alloc_arr<uint32_t>(R); t->left = alloc_arr<uint32_t>(R); t->len = alloc_arr<uint32_t>(R); t->peak = alloc_arr<uint32_t>(R);
-  t->cand_index = alloc_arr<uint64_t>(R); t->peak_score = alloc_arr<double>(R); t->kurtosis = alloc_arr<double>(R); t->corr = alloc_arr<double>(R);
-  t->counts = alloc_arr<uint32_t>(R * n); t->tags_in_regions = alloc_arr<uint64_t>(n);
-  t->unit_candidates = alloc_arr<uint64_t>(2 * (size_t)C); t->unit_last_tag = alloc_arr<uint32_t>(2 * (size_t)C);
-  if (!t->buffer || !t->forward_label || !t->dropped || !t->contig || !t->left || !t->len || !t->peak || !t->cand_index || !t->peak_score ||
-      !t->kurtosis || !t->corr || !t->counts || !t->tags_in_regions || !t->unit_candidates || !t->unit_last_tag) {
-    upb_free_region_table(t);
-    return fail(ctx, UPB_ERR_NOMEM, "out of host memory for the region table");
-  }
-  for (size_t i = 0; i < R; ++i) {
-    const HostRegion& h = po.regions[i];
-    t->buffer[i] = (uint8_t)h.buffer; t->forward_label[i] = h.buffer == 0; t->contig[i] = h.contig; t->left[i] = h.left; t->len[i] = h.len;
-    t->peak[i] = h.peak; t->cand_index[i] = h.candIndex; t->peak_score[i] = h.score; t->kurtosis[i] = h.kurt; t->corr[i] = h.corr;
-    for (uint32_t s = 0; s < n; ++s) { t->counts[i * n + s] = h.counts[s]; t->tags_in_regions[s] += h.counts[s]; }   // misc/peakcall.cpp:44
-  }
+}
+
+static void fill_table (upb_ctx* ctx, const PipeOut& po, upb_region_table* t) {
+  const uint32_t n = ctx->nSamples, C = (uint32_t)ctx->sizes.size();
+  const SlabLayout& L = po.layout;
+  memset(t, 0, sizeof *t);
+  t->n_rows = po.R; t->n_samples = n;
+  t->buffer = po.col<uint8_t>(L.oBuffer); t->forward_label = po.col<uint8_t>(L.oLabel); t->dropped = po.col<uint8_t>(L.oDropped);
+  t->contig = po.col<uint32_t>(L.oContig); t->left = po.col<uint32_t>(L.oLeft); t->len = po.col<uint32_t>(L.oLen); t->peak = po.col<uint32_t>(L.oPeak);
+  t->hit_sum = po.col<uint32_t>(L.oWsum);
+  t->cand_index = po.col<uint64_t>(L.oCandIndex); t->peak_score = po.col<double>(L.oPeakScore); t->kurtosis = po.col<double>(L.oKurt);
+  t->corr = po.col<double>(L.oCorr); t->counts = po.col<uint32_t>(L.oCounts); t->tags_in_regions = po.col<uint64_t>(L.oTags);
+  t->unit_candidates = po.col<uint64_t>(L.oUnitCand); t->unit_last_tag = po.col<uint32_t>(L.oUnitLast);
+  t->_slab = po.slab.p; t->_slab_bytes = po.slab.cap; t->_ctx = ctx;
+  for (uint64_t i = 0; i < po.R; ++i) t->forward_label[i] = t->buffer[i] == 0;
   for (size_t u = 0; u < po.units.size(); ++u) t->unit_candidates[(size_t)po.units[u].buffer * C + po.units[u].contig] = po.unitCand[u];
-  t->n_passed = R;
-  t->n_rejected = po.nCand - R;
-  return UPB_OK;
+  t->n_passed = po.R;
+  t->n_rejected = po.nCand - po.R;
 }
 
 extern "C" int upb_call_regions (upb_ctx* ctx, const upb_region_params* p, upb_region_table* out) {
@@ -813,35 +864,34 @@ extern "C" int upb_call_regions (upb_ctx* ctx, const upb_region_params* p, upb_r
   cfg.hitThr = p->hit_threshold; cfg.background = p->background; cfg.nondir = !p->directional; cfg.control = p->control;
   cfg.needCorr = cfg.nondir;        // -D: the filter (if corr_threshold > -1) and the optional correlation column
   PipeOut po;
-  int r = run_pipeline(ctx, cfg, po);
+  Prep pr;
+  int r = run_pipeline(ctx, cfg, pr, po);
   if (r) return r;
-  // canonical order: (buffer, contig, left) — units are already in that order and candidates are position-ordered
-  if ((r = fill_table(ctx, po, out))) return r;
+  // canonical order: (buffer, contig, left) — units are in that order and candidates are position-ordered
+  fill_table(ctx, po, out);
   const uint32_t C = (uint32_t)ctx->sizes.size(), n = ctx->nSamples;
   for (uint32_t s = 0; s < n; ++s) for (uint32_t d = 0; d < 2; ++d) for (uint32_t c = 0; c < C; ++c) {
     const uint32_t lp = ctx->lastPos[((size_t)s * 2 + d) * C + c];
     const uint32_t b = p->directional ? d : 0;
     if (lp > out->unit_last_tag[(size_t)b * C + c]) out->unit_last_tag[(size_t)b * C + c] = lp;
   }
-  if (p->reference_order && out->n_rows) {
-    std::vector<uint64_t> perm(out->n_rows);
+  if (p->reference_order) {
+    std::vector<uint64_t> perm(out->n_rows + 1);
     r = upb_reference_order(C, n, p->directional, p->bandwidth, ctx->firstPos.data(), ctx->lastPos.data(), out, perm.data());
     if (r) { upb_free_region_table(out); return fail(ctx, r, "the reference's merge loop would abort on this input (several directional samples whose '-' track is read during pass 1; SURVEY Q7)"); }
-    // apply the permutation to every column
     const uint64_t R = out->n_rows;
-    auto permute = [&] (auto* col, size_t width) {
-      typedef typename std::remove_pointer<decltype(col)>::type T;
-      std::vector<T> tmp(col, col + R * width);
-      for (uint64_t k = 0; k < R; ++k) for (size_t w = 0; w < width; ++w) col[k * width + w] = tmp[perm[k] * width + w];
-    };
-    permute(out->buffer, 1); permute(out->forward_label, 1); permute(out->dropped, 1); permute(out->contig, 1); permute(out->left, 1);
-    permute(out->len, 1); permute(out->peak, 1); permute(out->cand_index, 1); permute(out->peak_score, 1); permute(out->kurtosis, 1);
-    permute(out->corr, 1); permute(out->counts, n);
-  } else if (p->reference_order && p->directional) {
-    // still report the abort condition even when nothing was called
-    std::vector<uint64_t> none(1);
-    r = upb_reference_order(C, n, p->directional, p->bandwidth, ctx->firstPos.data(), ctx->lastPos.data(), out, none.data());
-    if (r) { upb_free_region_table(out); return fail(ctx, r, "the reference's merge loop would abort on this input (SURVEY Q7)"); }
+    bool identity = true;
+    for (uint64_t k = 0; k < R && identity; ++k) identity = perm[k] == k;
+    if (!identity) {
+      auto permute = [&] (auto* col, size_t width) {
+        typedef typename std::remove_pointer<decltype(col)>::type T;
+        std::vector<T> tmp(col, col + R * width);
+        for (uint64_t k = 0; k < R; ++k) for (size_t w = 0; w < width; ++w) col[k * width + w] = tmp[perm[k] * width + w];
+      };
+      permute(out->buffer, 1); permute(out->forward_label, 1); permute(out->dropped, 1); permute(out->contig, 1); permute(out->left, 1);
+      permute(out->len, 1); permute(out->peak, 1); permute(out->hit_sum, 1); permute(out->cand_index, 1); permute(out->peak_score, 1);
+      permute(out->kurtosis, 1); permute(out->corr, 1); permute(out->counts, n);
+    }
   }
   return UPB_OK;
 }
@@ -855,6 +905,8 @@ extern "C" void upb_free_shift_report (upb_shift_report* r) {
   memset(r, 0, sizeof *r);
 }
 
+template <class T> static T* alloc_arr (size_t n) { return (T*)calloc(n ? n : 1, sizeof(T)); }
+
 struct SumIdx { uint32_t sum; uint32_t idx; };
 static bool compareRegionCounts (const SumIdx& i, const SumIdx& j) { return i.sum > j.sum; }   // src/strand_shift.cpp:26-29
 
@@ -866,9 +918,17 @@ extern "C" int upb_strand_shift (upb_ctx* ctx, const upb_shift_params* p, upb_sh
   cfg.bw = p->bandwidth; cfg.thr = p->region_threshold; cfg.kurtThr = p->kurtosis_threshold; cfg.corrThr = -1;   // :142
   cfg.hitThr = (double)p->hit_threshold; cfg.background = p->background; cfg.nondir = true; cfg.control = nullptr; cfg.needCorr = false;
   PipeOut po;
-  int r = run_pipeline(ctx, cfg, po);
+  Prep pr;
+  int r = run_pipeline(ctx, cfg, pr, po);
   if (r) return r;
-  const size_t R = po.regions.size();
+  struct SlabGuard { upb_ctx* c; HostSlab h; ~SlabGuard () { if (h.p) c->slabPool.push_back(h); } } guard{ctx, po.slab};
+  const size_t R = po.R;
+  const uint32_t* rContig = po.col<uint32_t>(po.layout.oContig);
+  const uint32_t* rLeft = po.col<uint32_t>(po.layout.oLeft);
+  const uint32_t* rLen = po.col<uint32_t>(po.layout.oLen);
+  const uint32_t* rSum = po.col<uint32_t>(po.layout.oWsum);
+  std::vector<uint32_t> unitOfContig(ctx->sizes.size(), 0);
+  for (size_t u = 0; u < po.units.size(); ++u) unitOfContig[po.units[u].contig] = (uint32_t)u;
   out->n_regions_found = R;
   out->n_freq = p->max_shift + 1;
   out->shift_freq = alloc_arr<uint64_t>(out->n_freq);
@@ -880,53 +940,53 @@ extern "C" int upb_strand_shift (upb_ctx* ctx, const upb_shift_params* p, upb_sh
   // :198 std::sort by Region::sum() descending — same comparator outcomes, same libstdc++ algorithm, hence
   // the same permutation as the reference's sort of Region pointers
   std::vector<SumIdx> order(R);
-  for (size_t i = 0; i < R; ++i) { order[i].sum = po.regions[i].wsum; order[i].idx = (uint32_t)i; }   // no controls: sum() == pooled weight
+  for (size_t i = 0; i < R; ++i) { order[i].sum = rSum[i]; order[i].idx = (uint32_t)i; }   // no controls: sum() == pooled weight
   std::sort(order.begin(), order.end(), compareRegionCounts);
 
   // :201-226 — regions are examined in sorted order until enough qualify; the device sweeps a batch at a time
   uint16_t tested = 0;
   size_t cursor = 0;
   uint32_t launches = ctx->stats.launches;
-  KdeBase kb;
-  if (R && toTest) { uint32_t l2 = 0; if ((r = prepare_kde(ctx, cfg, kb, &l2))) return r; launches += l2; }
   const uint32_t nShifts = p->max_shift + 1;
   while (tested < toTest && cursor < R) {
-    std::vector<uint32_t> batch;                                     // indices into po.regions
+    std::vector<uint32_t> batch;                                     // row indices
     const size_t want = (size_t)(toTest - tested) + (size_t)(toTest - tested) / 4 + 8;
     while (cursor < R && batch.size() < want) {
-      const HostRegion& h = po.regions[order[cursor].idx];
-      if (h.len > 2 * p->max_shift + 3) batch.push_back(order[cursor].idx);   // :206 large enough to try all shifts
+      const uint32_t i = order[cursor].idx;
+      if (rLen[i] > 2 * p->max_shift + 3) batch.push_back(i);          // :206 large enough to try all shifts
       ++cursor;
     }
     if (batch.empty()) break;
     const uint32_t nb = (uint32_t)batch.size();
-    std::vector<uint32_t> dUnit(nb), dLeft(nb), dLen(nb), dChunks(nb);
+    std::vector<uint32_t> hUnit(nb), hLeft(nb), hLen(nb), hChunks(nb);
     for (uint32_t k = 0; k < nb; ++k) {
-      const HostRegion& h = po.regions[batch[k]];
-      dUnit[k] = h.unit; dLeft[k] = h.left; dLen[k] = h.len; dChunks[k] = (h.len + TILE - 1) / TILE;
+      const uint32_t i = batch[k];
+      hUnit[k] = unitOfContig[rContig[i]]; hLeft[k] = rLeft[i]; hLen[k] = rLen[i]; hChunks[k] = (rLen[i] + TILE - 1) / TILE;
     }
-    ENSURE(ctx->d_dUnit, (size_t)nb * 4); ENSURE(ctx->d_dLeft, (size_t)nb * 4); ENSURE(ctx->d_dLen, (size_t)nb * 4); ENSURE(ctx->d_dChunks, (size_t)nb * 4);
-    CU(cudaMemcpyAsync(ctx->d_dUnit.p, dUnit.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->d_dLeft.p, dLeft.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->d_dLen.p, dLen.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->d_dChunks.p, dChunks.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, ctx->stream));
-    if ((r = dump_and_corr(ctx, kb.ka, true, nb, nShifts, &launches, nullptr))) return r;
-    ENSURE(ctx->d_bestShift, (size_t)nb * 4);
-    ENSURE(ctx->d_bestCorr, (size_t)nb * 8);
-    best_shift_kernel<<<(nb + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_corr.as<double>(), nb, nShifts, ctx->d_bestShift.as<uint32_t>(), ctx->d_bestCorr.as<double>());
+    uint32_t* dUnit = SCR("dUnit", uint32_t, nb); uint32_t* dLeft = SCR("dLeft", uint32_t, nb);
+    uint32_t* dLen = SCR("dLen", uint32_t, nb); uint32_t* dChunks = SCR("dChunks", uint32_t, nb);
+    CU(cudaMemcpyAsync(dUnit, hUnit.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dLeft, hLeft.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dLen, hLen.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dChunks, hChunks.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));                           // the host vectors go out of scope below
+    if ((r = dump_and_corr(ctx, pr.dens, true, nb, nShifts, &launches))) return r;
+    uint32_t* dBestShift = SCR("bestShift", uint32_t, nb);
+    double* dBestCorr = SCR("bestCorr", double, nb);
+    best_shift_kernel<<<(nb + 255) / 256, 256, 0, ctx->stream>>>(ctx->scratch["corr"].as<double>(), nb, nShifts, dBestShift, dBestCorr);
     CU(cudaGetLastError());
     launches += 1;
     std::vector<uint32_t> bs(nb);
     std::vector<double> bc(nb);
-    CU(cudaMemcpyAsync(bs.data(), ctx->d_bestShift.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(bc.data(), ctx->d_bestCorr.p, (size_t)nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(bs.data(), dBestShift, (size_t)nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(bc.data(), dBestCorr, (size_t)nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     for (uint32_t k = 0; k < nb && tested < toTest; ++k) {
       if (bc[k] >= p->corr_threshold) {                              // :220 disqualify regions under threshold
-        const HostRegion& h = po.regions[batch[k]];
+        const uint32_t i = batch[k];
         ++out->shift_freq[bs[k]];
-        out->n_tags_in_regions += h.wsum;
-        out->tested_contig[tested] = h.contig; out->tested_left[tested] = h.left; out->tested_len[tested] = h.len;
+        out->n_tags_in_regions += rSum[i];
+        out->tested_contig[tested] = rContig[i]; out->tested_left[tested] = rLeft[i]; out->tested_len[tested] = rLen[i];
         out->tested_best_shift[tested] = bs[k]; out->tested_best_corr[tested] = bc[k];
         ++tested;
       }
@@ -954,7 +1014,7 @@ extern "C" int upb_strand_shift (upb_ctx* ctx, const upb_shift_params* p, upb_sh
 }
 
 // ------------------------------------------------------------------------------------------------
-// not yet implemented entry points (declared in the header so the ABI is stable)
+// bin/regions -w: every position with score != 0 of one (buffer, contig) — misc/peakcall.cpp:81-84
 // ------------------------------------------------------------------------------------------------
 extern "C" void upb_free_profile (upb_profile* p) { if (!p) return; free(p->pos); free(p->score); memset(p, 0, sizeof *p); }
 
@@ -969,12 +1029,12 @@ extern "C" int upb_profile_contig (upb_ctx* ctx, const upb_region_params* p, int
   PipeCfg cfg;
   cfg.bw = p->bandwidth; cfg.thr = p->region_threshold; cfg.kurtThr = p->kurtosis_threshold; cfg.corrThr = p->corr_threshold;
   cfg.hitThr = p->hit_threshold; cfg.background = p->background; cfg.nondir = !p->directional; cfg.control = p->control; cfg.needCorr = false;
-  KdeBase kb;
+  Prep pr;
   uint32_t launches = 0;
-  int r = prepare_kde(ctx, cfg, kb, &launches);
+  int r = prepare(ctx, cfg, pr, &launches);
   if (r) return r;
   int unit = -1;
-  for (size_t u = 0; u < kb.units.size(); ++u) if (kb.units[u].contig == contig && kb.units[u].buffer == (uint32_t)buffer) unit = (int)u;
+  for (size_t u = 0; u < pr.units.size(); ++u) if (pr.units[u].contig == contig && pr.units[u].buffer == (uint32_t)buffer) unit = (int)u;
   if (unit < 0) return UPB_OK;      // no non-control tags: the reference writes nothing for it
   // evaluate the contig in slabs of 8M positions; the reference evaluates firstTag-bw .. lastTag+bw (Q20)
   const uint64_t last = (uint64_t)ctx->sizes[contig] + cfg.bw;
@@ -984,16 +1044,17 @@ extern "C" int upb_profile_contig (upb_ctx* ctx, const upb_region_params* p, int
   std::vector<double> hF, hR;
   for (uint64_t start = 1; start <= last; start += SLAB) {
     const uint32_t len = (uint32_t)std::min<uint64_t>(SLAB, last - start + 1);
-    const uint32_t dUnit = (uint32_t)unit, dLeft = (uint32_t)start, dLen = len, dChunks = (len + TILE - 1) / TILE;
-    ENSURE(ctx->d_dUnit, 4); ENSURE(ctx->d_dLeft, 4); ENSURE(ctx->d_dLen, 4); ENSURE(ctx->d_dChunks, 4);
-    CU(cudaMemcpyAsync(ctx->d_dUnit.p, &dUnit, 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->d_dLeft.p, &dLeft, 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->d_dLen.p, &dLen, 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->d_dChunks.p, &dChunks, 4, cudaMemcpyHostToDevice, ctx->stream));
-    if ((r = dump_and_corr(ctx, kb.ka, cfg.nondir, 1, 0, &launches, nullptr))) return r;
+    const uint32_t desc[4] = {(uint32_t)unit, (uint32_t)start, len, (len + TILE - 1) / TILE};
+    uint32_t* dUnit = SCR("dUnit", uint32_t, 1); uint32_t* dLeft = SCR("dLeft", uint32_t, 1);
+    uint32_t* dLen = SCR("dLen", uint32_t, 1); uint32_t* dChunks = SCR("dChunks", uint32_t, 1);
+    CU(cudaMemcpyAsync(dUnit, &desc[0], 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dLeft, &desc[1], 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dLen, &desc[2], 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dChunks, &desc[3], 4, cudaMemcpyHostToDevice, ctx->stream));
+    if ((r = dump_and_corr(ctx, pr.dens, cfg.nondir, 1, 0, &launches))) return r;
     hF.resize(len); hR.resize(len);
-    CU(cudaMemcpyAsync(hF.data(), ctx->d_F.p, (size_t)len * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(hR.data(), ctx->d_R.p, (size_t)len * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(hF.data(), ctx->scratch["F"].p, (size_t)len * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(hR.data(), ctx->scratch["R"].p, (size_t)len * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     for (uint32_t i = 0; i < len; ++i) {
       volatile double scv = hF[i] + hR[i];                           // misc/peakcall.cpp:57

@@ -24,13 +24,8 @@ struct Unit {                       // one (ProfileBuffer, contig) pair
   uint32_t contig;
   uint32_t buffer;                  // 0 forwardBuffer, 1 reverseBuffer
   uint32_t size;                    // contig size
-  uint32_t nTiles;                  // ceil((size + bw) / TILE): the reference evaluates up to lastTag+bw (Q20)
-  uint32_t tileStart;               // first global tile index of this unit
-};
-
-struct RunRec {                     // a run of above-threshold positions inside one tile
-  uint32_t left, len, peak, wsum;
-  double score;                     // score at `peak`
+  uint32_t nSpans;                  // ceil((size + bw) / SPAN_LEN): the reference evaluates up to lastTag+bw (Q20)
+  uint32_t spanStart;               // first global span index of this unit
 };
 
 struct Tags {                       // resident tag-frequency data (see upb_load_tags)
@@ -175,32 +170,20 @@ __global__ void control_filter_kernel (ControlArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1: fused pool + KDE + threshold + run extraction.  Also used (DUMP mode) to write exact F/R
-// densities of selected position ranges for the strand-correlation statistics.
+// density kernel: exact F/R densities of selected position ranges, written to global memory.  Used where
+// the reference itself needs every value: strandCorr (misc/data.cpp:184-193), the strand-shift sweep
+// (src/strand_shift.cpp:211-218) and the -w profile (misc/peakcall.cpp:81-84).  Region calling never
+// goes through here (upb_span.cuh does not materialise the profile).
 // ------------------------------------------------------------------------------------------------
-struct KdeArgs {
+struct DensArgs {
   Tags T;
   const Unit* units;
   const uint32_t* nTilesIdx;        // [C] tiles covered by the search index of contig c
-  uint32_t nUnits;
-  uint32_t totalTiles;
   const uint32_t* srcSample;        // non-control sample ids (they alone feed the density)
   uint32_t nSrc;
   uint32_t bw;
   const double* taps;               // 2bw+1 (host-computed, misc/kernel.cpp:16-35)
-  double thr;
-  double kmaxBound;                 // max tap * (1 + 1e-9): upper bound factor for the cold-block test
-  int nondir;
-  // run mode outputs
   uint32_t* ticket;
-  RunRec* runs;
-  uint32_t runCap;
-  uint32_t* runCount;
-  uint32_t* tileRunBase;            // [totalTiles]
-  uint32_t* tileRunCount;           // [totalTiles]
-  uint32_t* flags;
-  unsigned long long* statHotTiles;
-  // dump mode inputs/outputs
   const uint32_t* dumpUnit;         // [nDump] unit of each range
   const uint32_t* dumpLeft;         // first position
   const uint32_t* dumpLen;
@@ -209,119 +192,39 @@ struct KdeArgs {
   uint32_t nDump;
   double* dumpF;
   double* dumpR;
-  uint32_t* dumpNonzero;            // optional [sum len] : 1 where score != 0 (profile output), else NULL
 };
 
-struct KdeSmem {                    // byte offsets inside dynamic shared memory
-  uint32_t taps, score, twF, twR, wdF, wdR, cltF, cltR, tpF, tpR, mask, hot, hotList, startPref, ranges, total;
-};
+struct DensSmem { uint32_t taps, wdF, wdR, ranges, total; };
 
-__host__ __device__ inline KdeSmem kde_smem_layout (uint32_t bw, uint32_t nSrcStrands, bool nondir) {
-  KdeSmem L;
-  const uint32_t W = TILE + 2 * bw;
-  const uint32_t Wp = (W + 8) & ~7u;               // cells, padded (+1 for the prefix sentinel)
+__host__ __device__ inline DensSmem dens_smem_layout (uint32_t bw, uint32_t nRanges, bool nondir) {
+  DensSmem L;
+  const uint32_t W = TILE + 2 * bw + 4;
   uint32_t o = 0;
-  L.taps = o;   o += ((2 * bw + 1 + 1) & ~1u) * 8;
-  L.score = o;  o += TILE * 8;
-  L.twF = o;    o += Wp * 8;
-  L.twR = o;    o += nondir ? Wp * 8 : 0;
-  L.wdF = o;    o += Wp * 4;
-  L.wdR = o;    o += nondir ? Wp * 4 : 0;
-  L.cltF = o;   o += Wp * 2;
-  L.cltR = o;   o += nondir ? Wp * 2 : 0;
-  L.tpF = o;    o += Wp * 2;
-  L.tpR = o;    o += nondir ? Wp * 2 : 0;
+  L.taps = o;   o += ((2 * bw + 2) & ~1u) * 8;
+  L.wdF = o;    o += W * 4;
+  L.wdR = o;    o += nondir ? W * 4 : 0;
   o = (o + 15) & ~15u;
-  L.mask = o;   o += TILE_BLOCKS * 4;
-  L.hot = o;    o += TILE_BLOCKS * 4;
-  L.hotList = o; o += TILE_BLOCKS * 4;
-  L.startPref = o; o += (TILE_BLOCKS + 1) * 4;
-  o = (o + 15) & ~15u;
-  L.ranges = o; o += nSrcStrands * 16;
+  L.ranges = o; o += nRanges * 16;
   L.total = o;
   return L;
 }
 
-// block-wide exclusive scan of one uint32 per thread (KDE_THREADS threads); returns the exclusive prefix, total in *total
-__device__ __forceinline__ uint32_t block_excl_scan (uint32_t v, uint32_t* warpTotals /*[KDE_WARPS+1] smem*/, uint32_t* total) {
-  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-  uint32_t inc = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (uint32_t)o) inc += n; }
-  if (lane == 31) warpTotals[warp] = inc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t run = 0;
-    for (int w = 0; w < KDE_WARPS; ++w) { const uint32_t t = warpTotals[w]; warpTotals[w] = run; run += t; }
-    warpTotals[KDE_WARPS] = run;
-  }
-  __syncthreads();
-  const uint32_t res = warpTotals[warp] + inc - v;
-  *total = warpTotals[KDE_WARPS];
-  __syncthreads();
-  return res;
-}
-
-// dense cells -> sorted sparse tag list (tp = cell index, tw = weight as double) and clt[cell] = number
-// of tags strictly before `cell`; clt[W] = number of tags
-__device__ __forceinline__ void compact_cells (const uint32_t* __restrict__ wd, uint16_t* clt, uint16_t* tp, double* tw,
-                                               uint32_t W, uint32_t* warpTotals) {
-  const uint32_t cpt = (W + KDE_THREADS - 1) / KDE_THREADS;
-  const uint32_t c0 = threadIdx.x * cpt;
-  const uint32_t c1 = min(W, c0 + cpt);
-  uint32_t n = 0;
-  for (uint32_t c = c0; c < c1; ++c) n += (wd[c] != 0);
-  uint32_t total;
-  uint32_t run = block_excl_scan(n, warpTotals, &total);
-  for (uint32_t c = c0; c < c1; ++c) {
-    clt[c] = (uint16_t)run;
-    const uint32_t w = wd[c];
-    if (w) { tp[run] = (uint16_t)c; tw[run] = (double)w; ++run; }
-  }
-  if (threadIdx.x == 0) clt[W] = (uint16_t)total;
-}
-
-// exact-order density of the position whose own cell index is pc (tags at cells pc-bw .. pc+bw)
-__device__ __forceinline__ double eval_exact (const double* __restrict__ Ks, const uint16_t* __restrict__ clt,
-                                              const uint16_t* __restrict__ tp, const double* __restrict__ tw,
-                                              uint32_t pc, uint32_t bw) {
-  const uint32_t lo = clt[pc - bw], hi = clt[pc + bw + 1];
-  double s = 0.0;
-  for (uint32_t q = lo; q < hi; ++q) s = __dadd_rn(s, __dmul_rn(Ks[pc + bw - tp[q]], tw[q]));
-  return s;
-}
-
-template <bool NONDIR, bool DUMP>
-__global__ void __launch_bounds__(KDE_THREADS) kde_kernel (const __grid_constant__ KdeArgs a) {
+template <bool NONDIR>
+__global__ void __launch_bounds__(KDE_THREADS) density_kernel (const __grid_constant__ DensArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ uint32_t s_ticket, s_nHot, s_nRuns, s_base, s_any;
-  __shared__ uint32_t s_warpTotals[KDE_WARPS + 1];
-
+  __shared__ uint32_t s_ticket;
   const uint32_t bw = a.bw;
   const uint32_t W = TILE + 2 * bw;
   const uint32_t nStr = NONDIR ? 2u : 1u;
   const uint32_t nRanges = a.nSrc * nStr;
-  const KdeSmem L = kde_smem_layout(bw, nRanges, NONDIR);
+  const DensSmem L = dens_smem_layout(bw, nRanges, NONDIR);
   double* Ks = (double*)(smem + L.taps);
-  double* score = (double*)(smem + L.score);
-  double* twF = (double*)(smem + L.twF);
-  double* twR = (double*)(smem + L.twR);
   uint32_t* wdF = (uint32_t*)(smem + L.wdF);
   uint32_t* wdR = (uint32_t*)(smem + L.wdR);
-  uint16_t* cltF = (uint16_t*)(smem + L.cltF);
-  uint16_t* cltR = (uint16_t*)(smem + L.cltR);
-  uint16_t* tpF = (uint16_t*)(smem + L.tpF);
-  uint16_t* tpR = (uint16_t*)(smem + L.tpR);
-  uint32_t* mask = (uint32_t*)(smem + L.mask);
-  uint32_t* hot = (uint32_t*)(smem + L.hot);
-  uint32_t* hotList = (uint32_t*)(smem + L.hotList);
-  uint32_t* startPref = (uint32_t*)(smem + L.startPref);
   ulonglong2* ranges = (ulonglong2*)(smem + L.ranges);
-
   const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
   for (uint32_t i = tid; i < 2 * bw + 1; i += KDE_THREADS) Ks[i] = a.taps[i];
-
-  const uint32_t totalWork = DUMP ? (uint32_t)a.dumpChunkStart[a.nDump] : a.totalTiles;
+  const uint32_t totalWork = (uint32_t)a.dumpChunkStart[a.nDump];
 
   for (;;) {
     __syncthreads();
@@ -329,32 +232,16 @@ __global__ void __launch_bounds__(KDE_THREADS) kde_kernel (const __grid_constant
     __syncthreads();
     const uint32_t work = s_ticket;
     if (work >= totalWork) break;
-
-    // ---- locate the work item: unit, first position ts, number of positions np ------------------
-    uint32_t ui, ts, np;
-    uint64_t dumpBase = 0;
-    if (!DUMP) {
-      uint32_t lo = 0, hi = a.nUnits;
-      while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.units[mid].tileStart <= work) lo = mid; else hi = mid; }
-      ui = lo;
-      const uint32_t t = work - a.units[ui].tileStart;
-      ts = t * TILE + 1;
-      const uint64_t lastPos = (uint64_t)a.units[ui].size + bw;      // Q20: evaluated through lastTag+bw, no clamp
-      np = (uint32_t)min((uint64_t)TILE, lastPos - (ts - 1));
-    } else {
-      uint32_t lo = 0, hi = a.nDump;
-      while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.dumpChunkStart[mid] <= work) lo = mid; else hi = mid; }
-      const uint32_t r = lo;
-      const uint32_t chunk = work - (uint32_t)a.dumpChunkStart[r];
-      ui = a.dumpUnit[r];
-      ts = a.dumpLeft[r] + chunk * TILE;
-      np = min((uint32_t)TILE, a.dumpLen[r] - chunk * TILE);
-      dumpBase = a.dumpOff[r] + (uint64_t)chunk * TILE;
-    }
-    const Unit U = a.units[ui];
+    uint32_t lo = 0, hi = a.nDump;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.dumpChunkStart[mid] <= work) lo = mid; else hi = mid; }
+    const uint32_t r = lo;
+    const uint32_t chunk = work - (uint32_t)a.dumpChunkStart[r];
+    const Unit U = a.units[a.dumpUnit[r]];
+    const uint32_t ts = a.dumpLeft[r] + chunk * TILE;
+    const uint32_t np = min((uint32_t)TILE, a.dumpLen[r] - chunk * TILE);
+    const uint64_t dumpBase = a.dumpOff[r] + (uint64_t)chunk * TILE;
     const int64_t cell0 = (int64_t)ts - bw;                           // position of cell 0
 
-    // ---- A: entry ranges of every source (sample, strand) -----------------------------------------
     uint32_t myCount = 0;
     for (uint32_t j = tid; j < nRanges; j += KDE_THREADS) {
       const uint32_t s = a.srcSample[j / nStr];
@@ -364,19 +251,13 @@ __global__ void __launch_bounds__(KDE_THREADS) kde_kernel (const __grid_constant
       ranges[j] = make_ulonglong2(x, y - x);
       myCount += (uint32_t)(y - x);
     }
-    // ---- B: clear the dense cells -------------------------------------------------------------------
     for (uint32_t i = tid; i < W + 1; i += KDE_THREADS) { wdF[i] = 0; if (NONDIR) wdR[i] = 0; }
-    for (uint32_t i = tid; i < TILE_BLOCKS; i += KDE_THREADS) { mask[i] = 0; hot[i] = 0; }
     const uint32_t any = __syncthreads_or(myCount != 0);
-    if (!any) {                                                      // nothing within bw of this tile
-      if (!DUMP) { if (tid == 0) { a.tileRunBase[work] = 0; a.tileRunCount[work] = 0; } }
-      else {
-        for (uint32_t i = tid; i < np; i += KDE_THREADS) { a.dumpF[dumpBase + i] = 0.0; a.dumpR[dumpBase + i] = 0.0; if (a.dumpNonzero) a.dumpNonzero[dumpBase + i] = 0; }
-      }
+    if (!any) {                                                      // nothing within bw of this chunk
+      for (uint32_t i = tid; i < np; i += KDE_THREADS) { a.dumpF[dumpBase + i] = 0.0; a.dumpR[dumpBase + i] = 0.0; }
       continue;
     }
-
-    // ---- C: pool the samples: dense per-position weight (integer sum of non-control counts) ---------
+    // pool the samples: dense per-position weight (integer sum of non-control counts)
     for (uint32_t j = warp; j < nRanges; j += KDE_WARPS) {
       const ulonglong2 rg = ranges[j];
       uint32_t* wd = (NONDIR && (j & 1)) ? wdR : wdF;
@@ -387,123 +268,19 @@ __global__ void __launch_bounds__(KDE_THREADS) kde_kernel (const __grid_constant
       }
     }
     __syncthreads();
-
-    // ---- D: cold-block test: no position of a 32-position block can reach the threshold if
-    //         maxTap * (sum of weights within bw of the block) < threshold ------------------------------
-    const uint32_t nBlk = (np + 31) / 32;
-    if (!DUMP) {
-      for (uint32_t k = warp; k < nBlk; k += KDE_WARPS) {
-        unsigned long long sum = 0;
-        const uint32_t cEnd = min(W, 32 * k + 32 + 2 * bw);
-        for (uint32_t c = 32 * k + lane; c < cEnd; c += 32) sum += (unsigned long long)wdF[c] + (NONDIR ? (unsigned long long)wdR[c] : 0ull);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (lane == 0) hot[k] = (__dmul_rn((double)sum, a.kmaxBound) >= a.thr) ? 1u : 0u;
-      }
-    } else {
-      for (uint32_t k = tid; k < nBlk; k += KDE_THREADS) hot[k] = 1u;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      const uint32_t f0 = lane < nBlk ? hot[lane] : 0u;
-      const uint32_t f1 = lane + 32 < nBlk ? hot[lane + 32] : 0u;
-      const uint32_t m0 = __ballot_sync(0xffffffffu, f0), m1 = __ballot_sync(0xffffffffu, f1);
-      if (f0) hotList[__popc(m0 & lanemask_lt())] = lane;
-      if (f1) hotList[__popc(m0) + __popc(m1 & lanemask_lt())] = lane + 32;
-      if (lane == 0) s_nHot = __popc(m0) + __popc(m1);
-    }
-    __syncthreads();
-    const uint32_t nHot = s_nHot;
-    if (nHot == 0) {
-      if (tid == 0) { a.tileRunBase[work] = 0; a.tileRunCount[work] = 0; }
-      continue;
-    }
-    if (!DUMP && tid == 0) atomicAdd(a.statHotTiles, 1ull);
-
-    // ---- E: dense -> sparse sorted tag list ------------------------------------------------------------
-    compact_cells(wdF, cltF, tpF, twF, W, s_warpTotals);
-    if (NONDIR) compact_cells(wdR, cltR, tpR, twR, W, s_warpTotals);
-    __syncthreads();
-
-    // ---- F: exact-order evaluation of the hot blocks, one warp per block of 32 positions ---------------
-    for (uint32_t h = warp; h < nHot; h += KDE_WARPS) {
-      const uint32_t k = hotList[h];
-      const uint32_t po = 32 * k + lane;                            // offset of this lane's position in the tile
-      const bool valid = po < np;
+    // exact-order evaluation (misc/peakcall.cpp:203-209); cells without tags add +0.0
+    for (uint32_t po = tid; po < np; po += KDE_THREADS) {
       double sF = 0.0, sR = 0.0;
-      if (valid) {
-        sF = eval_exact(Ks, cltF, tpF, twF, po + bw, bw);
-        if (NONDIR) sR = eval_exact(Ks, cltR, tpR, twR, po + bw, bw);
+      const uint32_t n2 = 2 * bw;
+      for (uint32_t k = 0; k <= n2; ++k) {
+        const uint32_t w = wdF[po + k];
+        if (w) sF = __dadd_rn(sF, __dmul_rn(Ks[n2 - k], (double)w));
+        if (NONDIR) { const uint32_t v = wdR[po + k]; if (v) sR = __dadd_rn(sR, __dmul_rn(Ks[n2 - k], (double)v)); }
       }
-      const double sc = NONDIR ? __dadd_rn(sF, sR) : sF;            // misc/peakcall.cpp:57
-      if (!DUMP) {
-        score[po] = sc;
-        const uint32_t m = __ballot_sync(0xffffffffu, valid && sc >= a.thr);
-        if (lane == 0) mask[k] = m;
-      } else if (valid) {
-        // a forward-strand buffer in directional mode has only F; reverseBuffer only R (src/regions.cpp:356-358)
-        const bool rev = (!NONDIR) && U.buffer == 1;
-        a.dumpF[dumpBase + po] = rev ? 0.0 : sF;
-        a.dumpR[dumpBase + po] = NONDIR ? sR : (rev ? sF : 0.0);
-        if (a.dumpNonzero) a.dumpNonzero[dumpBase + po] = (sc != 0.0) ? 1u : 0u;
-      }
-    }
-    if (DUMP) continue;
-    __syncthreads();
-
-    // ---- G: maximal runs of above-threshold positions inside the tile ------------------------------------
-    if (warp == 0) {
-      uint32_t cnt2[2];
-#pragma unroll
-      for (int hlf = 0; hlf < 2; ++hlf) {
-        const uint32_t k = lane + 32 * hlf;
-        const uint32_t m = mask[k];
-        const uint32_t prev = k > 0 ? (mask[k - 1] >> 31) : 0u;
-        cnt2[hlf] = __popc(m & ~((m << 1) | prev));
-      }
-      uint32_t inc0 = cnt2[0], inc1 = cnt2[1];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t n0 = __shfl_up_sync(0xffffffffu, inc0, o), n1 = __shfl_up_sync(0xffffffffu, inc1, o);
-        if (lane >= (uint32_t)o) { inc0 += n0; inc1 += n1; }
-      }
-      const uint32_t tot0 = __shfl_sync(0xffffffffu, inc0, 31), tot1 = __shfl_sync(0xffffffffu, inc1, 31);
-      startPref[lane] = inc0 - cnt2[0];
-      startPref[lane + 32] = tot0 + inc1 - cnt2[1];
-      if (lane == 0) {
-        const uint32_t nRuns = tot0 + tot1;
-        s_nRuns = nRuns;
-        uint32_t base = 0;
-        if (nRuns) base = atomicAdd(a.runCount, nRuns);
-        s_base = base;
-        a.tileRunBase[work] = base;
-        a.tileRunCount[work] = nRuns;
-      }
-    }
-    __syncthreads();
-    const uint32_t nRuns = s_nRuns, base = s_base;
-    if (nRuns == 0) continue;
-    if ((uint64_t)base + nRuns > a.runCap) { if (tid == 0) atomicOr(a.flags, FLAG_RUN_OVERFLOW); continue; }
-    for (uint32_t k = warp; k < TILE_BLOCKS; k += KDE_WARPS) {
-      const uint32_t m = mask[k];
-      const uint32_t prev = k > 0 ? (mask[k - 1] >> 31) : 0u;
-      const uint32_t startm = m & ~((m << 1) | prev);
-      if ((startm >> lane) & 1u) {
-        const uint32_t rank = startPref[k] + __popc(startm & lanemask_lt());
-        uint32_t q = 32 * k + lane;
-        const uint32_t q0 = q;
-        double best = score[q];
-        uint32_t bestq = q, wsum = 0;
-        while (q < TILE && ((mask[q >> 5] >> (q & 31)) & 1u)) {
-          const double sc = score[q];
-          if (sc > best) { best = sc; bestq = q; }                 // first strict maximum (misc/data.cpp:97-101)
-          wsum += wdF[q + bw] + (NONDIR ? wdR[q + bw] : 0u);
-          ++q;
-        }
-        RunRec r;
-        r.left = ts + q0; r.len = q - q0; r.peak = ts + bestq; r.wsum = wsum; r.score = best;
-        a.runs[base + rank] = r;
-      }
+      // a forward-strand buffer in directional mode has only F; reverseBuffer only R (src/regions.cpp:356-358)
+      const bool rev = (!NONDIR) && U.buffer == 1;
+      a.dumpF[dumpBase + po] = rev ? 0.0 : sF;
+      a.dumpR[dumpBase + po] = NONDIR ? sR : (rev ? sF : 0.0);
     }
   }
 }
@@ -572,175 +349,16 @@ __global__ void scan_final_kernel (const uint32_t* __restrict__ in, uint64_t n, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2: tile-ordered runs -> candidate regions (stitch runs split at tile boundaries)
+// small generic kernels
 // ------------------------------------------------------------------------------------------------
-struct Cand {                       // a candidate region == one Region object of the reference
-  uint32_t unit, left, len, peak, wsum;
-  uint32_t pad;
-  double score;
-};
-
-__global__ void order_runs_kernel (const RunRec* __restrict__ runs, const uint32_t* __restrict__ tileRunBase,
-                                   const uint32_t* __restrict__ tileRunCount, const unsigned long long* __restrict__ tileOrd,
-                                   const Unit* __restrict__ units, uint32_t nUnits, uint32_t totalTiles,
-                                   RunRec* __restrict__ ordRuns, uint32_t* __restrict__ ordUnit) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= totalTiles) return;
-  const uint32_t n = tileRunCount[t];
-  if (!n) return;
-  uint32_t lo = 0, hi = nUnits;
-  while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (units[mid].tileStart <= t) lo = mid; else hi = mid; }
-  const uint32_t b = tileRunBase[t];
-  const unsigned long long o = tileOrd[t];
-  for (uint32_t i = 0; i < n; ++i) { ordRuns[o + i] = runs[b + i]; ordUnit[o + i] = lo; }
-}
-
-__global__ void run_heads_kernel (const RunRec* __restrict__ r, const uint32_t* __restrict__ unit, uint32_t n, uint32_t* __restrict__ head) {
-  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  bool cont = false;
-  if (j > 0) cont = unit[j] == unit[j - 1] && r[j].left == r[j - 1].left + r[j - 1].len;
-  head[j] = cont ? 0u : 1u;
-}
-
-__global__ void merge_runs_kernel (const RunRec* __restrict__ r, const uint32_t* __restrict__ unit, const uint32_t* __restrict__ head,
-                                   const unsigned long long* __restrict__ headScan, uint32_t n, Cand* __restrict__ cand,
-                                   unsigned long long* __restrict__ unitCand) {
-  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n || !head[j]) return;
-  Cand c;
-  c.unit = unit[j]; c.left = r[j].left; c.len = r[j].len; c.peak = r[j].peak; c.wsum = r[j].wsum; c.score = r[j].score; c.pad = 0;
-  for (uint32_t q = j + 1; q < n && !head[q]; ++q) {
-    c.len += r[q].len;
-    c.wsum += r[q].wsum;                                            // HitCount wraps mod 2^32 (misc/peakcall.cpp:36-40)
-    if (r[q].score > c.score) { c.score = r[q].score; c.peak = r[q].peak; }
-  }
-  cand[headScan[j]] = c;
-  atomicAdd(&unitCand[c.unit], 1ull);
-}
-
-// ------------------------------------------------------------------------------------------------
-// K3: region filters and statistics
-// ------------------------------------------------------------------------------------------------
-__global__ void hit_filter_kernel (const Cand* __restrict__ cand, uint32_t n, double hitThr, uint32_t* __restrict__ pass) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  pass[i] = ((double)cand[i].wsum >= hitThr) ? 1u : 0u;             // misc/peakcall.cpp:41 first clause
-}
-
 __global__ void compact_index_kernel (const uint32_t* __restrict__ pass, const unsigned long long* __restrict__ scan, uint32_t n, uint32_t* __restrict__ list) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (pass[i]) list[scan[i]] = i;
 }
 
-// per (surviving region, sample): Region::exptSums (misc/data.cpp:116-131) and the pieces of posMean
-// (misc/data.cpp:133-148): sum of counts and sum of count*offset, offsets as UShort, both mod 2^32
-struct CountArgs {
-  Tags T;
-  const Unit* units;
-  const uint32_t* nTilesIdx;
-  const Cand* cand;
-  const uint32_t* list;             // surviving candidate indices
-  uint32_t nList;
-  int nondir;
-  uint32_t* counts;                 // [nList * nSamples]
-  uint32_t* offsum;                 // [nList * nSamples]
-};
-
-__global__ void region_counts_kernel (CountArgs a) {
-  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t n = a.T.nSamples;
-  if (g >= (uint64_t)a.nList * n) return;
-  const uint32_t i = (uint32_t)(g / n), s = (uint32_t)(g % n);
-  const Cand c = a.cand[a.list[i]];
-  const Unit U = a.units[c.unit];
-  uint32_t cs = 0, os = 0;
-  const uint32_t d0 = a.nondir ? 0u : U.buffer, d1 = a.nondir ? 1u : U.buffer;
-  for (uint32_t d = d0; d <= d1; ++d) {
-    uint64_t x, y;
-    seg_range(a.T, s, d, U.contig, a.nTilesIdx[U.contig], c.left, (int64_t)c.left + c.len - 1, x, y);
-    for (uint64_t e = x; e < y; ++e) {
-      const uint32_t k = a.T.cntEff[e];
-      cs += k;
-      os += k * ((a.T.pos[e] - c.left) & 0xFFFFu);
-    }
-  }
-  a.counts[g] = cs;
-  a.offsum[g] = os;
-}
-
-// Region::posKurtosis (misc/data.cpp:164-182): sequential FP64 sums over the positions that hold tags, in
-// position order; one warp per region, positions pooled in shared memory 1024 at a time
-struct KurtArgs {
-  Tags T;
-  const Unit* units;
-  const uint32_t* nTilesIdx;
-  const Cand* cand;
-  const uint32_t* list;
-  uint32_t nList;
-  int nondir;
-  const uint32_t* counts;
-  const uint32_t* offsum;
-  double kurtThr;
-  double* kurt;                     // [nList]
-  uint32_t* pass;                   // [nList]
-};
-
 constexpr int KURT_CHUNK = 1024;
 constexpr int KURT_WARPS = 8;
-
-__global__ void __launch_bounds__(KURT_WARPS * 32) region_kurtosis_kernel (KurtArgs a) {
-  __shared__ uint32_t cells[KURT_WARPS][KURT_CHUNK];
-  const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-  const uint32_t i = blockIdx.x * KURT_WARPS + warp;
-  if (i >= a.nList) return;
-  const uint32_t n = a.T.nSamples;
-  const Cand c = a.cand[a.list[i]];
-  const Unit U = a.units[c.unit];
-  uint32_t count = 0, sum = 0;
-  for (uint32_t s = lane; s < n; s += 32) { count += a.counts[(uint64_t)i * n + s]; sum += a.offsum[(uint64_t)i * n + s]; }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { count += __shfl_xor_sync(0xffffffffu, count, o); sum += __shfl_xor_sync(0xffffffffu, sum, o); }
-  const double xbar = (double)sum / (double)count;                  // misc/data.cpp:147
-  double sum2 = 0.0, sum4 = 0.0;
-  uint32_t* cell = cells[warp];
-  const uint32_t d0 = a.nondir ? 0u : U.buffer, d1 = a.nondir ? 1u : U.buffer;
-  for (uint32_t o0 = 0; o0 < c.len; o0 += KURT_CHUNK) {
-    const uint32_t oc = min((uint32_t)KURT_CHUNK, c.len - o0);
-    for (uint32_t k = lane; k < KURT_CHUNK; k += 32) cell[k] = 0;
-    __syncwarp();
-    for (uint32_t s = 0; s < n; ++s)
-      for (uint32_t d = d0; d <= d1; ++d) {
-        uint64_t x, y;
-        seg_range(a.T, s, d, U.contig, a.nTilesIdx[U.contig], (int64_t)c.left + o0, (int64_t)c.left + o0 + oc - 1, x, y);
-        for (uint64_t e = x + lane; e < y; e += 32) atomicAdd(&cell[a.T.pos[e] - c.left - o0], a.T.cntEff[e]);
-      }
-    __syncwarp();
-    for (uint32_t g = 0; g < oc; g += 32) {
-      const uint32_t o = o0 + g + lane;
-      const uint32_t pc = (g + lane < oc) ? cell[g + lane] : 0u;
-      const double dd = __dsub_rn((double)(o & 0xFFFFu), xbar);     // offset counter is a UShort (Q8)
-      const double d2 = __dmul_rn(dd, dd);
-      const double d4 = __dmul_rn(d2, d2);                          // pow(x,4) == (x*x)*(x*x) in the reference build (Q9)
-      const double t2 = __dmul_rn((double)pc, d2);
-      const double t4 = __dmul_rn((double)pc, d4);
-      uint32_t nz = __ballot_sync(0xffffffffu, pc != 0);
-      while (nz) {
-        const int b = __ffs(nz) - 1;
-        sum2 = __dadd_rn(sum2, __shfl_sync(0xffffffffu, t2, b));
-        sum4 = __dadd_rn(sum4, __shfl_sync(0xffffffffu, t4, b));
-        nz &= nz - 1;
-      }
-    }
-    __syncwarp();
-  }
-  const double k = __ddiv_rn(__dmul_rn(__dsub_rn((double)count, 1.0), sum4), __dmul_rn(sum2, sum2));   // misc/data.cpp:181
-  if (lane == 0) {
-    a.kurt[i] = k;
-    a.pass[i] = (a.kurtThr == 0.0 || (c.len > 1 && k <= a.kurtThr)) ? 1u : 0u;   // misc/peakcall.cpp:41 second clause
-  }
-}
 
 // Pearson correlation exactly as misc/data.cpp:22-58 computes it: sequential sums.  One warp per
 // (region, shift); lanes fetch 32 values at a time and the additions are chained in index order.
@@ -791,12 +409,6 @@ __global__ void strand_corr_kernel (CorrArgs a) {
   if (lane_id() == 0) a.corr[w] = c;
 }
 
-__global__ void corr_filter_kernel (const double* __restrict__ corr, uint32_t n, double thr, uint32_t* __restrict__ pass) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  pass[i] = (corr[i] >= thr) ? 1u : 0u;                             // NaN fails (misc/peakcall.cpp:41 third clause)
-}
-
 // per region: first strict maximum over shifts (src/strand_shift.cpp:209-218)
 __global__ void best_shift_kernel (const double* __restrict__ corr, uint32_t n, uint32_t nShifts, uint32_t* __restrict__ bestShift, double* __restrict__ bestCorr) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -809,19 +421,4 @@ __global__ void best_shift_kernel (const double* __restrict__ corr, uint32_t n, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// gather helpers
-// ------------------------------------------------------------------------------------------------
-__global__ void gather_u32_kernel (const uint32_t* __restrict__ src, const uint32_t* __restrict__ list, uint32_t n, uint32_t* __restrict__ dst) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = src[list[i]];
-}
-
-__global__ void dump_desc_kernel (const Cand* __restrict__ cand, const uint32_t* __restrict__ list, uint32_t n,
-                                  uint32_t* __restrict__ dUnit, uint32_t* __restrict__ dLeft, uint32_t* __restrict__ dLen, uint32_t* __restrict__ dChunks) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const Cand c = cand[list[i]];
-  dUnit[i] = c.unit; dLeft[i] = c.left; dLen[i] = c.len; dChunks[i] = (c.len + TILE - 1) / TILE;
-}
-
 }  // namespace upb

@@ -1,0 +1,620 @@
+// upb_span.cuh — the fused region-calling kernel (sm_100a) and the small kernels that order, stitch and
+// filter its output.
+//
+// span_kernel: ONE WARP works on one span (two index tiles = 4096 positions of one (ProfileBuffer, contig)
+// unit) at a time, spans handed out by a global ticket.  There is no block-level barrier anywhere on the
+// path: the warps of a CTA only share the read-only tap table.  (v2 of this kernel gave a whole CTA one
+// 16384-position span and lost 63 % of its issue slots at __syncthreads — profiles/r01_v2_*.)
+//
+//   phase A  every tag entry of every density source (non-control sample) inside the span +- bandwidth is
+//            read once, coalesced, and pooled into 8-position bins in shared memory (shared-memory atomics
+//            run at ~8 lane-ops/clk/SM on B200, profiles/r01_microbench_b200.txt).  A 32-position block is
+//            "hot" when  maxTap * (pooled weight within bandwidth of the block) >= threshold; a block that
+//            is not hot cannot hold a position of a region (misc/peakcall.cpp:57-60) and is never looked at
+//            again.  Maximal groups of hot blocks are cut into pieces of <= 16 blocks.
+//   phase B  per piece: its tags (L1/L2 hits — the same warp just read them) are pooled into dense
+//            per-position cells; every position is classified against the threshold with the O(1) integer
+//            moment form of the Epanechnikov sum (exact in 64-bit integers, window sums carried by warp
+//            scans), and re-evaluated in the reference's own floating-point order (ascending tag position,
+//            product and sum rounded separately, misc/peakcall.cpp:203-209) only where the fast value is
+//            within its error bound of the threshold or of the run maximum.  Runs of above-threshold
+//            positions are written out with their first strict maximum (misc/data.cpp:97-101) and pooled
+//            hit sum.
+//
+// The genome-wide profile is never materialised.  Runs cut by a piece or span boundary are stitched by
+// merge_runs2_kernel; region_stats_kernel then computes Region::exptSums and posKurtosis for the candidates
+// that pass the hit filter.
+#pragma once
+
+#include "upb_device.cuh"
+
+namespace upb {
+
+constexpr int SP_THREADS = 256;
+constexpr int SP_WARPS = SP_THREADS / 32;
+constexpr int SPAN_TILES = 2;                       // index tiles per span
+constexpr int SPAN_LEN = SPAN_TILES * TILE;         // 4096 positions
+constexpr int SPAN_BLOCKS = SPAN_LEN / 32;          // 128 blocks of 32 positions
+constexpr int SPAN_WORDS = SPAN_BLOCKS / 32;
+constexpr int PIECE_BLOCKS = 16;                    // <= 512 positions per piece
+constexpr int PIECE_LEN = PIECE_BLOCKS * 32;
+constexpr int MAX_BW_FAST = 448;                    // piece cells = PIECE_LEN + 2*bw <= 1408
+
+typedef Unit SpanUnit;                              // one (ProfileBuffer, contig) pair; nSpans = ceil((size + bw) / SPAN_LEN)
+
+struct SpanRun {                                    // a run of above-threshold positions inside one piece
+  uint32_t left, len, peak, wsum;
+  double score;                                     // exact-order score at `peak`
+  uint32_t span;                                    // work item that produced it
+  uint32_t rank;                                    // ordinal among the runs of that span (position order)
+};
+
+struct SpanArgs {
+  Tags T;
+  const SpanUnit* units;
+  const uint32_t* nTilesIdx;                        // [C]
+  const uint32_t* srcSample;                        // [nSrc] density sources (non-control samples)
+  uint32_t nSrc;
+  uint32_t nUnits, totalSpans;
+  uint32_t bw;
+  const double* taps;                               // 2bw+1, host-computed exactly as misc/kernel.cpp:16-35
+  double thr;                                       // region threshold
+  double kmaxBound;                                 // taps[bw] * (1 + 1e-9): cold-block bound per unit of pooled weight
+  double cN;                                        // taps[bw] / bw^2: moment-form scale
+  double dS;                                        // error bound of the moment form per unit of window weight
+  // outputs
+  uint32_t* ticket;
+  SpanRun* runs;
+  uint32_t runCap;
+  uint32_t* runCount;
+  uint32_t* spanRunCount;                           // [totalSpans]
+  uint32_t* flags;
+  unsigned long long* stat;                         // [0] hot blocks, [1] pieces, [2] exact evaluations, [3] spans with tags
+};
+
+struct SpanSmem { uint32_t taps, warp0, warpStride, oRs, oRx, oBins, oD, oDR, oSc, oMw, oHm, total; };
+
+__host__ __device__ inline SpanSmem span_smem_layout (uint32_t bw, uint32_t nRs, bool nondir) {
+  SpanSmem L;
+  uint32_t o = 0;
+  L.taps = o;      o += ((2 * bw + 2) & ~1u) * 8;
+  o = (o + 15) & ~15u;
+  L.warp0 = o;
+  const uint32_t W = PIECE_LEN + 2 * bw + 4;
+  uint32_t w = 0;
+  L.oRs = w;   w += ((nRs + 1) & ~1u) * 8;
+  L.oRx = w;   w += ((nRs + 2) & ~1u) * 4;
+  L.oBins = w; w += ((((SPAN_LEN + 2 * bw) >> 3) + 3) & ~1u) * 4;
+  L.oD = w;    w += W * 4;
+  L.oDR = w;   w += nondir ? W * 4 : 0;
+  L.oSc = w;   w += PIECE_LEN * 4;
+  L.oMw = w;   w += (PIECE_BLOCKS + 2) * 4;
+  L.oHm = w;   w += (SPAN_WORDS + 2) * 4;
+  w = (w + 15) & ~15u;
+  L.warpStride = w;
+  L.total = o + w * SP_WARPS;
+  return L;
+}
+
+__device__ __forceinline__ unsigned long long warp_sum_u64 (unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_sum_u32 (uint32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ unsigned long long warp_incl_scan_u64 (unsigned long long v, uint32_t lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const unsigned long long n = __shfl_up_sync(0xffffffffu, v, o); if (lane >= (uint32_t)o) v += n; }
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_incl_scan_u32 (uint32_t v, uint32_t lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, v, o); if (lane >= (uint32_t)o) v += n; }
+  return v;
+}
+
+// exact-order density of the position whose window starts at cell u0 (cells u0 .. u0+2bw), dense form:
+// a cell without tags contributes +0.0, which leaves the running sum unchanged, so this equals the
+// reference's sum over the tags in ascending position (misc/peakcall.cpp:203-209)
+__device__ __forceinline__ double exact_dense (const double* __restrict__ Ks, const uint32_t* __restrict__ cells, uint32_t u0, uint32_t bw) {
+  double s = 0.0;
+  const uint32_t n = 2 * bw;
+  for (uint32_t k = 0; k <= n; ++k) {
+    const uint32_t w = cells[u0 + k];
+    if (w) s = __dadd_rn(s, __dmul_rn(Ks[n - k], (double)w));
+  }
+  return s;
+}
+
+template <bool NONDIR>
+__global__ void __launch_bounds__(SP_THREADS) span_kernel (const __grid_constant__ SpanArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const uint32_t bw = a.bw;
+  const uint32_t nStr = NONDIR ? 2u : 1u;
+  const uint32_t nRs = a.nSrc * nStr;
+  const SpanSmem L = span_smem_layout(bw, nRs, NONDIR);
+  double* Ks = (double*)(smem + L.taps);
+  const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+  unsigned char* wbase = smem + L.warp0 + (size_t)warp * L.warpStride;
+  unsigned long long* rs = (unsigned long long*)(wbase + L.oRs);    // first entry of each source range
+  uint32_t* rx = (uint32_t*)(wbase + L.oRx);                         // exclusive prefix of the range lengths
+  uint32_t* bins = (uint32_t*)(wbase + L.oBins);
+  uint32_t* D = (uint32_t*)(wbase + L.oD);
+  uint32_t* DR = (uint32_t*)(wbase + L.oDR);
+  float* scf = (float*)(wbase + L.oSc);
+  uint32_t* mw = (uint32_t*)(wbase + L.oMw);
+  uint32_t* hm = (uint32_t*)(wbase + L.oHm);
+
+  for (uint32_t i = tid; i < 2 * bw + 1; i += SP_THREADS) Ks[i] = a.taps[i];
+  __syncthreads();                                                    // the only block-level barrier
+  const uint32_t nBins = ((SPAN_LEN + 2 * bw) >> 3) + 2;
+  const uint32_t nb8 = ((31 + 2 * bw) >> 3) + 1;                      // bins covering one block's window
+  const unsigned long long bw2 = (unsigned long long)bw * bw;
+  unsigned long long stHot = 0, stPieces = 0, stExact = 0, stSpans = 0;
+
+  for (;;) {
+    uint32_t work = 0;
+    if (lane == 0) work = atomicAdd(a.ticket, 1u);
+    work = __shfl_sync(0xffffffffu, work, 0);
+    if (work >= a.totalSpans) break;
+
+    uint32_t ui;
+    { uint32_t lo = 0, hi = a.nUnits; while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(&a.units[mid].spanStart) <= work) lo = mid; else hi = mid; } ui = lo; }
+    const SpanUnit U = a.units[ui];
+    const uint32_t ts = (work - U.spanStart) * SPAN_LEN + 1;           // first position of the span
+    const uint64_t lastPos = (uint64_t)U.size + bw;                   // Q20: evaluated through lastTag+bw
+    const uint32_t np = (uint32_t)min((uint64_t)SPAN_LEN, lastPos - (ts - 1));
+    const int64_t cell0 = (int64_t)ts - bw;                           // position of bin cell 0
+    const uint32_t nTi = a.nTilesIdx[U.contig];
+
+    // ---- A1: entry range of every source (sample, strand) over [ts-bw, te+bw]; flat index over all of them ----
+    uint32_t total = 0;
+    for (uint32_t g0 = 0; g0 < nRs; g0 += 32) {
+      const uint32_t j = g0 + lane;
+      uint64_t x = 0, y = 0;
+      if (j < nRs) {
+        const uint32_t s = __ldg(a.srcSample + j / nStr);
+        const uint32_t d = NONDIR ? (j % nStr) : U.buffer;
+        seg_range(a.T, s, d, U.contig, nTi, cell0, (int64_t)ts + np - 1 + bw, x, y);
+      }
+      const uint32_t c = (uint32_t)(y - x);
+      const uint32_t inc = warp_incl_scan_u32(c, lane);
+      if (j < nRs) { rs[j] = x; rx[j] = total + inc - c; }
+      total += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) rx[nRs] = total;
+    if (total == 0) { if (lane == 0) a.spanRunCount[work] = 0; continue; }
+    ++stSpans;
+    for (uint32_t i = lane; i < nBins; i += 32) bins[i] = 0;
+    __syncwarp();
+
+    // ---- A2: pool the density sources into 8-position bins --------------------------------------------------------
+    {
+      uint32_t j = 0;
+      for (uint32_t t = lane; t < total; t += 32) {
+        while (rx[j + 1] <= t) ++j;
+        const uint64_t e = rs[j] + (t - rx[j]);
+        const uint32_t p = __ldg(a.T.pos + e);
+        const uint32_t c = __ldg(a.T.cnt + e);
+        atomicAdd(&bins[(uint32_t)((int64_t)p - cell0) >> 3], c);
+      }
+    }
+    __syncwarp();
+
+    // ---- A3: hot blocks ------------------------------------------------------------------------------------------
+    const uint32_t nBlk = (np + 31) >> 5;
+    uint32_t anyHot = 0;
+#pragma unroll
+    for (uint32_t m = 0; m < (uint32_t)SPAN_WORDS; ++m) {
+      const uint32_t k = 32 * m + lane;
+      bool hot = false;
+      if (k < nBlk) {
+        unsigned long long sum = 0;
+        const uint32_t b0 = 4 * k;
+        for (uint32_t q = 0; q < nb8; ++q) sum += bins[b0 + q];
+        hot = __dmul_rn((double)sum, a.kmaxBound) >= a.thr;
+      }
+      const uint32_t msk = __ballot_sync(0xffffffffu, hot);
+      if (lane == 0) hm[m] = msk;
+      anyHot |= msk;
+    }
+    if (lane == 0) hm[SPAN_WORDS] = 0;
+    __syncwarp();
+    if (!anyHot) { if (lane == 0) a.spanRunCount[work] = 0; continue; }
+
+    // ---- B: pieces, in position order -------------------------------------------------------------------------------
+    uint32_t spanRuns = 0;
+    uint32_t kb = 0;
+    while (kb < nBlk) {
+      // next maximal group of hot blocks [zs, ze) (uniform scalar code over the mask words)
+      { uint32_t m = hm[kb >> 5] >> (kb & 31);
+        if (!m) { kb = ((kb >> 5) + 1) << 5; continue; }
+        kb += __ffs(m) - 1; }
+      const uint32_t zs = kb;
+      for (;;) {
+        const uint32_t x = ~(hm[kb >> 5] >> (kb & 31));
+        kb += x ? (uint32_t)(__ffs(x) - 1) : 32u;
+        if ((kb & 31) != 0 || kb >= nBlk || !(hm[kb >> 5] & 1u)) break;
+      }
+      if (kb > nBlk) kb = nBlk;
+      const uint32_t ze = kb;
+      stHot += ze - zs;
+
+      for (uint32_t pb = zs; pb < ze; pb += PIECE_BLOCKS) {
+        const uint32_t nb = min((uint32_t)PIECE_BLOCKS, ze - pb);
+        ++stPieces;
+        const uint32_t P = min(32 * nb, np - 32 * pb);                // positions of this piece
+        const uint32_t q0 = ts + 32 * pb;                             // first position
+        const int64_t cbase = (int64_t)q0 - bw;                       // position of cell 0
+        const uint32_t W = 32 * nb + 2 * bw;                          // cells
+        const uint32_t nbEff = (P + 31) >> 5;
+
+        for (uint32_t u = lane; u < W + 2; u += 32) { D[u] = 0; if (NONDIR) DR[u] = 0; }
+        __syncwarp();
+
+        // B1: the piece's tags -> dense cells (the span's entries are L1/L2 hits by now)
+        {
+          uint32_t j = 0;
+          for (uint32_t t = lane; t < total; t += 32) {
+            while (rx[j + 1] <= t) ++j;
+            const uint64_t e = rs[j] + (t - rx[j]);
+            const int64_t u = (int64_t)__ldg(a.T.pos + e) - cbase;
+            if (u >= 0 && u < (int64_t)W) atomicAdd((NONDIR && (j & 1u)) ? &DR[u] : &D[u], __ldg(a.T.cnt + e));
+          }
+        }
+        __syncwarp();
+
+        // B2: window sums of position 0 (cells 0 .. 2bw) and the piece's total weight
+        unsigned long long c0 = 0, c1 = 0, c2 = 0, tot = 0;
+        for (uint32_t u = lane; u < W; u += 32) {
+          const unsigned long long w = (unsigned long long)D[u] + (NONDIR ? (unsigned long long)DR[u] : 0ull);
+          tot += w;
+          if (u <= 2 * bw) { c0 += w; c1 += w * u; c2 += w * u * u; }
+        }
+        c0 = warp_sum_u64(c0); c1 = warp_sum_u64(c1); c2 = warp_sum_u64(c2); tot = warp_sum_u64(tot);
+        const double dPiece = __dmul_rn((double)tot, a.dS);           // one conservative error bound for the whole piece
+
+        // B3: classify every position: moment form, exact order only inside the error band
+        for (uint32_t b = 0; b < nbEff; ++b) {
+          const uint32_t i = 32 * b + lane;
+          unsigned long long d0 = 0, d1 = 0, d2 = 0;
+          if (i >= 1) {
+            const unsigned long long ue = i + 2 * bw, ul = i - 1;
+            const unsigned long long we = (unsigned long long)D[ue] + (NONDIR ? (unsigned long long)DR[ue] : 0ull);
+            const unsigned long long wl = (unsigned long long)D[ul] + (NONDIR ? (unsigned long long)DR[ul] : 0ull);
+            d0 = we - wl; d1 = we * ue - wl * ul; d2 = we * ue * ue - wl * ul * ul;
+          }
+          const unsigned long long S0 = c0 + warp_incl_scan_u64(d0, lane);
+          const unsigned long long S1 = c1 + warp_incl_scan_u64(d1, lane);
+          const unsigned long long S2 = c2 + warp_incl_scan_u64(d2, lane);
+          c0 = __shfl_sync(0xffffffffu, S0, 31); c1 = __shfl_sync(0xffffffffu, S1, 31); c2 = __shfl_sync(0xffffffffu, S2, 31);
+          const unsigned long long x = i + bw;
+          const unsigned long long N = bw2 * S0 - (x * x * S0 - 2ull * x * S1 + S2);
+          double v = __dmul_rn((double)(long long)N, a.cN);
+          const bool valid = i < P;
+          bool above = valid && v >= a.thr + dPiece;
+          if (valid && !above && v >= a.thr - dPiece) {                // too close to call: the reference's own arithmetic decides
+            const double f = exact_dense(Ks, D, i, bw);
+            v = NONDIR ? __dadd_rn(f, exact_dense(Ks, DR, i, bw)) : f; // misc/peakcall.cpp:57
+            above = v >= a.thr;
+            ++stExact;
+          }
+          if (valid) scf[i] = (float)v;
+          const uint32_t m = __ballot_sync(0xffffffffu, above);
+          if (lane == 0) mw[b] = m;
+        }
+        if (lane == 0) mw[nbEff] = 0;
+        __syncwarp();
+
+        // B4: runs of above-threshold positions
+        uint32_t nRuns = 0;
+        {
+          uint32_t n = 0;
+          if (lane < nbEff) { const uint32_t m = mw[lane]; const uint32_t prev = lane > 0 ? (mw[lane - 1] >> 31) : 0u; n = __popc(m & ~((m << 1) | prev)); }
+          nRuns = warp_sum_u32(n);
+        }
+        if (nRuns == 0) continue;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(a.runCount, nRuns);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const bool room = (uint64_t)base + nRuns <= a.runCap;
+        if (!room && lane == 0) atomicOr(a.flags, FLAG_RUN_OVERFLOW);
+
+        uint32_t cursor = 0;
+        for (uint32_t r = 0; r < nRuns; ++r) {
+          // next run [r0, r1) in position order (uniform across the warp)
+          { uint32_t w = cursor >> 5; uint32_t m = mw[w] >> (cursor & 31);
+            while (!m) { ++w; cursor = w << 5; m = mw[w]; }
+            cursor += __ffs(m) - 1; }
+          const uint32_t r0 = cursor;
+          for (;;) {
+            const uint32_t x = ~(mw[cursor >> 5] >> (cursor & 31));
+            cursor += x ? (uint32_t)(__ffs(x) - 1) : 32u;
+            if ((cursor & 31) != 0 || cursor >= 32 * nbEff || !(mw[cursor >> 5] & 1u)) break;
+          }
+          const uint32_t r1 = cursor;
+          if (!room) continue;
+
+          // pooled hit sum of the density sources == nonControlSum of misc/peakcall.cpp:36-40 (HitCount wraps mod 2^32)
+          uint32_t wsum = 0;
+          float fmax_ = -1.0f;
+          for (uint32_t i = r0 + lane; i < r1; i += 32) { wsum += D[bw + i] + (NONDIR ? DR[bw + i] : 0u); fmax_ = fmaxf(fmax_, scf[i]); }
+          wsum = warp_sum_u32(wsum);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) fmax_ = fmaxf(fmax_, __shfl_xor_sync(0xffffffffu, fmax_, o));
+
+          // peak: first strict maximum of the exact-order score (misc/data.cpp:97-101).  Candidates are the positions
+          // whose fast value (kept as float) could still be the maximum; they alone are evaluated exactly:
+          // exact_i <= f_i (1+2^-24) + dPiece and exact_max >= f_max (1-2^-24) - dPiece.
+          const double cut = (double)fmax_ * (1.0 - 0x1p-22) - 2.5 * dPiece;
+          double best = -1.0; uint32_t bestI = r0;
+          for (uint32_t g = r0; g < r1; g += 32) {
+            const uint32_t i = g + lane;
+            double e = -1.0;
+            if (i < r1 && (double)scf[i] >= cut) {
+              const double f = exact_dense(Ks, D, i, bw);
+              e = NONDIR ? __dadd_rn(f, exact_dense(Ks, DR, i, bw)) : f;
+              ++stExact;
+            }
+            uint32_t ei = i;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const double oe = __shfl_xor_sync(0xffffffffu, e, o);
+              const uint32_t oi = __shfl_xor_sync(0xffffffffu, ei, o);
+              if (oe > e || (oe == e && oi < ei)) { e = oe; ei = oi; }
+            }
+            if (e > best) { best = e; bestI = ei; }
+          }
+          if (lane == 0) {
+            SpanRun rr;
+            rr.left = q0 + r0; rr.len = r1 - r0; rr.peak = q0 + bestI; rr.wsum = wsum; rr.score = best; rr.span = work; rr.rank = spanRuns + r;
+            a.runs[base + r] = rr;
+          }
+        }
+        spanRuns += nRuns;
+      }
+    }
+    if (lane == 0) a.spanRunCount[work] = spanRuns;
+  }
+  stHot = warp_sum_u64(stHot) / 32; stPieces = warp_sum_u64(stPieces) / 32; stSpans = warp_sum_u64(stSpans) / 32; stExact = warp_sum_u64(stExact);
+  if (lane == 0) {
+    if (stHot) atomicAdd(a.stat + 0, stHot);
+    if (stPieces) atomicAdd(a.stat + 1, stPieces);
+    if (stExact) atomicAdd(a.stat + 2, stExact);
+    if (stSpans) atomicAdd(a.stat + 3, stSpans);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ordering, stitching, filtering
+// ------------------------------------------------------------------------------------------------
+struct Cand2 {                      // a candidate region == one Region object of the reference
+  uint32_t unit, left, len, peak, wsum;
+  uint32_t slot;                    // run slot of the first piece (row of runCounts / runKurt)
+  uint32_t nPieces, pad;
+  double score;
+};
+
+// position of every run in (span, rank) order
+__global__ void run_order_kernel (const SpanRun* __restrict__ runs, uint32_t nRuns, const unsigned long long* __restrict__ spanOrd, uint32_t* __restrict__ ordIdx) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nRuns) return;
+  ordIdx[spanOrd[runs[i].span] + runs[i].rank] = i;
+}
+
+__device__ __forceinline__ uint32_t unit_of_span (const SpanUnit* __restrict__ units, uint32_t nUnits, uint32_t span) {
+  uint32_t lo = 0, hi = nUnits;
+  while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (units[mid].spanStart <= span) lo = mid; else hi = mid; }
+  return lo;
+}
+
+__global__ void run_heads2_kernel (const SpanRun* __restrict__ runs, const uint32_t* __restrict__ ordIdx, uint32_t nRuns,
+                                   const SpanUnit* __restrict__ units, uint32_t nUnits, uint32_t* __restrict__ head) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nRuns) return;
+  bool cont = false;
+  if (j > 0) {
+    const SpanRun a = runs[ordIdx[j]], p = runs[ordIdx[j - 1]];
+    cont = a.left == p.left + p.len && unit_of_span(units, nUnits, a.span) == unit_of_span(units, nUnits, p.span);
+  }
+  head[j] = cont ? 0u : 1u;
+}
+
+__global__ void merge_runs2_kernel (const SpanRun* __restrict__ runs, const uint32_t* __restrict__ ordIdx, const uint32_t* __restrict__ head,
+                                    const unsigned long long* __restrict__ headScan, uint32_t nRuns, const SpanUnit* __restrict__ units, uint32_t nUnits,
+                                    Cand2* __restrict__ cand, unsigned long long* __restrict__ unitCand) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nRuns || !head[j]) return;
+  const SpanRun f = runs[ordIdx[j]];
+  Cand2 c;
+  c.unit = unit_of_span(units, nUnits, f.span); c.left = f.left; c.len = f.len; c.peak = f.peak; c.wsum = f.wsum; c.score = f.score;
+  c.slot = ordIdx[j]; c.nPieces = 1; c.pad = 0;
+  for (uint32_t q = j + 1; q < nRuns && !head[q]; ++q) {
+    const SpanRun r = runs[ordIdx[q]];
+    c.len += r.len;
+    c.wsum += r.wsum;                                                 // HitCount wraps mod 2^32 (misc/peakcall.cpp:36-40)
+    if (r.score > c.score) { c.score = r.score; c.peak = r.peak; }    // first strict maximum (misc/data.cpp:97-101)
+    ++c.nPieces;
+  }
+  cand[headScan[j]] = c;
+  atomicAdd(&unitCand[c.unit], 1ull);
+}
+
+// hit filter (misc/peakcall.cpp:41 first clause)
+__global__ void cand_hit_kernel (const Cand2* __restrict__ cand, uint32_t n, double hitThr, uint32_t* __restrict__ pass) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  pass[i] = ((double)cand[i].wsum >= hitThr) ? 1u : 0u;
+}
+
+// Region::exptSums (misc/data.cpp:116-131) and Region::posKurtosis (misc/data.cpp:133-182) of the candidates that
+// passed the hit filter: one warp per region.  Lanes take the (sample, strand) tracks, sum their entries
+// inside the region (counts, and count*offset with offsets as UShort and both sums as HitCount),
+// then the region's positions are pooled over ALL samples (controls included, minus the tags the reference
+// forgets, Q4) in shared memory 1024 at a time and the two central moments are accumulated sequentially in
+// position order, exactly as the reference does.
+struct StatArgs {
+  Tags T;
+  const SpanUnit* units;
+  const uint32_t* nTilesIdx;
+  const Cand2* cand;
+  const uint32_t* list;             // hit-filter survivors (candidate indices, ascending)
+  uint32_t nList;
+  int nondir;
+  double kurtThr;
+  uint32_t* counts;                 // [nList * nSamples]
+  double* kurt;                     // [nList]
+  uint32_t* pass;                   // [nList] kurtosis filter (misc/peakcall.cpp:41 second clause)
+};
+
+__global__ void __launch_bounds__(KURT_WARPS * 32) region_stats_kernel (StatArgs a) {
+  __shared__ uint32_t cells[KURT_WARPS][KURT_CHUNK];
+  const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+  const uint32_t i = blockIdx.x * KURT_WARPS + warp;
+  if (i >= a.nList) return;
+  const uint32_t n = a.T.nSamples;
+  const uint32_t nStr = a.nondir ? 2u : 1u;
+  const uint32_t nR = n * nStr;
+  const Cand2 c = a.cand[a.list[i]];
+  const SpanUnit U = a.units[c.unit];
+  const uint32_t nTi = a.nTilesIdx[U.contig];
+  uint32_t* cell = cells[warp];
+  const bool small = c.len <= (uint32_t)KURT_CHUNK;
+  if (small) { for (uint32_t k = lane; k < c.len; k += 32) cell[k] = 0; __syncwarp(); }
+  uint32_t count = 0, sum = 0;
+  for (uint32_t g0 = 0; g0 < nR; g0 += 32) {
+    const uint32_t j = g0 + lane;
+    uint32_t cs = 0, os = 0;
+    if (j < nR) {
+      const uint32_t s = j / nStr, d = a.nondir ? (j % nStr) : U.buffer;
+      uint64_t x, y;
+      seg_range(a.T, s, d, U.contig, nTi, c.left, (int64_t)c.left + c.len - 1, x, y);
+      for (uint64_t e = x; e < y; ++e) {
+        const uint32_t k = __ldg(a.T.cntEff + e);
+        const uint32_t o = __ldg(a.T.pos + e) - c.left;
+        cs += k;
+        os += k * (o & 0xFFFFu);
+        if (small && k) atomicAdd(&cell[o], k);
+      }
+    }
+    if (nStr == 2) { cs += __shfl_xor_sync(0xffffffffu, cs, 1); os += __shfl_xor_sync(0xffffffffu, os, 1); }
+    const bool owner = j < nR && (nStr == 1 || !(j & 1u));
+    if (owner) a.counts[(uint64_t)i * n + j / nStr] = cs;
+    count += warp_sum_u32(owner ? cs : 0u);
+    sum += warp_sum_u32(owner ? os : 0u);
+  }
+  __syncwarp();
+  const double xbar = (double)sum / (double)count;                   // misc/data.cpp:147
+  double sum2 = 0.0, sum4 = 0.0;
+  for (uint32_t o0 = 0; o0 < c.len; o0 += KURT_CHUNK) {
+    const uint32_t oc = min((uint32_t)KURT_CHUNK, c.len - o0);
+    if (!small) {                                                     // long region: pool one chunk of positions at a time
+      for (uint32_t k = lane; k < KURT_CHUNK; k += 32) cell[k] = 0;
+      __syncwarp();
+      for (uint32_t j = 0; j < nR; ++j) {
+        const uint32_t s = j / nStr, d = a.nondir ? (j % nStr) : U.buffer;
+        uint64_t x, y;
+        seg_range(a.T, s, d, U.contig, nTi, (int64_t)c.left + o0, (int64_t)c.left + o0 + oc - 1, x, y);
+        for (uint64_t e = x + lane; e < y; e += 32) atomicAdd(&cell[a.T.pos[e] - c.left - o0], a.T.cntEff[e]);
+      }
+      __syncwarp();
+    }
+    for (uint32_t g = 0; g < oc; g += 32) {
+      const uint32_t o = o0 + g + lane;
+      const uint32_t pc = (g + lane < oc) ? cell[g + lane] : 0u;
+      uint32_t nz = __ballot_sync(0xffffffffu, pc != 0);
+      if (!nz) continue;
+      const double dd = __dsub_rn((double)(o & 0xFFFFu), xbar);     // offset counter is a UShort (Q8)
+      const double d2 = __dmul_rn(dd, dd);
+      const double d4 = __dmul_rn(d2, d2);                          // pow(x,4) == (x*x)*(x*x) in the reference build (Q9)
+      const double t2 = __dmul_rn((double)pc, d2);
+      const double t4 = __dmul_rn((double)pc, d4);
+      while (nz) {
+        const int b = __ffs(nz) - 1;
+        sum2 = __dadd_rn(sum2, __shfl_sync(0xffffffffu, t2, b));
+        sum4 = __dadd_rn(sum4, __shfl_sync(0xffffffffu, t4, b));
+        nz &= nz - 1;
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    const double k = __ddiv_rn(__dmul_rn(__dsub_rn((double)count, 1.0), sum4), __dmul_rn(sum2, sum2));   // misc/data.cpp:181
+    a.kurt[i] = k;
+    a.pass[i] = (a.kurtThr == 0.0 || (c.len > 1 && k <= a.kurtThr)) ? 1u : 0u;
+  }
+}
+
+// strand-correlation filter (third clause); list2 holds positions in list1 space, corr[k] belongs to list2[k]
+__global__ void cand_corr_kernel (const uint32_t* __restrict__ list2, uint32_t n2, const double* __restrict__ corr, double corrThr,
+                                  uint32_t* __restrict__ pass, double* __restrict__ rowCorr) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n2) return;
+  const uint32_t i = list2[k];
+  rowCorr[i] = corr[k];
+  if (corrThr > -1.0 && !(corr[k] >= corrThr)) pass[i] = 0;         // NaN fails
+}
+
+__global__ void dump_desc2_kernel (const Cand2* __restrict__ cand, const uint32_t* __restrict__ list1, const uint32_t* __restrict__ list2, uint32_t n,
+                                   uint32_t* __restrict__ dUnit, uint32_t* __restrict__ dLeft, uint32_t* __restrict__ dLen, uint32_t* __restrict__ dChunks) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Cand2 c = cand[list1[list2[i]]];
+  dUnit[i] = c.unit; dLeft[i] = c.left; dLen[i] = c.len; dChunks[i] = (c.len + TILE - 1) / TILE;
+}
+
+// accepted candidates -> the column arrays of the result table (canonical order: buffer, contig, left)
+struct EmitArgs {
+  const Cand2* cand;
+  const uint32_t* list;                  // hit-filter survivors
+  const uint32_t* pass;                  // [nList] after the kurtosis (and correlation) filters
+  const unsigned long long* passScan;
+  uint32_t nList;
+  const SpanUnit* units;
+  const unsigned long long* unitFirst;   // [nUnits] ordinal of the first candidate of each unit
+  const uint32_t* statCounts;            // [nList * nSamples]
+  const double* statKurt;                // [nList]
+  const double* rowCorr;                 // [nList] or NULL
+  uint32_t nSamples;
+  // outputs (device slab)
+  uint8_t* buffer; uint32_t* contig; uint32_t* left; uint32_t* len; uint32_t* peak; unsigned long long* candIndex;
+  double* peakScore; double* kurt; double* corr; uint32_t* counts; uint32_t* wsum;
+};
+
+__global__ void emit_rows_kernel (EmitArgs a) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.nList || !a.pass[i]) return;
+  const uint32_t ci = a.list[i];
+  const Cand2 c = a.cand[ci];
+  const unsigned long long o = a.passScan[i];
+  a.buffer[o] = (uint8_t)a.units[c.unit].buffer;
+  a.contig[o] = a.units[c.unit].contig;
+  a.left[o] = c.left; a.len[o] = c.len; a.peak[o] = c.peak; a.wsum[o] = c.wsum;
+  a.candIndex[o] = (unsigned long long)ci - a.unitFirst[c.unit];
+  a.peakScore[o] = c.score;
+  a.kurt[o] = a.statKurt[i];
+  a.corr[o] = a.rowCorr ? a.rowCorr[i] : __longlong_as_double(0x7ff8000000000000ll);
+  for (uint32_t s = 0; s < a.nSamples; ++s) a.counts[o * a.nSamples + s] = a.statCounts[(uint64_t)i * a.nSamples + s];
+}
+
+// per-sample totals of the accepted rows (ProfileBuffer::nTagsInRegions, misc/peakcall.cpp:44)
+__global__ void tags_in_regions_kernel (const uint32_t* __restrict__ counts, unsigned long long nRows, uint32_t nSamples, unsigned long long* __restrict__ out) {
+  extern __shared__ unsigned long long sh[];
+  for (uint32_t s = threadIdx.x; s < nSamples; s += blockDim.x) sh[s] = 0;
+  __syncthreads();
+  const unsigned long long total = nRows * nSamples;
+  for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (unsigned long long)gridDim.x * blockDim.x)
+    atomicAdd(&sh[g % nSamples], (unsigned long long)counts[g]);
+  __syncthreads();
+  for (uint32_t s = threadIdx.x; s < nSamples; s += blockDim.x) if (sh[s]) atomicAdd(&out[s], sh[s]);
+}
+
+__global__ void unit_first_kernel (const unsigned long long* __restrict__ unitCand, uint32_t nUnits, unsigned long long* __restrict__ unitFirst) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long run = 0; for (uint32_t u = 0; u < nUnits; ++u) { unitFirst[u] = run; run += unitCand[u]; } }
+}
+
+}  // namespace upb
