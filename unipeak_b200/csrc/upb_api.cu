@@ -45,7 +45,9 @@ struct upb_ctx {
   bool loaded = false;
   std::vector<uint64_t> off;            // host copy
   std::vector<uint32_t> firstPos, lastPos;   // [(s*2+d)*C + c], 0 if empty
-  DevBuf d_pos, d_cnt, d_cntEff, d_off, d_segStart, d_tidx, d_tidxBase, d_sizes, d_nTilesIdx, d_small;
+  DevBuf d_pos, d_cnt, d_off, d_segStart, d_tidx, d_tidxBase, d_sizes, d_nTilesIdx, d_small;
+  DevBuf d_ment, d_mtOff, d_mtBase, d_mtCount, d_mEff;   // tile-major copy (upb_device.cuh)
+  std::vector<uint32_t> mtBase;         // [2*C+1]
   std::map<std::string, DevBuf> scratch;     // grow-only device scratch, by name
   unsigned char* h_small = nullptr;          // 4 KB of pinned host memory for small read-backs
   std::vector<HostSlab> slabPool;            // pinned host slabs of freed region tables, reused by the next call
@@ -110,7 +112,7 @@ extern "C" int upb_create (int device, upb_ctx** out) {
 extern "C" void upb_destroy (upb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  DevBuf* all[] = {&ctx->d_pos, &ctx->d_cnt, &ctx->d_cntEff, &ctx->d_off, &ctx->d_segStart, &ctx->d_tidx, &ctx->d_tidxBase, &ctx->d_sizes,
+  DevBuf* all[] = {&ctx->d_ment, &ctx->d_mtOff, &ctx->d_mtBase, &ctx->d_mtCount, &ctx->d_mEff, &ctx->d_pos, &ctx->d_cnt, &ctx->d_off, &ctx->d_segStart, &ctx->d_tidx, &ctx->d_tidxBase, &ctx->d_sizes,
     &ctx->d_nTilesIdx, &ctx->d_small};
   for (DevBuf* b : all) release(*b);
   for (auto& kv : ctx->scratch) release(kv.second);
@@ -192,7 +194,10 @@ static Tags make_tags (const upb_ctx* ctx, bool useEff) {
   Tags T;
   T.pos = ctx->d_pos.as<uint32_t>();
   T.cnt = ctx->d_cnt.as<uint32_t>();
-  T.cntEff = useEff ? ctx->d_cntEff.as<uint32_t>() : ctx->d_cnt.as<uint32_t>();
+  T.ment = ctx->d_ment.as<uint2>();
+  T.mtOff = ctx->d_mtOff.as<unsigned long long>();
+  T.mtBase = ctx->d_mtBase.as<uint32_t>();
+  T.mEff = useEff ? ctx->d_mEff.as<uint32_t>() : nullptr;
   T.off = ctx->d_off.as<uint64_t>();
   T.tidx = ctx->d_tidx.as<uint32_t>();
   T.tidxBase = ctx->d_tidxBase.as<uint32_t>();
@@ -201,6 +206,8 @@ static Tags make_tags (const upb_ctx* ctx, bool useEff) {
   T.nSamples = ctx->nSamples;
   return T;
 }
+
+static int scan_u32 (upb_ctx* ctx, const uint32_t* d_in, uint64_t n, unsigned long long* d_out, unsigned long long* d_total, uint32_t* launches);
 
 extern "C" int upb_load_tags (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt) {
   if (!ctx) return UPB_ERR_BAD_ARG;
@@ -263,6 +270,35 @@ extern "C" int upb_load_tags (upb_ctx* ctx, uint32_t n_samples, const uint64_t* 
   if (E) {
     const uint64_t blocks = (E + 255) / 256;
     index_build_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(ia);
+    CU(cudaGetLastError());
+  }
+  // tile-major copy: counting sort of the entries by (strand, contig, 512-position mini-tile)
+  if (n_samples > (1u << 20)) return fail(ctx, UPB_ERR_UNSUPPORTED, "more than 2^20 samples");
+  ctx->mtBase.assign(2 * (size_t)C + 1, 0);
+  { uint64_t run = 0;
+    for (uint32_t d = 0; d < 2; ++d) for (uint32_t c = 0; c < C; ++c) { ctx->mtBase[(size_t)d * C + c] = (uint32_t)run; run += ((uint64_t)(ctx->sizes[c] - 1) >> MT_SHIFT) + 1; }
+    if (run > 0xFFFFFFF0ull) return fail(ctx, UPB_ERR_UNSUPPORTED, "genome too large for the mini-tile index");
+    ctx->mtBase[2 * (size_t)C] = (uint32_t)run; }
+  const uint32_t nMtTotal = ctx->mtBase.back();
+  ENSURE(ctx->d_mtBase, (2 * (size_t)C + 1) * 4);
+  ENSURE(ctx->d_mtCount, ((size_t)nMtTotal + 1) * 4);
+  ENSURE(ctx->d_mtOff, ((size_t)nMtTotal + 2) * 8);
+  ENSURE(ctx->d_ment, (E ? E : 1) * 8);
+  CU(cudaMemcpyAsync(ctx->d_mtBase.p, ctx->mtBase.data(), (2 * (size_t)C + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_mtCount.p, 0, ((size_t)nMtTotal + 1) * 4, ctx->stream));
+  {
+    MtArgs ma;
+    ma.pos = ctx->d_pos.as<uint32_t>(); ma.cnt = ctx->d_cnt.as<uint32_t>(); ma.segStart = ctx->d_segStart.as<uint64_t>(); ma.mtBase = ctx->d_mtBase.as<uint32_t>();
+    ma.mtCount = ctx->d_mtCount.as<uint32_t>(); ma.mtOff = ctx->d_mtOff.as<unsigned long long>(); ma.ment = ctx->d_ment.as<uint2>();
+    ma.C = C; ma.nSeg = nSeg; ma.nEntries = E;
+    const uint64_t blocks = (E + 255) / 256;
+    uint32_t l = 0;
+    if (E) mt_build_kernel<false><<<(unsigned)blocks, 256, 0, ctx->stream>>>(ma);
+    unsigned long long* d_tot = ctx->d_small.as<unsigned long long>() + 16;
+    int r = scan_u32(ctx, ma.mtCount, nMtTotal, ctx->d_mtOff.as<unsigned long long>(), d_tot, &l);
+    if (r) return r;
+    CU(cudaMemcpyAsync(ctx->d_mtOff.as<unsigned long long>() + nMtTotal, d_tot, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (E) mt_build_kernel<true><<<(unsigned)blocks, 256, 0, ctx->stream>>>(ma);
     CU(cudaGetLastError());
   }
   uint32_t flags = 0;
@@ -436,15 +472,11 @@ static int prepare (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, uint32_t* launch
 
   // Q4: zero the control tags the reference forgets
   if (haveControl && !(ctx->cntEffValid && ctx->lastControl == control)) {
-    ENSURE(ctx->d_cntEff, (ctx->nEntries ? ctx->nEntries : 1) * 4);
+    ENSURE(ctx->d_mEff, (ctx->nEntries ? ctx->nEntries : 1) * 4);
+    const uint32_t nMtTotal = ctx->mtBase.back();
     if (ctx->nEntries) {
-      ControlArgs ca;
-      ca.T = make_tags(ctx, false);
-      ca.nTilesIdx = ctx->d_nTilesIdx.as<uint32_t>(); ca.segStart = ctx->d_segStart.as<uint64_t>();
-      ca.control = d_control; ca.srcSample = d_src; ca.nSrc = (uint32_t)src.size();
-      ca.cntEff = ctx->d_cntEff.as<uint32_t>(); ca.nSeg = n * 2 * C; ca.nEntries = ctx->nEntries;
-      const uint64_t blocks = (ctx->nEntries + 255) / 256;
-      control_filter_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(ca);
+      mt_control_kernel<<<(nMtTotal + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_ment.as<uint2>(), ctx->d_mtOff.as<unsigned long long>(), nMtTotal, d_control,
+                                                                        ctx->d_mEff.as<uint32_t>());
       CU(cudaGetLastError());
       *launches += 1;
     }
@@ -524,7 +556,7 @@ static int dump_and_corr (upb_ctx* ctx, const DensArgs& base, bool nondir, uint3
 }
 
 static int launch_span (upb_ctx* ctx, const SpanArgs& sa, bool nondir, uint32_t* launches) {
-  const SpanSmem L = span_smem_layout(sa.bw, sa.nSrc * (nondir ? 2u : 1u), nondir);
+  const SpanSmem L = span_smem_layout(sa.bw, sa.nSamples, nondir, sa.nUnits);
   const size_t smem = L.total;
   if (smem > 227 * 1024) return fail(ctx, UPB_ERR_UNSUPPORTED, "bandwidth / sample count need more shared memory than one SM has");
   void (*kern)(const SpanArgs) = nondir ? span_kernel<true> : span_kernel<false>;
@@ -577,7 +609,7 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
   SpanArgs sa;
   memset(&sa, 0, sizeof sa);
   sa.T = pr.T; sa.units = d_units; sa.nTilesIdx = ctx->d_nTilesIdx.as<uint32_t>();
-  sa.srcSample = ctx->scratch["src"].as<uint32_t>(); sa.nSrc = pr.nSrc;
+  sa.control = ctx->scratch["control"].as<uint8_t>(); sa.nSamples = n;
   sa.nUnits = nUnits; sa.totalSpans = pr.totalSpans; sa.bw = cfg.bw;
   sa.taps = ctx->scratch["taps"].as<double>();
   sa.thr = cfg.thr;
@@ -669,9 +701,12 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
     pass2 = SCR("pass2", uint32_t, n1);
     pass2Scan = SCR("pass2Scan", unsigned long long, n1);
     StatArgs st;
-    st.T = pr.T; st.units = d_units; st.nTilesIdx = ctx->d_nTilesIdx.as<uint32_t>(); st.cand = cand; st.list = list1; st.nList = n1;
+    st.T = pr.T; st.units = d_units; st.cand = cand; st.list = list1; st.nList = n1;
     st.nondir = cfg.nondir ? 1 : 0; st.kurtThr = cfg.kurtThr; st.counts = statCounts; st.kurt = statKurt; st.pass = pass2;
-    region_stats_kernel<<<(n1 + KURT_WARPS - 1) / KURT_WARPS, KURT_WARPS * 32, 0, ctx->stream>>>(st);
+    const size_t statSmem = (size_t)KURT_WARPS * (KURT_CHUNK + n) * 4;
+    if (statSmem > 200 * 1024) return fail(ctx, UPB_ERR_UNSUPPORTED, "too many samples for the region statistics kernel");
+    CU(cudaFuncSetAttribute(region_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)statSmem));
+    region_stats_kernel<<<(n1 + KURT_WARPS - 1) / KURT_WARPS, KURT_WARPS * 32, statSmem, ctx->stream>>>(st);
     CU(cudaGetLastError());
     launches += 1;
 

@@ -28,10 +28,20 @@ struct Unit {                       // one (ProfileBuffer, contig) pair
   uint32_t spanStart;               // first global span index of this unit
 };
 
+constexpr int MT_SHIFT = 9;         // mini-tile: 512 positions, the granule of the tile-major copy
+constexpr int SPAN_SHIFT = 12;      // span: 4096 positions = 8 mini-tiles; entries carry their offset inside the span
+constexpr int SPAN_LEN = 1 << SPAN_SHIFT;
+constexpr int SPAN_MT = 1 << (SPAN_SHIFT - MT_SHIFT);
+
 struct Tags {                       // resident tag-frequency data (see upb_load_tags)
-  const uint32_t* pos;
-  const uint32_t* cnt;              // counts as loaded
-  const uint32_t* cntEff;           // counts with control-only positions zeroed (Q4); == cnt when no controls
+  const uint32_t* pos;              // sample-major arrays exactly as loaded (density kernel, validation)
+  const uint32_t* cnt;
+  // tile-major copy used by region calling: all samples' entries of one (strand, contig, mini-tile) are contiguous.
+  //   ment[e].x = count, ment[e].y = (sample << 12) | ((pos - 1) & 4095);   order inside a mini-tile is arbitrary
+  const uint2* ment;
+  const unsigned long long* mtOff;  // [nMtTotal + 1] first entry of every mini-tile
+  const uint32_t* mtBase;           // [2*C + 1] first mini-tile of (strand d, contig c) at d*C + c
+  const uint32_t* mEff;             // [E] counts with the control tags the reference forgets zeroed (Q4); NULL when no controls
   const uint64_t* off;              // [(s*2+d)*(C+1)+c]
   const uint32_t* tidx;             // per (s,d): tidxStride entries; per contig: nTiles0+3 entries
   const uint32_t* tidxBase;         // [C] offset of contig c inside one (s,d) index block
@@ -131,42 +141,58 @@ __global__ void index_build_kernel (IndexArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// control filter: a control sample's tag is remembered by the reference only when the same
-// add() call carried a non-zero non-control sum, i.e. when a non-control sample has a tag at the same
-// (strand, contig, position) (misc/peakcall.cpp:203-220).  cntEff = cnt with the others zeroed.
+// tile-major copy (built once per upb_load_tags): a counting sort of all entries by (strand, contig, mini-tile)
 // ------------------------------------------------------------------------------------------------
-struct ControlArgs {
-  Tags T;
-  const uint32_t* nTilesIdx;        // [C]
+struct MtArgs {
+  const uint32_t* pos;
+  const uint32_t* cnt;
   const uint64_t* segStart;         // [nSeg+1]
-  const uint8_t* control;           // [nSamples]
-  const uint32_t* srcSample;        // non-control samples
-  uint32_t nSrc;
-  uint32_t* cntEff;
-  uint32_t nSeg;
+  const uint32_t* mtBase;           // [2*C+1]
+  uint32_t* mtCount;                // [nMtTotal] histogram, then per-tile cursors
+  const unsigned long long* mtOff;  // [nMtTotal+1]
+  uint2* ment;
+  uint32_t C, nSeg;
   uint64_t nEntries;
 };
 
-__global__ void control_filter_kernel (ControlArgs a) {
+__device__ __forceinline__ uint32_t seg_of_entry (const uint64_t* __restrict__ segStart, uint32_t nSeg, uint64_t i) {
+  uint32_t lo = 0, hi = nSeg;       // largest g with segStart[g] <= i (empty segments are skipped by taking the largest)
+  while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (segStart[mid] <= i) lo = mid; else hi = mid; }
+  return lo;
+}
+
+template <bool SCATTER>
+__global__ void mt_build_kernel (MtArgs a) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.nEntries) return;
-  uint32_t lo = 0, hi = a.nSeg;
-  while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.segStart[mid] <= i) lo = mid; else hi = mid; }
-  const uint32_t c = lo % a.T.C;
-  const uint32_t sd = lo / a.T.C;
-  const uint32_t s = sd >> 1, d = sd & 1;
-  uint32_t v = a.T.cnt[i];
-  if (a.control[s]) {
-    const uint32_t p = a.T.pos[i];
-    bool found = false;
-    for (uint32_t j = 0; j < a.nSrc && !found; ++j) {
-      uint64_t x, y;
-      seg_range(a.T, a.srcSample[j], d, c, a.nTilesIdx[c], p, p, x, y);
-      found = y > x;
+  const uint32_t g = seg_of_entry(a.segStart, a.nSeg, i);
+  const uint32_t c = g % a.C, sd = g / a.C, d = sd & 1u, s = sd >> 1;
+  const uint32_t p = a.pos[i] - 1;
+  const uint32_t mt = a.mtBase[d * a.C + c] + (p >> MT_SHIFT);
+  if (!SCATTER) { atomicAdd(&a.mtCount[mt], 1u); return; }
+  const unsigned long long slot = a.mtOff[mt] + (atomicSub(&a.mtCount[mt], 1u) - 1u);
+  a.ment[slot] = make_uint2(a.cnt[i], (s << SPAN_SHIFT) | (p & (SPAN_LEN - 1)));
+}
+
+// control filter: a control sample's tag is remembered by the reference only when the same add()
+// call carried a non-zero non-control sum, i.e. when a non-control sample has a tag at the same (strand,
+// contig, position) (misc/peakcall.cpp:203-220).  mEff = count with the others zeroed.  One thread per mini-tile.
+__global__ void mt_control_kernel (const uint2* __restrict__ ment, const unsigned long long* __restrict__ mtOff, uint32_t nMt,
+                                   const uint8_t* __restrict__ control, uint32_t* __restrict__ mEff) {
+  const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= nMt) return;
+  const unsigned long long e0 = mtOff[m], e1 = mtOff[m + 1];
+  for (unsigned long long e = e0; e < e1; ++e) {
+    const uint2 x = ment[e];
+    uint32_t v = x.x;
+    if (control[x.y >> SPAN_SHIFT]) {
+      bool found = false;
+      const uint32_t rel = x.y & (SPAN_LEN - 1);
+      for (unsigned long long f = e0; f < e1 && !found; ++f) { const uint32_t y = ment[f].y; found = (y & (SPAN_LEN - 1)) == rel && !control[y >> SPAN_SHIFT]; }
+      if (!found) v = 0;
     }
-    if (!found) v = 0;
+    mEff[e] = v;
   }
-  a.cntEff[i] = v;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -6,8 +6,10 @@
 // path: the warps of a CTA only share the read-only tap table.  (v2 of this kernel gave a whole CTA one
 // 16384-position span and lost 63 % of its issue slots at __syncthreads — profiles/r01_v2_*.)
 //
-//   phase A  every tag entry of every density source (non-control sample) inside the span +- bandwidth is
-//            read once, coalesced, and pooled into 8-position bins in shared memory (shared-memory atomics
+//   phase A  the span's tag entries — ONE contiguous chunk of the tile-major copy built at load time
+//            (upb_device.cuh mt_build_kernel), plus one 512-position mini-tile of halo on either side — are
+//            read once, coalesced, 8 bytes per entry, and the density sources (non-control samples) are
+//            pooled into 8-position bins in shared memory (shared-memory atomics
 //            run at ~8 lane-ops/clk/SM on B200, profiles/r01_microbench_b200.txt).  A 32-position block is
 //            "hot" when  maxTap * (pooled weight within bandwidth of the block) >= threshold; a block that
 //            is not hot cannot hold a position of a region (misc/peakcall.cpp:57-60) and is never looked at
@@ -32,8 +34,6 @@ namespace upb {
 
 constexpr int SP_THREADS = 256;
 constexpr int SP_WARPS = SP_THREADS / 32;
-constexpr int SPAN_TILES = 2;                       // index tiles per span
-constexpr int SPAN_LEN = SPAN_TILES * TILE;         // 4096 positions
 constexpr int SPAN_BLOCKS = SPAN_LEN / 32;          // 128 blocks of 32 positions
 constexpr int SPAN_WORDS = SPAN_BLOCKS / 32;
 constexpr int PIECE_BLOCKS = 16;                    // <= 512 positions per piece
@@ -53,8 +53,8 @@ struct SpanArgs {
   Tags T;
   const SpanUnit* units;
   const uint32_t* nTilesIdx;                        // [C]
-  const uint32_t* srcSample;                        // [nSrc] density sources (non-control samples)
-  uint32_t nSrc;
+  const uint8_t* control;                           // [nSamples] 1 = negative control (not a density source)
+  uint32_t nSamples;
   uint32_t nUnits, totalSpans;
   uint32_t bw;
   const double* taps;                               // 2bw+1, host-computed exactly as misc/kernel.cpp:16-35
@@ -72,18 +72,18 @@ struct SpanArgs {
   unsigned long long* stat;                         // [0] hot blocks, [1] pieces, [2] exact evaluations, [3] spans with tags
 };
 
-struct SpanSmem { uint32_t taps, warp0, warpStride, oRs, oRx, oBins, oD, oDR, oSc, oMw, oHm, total; };
+struct SpanSmem { uint32_t taps, ustart, ctl, warp0, warpStride, oBins, oD, oDR, oSc, oMw, oHm, total; };
 
-__host__ __device__ inline SpanSmem span_smem_layout (uint32_t bw, uint32_t nRs, bool nondir) {
+__host__ __device__ inline SpanSmem span_smem_layout (uint32_t bw, uint32_t nSamples, bool nondir, uint32_t nUnits) {
   SpanSmem L;
   uint32_t o = 0;
   L.taps = o;      o += ((2 * bw + 2) & ~1u) * 8;
+  L.ustart = o;    o += (nUnits + 1) * 4;
+  L.ctl = o;       o += (nSamples + 3) & ~3u;
   o = (o + 15) & ~15u;
   L.warp0 = o;
   const uint32_t W = PIECE_LEN + 2 * bw + 4;
   uint32_t w = 0;
-  L.oRs = w;   w += ((nRs + 1) & ~1u) * 8;
-  L.oRx = w;   w += ((nRs + 2) & ~1u) * 4;
   L.oBins = w; w += ((((SPAN_LEN + 2 * bw) >> 3) + 3) & ~1u) * 4;
   L.oD = w;    w += W * 4;
   L.oDR = w;   w += nondir ? W * 4 : 0;
@@ -130,18 +130,31 @@ __device__ __forceinline__ double exact_dense (const double* __restrict__ Ks, co
   return s;
 }
 
+// entries of the span's chunk of one strand: [e0, e0+total); the first nPrev lie in the mini-tile before the span,
+// the next nOwn inside it, the rest in the mini-tile after it
+struct SpanChunk { unsigned long long e0; uint32_t nPrev, nOwn, total; };
+
+__device__ __forceinline__ SpanChunk span_chunk (const Tags& T, uint32_t d, uint32_t c, uint32_t k) {
+  const uint32_t gb = __ldg(T.mtBase + d * T.C + c);
+  const uint32_t nMt = __ldg(T.mtBase + d * T.C + c + 1) - gb;
+  const uint32_t m0 = k * SPAN_MT;
+  const uint32_t a0 = min(m0 > 0 ? m0 - 1 : 0u, nMt), a1 = min(m0, nMt), a2 = min(m0 + SPAN_MT, nMt), a3 = min(m0 + SPAN_MT + 1, nMt);
+  const unsigned long long o0 = __ldg(T.mtOff + gb + a0), o1 = __ldg(T.mtOff + gb + a1), o2 = __ldg(T.mtOff + gb + a2), o3 = __ldg(T.mtOff + gb + a3);
+  SpanChunk ch;
+  ch.e0 = o0; ch.nPrev = (uint32_t)(o1 - o0); ch.nOwn = (uint32_t)(o2 - o1); ch.total = (uint32_t)(o3 - o0);
+  return ch;
+}
+
 template <bool NONDIR>
-__global__ void __launch_bounds__(SP_THREADS) span_kernel (const __grid_constant__ SpanArgs a) {
+__global__ void __launch_bounds__(SP_THREADS, 4) span_kernel (const __grid_constant__ SpanArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const uint32_t bw = a.bw;
-  const uint32_t nStr = NONDIR ? 2u : 1u;
-  const uint32_t nRs = a.nSrc * nStr;
-  const SpanSmem L = span_smem_layout(bw, nRs, NONDIR);
+  const SpanSmem L = span_smem_layout(bw, a.nSamples, NONDIR, a.nUnits);
   double* Ks = (double*)(smem + L.taps);
+  uint32_t* ustart = (uint32_t*)(smem + L.ustart);                   // first span of every unit (CTA-shared, read-only)
+  uint8_t* isCtl = (uint8_t*)(smem + L.ctl);                          // control flag of every sample (CTA-shared, read-only)
   const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
   unsigned char* wbase = smem + L.warp0 + (size_t)warp * L.warpStride;
-  unsigned long long* rs = (unsigned long long*)(wbase + L.oRs);    // first entry of each source range
-  uint32_t* rx = (uint32_t*)(wbase + L.oRx);                         // exclusive prefix of the range lengths
   uint32_t* bins = (uint32_t*)(wbase + L.oBins);
   uint32_t* D = (uint32_t*)(wbase + L.oD);
   uint32_t* DR = (uint32_t*)(wbase + L.oDR);
@@ -150,8 +163,11 @@ __global__ void __launch_bounds__(SP_THREADS) span_kernel (const __grid_constant
   uint32_t* hm = (uint32_t*)(wbase + L.oHm);
 
   for (uint32_t i = tid; i < 2 * bw + 1; i += SP_THREADS) Ks[i] = a.taps[i];
+  for (uint32_t i = tid; i < a.nUnits; i += SP_THREADS) ustart[i] = a.units[i].spanStart;
+  for (uint32_t i = tid; i < a.nSamples; i += SP_THREADS) isCtl[i] = a.control[i];
   __syncthreads();                                                    // the only block-level barrier
-  const uint32_t nBins = ((SPAN_LEN + 2 * bw) >> 3) + 2;
+  const uint32_t nCells = SPAN_LEN + 2 * bw;                          // cells of a span: positions ts-bw .. ts+4095+bw
+  const uint32_t nBins = (nCells >> 3) + 2;
   const uint32_t nb8 = ((31 + 2 * bw) >> 3) + 1;                      // bins covering one block's window
   const unsigned long long bw2 = (unsigned long long)bw * bw;
   unsigned long long stHot = 0, stPieces = 0, stExact = 0, stSpans = 0;
@@ -163,59 +179,54 @@ __global__ void __launch_bounds__(SP_THREADS) span_kernel (const __grid_constant
     if (work >= a.totalSpans) break;
 
     uint32_t ui;
-    { uint32_t lo = 0, hi = a.nUnits; while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(&a.units[mid].spanStart) <= work) lo = mid; else hi = mid; } ui = lo; }
+    { uint32_t lo = 0, hi = a.nUnits; while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (ustart[mid] <= work) lo = mid; else hi = mid; } ui = lo; }
     const SpanUnit U = a.units[ui];
-    const uint32_t ts = (work - U.spanStart) * SPAN_LEN + 1;           // first position of the span
+    const uint32_t k = work - U.spanStart;                            // span index inside the contig
+    const uint32_t ts = k * SPAN_LEN + 1;                             // first position of the span
     const uint64_t lastPos = (uint64_t)U.size + bw;                   // Q20: evaluated through lastTag+bw
     const uint32_t np = (uint32_t)min((uint64_t)SPAN_LEN, lastPos - (ts - 1));
-    const int64_t cell0 = (int64_t)ts - bw;                           // position of bin cell 0
-    const uint32_t nTi = a.nTilesIdx[U.contig];
 
-    // ---- A1: entry range of every source (sample, strand) over [ts-bw, te+bw]; flat index over all of them ----
-    uint32_t total = 0;
-    for (uint32_t g0 = 0; g0 < nRs; g0 += 32) {
-      const uint32_t j = g0 + lane;
-      uint64_t x = 0, y = 0;
-      if (j < nRs) {
-        const uint32_t s = __ldg(a.srcSample + j / nStr);
-        const uint32_t d = NONDIR ? (j % nStr) : U.buffer;
-        seg_range(a.T, s, d, U.contig, nTi, cell0, (int64_t)ts + np - 1 + bw, x, y);
-      }
-      const uint32_t c = (uint32_t)(y - x);
-      const uint32_t inc = warp_incl_scan_u32(c, lane);
-      if (j < nRs) { rs[j] = x; rx[j] = total + inc - c; }
-      total += __shfl_sync(0xffffffffu, inc, 31);
-    }
-    if (lane == 0) rx[nRs] = total;
-    if (total == 0) { if (lane == 0) a.spanRunCount[work] = 0; continue; }
+    // ---- A1: the span's chunk(s) of the tile-major copy --------------------------------------------------------
+    const SpanChunk chF = span_chunk(a.T, NONDIR ? 0u : U.buffer, U.contig, k);
+    SpanChunk chR; chR.e0 = 0; chR.nPrev = chR.nOwn = chR.total = 0;
+    if (NONDIR) chR = span_chunk(a.T, 1u, U.contig, k);
+    if (chF.total + chR.total == 0) { if (lane == 0) a.spanRunCount[work] = 0; continue; }
     ++stSpans;
     for (uint32_t i = lane; i < nBins; i += 32) bins[i] = 0;
     __syncwarp();
 
-    // ---- A2: pool the density sources into 8-position bins --------------------------------------------------------
-    {
-      uint32_t j = 0;
-      for (uint32_t t = lane; t < total; t += 32) {
-        while (rx[j + 1] <= t) ++j;
-        const uint64_t e = rs[j] + (t - rx[j]);
-        const uint32_t p = __ldg(a.T.pos + e);
-        const uint32_t c = __ldg(a.T.cnt + e);
-        atomicAdd(&bins[(uint32_t)((int64_t)p - cell0) >> 3], c);
+    // ---- A2: pool the density sources into 8-position bins: cell = position - (ts - bw) ------------------------
+#pragma unroll
+    for (int str = 0; str < (NONDIR ? 2 : 1); ++str) {
+      const SpanChunk ch = str ? chR : chF;
+      for (uint32_t t = lane; t < ch.total; t += 32) {
+        const uint2 en = __ldg(a.T.ment + ch.e0 + t);
+        const int32_t cell = (int32_t)(en.y & (SPAN_LEN - 1)) + (int32_t)bw + (t < ch.nPrev ? -SPAN_LEN : (t < ch.nPrev + ch.nOwn ? 0 : SPAN_LEN));
+        if ((uint32_t)cell < nCells && !isCtl[en.y >> SPAN_SHIFT]) atomicAdd(&bins[(uint32_t)cell >> 3], en.x);
       }
     }
     __syncwarp();
 
-    // ---- A3: hot blocks ------------------------------------------------------------------------------------------
+    // ---- A3: hot blocks: in-place inclusive prefix over the bins, then two look-ups per block ----------------------
     const uint32_t nBlk = (np + 31) >> 5;
+    {
+      const uint32_t per = (nBins + 31) >> 5;
+      const uint32_t u0 = lane * per, u1 = min(nBins, u0 + per);
+      uint32_t run = 0;
+      for (uint32_t u = u0; u < u1; ++u) run += bins[u];
+      const uint32_t inc = warp_incl_scan_u32(run, lane);
+      run = inc - run;
+      for (uint32_t u = u0; u < u1; ++u) { run += bins[u]; bins[u] = run; }
+    }
+    __syncwarp();
     uint32_t anyHot = 0;
 #pragma unroll
     for (uint32_t m = 0; m < (uint32_t)SPAN_WORDS; ++m) {
       const uint32_t k = 32 * m + lane;
       bool hot = false;
       if (k < nBlk) {
-        unsigned long long sum = 0;
-        const uint32_t b0 = 4 * k;
-        for (uint32_t q = 0; q < nb8; ++q) sum += bins[b0 + q];
+        const uint32_t b0 = 4 * k;                                    // window of block k: cells 32k .. 32k+31+2bw -> bins b0 .. b0+nb8-1
+        const uint32_t sum = bins[b0 + nb8 - 1] - (b0 ? bins[b0 - 1] : 0u);   // wraps like the counts do; a window holding >= 2^32 tags is not supported
         hot = __dmul_rn((double)sum, a.kmaxBound) >= a.thr;
       }
       const uint32_t msk = __ballot_sync(0xffffffffu, hot);
@@ -249,21 +260,21 @@ __global__ void __launch_bounds__(SP_THREADS) span_kernel (const __grid_constant
         ++stPieces;
         const uint32_t P = min(32 * nb, np - 32 * pb);                // positions of this piece
         const uint32_t q0 = ts + 32 * pb;                             // first position
-        const int64_t cbase = (int64_t)q0 - bw;                       // position of cell 0
         const uint32_t W = 32 * nb + 2 * bw;                          // cells
         const uint32_t nbEff = (P + 31) >> 5;
 
         for (uint32_t u = lane; u < W + 2; u += 32) { D[u] = 0; if (NONDIR) DR[u] = 0; }
         __syncwarp();
 
-        // B1: the piece's tags -> dense cells (the span's entries are L1/L2 hits by now)
-        {
-          uint32_t j = 0;
-          for (uint32_t t = lane; t < total; t += 32) {
-            while (rx[j + 1] <= t) ++j;
-            const uint64_t e = rs[j] + (t - rx[j]);
-            const int64_t u = (int64_t)__ldg(a.T.pos + e) - cbase;
-            if (u >= 0 && u < (int64_t)W) atomicAdd((NONDIR && (j & 1u)) ? &DR[u] : &D[u], __ldg(a.T.cnt + e));
+        // B1: the piece's tags -> dense cells (the chunk is an L1/L2 hit by now): u = cell - 32*pb
+#pragma unroll
+        for (int str = 0; str < (NONDIR ? 2 : 1); ++str) {
+          const SpanChunk ch = str ? chR : chF;
+          uint32_t* dst = str ? DR : D;
+          for (uint32_t t = lane; t < ch.total; t += 32) {
+            const uint2 en = __ldg(a.T.ment + ch.e0 + t);
+            const int32_t u = (int32_t)(en.y & (SPAN_LEN - 1)) + (int32_t)bw + (t < ch.nPrev ? -SPAN_LEN : (t < ch.nPrev + ch.nOwn ? 0 : SPAN_LEN)) - (int32_t)(32 * pb);
+            if ((uint32_t)u < W && !isCtl[en.y >> SPAN_SHIFT]) atomicAdd(&dst[u], en.x);
           }
         }
         __syncwarp();
@@ -452,15 +463,15 @@ __global__ void cand_hit_kernel (const Cand2* __restrict__ cand, uint32_t n, dou
 }
 
 // Region::exptSums (misc/data.cpp:116-131) and Region::posKurtosis (misc/data.cpp:133-182) of the candidates that
-// passed the hit filter: one warp per region.  Lanes take the (sample, strand) tracks, sum their entries
-// inside the region (counts, and count*offset with offsets as UShort and both sums as HitCount),
-// then the region's positions are pooled over ALL samples (controls included, minus the tags the reference
-// forgets, Q4) in shared memory 1024 at a time and the two central moments are accumulated sequentially in
-// position order, exactly as the reference does.
+// passed the hit filter: one warp per region.  The region's entries are a contiguous chunk of the tile-major
+// copy (the mini-tiles it touches); every lane takes entries, adds the count to its sample's slot (shared-memory
+// atomics) and keeps count*offset (offsets as UShort, both sums as HitCount); the region's positions
+// are pooled over ALL samples (controls included, minus the tags the reference forgets, Q4) in shared memory
+// 1024 at a time and the two central moments are accumulated sequentially in position order, exactly as the
+// reference does.
 struct StatArgs {
   Tags T;
   const SpanUnit* units;
-  const uint32_t* nTilesIdx;
   const Cand2* cand;
   const uint32_t* list;             // hit-filter survivors (candidate indices, ascending)
   uint32_t nList;
@@ -471,43 +482,54 @@ struct StatArgs {
   uint32_t* pass;                   // [nList] kurtosis filter (misc/peakcall.cpp:41 second clause)
 };
 
+// visit the entries of (strand d, contig c) with position in [lo, hi] (1-based, inclusive): f(position, entry index, y)
+template <class F>
+__device__ __forceinline__ void for_entries (const Tags& T, uint32_t d, uint32_t c, uint32_t lo, uint32_t hi, uint32_t lane, F f) {
+  const uint32_t gb = T.mtBase[d * T.C + c];
+  const uint32_t nMt = T.mtBase[d * T.C + c + 1] - gb;
+  if (nMt == 0) return;
+  const uint32_t ma = min((lo - 1) >> MT_SHIFT, nMt - 1), mb = min((hi - 1) >> MT_SHIFT, nMt - 1);
+  for (uint32_t sp = ma / SPAN_MT; sp <= mb / SPAN_MT; ++sp) {      // entries carry their offset inside a 4096-position span
+    const uint32_t m0 = max(ma, sp * SPAN_MT), m1 = min(mb, sp * SPAN_MT + SPAN_MT - 1);
+    const unsigned long long e0 = T.mtOff[gb + m0], e1 = T.mtOff[gb + m1 + 1];
+    for (unsigned long long e = e0 + lane; e < e1; e += 32) {
+      const uint2 en = __ldg(T.ment + e);
+      const uint32_t p = sp * SPAN_LEN + (en.y & (SPAN_LEN - 1)) + 1;
+      if (p >= lo && p <= hi) f(p, e, en);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(KURT_WARPS * 32) region_stats_kernel (StatArgs a) {
-  __shared__ uint32_t cells[KURT_WARPS][KURT_CHUNK];
+  extern __shared__ uint32_t stat_smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
   const uint32_t i = blockIdx.x * KURT_WARPS + warp;
   if (i >= a.nList) return;
   const uint32_t n = a.T.nSamples;
-  const uint32_t nStr = a.nondir ? 2u : 1u;
-  const uint32_t nR = n * nStr;
+  uint32_t* cell = stat_smem + (size_t)warp * (KURT_CHUNK + n);
+  uint32_t* cnts = cell + KURT_CHUNK;
   const Cand2 c = a.cand[a.list[i]];
   const SpanUnit U = a.units[c.unit];
-  const uint32_t nTi = a.nTilesIdx[U.contig];
-  uint32_t* cell = cells[warp];
   const bool small = c.len <= (uint32_t)KURT_CHUNK;
-  if (small) { for (uint32_t k = lane; k < c.len; k += 32) cell[k] = 0; __syncwarp(); }
-  uint32_t count = 0, sum = 0;
-  for (uint32_t g0 = 0; g0 < nR; g0 += 32) {
-    const uint32_t j = g0 + lane;
-    uint32_t cs = 0, os = 0;
-    if (j < nR) {
-      const uint32_t s = j / nStr, d = a.nondir ? (j % nStr) : U.buffer;
-      uint64_t x, y;
-      seg_range(a.T, s, d, U.contig, nTi, c.left, (int64_t)c.left + c.len - 1, x, y);
-      for (uint64_t e = x; e < y; ++e) {
-        const uint32_t k = __ldg(a.T.cntEff + e);
-        const uint32_t o = __ldg(a.T.pos + e) - c.left;
-        cs += k;
-        os += k * (o & 0xFFFFu);
-        if (small && k) atomicAdd(&cell[o], k);
-      }
-    }
-    if (nStr == 2) { cs += __shfl_xor_sync(0xffffffffu, cs, 1); os += __shfl_xor_sync(0xffffffffu, os, 1); }
-    const bool owner = j < nR && (nStr == 1 || !(j & 1u));
-    if (owner) a.counts[(uint64_t)i * n + j / nStr] = cs;
-    count += warp_sum_u32(owner ? cs : 0u);
-    sum += warp_sum_u32(owner ? os : 0u);
-  }
+  const uint32_t right = c.left + c.len - 1;
+  if (small) for (uint32_t k = lane; k < c.len; k += 32) cell[k] = 0;
+  for (uint32_t s = lane; s < n; s += 32) cnts[s] = 0;
   __syncwarp();
+  uint32_t count = 0, sum = 0;
+  const uint32_t d0 = a.nondir ? 0u : U.buffer, d1 = a.nondir ? 1u : U.buffer;
+  for (uint32_t d = d0; d <= d1; ++d)
+    for_entries(a.T, d, U.contig, c.left, right, lane, [&] (uint32_t p, unsigned long long e, const uint2& en) {
+      const uint32_t k = a.T.mEff ? __ldg(a.T.mEff + e) : en.x;
+      if (!k) return;
+      const uint32_t o = p - c.left;
+      count += k;
+      sum += k * (o & 0xFFFFu);
+      atomicAdd(&cnts[en.y >> SPAN_SHIFT], k);
+      if (small) atomicAdd(&cell[o], k);
+    });
+  count = warp_sum_u32(count); sum = warp_sum_u32(sum);
+  __syncwarp();
+  for (uint32_t s = lane; s < n; s += 32) a.counts[(uint64_t)i * n + s] = cnts[s];
   const double xbar = (double)sum / (double)count;                   // misc/data.cpp:147
   double sum2 = 0.0, sum4 = 0.0;
   for (uint32_t o0 = 0; o0 < c.len; o0 += KURT_CHUNK) {
@@ -515,12 +537,11 @@ __global__ void __launch_bounds__(KURT_WARPS * 32) region_stats_kernel (StatArgs
     if (!small) {                                                     // long region: pool one chunk of positions at a time
       for (uint32_t k = lane; k < KURT_CHUNK; k += 32) cell[k] = 0;
       __syncwarp();
-      for (uint32_t j = 0; j < nR; ++j) {
-        const uint32_t s = j / nStr, d = a.nondir ? (j % nStr) : U.buffer;
-        uint64_t x, y;
-        seg_range(a.T, s, d, U.contig, nTi, (int64_t)c.left + o0, (int64_t)c.left + o0 + oc - 1, x, y);
-        for (uint64_t e = x + lane; e < y; e += 32) atomicAdd(&cell[a.T.pos[e] - c.left - o0], a.T.cntEff[e]);
-      }
+      for (uint32_t d = d0; d <= d1; ++d)
+        for_entries(a.T, d, U.contig, c.left + o0, c.left + o0 + oc - 1, lane, [&] (uint32_t p, unsigned long long e, const uint2& en) {
+          const uint32_t k = a.T.mEff ? __ldg(a.T.mEff + e) : en.x;
+          if (k) atomicAdd(&cell[p - c.left - o0], k);
+        });
       __syncwarp();
     }
     for (uint32_t g = 0; g < oc; g += 32) {
