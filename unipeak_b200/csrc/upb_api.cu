@@ -609,7 +609,7 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
   SpanArgs sa;
   memset(&sa, 0, sizeof sa);
   sa.T = pr.T; sa.units = d_units; sa.nTilesIdx = ctx->d_nTilesIdx.as<uint32_t>();
-  sa.control = ctx->scratch["control"].as<uint8_t>(); sa.nSamples = n;
+  sa.control = ctx->scratch["control"].as<uint8_t>(); sa.nSamples = n; sa.hasControl = pr.haveControl ? 1 : 0;
   sa.nUnits = nUnits; sa.totalSpans = pr.totalSpans; sa.bw = cfg.bw;
   sa.taps = ctx->scratch["taps"].as<double>();
   sa.thr = cfg.thr;

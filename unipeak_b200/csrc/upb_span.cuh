@@ -34,6 +34,7 @@ namespace upb {
 
 constexpr int SP_THREADS = 256;
 constexpr int SP_WARPS = SP_THREADS / 32;
+constexpr int BIN_SHIFT = 4;                        // phase A pools into 16-position bins
 constexpr int SPAN_BLOCKS = SPAN_LEN / 32;          // 128 blocks of 32 positions
 constexpr int SPAN_WORDS = SPAN_BLOCKS / 32;
 constexpr int PIECE_BLOCKS = 16;                    // <= 512 positions per piece
@@ -55,6 +56,7 @@ struct SpanArgs {
   const uint32_t* nTilesIdx;                        // [C]
   const uint8_t* control;                           // [nSamples] 1 = negative control (not a density source)
   uint32_t nSamples;
+  int hasControl;
   uint32_t nUnits, totalSpans;
   uint32_t bw;
   const double* taps;                               // 2bw+1, host-computed exactly as misc/kernel.cpp:16-35
@@ -84,7 +86,7 @@ __host__ __device__ inline SpanSmem span_smem_layout (uint32_t bw, uint32_t nSam
   L.warp0 = o;
   const uint32_t W = PIECE_LEN + 2 * bw + 4;
   uint32_t w = 0;
-  L.oBins = w; w += ((((SPAN_LEN + 2 * bw) >> 3) + 3) & ~1u) * 4;
+  L.oBins = w; w += ((((SPAN_LEN + 2 * bw) >> BIN_SHIFT) + 3) & ~1u) * 4;
   L.oD = w;    w += W * 4;
   L.oDR = w;   w += nondir ? W * 4 : 0;
   L.oSc = w;   w += PIECE_LEN * 4;
@@ -130,6 +132,25 @@ __device__ __forceinline__ double exact_dense (const double* __restrict__ Ks, co
   return s;
 }
 
+// the same sum computed by the whole warp for ONE position (u0 uniform): the products are independent, so every
+// lane rounds one product per 32 taps; the additions stay a single chain in ascending tag order, fed by shuffles
+__device__ __forceinline__ double exact_dense_warp (const double* __restrict__ Ks, const uint32_t* __restrict__ cells, uint32_t u0, uint32_t bw, uint32_t lane) {
+  double s = 0.0;
+  const uint32_t n = 2 * bw;
+  for (uint32_t k0 = 0; k0 <= n; k0 += 32) {
+    const uint32_t k = k0 + lane;
+    const uint32_t w = k <= n ? cells[u0 + k] : 0u;
+    const double p = w ? __dmul_rn(Ks[n - k], (double)w) : 0.0;
+    uint32_t nz = __ballot_sync(0xffffffffu, w != 0);
+    while (nz) {
+      const int b = __ffs(nz) - 1;
+      s = __dadd_rn(s, __shfl_sync(0xffffffffu, p, b));
+      nz &= nz - 1;
+    }
+  }
+  return s;
+}
+
 // entries of the span's chunk of one strand: [e0, e0+total); the first nPrev lie in the mini-tile before the span,
 // the next nOwn inside it, the rest in the mini-tile after it
 struct SpanChunk { unsigned long long e0; uint32_t nPrev, nOwn, total; };
@@ -167,10 +188,12 @@ __global__ void __launch_bounds__(SP_THREADS, 4) span_kernel (const __grid_const
   for (uint32_t i = tid; i < a.nSamples; i += SP_THREADS) isCtl[i] = a.control[i];
   __syncthreads();                                                    // the only block-level barrier
   const uint32_t nCells = SPAN_LEN + 2 * bw;                          // cells of a span: positions ts-bw .. ts+4095+bw
-  const uint32_t nBins = (nCells >> 3) + 2;
-  const uint32_t nb8 = ((31 + 2 * bw) >> 3) + 1;                      // bins covering one block's window
+  const uint32_t nBins = (nCells >> BIN_SHIFT) + 2;
+  const uint32_t nbw = ((31 + 2 * bw) >> BIN_SHIFT) + 1;              // bins covering one block's window
   const unsigned long long bw2 = (unsigned long long)bw * bw;
   unsigned long long stHot = 0, stPieces = 0, stExact = 0, stSpans = 0;
+  uint32_t ui = 0;
+  SpanUnit U = a.units[0];
 
   for (;;) {
     uint32_t work = 0;
@@ -178,9 +201,10 @@ __global__ void __launch_bounds__(SP_THREADS, 4) span_kernel (const __grid_const
     work = __shfl_sync(0xffffffffu, work, 0);
     if (work >= a.totalSpans) break;
 
-    uint32_t ui;
-    { uint32_t lo = 0, hi = a.nUnits; while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (ustart[mid] <= work) lo = mid; else hi = mid; } ui = lo; }
-    const SpanUnit U = a.units[ui];
+    if (!(work >= ustart[ui] && (ui + 1 == a.nUnits || work < ustart[ui + 1]))) {   // tickets are mostly consecutive: same unit as last time
+      uint32_t lo = 0, hi = a.nUnits; while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (ustart[mid] <= work) lo = mid; else hi = mid; } ui = lo;
+      U = a.units[ui];
+    }
     const uint32_t k = work - U.spanStart;                            // span index inside the contig
     const uint32_t ts = k * SPAN_LEN + 1;                             // first position of the span
     const uint64_t lastPos = (uint64_t)U.size + bw;                   // Q20: evaluated through lastTag+bw
@@ -195,38 +219,37 @@ __global__ void __launch_bounds__(SP_THREADS, 4) span_kernel (const __grid_const
     for (uint32_t i = lane; i < nBins; i += 32) bins[i] = 0;
     __syncwarp();
 
-    // ---- A2: pool the density sources into 8-position bins: cell = position - (ts - bw) ------------------------
+    // ---- A2: pool the density sources into 16-position bins: cell = position - (ts - bw).  Four loads are in flight
+    //      per lane before the first atomic, so one round trip to L2/HBM covers 128 entries -------------------------
 #pragma unroll
     for (int str = 0; str < (NONDIR ? 2 : 1); ++str) {
       const SpanChunk ch = str ? chR : chF;
-      for (uint32_t t = lane; t < ch.total; t += 32) {
-        const uint2 en = __ldg(a.T.ment + ch.e0 + t);
-        const int32_t cell = (int32_t)(en.y & (SPAN_LEN - 1)) + (int32_t)bw + (t < ch.nPrev ? -SPAN_LEN : (t < ch.nPrev + ch.nOwn ? 0 : SPAN_LEN));
-        if ((uint32_t)cell < nCells && !isCtl[en.y >> SPAN_SHIFT]) atomicAdd(&bins[(uint32_t)cell >> 3], en.x);
+      const uint2* __restrict__ src = a.T.ment + ch.e0;
+      for (uint32_t t0 = 0; t0 < ch.total; t0 += 128) {
+        uint2 en[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const uint32_t t = t0 + 32 * q + lane; en[q] = t < ch.total ? __ldg(src + t) : make_uint2(0u, 0u); }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t t = t0 + 32 * q + lane;
+          const int32_t cell = (int32_t)(en[q].y & (SPAN_LEN - 1)) + (int32_t)bw + (t < ch.nPrev ? -SPAN_LEN : (t < ch.nPrev + ch.nOwn ? 0 : SPAN_LEN));
+          if (en[q].x && (uint32_t)cell < nCells && !(a.hasControl && isCtl[en[q].y >> SPAN_SHIFT])) atomicAdd(&bins[(uint32_t)cell >> BIN_SHIFT], en[q].x);
+        }
       }
     }
     __syncwarp();
 
-    // ---- A3: hot blocks: in-place inclusive prefix over the bins, then two look-ups per block ----------------------
+    // ---- A3: hot blocks: window of block k = cells 32k .. 32k+31+2bw = bins 2k .. 2k+nbw-1 ------------------------
     const uint32_t nBlk = (np + 31) >> 5;
-    {
-      const uint32_t per = (nBins + 31) >> 5;
-      const uint32_t u0 = lane * per, u1 = min(nBins, u0 + per);
-      uint32_t run = 0;
-      for (uint32_t u = u0; u < u1; ++u) run += bins[u];
-      const uint32_t inc = warp_incl_scan_u32(run, lane);
-      run = inc - run;
-      for (uint32_t u = u0; u < u1; ++u) { run += bins[u]; bins[u] = run; }
-    }
-    __syncwarp();
     uint32_t anyHot = 0;
 #pragma unroll
     for (uint32_t m = 0; m < (uint32_t)SPAN_WORDS; ++m) {
-      const uint32_t k = 32 * m + lane;
+      const uint32_t kblk = 32 * m + lane;
       bool hot = false;
-      if (k < nBlk) {
-        const uint32_t b0 = 4 * k;                                    // window of block k: cells 32k .. 32k+31+2bw -> bins b0 .. b0+nb8-1
-        const uint32_t sum = bins[b0 + nb8 - 1] - (b0 ? bins[b0 - 1] : 0u);   // wraps like the counts do; a window holding >= 2^32 tags is not supported
+      if (kblk < nBlk) {
+        unsigned long long sum = 0;
+        const uint32_t b0 = kblk << (5 - BIN_SHIFT);
+        for (uint32_t q = 0; q < nbw; ++q) sum += bins[b0 + q];
         hot = __dmul_rn((double)sum, a.kmaxBound) >= a.thr;
       }
       const uint32_t msk = __ballot_sync(0xffffffffu, hot);
@@ -270,11 +293,18 @@ __global__ void __launch_bounds__(SP_THREADS, 4) span_kernel (const __grid_const
 #pragma unroll
         for (int str = 0; str < (NONDIR ? 2 : 1); ++str) {
           const SpanChunk ch = str ? chR : chF;
+          const uint2* __restrict__ src = a.T.ment + ch.e0;
           uint32_t* dst = str ? DR : D;
-          for (uint32_t t = lane; t < ch.total; t += 32) {
-            const uint2 en = __ldg(a.T.ment + ch.e0 + t);
-            const int32_t u = (int32_t)(en.y & (SPAN_LEN - 1)) + (int32_t)bw + (t < ch.nPrev ? -SPAN_LEN : (t < ch.nPrev + ch.nOwn ? 0 : SPAN_LEN)) - (int32_t)(32 * pb);
-            if ((uint32_t)u < W && !isCtl[en.y >> SPAN_SHIFT]) atomicAdd(&dst[u], en.x);
+          for (uint32_t t0 = 0; t0 < ch.total; t0 += 128) {
+            uint2 en[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const uint32_t t = t0 + 32 * q + lane; en[q] = t < ch.total ? __ldg(src + t) : make_uint2(0u, 0u); }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t t = t0 + 32 * q + lane;
+              const int32_t u = (int32_t)(en[q].y & (SPAN_LEN - 1)) + (int32_t)bw + (t < ch.nPrev ? -SPAN_LEN : (t < ch.nPrev + ch.nOwn ? 0 : SPAN_LEN)) - (int32_t)(32 * pb);
+              if (en[q].x && (uint32_t)u < W && !(a.hasControl && isCtl[en[q].y >> SPAN_SHIFT])) atomicAdd(&dst[u], en[q].x);
+            }
           }
         }
         __syncwarp();
@@ -312,7 +342,7 @@ __global__ void __launch_bounds__(SP_THREADS, 4) span_kernel (const __grid_const
             const double f = exact_dense(Ks, D, i, bw);
             v = NONDIR ? __dadd_rn(f, exact_dense(Ks, DR, i, bw)) : f; // misc/peakcall.cpp:57
             above = v >= a.thr;
-            ++stExact;
+            stExact += 32;
           }
           if (valid) scf[i] = (float)v;
           const uint32_t m = __ballot_sync(0xffffffffu, above);
@@ -365,20 +395,15 @@ __global__ void __launch_bounds__(SP_THREADS, 4) span_kernel (const __grid_const
           double best = -1.0; uint32_t bestI = r0;
           for (uint32_t g = r0; g < r1; g += 32) {
             const uint32_t i = g + lane;
-            double e = -1.0;
-            if (i < r1 && (double)scf[i] >= cut) {
-              const double f = exact_dense(Ks, D, i, bw);
-              e = NONDIR ? __dadd_rn(f, exact_dense(Ks, DR, i, bw)) : f;
+            uint32_t cm = __ballot_sync(0xffffffffu, i < r1 && (double)scf[i] >= cut);
+            while (cm) {                                               // ascending position: a later tie never replaces an earlier maximum
+              const uint32_t ci = g + (uint32_t)(__ffs(cm) - 1);
+              const double f = exact_dense_warp(Ks, D, ci, bw, lane);
+              const double e = NONDIR ? __dadd_rn(f, exact_dense_warp(Ks, DR, ci, bw, lane)) : f;
+              if (e > best) { best = e; bestI = ci; }
               ++stExact;
+              cm &= cm - 1;
             }
-            uint32_t ei = i;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              const double oe = __shfl_xor_sync(0xffffffffu, e, o);
-              const uint32_t oi = __shfl_xor_sync(0xffffffffu, ei, o);
-              if (oe > e || (oe == e && oi < ei)) { e = oe; ei = oi; }
-            }
-            if (e > best) { best = e; bestI = ei; }
           }
           if (lane == 0) {
             SpanRun rr;
@@ -391,11 +416,11 @@ __global__ void __launch_bounds__(SP_THREADS, 4) span_kernel (const __grid_const
     }
     if (lane == 0) a.spanRunCount[work] = spanRuns;
   }
-  stHot = warp_sum_u64(stHot) / 32; stPieces = warp_sum_u64(stPieces) / 32; stSpans = warp_sum_u64(stSpans) / 32; stExact = warp_sum_u64(stExact);
+  stExact = warp_sum_u64(stExact);                                    // lane-divergent (uncertain positions) + 32 x uniform (peak candidates)
   if (lane == 0) {
     if (stHot) atomicAdd(a.stat + 0, stHot);
     if (stPieces) atomicAdd(a.stat + 1, stPieces);
-    if (stExact) atomicAdd(a.stat + 2, stExact);
+    if (stExact) atomicAdd(a.stat + 2, stExact / 32);
     if (stSpans) atomicAdd(a.stat + 3, stSpans);
   }
 }
