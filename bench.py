@@ -338,7 +338,7 @@ def main():
                 "gpu_launches": launches, "roofline": roofline,
                 "result": {"regions": n_rows, "candidates": stats["n_candidates"], "tag_entries_rank0": E, "spans": stats["kde_tiles"], "pieces": stats["kde_hot_tiles"],
                            "hot_blocks": stats["hot_blocks"], "exact_evals": stats["exact_evals"], "stitched": stats["n_stitched"],
-                           "device_ms_per_step_rank0": stats["ms_total"]}}
+                           "device_ms_per_step_rank0": stats["ms_total"], "call_ms_rank0": stats["ms_call"]}}
         if world == 1 and not args.no_cpu:
             cs = CPU_SAMPLE_CONTIGS[args.workload]
             sample = cpu_sample(data, cs)

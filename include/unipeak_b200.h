@@ -202,7 +202,8 @@ typedef struct {
   uint64_t hot_blocks;          /* 32-position blocks that could reach the threshold */
   uint64_t exact_evals;         /* positions evaluated in the reference's own summation order */
   uint64_t spans_with_tags;
-  uint64_t n_stitched;          /* candidates cut by a piece / span boundary (statistics by the generic kernels) */
+  uint64_t n_stitched;          /* run pieces merged into a neighbour (runs cut by a piece / span boundary) */
+  float ms_call;                /* host wall clock of the last upb_call_regions, entry to return */
 } upb_stats;
 int upb_last_stats (const upb_ctx* ctx, upb_stats* out);
 

@@ -68,7 +68,7 @@ class RegionKey(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("ms_total", C.c_float), ("ms_kde", C.c_float), ("launches", C.c_uint32), ("kde_tiles", C.c_uint64),
                 ("kde_hot_tiles", C.c_uint64), ("n_candidates", C.c_uint64), ("n_entries", C.c_uint64), ("hot_blocks", C.c_uint64),
-                ("exact_evals", C.c_uint64), ("spans_with_tags", C.c_uint64), ("n_stitched", C.c_uint64)]
+                ("exact_evals", C.c_uint64), ("spans_with_tags", C.c_uint64), ("n_stitched", C.c_uint64), ("ms_call", C.c_float)]
 
 
 EXPORTS = [
@@ -128,6 +128,28 @@ def _np(ptr, n, dtype):
     if n == 0:
         return np.zeros(0, dtype=dtype)
     return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+
+
+class RegionView:
+    """Lazy, zero-copy access to a upb_region_table (see Context.call_regions_view)."""
+
+    def __init__(self, table, n_contigs):
+        self._t = table
+        self._n_contigs = n_contigs
+        self._cols = None
+        self.n_rows = int(table.n_rows)
+        self.n_passed = int(table.n_passed)
+        self.n_rejected = int(table.n_rejected)
+
+    def columns(self) -> Dict:
+        if self._cols is None:
+            self._cols = Context._views(self._t, self._n_contigs)
+        return self._cols
+
+    def __getitem__(self, key):
+        if key in ("n_rows", "n_passed", "n_rejected"):
+            return getattr(self, key)
+        return self.columns()[key]
 
 
 class Context:
@@ -207,18 +229,17 @@ class Context:
 
     def call_regions_view(self, *, bandwidth=50, region_threshold=25.0, kurtosis_threshold=50.0, corr_threshold=-1.0, hit_threshold=10.0,
                           directional=True, control: Optional[Sequence[int]] = None, coeffs: Optional[Sequence[float]] = None,
-                          background: float, reference_order=True, **_ignored) -> Dict:
-        """upb_call_regions without any Python-side copy: the returned arrays are views of the library's pinned
-        result slab and stay valid until the next call_regions_view / close on this context."""
+                          background: float, reference_order=True, **_ignored) -> "RegionView":
+        """upb_call_regions without any Python-side copy: the returned object exposes the table's columns as numpy views
+        of the library's pinned result slab (created on first access); they stay valid until the next
+        call_regions_view / release_view / close on this context."""
         self.release_view()
         p, keep = self._region_params(bandwidth, region_threshold, kurtosis_threshold, corr_threshold, hit_threshold, directional, control,
                                       coeffs, background, reference_order)
         t = RegionTable()
         self._check(self._lib.upb_call_regions(self._h, C.byref(p), C.byref(t)))
         self._view_table = t
-        out = self._views(t, self.n_contigs)
-        out.update(n_rows=int(t.n_rows), n_passed=int(t.n_passed), n_rejected=int(t.n_rejected))
-        return out
+        return RegionView(t, self.n_contigs)
 
     def release_view(self):
         t = getattr(self, "_view_table", None)
@@ -295,4 +316,4 @@ class Context:
         return dict(ms_total=float(s.ms_total), ms_kde=float(s.ms_kde), launches=int(s.launches), kde_tiles=int(s.kde_tiles),
                     kde_hot_tiles=int(s.kde_hot_tiles), n_candidates=int(s.n_candidates), n_entries=int(s.n_entries),
                     hot_blocks=int(s.hot_blocks), exact_evals=int(s.exact_evals), spans_with_tags=int(s.spans_with_tags),
-                    n_stitched=int(s.n_stitched))
+                    n_stitched=int(s.n_stitched), ms_call=float(s.ms_call))

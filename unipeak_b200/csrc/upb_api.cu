@@ -8,6 +8,7 @@
 #include "upb_span.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -703,10 +704,12 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
     StatArgs st;
     st.T = pr.T; st.units = d_units; st.cand = cand; st.list = list1; st.nList = n1;
     st.nondir = cfg.nondir ? 1 : 0; st.kurtThr = cfg.kurtThr; st.counts = statCounts; st.kurt = statKurt; st.pass = pass2;
-    const size_t statSmem = (size_t)KURT_WARPS * (KURT_CHUNK + n) * 4;
+    const size_t groupBytes = ((size_t)(ST_CHUNK + n) * 4 + 15) / 16 * 16 + 2 * ST_GROUP * 8;
+    const size_t statSmem = (size_t)ST_WARPS * ST_PER_WARP * groupBytes;
     if (statSmem > 200 * 1024) return fail(ctx, UPB_ERR_UNSUPPORTED, "too many samples for the region statistics kernel");
     CU(cudaFuncSetAttribute(region_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)statSmem));
-    region_stats_kernel<<<(n1 + KURT_WARPS - 1) / KURT_WARPS, KURT_WARPS * 32, statSmem, ctx->stream>>>(st);
+    const uint32_t perBlock = ST_WARPS * ST_PER_WARP;
+    region_stats_kernel<<<(n1 + perBlock - 1) / perBlock, ST_WARPS * 32, statSmem, ctx->stream>>>(st);
     CU(cudaGetLastError());
     launches += 1;
 
@@ -803,7 +806,8 @@ extern "C" int upb_reference_order (uint32_t C, uint32_t n, int directional, uin
     const uint32_t L = lastTag[(size_t)t->buffer[i] * C + t->contig[i]];
     return right + bw + 2 > (uint64_t)L;
   };
-  for (uint64_t i = 0; i < R; ++i) { t->forward_label[i] = t->buffer[i] == 0 ? 1 : 0; t->dropped[i] = 0; }
+  for (uint64_t i = 0; i < R; ++i) t->forward_label[i] = t->buffer[i] == 0 ? 1 : 0;
+  memset(t->dropped, 0, R);
 
   // which samples read their '-' track during pass 1 (Q7)
   bool anyEarly = false;
@@ -819,42 +823,44 @@ extern "C" int upb_reference_order (uint32_t C, uint32_t n, int directional, uin
     if (anyEarly && nWithTags > 1) return UPB_ERR_REFERENCE_ABORTS;
   }
 
+  // canonical rows are sorted by (buffer, contig, left): first row of the reverse buffer by binary search
+  uint64_t firstRev = R;
+  { uint64_t lo = 0, hi = R; while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (t->buffer[mid] == 0) lo = mid + 1; else hi = mid; } firstRev = lo; }
+
   // Q5: the first Region object of reverseBuffer is constructed forward (misc/peakcall.cpp:103); if the
   // first candidate of the reverse buffer is accepted it is printed left-right
   if (directional && t->unit_candidates) {
     for (uint32_t c = 0; c < C; ++c) {
       if (t->unit_candidates[(size_t)C + c] == 0) continue;
-      for (uint64_t i = 0; i < R; ++i)
-        if (t->buffer[i] == 1 && t->contig[i] == c && t->cand_index[i] == 0) t->forward_label[i] = 1;
+      for (uint64_t i = firstRev; i < R && t->contig[i] <= c; ++i)
+        if (t->contig[i] == c && t->cand_index[i] == 0) t->forward_label[i] = 1;
       break;
     }
   }
 
-  // canonical rows are sorted by (buffer, contig, left)
+  if (!directional || !anyEarly) {
+    // rows are written in canonical order ('+' regions by contig, then '-' regions); only what the very last
+    // flushContig() finalises is lost (Q6): the tail of the last contig of the last buffer — a suffix of the table
+    for (uint64_t i = R; i-- > 0;) {
+      if (t->contig[i] != C - 1 || (directional && t->buffer[i] != 1) || !tail(i)) break;
+      t->dropped[i] = 1;
+    }
+    for (uint64_t i = 0; i < R; ++i) perm[i] = i;                     // dropped rows already sit at the end
+    return UPB_OK;
+  }
+  // single sample whose '-' track is read in pass 1: per contig iteration the '+' tags come first, then
+  // the '-' tags; regions closed by add() are written at once, the two flushes at the end of the
+  // iteration hand over the '+' tail and then the '-' tail; pass 2 then writes what is pending (nothing is lost)
   std::vector<uint64_t> order;
   order.reserve(R);
-  if (!directional) {
-    for (uint64_t i = 0; i < R; ++i) order.push_back(i);
-    // only what the last contig's flush finalises is lost (Q6)
-    for (uint64_t i = 0; i < R; ++i) if (t->contig[i] == C - 1 && tail(i)) t->dropped[i] = 1;
-  } else if (!anyEarly) {
-    for (uint64_t i = 0; i < R; ++i) order.push_back(i);            // all '+' regions, then all '-' regions
-    for (uint64_t i = 0; i < R; ++i) if (t->buffer[i] == 1 && t->contig[i] == C - 1 && tail(i)) t->dropped[i] = 1;
-  } else {
-    // single sample whose '-' track is read in pass 1: per contig iteration the '+' tags come first, then
-    // the '-' tags; regions closed by add() are written at once, the two flushes at the end of the
-    // iteration hand over the '+' tail and then the '-' tail; pass 2 then writes what is pending (nothing is lost)
-    std::vector<std::vector<uint64_t>> byUnit(2 * (size_t)C);
-    for (uint64_t i = 0; i < R; ++i) byUnit[(size_t)t->buffer[i] * C + t->contig[i]].push_back(i);
-    for (uint32_t c = 0; c < C; ++c) {
-      for (int b = 0; b < 2; ++b) for (uint64_t i : byUnit[(size_t)b * C + c]) if (!tail(i)) order.push_back(i);
-      for (int b = 0; b < 2; ++b) for (uint64_t i : byUnit[(size_t)b * C + c]) if (tail(i)) order.push_back(i);
-    }
+  std::vector<std::vector<uint64_t>> byUnit(2 * (size_t)C);
+  for (uint64_t i = 0; i < R; ++i) byUnit[(size_t)t->buffer[i] * C + t->contig[i]].push_back(i);
+  for (uint32_t c = 0; c < C; ++c) {
+    for (int b = 0; b < 2; ++b) for (uint64_t i : byUnit[(size_t)b * C + c]) if (!tail(i)) order.push_back(i);
+    for (int b = 0; b < 2; ++b) for (uint64_t i : byUnit[(size_t)b * C + c]) if (tail(i)) order.push_back(i);
   }
-  // dropped rows keep their slot at the end so that callers can still inspect them
   uint64_t k = 0;
-  for (uint64_t i : order) if (!t->dropped[i]) perm[k++] = i;
-  for (uint64_t i : order) if (t->dropped[i]) perm[k++] = i;
+  for (uint64_t i : order) perm[k++] = i;
   return UPB_OK;
 }
 
@@ -893,6 +899,7 @@ extern "C" int upb_call_regions (upb_ctx* ctx, const upb_region_params* p, upb_r
   if (!ctx) return UPB_ERR_BAD_ARG;
   if (!p || !out) return fail(ctx, UPB_ERR_BAD_ARG, "upb_call_regions: NULL argument");
   memset(out, 0, sizeof *out);
+  const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
   if (p->n_coeffs != 0) return fail(ctx, UPB_ERR_UNSUPPORTED, "scaling coefficients (-z) are not implemented yet");
   PipeCfg cfg;
   cfg.bw = p->bandwidth; cfg.thr = p->region_threshold; cfg.kurtThr = p->kurtosis_threshold; cfg.corrThr = p->corr_threshold;
@@ -928,6 +935,7 @@ extern "C" int upb_call_regions (upb_ctx* ctx, const upb_region_params* p, upb_r
       permute(out->kurtosis, 1); permute(out->corr, 1); permute(out->counts, n);
     }
   }
+  ctx->stats.ms_call = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return UPB_OK;
 }
 

@@ -507,88 +507,129 @@ struct StatArgs {
   uint32_t* pass;                   // [nList] kurtosis filter (misc/peakcall.cpp:41 second clause)
 };
 
-// visit the entries of (strand d, contig c) with position in [lo, hi] (1-based, inclusive): f(position, entry index, y)
+// Eight lanes work on one region (four regions per warp): most regions are ~130 positions with a few hundred
+// entries, and the two moment sums are sequential chains, so narrow groups keep the lanes busy and let one
+// leader lane per group run its chain while the other groups run theirs.
+constexpr int ST_GROUP = 8;                         // lanes per region
+constexpr int ST_PER_WARP = 32 / ST_GROUP;
+constexpr int ST_CHUNK = 256;                       // positions pooled in shared memory at a time
+constexpr int ST_WARPS = 8;
+
+__device__ __forceinline__ uint32_t group_sum_u32 (uint32_t v) {
+#pragma unroll
+  for (int o = ST_GROUP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// entries of (strand d, contig c) with position in [lo, hi] (1-based, inclusive), visited by the ST_GROUP lanes of a
+// group: f(position, entry index, entry).  Entries carry their offset inside a 4096-position span, so the mini-tiles
+// the interval touches are walked span by span.
 template <class F>
-__device__ __forceinline__ void for_entries (const Tags& T, uint32_t d, uint32_t c, uint32_t lo, uint32_t hi, uint32_t lane, F f) {
-  const uint32_t gb = T.mtBase[d * T.C + c];
-  const uint32_t nMt = T.mtBase[d * T.C + c + 1] - gb;
+__device__ __forceinline__ void group_entries (const Tags& T, uint32_t d, uint32_t c, uint32_t lo, uint32_t hi, uint32_t gl, F f) {
+  const uint32_t gb = __ldg(T.mtBase + d * T.C + c);
+  const uint32_t nMt = __ldg(T.mtBase + d * T.C + c + 1) - gb;
   if (nMt == 0) return;
   const uint32_t ma = min((lo - 1) >> MT_SHIFT, nMt - 1), mb = min((hi - 1) >> MT_SHIFT, nMt - 1);
-  for (uint32_t sp = ma / SPAN_MT; sp <= mb / SPAN_MT; ++sp) {      // entries carry their offset inside a 4096-position span
+  for (uint32_t sp = ma / SPAN_MT; sp <= mb / SPAN_MT; ++sp) {
     const uint32_t m0 = max(ma, sp * SPAN_MT), m1 = min(mb, sp * SPAN_MT + SPAN_MT - 1);
-    const unsigned long long e0 = T.mtOff[gb + m0], e1 = T.mtOff[gb + m1 + 1];
-    for (unsigned long long e = e0 + lane; e < e1; e += 32) {
-      const uint2 en = __ldg(T.ment + e);
-      const uint32_t p = sp * SPAN_LEN + (en.y & (SPAN_LEN - 1)) + 1;
-      if (p >= lo && p <= hi) f(p, e, en);
+    const unsigned long long e0 = __ldg(T.mtOff + gb + m0), e1 = __ldg(T.mtOff + gb + m1 + 1);
+    for (unsigned long long eb = e0 + gl; eb < e1; eb += 4 * ST_GROUP) {
+      uint2 en[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) en[q] = (eb + q * ST_GROUP < e1) ? __ldg(T.ment + eb + q * ST_GROUP) : make_uint2(0u, 0u);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t p = sp * SPAN_LEN + (en[q].y & (SPAN_LEN - 1)) + 1;
+        if (en[q].x && p >= lo && p <= hi) f(p, eb + q * ST_GROUP, en[q]);
+      }
     }
   }
 }
 
-__global__ void __launch_bounds__(KURT_WARPS * 32) region_stats_kernel (StatArgs a) {
-  extern __shared__ uint32_t stat_smem[];
+__global__ void __launch_bounds__(ST_WARPS * 32) region_stats_kernel (StatArgs a) {
+  extern __shared__ __align__(16) unsigned char stat_smem_raw[];
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-  const uint32_t i = blockIdx.x * KURT_WARPS + warp;
-  if (i >= a.nList) return;
+  const uint32_t g = lane / ST_GROUP, gl = lane % ST_GROUP;
   const uint32_t n = a.T.nSamples;
-  uint32_t* cell = stat_smem + (size_t)warp * (KURT_CHUNK + n);
-  uint32_t* cnts = cell + KURT_CHUNK;
-  const Cand2 c = a.cand[a.list[i]];
+  // per group: cell[ST_CHUNK] u32, cnts[n] u32, stage[2*ST_GROUP] f64
+  const size_t groupBytes = ((size_t)(ST_CHUNK + n) * 4 + 15) / 16 * 16 + 2 * ST_GROUP * 8;
+  unsigned char* gbase = stat_smem_raw + ((size_t)warp * ST_PER_WARP + g) * groupBytes;
+  uint32_t* cell = (uint32_t*)gbase;
+  uint32_t* cnts = cell + ST_CHUNK;
+  double* stage = (double*)(gbase + ((size_t)(ST_CHUNK + n) * 4 + 15) / 16 * 16);
+  const uint32_t i = (blockIdx.x * ST_WARPS + warp) * ST_PER_WARP + g;
+  const bool live = i < a.nList;                                      // whole groups idle at the tail; no early return (warp-wide syncs below)
+  Cand2 c; c.unit = 0; c.left = 1; c.len = 0;
+  if (live) c = a.cand[a.list[i]];
   const SpanUnit U = a.units[c.unit];
-  const bool small = c.len <= (uint32_t)KURT_CHUNK;
-  const uint32_t right = c.left + c.len - 1;
-  if (small) for (uint32_t k = lane; k < c.len; k += 32) cell[k] = 0;
-  for (uint32_t s = lane; s < n; s += 32) cnts[s] = 0;
+  const uint32_t d0 = a.nondir ? 0u : U.buffer, d1 = a.nondir ? 1u : U.buffer;
+  for (uint32_t s = gl; s < n; s += ST_GROUP) cnts[s] = 0;
   __syncwarp();
   uint32_t count = 0, sum = 0;
-  const uint32_t d0 = a.nondir ? 0u : U.buffer, d1 = a.nondir ? 1u : U.buffer;
-  for (uint32_t d = d0; d <= d1; ++d)
-    for_entries(a.T, d, U.contig, c.left, right, lane, [&] (uint32_t p, unsigned long long e, const uint2& en) {
-      const uint32_t k = a.T.mEff ? __ldg(a.T.mEff + e) : en.x;
-      if (!k) return;
-      const uint32_t o = p - c.left;
-      count += k;
-      sum += k * (o & 0xFFFFu);
-      atomicAdd(&cnts[en.y >> SPAN_SHIFT], k);
-      if (small) atomicAdd(&cell[o], k);
-    });
-  count = warp_sum_u32(count); sum = warp_sum_u32(sum);
-  __syncwarp();
-  for (uint32_t s = lane; s < n; s += 32) a.counts[(uint64_t)i * n + s] = cnts[s];
-  const double xbar = (double)sum / (double)count;                   // misc/data.cpp:147
   double sum2 = 0.0, sum4 = 0.0;
-  for (uint32_t o0 = 0; o0 < c.len; o0 += KURT_CHUNK) {
-    const uint32_t oc = min((uint32_t)KURT_CHUNK, c.len - o0);
-    if (!small) {                                                     // long region: pool one chunk of positions at a time
-      for (uint32_t k = lane; k < KURT_CHUNK; k += 32) cell[k] = 0;
-      __syncwarp();
+  const bool single = c.len <= (uint32_t)ST_CHUNK;                    // fits one chunk: positions are pooled during the counting pass
+  const uint32_t right = c.left + c.len - 1;
+
+  // pass 1: per-sample sums, count and count*offset (and the pooled positions of a single-chunk region)
+  if (live && single) for (uint32_t k = gl; k < ST_CHUNK; k += ST_GROUP) cell[k] = 0;
+  __syncwarp();
+  if (live)
+    for (uint32_t d = d0; d <= d1; ++d)
+      group_entries(a.T, d, U.contig, c.left, right, gl, [&] (uint32_t p, unsigned long long e, const uint2& en) {
+        const uint32_t k = a.T.mEff ? __ldg(a.T.mEff + e) : en.x;
+        if (!k) return;
+        const uint32_t o = p - c.left;
+        count += k;
+        sum += k * (o & 0xFFFFu);
+        atomicAdd(&cnts[en.y >> SPAN_SHIFT], k);
+        if (single) atomicAdd(&cell[o], k);
+      });
+  __syncwarp();
+  count = group_sum_u32(count); sum = group_sum_u32(sum);
+  const double xbar = (double)sum / (double)count;                   // misc/data.cpp:147
+  if (live) for (uint32_t s = gl; s < n; s += ST_GROUP) a.counts[(uint64_t)i * n + s] = cnts[s];
+
+  // pass 2: the two central-moment chains, one chunk of positions at a time (loop bounds made warp-uniform)
+  const uint32_t nChunks = live ? (c.len + ST_CHUNK - 1) / ST_CHUNK : 0u;
+  uint32_t maxChunks = nChunks;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) maxChunks = max(maxChunks, __shfl_xor_sync(0xffffffffu, maxChunks, o));
+  for (uint32_t ch = 0; ch < maxChunks; ++ch) {
+    const bool act = ch < nChunks;
+    const uint32_t o0 = ch * ST_CHUNK;
+    const uint32_t oc = act ? min((uint32_t)ST_CHUNK, c.len - o0) : 0u;
+    if (act && !single) for (uint32_t k = gl; k < ST_CHUNK; k += ST_GROUP) cell[k] = 0;
+    __syncwarp();
+    if (act && !single)
       for (uint32_t d = d0; d <= d1; ++d)
-        for_entries(a.T, d, U.contig, c.left + o0, c.left + o0 + oc - 1, lane, [&] (uint32_t p, unsigned long long e, const uint2& en) {
+        group_entries(a.T, d, U.contig, c.left + o0, c.left + o0 + oc - 1, gl, [&] (uint32_t p, unsigned long long e, const uint2& en) {
           const uint32_t k = a.T.mEff ? __ldg(a.T.mEff + e) : en.x;
           if (k) atomicAdd(&cell[p - c.left - o0], k);
         });
+    __syncwarp();
+    // ST_GROUP positions per step: every lane prepares its position's terms, the group's leader adds them in
+    // position order (a position without tags adds +0.0, which changes nothing)
+    const uint32_t steps = (oc + ST_GROUP - 1) / ST_GROUP;
+    uint32_t maxSteps = steps;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxSteps = max(maxSteps, __shfl_xor_sync(0xffffffffu, maxSteps, o));
+    for (uint32_t st = 0; st < maxSteps; ++st) {
+      const uint32_t k = st * ST_GROUP + gl;
+      const uint32_t pc = k < oc ? cell[k] : 0u;
+      const double dd = __dsub_rn((double)((o0 + k) & 0xFFFFu), xbar); // offset counter is a UShort (Q8)
+      const double d2 = __dmul_rn(dd, dd);
+      const double d4 = __dmul_rn(d2, d2);                            // pow(x,4) == (x*x)*(x*x) in the reference build (Q9)
+      stage[gl] = pc ? __dmul_rn((double)pc, d2) : 0.0;
+      stage[ST_GROUP + gl] = pc ? __dmul_rn((double)pc, d4) : 0.0;
+      __syncwarp();
+      if (gl == 0 && st < steps) {
+#pragma unroll
+        for (int q = 0; q < ST_GROUP; ++q) { sum2 = __dadd_rn(sum2, stage[q]); sum4 = __dadd_rn(sum4, stage[ST_GROUP + q]); }
+      }
       __syncwarp();
     }
-    for (uint32_t g = 0; g < oc; g += 32) {
-      const uint32_t o = o0 + g + lane;
-      const uint32_t pc = (g + lane < oc) ? cell[g + lane] : 0u;
-      uint32_t nz = __ballot_sync(0xffffffffu, pc != 0);
-      if (!nz) continue;
-      const double dd = __dsub_rn((double)(o & 0xFFFFu), xbar);     // offset counter is a UShort (Q8)
-      const double d2 = __dmul_rn(dd, dd);
-      const double d4 = __dmul_rn(d2, d2);                          // pow(x,4) == (x*x)*(x*x) in the reference build (Q9)
-      const double t2 = __dmul_rn((double)pc, d2);
-      const double t4 = __dmul_rn((double)pc, d4);
-      while (nz) {
-        const int b = __ffs(nz) - 1;
-        sum2 = __dadd_rn(sum2, __shfl_sync(0xffffffffu, t2, b));
-        sum4 = __dadd_rn(sum4, __shfl_sync(0xffffffffu, t4, b));
-        nz &= nz - 1;
-      }
-    }
-    __syncwarp();
   }
-  if (lane == 0) {
+  if (live && gl == 0) {
     const double k = __ddiv_rn(__dmul_rn(__dsub_rn((double)count, 1.0), sum4), __dmul_rn(sum2, sum2));   // misc/data.cpp:181
     a.kurt[i] = k;
     a.pass[i] = (a.kurtThr == 0.0 || (c.len > 1 && k <= a.kurtThr)) ? 1u : 0u;
