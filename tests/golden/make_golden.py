@@ -75,6 +75,31 @@ def save_shift(name, data: TagData, **kw):
     print("%-28s %6d entries, %d regions tested, best shift %d" % (name, data.pos.shape[0], ref["n_regions_tested"], ref["best_shift"]))
 
 
+def save_tags_in_regions(name, data: TagData, base_samples, extra_samples, directional=True, extension=0):
+    """bin/regions on the base samples, then bin/tags_in_regions (the real reference CLIs) for the extra samples."""
+    import re
+    base = data.subset_samples(base_samples)
+    extra = data.subset_samples(extra_samples)
+    with tempfile.TemporaryDirectory() as wd:
+        f0 = refutil.write_inputs(base, os.path.join(wd, "base"))
+        f1 = refutil.write_inputs(extra, os.path.join(wd, "extra"), prefix="x")
+        table = os.path.join(wd, "regions.txt")
+        refutil.run_ref_cli("regions", ["-q", "-o", table, "-c", f0["contigs"]] + (["-D"] if not directional else []) + f0["wigs"])
+        out = os.path.join(wd, "more.txt")
+        refutil.run_ref_cli("tags_in_regions", ["-f", table, "-o", out, "-c", f0["contigs"], "-e", str(extension)] + (["-D"] if not directional else []) + f1["wigs"])
+        names = data.names()
+        keys = []
+        for row in refutil.read_table_rows(table):
+            m = re.match(r"(\w+):(\d+)-(\d+)", row)
+            keys.append((names.index(m.group(1)), int(m.group(2)), int(m.group(3))))
+        n = len(extra_samples)
+        got = [[int(x) for x in row.split("\t")[-n:]] for row in refutil.read_table_rows(out)]
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), kind=np.array("tir"), contig_sizes=extra.contig_sizes, n_samples=np.array(extra.n_samples),
+                        off=extra.off, pos=extra.pos, cnt=extra.cnt, directional=np.array(int(directional)), extension=np.array(extension),
+                        keys=np.array(keys, np.uint32).reshape(len(keys), 3), counts=np.array(got, np.uint32).reshape(len(keys), n))
+    print("%-28s %6d entries, %4d region rows x %d extra samples" % (name, extra.pos.shape[0], len(keys), n))
+
+
 def dense(sizes, n_samples, seed, fill, max_count):
     rng = np.random.default_rng(seed)
     segs = []
@@ -103,6 +128,13 @@ def main():
     d = dense([70000, 3000], 1, 109, 0.9, 3)
     save_regions("regions_long_q8", d, mappable=100 * d.genome_size())
     save_regions("regions_long_q8_nondir", d, mappable=100 * d.genome_size(), directional=False, corr_threshold=-0.5)
+    d3 = make_synthetic([120000, 60000], 4, 12000, directional=True, seed=111, peak_spacing=4000, contig_names=["chrA", "chrB"])
+    save_tags_in_regions("tir_directional", d3, [0, 1], [2, 3])
+    save_tags_in_regions("tir_directional_ext", d3, [0], [1, 2, 3], extension=75)
+    d4 = make_synthetic([120000, 60000], 3, 16000, directional=False, seed=112, peak_spacing=4000, contig_names=["chrA", "chrB"])
+    save_tags_in_regions("tir_nondirectional", d4, [0], [1, 2], directional=False, extension=20)
+    d5 = make_synthetic([300000], 3, 16000, directional=True, seed=113, peak_spacing=6000, contig_names=["chrA"])
+    save_tags_in_regions("tir_one_contig_q13", d5.subset_samples([0, 1, 2]), [0], [1, 2])
     save_shift("shift_chip", make_synthetic([1500000], 1, 150000, directional=False, seed=110, peak_spacing=10000),
                n_regions_to_test=25, region_threshold=8.0, corr_threshold=0.1)
 

@@ -364,6 +364,9 @@ def load_golden(name: str):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     data = TagData(z["contig_sizes"].astype(np.uint32), int(z["n_samples"]), z["off"].astype(np.uint64), z["pos"].astype(np.uint32), z["cnt"].astype(np.uint32))
     kind = str(z["kind"])
+    if kind == "tir":
+        keys = [tuple(int(x) for x in row) for row in z["keys"]]
+        return data, dict(directional=bool(int(z["directional"])), extension=int(z["extension"]), keys=keys), z["counts"].astype(np.uint32)
     if kind == "regions":
         st = dict(bandwidth=int(z["bandwidth"]), region_threshold=_f(z["region_threshold"]), kurtosis_threshold=_f(z["kurtosis_threshold"]),
                   corr_threshold=_f(z["corr_threshold"]), hit_threshold=_f(z["hit_threshold"]), directional=bool(int(z["directional"])),

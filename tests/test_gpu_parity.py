@@ -229,3 +229,70 @@ def test_fast_classification_is_what_runs(gpu_ctx):
     assert s["exact_evals"] < 32 * s["hot_blocks"] / 4, s
     want = oracle_regions(d, st)
     assert_rows_equal(got["rows"], want["rows"], "written")
+
+
+# ---- bin/tags_in_regions ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names("tir"))
+def test_golden_tags_in_regions(gpu_ctx, name):
+    data, p, want = load_golden(name)
+    gpu_ctx.load(data)
+    got = gpu_ctx.count_tags_in_regions(p["keys"], directional=p["directional"], extension=p["extension"])
+    assert got.tolist() == want.tolist()
+
+
+def _tir_check(ctx, data, keys, **kw):
+    from refutil import oracle_tags_in_regions
+    status, want = oracle_tags_in_regions(data, keys, **kw)
+    ctx.load(data)
+    if status != 0:
+        import unipeak_b200
+        with pytest.raises(unipeak_b200.UpbError) as ei:
+            ctx.count_tags_in_regions(keys, **kw)
+        assert ei.value.code == -9
+        return None
+    got = ctx.count_tags_in_regions(keys, **kw)
+    assert got.tolist() == want.tolist()
+    return got
+
+
+def test_tags_in_regions_stream_order_quirks(gpu_ctx):
+    # rows out of stream order, overlapping rows, a '+' row after '-' rows (eats nothing / everything),
+    # rows past the last tag, extension reaching below position 1
+    rng = np.random.default_rng(5)
+    d = make_synthetic([200000, 80000], 3, 20000, directional=True, seed=41, peak_spacing=5000)
+    keys = []
+    for _ in range(300):
+        c = int(rng.integers(0, 2))
+        a = int(rng.integers(1, 79000 if c else 199000))
+        b = a + int(rng.integers(0, 900))
+        keys.append((c, a, b) if rng.random() < 0.6 else (c, b, a))          # '+' and '-' rows interleaved at random
+    _tir_check(gpu_ctx, d, keys, directional=True, extension=0)
+    _tir_check(gpu_ctx, d, keys, directional=True, extension=400)
+    fwd_sorted = sorted([k for k in keys if k[2] >= k[1]])
+    rev_sorted = sorted([k for k in keys if k[2] < k[1]])
+    got = _tir_check(gpu_ctx, d, fwd_sorted + rev_sorted, directional=True, extension=0)
+    assert got.sum() > 0
+    _tir_check(gpu_ctx, d, rev_sorted + fwd_sorted, directional=True, extension=0)   # every '+' row after the '-' rows counts 0
+
+
+def test_tags_in_regions_nondirectional(gpu_ctx):
+    rng = np.random.default_rng(6)
+    d = make_synthetic([200000, 80000], 2, 30000, directional=False, seed=42, peak_spacing=5000)
+    keys = []
+    for _ in range(300):
+        c = int(rng.integers(0, 2))
+        a = int(rng.integers(1, 79000 if c else 199000))
+        keys.append((c, a, a + int(rng.integers(0, 900))))
+    _tir_check(gpu_ctx, d, keys, directional=False, extension=0)
+    got = _tir_check(gpu_ctx, d, sorted(keys), directional=False, extension=30)
+    assert got.sum() > 0
+    assert _tir_check(gpu_ctx, d, [(0, 500, 100)], directional=False, extension=0) is None   # reverse row in a -D analysis
+
+
+def test_tags_in_regions_single_contig_plus_row_eats_minus_track(gpu_ctx):
+    # Q13 (ii): on a one-contig table the count loop of the last '+' row runs on into the '-' track
+    d = make_synthetic([300000], 2, 20000, directional=True, seed=43, peak_spacing=6000)
+    last_plus = int(d.seg(0, 0, 0)[0][-1])
+    keys = [(0, 1000, 5000), (0, last_plus - 10, 299000), (0, 100, 200000), (0, 250000, 1000)]
+    got = _tir_check(gpu_ctx, d, keys, directional=True, extension=0)
+    assert got[1, 0] > int(d.seg(0, 0, 0)[1][-1])

@@ -33,3 +33,12 @@ def test_fixture_set_is_complete():
     for needed in ("regions_directional", "regions_nondirectional", "regions_controls_q4", "regions_coeffs_q3", "regions_left_edge_q2",
                    "regions_one_contig_q7", "regions_long_q8"):
         assert needed in names
+
+
+@pytest.mark.parametrize("name", golden_names("tir"))
+def test_oracle_tags_in_regions_golden(name):
+    from refutil import oracle_tags_in_regions
+    data, p, want = load_golden(name)
+    status, got = oracle_tags_in_regions(data, p["keys"], directional=p["directional"], extension=p["extension"])
+    assert status == 0
+    assert got.tolist() == want.tolist()

@@ -1116,7 +1116,45 @@ extern "C" int upb_profile_contig (upb_ctx* ctx, const upb_region_params* p, int
 
 extern "C" int upb_count_tags_in_regions (upb_ctx* ctx, int directional, uint32_t extension, uint64_t n_regions,
                                           const upb_region_key* regions, uint32_t* counts_out) {
-  (void)directional; (void)extension; (void)n_regions; (void)regions; (void)counts_out;
   if (!ctx) return UPB_ERR_BAD_ARG;
-  return fail(ctx, UPB_ERR_UNSUPPORTED, "upb_count_tags_in_regions is not implemented yet");
+  if (!ctx->loaded) return fail(ctx, UPB_ERR_NOT_LOADED, "no tags loaded (upb_set_contigs + upb_load_tags first)");
+  if (n_regions && (!regions || !counts_out)) return fail(ctx, UPB_ERR_BAD_ARG, "upb_count_tags_in_regions: NULL argument");
+  CU(cudaSetDevice(ctx->device));
+  const uint32_t C = (uint32_t)ctx->sizes.size(), n = ctx->nSamples;
+  if (C >= (1u << 28)) return fail(ctx, UPB_ERR_UNSUPPORTED, "too many contigs");
+  if (n_regions == 0) return UPB_OK;
+  // src/tags_in_regions.cpp:141-172: strand from the coordinate order, optional extension (Pos arithmetic wraps like the reference's)
+  std::vector<TirRegion> tr(n_regions);
+  for (uint64_t k = 0; k < n_regions; ++k) {
+    const upb_region_key& q = regions[k];
+    if (q.contig >= C) return fail(ctx, UPB_ERR_BAD_ARG, "upb_count_tags_in_regions: contig not in table");
+    const bool forward = q.end >= q.start;
+    if (!forward && !directional) return fail(ctx, UPB_ERR_REVERSE_NONDIR, "reverse regions in non-directional analysis");   // :167-170
+    const uint32_t lo = forward ? q.start : q.end;
+    tr[k].contig = q.contig;
+    tr[k].left = lo < extension ? 0u : lo - extension;
+    tr[k].right = (forward ? q.end : q.start) + extension;
+    tr[k].strand = forward ? 0u : 1u;
+  }
+  TirArgs ta;
+  ta.T = make_tags(ctx, false);
+  TirRegion* d_regions = SCR("tirRegions", TirRegion, n_regions);
+  ta.regions = d_regions; ta.nRegions = n_regions; ta.directional = directional ? 1 : 0;
+  ta.hits = SCR("tirHits", uint32_t, n_regions * n);
+  ta.E = SCR("tirE", unsigned long long, n_regions * n);
+  ta.M = SCR("tirM", unsigned long long, n_regions * n);
+  CU(cudaMemcpyAsync(d_regions, tr.data(), n_regions * sizeof(TirRegion), cudaMemcpyHostToDevice, ctx->stream));
+  const uint64_t total = n_regions * n;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  ta.firstDead = SCR("tirDead", unsigned long long, n);
+  CU(cudaMemsetAsync(ta.firstDead, 0xFF, (size_t)n * 8, ctx->stream));
+  tir_eval_kernel<<<blocks, 256, 0, ctx->stream>>>(ta, 0);
+  tir_scan_kernel<<<n, 1024, 0, ctx->stream>>>(ta.E, ta.M, n_regions);
+  if (directional) tir_dead_kernel<<<blocks, 256, 0, ctx->stream>>>(ta);
+  tir_eval_kernel<<<blocks, 256, 0, ctx->stream>>>(ta, 1);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(counts_out, ta.hits, total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->stats.launches = directional ? 4 : 3;
+  return UPB_OK;
 }

@@ -447,4 +447,155 @@ __global__ void best_shift_kernel (const double* __restrict__ corr, uint32_t n, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// bin/tags_in_regions (src/tags_in_regions.cpp:131-199).  The reference walks every extra sample's stream once,
+// with a cursor that only moves forward: per region it SKIPS entries until one has the region's strand and lies at
+// or after the region's left edge (a strand mismatch also skips, SURVEY Q13 i), then COUNTS entries while they are
+// on the region's contig at or before its right edge — without looking at the strand (Q13 ii).
+//
+// Cursor positions are handled as keys in the stream's order: directional streams are strand-major
+// (misc/format.cpp:503-565), key = (strand, contig, pos); NondirParseAlignStream merges the strands by position,
+// forward first on ties (misc/format.cpp:832-850), key = (contig, pos, strand).  For a cursor at or before the
+// region's own lower key L the outcome does not depend on the cursor, so pass 1 evaluates every (region, sample)
+// independently from L and reports where the cursor ends up (E); the cursor seen by region k is then the running
+// maximum of the earlier E (pass 2, one block per sample), and pass 3 re-evaluates only the rare pairs whose cursor
+// had already overtaken L (overlapping or unsorted rows, or a '+' row met after the stream reached its '-' track).
+// ------------------------------------------------------------------------------------------------
+struct TirRegion { uint32_t contig, left, right, strand; };          // strand 0 '+', 1 '-'
+
+__device__ __forceinline__ unsigned long long tir_key (bool directional, uint32_t d, uint32_t c, uint64_t p) {
+  return directional ? (((unsigned long long)d << 62) | ((unsigned long long)c << 33) | p) : (((unsigned long long)c << 34) | (p << 1) | d);
+}
+constexpr unsigned long long TIR_END = ~0ull;
+
+// first entry index (absolute) of sample s, strand d with (contig, pos) >= (c, p); strand end if none
+__device__ __forceinline__ uint64_t tir_lb (const Tags& T, uint32_t s, uint32_t d, uint32_t c, uint64_t p) {
+  const uint64_t* o = T.off + (uint64_t)(s * 2 + d) * (T.C + 1);
+  if (c >= T.C) return o[T.C];
+  if (p > 0xFFFFFFFFull) return o[c + 1];
+  return lower_bound_u32(T.pos, o[c], o[c + 1], (uint32_t)p);
+}
+__device__ __forceinline__ uint32_t tir_contig_of (const Tags& T, uint32_t s, uint32_t d, uint64_t idx) {
+  const uint64_t* o = T.off + (uint64_t)(s * 2 + d) * (T.C + 1);
+  uint32_t lo = 0, hi = T.C;                                         // largest c with o[c] <= idx
+  while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (o[mid] <= idx) lo = mid; else hi = mid; }
+  return lo;
+}
+__device__ __forceinline__ uint32_t tir_sum (const Tags& T, uint64_t a, uint64_t b) {
+  uint32_t h = 0;
+  for (uint64_t e = a; e < b; ++e) h += __ldg(T.cnt + e);             // HitCount wraps mod 2^32
+  return h;
+}
+
+// one region, one sample, cursor at key bound `cur` (<= L means "not past the region's own lower key")
+__device__ __forceinline__ void tir_eval (const Tags& T, bool directional, uint32_t s, const TirRegion& r, unsigned long long cur,
+                                          uint32_t& hits, unsigned long long& E) {
+  hits = 0;
+  const uint32_t C = T.C;
+  uint32_t bc = r.contig; uint64_t bp = r.left;                      // bound inside the region's strand: max(cur, L)
+  if (cur > tir_key(directional, r.strand, r.contig, r.left)) {
+    if (cur == TIR_END) { E = TIR_END; return; }
+    if (directional) {
+      const uint32_t dc = (uint32_t)(cur >> 62);
+      if (dc > r.strand) { E = TIR_END; return; }                    // a '+' row after the cursor reached the '-' track: nothing matches any more
+      bc = (uint32_t)((cur >> 33) & 0x1FFFFFFFu); bp = cur & 0x1FFFFFFFFull;
+    } else {
+      bc = (uint32_t)(cur >> 34); bp = ((cur >> 1) & 0x1FFFFFFFFull) + (cur & 1ull);   // past a '-' entry at p: the next '+' entry is beyond p
+    }
+  }
+  const uint64_t* o = T.off + (uint64_t)(s * 2 + r.strand) * (C + 1);
+  const uint64_t t = tir_lb(T, s, r.strand, bc, bp);                 // SKIP ends here
+  if (t >= o[C]) { E = TIR_END; return; }
+  const uint32_t tc = tir_contig_of(T, s, r.strand, t);
+  const uint32_t tp = T.pos[t];
+  if (tc != r.contig || tp > r.right) { E = tir_key(directional, r.strand, tc, tp); return; }
+  // COUNT: same contig, position <= right, strand not examined
+  const uint64_t a1 = upper_bound_u32(T.pos, t, o[r.contig + 1], r.right);
+  hits = tir_sum(T, t, a1);
+  E = tir_key(directional, r.strand, r.contig, (uint64_t)r.right + 1);
+  if (directional) {
+    if (r.strand == 0 && a1 == o[C]) {                                // ran off the end of the '+' track: the '-' track follows in the stream
+      const uint64_t* om = T.off + (uint64_t)(s * 2 + 1) * (C + 1);
+      const uint64_t b0 = om[0];
+      if (b0 < om[C] && tir_contig_of(T, s, 1, b0) == r.contig && T.pos[b0] <= r.right) {
+        const uint64_t b1 = upper_bound_u32(T.pos, b0, om[r.contig + 1], r.right);
+        hits += tir_sum(T, b0, b1);
+        E = tir_key(true, 1, r.contig, (uint64_t)r.right + 1);
+      }
+    }
+  } else {
+    // merged stream: every '-' entry from (contig, tp) on ('-' follows '+' at equal positions) up to right
+    const uint64_t* om = T.off + (uint64_t)(s * 2 + 1) * (C + 1);
+    const uint64_t b0 = lower_bound_u32(T.pos, om[r.contig], om[r.contig + 1], tp);
+    const uint64_t b1 = upper_bound_u32(T.pos, b0, om[r.contig + 1], r.right);
+    hits += tir_sum(T, b0, b1);
+  }
+}
+
+struct TirArgs {
+  Tags T;
+  const TirRegion* regions;
+  uint64_t nRegions;
+  int directional;
+  uint32_t* hits;                    // [nRegions * nSamples]
+  unsigned long long* E;             // [nSamples * nRegions] (sample-major for the scan)
+  unsigned long long* M;             // [nSamples * nRegions] exclusive running maximum of E
+  unsigned long long* firstDead;     // [nSamples] first '+' row met with the cursor already in the '-' track: it and every later row count 0
+};
+
+// a directional '+' row whose cursor already sits in the '-' track skips to the end of the stream (Q13 i)
+__global__ void tir_dead_kernel (TirArgs a) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n = a.T.nSamples;
+  if (g >= a.nRegions * n) return;
+  const uint64_t k = g / n; const uint32_t s = (uint32_t)(g % n);
+  if (a.regions[k].strand == 0 && (a.M[(uint64_t)s * a.nRegions + k] >> 62) != 0) atomicMin(&a.firstDead[s], (unsigned long long)k);
+}
+
+__global__ void tir_eval_kernel (TirArgs a, int fixup) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n = a.T.nSamples;
+  if (g >= a.nRegions * n) return;
+  const uint64_t k = g / n; const uint32_t s = (uint32_t)(g % n);
+  const TirRegion r = a.regions[k];
+  unsigned long long cur = 0;
+  if (fixup) {
+    if (a.directional && k >= a.firstDead[s]) { a.hits[g] = 0; return; }
+    cur = a.M[(uint64_t)s * a.nRegions + k];
+    if (cur <= tir_key(a.directional != 0, r.strand, r.contig, r.left)) return;   // pass 1 already holds the answer
+  }
+  uint32_t h; unsigned long long E;
+  tir_eval(a.T, a.directional != 0, s, r, cur, h, E);
+  a.hits[g] = h;
+  if (!fixup) a.E[(uint64_t)s * a.nRegions + k] = E;
+}
+
+// exclusive running maximum per sample: one block per sample walks its row in chunks
+__global__ void tir_scan_kernel (const unsigned long long* __restrict__ E, unsigned long long* __restrict__ M, uint64_t nRegions) {
+  __shared__ unsigned long long sh[33];
+  __shared__ unsigned long long carry;
+  const uint32_t s = blockIdx.x, lane = lane_id(), warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const unsigned long long* e = E + (uint64_t)s * nRegions;
+  unsigned long long* m = M + (uint64_t)s * nRegions;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint64_t b0 = 0; b0 < nRegions; b0 += blockDim.x) {
+    const uint64_t i = b0 + threadIdx.x;
+    const unsigned long long v = i < nRegions ? e[i] : 0ull;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (uint32_t)o) inc = max(inc, x); }
+    if (lane == 31) sh[warp] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned long long run = carry; for (uint32_t w = 0; w < nw; ++w) { const unsigned long long t = sh[w]; sh[w] = run; run = max(run, t); } sh[32] = run; }
+    __syncthreads();
+    unsigned long long ex = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) ex = 0;
+    if (i < nRegions) m[i] = max(sh[warp], ex);
+    __syncthreads();
+    if (threadIdx.x == 0) carry = sh[32];
+    __syncthreads();
+  }
+}
+
 }  // namespace upb
