@@ -57,16 +57,7 @@ def env_int(name, default):
         return default
 
 
-def shard_contigs(sizes, world):
-    """Longest-processing-time assignment of whole contigs to ranks (tag density is uniform in the workload)."""
-    order = sorted(range(len(sizes)), key=lambda c: -sizes[c])
-    load = [0] * world
-    owner = [0] * len(sizes)
-    for c in order:
-        r = min(range(world), key=lambda k: load[k])
-        owner[c] = r
-        load[r] += sizes[c]
-    return owner
+from unipeak_b200.multi import gather_region_rows, shard_contigs  # noqa: E402
 
 
 class ClockSampler:
@@ -246,34 +237,9 @@ def main():
         res = ctx.call_regions_view(**dict(st, reference_order=(world == 1)))
         if world == 1:
             return res
-        # gather the canonical rows on rank 0 (NCCL), total the per-sample tags-in-regions (NCCL)
-        cols = res
-        R = int(res["n_rows"])
-        tir = torch.from_numpy(res["tags_in_regions"].astype(np.int64)).to(dev)
-        dist.all_reduce(tir)
-        nrows = torch.tensor([R], dtype=torch.int64, device=dev)
-        allrows = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(allrows, nrows)
-        counts = [int(x.item()) for x in allrows]
-        rmax = max(counts + [1])
-        # one packed int64 matrix per rank: buffer, contig, left, len, peak, cand_index, kurtosis bits, corr bits, score bits, counts...
-        width = 9 + n_samples
-        pack = np.zeros((rmax, width), dtype=np.int64)
-        if R:
-            pack[:R, 0] = cols["buffer"]; pack[:R, 1] = cols["contig"]; pack[:R, 2] = cols["left"]; pack[:R, 3] = cols["len"]
-            pack[:R, 4] = cols["peak"]; pack[:R, 5] = cols["cand_index"].astype(np.int64)
-            pack[:R, 6] = cols["kurtosis"].view(np.int64); pack[:R, 7] = cols["corr"].view(np.int64); pack[:R, 8] = cols["peak_score"].view(np.int64)
-            pack[:R, 9:] = cols["counts"]
-        t = torch.from_numpy(pack).to(dev)
-        gathered = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
-        dist.gather(t, gathered, dst=0)
-        uc = torch.from_numpy(res["unit_candidates"].astype(np.int64)).to(dev)
-        dist.all_reduce(uc)
-        if rank != 0:
-            return None
-        rows = np.concatenate([g.cpu().numpy()[:k] for g, k in zip(gathered, counts)], axis=0)
-        order = np.lexsort((rows[:, 2], rows[:, 1], rows[:, 0]))       # canonical: buffer, contig, left
-        return {"n_rows": int(rows.shape[0]), "rows_packed": rows[order], "tags_in_regions": tir.cpu().tolist(), "unit_candidates": uc.cpu().numpy()}
+        # gather the canonical rows on rank 0 and total the per-sample tags-in-regions / candidate counts (NCCL)
+        return gather_region_rows(res.columns(), n_samples, res["tags_in_regions"], res["unit_candidates"],
+                                  dist=dist, rank=rank, world=world, device=dev)
 
     def barrier():
         if world > 1:

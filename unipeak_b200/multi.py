@@ -1,0 +1,82 @@
+"""Multi-GPU plumbing of the region-calling path (one process per GPU, torch.distributed).
+
+The path shards by (ProfileBuffer, contig) with no data-path exchange: every rank loads and
+calls only its own contigs.  Three small, latency-bound collectives remain:
+  * per-sample tag totals -> background (src/regions.cpp:190-210), all-reduce before the call;
+  * per-sample tags-in-regions totals and per-(buffer, contig) candidate counts, all-reduce after it;
+  * the gather of the region rows to rank 0, which puts them in canonical order (buffer, contig, left).
+Works on any backend (NCCL on the GPUs; gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+
+def shard_contigs(sizes: Sequence[int], world: int) -> List[int]:
+    """Longest-processing-time assignment of whole contigs to ranks (tag density is roughly uniform).
+    Returns owner[c]."""
+    order = sorted(range(len(sizes)), key=lambda c: (-int(sizes[c]), c))
+    load = [0] * world
+    owner = [0] * len(sizes)
+    for c in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        owner[c] = r
+        load[r] += int(sizes[c])
+    return owner
+
+
+ROW_FIELDS = ("buffer", "contig", "left", "len", "peak", "cand_index", "hit_sum")
+FP_FIELDS = ("kurtosis", "corr", "peak_score")
+
+
+def pack_rows(cols, n_samples: int) -> np.ndarray:
+    """One int64 matrix per rank: integer fields, FP64 fields as bit patterns, then the per-sample counts."""
+    R = int(cols["left"].shape[0])
+    width = len(ROW_FIELDS) + len(FP_FIELDS) + n_samples
+    pack = np.zeros((R, width), dtype=np.int64)
+    for j, k in enumerate(ROW_FIELDS):
+        pack[:, j] = cols[k].astype(np.int64)
+    for j, k in enumerate(FP_FIELDS):
+        pack[:, len(ROW_FIELDS) + j] = np.ascontiguousarray(cols[k], dtype=np.float64).view(np.int64)
+    pack[:, len(ROW_FIELDS) + len(FP_FIELDS):] = cols["counts"]
+    return pack
+
+
+def unpack_rows(pack: np.ndarray, n_samples: int) -> Dict[str, np.ndarray]:
+    out = {}
+    for j, k in enumerate(ROW_FIELDS):
+        out[k] = pack[:, j].copy()
+    for j, k in enumerate(FP_FIELDS):
+        out[k] = pack[:, len(ROW_FIELDS) + j].copy().view(np.float64)
+    out["counts"] = pack[:, len(ROW_FIELDS) + len(FP_FIELDS):].astype(np.uint32)
+    return out
+
+
+def gather_region_rows(cols, n_samples: int, tags_in_regions, unit_candidates, *, dist, rank: int, world: int, device) -> Optional[Dict]:
+    """Collects every rank's canonical rows on rank 0.  Returns None on the other ranks."""
+    import torch
+    pack = pack_rows(cols, n_samples)
+    R = pack.shape[0]
+    tir = torch.as_tensor(np.asarray(tags_in_regions, dtype=np.int64)).to(device)
+    uc = torch.as_tensor(np.asarray(unit_candidates, dtype=np.int64)).to(device)
+    nrows = torch.tensor([R], dtype=torch.int64, device=device)
+    allrows = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_reduce(tir)
+    dist.all_reduce(uc)
+    dist.all_gather(allrows, nrows)
+    counts = [int(x.item()) for x in allrows]
+    rmax = max(counts + [1])
+    padded = np.zeros((rmax, pack.shape[1]), dtype=np.int64)
+    padded[:R] = pack
+    t = torch.from_numpy(padded).to(device)
+    gathered = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+    dist.gather(t, gathered, dst=0)
+    if rank != 0:
+        return None
+    rows = np.concatenate([g.cpu().numpy()[:k] for g, k in zip(gathered, counts)], axis=0)
+    order = np.lexsort((rows[:, 2], rows[:, 1], rows[:, 0]))       # canonical: buffer, contig, left
+    out = unpack_rows(rows[order], n_samples)
+    out.update(n_rows=int(rows.shape[0]), tags_in_regions=tir.cpu().numpy(), unit_candidates=uc.cpu().numpy())
+    return out
