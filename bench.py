@@ -57,7 +57,7 @@ def env_int(name, default):
         return default
 
 
-from unipeak_b200.multi import gather_region_rows, shard_contigs  # noqa: E402
+from unipeak_b200.multi import DeviceGather, shard_contigs  # noqa: E402
 
 
 class ClockSampler:
@@ -231,15 +231,14 @@ def main():
         ctx.load_tags_ptr(n_samples, h_off.data_ptr(), h_pos.data_ptr(), h_cnt.data_ptr())
 
     C = len(sizes)
-    first_last = None
+    gather = DeviceGather(ctx, n_samples, C, dist=dist, rank=rank, world=world, device=dev) if world > 1 else None
 
     def step():
         res = ctx.call_regions_view(**dict(st, reference_order=(world == 1)))
         if world == 1:
             return res
-        # gather the canonical rows on rank 0 and total the per-sample tags-in-regions / candidate counts (NCCL)
-        return gather_region_rows(res.columns(), n_samples, res["tags_in_regions"], res["unit_candidates"],
-                                  dist=dist, rank=rank, world=world, device=dev)
+        # NCCL: one small all-reduce (rows / candidates per unit, tags in regions) + one reduce of the table-wide slab to rank 0
+        return gather(res)
 
     def barrier():
         if world > 1:

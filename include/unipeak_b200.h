@@ -111,6 +111,7 @@ typedef struct {
   uint64_t* tags_in_regions;    /* [n_samples] ProfileBuffer::nTagsInRegions() */
   uint64_t* unit_candidates;    /* [2 * n_contigs] candidate regions per (buffer, contig) */
   uint32_t* unit_last_tag;      /* [2 * n_contigs] last add() position per (buffer, contig), 0 if none */
+  uint64_t* unit_rows;          /* [2 * n_contigs] accepted rows per (buffer, contig) */
   void* _slab;                  /* private: the slab, its size and its owner */
   uint64_t _slab_bytes;
   void* _ctx;
@@ -126,6 +127,22 @@ void upb_free_region_table (upb_region_table* t);
 int upb_reference_order (uint32_t n_contigs, uint32_t n_samples, int directional, uint32_t bandwidth,
                          const uint32_t* first_pos, const uint32_t* last_pos,
                          upb_region_table* t, uint64_t* perm_out);
+
+/* ---- several GPUs: one table out of the ranks' tables ---------------------------------------- */
+/* Every rank calls upb_call_regions on the contigs it loaded (reference_order = 0), the ranks sum their unit_rows
+ * (one small all-reduce), and each rank scatters its rows to their place in ONE table-wide device slab that the
+ * caller zeroed: slab columns are laid out as upb_slab_layout says, rows in canonical order (buffer, contig, left).
+ * Summing the slabs over the ranks (ncclReduce on 64-bit words; the row sets are disjoint) gives rank 0 the whole
+ * table without a host round trip; upb_table_from_slab wraps a host copy of it. */
+enum { UPB_COL_CAND_INDEX = 0, UPB_COL_PEAK_SCORE, UPB_COL_KURTOSIS, UPB_COL_CORR, UPB_COL_CONTIG, UPB_COL_LEFT, UPB_COL_LEN,
+       UPB_COL_PEAK, UPB_COL_HIT_SUM, UPB_COL_COUNTS, UPB_COL_BUFFER, UPB_COL_END /* = bytes of the slab */, UPB_N_COLS };
+int upb_slab_layout (uint64_t n_rows, uint32_t n_samples, uint64_t* offsets_out /* [UPB_N_COLS] byte offsets */);
+int upb_scatter_rows (upb_ctx* ctx, uint64_t total_rows, const uint64_t* unit_rows_total /* [2 * n_contigs] summed over ranks */,
+                      const uint64_t* unit_rows_local /* [2 * n_contigs] of this rank's last upb_call_regions (its table's unit_rows) */,
+                      void* d_slab /* device, upb_slab_layout(total_rows) bytes, zeroed */);
+/* Host-only: column pointers of `out` into a host copy of the summed slab (the caller keeps the memory alive; do not
+ * pass such a table to upb_free_region_table). forward_label / dropped / unit arrays are left NULL. */
+int upb_table_from_slab (void* h_slab, uint64_t n_rows, uint32_t n_samples, upb_region_table* out);
 
 /* ---- bin/regions -w (profile) -------------------------------------------------------------- */
 /* Replaces the FormatOutStream::write(PosScore) calls of ProfileBuffer::processPosition

@@ -296,3 +296,40 @@ def test_tags_in_regions_single_contig_plus_row_eats_minus_track(gpu_ctx):
     keys = [(0, 1000, 5000), (0, last_plus - 10, 299000), (0, 100, 200000), (0, 250000, 1000)]
     got = _tir_check(gpu_ctx, d, keys, directional=True, extension=0)
     assert got[1, 0] > int(d.seg(0, 0, 0)[1][-1])
+
+
+def test_scatter_rows_rebuilds_the_single_gpu_table(gpu_ctx):
+    # two "ranks" emulated on one GPU: each loads half of the contigs, both scatter into one table-wide slab
+    import torch
+    import unipeak_b200
+    from unipeak_b200.multi import shard_contigs
+    sizes = [400000, 300000, 200000, 100000]
+    d = make_synthetic(sizes, 3, 60000, directional=True, seed=51, peak_spacing=5000)
+    st = region_settings(d)
+    gpu_ctx.load(d)
+    full = gpu_ctx.call_regions(**dict(st, reference_order=False))["columns"]
+    owner = shard_contigs(sizes, 2)
+    ctxs, views = [], []
+    for r in range(2):
+        keep = [c for c in range(4) if owner[c] == r]
+        segs = [[[d.seg(s, dd, c) if c in keep else (np.zeros(0, np.uint32), np.zeros(0, np.uint32)) for c in range(4)] for dd in range(2)] for s in range(3)]
+        part = TagData.from_segments(sizes, segs)
+        cx = unipeak_b200.Context(0)
+        cx.load(part)
+        views.append(cx.call_regions_view(**dict(st, reference_order=False)))
+        ctxs.append(cx)
+    unit_total = sum(np.asarray(v["unit_rows"], dtype=np.uint64) for v in views)
+    R = int(unit_total.sum())
+    assert R == full["left"].shape[0]
+    nbytes = unipeak_b200.slab_layout(R, 3)["end"]
+    slab = torch.zeros((nbytes + 7) // 8, dtype=torch.int64, device="cuda:0")
+    torch.cuda.synchronize()
+    for cx, v in zip(ctxs, views):
+        cx.scatter_rows(R, unit_total, np.asarray(v["unit_rows"], dtype=np.uint64), slab.data_ptr())
+    cols = unipeak_b200.slab_columns(slab.cpu().numpy().view(np.uint8), R, 3)
+    for k in ("buffer", "contig", "left", "len", "peak", "hit_sum", "counts", "cand_index"):
+        assert np.array_equal(cols[k], full[k]), k
+    for k in ("kurtosis", "peak_score"):
+        assert np.array_equal(cols[k].view(np.uint64), full[k].view(np.uint64)), k
+    for cx in ctxs:
+        cx.close()

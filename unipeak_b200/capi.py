@@ -41,7 +41,7 @@ class RegionTable(C.Structure):
                 ("hit_sum", C.POINTER(C.c_uint32)), ("cand_index", C.POINTER(C.c_uint64)), ("peak_score", C.POINTER(C.c_double)), ("kurtosis", C.POINTER(C.c_double)),
                 ("corr", C.POINTER(C.c_double)), ("counts", C.POINTER(C.c_uint32)), ("n_passed", C.c_uint64),
                 ("n_rejected", C.c_uint64), ("tags_in_regions", C.POINTER(C.c_uint64)), ("unit_candidates", C.POINTER(C.c_uint64)),
-                ("unit_last_tag", C.POINTER(C.c_uint32)), ("_slab", C.c_void_p), ("_slab_bytes", C.c_uint64), ("_ctx", C.c_void_p)]
+                ("unit_last_tag", C.POINTER(C.c_uint32)), ("unit_rows", C.POINTER(C.c_uint64)), ("_slab", C.c_void_p), ("_slab_bytes", C.c_uint64), ("_ctx", C.c_void_p)]
 
 
 class Profile(C.Structure):
@@ -75,7 +75,11 @@ EXPORTS = [
     "upb_create", "upb_destroy", "upb_last_error", "upb_device_count", "upb_host_alloc", "upb_host_free", "upb_set_contigs",
     "upb_load_tags", "upb_call_regions", "upb_free_region_table", "upb_reference_order", "upb_profile_contig", "upb_free_profile",
     "upb_strand_shift", "upb_free_shift_report", "upb_count_tags_in_regions", "upb_kernel_taps", "upb_last_stats",
+    "upb_slab_layout", "upb_scatter_rows", "upb_table_from_slab",
 ]
+SLAB_COLS = ("cand_index", "peak_score", "kurtosis", "corr", "contig", "left", "len", "peak", "hit_sum", "counts", "buffer", "end")
+SLAB_DTYPES = dict(cand_index=np.uint64, peak_score=np.float64, kurtosis=np.float64, corr=np.float64, contig=np.uint32, left=np.uint32,
+                   len=np.uint32, peak=np.uint32, hit_sum=np.uint32, counts=np.uint32, buffer=np.uint8)
 
 _lib = None
 
@@ -110,9 +114,32 @@ def lib():
         L.upb_count_tags_in_regions.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint64, C.POINTER(RegionKey), C.c_void_p]
         L.upb_kernel_taps.argtypes = [C.c_uint32, C.c_double, C.POINTER(C.c_double)]
         L.upb_last_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.upb_slab_layout.argtypes = [C.c_uint64, C.c_uint32, C.c_void_p]
+        L.upb_scatter_rows.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.upb_table_from_slab.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(RegionTable)]
         L.upb_reference_order.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(RegionTable), C.c_void_p]
         _lib = L
     return _lib
+
+
+def slab_layout(n_rows: int, n_samples: int) -> Dict[str, int]:
+    """Byte offsets of the columns of a table-wide result slab (upb_slab_layout); 'end' = its size."""
+    off = np.zeros(len(SLAB_COLS), dtype=np.uint64)
+    rc = lib().upb_slab_layout(int(n_rows), int(n_samples), off.ctypes.data)
+    if rc:
+        raise UpbError(rc, "upb_slab_layout")
+    return {k: int(v) for k, v in zip(SLAB_COLS, off)}
+
+
+def slab_columns(buf: np.ndarray, n_rows: int, n_samples: int) -> Dict[str, np.ndarray]:
+    """numpy views of the columns of a host copy (uint8 array) of a table-wide slab."""
+    L = slab_layout(n_rows, n_samples)
+    out = {}
+    for k, dt in SLAB_DTYPES.items():
+        count = n_rows * (n_samples if k == "counts" else 1)
+        out[k] = buf[L[k]:L[k] + count * np.dtype(dt).itemsize].view(dt)
+    out["counts"] = out["counts"].reshape(n_rows, n_samples)
+    return out
 
 
 def kernel_taps(bandwidth: int, total: float = 1.0) -> np.ndarray:
@@ -225,7 +252,7 @@ class Context:
                     hit_sum=v(t.hit_sum, R, np.uint32), cand_index=v(t.cand_index, R, np.uint64), peak_score=v(t.peak_score, R, np.float64),
                     kurtosis=v(t.kurtosis, R, np.float64), corr=v(t.corr, R, np.float64), counts=v(t.counts, R * n, np.uint32).reshape(R, n),
                     tags_in_regions=v(t.tags_in_regions, n, np.uint64), unit_candidates=v(t.unit_candidates, 2 * n_contigs, np.uint64),
-                    unit_last_tag=v(t.unit_last_tag, 2 * n_contigs, np.uint32))
+                    unit_last_tag=v(t.unit_last_tag, 2 * n_contigs, np.uint32), unit_rows=v(t.unit_rows, 2 * n_contigs, np.uint64))
 
     def call_regions_view(self, *, bandwidth=50, region_threshold=25.0, kurtosis_threshold=50.0, corr_threshold=-1.0, hit_threshold=10.0,
                           directional=True, control: Optional[Sequence[int]] = None, coeffs: Optional[Sequence[float]] = None,
@@ -309,6 +336,12 @@ class Context:
         out = np.zeros(max(1, len(keys) * self.n_samples), dtype=np.uint32)
         self._check(self._lib.upb_count_tags_in_regions(self._h, 1 if directional else 0, extension, len(keys), arr, out.ctypes.data))
         return out[:len(keys) * self.n_samples].reshape(len(keys), self.n_samples)
+
+    def scatter_rows(self, total_rows: int, unit_rows_total: np.ndarray, unit_rows_local: np.ndarray, d_slab_ptr: int):
+        """Scatter the rows of the last call_regions(_view) on this context into a table-wide device slab (see upb_scatter_rows)."""
+        tot = np.ascontiguousarray(unit_rows_total, dtype=np.uint64)
+        loc = np.ascontiguousarray(unit_rows_local, dtype=np.uint64)
+        self._check(self._lib.upb_scatter_rows(self._h, int(total_rows), tot.ctypes.data, loc.ctypes.data, C.c_void_p(d_slab_ptr)))
 
     def stats(self) -> Dict:
         s = Stats()

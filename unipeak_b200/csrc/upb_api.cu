@@ -53,6 +53,7 @@ struct upb_ctx {
   unsigned char* h_small = nullptr;          // 4 KB of pinned host memory for small read-backs
   std::vector<HostSlab> slabPool;            // pinned host slabs of freed region tables, reused by the next call
   upb_stats stats;
+  uint64_t lastRows = 0;                // rows of the last upb_call_regions still sitting in the device slab (scratch "slab")
   std::vector<uint8_t> lastControl;     // control set cntEff was built for
   bool cntEffValid = false;
 };
@@ -346,7 +347,7 @@ struct PipeCfg {
 // column layout of one result slab (device copy and pinned host copy share it)
 struct SlabLayout {
   size_t oContig, oLeft, oLen, oPeak, oWsum, oCandIndex, oPeakScore, oKurt, oCorr, oCounts, oBuffer, devBytes;
-  size_t oLabel, oDropped, oTags, oUnitCand, oUnitLast, totalBytes;   // host-only tail
+  size_t oLabel, oDropped, oTags, oUnitCand, oUnitRows, oUnitLast, totalBytes;   // host-only tail
 };
 
 static SlabLayout slab_layout (size_t R, uint32_t n, uint32_t C) {
@@ -369,6 +370,7 @@ static SlabLayout slab_layout (size_t R, uint32_t n, uint32_t C) {
   L.oDropped = o;   o += Rp;
   L.oTags = o;      o += (size_t)n * 8;
   L.oUnitCand = o;  o += 2 * (size_t)C * 8;
+  L.oUnitRows = o;  o += 2 * (size_t)C * 8;
   L.oUnitLast = o;  o += ((2 * (size_t)C + 1) & ~(size_t)1) * 4;
   L.totalBytes = o + 64;
   return L;
@@ -591,6 +593,7 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
   out.units = pr.units;
   out.unitCand.assign(nUnits, 0);
   out.nCand = 0; out.R = 0;
+  ctx->lastRows = 0;
   memset(&ctx->stats, 0, sizeof ctx->stats);
   ctx->stats.n_entries = ctx->nEntries;
   ctx->stats.kde_tiles = pr.totalSpans;
@@ -744,6 +747,7 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
 
   // ---- accepted rows -> result slab -------------------------------------------------------------------------
   out.R = R;
+  ctx->lastRows = R;
   out.layout = slab_layout(R, n, C);
   const SlabLayout& SL = out.layout;
   if ((r = acquire_slab(ctx, SL.totalBytes, out.slab))) return r;
@@ -887,9 +891,9 @@ static void fill_table (upb_ctx* ctx, const PipeOut& po, upb_region_table* t) {
   t->hit_sum = po.col<uint32_t>(L.oWsum);
   t->cand_index = po.col<uint64_t>(L.oCandIndex); t->peak_score = po.col<double>(L.oPeakScore); t->kurtosis = po.col<double>(L.oKurt);
   t->corr = po.col<double>(L.oCorr); t->counts = po.col<uint32_t>(L.oCounts); t->tags_in_regions = po.col<uint64_t>(L.oTags);
-  t->unit_candidates = po.col<uint64_t>(L.oUnitCand); t->unit_last_tag = po.col<uint32_t>(L.oUnitLast);
+  t->unit_candidates = po.col<uint64_t>(L.oUnitCand); t->unit_last_tag = po.col<uint32_t>(L.oUnitLast); t->unit_rows = po.col<uint64_t>(L.oUnitRows);
   t->_slab = po.slab.p; t->_slab_bytes = po.slab.cap; t->_ctx = ctx;
-  for (uint64_t i = 0; i < po.R; ++i) t->forward_label[i] = t->buffer[i] == 0;
+  for (uint64_t i = 0; i < po.R; ++i) { t->forward_label[i] = t->buffer[i] == 0; ++t->unit_rows[(size_t)t->buffer[i] * C + t->contig[i]]; }
   for (size_t u = 0; u < po.units.size(); ++u) t->unit_candidates[(size_t)po.units[u].buffer * C + po.units[u].contig] = po.unitCand[u];
   t->n_passed = po.R;
   t->n_rejected = po.nCand - po.R;
@@ -936,6 +940,81 @@ extern "C" int upb_call_regions (upb_ctx* ctx, const upb_region_params* p, upb_r
     }
   }
   ctx->stats.ms_call = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return UPB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// several GPUs: one table out of the ranks' tables
+// ------------------------------------------------------------------------------------------------
+extern "C" int upb_slab_layout (uint64_t n_rows, uint32_t n_samples, uint64_t* off) {
+  if (!off) return UPB_ERR_BAD_ARG;
+  const SlabLayout L = slab_layout((size_t)n_rows, n_samples, 1);
+  off[UPB_COL_CAND_INDEX] = L.oCandIndex; off[UPB_COL_PEAK_SCORE] = L.oPeakScore; off[UPB_COL_KURTOSIS] = L.oKurt; off[UPB_COL_CORR] = L.oCorr;
+  off[UPB_COL_CONTIG] = L.oContig; off[UPB_COL_LEFT] = L.oLeft; off[UPB_COL_LEN] = L.oLen; off[UPB_COL_PEAK] = L.oPeak; off[UPB_COL_HIT_SUM] = L.oWsum;
+  off[UPB_COL_COUNTS] = L.oCounts; off[UPB_COL_BUFFER] = L.oBuffer; off[UPB_COL_END] = L.devBytes;
+  return UPB_OK;
+}
+
+struct ScatterArgs {
+  const unsigned char* src; unsigned char* dst;
+  SlabLayout ls, ld;
+  unsigned long long R;
+  uint32_t n, C;
+  const unsigned long long* unitDst;   // [2C] first table-wide row of each (buffer, contig)
+  const unsigned long long* unitSrc;   // [2C] first local row of each (buffer, contig)
+};
+
+__global__ void scatter_rows_kernel (ScatterArgs a) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.R) return;
+  const uint32_t b = a.src[a.ls.oBuffer + i];
+  const uint32_t c = ((const uint32_t*)(a.src + a.ls.oContig))[i];
+  const size_t u = (size_t)b * a.C + c;
+  const unsigned long long o = a.unitDst[u] + (i - a.unitSrc[u]);
+#define UPB_MOVE(T, off) ((T*)(a.dst + a.ld.off))[o] = ((const T*)(a.src + a.ls.off))[i]
+  UPB_MOVE(unsigned long long, oCandIndex); UPB_MOVE(double, oPeakScore); UPB_MOVE(double, oKurt); UPB_MOVE(double, oCorr);
+  UPB_MOVE(uint32_t, oContig); UPB_MOVE(uint32_t, oLeft); UPB_MOVE(uint32_t, oLen); UPB_MOVE(uint32_t, oPeak); UPB_MOVE(uint32_t, oWsum);
+  UPB_MOVE(uint8_t, oBuffer);
+#undef UPB_MOVE
+  const uint32_t* sc = (const uint32_t*)(a.src + a.ls.oCounts) + i * a.n;
+  uint32_t* dc = (uint32_t*)(a.dst + a.ld.oCounts) + o * a.n;
+  for (uint32_t s = 0; s < a.n; ++s) dc[s] = sc[s];
+}
+
+extern "C" int upb_scatter_rows (upb_ctx* ctx, uint64_t total_rows, const uint64_t* unit_rows_total, const uint64_t* unit_rows_local, void* d_slab) {
+  if (!ctx) return UPB_ERR_BAD_ARG;
+  if (!unit_rows_total || !unit_rows_local || !d_slab) return fail(ctx, UPB_ERR_BAD_ARG, "upb_scatter_rows: NULL argument");
+  CU(cudaSetDevice(ctx->device));
+  const uint32_t C = (uint32_t)ctx->sizes.size(), n = ctx->nSamples;
+  const uint64_t R = ctx->lastRows;
+  if (R == 0) return UPB_OK;
+  ScatterArgs sa;
+  sa.src = ctx->scratch["slab"].as<unsigned char>(); sa.dst = (unsigned char*)d_slab;
+  sa.ls = slab_layout(R, n, C); sa.ld = slab_layout(total_rows, n, C);
+  sa.R = R; sa.n = n; sa.C = C;
+  // local first row of each unit: rows are in canonical order, so count them from the buffer / contig columns
+  std::vector<unsigned long long> h(4 * (size_t)C, 0);
+  { unsigned long long run = 0; for (size_t u = 0; u < 2 * (size_t)C; ++u) { h[u] = run; run += unit_rows_total[u]; } if (run != total_rows) return fail(ctx, UPB_ERR_BAD_ARG, "upb_scatter_rows: unit_rows_total does not add up to total_rows"); }
+  { unsigned long long run = 0; for (size_t u = 0; u < 2 * (size_t)C; ++u) { h[2 * (size_t)C + u] = run; run += unit_rows_local[u]; } if (run != R) return fail(ctx, UPB_ERR_BAD_ARG, "upb_scatter_rows: unit_rows_local does not match the last upb_call_regions on this context"); }
+  unsigned long long* d_u = SCR("scatterUnits", unsigned long long, 4 * (size_t)C);
+  CU(cudaMemcpyAsync(d_u, h.data(), 4 * (size_t)C * 8, cudaMemcpyHostToDevice, ctx->stream));
+  sa.unitDst = d_u; sa.unitSrc = d_u + 2 * (size_t)C;
+  scatter_rows_kernel<<<(unsigned)((R + 255) / 256), 256, 0, ctx->stream>>>(sa);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(ctx->stream));
+  return UPB_OK;
+}
+
+extern "C" int upb_table_from_slab (void* h_slab, uint64_t n_rows, uint32_t n_samples, upb_region_table* t) {
+  if (!h_slab || !t) return UPB_ERR_BAD_ARG;
+  const SlabLayout L = slab_layout((size_t)n_rows, n_samples, 1);
+  unsigned char* b = (unsigned char*)h_slab;
+  memset(t, 0, sizeof *t);
+  t->n_rows = n_rows; t->n_samples = n_samples;
+  t->buffer = b + L.oBuffer; t->contig = (uint32_t*)(b + L.oContig); t->left = (uint32_t*)(b + L.oLeft); t->len = (uint32_t*)(b + L.oLen);
+  t->peak = (uint32_t*)(b + L.oPeak); t->hit_sum = (uint32_t*)(b + L.oWsum); t->cand_index = (uint64_t*)(b + L.oCandIndex);
+  t->peak_score = (double*)(b + L.oPeakScore); t->kurtosis = (double*)(b + L.oKurt); t->corr = (double*)(b + L.oCorr); t->counts = (uint32_t*)(b + L.oCounts);
+  t->n_passed = n_rows;
   return UPB_OK;
 }
 

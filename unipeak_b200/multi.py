@@ -80,3 +80,54 @@ def gather_region_rows(cols, n_samples: int, tags_in_regions, unit_candidates, *
     out = unpack_rows(rows[order], n_samples)
     out.update(n_rows=int(rows.shape[0]), tags_in_regions=tir.cpu().numpy(), unit_candidates=uc.cpu().numpy())
     return out
+
+
+class DeviceGather:
+    """The fast path on GPUs: every rank scatters its rows into ONE table-wide device slab (rows in canonical
+    order), the slabs are summed over the ranks with a single NCCL reduce (disjoint rows, so the sum is the union),
+    and rank 0 copies the result into pinned host memory.  No host staging, no sort."""
+
+    def __init__(self, ctx, n_samples: int, n_contigs: int, *, dist, rank: int, world: int, device):
+        import torch
+        self.ctx, self.n, self.C, self.dist, self.rank, self.world, self.device = ctx, n_samples, n_contigs, dist, rank, world, device
+        self.torch = torch
+        self._slab = None
+        self._host = None
+        self._small = torch.zeros(2 * n_contigs * 2 + n_samples, dtype=torch.int64, device=device)
+
+    def _ensure(self, nbytes: int):
+        torch = self.torch
+        words = (nbytes + 7) // 8 + 1
+        if self._slab is None or self._slab.shape[0] < words:
+            words = int(words * 1.25) + 1024
+            self._slab = torch.zeros(words, dtype=torch.int64, device=self.device)
+            self._host = torch.zeros(words, dtype=torch.int64).pin_memory() if self.rank == 0 else None
+        return self._slab
+
+    def __call__(self, view):
+        """`view`: the RegionView of this rank's call_regions_view(reference_order=False).  Returns the table-wide
+        columns on rank 0, None elsewhere."""
+        torch, dist = self.torch, self.dist
+        C2 = 2 * self.C
+        local_rows = np.asarray(view["unit_rows"], dtype=np.int64)
+        small = np.concatenate([local_rows, np.asarray(view["unit_candidates"], dtype=np.int64), np.asarray(view["tags_in_regions"], dtype=np.int64)])
+        self._small.copy_(torch.from_numpy(small))
+        dist.all_reduce(self._small)                                   # unit rows, unit candidates, tags in regions: one small all-reduce
+        tot = self._small.cpu().numpy()
+        unit_rows_total = tot[:C2].astype(np.uint64)
+        R = int(unit_rows_total.sum())
+        from .capi import slab_columns, slab_layout
+        nbytes = slab_layout(R, self.n)["end"]
+        slab = self._ensure(nbytes)
+        words = (nbytes + 7) // 8
+        slab[:words].zero_()
+        torch.cuda.current_stream().synchronize()
+        self.ctx.scatter_rows(R, unit_rows_total, local_rows.astype(np.uint64), slab.data_ptr())
+        dist.reduce(slab[:words], dst=0)                               # region-list gather (NCCL over NVLink)
+        if self.rank != 0:
+            return None
+        self._host[:words].copy_(slab[:words], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        cols = slab_columns(self._host.numpy().view(np.uint8), R, self.n)
+        cols.update(n_rows=R, unit_candidates=tot[C2:2 * C2], tags_in_regions=tot[2 * C2:])
+        return cols
