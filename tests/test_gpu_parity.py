@@ -86,6 +86,18 @@ def test_thresholds_disabled_and_tight(gpu_ctx):
     check_regions(gpu_ctx, d, directional=False, kurtosis_threshold=2.5, corr_threshold=0.8, hit_threshold=30.0, region_threshold=40.0)
 
 
+def test_scaling_coefficients_q3(gpu_ctx):
+    # -z: weights become doubles (sum c*coeff + sum c); accumulation order per position is the sample order
+    d = make_synthetic([300000, 150000], 3, 25000, directional=True, seed=15, peak_spacing=5000)
+    check_regions(gpu_ctx, d, coeffs=[1.0, 2.0, 0.5])
+    check_regions(gpu_ctx, d, proportional=True)
+    d3 = make_synthetic([300000, 150000], 3, 25000, directional=True, seed=18, peak_spacing=5000, bandwidth=120)
+    check_regions(gpu_ctx, d3, coeffs=[0.37, 1.91, 0.73], bandwidth=120)
+    d2 = make_synthetic([300000, 150000], 3, 30000, directional=False, seed=16, peak_spacing=5000)
+    check_regions(gpu_ctx, d2, directional=False, coeffs=[0.7, 1.3], control=[1])
+    check_regions(gpu_ctx, d2, directional=False, proportional=True, corr_threshold=0.1)
+
+
 def dense_data(sizes, n_samples, seed, fill=0.8, max_count=4, bandwidth=50):
     rng = np.random.default_rng(seed)
     segs = []
@@ -177,7 +189,7 @@ def test_strand_shift_no_regions(gpu_ctx):
 # ---- golden fixtures: outputs of the unmodified reference itself (tests/golden/make_golden.py) -------------------
 from refutil import golden_names, load_golden  # noqa: E402
 
-NOT_YET = {"regions_coeffs_q3": -11, "regions_left_edge_q2": -6}   # fixtures the CUDA path still refuses (error code asserted)
+NOT_YET = {"regions_left_edge_q2": -6}   # fixtures the CUDA path still refuses (error code asserted)
 
 
 @pytest.mark.parametrize("name", golden_names("regions"))

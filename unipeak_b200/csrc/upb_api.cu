@@ -342,6 +342,8 @@ struct PipeCfg {
   bool nondir;
   bool needCorr;                     // compute strandCorr(0) for regions passing the earlier filters
   const uint8_t* control;            // may be NULL
+  uint32_t nCoeffs = 0;              // 0, or the number of non-control samples (-z)
+  const double* coeffs = nullptr;    // already normalised as src/regions.cpp:216-229
 };
 
 // column layout of one result slab (device copy and pinned host copy share it)
@@ -413,6 +415,8 @@ static int check_left_edge (upb_ctx* ctx, uint32_t bw) {
 struct Prep {
   std::vector<Unit> units;
   std::vector<double> taps;
+  double maxCoeff = 0;               // -z: largest coefficient (bounds the weight of a position)
+  const double* d_coeffBySample = nullptr;
   uint32_t totalSpans = 0;
   uint32_t nSrc = 0;
   bool haveControl = false;
@@ -437,6 +441,16 @@ static int prepare (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, uint32_t* launch
   for (uint32_t s = 0; s < n; ++s) { if (cfg.control && cfg.control[s]) { control[s] = 1; haveControl = true; } else src.push_back(s); }
   pr.haveControl = haveControl;
   pr.nSrc = (uint32_t)src.size();
+  std::vector<double> coeffBySample(n, 0.0), coeffBySrc(src.size(), 0.0);
+  pr.maxCoeff = 0; pr.d_coeffBySample = nullptr;
+  if (cfg.nCoeffs) {
+    if (cfg.nCoeffs != src.size() || !cfg.coeffs) return fail(ctx, UPB_ERR_BAD_ARG, "n_coeffs must equal the number of non-control samples (src/regions.cpp:221)");
+    for (size_t k = 0; k < src.size(); ++k) {
+      if (!(cfg.coeffs[k] >= 0)) return fail(ctx, UPB_ERR_BAD_ARG, "scaling coefficients must be >= 0");
+      coeffBySample[src[k]] = cfg.coeffs[k]; coeffBySrc[k] = cfg.coeffs[k];
+      pr.maxCoeff = std::max(pr.maxCoeff, cfg.coeffs[k]);
+    }
+  }
 
   // units: one per (buffer, contig) that holds at least one non-control tag
   pr.units.clear();
@@ -471,6 +485,15 @@ static int prepare (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, uint32_t* launch
   if (!src.empty()) CU(cudaMemcpyAsync(d_src, src.data(), src.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
   if (!pr.units.empty()) CU(cudaMemcpyAsync(d_units, pr.units.data(), pr.units.size() * sizeof(Unit), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(d_control, control.data(), n, cudaMemcpyHostToDevice, ctx->stream));
+  double* d_coefSrc = nullptr;
+  if (cfg.nCoeffs) {
+    double* d_coefSample = SCR("coefSample", double, n);
+    d_coefSrc = SCR("coefSrc", double, src.size() + 1);
+    CU(cudaMemcpyAsync(d_coefSample, coeffBySample.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_coefSrc, coeffBySrc.data(), src.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));                             // the host vectors go out of scope
+    pr.d_coeffBySample = d_coefSample;
+  }
   CU(cudaMemsetAsync(ctx->d_small.p, 0, 4096, ctx->stream));
 
   // Q4: zero the control tags the reference forgets
@@ -497,13 +520,14 @@ static int prepare (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, uint32_t* launch
   da.nSrc = (uint32_t)src.size();
   da.bw = cfg.bw;
   da.taps = d_taps;
+  da.srcCoeff = d_coefSrc;
   // d_small layout (4 KB): [0] flags u32, [1] ticket u32, [2] runCount u32, [3] multiCount u32, [4..11] span stats u64 x4, [16..] scan totals u64
   da.ticket = ctx->d_small.as<uint32_t>() + 1;
   return UPB_OK;
 }
 
 static int launch_density (upb_ctx* ctx, DensArgs& da, bool nondir, uint32_t totalWork, uint32_t* launches) {
-  const DensSmem L = dens_smem_layout(da.bw, da.nSrc * (nondir ? 2u : 1u), nondir);
+  const DensSmem L = dens_smem_layout(da.bw, da.nSrc * (nondir ? 2u : 1u), nondir, da.srcCoeff != nullptr);
   const size_t smem = L.total;
   if (smem > 227 * 1024) return fail(ctx, UPB_ERR_UNSUPPORTED, "bandwidth / sample count need more shared memory than one SM has");
   void (*kern)(const DensArgs) = nondir ? density_kernel<true> : density_kernel<false>;
@@ -559,10 +583,11 @@ static int dump_and_corr (upb_ctx* ctx, const DensArgs& base, bool nondir, uint3
 }
 
 static int launch_span (upb_ctx* ctx, const SpanArgs& sa, bool nondir, uint32_t* launches) {
-  const SpanSmem L = span_smem_layout(sa.bw, sa.nSamples, nondir, sa.nUnits);
+  const bool coeff = sa.coeff != nullptr;
+  const SpanSmem L = span_smem_layout(sa.bw, sa.nSamples, nondir, sa.nUnits, coeff);
   const size_t smem = L.total;
   if (smem > 227 * 1024) return fail(ctx, UPB_ERR_UNSUPPORTED, "bandwidth / sample count need more shared memory than one SM has");
-  void (*kern)(const SpanArgs) = nondir ? span_kernel<true> : span_kernel<false>;
+  void (*kern)(const SpanArgs) = coeff ? (nondir ? span_kernel<true, true> : span_kernel<false, true>) : (nondir ? span_kernel<true, false> : span_kernel<false, false>);
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int perSm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, SP_THREADS, smem));
@@ -618,7 +643,8 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
   sa.taps = ctx->scratch["taps"].as<double>();
   sa.thr = cfg.thr;
   const double kmax = pr.taps[cfg.bw];                                // K(0) = 0.75 * scale
-  sa.kmaxBound = kmax * (1.0 + 1e-9);
+  sa.kmaxBound = kmax * (1.0 + pr.maxCoeff) * (1.0 + 1e-9);           // -z: a count c weighs at most c*(coeff+1)
+  sa.coeff = pr.d_coeffBySample;
   sa.cN = kmax / ((double)cfg.bw * (double)cfg.bw);
   sa.dS = kmax * 1e-11;                                               // >= 100x the worst-case rounding difference between the two forms
   sa.flags = small32; sa.ticket = small32 + 1; sa.runCount = small32 + 2; sa.stat = (unsigned long long*)(small32 + 4);
@@ -904,10 +930,10 @@ extern "C" int upb_call_regions (upb_ctx* ctx, const upb_region_params* p, upb_r
   if (!p || !out) return fail(ctx, UPB_ERR_BAD_ARG, "upb_call_regions: NULL argument");
   memset(out, 0, sizeof *out);
   const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
-  if (p->n_coeffs != 0) return fail(ctx, UPB_ERR_UNSUPPORTED, "scaling coefficients (-z) are not implemented yet");
   PipeCfg cfg;
   cfg.bw = p->bandwidth; cfg.thr = p->region_threshold; cfg.kurtThr = p->kurtosis_threshold; cfg.corrThr = p->corr_threshold;
   cfg.hitThr = p->hit_threshold; cfg.background = p->background; cfg.nondir = !p->directional; cfg.control = p->control;
+  cfg.nCoeffs = p->n_coeffs; cfg.coeffs = p->coeffs;
   cfg.needCorr = cfg.nondir;        // -D: the filter (if corr_threshold > -1) and the optional correlation column
   PipeOut po;
   Prep pr;
@@ -1146,11 +1172,11 @@ extern "C" int upb_profile_contig (upb_ctx* ctx, const upb_region_params* p, int
   memset(out, 0, sizeof *out);
   const uint32_t C = (uint32_t)ctx->sizes.size();
   if (contig >= C || buffer < 0 || buffer > 1 || (!p->directional && buffer != 0)) return fail(ctx, UPB_ERR_BAD_ARG, "upb_profile_contig: bad buffer/contig");
-  if (p->n_coeffs != 0) return fail(ctx, UPB_ERR_UNSUPPORTED, "scaling coefficients (-z) are not implemented yet");
   CU(cudaSetDevice(ctx->device));
   PipeCfg cfg;
   cfg.bw = p->bandwidth; cfg.thr = p->region_threshold; cfg.kurtThr = p->kurtosis_threshold; cfg.corrThr = p->corr_threshold;
   cfg.hitThr = p->hit_threshold; cfg.background = p->background; cfg.nondir = !p->directional; cfg.control = p->control; cfg.needCorr = false;
+  cfg.nCoeffs = p->n_coeffs; cfg.coeffs = p->coeffs;
   Prep pr;
   uint32_t launches = 0;
   int r = prepare(ctx, cfg, pr, &launches);

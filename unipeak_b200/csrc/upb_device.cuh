@@ -209,6 +209,7 @@ struct DensArgs {
   uint32_t nSrc;
   uint32_t bw;
   const double* taps;               // 2bw+1 (host-computed, misc/kernel.cpp:16-35)
+  const double* srcCoeff;           // [nSrc] -z scaling coefficients of the sources, NULL otherwise
   uint32_t* ticket;
   const uint32_t* dumpUnit;         // [nDump] unit of each range
   const uint32_t* dumpLeft;         // first position
@@ -220,13 +221,15 @@ struct DensArgs {
   double* dumpR;
 };
 
-struct DensSmem { uint32_t taps, wdF, wdR, ranges, total; };
+struct DensSmem { uint32_t taps, wdF, wdR, wfF, wfR, ranges, total; };
 
-__host__ __device__ inline DensSmem dens_smem_layout (uint32_t bw, uint32_t nRanges, bool nondir) {
+__host__ __device__ inline DensSmem dens_smem_layout (uint32_t bw, uint32_t nRanges, bool nondir, bool coeff) {
   DensSmem L;
   const uint32_t W = TILE + 2 * bw + 4;
   uint32_t o = 0;
   L.taps = o;   o += ((2 * bw + 2) & ~1u) * 8;
+  L.wfF = o;    o += coeff ? W * 8 : 0;
+  L.wfR = o;    o += (coeff && nondir) ? W * 8 : 0;
   L.wdF = o;    o += W * 4;
   L.wdR = o;    o += nondir ? W * 4 : 0;
   o = (o + 15) & ~15u;
@@ -243,8 +246,11 @@ __global__ void __launch_bounds__(KDE_THREADS) density_kernel (const __grid_cons
   const uint32_t W = TILE + 2 * bw;
   const uint32_t nStr = NONDIR ? 2u : 1u;
   const uint32_t nRanges = a.nSrc * nStr;
-  const DensSmem L = dens_smem_layout(bw, nRanges, NONDIR);
+  const bool coeff = a.srcCoeff != nullptr;
+  const DensSmem L = dens_smem_layout(bw, nRanges, NONDIR, coeff);
   double* Ks = (double*)(smem + L.taps);
+  double* wfF = (double*)(smem + L.wfF);
+  double* wfR = (double*)(smem + L.wfR);
   uint32_t* wdF = (uint32_t*)(smem + L.wdF);
   uint32_t* wdR = (uint32_t*)(smem + L.wdR);
   ulonglong2* ranges = (ulonglong2*)(smem + L.ranges);
@@ -281,6 +287,37 @@ __global__ void __launch_bounds__(KDE_THREADS) density_kernel (const __grid_cons
     const uint32_t any = __syncthreads_or(myCount != 0);
     if (!any) {                                                      // nothing within bw of this chunk
       for (uint32_t i = tid; i < np; i += KDE_THREADS) { a.dumpF[dumpBase + i] = 0.0; a.dumpR[dumpBase + i] = 0.0; }
+      continue;
+    }
+    if (coeff) {
+      // -z (misc/peakcall.cpp:191-200): weight = sum_s c_s*coeff_s, then + sum_s c_s, in sample order, every step rounded.
+      // One source range at a time (a range has at most one entry per position, so there are no conflicts).
+      for (uint32_t i = tid; i < W + 1; i += KDE_THREADS) { wfF[i] = 0.0; if (NONDIR) wfR[i] = 0.0; }
+      __syncthreads();
+      for (int phase = 0; phase < 2; ++phase)
+        for (uint32_t j = 0; j < nRanges; ++j) {
+          const ulonglong2 rg = ranges[j];
+          double* wf = (NONDIR && (j & 1)) ? wfR : wfF;
+          const double cf = a.srcCoeff[j / nStr];
+          for (uint64_t i = tid; i < rg.y; i += KDE_THREADS) {
+            const uint32_t cell = (uint32_t)((int64_t)__ldg(a.T.pos + rg.x + i) - cell0);
+            const double c = (double)__ldg(a.T.cnt + rg.x + i);
+            wf[cell] = __dadd_rn(wf[cell], phase ? c : __dmul_rn(c, cf));
+          }
+          __syncthreads();
+        }
+      for (uint32_t po = tid; po < np; po += KDE_THREADS) {
+        double sF = 0.0, sR = 0.0;
+        const uint32_t n2 = 2 * bw;
+        for (uint32_t k = 0; k <= n2; ++k) {
+          const double w = wfF[po + k];
+          if (w != 0.0) sF = __dadd_rn(sF, __dmul_rn(Ks[n2 - k], w));
+          if (NONDIR) { const double v = wfR[po + k]; if (v != 0.0) sR = __dadd_rn(sR, __dmul_rn(Ks[n2 - k], v)); }
+        }
+        const bool rev = (!NONDIR) && U.buffer == 1;
+        a.dumpF[dumpBase + po] = rev ? 0.0 : sF;
+        a.dumpR[dumpBase + po] = NONDIR ? sR : (rev ? sF : 0.0);
+      }
       continue;
     }
     // pool the samples: dense per-position weight (integer sum of non-control counts)

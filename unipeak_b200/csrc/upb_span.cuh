@@ -57,6 +57,7 @@ struct SpanArgs {
   const uint8_t* control;                           // [nSamples] 1 = negative control (not a density source)
   uint32_t nSamples;
   int hasControl;
+  const double* coeff;                              // [nSamples] scaling coefficient of every non-control sample (-z), NULL otherwise
   uint32_t nUnits, totalSpans;
   uint32_t bw;
   const double* taps;                               // 2bw+1, host-computed exactly as misc/kernel.cpp:16-35
@@ -74,14 +75,16 @@ struct SpanArgs {
   unsigned long long* stat;                         // [0] hot blocks, [1] pieces, [2] exact evaluations, [3] spans with tags
 };
 
-struct SpanSmem { uint32_t taps, ustart, ctl, warp0, warpStride, oBins, oD, oDR, oSc, oMw, oHm, total; };
+struct SpanSmem { uint32_t taps, ustart, ctl, coef, warp0, warpStride, oBins, oD, oDR, oWf, oWr, oSc, oMw, oHm, total; };
 
-__host__ __device__ inline SpanSmem span_smem_layout (uint32_t bw, uint32_t nSamples, bool nondir, uint32_t nUnits) {
+__host__ __device__ inline SpanSmem span_smem_layout (uint32_t bw, uint32_t nSamples, bool nondir, uint32_t nUnits, bool coeff) {
   SpanSmem L;
   uint32_t o = 0;
   L.taps = o;      o += ((2 * bw + 2) & ~1u) * 8;
   L.ustart = o;    o += (nUnits + 1) * 4;
   L.ctl = o;       o += (nSamples + 3) & ~3u;
+  o = (o + 15) & ~15u;
+  L.coef = o;      o += coeff ? nSamples * 8 : 0;
   o = (o + 15) & ~15u;
   L.warp0 = o;
   const uint32_t W = PIECE_LEN + 2 * bw + 4;
@@ -89,7 +92,10 @@ __host__ __device__ inline SpanSmem span_smem_layout (uint32_t bw, uint32_t nSam
   L.oBins = w; w += ((((SPAN_LEN + 2 * bw) >> BIN_SHIFT) + 3) & ~1u) * 4;
   L.oD = w;    w += W * 4;
   L.oDR = w;   w += nondir ? W * 4 : 0;
-  L.oSc = w;   w += PIECE_LEN * 4;
+  w = (w + 7) & ~7u;
+  L.oWf = w;   w += coeff ? W * 8 : 0;              // -z: per-position weights are doubles
+  L.oWr = w;   w += (coeff && nondir) ? W * 8 : 0;
+  L.oSc = w;   w += coeff ? PIECE_LEN * 8 : PIECE_LEN * 4;
   L.oMw = w;   w += (PIECE_BLOCKS + 2) * 4;
   L.oHm = w;   w += (SPAN_WORDS + 2) * 4;
   w = (w + 15) & ~15u;
@@ -132,6 +138,17 @@ __device__ __forceinline__ double exact_dense (const double* __restrict__ Ks, co
   return s;
 }
 
+// -z: the weights are doubles (misc/peakcall.cpp:191-200)
+__device__ __noinline__ double exact_dense_f64 (const double* __restrict__ Ks, const double* __restrict__ cells, uint32_t u0, uint32_t bw) {
+  double s = 0.0;
+  const uint32_t n = 2 * bw;
+  for (uint32_t k = 0; k <= n; ++k) {
+    const double w = cells[u0 + k];
+    if (w != 0.0) s = __dadd_rn(s, __dmul_rn(Ks[n - k], w));
+  }
+  return s;
+}
+
 // the same sum computed by the whole warp for ONE position (u0 uniform): the products are independent, so every
 // lane rounds one product per 32 taps; the additions stay a single chain in ascending tag order, fed by shuffles
 __device__ __forceinline__ double exact_dense_warp (const double* __restrict__ Ks, const uint32_t* __restrict__ cells, uint32_t u0, uint32_t bw, uint32_t lane) {
@@ -166,12 +183,13 @@ __device__ __forceinline__ SpanChunk span_chunk (const Tags& T, uint32_t d, uint
   return ch;
 }
 
-template <bool NONDIR>
-__global__ void __launch_bounds__(SP_THREADS, 4) span_kernel (const __grid_constant__ SpanArgs a) {
+template <bool NONDIR, bool COEFF>
+__global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : 4) span_kernel (const __grid_constant__ SpanArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const uint32_t bw = a.bw;
-  const SpanSmem L = span_smem_layout(bw, a.nSamples, NONDIR, a.nUnits);
+  const SpanSmem L = span_smem_layout(bw, a.nSamples, NONDIR, a.nUnits, COEFF);
   double* Ks = (double*)(smem + L.taps);
+  double* coef = (double*)(smem + L.coef);
   uint32_t* ustart = (uint32_t*)(smem + L.ustart);                   // first span of every unit (CTA-shared, read-only)
   uint8_t* isCtl = (uint8_t*)(smem + L.ctl);                          // control flag of every sample (CTA-shared, read-only)
   const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
@@ -180,12 +198,16 @@ __global__ void __launch_bounds__(SP_THREADS, 4) span_kernel (const __grid_const
   uint32_t* D = (uint32_t*)(wbase + L.oD);
   uint32_t* DR = (uint32_t*)(wbase + L.oDR);
   float* scf = (float*)(wbase + L.oSc);
+  double* scd = (double*)(wbase + L.oSc);                             // -z keeps exact doubles instead
+  double* Wf = (double*)(wbase + L.oWf);
+  double* Wr = (double*)(wbase + L.oWr);
   uint32_t* mw = (uint32_t*)(wbase + L.oMw);
   uint32_t* hm = (uint32_t*)(wbase + L.oHm);
 
   for (uint32_t i = tid; i < 2 * bw + 1; i += SP_THREADS) Ks[i] = a.taps[i];
   for (uint32_t i = tid; i < a.nUnits; i += SP_THREADS) ustart[i] = a.units[i].spanStart;
   for (uint32_t i = tid; i < a.nSamples; i += SP_THREADS) isCtl[i] = a.control[i];
+  if (COEFF) for (uint32_t i = tid; i < a.nSamples; i += SP_THREADS) coef[i] = a.coeff[i];
   __syncthreads();                                                    // the only block-level barrier
   const uint32_t nCells = SPAN_LEN + 2 * bw;                          // cells of a span: positions ts-bw .. ts+4095+bw
   const uint32_t nBins = (nCells >> BIN_SHIFT) + 2;
@@ -309,6 +331,46 @@ __global__ void __launch_bounds__(SP_THREADS, 4) span_kernel (const __grid_const
         }
         __syncwarp();
 
+        double dPiece = 0.0;
+        if (COEFF) {
+          // -z (misc/peakcall.cpp:191-200): the weight of a position is  sum_s c_s*coeff_s  followed by  + sum_s c_s,
+          // both accumulated in sample order with every product and sum rounded.  One pass over the chunk per sample and
+          // phase keeps that order (a sample has at most one entry per strand and position, so a pass has no conflicts).
+          for (uint32_t u = lane; u < W + 2; u += 32) { Wf[u] = 0.0; if (NONDIR) Wr[u] = 0.0; }
+          __syncwarp();
+          for (int phase = 0; phase < 2; ++phase)
+            for (uint32_t sm = 0; sm < a.nSamples; ++sm) {
+              if (isCtl[sm]) continue;
+              const double cf = coef[sm];
+#pragma unroll
+              for (int str = 0; str < (NONDIR ? 2 : 1); ++str) {
+                const SpanChunk ch = str ? chR : chF;
+                const uint2* __restrict__ src = a.T.ment + ch.e0;
+                double* dst = str ? Wr : Wf;
+                for (uint32_t t = lane; t < ch.total; t += 32) {
+                  const uint2 en = __ldg(src + t);
+                  if ((en.y >> SPAN_SHIFT) != sm) continue;
+                  const int32_t u = (int32_t)(en.y & (SPAN_LEN - 1)) + (int32_t)bw + (t < ch.nPrev ? -SPAN_LEN : (t < ch.nPrev + ch.nOwn ? 0 : SPAN_LEN)) - (int32_t)(32 * pb);
+                  if ((uint32_t)u < W) dst[u] = __dadd_rn(dst[u], phase ? (double)en.x : __dmul_rn((double)en.x, cf));
+                }
+              }
+              __syncwarp();
+            }
+          // every position of the piece in the reference's own order
+          for (uint32_t b = 0; b < nbEff; ++b) {
+            const uint32_t i = 32 * b + lane;
+            const bool valid = i < P;
+            double v = 0.0;
+            if (valid) {
+              const double f = exact_dense_f64(Ks, Wf, i, bw);
+              v = NONDIR ? __dadd_rn(f, exact_dense_f64(Ks, Wr, i, bw)) : f;
+              scd[i] = v;
+              stExact += 32;
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, valid && v >= a.thr);
+            if (lane == 0) mw[b] = m;
+          }
+        } else {
         // B2: window sums of position 0 (cells 0 .. 2bw) and the piece's total weight
         unsigned long long c0 = 0, c1 = 0, c2 = 0, tot = 0;
         for (uint32_t u = lane; u < W; u += 32) {
@@ -317,7 +379,7 @@ __global__ void __launch_bounds__(SP_THREADS, 4) span_kernel (const __grid_const
           if (u <= 2 * bw) { c0 += w; c1 += w * u; c2 += w * u * u; }
         }
         c0 = warp_sum_u64(c0); c1 = warp_sum_u64(c1); c2 = warp_sum_u64(c2); tot = warp_sum_u64(tot);
-        const double dPiece = __dmul_rn((double)tot, a.dS);           // one conservative error bound for the whole piece
+        dPiece = __dmul_rn((double)tot, a.dS);           // one conservative error bound for the whole piece
 
         // B3: classify every position: moment form, exact order only inside the error band
         for (uint32_t b = 0; b < nbEff; ++b) {
@@ -347,6 +409,7 @@ __global__ void __launch_bounds__(SP_THREADS, 4) span_kernel (const __grid_const
           if (valid) scf[i] = (float)v;
           const uint32_t m = __ballot_sync(0xffffffffu, above);
           if (lane == 0) mw[b] = m;
+        }
         }
         if (lane == 0) mw[nbEff] = 0;
         __syncwarp();
@@ -382,6 +445,20 @@ __global__ void __launch_bounds__(SP_THREADS, 4) span_kernel (const __grid_const
 
           // pooled hit sum of the density sources == nonControlSum of misc/peakcall.cpp:36-40 (HitCount wraps mod 2^32)
           uint32_t wsum = 0;
+          double best = -1.0; uint32_t bestI = r0;
+          if (COEFF) {
+            for (uint32_t i = r0 + lane; i < r1; i += 32) {
+              wsum += D[bw + i] + (NONDIR ? DR[bw + i] : 0u);
+              if (scd[i] > best) { best = scd[i]; bestI = i; }          // ascending i per lane: first strict maximum
+            }
+            wsum = warp_sum_u32(wsum);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const double oe = __shfl_xor_sync(0xffffffffu, best, o);
+              const uint32_t oi = __shfl_xor_sync(0xffffffffu, bestI, o);
+              if (oe > best || (oe == best && oi < bestI)) { best = oe; bestI = oi; }
+            }
+          } else {
           float fmax_ = -1.0f;
           for (uint32_t i = r0 + lane; i < r1; i += 32) { wsum += D[bw + i] + (NONDIR ? DR[bw + i] : 0u); fmax_ = fmaxf(fmax_, scf[i]); }
           wsum = warp_sum_u32(wsum);
@@ -392,7 +469,6 @@ __global__ void __launch_bounds__(SP_THREADS, 4) span_kernel (const __grid_const
           // whose fast value (kept as float) could still be the maximum; they alone are evaluated exactly:
           // exact_i <= f_i (1+2^-24) + dPiece and exact_max >= f_max (1-2^-24) - dPiece.
           const double cut = (double)fmax_ * (1.0 - 0x1p-22) - 2.5 * dPiece;
-          double best = -1.0; uint32_t bestI = r0;
           for (uint32_t g = r0; g < r1; g += 32) {
             const uint32_t i = g + lane;
             uint32_t cm = __ballot_sync(0xffffffffu, i < r1 && (double)scf[i] >= cut);
@@ -404,6 +480,7 @@ __global__ void __launch_bounds__(SP_THREADS, 4) span_kernel (const __grid_const
               ++stExact;
               cm &= cm - 1;
             }
+          }
           }
           if (lane == 0) {
             SpanRun rr;
