@@ -11,7 +11,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libunipeak_b200.so")
+LIB_PATH = os.environ.get("UPB_LIB") or os.path.join(_HERE, "libunipeak_b200.so")   # UPB_LIB: experiment builds (tools/)
 
 UPB_OK = 0
 ERRORS = {

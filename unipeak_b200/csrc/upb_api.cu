@@ -643,7 +643,27 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
   sa.taps = ctx->scratch["taps"].as<double>();
   sa.thr = cfg.thr;
   const double kmax = pr.taps[cfg.bw];                                // K(0) = 0.75 * scale
-  sa.kmaxBound = kmax * (1.0 + pr.maxCoeff) * (1.0 + 1e-9);           // -z: a count c weighs at most c*(coeff+1)
+  {
+    // cold-block bound: for bin q of a block's window, the largest tap any (cell of the bin, position of the block) pair can
+    // have; cell u, position index i: tag offset d = u - i - bw with u in [16q, 16q+15], i in [0, 31]
+    const int bwI = (int)cfg.bw, nbw = ((31 + 2 * bwI) >> BIN_SHIFT) + 1, bin = 1 << BIN_SHIFT;
+    std::vector<double> hc(nbw);
+    for (int q = 0; q < nbw; ++q) {
+      const int lo = bin * q - 31 - bwI, hi = bin * q + bin - 1 - bwI;
+      const int m = (lo <= 0 && hi >= 0) ? 0 : std::min(std::abs(lo), std::abs(hi));
+      hc[q] = m > bwI ? 0.0 : pr.taps[bwI - m] * (1.0 + pr.maxCoeff) * (1.0 + 1e-9);   // -z: a count c weighs at most c*(coeff+1)
+    }
+    std::vector<float> hf(nbw);
+    for (int q = 0; q < nbw; ++q) hf[q] = std::nextafter((float)(hc[q] * (1.0 + 1e-5)), INFINITY);   // float sum of <= 58 terms: 1e-5 covers its rounding
+    double* d_hc = SCR("hotCoef", double, nbw);
+    float* d_hf = SCR("hotCoefF", float, nbw);
+    CU(cudaMemcpyAsync(d_hc, hc.data(), (size_t)nbw * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_hf, hf.data(), (size_t)nbw * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    sa.hotCoef = d_hc; sa.hotCoefF = d_hf;
+    sa.thrLow = std::nextafter((float)cfg.thr, -INFINITY);
+    sa.flatBound = kmax * (1.0 + pr.maxCoeff) * (1.0 + 1e-9);
+  }
   sa.coeff = pr.d_coeffBySample;
   sa.cN = kmax / ((double)cfg.bw * (double)cfg.bw);
   sa.dS = kmax * 1e-11;                                               // >= 100x the worst-case rounding difference between the two forms

@@ -30,6 +30,13 @@
 
 #include "upb_device.cuh"
 
+#ifndef UPB_EXP_EXACT
+#define UPB_EXP_EXACT 1
+#endif
+#ifndef UPB_EXP_HOT
+#define UPB_EXP_HOT 0
+#endif
+
 namespace upb {
 
 constexpr int SP_THREADS = 256;
@@ -62,7 +69,10 @@ struct SpanArgs {
   uint32_t bw;
   const double* taps;                               // 2bw+1, host-computed exactly as misc/kernel.cpp:16-35
   double thr;                                       // region threshold
-  double kmaxBound;                                 // taps[bw] * (1 + 1e-9): cold-block bound per unit of pooled weight
+  double flatBound;                                 // largest tap (with margin): maxTap * window weight bounds every score
+  float thrLow;                                     // threshold rounded down to float
+  const float* hotCoefF;                            // the same envelope in single precision, rounded up with a 1e-5 margin
+  const double* hotCoef;                            // [nbw] upper envelope of the taps per 16-position bin of a block's window (cold-block bound)
   double cN;                                        // taps[bw] / bw^2: moment-form scale
   double dS;                                        // error bound of the moment form per unit of window weight
   // outputs
@@ -75,12 +85,13 @@ struct SpanArgs {
   unsigned long long* stat;                         // [0] hot blocks, [1] pieces, [2] exact evaluations, [3] spans with tags
 };
 
-struct SpanSmem { uint32_t taps, ustart, ctl, coef, warp0, warpStride, oBins, oD, oDR, oWf, oWr, oSc, oMw, oHm, total; };
+struct SpanSmem { uint32_t taps, hotc, ustart, ctl, coef, warp0, warpStride, oBins, oD, oDR, oWf, oWr, oSt, oSc, oMw, oHm, total; };
 
 __host__ __device__ inline SpanSmem span_smem_layout (uint32_t bw, uint32_t nSamples, bool nondir, uint32_t nUnits, bool coeff) {
   SpanSmem L;
   uint32_t o = 0;
   L.taps = o;      o += ((2 * bw + 2) & ~1u) * 8;
+  L.hotc = o;      o += ((((31 + 2 * bw) >> BIN_SHIFT) + 2) & ~1u) * 8;
   L.ustart = o;    o += (nUnits + 1) * 4;
   L.ctl = o;       o += (nSamples + 3) & ~3u;
   o = (o + 15) & ~15u;
@@ -95,6 +106,7 @@ __host__ __device__ inline SpanSmem span_smem_layout (uint32_t bw, uint32_t nSam
   w = (w + 7) & ~7u;
   L.oWf = w;   w += coeff ? W * 8 : 0;              // -z: per-position weights are doubles
   L.oWr = w;   w += (coeff && nondir) ? W * 8 : 0;
+  L.oSt = w;   w += 64 * 8;                         // products of 64 taps (exact_dense_warp)
   L.oSc = w;   w += coeff ? PIECE_LEN * 8 : PIECE_LEN * 4;
   L.oMw = w;   w += (PIECE_BLOCKS + 2) * 4;
   L.oHm = w;   w += (SPAN_WORDS + 2) * 4;
@@ -149,11 +161,14 @@ __device__ __noinline__ double exact_dense_f64 (const double* __restrict__ Ks, c
   return s;
 }
 
-// the same sum computed by the whole warp for ONE position (u0 uniform): the products are independent, so every
-// lane rounds one product per 32 taps; the additions stay a single chain in ascending tag order, fed by shuffles
-__device__ __forceinline__ double exact_dense_warp (const double* __restrict__ Ks, const uint32_t* __restrict__ cells, uint32_t u0, uint32_t bw, uint32_t lane) {
+// the same sum computed by the whole warp for ONE position (u0 uniform): the products are independent, so the lanes round
+// 64 of them at a time into `stage`; the additions stay a single chain in ascending tag order (a product of an empty cell
+// is +0.0 and changes nothing), run by every lane on the broadcast values
+__device__ __forceinline__ double exact_dense_warp (const double* __restrict__ Ks, const uint32_t* __restrict__ cells, double* stage /* [64] */,
+                                                    uint32_t u0, uint32_t bw, uint32_t lane) {
   double s = 0.0;
   const uint32_t n = 2 * bw;
+#if UPB_EXP_EXACT == 0
   for (uint32_t k0 = 0; k0 <= n; k0 += 32) {
     const uint32_t k = k0 + lane;
     const uint32_t w = k <= n ? cells[u0 + k] : 0u;
@@ -164,6 +179,21 @@ __device__ __forceinline__ double exact_dense_warp (const double* __restrict__ K
       s = __dadd_rn(s, __shfl_sync(0xffffffffu, p, b));
       nz &= nz - 1;
     }
+  }
+  return s;
+#endif
+  for (uint32_t k0 = 0; k0 <= n; k0 += 64) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t k = k0 + 32 * h + lane;
+      const uint32_t w = k <= n ? cells[u0 + k] : 0u;
+      stage[32 * h + lane] = w ? __dmul_rn(Ks[n - k], (double)w) : 0.0;
+    }
+    __syncwarp();
+    const uint32_t m = min(64u, n + 1 - k0);
+#pragma unroll 4
+    for (uint32_t q = 0; q < m; ++q) s = __dadd_rn(s, stage[q]);
+    __syncwarp();
   }
   return s;
 }
@@ -190,6 +220,8 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : 4) span_kernel (const 
   const SpanSmem L = span_smem_layout(bw, a.nSamples, NONDIR, a.nUnits, COEFF);
   double* Ks = (double*)(smem + L.taps);
   double* coef = (double*)(smem + L.coef);
+  double* hotc = (double*)(smem + L.hotc);
+  float* hotf = (float*)(smem + L.hotc);                              // single precision is enough for a bound (margins folded in on the host)
   uint32_t* ustart = (uint32_t*)(smem + L.ustart);                   // first span of every unit (CTA-shared, read-only)
   uint8_t* isCtl = (uint8_t*)(smem + L.ctl);                          // control flag of every sample (CTA-shared, read-only)
   const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
@@ -199,6 +231,7 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : 4) span_kernel (const 
   uint32_t* DR = (uint32_t*)(wbase + L.oDR);
   float* scf = (float*)(wbase + L.oSc);
   double* scd = (double*)(wbase + L.oSc);                             // -z keeps exact doubles instead
+  double* stage = (double*)(wbase + L.oSt);
   double* Wf = (double*)(wbase + L.oWf);
   double* Wr = (double*)(wbase + L.oWr);
   uint32_t* mw = (uint32_t*)(wbase + L.oMw);
@@ -208,6 +241,8 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : 4) span_kernel (const 
   for (uint32_t i = tid; i < a.nUnits; i += SP_THREADS) ustart[i] = a.units[i].spanStart;
   for (uint32_t i = tid; i < a.nSamples; i += SP_THREADS) isCtl[i] = a.control[i];
   if (COEFF) for (uint32_t i = tid; i < a.nSamples; i += SP_THREADS) coef[i] = a.coeff[i];
+  if (UPB_EXP_HOT) { for (uint32_t i = tid; i < ((31 + 2 * bw) >> BIN_SHIFT) + 1; i += SP_THREADS) hotc[i] = a.hotCoef[i]; }
+  else { for (uint32_t i = tid; i < ((31 + 2 * bw) >> BIN_SHIFT) + 1; i += SP_THREADS) hotf[i] = a.hotCoefF[i]; }
   __syncthreads();                                                    // the only block-level barrier
   const uint32_t nCells = SPAN_LEN + 2 * bw;                          // cells of a span: positions ts-bw .. ts+4095+bw
   const uint32_t nBins = (nCells >> BIN_SHIFT) + 2;
@@ -242,26 +277,48 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : 4) span_kernel (const 
     __syncwarp();
 
     // ---- A2: pool the density sources into 16-position bins: cell = position - (ts - bw).  Four loads are in flight
-    //      per lane before the first atomic, so one round trip to L2/HBM covers 128 entries -------------------------
+    //      per lane before the first atomic, so one round trip to L2/HBM covers 128 entries.  The span's own entries need
+    //      no range check; the two halo mini-tiles (the first nPrev and the last entries of the chunk) do ---------------
 #pragma unroll
     for (int str = 0; str < (NONDIR ? 2 : 1); ++str) {
       const SpanChunk ch = str ? chR : chF;
       const uint2* __restrict__ src = a.T.ment + ch.e0;
-      for (uint32_t t0 = 0; t0 < ch.total; t0 += 128) {
-        uint2 en[4];
+      const uint2* __restrict__ own = src + ch.nPrev;
+      const uint2* __restrict__ nxt = own + ch.nOwn;
+      const uint32_t nNext = ch.total - ch.nPrev - ch.nOwn;
+      // first round trip: both halo mini-tiles (usually < 32 entries each) and the first 128 entries of the span together
+      uint2 hp = make_uint2(0u, 0u), hn = make_uint2(0u, 0u), en[4];
+      if (lane < ch.nPrev) hp = __ldg(src + lane);
+      if (lane < nNext) hn = __ldg(nxt + lane);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { const uint32_t t = t0 + 32 * q + lane; en[q] = t < ch.total ? __ldg(src + t) : make_uint2(0u, 0u); }
+      for (int q = 0; q < 4; ++q) { const uint32_t t = 32 * q + lane; en[q] = t < ch.nOwn ? __ldg(own + t) : make_uint2(0u, 0u); }
+      for (uint32_t t0 = 0;;) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t t = t0 + 32 * q + lane;
-          const int32_t cell = (int32_t)(en[q].y & (SPAN_LEN - 1)) + (int32_t)bw + (t < ch.nPrev ? -SPAN_LEN : (t < ch.nPrev + ch.nOwn ? 0 : SPAN_LEN));
-          if (en[q].x && (uint32_t)cell < nCells && !(a.hasControl && isCtl[en[q].y >> SPAN_SHIFT])) atomicAdd(&bins[(uint32_t)cell >> BIN_SHIFT], en[q].x);
-        }
+        for (int q = 0; q < 4; ++q)
+          if (en[q].x && !(a.hasControl && isCtl[en[q].y >> SPAN_SHIFT])) atomicAdd(&bins[((en[q].y & (SPAN_LEN - 1)) + bw) >> BIN_SHIFT], en[q].x);
+        t0 += 128;
+        if (t0 >= ch.nOwn) break;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const uint32_t t = t0 + 32 * q + lane; en[q] = t < ch.nOwn ? __ldg(own + t) : make_uint2(0u, 0u); }
+      }
+      for (uint32_t t = lane;;) {                                     // halo before: positions ts-512 .. ts-1
+        const int32_t cell = (int32_t)(hp.y & (SPAN_LEN - 1)) + (int32_t)bw - SPAN_LEN;
+        if (hp.x && cell >= 0 && !(a.hasControl && isCtl[hp.y >> SPAN_SHIFT])) atomicAdd(&bins[(uint32_t)cell >> BIN_SHIFT], hp.x);
+        t += 32;
+        if (t - lane >= ch.nPrev) break;
+        hp = t < ch.nPrev ? __ldg(src + t) : make_uint2(0u, 0u);
+      }
+      for (uint32_t t = lane;;) {                                     // halo after: positions ts+4096 .. ts+4607
+        const uint32_t cell = (hn.y & (SPAN_LEN - 1)) + bw + SPAN_LEN;
+        if (hn.x && cell < nCells && !(a.hasControl && isCtl[hn.y >> SPAN_SHIFT])) atomicAdd(&bins[cell >> BIN_SHIFT], hn.x);
+        t += 32;
+        if (t - lane >= nNext) break;
+        hn = t < nNext ? __ldg(nxt + t) : make_uint2(0u, 0u);
       }
     }
     __syncwarp();
 
-    // ---- A3: hot blocks: window of block k = cells 32k .. 32k+31+2bw = bins 2k .. 2k+nbw-1 ------------------------
+    // ---- A3: hot blocks: window of block k = cells 32k .. 32k+31+2bw = bins 2k .. 2k+nbw-1 (16-position bins) ----------
     const uint32_t nBlk = (np + 31) >> 5;
     uint32_t anyHot = 0;
 #pragma unroll
@@ -269,10 +326,22 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : 4) span_kernel (const 
       const uint32_t kblk = 32 * m + lane;
       bool hot = false;
       if (kblk < nBlk) {
-        unsigned long long sum = 0;
+        // no position of the block can score more than  sum_bins weight(bin) * (largest tap any of its cells has for any
+        // position of the block): a bound, so plain FMA arithmetic with the margin folded into hotCoef
         const uint32_t b0 = kblk << (5 - BIN_SHIFT);
+#if UPB_EXP_HOT == 1
+        unsigned long long sum = 0;
         for (uint32_t q = 0; q < nbw; ++q) sum += bins[b0 + q];
-        hot = __dmul_rn((double)sum, a.kmaxBound) >= a.thr;
+        if ((double)sum * a.flatBound >= a.thr) {                       // cheap necessary condition first (maxTap * window weight)
+          double bound = 0.0;
+          for (uint32_t q = 0; q < nbw; ++q) bound = fma((double)bins[b0 + q], hotc[q], bound);
+          hot = bound >= a.thr;
+        }
+#else
+        float bound = 0.0f;
+        for (uint32_t q = 0; q < nbw; ++q) bound = fmaf(__uint2float_ru(bins[b0 + q]), hotf[q], bound);
+        hot = bound >= a.thrLow;
+#endif
       }
       const uint32_t msk = __ballot_sync(0xffffffffu, hot);
       if (lane == 0) hm[m] = msk;
@@ -474,8 +543,8 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : 4) span_kernel (const 
             uint32_t cm = __ballot_sync(0xffffffffu, i < r1 && (double)scf[i] >= cut);
             while (cm) {                                               // ascending position: a later tie never replaces an earlier maximum
               const uint32_t ci = g + (uint32_t)(__ffs(cm) - 1);
-              const double f = exact_dense_warp(Ks, D, ci, bw, lane);
-              const double e = NONDIR ? __dadd_rn(f, exact_dense_warp(Ks, DR, ci, bw, lane)) : f;
+              const double f = exact_dense_warp(Ks, D, stage, ci, bw, lane);
+              const double e = NONDIR ? __dadd_rn(f, exact_dense_warp(Ks, DR, stage, ci, bw, lane)) : f;
               if (e > best) { best = e; bestI = ci; }
               ++stExact;
               cm &= cm - 1;
