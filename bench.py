@@ -301,7 +301,7 @@ def main():
                 "config": config, "clocks": clocks.summary(),
                 "e2e": {"value": genome / (e2e_ms * 1e-3), "unit": "bp/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": 8 * E + 8 * int(data.off.shape[0]), "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "roofline": roofline,
-                "result": {"regions": n_rows, "candidates": stats["n_candidates"], "tag_entries_rank0": E, "spans": stats["kde_tiles"], "pieces": stats["kde_hot_tiles"],
+                "result": {"regions": n_rows, "candidates": stats["n_candidates"], "tag_entries_rank0": E, "spans": stats["kde_tiles"], "warm_spans": stats["warm_spans"], "pieces": stats["kde_hot_tiles"],
                            "hot_blocks": stats["hot_blocks"], "exact_evals": stats["exact_evals"], "stitched": stats["n_stitched"],
                            "device_ms_per_step_rank0": stats["ms_total"], "call_ms_rank0": stats["ms_call"]}}
         if world == 1 and not args.no_cpu:

@@ -220,6 +220,7 @@ typedef struct {
   uint64_t exact_evals;         /* positions evaluated in the reference's own summation order */
   uint64_t spans_with_tags;
   uint64_t n_stitched;          /* run pieces merged into a neighbour (runs cut by a piece / span boundary) */
+  uint64_t warm_spans;          /* spans that survived the zone-map prefilter */
   float ms_call;                /* host wall clock of the last upb_call_regions, entry to return */
 } upb_stats;
 int upb_last_stats (const upb_ctx* ctx, upb_stats* out);

@@ -68,7 +68,7 @@ class RegionKey(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("ms_total", C.c_float), ("ms_kde", C.c_float), ("launches", C.c_uint32), ("kde_tiles", C.c_uint64),
                 ("kde_hot_tiles", C.c_uint64), ("n_candidates", C.c_uint64), ("n_entries", C.c_uint64), ("hot_blocks", C.c_uint64),
-                ("exact_evals", C.c_uint64), ("spans_with_tags", C.c_uint64), ("n_stitched", C.c_uint64), ("ms_call", C.c_float)]
+                ("exact_evals", C.c_uint64), ("spans_with_tags", C.c_uint64), ("n_stitched", C.c_uint64), ("warm_spans", C.c_uint64), ("ms_call", C.c_float)]
 
 
 EXPORTS = [
@@ -349,4 +349,4 @@ class Context:
         return dict(ms_total=float(s.ms_total), ms_kde=float(s.ms_kde), launches=int(s.launches), kde_tiles=int(s.kde_tiles),
                     kde_hot_tiles=int(s.kde_hot_tiles), n_candidates=int(s.n_candidates), n_entries=int(s.n_entries),
                     hot_blocks=int(s.hot_blocks), exact_evals=int(s.exact_evals), spans_with_tags=int(s.spans_with_tags),
-                    n_stitched=int(s.n_stitched), ms_call=float(s.ms_call))
+                    n_stitched=int(s.n_stitched), warm_spans=int(s.warm_spans), ms_call=float(s.ms_call))

@@ -47,7 +47,7 @@ struct upb_ctx {
   std::vector<uint64_t> off;            // host copy
   std::vector<uint32_t> firstPos, lastPos;   // [(s*2+d)*C + c], 0 if empty
   DevBuf d_pos, d_cnt, d_off, d_segStart, d_tidx, d_tidxBase, d_sizes, d_nTilesIdx, d_small;
-  DevBuf d_ment, d_mtOff, d_mtBase, d_mtCount, d_mEff;   // tile-major copy (upb_device.cuh)
+  DevBuf d_ment, d_mtOff, d_mtBase, d_mtCount, d_mEff, d_mtW;   // tile-major copy (upb_device.cuh)
   std::vector<uint32_t> mtBase;         // [2*C+1]
   std::map<std::string, DevBuf> scratch;     // grow-only device scratch, by name
   unsigned char* h_small = nullptr;          // 4 KB of pinned host memory for small read-backs
@@ -114,7 +114,7 @@ extern "C" int upb_create (int device, upb_ctx** out) {
 extern "C" void upb_destroy (upb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  DevBuf* all[] = {&ctx->d_ment, &ctx->d_mtOff, &ctx->d_mtBase, &ctx->d_mtCount, &ctx->d_mEff, &ctx->d_pos, &ctx->d_cnt, &ctx->d_off, &ctx->d_segStart, &ctx->d_tidx, &ctx->d_tidxBase, &ctx->d_sizes,
+  DevBuf* all[] = {&ctx->d_mtW, &ctx->d_ment, &ctx->d_mtOff, &ctx->d_mtBase, &ctx->d_mtCount, &ctx->d_mEff, &ctx->d_pos, &ctx->d_cnt, &ctx->d_off, &ctx->d_segStart, &ctx->d_tidx, &ctx->d_tidxBase, &ctx->d_sizes,
     &ctx->d_nTilesIdx, &ctx->d_small};
   for (DevBuf* b : all) release(*b);
   for (auto& kv : ctx->scratch) release(kv.second);
@@ -200,6 +200,7 @@ static Tags make_tags (const upb_ctx* ctx, bool useEff) {
   T.mtOff = ctx->d_mtOff.as<unsigned long long>();
   T.mtBase = ctx->d_mtBase.as<uint32_t>();
   T.mEff = useEff ? ctx->d_mEff.as<uint32_t>() : nullptr;
+  T.mtW = ctx->d_mtW.as<unsigned long long>();
   T.off = ctx->d_off.as<uint64_t>();
   T.tidx = ctx->d_tidx.as<uint32_t>();
   T.tidxBase = ctx->d_tidxBase.as<uint32_t>();
@@ -286,11 +287,14 @@ extern "C" int upb_load_tags (upb_ctx* ctx, uint32_t n_samples, const uint64_t* 
   ENSURE(ctx->d_mtCount, ((size_t)nMtTotal + 1) * 4);
   ENSURE(ctx->d_mtOff, ((size_t)nMtTotal + 2) * 8);
   ENSURE(ctx->d_ment, (E ? E : 1) * 8);
+  ENSURE(ctx->d_mtW, ((size_t)nMtTotal + 1) * 8);
+  CU(cudaMemsetAsync(ctx->d_mtW.p, 0, ((size_t)nMtTotal + 1) * 8, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_mtBase.p, ctx->mtBase.data(), (2 * (size_t)C + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemsetAsync(ctx->d_mtCount.p, 0, ((size_t)nMtTotal + 1) * 4, ctx->stream));
   {
     MtArgs ma;
     ma.pos = ctx->d_pos.as<uint32_t>(); ma.cnt = ctx->d_cnt.as<uint32_t>(); ma.segStart = ctx->d_segStart.as<uint64_t>(); ma.mtBase = ctx->d_mtBase.as<uint32_t>();
+    ma.mtW = ctx->d_mtW.as<unsigned long long>();
     ma.mtCount = ctx->d_mtCount.as<uint32_t>(); ma.mtOff = ctx->d_mtOff.as<unsigned long long>(); ma.ment = ctx->d_ment.as<uint2>();
     ma.C = C; ma.nSeg = nSeg; ma.nEntries = E;
     const uint64_t blocks = (E + 255) / 256;
@@ -669,6 +673,12 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
   sa.dS = kmax * 1e-11;                                               // >= 100x the worst-case rounding difference between the two forms
   sa.flags = small32; sa.ticket = small32 + 1; sa.runCount = small32 + 2; sa.stat = (unsigned long long*)(small32 + 4);
   sa.spanRunCount = SCR("spanRunCount", uint32_t, pr.totalSpans);
+  uint32_t* warmList = SCR("warmList", uint32_t, pr.totalSpans);
+  sa.warmList = warmList; sa.nWarm = small32 + 12;
+  WarmArgs wa;
+  wa.T = pr.T; wa.units = d_units; wa.nUnits = nUnits; wa.totalSpans = pr.totalSpans; wa.nondir = cfg.nondir ? 1 : 0;
+  wa.nAdj = ((31 + 2 * cfg.bw) >> MT_SHIFT) + 2;
+  wa.warmList = warmList; wa.nWarm = small32 + 12; wa.spanRunCount = sa.spanRunCount;
 
   size_t runCap = std::max<size_t>(1u << 18, (size_t)(ctx->nEntries / 64));
   { const size_t have = ctx->scratch["runs"].cap / sizeof(SpanRun); if (have > runCap) runCap = have; }
@@ -677,6 +687,9 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
     sa.runs = SCR("runs", SpanRun, runCap);
     sa.runCap = (uint32_t)std::min<size_t>(runCap, 0xFFFFFFF0u);
     CU(cudaMemsetAsync(ctx->d_small.p, 0, 256, ctx->stream));
+    wa.flatBound = sa.flatBound; wa.thr = cfg.thr;
+    warm_span_kernel<<<(pr.totalSpans + 255) / 256, 256, 0, ctx->stream>>>(wa);
+    launches += 1;
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     if ((r = launch_span(ctx, sa, cfg.nondir, &launches))) return r;
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -687,6 +700,7 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
     if (attempt == 1) return fail(ctx, UPB_ERR_NOMEM, "run buffer overflow after resize");
     runCap = (size_t)nRuns + 1024;                                    // the counter holds the exact need
   }
+  ctx->stats.warm_spans = h32[12];
   { unsigned long long st[4]; memcpy(st, h32 + 4, 32); ctx->stats.kde_hot_tiles = st[1]; ctx->stats.hot_blocks = st[0]; ctx->stats.exact_evals = st[2]; ctx->stats.spans_with_tags = st[3]; }
   { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->stats.ms_kde = ms; }
   if (nRuns == 0) {

@@ -41,6 +41,7 @@ struct Tags {                       // resident tag-frequency data (see upb_load
   const uint2* ment;
   const unsigned long long* mtOff;  // [nMtTotal + 1] first entry of every mini-tile
   const uint32_t* mtBase;           // [2*C + 1] first mini-tile of (strand d, contig c) at d*C + c
+  const unsigned long long* mtW;    // [nMtTotal] zone map: total count (all samples) per mini-tile — lets whole spans be skipped
   const uint32_t* mEff;             // [E] counts with the control tags the reference forgets zeroed (Q4); NULL when no controls
   const uint64_t* off;              // [(s*2+d)*(C+1)+c]
   const uint32_t* tidx;             // per (s,d): tidxStride entries; per contig: nTiles0+3 entries
@@ -149,6 +150,7 @@ struct MtArgs {
   const uint64_t* segStart;         // [nSeg+1]
   const uint32_t* mtBase;           // [2*C+1]
   uint32_t* mtCount;                // [nMtTotal] histogram, then per-tile cursors
+  unsigned long long* mtW;          // [nMtTotal] zone map: total count of all samples' entries in the mini-tile
   const unsigned long long* mtOff;  // [nMtTotal+1]
   uint2* ment;
   uint32_t C, nSeg;
@@ -169,7 +171,7 @@ __global__ void mt_build_kernel (MtArgs a) {
   const uint32_t c = g % a.C, sd = g / a.C, d = sd & 1u, s = sd >> 1;
   const uint32_t p = a.pos[i] - 1;
   const uint32_t mt = a.mtBase[d * a.C + c] + (p >> MT_SHIFT);
-  if (!SCATTER) { atomicAdd(&a.mtCount[mt], 1u); return; }
+  if (!SCATTER) { atomicAdd(&a.mtCount[mt], 1u); atomicAdd(&a.mtW[mt], (unsigned long long)a.cnt[i]); return; }
   const unsigned long long slot = a.mtOff[mt] + (atomicSub(&a.mtCount[mt], 1u) - 1u);
   a.ment[slot] = make_uint2(a.cnt[i], (s << SPAN_SHIFT) | (p & (SPAN_LEN - 1)));
 }

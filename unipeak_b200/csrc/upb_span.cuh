@@ -66,6 +66,8 @@ struct SpanArgs {
   int hasControl;
   const double* coeff;                              // [nSamples] scaling coefficient of every non-control sample (-z), NULL otherwise
   uint32_t nUnits, totalSpans;
+  const uint32_t* warmList;                         // spans that survived the zone-map prefilter
+  const uint32_t* nWarm;
   uint32_t bw;
   const double* taps;                               // 2bw+1, host-computed exactly as misc/kernel.cpp:16-35
   double thr;                                       // region threshold
@@ -213,6 +215,58 @@ __device__ __forceinline__ SpanChunk span_chunk (const Tags& T, uint32_t d, uint
   return ch;
 }
 
+// Zone-map prefilter: a block's window (32 + 2bw positions) lies inside `nAdj` consecutive 512-position mini-tiles, so a
+// span none of whose runs of nAdj mini-tiles (its own 8 plus one of halo on either side) weighs enough for
+// maxTap * weight >= threshold has no hot block and is skipped without touching its entries — the device-side analogue
+// of the reference leaping over empty stretches (misc/peakcall.cpp:172-173).  The weights count every sample (controls
+// too), which only makes the bound more conservative.
+struct WarmArgs {
+  Tags T;
+  const SpanUnit* units;
+  uint32_t nUnits, totalSpans;
+  int nondir;
+  uint32_t nAdj;
+  double flatBound, thr;
+  uint32_t* warmList;               // spans that have to be looked at, any order
+  uint32_t* nWarm;
+  uint32_t* spanRunCount;           // zeroed here for the spans that are skipped
+};
+
+__global__ void warm_span_kernel (WarmArgs a) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  bool warm = false;
+  if (w < a.totalSpans) {
+    uint32_t lo = 0, hi = a.nUnits;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.units[mid].spanStart <= w) lo = mid; else hi = mid; }
+    const SpanUnit U = a.units[lo];
+    const uint32_t k = w - U.spanStart;
+    const int m0 = (int)(k * SPAN_MT) - 1, m1 = (int)(k * SPAN_MT + SPAN_MT);     // inclusive mini-tile range with halo
+    const uint32_t d0 = a.nondir ? 0u : U.buffer, d1 = a.nondir ? 1u : U.buffer;
+    unsigned long long win[4] = {0, 0, 0, 0};                        // sliding window of the last nAdj (<= 4) mini-tile weights
+    unsigned long long run = 0;
+    for (int m = m0; m <= m1; ++m) {
+      unsigned long long wgt = 0;
+      for (uint32_t d = d0; d <= d1; ++d) {
+        const uint32_t gb = a.T.mtBase[d * a.T.C + U.contig], nMt = a.T.mtBase[d * a.T.C + U.contig + 1] - gb;
+        if (m >= 0 && (uint32_t)m < nMt) wgt += a.T.mtW[gb + m];
+      }
+      const uint32_t slot = (uint32_t)(m - m0) % a.nAdj;
+      run += wgt - win[slot];
+      win[slot] = wgt;
+      if ((double)run * a.flatBound >= a.thr) { warm = true; break; }
+    }
+    if (!warm) a.spanRunCount[w] = 0;
+  }
+  // compact the warm spans: one atomic per warp
+  const uint32_t msk = __ballot_sync(0xffffffffu, warm);
+  if (msk) {
+    uint32_t base = 0;
+    if ((threadIdx.x & 31) == (uint32_t)(__ffs(msk) - 1)) base = atomicAdd(a.nWarm, __popc(msk));
+    base = __shfl_sync(0xffffffffu, base, __ffs(msk) - 1);
+    if (warm) a.warmList[base + __popc(msk & ((1u << (threadIdx.x & 31)) - 1))] = w;
+  }
+}
+
 template <bool NONDIR, bool COEFF>
 __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : 4) span_kernel (const __grid_constant__ SpanArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -249,6 +303,7 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : 4) span_kernel (const 
   const uint32_t nbw = ((31 + 2 * bw) >> BIN_SHIFT) + 1;              // bins covering one block's window
   const unsigned long long bw2 = (unsigned long long)bw * bw;
   unsigned long long stHot = 0, stPieces = 0, stExact = 0, stSpans = 0;
+  const uint32_t nWarm = *a.nWarm;
   uint32_t ui = 0;
   SpanUnit U = a.units[0];
 
@@ -256,7 +311,8 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : 4) span_kernel (const 
     uint32_t work = 0;
     if (lane == 0) work = atomicAdd(a.ticket, 1u);
     work = __shfl_sync(0xffffffffu, work, 0);
-    if (work >= a.totalSpans) break;
+    if (work >= nWarm) break;
+    work = __ldg(a.warmList + work);                                  // span index (all later uses)
 
     if (!(work >= ustart[ui] && (ui + 1 == a.nUnits || work < ustart[ui + 1]))) {   // tickets are mostly consecutive: same unit as last time
       uint32_t lo = 0, hi = a.nUnits; while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (ustart[mid] <= work) lo = mid; else hi = mid; } ui = lo;
