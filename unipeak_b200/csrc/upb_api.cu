@@ -771,8 +771,13 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
     const size_t statSmem = (size_t)ST_WARPS * ST_PER_WARP * groupBytes;
     if (statSmem > 200 * 1024) return fail(ctx, UPB_ERR_UNSUPPORTED, "too many samples for the region statistics kernel");
     CU(cudaFuncSetAttribute(region_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)statSmem));
+    st.ticket = small32 + 13;
+    CU(cudaMemsetAsync(st.ticket, 0, 4, ctx->stream));
+    int perSm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, region_stats_kernel, ST_WARPS * 32, statSmem));
     const uint32_t perBlock = ST_WARPS * ST_PER_WARP;
-    region_stats_kernel<<<(n1 + perBlock - 1) / perBlock, ST_WARPS * 32, statSmem, ctx->stream>>>(st);
+    const uint32_t gridS = std::min<uint32_t>((n1 + perBlock - 1) / perBlock, (uint32_t)(ctx->smCount * std::max(perSm, 1)));
+    region_stats_kernel<<<gridS, ST_WARPS * 32, statSmem, ctx->stream>>>(st);
     CU(cudaGetLastError());
     launches += 1;
 

@@ -707,6 +707,7 @@ struct StatArgs {
   uint32_t* counts;                 // [nList * nSamples]
   double* kurt;                     // [nList]
   uint32_t* pass;                   // [nList] kurtosis filter (misc/peakcall.cpp:41 second clause)
+  uint32_t* ticket;
 };
 
 // Eight lanes work on one region (four regions per warp): most regions are ~130 positions with a few hundred
@@ -735,12 +736,12 @@ __device__ __forceinline__ void group_entries (const Tags& T, uint32_t d, uint32
   for (uint32_t sp = ma / SPAN_MT; sp <= mb / SPAN_MT; ++sp) {
     const uint32_t m0 = max(ma, sp * SPAN_MT), m1 = min(mb, sp * SPAN_MT + SPAN_MT - 1);
     const unsigned long long e0 = __ldg(T.mtOff + gb + m0), e1 = __ldg(T.mtOff + gb + m1 + 1);
-    for (unsigned long long eb = e0 + gl; eb < e1; eb += 4 * ST_GROUP) {
-      uint2 en[4];
+    for (unsigned long long eb = e0 + gl; eb < e1; eb += 8 * ST_GROUP) {
+      uint2 en[8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) en[q] = (eb + q * ST_GROUP < e1) ? __ldg(T.ment + eb + q * ST_GROUP) : make_uint2(0u, 0u);
+      for (int q = 0; q < 8; ++q) en[q] = (eb + q * ST_GROUP < e1) ? __ldg(T.ment + eb + q * ST_GROUP) : make_uint2(0u, 0u);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 8; ++q) {
         const uint32_t p = sp * SPAN_LEN + (en[q].y & (SPAN_LEN - 1)) + 1;
         if (en[q].x && p >= lo && p <= hi) f(p, eb + q * ST_GROUP, en[q]);
       }
@@ -759,7 +760,12 @@ __global__ void __launch_bounds__(ST_WARPS * 32) region_stats_kernel (StatArgs a
   uint32_t* cell = (uint32_t*)gbase;
   uint32_t* cnts = cell + ST_CHUNK;
   double* stage = (double*)(gbase + ((size_t)(ST_CHUNK + n) * 4 + 15) / 16 * 16);
-  const uint32_t i = (blockIdx.x * ST_WARPS + warp) * ST_PER_WARP + g;
+  for (;;) {                                                          // persistent warps: four regions per ticket
+  uint32_t tk = 0;
+  if (lane == 0) tk = atomicAdd(a.ticket, (uint32_t)ST_PER_WARP);
+  tk = __shfl_sync(0xffffffffu, tk, 0);
+  if (tk >= a.nList) break;
+  const uint32_t i = tk + g;
   const bool live = i < a.nList;                                      // whole groups idle at the tail; no early return (warp-wide syncs below)
   Cand2 c; c.unit = 0; c.left = 1; c.len = 0;
   if (live) c = a.cand[a.list[i]];
@@ -835,6 +841,8 @@ __global__ void __launch_bounds__(ST_WARPS * 32) region_stats_kernel (StatArgs a
     const double k = __ddiv_rn(__dmul_rn(__dsub_rn((double)count, 1.0), sum4), __dmul_rn(sum2, sum2));   // misc/data.cpp:181
     a.kurt[i] = k;
     a.pass[i] = (a.kurtThr == 0.0 || (c.len > 1 && k <= a.kurtThr)) ? 1u : 0u;
+  }
+  __syncwarp();
   }
 }
 
