@@ -855,9 +855,24 @@ static bool early_reverse (uint32_t C, const uint32_t* firstPos /* [2*C] of this
   return firstMinus >= lastPlus;     // lastPlus == -1 (no '+' tags at all) also lands here
 }
 
+static int reference_order_impl (uint32_t C, uint32_t n, int directional, uint32_t bw, const uint32_t* firstPos, const uint32_t* lastPos,
+                                 upb_region_table* t, std::vector<uint64_t>* permOut, bool* identity);
+
 extern "C" int upb_reference_order (uint32_t C, uint32_t n, int directional, uint32_t bw, const uint32_t* firstPos, const uint32_t* lastPos,
                                     upb_region_table* t, uint64_t* perm) {
   if (!t || !perm || !firstPos || !lastPos) return UPB_ERR_BAD_ARG;
+  std::vector<uint64_t> p;
+  bool identity = true;
+  const int r = reference_order_impl(C, n, directional, bw, firstPos, lastPos, t, &p, &identity);
+  if (r) return r;
+  if (identity) { for (uint64_t i = 0; i < t->n_rows; ++i) perm[i] = i; }
+  else memcpy(perm, p.data(), t->n_rows * 8);
+  return UPB_OK;
+}
+
+static int reference_order_impl (uint32_t C, uint32_t n, int directional, uint32_t bw, const uint32_t* firstPos, const uint32_t* lastPos,
+                                 upb_region_table* t, std::vector<uint64_t>* permOut, bool* identity) {
+  *identity = true;
   const uint64_t R = t->n_rows;
   // last add() position per (buffer, contig): every sample counts, controls included
   std::vector<uint32_t> lastTag(2 * (size_t)C, 0);
@@ -875,7 +890,6 @@ extern "C" int upb_reference_order (uint32_t C, uint32_t n, int directional, uin
     const uint32_t L = lastTag[(size_t)t->buffer[i] * C + t->contig[i]];
     return right + bw + 2 > (uint64_t)L;
   };
-  for (uint64_t i = 0; i < R; ++i) t->forward_label[i] = t->buffer[i] == 0 ? 1 : 0;
   memset(t->dropped, 0, R);
 
   // which samples read their '-' track during pass 1 (Q7)
@@ -895,6 +909,8 @@ extern "C" int upb_reference_order (uint32_t C, uint32_t n, int directional, uin
   // canonical rows are sorted by (buffer, contig, left): first row of the reverse buffer by binary search
   uint64_t firstRev = R;
   { uint64_t lo = 0, hi = R; while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (t->buffer[mid] == 0) lo = mid + 1; else hi = mid; } firstRev = lo; }
+  memset(t->forward_label, 1, firstRev);
+  memset(t->forward_label + firstRev, 0, R - firstRev);
 
   // Q5: the first Region object of reverseBuffer is constructed forward (misc/peakcall.cpp:103); if the
   // first candidate of the reverse buffer is accepted it is printed left-right
@@ -914,8 +930,7 @@ extern "C" int upb_reference_order (uint32_t C, uint32_t n, int directional, uin
       if (t->contig[i] != C - 1 || (directional && t->buffer[i] != 1) || !tail(i)) break;
       t->dropped[i] = 1;
     }
-    for (uint64_t i = 0; i < R; ++i) perm[i] = i;                     // dropped rows already sit at the end
-    return UPB_OK;
+    return UPB_OK;                                                    // canonical order; dropped rows already sit at the end
   }
   // single sample whose '-' track is read in pass 1: per contig iteration the '+' tags come first, then
   // the '-' tags; regions closed by add() are written at once, the two flushes at the end of the
@@ -928,8 +943,8 @@ extern "C" int upb_reference_order (uint32_t C, uint32_t n, int directional, uin
     for (int b = 0; b < 2; ++b) for (uint64_t i : byUnit[(size_t)b * C + c]) if (!tail(i)) order.push_back(i);
     for (int b = 0; b < 2; ++b) for (uint64_t i : byUnit[(size_t)b * C + c]) if (tail(i)) order.push_back(i);
   }
-  uint64_t k = 0;
-  for (uint64_t i : order) perm[k++] = i;
+  *identity = false;
+  permOut->assign(order.begin(), order.end());
   return UPB_OK;
 }
 
@@ -958,7 +973,23 @@ static void fill_table (upb_ctx* ctx, const PipeOut& po, upb_region_table* t) {
   t->corr = po.col<double>(L.oCorr); t->counts = po.col<uint32_t>(L.oCounts); t->tags_in_regions = po.col<uint64_t>(L.oTags);
   t->unit_candidates = po.col<uint64_t>(L.oUnitCand); t->unit_last_tag = po.col<uint32_t>(L.oUnitLast); t->unit_rows = po.col<uint64_t>(L.oUnitRows);
   t->_slab = po.slab.p; t->_slab_bytes = po.slab.cap; t->_ctx = ctx;
-  for (uint64_t i = 0; i < po.R; ++i) { t->forward_label[i] = t->buffer[i] == 0; ++t->unit_rows[(size_t)t->buffer[i] * C + t->contig[i]]; }
+  // rows are sorted by (buffer, contig, left): unit boundaries by binary search instead of a pass over the rows
+  {
+    auto lower = [&] (uint32_t b, uint32_t c) -> uint64_t {           // first row with (buffer, contig) >= (b, c)
+      uint64_t lo = 0, hi = po.R;
+      while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (t->buffer[mid] < b || (t->buffer[mid] == b && t->contig[mid] < c)) lo = mid + 1; else hi = mid; }
+      return lo;
+    };
+    uint64_t prev = 0;
+    for (uint32_t b = 0; b < 2; ++b) for (uint32_t c = 0; c < C; ++c) {
+      const uint64_t nxt = (b == 1 && c == C - 1) ? po.R : lower(c + 1 == C ? b + 1 : b, c + 1 == C ? 0 : c + 1);
+      t->unit_rows[(size_t)b * C + c] = nxt - prev;
+      prev = nxt;
+    }
+    const uint64_t firstRev = lower(1, 0);
+    memset(t->forward_label, 1, firstRev);
+    memset(t->forward_label + firstRev, 0, po.R - firstRev);
+  }
   for (size_t u = 0; u < po.units.size(); ++u) t->unit_candidates[(size_t)po.units[u].buffer * C + po.units[u].contig] = po.unitCand[u];
   t->n_passed = po.R;
   t->n_rejected = po.nCand - po.R;
@@ -987,12 +1018,11 @@ extern "C" int upb_call_regions (upb_ctx* ctx, const upb_region_params* p, upb_r
     if (lp > out->unit_last_tag[(size_t)b * C + c]) out->unit_last_tag[(size_t)b * C + c] = lp;
   }
   if (p->reference_order) {
-    std::vector<uint64_t> perm(out->n_rows + 1);
-    r = upb_reference_order(C, n, p->directional, p->bandwidth, ctx->firstPos.data(), ctx->lastPos.data(), out, perm.data());
+    std::vector<uint64_t> perm;
+    bool identity = true;
+    r = reference_order_impl(C, n, p->directional, p->bandwidth, ctx->firstPos.data(), ctx->lastPos.data(), out, &perm, &identity);
     if (r) { upb_free_region_table(out); return fail(ctx, r, "the reference's merge loop would abort on this input (several directional samples whose '-' track is read during pass 1; SURVEY Q7)"); }
     const uint64_t R = out->n_rows;
-    bool identity = true;
-    for (uint64_t k = 0; k < R && identity; ++k) identity = perm[k] == k;
     if (!identity) {
       auto permute = [&] (auto* col, size_t width) {
         typedef typename std::remove_pointer<decltype(col)>::type T;
