@@ -102,13 +102,13 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def settings_from_totals(tags, n_samples, directional, mappable, genome):
+def settings_from_totals(tags, n_samples, directional, mappable, genome, bandwidth=50):
     """What src/regions.cpp:152-232 derives with default flags (no controls, no coefficients)."""
     total = int(sum(tags))
     background = float(total) / float(mappable or genome)
     if directional:
         background /= 2
-    return dict(bandwidth=50, region_threshold=25.0, kurtosis_threshold=50.0, corr_threshold=(-1.0 if directional else 0.3),
+    return dict(bandwidth=bandwidth, region_threshold=25.0, kurtosis_threshold=50.0, corr_threshold=(-1.0 if directional else 0.3),
                 hit_threshold=10.0 * n_samples, directional=directional, control=np.zeros(n_samples, np.uint8), coeffs=[],
                 background=background)
 
@@ -150,6 +150,7 @@ def main():
     ap.add_argument("--tags", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--seed", type=int, default=20261018)
+    ap.add_argument("--bandwidth", type=int, default=50, help="-b (config 5 sweeps 10..200)")
     args = ap.parse_args()
 
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -159,7 +160,7 @@ def main():
     genome = int(sum(sizes))
     metric = "genome bp/s for pooled KDE+region calling"
     config = {"workload": desc if not (args.samples or args.tags) else "%s [overridden: %d samples x %d tags]" % (desc, n_samples, tags_per_sample),
-              "samples": n_samples, "tags_per_sample": tags_per_sample, "genome_bp": genome, "bandwidth": 50,
+              "samples": n_samples, "tags_per_sample": tags_per_sample, "genome_bp": genome, "bandwidth": args.bandwidth,
               "l2": "inputs (GBs of tag entries) are far larger than the 126 MB L2; no explicit flush",
               "parallelism": "contig-sharded x%d" % world if world > 1 else "single GPU"}
 
@@ -171,12 +172,12 @@ def main():
         cs = CPU_SAMPLE_CONTIGS[args.workload]
         if torch.cuda.is_available():
             from unipeak_b200.synth_gpu import make_synthetic_gpu
-            data = make_synthetic_gpu(sizes, n_samples, tags_per_sample, directional=directional, seed=args.seed, device="cuda:%d" % local_rank)
+            data = make_synthetic_gpu(sizes, n_samples, tags_per_sample, directional=directional, seed=args.seed, device="cuda:%d" % local_rank, bandwidth=max(50, args.bandwidth))
         else:
             from unipeak_b200.synth import make_synthetic
-            data = make_synthetic(sizes, n_samples, tags_per_sample, directional=directional, seed=args.seed)
+            data = make_synthetic(sizes, n_samples, tags_per_sample, directional=directional, seed=args.seed, bandwidth=max(50, args.bandwidth))
         # thresholds come from the whole workload's tag totals, exactly as in our arm
-        st = settings_from_totals([data.tags(s) for s in range(n_samples)], n_samples, directional, mappable, genome)
+        st = settings_from_totals([data.tags(s) for s in range(n_samples)], n_samples, directional, mappable, genome, args.bandwidth)
         sample = cpu_sample(data, cs)
         del data
         with tempfile.TemporaryDirectory() as wd:
@@ -210,7 +211,7 @@ def main():
 
     owner = shard_contigs(sizes, world)
     mine = [c for c in range(len(sizes)) if owner[c] == rank]
-    data = make_synthetic_gpu(sizes, n_samples, tags_per_sample, directional=directional, seed=args.seed, contigs=mine, device=str(dev))
+    data = make_synthetic_gpu(sizes, n_samples, tags_per_sample, directional=directional, seed=args.seed, contigs=mine, device=str(dev), bandwidth=max(50, args.bandwidth))
 
     # pinned host copies (the e2e leg copies from these every step)
     h_off = torch.from_numpy(data.off.view(np.int64)).pin_memory()
@@ -222,7 +223,7 @@ def main():
     tags = torch.tensor([data.tags(s) for s in range(n_samples)], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(tags)
-    st = settings_from_totals(tags.cpu().tolist(), n_samples, directional, mappable, genome)
+    st = settings_from_totals(tags.cpu().tolist(), n_samples, directional, mappable, genome, args.bandwidth)
 
     ctx = unipeak_b200.Context(local_rank)
     ctx.set_contigs(sizes)
