@@ -86,6 +86,41 @@ def test_thresholds_disabled_and_tight(gpu_ctx):
     check_regions(gpu_ctx, d, directional=False, kurtosis_threshold=2.5, corr_threshold=0.8, hit_threshold=30.0, region_threshold=40.0)
 
 
+def test_left_edge_q2(gpu_ctx):
+    # tags inside the first `bandwidth` positions of a contig: the reference's window does not slide there; densities
+    # and hit vectors are displaced and stale cells surface before the next tag (misc/peakcall.cpp:176-184)
+    d = make_synthetic([60000, 30000], 2, 30000, directional=True, seed=21, peak_spacing=2000, keep_clear_of_edges=False)
+    assert min(int(d.seg(s, dd, c)[0][0]) for s in range(2) for dd in range(2) for c in range(2)) <= 50
+    check_regions(gpu_ctx, d)
+    check_regions(gpu_ctx, d, directional=False)
+    check_regions(gpu_ctx, d, directional=False, corr_threshold=-1.0, kurtosis_threshold=0.0, hit_threshold=1.0, region_threshold=3.0)
+    check_regions(gpu_ctx, d, control=[1], bandwidth=80, region_threshold=5.0, hit_threshold=2.0)
+    check_regions(gpu_ctx, d, coeffs=[0.8, 1.7])
+
+
+def test_left_edge_stale_cells_far_away_and_dense_start(gpu_ctx):
+    rng = np.random.default_rng(77)
+    # (a) a pile of early tags, then nothing for a long stretch: the stale cells surface just before the next tag
+    sizes = [400000, 9000]
+    segs = []
+    for s in range(2):
+        per = [[None, None], [None, None]]
+        for dd in range(2):
+            early = np.sort(rng.choice(np.arange(1, 51), size=20, replace=False)).astype(np.uint32)
+            far = np.sort(rng.choice(np.arange(200000, 200300), size=150, replace=False)).astype(np.uint32)
+            pos = np.concatenate([early, far])
+            per[dd][0] = (pos, rng.integers(1, 6, size=pos.shape[0]).astype(np.uint32))
+            # (b) contig 1: dense from position 1 on (a chrM-like contig): one region from the very first position
+            p1 = np.arange(1, 8900, dtype=np.uint32)
+            p1 = p1[rng.random(p1.shape[0]) < 0.85]
+            per[dd][1] = (p1, rng.integers(1, 4, size=p1.shape[0]).astype(np.uint32))
+        segs.append(per)
+    d = TagData.from_segments(sizes, segs)
+    got, want = check_regions(gpu_ctx, d, mappable=50 * d.genome_size(), region_threshold=5.0, hit_threshold=1.0)
+    assert len(want["rows"]) + len(want["dropped"]) >= 3
+    check_regions(gpu_ctx, d, mappable=50 * d.genome_size(), directional=False, region_threshold=5.0, hit_threshold=1.0, corr_threshold=-0.9)
+
+
 def test_scaling_coefficients_q3(gpu_ctx):
     # -z: weights become doubles (sum c*coeff + sum c); accumulation order per position is the sample order
     d = make_synthetic([300000, 150000], 3, 25000, directional=True, seed=15, peak_spacing=5000)
@@ -189,7 +224,7 @@ def test_strand_shift_no_regions(gpu_ctx):
 # ---- golden fixtures: outputs of the unmodified reference itself (tests/golden/make_golden.py) -------------------
 from refutil import golden_names, load_golden  # noqa: E402
 
-NOT_YET = {"regions_left_edge_q2": -6}   # fixtures the CUDA path still refuses (error code asserted)
+NOT_YET = {}   # fixtures the CUDA path still refuses (error code asserted)
 
 
 @pytest.mark.parametrize("name", golden_names("regions"))

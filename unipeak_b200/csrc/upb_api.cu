@@ -346,6 +346,7 @@ struct PipeCfg {
   bool nondir;
   bool needCorr;                     // compute strandCorr(0) for regions passing the earlier filters
   const uint8_t* control;            // may be NULL
+  bool allowLeftEdge = false;        // replay the reference's left-edge behaviour (Q2) instead of refusing such inputs
   uint32_t nCoeffs = 0;              // 0, or the number of non-control samples (-z)
   const double* coeffs = nullptr;    // already normalised as src/regions.cpp:216-229
 };
@@ -419,6 +420,7 @@ static int check_left_edge (upb_ctx* ctx, uint32_t bw) {
 struct Prep {
   std::vector<Unit> units;
   std::vector<double> taps;
+  std::vector<uint32_t> affected;    // units with a tag within `bandwidth` of the contig start: replayed by left_edge_kernel
   double maxCoeff = 0;               // -z: largest coefficient (bounds the weight of a position)
   const double* d_coeffBySample = nullptr;
   uint32_t totalSpans = 0;
@@ -429,7 +431,7 @@ struct Prep {
 };
 
 // common set-up: units, taps, source list, control filter
-static int prepare (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, uint32_t* launches) {
+static int prepare (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, uint32_t* launches, bool allowLeftEdge = false) {
   const uint32_t C = (uint32_t)ctx->sizes.size();
   const uint32_t n = ctx->nSamples;
   if (!ctx->loaded) return fail(ctx, UPB_ERR_NOT_LOADED, "no tags loaded (upb_set_contigs + upb_load_tags first)");
@@ -437,7 +439,7 @@ static int prepare (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, uint32_t* launch
   if (!(cfg.thr > 0)) return fail(ctx, UPB_ERR_BAD_ARG, "region threshold must be > 0 (the reference's leap handling relies on it, SURVEY Q10)");
   if (!(cfg.background > 0)) return fail(ctx, UPB_ERR_BAD_ARG, "background must be > 0");
   int r;
-  if ((r = check_left_edge(ctx, cfg.bw))) return r;
+  if (!allowLeftEdge && (r = check_left_edge(ctx, cfg.bw))) return r;
 
   std::vector<uint32_t> src;
   std::vector<uint8_t> control(n, 0);
@@ -458,6 +460,7 @@ static int prepare (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, uint32_t* launch
 
   // units: one per (buffer, contig) that holds at least one non-control tag
   pr.units.clear();
+  pr.affected.clear();
   uint64_t spanStart = 0;
   const uint32_t nBuf = cfg.nondir ? 1u : 2u;
   for (uint32_t b = 0; b < nBuf; ++b)
@@ -474,6 +477,16 @@ static int prepare (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, uint32_t* launch
       u.spanStart = (uint32_t)spanStart;
       spanStart += u.nSpans;
       if (spanStart > 0xFFFFFFF0ull) return fail(ctx, UPB_ERR_UNSUPPORTED, "too many spans");
+      // Q2: every add() moves the window, control samples included (src/regions.cpp:356-359)
+      uint32_t first = 0xFFFFFFFFu, last = 0;
+      for (uint32_t s = 0; s < n; ++s) for (uint32_t d = (cfg.nondir ? 0u : b); d <= (cfg.nondir ? 1u : b); ++d) {
+        const uint32_t fp = ctx->firstPos[(size_t)(s * 2 + d) * C + c], lp = ctx->lastPos[(size_t)(s * 2 + d) * C + c];
+        if (fp) { first = std::min(first, fp); last = std::max(last, lp); }
+      }
+      if (first <= cfg.bw) {
+        if (last <= cfg.bw) return fail(ctx, UPB_ERR_LEFT_EDGE, "every tag of a contig lies within `bandwidth` of its start: the reference then leaks window cells into the next contig (misc/peakcall.cpp:176-184,224-231), which is not emulated");
+        pr.affected.push_back((uint32_t)pr.units.size());
+      }
       pr.units.push_back(u);
     }
   pr.totalSpans = (uint32_t)spanStart;
@@ -615,7 +628,7 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
   CU(cudaSetDevice(ctx->device));
   uint32_t launches = 0;
   CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-  int r = prepare(ctx, cfg, pr, &launches);
+  int r = prepare(ctx, cfg, pr, &launches, cfg.allowLeftEdge);
   if (r) return r;
   const uint32_t n = ctx->nSamples, C = (uint32_t)ctx->sizes.size();
   const uint32_t nUnits = (uint32_t)pr.units.size();
@@ -680,6 +693,44 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
   wa.nAdj = ((31 + 2 * cfg.bw) >> MT_SHIFT) + 2;
   wa.warmList = warmList; wa.nWarm = small32 + 12; wa.spanRunCount = sa.spanRunCount;
 
+  // ---- K0: left-edge replay for the units that need it ------------------------------------
+  const uint32_t nAff = (uint32_t)pr.affected.size();
+  const uint32_t EDGE_REG_CAP = 1u << 18, EDGE_ROW_CAP = 1024;
+  EdgeArgs eg;
+  memset(&eg, 0, sizeof eg);
+  uint32_t* d_affected = nullptr;
+  std::vector<uint32_t> edgeStop(nAff, 0), edgeCand(nAff, 0), edgeRows(nAff, 0);
+  if (nAff) {
+    const uint32_t w = 2 * cfg.bw + 1;
+    d_affected = SCR("edgeAffected", uint32_t, nAff);
+    CU(cudaMemcpyAsync(d_affected, pr.affected.data(), (size_t)nAff * 4, cudaMemcpyHostToDevice, ctx->stream));
+    eg.T = pr.T; eg.units = d_units; eg.affected = d_affected; eg.nAffected = nAff; eg.control = ctx->scratch["control"].as<uint8_t>();
+    eg.coeffBySample = pr.d_coeffBySample; eg.taps = ctx->scratch["taps"].as<double>(); eg.bw = cfg.bw; eg.nondir = cfg.nondir ? 1 : 0;
+    eg.thr = cfg.thr; eg.kurtThr = cfg.kurtThr; eg.corrThr = cfg.nondir ? cfg.corrThr : -1.0; eg.hitThr = cfg.hitThr;
+    eg.cursors = SCR("edgeCursors", unsigned long long, (size_t)nAff * 2 * n);
+    eg.ringF = SCR("edgeRingF", double, (size_t)nAff * w); eg.ringR = SCR("edgeRingR", double, (size_t)nAff * w);
+    eg.ringHits = SCR("edgeRingHits", uint32_t, (size_t)nAff * w * n); eg.ringHas = SCR("edgeRingHas", uint8_t, (size_t)nAff * w);
+    eg.regPc = SCR("edgeRegPc", uint32_t, (size_t)nAff * EDGE_REG_CAP); eg.regHas = SCR("edgeRegHas", uint8_t, (size_t)nAff * EDGE_REG_CAP);
+    eg.regF = SCR("edgeRegF", double, (size_t)nAff * EDGE_REG_CAP); eg.regR = SCR("edgeRegR", double, (size_t)nAff * EDGE_REG_CAP);
+    eg.regSums = SCR("edgeRegSums", uint32_t, (size_t)nAff * n); eg.callCounts = SCR("edgeCall", uint32_t, (size_t)nAff * n);
+    eg.regCap = EDGE_REG_CAP; eg.rowCap = EDGE_ROW_CAP; eg.maxPositions = 1ull << 23;
+    uint32_t* eo = SCR("edgeOut", uint32_t, (size_t)3 * nAff + 4);
+    CU(cudaMemsetAsync(eo, 0, ((size_t)3 * nAff + 4) * 4, ctx->stream));
+    eg.stop = eo; eg.nCand = eo + nAff; eg.nRows = eo + 2 * nAff; eg.flags = eo + 3 * nAff;
+    eg.rows = SCR("edgeRows", EdgeRow, (size_t)nAff * EDGE_ROW_CAP);
+    eg.rowCounts = SCR("edgeRowCounts", uint32_t, (size_t)nAff * EDGE_ROW_CAP * n);
+    left_edge_kernel<<<nAff, 32, 0, ctx->stream>>>(eg);
+    CU(cudaGetLastError());
+    launches += 1;
+    std::vector<uint32_t> eoh((size_t)3 * nAff + 4);
+    CU(cudaMemcpyAsync(eoh.data(), eo, eoh.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (eoh[3 * nAff]) return fail(ctx, UPB_ERR_UNSUPPORTED, "left-edge replay (SURVEY Q2) ran out of its scratch or position budget");
+    for (uint32_t k = 0; k < nAff; ++k) { edgeStop[k] = eoh[k]; edgeCand[k] = eoh[nAff + k]; edgeRows[k] = eoh[2 * nAff + k]; }
+  }
+  uint64_t edgeRowsTotal = 0;
+  for (uint32_t k = 0; k < nAff; ++k) edgeRowsTotal += edgeRows[k];
+
   size_t runCap = std::max<size_t>(1u << 18, (size_t)(ctx->nEntries / 64));
   { const size_t have = ctx->scratch["runs"].cap / sizeof(SpanRun); if (have > runCap) runCap = have; }
   uint32_t nRuns = 0;
@@ -703,13 +754,20 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
   ctx->stats.warm_spans = h32[12];
   { unsigned long long st[4]; memcpy(st, h32 + 4, 32); ctx->stats.kde_hot_tiles = st[1]; ctx->stats.hot_blocks = st[0]; ctx->stats.exact_evals = st[2]; ctx->stats.spans_with_tags = st[3]; }
   { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->stats.ms_kde = ms; }
-  if (nRuns == 0) {
+  if (nRuns == 0 && edgeRowsTotal == 0) {
+    for (uint32_t k = 0; k < nAff; ++k) { out.unitCand[pr.affected[k]] = edgeCand[k]; out.nCand += edgeCand[k]; }
     if ((r = acquire_slab(ctx, out.layout.totalBytes, out.slab))) return r;
     memset(out.slab.p, 0, out.layout.totalBytes);
     finish_stats(ctx, launches);
     return UPB_OK;
   }
-
+  unsigned long long* h64 = (unsigned long long*)ctx->h_small;
+  uint32_t nCand = 0, n1 = 0;
+  uint64_t R = 0;
+  Cand2* cand = nullptr; uint32_t* list1 = nullptr; unsigned long long* unitFirst = nullptr;
+  uint32_t* statCounts = nullptr; double* statKurt = nullptr; uint32_t* pass2 = nullptr; unsigned long long* pass2Scan = nullptr; double* rowCorr = nullptr;
+  std::vector<uint32_t> edgeDrop(nAff, 0);
+  if (nRuns) {
   // ---- K2: (span, rank) order, stitch runs cut by piece / span boundaries ------------------------------
   unsigned long long* spanOrd = SCR("spanOrd", unsigned long long, pr.totalSpans);
   if ((r = scan_u32(ctx, sa.spanRunCount, pr.totalSpans, spanOrd, d_tot, &launches))) return r;
@@ -722,18 +780,17 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
   CU(cudaGetLastError());
   launches += 2;
   if ((r = scan_u32(ctx, head, nRuns, headScan, d_tot, &launches))) return r;
-  Cand2* cand = SCR("cand", Cand2, nRuns);                            // nCand <= nRuns
+  cand = SCR("cand", Cand2, nRuns);                                   // nCand <= nRuns
   unsigned long long* unitCand = SCR("unitCand", unsigned long long, 2 * (size_t)nUnits + 2);
-  unsigned long long* unitFirst = unitCand + nUnits + 1;
+  unitFirst = unitCand + nUnits + 1;
   CU(cudaMemsetAsync(unitCand, 0, (2 * (size_t)nUnits + 2) * 8, ctx->stream));
   merge_runs2_kernel<<<gRuns, 256, 0, ctx->stream>>>(sa.runs, ordIdx, head, headScan, nRuns, d_units, nUnits, cand, unitCand);
   unit_first_kernel<<<1, 32, 0, ctx->stream>>>(unitCand, nUnits, unitFirst);
   CU(cudaGetLastError());
   launches += 2;
-  unsigned long long* h64 = (unsigned long long*)ctx->h_small;
   CU(cudaMemcpyAsync(h64, d_tot, 8, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  const uint32_t nCand = (uint32_t)h64[0];
+  nCand = (uint32_t)h64[0];
   out.nCand = nCand;
   ctx->stats.n_candidates = nCand;
   ctx->stats.n_stitched = nRuns - nCand;
@@ -742,22 +799,28 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
   // ---- K3: hit filter (misc/peakcall.cpp:41), then per-region statistics for the survivors ------------------
   uint32_t* pass = SCR("pass", uint32_t, nCand);
   unsigned long long* passScan = SCR("passScan", unsigned long long, nCand);
-  uint32_t* list1 = SCR("list1", uint32_t, nCand);
+  list1 = SCR("list1", uint32_t, nCand);
   cand_hit_kernel<<<gCand, 256, 0, ctx->stream>>>(cand, nCand, cfg.hitThr, pass);
   launches += 1;
+  uint32_t* d_drop = nullptr;
+  if (nAff) {                                                         // what the replay owns is not a Region of the reference
+    d_drop = SCR("edgeDrop", uint32_t, nAff);
+    CU(cudaMemsetAsync(d_drop, 0, (size_t)nAff * 4, ctx->stream));
+    edge_drop_kernel<<<gCand, 256, 0, ctx->stream>>>(d_affected, eg.stop, nAff, cand, nCand, pass, d_drop);
+    launches += 1;
+  }
   if ((r = scan_u32(ctx, pass, nCand, passScan, d_tot, &launches))) return r;
   compact_index_kernel<<<gCand, 256, 0, ctx->stream>>>(pass, passScan, nCand, list1);
   CU(cudaGetLastError());
   launches += 1;
   CU(cudaMemcpyAsync(h64, d_tot, 8, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(h64 + 8, unitCand, std::min<size_t>((size_t)nUnits, 400) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (nAff) CU(cudaMemcpyAsync(edgeDrop.data(), d_drop, (size_t)nAff * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  const uint32_t n1 = (uint32_t)h64[0];
+  n1 = (uint32_t)h64[0];
   if (nUnits <= 400) for (uint32_t u = 0; u < nUnits; ++u) out.unitCand[u] = h64[8 + u];
   else { CU(cudaMemcpy(out.unitCand.data(), unitCand, (size_t)nUnits * 8, cudaMemcpyDeviceToHost)); }
 
-  uint64_t R = 0;
-  uint32_t* statCounts = nullptr; double* statKurt = nullptr; uint32_t* pass2 = nullptr; unsigned long long* pass2Scan = nullptr; double* rowCorr = nullptr;
   if (n1) {
     const unsigned g1 = (n1 + 255) / 256;
     statCounts = SCR("statCounts", uint32_t, (size_t)n1 * n);
@@ -810,7 +873,11 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
     R = h64[0];
   }
 
+  }  // nRuns
+
   // ---- accepted rows -> result slab -------------------------------------------------------------------------
+  const uint64_t Rnormal = R;
+  R += edgeRowsTotal;
   out.R = R;
   ctx->lastRows = R;
   out.layout = slab_layout(R, n, C);
@@ -818,24 +885,76 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
   if ((r = acquire_slab(ctx, SL.totalBytes, out.slab))) return r;
   unsigned char* hs = (unsigned char*)out.slab.p;
   memset(hs + SL.devBytes, 0, SL.totalBytes - SL.devBytes);
+  // replay bookkeeping: its candidates replace the dropped ones, its rows precede the unit's other rows
+  long long* d_shift = nullptr;
+  if (nAff) {
+    std::vector<long long> shift(2 * (size_t)nUnits, 0);
+    long long runRows = 0;
+    size_t k = 0;
+    for (uint32_t u = 0; u < nUnits; ++u) {
+      if (k < nAff && pr.affected[k] == u) { runRows += edgeRows[k]; shift[nUnits + u] = (long long)edgeCand[k] - (long long)edgeDrop[k]; ++k; }
+      shift[u] = runRows;
+    }
+    for (k = 0; k < nAff; ++k) {
+      const uint32_t u = pr.affected[k];
+      out.unitCand[u] = (uint64_t)((long long)out.unitCand[u] + shift[nUnits + u]);
+      out.nCand = (uint64_t)((long long)out.nCand + shift[nUnits + u]);
+    }
+    d_shift = SCR("edgeShift", long long, 2 * (size_t)nUnits);
+    CU(cudaMemcpyAsync(d_shift, shift.data(), shift.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
   if (R) {
     unsigned char* ds = SCR("slab", unsigned char, SL.devBytes);
     unsigned long long* d_tir = SCR("tir", unsigned long long, n);
     CU(cudaMemsetAsync(d_tir, 0, (size_t)n * 8, ctx->stream));
     EmitArgs ea;
     ea.cand = cand; ea.list = list1; ea.pass = pass2; ea.passScan = pass2Scan; ea.nList = n1; ea.units = d_units; ea.unitFirst = unitFirst;
+    ea.unitRowShift = d_shift; ea.unitCandShift = d_shift ? d_shift + nUnits : nullptr;
     ea.statCounts = statCounts; ea.statKurt = statKurt; ea.rowCorr = rowCorr; ea.nSamples = n;
     ea.buffer = ds + SL.oBuffer; ea.contig = (uint32_t*)(ds + SL.oContig); ea.left = (uint32_t*)(ds + SL.oLeft); ea.len = (uint32_t*)(ds + SL.oLen);
     ea.peak = (uint32_t*)(ds + SL.oPeak); ea.wsum = (uint32_t*)(ds + SL.oWsum); ea.candIndex = (unsigned long long*)(ds + SL.oCandIndex);
     ea.peakScore = (double*)(ds + SL.oPeakScore); ea.kurt = (double*)(ds + SL.oKurt); ea.corr = (double*)(ds + SL.oCorr);
     ea.counts = (uint32_t*)(ds + SL.oCounts);
-    emit_rows_kernel<<<(n1 + 255) / 256, 256, 0, ctx->stream>>>(ea);
+    if (n1) { emit_rows_kernel<<<(n1 + 255) / 256, 256, 0, ctx->stream>>>(ea); launches += 1; }
+    if (edgeRowsTotal) {
+      // first table row of each unit's replay rows = accepted rows of span_kernel in earlier units + replay rows of earlier units
+      std::vector<unsigned long long> rowBase(nAff, 0);
+      std::vector<uint32_t> l1(n1), p2(n1);
+      std::vector<Cand2> hc;                                          // rare path: a few small host look-ups are fine
+      unsigned long long before = 0;
+      if (n1) {
+        CU(cudaMemcpyAsync(l1.data(), list1, (size_t)n1 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(p2.data(), pass2, (size_t)n1 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        hc.resize(nCand);
+        CU(cudaMemcpyAsync(hc.data(), cand, (size_t)nCand * sizeof(Cand2), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+      }
+      size_t j = 0; unsigned long long acc = 0;
+      for (uint32_t k = 0; k < nAff; ++k) {
+        const uint32_t u = pr.affected[k];
+        while (j < n1 && hc[l1[j]].unit < u) { acc += p2[j]; ++j; }
+        rowBase[k] = acc + before;
+        before += edgeRows[k];
+      }
+      unsigned long long* d_rowBase = SCR("edgeRowBase", unsigned long long, nAff);
+      CU(cudaMemcpyAsync(d_rowBase, rowBase.data(), (size_t)nAff * 8, cudaMemcpyHostToDevice, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      EdgeEmitArgs ee;
+      ee.rows = eg.rows; ee.rowCounts = eg.rowCounts; ee.rowCap = EDGE_ROW_CAP; ee.nSamples = n; ee.nAffected = nAff; ee.affected = d_affected; ee.nRows = eg.nRows;
+      ee.rowBase = d_rowBase; ee.units = d_units;
+      ee.buffer = ea.buffer; ee.contig = ea.contig; ee.left = ea.left; ee.len = ea.len; ee.peak = ea.peak; ee.candIndex = ea.candIndex;
+      ee.peakScore = ea.peakScore; ee.kurt = ea.kurt; ee.corr = ea.corr; ee.counts = ea.counts; ee.wsum = ea.wsum;
+      edge_emit_kernel<<<dim3((EDGE_ROW_CAP + 127) / 128, nAff), 128, 0, ctx->stream>>>(ee);
+      launches += 1;
+    }
     tags_in_regions_kernel<<<std::min<unsigned>(ctx->smCount * 4, (unsigned)((R * n + 255) / 256)), 256, (size_t)n * 8, ctx->stream>>>(ea.counts, R, n, d_tir);
     CU(cudaGetLastError());
-    launches += 2;
+    launches += 1;
     CU(cudaMemcpyAsync(hs, ds, SL.devBytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(hs + SL.oTags, d_tir, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
   }
+  (void)Rnormal;
   finish_stats(ctx, launches);
   return UPB_OK;
 }
@@ -1005,6 +1124,7 @@ extern "C" int upb_call_regions (upb_ctx* ctx, const upb_region_params* p, upb_r
   cfg.hitThr = p->hit_threshold; cfg.background = p->background; cfg.nondir = !p->directional; cfg.control = p->control;
   cfg.nCoeffs = p->n_coeffs; cfg.coeffs = p->coeffs;
   cfg.needCorr = cfg.nondir;        // -D: the filter (if corr_threshold > -1) and the optional correlation column
+  cfg.allowLeftEdge = true;
   PipeOut po;
   Prep pr;
   int r = run_pipeline(ctx, cfg, pr, po);

@@ -29,6 +29,7 @@
 #pragma once
 
 #include "upb_device.cuh"
+#include "upb_edge.cuh"
 
 #ifndef UPB_EXP_EXACT
 #define UPB_EXP_EXACT 1
@@ -682,6 +683,17 @@ __global__ void merge_runs2_kernel (const SpanRun* __restrict__ runs, const uint
   atomicAdd(&unitCand[c.unit], 1ull);
 }
 
+// candidates of span_kernel that lie in the stretch the left-edge replay owns (upb_edge.cuh) are not Region objects of the
+// reference: they are dropped and counted per affected unit
+__global__ void edge_drop_kernel (const uint32_t* __restrict__ affected, const uint32_t* __restrict__ stop, uint32_t nAffected,
+                                  const Cand2* __restrict__ cand, uint32_t nCand, uint32_t* __restrict__ pass, uint32_t* __restrict__ dropCount) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nCand) return;
+  const uint32_t unit = cand[i].unit;
+  for (uint32_t k = 0; k < nAffected; ++k)
+    if (affected[k] == unit) { if (cand[i].left <= stop[k]) { pass[i] = 0; atomicAdd(&dropCount[k], 1u); } break; }
+}
+
 // hit filter (misc/peakcall.cpp:41 first clause)
 __global__ void cand_hit_kernel (const Cand2* __restrict__ cand, uint32_t n, double hitThr, uint32_t* __restrict__ pass) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -873,6 +885,8 @@ struct EmitArgs {
   uint32_t nList;
   const SpanUnit* units;
   const unsigned long long* unitFirst;   // [nUnits] ordinal of the first candidate of each unit
+  const long long* unitRowShift;         // [nUnits] left-edge replay: rows it contributes to this and earlier units (NULL if none)
+  const long long* unitCandShift;        // [nUnits] left-edge replay: its candidates minus the dropped ones of this unit
   const uint32_t* statCounts;            // [nList * nSamples]
   const double* statKurt;                // [nList]
   const double* rowCorr;                 // [nList] or NULL
@@ -887,15 +901,38 @@ __global__ void emit_rows_kernel (EmitArgs a) {
   if (i >= a.nList || !a.pass[i]) return;
   const uint32_t ci = a.list[i];
   const Cand2 c = a.cand[ci];
-  const unsigned long long o = a.passScan[i];
+  const unsigned long long o = a.passScan[i] + (a.unitRowShift ? (unsigned long long)a.unitRowShift[c.unit] : 0ull);
   a.buffer[o] = (uint8_t)a.units[c.unit].buffer;
   a.contig[o] = a.units[c.unit].contig;
   a.left[o] = c.left; a.len[o] = c.len; a.peak[o] = c.peak; a.wsum[o] = c.wsum;
-  a.candIndex[o] = (unsigned long long)ci - a.unitFirst[c.unit];
+  a.candIndex[o] = (unsigned long long)((long long)((unsigned long long)ci - a.unitFirst[c.unit]) + (a.unitCandShift ? a.unitCandShift[c.unit] : 0ll));
   a.peakScore[o] = c.score;
   a.kurt[o] = a.statKurt[i];
   a.corr[o] = a.rowCorr ? a.rowCorr[i] : __longlong_as_double(0x7ff8000000000000ll);
   for (uint32_t s = 0; s < a.nSamples; ++s) a.counts[o * a.nSamples + s] = a.statCounts[(uint64_t)i * a.nSamples + s];
+}
+
+// rows of the left-edge replay -> their slots in the table (they precede span_kernel's rows of the same unit)
+struct EdgeEmitArgs {
+  const EdgeRow* rows; const uint32_t* rowCounts;
+  uint32_t rowCap, nSamples, nAffected;
+  const uint32_t* affected; const uint32_t* nRows;
+  const unsigned long long* rowBase;     // [nAffected] first table row of the unit's replay rows
+  const SpanUnit* units;
+  uint8_t* buffer; uint32_t* contig; uint32_t* left; uint32_t* len; uint32_t* peak; unsigned long long* candIndex;
+  double* peakScore; double* kurt; double* corr; uint32_t* counts; uint32_t* wsum;
+};
+
+__global__ void edge_emit_kernel (EdgeEmitArgs a) {
+  const uint32_t ai = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ai >= a.nAffected || k >= a.nRows[ai]) return;
+  const EdgeRow r = a.rows[(size_t)ai * a.rowCap + k];
+  const SpanUnit U = a.units[a.affected[ai]];
+  const unsigned long long o = a.rowBase[ai] + k;
+  a.buffer[o] = (uint8_t)U.buffer; a.contig[o] = U.contig;
+  a.left[o] = r.left; a.len[o] = r.len; a.peak[o] = r.peak; a.wsum[o] = r.wsum; a.candIndex[o] = r.candIndex;
+  a.peakScore[o] = r.score; a.kurt[o] = r.kurt; a.corr[o] = r.corr;
+  for (uint32_t s = 0; s < a.nSamples; ++s) a.counts[o * a.nSamples + s] = a.rowCounts[((size_t)ai * a.rowCap + k) * a.nSamples + s];
 }
 
 // per-sample totals of the accepted rows (ProfileBuffer::nTagsInRegions, misc/peakcall.cpp:44)
