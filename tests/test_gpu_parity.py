@@ -86,6 +86,19 @@ def test_thresholds_disabled_and_tight(gpu_ctx):
     check_regions(gpu_ctx, d, directional=False, kurtosis_threshold=2.5, corr_threshold=0.8, hit_threshold=30.0, region_threshold=40.0)
 
 
+def test_many_samples(gpu_ctx):
+    # more samples than lanes (config 4 has 96): per-sample slots, control tables and row widths beyond 32
+    d = make_synthetic([300000, 100000], 40, 4000, directional=True, seed=61, peak_spacing=5000)
+    check_regions(gpu_ctx, d, control=[3, 17, 39])
+    d2 = make_synthetic([200000], 70, 2500, directional=False, seed=62, peak_spacing=5000)
+    check_regions(gpu_ctx, d2, directional=False, corr_threshold=0.0)
+    from refutil import oracle_tags_in_regions
+    keys = [(0, 1000 + 3000 * i, 1400 + 3000 * i) for i in range(60)]
+    status, want = oracle_tags_in_regions(d2, keys, directional=False, extension=10)
+    got = gpu_ctx.count_tags_in_regions(keys, directional=False, extension=10)
+    assert status == 0 and got.tolist() == want.tolist()
+
+
 def test_left_edge_q2(gpu_ctx):
     # tags inside the first `bandwidth` positions of a contig: the reference's window does not slide there; densities
     # and hit vectors are displaced and stale cells surface before the next tag (misc/peakcall.cpp:176-184)
@@ -380,3 +393,28 @@ def test_scatter_rows_rebuilds_the_single_gpu_table(gpu_ctx):
         assert np.array_equal(cols[k].view(np.uint64), full[k].view(np.uint64)), k
     for cx in ctxs:
         cx.close()
+
+
+def test_load_validation(gpu_ctx):
+    # what the reference's parser / asserts guarantee is checked at load time; nothing is indexed with a bad position
+    import unipeak_b200
+    sizes = [50000, 20000]
+    good = make_synthetic(sizes, 2, 3000, directional=True, seed=71, peak_spacing=4000)
+
+    def broken(mutate):
+        pos, cnt = good.pos.copy(), good.cnt.copy()
+        mutate(pos, cnt)
+        return TagData(good.contig_sizes, good.n_samples, good.off, pos, cnt)
+    a = int(good.off[0]) + 5
+    cases = [(lambda p, c: p.__setitem__(a, p[a - 1]), -5),                 # not strictly ascending
+             (lambda p, c: p.__setitem__(a, 0), -2),                        # position 0
+             (lambda p, c: p.__setitem__(int(good.off[1]) - 1, 50001), -2),   # beyond the contig
+             (lambda p, c: c.__setitem__(a, 0), -2)]                        # zero count
+    for mutate, code in cases:
+        with pytest.raises(unipeak_b200.UpbError) as ei:
+            gpu_ctx.load(broken(mutate))
+        assert ei.value.code == code
+        with pytest.raises(unipeak_b200.UpbError) as ei:
+            gpu_ctx.call_regions(**region_settings(good))
+        assert ei.value.code == -4                                          # nothing usable is loaded after a failed load
+    check_regions(gpu_ctx, good)

@@ -56,6 +56,7 @@ struct upb_ctx {
   uint64_t lastRows = 0;                // rows of the last upb_call_regions still sitting in the device slab (scratch "slab")
   std::vector<uint8_t> lastControl;     // control set cntEff was built for
   bool cntEffValid = false;
+  bool tidxBuilt = false;               // per-2048-tile entry offsets of the sample-major arrays: built on first use (density kernel only)
 };
 
 static thread_local std::string g_createErr;
@@ -249,9 +250,6 @@ extern "C" int upb_load_tags (upb_ctx* ctx, uint32_t n_samples, const uint64_t* 
   ENSURE(ctx->d_cnt, (E ? E : 1) * 4);
   ENSURE(ctx->d_off, nOff * 8);
   ENSURE(ctx->d_segStart, ((size_t)nSeg + 1) * 8);
-  const uint64_t stride = ctx->tidxBase.back();
-  const uint64_t idxTotal = stride * n_samples * 2;
-  ENSURE(ctx->d_tidx, idxTotal * 4);
   ENSURE(ctx->d_small, 4096);
   if (E) {
     CU(cudaMemcpyAsync(ctx->d_pos.p, pos, E * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -261,20 +259,6 @@ extern "C" int upb_load_tags (upb_ctx* ctx, uint32_t n_samples, const uint64_t* 
   CU(cudaMemcpyAsync(ctx->d_segStart.p, segStart.data(), ((size_t)nSeg + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemsetAsync(ctx->d_small.p, 0, 4096, ctx->stream));
 
-  IndexArgs ia;
-  ia.pos = ctx->d_pos.as<uint32_t>(); ia.cnt = ctx->d_cnt.as<uint32_t>(); ia.segStart = ctx->d_segStart.as<uint64_t>();
-  ia.sizes = ctx->d_sizes.as<uint32_t>(); ia.tidxBase = ctx->d_tidxBase.as<uint32_t>(); ia.tidx = ctx->d_tidx.as<uint32_t>();
-  ia.tidxStride = stride; ia.C = C; ia.nSeg = nSeg; ia.nEntries = E; ia.flags = ctx->d_small.as<uint32_t>();
-  {
-    const uint64_t blocks = (idxTotal + 255) / 256;
-    index_fill_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(ia, idxTotal);
-    CU(cudaGetLastError());
-  }
-  if (E) {
-    const uint64_t blocks = (E + 255) / 256;
-    index_build_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(ia);
-    CU(cudaGetLastError());
-  }
   // tile-major copy: counting sort of the entries by (strand, contig, 512-position mini-tile)
   if (n_samples > (1u << 20)) return fail(ctx, UPB_ERR_UNSUPPORTED, "more than 2^20 samples");
   ctx->mtBase.assign(2 * (size_t)C + 1, 0);
@@ -296,6 +280,7 @@ extern "C" int upb_load_tags (upb_ctx* ctx, uint32_t n_samples, const uint64_t* 
     ma.pos = ctx->d_pos.as<uint32_t>(); ma.cnt = ctx->d_cnt.as<uint32_t>(); ma.segStart = ctx->d_segStart.as<uint64_t>(); ma.mtBase = ctx->d_mtBase.as<uint32_t>();
     ma.mtW = ctx->d_mtW.as<unsigned long long>();
     ma.mtCount = ctx->d_mtCount.as<uint32_t>(); ma.mtOff = ctx->d_mtOff.as<unsigned long long>(); ma.ment = ctx->d_ment.as<uint2>();
+    ma.sizes = ctx->d_sizes.as<uint32_t>(); ma.flags = ctx->d_small.as<uint32_t>();
     ma.C = C; ma.nSeg = nSeg; ma.nEntries = E;
     const uint64_t blocks = (E + 255) / 256;
     uint32_t l = 0;
@@ -312,6 +297,7 @@ extern "C" int upb_load_tags (upb_ctx* ctx, uint32_t n_samples, const uint64_t* 
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->loaded = false;
   ctx->cntEffValid = false;
+  ctx->tidxBuilt = false;
   if (flags & FLAG_UNSORTED) return fail(ctx, UPB_ERR_UNSORTED, "upb_load_tags: positions must be strictly ascending within each (sample, strand, contig) — the reference asserts on unsorted input (misc/peakcall.cpp:171)");
   if (flags & FLAG_BAD_POS) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags: position outside 1..contig size (the reference's parser drops those, misc/format.cpp:670-676)");
   if (flags & FLAG_ZERO_COUNT) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags: zero count (the reference's parser never delivers those, misc/format.cpp:710)");
@@ -543,7 +529,27 @@ static int prepare (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, uint32_t* launch
   return UPB_OK;
 }
 
+static int ensure_tidx (upb_ctx* ctx, uint32_t* launches) {
+  if (ctx->tidxBuilt) return UPB_OK;
+  const uint32_t C = (uint32_t)ctx->sizes.size(), n = ctx->nSamples;
+  const uint64_t stride = ctx->tidxBase.back();
+  const uint64_t idxTotal = stride * n * 2;
+  ENSURE(ctx->d_tidx, idxTotal * 4);
+  IndexArgs ia;
+  ia.pos = ctx->d_pos.as<uint32_t>(); ia.cnt = ctx->d_cnt.as<uint32_t>(); ia.segStart = ctx->d_segStart.as<uint64_t>();
+  ia.sizes = ctx->d_sizes.as<uint32_t>(); ia.tidxBase = ctx->d_tidxBase.as<uint32_t>(); ia.tidx = ctx->d_tidx.as<uint32_t>();
+  ia.tidxStride = stride; ia.C = C; ia.nSeg = n * 2 * C; ia.nEntries = ctx->nEntries;
+  ia.flags = ctx->d_small.as<uint32_t>() + 15;                        // validation already happened in mt_build_kernel
+  index_fill_kernel<<<(unsigned)((idxTotal + 255) / 256), 256, 0, ctx->stream>>>(ia, idxTotal);
+  if (ctx->nEntries) index_build_kernel<<<(unsigned)((ctx->nEntries + 255) / 256), 256, 0, ctx->stream>>>(ia);
+  CU(cudaGetLastError());
+  *launches += 2;
+  ctx->tidxBuilt = true;
+  return UPB_OK;
+}
+
 static int launch_density (upb_ctx* ctx, DensArgs& da, bool nondir, uint32_t totalWork, uint32_t* launches) {
+  { int rr = ensure_tidx(ctx, launches); if (rr) return rr; da.T.tidx = ctx->d_tidx.as<uint32_t>(); }
   const DensSmem L = dens_smem_layout(da.bw, da.nSrc * (nondir ? 2u : 1u), nondir, da.srcCoeff != nullptr);
   const size_t smem = L.total;
   if (smem > 227 * 1024) return fail(ctx, UPB_ERR_UNSUPPORTED, "bandwidth / sample count need more shared memory than one SM has");

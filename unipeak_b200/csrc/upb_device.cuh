@@ -153,6 +153,8 @@ struct MtArgs {
   unsigned long long* mtW;          // [nMtTotal] zone map: total count of all samples' entries in the mini-tile
   const unsigned long long* mtOff;  // [nMtTotal+1]
   uint2* ment;
+  const uint32_t* sizes;            // [C]
+  uint32_t* flags;                  // validation results (FLAG_*)
   uint32_t C, nSeg;
   uint64_t nEntries;
 };
@@ -163,15 +165,33 @@ __device__ __forceinline__ uint32_t seg_of_entry (const uint64_t* __restrict__ s
   return lo;
 }
 
+// Pass 1 (SCATTER = false) validates what the reference's parser guarantees (positions inside the contig and strictly
+// ascending per (sample, strand, contig), non-zero counts: misc/format.cpp:654-710, misc/peakcall.cpp:171) and builds
+// the per-mini-tile histogram and zone map; pass 2 scatters.  Entries that fail validation are never used as indices.
 template <bool SCATTER>
 __global__ void mt_build_kernel (MtArgs a) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.nEntries) return;
-  const uint32_t g = seg_of_entry(a.segStart, a.nSeg, i);
+  // consecutive entries almost always share their segment: one search per warp, the lanes only check
+  uint32_t g = 0;
+  { const uint64_t i0 = i & ~(uint64_t)31;
+    g = seg_of_entry(a.segStart, a.nSeg, i0);
+    if (i >= a.segStart[g + 1]) g = seg_of_entry(a.segStart, a.nSeg, i); }
   const uint32_t c = g % a.C, sd = g / a.C, d = sd & 1u, s = sd >> 1;
-  const uint32_t p = a.pos[i] - 1;
+  const uint32_t pos1 = a.pos[i];
+  const uint32_t p = pos1 - 1;
+  if (pos1 < 1 || pos1 > a.sizes[c]) { if (!SCATTER) atomicOr(a.flags, FLAG_BAD_POS); return; }
   const uint32_t mt = a.mtBase[d * a.C + c] + (p >> MT_SHIFT);
-  if (!SCATTER) { atomicAdd(&a.mtCount[mt], 1u); atomicAdd(&a.mtW[mt], (unsigned long long)a.cnt[i]); return; }
+  if (!SCATTER) {
+    uint32_t f = 0;
+    const uint32_t k = a.cnt[i];
+    if (k == 0) f |= FLAG_ZERO_COUNT;
+    if (i > a.segStart[g] && a.pos[i - 1] >= pos1) f |= FLAG_UNSORTED;
+    if (f) atomicOr(a.flags, f);
+    atomicAdd(&a.mtCount[mt], 1u);
+    atomicAdd(&a.mtW[mt], (unsigned long long)k);
+    return;
+  }
   const unsigned long long slot = a.mtOff[mt] + (atomicSub(&a.mtCount[mt], 1u) - 1u);
   a.ment[slot] = make_uint2(a.cnt[i], (s << SPAN_SHIFT) | (p & (SPAN_LEN - 1)));
 }
