@@ -1,0 +1,251 @@
+"""Drop-in command-line drivers (bin/regions, bin/strand_shift, bin/tags_in_regions built from unipeak_b200/host) against
+the reference's real binaries (oracle/_ref): same arguments, same working directory -> the output files and stderr must be
+byte-identical.  The CPU part checks what needs no device (flag handling, usage text, wiggle reader, %g formatter)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import refutil
+from refutil import REF_DIR, ROOT, write_inputs
+from unipeak_b200.synth import TagData, make_synthetic
+
+BIN = os.path.join(ROOT, "bin")
+TOOLS = ("regions", "strand_shift", "tags_in_regions")
+
+
+def have_bins() -> bool:
+    return all(os.access(os.path.join(BIN, t), os.X_OK) for t in TOOLS + ("host_selftest",))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    if not have_bins():
+        from unipeak_b200 import build
+        build.build_library()
+        build.build_host()
+    assert have_bins()
+
+
+def run(tool_dir, tool, args, cwd, check=None):
+    p = subprocess.run([os.path.join(tool_dir, tool)] + list(args), cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    if check is not None:
+        assert p.returncode == check, (tool, args, p.returncode, p.stderr.decode()[-2000:])
+    return p
+
+
+def side_by_side(tmp_path):
+    """Two directories holding symlinks named alike, so argv[0] has the same length in both usage texts."""
+    a, b = tmp_path / "ref", tmp_path / "new"
+    a.mkdir(), b.mkdir()
+    for t in TOOLS:
+        os.symlink(os.path.join(REF_DIR, t), a / t)
+        os.symlink(os.path.join(BIN, t), b / t)
+    return str(a), str(b)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU: no device call on these paths
+# ---------------------------------------------------------------------------------------------------------
+def test_g6_formatter_equals_printf():
+    p = run(BIN, "host_selftest", ["g6", "2000000"], ROOT, check=0)
+    assert b"bad=0" in p.stdout
+
+
+@pytest.mark.skipif(not refutil.have_ref(), reason="compiled reference (oracle/_ref) not present")
+@pytest.mark.parametrize("args", [["-h"], ["--version"], [], ["-c", "x", "-b", "abc", "f.wig"], ["-c", "x", "-c", "y", "f.wig"],
+                                  ["-c", "x", "f.wig", "-s"], ["-c", "x", "-l", "70000", "f.wig"], ["-c", "x", "-s", "1,2,3", "-o", "o", "-f", "i", "f.wig"],
+                                  ["-c", "x", "-s", "1,b", "-o", "o", "-f", "i", "f.wig"], ["-c", "nonexistent.txt", "-o", "o", "-f", "i", "f.wig"]])
+def test_flag_handling_matches_reference(tmp_path, args):
+    a, b = side_by_side(tmp_path)
+    for t in TOOLS:
+        ra = subprocess.run(["./" + t] + args, cwd=a, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        rb = subprocess.run(["./" + t] + args, cwd=b, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert (ra.returncode, ra.stdout, ra.stderr) == (rb.returncode, rb.stdout, rb.stderr), (t, args, ra.stderr, rb.stderr)
+
+
+def test_wiggle_reader_arrays(tmp_path):
+    d = make_synthetic([120000, 60000, 30000], 1, 30000, directional=True, seed=9, peak_spacing=4000, contig_names=["chrA", "chrB", "chrC"],
+                       keep_clear_of_edges=False)
+    f = write_inputs(d, str(tmp_path))
+    p = run(BIN, "host_selftest", ["wig", f["contigs"], f["wigs"][0]], str(tmp_path), check=0)
+    lines = p.stdout.decode().splitlines()
+    head = dict(l.split("\t") for l in lines[:5])
+    assert head["name"] == "s0" and int(head["expected"]) == d.tags(0) == int(head["confident"]) and int(head["oob"]) == 0
+    got = np.array([[int(x) for x in l.split("\t")] for l in lines[5:]], dtype=np.int64)
+    want = []
+    for dd in range(2):
+        for c in range(3):
+            pos, cnt = d.seg(0, dd, c)
+            want += [[dd, c, int(a), int(b)] for a, b in zip(pos, cnt)]
+    assert got.tolist() == want
+
+
+def test_wiggle_reader_offset_bounds_and_skipped_contigs(tmp_path):
+    # -s moves '+' tags right and '-' tags left; tags pushed off either end are counted out of bounds (misc/format.cpp:654-678);
+    # contigs missing from the table are skipped without counting (:506)
+    (tmp_path / "c.txt").write_text("# comment\nchrA\t1000\nchrB 500\n")
+    (tmp_path / "x.wig").write_text(
+        "# original_file=x.bed\n# tags=21\n"
+        'track name="x +" description="x" priority=3 visibility=full type=wiggle_0 alwaysZero=on color=0,0,255\n'
+        "variableStep chrom=chrA\n5 2\n990 3\n1000 1\nvariableStep chrom=chrZ\n7 9\nvariableStep chrom=chrB\n100 1\n100 2\n"
+        'track name="x -" description=" " priority=3 visibility=full type=wiggle_0 alwaysZero=on color=255,0,0 altColor=255,0,0\n'
+        "variableStep chrom=chrA\n10 -4\n11 -1\n500\t-2\nvariableStep chrom=chrB\n500 -5\n")
+    p = run(BIN, "host_selftest", ["wig", "c.txt", "x.wig", "10"], str(tmp_path), check=0)
+    lines = p.stdout.decode().splitlines()
+    head = dict(l.split("\t") for l in lines[:5])
+    # '+': 5->15, 990->1000, 1000->1010 (out); chrB 100->110 twice (merged).  '-': 10->0 (out: lastPos 10 > 10 is false), 11->1, 500->490; chrB 500->490
+    assert head == dict(name="x", expected="21", confident="16", oob="5", total="21")
+    assert [l.split("\t") for l in lines[5:]] == [["0", "0", "15", "2"], ["0", "0", "1000", "3"], ["0", "1", "110", "3"],
+                                                  ["1", "0", "1", "1"], ["1", "0", "490", "2"], ["1", "1", "490", "5"]]
+
+
+def test_wiggle_reader_errors(tmp_path):
+    (tmp_path / "c.txt").write_text("chrA\t1000\n")
+    hdr = 'track name="x +" description="x" priority=3 visibility=full type=wiggle_0 alwaysZero=on color=0,0,255\nvariableStep chrom=chrA\n'
+    cases = {"dup.wig": ("# tags=3\n# tags=4\n" + hdr + "5 3\n", "multiple tag count headers in dup.wig line 2"),
+             "zero.wig": ("# tags=0\n" + hdr, "zero tag count in zero.wig line 1"),
+             "bad.wig": ("# tags=3\n" + hdr + "5  3\n", "bad format in bad.wig line 4"),
+             "order.wig": ("# tags=3\n" + hdr + "50 1\n40 2\n", "alignments out of order in order.wig line 5"),
+             "junk.wig": ("# tags=3\n" + hdr + "hello\n", "bad format in junk.wig line 4")}
+    for name, (text, msg) in cases.items():
+        (tmp_path / name).write_text(text)
+        p = run(BIN, "host_selftest", ["wig", "c.txt", name], str(tmp_path), check=0)
+        assert p.stdout.decode().strip() == "error\t" + msg, name
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU: whole programs against the reference's
+# ---------------------------------------------------------------------------------------------------------
+needs_ref = pytest.mark.skipif(not refutil.have_ref(), reason="compiled reference (oracle/_ref) not present")
+
+
+def both(tmp_path, tool, args, outputs, rc=0):
+    """Run the reference's and our binary with identical argv in sibling directories that hold the same inputs."""
+    res = []
+    for which, d in (("ref", REF_DIR), ("new", BIN)):
+        cwd = tmp_path / which
+        p = run(d, tool, args, str(cwd))
+        res.append((p.returncode, p.stderr.decode(), {o: (cwd / o).read_bytes() if (cwd / o).exists() else None for o in outputs}, p.stdout))
+    (rca, erra, outa, soa), (rcb, errb, outb, sob) = res
+    assert rca == rc, erra
+    assert rcb == rc, errb
+    for o in outputs:
+        assert outa[o] is not None and outa[o] == outb[o], "%s differs:\n%s\n---\n%s" % (o, (outa[o] or b"")[:3000].decode(), (outb[o] or b"")[:3000].decode())
+    assert erra == errb
+    assert soa == sob
+    return outa
+
+
+def stage(tmp_path, data: TagData, prefix="s", sub=""):
+    """Same input files (relative names) in both working directories."""
+    files = None
+    for which in ("ref", "new"):
+        files = write_inputs(data, str(tmp_path / which / sub) if sub else str(tmp_path / which), prefix=prefix)
+    rel = lambda p: os.path.relpath(p, str(tmp_path / "new"))
+    return dict(contigs=rel(files["contigs"]), wigs=[rel(w) for w in files["wigs"]])
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_cli_regions_directional(tmp_path):
+    d = make_synthetic([200000, 100000, 50000], 3, 20000, directional=True, seed=1, peak_spacing=5000, contig_names=["chrA", "chrB", "chrC"])
+    f = stage(tmp_path, d)
+    out = both(tmp_path, "regions", ["-f", "-o", "regions.txt", "-c", f["contigs"]] + f["wigs"], ["regions.txt"])
+    assert out["regions.txt"].count(b"\n") > 30
+    both(tmp_path, "regions", ["-q", "-o", "r2.txt", "-c", f["contigs"], "-b", "20", "-r", "12.5", "-k", "0", "-t", "3", "-m", "100000000"] + f["wigs"], ["r2.txt"])
+    both(tmp_path, "regions", ["-q", "-o", "stdout", "-c", f["contigs"], "-u", "0.5", "-y"] + f["wigs"], [])
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_cli_regions_nondirectional_shifts_controls_coeffs(tmp_path):
+    d = make_synthetic([200000, 100000], 4, 30000, directional=False, seed=2, peak_spacing=5000, contig_names=["chrA", "chrB"])
+    f = stage(tmp_path, d)
+    both(tmp_path, "regions", ["-D", "-y", "-f", "-o", "a.txt", "-c", f["contigs"], "-s", "90"] + f["wigs"], ["a.txt"])
+    both(tmp_path, "regions", ["-D", "-y", "-o", "b.txt", "-c", f["contigs"], "-s", "80,90,100,-5", "-e", "2,4", "-u", "0.1"] + f["wigs"], ["b.txt"])
+    both(tmp_path, "regions", ["-q", "-o", "c.txt", "-c", f["contigs"], "-z", "p", "-e", "3"] + f["wigs"], ["c.txt"])
+    both(tmp_path, "regions", ["-q", "-D", "-o", "d.txt", "-c", f["contigs"], "-z", "1,2.5,0.25,1"] + f["wigs"], ["d.txt"])
+    both(tmp_path, "regions", ["-q", "-o", "e.txt", "-c", f["contigs"], "-z", "1,2.5,0.25", "-e", "1"] + f["wigs"], ["e.txt"])
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_cli_regions_profile_wiggle(tmp_path):
+    d = make_synthetic([150000, 80000], 2, 15000, directional=True, seed=4, peak_spacing=5000, contig_names=["chrA", "chrB"])
+    f = stage(tmp_path, d)
+    out = both(tmp_path, "regions", ["-q", "-o", "r.txt", "-w", "prof.wig", "-a", "hg19", "-c", f["contigs"]] + f["wigs"], ["r.txt", "prof.wig"])
+    assert out["prof.wig"].count(b"\n") > 10000
+    both(tmp_path, "regions", ["-q", "-D", "-o", "rd.txt", "-w", "profd.wig", "-n", "pooled", "-c", f["contigs"]] + f["wigs"], ["rd.txt", "profd.wig"])
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_cli_regions_single_contig_q7_and_profile(tmp_path):
+    # one sample, one contig: the '-' track is consumed in pass 1; emission order, progress lines and the profile interleave
+    d = make_synthetic([2000000], 1, 60000, directional=True, seed=3, peak_spacing=10000, contig_names=["chr21"])
+    f = stage(tmp_path, d)
+    both(tmp_path, "regions", ["-f", "-o", "r.txt", "-w", "p.wig", "-m", "300000000", "-c", f["contigs"]] + f["wigs"], ["r.txt", "p.wig"])
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_cli_regions_left_edge_q2(tmp_path):
+    d = make_synthetic([60000, 30000], 2, 30000, directional=True, seed=21, peak_spacing=2000, keep_clear_of_edges=False, contig_names=["chrA", "chrB"])
+    f = stage(tmp_path, d)
+    both(tmp_path, "regions", ["-f", "-o", "r.txt", "-c", f["contigs"]] + f["wigs"], ["r.txt"])
+    both(tmp_path, "regions", ["-D", "-y", "-q", "-o", "rd.txt", "-c", f["contigs"]] + f["wigs"], ["rd.txt"])
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_cli_regions_header_mismatch_warning(tmp_path):
+    d = make_synthetic([200000], 2, 20000, directional=True, seed=6, peak_spacing=5000, contig_names=["chrA"])
+    for which in ("ref", "new"):
+        wd = tmp_path / which
+        wd.mkdir()
+        d.write_contig_table(str(wd / "contigs.txt"))
+        d.write_wig(str(wd / "s0.wig"), 0, "s0", tags_header=d.tags(0) + 17)
+        d.write_wig(str(wd / "s1.wig"), 1, "s1")
+    # several directional samples on a one-contig table trip the reference's own assert: use two contigs' worth instead
+    both(tmp_path, "regions", ["-q", "-D", "-o", "r.txt", "-c", "contigs.txt", "s0.wig", "s1.wig"], ["r.txt"])
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_cli_strand_shift(tmp_path):
+    d = make_synthetic([3000000], 1, 300000, directional=False, seed=11, peak_spacing=10000, contig_names=["chrA"])
+    f = stage(tmp_path, d)
+    both(tmp_path, "strand_shift", ["-o", "shift.txt", "-c", f["contigs"], "-g", "30", "-r", "8", "-u", "0.1"] + f["wigs"], ["shift.txt"])
+    both(tmp_path, "strand_shift", ["-o", "shift2.txt", "-c", f["contigs"], "-g", "2000", "-r", "8", "-u", "0.1", "-x", "120", "-n", "10", "-s", "3"] + f["wigs"], ["shift2.txt"])
+    # nothing qualifies: same message, same exit code
+    both(tmp_path, "strand_shift", ["-c", f["contigs"], "-r", "100000"] + f["wigs"], [], rc=1)
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_cli_tags_in_regions(tmp_path):
+    d = make_synthetic([200000, 100000], 3, 20000, directional=True, seed=31, peak_spacing=5000, contig_names=["chrA", "chrB"])
+    f0 = stage(tmp_path, d.subset_samples([0]), sub="base")
+    f1 = stage(tmp_path, d.subset_samples([1, 2]), prefix="x", sub="extra")
+    both(tmp_path, "regions", ["-q", "-o", "regions.txt", "-c", f0["contigs"]] + f0["wigs"], ["regions.txt"])
+    both(tmp_path, "tags_in_regions", ["-f", "regions.txt", "-o", "more.txt", "-c", f0["contigs"]] + f1["wigs"], ["more.txt"])
+    both(tmp_path, "tags_in_regions", ["-f", "regions.txt", "-o", "more2.txt", "-e", "25", "-s", "2,-2", "-c", f0["contigs"]] + f1["wigs"], ["more2.txt"])
+    # a table with '-' rows under -D is refused the same way
+    both(tmp_path, "tags_in_regions", ["-D", "-f", "regions.txt", "-o", "more3.txt", "-c", f0["contigs"]] + f1["wigs"], [], rc=1)
+
+
+@pytest.mark.gpu
+def test_cli_gzip_roundtrip(tmp_path):
+    import gzip
+    d = make_synthetic([200000, 100000], 2, 20000, directional=True, seed=8, peak_spacing=5000, contig_names=["chrA", "chrB"])
+    f = write_inputs(d, str(tmp_path))
+    for w in f["wigs"]:
+        with open(w, "rb") as src, gzip.open(w + ".gz", "wb") as dst:
+            dst.write(src.read())
+    run(BIN, "regions", ["-q", "-o", "plain.txt", "-c", "contigs.txt", "s0.wig", "s1.wig"], str(tmp_path), check=0)
+    run(BIN, "regions", ["-q", "-o", "z.txt.gz", "-c", "contigs.txt", "s0.wig.gz", "s1.wig.gz"], str(tmp_path), check=0)
+    plain = [l for l in (tmp_path / "plain.txt").read_bytes().splitlines() if not l.startswith(b"# align_file")]
+    z = [l for l in gzip.open(tmp_path / "z.txt.gz").read().splitlines() if not l.startswith(b"# align_file")]
+    assert plain == z and len(plain) > 20

@@ -64,7 +64,7 @@ def build_host(force: bool = False) -> None:
         if not force and _newer(exe, srcs + hdrs + [LIB]):
             continue
         cmd = [gxx, "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", exe] + srcs + \
-              ["-L", HERE, "-lunipeak_b200", "-Wl,-rpath," + HERE, "-lz"]
+              ["-L", HERE, "-lunipeak_b200", "-Wl,-rpath,$ORIGIN/../unipeak_b200", "-lz", "-lpthread"]
         subprocess.check_call(cmd, cwd=ROOT)
 
 

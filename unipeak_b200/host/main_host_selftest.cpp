@@ -1,0 +1,49 @@
+// bin/host_selftest — CPU-only checks of the host front end (no device call): the %g formatter against printf, and a dump
+// of what the wiggle reader hands to upb_load_tags, for tests/test_host_cli.py.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+
+#include "upb_host.hpp"
+
+using namespace upbhost;
+
+int main (int argc, char** argv) {
+  if (argc >= 2 && !strcmp(argv[1], "g6")) {
+    const long n = argc > 2 ? atol(argv[2]) : 1000000;
+    std::mt19937_64 rng(12345);
+    long bad = 0;
+    char a[64], b[64];
+    for (long i = 0; i < n; ++i) {
+      double x;
+      switch (i % 4) {
+        case 0: x = std::ldexp((double)(rng() >> 11), (int)(rng() % 100) - 80); break;      // wide range of magnitudes
+        case 1: x = (double)(rng() % 2000000) / 1000.0; break;                              // short decimals (ties after scaling)
+        case 2: x = (double)(rng() % 100000000) * 1e-7; break;
+        default: x = std::exp(((double)(rng() % 2000000) / 1e6 - 1.0) * 30.0); break;
+      }
+      snprintf(a, sizeof a, "%g", x);
+      fast_g6(x, b);
+      if (strcmp(a, b)) { if (++bad < 10) fprintf(stderr, "g6 mismatch: %.17g printf=%s fast=%s\n", x, a, b); }
+    }
+    printf("g6 checked=%ld bad=%ld\n", n, bad);
+    return bad ? 1 : 0;
+  }
+  if (argc >= 4 && !strcmp(argv[1], "wig")) {
+    const ContigTable contigs = parse_contig_table(argv[2]);
+    Sample s;
+    read_wig(argv[3], contigs, argc > 4 ? atoi(argv[4]) : 0, argc > 5 ? (unsigned)atoi(argv[5]) : 0, &s);
+    if (!s.error.empty()) { printf("error\t%s\n", s.error.c_str()); return 0; }
+    printf("name\t%s\nexpected\t%llu\nconfident\t%llu\noob\t%llu\ntotal\t%llu\n", s.name.c_str(), (unsigned long long)s.expectedTags,
+           (unsigned long long)s.confidentTags, (unsigned long long)s.outOfBoundsTags, (unsigned long long)s.totalTags);
+    for (int d = 0; d < 2; ++d)
+      for (uint32_t c = 0; c < contigs.size(); ++c)
+        for (size_t i = 0; i < s.pos[d][c].size(); ++i) printf("%d\t%u\t%u\t%u\n", d, c, s.pos[d][c][i], s.cnt[d][c][i]);
+    return 0;
+  }
+  fprintf(stderr, "usage: host_selftest g6 [n] | wig <contig table> <wig> [offset] [length]\n");
+  return 2;
+}

@@ -1,0 +1,681 @@
+// upb_host.cpp — see upb_host.hpp.  Host-only code: flags, contig table, wiggle reader, number formatting, output files.
+#include "upb_host.hpp"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <cctype>
+#include <cerrno>
+#include <climits>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <sstream>
+#include <thread>
+
+namespace upbhost {
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------------------------
+void die (const std::string& msg) {
+  fflush(stdout);
+  fprintf(stderr, "error: %s\n\n", msg.c_str());
+  exit(1);
+}
+
+void die_upb (upb_ctx* ctx, int code) {
+  const char* m = upb_last_error(ctx);
+  std::string msg = (m && *m) ? m : "device call failed";
+  msg += " (unipeak_b200 error " + std::to_string(code) + ")";
+  die(msg);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// flags: the observable behaviour of TCLAP::CmdLine + StdOutput (misc/tclap/CmdLine.h, StdOutput.h) for the argument kinds
+// the three mains declare.  Unknown "-x" tokens are swallowed by the unlabeled multi-argument, as in the reference.
+// ---------------------------------------------------------------------------------------------------------------------------
+CmdLine::CmdLine (const std::vector<ArgSpec>& specs, const char* unlabeledDesc, const char* unlabeledType)
+    : specs_(specs), unlabeledDesc_(unlabeledDesc), unlabeledType_(unlabeledType) {}
+
+std::string CmdLine::argId (const ArgSpec& a) const { return std::string("Argument: -") + a.flag + " (--" + a.name + ")"; }
+
+// word wrap of StdOutput::spacePrint: break at ' ', ',' or '|', indent the continuation lines further
+static void space_print (FILE* f, const std::string& s, int maxWidth, int indent, int secondLineOffset) {
+  const int len = (int)s.size();
+  if (len + indent <= maxWidth || maxWidth <= 0) { fprintf(f, "%*s%s\n", indent, "", s.c_str()); return; }
+  int allowed = maxWidth - indent, start = 0;
+  while (start < len) {
+    int n = std::min(len - start, allowed);
+    if (n == allowed) while (n >= 0 && s.c_str()[n + start] != ' ' && s.c_str()[n + start] != ',' && s.c_str()[n + start] != '|') --n;
+    if (n <= 0) n = allowed;
+    for (int i = 0; i < n; ++i) if (s[start + i] == '\n') n = i + 1;
+    fprintf(f, "%*s", indent, "");
+    if (start == 0) { indent += secondLineOffset; allowed -= secondLineOffset; }
+    fprintf(f, "%s\n", s.substr(start, n).c_str());
+    while (start < len && s.c_str()[n + start] == ' ') ++start;
+    start += n;
+  }
+}
+
+static std::string short_id (const ArgSpec& a) {
+  std::string id = std::string("-") + a.flag;
+  if (a.kind != ARG_SWITCH) id += std::string(" <") + a.typeDesc + ">";
+  return a.required ? id : "[" + id + "]";
+}
+
+void CmdLine::shortUsage (FILE* f) const {
+  std::string s = prog_ + " ";
+  for (size_t i = specs_.size(); i-- > 0;) s += " " + short_id(specs_[i]);
+  s += " [--] [--version] [-h] <" + unlabeledType_ + "> ...";
+  int second = (int)prog_.size() + 2;
+  if (second > 75 / 2) second = 75 / 2;
+  space_print(f, s, 75, 3, second);
+}
+
+void CmdLine::longUsage (FILE* f) const {
+  for (size_t i = specs_.size(); i-- > 0;) {
+    const ArgSpec& a = specs_[i];
+    std::string id = std::string("-") + a.flag, tail = std::string("--") + a.name;
+    if (a.kind != ARG_SWITCH) { id += std::string(" <") + a.typeDesc + ">"; tail += std::string(" <") + a.typeDesc + ">"; }
+    space_print(f, id + ",  " + tail, 75, 3, 3);
+    space_print(f, std::string(a.required ? "(required)  " : "") + a.desc, 75, 5, 0);
+    fputc('\n', f);
+  }
+  space_print(f, "--,  --ignore_rest", 75, 3, 3);
+  space_print(f, "Ignores the rest of the labeled arguments following this flag.", 75, 5, 0);
+  fputc('\n', f);
+  space_print(f, "--version", 75, 3, 3);
+  space_print(f, "Displays version information and exits.", 75, 5, 0);
+  fputc('\n', f);
+  space_print(f, "-h,  --help", 75, 3, 3);
+  space_print(f, "Displays usage information and exits.", 75, 5, 0);
+  fputc('\n', f);
+  space_print(f, "<" + unlabeledType_ + ">  (accepted multiple times)", 75, 3, 3);
+  space_print(f, "(required)  " + unlabeledDesc_, 75, 5, 0);
+  fputc('\n', f);
+  fputc('\n', f);
+  space_print(f, "See README.TXT for more information", 75, 3, 0);
+}
+
+void CmdLine::failure (const std::string& id, const std::string& what) const {
+  fflush(stdout);
+  fprintf(stderr, "PARSE ERROR: %s\n             %s\n\n", id.c_str(), what.c_str());
+  fprintf(stderr, "Brief USAGE: \n");
+  shortUsage(stderr);
+  fprintf(stderr, "\nFor complete USAGE and HELP type: \n   %s --help\n\n", prog_.c_str());
+  exit(1);
+}
+
+// TCLAP::ValueArg<T>::_extractValue for value-like T: stream extraction, every token must convert, exactly one value
+template <class T> static bool extract_ok (const std::string& val, bool* several) {
+  std::istringstream is(val);
+  T dest;
+  int n = 0;
+  while (is.good()) {
+    if (is.peek() != EOF) is >> dest; else break;
+    ++n;
+  }
+  if (is.fail()) return false;
+  *several = n > 1;
+  return true;
+}
+
+void CmdLine::parse (int argc, char** argv) {
+  prog_ = argc > 0 ? argv[0] : "";
+  bool ignoreRest = false;
+  auto bySpec = [&] (const std::string& tok) -> const ArgSpec* {
+    for (const ArgSpec& a : specs_) {
+      if (tok.size() == 2 && tok[0] == '-' && tok[1] == a.flag) return &a;
+      if (tok.size() > 2 && tok[0] == '-' && tok[1] == '-' && tok.substr(2) == a.name) return &a;
+    }
+    return nullptr;
+  };
+  for (int i = 1; i < argc; ++i) {
+    const std::string tok = argv[i];
+    if (ignoreRest) { unlabeled_.push_back(tok); continue; }
+    if (tok == "--" || tok == "--ignore_rest") { ignoreRest = true; continue; }
+    if (tok == "--version") { printf("\n%s  version: 1.0\n\n", prog_.c_str()); exit(0); }
+    if (tok == "-h" || tok == "--help") {
+      printf("\nUSAGE: \n\n");
+      shortUsage(stdout);
+      printf("\n\nWhere: \n\n");
+      longUsage(stdout);
+      printf("\n");
+      exit(0);
+    }
+    const ArgSpec* a = bySpec(tok);
+    if (a) {
+      if (a->kind == ARG_SWITCH) {
+        if (switches_.count(a->flag)) failure(argId(*a), "Argument already set!");
+        switches_[a->flag] = true;
+        continue;
+      }
+      if (values_.count(a->flag)) failure(argId(*a), "Argument already set!");
+      if (i + 1 >= argc) failure(argId(*a), "Missing a value for this argument!");
+      const std::string val = argv[++i];
+      bool ok = true, several = false;
+      switch (a->kind) {
+        case ARG_U16: ok = extract_ok<unsigned short>(val, &several); break;
+        case ARG_U32: ok = extract_ok<unsigned int>(val, &several); break;
+        case ARG_DOUBLE: ok = extract_ok<double>(val, &several); break;
+        default: break;
+      }
+      if (!ok) failure(argId(*a), "Couldn't read argument value from string '" + val + "'");
+      if (several) failure(argId(*a), "More than one valid value parsed from string '" + val + "'");
+      values_[a->flag] = val;
+      continue;
+    }
+    // combined switches, e.g. -qD
+    if (tok.size() > 2 && tok[0] == '-' && tok[1] != '-') {
+      bool all = true;
+      for (size_t k = 1; k < tok.size() && all; ++k) {
+        bool found = false;
+        for (const ArgSpec& s : specs_) if (s.kind == ARG_SWITCH && s.flag == tok[k]) found = true;
+        all = found;
+      }
+      if (all) { for (size_t k = 1; k < tok.size(); ++k) switches_[tok[k]] = true; continue; }
+    }
+    unlabeled_.push_back(tok);
+  }
+  // required arguments, listed in TCLAP's (reverse-declaration) order; the unlabeled argument has an empty name
+  std::string missing;
+  int nMissing = 0;
+  for (size_t i = specs_.size(); i-- > 0;)
+    if (specs_[i].required && !values_.count(specs_[i].flag)) { missing += std::string(specs_[i].name) + ", "; ++nMissing; }
+  if (unlabeled_.empty()) { missing += ", "; ++nMissing; }
+  if (nMissing > 0)
+    failure(" ", std::string(nMissing > 1 ? "Required arguments missing: " : "Required argument missing: ") + missing.substr(0, missing.size() - 2));
+}
+
+std::string CmdLine::str (char flag, const std::string& dflt) const {
+  auto it = values_.find(flag);
+  return it == values_.end() ? dflt : it->second;
+}
+template <class T> static T extract (const std::string& val) { std::istringstream is(val); T v = T(); is >> v; return v; }
+double CmdLine::dbl (char flag, double dflt) const { auto it = values_.find(flag); return it == values_.end() ? dflt : extract<double>(it->second); }
+uint32_t CmdLine::u32 (char flag, uint32_t dflt) const { auto it = values_.find(flag); return it == values_.end() ? dflt : extract<unsigned int>(it->second); }
+uint16_t CmdLine::u16 (char flag, uint16_t dflt) const { auto it = values_.find(flag); return it == values_.end() ? dflt : extract<unsigned short>(it->second); }
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// lexical_cast / tokenizer behaviour used by the mains
+// ---------------------------------------------------------------------------------------------------------------------------
+std::vector<std::string> split_commas (const std::string& s) {
+  std::vector<std::string> out;
+  size_t i = 0;
+  while (i <= s.size()) {
+    size_t j = s.find(',', i);
+    if (j == std::string::npos) j = s.size();
+    if (j > i) out.push_back(s.substr(i, j - i));
+    i = j + 1;
+  }
+  return out;
+}
+
+bool lexical_short (const std::string& s, short* out) {
+  if (s.empty() || isspace((unsigned char)s[0])) return false;
+  errno = 0;
+  char* end = nullptr;
+  const long v = strtol(s.c_str(), &end, 10);
+  if (errno || end == s.c_str() || *end != '\0' || v < SHRT_MIN || v > SHRT_MAX) return false;
+  *out = (short)v;
+  return true;
+}
+
+bool lexical_double (const std::string& s, double* out) {
+  if (s.empty() || isspace((unsigned char)s[0])) return false;
+  char* end = nullptr;
+  const double v = strtod(s.c_str(), &end);
+  if (end == s.c_str() || *end != '\0') return false;
+  *out = v;
+  return true;
+}
+
+bool lexical_u32 (const char* s, size_t n, uint32_t* out) {
+  size_t i = 0;
+  if (n && s[0] == '+') i = 1;
+  if (i >= n) return false;
+  uint64_t v = 0;
+  for (; i < n; ++i) {
+    const unsigned d = (unsigned)s[i] - '0';
+    if (d > 9) return false;
+    v = v * 10 + d;
+    if (v > 0xFFFFFFFFull) return false;
+  }
+  *out = (uint32_t)v;
+  return true;
+}
+
+std::vector<short> parse_offsets (const std::string& s, size_t nFiles) {
+  std::vector<short> offsets;
+  if (s.empty()) return offsets;
+  for (const std::string& tok : split_commas(s)) {
+    short v;
+    if (!lexical_short(tok, &v)) { fprintf(stderr, "error: bad offset argument\n\n"); exit(1); }
+    offsets.push_back(v);
+  }
+  if (!(offsets.size() == nFiles || offsets.size() == 1)) {
+    fprintf(stderr, "error: wrong number of offset arguments\nmust have same number as alignment files or just one\n\n");
+    exit(1);
+  }
+  return offsets;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// whole-file reader (InStream, misc/filterstream.cpp:30-50): plain, gzip by suffix, "stdin"
+// ---------------------------------------------------------------------------------------------------------------------------
+static bool ends_with (const std::string& s, const char* suf) {
+  const size_t n = strlen(suf);
+  return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+}
+
+static bool slurp (const std::string& fname, std::vector<char>* buf, std::string* shownName, std::string* err) {
+  buf->clear();
+  *shownName = fname;
+  if (fname == "stdin") {
+    *shownName = "standard input stream";
+    char tmp[1 << 16];
+    size_t k;
+    while ((k = fread(tmp, 1, sizeof tmp, stdin)) > 0) buf->insert(buf->end(), tmp, tmp + k);
+    return true;
+  }
+  if (ends_with(fname, ".bz2")) { *err = "bzip2 input is not supported by this build (no bzlib.h): " + fname; return false; }
+  if (ends_with(fname, ".gz")) {
+    gzFile g = gzopen(fname.c_str(), "rb");
+    if (!g) { *err = "could not read " + fname; return false; }
+    gzbuffer(g, 1 << 20);
+    std::vector<char> tmp(1 << 22);
+    int k;
+    while ((k = gzread(g, tmp.data(), (unsigned)tmp.size())) > 0) buf->insert(buf->end(), tmp.begin(), tmp.begin() + k);
+    gzclose(g);
+    return true;
+  }
+  FILE* f = fopen(fname.c_str(), "rb");
+  if (!f) { *err = "could not read " + fname; return false; }
+  if (fseek(f, 0, SEEK_END) == 0) {
+    const long sz = ftell(f);
+    if (sz > 0) buf->reserve((size_t)sz);
+    fseek(f, 0, SEEK_SET);
+  }
+  std::vector<char> tmp(1 << 22);
+  size_t k;
+  while ((k = fread(tmp.data(), 1, tmp.size(), f)) > 0) buf->insert(buf->end(), tmp.begin(), tmp.begin() + k);
+  fclose(f);
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// contig table (misc/format.cpp:27-57; CONTIG_TABLE_REGEX "^(\w+)\W+(\d+)", misc/format.hpp:22)
+// ---------------------------------------------------------------------------------------------------------------------------
+static inline bool is_word (char c) { return isalnum((unsigned char)c) || c == '_'; }
+
+ContigTable parse_contig_table (const std::string& fname) {
+  fprintf(stderr, "reading %s... ", fname.c_str());
+  fflush(stderr);
+  ContigTable t;
+  std::vector<char> buf;
+  std::string shown, err;
+  if (!slurp(fname, &buf, &shown, &err)) { fprintf(stderr, "error: %s\n\n", err.c_str()); exit(1); }
+  size_t p = 0;
+  while (p < buf.size()) {
+    const char* nl = (const char*)memchr(buf.data() + p, '\n', buf.size() - p);
+    const size_t e = nl ? (size_t)(nl - buf.data()) : buf.size();
+    const char* s = buf.data() + p;
+    const size_t len = e - p;
+    p = e + 1;
+    if (!len || s[0] == '#') continue;
+    size_t i = 0;
+    while (i < len && is_word(s[i])) ++i;
+    if (i == 0) continue;
+    size_t j = i;
+    while (j < len && !is_word(s[j])) ++j;
+    if (j == i) continue;
+    size_t k = j;
+    while (k < len && isdigit((unsigned char)s[k])) ++k;
+    if (k == j) continue;
+    const std::string name(s, i);
+    uint32_t size;
+    if (!lexical_u32(s + j, k - j, &size)) die("bad contig size for " + name + " in " + fname);
+    if (t.index.count(name)) { fprintf(stderr, "error: %s defined twice in contig table\n\n", name.c_str()); exit(1); }
+    t.index[name] = t.size();
+    t.names.push_back(name);
+    t.sizes.push_back(size);
+  }
+  if (t.size() == 0) { fprintf(stderr, "error: no contigs in table\n\n"); exit(1); }
+  fprintf(stderr, "%u contigs\n", t.size());
+  return t;
+}
+
+std::string fname_prefix (const std::string& name) {
+  std::string r = name;
+  const size_t slash = r.rfind('/');
+  if (slash != std::string::npos) r = r.substr(slash + 1);
+  const size_t dot = r.find('.');
+  if (dot != std::string::npos) r = r.substr(0, dot);
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// tag-frequency wiggle (misc/format.cpp:242-286 format detection, :503-565 the two wiggle cases, :654-678 offset and
+// bounds, :737-766 the "# tags=" header).  The reference streams one Alignment at a time into the merge loop; here the
+// whole file becomes per-(strand, contig) arrays, which is what the device path consumes.
+// ---------------------------------------------------------------------------------------------------------------------------
+// NAME_REGEX1 name="(.+?)"  /  NAME_REGEX2 name=(.+?)<space>   (misc/format.hpp:31-32)
+static bool match_name (const char* s, size_t len, const char* open, char closer, std::string* out) {
+  const size_t lo = strlen(open);
+  for (size_t p = 0; p + lo < len; ++p) {
+    if (memcmp(s + p, open, lo) != 0) continue;
+    for (size_t q = p + lo + 1; q < len; ++q)
+      if (s[q] == closer) { out->assign(s + p + lo, q - p - lo); return true; }
+  }
+  return false;
+}
+
+// DIRECTIONAL_WIG_NAME_REGEX "(.+) ([+-])" searched in the track name: the last " +"/" -" that has a character before it
+static bool split_directional (const std::string& name, std::string* base, bool* forward) {
+  for (size_t i = name.size(); i-- > 1;)
+    if (name[i] == ' ' && i + 1 < name.size() && (name[i + 1] == '+' || name[i + 1] == '-')) {
+      *base = name.substr(0, i);
+      *forward = name[i + 1] == '+';
+      return true;
+    }
+  return false;
+}
+
+static std::string line_error (const std::string& msg, const std::string& shown, uint64_t lineNo) {
+  return msg + " in " + shown + " line " + std::to_string(lineNo);
+}
+
+void read_wig (const std::string& fname, const ContigTable& contigs, int offset, unsigned useLength, Sample* out) {
+  Sample& S = *out;
+  S = Sample();
+  S.fname = fname;
+  S.name = fname_prefix(fname);
+  const uint32_t C = contigs.size();
+  for (int d = 0; d < 2; ++d) { S.pos[d].assign(C, std::vector<uint32_t>()); S.cnt[d].assign(C, std::vector<uint32_t>()); }
+  std::vector<char> buf;
+  std::string shown;
+  if (!slurp(fname, &buf, &shown, &S.error)) return;
+
+  int format = 0;                   // 0 unknown, 6 directional wiggle, 7 non-directional wiggle
+  bool forward = true;
+  uint32_t contig = 0;              // ParseAlignStream::open resets the Alignment to contig 0 (misc/format.cpp:122-127)
+  bool inHeader = true;             // getExpectedTags only looks at the '#' lines before the first other line
+  uint64_t lineNo = 0;
+  long lastKey = -1;                // (strand, contig) blocks must come in stream order
+  std::vector<uint32_t>* vp = nullptr;
+  std::vector<uint32_t>* vc = nullptr;
+  const char* base = buf.data();
+  size_t p = 0;
+  const size_t N = buf.size();
+  // InStream::good() is still true after the last '\n', so the reference reads one more (empty) line; it changes nothing
+  while (p < N) {
+    const char* nl = (const char*)memchr(base + p, '\n', N - p);
+    const size_t e = nl ? (size_t)(nl - base) : N;
+    const char* s = base + p;
+    const size_t len = e - p;
+    p = e + 1;
+    ++lineNo;
+    if (len == 0) { inHeader = false; continue; }              // an empty line ends getExpectedTags' header scan too
+    if (s[0] == '#') {
+      if (inHeader) {
+        // TAG_COUNT_REGEX "# tags=(\d+)" anywhere in the line
+        const std::string line(s, len);
+        size_t q = 0;
+        while ((q = line.find("# tags=", q)) != std::string::npos) {
+          size_t k = q + 7;
+          while (k < line.size() && isdigit((unsigned char)line[k])) ++k;
+          if (k > q + 7) {
+            if (S.expectedTags != 0) { S.error = line_error("multiple tag count headers", shown, lineNo); return; }
+            S.expectedTags = strtoull(line.c_str() + q + 7, nullptr, 10);
+            if (S.expectedTags == 0) { S.error = line_error("zero tag count", shown, lineNo); return; }
+            break;
+          }
+          ++q;
+        }
+      }
+      continue;
+    }
+    inHeader = false;
+    if (format == 0) {
+      if (len >= 5 && memcmp(s, "track", 5) == 0) {
+        std::string nm;
+        const bool named = match_name(s, len, "name=\"", '"', &nm) || match_name(s, len, "name=", ' ', &nm);
+        if (named) S.name = nm;
+        const std::string line(s, len);
+        if (line.find("type=wiggle_0") == std::string::npos) {
+          S.error = fname + " is not a tag-frequency wiggle file; this build reads only the output of convert_align";
+          return;
+        }
+        std::string b;
+        bool f;
+        if (split_directional(S.name, &b, &f)) { format = 6; S.name = b; forward = f; }
+        else { format = 7; S.name = named ? nm : std::string(); forward = true; }
+        continue;
+      }
+      S.error = fname + " is not a tag-frequency wiggle file; this build reads only the output of convert_align";
+      return;
+    }
+    if (isdigit((unsigned char)s[0])) {
+      if (contig == C) continue;                                   // contig not in the table: skipped
+      size_t delim = len;
+      while (delim-- > 0) if (s[delim] == '\t' || s[delim] == ' ') break;
+      if (delim == (size_t)-1) { S.error = line_error("bad format", shown, lineNo); return; }
+      uint32_t first, count;
+      const size_t cs = delim + ((delim + 1 < len && s[delim + 1] == '-') ? 2 : 1);
+      if (!lexical_u32(s, delim, &first) || cs > len || !lexical_u32(s + cs, len - cs, &count)) { S.error = line_error("bad format", shown, lineNo); return; }
+      S.totalTags += count;
+      if (count == 0) continue;
+      uint32_t last = first;
+      if (useLength != 0) last = forward ? first + (useLength - 1) : first - (useLength - 1);
+      if (offset != 0) {
+        if ((forward && (int)first > -offset) || (!forward && (int)last > offset)) {
+          first += (uint32_t)(forward ? offset : -offset);
+          last += (uint32_t)(forward ? offset : -offset);
+        } else { S.outOfBoundsTags += count; continue; }
+      }
+      const uint32_t size = contigs.sizes[contig];
+      if (first == 0 || first > size || last == 0 || last > size) { S.outOfBoundsTags += count; continue; }
+      S.confidentTags += count;
+      if (!vp) {
+        const long key = (long)(forward ? 0 : 1) * (long)C + contig;
+        if (key <= lastKey) { S.error = "alignments out of order in " + shown + " line " + std::to_string(lineNo) + " (strand/contig blocks must follow the contig table, '+' track first)"; return; }
+        lastKey = key;
+        vp = &S.pos[forward ? 0 : 1][contig];
+        vc = &S.cnt[forward ? 0 : 1][contig];
+      }
+      if (!vp->empty() && first <= vp->back()) {
+        if (first == vp->back()) { vc->back() += count; continue; }   // the merge loop adds up equal positions (src/regions.cpp:341-350)
+        S.error = line_error("alignments out of order", shown, lineNo);
+        return;
+      }
+      vp->push_back(first);
+      vc->push_back(count);
+      continue;
+    }
+    if (len > 19 && memcmp(s, "variableStep chrom=", 19) == 0) {
+      contig = contigs.find(std::string(s + 19, len - 19));
+      vp = vc = nullptr;
+      continue;
+    }
+    if (len >= 5 && memcmp(s, "track", 5) == 0) {
+      std::string nm;
+      if (match_name(s, len, "name=\"", '"', &nm)) {
+        contig = C;
+        vp = vc = nullptr;
+        if (format == 6) {
+          std::string b;
+          bool f;
+          if (!split_directional(nm, &b, &f)) { S.error = line_error("strand not defined", shown, lineNo); return; }
+          S.name = b;
+          forward = f;
+        } else {
+          S.name = nm;
+        }
+        continue;
+      }
+    }
+    S.error = line_error("bad format", shown, lineNo);
+    return;
+  }
+  if (S.expectedTags == 0) S.expectedTags = S.confidentTags;       // "count tags the hard way", misc/format.cpp:754-758
+}
+
+std::vector<Sample> read_samples (const std::vector<std::string>& fnames, const ContigTable& contigs,
+                                  const std::vector<short>& offsets, unsigned useLength) {
+  std::vector<Sample> samples(fnames.size());
+  unsigned nThreads = std::thread::hardware_concurrency();
+  if (nThreads == 0) nThreads = 4;
+  nThreads = std::min<unsigned>(nThreads, (unsigned)fnames.size());
+  int nStdin = 0;
+  for (const std::string& f : fnames) nStdin += f == "stdin";
+  if (nStdin) nThreads = 1;
+  std::vector<std::thread> pool;
+  for (unsigned t = 0; t < nThreads; ++t)
+    pool.emplace_back([&, t] () {
+      for (size_t i = t; i < fnames.size(); i += nThreads) {
+        const int off = offsets.empty() ? 0 : (offsets.size() > 1 ? offsets[i] : offsets[0]);
+        read_wig(fnames[i], contigs, off, useLength, &samples[i]);
+      }
+    });
+  for (std::thread& th : pool) th.join();
+  return samples;
+}
+
+Flat::~Flat () {
+  if (pinned) { upb_host_free(pos); upb_host_free(cnt); } else { free(pos); free(cnt); }
+}
+
+void flatten (const std::vector<Sample>& samples, uint32_t C, Flat* out) {
+  const size_t n = samples.size();
+  out->off.assign(n * 2 * ((size_t)C + 1), 0);
+  uint64_t run = 0;
+  for (size_t s = 0; s < n; ++s)
+    for (int d = 0; d < 2; ++d) {
+      uint64_t* o = &out->off[(s * 2 + d) * ((size_t)C + 1)];
+      for (uint32_t c = 0; c < C; ++c) { o[c] = run; run += samples[s].pos[d][c].size(); }
+      o[C] = run;
+    }
+  out->n = run;
+  const size_t bytes = (size_t)(run ? run : 1) * 4;
+  void *pp = nullptr, *pc = nullptr;
+  if (upb_host_alloc(&pp, bytes) == UPB_OK && upb_host_alloc(&pc, bytes) == UPB_OK) out->pinned = true;
+  else { if (pp) upb_host_free(pp); pp = malloc(bytes); pc = malloc(bytes); out->pinned = false; }
+  if (!pp || !pc) die("out of host memory");
+  out->pos = (uint32_t*)pp;
+  out->cnt = (uint32_t*)pc;
+  for (size_t s = 0; s < n; ++s)
+    for (int d = 0; d < 2; ++d) {
+      const uint64_t* o = &out->off[(s * 2 + d) * ((size_t)C + 1)];
+      for (uint32_t c = 0; c < C; ++c) {
+        const std::vector<uint32_t>& vp = samples[s].pos[d][c];
+        if (vp.empty()) continue;
+        memcpy(out->pos + o[c], vp.data(), vp.size() * 4);
+        memcpy(out->cnt + o[c], samples[s].cnt[d][c].data(), vp.size() * 4);
+      }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// number formatting
+// ---------------------------------------------------------------------------------------------------------------------------
+std::string fmt_lexical (double x) { char b[64]; snprintf(b, sizeof b, "%.17g", x); return b; }
+std::string fmt_g (double x) { char b[64]; snprintf(b, sizeof b, "%g", x); return b; }
+std::string fmt_fixed (double x, int digits) { char b[400]; snprintf(b, sizeof b, "%.*f", digits, x); return b; }
+
+// %g with the default precision 6 for a finite, non-negative double — the profile wiggle writes one per non-zero position
+// (misc/format.cpp:1112-1129), so it is worth not going through printf: scale to a 6-digit integer, round half to even on
+// the exact value (via long double / fma-free remainder check), strip trailing zeros.  Falls back to snprintf in the rare
+// cases where the fast scaling cannot guarantee printf's correctly rounded result.
+int fast_g6 (double x, char* buf) {
+  if (!(x > 0) || !std::isfinite(x) || x < 1e-4 || x >= 1e15) return snprintf(buf, 32, "%g", x);
+  // decimal exponent e with 10^e <= x < 10^(e+1)
+  int e = (int)std::floor(std::log10(x));
+  static const double P10[] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+  auto scaled = [&] (int ee) -> long double {                      // x * 10^(5-ee) in extended precision (64-bit mantissa)
+    const int k = 5 - ee;
+    return k >= 0 ? (long double)x * (long double)P10[k] : (long double)x / (long double)P10[-k];
+  };
+  long double v = scaled(e);
+  if (v < 100000.0L) { --e; v = scaled(e); } else if (v >= 1000000.0L) { ++e; v = scaled(e); }
+  const long double fl = std::floor(v);
+  const long double frac = v - fl;
+  // the extended product carries ~1e-19 relative error; anything that close to a tie goes to printf
+  if (std::fabs((double)(frac - 0.5L)) < 1e-9) return snprintf(buf, 32, "%g", x);
+  long m = (long)fl + (frac > 0.5L ? 1 : 0);
+  if (m >= 1000000) { m /= 10; ++e; }
+  if (e < -4 || e >= 6) {
+    // scientific: d.ddddde+XX with trailing zeros removed
+    char digits[8];
+    for (int i = 5; i >= 0; --i) { digits[i] = (char)('0' + m % 10); m /= 10; }
+    int nd = 6;
+    while (nd > 1 && digits[nd - 1] == '0') --nd;
+    char* o = buf;
+    *o++ = digits[0];
+    if (nd > 1) { *o++ = '.'; for (int i = 1; i < nd; ++i) *o++ = digits[i]; }
+    *o++ = 'e';
+    *o++ = e < 0 ? '-' : '+';
+    const int ae = e < 0 ? -e : e;
+    if (ae >= 100) { *o++ = (char)('0' + ae / 100); }
+    *o++ = (char)('0' + (ae / 10) % 10);
+    *o++ = (char)('0' + ae % 10);
+    *o = 0;
+    return (int)(o - buf);
+  }
+  char digits[8];
+  for (int i = 5; i >= 0; --i) { digits[i] = (char)('0' + m % 10); m /= 10; }
+  char* o = buf;
+  if (e >= 0) {
+    for (int i = 0; i <= e; ++i) *o++ = digits[i];
+    int nd = 6;
+    while (nd > e + 1 && digits[nd - 1] == '0') --nd;
+    if (nd > e + 1) { *o++ = '.'; for (int i = e + 1; i < nd; ++i) *o++ = digits[i]; }
+  } else {
+    *o++ = '0'; *o++ = '.';
+    for (int i = -1; i > e; --i) *o++ = '0';
+    int nd = 6;
+    while (nd > 1 && digits[nd - 1] == '0') --nd;
+    for (int i = 0; i < nd; ++i) *o++ = digits[i];
+  }
+  *o = 0;
+  return (int)(o - buf);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// output file
+// ---------------------------------------------------------------------------------------------------------------------------
+Out::Out (const std::string& fname) {
+  buf_.reserve(1 << 20);
+  if (fname == "stdout") { f_ = stdout; isStdout_ = true; return; }
+  if (ends_with(fname, ".bz2")) die("bzip2 output is not supported by this build (no bzlib.h): " + fname);
+  if (ends_with(fname, ".gz")) {
+    gz_ = gzopen(fname.c_str(), "wb");
+    if (!gz_) { fprintf(stderr, "error: could not write %s\n\n", fname.c_str()); exit(1); }
+    return;
+  }
+  f_ = fopen(fname.c_str(), "wb");
+  if (!f_) { fprintf(stderr, "error: could not write %s\n\n", fname.c_str()); exit(1); }
+}
+
+void Out::flush () {
+  if (buf_.empty()) return;
+  if (gz_) gzwrite((gzFile)gz_, buf_.data(), (unsigned)buf_.size());
+  else if (f_) fwrite(buf_.data(), 1, buf_.size(), f_);
+  buf_.clear();
+}
+
+void Out::write (const char* p, size_t n) {
+  if (buf_.size() + n > (1u << 20)) flush();
+  if (n > (1u << 20)) { if (gz_) gzwrite((gzFile)gz_, p, (unsigned)n); else if (f_) fwrite(p, 1, n, f_); return; }
+  buf_.insert(buf_.end(), p, p + n);
+}
+
+void Out::close () {
+  flush();
+  if (gz_) { gzclose((gzFile)gz_); gz_ = nullptr; }
+  if (f_) { if (isStdout_) fflush(f_); else fclose(f_); f_ = nullptr; }
+}
+
+Out::~Out () { close(); }
+
+}  // namespace upbhost
