@@ -47,7 +47,7 @@ struct upb_ctx {
   std::vector<uint64_t> off;            // host copy
   std::vector<uint32_t> firstPos, lastPos;   // [(s*2+d)*C + c], 0 if empty
   DevBuf d_pos, d_cnt, d_off, d_segStart, d_tidx, d_tidxBase, d_sizes, d_nTilesIdx, d_small;
-  DevBuf d_ment, d_mtOff, d_mtBase, d_mtCount, d_mEff, d_mtW;   // tile-major copy (upb_device.cuh)
+  DevBuf d_ment, d_mtOff, d_mtBase, d_mtCount, d_mEff, d_mtW, d_blkW;   // tile-major copy and its zone maps (upb_device.cuh)
   std::vector<uint32_t> mtBase;         // [2*C+1]
   std::map<std::string, DevBuf> scratch;     // grow-only device scratch, by name
   unsigned char* h_small = nullptr;          // 4 KB of pinned host memory for small read-backs
@@ -115,7 +115,7 @@ extern "C" int upb_create (int device, upb_ctx** out) {
 extern "C" void upb_destroy (upb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  DevBuf* all[] = {&ctx->d_mtW, &ctx->d_ment, &ctx->d_mtOff, &ctx->d_mtBase, &ctx->d_mtCount, &ctx->d_mEff, &ctx->d_pos, &ctx->d_cnt, &ctx->d_off, &ctx->d_segStart, &ctx->d_tidx, &ctx->d_tidxBase, &ctx->d_sizes,
+  DevBuf* all[] = {&ctx->d_mtW, &ctx->d_blkW, &ctx->d_ment, &ctx->d_mtOff, &ctx->d_mtBase, &ctx->d_mtCount, &ctx->d_mEff, &ctx->d_pos, &ctx->d_cnt, &ctx->d_off, &ctx->d_segStart, &ctx->d_tidx, &ctx->d_tidxBase, &ctx->d_sizes,
     &ctx->d_nTilesIdx, &ctx->d_small};
   for (DevBuf* b : all) release(*b);
   for (auto& kv : ctx->scratch) release(kv.second);
@@ -202,6 +202,7 @@ static Tags make_tags (const upb_ctx* ctx, bool useEff) {
   T.mtBase = ctx->d_mtBase.as<uint32_t>();
   T.mEff = useEff ? ctx->d_mEff.as<uint32_t>() : nullptr;
   T.mtW = ctx->d_mtW.as<unsigned long long>();
+  T.blkW = ctx->d_blkW.as<float>();
   T.off = ctx->d_off.as<uint64_t>();
   T.tidx = ctx->d_tidx.as<uint32_t>();
   T.tidxBase = ctx->d_tidxBase.as<uint32_t>();
@@ -272,13 +273,12 @@ extern "C" int upb_load_tags (upb_ctx* ctx, uint32_t n_samples, const uint64_t* 
   ENSURE(ctx->d_mtOff, ((size_t)nMtTotal + 2) * 8);
   ENSURE(ctx->d_ment, (E ? E : 1) * 8);
   ENSURE(ctx->d_mtW, ((size_t)nMtTotal + 1) * 8);
-  CU(cudaMemsetAsync(ctx->d_mtW.p, 0, ((size_t)nMtTotal + 1) * 8, ctx->stream));
+  ENSURE(ctx->d_blkW, ((size_t)nMtTotal + 1) * BLK_PER_MT * 4);
   CU(cudaMemcpyAsync(ctx->d_mtBase.p, ctx->mtBase.data(), (2 * (size_t)C + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemsetAsync(ctx->d_mtCount.p, 0, ((size_t)nMtTotal + 1) * 4, ctx->stream));
   {
     MtArgs ma;
     ma.pos = ctx->d_pos.as<uint32_t>(); ma.cnt = ctx->d_cnt.as<uint32_t>(); ma.segStart = ctx->d_segStart.as<uint64_t>(); ma.mtBase = ctx->d_mtBase.as<uint32_t>();
-    ma.mtW = ctx->d_mtW.as<unsigned long long>();
     ma.mtCount = ctx->d_mtCount.as<uint32_t>(); ma.mtOff = ctx->d_mtOff.as<unsigned long long>(); ma.ment = ctx->d_ment.as<uint2>();
     ma.sizes = ctx->d_sizes.as<uint32_t>(); ma.flags = ctx->d_small.as<uint32_t>();
     ma.C = C; ma.nSeg = nSeg; ma.nEntries = E;
@@ -290,6 +290,9 @@ extern "C" int upb_load_tags (upb_ctx* ctx, uint32_t n_samples, const uint64_t* 
     if (r) return r;
     CU(cudaMemcpyAsync(ctx->d_mtOff.as<unsigned long long>() + nMtTotal, d_tot, 8, cudaMemcpyDeviceToDevice, ctx->stream));
     if (E) mt_build_kernel<true><<<(unsigned)blocks, 256, 0, ctx->stream>>>(ma);
+    // zone maps (per mini-tile and per 32-position block) from the sorted copy
+    mt_zone_kernel<<<(nMtTotal + 7) / 8, 256, 0, ctx->stream>>>(ctx->d_ment.as<uint2>(), ctx->d_mtOff.as<unsigned long long>(), nMtTotal,
+                                                               ctx->d_mtW.as<unsigned long long>(), ctx->d_blkW.as<float>());
     CU(cudaGetLastError());
   }
   uint32_t flags = 0;
@@ -667,26 +670,22 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
   sa.thr = cfg.thr;
   const double kmax = pr.taps[cfg.bw];                                // K(0) = 0.75 * scale
   {
-    // cold-block bound: for bin q of a block's window, the largest tap any (cell of the bin, position of the block) pair can
-    // have; cell u, position index i: tag offset d = u - i - bw with u in [16q, 16q+15], i in [0, 31]
-    const int bwI = (int)cfg.bw, nbw = ((31 + 2 * bwI) >> BIN_SHIFT) + 1, bin = 1 << BIN_SHIFT;
-    std::vector<double> hc(nbw);
-    for (int q = 0; q < nbw; ++q) {
-      const int lo = bin * q - 31 - bwI, hi = bin * q + bin - 1 - bwI;
-      const int m = (lo <= 0 && hi >= 0) ? 0 : std::min(std::abs(lo), std::abs(hi));
-      hc[q] = m > bwI ? 0.0 : pr.taps[bwI - m] * (1.0 + pr.maxCoeff) * (1.0 + 1e-9);   // -z: a count c weighs at most c*(coeff+1)
+    // cold-block bound: a tag j blocks (of 32 positions) away from block B is at least 32(|j|-1)+1 positions from every position of
+    // B (0 for j = 0); blocks further than J = (bw-2)/32+1 away cannot reach it (the taps at +-bw are exactly 0, misc/kernel.cpp:12-14)
+    const int bwI = (int)cfg.bw, J = bwI >= 2 ? (bwI - 2) / 32 + 1 : 0;
+    std::vector<float> hf(J + 1);
+    for (int j = 0; j <= J; ++j) {
+      const int m = j == 0 ? 0 : 32 * (j - 1) + 1;
+      const double hc = pr.taps[bwI - m] * (1.0 + pr.maxCoeff) * (1.0 + 1e-9);   // -z: a count c weighs at most c*(coeff+1)
+      hf[j] = std::nextafter((float)(hc * (1.0 + 1e-5)), INFINITY);              // float sum of <= 58 terms: 1e-5 covers its rounding
     }
-    std::vector<float> hf(nbw);
-    for (int q = 0; q < nbw; ++q) hf[q] = std::nextafter((float)(hc[q] * (1.0 + 1e-5)), INFINITY);   // float sum of <= 58 terms: 1e-5 covers its rounding
-    double* d_hc = SCR("hotCoef", double, nbw);
-    float* d_hf = SCR("hotCoefF", float, nbw);
-    CU(cudaMemcpyAsync(d_hc, hc.data(), (size_t)nbw * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(d_hf, hf.data(), (size_t)nbw * 4, cudaMemcpyHostToDevice, ctx->stream));
+    float* d_hf = SCR("hotCoefF", float, J + 1);
+    CU(cudaMemcpyAsync(d_hf, hf.data(), (size_t)(J + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    sa.hotCoef = d_hc; sa.hotCoefF = d_hf;
+    sa.hotCoefF = d_hf; sa.hotJ = (uint32_t)J;
     sa.thrLow = std::nextafter((float)cfg.thr, -INFINITY);
-    sa.flatBound = kmax * (1.0 + pr.maxCoeff) * (1.0 + 1e-9);
   }
+  const double flatBound = kmax * (1.0 + pr.maxCoeff) * (1.0 + 1e-9);  // largest tap: maxTap * window weight bounds every score (zone-map prefilter)
   sa.coeff = pr.d_coeffBySample;
   sa.cN = kmax / ((double)cfg.bw * (double)cfg.bw);
   sa.dS = kmax * 1e-11;                                               // >= 100x the worst-case rounding difference between the two forms
@@ -744,7 +743,7 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
     sa.runs = SCR("runs", SpanRun, runCap);
     sa.runCap = (uint32_t)std::min<size_t>(runCap, 0xFFFFFFF0u);
     CU(cudaMemsetAsync(ctx->d_small.p, 0, 256, ctx->stream));
-    wa.flatBound = sa.flatBound; wa.thr = cfg.thr;
+    wa.flatBound = flatBound; wa.thr = cfg.thr;
     warm_span_kernel<<<(pr.totalSpans + 255) / 256, 256, 0, ctx->stream>>>(wa);
     launches += 1;
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));

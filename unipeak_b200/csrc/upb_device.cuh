@@ -42,6 +42,8 @@ struct Tags {                       // resident tag-frequency data (see upb_load
   const unsigned long long* mtOff;  // [nMtTotal + 1] first entry of every mini-tile
   const uint32_t* mtBase;           // [2*C + 1] first mini-tile of (strand d, contig c) at d*C + c
   const unsigned long long* mtW;    // [nMtTotal] zone map: total count (all samples) per mini-tile — lets whole spans be skipped
+  const float* blkW;                // [nMtTotal * 16] fine zone map: total count (all samples) per 32-position block, rounded UP to float
+                                    //   (+inf where a 32-bit sum could have wrapped) — hot blocks are found without touching the entries
   const uint32_t* mEff;             // [E] counts with the control tags the reference forgets zeroed (Q4); NULL when no controls
   const uint64_t* off;              // [(s*2+d)*(C+1)+c]
   const uint32_t* tidx;             // per (s,d): tidxStride entries; per contig: nTiles0+3 entries
@@ -150,7 +152,6 @@ struct MtArgs {
   const uint64_t* segStart;         // [nSeg+1]
   const uint32_t* mtBase;           // [2*C+1]
   uint32_t* mtCount;                // [nMtTotal] histogram, then per-tile cursors
-  unsigned long long* mtW;          // [nMtTotal] zone map: total count of all samples' entries in the mini-tile
   const unsigned long long* mtOff;  // [nMtTotal+1]
   uint2* ment;
   const uint32_t* sizes;            // [C]
@@ -167,7 +168,7 @@ __device__ __forceinline__ uint32_t seg_of_entry (const uint64_t* __restrict__ s
 
 // Pass 1 (SCATTER = false) validates what the reference's parser guarantees (positions inside the contig and strictly
 // ascending per (sample, strand, contig), non-zero counts: misc/format.cpp:654-710, misc/peakcall.cpp:171) and builds
-// the per-mini-tile histogram and zone map; pass 2 scatters.  Entries that fail validation are never used as indices.
+// the per-mini-tile histogram; pass 2 scatters (the zone maps are built from the sorted copy by mt_zone_kernel).  Entries that fail validation are never used as indices.
 template <bool SCATTER>
 __global__ void mt_build_kernel (MtArgs a) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -189,11 +190,37 @@ __global__ void mt_build_kernel (MtArgs a) {
     if (i > a.segStart[g] && a.pos[i - 1] >= pos1) f |= FLAG_UNSORTED;
     if (f) atomicOr(a.flags, f);
     atomicAdd(&a.mtCount[mt], 1u);
-    atomicAdd(&a.mtW[mt], (unsigned long long)k);
     return;
   }
   const unsigned long long slot = a.mtOff[mt] + (atomicSub(&a.mtCount[mt], 1u) - 1u);
   a.ment[slot] = make_uint2(a.cnt[i], (s << SPAN_SHIFT) | (p & (SPAN_LEN - 1)));
+}
+
+// Zone maps of the tile-major copy, one warp per mini-tile: mtW[m] = total count of the mini-tile (all samples), blkW[16m + j] =
+// total count of its j-th 32-position block as a float rounded up.  Both only ever feed upper bounds (a span / block whose
+// bound stays below the threshold is never evaluated), so rounding up and +inf for sums that could wrap are safe.
+constexpr int BLK_PER_MT = 1 << (MT_SHIFT - 5);
+__global__ void mt_zone_kernel (const uint2* __restrict__ ment, const unsigned long long* __restrict__ mtOff, uint32_t nMt,
+                                unsigned long long* __restrict__ mtW, float* __restrict__ blkW) {
+  __shared__ uint32_t acc[8][BLK_PER_MT];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t m = blockIdx.x * 8 + warp;
+  if (m >= nMt) return;
+  if (lane < BLK_PER_MT) acc[warp][lane] = 0;
+  __syncwarp();
+  const unsigned long long e0 = mtOff[m], e1 = mtOff[m + 1];
+  unsigned long long tot = 0;
+  for (unsigned long long e = e0 + lane; e < e1; e += 32) {
+    const uint2 x = __ldg(ment + e);
+    tot += x.x;
+    atomicAdd(&acc[warp][(x.y >> 5) & (BLK_PER_MT - 1)], x.x);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+  __syncwarp();
+  const bool wrap = tot > 0xFFFFFFFFull;                              // a block's 32-bit sum may have wrapped: call all of them unbounded
+  if (lane == 0) mtW[m] = tot;
+  if (lane < BLK_PER_MT) blkW[(size_t)m * BLK_PER_MT + lane] = wrap ? __int_as_float(0x7f800000) : __uint2float_ru(acc[warp][lane]);
 }
 
 // control filter: a control sample's tag is remembered by the reference only when the same add()

@@ -6,15 +6,14 @@
 // path: the warps of a CTA only share the read-only tap table.  (v2 of this kernel gave a whole CTA one
 // 16384-position span and lost 63 % of its issue slots at __syncthreads — profiles/r01_v2_*.)
 //
-//   phase A  the span's tag entries — ONE contiguous chunk of the tile-major copy built at load time
-//            (upb_device.cuh mt_build_kernel), plus one 512-position mini-tile of halo on either side — are
-//            read once, coalesced, 8 bytes per entry, and the density sources (non-control samples) are
-//            pooled into 8-position bins in shared memory (shared-memory atomics
-//            run at ~8 lane-ops/clk/SM on B200, profiles/r01_microbench_b200.txt).  A 32-position block is
-//            "hot" when  maxTap * (pooled weight within bandwidth of the block) >= threshold; a block that
-//            is not hot cannot hold a position of a region (misc/peakcall.cpp:57-60) and is never looked at
-//            again.  Maximal groups of hot blocks are cut into pieces of <= 16 blocks.
-//   phase B  per piece: its tags (L1/L2 hits — the same warp just read them) are pooled into dense
+//   phase A  hot blocks WITHOUT touching the entries: the load step keeps the pooled tag count of every 32-position block
+//            (Tags::blkW, all samples, float rounded up).  A block is "hot" when  sum_j blkW[B+j] * (largest tap any tag of
+//            block B+j can have for any position of block B) >= threshold  — an upper envelope of every score in the block
+//            (control samples and rounding only loosen it); a block that is not hot cannot hold a position of a region
+//            (misc/peakcall.cpp:57-60) and is never looked at again.  One coalesced read of 128 + halo floats per span.
+//            Maximal groups of hot blocks are cut into pieces of <= 16 blocks.
+//   phase B  per piece: the tags of the mini-tiles its window touches (one contiguous chunk of the tile-major copy per
+//            4096-position span, 8 bytes per entry, four loads in flight per lane) are pooled into dense
 //            per-position cells; every position is classified against the threshold with the O(1) integer
 //            moment form of the Epanechnikov sum (exact in 64-bit integers, window sums carried by warp
 //            scans), and re-evaluated in the reference's own floating-point order (ascending tag position,
@@ -34,15 +33,12 @@
 #ifndef UPB_EXP_EXACT
 #define UPB_EXP_EXACT 1
 #endif
-#ifndef UPB_EXP_HOT
-#define UPB_EXP_HOT 0
-#endif
 
 namespace upb {
 
 constexpr int SP_THREADS = 256;
 constexpr int SP_WARPS = SP_THREADS / 32;
-constexpr int BIN_SHIFT = 4;                        // phase A pools into 16-position bins
+constexpr int HOT_JMAX = (448 - 1) / 32 + 1;        // blocks on either side whose tags can reach a block's positions (bandwidth <= 448)
 constexpr int SPAN_BLOCKS = SPAN_LEN / 32;          // 128 blocks of 32 positions
 constexpr int SPAN_WORDS = SPAN_BLOCKS / 32;
 constexpr int PIECE_BLOCKS = 16;                    // <= 512 positions per piece
@@ -72,10 +68,9 @@ struct SpanArgs {
   uint32_t bw;
   const double* taps;                               // 2bw+1, host-computed exactly as misc/kernel.cpp:16-35
   double thr;                                       // region threshold
-  double flatBound;                                 // largest tap (with margin): maxTap * window weight bounds every score
   float thrLow;                                     // threshold rounded down to float
-  const float* hotCoefF;                            // the same envelope in single precision, rounded up with a 1e-5 margin
-  const double* hotCoef;                            // [nbw] upper envelope of the taps per 16-position bin of a block's window (cold-block bound)
+  const float* hotCoefF;                            // [hotJ+1] largest tap a tag |j| blocks away can have for a position of the block, rounded up (1e-5 margin)
+  uint32_t hotJ;                                    // blocks on either side that can reach a block: (bw-1)/32 + 1
   double cN;                                        // taps[bw] / bw^2: moment-form scale
   double dS;                                        // error bound of the moment form per unit of window weight
   // outputs
@@ -88,13 +83,13 @@ struct SpanArgs {
   unsigned long long* stat;                         // [0] hot blocks, [1] pieces, [2] exact evaluations, [3] spans with tags
 };
 
-struct SpanSmem { uint32_t taps, hotc, ustart, ctl, coef, warp0, warpStride, oBins, oD, oDR, oWf, oWr, oSt, oSc, oMw, oHm, total; };
+struct SpanSmem { uint32_t taps, hotc, ustart, ctl, coef, warp0, warpStride, oWb, oD, oDR, oWf, oWr, oSt, oSc, oMw, oHm, total; };
 
 __host__ __device__ inline SpanSmem span_smem_layout (uint32_t bw, uint32_t nSamples, bool nondir, uint32_t nUnits, bool coeff) {
   SpanSmem L;
   uint32_t o = 0;
   L.taps = o;      o += ((2 * bw + 2) & ~1u) * 8;
-  L.hotc = o;      o += ((((31 + 2 * bw) >> BIN_SHIFT) + 2) & ~1u) * 8;
+  L.hotc = o;      o += ((HOT_JMAX + 2) & ~1u) * 4;
   L.ustart = o;    o += (nUnits + 1) * 4;
   L.ctl = o;       o += (nSamples + 3) & ~3u;
   o = (o + 15) & ~15u;
@@ -103,7 +98,7 @@ __host__ __device__ inline SpanSmem span_smem_layout (uint32_t bw, uint32_t nSam
   L.warp0 = o;
   const uint32_t W = PIECE_LEN + 2 * bw + 4;
   uint32_t w = 0;
-  L.oBins = w; w += ((((SPAN_LEN + 2 * bw) >> BIN_SHIFT) + 3) & ~1u) * 4;
+  L.oWb = w;   w += ((SPAN_BLOCKS + 2 * HOT_JMAX + 3) & ~1u) * 4;
   L.oD = w;    w += W * 4;
   L.oDR = w;   w += nondir ? W * 4 : 0;
   w = (w + 7) & ~7u;
@@ -201,19 +196,30 @@ __device__ __forceinline__ double exact_dense_warp (const double* __restrict__ K
   return s;
 }
 
-// entries of the span's chunk of one strand: [e0, e0+total); the first nPrev lie in the mini-tile before the span,
-// the next nOwn inside it, the rest in the mini-tile after it
-struct SpanChunk { unsigned long long e0; uint32_t nPrev, nOwn, total; };
-
-__device__ __forceinline__ SpanChunk span_chunk (const Tags& T, uint32_t d, uint32_t c, uint32_t k) {
+// Entries of (strand d, contig c) whose mini-tile overlaps positions [lo, hi] (1-based, inclusive; lo may be <= 0), visited by
+// the 32 lanes with four loads in flight each: f(position, entry).  Entries carry their offset inside a 4096-position span, so
+// the mini-tiles are walked span by span (a piece window touches at most two spans).
+template <class F>
+__device__ __forceinline__ void piece_entries (const Tags& T, uint32_t d, uint32_t c, int64_t lo, int64_t hi, uint32_t lane, F f) {
   const uint32_t gb = __ldg(T.mtBase + d * T.C + c);
   const uint32_t nMt = __ldg(T.mtBase + d * T.C + c + 1) - gb;
-  const uint32_t m0 = k * SPAN_MT;
-  const uint32_t a0 = min(m0 > 0 ? m0 - 1 : 0u, nMt), a1 = min(m0, nMt), a2 = min(m0 + SPAN_MT, nMt), a3 = min(m0 + SPAN_MT + 1, nMt);
-  const unsigned long long o0 = __ldg(T.mtOff + gb + a0), o1 = __ldg(T.mtOff + gb + a1), o2 = __ldg(T.mtOff + gb + a2), o3 = __ldg(T.mtOff + gb + a3);
-  SpanChunk ch;
-  ch.e0 = o0; ch.nPrev = (uint32_t)(o1 - o0); ch.nOwn = (uint32_t)(o2 - o1); ch.total = (uint32_t)(o3 - o0);
-  return ch;
+  if (nMt == 0 || hi < 1) return;
+  if (lo < 1) lo = 1;
+  const uint32_t ma = (uint32_t)((lo - 1) >> MT_SHIFT);
+  if (ma >= nMt) return;
+  const uint32_t mb = min((uint32_t)((hi - 1) >> MT_SHIFT), nMt - 1);
+  for (uint32_t sp = ma / SPAN_MT; sp <= mb / SPAN_MT; ++sp) {
+    const uint32_t m0 = max(ma, sp * SPAN_MT), m1 = min(mb, sp * SPAN_MT + SPAN_MT - 1);
+    const unsigned long long e0 = __ldg(T.mtOff + gb + m0), e1 = __ldg(T.mtOff + gb + m1 + 1);
+    const uint32_t base = sp * SPAN_LEN + 1;
+    for (unsigned long long eb = e0 + lane; eb - lane < e1; eb += 128) {
+      uint2 en[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) en[q] = (eb + 32 * q < e1) ? __ldg(T.ment + eb + 32 * q) : make_uint2(0u, 0u);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (en[q].x) f(base + (en[q].y & (SPAN_LEN - 1)), en[q]);
+    }
+  }
 }
 
 // Zone-map prefilter: a block's window (32 + 2bw positions) lies inside `nAdj` consecutive 512-position mini-tiles, so a
@@ -275,13 +281,12 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : 4) span_kernel (const 
   const SpanSmem L = span_smem_layout(bw, a.nSamples, NONDIR, a.nUnits, COEFF);
   double* Ks = (double*)(smem + L.taps);
   double* coef = (double*)(smem + L.coef);
-  double* hotc = (double*)(smem + L.hotc);
   float* hotf = (float*)(smem + L.hotc);                              // single precision is enough for a bound (margins folded in on the host)
   uint32_t* ustart = (uint32_t*)(smem + L.ustart);                   // first span of every unit (CTA-shared, read-only)
   uint8_t* isCtl = (uint8_t*)(smem + L.ctl);                          // control flag of every sample (CTA-shared, read-only)
   const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
   unsigned char* wbase = smem + L.warp0 + (size_t)warp * L.warpStride;
-  uint32_t* bins = (uint32_t*)(wbase + L.oBins);
+  float* wb = (float*)(wbase + L.oWb);                                // block weights of the span with hotJ blocks of halo on either side
   uint32_t* D = (uint32_t*)(wbase + L.oD);
   uint32_t* DR = (uint32_t*)(wbase + L.oDR);
   float* scf = (float*)(wbase + L.oSc);
@@ -296,12 +301,9 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : 4) span_kernel (const 
   for (uint32_t i = tid; i < a.nUnits; i += SP_THREADS) ustart[i] = a.units[i].spanStart;
   for (uint32_t i = tid; i < a.nSamples; i += SP_THREADS) isCtl[i] = a.control[i];
   if (COEFF) for (uint32_t i = tid; i < a.nSamples; i += SP_THREADS) coef[i] = a.coeff[i];
-  if (UPB_EXP_HOT) { for (uint32_t i = tid; i < ((31 + 2 * bw) >> BIN_SHIFT) + 1; i += SP_THREADS) hotc[i] = a.hotCoef[i]; }
-  else { for (uint32_t i = tid; i < ((31 + 2 * bw) >> BIN_SHIFT) + 1; i += SP_THREADS) hotf[i] = a.hotCoefF[i]; }
+  for (uint32_t i = tid; i <= a.hotJ; i += SP_THREADS) hotf[i] = a.hotCoefF[i];
   __syncthreads();                                                    // the only block-level barrier
-  const uint32_t nCells = SPAN_LEN + 2 * bw;                          // cells of a span: positions ts-bw .. ts+4095+bw
-  const uint32_t nBins = (nCells >> BIN_SHIFT) + 2;
-  const uint32_t nbw = ((31 + 2 * bw) >> BIN_SHIFT) + 1;              // bins covering one block's window
+  const int J = (int)a.hotJ;
   const unsigned long long bw2 = (unsigned long long)bw * bw;
   unsigned long long stHot = 0, stPieces = 0, stExact = 0, stSpans = 0;
   const uint32_t nWarm = *a.nWarm;
@@ -324,89 +326,44 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : 4) span_kernel (const 
     const uint64_t lastPos = (uint64_t)U.size + bw;                   // Q20: evaluated through lastTag+bw
     const uint32_t np = (uint32_t)min((uint64_t)SPAN_LEN, lastPos - (ts - 1));
 
-    // ---- A1: the span's chunk(s) of the tile-major copy --------------------------------------------------------
-    const SpanChunk chF = span_chunk(a.T, NONDIR ? 0u : U.buffer, U.contig, k);
-    SpanChunk chR; chR.e0 = 0; chR.nPrev = chR.nOwn = chR.total = 0;
-    if (NONDIR) chR = span_chunk(a.T, 1u, U.contig, k);
-    if (chF.total + chR.total == 0) { if (lane == 0) a.spanRunCount[work] = 0; continue; }
-    ++stSpans;
-    for (uint32_t i = lane; i < nBins; i += 32) bins[i] = 0;
-    __syncwarp();
-
-    // ---- A2: pool the density sources into 16-position bins: cell = position - (ts - bw).  Four loads are in flight
-    //      per lane before the first atomic, so one round trip to L2/HBM covers 128 entries.  The span's own entries need
-    //      no range check; the two halo mini-tiles (the first nPrev and the last entries of the chunk) do ---------------
+    // ---- A: hot blocks from the block-weight zone map.  Block B of the contig = positions 32B+1 .. 32B+32; a tag of block B+j
+    //      is at least 32(|j|-1)+1 positions away from every position of block B (0 for j = 0), so
+    //      bound(B) = sum_j blkW[B+j] * tap(that distance) >= every score in B.  One round trip: 128 + 2J floats per strand ------
+    const uint32_t nBlk = (np + 31) >> 5;
+    {
+      const int B0 = (int)(k * SPAN_BLOCKS) - J;                       // block held by wb[0]
 #pragma unroll
-    for (int str = 0; str < (NONDIR ? 2 : 1); ++str) {
-      const SpanChunk ch = str ? chR : chF;
-      const uint2* __restrict__ src = a.T.ment + ch.e0;
-      const uint2* __restrict__ own = src + ch.nPrev;
-      const uint2* __restrict__ nxt = own + ch.nOwn;
-      const uint32_t nNext = ch.total - ch.nPrev - ch.nOwn;
-      // first round trip: both halo mini-tiles (usually < 32 entries each) and the first 128 entries of the span together
-      uint2 hp = make_uint2(0u, 0u), hn = make_uint2(0u, 0u), en[4];
-      if (lane < ch.nPrev) hp = __ldg(src + lane);
-      if (lane < nNext) hn = __ldg(nxt + lane);
+      for (int q = 0; q < (SPAN_BLOCKS + 2 * HOT_JMAX + 31) / 32; ++q) {
+        const int i = 32 * q + (int)lane;
+        if (i < SPAN_BLOCKS + 2 * J) {
+          const int B = B0 + i;
+          float w = 0.0f;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { const uint32_t t = 32 * q + lane; en[q] = t < ch.nOwn ? __ldg(own + t) : make_uint2(0u, 0u); }
-      for (uint32_t t0 = 0;;) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (en[q].x && !(a.hasControl && isCtl[en[q].y >> SPAN_SHIFT])) atomicAdd(&bins[((en[q].y & (SPAN_LEN - 1)) + bw) >> BIN_SHIFT], en[q].x);
-        t0 += 128;
-        if (t0 >= ch.nOwn) break;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { const uint32_t t = t0 + 32 * q + lane; en[q] = t < ch.nOwn ? __ldg(own + t) : make_uint2(0u, 0u); }
-      }
-      for (uint32_t t = lane;;) {                                     // halo before: positions ts-512 .. ts-1
-        const int32_t cell = (int32_t)(hp.y & (SPAN_LEN - 1)) + (int32_t)bw - SPAN_LEN;
-        if (hp.x && cell >= 0 && !(a.hasControl && isCtl[hp.y >> SPAN_SHIFT])) atomicAdd(&bins[(uint32_t)cell >> BIN_SHIFT], hp.x);
-        t += 32;
-        if (t - lane >= ch.nPrev) break;
-        hp = t < ch.nPrev ? __ldg(src + t) : make_uint2(0u, 0u);
-      }
-      for (uint32_t t = lane;;) {                                     // halo after: positions ts+4096 .. ts+4607
-        const uint32_t cell = (hn.y & (SPAN_LEN - 1)) + bw + SPAN_LEN;
-        if (hn.x && cell < nCells && !(a.hasControl && isCtl[hn.y >> SPAN_SHIFT])) atomicAdd(&bins[cell >> BIN_SHIFT], hn.x);
-        t += 32;
-        if (t - lane >= nNext) break;
-        hn = t < nNext ? __ldg(nxt + t) : make_uint2(0u, 0u);
+          for (int str = 0; str < (NONDIR ? 2 : 1); ++str) {
+            const uint32_t d = NONDIR ? (uint32_t)str : U.buffer;
+            const uint32_t gb = __ldg(a.T.mtBase + d * a.T.C + U.contig);
+            const uint32_t nB = (__ldg(a.T.mtBase + d * a.T.C + U.contig + 1) - gb) * BLK_PER_MT;
+            if (B >= 0 && (uint32_t)B < nB) w += __ldg(a.T.blkW + (size_t)gb * BLK_PER_MT + (uint32_t)B);   // two rounded-up floats: the sum may round down by 2^-24, inside the margin
+          }
+          wb[i] = w;
+        }
       }
     }
     __syncwarp();
-
-    // ---- A3: hot blocks: window of block k = cells 32k .. 32k+31+2bw = bins 2k .. 2k+nbw-1 (16-position bins) ----------
-    const uint32_t nBlk = (np + 31) >> 5;
     uint32_t anyHot = 0;
 #pragma unroll
     for (uint32_t m = 0; m < (uint32_t)SPAN_WORDS; ++m) {
       const uint32_t kblk = 32 * m + lane;
-      bool hot = false;
-      if (kblk < nBlk) {
-        // no position of the block can score more than  sum_bins weight(bin) * (largest tap any of its cells has for any
-        // position of the block): a bound, so plain FMA arithmetic with the margin folded into hotCoef
-        const uint32_t b0 = kblk << (5 - BIN_SHIFT);
-#if UPB_EXP_HOT == 1
-        unsigned long long sum = 0;
-        for (uint32_t q = 0; q < nbw; ++q) sum += bins[b0 + q];
-        if ((double)sum * a.flatBound >= a.thr) {                       // cheap necessary condition first (maxTap * window weight)
-          double bound = 0.0;
-          for (uint32_t q = 0; q < nbw; ++q) bound = fma((double)bins[b0 + q], hotc[q], bound);
-          hot = bound >= a.thr;
-        }
-#else
-        float bound = 0.0f;
-        for (uint32_t q = 0; q < nbw; ++q) bound = fmaf(__uint2float_ru(bins[b0 + q]), hotf[q], bound);
-        hot = bound >= a.thrLow;
-#endif
-      }
-      const uint32_t msk = __ballot_sync(0xffffffffu, hot);
+      float bound = wb[kblk + J] * hotf[0];
+      for (int j = 1; j <= J; ++j) bound = fmaf(wb[kblk + J - j] + wb[kblk + J + j], hotf[j], bound);
+      const uint32_t msk = __ballot_sync(0xffffffffu, kblk < nBlk && !(bound < a.thrLow));   // NaN (inf * 0 cannot occur, but) counts as hot
       if (lane == 0) hm[m] = msk;
       anyHot |= msk;
     }
     if (lane == 0) hm[SPAN_WORDS] = 0;
     __syncwarp();
     if (!anyHot) { if (lane == 0) a.spanRunCount[work] = 0; continue; }
+    ++stSpans;
 
     // ---- B: pieces, in position order -------------------------------------------------------------------------------
     uint32_t spanRuns = 0;
@@ -437,22 +394,17 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : 4) span_kernel (const 
         for (uint32_t u = lane; u < W + 2; u += 32) { D[u] = 0; if (NONDIR) DR[u] = 0; }
         __syncwarp();
 
-        // B1: the piece's tags -> dense cells (the chunk is an L1/L2 hit by now): u = cell - 32*pb
+        // B1: the tags within bandwidth of the piece -> dense cells: cell u holds position q0 - bw + u
+        {
+          const int64_t lo = (int64_t)q0 - bw, hi = (int64_t)q0 + 32 * nb - 1 + bw;
+          const uint32_t cell0 = q0 - bw;                              // may wrap below 0: the unsigned difference below is still right
 #pragma unroll
-        for (int str = 0; str < (NONDIR ? 2 : 1); ++str) {
-          const SpanChunk ch = str ? chR : chF;
-          const uint2* __restrict__ src = a.T.ment + ch.e0;
-          uint32_t* dst = str ? DR : D;
-          for (uint32_t t0 = 0; t0 < ch.total; t0 += 128) {
-            uint2 en[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { const uint32_t t = t0 + 32 * q + lane; en[q] = t < ch.total ? __ldg(src + t) : make_uint2(0u, 0u); }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint32_t t = t0 + 32 * q + lane;
-              const int32_t u = (int32_t)(en[q].y & (SPAN_LEN - 1)) + (int32_t)bw + (t < ch.nPrev ? -SPAN_LEN : (t < ch.nPrev + ch.nOwn ? 0 : SPAN_LEN)) - (int32_t)(32 * pb);
-              if (en[q].x && (uint32_t)u < W && !(a.hasControl && isCtl[en[q].y >> SPAN_SHIFT])) atomicAdd(&dst[u], en[q].x);
-            }
+          for (int str = 0; str < (NONDIR ? 2 : 1); ++str) {
+            uint32_t* dst = str ? DR : D;
+            piece_entries(a.T, NONDIR ? (uint32_t)str : U.buffer, U.contig, lo, hi, lane, [&] (uint32_t pos, const uint2& en) {
+              const uint32_t u = pos - cell0;
+              if (u < W && !(a.hasControl && isCtl[en.y >> SPAN_SHIFT])) atomicAdd(&dst[u], en.x);
+            });
           }
         }
         __syncwarp();
@@ -470,15 +422,13 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : 4) span_kernel (const 
               const double cf = coef[sm];
 #pragma unroll
               for (int str = 0; str < (NONDIR ? 2 : 1); ++str) {
-                const SpanChunk ch = str ? chR : chF;
-                const uint2* __restrict__ src = a.T.ment + ch.e0;
                 double* dst = str ? Wr : Wf;
-                for (uint32_t t = lane; t < ch.total; t += 32) {
-                  const uint2 en = __ldg(src + t);
-                  if ((en.y >> SPAN_SHIFT) != sm) continue;
-                  const int32_t u = (int32_t)(en.y & (SPAN_LEN - 1)) + (int32_t)bw + (t < ch.nPrev ? -SPAN_LEN : (t < ch.nPrev + ch.nOwn ? 0 : SPAN_LEN)) - (int32_t)(32 * pb);
-                  if ((uint32_t)u < W) dst[u] = __dadd_rn(dst[u], phase ? (double)en.x : __dmul_rn((double)en.x, cf));
-                }
+                const uint32_t cell0 = q0 - bw;
+                piece_entries(a.T, NONDIR ? (uint32_t)str : U.buffer, U.contig, (int64_t)q0 - bw, (int64_t)q0 + 32 * nb - 1 + bw, lane, [&] (uint32_t pos, const uint2& en) {
+                  if ((en.y >> SPAN_SHIFT) != sm) return;
+                  const uint32_t u = pos - cell0;
+                  if (u < W) dst[u] = __dadd_rn(dst[u], phase ? (double)en.x : __dmul_rn((double)en.x, cf));
+                });
               }
               __syncwarp();
             }
