@@ -610,7 +610,7 @@ static int dump_and_corr (upb_ctx* ctx, const DensArgs& base, bool nondir, uint3
 
 static int launch_span (upb_ctx* ctx, const SpanArgs& sa, bool nondir, uint32_t* launches) {
   const bool coeff = sa.coeff != nullptr;
-  const SpanSmem L = span_smem_layout(sa.bw, sa.nSamples, nondir, sa.nUnits, coeff);
+  const SpanSmem L = span_smem_layout(sa.bw, sa.nSamples, nondir, coeff);
   const size_t smem = L.total;
   if (smem > 227 * 1024) return fail(ctx, UPB_ERR_UNSUPPORTED, "bandwidth / sample count need more shared memory than one SM has");
   void (*kern)(const SpanArgs) = coeff ? (nondir ? span_kernel<true, true> : span_kernel<false, true>) : (nondir ? span_kernel<true, false> : span_kernel<false, false>);
@@ -669,6 +669,8 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
   sa.taps = ctx->scratch["taps"].as<double>();
   sa.thr = cfg.thr;
   const double kmax = pr.taps[cfg.bw];                                // K(0) = 0.75 * scale
+  HotArgs ha;
+  memset(&ha, 0, sizeof ha);
   {
     // cold-block bound: a tag j blocks (of 32 positions) away from block B is at least 32(|j|-1)+1 positions from every position of
     // B (0 for j = 0); blocks further than J = (bw-2)/32+1 away cannot reach it (the taps at +-bw are exactly 0, misc/kernel.cpp:12-14)
@@ -682,8 +684,8 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
     float* d_hf = SCR("hotCoefF", float, J + 1);
     CU(cudaMemcpyAsync(d_hf, hf.data(), (size_t)(J + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    sa.hotCoefF = d_hf; sa.hotJ = (uint32_t)J;
-    sa.thrLow = std::nextafter((float)cfg.thr, -INFINITY);
+    ha.hotCoefF = d_hf; ha.hotJ = (uint32_t)J;
+    ha.thrLow = std::nextafter((float)cfg.thr, -INFINITY);
   }
   const double flatBound = kmax * (1.0 + pr.maxCoeff) * (1.0 + 1e-9);  // largest tap: maxTap * window weight bounds every score (zone-map prefilter)
   sa.coeff = pr.d_coeffBySample;
@@ -691,8 +693,12 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
   sa.dS = kmax * 1e-11;                                               // >= 100x the worst-case rounding difference between the two forms
   sa.flags = small32; sa.ticket = small32 + 1; sa.runCount = small32 + 2; sa.stat = (unsigned long long*)(small32 + 4);
   sa.spanRunCount = SCR("spanRunCount", uint32_t, pr.totalSpans);
-  uint32_t* warmList = SCR("warmList", uint32_t, pr.totalSpans);
-  sa.warmList = warmList; sa.nWarm = small32 + 12;
+  uint2* warmList = SCR("warmList", uint2, pr.totalSpans);
+  uint2* hotList = SCR("hotList", uint2, pr.totalSpans);
+  uint32_t* hotMask = SCR("hotMask", uint32_t, (size_t)pr.totalSpans * SPAN_WORDS);
+  sa.hotList = hotList; sa.nHot = small32 + 14; sa.hotMask = hotMask;
+  ha.T = pr.T; ha.units = d_units; ha.warmList = warmList; ha.nWarm = small32 + 12; ha.bw = cfg.bw; ha.nondir = cfg.nondir ? 1 : 0;
+  ha.hotMask = hotMask; ha.hotList = hotList; ha.nHot = small32 + 14; ha.spanRunCount = sa.spanRunCount; ha.stat = sa.stat;
   WarmArgs wa;
   wa.T = pr.T; wa.units = d_units; wa.nUnits = nUnits; wa.totalSpans = pr.totalSpans; wa.nondir = cfg.nondir ? 1 : 0;
   wa.nAdj = ((31 + 2 * cfg.bw) >> MT_SHIFT) + 2;
@@ -745,7 +751,8 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
     CU(cudaMemsetAsync(ctx->d_small.p, 0, 256, ctx->stream));
     wa.flatBound = flatBound; wa.thr = cfg.thr;
     warm_span_kernel<<<(pr.totalSpans + 255) / 256, 256, 0, ctx->stream>>>(wa);
-    launches += 1;
+    hot_span_kernel<<<ctx->smCount * 8, HOT_THREADS, 0, ctx->stream>>>(ha);
+    launches += 2;
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     if ((r = launch_span(ctx, sa, cfg.nondir, &launches))) return r;
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));

@@ -63,14 +63,12 @@ struct SpanArgs {
   int hasControl;
   const double* coeff;                              // [nSamples] scaling coefficient of every non-control sample (-z), NULL otherwise
   uint32_t nUnits, totalSpans;
-  const uint32_t* warmList;                         // spans that survived the zone-map prefilter
-  const uint32_t* nWarm;
+  const uint2* hotList;                             // (span, unit) of the spans that hold at least one hot block (hot_span_kernel), any order
+  const uint32_t* nHot;
+  const uint32_t* hotMask;                          // [totalSpans * 4] hot-block bits of those spans
   uint32_t bw;
   const double* taps;                               // 2bw+1, host-computed exactly as misc/kernel.cpp:16-35
   double thr;                                       // region threshold
-  float thrLow;                                     // threshold rounded down to float
-  const float* hotCoefF;                            // [hotJ+1] largest tap a tag |j| blocks away can have for a position of the block, rounded up (1e-5 margin)
-  uint32_t hotJ;                                    // blocks on either side that can reach a block: (bw-1)/32 + 1
   double cN;                                        // taps[bw] / bw^2: moment-form scale
   double dS;                                        // error bound of the moment form per unit of window weight
   // outputs
@@ -83,14 +81,12 @@ struct SpanArgs {
   unsigned long long* stat;                         // [0] hot blocks, [1] pieces, [2] exact evaluations, [3] spans with tags
 };
 
-struct SpanSmem { uint32_t taps, hotc, ustart, ctl, coef, warp0, warpStride, oWb, oD, oDR, oWf, oWr, oSt, oSc, oMw, oHm, total; };
+struct SpanSmem { uint32_t taps, ctl, coef, warp0, warpStride, oD, oDR, oWf, oWr, oSt, oSc, oMw, oHm, total; };
 
-__host__ __device__ inline SpanSmem span_smem_layout (uint32_t bw, uint32_t nSamples, bool nondir, uint32_t nUnits, bool coeff) {
+__host__ __device__ inline SpanSmem span_smem_layout (uint32_t bw, uint32_t nSamples, bool nondir, bool coeff) {
   SpanSmem L;
   uint32_t o = 0;
   L.taps = o;      o += ((2 * bw + 2) & ~1u) * 8;
-  L.hotc = o;      o += ((HOT_JMAX + 2) & ~1u) * 4;
-  L.ustart = o;    o += (nUnits + 1) * 4;
   L.ctl = o;       o += (nSamples + 3) & ~3u;
   o = (o + 15) & ~15u;
   L.coef = o;      o += coeff ? nSamples * 8 : 0;
@@ -98,7 +94,6 @@ __host__ __device__ inline SpanSmem span_smem_layout (uint32_t bw, uint32_t nSam
   L.warp0 = o;
   const uint32_t W = PIECE_LEN + 2 * bw + 4;
   uint32_t w = 0;
-  L.oWb = w;   w += ((SPAN_BLOCKS + 2 * HOT_JMAX + 3) & ~1u) * 4;
   L.oD = w;    w += W * 4;
   L.oDR = w;   w += nondir ? W * 4 : 0;
   w = (w + 7) & ~7u;
@@ -124,14 +119,14 @@ __device__ __forceinline__ uint32_t warp_sum_u32 (uint32_t v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ unsigned long long warp_incl_scan_u64 (unsigned long long v, uint32_t lane) {
+template <class T> __device__ __forceinline__ T warp_incl_scan (T v, uint32_t lane) {
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const unsigned long long n = __shfl_up_sync(0xffffffffu, v, o); if (lane >= (uint32_t)o) v += n; }
+  for (int o = 1; o < 32; o <<= 1) { const T n = __shfl_up_sync(0xffffffffu, v, o); if (lane >= (uint32_t)o) v += n; }
   return v;
 }
-__device__ __forceinline__ uint32_t warp_incl_scan_u32 (uint32_t v, uint32_t lane) {
+template <class T> __device__ __forceinline__ T warp_sum (T v) {
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, v, o); if (lane >= (uint32_t)o) v += n; }
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
@@ -234,7 +229,7 @@ struct WarmArgs {
   int nondir;
   uint32_t nAdj;
   double flatBound, thr;
-  uint32_t* warmList;               // spans that have to be looked at, any order
+  uint2* warmList;                  // (span, unit) of the spans that have to be looked at, any order
   uint32_t* nWarm;
   uint32_t* spanRunCount;           // zeroed here for the spans that are skipped
 };
@@ -242,10 +237,12 @@ struct WarmArgs {
 __global__ void warm_span_kernel (WarmArgs a) {
   const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
   bool warm = false;
+  uint32_t unit = 0;
   if (w < a.totalSpans) {
     uint32_t lo = 0, hi = a.nUnits;
     while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.units[mid].spanStart <= w) lo = mid; else hi = mid; }
     const SpanUnit U = a.units[lo];
+    unit = lo;
     const uint32_t k = w - U.spanStart;
     const int m0 = (int)(k * SPAN_MT) - 1, m1 = (int)(k * SPAN_MT + SPAN_MT);     // inclusive mini-tile range with halo
     const uint32_t d0 = a.nondir ? 0u : U.buffer, d1 = a.nondir ? 1u : U.buffer;
@@ -270,23 +267,106 @@ __global__ void warm_span_kernel (WarmArgs a) {
     uint32_t base = 0;
     if ((threadIdx.x & 31) == (uint32_t)(__ffs(msk) - 1)) base = atomicAdd(a.nWarm, __popc(msk));
     base = __shfl_sync(0xffffffffu, base, __ffs(msk) - 1);
-    if (warm) a.warmList[base + __popc(msk & ((1u << (threadIdx.x & 31)) - 1))] = w;
+    if (warm) a.warmList[base + __popc(msk & ((1u << (threadIdx.x & 31)) - 1))] = make_uint2(w, unit);
   }
+}
+
+// Hot blocks of the warm spans from the block-weight zone map, one warp per span, without touching the entries.  Block B of the
+// contig = positions 32B+1 .. 32B+32; a tag of block B+j is at least 32(|j|-1)+1 positions away from every position of block B
+// (0 for j = 0), so  bound(B) = sum_j blkW[B+j] * tap(that distance)  is an upper envelope of every score in B: a block whose
+// bound stays below the threshold cannot hold a position of a region (misc/peakcall.cpp:57-60).  Control samples, float
+// rounding (upwards, margins folded into the coefficients on the host) and -z coefficients only loosen the bound.
+struct HotArgs {
+  Tags T;
+  const SpanUnit* units;
+  const uint2* warmList;
+  const uint32_t* nWarm;
+  uint32_t bw;
+  int nondir;
+  const float* hotCoefF;            // [hotJ+1] largest tap a tag |j| blocks away can have for a position of the block, rounded up
+  uint32_t hotJ;                    // blocks on either side that can reach a block: (bw-2)/32 + 1
+  float thrLow;                     // threshold rounded down to float
+  uint32_t* hotMask;                // [totalSpans * 4]
+  uint2* hotList;
+  uint32_t* nHot;
+  uint32_t* spanRunCount;           // zeroed here for the spans without a hot block
+  unsigned long long* stat;         // [0] hot blocks
+};
+
+constexpr int HOT_THREADS = 256;
+constexpr int HOT_WB = (SPAN_BLOCKS + 2 * HOT_JMAX + 3) & ~1;
+
+__global__ void __launch_bounds__(HOT_THREADS) hot_span_kernel (const __grid_constant__ HotArgs a) {
+  __shared__ float hotf[HOT_JMAX + 2];
+  __shared__ float wbAll[HOT_THREADS / 32][HOT_WB];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* wb = wbAll[warp];
+  for (uint32_t i = threadIdx.x; i <= a.hotJ; i += HOT_THREADS) hotf[i] = a.hotCoefF[i];
+  __syncthreads();
+  const int J = (int)a.hotJ;
+  const uint32_t nWarm = *a.nWarm;
+  const uint32_t nWarps = gridDim.x * (HOT_THREADS / 32);
+  unsigned long long stHot = 0;
+  for (uint32_t it = blockIdx.x * (HOT_THREADS / 32) + warp; it < nWarm; it += nWarps) {
+    const uint2 item = __ldg(a.warmList + it);
+    const SpanUnit U = a.units[item.y];
+    const uint32_t k = item.x - U.spanStart;
+    const uint32_t ts = k * SPAN_LEN + 1;
+    const uint64_t lastPos = (uint64_t)U.size + a.bw;                 // Q20: evaluated through lastTag+bw
+    const uint32_t np = (uint32_t)min((uint64_t)SPAN_LEN, lastPos - (ts - 1));
+    const uint32_t nBlk = (np + 31) >> 5;
+    const int B0 = (int)(k * SPAN_BLOCKS) - J;                         // block held by wb[0]
+    uint32_t gb[2], nB[2];
+#pragma unroll
+    for (int str = 0; str < 2; ++str) {
+      const uint32_t d = a.nondir ? (uint32_t)str : U.buffer;
+      gb[str] = __ldg(a.T.mtBase + d * a.T.C + U.contig);
+      nB[str] = (__ldg(a.T.mtBase + d * a.T.C + U.contig + 1) - gb[str]) * BLK_PER_MT;
+    }
+    float wv[(SPAN_BLOCKS + 2 * HOT_JMAX + 31) / 32];
+#pragma unroll
+    for (int q = 0; q < (SPAN_BLOCKS + 2 * HOT_JMAX + 31) / 32; ++q) {   // one round trip: 128 + 2J floats per strand
+      const int i = 32 * q + (int)lane, B = B0 + i;
+      float w = 0.0f;
+      if (i < SPAN_BLOCKS + 2 * J && B >= 0) {
+        if ((uint32_t)B < nB[0]) w = __ldg(a.T.blkW + (size_t)gb[0] * BLK_PER_MT + (uint32_t)B);
+        if (a.nondir && (uint32_t)B < nB[1]) w += __ldg(a.T.blkW + (size_t)gb[1] * BLK_PER_MT + (uint32_t)B);   // may round down by 2^-24: inside the margin
+      }
+      wv[q] = w;
+    }
+#pragma unroll
+    for (int q = 0; q < (SPAN_BLOCKS + 2 * HOT_JMAX + 31) / 32; ++q) { const int i = 32 * q + (int)lane; if (i < HOT_WB) wb[i] = wv[q]; }
+    __syncwarp();
+    uint32_t any = 0, mine = 0;
+#pragma unroll
+    for (uint32_t m = 0; m < (uint32_t)SPAN_WORDS; ++m) {
+      const uint32_t kblk = 32 * m + lane;
+      float bound = wb[kblk + J] * hotf[0];
+      for (int j = 1; j <= J; ++j) bound = fmaf(wb[kblk + J - j] + wb[kblk + J + j], hotf[j], bound);
+      const uint32_t msk = __ballot_sync(0xffffffffu, kblk < nBlk && !(bound < a.thrLow));   // a NaN would count as hot
+      any |= msk;
+      if (lane == m) mine = msk;
+      stHot += __popc(msk);
+    }
+    __syncwarp();
+    if (any) {
+      if (lane < (uint32_t)SPAN_WORDS) a.hotMask[(size_t)item.x * SPAN_WORDS + lane] = mine;
+      if (lane == 0) a.hotList[atomicAdd(a.nHot, 1u)] = item;
+    } else if (lane == 0) a.spanRunCount[item.x] = 0;
+  }
+  if (lane == 0 && stHot) atomicAdd(a.stat + 0, stHot);
 }
 
 template <bool NONDIR, bool COEFF>
 __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : 4) span_kernel (const __grid_constant__ SpanArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const uint32_t bw = a.bw;
-  const SpanSmem L = span_smem_layout(bw, a.nSamples, NONDIR, a.nUnits, COEFF);
+  const SpanSmem L = span_smem_layout(bw, a.nSamples, NONDIR, COEFF);
   double* Ks = (double*)(smem + L.taps);
   double* coef = (double*)(smem + L.coef);
-  float* hotf = (float*)(smem + L.hotc);                              // single precision is enough for a bound (margins folded in on the host)
-  uint32_t* ustart = (uint32_t*)(smem + L.ustart);                   // first span of every unit (CTA-shared, read-only)
   uint8_t* isCtl = (uint8_t*)(smem + L.ctl);                          // control flag of every sample (CTA-shared, read-only)
   const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
   unsigned char* wbase = smem + L.warp0 + (size_t)warp * L.warpStride;
-  float* wb = (float*)(wbase + L.oWb);                                // block weights of the span with hotJ blocks of halo on either side
   uint32_t* D = (uint32_t*)(wbase + L.oD);
   uint32_t* DR = (uint32_t*)(wbase + L.oDR);
   float* scf = (float*)(wbase + L.oSc);
@@ -298,71 +378,37 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : 4) span_kernel (const 
   uint32_t* hm = (uint32_t*)(wbase + L.oHm);
 
   for (uint32_t i = tid; i < 2 * bw + 1; i += SP_THREADS) Ks[i] = a.taps[i];
-  for (uint32_t i = tid; i < a.nUnits; i += SP_THREADS) ustart[i] = a.units[i].spanStart;
   for (uint32_t i = tid; i < a.nSamples; i += SP_THREADS) isCtl[i] = a.control[i];
   if (COEFF) for (uint32_t i = tid; i < a.nSamples; i += SP_THREADS) coef[i] = a.coeff[i];
-  for (uint32_t i = tid; i <= a.hotJ; i += SP_THREADS) hotf[i] = a.hotCoefF[i];
   __syncthreads();                                                    // the only block-level barrier
-  const int J = (int)a.hotJ;
   const unsigned long long bw2 = (unsigned long long)bw * bw;
-  unsigned long long stHot = 0, stPieces = 0, stExact = 0, stSpans = 0;
-  const uint32_t nWarm = *a.nWarm;
-  uint32_t ui = 0;
-  SpanUnit U = a.units[0];
+  unsigned long long stPieces = 0, stExact = 0, stSpans = 0;
+  const uint32_t nHot = *a.nHot;
+  constexpr uint32_t BATCH = 4;                                        // hot spans per ticket: one atomic and two dependent loads per four spans
 
   for (;;) {
-    uint32_t work = 0;
-    if (lane == 0) work = atomicAdd(a.ticket, 1u);
-    work = __shfl_sync(0xffffffffu, work, 0);
-    if (work >= nWarm) break;
-    work = __ldg(a.warmList + work);                                  // span index (all later uses)
-
-    if (!(work >= ustart[ui] && (ui + 1 == a.nUnits || work < ustart[ui + 1]))) {   // tickets are mostly consecutive: same unit as last time
-      uint32_t lo = 0, hi = a.nUnits; while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (ustart[mid] <= work) lo = mid; else hi = mid; } ui = lo;
-      U = a.units[ui];
-    }
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(a.ticket, BATCH);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= nHot) break;
+    const uint32_t nIn = min(BATCH, nHot - base);
+    uint2 item = make_uint2(0u, 0u);
+    if (lane < nIn) item = __ldg(a.hotList + base + lane);
+    uint32_t maskWord = 0;                                            // lane 4t+m holds word m of the t-th span's hot-block mask
+    { const uint32_t sp = __shfl_sync(0xffffffffu, item.x, lane >> 2);
+      if ((lane >> 2) < nIn) maskWord = __ldg(a.hotMask + (size_t)sp * SPAN_WORDS + (lane & 3)); }
+  for (uint32_t tb = 0; tb < nIn; ++tb) {
+    const uint32_t work = __shfl_sync(0xffffffffu, item.x, tb);        // span index
+    const SpanUnit U = a.units[__shfl_sync(0xffffffffu, item.y, tb)];
     const uint32_t k = work - U.spanStart;                            // span index inside the contig
     const uint32_t ts = k * SPAN_LEN + 1;                             // first position of the span
     const uint64_t lastPos = (uint64_t)U.size + bw;                   // Q20: evaluated through lastTag+bw
     const uint32_t np = (uint32_t)min((uint64_t)SPAN_LEN, lastPos - (ts - 1));
-
-    // ---- A: hot blocks from the block-weight zone map.  Block B of the contig = positions 32B+1 .. 32B+32; a tag of block B+j
-    //      is at least 32(|j|-1)+1 positions away from every position of block B (0 for j = 0), so
-    //      bound(B) = sum_j blkW[B+j] * tap(that distance) >= every score in B.  One round trip: 128 + 2J floats per strand ------
     const uint32_t nBlk = (np + 31) >> 5;
-    {
-      const int B0 = (int)(k * SPAN_BLOCKS) - J;                       // block held by wb[0]
-#pragma unroll
-      for (int q = 0; q < (SPAN_BLOCKS + 2 * HOT_JMAX + 31) / 32; ++q) {
-        const int i = 32 * q + (int)lane;
-        if (i < SPAN_BLOCKS + 2 * J) {
-          const int B = B0 + i;
-          float w = 0.0f;
-#pragma unroll
-          for (int str = 0; str < (NONDIR ? 2 : 1); ++str) {
-            const uint32_t d = NONDIR ? (uint32_t)str : U.buffer;
-            const uint32_t gb = __ldg(a.T.mtBase + d * a.T.C + U.contig);
-            const uint32_t nB = (__ldg(a.T.mtBase + d * a.T.C + U.contig + 1) - gb) * BLK_PER_MT;
-            if (B >= 0 && (uint32_t)B < nB) w += __ldg(a.T.blkW + (size_t)gb * BLK_PER_MT + (uint32_t)B);   // two rounded-up floats: the sum may round down by 2^-24, inside the margin
-          }
-          wb[i] = w;
-        }
-      }
-    }
     __syncwarp();
-    uint32_t anyHot = 0;
-#pragma unroll
-    for (uint32_t m = 0; m < (uint32_t)SPAN_WORDS; ++m) {
-      const uint32_t kblk = 32 * m + lane;
-      float bound = wb[kblk + J] * hotf[0];
-      for (int j = 1; j <= J; ++j) bound = fmaf(wb[kblk + J - j] + wb[kblk + J + j], hotf[j], bound);
-      const uint32_t msk = __ballot_sync(0xffffffffu, kblk < nBlk && !(bound < a.thrLow));   // NaN (inf * 0 cannot occur, but) counts as hot
-      if (lane == 0) hm[m] = msk;
-      anyHot |= msk;
-    }
+    if ((lane >> 2) == tb) hm[lane & 3] = maskWord;
     if (lane == 0) hm[SPAN_WORDS] = 0;
     __syncwarp();
-    if (!anyHot) { if (lane == 0) a.spanRunCount[work] = 0; continue; }
     ++stSpans;
 
     // ---- B: pieces, in position order -------------------------------------------------------------------------------
@@ -381,7 +427,6 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : 4) span_kernel (const 
       }
       if (kb > nBlk) kb = nBlk;
       const uint32_t ze = kb;
-      stHot += ze - zs;
 
       for (uint32_t pb = zs; pb < ze; pb += PIECE_BLOCKS) {
         const uint32_t nb = min((uint32_t)PIECE_BLOCKS, ze - pb);
@@ -395,6 +440,7 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : 4) span_kernel (const 
         __syncwarp();
 
         // B1: the tags within bandwidth of the piece -> dense cells: cell u holds position q0 - bw + u
+        unsigned long long tot = 0;                                    // pooled weight of the piece's cells
         {
           const int64_t lo = (int64_t)q0 - bw, hi = (int64_t)q0 + 32 * nb - 1 + bw;
           const uint32_t cell0 = q0 - bw;                              // may wrap below 0: the unsigned difference below is still right
@@ -403,10 +449,11 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : 4) span_kernel (const 
             uint32_t* dst = str ? DR : D;
             piece_entries(a.T, NONDIR ? (uint32_t)str : U.buffer, U.contig, lo, hi, lane, [&] (uint32_t pos, const uint2& en) {
               const uint32_t u = pos - cell0;
-              if (u < W && !(a.hasControl && isCtl[en.y >> SPAN_SHIFT])) atomicAdd(&dst[u], en.x);
+              if (u < W && !(a.hasControl && isCtl[en.y >> SPAN_SHIFT])) { atomicAdd(&dst[u], en.x); tot += en.x; }
             });
           }
         }
+        tot = warp_sum(tot);                                           // also orders the atomics before the reads below
         __syncwarp();
 
         double dPiece = 0.0;
@@ -447,45 +494,49 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : 4) span_kernel (const 
             if (lane == 0) mw[b] = m;
           }
         } else {
-        // B2: window sums of position 0 (cells 0 .. 2bw) and the piece's total weight
-        unsigned long long c0 = 0, c1 = 0, c2 = 0, tot = 0;
-        for (uint32_t u = lane; u < W; u += 32) {
-          const unsigned long long w = (unsigned long long)D[u] + (NONDIR ? (unsigned long long)DR[u] : 0ull);
-          tot += w;
-          if (u <= 2 * bw) { c0 += w; c1 += w * u; c2 += w * u * u; }
-        }
-        c0 = warp_sum_u64(c0); c1 = warp_sum_u64(c1); c2 = warp_sum_u64(c2); tot = warp_sum_u64(tot);
         dPiece = __dmul_rn((double)tot, a.dS);           // one conservative error bound for the whole piece
-
-        // B3: classify every position: moment form, exact order only inside the error band
-        for (uint32_t b = 0; b < nbEff; ++b) {
-          const uint32_t i = 32 * b + lane;
-          unsigned long long d0 = 0, d1 = 0, d2 = 0;
-          if (i >= 1) {
-            const unsigned long long ue = i + 2 * bw, ul = i - 1;
-            const unsigned long long we = (unsigned long long)D[ue] + (NONDIR ? (unsigned long long)DR[ue] : 0ull);
-            const unsigned long long wl = (unsigned long long)D[ul] + (NONDIR ? (unsigned long long)DR[ul] : 0ull);
-            d0 = we - wl; d1 = we * ue - wl * ul; d2 = we * ue * ue - wl * ul * ul;
+        // B2 + B3 with the window sums S0 = sum w, S1 = sum w*u, S2 = sum w*u^2 (u = cell index) held in type S: they are bounded by
+        // tot, tot*W and tot*W^2, so 32-bit (wrapping differences, exact sums) is enough for all but the heaviest pieces
+        auto classify = [&] (auto tag) {
+          typedef decltype(tag) S;
+          // B2: window sums of position 0 (cells 0 .. 2bw)
+          S c0 = 0, c1 = 0, c2 = 0;
+          for (uint32_t u = lane; u <= 2 * bw; u += 32) {
+            const S w = (S)D[u] + (NONDIR ? (S)DR[u] : (S)0);
+            c0 += w; c1 += w * (S)u; c2 += w * (S)u * (S)u;
           }
-          const unsigned long long S0 = c0 + warp_incl_scan_u64(d0, lane);
-          const unsigned long long S1 = c1 + warp_incl_scan_u64(d1, lane);
-          const unsigned long long S2 = c2 + warp_incl_scan_u64(d2, lane);
-          c0 = __shfl_sync(0xffffffffu, S0, 31); c1 = __shfl_sync(0xffffffffu, S1, 31); c2 = __shfl_sync(0xffffffffu, S2, 31);
-          const unsigned long long x = i + bw;
-          const unsigned long long N = bw2 * S0 - (x * x * S0 - 2ull * x * S1 + S2);
-          double v = __dmul_rn((double)(long long)N, a.cN);
-          const bool valid = i < P;
-          bool above = valid && v >= a.thr + dPiece;
-          if (valid && !above && v >= a.thr - dPiece) {                // too close to call: the reference's own arithmetic decides
-            const double f = exact_dense(Ks, D, i, bw);
-            v = NONDIR ? __dadd_rn(f, exact_dense(Ks, DR, i, bw)) : f; // misc/peakcall.cpp:57
-            above = v >= a.thr;
-            stExact += 32;
+          c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2);
+          // B3: classify every position: moment form, exact order only inside the error band
+          for (uint32_t b = 0; b < nbEff; ++b) {
+            const uint32_t i = 32 * b + lane;
+            S d0 = 0, d1 = 0, d2 = 0;
+            if (i >= 1) {
+              const S ue = (S)(i + 2 * bw), ul = (S)(i - 1);
+              const S we = (S)D[i + 2 * bw] + (NONDIR ? (S)DR[i + 2 * bw] : (S)0);
+              const S wl = (S)D[i - 1] + (NONDIR ? (S)DR[i - 1] : (S)0);
+              d0 = we - wl; d1 = we * ue - wl * ul; d2 = we * ue * ue - wl * ul * ul;
+            }
+            const S S0 = c0 + warp_incl_scan(d0, lane);
+            const S S1 = c1 + warp_incl_scan(d1, lane);
+            const S S2 = c2 + warp_incl_scan(d2, lane);
+            c0 = __shfl_sync(0xffffffffu, S0, 31); c1 = __shfl_sync(0xffffffffu, S1, 31); c2 = __shfl_sync(0xffffffffu, S2, 31);
+            const unsigned long long x = i + bw;
+            const unsigned long long N = bw2 * (unsigned long long)S0 - (x * x * (unsigned long long)S0 - 2ull * x * (unsigned long long)S1 + (unsigned long long)S2);
+            double v = __dmul_rn((double)(long long)N, a.cN);
+            const bool valid = i < P;
+            bool above = valid && v >= a.thr + dPiece;
+            if (valid && !above && v >= a.thr - dPiece) {              // too close to call: the reference's own arithmetic decides
+              const double f = exact_dense(Ks, D, i, bw);
+              v = NONDIR ? __dadd_rn(f, exact_dense(Ks, DR, i, bw)) : f; // misc/peakcall.cpp:57
+              above = v >= a.thr;
+              stExact += 32;
+            }
+            if (valid) scf[i] = (float)v;
+            const uint32_t m = __ballot_sync(0xffffffffu, above);
+            if (lane == 0) mw[b] = m;
           }
-          if (valid) scf[i] = (float)v;
-          const uint32_t m = __ballot_sync(0xffffffffu, above);
-          if (lane == 0) mw[b] = m;
-        }
+        };
+        if (tot * (unsigned long long)W * (unsigned long long)W < 0x100000000ull) classify((uint32_t)0); else classify((unsigned long long)0);
         }
         if (lane == 0) mw[nbEff] = 0;
         __syncwarp();
@@ -569,9 +620,9 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : 4) span_kernel (const 
     }
     if (lane == 0) a.spanRunCount[work] = spanRuns;
   }
+  }
   stExact = warp_sum_u64(stExact);                                    // lane-divergent (uncertain positions) + 32 x uniform (peak candidates)
   if (lane == 0) {
-    if (stHot) atomicAdd(a.stat + 0, stHot);
     if (stPieces) atomicAdd(a.stat + 1, stPieces);
     if (stExact) atomicAdd(a.stat + 2, stExact / 32);
     if (stSpans) atomicAdd(a.stat + 3, stSpans);
