@@ -235,7 +235,7 @@ def main():
     gather = DeviceGather(ctx, n_samples, C, dist=dist, rank=rank, world=world, device=dev) if world > 1 else None
 
     def step():
-        res = ctx.call_regions_view(**dict(st, reference_order=(world == 1)))
+        res = ctx.call_regions_view(**dict(st, reference_order=(1 if world == 1 else 2)))   # ranks of a multi-GPU job keep their rows on the device
         if world == 1:
             return res
         # NCCL: one small all-reduce (rows / candidates per unit, tags in regions) + one reduce of the table-wide slab to rank 0
@@ -246,6 +246,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # device timing: CUDA events on the stream the library launches on (torch's current stream never sees those kernels).
+    # Every call returns only when its table is in host memory, so the events bracket kernels, copies and the host gaps between
+    # steps; the wall clock around the same region is reported next to it as a cross-check.
+    lib_stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
     load()
     for _ in range(args.warmup):
         last = step()
@@ -253,31 +259,45 @@ def main():
     barrier()
     with ClockSampler(local_rank) as clocks:
         t0 = time.perf_counter()
+        ev0.record(lib_stream)
         for _ in range(args.steps):
             last = step()
             s = ctx.stats()
             kde_ms.append(s["ms_kde"]); launches += s["launches"]
+        if world > 1:
+            lib_stream.wait_stream(torch.cuda.current_stream())      # the NCCL gather of the last step runs on torch's stream
+        ev1.record(lib_stream)
         barrier()
-        dt = time.perf_counter() - t0
+        dt_wall = time.perf_counter() - t0
     stats = ctx.stats()
-    tmax = torch.tensor([dt], dtype=torch.float64, device=dev)
+    ev1.synchronize()
+    dt = ev0.elapsed_time(ev1) * 1e-3
+    tmax = torch.tensor([dt, dt_wall], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    dt = float(tmax.item())
+    dt, dt_wall = float(tmax[0].item()), float(tmax[1].item())
     ms_per_step = dt / args.steps * 1e3
+    wall_ms_per_step = dt_wall / args.steps * 1e3
 
-    # e2e: pinned host arrays -> device every step
+    # e2e: pinned host arrays -> device every step (same two clocks)
     barrier()
     t0 = time.perf_counter()
+    ev0.record(lib_stream)
     e2e_steps = max(1, min(args.steps, 3))
     for _ in range(e2e_steps):
         load()
         last = step()
+    if world > 1:
+        lib_stream.wait_stream(torch.cuda.current_stream())
+    ev1.record(lib_stream)
     barrier()
-    e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    e2e_wall = time.perf_counter() - t0
+    ev1.synchronize()
+    e2e = torch.tensor([ev0.elapsed_time(ev1) * 1e-3, e2e_wall], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
-    e2e_ms = float(e2e.item()) / e2e_steps * 1e3
+    e2e_ms = float(e2e[0].item()) / e2e_steps * 1e3
+    e2e_wall_ms = float(e2e[1].item()) / e2e_steps * 1e3
     n_rows = int(last["n_rows"]) if last else 0
     d2h = n_rows * (41 + 4 * n_samples)
 
@@ -288,19 +308,28 @@ def main():
     except Exception:
         pass
     peak_gbs, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
+    traffic = None
+    try:    # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on this workload (profiles/)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = "%s_bw%d" % (args.workload, args.bandwidth)
+        if world == 1 and not (args.samples or args.tags) and key in tj:
+            traffic = tj[key]["span_kernel_dram_bytes"]
+    except Exception:
+        pass
     kde_avg_ms = float(np.mean(kde_ms)) if kde_ms else float("nan")
     n_runs_bytes = (40 + 4 * n_samples) * stats["n_candidates"]     # run record + kurtosis + per-sample hits
     alg_bytes = 8 * E + n_runs_bytes
     achieved = alg_bytes / (kde_avg_ms * 1e-3) / 1e9 if kde_avg_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "span_kernel<directional>" if directional else "span_kernel<nondirectional>", "achieved": achieved, "peak": peak_gbs,
-                "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None,
+                "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kde_avg_ms, "kernel_share_of_step": kde_avg_ms / ms_per_step}
 
     if rank == 0:
         line = {"metric": metric, "value": genome / (ms_per_step * 1e-3), "unit": "bp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "ms_per_step": ms_per_step, "wall_ms_per_step": wall_ms_per_step, "timing": "CUDA events on the library's stream around the K steps (max over ranks); wall clock alongside",
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config, "clocks": clocks.summary(),
-                "e2e": {"value": genome / (e2e_ms * 1e-3), "unit": "bp/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": 8 * E + 8 * int(data.off.shape[0]), "d2h_bytes_per_step": d2h},
+                "e2e": {"value": genome / (e2e_ms * 1e-3), "unit": "bp/s", "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall_ms, "h2d_bytes_per_step": 8 * E + 8 * int(data.off.shape[0]), "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "roofline": roofline,
                 "result": {"regions": n_rows, "candidates": stats["n_candidates"], "tag_entries_rank0": E, "spans": stats["kde_tiles"], "warm_spans": stats["warm_spans"], "pieces": stats["kde_hot_tiles"],
                            "hot_blocks": stats["hot_blocks"], "exact_evals": stats["exact_evals"], "stitched": stats["n_stitched"],

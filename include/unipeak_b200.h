@@ -83,7 +83,10 @@ typedef struct {
   double background;            /* tags per mappable position, halved if directional (src/regions.cpp:209-210) */
   int reference_order;          /* 1: rows come back in the reference's emission order with its labels and its
                                    dropped tail; needs every contig loaded in this context.
-                                   0: canonical order (buffer, contig, left), nothing dropped. */
+                                   0: canonical order (buffer, contig, left), nothing dropped.
+                                   2: as 0, but the rows stay in device memory only — for a rank of a multi-GPU job that hands them
+                                      to upb_scatter_rows; n_rows, the totals and the unit_* arrays of the returned table are valid,
+                                      the per-row columns are not filled. */
 } upb_region_params;
 
 /* One row per accepted region == one Region the reference pushes into regionsOut (misc/peakcall.cpp:45)
@@ -224,6 +227,10 @@ typedef struct {
   float ms_call;                /* host wall clock of the last upb_call_regions, entry to return */
 } upb_stats;
 int upb_last_stats (const upb_ctx* ctx, upb_stats* out);
+
+/* The CUDA stream (cudaStream_t) every kernel and copy of this context is issued on, so that a caller can bracket calls with
+ * its own CUDA events (bench.py times the step this way).  No reference counterpart: instrumentation only. */
+void* upb_stream (const upb_ctx* ctx);
 
 #ifdef __cplusplus
 }

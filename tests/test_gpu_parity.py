@@ -376,7 +376,7 @@ def test_scatter_rows_rebuilds_the_single_gpu_table(gpu_ctx):
         part = TagData.from_segments(sizes, segs)
         cx = unipeak_b200.Context(0)
         cx.load(part)
-        views.append(cx.call_regions_view(**dict(st, reference_order=False)))
+        views.append(cx.call_regions_view(**dict(st, reference_order=(2 if r else 0))))   # 2: rows stay on the device (what a rank of a multi-GPU job asks for)
         ctxs.append(cx)
     unit_total = sum(np.asarray(v["unit_rows"], dtype=np.uint64) for v in views)
     R = int(unit_total.sum())

@@ -75,7 +75,7 @@ EXPORTS = [
     "upb_create", "upb_destroy", "upb_last_error", "upb_device_count", "upb_host_alloc", "upb_host_free", "upb_set_contigs",
     "upb_load_tags", "upb_call_regions", "upb_free_region_table", "upb_reference_order", "upb_profile_contig", "upb_free_profile",
     "upb_strand_shift", "upb_free_shift_report", "upb_count_tags_in_regions", "upb_kernel_taps", "upb_last_stats",
-    "upb_slab_layout", "upb_scatter_rows", "upb_table_from_slab",
+    "upb_slab_layout", "upb_scatter_rows", "upb_table_from_slab", "upb_stream",
 ]
 SLAB_COLS = ("cand_index", "peak_score", "kurtosis", "corr", "contig", "left", "len", "peak", "hit_sum", "counts", "buffer", "end")
 SLAB_DTYPES = dict(cand_index=np.uint64, peak_score=np.float64, kurtosis=np.float64, corr=np.float64, contig=np.uint32, left=np.uint32,
@@ -114,6 +114,8 @@ def lib():
         L.upb_count_tags_in_regions.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint64, C.POINTER(RegionKey), C.c_void_p]
         L.upb_kernel_taps.argtypes = [C.c_uint32, C.c_double, C.POINTER(C.c_double)]
         L.upb_last_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.upb_stream.argtypes = [C.c_void_p]
+        L.upb_stream.restype = C.c_void_p
         L.upb_slab_layout.argtypes = [C.c_uint64, C.c_uint32, C.c_void_p]
         L.upb_scatter_rows.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.upb_table_from_slab.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(RegionTable)]
@@ -235,7 +237,7 @@ class Context:
         cf = np.ascontiguousarray(coeffs if coeffs is not None else [], dtype=np.float64)
         p = RegionParams(bandwidth, region_threshold, kurtosis_threshold, corr_threshold, hit_threshold, 1 if directional else 0,
                          ctrl.ctypes.data_as(C.POINTER(C.c_uint8)), cf.shape[0], cf.ctypes.data_as(C.POINTER(C.c_double)),
-                         background, 1 if reference_order else 0)
+                         background, int(reference_order) if reference_order in (0, 1, 2) and not isinstance(reference_order, bool) else (1 if reference_order else 0))
         return p, (ctrl, cf)
 
     @staticmethod
@@ -342,6 +344,10 @@ class Context:
         tot = np.ascontiguousarray(unit_rows_total, dtype=np.uint64)
         loc = np.ascontiguousarray(unit_rows_local, dtype=np.uint64)
         self._check(self._lib.upb_scatter_rows(self._h, int(total_rows), tot.ctypes.data, loc.ctypes.data, C.c_void_p(d_slab_ptr)))
+
+    def stream_ptr(self) -> int:
+        """cudaStream_t of this context (for CUDA-event timing by the caller)."""
+        return int(self._lib.upb_stream(self._h) or 0)
 
     def stats(self) -> Dict:
         s = Stats()

@@ -136,6 +136,8 @@ extern "C" int upb_host_alloc (void** out, size_t bytes) {
 }
 extern "C" void upb_host_free (void* p) { if (p) cudaFreeHost(p); }
 
+extern "C" void* upb_stream (const upb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
 extern "C" int upb_last_stats (const upb_ctx* ctx, upb_stats* out) {
   if (!ctx || !out) return UPB_ERR_BAD_ARG;
   *out = ctx->stats;
@@ -335,6 +337,7 @@ struct PipeCfg {
   bool nondir;
   bool needCorr;                     // compute strandCorr(0) for regions passing the earlier filters
   const uint8_t* control;            // may be NULL
+  bool deviceOnly = false;           // leave the rows in the device slab (multi-GPU ranks: upb_scatter_rows reads them there)
   bool allowLeftEdge = false;        // replay the reference's left-edge behaviour (Q2) instead of refusing such inputs
   uint32_t nCoeffs = 0;              // 0, or the number of non-control samples (-z)
   const double* coeffs = nullptr;    // already normalised as src/regions.cpp:216-229
@@ -691,9 +694,9 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
   sa.coeff = pr.d_coeffBySample;
   sa.cN = kmax / ((double)cfg.bw * (double)cfg.bw);
   sa.dS = kmax * 1e-11;                                               // >= 100x the worst-case rounding difference between the two forms
-  sa.flags = small32; sa.ticket = small32 + 1; sa.runCount = small32 + 2; sa.stat = (unsigned long long*)(small32 + 4);
+  sa.flags = small32; sa.ticket = small32 + 1; sa.runCount = small32 + 2; sa.runReal = small32 + 3; sa.stat = (unsigned long long*)(small32 + 4);
   sa.spanRunCount = SCR("spanRunCount", uint32_t, pr.totalSpans);
-  uint2* warmList = SCR("warmList", uint2, pr.totalSpans);
+  WarmRec* warmList = SCR("warmList", WarmRec, pr.totalSpans);
   uint2* hotList = SCR("hotList", uint2, pr.totalSpans);
   uint32_t* hotMask = SCR("hotMask", uint32_t, (size_t)pr.totalSpans * SPAN_WORDS);
   sa.hotList = hotList; sa.nHot = small32 + 14; sa.hotMask = hotMask;
@@ -702,7 +705,7 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
   WarmArgs wa;
   wa.T = pr.T; wa.units = d_units; wa.nUnits = nUnits; wa.totalSpans = pr.totalSpans; wa.nondir = cfg.nondir ? 1 : 0;
   wa.nAdj = ((31 + 2 * cfg.bw) >> MT_SHIFT) + 2;
-  wa.warmList = warmList; wa.nWarm = small32 + 12; wa.spanRunCount = sa.spanRunCount;
+  wa.warmList = warmList; wa.nWarm = small32 + 12; wa.spanRunCount = sa.spanRunCount; wa.bw = cfg.bw;
 
   // ---- K0: left-edge replay for the units that need it ------------------------------------
   const uint32_t nAff = (uint32_t)pr.affected.size();
@@ -744,24 +747,27 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
 
   size_t runCap = std::max<size_t>(1u << 18, (size_t)(ctx->nEntries / 64));
   { const size_t have = ctx->scratch["runs"].cap / sizeof(SpanRun); if (have > runCap) runCap = have; }
-  uint32_t nRuns = 0;
+  uint32_t nRuns = 0, runSlots = 0;
   for (int attempt = 0; attempt < 2; ++attempt) {
     sa.runs = SCR("runs", SpanRun, runCap);
     sa.runCap = (uint32_t)std::min<size_t>(runCap, 0xFFFFFFF0u);
     CU(cudaMemsetAsync(ctx->d_small.p, 0, 256, ctx->stream));
     wa.flatBound = flatBound; wa.thr = cfg.thr;
     warm_span_kernel<<<(pr.totalSpans + 255) / 256, 256, 0, ctx->stream>>>(wa);
-    hot_span_kernel<<<ctx->smCount * 8, HOT_THREADS, 0, ctx->stream>>>(ha);
+    { int perSm = 0;
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, hot_span_kernel, HOT_THREADS, 0));
+      hot_span_kernel<<<ctx->smCount * std::max(perSm, 1), HOT_THREADS, 0, ctx->stream>>>(ha); }
     launches += 2;
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     if ((r = launch_span(ctx, sa, cfg.nondir, &launches))) return r;
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     CU(cudaMemcpyAsync(h32, ctx->d_small.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    nRuns = h32[2];
+    nRuns = h32[3];                                                   // runs written
+    runSlots = h32[2];                                                // slots handed out (a warp reserves RUN_CHUNK at a time)
     if (!(h32[0] & FLAG_RUN_OVERFLOW)) break;
     if (attempt == 1) return fail(ctx, UPB_ERR_NOMEM, "run buffer overflow after resize");
-    runCap = (size_t)nRuns + 1024;                                    // the counter holds the exact need
+    runCap = (size_t)runSlots + (1u << 20);                           // the counter holds the need; chunks may fall differently next time
   }
   ctx->stats.warm_spans = h32[12];
   { unsigned long long st[4]; memcpy(st, h32 + 4, 32); ctx->stats.kde_hot_tiles = st[1]; ctx->stats.hot_blocks = st[0]; ctx->stats.exact_evals = st[2]; ctx->stats.spans_with_tags = st[3]; }
@@ -787,7 +793,7 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
   uint32_t* head = SCR("head", uint32_t, nRuns);
   unsigned long long* headScan = SCR("headScan", unsigned long long, nRuns);
   const unsigned gRuns = (nRuns + 255) / 256;
-  run_order_kernel<<<gRuns, 256, 0, ctx->stream>>>(sa.runs, nRuns, spanOrd, ordIdx);
+  run_order_kernel<<<(runSlots + 255) / 256, 256, 0, ctx->stream>>>(sa.runs, runSlots, spanOrd, ordIdx);
   run_heads2_kernel<<<gRuns, 256, 0, ctx->stream>>>(sa.runs, ordIdx, nRuns, d_units, nUnits, head);
   CU(cudaGetLastError());
   launches += 2;
@@ -963,7 +969,12 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
     tags_in_regions_kernel<<<std::min<unsigned>(ctx->smCount * 4, (unsigned)((R * n + 255) / 256)), 256, (size_t)n * 8, ctx->stream>>>(ea.counts, R, n, d_tir);
     CU(cudaGetLastError());
     launches += 1;
-    CU(cudaMemcpyAsync(hs, ds, SL.devBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!cfg.deviceOnly) CU(cudaMemcpyAsync(hs, ds, SL.devBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    else {                                                            // only what the per-unit row counts need (5 bytes per row)
+      const size_t Rp = (R + 7) & ~(size_t)7;
+      CU(cudaMemcpyAsync(hs + SL.oContig, ds + SL.oContig, Rp * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaMemcpyAsync(hs + SL.oBuffer, ds + SL.oBuffer, Rp, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CU(cudaMemcpyAsync(hs + SL.oTags, d_tir, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
   }
   (void)Rnormal;
@@ -1137,6 +1148,7 @@ extern "C" int upb_call_regions (upb_ctx* ctx, const upb_region_params* p, upb_r
   cfg.nCoeffs = p->n_coeffs; cfg.coeffs = p->coeffs;
   cfg.needCorr = cfg.nondir;        // -D: the filter (if corr_threshold > -1) and the optional correlation column
   cfg.allowLeftEdge = true;
+  cfg.deviceOnly = p->reference_order == 2;
   PipeOut po;
   Prep pr;
   int r = run_pipeline(ctx, cfg, pr, po);
@@ -1149,7 +1161,7 @@ extern "C" int upb_call_regions (upb_ctx* ctx, const upb_region_params* p, upb_r
     const uint32_t b = p->directional ? d : 0;
     if (lp > out->unit_last_tag[(size_t)b * C + c]) out->unit_last_tag[(size_t)b * C + c] = lp;
   }
-  if (p->reference_order) {
+  if (p->reference_order == 1) {
     std::vector<uint64_t> perm;
     bool identity = true;
     r = reference_order_impl(C, n, p->directional, p->bandwidth, ctx->firstPos.data(), ctx->lastPos.data(), out, &perm, &identity);

@@ -43,6 +43,8 @@ constexpr int SPAN_BLOCKS = SPAN_LEN / 32;          // 128 blocks of 32 position
 constexpr int SPAN_WORDS = SPAN_BLOCKS / 32;
 constexpr int PIECE_BLOCKS = 16;                    // <= 512 positions per piece
 constexpr int PIECE_LEN = PIECE_BLOCKS * 32;
+constexpr uint32_t RUN_CHUNK = 32;                  // run slots a warp reserves at a time
+constexpr uint32_t RUN_INVALID = 0xFFFFFFFFu;       // SpanRun::span of a reserved slot that was never filled
 constexpr int MAX_BW_FAST = 448;                    // piece cells = PIECE_LEN + 2*bw <= 1408
 
 typedef Unit SpanUnit;                              // one (ProfileBuffer, contig) pair; nSpans = ceil((size + bw) / SPAN_LEN)
@@ -75,7 +77,8 @@ struct SpanArgs {
   uint32_t* ticket;
   SpanRun* runs;
   uint32_t runCap;
-  uint32_t* runCount;
+  uint32_t* runCount;                               // run slots handed out (chunks of RUN_CHUNK per warp; unused slots are marked invalid)
+  uint32_t* runReal;                                // runs actually written
   uint32_t* spanRunCount;                           // [totalSpans]
   uint32_t* flags;
   unsigned long long* stat;                         // [0] hot blocks, [1] pieces, [2] exact evaluations, [3] spans with tags
@@ -222,6 +225,14 @@ __device__ __forceinline__ void piece_entries (const Tags& T, uint32_t d, uint32
 // maxTap * weight >= threshold has no hot block and is skipped without touching its entries — the device-side analogue
 // of the reference leaping over empty stretches (misc/peakcall.cpp:172-173).  The weights count every sample (controls
 // too), which only makes the bound more conservative.
+struct WarmRec {                    // everything hot_span_kernel needs about one warm span: no dependent look-ups there
+  uint32_t span, unit;
+  uint32_t blk0, blk1;              // index into Tags::blkW of the span's first block, strand 0 / 1 of the unit (blk1 unused unless -D)
+  int32_t left;                     // blocks of the contig before the span
+  int32_t right0, right1;           // blocks of the contig from the span's first block to the end of the mini-tile table (may be <= 0), per strand
+  uint32_t nBlk;                    // blocks of the span that hold evaluated positions (Q20: through size + bw)
+};
+
 struct WarmArgs {
   Tags T;
   const SpanUnit* units;
@@ -229,7 +240,8 @@ struct WarmArgs {
   int nondir;
   uint32_t nAdj;
   double flatBound, thr;
-  uint2* warmList;                  // (span, unit) of the spans that have to be looked at, any order
+  WarmRec* warmList;                // the spans that have to be looked at, any order
+  uint32_t bw;
   uint32_t* nWarm;
   uint32_t* spanRunCount;           // zeroed here for the spans that are skipped
 };
@@ -261,13 +273,35 @@ __global__ void warm_span_kernel (WarmArgs a) {
     }
     if (!warm) a.spanRunCount[w] = 0;
   }
-  // compact the warm spans: one atomic per warp
+  // compact the warm spans: one atomic per block (atomics on one address serialise: ~1 ns each)
+  __shared__ uint32_t s_warp[8], s_base;
   const uint32_t msk = __ballot_sync(0xffffffffu, warm);
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = __popc(msk);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int q = 0; q < 8; ++q) { const uint32_t c = s_warp[q]; s_warp[q] = run; run += c; }
+    s_base = run ? atomicAdd(a.nWarm, run) : 0u;
+  }
+  __syncthreads();
   if (msk) {
-    uint32_t base = 0;
-    if ((threadIdx.x & 31) == (uint32_t)(__ffs(msk) - 1)) base = atomicAdd(a.nWarm, __popc(msk));
-    base = __shfl_sync(0xffffffffu, base, __ffs(msk) - 1);
-    if (warm) a.warmList[base + __popc(msk & ((1u << (threadIdx.x & 31)) - 1))] = make_uint2(w, unit);
+    const uint32_t base = s_base + s_warp[threadIdx.x >> 5];
+    if (warm) {
+      const SpanUnit U = a.units[unit];
+      const uint32_t k = w - U.spanStart;
+      const uint32_t d0 = a.nondir ? 0u : U.buffer, d1 = a.nondir ? 1u : U.buffer;
+      const uint32_t gb0 = a.T.mtBase[d0 * a.T.C + U.contig], gb1 = a.T.mtBase[d1 * a.T.C + U.contig];
+      const uint32_t nB0 = (a.T.mtBase[d0 * a.T.C + U.contig + 1] - gb0) * BLK_PER_MT, nB1 = (a.T.mtBase[d1 * a.T.C + U.contig + 1] - gb1) * BLK_PER_MT;
+      const uint64_t lastPos = (uint64_t)U.size + a.bw;
+      const uint32_t np = (uint32_t)min((uint64_t)SPAN_LEN, lastPos - (uint64_t)k * SPAN_LEN);
+      WarmRec r;
+      r.span = w; r.unit = unit;
+      r.blk0 = gb0 * BLK_PER_MT + k * SPAN_BLOCKS; r.blk1 = gb1 * BLK_PER_MT + k * SPAN_BLOCKS;
+      r.left = (int32_t)(k * SPAN_BLOCKS);
+      r.right0 = (int32_t)nB0 - (int32_t)(k * SPAN_BLOCKS); r.right1 = (int32_t)nB1 - (int32_t)(k * SPAN_BLOCKS);
+      r.nBlk = (np + 31) >> 5;
+      a.warmList[base + __popc(msk & ((1u << (threadIdx.x & 31)) - 1))] = r;
+    }
   }
 }
 
@@ -279,7 +313,7 @@ __global__ void warm_span_kernel (WarmArgs a) {
 struct HotArgs {
   Tags T;
   const SpanUnit* units;
-  const uint2* warmList;
+  const WarmRec* warmList;
   const uint32_t* nWarm;
   uint32_t bw;
   int nondir;
@@ -296,46 +330,52 @@ struct HotArgs {
 constexpr int HOT_THREADS = 256;
 constexpr int HOT_WB = (SPAN_BLOCKS + 2 * HOT_JMAX + 3) & ~1;
 
-__global__ void __launch_bounds__(HOT_THREADS) hot_span_kernel (const __grid_constant__ HotArgs a) {
+__global__ void __launch_bounds__(HOT_THREADS, 6) hot_span_kernel (const __grid_constant__ HotArgs a) {
   __shared__ float hotf[HOT_JMAX + 2];
   __shared__ float wbAll[HOT_THREADS / 32][HOT_WB];
+  __shared__ uint2 outAll[HOT_THREADS / 32][32];                      // hot spans found by this warp, flushed with one atomic per 32
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* wb = wbAll[warp];
+  uint2* outBuf = outAll[warp];
+  uint32_t nOut = 0;
   for (uint32_t i = threadIdx.x; i <= a.hotJ; i += HOT_THREADS) hotf[i] = a.hotCoefF[i];
   __syncthreads();
   const int J = (int)a.hotJ;
   const uint32_t nWarm = *a.nWarm;
   const uint32_t nWarps = gridDim.x * (HOT_THREADS / 32);
   unsigned long long stHot = 0;
-  for (uint32_t it = blockIdx.x * (HOT_THREADS / 32) + warp; it < nWarm; it += nWarps) {
-    const uint2 item = __ldg(a.warmList + it);
-    const SpanUnit U = a.units[item.y];
-    const uint32_t k = item.x - U.spanStart;
-    const uint32_t ts = k * SPAN_LEN + 1;
-    const uint64_t lastPos = (uint64_t)U.size + a.bw;                 // Q20: evaluated through lastTag+bw
-    const uint32_t np = (uint32_t)min((uint64_t)SPAN_LEN, lastPos - (ts - 1));
-    const uint32_t nBlk = (np + 31) >> 5;
-    const int B0 = (int)(k * SPAN_BLOCKS) - J;                         // block held by wb[0]
-    uint32_t gb[2], nB[2];
-#pragma unroll
-    for (int str = 0; str < 2; ++str) {
-      const uint32_t d = a.nondir ? (uint32_t)str : U.buffer;
-      gb[str] = __ldg(a.T.mtBase + d * a.T.C + U.contig);
-      nB[str] = (__ldg(a.T.mtBase + d * a.T.C + U.contig + 1) - gb[str]) * BLK_PER_MT;
-    }
-    float wv[(SPAN_BLOCKS + 2 * HOT_JMAX + 31) / 32];
-#pragma unroll
-    for (int q = 0; q < (SPAN_BLOCKS + 2 * HOT_JMAX + 31) / 32; ++q) {   // one round trip: 128 + 2J floats per strand
-      const int i = 32 * q + (int)lane, B = B0 + i;
-      float w = 0.0f;
-      if (i < SPAN_BLOCKS + 2 * J && B >= 0) {
-        if ((uint32_t)B < nB[0]) w = __ldg(a.T.blkW + (size_t)gb[0] * BLK_PER_MT + (uint32_t)B);
-        if (a.nondir && (uint32_t)B < nB[1]) w += __ldg(a.T.blkW + (size_t)gb[1] * BLK_PER_MT + (uint32_t)B);   // may round down by 2^-24: inside the margin
+  uint32_t it = blockIdx.x * (HOT_THREADS / 32) + warp;
+  uint4 ra = make_uint4(0, 0, 0, 0), rb = ra;
+  if (it < nWarm) { const uint4* rp = (const uint4*)(a.warmList + it); ra = __ldg(rp); rb = __ldg(rp + 1); }
+  for (; it < nWarm; it += nWarps) {
+    const uint32_t span = ra.x, unitOf = ra.y, blk0 = ra.z, blk1 = ra.w, nBlk = rb.w;
+    const int left = (int)rb.x, right0 = (int)rb.y, right1 = (int)rb.z;
+    if (it + nWarps < nWarm) { const uint4* rp = (const uint4*)(a.warmList + it + nWarps); ra = __ldg(rp); rb = __ldg(rp + 1); }   // next record: in flight during this span
+    // one round trip: 128 + 2J floats per strand, straight into shared memory
+    const bool interior = left >= J && right0 >= SPAN_BLOCKS + J && (!a.nondir || right1 >= SPAN_BLOCKS + J);
+    if (interior && J <= 16) {                                         // the common case: no bounds to check, 160 consecutive floats
+      const float* __restrict__ p0 = a.T.blkW + (size_t)blk0 - J;
+      const float* __restrict__ p1 = a.T.blkW + (size_t)blk1 - J;
+      float w0 = __ldg(p0 + lane), w1 = __ldg(p0 + 32 + lane), w2 = __ldg(p0 + 64 + lane), w3 = __ldg(p0 + 96 + lane);
+      float w4 = lane < (uint32_t)(2 * J) ? __ldg(p0 + 128 + lane) : 0.0f;
+      if (a.nondir) {
+        w0 += __ldg(p1 + lane); w1 += __ldg(p1 + 32 + lane); w2 += __ldg(p1 + 64 + lane); w3 += __ldg(p1 + 96 + lane);   // may round down by 2^-24: inside the margin
+        if (lane < (uint32_t)(2 * J)) w4 += __ldg(p1 + 128 + lane);
       }
-      wv[q] = w;
-    }
+      wb[lane] = w0; wb[32 + lane] = w1; wb[64 + lane] = w2; wb[96 + lane] = w3;
+      if (128 + lane < (uint32_t)HOT_WB) wb[128 + lane] = w4;
+    } else {
 #pragma unroll
-    for (int q = 0; q < (SPAN_BLOCKS + 2 * HOT_JMAX + 31) / 32; ++q) { const int i = 32 * q + (int)lane; if (i < HOT_WB) wb[i] = wv[q]; }
+      for (int q = 0; q < (SPAN_BLOCKS + 2 * HOT_JMAX + 31) / 32; ++q) {
+        const int i = 32 * q + (int)lane, r = i - J;                 // block r of the span (r < 0: halo before it)
+        float w = 0.0f;
+        if (i < SPAN_BLOCKS + 2 * J && r >= -left) {
+          if (r < right0) w = __ldg(a.T.blkW + (size_t)blk0 + r);
+          if (a.nondir && r < right1) w += __ldg(a.T.blkW + (size_t)blk1 + r);
+        }
+        if (i < HOT_WB) wb[i] = w;
+      }
+    }
     __syncwarp();
     uint32_t any = 0, mine = 0;
 #pragma unroll
@@ -350,9 +390,25 @@ __global__ void __launch_bounds__(HOT_THREADS) hot_span_kernel (const __grid_con
     }
     __syncwarp();
     if (any) {
-      if (lane < (uint32_t)SPAN_WORDS) a.hotMask[(size_t)item.x * SPAN_WORDS + lane] = mine;
-      if (lane == 0) a.hotList[atomicAdd(a.nHot, 1u)] = item;
-    } else if (lane == 0) a.spanRunCount[item.x] = 0;
+      if (lane < (uint32_t)SPAN_WORDS) a.hotMask[(size_t)span * SPAN_WORDS + lane] = mine;
+      if (lane == 0) outBuf[nOut] = make_uint2(span, unitOf);
+      if (++nOut == 32) {
+        __syncwarp();
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(a.nHot, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        a.hotList[base + lane] = outBuf[lane];
+        nOut = 0;
+        __syncwarp();
+      }
+    } else if (lane == 0) a.spanRunCount[span] = 0;
+  }
+  if (nOut) {
+    __syncwarp();
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(a.nHot, nOut);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (lane < nOut) a.hotList[base + lane] = outBuf[lane];
   }
   if (lane == 0 && stHot) atomicAdd(a.stat + 0, stHot);
 }
@@ -384,6 +440,8 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : 4) span_kernel (const 
   const unsigned long long bw2 = (unsigned long long)bw * bw;
   unsigned long long stPieces = 0, stExact = 0, stSpans = 0;
   const uint32_t nHot = *a.nHot;
+  uint32_t rBase = 0, rUsed = RUN_CHUNK, rTotal = 0;                   // current chunk of run slots: [rBase, rBase + RUN_CHUNK), rUsed taken
+  bool rRoom = true;
   constexpr uint32_t BATCH = 4;                                        // hot spans per ticket: one atomic and two dependent loads per four spans
 
   for (;;) {
@@ -549,11 +607,27 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : 4) span_kernel (const 
           nRuns = warp_sum_u32(n);
         }
         if (nRuns == 0) continue;
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(a.runCount, nRuns);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        const bool room = (uint64_t)base + nRuns <= a.runCap;
+        uint32_t base;
+        bool room;
+        if (nRuns > RUN_CHUNK) {                                       // rare: more runs than a chunk holds get their own reservation
+          base = 0;
+          if (lane == 0) base = atomicAdd(a.runCount, nRuns);
+          base = __shfl_sync(0xffffffffu, base, 0);
+          room = (uint64_t)base + nRuns <= a.runCap;
+        } else {
+          if (rUsed + nRuns > RUN_CHUNK) {                             // next chunk; what is left of the old one is marked unused
+            if (rRoom && rUsed + lane < RUN_CHUNK) a.runs[rBase + rUsed + lane].span = RUN_INVALID;
+            if (lane == 0) rBase = atomicAdd(a.runCount, RUN_CHUNK);
+            rBase = __shfl_sync(0xffffffffu, rBase, 0);
+            rUsed = 0;
+            rRoom = (uint64_t)rBase + RUN_CHUNK <= a.runCap;
+          }
+          base = rBase + rUsed;
+          rUsed += nRuns;
+          room = rRoom;
+        }
         if (!room && lane == 0) atomicOr(a.flags, FLAG_RUN_OVERFLOW);
+        if (room) rTotal += nRuns;
 
         uint32_t cursor = 0;
         for (uint32_t r = 0; r < nRuns; ++r) {
@@ -621,6 +695,8 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : 4) span_kernel (const 
     if (lane == 0) a.spanRunCount[work] = spanRuns;
   }
   }
+  if (rRoom && rUsed + lane < RUN_CHUNK) a.runs[rBase + rUsed + lane].span = RUN_INVALID;
+  if (lane == 0 && rTotal) atomicAdd(a.runReal, rTotal);
   stExact = warp_sum_u64(stExact);                                    // lane-divergent (uncertain positions) + 32 x uniform (peak candidates)
   if (lane == 0) {
     if (stPieces) atomicAdd(a.stat + 1, stPieces);
@@ -642,7 +718,7 @@ struct Cand2 {                      // a candidate region == one Region object o
 // position of every run in (span, rank) order
 __global__ void run_order_kernel (const SpanRun* __restrict__ runs, uint32_t nRuns, const unsigned long long* __restrict__ spanOrd, uint32_t* __restrict__ ordIdx) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nRuns) return;
+  if (i >= nRuns || runs[i].span == RUN_INVALID) return;              // nRuns = slots handed out; unfilled ones are skipped
   ordIdx[spanOrd[runs[i].span] + runs[i].rank] = i;
 }
 
@@ -668,10 +744,17 @@ __global__ void merge_runs2_kernel (const SpanRun* __restrict__ runs, const uint
                                     const unsigned long long* __restrict__ headScan, uint32_t nRuns, const SpanUnit* __restrict__ units, uint32_t nUnits,
                                     Cand2* __restrict__ cand, unsigned long long* __restrict__ unitCand) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= nRuns || !head[j]) return;
+  const bool isHead = j < nRuns && head[j];
+  uint32_t myUnit = 0xFFFFFFFFu;
+  if (isHead) myUnit = unit_of_span(units, nUnits, runs[ordIdx[j]].span);
+  {                                                                   // candidates per unit: one atomic per (warp, unit) instead of one per candidate
+    const uint32_t peers = __match_any_sync(0xffffffffu, myUnit);
+    if (isHead && (threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&unitCand[myUnit], (unsigned long long)__popc(peers));
+  }
+  if (!isHead) return;
   const SpanRun f = runs[ordIdx[j]];
   Cand2 c;
-  c.unit = unit_of_span(units, nUnits, f.span); c.left = f.left; c.len = f.len; c.peak = f.peak; c.wsum = f.wsum; c.score = f.score;
+  c.unit = myUnit; c.left = f.left; c.len = f.len; c.peak = f.peak; c.wsum = f.wsum; c.score = f.score;
   c.slot = ordIdx[j]; c.nPieces = 1; c.pad = 0;
   for (uint32_t q = j + 1; q < nRuns && !head[q]; ++q) {
     const SpanRun r = runs[ordIdx[q]];
@@ -681,7 +764,6 @@ __global__ void merge_runs2_kernel (const SpanRun* __restrict__ runs, const uint
     ++c.nPieces;
   }
   cand[headScan[j]] = c;
-  atomicAdd(&unitCand[c.unit], 1ull);
 }
 
 // candidates of span_kernel that lie in the stretch the left-edge replay owns (upb_edge.cuh) are not Region objects of the
