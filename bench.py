@@ -57,7 +57,7 @@ def env_int(name, default):
         return default
 
 
-from unipeak_b200.multi import DeviceGather, shard_contigs  # noqa: E402
+from unipeak_b200.multi import DeviceGather, HostGather, shard_contigs  # noqa: E402
 
 
 class ClockSampler:
@@ -151,6 +151,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--bandwidth", type=int, default=50, help="-b (config 5 sweeps 10..200)")
+    ap.add_argument("--gather", default="host", choices=["host", "nccl"],
+                    help="N > 1 region-list gather: every rank writes its rows into one shared, mapped host table (host), or one NCCL reduce of a device slab + D2H on rank 0 (nccl)")
     args = ap.parse_args()
 
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -232,7 +234,10 @@ def main():
         ctx.load_tags_ptr(n_samples, h_off.data_ptr(), h_pos.data_ptr(), h_cnt.data_ptr())
 
     C = len(sizes)
-    gather = DeviceGather(ctx, n_samples, C, dist=dist, rank=rank, world=world, device=dev) if world > 1 else None
+    gather = None
+    if world > 1:
+        gather = (HostGather if args.gather == "host" else DeviceGather)(ctx, n_samples, C, dist=dist, rank=rank, world=world, device=dev)
+        config["parallelism"] += ", region-list gather: " + ("rows written by every rank into one shared mapped host table, two small NCCL all-reduces" if args.gather == "host" else "one NCCL reduce of a device slab + D2H on rank 0")
 
     def step():
         res = ctx.call_regions_view(**dict(st, reference_order=(1 if world == 1 else 2)))   # ranks of a multi-GPU job keep their rows on the device
@@ -352,7 +357,12 @@ def main():
                                     "sample": "contigs %s (%d bp, %d tag entries) of the workload, all samples, workload-wide thresholds"
                                               % ("+".join(names[c] for c in cs), bp, int(sample.pos.shape[0])),
                                     "host_cores_available": os.cpu_count(), "rows_match_gpu": bool(same), "rows": len(theirs)}
+        if gather is not None and getattr(gather, "times", None):
+            k = max(1, gather.times[3])
+            line["result"]["gather_ms_rank0"] = {"allreduce_counts": gather.times[0] / k * 1e3, "scatter": gather.times[1] / k * 1e3, "completion": gather.times[2] / k * 1e3}
         print(json.dumps(line))
+    if gather is not None and hasattr(gather, "close"):
+        gather.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

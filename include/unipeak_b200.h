@@ -53,6 +53,11 @@ int upb_device_count (void);
 /* pinned host memory for the arrays handed to upb_load_tags (optional; any host memory works) */
 int upb_host_alloc (void** out, size_t bytes);
 void upb_host_free (void* p);
+/* page-lock and map host memory the caller owns — e.g. a POSIX shared-memory segment shared by the ranks of a multi-GPU job, so that
+ * every rank's upb_scatter_rows writes its rows straight into ONE host table (the destination of the region-list gather);
+ * *device_ptr is the address to hand to upb_scatter_rows */
+int upb_host_register (void* p, size_t bytes, void** device_ptr);
+void upb_host_unregister (void* p);
 
 /* ---- inputs -------------------------------------------------------------------------------- */
 /* Replaces ContigTable (misc/data.hpp:75-100, filled by parseContigTable, misc/format.cpp:27-57):
@@ -134,7 +139,8 @@ int upb_reference_order (uint32_t n_contigs, uint32_t n_samples, int directional
 /* ---- several GPUs: one table out of the ranks' tables ---------------------------------------- */
 /* Every rank calls upb_call_regions on the contigs it loaded (reference_order = 0), the ranks sum their unit_rows
  * (one small all-reduce), and each rank scatters its rows to their place in ONE table-wide device slab that the
- * caller zeroed: slab columns are laid out as upb_slab_layout says, rows in canonical order (buffer, contig, left).
+ * caller zeroed (or, when every row is written by exactly one rank, simply allocated — device memory or mapped host memory from
+ * upb_host_register): slab columns are laid out as upb_slab_layout says, rows in canonical order (buffer, contig, left).
  * Summing the slabs over the ranks (ncclReduce on 64-bit words; the row sets are disjoint) gives rank 0 the whole
  * table without a host round trip; upb_table_from_slab wraps a host copy of it. */
 enum { UPB_COL_CAND_INDEX = 0, UPB_COL_PEAK_SCORE, UPB_COL_KURTOSIS, UPB_COL_CORR, UPB_COL_CONTIG, UPB_COL_LEFT, UPB_COL_LEN,

@@ -391,6 +391,22 @@ def test_scatter_rows_rebuilds_the_single_gpu_table(gpu_ctx):
         assert np.array_equal(cols[k], full[k]), k
     for k in ("kurtosis", "peak_score"):
         assert np.array_equal(cols[k].view(np.uint64), full[k].view(np.uint64)), k
+    # the same scatter straight into mapped host memory (what HostGather does with a segment shared by the ranks)
+    from unipeak_b200.capi import host_register, host_unregister
+    host = np.zeros(((nbytes + 4095) // 4096) * 4096 + 4096, dtype=np.uint8)
+    base = (-host.ctypes.data) % 4096
+    host = host[base:base + ((nbytes + 4095) // 4096) * 4096]
+    dev_ptr = host_register(host.ctypes.data, host.shape[0])
+    try:
+        for cx, v in zip(ctxs, views):
+            cx.scatter_rows(R, unit_total, np.asarray(v["unit_rows"], dtype=np.uint64), dev_ptr)
+        cols = unipeak_b200.slab_columns(host, R, 3)
+        for k in ("buffer", "contig", "left", "len", "peak", "hit_sum", "counts", "cand_index"):
+            assert np.array_equal(cols[k], full[k]), k
+        for k in ("kurtosis", "peak_score"):
+            assert np.array_equal(cols[k].view(np.uint64), full[k].view(np.uint64)), k
+    finally:
+        host_unregister(host.ctypes.data)
     for cx in ctxs:
         cx.close()
 

@@ -75,13 +75,26 @@ EXPORTS = [
     "upb_create", "upb_destroy", "upb_last_error", "upb_device_count", "upb_host_alloc", "upb_host_free", "upb_set_contigs",
     "upb_load_tags", "upb_call_regions", "upb_free_region_table", "upb_reference_order", "upb_profile_contig", "upb_free_profile",
     "upb_strand_shift", "upb_free_shift_report", "upb_count_tags_in_regions", "upb_kernel_taps", "upb_last_stats",
-    "upb_slab_layout", "upb_scatter_rows", "upb_table_from_slab", "upb_stream",
+    "upb_slab_layout", "upb_scatter_rows", "upb_table_from_slab", "upb_stream", "upb_host_register", "upb_host_unregister",
 ]
 SLAB_COLS = ("cand_index", "peak_score", "kurtosis", "corr", "contig", "left", "len", "peak", "hit_sum", "counts", "buffer", "end")
 SLAB_DTYPES = dict(cand_index=np.uint64, peak_score=np.float64, kurtosis=np.float64, corr=np.float64, contig=np.uint32, left=np.uint32,
                    len=np.uint32, peak=np.uint32, hit_sum=np.uint32, counts=np.uint32, buffer=np.uint8)
 
 _lib = None
+
+
+def host_register(ptr: int, nbytes: int) -> int:
+    """Page-lock + map caller-owned host memory (upb_host_register); returns the device-side address of it."""
+    dp = C.c_void_p()
+    rc = lib().upb_host_register(C.c_void_p(ptr), nbytes, C.byref(dp))
+    if rc:
+        raise UpbError(rc, lib().upb_last_error(None).decode())
+    return int(dp.value)
+
+
+def host_unregister(ptr: int) -> None:
+    lib().upb_host_unregister(C.c_void_p(ptr))
 
 
 def lib():
@@ -115,6 +128,9 @@ def lib():
         L.upb_kernel_taps.argtypes = [C.c_uint32, C.c_double, C.POINTER(C.c_double)]
         L.upb_last_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.upb_stream.argtypes = [C.c_void_p]
+        L.upb_host_register.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.upb_host_unregister.argtypes = [C.c_void_p]
+        L.upb_host_unregister.restype = None
         L.upb_stream.restype = C.c_void_p
         L.upb_slab_layout.argtypes = [C.c_uint64, C.c_uint32, C.c_void_p]
         L.upb_scatter_rows.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -136,6 +136,18 @@ extern "C" int upb_host_alloc (void** out, size_t bytes) {
 }
 extern "C" void upb_host_free (void* p) { if (p) cudaFreeHost(p); }
 
+extern "C" int upb_host_register (void* p, size_t bytes, void** device_ptr) {
+  if (!p || !bytes) return UPB_ERR_BAD_ARG;
+  cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+  if (e != cudaSuccess) return fail(nullptr, UPB_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e));
+  if (device_ptr) {
+    e = cudaHostGetDevicePointer(device_ptr, p, 0);
+    if (e != cudaSuccess) { cudaHostUnregister(p); return fail(nullptr, UPB_ERR_CUDA, std::string("cudaHostGetDevicePointer: ") + cudaGetErrorString(e)); }
+  }
+  return UPB_OK;
+}
+extern "C" void upb_host_unregister (void* p) { if (p) cudaHostUnregister(p); }
+
 extern "C" void* upb_stream (const upb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 extern "C" int upb_last_stats (const upb_ctx* ctx, upb_stats* out) {
@@ -1215,9 +1227,21 @@ __global__ void scatter_rows_kernel (ScatterArgs a) {
   UPB_MOVE(uint32_t, oContig); UPB_MOVE(uint32_t, oLeft); UPB_MOVE(uint32_t, oLen); UPB_MOVE(uint32_t, oPeak); UPB_MOVE(uint32_t, oWsum);
   UPB_MOVE(uint8_t, oBuffer);
 #undef UPB_MOVE
-  const uint32_t* sc = (const uint32_t*)(a.src + a.ls.oCounts) + i * a.n;
-  uint32_t* dc = (uint32_t*)(a.dst + a.ld.oCounts) + o * a.n;
-  for (uint32_t s = 0; s < a.n; ++s) dc[s] = sc[s];
+}
+
+// the counts matrix, one thread per element: consecutive threads write consecutive words (the destination may be mapped host
+// memory, where only coalesced stores travel well over PCIe)
+__global__ void scatter_counts_kernel (ScatterArgs a) {
+  const unsigned long long total = a.R * a.n;
+  const uint32_t* sc = (const uint32_t*)(a.src + a.ls.oCounts);
+  uint32_t* dc = (uint32_t*)(a.dst + a.ld.oCounts);
+  for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long i = g / a.n;
+    const uint32_t b = a.src[a.ls.oBuffer + i];
+    const uint32_t c = ((const uint32_t*)(a.src + a.ls.oContig))[i];
+    const size_t u = (size_t)b * a.C + c;
+    dc[(a.unitDst[u] + (i - a.unitSrc[u])) * a.n + (g - i * a.n)] = sc[g];
+  }
 }
 
 extern "C" int upb_scatter_rows (upb_ctx* ctx, uint64_t total_rows, const uint64_t* unit_rows_total, const uint64_t* unit_rows_local, void* d_slab) {
@@ -1239,6 +1263,7 @@ extern "C" int upb_scatter_rows (upb_ctx* ctx, uint64_t total_rows, const uint64
   CU(cudaMemcpyAsync(d_u, h.data(), 4 * (size_t)C * 8, cudaMemcpyHostToDevice, ctx->stream));
   sa.unitDst = d_u; sa.unitSrc = d_u + 2 * (size_t)C;
   scatter_rows_kernel<<<(unsigned)((R + 255) / 256), 256, 0, ctx->stream>>>(sa);
+  scatter_counts_kernel<<<(unsigned)std::min<uint64_t>((R * n + 255) / 256, (uint64_t)ctx->smCount * 16), 256, 0, ctx->stream>>>(sa);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(ctx->stream));
   return UPB_OK;

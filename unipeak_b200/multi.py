@@ -6,6 +6,10 @@ calls only its own contigs.  Three small, latency-bound collectives remain:
   * per-sample tags-in-regions totals and per-(buffer, contig) candidate counts, all-reduce after it;
   * the gather of the region rows to rank 0, which puts them in canonical order (buffer, contig, left).
 Works on any backend (NCCL on the GPUs; gloo in the CPU tests).
+
+Two device-side gathers: DeviceGather (one NCCL reduce of a table-wide device slab, then rank 0 copies it to the host) and
+HostGather (the table lives in ONE host segment shared by the ranks and mapped into every GPU; each rank's scatter kernel
+writes its rows there directly over its own PCIe link — the destination is host memory either way, and eight links beat one).
 """
 from __future__ import annotations
 
@@ -129,5 +133,72 @@ class DeviceGather:
         self._host[:words].copy_(slab[:words], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         cols = slab_columns(self._host.numpy().view(np.uint8), R, self.n)
+        cols.update(n_rows=R, unit_candidates=tot[C2:2 * C2], tags_in_regions=tot[2 * C2:])
+        return cols
+
+
+class HostGather:
+    """Region-list gather without the detour through GPU 0: the table-wide slab is a POSIX shared-memory segment that every
+    rank page-locks and maps (upb_host_register); after one small all-reduce (rows per unit, candidates per unit, tags in
+    regions) each rank's upb_scatter_rows kernel writes its rows to their canonical place over its own PCIe link, and a
+    second small all-reduce tells rank 0 that every rank is done."""
+
+    def __init__(self, ctx, n_samples: int, n_contigs: int, *, dist, rank: int, world: int, device, capacity_bytes: int = 256 << 20, name: str = None):
+        import os
+        import torch
+        from .capi import host_register
+        self.ctx, self.n, self.C, self.dist, self.rank, self.world, self.device = ctx, n_samples, n_contigs, dist, rank, world, device
+        self.torch = torch
+        self.cap = int(capacity_bytes)
+        name = name or "upb_gather_%s" % os.environ.get("MASTER_PORT", "0")
+        self.path = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp", name)
+        if rank == 0:
+            with open(self.path, "wb") as f:
+                f.truncate(self.cap)
+        dist.barrier()
+        self.host = np.memmap(self.path, dtype=np.uint8, mode="r+", shape=(self.cap,))
+        self.host_ptr = self.host.ctypes.data
+        self.dev_ptr = host_register(self.host_ptr, self.cap)
+        self._small = torch.zeros(2 * n_contigs * 2 + n_samples, dtype=torch.int64, device=device)
+        self._done = torch.zeros(1, dtype=torch.int64, device=device)
+        dist.barrier()
+
+    def close(self):
+        from .capi import host_unregister
+        import os
+        if self.host is not None:
+            host_unregister(self.host_ptr)
+            self.host = None
+            self.dist.barrier()
+            if self.rank == 0 and os.path.exists(self.path):
+                os.unlink(self.path)
+
+    def __call__(self, view):
+        import time
+        torch, dist = self.torch, self.dist
+        C2 = 2 * self.C
+        t0 = time.perf_counter()
+        local_rows = np.asarray(view["unit_rows"], dtype=np.int64)
+        small = np.concatenate([local_rows, np.asarray(view["unit_candidates"], dtype=np.int64), np.asarray(view["tags_in_regions"], dtype=np.int64)])
+        self._small.copy_(torch.from_numpy(small))
+        dist.all_reduce(self._small)                                   # unit rows, unit candidates, tags in regions
+        tot = self._small.cpu().numpy()
+        t1 = time.perf_counter()
+        unit_rows_total = tot[:C2].astype(np.uint64)
+        R = int(unit_rows_total.sum())
+        from .capi import slab_columns, slab_layout
+        nbytes = slab_layout(R, self.n)["end"]
+        if nbytes > self.cap:
+            raise RuntimeError("region table (%d bytes) exceeds the shared gather segment (%d bytes)" % (nbytes, self.cap))
+        self.ctx.scatter_rows(R, unit_rows_total, local_rows.astype(np.uint64), self.dev_ptr)   # returns when this rank's rows are in host memory
+        t2 = time.perf_counter()
+        dist.all_reduce(self._done)                                    # completion: every rank's rows have landed
+        torch.cuda.current_stream().synchronize()
+        t3 = time.perf_counter()
+        self.times = getattr(self, "times", [0.0, 0.0, 0.0, 0])
+        self.times[0] += t1 - t0; self.times[1] += t2 - t1; self.times[2] += t3 - t2; self.times[3] += 1
+        if self.rank != 0:
+            return None
+        cols = slab_columns(self.host, R, self.n)
         cols.update(n_rows=R, unit_candidates=tot[C2:2 * C2], tags_in_regions=tot[2 * C2:])
         return cols
