@@ -841,13 +841,20 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
   }
   if ((r = scan_u32(ctx, pass, nCand, passScan, d_tot, &launches))) return r;
   compact_index_kernel<<<gCand, 256, 0, ctx->stream>>>(pass, passScan, nCand, list1);
+  // pooled position cells of the survivors live back to back in one scratch array: offsets by a scan of their lengths
+  uint32_t* candLen = SCR("candLen", uint32_t, nCand);
+  unsigned long long* cellOff = SCR("cellOff", unsigned long long, nCand);
+  cand_len_kernel<<<gCand, 256, 0, ctx->stream>>>(cand, pass, nCand, candLen);
+  if ((r = scan_u32(ctx, candLen, nCand, cellOff, d_tot + 2, &launches))) return r;
   CU(cudaGetLastError());
-  launches += 1;
+  launches += 2;
   CU(cudaMemcpyAsync(h64, d_tot, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(h64 + 2, d_tot + 2, 8, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(h64 + 8, unitCand, std::min<size_t>((size_t)nUnits, 400) * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (nAff) CU(cudaMemcpyAsync(edgeDrop.data(), d_drop, (size_t)nAff * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   n1 = (uint32_t)h64[0];
+  const unsigned long long totalCells = h64[2];
   if (nUnits <= 400) for (uint32_t u = 0; u < nUnits; ++u) out.unitCand[u] = h64[8 + u];
   else { CU(cudaMemcpy(out.unitCand.data(), unitCand, (size_t)nUnits * 8, cudaMemcpyDeviceToHost)); }
 
@@ -860,19 +867,21 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
     StatArgs st;
     st.T = pr.T; st.units = d_units; st.cand = cand; st.list = list1; st.nList = n1;
     st.nondir = cfg.nondir ? 1 : 0; st.kurtThr = cfg.kurtThr; st.counts = statCounts; st.kurt = statKurt; st.pass = pass2;
-    const size_t groupBytes = ((size_t)(ST_CHUNK + n) * 4 + 15) / 16 * 16 + 2 * ST_GROUP * 8;
+    st.cellOff = cellOff; st.cells = SCR("statCells", uint32_t, (size_t)totalCells + 1);
+    const size_t groupBytes = ((size_t)(ST_CHUNK + n) * 4 + 15) / 16 * 16;
     const size_t statSmem = (size_t)ST_WARPS * ST_PER_WARP * groupBytes;
     if (statSmem > 200 * 1024) return fail(ctx, UPB_ERR_UNSUPPORTED, "too many samples for the region statistics kernel");
-    CU(cudaFuncSetAttribute(region_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)statSmem));
+    CU(cudaFuncSetAttribute(region_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)statSmem));
     st.ticket = small32 + 13;
     CU(cudaMemsetAsync(st.ticket, 0, 4, ctx->stream));
     int perSm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, region_stats_kernel, ST_WARPS * 32, statSmem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, region_pool_kernel, ST_WARPS * 32, statSmem));
     const uint32_t perBlock = ST_WARPS * ST_PER_WARP;
     const uint32_t gridS = std::min<uint32_t>((n1 + perBlock - 1) / perBlock, (uint32_t)(ctx->smCount * std::max(perSm, 1)));
-    region_stats_kernel<<<gridS, ST_WARPS * 32, statSmem, ctx->stream>>>(st);
+    region_pool_kernel<<<gridS, ST_WARPS * 32, statSmem, ctx->stream>>>(st);
+    region_moment_kernel<<<g1, 256, 0, ctx->stream>>>(st);
     CU(cudaGetLastError());
-    launches += 1;
+    launches += 2;
 
     // strand correlation for the regions that got this far (misc/peakcall.cpp:41 evaluates it last)
     if (cfg.needCorr) {

@@ -36,7 +36,11 @@
 
 namespace upb {
 
+#ifndef UPB_SP_MIN_BLOCKS
+#define UPB_SP_MIN_BLOCKS 4
+#endif
 constexpr int SP_THREADS = 256;
+constexpr int SP_MIN_BLOCKS = UPB_SP_MIN_BLOCKS;
 constexpr int SP_WARPS = SP_THREADS / 32;
 constexpr int HOT_JMAX = (448 - 1) / 32 + 1;        // blocks on either side whose tags can reach a block's positions (bandwidth <= 448)
 constexpr int SPAN_BLOCKS = SPAN_LEN / 32;          // 128 blocks of 32 positions
@@ -414,7 +418,7 @@ __global__ void __launch_bounds__(HOT_THREADS, 6) hot_span_kernel (const __grid_
 }
 
 template <bool NONDIR, bool COEFF>
-__global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : 4) span_kernel (const __grid_constant__ SpanArgs a) {
+__global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : SP_MIN_BLOCKS) span_kernel (const __grid_constant__ SpanArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const uint32_t bw = a.bw;
   const SpanSmem L = span_smem_layout(bw, a.nSamples, NONDIR, COEFF);
@@ -784,13 +788,18 @@ __global__ void cand_hit_kernel (const Cand2* __restrict__ cand, uint32_t n, dou
   pass[i] = ((double)cand[i].wsum >= hitThr) ? 1u : 0u;
 }
 
-// Region::exptSums (misc/data.cpp:116-131) and Region::posKurtosis (misc/data.cpp:133-182) of the candidates that
-// passed the hit filter: one warp per region.  The region's entries are a contiguous chunk of the tile-major
-// copy (the mini-tiles it touches); every lane takes entries, adds the count to its sample's slot (shared-memory
-// atomics) and keeps count*offset (offsets as UShort, both sums as HitCount); the region's positions
-// are pooled over ALL samples (controls included, minus the tags the reference forgets, Q4) in shared memory
-// 1024 at a time and the two central moments are accumulated sequentially in position order, exactly as the
-// reference does.
+// Region::exptSums (misc/data.cpp:116-131) and Region::posKurtosis (misc/data.cpp:133-182) of the candidates that passed the
+// hit filter, in two kernels.
+//
+// region_pool_kernel: eight lanes work on one region.  The region's entries are contiguous chunks of the tile-major copy (the
+// mini-tiles it touches, one chunk per 4096-position span); every lane takes entries, adds the count to its sample's slot
+// (shared-memory atomics, -> the regions x samples matrix row) and to the region's pooled position cell (ALL samples, controls
+// included, minus the tags the reference forgets, Q4).  The four groups of a warp run as independent state machines inside one
+// lock-step loop — fetch a region / pool one batch of 64 entries / write the finished region out — so a group that finishes a
+// small region takes the next one at once instead of idling until its warp-mates are through a big one (v5–v16 handed a warp
+// four regions at a time: 14.7 of 32 lanes active on average, 433 M warp instructions).
+// region_moment_kernel: one thread per region walks its pooled cells in position order: count and count*offset (offsets as
+// UShort, both sums as HitCount), then the two central-moment sums added sequentially exactly as the reference does.
 struct StatArgs {
   Tags T;
   const SpanUnit* units;
@@ -799,146 +808,160 @@ struct StatArgs {
   uint32_t nList;
   int nondir;
   double kurtThr;
+  const unsigned long long* cellOff;   // [nCand] first pooled cell of every surviving candidate (exclusive scan of len over the survivors)
+  uint32_t* cells;                  // pooled counts per position of every surviving candidate
   uint32_t* counts;                 // [nList * nSamples]
   double* kurt;                     // [nList]
   uint32_t* pass;                   // [nList] kurtosis filter (misc/peakcall.cpp:41 second clause)
   uint32_t* ticket;
 };
 
-// Eight lanes work on one region (four regions per warp): most regions are ~130 positions with a few hundred
-// entries, and the two moment sums are sequential chains, so narrow groups keep the lanes busy and let one
-// leader lane per group run its chain while the other groups run theirs.
 constexpr int ST_GROUP = 8;                         // lanes per region
 constexpr int ST_PER_WARP = 32 / ST_GROUP;
-constexpr int ST_CHUNK = 256;                       // positions pooled in shared memory at a time
+constexpr int ST_CHUNK = 256;                       // regions up to this long pool their positions in shared memory; longer ones straight in global memory
 constexpr int ST_WARPS = 8;
+constexpr uint32_t ST_TICKET = 4;                   // regions a group takes per atomic
 
-__device__ __forceinline__ uint32_t group_sum_u32 (uint32_t v) {
-#pragma unroll
-  for (int o = ST_GROUP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// entries of (strand d, contig c) with position in [lo, hi] (1-based, inclusive), visited by the ST_GROUP lanes of a
-// group: f(position, entry index, entry).  Entries carry their offset inside a 4096-position span, so the mini-tiles
-// the interval touches are walked span by span.
-template <class F>
-__device__ __forceinline__ void group_entries (const Tags& T, uint32_t d, uint32_t c, uint32_t lo, uint32_t hi, uint32_t gl, F f) {
-  const uint32_t gb = __ldg(T.mtBase + d * T.C + c);
-  const uint32_t nMt = __ldg(T.mtBase + d * T.C + c + 1) - gb;
-  if (nMt == 0) return;
-  const uint32_t ma = min((lo - 1) >> MT_SHIFT, nMt - 1), mb = min((hi - 1) >> MT_SHIFT, nMt - 1);
-  for (uint32_t sp = ma / SPAN_MT; sp <= mb / SPAN_MT; ++sp) {
-    const uint32_t m0 = max(ma, sp * SPAN_MT), m1 = min(mb, sp * SPAN_MT + SPAN_MT - 1);
-    const unsigned long long e0 = __ldg(T.mtOff + gb + m0), e1 = __ldg(T.mtOff + gb + m1 + 1);
-    for (unsigned long long eb = e0 + gl; eb < e1; eb += 8 * ST_GROUP) {
-      uint2 en[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) en[q] = (eb + q * ST_GROUP < e1) ? __ldg(T.ment + eb + q * ST_GROUP) : make_uint2(0u, 0u);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const uint32_t p = sp * SPAN_LEN + (en[q].y & (SPAN_LEN - 1)) + 1;
-        if (en[q].x && p >= lo && p <= hi) f(p, eb + q * ST_GROUP, en[q]);
-      }
-    }
-  }
-}
-
-__global__ void __launch_bounds__(ST_WARPS * 32) region_stats_kernel (StatArgs a) {
+__global__ void __launch_bounds__(ST_WARPS * 32) region_pool_kernel (StatArgs a) {
   extern __shared__ __align__(16) unsigned char stat_smem_raw[];
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-  const uint32_t g = lane / ST_GROUP, gl = lane % ST_GROUP;
+  const uint32_t g = lane / ST_GROUP, gl = lane % ST_GROUP, leader = lane & ~(uint32_t)(ST_GROUP - 1);
   const uint32_t n = a.T.nSamples;
-  // per group: cell[ST_CHUNK] u32, cnts[n] u32, stage[2*ST_GROUP] f64
-  const size_t groupBytes = ((size_t)(ST_CHUNK + n) * 4 + 15) / 16 * 16 + 2 * ST_GROUP * 8;
+  const size_t groupBytes = ((size_t)(ST_CHUNK + n) * 4 + 15) / 16 * 16;   // per group: cell[ST_CHUNK] u32, cnts[n] u32
   unsigned char* gbase = stat_smem_raw + ((size_t)warp * ST_PER_WARP + g) * groupBytes;
   uint32_t* cell = (uint32_t*)gbase;
   uint32_t* cnts = cell + ST_CHUNK;
-  double* stage = (double*)(gbase + ((size_t)(ST_CHUNK + n) * 4 + 15) / 16 * 16);
-  for (;;) {                                                          // persistent warps: four regions per ticket
-  uint32_t tk = 0;
-  if (lane == 0) tk = atomicAdd(a.ticket, (uint32_t)ST_PER_WARP);
-  tk = __shfl_sync(0xffffffffu, tk, 0);
-  if (tk >= a.nList) break;
-  const uint32_t i = tk + g;
-  const bool live = i < a.nList;                                      // whole groups idle at the tail; no early return (warp-wide syncs below)
-  Cand2 c; c.unit = 0; c.left = 1; c.len = 0;
-  if (live) c = a.cand[a.list[i]];
-  const SpanUnit U = a.units[c.unit];
-  const uint32_t d0 = a.nondir ? 0u : U.buffer, d1 = a.nondir ? 1u : U.buffer;
-  for (uint32_t s = gl; s < n; s += ST_GROUP) cnts[s] = 0;
-  __syncwarp();
-  uint32_t count = 0, sum = 0;
-  double sum2 = 0.0, sum4 = 0.0;
-  const bool single = c.len <= (uint32_t)ST_CHUNK;                    // fits one chunk: positions are pooled during the counting pass
-  const uint32_t right = c.left + c.len - 1;
 
-  // pass 1: per-sample sums, count and count*offset (and the pooled positions of a single-chunk region)
-  if (live && single) for (uint32_t k = gl; k < ST_CHUNK; k += ST_GROUP) cell[k] = 0;
-  __syncwarp();
-  if (live)
-    for (uint32_t d = d0; d <= d1; ++d)
-      group_entries(a.T, d, U.contig, c.left, right, gl, [&] (uint32_t p, unsigned long long e, const uint2& en) {
-        const uint32_t k = a.T.mEff ? __ldg(a.T.mEff + e) : en.x;
-        if (!k) return;
-        const uint32_t o = p - c.left;
-        count += k;
-        sum += k * (o & 0xFFFFu);
-        atomicAdd(&cnts[en.y >> SPAN_SHIFT], k);
-        if (single) atomicAdd(&cell[o], k);
-      });
-  __syncwarp();
-  count = group_sum_u32(count); sum = group_sum_u32(sum);
-  const double xbar = (double)sum / (double)count;                   // misc/data.cpp:147
-  if (live) for (uint32_t s = gl; s < n; s += ST_GROUP) a.counts[(uint64_t)i * n + s] = cnts[s];
+  // group state (identical in the lanes of a group)
+  bool active = false, exhausted = false;
+  uint32_t tkNext = 0, tkEnd = 0;
+  uint32_t i = 0, left = 1, right = 0, contig = 0;
+  bool single = true;
+  uint32_t d = 0, dEnd = 0, sp = 0, spEnd = 0, ma = 0, mb = 0, gb = 0;
+  unsigned long long eb = 0, e1 = 0, cellBase = 0;
 
-  // pass 2: the two central-moment chains, one chunk of positions at a time (loop bounds made warp-uniform)
-  const uint32_t nChunks = live ? (c.len + ST_CHUNK - 1) / ST_CHUNK : 0u;
-  uint32_t maxChunks = nChunks;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) maxChunks = max(maxChunks, __shfl_xor_sync(0xffffffffu, maxChunks, o));
-  for (uint32_t ch = 0; ch < maxChunks; ++ch) {
-    const bool act = ch < nChunks;
-    const uint32_t o0 = ch * ST_CHUNK;
-    const uint32_t oc = act ? min((uint32_t)ST_CHUNK, c.len - o0) : 0u;
-    if (act && !single) for (uint32_t k = gl; k < ST_CHUNK; k += ST_GROUP) cell[k] = 0;
-    __syncwarp();
-    if (act && !single)
-      for (uint32_t d = d0; d <= d1; ++d)
-        group_entries(a.T, d, U.contig, c.left + o0, c.left + o0 + oc - 1, gl, [&] (uint32_t p, unsigned long long e, const uint2& en) {
-          const uint32_t k = a.T.mEff ? __ldg(a.T.mEff + e) : en.x;
-          if (k) atomicAdd(&cell[p - c.left - o0], k);
-        });
-    __syncwarp();
-    // ST_GROUP positions per step: every lane prepares its position's terms, the group's leader adds them in
-    // position order (a position without tags adds +0.0, which changes nothing)
-    const uint32_t steps = (oc + ST_GROUP - 1) / ST_GROUP;
-    uint32_t maxSteps = steps;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) maxSteps = max(maxSteps, __shfl_xor_sync(0xffffffffu, maxSteps, o));
-    for (uint32_t st = 0; st < maxSteps; ++st) {
-      const uint32_t k = st * ST_GROUP + gl;
-      const uint32_t pc = k < oc ? cell[k] : 0u;
-      const double dd = __dsub_rn((double)((o0 + k) & 0xFFFFu), xbar); // offset counter is a UShort (Q8)
-      const double d2 = __dmul_rn(dd, dd);
-      const double d4 = __dmul_rn(d2, d2);                            // pow(x,4) == (x*x)*(x*x) in the reference build (Q9)
-      stage[gl] = pc ? __dmul_rn((double)pc, d2) : 0.0;
-      stage[ST_GROUP + gl] = pc ? __dmul_rn((double)pc, d4) : 0.0;
-      __syncwarp();
-      if (gl == 0 && st < steps) {
-#pragma unroll
-        for (int q = 0; q < ST_GROUP; ++q) { sum2 = __dadd_rn(sum2, stage[q]); sum4 = __dadd_rn(sum4, stage[ST_GROUP + q]); }
-      }
-      __syncwarp();
+  for (;;) {
+    // ---- fetch: a group without a region takes the next one -------------------------------------------------------------------
+    uint32_t t = 0;
+    const bool wantTicket = !active && !exhausted && tkNext == tkEnd;
+    if (wantTicket && gl == 0) t = atomicAdd(a.ticket, ST_TICKET);
+    t = __shfl_sync(0xffffffffu, t, leader);
+    if (wantTicket) { tkNext = t; tkEnd = min(t + ST_TICKET, a.nList); if (t >= a.nList) { exhausted = true; tkEnd = tkNext; } }
+    bool needSeg = false;                                             // (re)load the entry range of segment (d, sp)
+    if (!active && tkNext < tkEnd) {
+      i = tkNext++;
+      const uint32_t ci = __ldg(a.list + i);
+      const Cand2 c = a.cand[ci];
+      const SpanUnit U = a.units[c.unit];
+      left = c.left; right = c.left + c.len - 1; contig = U.contig;
+      single = c.len <= (uint32_t)ST_CHUNK;
+      cellBase = a.cellOff[ci];
+      d = a.nondir ? 0u : U.buffer; dEnd = a.nondir ? 1u : U.buffer;
+      for (uint32_t s2 = gl; s2 < n; s2 += ST_GROUP) cnts[s2] = 0;
+      if (single) { for (uint32_t k = gl; k < (uint32_t)ST_CHUNK; k += ST_GROUP) cell[k] = 0; }
+      else { for (unsigned long long k = gl; k < c.len; k += ST_GROUP) a.cells[cellBase + k] = 0; }
+      active = true;
+      needSeg = true;
+      sp = 0xFFFFFFFFu;                                               // "strand d not opened yet"
     }
+    if (!__any_sync(0xffffffffu, active)) break;
+    __syncwarp();
+
+    // ---- segment: entries of strand d, span sp that lie in the region's mini-tiles --------------------------------------------
+    if (active && needSeg) {
+      for (;;) {
+        if (sp == 0xFFFFFFFFu) {                                      // open strand d
+          gb = __ldg(a.T.mtBase + d * a.T.C + contig);
+          const uint32_t nMt = __ldg(a.T.mtBase + d * a.T.C + contig + 1) - gb;
+          if (nMt == 0) { if (d == dEnd) { eb = e1 = 0; break; } ++d; continue; }
+          ma = min((left - 1) >> MT_SHIFT, nMt - 1); mb = min((right - 1) >> MT_SHIFT, nMt - 1);
+          sp = ma / SPAN_MT; spEnd = mb / SPAN_MT;
+        }
+        const uint32_t m0 = max(ma, sp * SPAN_MT), m1 = min(mb, sp * SPAN_MT + SPAN_MT - 1);
+        eb = __ldg(a.T.mtOff + gb + m0); e1 = __ldg(a.T.mtOff + gb + m1 + 1);
+        break;
+      }
+    }
+
+    // ---- pool one batch of up to 8 * ST_GROUP entries ----------------------------------------------------------------------------
+    if (active) {
+      uint2 en[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { const unsigned long long e = eb + gl + q * ST_GROUP; en[q] = e < e1 ? __ldg(a.T.ment + e) : make_uint2(0u, 0u); }
+      uint32_t eff[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { const unsigned long long e = eb + gl + q * ST_GROUP; eff[q] = (a.T.mEff && e < e1) ? __ldg(a.T.mEff + e) : en[q].x; }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint32_t p = sp * SPAN_LEN + (en[q].y & (SPAN_LEN - 1)) + 1;
+        if (eff[q] && p >= left && p <= right) {
+          atomicAdd(&cnts[en[q].y >> SPAN_SHIFT], eff[q]);
+          if (single) atomicAdd(&cell[p - left], eff[q]); else atomicAdd(&a.cells[cellBase + (p - left)], eff[q]);
+        }
+      }
+      eb += 8 * ST_GROUP;
+    }
+    __syncwarp();
+
+    // ---- segment / region finished? ----------------------------------------------------------------------------------------------
+    if (active && eb >= e1) {
+      bool done = false;
+      if (sp != 0xFFFFFFFFu && sp < spEnd) { ++sp; }
+      else if (d < dEnd) { ++d; sp = 0xFFFFFFFFu; }
+      else done = true;
+      if (!done) {
+        for (;;) {                                                    // same walk as above (kept in one place would need a lambda with many captures)
+          if (sp == 0xFFFFFFFFu) {
+            gb = __ldg(a.T.mtBase + d * a.T.C + contig);
+            const uint32_t nMt = __ldg(a.T.mtBase + d * a.T.C + contig + 1) - gb;
+            if (nMt == 0) { if (d == dEnd) { done = true; break; } ++d; continue; }
+            ma = min((left - 1) >> MT_SHIFT, nMt - 1); mb = min((right - 1) >> MT_SHIFT, nMt - 1);
+            sp = ma / SPAN_MT; spEnd = mb / SPAN_MT;
+          }
+          const uint32_t m0 = max(ma, sp * SPAN_MT), m1 = min(mb, sp * SPAN_MT + SPAN_MT - 1);
+          eb = __ldg(a.T.mtOff + gb + m0); e1 = __ldg(a.T.mtOff + gb + m1 + 1);
+          break;
+        }
+      }
+      if (done) {                                                     // write the region out: matrix row and (short regions) the pooled cells
+        for (uint32_t s2 = gl; s2 < n; s2 += ST_GROUP) a.counts[(uint64_t)i * n + s2] = cnts[s2];
+        if (single) { const uint32_t len = right - left + 1; for (uint32_t k = gl; k < len; k += ST_GROUP) a.cells[cellBase + k] = cell[k]; }
+        active = false;
+      }
+    }
+    __syncwarp();
   }
-  if (live && gl == 0) {
-    const double k = __ddiv_rn(__dmul_rn(__dsub_rn((double)count, 1.0), sum4), __dmul_rn(sum2, sum2));   // misc/data.cpp:181
-    a.kurt[i] = k;
-    a.pass[i] = (a.kurtThr == 0.0 || (c.len > 1 && k <= a.kurtThr)) ? 1u : 0u;
+}
+
+__global__ void region_moment_kernel (StatArgs a) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.nList) return;
+  const uint32_t ci = a.list[i];
+  const uint32_t len = a.cand[ci].len;
+  const uint32_t* __restrict__ cells = a.cells + a.cellOff[ci];
+  uint32_t count = 0, sum = 0;                                        // HitCount arithmetic (wraps), offsets as UShort (Q8)
+  for (uint32_t o = 0; o < len; ++o) { const uint32_t k = cells[o]; count += k; sum += k * (o & 0xFFFFu); }
+  const double xbar = (double)sum / (double)count;                   // misc/data.cpp:147
+  double sum2 = 0.0, sum4 = 0.0;
+  for (uint32_t o = 0; o < len; ++o) {
+    const uint32_t pc = cells[o];
+    if (!pc) continue;                                                // positions without a stored hit vector are not visited (misc/data.cpp:171-173)
+    const double dd = __dsub_rn((double)(o & 0xFFFFu), xbar);
+    const double d2 = __dmul_rn(dd, dd);
+    const double d4 = __dmul_rn(d2, d2);                              // pow(x,4) == (x*x)*(x*x) in the reference build (Q9)
+    sum2 = __dadd_rn(sum2, __dmul_rn((double)pc, d2));
+    sum4 = __dadd_rn(sum4, __dmul_rn((double)pc, d4));
   }
-  __syncwarp();
-  }
+  const double k = __ddiv_rn(__dmul_rn(__dsub_rn((double)count, 1.0), sum4), __dmul_rn(sum2, sum2));   // misc/data.cpp:181
+  a.kurt[i] = k;
+  a.pass[i] = (a.kurtThr == 0.0 || (len > 1 && k <= a.kurtThr)) ? 1u : 0u;
+}
+
+// len of the candidates that passed the hit filter, 0 for the others (scanned into StatArgs::cellOff)
+__global__ void cand_len_kernel (const Cand2* __restrict__ cand, const uint32_t* __restrict__ pass, uint32_t n, uint32_t* __restrict__ lenOut) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  lenOut[i] = pass[i] ? cand[i].len : 0u;
 }
 
 // strand-correlation filter (third clause); list2 holds positions in list1 space, corr[k] belongs to list2[k]
