@@ -73,6 +73,18 @@ int upb_set_contigs (upb_ctx* ctx, uint32_t n_contigs, const uint32_t* sizes);
  * A rank of a multi-GPU job loads only the contigs it owns (empty segments elsewhere). */
 int upb_load_tags (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt);
 
+/* The same tag streams in the compact host form (3 bytes per entry instead of 8 — the load is PCIe-bound): dpos[e] = position
+ * minus the previous position of the same (sample, strand, contig) segment, cnt8[e] = count; 0xFFFF / 0xFF are escapes whose
+ * absolute position / full count sit in `exceptions` (sorted by entry index; pos or cnt is 0 where that field is not escaped).
+ * The FIRST entry of every segment must be a position escape.  Decoded on the device (segmented scan), validated exactly as
+ * upb_load_tags validates.  upb_pack_tags is the host-only encoder a front end runs while it parses (pass exc_cap = 0 to
+ * count the exceptions first; returns UPB_ERR_NOMEM with *n_exc_out set when exc_cap is too small). */
+typedef struct { uint64_t index; uint32_t pos; uint32_t cnt; } upb_packed_exception;
+int upb_load_tags_packed (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off, const uint16_t* dpos, const uint8_t* cnt8,
+                          uint64_t n_exceptions, const upb_packed_exception* exceptions);
+int upb_pack_tags (uint32_t n_samples, uint32_t n_contigs, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt,
+                   uint16_t* dpos_out, uint8_t* cnt8_out, upb_packed_exception* exc_out, uint64_t exc_cap, uint64_t* n_exc_out);
+
 /* ---- bin/regions --------------------------------------------------------------------------- */
 /* What src/regions.cpp:104-232 derives from its flags before the hot loop. */
 typedef struct {

@@ -434,3 +434,46 @@ def test_load_validation(gpu_ctx):
             gpu_ctx.call_regions(**region_settings(good))
         assert ei.value.code == -4                                          # nothing usable is loaded after a failed load
     check_regions(gpu_ctx, good)
+
+
+def test_packed_load_equals_plain_load(gpu_ctx):
+    # the compact host form (16-bit deltas, 8-bit counts, exception list) decodes to exactly the arrays of the plain path:
+    # large gaps (>= 65535), large counts (>= 255), empty segments, several samples
+    import unipeak_b200
+    rng = np.random.default_rng(5)
+    sizes = [3000000, 200000, 90000]
+    d = make_synthetic(sizes, 3, 40000, directional=True, seed=77, peak_spacing=6000)
+    pos, cnt = d.pos.copy(), d.cnt.copy()
+    big = rng.choice(pos.shape[0], size=50, replace=False)
+    cnt[big] = rng.integers(255, 100000, size=50).astype(np.uint32)
+    segs = [[[None] * 3 for _ in range(2)] for _ in range(3)]
+    for s in range(3):
+        for dd in range(2):
+            for c in range(3):
+                a, b = int(d.off[(s * 2 + dd) * 4 + c]), int(d.off[(s * 2 + dd) * 4 + c + 1])
+                p, k = pos[a:b], cnt[a:b]
+                if c == 0:                                        # thin chr0 out so that gaps exceed 65535
+                    keep = (p < 400000) | (p > 2500000)
+                    p, k = p[keep], k[keep]
+                if s == 1 and c == 2:
+                    p, k = p[:0], k[:0]                           # an empty segment
+                segs[s][dd][c] = (p, k)
+    data = TagData.from_segments(sizes, segs)
+    dpos, cnt8, exc = unipeak_b200.pack_tags(3, 3, data.off, data.pos, data.cnt)
+    assert exc.shape[0] >= 3 * 2 * 3 - 2 + 5 and (dpos == 0xFFFF).sum() >= 16 + 6 and (cnt8 == 0xFF).sum() >= 5
+    st = region_settings(data)
+    gpu_ctx.load(data)
+    want = gpu_ctx.call_regions(**st)
+    tir_keys = [(r["contig"], r["left"], r["left"] + r["len"] - 1) for r in want["rows"] if r["forward_label"]][:50]
+    tir_want = gpu_ctx.count_tags_in_regions(tir_keys, directional=True, extension=0)
+    gpu_ctx.load_packed(data)
+    got = gpu_ctx.call_regions(**st)
+    assert_rows_equal(got["rows"], want["rows"], "packed load")
+    assert_rows_equal(got["dropped"], want["dropped"], "packed load (dropped)")
+    assert got["tags_in_regions"] == want["tags_in_regions"] and len(got["rows"]) > 3
+    assert np.array_equal(gpu_ctx.count_tags_in_regions(tir_keys, directional=True, extension=0), tir_want)   # reads the decoded pos[] / cnt[] directly
+    # a broken stream is refused: an escape without its exception entry
+    with pytest.raises(unipeak_b200.UpbError):
+        off = np.ascontiguousarray(data.off, dtype=np.uint64)
+        gpu_ctx.load_tags_packed_ptr(3, off.ctypes.data, dpos.ctypes.data, cnt8.ctypes.data, exc.shape[0] - 1, exc.ctypes.data)
+    check_regions(gpu_ctx, d)

@@ -75,13 +75,35 @@ EXPORTS = [
     "upb_create", "upb_destroy", "upb_last_error", "upb_device_count", "upb_host_alloc", "upb_host_free", "upb_set_contigs",
     "upb_load_tags", "upb_call_regions", "upb_free_region_table", "upb_reference_order", "upb_profile_contig", "upb_free_profile",
     "upb_strand_shift", "upb_free_shift_report", "upb_count_tags_in_regions", "upb_kernel_taps", "upb_last_stats",
-    "upb_slab_layout", "upb_scatter_rows", "upb_table_from_slab", "upb_stream", "upb_host_register", "upb_host_unregister",
+    "upb_slab_layout", "upb_scatter_rows", "upb_table_from_slab", "upb_stream", "upb_host_register", "upb_host_unregister", "upb_load_tags_packed", "upb_pack_tags",
 ]
 SLAB_COLS = ("cand_index", "peak_score", "kurtosis", "corr", "contig", "left", "len", "peak", "hit_sum", "counts", "buffer", "end")
 SLAB_DTYPES = dict(cand_index=np.uint64, peak_score=np.float64, kurtosis=np.float64, corr=np.float64, contig=np.uint32, left=np.uint32,
                    len=np.uint32, peak=np.uint32, hit_sum=np.uint32, counts=np.uint32, buffer=np.uint8)
 
 _lib = None
+
+
+PACKED_EXC_DTYPE = np.dtype([("index", np.uint64), ("pos", np.uint32), ("cnt", np.uint32)])
+
+
+def pack_tags(n_samples: int, n_contigs: int, off, pos, cnt, out=None):
+    """upb_pack_tags: (dpos u16, cnt8 u8, exceptions) of the plain arrays.  `out` may supply preallocated (dpos, cnt8) arrays
+    (e.g. pinned); the exception list is sized by a counting pass first."""
+    L = lib()
+    off = np.ascontiguousarray(off, dtype=np.uint64)
+    pos = np.ascontiguousarray(pos, dtype=np.uint32)
+    cnt = np.ascontiguousarray(cnt, dtype=np.uint32)
+    E = int(pos.shape[0])
+    n_exc = C.c_uint64(0)
+    L.upb_pack_tags(n_samples, n_contigs, off.ctypes.data, pos.ctypes.data, cnt.ctypes.data, None, None, None, 0, C.byref(n_exc))
+    dpos, cnt8 = out if out is not None else (np.empty(max(E, 1), np.uint16), np.empty(max(E, 1), np.uint8))
+    exc = np.zeros(max(int(n_exc.value), 1), dtype=PACKED_EXC_DTYPE)
+    rc = L.upb_pack_tags(n_samples, n_contigs, off.ctypes.data, pos.ctypes.data, cnt.ctypes.data, dpos.ctypes.data, cnt8.ctypes.data,
+                         exc.ctypes.data, int(n_exc.value), C.byref(n_exc))
+    if rc:
+        raise UpbError(rc, "upb_pack_tags failed")
+    return dpos, cnt8, exc[:int(n_exc.value)]
 
 
 def host_register(ptr: int, nbytes: int) -> int:
@@ -128,6 +150,8 @@ def lib():
         L.upb_kernel_taps.argtypes = [C.c_uint32, C.c_double, C.POINTER(C.c_double)]
         L.upb_last_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.upb_stream.argtypes = [C.c_void_p]
+        L.upb_load_tags_packed.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.upb_pack_tags.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.upb_host_register.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
         L.upb_host_unregister.argtypes = [C.c_void_p]
         L.upb_host_unregister.restype = None
@@ -241,6 +265,18 @@ class Context:
         """Same, from raw host addresses (e.g. pinned buffers owned by the caller)."""
         self._check(self._lib.upb_load_tags(self._h, n_samples, C.c_void_p(off_ptr), C.c_void_p(pos_ptr), C.c_void_p(cnt_ptr)))
         self.n_samples = n_samples
+
+    def load_tags_packed_ptr(self, n_samples: int, off_ptr: int, dpos_ptr: int, cnt8_ptr: int, n_exc: int, exc_ptr: int):
+        """upb_load_tags_packed from raw host addresses (see pack_tags)."""
+        self._check(self._lib.upb_load_tags_packed(self._h, n_samples, C.c_void_p(off_ptr), C.c_void_p(dpos_ptr), C.c_void_p(cnt8_ptr), n_exc, C.c_void_p(exc_ptr)))
+        self.n_samples = n_samples
+
+    def load_packed(self, data) -> None:
+        """Load a TagData through the compact host form (encode on the host, decode on the device)."""
+        self.set_contigs(data.contig_sizes)
+        off = np.ascontiguousarray(data.off, dtype=np.uint64)
+        dpos, cnt8, exc = pack_tags(data.n_samples, self.n_contigs, off, data.pos, data.cnt)
+        self.load_tags_packed_ptr(data.n_samples, off.ctypes.data, dpos.ctypes.data, cnt8.ctypes.data, exc.shape[0], exc.ctypes.data)
 
     def load(self, data) -> None:
         """Load a unipeak_b200.synth.TagData."""

@@ -6,6 +6,7 @@
 #include "../../include/unipeak_b200.h"
 #include "upb_device.cuh"
 #include "upb_span.cuh"
+#include "upb_pack.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -34,6 +35,8 @@ struct upb_ctx {
   int device = 0;
   int smCount = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t copyStream = nullptr;    // H2D copies of upb_load_tags run here, one sample ahead of the kernels that consume them
+  cudaEvent_t copyEv = nullptr, doneEv = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::string err;
   // contigs
@@ -47,6 +50,7 @@ struct upb_ctx {
   std::vector<uint64_t> off;            // host copy
   std::vector<uint32_t> firstPos, lastPos;   // [(s*2+d)*C + c], 0 if empty
   DevBuf d_pos, d_cnt, d_off, d_segStart, d_tidx, d_tidxBase, d_sizes, d_nTilesIdx, d_small;
+  DevBuf d_pk16, d_pk8, d_pkExc, d_pkAgg, d_segEnds;                  // packed load (upb_pack.cuh)
   DevBuf d_ment, d_mtOff, d_mtBase, d_mtCount, d_mEff, d_mtW, d_blkW;   // tile-major copy and its zone maps (upb_device.cuh)
   std::vector<uint32_t> mtBase;         // [2*C+1]
   std::map<std::string, DevBuf> scratch;     // grow-only device scratch, by name
@@ -106,6 +110,9 @@ extern "C" int upb_create (int device, upb_ctx** out) {
   ctx->smCount = prop.multiProcessorCount;
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return fail(nullptr, UPB_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
   for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
+  cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&ctx->copyEv, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->doneEv, cudaEventDisableTiming);
   if ((e = cudaMallocHost((void**)&ctx->h_small, 4096)) != cudaSuccess) { upb_destroy(ctx); return fail(nullptr, UPB_ERR_NOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e)); }
   memset(&ctx->stats, 0, sizeof ctx->stats);
   *out = ctx;
@@ -115,13 +122,16 @@ extern "C" int upb_create (int device, upb_ctx** out) {
 extern "C" void upb_destroy (upb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  DevBuf* all[] = {&ctx->d_mtW, &ctx->d_blkW, &ctx->d_ment, &ctx->d_mtOff, &ctx->d_mtBase, &ctx->d_mtCount, &ctx->d_mEff, &ctx->d_pos, &ctx->d_cnt, &ctx->d_off, &ctx->d_segStart, &ctx->d_tidx, &ctx->d_tidxBase, &ctx->d_sizes,
+  DevBuf* all[] = {&ctx->d_pk16, &ctx->d_pk8, &ctx->d_pkExc, &ctx->d_pkAgg, &ctx->d_segEnds, &ctx->d_mtW, &ctx->d_blkW, &ctx->d_ment, &ctx->d_mtOff, &ctx->d_mtBase, &ctx->d_mtCount, &ctx->d_mEff, &ctx->d_pos, &ctx->d_cnt, &ctx->d_off, &ctx->d_segStart, &ctx->d_tidx, &ctx->d_tidxBase, &ctx->d_sizes,
     &ctx->d_nTilesIdx, &ctx->d_small};
   for (DevBuf* b : all) release(*b);
   for (auto& kv : ctx->scratch) release(kv.second);
   for (HostSlab& h : ctx->slabPool) if (h.p) cudaFreeHost(h.p);
   if (ctx->h_small) cudaFreeHost(ctx->h_small);
   for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->copyEv) cudaEventDestroy(ctx->copyEv);
+  if (ctx->doneEv) cudaEventDestroy(ctx->doneEv);
+  if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -228,7 +238,12 @@ static Tags make_tags (const upb_ctx* ctx, bool useEff) {
 
 static int scan_u32 (upb_ctx* ctx, const uint32_t* d_in, uint64_t n, unsigned long long* d_out, unsigned long long* d_total, uint32_t* launches);
 
-extern "C" int upb_load_tags (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt) {
+// Both load paths: validate the offsets, bring pos[] / cnt[] to the device SAMPLE BY SAMPLE on the copy stream (plain: two
+// copies; packed: the 3-byte form, decoded by upb_pack.cuh) with the validation + histogram pass of the counting sort running
+// one sample behind on the compute stream, then the scan, the scatter pass and the zone maps.
+struct PackedSrc { const uint16_t* dpos; const uint8_t* cnt8; uint64_t nExc; const upb_packed_exception* exc; };
+
+static int load_tags_impl (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt, const PackedSrc* pk) {
   if (!ctx) return UPB_ERR_BAD_ARG;
   if (ctx->sizes.empty()) return fail(ctx, UPB_ERR_NOT_LOADED, "upb_load_tags: call upb_set_contigs first");
   if (n_samples == 0 || !off) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags: no samples");
@@ -252,30 +267,24 @@ extern "C" int upb_load_tags (upb_ctx* ctx, uint32_t n_samples, const uint64_t* 
   }
   const uint64_t E = expect;
   segStart[nSeg] = E;
-  if (E && (!pos || !cnt)) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags: pos/cnt are NULL");
+  if (E && !pk && (!pos || !cnt)) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags: pos/cnt are NULL");
+  if (E && pk && (!pk->dpos || !pk->cnt8 || (pk->nExc && !pk->exc))) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags_packed: NULL argument");
+  if (n_samples > (1u << 20)) return fail(ctx, UPB_ERR_UNSUPPORTED, "more than 2^20 samples");
+  ctx->loaded = false;
   ctx->nSamples = n_samples;
   ctx->nEntries = E;
   ctx->off.assign(off, off + nOff);
   ctx->firstPos.assign(nSeg, 0);
   ctx->lastPos.assign(nSeg, 0);
-  for (uint32_t g = 0; g < nSeg; ++g)
-    if (segStart[g + 1] > segStart[g]) { ctx->firstPos[g] = pos[segStart[g]]; ctx->lastPos[g] = pos[segStart[g + 1] - 1]; }
+  if (!pk)
+    for (uint32_t g = 0; g < nSeg; ++g)
+      if (segStart[g + 1] > segStart[g]) { ctx->firstPos[g] = pos[segStart[g]]; ctx->lastPos[g] = pos[segStart[g + 1] - 1]; }
 
   ENSURE(ctx->d_pos, (E ? E : 1) * 4);
   ENSURE(ctx->d_cnt, (E ? E : 1) * 4);
   ENSURE(ctx->d_off, nOff * 8);
   ENSURE(ctx->d_segStart, ((size_t)nSeg + 1) * 8);
   ENSURE(ctx->d_small, 4096);
-  if (E) {
-    CU(cudaMemcpyAsync(ctx->d_pos.p, pos, E * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->d_cnt.p, cnt, E * 4, cudaMemcpyHostToDevice, ctx->stream));
-  }
-  CU(cudaMemcpyAsync(ctx->d_off.p, off, nOff * 8, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->d_segStart.p, segStart.data(), ((size_t)nSeg + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemsetAsync(ctx->d_small.p, 0, 4096, ctx->stream));
-
-  // tile-major copy: counting sort of the entries by (strand, contig, 512-position mini-tile)
-  if (n_samples > (1u << 20)) return fail(ctx, UPB_ERR_UNSUPPORTED, "more than 2^20 samples");
   ctx->mtBase.assign(2 * (size_t)C + 1, 0);
   { uint64_t run = 0;
     for (uint32_t d = 0; d < 2; ++d) for (uint32_t c = 0; c < C; ++c) { ctx->mtBase[(size_t)d * C + c] = (uint32_t)run; run += ((uint64_t)(ctx->sizes[c] - 1) >> MT_SHIFT) + 1; }
@@ -288,22 +297,65 @@ extern "C" int upb_load_tags (upb_ctx* ctx, uint32_t n_samples, const uint64_t* 
   ENSURE(ctx->d_ment, (E ? E : 1) * 8);
   ENSURE(ctx->d_mtW, ((size_t)nMtTotal + 1) * 8);
   ENSURE(ctx->d_blkW, ((size_t)nMtTotal + 1) * BLK_PER_MT * 4);
+  uint64_t maxChunk = 0;
+  for (uint32_t s = 0; s < n_samples; ++s) maxChunk = std::max(maxChunk, segStart[(size_t)(s + 1) * 2 * C] - segStart[(size_t)s * 2 * C]);
+  if (pk) {
+    ENSURE(ctx->d_pk16, (E ? E : 1) * 2);
+    ENSURE(ctx->d_pk8, (E ? E : 1));
+    ENSURE(ctx->d_pkExc, (pk->nExc ? pk->nExc : 1) * sizeof(PkException));
+    ENSURE(ctx->d_pkAgg, 2 * (maxChunk / PK_TILE + 2) * sizeof(PkAgg));
+    ENSURE(ctx->d_segEnds, 2 * ((size_t)nSeg + 1) * 4);
+    if (pk->nExc) CU(cudaMemcpyAsync(ctx->d_pkExc.p, pk->exc, pk->nExc * sizeof(PkException), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CU(cudaMemcpyAsync(ctx->d_off.p, off, nOff * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_segStart.p, segStart.data(), ((size_t)nSeg + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_small.p, 0, 4096, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_mtBase.p, ctx->mtBase.data(), (2 * (size_t)C + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemsetAsync(ctx->d_mtCount.p, 0, ((size_t)nMtTotal + 1) * 4, ctx->stream));
+  // the copy stream starts after whatever still reads the old arrays on the compute stream
+  CU(cudaEventRecord(ctx->doneEv, ctx->stream));
+  CU(cudaStreamWaitEvent(ctx->copyStream, ctx->doneEv, 0));
+
+  MtArgs ma;
+  ma.pos = ctx->d_pos.as<uint32_t>(); ma.cnt = ctx->d_cnt.as<uint32_t>(); ma.segStart = ctx->d_segStart.as<uint64_t>(); ma.mtBase = ctx->d_mtBase.as<uint32_t>();
+  ma.mtCount = ctx->d_mtCount.as<uint32_t>(); ma.mtOff = ctx->d_mtOff.as<unsigned long long>(); ma.ment = ctx->d_ment.as<uint2>();
+  ma.sizes = ctx->d_sizes.as<uint32_t>(); ma.flags = ctx->d_small.as<uint32_t>();
+  ma.C = C; ma.nSeg = nSeg;
+  // tile-major copy, pass 1 (validation + per-mini-tile histogram), one sample behind the copies
+  for (uint32_t s = 0; s < n_samples; ++s) {
+    const uint64_t first = segStart[(size_t)s * 2 * C], n = segStart[(size_t)(s + 1) * 2 * C] - first;
+    if (!n) continue;
+    if (!pk) {
+      CU(cudaMemcpyAsync(ctx->d_pos.as<uint32_t>() + first, pos + first, n * 4, cudaMemcpyHostToDevice, ctx->copyStream));
+      CU(cudaMemcpyAsync(ctx->d_cnt.as<uint32_t>() + first, cnt + first, n * 4, cudaMemcpyHostToDevice, ctx->copyStream));
+    } else {
+      CU(cudaMemcpyAsync(ctx->d_pk16.as<uint16_t>() + first, pk->dpos + first, n * 2, cudaMemcpyHostToDevice, ctx->copyStream));
+      CU(cudaMemcpyAsync(ctx->d_pk8.as<uint8_t>() + first, pk->cnt8 + first, n, cudaMemcpyHostToDevice, ctx->copyStream));
+    }
+    CU(cudaEventRecord(ctx->copyEv, ctx->copyStream));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->copyEv, 0));
+    if (pk) {
+      PkArgs pa;
+      pa.dpos = ctx->d_pk16.as<uint16_t>(); pa.cnt8 = ctx->d_pk8.as<uint8_t>(); pa.exc = ctx->d_pkExc.as<PkException>(); pa.nExc = pk->nExc;
+      pa.first = first; pa.E = n; pa.pos = ctx->d_pos.as<uint32_t>(); pa.cnt = ctx->d_cnt.as<uint32_t>(); pa.flags = ctx->d_small.as<uint32_t>();
+      const uint32_t nTiles = (uint32_t)((n + PK_TILE - 1) / PK_TILE);
+      pa.agg = ctx->d_pkAgg.as<PkAgg>(); pa.carry = pa.agg + (maxChunk / PK_TILE + 2);
+      pk_tile_kernel<<<nTiles, PK_THREADS, 0, ctx->stream>>>(pa);
+      pk_top_kernel<<<1, 1024, 0, ctx->stream>>>(pa.agg, nTiles, pa.carry);
+      pk_final_kernel<<<nTiles, PK_THREADS, 0, ctx->stream>>>(pa);
+    }
+    ma.first = first; ma.nEntries = n;
+    mt_build_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ma);
+    CU(cudaGetLastError());
+  }
   {
-    MtArgs ma;
-    ma.pos = ctx->d_pos.as<uint32_t>(); ma.cnt = ctx->d_cnt.as<uint32_t>(); ma.segStart = ctx->d_segStart.as<uint64_t>(); ma.mtBase = ctx->d_mtBase.as<uint32_t>();
-    ma.mtCount = ctx->d_mtCount.as<uint32_t>(); ma.mtOff = ctx->d_mtOff.as<unsigned long long>(); ma.ment = ctx->d_ment.as<uint2>();
-    ma.sizes = ctx->d_sizes.as<uint32_t>(); ma.flags = ctx->d_small.as<uint32_t>();
-    ma.C = C; ma.nSeg = nSeg; ma.nEntries = E;
-    const uint64_t blocks = (E + 255) / 256;
     uint32_t l = 0;
-    if (E) mt_build_kernel<false><<<(unsigned)blocks, 256, 0, ctx->stream>>>(ma);
     unsigned long long* d_tot = ctx->d_small.as<unsigned long long>() + 16;
     int r = scan_u32(ctx, ma.mtCount, nMtTotal, ctx->d_mtOff.as<unsigned long long>(), d_tot, &l);
     if (r) return r;
     CU(cudaMemcpyAsync(ctx->d_mtOff.as<unsigned long long>() + nMtTotal, d_tot, 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    if (E) mt_build_kernel<true><<<(unsigned)blocks, 256, 0, ctx->stream>>>(ma);
+    ma.first = 0; ma.nEntries = E;
+    if (E) mt_build_kernel<true><<<(unsigned)((E + 255) / 256), 256, 0, ctx->stream>>>(ma);
     // zone maps (per mini-tile and per 32-position block) from the sorted copy
     mt_zone_kernel<<<(nMtTotal + 7) / 8, 256, 0, ctx->stream>>>(ctx->d_ment.as<uint2>(), ctx->d_mtOff.as<unsigned long long>(), nMtTotal,
                                                                ctx->d_mtW.as<unsigned long long>(), ctx->d_blkW.as<float>());
@@ -311,16 +363,58 @@ extern "C" int upb_load_tags (upb_ctx* ctx, uint32_t n_samples, const uint64_t* 
   }
   uint32_t flags = 0;
   CU(cudaMemcpyAsync(&flags, ctx->d_small.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (pk) {   // first / last position of every segment come back from the decoded arrays
+    uint32_t* ends = ctx->d_segEnds.as<uint32_t>();
+    seg_ends_kernel<<<(nSeg + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_pos.as<uint32_t>(), ctx->d_segStart.as<uint64_t>(), nSeg, ends, ends + nSeg);
+    CU(cudaMemcpyAsync(ctx->firstPos.data(), ends, (size_t)nSeg * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->lastPos.data(), ends + nSeg, (size_t)nSeg * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
   CU(cudaStreamSynchronize(ctx->stream));
-  ctx->loaded = false;
   ctx->cntEffValid = false;
   ctx->tidxBuilt = false;
+  if (flags & FLAG_BAD_PACK) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags_packed: an escape code (0xFFFF / 0xFF) without its exception entry");
   if (flags & FLAG_UNSORTED) return fail(ctx, UPB_ERR_UNSORTED, "upb_load_tags: positions must be strictly ascending within each (sample, strand, contig) — the reference asserts on unsorted input (misc/peakcall.cpp:171)");
   if (flags & FLAG_BAD_POS) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags: position outside 1..contig size (the reference's parser drops those, misc/format.cpp:670-676)");
   if (flags & FLAG_ZERO_COUNT) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags: zero count (the reference's parser never delivers those, misc/format.cpp:710)");
   ctx->loaded = true;
   ctx->stats.n_entries = E;
   return UPB_OK;
+}
+
+extern "C" int upb_load_tags (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt) {
+  return load_tags_impl(ctx, n_samples, off, pos, cnt, nullptr);
+}
+
+extern "C" int upb_load_tags_packed (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off, const uint16_t* dpos, const uint8_t* cnt8,
+                                     uint64_t n_exceptions, const upb_packed_exception* exceptions) {
+  PackedSrc pk; pk.dpos = dpos; pk.cnt8 = cnt8; pk.nExc = n_exceptions; pk.exc = exceptions;
+  return load_tags_impl(ctx, n_samples, off, nullptr, nullptr, &pk);
+}
+
+// host-only encoder of the packed form (what a front end does while it parses)
+extern "C" int upb_pack_tags (uint32_t n_samples, uint32_t n_contigs, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt,
+                              uint16_t* dpos_out, uint8_t* cnt8_out, upb_packed_exception* exc_out, uint64_t exc_cap, uint64_t* n_exc_out) {
+  if (!off || !n_exc_out || (exc_cap && !exc_out)) return UPB_ERR_BAD_ARG;
+  uint64_t nExc = 0;
+  for (uint32_t sd = 0; sd < n_samples * 2; ++sd)
+    for (uint32_t c = 0; c < n_contigs; ++c) {
+      const uint64_t a = off[(size_t)sd * (n_contigs + 1) + c], b = off[(size_t)sd * (n_contigs + 1) + c + 1];
+      uint32_t prev = 0;
+      for (uint64_t e = a; e < b; ++e) {
+        const uint32_t p = pos[e], k = cnt[e];
+        const bool escP = e == a || p < prev || p - prev >= PK_DPOS_ESC;   // unsorted input is kept verbatim: the load then reports it
+        const bool escC = k >= PK_CNT_ESC;
+        if (escP || escC) {
+          if (nExc < exc_cap) { exc_out[nExc].index = e; exc_out[nExc].pos = escP ? p : 0u; exc_out[nExc].cnt = escC ? k : 0u; }
+          ++nExc;
+        }
+        if (dpos_out) dpos_out[e] = escP ? (uint16_t)PK_DPOS_ESC : (uint16_t)(p - prev);
+        if (cnt8_out) cnt8_out[e] = escC ? (uint8_t)PK_CNT_ESC : (uint8_t)k;
+        prev = p;
+      }
+    }
+  *n_exc_out = nExc;
+  return nExc <= exc_cap ? UPB_OK : UPB_ERR_NOMEM;
 }
 
 // ------------------------------------------------------------------------------------------------

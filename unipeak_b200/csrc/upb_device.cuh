@@ -157,6 +157,7 @@ struct MtArgs {
   const uint32_t* sizes;            // [C]
   uint32_t* flags;                  // validation results (FLAG_*)
   uint32_t C, nSeg;
+  uint64_t first;                   // entries [first, first + nEntries) are processed (pass 1 runs sample by sample behind the H2D copies)
   uint64_t nEntries;
 };
 
@@ -171,11 +172,12 @@ __device__ __forceinline__ uint32_t seg_of_entry (const uint64_t* __restrict__ s
 // the per-mini-tile histogram; pass 2 scatters (the zone maps are built from the sorted copy by mt_zone_kernel).  Entries that fail validation are never used as indices.
 template <bool SCATTER>
 __global__ void mt_build_kernel (MtArgs a) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.nEntries) return;
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.nEntries) return;
+  const uint64_t i = a.first + k;
   // consecutive entries almost always share their segment: one search per warp, the lanes only check
   uint32_t g = 0;
-  { const uint64_t i0 = i & ~(uint64_t)31;
+  { const uint64_t i0 = a.first + (k & ~(uint64_t)31);
     g = seg_of_entry(a.segStart, a.nSeg, i0);
     if (i >= a.segStart[g + 1]) g = seg_of_entry(a.segStart, a.nSeg, i); }
   const uint32_t c = g % a.C, sd = g / a.C, d = sd & 1u, s = sd >> 1;
