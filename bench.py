@@ -278,19 +278,23 @@ def main():
         last = step()
     kde_ms, launches = [], 0
     barrier()
+    if gather is not None:
+        gather.times = [0.0, 0.0, 0.0, 0]                             # per-phase host clocks of the timed steps only
+    call_ms = []
     with ClockSampler(local_rank) as clocks:
         t0 = time.perf_counter()
         ev0.record(lib_stream)
         for _ in range(args.steps):
             last = step()
             s = ctx.stats()
-            kde_ms.append(s["ms_kde"]); launches += s["launches"]
+            kde_ms.append(s["ms_kde"]); launches += s["launches"]; call_ms.append(s["ms_call"])
         if world > 1:
             lib_stream.wait_stream(torch.cuda.current_stream())      # the NCCL gather of the last step runs on torch's stream
         ev1.record(lib_stream)
         barrier()
         dt_wall = time.perf_counter() - t0
     stats = ctx.stats()
+    gather_times = list(gather.times) if gather is not None and getattr(gather, "times", None) else [0.0, 0.0, 0.0, 1]
     ev1.synchronize()
     dt = ev0.elapsed_time(ev1) * 1e-3
     tmax = torch.tensor([dt, dt_wall], dtype=torch.float64, device=dev)
@@ -351,6 +355,17 @@ def main():
                 "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kde_avg_ms, "kernel_share_of_step": kde_avg_ms / ms_per_step}
 
+    # where the step goes on every rank (host clocks of the last call and of the gather phases, averaged over the gather's calls)
+    per_rank = None
+    if world > 1:
+        gt = gather_times
+        k = max(1, gt[3])
+        mine = torch.tensor([float(np.mean(call_ms)) if call_ms else 0.0, stats["ms_total"], gt[0] / k * 1e3, gt[1] / k * 1e3, gt[2] / k * 1e3, float(E)], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"columns": ["call_ms", "device_ms", "allreduce_counts_ms", "scatter_ms", "completion_ms", "tag_entries"],
+                    "rows": [[round(float(x), 4) for x in t.cpu().tolist()] for t in allr]}
+
     if rank == 0:
         line = {"metric": metric, "value": genome / (ms_per_step * 1e-3), "unit": "bp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "wall_ms_per_step": wall_ms_per_step, "timing": "CUDA events on the library's stream around the K steps (max over ranks); wall clock alongside",
@@ -381,9 +396,8 @@ def main():
                                     "sample": "contigs %s (%d bp, %d tag entries) of the workload, all samples, workload-wide thresholds"
                                               % ("+".join(names[c] for c in cs), bp, int(sample.pos.shape[0])),
                                     "host_cores_available": os.cpu_count(), "rows_match_gpu": bool(same), "rows": len(theirs)}
-        if gather is not None and getattr(gather, "times", None):
-            k = max(1, gather.times[3])
-            line["result"]["gather_ms_rank0"] = {"allreduce_counts": gather.times[0] / k * 1e3, "scatter": gather.times[1] / k * 1e3, "completion": gather.times[2] / k * 1e3}
+        if per_rank is not None:
+            line["result"]["per_rank_ms"] = per_rank
         print(json.dumps(line))
     if gather is not None and hasattr(gather, "close"):
         gather.close()

@@ -357,7 +357,7 @@ static int load_tags_impl (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off
     ma.first = 0; ma.nEntries = E;
     if (E) mt_build_kernel<true><<<(unsigned)((E + 255) / 256), 256, 0, ctx->stream>>>(ma);
     // zone maps (per mini-tile and per 32-position block) from the sorted copy
-    mt_zone_kernel<<<(nMtTotal + 7) / 8, 256, 0, ctx->stream>>>(ctx->d_ment.as<uint2>(), ctx->d_mtOff.as<unsigned long long>(), nMtTotal,
+    mt_zone_kernel<<<(nMtTotal + ZONE_MT_PER_BLOCK - 1) / ZONE_MT_PER_BLOCK, 256, 0, ctx->stream>>>(ctx->d_ment.as<uint2>(), ctx->d_mtOff.as<unsigned long long>(), nMtTotal,
                                                                ctx->d_mtW.as<unsigned long long>(), ctx->d_blkW.as<float>());
     CU(cudaGetLastError());
   }

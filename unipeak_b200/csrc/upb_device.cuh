@@ -198,31 +198,36 @@ __global__ void mt_build_kernel (MtArgs a) {
   a.ment[slot] = make_uint2(a.cnt[i], (s << SPAN_SHIFT) | (p & (SPAN_LEN - 1)));
 }
 
-// Zone maps of the tile-major copy, one warp per mini-tile: mtW[m] = total count of the mini-tile (all samples), blkW[16m + j] =
+// Zone maps of the tile-major copy, eight lanes per mini-tile: mtW[m] = total count of the mini-tile (all samples), blkW[16m + j] =
 // total count of its j-th 32-position block as a float rounded up.  Both only ever feed upper bounds (a span / block whose
 // bound stays below the threshold is never evaluated), so rounding up and +inf for sums that could wrap are safe.
 constexpr int BLK_PER_MT = 1 << (MT_SHIFT - 5);
-__global__ void mt_zone_kernel (const uint2* __restrict__ ment, const unsigned long long* __restrict__ mtOff, uint32_t nMt,
-                                unsigned long long* __restrict__ mtW, float* __restrict__ blkW) {
-  __shared__ uint32_t acc[8][BLK_PER_MT];
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t m = blockIdx.x * 8 + warp;
-  if (m >= nMt) return;
-  if (lane < BLK_PER_MT) acc[warp][lane] = 0;
+constexpr int ZONE_MT_PER_BLOCK = 32;               // 8 warps x 4 mini-tiles: eight lanes per mini-tile (a mini-tile holds ~27 entries on C3)
+__global__ void __launch_bounds__(256) mt_zone_kernel (const uint2* __restrict__ ment, const unsigned long long* __restrict__ mtOff, uint32_t nMt,
+                                                       unsigned long long* __restrict__ mtW, float* __restrict__ blkW) {
+  __shared__ uint32_t acc[8][4][BLK_PER_MT];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3, gl = lane & 7;
+  const uint32_t m = (blockIdx.x * 8 + warp) * 4 + g;
+  const bool valid = m < nMt;
+  acc[warp][g][gl] = 0; acc[warp][g][gl + 8] = 0;
   __syncwarp();
-  const unsigned long long e0 = mtOff[m], e1 = mtOff[m + 1];
+  unsigned long long e0 = 0, e1 = 0;
+  if (valid) { e0 = __ldg(mtOff + m); e1 = __ldg(mtOff + m + 1); }
   unsigned long long tot = 0;
-  for (unsigned long long e = e0 + lane; e < e1; e += 32) {
-    const uint2 x = __ldg(ment + e);
-    tot += x.x;
-    atomicAdd(&acc[warp][(x.y >> 5) & (BLK_PER_MT - 1)], x.x);
-  }
+  for (unsigned long long e = e0 + gl; __any_sync(0xffffffffu, e < e1); e += 8)
+    if (e < e1) {
+      const uint2 x = __ldg(ment + e);
+      tot += x.x;
+      atomicAdd(&acc[warp][g][(x.y >> 5) & (BLK_PER_MT - 1)], x.x);
+    }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+  for (int o = 4; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
   __syncwarp();
+  if (!valid) return;
   const bool wrap = tot > 0xFFFFFFFFull;                              // a block's 32-bit sum may have wrapped: call all of them unbounded
-  if (lane == 0) mtW[m] = tot;
-  if (lane < BLK_PER_MT) blkW[(size_t)m * BLK_PER_MT + lane] = wrap ? __int_as_float(0x7f800000) : __uint2float_ru(acc[warp][lane]);
+  if (gl == 0) mtW[m] = tot;
+  blkW[(size_t)m * BLK_PER_MT + gl] = wrap ? __int_as_float(0x7f800000) : __uint2float_ru(acc[warp][g][gl]);
+  blkW[(size_t)m * BLK_PER_MT + gl + 8] = wrap ? __int_as_float(0x7f800000) : __uint2float_ru(acc[warp][g][gl + 8]);
 }
 
 // control filter: a control sample's tag is remembered by the reference only when the same add()

@@ -195,7 +195,8 @@ class HostGather:
         dist.all_reduce(self._done)                                    # completion: every rank's rows have landed
         torch.cuda.current_stream().synchronize()
         t3 = time.perf_counter()
-        self.times = getattr(self, "times", [0.0, 0.0, 0.0, 0])
+        if getattr(self, "times", None) is None:
+            self.times = [0.0, 0.0, 0.0, 0]
         self.times[0] += t1 - t0; self.times[1] += t2 - t1; self.times[2] += t3 - t2; self.times[3] += 1
         if self.rank != 0:
             return None
