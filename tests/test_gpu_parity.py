@@ -9,7 +9,7 @@ import math
 import numpy as np
 import pytest
 
-from refutil import oracle_regions, oracle_strand_shift, region_settings
+from refutil import oracle_regions, oracle_strand_shift, oracle_tags_in_regions, region_settings
 from unipeak_b200.synth import TagData, make_synthetic
 
 pytestmark = pytest.mark.gpu
@@ -477,3 +477,17 @@ def test_packed_load_equals_plain_load(gpu_ctx):
         off = np.ascontiguousarray(data.off, dtype=np.uint64)
         gpu_ctx.load_tags_packed_ptr(3, off.ctypes.data, dpos.ctypes.data, cnt8.ctypes.data, exc.shape[0] - 1, exc.ctypes.data)
     check_regions(gpu_ctx, d)
+
+
+def test_many_samples_c4_shape(gpu_ctx):
+    # config 4 has 96 samples (+32 held out for tags_in_regions): sample ids beyond 6 bits, shared-memory sizing of the matrix rows
+    d = make_synthetic([300000, 120000], 96, 2500, directional=True, seed=96, peak_spacing=4000)
+    got, want = check_regions(gpu_ctx, d)
+    assert len(want["rows"]) > 20 and len(want["rows"][0]["counts"]) == 96
+    check_regions(gpu_ctx, d, control=[0, 17, 95])
+    held = make_synthetic([300000, 120000], 32, 2500, directional=True, seed=97, peak_spacing=4000)
+    keys = [(r["contig"], r["left"], r["left"] + r["len"] - 1) if r["forward_label"] else (r["contig"], r["left"] + r["len"] - 1, r["left"]) for r in want["rows"]]
+    status, tir_want = oracle_tags_in_regions(held, keys, directional=True, extension=0)
+    assert status == 0
+    gpu_ctx.load(held)
+    assert np.array_equal(gpu_ctx.count_tags_in_regions(keys, directional=True, extension=0), tir_want)

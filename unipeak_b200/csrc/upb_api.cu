@@ -50,6 +50,7 @@ struct upb_ctx {
   std::vector<uint64_t> off;            // host copy
   std::vector<uint32_t> firstPos, lastPos;   // [(s*2+d)*C + c], 0 if empty
   DevBuf d_pos, d_cnt, d_off, d_segStart, d_tidx, d_tidxBase, d_sizes, d_nTilesIdx, d_small;
+  DevBuf d_winBase, d_wEnt;                                          // per-sample window index of the scatter pass
   DevBuf d_pk16, d_pk8, d_pkExc, d_pkAgg, d_segEnds;                  // packed load (upb_pack.cuh)
   DevBuf d_ment, d_mtOff, d_mtBase, d_mtCount, d_mEff, d_mtW, d_blkW;   // tile-major copy and its zone maps (upb_device.cuh)
   std::vector<uint32_t> mtBase;         // [2*C+1]
@@ -122,7 +123,7 @@ extern "C" int upb_create (int device, upb_ctx** out) {
 extern "C" void upb_destroy (upb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  DevBuf* all[] = {&ctx->d_pk16, &ctx->d_pk8, &ctx->d_pkExc, &ctx->d_pkAgg, &ctx->d_segEnds, &ctx->d_mtW, &ctx->d_blkW, &ctx->d_ment, &ctx->d_mtOff, &ctx->d_mtBase, &ctx->d_mtCount, &ctx->d_mEff, &ctx->d_pos, &ctx->d_cnt, &ctx->d_off, &ctx->d_segStart, &ctx->d_tidx, &ctx->d_tidxBase, &ctx->d_sizes,
+  DevBuf* all[] = {&ctx->d_winBase, &ctx->d_wEnt, &ctx->d_pk16, &ctx->d_pk8, &ctx->d_pkExc, &ctx->d_pkAgg, &ctx->d_segEnds, &ctx->d_mtW, &ctx->d_blkW, &ctx->d_ment, &ctx->d_mtOff, &ctx->d_mtBase, &ctx->d_mtCount, &ctx->d_mEff, &ctx->d_pos, &ctx->d_cnt, &ctx->d_off, &ctx->d_segStart, &ctx->d_tidx, &ctx->d_tidxBase, &ctx->d_sizes,
     &ctx->d_nTilesIdx, &ctx->d_small};
   for (DevBuf* b : all) release(*b);
   for (auto& kv : ctx->scratch) release(kv.second);
@@ -291,7 +292,14 @@ static int load_tags_impl (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off
     if (run > 0xFFFFFFF0ull) return fail(ctx, UPB_ERR_UNSUPPORTED, "genome too large for the mini-tile index");
     ctx->mtBase[2 * (size_t)C] = (uint32_t)run; }
   const uint32_t nMtTotal = ctx->mtBase.back();
+  std::vector<uint32_t> winBase(2 * (size_t)C + 1, 0);
+  { uint32_t run = 0;
+    for (size_t dc = 0; dc < 2 * (size_t)C; ++dc) { winBase[dc] = run; run += (ctx->mtBase[dc + 1] - ctx->mtBase[dc] + WIN_MT - 1) / WIN_MT; }
+    winBase[2 * (size_t)C] = run; }
+  const uint32_t nWinTotal = winBase.back();
   ENSURE(ctx->d_mtBase, (2 * (size_t)C + 1) * 4);
+  ENSURE(ctx->d_winBase, (2 * (size_t)C + 1) * 4);
+  ENSURE(ctx->d_wEnt, ((size_t)n_samples * nWinTotal + 2) * 4);
   ENSURE(ctx->d_mtCount, ((size_t)nMtTotal + 1) * 4);
   ENSURE(ctx->d_mtOff, ((size_t)nMtTotal + 2) * 8);
   ENSURE(ctx->d_ment, (E ? E : 1) * 8);
@@ -312,6 +320,7 @@ static int load_tags_impl (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off
   CU(cudaMemsetAsync(ctx->d_small.p, 0, 4096, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_mtBase.p, ctx->mtBase.data(), (2 * (size_t)C + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemsetAsync(ctx->d_mtCount.p, 0, ((size_t)nMtTotal + 1) * 4, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_winBase.p, winBase.data(), (2 * (size_t)C + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
   // the copy stream starts after whatever still reads the old arrays on the compute stream
   CU(cudaEventRecord(ctx->doneEv, ctx->stream));
   CU(cudaStreamWaitEvent(ctx->copyStream, ctx->doneEv, 0));
@@ -321,6 +330,10 @@ static int load_tags_impl (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off
   ma.mtCount = ctx->d_mtCount.as<uint32_t>(); ma.mtOff = ctx->d_mtOff.as<unsigned long long>(); ma.ment = ctx->d_ment.as<uint2>();
   ma.sizes = ctx->d_sizes.as<uint32_t>(); ma.flags = ctx->d_small.as<uint32_t>();
   ma.C = C; ma.nSeg = nSeg;
+  ma.mtW = ctx->d_mtW.as<unsigned long long>(); ma.blkW = ctx->d_blkW.as<float>();
+  ma.winBase = ctx->d_winBase.as<uint32_t>(); ma.wEnt = ctx->d_wEnt.as<uint32_t>(); ma.nWinTotal = nWinTotal;
+  ma.first = 0; ma.nEntries = 0;
+  win_fill_kernel<<<(unsigned)(((uint64_t)n_samples * nWinTotal + 255) / 256), 256, 0, ctx->stream>>>(ma, n_samples);
   // tile-major copy, pass 1 (validation + per-mini-tile histogram), one sample behind the copies
   for (uint32_t s = 0; s < n_samples; ++s) {
     const uint64_t first = segStart[(size_t)s * 2 * C], n = segStart[(size_t)(s + 1) * 2 * C] - first;
@@ -355,10 +368,7 @@ static int load_tags_impl (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off
     if (r) return r;
     CU(cudaMemcpyAsync(ctx->d_mtOff.as<unsigned long long>() + nMtTotal, d_tot, 8, cudaMemcpyDeviceToDevice, ctx->stream));
     ma.first = 0; ma.nEntries = E;
-    if (E) mt_build_kernel<true><<<(unsigned)((E + 255) / 256), 256, 0, ctx->stream>>>(ma);
-    // zone maps (per mini-tile and per 32-position block) from the sorted copy
-    mt_zone_kernel<<<(nMtTotal + ZONE_MT_PER_BLOCK - 1) / ZONE_MT_PER_BLOCK, 256, 0, ctx->stream>>>(ctx->d_ment.as<uint2>(), ctx->d_mtOff.as<unsigned long long>(), nMtTotal,
-                                                               ctx->d_mtW.as<unsigned long long>(), ctx->d_blkW.as<float>());
+    if (E) mt_scatter_kernel<<<nWinTotal, 256, 0, ctx->stream>>>(ma, n_samples);
     CU(cudaGetLastError());
   }
   uint32_t flags = 0;

@@ -156,6 +156,11 @@ struct MtArgs {
   uint2* ment;
   const uint32_t* sizes;            // [C]
   uint32_t* flags;                  // validation results (FLAG_*)
+  unsigned long long* mtW;          // [nMtTotal] zone map per mini-tile (written by the scatter pass)
+  float* blkW;                      // [nMtTotal * 16] zone map per 32-position block
+  const uint32_t* winBase;          // [2*C+1] first window (WIN_MT mini-tiles) of (strand d, contig c)
+  uint32_t* wEnt;                   // [nSamples * nWinTotal] first entry (relative to its segment) of sample s at or after each window
+  uint32_t nWinTotal;
   uint32_t C, nSeg;
   uint64_t first;                   // entries [first, first + nEntries) are processed (pass 1 runs sample by sample behind the H2D copies)
   uint64_t nEntries;
@@ -166,6 +171,9 @@ __device__ __forceinline__ uint32_t seg_of_entry (const uint64_t* __restrict__ s
   while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (segStart[mid] <= i) lo = mid; else hi = mid; }
   return lo;
 }
+
+constexpr int WIN_SHIFT = 16;       // scatter window: 65536 positions = 128 mini-tiles, one CTA of mt_scatter_kernel
+constexpr int WIN_MT = 1 << (WIN_SHIFT - MT_SHIFT);
 
 // Pass 1 (SCATTER = false) validates what the reference's parser guarantees (positions inside the contig and strictly
 // ascending per (sample, strand, contig), non-zero counts: misc/format.cpp:654-710, misc/peakcall.cpp:171) and builds
@@ -192,43 +200,83 @@ __global__ void mt_build_kernel (MtArgs a) {
     if (i > a.segStart[g] && a.pos[i - 1] >= pos1) f |= FLAG_UNSORTED;
     if (f) atomicOr(a.flags, f);
     atomicAdd(&a.mtCount[mt], 1u);
+    if (!(f & FLAG_UNSORTED)) {     // per-sample window index: the first entry of every window this entry opens
+      const int64_t w = (int64_t)(p >> WIN_SHIFT);
+      const int64_t pw = i > a.segStart[g] ? (int64_t)((a.pos[i - 1] - 1) >> WIN_SHIFT) : -1;
+      uint32_t* we = a.wEnt + (size_t)s * a.nWinTotal + a.winBase[d * a.C + c];
+      for (int64_t t = pw + 1; t <= w; ++t) we[t] = (uint32_t)(i - a.segStart[g]);
+    }
     return;
   }
   const unsigned long long slot = a.mtOff[mt] + (atomicSub(&a.mtCount[mt], 1u) - 1u);
   a.ment[slot] = make_uint2(a.cnt[i], (s << SPAN_SHIFT) | (p & (SPAN_LEN - 1)));
 }
 
-// Zone maps of the tile-major copy, eight lanes per mini-tile: mtW[m] = total count of the mini-tile (all samples), blkW[16m + j] =
-// total count of its j-th 32-position block as a float rounded up.  Both only ever feed upper bounds (a span / block whose
-// bound stays below the threshold is never evaluated), so rounding up and +inf for sums that could wrap are safe.
-constexpr int BLK_PER_MT = 1 << (MT_SHIFT - 5);
-constexpr int ZONE_MT_PER_BLOCK = 32;               // 8 warps x 4 mini-tiles: eight lanes per mini-tile (a mini-tile holds ~27 entries on C3)
-__global__ void __launch_bounds__(256) mt_zone_kernel (const uint2* __restrict__ ment, const unsigned long long* __restrict__ mtOff, uint32_t nMt,
-                                                       unsigned long long* __restrict__ mtW, float* __restrict__ blkW) {
-  __shared__ uint32_t acc[8][4][BLK_PER_MT];
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3, gl = lane & 7;
-  const uint32_t m = (blockIdx.x * 8 + warp) * 4 + g;
-  const bool valid = m < nMt;
-  acc[warp][g][gl] = 0; acc[warp][g][gl + 8] = 0;
-  __syncwarp();
-  unsigned long long e0 = 0, e1 = 0;
-  if (valid) { e0 = __ldg(mtOff + m); e1 = __ldg(mtOff + m + 1); }
-  unsigned long long tot = 0;
-  for (unsigned long long e = e0 + gl; __any_sync(0xffffffffu, e < e1); e += 8)
-    if (e < e1) {
-      const uint2 x = __ldg(ment + e);
-      tot += x.x;
-      atomicAdd(&acc[warp][g][(x.y >> 5) & (BLK_PER_MT - 1)], x.x);
-    }
-#pragma unroll
-  for (int o = 4; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-  __syncwarp();
-  if (!valid) return;
-  const bool wrap = tot > 0xFFFFFFFFull;                              // a block's 32-bit sum may have wrapped: call all of them unbounded
-  if (gl == 0) mtW[m] = tot;
-  blkW[(size_t)m * BLK_PER_MT + gl] = wrap ? __int_as_float(0x7f800000) : __uint2float_ru(acc[warp][g][gl]);
-  blkW[(size_t)m * BLK_PER_MT + gl + 8] = wrap ? __int_as_float(0x7f800000) : __uint2float_ru(acc[warp][g][gl + 8]);
+// window index default: "no entry at or after this window" = the segment's length
+__global__ void win_fill_kernel (MtArgs a, uint32_t nSamples) {
+  const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (uint64_t)nSamples * a.nWinTotal) return;
+  const uint32_t s = (uint32_t)(e / a.nWinTotal), gw = (uint32_t)(e % a.nWinTotal);
+  uint32_t lo = 0, hi = 2 * a.C;    // largest dc with winBase[dc] <= gw (empty ranges are skipped by taking the largest)
+  while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.winBase[mid] <= gw) lo = mid; else hi = mid; }
+  const uint32_t d = lo / a.C, c = lo % a.C;
+  const uint64_t g = (uint64_t)(s * 2 + d) * a.C + c;
+  a.wEnt[e] = (uint32_t)(a.segStart[g + 1] - a.segStart[g]);
 }
+
+// Pass 2 of the counting sort, window-major: one CTA per 65536-position window of one (strand, contig) moves the entries of
+// ALL samples that fall into it (one warp per sample at a time; each sample's entries of the window are one contiguous range of
+// its sorted segment, found through the window index) to their mini-tiles.  The CTA's output is one contiguous stretch of the
+// tile-major copy (~28 KB on C3), so the 8-byte stores merge into full sectors in L2, and the per-mini-tile cursors are
+// shared-memory atomics — the sample-major version (v1–v19) did 326 M global atomics and partial-sector writes: 5.3 ms.
+__global__ void __launch_bounds__(256) mt_scatter_kernel (MtArgs a, uint32_t nSamples) {
+  __shared__ uint32_t cursor[WIN_MT];
+  __shared__ unsigned long long base[WIN_MT];
+  __shared__ uint32_t big[WIN_MT];                                    // a count large enough that a 32-bit block sum could wrap
+  __shared__ uint32_t blk[WIN_MT * (1 << (MT_SHIFT - 5))];            // zone map per 32-position block
+  if (*a.flags & (FLAG_UNSORTED | FLAG_BAD_POS)) return;             // pass 1 found invalid input: its entries are never used as indices
+  const uint32_t gw = blockIdx.x;
+  uint32_t lo = 0, hi = 2 * a.C;
+  while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.winBase[mid] <= gw) lo = mid; else hi = mid; }
+  const uint32_t d = lo / a.C, c = lo % a.C, w = gw - a.winBase[lo];
+  const uint32_t gb = a.mtBase[lo], nMt = a.mtBase[lo + 1] - gb;
+  const uint32_t m0 = w * WIN_MT, nHere = min((uint32_t)WIN_MT, nMt - m0);
+  const bool lastWin = gw + 1 == a.winBase[lo + 1];
+  for (uint32_t k = threadIdx.x; k < (uint32_t)WIN_MT; k += blockDim.x) { cursor[k] = 0; big[k] = 0; base[k] = k < nHere ? a.mtOff[gb + m0 + k] : 0ull; }
+  for (uint32_t k = threadIdx.x; k < (uint32_t)(WIN_MT << (MT_SHIFT - 5)); k += blockDim.x) blk[k] = 0;
+  __syncthreads();
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t kBig = 0xFFFFFFFFu / (32u * nSamples);               // a block holds at most 32 * nSamples entries of one strand
+  for (uint32_t s = warp; s < nSamples; s += blockDim.x / 32) {
+    const uint64_t g = (uint64_t)(s * 2 + d) * a.C + c;
+    const uint64_t seg = a.segStart[g];
+    const uint32_t* we = a.wEnt + (size_t)s * a.nWinTotal + gw;
+    const uint64_t e0 = seg + we[0], e1 = lastWin ? a.segStart[g + 1] : seg + we[1];
+    for (uint64_t e = e0 + lane; e < e1; e += 32) {
+      const uint32_t p = a.pos[e] - 1;
+      const uint32_t lm = (p >> MT_SHIFT) - m0;
+      if (lm >= nHere) continue;                                      // cannot happen on validated input
+      const unsigned long long slot = base[lm] + atomicAdd(&cursor[lm], 1u);
+      const uint32_t k = a.cnt[e];
+      a.ment[slot] = make_uint2(k, (s << SPAN_SHIFT) | (p & (SPAN_LEN - 1)));
+      if (k >= kBig) big[lm] = 1;
+      atomicAdd(&blk[(lm << (MT_SHIFT - 5)) | ((p >> 5) & ((1u << (MT_SHIFT - 5)) - 1))], k);
+    }
+  }
+  // zone maps of the window: mtW[m] = total count of the mini-tile, blkW[16m + j] = total count of its j-th 32-position block as a
+  // float rounded up (+inf where a 32-bit block sum could have wrapped).  Both only ever feed upper bounds (a span / block whose
+  // bound stays below the threshold is never evaluated), so rounding up is safe.
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < nHere; k += blockDim.x) {
+    unsigned long long t = 0;
+    for (uint32_t j = 0; j < (1u << (MT_SHIFT - 5)); ++j) t += blk[(k << (MT_SHIFT - 5)) + j];
+    a.mtW[gb + m0 + k] = big[k] ? (1ull << 56) : t;
+  }
+  for (uint32_t k = threadIdx.x; k < (nHere << (MT_SHIFT - 5)); k += blockDim.x)
+    a.blkW[((size_t)(gb + m0) << (MT_SHIFT - 5)) + k] = big[k >> (MT_SHIFT - 5)] ? __int_as_float(0x7f800000) : __uint2float_ru(blk[k]);
+}
+
+constexpr int BLK_PER_MT = 1 << (MT_SHIFT - 5);
 
 // control filter: a control sample's tag is remembered by the reference only when the same add()
 // call carried a non-zero non-control sum, i.e. when a non-control sample has a tag at the same (strand,
