@@ -222,6 +222,23 @@ typedef struct {
 int upb_count_tags_in_regions (upb_ctx* ctx, int directional, uint32_t extension, uint64_t n_regions,
                                const upb_region_key* regions, uint32_t* counts_out);
 
+/* ---- bin/convert_align --------------------------------------------------------------------- */
+/* Replaces CountMap (misc/data.hpp, CountMap::add misc/data.cpp:301-314) as filled by src/convert_align.cpp:70-90: the number of
+ * tags per (strand, contig, 5' position) of a batch of alignments.  key[i] = strand * n_contigs + contig (strand 0 '+', 1 '-'),
+ * pos[i] the 1-based 5' position (offset applied, out-of-bounds tags already dropped, as ParseAlignStream delivers them),
+ * cnt[i] the multiplicity (NULL: 1 each).  combine_strands != 0 pools both strands on strand 0 (the -D output,
+ * CountMap::ConstNondirIterator).  Result: distinct positions ascending inside each (strand, contig), library-allocated. */
+typedef struct {
+  uint64_t n;                   /* distinct (strand, contig, position) */
+  uint64_t tag_count;           /* CountMap::tagCount() */
+  uint64_t* off;                /* [2 * n_contigs + 1] entries of (strand d, contig c): [off[d*C+c], off[d*C+c+1]) */
+  uint32_t* pos;
+  uint32_t* cnt;
+} upb_tag_counts;
+int upb_aggregate_tags (upb_ctx* ctx, uint64_t n, const uint32_t* key, const uint32_t* pos, const uint32_t* cnt, int combine_strands,
+                        upb_tag_counts* out);
+void upb_free_tag_counts (upb_tag_counts* t);
+
 /* ---- Kernel -------------------------------------------------------------------------------- */
 /* Replaces Kernel::Kernel (misc/kernel.cpp:16-35): 2*bandwidth+1 Epanechnikov taps scaled to `sum`.
  * Host arithmetic, identical expression order; the device uses exactly this table. */

@@ -491,3 +491,34 @@ def test_many_samples_c4_shape(gpu_ctx):
     assert status == 0
     gpu_ctx.load(held)
     assert np.array_equal(gpu_ctx.count_tags_in_regions(keys, directional=True, extension=0), tir_want)
+
+
+def test_aggregate_tags_equals_a_map(gpu_ctx):
+    # bin/convert_align's CountMap (misc/data.cpp:301-314): counts per (strand, contig, position), ascending positions
+    rng = np.random.default_rng(8)
+    sizes = [700000, 5000, 1, 130000]
+    gpu_ctx.set_contigs(sizes)
+    n = 400000
+    contig = rng.choice(4, size=n, p=[0.6, 0.1, 0.05, 0.25])
+    strand = rng.integers(0, 2, size=n)
+    pos = np.array([rng.integers(1, sizes[c] + 1) for c in contig], dtype=np.uint32)
+    pos[::7] = pos[3::7][:pos[::7].shape[0]] if pos[3::7].shape[0] >= pos[::7].shape[0] else pos[::7]    # plenty of repeats
+    pos = np.minimum(pos, np.array(sizes, dtype=np.uint32)[contig])
+    cnt = rng.integers(1, 5, size=n).astype(np.uint32)
+    cnt[::1000] = 0xFFFFFFF0                                                                           # HitCount arithmetic wraps
+    key = (strand * 4 + contig).astype(np.uint32)
+    for combine in (False, True):
+        off, opos, ocnt, total = gpu_ctx.aggregate_tags(key, pos, cnt, combine_strands=combine)
+        k2 = contig.astype(np.int64) if combine else key.astype(np.int64)
+        full = k2 * (1 << 32) + pos.astype(np.int64)
+        order = np.argsort(full, kind="stable")
+        u, start = np.unique(full[order], return_index=True)
+        sums = np.add.reduceat(cnt[order].astype(np.uint64), start) & 0xFFFFFFFF
+        u, sums = u[sums != 0], sums[sums != 0]                        # a count that wraps to exactly 0 (mod 2^32) is an empty cell on the device
+        assert np.array_equal(opos, (u & 0xFFFFFFFF).astype(np.uint32)) and np.array_equal(ocnt, sums.astype(np.uint32))
+        assert total == int(cnt.astype(np.uint64).sum())
+        want_off = np.searchsorted(u >> 32, np.arange(9), side="left")
+        assert np.array_equal(off, want_off.astype(np.uint64))
+    import unipeak_b200
+    with pytest.raises(unipeak_b200.UpbError):
+        gpu_ctx.aggregate_tags(np.array([0], np.uint32), np.array([700001], np.uint32))                # beyond the contig

@@ -12,7 +12,7 @@ from refutil import REF_DIR, ROOT, write_inputs
 from unipeak_b200.synth import TagData, make_synthetic
 
 BIN = os.path.join(ROOT, "bin")
-TOOLS = ("regions", "strand_shift", "tags_in_regions")
+TOOLS = ("regions", "strand_shift", "tags_in_regions", "convert_align")
 
 
 def have_bins() -> bool:
@@ -249,3 +249,84 @@ def test_cli_gzip_roundtrip(tmp_path):
     plain = [l for l in (tmp_path / "plain.txt").read_bytes().splitlines() if not l.startswith(b"# align_file")]
     z = [l for l in gzip.open(tmp_path / "z.txt.gz").read().splitlines() if not l.startswith(b"# align_file")]
     assert plain == z and len(plain) > 20
+
+
+# ---------------------------------------------------------------------------------------------------------
+# bin/convert_align: alignments -> tag-frequency wiggle (parsers on the host, aggregation on the device)
+# ---------------------------------------------------------------------------------------------------------
+def write_bed(path, data: TagData, sample=0, read_len=36, extra=()):
+    names = data.names()
+    rng = np.random.default_rng(11)
+    lines = []
+    for d in range(2):
+        for c in range(data.n_contigs):
+            pos, cnt = data.seg(sample, d, c)
+            for p, k in zip(pos.tolist(), cnt.tolist()):
+                for _ in range(k):
+                    if d == 0:
+                        lines.append("%s\t%d\t%d\tr\t0\t+" % (names[c], p - 1, p - 1 + read_len))
+                    else:
+                        lines.append("%s\t%d\t%d\tr\t0\t-" % (names[c], max(0, p - read_len), p))
+    lines += list(extra)
+    order = rng.permutation(len(lines))
+    with open(path, "w") as f:
+        f.write("".join(lines[i] + "\n" for i in order))
+
+
+def write_sam(path, data: TagData, sample=0, read_len=30):
+    names = data.names()
+    rng = np.random.default_rng(12)
+    out = ["@HD\tVN:1.0\tSO:unsorted"] + ["@SQ\tSN:%s\tLN:%d" % (n, s) for n, s in zip(names, data.contig_sizes.tolist())]
+    seq, qual = "A" * read_len, "I" * read_len
+    reads = []
+    for d in range(2):
+        for c in range(data.n_contigs):
+            pos, cnt = data.seg(sample, d, c)
+            for p, k in zip(pos.tolist(), cnt.tolist()):
+                for _ in range(k):
+                    start = p if d == 0 else p - read_len + 1
+                    if start < 1:
+                        continue
+                    flag = 16 if d else 0
+                    u = rng.random()
+                    if u < 0.05:
+                        flag |= 4                       # unmapped
+                    elif u < 0.10:
+                        flag |= 256                     # secondary: not even counted
+                    elif u < 0.13:
+                        flag |= 512                     # failed QC
+                    mapq = int(rng.choice([0, 3, 9, 10, 11, 30, 60]))
+                    nm = int(rng.choice([0, 0, 0, 1, 2, 3]))
+                    fields = ["r%d" % len(reads), str(flag), names[c] if rng.random() > 0.02 else "chrUn", str(start), str(mapq), "%dM" % read_len, "*", "0", "0", seq, qual]
+                    if rng.random() < 0.8:
+                        fields += ["XT:A:U", "NM:i:%d" % nm]
+                    reads.append("\t".join(fields))
+    order = rng.permutation(len(reads))
+    with open(path, "w") as f:
+        f.write("\n".join(out) + "\n" + "".join(reads[i] + "\n" for i in order))
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_cli_convert_align_bed_sam_wig(tmp_path):
+    d = make_synthetic([120000, 40000], 1, 6000, directional=True, seed=41, peak_spacing=4000, contig_names=["chrA", "chrB"], keep_clear_of_edges=False)
+    extra = ["chrZ\t10\t46\tr\t0\t+", "chrB\t39990\t40026\tr\t0\t+", "chrA\t0\t36\tr\t0\t-", "track name=ignored"]
+    for which in ("ref", "new"):
+        wd = tmp_path / which
+        wd.mkdir()
+        d.write_contig_table(str(wd / "contigs.txt"))
+        write_bed(str(wd / "reads.bed"), d, extra=extra)
+        write_sam(str(wd / "reads.sam"), d)
+    both(tmp_path, "convert_align", ["-q", "-c", "contigs.txt", "-o", "bed.wig", "reads.bed"], ["bed.wig"])
+    both(tmp_path, "convert_align", ["-c", "contigs.txt", "-o", "bed2.wig", "-s", "7", "-l", "25", "-a", "hg19", "-n", "trk", "reads.bed"], ["bed2.wig"])
+    both(tmp_path, "convert_align", ["-q", "-D", "-c", "contigs.txt", "-o", "bedD.wig", "reads.bed"], ["bedD.wig"])
+    both(tmp_path, "convert_align", ["-q", "-c", "contigs.txt", "-o", "sam.wig", "reads.sam"], ["sam.wig"])
+    both(tmp_path, "convert_align", ["-q", "-c", "contigs.txt", "-o", "sam2.wig", "-p", "0", "-i", "0", "-s", "-3", "reads.sam"], ["sam2.wig"])
+    both(tmp_path, "convert_align", ["-q", "-D", "-c", "contigs.txt", "-o", "samD.wig", "-p", "0.999", "-l", "20", "reads.sam", "reads.bed"], ["samD.wig"])
+    # a wiggle is also an alignment format: re-aggregating the converter's own output, then calling regions on it
+    both(tmp_path, "convert_align", ["-q", "-c", "contigs.txt", "-o", "again.wig", "-p", "0", "bed.wig", "sam.wig"], ["again.wig"])
+    both(tmp_path, "regions", ["-q", "-o", "regions.txt", "-c", "contigs.txt", "-m", "3000000", "bed.wig"], ["regions.txt"])
+    # nothing usable: same message, same exit code
+    (tmp_path / "ref" / "empty.bed").write_text("chrZ\t10\t46\tr\t0\t+\n")
+    (tmp_path / "new" / "empty.bed").write_text("chrZ\t10\t46\tr\t0\t+\n")
+    both(tmp_path, "convert_align", ["-q", "-c", "contigs.txt", "-o", "none.wig", "empty.bed"], [], rc=1)

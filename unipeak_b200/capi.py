@@ -75,13 +75,17 @@ EXPORTS = [
     "upb_create", "upb_destroy", "upb_last_error", "upb_device_count", "upb_host_alloc", "upb_host_free", "upb_set_contigs",
     "upb_load_tags", "upb_call_regions", "upb_free_region_table", "upb_reference_order", "upb_profile_contig", "upb_free_profile",
     "upb_strand_shift", "upb_free_shift_report", "upb_count_tags_in_regions", "upb_kernel_taps", "upb_last_stats",
-    "upb_slab_layout", "upb_scatter_rows", "upb_table_from_slab", "upb_stream", "upb_host_register", "upb_host_unregister", "upb_load_tags_packed", "upb_pack_tags",
+    "upb_slab_layout", "upb_scatter_rows", "upb_table_from_slab", "upb_stream", "upb_host_register", "upb_host_unregister", "upb_load_tags_packed", "upb_pack_tags", "upb_aggregate_tags", "upb_free_tag_counts",
 ]
 SLAB_COLS = ("cand_index", "peak_score", "kurtosis", "corr", "contig", "left", "len", "peak", "hit_sum", "counts", "buffer", "end")
 SLAB_DTYPES = dict(cand_index=np.uint64, peak_score=np.float64, kurtosis=np.float64, corr=np.float64, contig=np.uint32, left=np.uint32,
                    len=np.uint32, peak=np.uint32, hit_sum=np.uint32, counts=np.uint32, buffer=np.uint8)
 
 _lib = None
+
+
+class TagCounts(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("tag_count", C.c_uint64), ("off", C.POINTER(C.c_uint64)), ("pos", C.POINTER(C.c_uint32)), ("cnt", C.POINTER(C.c_uint32))]
 
 
 PACKED_EXC_DTYPE = np.dtype([("index", np.uint64), ("pos", np.uint32), ("cnt", np.uint32)])
@@ -277,6 +281,24 @@ class Context:
         off = np.ascontiguousarray(data.off, dtype=np.uint64)
         dpos, cnt8, exc = pack_tags(data.n_samples, self.n_contigs, off, data.pos, data.cnt)
         self.load_tags_packed_ptr(data.n_samples, off.ctypes.data, dpos.ctypes.data, cnt8.ctypes.data, exc.shape[0], exc.ctypes.data)
+
+    def aggregate_tags(self, key, pos, cnt=None, combine_strands=False):
+        """upb_aggregate_tags: (off[2C+1], pos, cnt, tag_count) — distinct 5' positions with their tag counts per (strand, contig)."""
+        key = np.ascontiguousarray(key, dtype=np.uint32)
+        pos = np.ascontiguousarray(pos, dtype=np.uint32)
+        cnt_p = None
+        if cnt is not None:
+            cnt = np.ascontiguousarray(cnt, dtype=np.uint32)
+            cnt_p = cnt.ctypes.data
+        t = TagCounts()
+        self._lib.upb_aggregate_tags.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(TagCounts)]
+        self._lib.upb_free_tag_counts.argtypes = [C.POINTER(TagCounts)]
+        self._check(self._lib.upb_aggregate_tags(self._h, int(key.shape[0]), key.ctypes.data, pos.ctypes.data, cnt_p, 1 if combine_strands else 0, C.byref(t)))
+        try:
+            n = int(t.n)
+            return (_np(t.off, 2 * self.n_contigs + 1, np.uint64), _np(t.pos, n, np.uint32), _np(t.cnt, n, np.uint32), int(t.tag_count))
+        finally:
+            self._lib.upb_free_tag_counts(C.byref(t))
 
     def load(self, data) -> None:
         """Load a unipeak_b200.synth.TagData."""

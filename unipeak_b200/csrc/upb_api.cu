@@ -7,6 +7,7 @@
 #include "upb_device.cuh"
 #include "upb_span.cuh"
 #include "upb_pack.cuh"
+#include "upb_aggr.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -1614,3 +1615,85 @@ extern "C" int upb_count_tags_in_regions (upb_ctx* ctx, int directional, uint32_
   ctx->stats.launches = directional ? 4 : 3;
   return UPB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// bin/convert_align: tag counts per (strand, contig, 5' position)
+// ------------------------------------------------------------------------------------------------
+extern "C" void upb_free_tag_counts (upb_tag_counts* t) {
+  if (!t) return;
+  free(t->off); free(t->pos); free(t->cnt);
+  memset(t, 0, sizeof *t);
+}
+
+extern "C" int upb_aggregate_tags (upb_ctx* ctx, uint64_t n, const uint32_t* key, const uint32_t* pos, const uint32_t* cnt, int combine_strands,
+                                   upb_tag_counts* out) {
+  if (!ctx) return UPB_ERR_BAD_ARG;
+  if (!out || (n && (!key || !pos))) return fail(ctx, UPB_ERR_BAD_ARG, "upb_aggregate_tags: NULL argument");
+  if (ctx->sizes.empty()) return fail(ctx, UPB_ERR_NOT_LOADED, "upb_aggregate_tags: call upb_set_contigs first");
+  memset(out, 0, sizeof *out);
+  CU(cudaSetDevice(ctx->device));
+  const uint32_t C = (uint32_t)ctx->sizes.size();
+  std::vector<uint32_t> mtBase(2 * (size_t)C + 1, 0);
+  { uint64_t run = 0;
+    for (uint32_t d = 0; d < 2; ++d) for (uint32_t c = 0; c < C; ++c) { mtBase[(size_t)d * C + c] = (uint32_t)run; run += ((uint64_t)(ctx->sizes[c] - 1) >> MT_SHIFT) + 1; }
+    if (run > 0xFFFFFFF0ull) return fail(ctx, UPB_ERR_UNSUPPORTED, "genome too large for the mini-tile index");
+    mtBase[2 * (size_t)C] = (uint32_t)run; }
+  const uint32_t nMt = mtBase.back();
+  out->off = (uint64_t*)calloc(2 * (size_t)C + 1, 8);
+  if (!out->off) return fail(ctx, UPB_ERR_NOMEM, "out of host memory");
+  if (n == 0) return UPB_OK;
+  AggrArgs a;
+  memset(&a, 0, sizeof a);
+  uint32_t* d_key = SCR("agKey", uint32_t, n); uint32_t* d_pos = SCR("agPos", uint32_t, n);
+  uint32_t* d_cnt = cnt ? SCR("agCnt", uint32_t, n) : nullptr;
+  uint32_t* d_mtBase = SCR("agMtBase", uint32_t, 2 * (size_t)C + 1);
+  uint32_t* d_count = SCR("agCount", uint32_t, (size_t)nMt + 1); uint32_t* d_cursor = SCR("agCursor", uint32_t, (size_t)nMt + 1);
+  unsigned long long* d_mtOff = SCR("agMtOff", unsigned long long, (size_t)nMt + 2);
+  uint2* d_ent = SCR("agEnt", uint2, n);
+  uint32_t* d_uniq = SCR("agUniq", uint32_t, (size_t)nMt + 1);
+  unsigned long long* d_outOff = SCR("agOutOff", unsigned long long, (size_t)nMt + 2);
+  unsigned long long* d_off = SCR("agOff", unsigned long long, 2 * (size_t)C + 2);
+  ENSURE(ctx->d_small, 4096);
+  CU(cudaMemcpyAsync(d_key, key, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_pos, pos, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (cnt) CU(cudaMemcpyAsync(d_cnt, cnt, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_mtBase, mtBase.data(), (2 * (size_t)C + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemsetAsync(d_count, 0, ((size_t)nMt + 1) * 4, ctx->stream));
+  CU(cudaMemsetAsync(d_cursor, 0, ((size_t)nMt + 1) * 4, ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_small.p, 0, 4096, ctx->stream));
+  a.key = d_key; a.pos = d_pos; a.cnt = d_cnt; a.n = n; a.sizes = ctx->d_sizes.as<uint32_t>(); a.mtBase = d_mtBase; a.C = C;
+  a.combine = combine_strands ? 1 : 0; a.mtCount = d_count; a.cursor = d_cursor; a.mtOff = d_mtOff; a.ent = d_ent; a.uniq = d_uniq;
+  a.outOff = d_outOff; a.nMt = nMt; a.flags = ctx->d_small.as<uint32_t>();
+  unsigned long long* d_tot = ctx->d_small.as<unsigned long long>() + 16;
+  a.tagCount = d_tot + 4;
+  uint32_t launches = 0;
+  const unsigned gN = (unsigned)((n + 255) / 256), gM = (nMt + AG_WARPS - 1) / AG_WARPS;
+  aggr_sort_kernel<false><<<gN, 256, 0, ctx->stream>>>(a);
+  int r = scan_u32(ctx, d_count, nMt, d_mtOff, d_tot, &launches);
+  if (r) return r;
+  CU(cudaMemcpyAsync(d_mtOff + nMt, d_tot, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  aggr_sort_kernel<true><<<gN, 256, 0, ctx->stream>>>(a);
+  aggr_reduce_kernel<false><<<gM, AG_WARPS * 32, 0, ctx->stream>>>(a);
+  if ((r = scan_u32(ctx, d_uniq, nMt, d_outOff, d_tot + 1, &launches))) return r;
+  CU(cudaMemcpyAsync(d_outOff + nMt, d_tot + 1, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  unsigned long long* h64 = (unsigned long long*)ctx->h_small;
+  CU(cudaMemcpyAsync(h64, d_tot, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(h64 + 8, ctx->d_small.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (((uint32_t*)(h64 + 8))[0] & FLAG_BAD_POS) return fail(ctx, UPB_ERR_BAD_ARG, "upb_aggregate_tags: strand/contig key or position out of range");
+  const uint64_t nOut = h64[1];
+  out->n = nOut; out->tag_count = h64[4];
+  out->pos = (uint32_t*)malloc((nOut ? nOut : 1) * 4); out->cnt = (uint32_t*)malloc((nOut ? nOut : 1) * 4);
+  if (!out->pos || !out->cnt) { upb_free_tag_counts(out); return fail(ctx, UPB_ERR_NOMEM, "out of host memory"); }
+  a.outPos = SCR("agOutPos", uint32_t, nOut + 1); a.outCnt = SCR("agOutCnt", uint32_t, nOut + 1);
+  aggr_reduce_kernel<true><<<gM, AG_WARPS * 32, 0, ctx->stream>>>(a);
+  aggr_offsets_kernel<<<(2 * C + 1 + 255) / 256, 256, 0, ctx->stream>>>(d_outOff, d_mtBase, 2 * C, d_off);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out->pos, a.outPos, nOut * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(out->cnt, a.outCnt, nOut * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(out->off, d_off, (2 * (size_t)C + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->stats.launches = launches + 6;
+  return UPB_OK;
+}
+

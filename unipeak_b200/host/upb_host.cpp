@@ -35,8 +35,8 @@ void die_upb (upb_ctx* ctx, int code) {
 // flags: the observable behaviour of TCLAP::CmdLine + StdOutput (misc/tclap/CmdLine.h, StdOutput.h) for the argument kinds
 // the three mains declare.  Unknown "-x" tokens are swallowed by the unlabeled multi-argument, as in the reference.
 // ---------------------------------------------------------------------------------------------------------------------------
-CmdLine::CmdLine (const std::vector<ArgSpec>& specs, const char* unlabeledDesc, const char* unlabeledType)
-    : specs_(specs), unlabeledDesc_(unlabeledDesc), unlabeledType_(unlabeledType) {}
+CmdLine::CmdLine (const std::vector<ArgSpec>& specs, const char* unlabeledDesc, const char* unlabeledType, const char* unlabeledName)
+    : specs_(specs), unlabeledDesc_(unlabeledDesc), unlabeledType_(unlabeledType), unlabeledName_(unlabeledName) {}
 
 std::string CmdLine::argId (const ArgSpec& a) const { return std::string("Argument: -") + a.flag + " (--" + a.name + ")"; }
 
@@ -159,6 +159,7 @@ void CmdLine::parse (int argc, char** argv) {
         case ARG_U16: ok = extract_ok<unsigned short>(val, &several); break;
         case ARG_U32: ok = extract_ok<unsigned int>(val, &several); break;
         case ARG_DOUBLE: ok = extract_ok<double>(val, &several); break;
+        case ARG_I16: ok = extract_ok<short>(val, &several); break;
         default: break;
       }
       if (!ok) failure(argId(*a), "Couldn't read argument value from string '" + val + "'");
@@ -183,7 +184,7 @@ void CmdLine::parse (int argc, char** argv) {
   int nMissing = 0;
   for (size_t i = specs_.size(); i-- > 0;)
     if (specs_[i].required && !values_.count(specs_[i].flag)) { missing += std::string(specs_[i].name) + ", "; ++nMissing; }
-  if (unlabeled_.empty()) { missing += ", "; ++nMissing; }
+  if (unlabeled_.empty()) { missing += unlabeledName_ + ", "; ++nMissing; }
   if (nMissing > 0)
     failure(" ", std::string(nMissing > 1 ? "Required arguments missing: " : "Required argument missing: ") + missing.substr(0, missing.size() - 2));
 }
@@ -195,6 +196,7 @@ std::string CmdLine::str (char flag, const std::string& dflt) const {
 template <class T> static T extract (const std::string& val) { std::istringstream is(val); T v = T(); is >> v; return v; }
 double CmdLine::dbl (char flag, double dflt) const { auto it = values_.find(flag); return it == values_.end() ? dflt : extract<double>(it->second); }
 uint32_t CmdLine::u32 (char flag, uint32_t dflt) const { auto it = values_.find(flag); return it == values_.end() ? dflt : extract<unsigned int>(it->second); }
+short CmdLine::i16 (char flag, short dflt) const { auto it = values_.find(flag); return it == values_.end() ? dflt : extract<short>(it->second); }
 uint16_t CmdLine::u16 (char flag, uint16_t dflt) const { auto it = values_.find(flag); return it == values_.end() ? dflt : extract<unsigned short>(it->second); }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -540,6 +542,204 @@ std::vector<Sample> read_samples (const std::vector<std::string>& fnames, const 
     });
   for (std::thread& th : pool) th.join();
   return samples;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// alignments: BED (misc/format.cpp:287-312), SAM (:567-610), tag-frequency wiggle; format detection :247-284; the common tail
+// (read length, -s offset, contig bounds) :654-678
+// ---------------------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct AlignSink {
+  const ContigTable& contigs;
+  const AlignOpts& o;
+  AlignBatch& b;
+  // returns false when the tag was dropped
+  bool add (bool forward, uint32_t contig, uint32_t first, uint32_t last, uint32_t count) {
+    if (count == 0 || contig == contigs.size()) return false;
+    if (o.useLength != 0) last = forward ? first + (o.useLength - 1) : first - (o.useLength - 1);
+    if (o.offset != 0) {
+      if ((forward && (int)first > -o.offset) || (!forward && (int)last > o.offset)) {
+        first += (uint32_t)(forward ? o.offset : -o.offset);
+        last += (uint32_t)(forward ? o.offset : -o.offset);
+      } else { b.outOfBoundsTags += count; return false; }
+    }
+    const uint32_t size = contigs.sizes[contig];
+    if (first == 0 || first > size || last == 0 || last > size) { b.outOfBoundsTags += count; return false; }
+    b.confidentTags += count;
+    b.key.push_back((forward ? 0u : contigs.size()) + contig);
+    b.pos.push_back(first);
+    b.cnt.push_back(count);
+    return true;
+  }
+};
+
+// boost::split(fields, line, is_any_of(seps)) without token compression: empty fields are kept
+void split_any (const char* s, size_t len, const char* seps, std::vector<std::pair<const char*, size_t> >* out) {
+  out->clear();
+  size_t a = 0;
+  for (size_t i = 0; i <= len; ++i)
+    if (i == len || strchr(seps, s[i])) { out->push_back(std::make_pair(s + a, i - a)); a = i + 1; }
+}
+
+bool all_digits (const char* s, size_t n) { if (!n) return false; for (size_t i = 0; i < n; ++i) if (!isdigit((unsigned char)s[i])) return false; return true; }
+
+// BED_REGEX  ^[^\s]+\s\d+\s\d+\s[^\s]*\s[^\s]*?\s[+-]   (misc/format.hpp:24)
+bool looks_like_bed (const char* s, size_t len) {
+  size_t i = 0;
+  auto nonspace = [&] (bool atLeastOne) { size_t a = i; while (i < len && !isspace((unsigned char)s[i])) ++i; return !atLeastOne || i > a; };
+  auto space = [&] () { if (i < len && isspace((unsigned char)s[i])) { ++i; return true; } return false; };
+  auto digits = [&] () { size_t a = i; while (i < len && isdigit((unsigned char)s[i])) ++i; return i > a; };
+  if (!nonspace(true) || !space() || !digits() || !space() || !digits() || !space()) return false;
+  nonspace(false); if (!space()) return false;
+  nonspace(false); if (!space()) return false;
+  return i < len && (s[i] == '+' || s[i] == '-');
+}
+
+// SAM_HEADER_REGEX  ^@[A-Za-z][A-Za-z](\t[A-Za-z][A-Za-z0-9]:[ -~]+)+$
+bool looks_like_sam_header (const char* s, size_t len) {
+  if (len < 3 || s[0] != '@' || !isalpha((unsigned char)s[1]) || !isalpha((unsigned char)s[2])) return false;
+  size_t i = 3;
+  int groups = 0;
+  while (i < len) {
+    if (s[i] != '\t' || i + 4 > len || !isalpha((unsigned char)s[i + 1]) || !isalnum((unsigned char)s[i + 2]) || s[i + 3] != ':') return false;
+    i += 4;
+    size_t a = i;
+    while (i < len && s[i] >= ' ' && s[i] <= '~') ++i;
+    if (i == a) return false;
+    ++groups;
+  }
+  return groups > 0;
+}
+
+}  // namespace
+
+void read_alignments (const std::string& fname, const ContigTable& contigs, const AlignOpts& opts, AlignBatch* out) {
+  AlignBatch& B = *out;
+  B = AlignBatch();
+  B.name = fname_prefix(fname);
+  if (ends_with(fname, ".bam")) { B.error = fname + ": BAM input is not supported by this build (convert it with samtools view -h)"; return; }
+  std::vector<char> buf;
+  std::string shown;
+  if (!slurp(fname, &buf, &shown, &B.error)) return;
+  AlignSink sink{contigs, opts, B};
+  const uint32_t C = contigs.size();
+  // MAPQ threshold exactly as the reference derives it (a double, misc/format.cpp:166-168)
+  const double phred = opts.probThreshold == 0 ? 0 : opts.probThreshold == 1 ? 255 : -10 * log10(1 - opts.probThreshold);
+  bool forward = true;              // wiggle state
+  uint32_t contig = 0;
+  uint64_t lineNo = 0;
+  std::vector<std::pair<const char*, size_t> > f;
+  const char* base = buf.data();
+  size_t p = 0;
+  const size_t N = buf.size();
+  auto fail = [&] (const char* msg) { B.error = line_error(msg, shown, lineNo); };
+  while (p < N) {
+    const char* nl = (const char*)memchr(base + p, '\n', N - p);
+    const size_t e = nl ? (size_t)(nl - base) : N;
+    const char* s = base + p;
+    const size_t len = e - p;
+    p = e + 1;
+    ++lineNo;
+    if (len == 0 || s[0] == '#') continue;
+    if (B.format == 0) {
+      if (len >= 5 && memcmp(s, "track", 5) == 0) {
+        std::string nm;
+        const bool named = match_name(s, len, "name=\"", '"', &nm) || match_name(s, len, "name=", ' ', &nm);
+        if (named) B.name = nm;
+        if (std::string(s, len).find("type=wiggle_0") != std::string::npos) {
+          std::string b2; bool fw;
+          if (split_directional(B.name, &b2, &fw)) { B.format = 6; B.name = b2; forward = fw; }
+          else { B.format = 7; B.name = named ? nm : std::string(); forward = true; }
+        } else B.format = 1;
+        continue;
+      } else if (looks_like_bed(s, len)) B.format = 1;
+      else if (looks_like_sam_header(s, len)) B.format = 4;
+      else if (s[0] == '>') { B.error = fname + ": Eland / Corona input is not supported by this build"; return; }
+      else { fail("bad format"); return; }
+    }
+    if (B.format == 1) {                                             // BED
+      if (len >= 5 && memcmp(s, "track", 5) == 0) continue;
+      split_any(s, len, "\t ", &f);
+      if (f.size() < 6) { fail("bad format"); return; }
+      const char strand = f[5].second ? f[5].first[0] : '\0';
+      if (strand != '+' && strand != '-') { fail("bad format"); return; }
+      const bool fw = strand == '+';
+      uint32_t a, b2;
+      if (!lexical_u32(f[1].first, f[1].second, &a) || !lexical_u32(f[2].first, f[2].second, &b2)) { fail("bad format"); return; }
+      ++B.totalTags;
+      sink.add(fw, contigs.find(std::string(f[0].first, f[0].second)), fw ? a + 1 : b2, fw ? b2 : a + 1, 1);
+    } else if (B.format == 4) {                                      // SAM
+      if (s[0] == '@') continue;
+      split_any(s, len, "\t", &f);
+      if (f.size() < 10) { fail("bad format"); return; }
+      uint32_t flag;
+      if (!lexical_u32(f[1].first, f[1].second, &flag) || flag > 0xFFFF) { fail("bad format"); return; }
+      if (flag & 0x0100) continue;                                   // non-primary
+      ++B.totalTags;
+      if (flag & (0x0004 + 0x0200)) continue;                        // unmapped or failed QC
+      if (f.size() > 11) {
+        long edit = 0;
+        for (size_t k = 0; k < f.size(); ++k)
+          if (f[k].second > 5 && memcmp(f[k].first, "NM:i:", 5) == 0 && all_digits(f[k].first + 5, f[k].second - 5)) { edit = strtol(std::string(f[k].first + 5, f[k].second - 5).c_str(), nullptr, 10); break; }
+        if (edit > (long)opts.mismatchTolerance) continue;
+      }
+      if (phred != 0 && phred != 255) {
+        uint32_t mapq;
+        if (!lexical_u32(f[4].first, f[4].second, &mapq) || mapq > 0xFFFF) { fail("bad format"); return; }
+        if ((double)mapq < phred) { ++B.rejectTags; continue; }
+      }
+      const uint32_t c = contigs.find(std::string(f[2].first, f[2].second));
+      if (c == C) continue;
+      const uint32_t seqLen = (uint32_t)f[9].second;
+      if (opts.useLength != 0 && seqLen < opts.useLength) { fail("sequence shorter than requested length"); return; }
+      const bool fw = !(flag & 0x0010);
+      uint32_t pos1;
+      if (!lexical_u32(f[3].first, f[3].second, &pos1)) { fail("bad format"); return; }
+      const uint32_t first = pos1 + (fw ? 0u : seqLen - 1);
+      const uint32_t span = (opts.useLength != 0 ? opts.useLength : seqLen) - 1;
+      sink.add(fw, c, first, fw ? first + span : first - span, 1);
+    } else {                                                          // tag-frequency wiggle (misc/format.cpp:503-565)
+      if (isdigit((unsigned char)s[0])) {
+        if (contig == C) continue;
+        size_t delim = len;
+        while (delim-- > 0) if (s[delim] == '\t' || s[delim] == ' ') break;
+        if (delim == (size_t)-1) { fail("bad format"); return; }
+        uint32_t first, count;
+        const size_t cs = delim + ((delim + 1 < len && s[delim + 1] == '-') ? 2 : 1);
+        if (!lexical_u32(s, delim, &first) || cs > len || !lexical_u32(s + cs, len - cs, &count)) { fail("bad format"); return; }
+        B.totalTags += count;
+        uint32_t last = first;
+        if (opts.useLength != 0) last = (B.format == 6 && !forward) ? first - (opts.useLength - 1) : first + (opts.useLength - 1);
+        sink.add(forward, contig, first, last, count);
+      } else if (len > 19 && memcmp(s, "variableStep chrom=", 19) == 0) {
+        contig = contigs.find(std::string(s + 19, len - 19));
+      } else if (len >= 5 && memcmp(s, "track", 5) == 0) {
+        std::string nm;
+        if (!match_name(s, len, "name=\"", '"', &nm)) { fail("bad format"); return; }
+        contig = C;
+        if (B.format == 6) {
+          std::string b2; bool fw;
+          if (!split_directional(nm, &b2, &fw)) { fail("strand not defined"); return; }
+          B.name = b2; forward = fw;
+        } else B.name = nm;
+      } else { fail("bad format"); return; }
+    }
+  }
+}
+
+std::string align_summary (const AlignBatch& b, double prob) {
+  std::string s;
+  if (!b.name.empty()) s += b.name + ": ";
+  s += std::to_string(b.totalTags) + " tags";
+  if (b.format == 4) {
+    s += "\n  " + std::to_string(b.confidentTags) + (prob != 0 ? " confidently mapped" : " unique best") + " hits (" +
+         fmt_fixed(100 * (double)b.confidentTags / (double)b.totalTags, 1) + "%)";
+    if (prob != 0) s += "\n  " + std::to_string(b.rejectTags) + " unique best hits rejected by filter (" + fmt_fixed(100 * (double)b.rejectTags / (double)b.totalTags, 1) + "%)";
+  }
+  if (b.outOfBoundsTags > 0) s += "\n" + std::to_string(b.outOfBoundsTags) + " out of contig bounds";
+  s += "\n";
+  return s;
 }
 
 Flat::~Flat () {

@@ -17,14 +17,14 @@
 namespace upbhost {
 
 // ---- flags (what TCLAP::CmdLine does for the three mains) ---------------------------------------------------------------
-enum ArgKind { ARG_SWITCH, ARG_STRING, ARG_U16, ARG_U32, ARG_DOUBLE };
+enum ArgKind { ARG_SWITCH, ARG_STRING, ARG_U16, ARG_U32, ARG_DOUBLE, ARG_I16 };
 struct ArgSpec {                           // in the order the reference declares them
   char flag; const char* name; ArgKind kind; bool required; const char* desc; const char* typeDesc;
 };
 
 class CmdLine {
  public:
-  CmdLine (const std::vector<ArgSpec>& specs, const char* unlabeledDesc, const char* unlabeledType);
+  CmdLine (const std::vector<ArgSpec>& specs, const char* unlabeledDesc, const char* unlabeledType, const char* unlabeledName = "");
   void parse (int argc, char** argv);      // prints TCLAP's messages and exits (1 on error, 0 for -h / --version)
   bool isSet (char flag) const { return values_.count(flag) != 0; }
   bool sw (char flag) const { return switches_.count(flag) != 0; }
@@ -32,6 +32,7 @@ class CmdLine {
   double dbl (char flag, double dflt) const;
   uint32_t u32 (char flag, uint32_t dflt) const;
   uint16_t u16 (char flag, uint16_t dflt) const;
+  short i16 (char flag, short dflt) const;
   const std::vector<std::string>& unlabeled () const { return unlabeled_; }
 
  private:
@@ -40,7 +41,7 @@ class CmdLine {
   void longUsage (FILE* f) const;
   std::string argId (const ArgSpec& a) const;
   std::vector<ArgSpec> specs_;
-  std::string unlabeledDesc_, unlabeledType_, prog_;
+  std::string unlabeledDesc_, unlabeledType_, unlabeledName_, prog_;
   std::map<char, std::string> values_;
   std::map<char, bool> switches_;
   std::vector<std::string> unlabeled_;
@@ -78,6 +79,20 @@ void read_wig (const std::string& fname, const ContigTable& contigs, int offset,
 // every file on its own thread; returns in input order; exits with the first file's error like the reference would
 std::vector<Sample> read_samples (const std::vector<std::string>& fnames, const ContigTable& contigs,
                                   const std::vector<short>& offsets, unsigned useLength);
+
+// ---- alignments (bin/convert_align) ------------------------------------------------------------------------------------------------
+// What ParseAlignStream delivers to CountMap::add (src/convert_align.cpp:70-90): one (strand, contig, 5' position, count) per usable
+// alignment, plus the counters printSummary reports (misc/format.cpp:213-232).  Formats: BED, SAM, tag-frequency wiggle.
+struct AlignOpts { unsigned mismatchTolerance = 1; unsigned useLength = 0; int offset = 0; double probThreshold = 0.9; };
+struct AlignBatch {
+  std::string name;                        // exptName()
+  int format = 0;                          // 1 BED, 4 SAM, 6 / 7 wiggle (misc/format.hpp:36-43)
+  uint64_t totalTags = 0, confidentTags = 0, rejectTags = 0, outOfBoundsTags = 0;
+  std::vector<uint32_t> key, pos, cnt;     // key = strand * nContigs + contig
+  std::string error;
+};
+void read_alignments (const std::string& fname, const ContigTable& contigs, const AlignOpts& opts, AlignBatch* out);
+std::string align_summary (const AlignBatch& b, double probThreshold);   // ParseAlignStream::printSummary
 
 // flat layout of upb_load_tags (include/unipeak_b200.h)
 struct Flat { std::vector<uint64_t> off; uint32_t* pos = nullptr; uint32_t* cnt = nullptr; uint64_t n = 0; bool pinned = false; ~Flat (); };
