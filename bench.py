@@ -10,9 +10,11 @@ N > 1 (torchrun, one process per GPU): contigs are sharded over the ranks (stron
 fixed); NCCL carries only the per-sample tag totals (background), the tags-in-regions totals and the
 gather of the region rows to rank 0.
 
-`value`  : genome bp / step time, inputs already resident in HBM (wall clock bracketed by barrier +
-           synchronize, max over ranks).
-`e2e`    : the same through the C-ABI from pinned HOST arrays: H2D copy + index build + call + table D2H.
+`value`  : genome bp / step time, inputs already resident in HBM (CUDA events on the library's stream around the K steps,
+           bracketed by barrier + synchronize, max over ranks; the wall clock of the same region is reported beside it).
+`e2e`    : the same through the C-ABI from pinned HOST buffers every step: H2D copy + decode + counting sort + zone maps +
+           call + table D2H.  Default host form: the compact one (upb_load_tags_packed: u16 position deltas + u8 counts +
+           exception list, 3 B per entry); `e2e_alt` is the plain form (upb_load_tags: u32 + u32, 8 B per entry).
 `roofline`: the fused span kernel, algorithmic bytes (8 B per tag entry read once + 40+4n B per candidate written)
            over its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
 `cpu_baseline` / --impl reference: the reference's own Kernel/ProfileBuffer/Region objects
