@@ -53,6 +53,12 @@ def test_g6_formatter_equals_printf():
     assert b"bad=0" in p.stdout
 
 
+def test_prefix_sort_equals_std_sort():
+    # strand_shift needs only the head of std::sort's (unstable) result: unipeak_b200/csrc/upb_introsort.hpp
+    p = run(BIN, "host_selftest", ["sort"], ROOT, check=0)
+    assert b"bad=0" in p.stdout
+
+
 @pytest.mark.skipif(not refutil.have_ref(), reason="compiled reference (oracle/_ref) not present")
 @pytest.mark.parametrize("args", [["-h"], ["--version"], [], ["-c", "x", "-b", "abc", "f.wig"], ["-c", "x", "-c", "y", "f.wig"],
                                   ["-c", "x", "f.wig", "-s"], ["-c", "x", "-l", "70000", "f.wig"], ["-c", "x", "-s", "1,2,3", "-o", "o", "-f", "i", "f.wig"],

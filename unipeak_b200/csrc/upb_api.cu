@@ -8,6 +8,7 @@
 #include "upb_span.cuh"
 #include "upb_pack.cuh"
 #include "upb_aggr.cuh"
+#include "upb_introsort.hpp"
 
 #include <algorithm>
 #include <chrono>
@@ -1437,11 +1438,16 @@ extern "C" int upb_strand_shift (upb_ctx* ctx, const upb_shift_params* p, upb_sh
   out->tested_contig = alloc_arr<uint32_t>(cap); out->tested_left = alloc_arr<uint32_t>(cap); out->tested_len = alloc_arr<uint32_t>(cap);
   out->tested_best_shift = alloc_arr<uint32_t>(cap); out->tested_best_corr = alloc_arr<double>(cap);
 
-  // :198 std::sort by Region::sum() descending — same comparator outcomes, same libstdc++ algorithm, hence
-  // the same permutation as the reference's sort of Region pointers
-  std::vector<SumIdx> order(R);
-  for (size_t i = 0; i < R; ++i) { order[i].sum = rSum[i]; order[i].idx = (uint32_t)i; }   // no controls: sum() == pooled weight
-  std::sort(order.begin(), order.end(), compareRegionCounts);
+  // :198 std::sort by Region::sum() descending — same comparator outcomes, same libstdc++ algorithm, hence the same
+  // permutation as the reference's sort of Region pointers; only as much of it as the examination below needs (upb_introsort.hpp)
+  std::vector<SumIdx> unsorted(R), order;
+  for (size_t i = 0; i < R; ++i) { unsorted[i].sum = rSum[i]; unsorted[i].idx = (uint32_t)i; }   // no controls: sum() == pooled weight
+  size_t sortedEnd = 0;
+  auto sort_more = [&] (size_t want) {
+    order = unsorted;
+    sortedEnd = sort_prefix_like_std_sort(order.begin(), order.end(), want, compareRegionCounts);
+  };
+  sort_more(std::min<size_t>(R, 2 * (size_t)toTest + 256));
 
   // :201-226 — regions are examined in sorted order until enough qualify; the device sweeps a batch at a time
   uint16_t tested = 0;
@@ -1452,6 +1458,7 @@ extern "C" int upb_strand_shift (upb_ctx* ctx, const upb_shift_params* p, upb_sh
     std::vector<uint32_t> batch;                                     // row indices
     const size_t want = (size_t)(toTest - tested) + (size_t)(toTest - tested) / 4 + 8;
     while (cursor < R && batch.size() < want) {
+      if (cursor >= sortedEnd) sort_more(std::min<size_t>(R, std::max<size_t>(2 * sortedEnd, cursor + 1024)));
       const uint32_t i = order[cursor].idx;
       if (rLen[i] > 2 * p->max_shift + 3) batch.push_back(i);          // :206 large enough to try all shifts
       ++cursor;

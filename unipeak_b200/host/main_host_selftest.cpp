@@ -8,6 +8,10 @@
 #include <string>
 
 #include "upb_host.hpp"
+#include "../csrc/upb_introsort.hpp"
+
+#include <algorithm>
+#include <vector>
 
 using namespace upbhost;
 
@@ -30,6 +34,31 @@ int main (int argc, char** argv) {
       if (strcmp(a, b)) { if (++bad < 10) fprintf(stderr, "g6 mismatch: %.17g printf=%s fast=%s\n", x, a, b); }
     }
     printf("g6 checked=%ld bad=%ld\n", n, bad);
+    return bad ? 1 : 0;
+  }
+  if (argc >= 2 && !strcmp(argv[1], "sort")) {
+    // the prefix sort against std::sort itself: unstable sort, heavy ties, the element order must be identical
+    struct SI { uint32_t sum, idx; };
+    auto cmp = [] (const SI& a, const SI& b) { return a.sum > b.sum; };
+    std::mt19937_64 rng(99);
+    long bad = 0, cases = 0;
+    for (int rep = 0; rep < 60; ++rep) {
+      const size_t n = rep < 6 ? (size_t)rep * 5 : 1000 + rng() % 120000;
+      const uint32_t range = rep % 3 == 0 ? 7 : (rep % 3 == 1 ? 500 : 1000000);
+      std::vector<SI> a(n);
+      for (size_t i = 0; i < n; ++i) { a[i].sum = (uint32_t)(rng() % range); a[i].idx = (uint32_t)i; }
+      if (rep % 5 == 4) std::sort(a.begin(), a.end(), [] (const SI& x, const SI& y) { return x.sum < y.sum; });   // adversarial: ascending input
+      std::vector<SI> full = a;
+      std::sort(full.begin(), full.end(), cmp);
+      for (size_t bound : {(size_t)0, (size_t)1, (size_t)17, (size_t)1000, (size_t)2256, n / 2, n}) {
+        std::vector<SI> b = a;
+        const size_t end = upb::sort_prefix_like_std_sort(b.begin(), b.end(), bound, cmp);
+        ++cases;
+        if (end < std::min(bound, n)) { ++bad; continue; }
+        for (size_t i = 0; i < end; ++i) if (b[i].idx != full[i].idx) { ++bad; break; }
+      }
+    }
+    printf("sort cases=%ld bad=%ld\n", cases, bad);
     return bad ? 1 : 0;
   }
   if (argc >= 4 && !strcmp(argv[1], "wig")) {
