@@ -88,7 +88,7 @@ struct SpanArgs {
   unsigned long long* stat;                         // [0] hot blocks, [1] pieces, [2] exact evaluations, [3] spans with tags
 };
 
-struct SpanSmem { uint32_t taps, ctl, coef, warp0, warpStride, oD, oDR, oWf, oWr, oSt, oSc, oMw, oHm, total; };
+struct SpanSmem { uint32_t taps, ctl, coef, warp0, warpStride, oD, oDR, oWf, oWr, oSt, oMo, oSc, oMw, oHm, total; };
 
 __host__ __device__ inline SpanSmem span_smem_layout (uint32_t bw, uint32_t nSamples, bool nondir, bool coeff) {
   SpanSmem L;
@@ -106,7 +106,9 @@ __host__ __device__ inline SpanSmem span_smem_layout (uint32_t bw, uint32_t nSam
   w = (w + 7) & ~7u;
   L.oWf = w;   w += coeff ? W * 8 : 0;              // -z: per-position weights are doubles
   L.oWr = w;   w += (coeff && nondir) ? W * 8 : 0;
-  L.oSt = w;   w += 64 * 8;                         // products of 64 taps (exact_dense_warp)
+  w = (w + 15) & ~15u;
+  L.oSt = w;   w += 128 * 8;                        // products of 128 taps (exact_dense_warp)
+  L.oMo = w;   w += 24 * 8;                         // mini-tile offsets of the span + one of halo on either side, per strand
   L.oSc = w;   w += coeff ? PIECE_LEN * 8 : PIECE_LEN * 4;
   L.oMw = w;   w += (PIECE_BLOCKS + 2) * 4;
   L.oHm = w;   w += (SPAN_WORDS + 2) * 4;
@@ -164,7 +166,7 @@ __device__ __noinline__ double exact_dense_f64 (const double* __restrict__ Ks, c
 // the same sum computed by the whole warp for ONE position (u0 uniform): the products are independent, so the lanes round
 // 64 of them at a time into `stage`; the additions stay a single chain in ascending tag order (a product of an empty cell
 // is +0.0 and changes nothing), run by every lane on the broadcast values
-__device__ __forceinline__ double exact_dense_warp (const double* __restrict__ Ks, const uint32_t* __restrict__ cells, double* stage /* [64] */,
+__device__ __forceinline__ double exact_dense_warp (const double* __restrict__ Ks, const uint32_t* __restrict__ cells, double* stage /* [128], 16-byte aligned */,
                                                     uint32_t u0, uint32_t bw, uint32_t lane) {
   double s = 0.0;
   const uint32_t n = 2 * bw;
@@ -182,17 +184,22 @@ __device__ __forceinline__ double exact_dense_warp (const double* __restrict__ K
   }
   return s;
 #endif
-  for (uint32_t k0 = 0; k0 <= n; k0 += 64) {
+  for (uint32_t k0 = 0; k0 <= n; k0 += 128) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < 4; ++h) {
       const uint32_t k = k0 + 32 * h + lane;
       const uint32_t w = k <= n ? cells[u0 + k] : 0u;
       stage[32 * h + lane] = w ? __dmul_rn(Ks[n - k], (double)w) : 0.0;
     }
     __syncwarp();
-    const uint32_t m = min(64u, n + 1 - k0);
-#pragma unroll 4
-    for (uint32_t q = 0; q < m; ++q) s = __dadd_rn(s, stage[q]);
+    // the chain, eight terms per step from four 16-byte loads; the stage is zero beyond tap n and s + (+0.0) == s
+    const uint32_t m8 = (min(128u, n + 1 - k0) + 7) >> 3;
+    const double2* __restrict__ st2 = (const double2*)stage;
+    for (uint32_t q = 0; q < m8; ++q) {
+      const double2 t0 = st2[4 * q], t1 = st2[4 * q + 1], t2 = st2[4 * q + 2], t3 = st2[4 * q + 3];
+      s = __dadd_rn(s, t0.x); s = __dadd_rn(s, t0.y); s = __dadd_rn(s, t1.x); s = __dadd_rn(s, t1.y);
+      s = __dadd_rn(s, t2.x); s = __dadd_rn(s, t2.y); s = __dadd_rn(s, t3.x); s = __dadd_rn(s, t3.y);
+    }
     __syncwarp();
   }
   return s;
@@ -218,6 +225,30 @@ __device__ __forceinline__ void piece_entries (const Tags& T, uint32_t d, uint32
       uint2 en[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) en[q] = (eb + 32 * q < e1) ? __ldg(T.ment + eb + 32 * q) : make_uint2(0u, 0u);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (en[q].x) f(base + (en[q].y & (SPAN_LEN - 1)), en[q]);
+    }
+  }
+}
+
+// The same walk with the mini-tile offsets taken from a table the warp loaded once per span: tab[j] = mtOff[gb + min(mBase + j, nMt)]
+// for j = 0 .. 11 (the span's 8 mini-tiles, one of halo on either side, and the end) — no dependent global look-up per piece.
+template <class F>
+__device__ __forceinline__ void piece_entries_tab (const uint2* __restrict__ ment, const unsigned long long* __restrict__ tab, int mBase, uint32_t nMt,
+                                                   int64_t lo, int64_t hi, uint32_t lane, F f) {
+  if (nMt == 0 || hi < 1) return;
+  if (lo < 1) lo = 1;
+  const uint32_t ma = (uint32_t)((lo - 1) >> MT_SHIFT);
+  if (ma >= nMt) return;
+  const uint32_t mb = min((uint32_t)((hi - 1) >> MT_SHIFT), nMt - 1);
+  for (uint32_t sp = ma / SPAN_MT; sp <= mb / SPAN_MT; ++sp) {
+    const uint32_t m0 = max(ma, sp * SPAN_MT), m1 = min(mb, sp * SPAN_MT + SPAN_MT - 1);
+    const unsigned long long e0 = tab[(int)m0 - mBase], e1 = tab[(int)m1 + 1 - mBase];
+    const uint32_t base = sp * SPAN_LEN + 1;
+    for (unsigned long long eb = e0 + lane; eb - lane < e1; eb += 128) {
+      uint2 en[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) en[q] = (eb + 32 * q < e1) ? __ldg(ment + eb + 32 * q) : make_uint2(0u, 0u);
 #pragma unroll
       for (int q = 0; q < 4; ++q) if (en[q].x) f(base + (en[q].y & (SPAN_LEN - 1)), en[q]);
     }
@@ -432,6 +463,7 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : SP_MIN_BLOCKS) span_ke
   float* scf = (float*)(wbase + L.oSc);
   double* scd = (double*)(wbase + L.oSc);                             // -z keeps exact doubles instead
   double* stage = (double*)(wbase + L.oSt);
+  unsigned long long* mo = (unsigned long long*)(wbase + L.oMo);
   double* Wf = (double*)(wbase + L.oWf);
   double* Wr = (double*)(wbase + L.oWr);
   uint32_t* mw = (uint32_t*)(wbase + L.oMw);
@@ -470,6 +502,15 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : SP_MIN_BLOCKS) span_ke
     __syncwarp();
     if ((lane >> 2) == tb) hm[lane & 3] = maskWord;
     if (lane == 0) hm[SPAN_WORDS] = 0;
+    const int mBase = (int)(k * SPAN_MT) - 1;
+    uint32_t nMtS[2] = {0u, 0u};
+#pragma unroll
+    for (int str = 0; str < (NONDIR ? 2 : 1); ++str) {
+      const uint32_t d = NONDIR ? (uint32_t)str : U.buffer;
+      const uint32_t gb = __ldg(a.T.mtBase + d * a.T.C + U.contig);
+      nMtS[str] = __ldg(a.T.mtBase + d * a.T.C + U.contig + 1) - gb;
+      if (lane < 12) mo[12 * str + lane] = __ldg(a.T.mtOff + gb + (uint32_t)min(max(mBase + (int)lane, 0), (int)nMtS[str]));
+    }
     __syncwarp();
     ++stSpans;
 
@@ -509,7 +550,7 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : SP_MIN_BLOCKS) span_ke
 #pragma unroll
           for (int str = 0; str < (NONDIR ? 2 : 1); ++str) {
             uint32_t* dst = str ? DR : D;
-            piece_entries(a.T, NONDIR ? (uint32_t)str : U.buffer, U.contig, lo, hi, lane, [&] (uint32_t pos, const uint2& en) {
+            piece_entries_tab(a.T.ment, mo + 12 * str, mBase, nMtS[str], lo, hi, lane, [&] (uint32_t pos, const uint2& en) {
               const uint32_t u = pos - cell0;
               if (u < W && !(a.hasControl && isCtl[en.y >> SPAN_SHIFT])) { atomicAdd(&dst[u], en.x); tot += en.x; }
             });
@@ -533,7 +574,7 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : SP_MIN_BLOCKS) span_ke
               for (int str = 0; str < (NONDIR ? 2 : 1); ++str) {
                 double* dst = str ? Wr : Wf;
                 const uint32_t cell0 = q0 - bw;
-                piece_entries(a.T, NONDIR ? (uint32_t)str : U.buffer, U.contig, (int64_t)q0 - bw, (int64_t)q0 + 32 * nb - 1 + bw, lane, [&] (uint32_t pos, const uint2& en) {
+                piece_entries_tab(a.T.ment, mo + 12 * str, mBase, nMtS[str], (int64_t)q0 - bw, (int64_t)q0 + 32 * nb - 1 + bw, lane, [&] (uint32_t pos, const uint2& en) {
                   if ((en.y >> SPAN_SHIFT) != sm) return;
                   const uint32_t u = pos - cell0;
                   if (u < W) dst[u] = __dadd_rn(dst[u], phase ? (double)en.x : __dmul_rn((double)en.x, cf));
