@@ -522,3 +522,59 @@ def test_aggregate_tags_equals_a_map(gpu_ctx):
     import unipeak_b200
     with pytest.raises(unipeak_b200.UpbError):
         gpu_ctx.aggregate_tags(np.array([0], np.uint32), np.array([700001], np.uint32))                # beyond the contig
+
+
+def test_full_size_properties_config3():
+    """BASELINE.json config 3 at full size (16 x 30 M tags, hg19): too big for the CPU oracle, so the checks are the
+    size-independent properties of the path — idempotence, shard independence (a contig's rows do not depend on what else is
+    loaded), the host-format invariance of the load, ordering / disjointness of the regions, and the count-matrix checksums."""
+    import torch
+    import unipeak_b200
+    from unipeak_b200.synth import HG19_SIZES
+    from unipeak_b200.synth_gpu import make_synthetic_gpu
+    if torch.cuda.mem_get_info()[0] < 40e9:
+        pytest.skip("needs ~40 GB of free HBM")
+    n, G = 16, int(sum(HG19_SIZES))
+    data = make_synthetic_gpu(HG19_SIZES, n, 30_000_000, directional=True, seed=20261018)
+    total = sum(data.tags(s) for s in range(n))
+    st = dict(bandwidth=50, region_threshold=25.0, kurtosis_threshold=50.0, corr_threshold=-1.0, hit_threshold=10.0 * n, directional=True,
+              control=np.zeros(n, np.uint8), coeffs=[], background=total / G / 2)
+    ctx = unipeak_b200.Context(0)
+    try:
+        ctx.load(data)
+        a = ctx.call_regions(**dict(st, reference_order=False, rows=False))["columns"]
+        b = ctx.call_regions(**dict(st, reference_order=False, rows=False))["columns"]
+        R = a["left"].shape[0]
+        assert R > 100000
+        for k in a:                                                       # idempotence, bit for bit
+            assert np.array_equal(a[k].view(np.uint8), b[k].view(np.uint8)), k
+        # canonical order, regions of one (buffer, contig) ascending and separated by at least one position below the threshold
+        key = a["buffer"].astype(np.int64) * 64 + a["contig"].astype(np.int64)
+        assert np.all(np.diff(key) >= 0)
+        same = np.diff(key) == 0
+        right = a["left"].astype(np.int64) + a["len"].astype(np.int64) - 1
+        assert np.all(a["left"].astype(np.int64)[1:][same] > right[:-1][same] + 1)
+        assert np.all((a["peak"] >= a["left"]) & (a["peak"].astype(np.int64) <= right))
+        # filters: every row meets the hit threshold and the kurtosis bound; the matrix sums back to the per-sample totals
+        assert np.all(a["hit_sum"] >= st["hit_threshold"]) and np.all(a["kurtosis"] <= st["kurtosis_threshold"])
+        assert np.array_equal(a["counts"].astype(np.uint64).sum(axis=1) & 0xFFFFFFFF, a["hit_sum"].astype(np.uint64))   # no controls: sum() of the row
+        assert np.array_equal(a["counts"].astype(np.uint64).sum(axis=0), np.asarray(a["tags_in_regions"], dtype=np.uint64))
+        # the compact host form decodes to the same table
+        ctx.load_packed(data)
+        c = ctx.call_regions(**dict(st, reference_order=False, rows=False))["columns"]
+        for k in a:
+            assert np.array_equal(a[k].view(np.uint8), c[k].view(np.uint8)), k
+        # shard independence: chr21 + chr22 alone (same thresholds) give exactly their rows of the whole-genome table
+        part = data.subset_contigs([20, 21])
+        ctx.load(part)
+        p = ctx.call_regions(**dict(st, reference_order=False, rows=False))["columns"]
+        sel = (a["contig"] == 20) | (a["contig"] == 21)
+        assert int(sel.sum()) == p["left"].shape[0] > 1000
+        remap = np.where(a["contig"][sel] == 20, 0, 1)
+        assert np.array_equal(p["contig"], remap.astype(p["contig"].dtype))
+        for k in ("buffer", "left", "len", "peak", "hit_sum", "counts", "cand_index"):
+            assert np.array_equal(p[k], a[k][sel]), k
+        for k in ("kurtosis", "peak_score"):
+            assert np.array_equal(p[k].view(np.uint64), a[k][sel].view(np.uint64)), k
+    finally:
+        ctx.close()

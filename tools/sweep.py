@@ -13,7 +13,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import unipeak_b200  # noqa: E402
-from unipeak_b200.synth import HG19_SIZES  # noqa: E402
+from unipeak_b200.synth import HG19_SIZES, MM9_SIZES  # noqa: E402
 from unipeak_b200.synth_gpu import make_synthetic_gpu  # noqa: E402
 
 PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
@@ -68,6 +68,29 @@ def main():
         s = ctx.stats()
         print(json.dumps({"config": "c2 regions -D, 2 x 20M tags, hg19 (no -s offsets applied)", "ms_per_step": ms, "genome_bp_per_s": G / ms * 1e3,
                           "span_kernel_ms": s["ms_kde"], "regions": v.n_rows, "candidates": s["n_candidates"], "estimated_shifts": shifts}))
+    if which in ("all", "c4"):
+        # config 4 scaled to one GPU's comfortable size: 96 samples x 5 M tags (the full 96 x 50 M is ~77 GB resident), mm9, then
+        # tags_in_regions of 32 held-out samples x 5 M tags over the resulting table
+        Gm = int(sum(MM9_SIZES))
+        data = make_synthetic_gpu(MM9_SIZES, 96, 5_000_000, directional=True, seed=20261020)
+        ctx.load(data)
+        total = sum(data.tags(s) for s in range(96))
+        st = dict(bandwidth=50, region_threshold=25.0, kurtosis_threshold=50.0, corr_threshold=-1.0, hit_threshold=960.0, directional=True, background=total / Gm / 2)
+        ms, v = timed(lambda: ctx.call_regions_view(**st), reps=3, warm=1)
+        s = ctx.stats()
+        cols = v.columns()
+        fwd = cols["forward_label"].astype(bool) & (cols["dropped"] == 0)
+        right = cols["left"] + cols["len"] - 1
+        keys = np.stack([cols["contig"], np.where(cols["forward_label"] != 0, cols["left"], right), np.where(cols["forward_label"] != 0, right, cols["left"])], axis=1)[cols["dropped"] == 0].astype(np.uint32)
+        print(json.dumps({"config": "c4 scaled: regions, 96 samples x 5M tags, mm9 (full config: 96 x 50M)", "ms_per_step": ms, "genome_bp_per_s": Gm / ms * 1e3,
+                          "span_kernel_ms": s["ms_kde"], "tag_entries": int(data.pos.shape[0]), "regions": v.n_rows, "candidates": s["n_candidates"]}))
+        ctx.release_view()
+        del data
+        held = make_synthetic_gpu(MM9_SIZES, 32, 5_000_000, directional=True, seed=20261021)
+        ctx.load(held)
+        ms, counts = timed(lambda: ctx.count_tags_in_regions_arr(keys, directional=True, extension=0), reps=3, warm=1)
+        print(json.dumps({"config": "c4 scaled: tags_in_regions, 32 held-out samples x 5M tags over the table above", "ms": ms, "rows": int(keys.shape[0]),
+                          "tag_entries": int(held.pos.shape[0]), "tags_counted": int(counts.astype(np.uint64).sum())}))
     ctx.close()
 
 

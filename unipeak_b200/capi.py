@@ -414,6 +414,13 @@ class Context:
         self._check(self._lib.upb_count_tags_in_regions(self._h, 1 if directional else 0, extension, len(keys), arr, out.ctypes.data))
         return out[:len(keys) * self.n_samples].reshape(len(keys), self.n_samples)
 
+    def count_tags_in_regions_arr(self, keys: np.ndarray, *, directional=True, extension=0) -> np.ndarray:
+        """Same, keys as a contiguous (n, 3) uint32 array of (contig, start, end) — no per-row Python work."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint32).reshape(-1, 3)
+        out = np.zeros(max(1, keys.shape[0] * self.n_samples), dtype=np.uint32)
+        self._check(self._lib.upb_count_tags_in_regions(self._h, 1 if directional else 0, extension, keys.shape[0], C.cast(keys.ctypes.data, C.POINTER(RegionKey)), out.ctypes.data))
+        return out[:keys.shape[0] * self.n_samples].reshape(keys.shape[0], self.n_samples)
+
     def scatter_rows(self, total_rows: int, unit_rows_total: np.ndarray, unit_rows_local: np.ndarray, d_slab_ptr: int):
         """Scatter the rows of the last call_regions(_view) on this context into a table-wide device slab (see upb_scatter_rows)."""
         tot = np.ascontiguousarray(unit_rows_total, dtype=np.uint64)

@@ -20,6 +20,10 @@ HG19_SIZES = [
     81195210, 78077248, 59128983, 63025520, 48129895, 51304566, 155270560, 59373566, 16571,
 ]
 HG19_NAMES = ["chr%s" % c for c in list(range(1, 23)) + ["X", "Y", "M"]]
+# UCSC mm9 chromosome sizes (the reference ships the same table as contig/mm9.txt): 22 contigs, 2 654 911 517 bp
+MM9_SIZES = [197195432, 181748087, 159599783, 155630120, 152537259, 149517037, 152524553, 131738871, 124076172, 129993255, 121843856,
+             121257530, 120284312, 125194864, 103494974, 98319150, 95272651, 90772031, 61342430, 166650296, 15902555, 16299]
+MM9_NAMES = ["chr%s" % c for c in list(range(1, 20)) + ["X", "Y", "M"]]
 
 
 @dataclasses.dataclass
