@@ -38,18 +38,19 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from unipeak_b200.synth import HG19_NAMES, HG19_SIZES, TagData  # noqa: E402
+from unipeak_b200.synth import HG19_NAMES, HG19_SIZES, MM9_NAMES, MM9_SIZES, TagData  # noqa: E402
 
 WORKLOADS = {
     # name: (description, n_samples, tags_per_sample, directional, contig sizes, names, mappable)
     "c3": ("3SEQ pooled region calling, 16 samples x 30M tags, full hg19, with regions x experiments count matrix", 16, 30_000_000, True, HG19_SIZES, HG19_NAMES, 0),
     "c2": ("regions -D on 2 non-directional ChIP-seq samples, full hg19, 20M tags each", 2, 20_000_000, False, HG19_SIZES, HG19_NAMES, 0),
+    "c4": ("RNA-seq mm9, 96 samples x 50M tags (regions part of config 4; sized for contig-sharding over 8 GPUs: ~77 GB resident on one)", 96, 50_000_000, True, MM9_SIZES, MM9_NAMES, 0),
     "c1": ("regions on one directional 3SEQ sample, chr21 only, 1M tags, -m whole-genome", 1, 1_000_000, True, [48129895], ["chr21"], 3095693983),
     "tiny": ("smoke-sized: 4 samples x 200k tags on 3 contigs", 4, 200_000, True, [5_000_000, 3_000_000, 1_000_000], ["cA", "cB", "cC"], 0),
 }
 # bounded CPU sample: chr21 + chr22 for the hg19 workloads.  Two contigs, not one: several directional samples on
 # a single-contig table make the reference's own merge loop assert.
-CPU_SAMPLE_CONTIGS = {"c3": [20, 21], "c2": [20, 21], "c1": [0], "tiny": [1, 2]}
+CPU_SAMPLE_CONTIGS = {"c3": [20, 21], "c2": [20, 21], "c4": [18, 20], "c1": [0], "tiny": [1, 2]}
 
 
 def env_int(name, default):

@@ -360,7 +360,7 @@ static int load_tags_impl (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off
       pk_final_kernel<<<nTiles, PK_THREADS, 0, ctx->stream>>>(pa);
     }
     ma.first = first; ma.nEntries = n;
-    mt_build_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ma);
+    mt_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ma);
     CU(cudaGetLastError());
   }
   {
@@ -1548,7 +1548,6 @@ extern "C" int upb_profile_contig (upb_ctx* ctx, const upb_region_params* p, int
   const uint32_t SLAB = 8u << 20;
   std::vector<uint32_t> posOut;
   std::vector<double> scoreOut;
-  std::vector<double> hF, hR;
   for (uint64_t start = 1; start <= last; start += SLAB) {
     const uint32_t len = (uint32_t)std::min<uint64_t>(SLAB, last - start + 1);
     const uint32_t desc[4] = {(uint32_t)unit, (uint32_t)start, len, (len + TILE - 1) / TILE};
@@ -1559,14 +1558,28 @@ extern "C" int upb_profile_contig (upb_ctx* ctx, const upb_region_params* p, int
     CU(cudaMemcpyAsync(dLen, &desc[2], 4, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(dChunks, &desc[3], 4, cudaMemcpyHostToDevice, ctx->stream));
     if ((r = dump_and_corr(ctx, pr.dens, cfg.nondir, 1, 0, &launches))) return r;
-    hF.resize(len); hR.resize(len);
-    CU(cudaMemcpyAsync(hF.data(), ctx->scratch["F"].p, (size_t)len * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(hR.data(), ctx->scratch["R"].p, (size_t)len * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    // compact the non-zero positions on the device; only those cross PCIe
+    uint32_t* d_flag = SCR("profFlag", uint32_t, len);
+    unsigned long long* d_poff = SCR("profOff", unsigned long long, len);
+    const double* dF = ctx->scratch["F"].as<double>();
+    const double* dR = ctx->scratch["R"].as<double>();
+    unsigned long long* d_tot = ctx->d_small.as<unsigned long long>() + 16;
+    profile_flag_kernel<<<(len + 255) / 256, 256, 0, ctx->stream>>>(dF, dR, len, d_flag);
+    if ((r = scan_u32(ctx, d_flag, len, d_poff, d_tot, &launches))) return r;
+    unsigned long long* h64 = (unsigned long long*)ctx->h_small;
+    CU(cudaMemcpyAsync(h64, d_tot, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    for (uint32_t i = 0; i < len; ++i) {
-      volatile double scv = hF[i] + hR[i];                           // misc/peakcall.cpp:57
-      const double sc = scv;
-      if (sc != 0) { posOut.push_back((uint32_t)(start + i)); scoreOut.push_back(sc); }
+    const size_t nz = (size_t)h64[0];
+    if (nz) {
+      uint32_t* d_pp = SCR("profPos", uint32_t, nz);
+      double* d_ps = SCR("profScore", double, nz);
+      profile_emit_kernel<<<(len + 255) / 256, 256, 0, ctx->stream>>>(dF, dR, len, (uint32_t)start, d_flag, d_poff, d_pp, d_ps);
+      CU(cudaGetLastError());
+      const size_t at = posOut.size();
+      posOut.resize(at + nz); scoreOut.resize(at + nz);
+      CU(cudaMemcpyAsync(posOut.data() + at, d_pp, nz * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaMemcpyAsync(scoreOut.data() + at, d_ps, nz * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
     }
   }
   out->n = posOut.size();

@@ -175,10 +175,9 @@ __device__ __forceinline__ uint32_t seg_of_entry (const uint64_t* __restrict__ s
 constexpr int WIN_SHIFT = 16;       // scatter window: 65536 positions = 128 mini-tiles, one CTA of mt_scatter_kernel
 constexpr int WIN_MT = 1 << (WIN_SHIFT - MT_SHIFT);
 
-// Pass 1 (SCATTER = false) validates what the reference's parser guarantees (positions inside the contig and strictly
+// Pass 1 validates what the reference's parser guarantees (positions inside the contig and strictly
 // ascending per (sample, strand, contig), non-zero counts: misc/format.cpp:654-710, misc/peakcall.cpp:171) and builds
-// the per-mini-tile histogram; pass 2 scatters (the zone maps are built from the sorted copy by mt_zone_kernel).  Entries that fail validation are never used as indices.
-template <bool SCATTER>
+// the per-mini-tile histogram and the per-sample window index; pass 2 (mt_scatter_kernel) scatters and builds the zone maps.  Entries that fail validation are never used as indices.
 __global__ void mt_build_kernel (MtArgs a) {
   const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= a.nEntries) return;
@@ -191,12 +190,11 @@ __global__ void mt_build_kernel (MtArgs a) {
   const uint32_t c = g % a.C, sd = g / a.C, d = sd & 1u, s = sd >> 1;
   const uint32_t pos1 = a.pos[i];
   const uint32_t p = pos1 - 1;
-  if (pos1 < 1 || pos1 > a.sizes[c]) { if (!SCATTER) atomicOr(a.flags, FLAG_BAD_POS); return; }
+  if (pos1 < 1 || pos1 > a.sizes[c]) { atomicOr(a.flags, FLAG_BAD_POS); return; }
   const uint32_t mt = a.mtBase[d * a.C + c] + (p >> MT_SHIFT);
-  if (!SCATTER) {
+  {
     uint32_t f = 0;
-    const uint32_t k = a.cnt[i];
-    if (k == 0) f |= FLAG_ZERO_COUNT;
+    if (a.cnt[i] == 0) f |= FLAG_ZERO_COUNT;
     if (i > a.segStart[g] && a.pos[i - 1] >= pos1) f |= FLAG_UNSORTED;
     if (f) atomicOr(a.flags, f);
     atomicAdd(&a.mtCount[mt], 1u);
@@ -208,8 +206,6 @@ __global__ void mt_build_kernel (MtArgs a) {
     }
     return;
   }
-  const unsigned long long slot = a.mtOff[mt] + (atomicSub(&a.mtCount[mt], 1u) - 1u);
-  a.ment[slot] = make_uint2(a.cnt[i], (s << SPAN_SHIFT) | (p & (SPAN_LEN - 1)));
 }
 
 // window index default: "no entry at or after this window" = the segment's length
@@ -739,4 +735,18 @@ __global__ void tir_scan_kernel (const unsigned long long* __restrict__ E, unsig
   }
 }
 
+}  // namespace upb
+
+namespace upb {
+// bin/regions -w: positions of a dumped range whose score F + R is not zero (misc/peakcall.cpp:57,81-84), compacted on the device so
+// that only what the wiggle will print crosses PCIe
+__global__ void profile_flag_kernel (const double* __restrict__ F, const double* __restrict__ R, uint32_t len, uint32_t* __restrict__ flag) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < len) flag[i] = __dadd_rn(F[i], R[i]) != 0.0 ? 1u : 0u;
+}
+__global__ void profile_emit_kernel (const double* __restrict__ F, const double* __restrict__ R, uint32_t len, uint32_t start, const uint32_t* __restrict__ flag,
+                                     const unsigned long long* __restrict__ off, uint32_t* __restrict__ outPos, double* __restrict__ outScore) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < len && flag[i]) { outPos[off[i]] = start + i; outScore[off[i]] = __dadd_rn(F[i], R[i]); }
+}
 }  // namespace upb
