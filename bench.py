@@ -64,24 +64,57 @@ from unipeak_b200.multi import DeviceGather, HostGather, shard_contigs  # noqa: 
 
 
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region, in-process through NVML (pynvml) every 10 ms — spawning
+    nvidia-smi five times a second from every rank, as this class did before, perturbed the launch-bound multi-GPU steps.
+    Falls back to nvidia-smi when pynvml is missing."""
     QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None):
         self.index = index
-        self.samples = []
+        self.samples = []          # (sm_mhz, max_mhz, set of reasons)
         self._stop = threading.Event()
         self._t = None
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)) if not str(uuid).startswith("GPU-") else str(uuid))
+                except Exception:
+                    h = None
+            self._h = h or pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._nvml = pynvml
+            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._h = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM))
+        try:
+            mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+        except Exception:
+            mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+        self.samples.append((sm, self._max, {name for bit, name in self.REASONS if mask & bit}))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits"],
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+        if out:
+            s = [x.strip() for x in out.split(",")]
+            self.samples.append((float(s[0]), float(s[1]), {name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7])
+                                                             if v.lower().startswith("active")}))
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits"],
-                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                self._sample_nvml() if self._h is not None else self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.01 if self._h is not None else 0.5)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -93,16 +126,22 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], 0, set()
-        for s in self.samples:
-            try:
-                sm.append(float(s[0])); mx = max(mx, float(s[1]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        sm = [s[0] for s in self.samples]
+        mx = max([s[1] for s in self.samples] + [0])
+        reasons = set().union(*[s[2] for s in self.samples]) if self.samples else set()
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvml" if self._h is not None else "nvidia-smi"}
+
+
+class NoSampler:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        pass
+
+    def summary(self):
+        return None
 
 
 def settings_from_totals(tags, n_samples, directional, mappable, genome, bandwidth=50):
@@ -284,7 +323,11 @@ def main():
     if gather is not None:
         gather.times = [0.0, 0.0, 0.0, 0]                             # per-phase host clocks of the timed steps only
     call_ms = []
-    with ClockSampler(local_rank) as clocks:
+    try:
+        gpu_uuid = torch.cuda.get_device_properties(dev).uuid
+    except Exception:
+        gpu_uuid = None
+    with (ClockSampler(local_rank, gpu_uuid) if rank == 0 else NoSampler()) as clocks:   # rank 0's GPU stands for the box
         t0 = time.perf_counter()
         ev0.record(lib_stream)
         for _ in range(args.steps):

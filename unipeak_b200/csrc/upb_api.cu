@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -63,7 +64,8 @@ struct upb_ctx {
   uint64_t lastRows = 0;                // rows of the last upb_call_regions still sitting in the device slab (scratch "slab")
   std::vector<uint8_t> lastControl;     // control set cntEff was built for
   bool cntEffValid = false;
-  bool tidxBuilt = false;               // per-2048-tile entry offsets of the sample-major arrays: built on first use (density kernel only)
+  bool tidxBuilt = false;
+  std::map<std::pair<const void*, size_t>, int> occCache;   // resident CTAs per SM of (kernel, dynamic shared memory)               // per-2048-tile entry offsets of the sample-major arrays: built on first use (density kernel only)
 };
 
 static thread_local std::string g_createErr;
@@ -672,16 +674,37 @@ static int ensure_tidx (upb_ctx* ctx, uint32_t* launches) {
   return UPB_OK;
 }
 
+// largest dynamic shared memory size each kernel has been opted into, per device — the attribute belongs to the function, not to
+// a context, and setting a smaller value would lower it under another context's feet: only ever raised
+static std::map<std::pair<int, const void*>, size_t> g_smemRaised;
+static std::mutex g_smemMutex;
+
+template <class K>
+static int cached_occupancy (upb_ctx* ctx, K kern, int threads, size_t smem, int* perSm) {
+  const std::pair<const void*, size_t> key((const void*)kern, smem);
+  if (smem > 48 * 1024) {
+    std::lock_guard<std::mutex> lock(g_smemMutex);
+    size_t& raised = g_smemRaised[std::make_pair(ctx->device, (const void*)kern)];
+    if (smem > raised) { CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); raised = smem; }
+  }
+  auto it = ctx->occCache.find(key);
+  if (it != ctx->occCache.end()) { *perSm = it->second; return UPB_OK; }
+  int v = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kern, threads, smem));
+  if (v < 1) v = 1;
+  ctx->occCache[key] = v;
+  *perSm = v;
+  return UPB_OK;
+}
+
 static int launch_density (upb_ctx* ctx, DensArgs& da, bool nondir, uint32_t totalWork, uint32_t* launches) {
   { int rr = ensure_tidx(ctx, launches); if (rr) return rr; da.T.tidx = ctx->d_tidx.as<uint32_t>(); }
   const DensSmem L = dens_smem_layout(da.bw, da.nSrc * (nondir ? 2u : 1u), nondir, da.srcCoeff != nullptr);
   const size_t smem = L.total;
   if (smem > 227 * 1024) return fail(ctx, UPB_ERR_UNSUPPORTED, "bandwidth / sample count need more shared memory than one SM has");
   void (*kern)(const DensArgs) = nondir ? density_kernel<true> : density_kernel<false>;
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int perSm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, KDE_THREADS, smem));
-  if (perSm < 1) perSm = 1;
+  { int rr = cached_occupancy(ctx, kern, KDE_THREADS, smem, &perSm); if (rr) return rr; }
   const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)ctx->smCount * perSm, std::max<uint32_t>(totalWork, 1u));
   kern<<<grid, KDE_THREADS, smem, ctx->stream>>>(da);
   CU(cudaGetLastError());
@@ -735,10 +758,8 @@ static int launch_span (upb_ctx* ctx, const SpanArgs& sa, bool nondir, uint32_t*
   const size_t smem = L.total;
   if (smem > 227 * 1024) return fail(ctx, UPB_ERR_UNSUPPORTED, "bandwidth / sample count need more shared memory than one SM has");
   void (*kern)(const SpanArgs) = coeff ? (nondir ? span_kernel<true, true> : span_kernel<false, true>) : (nondir ? span_kernel<true, false> : span_kernel<false, false>);
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int perSm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, SP_THREADS, smem));
-  if (perSm < 1) perSm = 1;
+  { int rr = cached_occupancy(ctx, kern, SP_THREADS, smem, &perSm); if (rr) return rr; }
   const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)ctx->smCount * perSm, std::max<uint32_t>(sa.totalSpans, 1u));
   kern<<<grid, SP_THREADS, smem, ctx->stream>>>(sa);
   CU(cudaGetLastError());
@@ -803,8 +824,7 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
       hf[j] = std::nextafter((float)(hc * (1.0 + 1e-5)), INFINITY);              // float sum of <= 58 terms: 1e-5 covers its rounding
     }
     float* d_hf = SCR("hotCoefF", float, J + 1);
-    CU(cudaMemcpyAsync(d_hf, hf.data(), (size_t)(J + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpyAsync(d_hf, hf.data(), (size_t)(J + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));   // pageable source: staged before the call returns
     ha.hotCoefF = d_hf; ha.hotJ = (uint32_t)J;
     ha.thrLow = std::nextafter((float)cfg.thr, -INFINITY);
   }
@@ -873,8 +893,8 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
     wa.flatBound = flatBound; wa.thr = cfg.thr;
     warm_span_kernel<<<(pr.totalSpans + 255) / 256, 256, 0, ctx->stream>>>(wa);
     { int perSm = 0;
-      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, hot_span_kernel, HOT_THREADS, 0));
-      hot_span_kernel<<<ctx->smCount * std::max(perSm, 1), HOT_THREADS, 0, ctx->stream>>>(ha); }
+      if ((r = cached_occupancy(ctx, hot_span_kernel, HOT_THREADS, 0, &perSm))) return r;
+      hot_span_kernel<<<ctx->smCount * perSm, HOT_THREADS, 0, ctx->stream>>>(ha); }
     launches += 2;
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     if ((r = launch_span(ctx, sa, cfg.nondir, &launches))) return r;
@@ -924,41 +944,44 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
   unit_first_kernel<<<1, 32, 0, ctx->stream>>>(unitCand, nUnits, unitFirst);
   CU(cudaGetLastError());
   launches += 2;
-  CU(cudaMemcpyAsync(h64, d_tot, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
-  nCand = (uint32_t)h64[0];
-  out.nCand = nCand;
-  ctx->stats.n_candidates = nCand;
-  ctx->stats.n_stitched = nRuns - nCand;
-  const unsigned gCand = (nCand + 255) / 256;
+  // the number of candidates stays on the device for now (one read-back fewer): what follows runs over nRuns >= nCand slots and
+  // looks the count up itself
+  const unsigned long long* d_nCand = d_tot + 5;
+  CU(cudaMemcpyAsync(d_tot + 5, d_tot, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  const unsigned gCand = gRuns;
 
   // ---- K3: hit filter (misc/peakcall.cpp:41), then per-region statistics for the survivors ------------------
-  uint32_t* pass = SCR("pass", uint32_t, nCand);
-  unsigned long long* passScan = SCR("passScan", unsigned long long, nCand);
-  list1 = SCR("list1", uint32_t, nCand);
-  cand_hit_kernel<<<gCand, 256, 0, ctx->stream>>>(cand, nCand, cfg.hitThr, pass);
+  uint32_t* pass = SCR("pass", uint32_t, nRuns);
+  unsigned long long* passScan = SCR("passScan", unsigned long long, nRuns);
+  list1 = SCR("list1", uint32_t, nRuns);
+  cand_hit_kernel<<<gCand, 256, 0, ctx->stream>>>(cand, d_nCand, nRuns, cfg.hitThr, pass);
   launches += 1;
   uint32_t* d_drop = nullptr;
   if (nAff) {                                                         // what the replay owns is not a Region of the reference
     d_drop = SCR("edgeDrop", uint32_t, nAff);
     CU(cudaMemsetAsync(d_drop, 0, (size_t)nAff * 4, ctx->stream));
-    edge_drop_kernel<<<gCand, 256, 0, ctx->stream>>>(d_affected, eg.stop, nAff, cand, nCand, pass, d_drop);
+    edge_drop_kernel<<<gCand, 256, 0, ctx->stream>>>(d_affected, eg.stop, nAff, cand, d_nCand, pass, d_drop);
     launches += 1;
   }
-  if ((r = scan_u32(ctx, pass, nCand, passScan, d_tot, &launches))) return r;
-  compact_index_kernel<<<gCand, 256, 0, ctx->stream>>>(pass, passScan, nCand, list1);
+  if ((r = scan_u32(ctx, pass, nRuns, passScan, d_tot, &launches))) return r;
+  compact_index_kernel<<<gCand, 256, 0, ctx->stream>>>(pass, passScan, nRuns, list1);
   // pooled position cells of the survivors live back to back in one scratch array: offsets by a scan of their lengths
-  uint32_t* candLen = SCR("candLen", uint32_t, nCand);
-  unsigned long long* cellOff = SCR("cellOff", unsigned long long, nCand);
-  cand_len_kernel<<<gCand, 256, 0, ctx->stream>>>(cand, pass, nCand, candLen);
-  if ((r = scan_u32(ctx, candLen, nCand, cellOff, d_tot + 2, &launches))) return r;
+  uint32_t* candLen = SCR("candLen", uint32_t, nRuns);
+  unsigned long long* cellOff = SCR("cellOff", unsigned long long, nRuns);
+  cand_len_kernel<<<gCand, 256, 0, ctx->stream>>>(cand, pass, nRuns, candLen);
+  if ((r = scan_u32(ctx, candLen, nRuns, cellOff, d_tot + 2, &launches))) return r;
   CU(cudaGetLastError());
   launches += 2;
   CU(cudaMemcpyAsync(h64, d_tot, 8, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(h64 + 2, d_tot + 2, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(h64 + 5, d_tot + 5, 8, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(h64 + 8, unitCand, std::min<size_t>((size_t)nUnits, 400) * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (nAff) CU(cudaMemcpyAsync(edgeDrop.data(), d_drop, (size_t)nAff * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  nCand = (uint32_t)h64[5];
+  out.nCand = nCand;
+  ctx->stats.n_candidates = nCand;
+  ctx->stats.n_stitched = nRuns - nCand;
   n1 = (uint32_t)h64[0];
   const unsigned long long totalCells = h64[2];
   if (nUnits <= 400) for (uint32_t u = 0; u < nUnits; ++u) out.unitCand[u] = h64[8 + u];
@@ -977,11 +1000,10 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
     const size_t groupBytes = ((size_t)(ST_CHUNK + n) * 4 + 15) / 16 * 16;
     const size_t statSmem = (size_t)ST_WARPS * ST_PER_WARP * groupBytes;
     if (statSmem > 200 * 1024) return fail(ctx, UPB_ERR_UNSUPPORTED, "too many samples for the region statistics kernel");
-    CU(cudaFuncSetAttribute(region_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)statSmem));
     st.ticket = small32 + 13;
     CU(cudaMemsetAsync(st.ticket, 0, 4, ctx->stream));
     int perSm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, region_pool_kernel, ST_WARPS * 32, statSmem));
+    if ((r = cached_occupancy(ctx, region_pool_kernel, ST_WARPS * 32, statSmem, &perSm))) return r;
     const uint32_t perBlock = ST_WARPS * ST_PER_WARP;
     const uint32_t gridS = std::min<uint32_t>((n1 + perBlock - 1) / perBlock, (uint32_t)(ctx->smCount * std::max(perSm, 1)));
     region_pool_kernel<<<gridS, ST_WARPS * 32, statSmem, ctx->stream>>>(st);

@@ -814,19 +814,20 @@ __global__ void merge_runs2_kernel (const SpanRun* __restrict__ runs, const uint
 // candidates of span_kernel that lie in the stretch the left-edge replay owns (upb_edge.cuh) are not Region objects of the
 // reference: they are dropped and counted per affected unit
 __global__ void edge_drop_kernel (const uint32_t* __restrict__ affected, const uint32_t* __restrict__ stop, uint32_t nAffected,
-                                  const Cand2* __restrict__ cand, uint32_t nCand, uint32_t* __restrict__ pass, uint32_t* __restrict__ dropCount) {
+                                  const Cand2* __restrict__ cand, const unsigned long long* __restrict__ nCand, uint32_t* __restrict__ pass, uint32_t* __restrict__ dropCount) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nCand) return;
+  if (i >= *nCand) return;
   const uint32_t unit = cand[i].unit;
   for (uint32_t k = 0; k < nAffected; ++k)
     if (affected[k] == unit) { if (cand[i].left <= stop[k]) { pass[i] = 0; atomicAdd(&dropCount[k], 1u); } break; }
 }
 
 // hit filter (misc/peakcall.cpp:41 first clause)
-__global__ void cand_hit_kernel (const Cand2* __restrict__ cand, uint32_t n, double hitThr, uint32_t* __restrict__ pass) {
+// n = the number of candidates (still on the device), bound = slots to fill: slots beyond the candidates get 0
+__global__ void cand_hit_kernel (const Cand2* __restrict__ cand, const unsigned long long* __restrict__ n, uint32_t bound, double hitThr, uint32_t* __restrict__ pass) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  pass[i] = ((double)cand[i].wsum >= hitThr) ? 1u : 0u;
+  if (i >= bound) return;
+  pass[i] = (i < *n && (double)cand[i].wsum >= hitThr) ? 1u : 0u;
 }
 
 // Region::exptSums (misc/data.cpp:116-131) and Region::posKurtosis (misc/data.cpp:133-182) of the candidates that passed the
