@@ -1,30 +1,25 @@
-// upb_span.cuh — the fused region-calling kernel (sm_100a) and the small kernels that order, stitch and
-// filter its output.
+// upb_span.cuh — the region-calling kernels (sm_100a) and the small kernels that order, stitch and filter their output.
 //
-// span_kernel: ONE WARP works on one span (two index tiles = 4096 positions of one (ProfileBuffer, contig)
-// unit) at a time, spans handed out by a global ticket.  There is no block-level barrier anywhere on the
-// path: the warps of a CTA only share the read-only tap table.  (v2 of this kernel gave a whole CTA one
-// 16384-position span and lost 63 % of its issue slots at __syncthreads — profiles/r01_v2_*.)
+//   warm_span_kernel   which 4096-position spans of a (ProfileBuffer, contig) unit can hold a region at all (per-mini-tile zone map)
+//   hot_span_kernel    which 32-position blocks of those spans can (per-block zone map, Tags::blkW): a block is "hot" when
+//                      sum_j blkW[B+j] * (largest tap any tag of block B+j can have for any position of block B) >= threshold — an
+//                      upper envelope of every score in the block (control samples and rounding only loosen it); a block that is
+//                      not hot cannot hold a position of a region (misc/peakcall.cpp:57-60) and is never looked at again.
+//                      Neither kernel touches a tag entry.
+//   span_kernel        ONE WARP works on one span that has a hot block, four spans per ticket; no block-level barrier anywhere: the
+//                      warps of a CTA only share the read-only tap table (v2 gave a whole CTA one 16384-position span and lost 63 %
+//                      of its issue slots at __syncthreads — profiles/r01_v2_*).  Maximal groups of hot blocks are cut into pieces
+//                      of <= 16 blocks; per piece the tags of the mini-tiles its window touches (one contiguous chunk of the
+//                      tile-major copy per span, 8 bytes per entry, four loads in flight per lane) are pooled into dense
+//                      per-position cells; every position is classified against the threshold with the O(1) integer moment form of
+//                      the Epanechnikov sum (exact integers, window sums carried by warp scans) and re-evaluated in the reference's
+//                      own floating-point order (ascending tag position, product and sum rounded separately,
+//                      misc/peakcall.cpp:203-209) only where the fast value is within its error bound of the threshold or of the
+//                      run maximum.  Runs of above-threshold positions are written out with their first strict maximum
+//                      (misc/data.cpp:97-101) and pooled hit sum.
 //
-//   phase A  hot blocks WITHOUT touching the entries: the load step keeps the pooled tag count of every 32-position block
-//            (Tags::blkW, all samples, float rounded up).  A block is "hot" when  sum_j blkW[B+j] * (largest tap any tag of
-//            block B+j can have for any position of block B) >= threshold  — an upper envelope of every score in the block
-//            (control samples and rounding only loosen it); a block that is not hot cannot hold a position of a region
-//            (misc/peakcall.cpp:57-60) and is never looked at again.  One coalesced read of 128 + halo floats per span.
-//            Maximal groups of hot blocks are cut into pieces of <= 16 blocks.
-//   phase B  per piece: the tags of the mini-tiles its window touches (one contiguous chunk of the tile-major copy per
-//            4096-position span, 8 bytes per entry, four loads in flight per lane) are pooled into dense
-//            per-position cells; every position is classified against the threshold with the O(1) integer
-//            moment form of the Epanechnikov sum (exact in 64-bit integers, window sums carried by warp
-//            scans), and re-evaluated in the reference's own floating-point order (ascending tag position,
-//            product and sum rounded separately, misc/peakcall.cpp:203-209) only where the fast value is
-//            within its error bound of the threshold or of the run maximum.  Runs of above-threshold
-//            positions are written out with their first strict maximum (misc/data.cpp:97-101) and pooled
-//            hit sum.
-//
-// The genome-wide profile is never materialised.  Runs cut by a piece or span boundary are stitched by
-// merge_runs2_kernel; region_stats_kernel then computes Region::exptSums and posKurtosis for the candidates
-// that pass the hit filter.
+// The genome-wide profile is never materialised.  Runs cut by a piece or span boundary are stitched by merge_runs2_kernel;
+// region_pool_kernel + region_moment_kernel then compute Region::exptSums and posKurtosis for the candidates that pass the hit filter.
 #pragma once
 
 #include "upb_device.cuh"
