@@ -333,7 +333,7 @@ def main():
         for _ in range(args.steps):
             last = step()
             s = ctx.stats()
-            kde_ms.append(s["ms_kde"]); launches += s["launches"]; call_ms.append(s["ms_call"])
+            kde_ms.append(s["ms_kde"]); launches += s["launches"] + (2 if world > 1 else 0); call_ms.append(s["ms_call"])   # + the two scatter kernels of the gather
         if world > 1:
             lib_stream.wait_stream(torch.cuda.current_stream())      # the NCCL gather of the last step runs on torch's stream
         ev1.record(lib_stream)
