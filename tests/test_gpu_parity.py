@@ -578,3 +578,21 @@ def test_full_size_properties_config3():
             assert np.array_equal(p[k].view(np.uint64), a[k][sel].view(np.uint64)), k
     finally:
         ctx.close()
+
+
+def test_strand_shift_with_left_edge_tags(gpu_ctx):
+    # tags within `bandwidth` of a contig start (chrM-like data): the regions there come from the left-edge replay (Q2); the
+    # calibration goes through as long as none of them is long enough to enter the shift sweep
+    d = make_synthetic([1500000, 40000], 1, 200000, directional=False, seed=13, peak_spacing=8000, keep_clear_of_edges=False)
+    assert min(int(d.seg(0, dd, c)[0][0]) for dd in range(2) for c in range(2)) <= 50
+    kw = dict(n_regions_to_test=40, region_threshold=8.0, corr_threshold=0.1)
+    want = oracle_strand_shift(d, **kw)
+    assert want["status"] == 0
+    gpu_ctx.load(d)
+    got = gpu_ctx.strand_shift(background=want["background"], **kw)
+    assert got["status"] == 0
+    for k in ("n_regions_found", "n_regions_tested", "n_tags_in_regions", "best_shift", "shift_freq"):
+        assert got[k] == want[k], k
+    for g, w in zip(got["tested"], want["tested"]):
+        assert (g["contig"], g["left"], g["len"], g["best_shift"]) == (w["contig"], w["left"], w["len"], w["best_shift"])
+        assert g["best_corr"] == w["best_corr"]

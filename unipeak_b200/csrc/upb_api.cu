@@ -500,6 +500,7 @@ struct PipeOut {
   std::vector<uint64_t> unitCand;    // [nUnits]
   uint64_t nCand = 0;
   uint64_t R = 0;                    // accepted regions, canonical order (buffer, contig, left)
+  std::vector<uint32_t> unitEdgeStop; // [nUnits] last position the left-edge replay owns in this unit, 0 if none
   HostSlab slab;                     // pinned; columns per `layout`
   SlabLayout layout;
   template <class T> T* col (size_t off) const { return (T*)((unsigned char*)slab.p + off); }
@@ -785,6 +786,7 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
   const uint32_t nUnits = (uint32_t)pr.units.size();
   out.units = pr.units;
   out.unitCand.assign(nUnits, 0);
+  out.unitEdgeStop.assign(nUnits, 0);
   out.nCand = 0; out.R = 0;
   ctx->lastRows = 0;
   memset(&ctx->stats, 0, sizeof ctx->stats);
@@ -878,7 +880,7 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
     CU(cudaMemcpyAsync(eoh.data(), eo, eoh.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     if (eoh[3 * nAff]) return fail(ctx, UPB_ERR_UNSUPPORTED, "left-edge replay (SURVEY Q2) ran out of its scratch or position budget");
-    for (uint32_t k = 0; k < nAff; ++k) { edgeStop[k] = eoh[k]; edgeCand[k] = eoh[nAff + k]; edgeRows[k] = eoh[2 * nAff + k]; }
+    for (uint32_t k = 0; k < nAff; ++k) { edgeStop[k] = eoh[k]; edgeCand[k] = eoh[nAff + k]; edgeRows[k] = eoh[2 * nAff + k]; out.unitEdgeStop[pr.affected[k]] = eoh[k]; }
   }
   uint64_t edgeRowsTotal = 0;
   for (uint32_t k = 0; k < nAff; ++k) edgeRowsTotal += edgeRows[k];
@@ -1440,6 +1442,7 @@ extern "C" int upb_strand_shift (upb_ctx* ctx, const upb_shift_params* p, upb_sh
   PipeCfg cfg;
   cfg.bw = p->bandwidth; cfg.thr = p->region_threshold; cfg.kurtThr = p->kurtosis_threshold; cfg.corrThr = -1;   // :142
   cfg.hitThr = (double)p->hit_threshold; cfg.background = p->background; cfg.nondir = true; cfg.control = nullptr; cfg.needCorr = false;
+  cfg.allowLeftEdge = true;          // regions at a contig start come from the replay of the reference's left-edge behaviour (Q2)
   PipeOut po;
   Prep pr;
   int r = run_pipeline(ctx, cfg, pr, po);
@@ -1482,7 +1485,12 @@ extern "C" int upb_strand_shift (upb_ctx* ctx, const upb_shift_params* p, upb_sh
     while (cursor < R && batch.size() < want) {
       if (cursor >= sortedEnd) sort_more(std::min<size_t>(R, std::max<size_t>(2 * sortedEnd, cursor + 1024)));
       const uint32_t i = order[cursor].idx;
-      if (rLen[i] > 2 * p->max_shift + 3) batch.push_back(i);          // :206 large enough to try all shifts
+      if (rLen[i] > 2 * p->max_shift + 3) {                            // :206 large enough to try all shifts
+        // a region the left-edge replay produced has displaced densities (Q2); its shift sweep is not replayed
+        if (rLeft[i] <= po.unitEdgeStop[unitOfContig[rContig[i]]])
+          return fail(ctx, UPB_ERR_LEFT_EDGE, "a region within `bandwidth` of a contig start is long enough for the shift sweep: the reference's left-edge densities (SURVEY Q2) are not emulated there");
+        batch.push_back(i);
+      }
       ++cursor;
     }
     if (batch.empty()) break;
