@@ -761,6 +761,10 @@ static int launch_span (upb_ctx* ctx, const SpanArgs& sa, bool nondir, uint32_t*
   void (*kern)(const SpanArgs) = coeff ? (nondir ? span_kernel<true, true> : span_kernel<false, true>) : (nondir ? span_kernel<true, false> : span_kernel<false, false>);
   int perSm = 0;
   { int rr = cached_occupancy(ctx, kern, SP_THREADS, smem, &perSm); if (rr) return rr; }
+  if (!coeff && perSm < SP_MIN_BLOCKS) {                              // shared memory admits fewer CTAs than the 64-register build is sized for: take the build without that cap
+    kern = nondir ? span_kernel<true, false, SP_MIN_BLOCKS - 1> : span_kernel<false, false, SP_MIN_BLOCKS - 1>;
+    int rr = cached_occupancy(ctx, kern, SP_THREADS, smem, &perSm); if (rr) return rr;
+  }
   const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)ctx->smCount * perSm, std::max<uint32_t>(sa.totalSpans, 1u));
   kern<<<grid, SP_THREADS, smem, ctx->stream>>>(sa);
   CU(cudaGetLastError());

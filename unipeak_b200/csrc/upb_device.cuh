@@ -28,10 +28,17 @@ struct Unit {                       // one (ProfileBuffer, contig) pair
   uint32_t spanStart;               // first global span index of this unit
 };
 
-constexpr int MT_SHIFT = 9;         // mini-tile: 512 positions, the granule of the tile-major copy
+#ifndef UPB_MT_SHIFT
+#define UPB_MT_SHIFT 9
+#endif
+constexpr int MT_SHIFT = UPB_MT_SHIFT;  // mini-tile: 512 positions, the granule of the tile-major copy.  256 (UPB_MT_SHIFT=8) is supported and passes the same
+                                    //   tests, but buys nothing: the entries a piece reads sit in the peak itself, and the zone map doubles (profiles/r01_v27_ab.txt)
 constexpr int SPAN_SHIFT = 12;      // span: 4096 positions = 8 mini-tiles; entries carry their offset inside the span
 constexpr int SPAN_LEN = 1 << SPAN_SHIFT;
 constexpr int SPAN_MT = 1 << (SPAN_SHIFT - MT_SHIFT);
+constexpr int MAX_BW_SPAN = 448;    // largest bandwidth of the region-calling kernels (upb_span.cuh: MAX_BW_FAST)
+constexpr int HALO_MT = (MAX_BW_SPAN + (1 << MT_SHIFT) - 1) >> MT_SHIFT;   // mini-tiles on either side of a span that a window of its positions can reach
+static_assert(MT_SHIFT >= 7 && MT_SHIFT <= 10, "mini-tile: 128 .. 1024 positions");
 
 struct Tags {                       // resident tag-frequency data (see upb_load_tags)
   const uint32_t* pos;              // sample-major arrays exactly as loaded (density kernel, validation)

@@ -28,6 +28,9 @@
 #ifndef UPB_EXP_EXACT
 #define UPB_EXP_EXACT 1
 #endif
+#ifndef UPB_EXP_ASYNC
+#define UPB_EXP_ASYNC 0                             // B1 of span_kernel: entries staged through shared memory with cp.async (0: register loads, v4-v24)
+#endif
 
 namespace upb {
 
@@ -44,7 +47,10 @@ constexpr int PIECE_BLOCKS = 16;                    // <= 512 positions per piec
 constexpr int PIECE_LEN = PIECE_BLOCKS * 32;
 constexpr uint32_t RUN_CHUNK = 32;                  // run slots a warp reserves at a time
 constexpr uint32_t RUN_INVALID = 0xFFFFFFFFu;       // SpanRun::span of a reserved slot that was never filled
-constexpr int MAX_BW_FAST = 448;                    // piece cells = PIECE_LEN + 2*bw <= 1408
+constexpr int MAX_BW_FAST = MAX_BW_SPAN;            // piece cells = PIECE_LEN + 2*bw <= 1408
+constexpr int MO_N = SPAN_MT + 2 * HALO_MT + 1;     // mini-tile offsets a span needs: its own mini-tiles, the halo on either side, and the end
+constexpr int MO_STRIDE = (MO_N + 3) & ~3;
+static_assert(MO_N <= 32, "one lane per mini-tile offset");
 
 typedef Unit SpanUnit;                              // one (ProfileBuffer, contig) pair; nSpans = ceil((size + bw) / SPAN_LEN)
 
@@ -102,9 +108,9 @@ __host__ __device__ inline SpanSmem span_smem_layout (uint32_t bw, uint32_t nSam
   L.oWf = w;   w += coeff ? W * 8 : 0;              // -z: per-position weights are doubles
   L.oWr = w;   w += (coeff && nondir) ? W * 8 : 0;
   w = (w + 15) & ~15u;
+  L.oMo = w;   w += 2 * MO_STRIDE * 8;              // mini-tile offsets of the span + its halo on either side, per strand
   L.oSt = w;   w += 128 * 8;                        // products of 128 taps (exact_dense_warp)
-  L.oMo = w;   w += 24 * 8;                         // mini-tile offsets of the span + one of halo on either side, per strand
-  L.oSc = w;   w += coeff ? PIECE_LEN * 8 : PIECE_LEN * 4;
+  L.oSc = w;   w += coeff ? PIECE_LEN * 8 : PIECE_LEN * 4;   // oSt + oSc together (>= 3 KB, contiguous) double as the entry staging ring of B1
   L.oMw = w;   w += (PIECE_BLOCKS + 2) * 4;
   L.oHm = w;   w += (SPAN_WORDS + 2) * 4;
   w = (w + 15) & ~15u;
@@ -126,6 +132,14 @@ __device__ __forceinline__ uint32_t warp_sum_u32 (uint32_t v) {
 template <class T> __device__ __forceinline__ T warp_incl_scan (T v, uint32_t lane) {
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const T n = __shfl_up_sync(0xffffffffu, v, o); if (lane >= (uint32_t)o) v += n; }
+  return v;
+}
+// the same scan for 32-bit values with the shuffle's own in-range predicate: one SHFL + one predicated IADD per step
+// (the generic form above compiles to SHFL + SEL + IADD and recomputes the five lane tests every time it is inlined in a loop)
+__device__ __forceinline__ uint32_t warp_incl_scan_u32 (uint32_t v) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+    asm volatile("{ .reg .u32 t; .reg .pred p; shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff; @p add.u32 %0, %0, t; }" : "+r"(v) : "r"(o));
   return v;
 }
 template <class T> __device__ __forceinline__ T warp_sum (T v) {
@@ -227,7 +241,7 @@ __device__ __forceinline__ void piece_entries (const Tags& T, uint32_t d, uint32
 }
 
 // The same walk with the mini-tile offsets taken from a table the warp loaded once per span: tab[j] = mtOff[gb + min(mBase + j, nMt)]
-// for j = 0 .. 11 (the span's 8 mini-tiles, one of halo on either side, and the end) — no dependent global look-up per piece.
+// for j = 0 .. MO_N - 1 (the span's mini-tiles, HALO_MT of halo on either side, and the end) — no dependent global look-up per piece.
 template <class F>
 __device__ __forceinline__ void piece_entries_tab (const uint2* __restrict__ ment, const unsigned long long* __restrict__ tab, int mBase, uint32_t nMt,
                                                    int64_t lo, int64_t hi, uint32_t lane, F f) {
@@ -240,18 +254,76 @@ __device__ __forceinline__ void piece_entries_tab (const uint2* __restrict__ men
     const uint32_t m0 = max(ma, sp * SPAN_MT), m1 = min(mb, sp * SPAN_MT + SPAN_MT - 1);
     const unsigned long long e0 = tab[(int)m0 - mBase], e1 = tab[(int)m1 + 1 - mBase];
     const uint32_t base = sp * SPAN_LEN + 1;
-    for (unsigned long long eb = e0 + lane; eb - lane < e1; eb += 128) {
+    // the chunk holds at most one entry per (sample, position) of one span and its halo: its length fits 32 bits
+    const uint32_t n = (uint32_t)(e1 - e0);
+    const uint2* __restrict__ src = ment + e0 + lane;
+    for (uint32_t k = lane; k - lane < n; k += 128, src += 128) {
       uint2 en[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) en[q] = (eb + 32 * q < e1) ? __ldg(ment + eb + 32 * q) : make_uint2(0u, 0u);
+      for (int q = 0; q < 4; ++q) en[q] = (k + 32 * q < n) ? __ldg(src + 32 * q) : make_uint2(0u, 0u);
 #pragma unroll
       for (int q = 0; q < 4; ++q) if (en[q].x) f(base + (en[q].y & (SPAN_LEN - 1)), en[q]);
     }
   }
 }
 
-// Zone-map prefilter: a block's window (32 + 2bw positions) lies inside `nAdj` consecutive 512-position mini-tiles, so a
-// span none of whose runs of nAdj mini-tiles (its own 8 plus one of halo on either side) weighs enough for
+// The same walk with the entries staged through shared memory: every lane copies its own entries (8 bytes each, cp.async) into a
+// ring of STAGE_SLOTS batches of 128 and consumes them STAGE_SLOTS - 1 batches later, so up to 12 loads per lane are in flight with no
+// registers held, instead of four that are waited for before the next four are issued.  A lane reads back only what it copied
+// itself: cp.async.wait_group is all the ordering this needs.  `pre` runs once, after the first batches are on their way (the
+// caller zeroes the piece's cells there, behind the loads).
+constexpr uint32_t STAGE_SLOTS = 3;
+static_assert(128 * 8 + PIECE_LEN * 4 >= STAGE_SLOTS * 128 * 8, "SpanSmem: oSt + oSc must hold the staging ring");
+
+__device__ __forceinline__ void cp_async8 (void* smemDst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((uint32_t)__cvta_generic_to_shared(smemDst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit () { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait () { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+template <class P, class F>
+__device__ __forceinline__ void piece_entries_async (const uint2* __restrict__ ment, const unsigned long long* __restrict__ tab, int mBase, uint32_t nMt,
+                                                     int64_t lo, int64_t hi, uint32_t lane, uint2* ring /* [STAGE_SLOTS * 128], 8-byte aligned, this warp's */,
+                                                     bool& preDone, P pre, F f) {
+  if (nMt == 0 || hi < 1) return;
+  if (lo < 1) lo = 1;
+  const uint32_t ma = (uint32_t)((lo - 1) >> MT_SHIFT);
+  if (ma >= nMt) return;
+  const uint32_t mb = min((uint32_t)((hi - 1) >> MT_SHIFT), nMt - 1);
+  for (uint32_t sp = ma / SPAN_MT; sp <= mb / SPAN_MT; ++sp) {
+    const uint32_t m0 = max(ma, sp * SPAN_MT), m1 = min(mb, sp * SPAN_MT + SPAN_MT - 1);
+    const unsigned long long e0 = tab[(int)m0 - mBase], e1 = tab[(int)m1 + 1 - mBase];
+    const uint32_t base = sp * SPAN_LEN + 1;
+    const uint32_t nB = (uint32_t)((e1 - e0 + 127) >> 7);             // batches of 128 entries
+    auto issue = [&] (uint32_t b) {                                    // batch b -> slot b % STAGE_SLOTS; always one group, empty beyond the end
+      if (b < nB) {
+        const unsigned long long eb = e0 + ((unsigned long long)b << 7) + lane;
+        uint2* dst = ring + (b % STAGE_SLOTS) * 128 + lane;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (eb + 32 * q < e1) cp_async8(dst + 32 * q, ment + eb + 32 * q);
+      }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (uint32_t b = 0; b < STAGE_SLOTS; ++b) issue(b);
+    if (!preDone) { pre(); preDone = true; }
+    for (uint32_t b = 0; b < nB; ++b) {
+      cp_async_wait<STAGE_SLOTS - 1>();                                // all but the newest STAGE_SLOTS - 1 groups have landed: batch b is here
+      const unsigned long long eb = e0 + ((unsigned long long)b << 7) + lane;
+      const uint2* src = ring + (b % STAGE_SLOTS) * 128 + lane;
+      uint2 en[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) en[q] = (eb + 32 * q < e1) ? src[32 * q] : make_uint2(0u, 0u);
+      issue(b + STAGE_SLOTS);                                          // refills the slot just read (same lane, same addresses)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (en[q].x) f(base + (en[q].y & (SPAN_LEN - 1)), en[q]);
+    }
+    cp_async_wait<0>();                                                // nothing of this walk is still on its way when the ring is reused
+  }
+}
+
+// Zone-map prefilter: a block's window (32 + 2bw positions) lies inside `nAdj` consecutive mini-tiles, so a
+// span none of whose runs of nAdj mini-tiles (its own plus HALO_MT of halo on either side) weighs enough for
 // maxTap * weight >= threshold has no hot block and is skipped without touching its entries — the device-side analogue
 // of the reference leaping over empty stretches (misc/peakcall.cpp:172-173).  The weights count every sample (controls
 // too), which only makes the bound more conservative.
@@ -276,6 +348,8 @@ struct WarmArgs {
   uint32_t* spanRunCount;           // zeroed here for the spans that are skipped
 };
 
+constexpr int WARM_ADJ_MAX = ((31 + 2 * MAX_BW_SPAN) >> MT_SHIFT) + 2;   // upb_api.cu: nAdj = ((31 + 2 bw) >> MT_SHIFT) + 2
+
 __global__ void warm_span_kernel (WarmArgs a) {
   const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
   bool warm = false;
@@ -286,9 +360,11 @@ __global__ void warm_span_kernel (WarmArgs a) {
     const SpanUnit U = a.units[lo];
     unit = lo;
     const uint32_t k = w - U.spanStart;
-    const int m0 = (int)(k * SPAN_MT) - 1, m1 = (int)(k * SPAN_MT + SPAN_MT);     // inclusive mini-tile range with halo
+    const int m0 = (int)(k * SPAN_MT) - HALO_MT, m1 = (int)(k * SPAN_MT + SPAN_MT) - 1 + HALO_MT;   // inclusive mini-tile range with halo
     const uint32_t d0 = a.nondir ? 0u : U.buffer, d1 = a.nondir ? 1u : U.buffer;
-    unsigned long long win[4] = {0, 0, 0, 0};                        // sliding window of the last nAdj (<= 4) mini-tile weights
+    unsigned long long win[WARM_ADJ_MAX];                            // sliding window of the last nAdj mini-tile weights
+#pragma unroll
+    for (int q = 0; q < WARM_ADJ_MAX; ++q) win[q] = 0;
     unsigned long long run = 0;
     for (int m = m0; m <= m1; ++m) {
       unsigned long long wgt = 0;
@@ -443,8 +519,11 @@ __global__ void __launch_bounds__(HOT_THREADS, 6) hot_span_kernel (const __grid_
   if (lane == 0 && stHot) atomicAdd(a.stat + 0, stHot);
 }
 
-template <bool NONDIR, bool COEFF>
-__global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : SP_MIN_BLOCKS) span_kernel (const __grid_constant__ SpanArgs a) {
+// MINB: CTAs per SM the register budget is sized for.  Four (64 registers) when the shared memory of four CTAs fits; where it
+// does not (bandwidth > ~150, or -D with its second cell array) the kernel is built for three (no spills, 78 registers): measured
+// on C3 at bandwidth 200 0.69 -> 0.60 ms, C2 0.57 -> 0.47 ms, while at bandwidth <= 150 four CTAs win (profiles/r01_v26_ab.txt).
+template <bool NONDIR, bool COEFF, int MINB = SP_MIN_BLOCKS>
+__global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : MINB) span_kernel (const __grid_constant__ SpanArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const uint32_t bw = a.bw;
   const SpanSmem L = span_smem_layout(bw, a.nSamples, NONDIR, COEFF);
@@ -497,14 +576,14 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : SP_MIN_BLOCKS) span_ke
     __syncwarp();
     if ((lane >> 2) == tb) hm[lane & 3] = maskWord;
     if (lane == 0) hm[SPAN_WORDS] = 0;
-    const int mBase = (int)(k * SPAN_MT) - 1;
+    const int mBase = (int)(k * SPAN_MT) - HALO_MT;
     uint32_t nMtS[2] = {0u, 0u};
 #pragma unroll
     for (int str = 0; str < (NONDIR ? 2 : 1); ++str) {
       const uint32_t d = NONDIR ? (uint32_t)str : U.buffer;
       const uint32_t gb = __ldg(a.T.mtBase + d * a.T.C + U.contig);
       nMtS[str] = __ldg(a.T.mtBase + d * a.T.C + U.contig + 1) - gb;
-      if (lane < 12) mo[12 * str + lane] = __ldg(a.T.mtOff + gb + (uint32_t)min(max(mBase + (int)lane, 0), (int)nMtS[str]));
+      if (lane < (uint32_t)MO_N) mo[MO_STRIDE * str + lane] = __ldg(a.T.mtOff + gb + (uint32_t)min(max(mBase + (int)lane, 0), (int)nMtS[str]));
     }
     __syncwarp();
     ++stSpans;
@@ -534,21 +613,41 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : SP_MIN_BLOCKS) span_ke
         const uint32_t W = 32 * nb + 2 * bw;                          // cells
         const uint32_t nbEff = (P + 31) >> 5;
 
-        for (uint32_t u = lane; u < W + 2; u += 32) { D[u] = 0; if (NONDIR) DR[u] = 0; }
-        __syncwarp();
+        auto zeroCells = [&] () {
+          for (uint32_t u = lane; u < W + 2; u += 32) { D[u] = 0; if (NONDIR) DR[u] = 0; }
+          __syncwarp();
+        };
 
         // B1: the tags within bandwidth of the piece -> dense cells: cell u holds position q0 - bw + u
         unsigned long long tot = 0;                                    // pooled weight of the piece's cells
         {
           const int64_t lo = (int64_t)q0 - bw, hi = (int64_t)q0 + 32 * nb - 1 + bw;
           const uint32_t cell0 = q0 - bw;                              // may wrap below 0: the unsigned difference below is still right
+#if UPB_EXP_ASYNC
+          bool zeroed = false;                                         // the cells are zeroed behind the first batches of loads
+          if (!COEFF) {
+            __syncwarp();                                              // the ring (stage + scf) was read by other lanes in B4 of the previous piece
+#pragma unroll
+            for (int str = 0; str < (NONDIR ? 2 : 1); ++str) {
+              uint32_t* dst = str ? DR : D;
+              piece_entries_async(a.T.ment, mo + MO_STRIDE * str, mBase, nMtS[str], lo, hi, lane, (uint2*)stage, zeroed, zeroCells, [&] (uint32_t pos, const uint2& en) {
+                const uint32_t u = pos - cell0;
+                if (u < W && !(a.hasControl && isCtl[en.y >> SPAN_SHIFT])) { atomicAdd(&dst[u], en.x); tot += en.x; }
+              });
+            }
+            if (!zeroed) zeroCells();
+          } else
+#endif
+          {
+          zeroCells();
 #pragma unroll
           for (int str = 0; str < (NONDIR ? 2 : 1); ++str) {
             uint32_t* dst = str ? DR : D;
-            piece_entries_tab(a.T.ment, mo + 12 * str, mBase, nMtS[str], lo, hi, lane, [&] (uint32_t pos, const uint2& en) {
+            piece_entries_tab(a.T.ment, mo + MO_STRIDE * str, mBase, nMtS[str], lo, hi, lane, [&] (uint32_t pos, const uint2& en) {
               const uint32_t u = pos - cell0;
               if (u < W && !(a.hasControl && isCtl[en.y >> SPAN_SHIFT])) { atomicAdd(&dst[u], en.x); tot += en.x; }
             });
+          }
           }
         }
         tot = warp_sum(tot);                                           // also orders the atomics before the reads below
@@ -569,7 +668,7 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : SP_MIN_BLOCKS) span_ke
               for (int str = 0; str < (NONDIR ? 2 : 1); ++str) {
                 double* dst = str ? Wr : Wf;
                 const uint32_t cell0 = q0 - bw;
-                piece_entries_tab(a.T.ment, mo + 12 * str, mBase, nMtS[str], (int64_t)q0 - bw, (int64_t)q0 + 32 * nb - 1 + bw, lane, [&] (uint32_t pos, const uint2& en) {
+                piece_entries_tab(a.T.ment, mo + MO_STRIDE * str, mBase, nMtS[str], (int64_t)q0 - bw, (int64_t)q0 + 32 * nb - 1 + bw, lane, [&] (uint32_t pos, const uint2& en) {
                   if ((en.y >> SPAN_SHIFT) != sm) return;
                   const uint32_t u = pos - cell0;
                   if (u < W) dst[u] = __dadd_rn(dst[u], phase ? (double)en.x : __dmul_rn((double)en.x, cf));
@@ -605,6 +704,7 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : SP_MIN_BLOCKS) span_ke
           }
           c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2);
           // B3: classify every position: moment form, exact order only inside the error band
+          const double thrHi = a.thr + dPiece, thrLo = a.thr - dPiece;
           for (uint32_t b = 0; b < nbEff; ++b) {
             const uint32_t i = 32 * b + lane;
             S d0 = 0, d1 = 0, d2 = 0;
@@ -614,16 +714,24 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : SP_MIN_BLOCKS) span_ke
               const S wl = (S)D[i - 1] + (NONDIR ? (S)DR[i - 1] : (S)0);
               d0 = we - wl; d1 = we * ue - wl * ul; d2 = we * ue * ue - wl * ul * ul;
             }
-            const S S0 = c0 + warp_incl_scan(d0, lane);
-            const S S1 = c1 + warp_incl_scan(d1, lane);
-            const S S2 = c2 + warp_incl_scan(d2, lane);
+            S S0, S1, S2;
+            double v;
+            if constexpr (sizeof(S) == 4) {
+              // tot * W^2 < 2^32: the sums and N itself (0 <= N <= bw^2 * S0) fit 32 bits, intermediate products may wrap
+              S0 = c0 + warp_incl_scan_u32(d0); S1 = c1 + warp_incl_scan_u32(d1); S2 = c2 + warp_incl_scan_u32(d2);
+              const uint32_t x = i + bw;
+              const uint32_t N = (uint32_t)bw2 * S0 - (x * x * S0 - 2u * x * S1 + S2);
+              v = __dmul_rn((double)N, a.cN);
+            } else {
+              S0 = c0 + warp_incl_scan(d0, lane); S1 = c1 + warp_incl_scan(d1, lane); S2 = c2 + warp_incl_scan(d2, lane);
+              const unsigned long long x = i + bw;
+              const unsigned long long N = bw2 * (unsigned long long)S0 - (x * x * (unsigned long long)S0 - 2ull * x * (unsigned long long)S1 + (unsigned long long)S2);
+              v = __dmul_rn((double)(long long)N, a.cN);
+            }
             c0 = __shfl_sync(0xffffffffu, S0, 31); c1 = __shfl_sync(0xffffffffu, S1, 31); c2 = __shfl_sync(0xffffffffu, S2, 31);
-            const unsigned long long x = i + bw;
-            const unsigned long long N = bw2 * (unsigned long long)S0 - (x * x * (unsigned long long)S0 - 2ull * x * (unsigned long long)S1 + (unsigned long long)S2);
-            double v = __dmul_rn((double)(long long)N, a.cN);
             const bool valid = i < P;
-            bool above = valid && v >= a.thr + dPiece;
-            if (valid && !above && v >= a.thr - dPiece) {              // too close to call: the reference's own arithmetic decides
+            bool above = valid && v >= thrHi;
+            if (valid && !above && v >= thrLo) {                       // too close to call: the reference's own arithmetic decides
               const double f = exact_dense(Ks, D, i, bw);
               v = NONDIR ? __dadd_rn(f, exact_dense(Ks, DR, i, bw)) : f; // misc/peakcall.cpp:57
               above = v >= a.thr;
