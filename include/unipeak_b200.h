@@ -211,6 +211,37 @@ typedef struct {
 int upb_strand_shift (upb_ctx* ctx, const upb_shift_params* params, upb_shift_report* out);
 void upb_free_shift_report (upb_shift_report* r);
 
+/* ---- bin/strand_shift over contig-sharded contexts (one per GPU) -----------------
+ * The same steps as upb_strand_shift, cut where the ranks have to exchange something:
+ *   1. upb_shift_regions        the Region vector of src/strand_shift.cpp:143-190 for the contigs loaded on this context,
+ *                               in the order the reference builds it (contig, left)
+ *   2. (caller) all-gather of the lists, 16 B per region; concatenated by contig they are the reference's whole vector
+ *   3. upb_shift_examine_order  the order in which src/strand_shift.cpp:198-226 examines that vector: the head of
+ *                               libstdc++'s std::sort by Region::sum() descending, ties as the reference leaves them (Q12)
+ *   4. upb_shift_sweep          src/strand_shift.cpp:206-219 for the regions of a batch that lie on this context's contigs;
+ *                               (caller) all-gather of the (best shift, best correlation) pairs
+ *   5. (caller) src/strand_shift.cpp:220-225 in examination order, then upb_shift_mode = src/strand_shift.cpp:239-258
+ * unipeak_b200/multi.py::strand_shift_sharded is this protocol over torch.distributed; with one rank it returns exactly
+ * what upb_strand_shift returns. */
+typedef struct {
+  uint64_t n;
+  uint32_t* contig;
+  uint32_t* left;
+  uint32_t* len;
+  uint32_t* sum;                /* Region::sum() (no controls in strand_shift: the pooled hit sum) */
+  uint8_t* replayed;            /* 1: produced by the left-edge replay (Q2); upb_strand_shift refuses to sweep such a region */
+} upb_shift_region_list;
+
+int upb_shift_regions (upb_ctx* ctx, const upb_shift_params* params, upb_shift_region_list* out);
+void upb_free_shift_regions (upb_shift_region_list* l);
+/* order_out[0 .. *sorted_end) = indices of the first *sorted_end (>= min(want, n)) elements of the reference's sorted vector;
+ * the rest of order_out is a permutation of the remaining indices in no particular order.  Host only. */
+int upb_shift_examine_order (uint64_t n, const uint32_t* sums, uint64_t want, uint32_t* order_out, uint64_t* sorted_end);
+/* every region must be longer than 2 * max_shift + 3 (src/strand_shift.cpp:206) and lie on a contig with tags on this context */
+int upb_shift_sweep (upb_ctx* ctx, const upb_shift_params* params, uint64_t n, const uint32_t* contig, const uint32_t* left,
+                     const uint32_t* len, uint32_t* best_shift_out, double* best_corr_out);
+int upb_shift_mode (const uint64_t* shift_freq, uint32_t n_freq, uint32_t min_shift, uint32_t* best_out);   /* host only */
+
 /* ---- bin/tags_in_regions ------------------------------------------------------------------- */
 typedef struct {
   uint32_t contig;

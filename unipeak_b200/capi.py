@@ -61,6 +61,11 @@ class ShiftReport(C.Structure):
                 ("tested_best_shift", C.POINTER(C.c_uint32)), ("tested_best_corr", C.POINTER(C.c_double))]
 
 
+class ShiftRegionList(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("contig", C.POINTER(C.c_uint32)), ("left", C.POINTER(C.c_uint32)), ("len", C.POINTER(C.c_uint32)),
+                ("sum", C.POINTER(C.c_uint32)), ("replayed", C.POINTER(C.c_uint8))]
+
+
 class RegionKey(C.Structure):
     _fields_ = [("contig", C.c_uint32), ("start", C.c_uint32), ("end", C.c_uint32)]
 
@@ -76,6 +81,7 @@ EXPORTS = [
     "upb_load_tags", "upb_call_regions", "upb_free_region_table", "upb_reference_order", "upb_profile_contig", "upb_free_profile",
     "upb_strand_shift", "upb_free_shift_report", "upb_count_tags_in_regions", "upb_kernel_taps", "upb_last_stats",
     "upb_slab_layout", "upb_scatter_rows", "upb_table_from_slab", "upb_stream", "upb_host_register", "upb_host_unregister", "upb_load_tags_packed", "upb_pack_tags", "upb_aggregate_tags", "upb_free_tag_counts",
+    "upb_shift_regions", "upb_free_shift_regions", "upb_shift_examine_order", "upb_shift_sweep", "upb_shift_mode",
 ]
 SLAB_COLS = ("cand_index", "peak_score", "kurtosis", "corr", "contig", "left", "len", "peak", "hit_sum", "counts", "buffer", "end")
 SLAB_DTYPES = dict(cand_index=np.uint64, peak_score=np.float64, kurtosis=np.float64, corr=np.float64, contig=np.uint32, left=np.uint32,
@@ -150,6 +156,12 @@ def lib():
         L.upb_strand_shift.argtypes = [C.c_void_p, C.POINTER(ShiftParams), C.POINTER(ShiftReport)]
         L.upb_free_shift_report.argtypes = [C.POINTER(ShiftReport)]
         L.upb_free_shift_report.restype = None
+        L.upb_shift_regions.argtypes = [C.c_void_p, C.POINTER(ShiftParams), C.POINTER(ShiftRegionList)]
+        L.upb_free_shift_regions.argtypes = [C.POINTER(ShiftRegionList)]
+        L.upb_free_shift_regions.restype = None
+        L.upb_shift_examine_order.argtypes = [C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.upb_shift_sweep.argtypes = [C.c_void_p, C.POINTER(ShiftParams), C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.upb_shift_mode.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
         L.upb_count_tags_in_regions.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint64, C.POINTER(RegionKey), C.c_void_p]
         L.upb_kernel_taps.argtypes = [C.c_uint32, C.c_double, C.POINTER(C.c_double)]
         L.upb_last_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
@@ -186,6 +198,28 @@ def slab_columns(buf: np.ndarray, n_rows: int, n_samples: int) -> Dict[str, np.n
         out[k] = buf[L[k]:L[k] + count * np.dtype(dt).itemsize].view(dt)
     out["counts"] = out["counts"].reshape(n_rows, n_samples)
     return out
+
+
+def shift_examine_order(sums: np.ndarray, want: int):
+    """upb_shift_examine_order (host only): (order, sorted_end) — order[:sorted_end] are the indices of the first sorted_end
+    elements of the reference's std::sort of the regions by Region::sum() descending (src/strand_shift.cpp:198, SURVEY Q12)."""
+    sums = np.ascontiguousarray(sums, dtype=np.uint32)
+    order = np.empty(sums.shape[0], dtype=np.uint32)
+    end = C.c_uint64(0)
+    rc = lib().upb_shift_examine_order(sums.shape[0], sums.ctypes.data, int(want), order.ctypes.data, C.byref(end))
+    if rc:
+        raise UpbError(rc, "upb_shift_examine_order failed")
+    return order, int(end.value)
+
+
+def shift_mode(shift_freq: np.ndarray, min_shift: int) -> int:
+    """upb_shift_mode (host only): src/strand_shift.cpp:239-258."""
+    f = np.ascontiguousarray(shift_freq, dtype=np.uint64)
+    best = C.c_uint32(0)
+    rc = lib().upb_shift_mode(f.ctypes.data, f.shape[0], int(min_shift), C.byref(best))
+    if rc:
+        raise UpbError(rc, "upb_shift_mode failed")
+    return int(best.value)
 
 
 def kernel_taps(bandwidth: int, total: float = 1.0) -> np.ndarray:
@@ -405,6 +439,36 @@ class Context:
         if rc and rc != -8:
             self._check(rc)
         return out
+
+    @staticmethod
+    def _shift_params(bandwidth=50, region_threshold=25.0, kurtosis_threshold=50.0, corr_threshold=0.3, hit_threshold=10,
+                      min_shift=25, max_shift=150, n_regions_to_test=1000, *, background: float) -> "ShiftParams":
+        return ShiftParams(bandwidth, region_threshold, kurtosis_threshold, corr_threshold, hit_threshold, min_shift, max_shift,
+                           n_regions_to_test, background)
+
+    def shift_regions(self, **params) -> Dict[str, np.ndarray]:
+        """upb_shift_regions: the regions of the contigs loaded on this context, in the reference's order (contig, left)."""
+        p = self._shift_params(**params)
+        l = ShiftRegionList()
+        self._check(self._lib.upb_shift_regions(self._h, C.byref(p), C.byref(l)))
+        try:
+            n = int(l.n)
+            return dict(contig=_np(l.contig, n, np.uint32), left=_np(l.left, n, np.uint32), len=_np(l.len, n, np.uint32),
+                        sum=_np(l.sum, n, np.uint32), replayed=_np(l.replayed, n, np.uint8))
+        finally:
+            self._lib.upb_free_shift_regions(C.byref(l))
+
+    def shift_sweep(self, contig: np.ndarray, left: np.ndarray, length: np.ndarray, **params):
+        """upb_shift_sweep: (best shift, best correlation) of every given region (src/strand_shift.cpp:206-219)."""
+        p = self._shift_params(**params)
+        contig = np.ascontiguousarray(contig, dtype=np.uint32); left = np.ascontiguousarray(left, dtype=np.uint32)
+        length = np.ascontiguousarray(length, dtype=np.uint32)
+        n = int(contig.shape[0])
+        bs = np.zeros(n, dtype=np.uint32); bc = np.zeros(n, dtype=np.float64)
+        if n:
+            self._check(self._lib.upb_shift_sweep(self._h, C.byref(p), n, contig.ctypes.data, left.ctypes.data, length.ctypes.data,
+                                                  bs.ctypes.data, bc.ctypes.data))
+        return bs, bc
 
     def count_tags_in_regions(self, keys: Sequence[Sequence[int]], *, directional=True, extension=0) -> np.ndarray:
         arr = (RegionKey * max(1, len(keys)))()

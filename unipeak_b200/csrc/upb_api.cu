@@ -1439,14 +1439,63 @@ template <class T> static T* alloc_arr (size_t n) { return (T*)calloc(n ? n : 1,
 struct SumIdx { uint32_t sum; uint32_t idx; };
 static bool compareRegionCounts (const SumIdx& i, const SumIdx& j) { return i.sum > j.sum; }   // src/strand_shift.cpp:26-29
 
-extern "C" int upb_strand_shift (upb_ctx* ctx, const upb_shift_params* p, upb_shift_report* out) {
-  if (!ctx) return UPB_ERR_BAD_ARG;
-  if (!p || !out) return fail(ctx, UPB_ERR_BAD_ARG, "upb_strand_shift: NULL argument");
-  memset(out, 0, sizeof *out);
+// the pipeline configuration of src/strand_shift.cpp:139-190: one non-directional buffer, no correlation filter (:142)
+static PipeCfg shift_cfg (const upb_shift_params* p) {
   PipeCfg cfg;
   cfg.bw = p->bandwidth; cfg.thr = p->region_threshold; cfg.kurtThr = p->kurtosis_threshold; cfg.corrThr = -1;   // :142
   cfg.hitThr = (double)p->hit_threshold; cfg.background = p->background; cfg.nondir = true; cfg.control = nullptr; cfg.needCorr = false;
   cfg.allowLeftEdge = true;          // regions at a contig start come from the replay of the reference's left-edge behaviour (Q2)
+  return cfg;
+}
+
+// :206-219 for a batch of regions that are long enough: strandCorr(shift) for every shift 0..max_shift on the device, then the
+// first strict maximum per region.  `dens` is the density template of a prepare() / run_pipeline() with shift_cfg.
+static int shift_sweep_batch (upb_ctx* ctx, const DensArgs& dens, const std::vector<uint32_t>& unitOfContig, uint32_t nb, const uint32_t* contig,
+                              const uint32_t* left, const uint32_t* len, uint32_t nShifts, uint32_t* bestShift, double* bestCorr, uint32_t* launches) {
+  if (!nb) return UPB_OK;
+  std::vector<uint32_t> hUnit(nb), hChunks(nb);
+  for (uint32_t k = 0; k < nb; ++k) { hUnit[k] = unitOfContig[contig[k]]; hChunks[k] = (len[k] + TILE - 1) / TILE; }
+  uint32_t* dUnit = SCR("dUnit", uint32_t, nb); uint32_t* dLeft = SCR("dLeft", uint32_t, nb);
+  uint32_t* dLen = SCR("dLen", uint32_t, nb); uint32_t* dChunks = SCR("dChunks", uint32_t, nb);
+  CU(cudaMemcpyAsync(dUnit, hUnit.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dLeft, left, (size_t)nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dLen, len, (size_t)nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dChunks, hChunks.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));                           // the host vectors go out of scope below
+  int r;
+  if ((r = dump_and_corr(ctx, dens, true, nb, nShifts, launches))) return r;
+  uint32_t* dBestShift = SCR("bestShift", uint32_t, nb);
+  double* dBestCorr = SCR("bestCorr", double, nb);
+  best_shift_kernel<<<(nb + 255) / 256, 256, 0, ctx->stream>>>(ctx->scratch["corr"].as<double>(), nb, nShifts, dBestShift, dBestCorr);
+  CU(cudaGetLastError());
+  *launches += 1;
+  CU(cudaMemcpyAsync(bestShift, dBestShift, (size_t)nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(bestCorr, dBestCorr, (size_t)nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return UPB_OK;
+}
+
+// :239-258 smooth the histogram of maxima with Kernel(5) and take the mode (151 numbers: host)
+static uint32_t shift_mode (const uint64_t* shiftFreq, size_t m, uint32_t minShift) {
+  double modeKernel[11];
+  upb_kernel_taps(5, 1, modeKernel);
+  std::vector<double> density(m, 0.0);
+  for (size_t i = 0; i < m; ++i)
+    for (int j = 0; j < 11; ++j) {
+      const long k = (long)i - 5 + j;
+      if (k >= 0 && k < (long)m) { volatile double term = (double)shiftFreq[i] * modeKernel[j]; density[k] = density[k] + term; }
+    }
+  double bestDensity = 0;
+  uint32_t best = 0;
+  if (m >= 5) for (size_t i = minShift; i < m - 5; ++i) if (density[i] > bestDensity) { best = (uint32_t)i; bestDensity = density[i]; }
+  return best;
+}
+
+extern "C" int upb_strand_shift (upb_ctx* ctx, const upb_shift_params* p, upb_shift_report* out) {
+  if (!ctx) return UPB_ERR_BAD_ARG;
+  if (!p || !out) return fail(ctx, UPB_ERR_BAD_ARG, "upb_strand_shift: NULL argument");
+  memset(out, 0, sizeof *out);
+  const PipeCfg cfg = shift_cfg(p);
   PipeOut po;
   Prep pr;
   int r = run_pipeline(ctx, cfg, pr, po);
@@ -1499,29 +1548,10 @@ extern "C" int upb_strand_shift (upb_ctx* ctx, const upb_shift_params* p, upb_sh
     }
     if (batch.empty()) break;
     const uint32_t nb = (uint32_t)batch.size();
-    std::vector<uint32_t> hUnit(nb), hLeft(nb), hLen(nb), hChunks(nb);
-    for (uint32_t k = 0; k < nb; ++k) {
-      const uint32_t i = batch[k];
-      hUnit[k] = unitOfContig[rContig[i]]; hLeft[k] = rLeft[i]; hLen[k] = rLen[i]; hChunks[k] = (rLen[i] + TILE - 1) / TILE;
-    }
-    uint32_t* dUnit = SCR("dUnit", uint32_t, nb); uint32_t* dLeft = SCR("dLeft", uint32_t, nb);
-    uint32_t* dLen = SCR("dLen", uint32_t, nb); uint32_t* dChunks = SCR("dChunks", uint32_t, nb);
-    CU(cudaMemcpyAsync(dUnit, hUnit.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(dLeft, hLeft.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(dLen, hLen.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(dChunks, hChunks.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));                           // the host vectors go out of scope below
-    if ((r = dump_and_corr(ctx, pr.dens, true, nb, nShifts, &launches))) return r;
-    uint32_t* dBestShift = SCR("bestShift", uint32_t, nb);
-    double* dBestCorr = SCR("bestCorr", double, nb);
-    best_shift_kernel<<<(nb + 255) / 256, 256, 0, ctx->stream>>>(ctx->scratch["corr"].as<double>(), nb, nShifts, dBestShift, dBestCorr);
-    CU(cudaGetLastError());
-    launches += 1;
-    std::vector<uint32_t> bs(nb);
+    std::vector<uint32_t> hContig(nb), hLeft(nb), hLen(nb), bs(nb);
     std::vector<double> bc(nb);
-    CU(cudaMemcpyAsync(bs.data(), dBestShift, (size_t)nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(bc.data(), dBestCorr, (size_t)nb * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t k = 0; k < nb; ++k) { const uint32_t i = batch[k]; hContig[k] = rContig[i]; hLeft[k] = rLeft[i]; hLen[k] = rLen[i]; }
+    if ((r = shift_sweep_batch(ctx, pr.dens, unitOfContig, nb, hContig.data(), hLeft.data(), hLen.data(), nShifts, bs.data(), bc.data(), &launches))) return r;
     for (uint32_t k = 0; k < nb && tested < toTest; ++k) {
       if (bc[k] >= p->corr_threshold) {                              // :220 disqualify regions under threshold
         const uint32_t i = batch[k];
@@ -1536,21 +1566,89 @@ extern "C" int upb_strand_shift (upb_ctx* ctx, const upb_shift_params* p, upb_sh
   ctx->stats.launches = launches;
   out->n_regions_tested = tested;
   if (tested == 0) return fail(ctx, UPB_ERR_NO_REGIONS, "no regions qualified with given settings");   // :228-230
+  out->best_shift = shift_mode(out->shift_freq, out->n_freq, p->min_shift);
+  return UPB_OK;
+}
 
-  // :239-258 smooth the histogram of maxima with Kernel(5) and take the mode (151 numbers: host)
-  double modeKernel[11];
-  upb_kernel_taps(5, 1, modeKernel);
-  const size_t m = out->n_freq;
-  std::vector<double> density(m, 0.0);
-  for (size_t i = 0; i < m; ++i)
-    for (int j = 0; j < 11; ++j) {
-      const long k = (long)i - 5 + j;
-      if (k >= 0 && k < (long)m) { volatile double term = (double)out->shift_freq[i] * modeKernel[j]; density[k] = density[k] + term; }
-    }
-  double bestDensity = 0;
-  uint32_t best = 0;
-  if (m >= 5) for (size_t i = p->min_shift; i < m - 5; ++i) if (density[i] > bestDensity) { best = (uint32_t)i; bestDensity = density[i]; }
-  out->best_shift = best;
+// ------------------------------------------------------------------------------------------------
+// bin/strand_shift over contig-sharded ranks: the same steps as upb_strand_shift, cut where the ranks have to
+// exchange something.  Protocol (unipeak_b200/multi.py::strand_shift_sharded runs it over torch.distributed):
+//   1. every rank: upb_shift_regions   — the Region vector of :143-190 for its contigs, canonical order (contig, left)
+//   2. all-gather of the lists (16 B per region); concatenated by contig they are the reference's vector, on every rank
+//   3. every rank: upb_shift_examine_order on the global sums — the head of the reference's std::sort, hence the same order everywhere
+//   4. per batch of regions to examine: each rank sweeps the ones on its contigs (upb_shift_sweep), all-gather of (shift, corr)
+//   5. every rank applies :220-225 in examination order and smooths the histogram (upb_shift_mode)
+// ------------------------------------------------------------------------------------------------
+extern "C" void upb_free_shift_regions (upb_shift_region_list* l) {
+  if (!l) return;
+  free(l->contig); free(l->left); free(l->len); free(l->sum); free(l->replayed);
+  memset(l, 0, sizeof *l);
+}
+
+extern "C" int upb_shift_regions (upb_ctx* ctx, const upb_shift_params* p, upb_shift_region_list* out) {
+  if (!ctx) return UPB_ERR_BAD_ARG;
+  if (!p || !out) return fail(ctx, UPB_ERR_BAD_ARG, "upb_shift_regions: NULL argument");
+  memset(out, 0, sizeof *out);
+  const PipeCfg cfg = shift_cfg(p);
+  PipeOut po;
+  Prep pr;
+  int r = run_pipeline(ctx, cfg, pr, po);
+  if (r) return r;
+  struct SlabGuard { upb_ctx* c; HostSlab h; ~SlabGuard () { if (h.p) c->slabPool.push_back(h); } } guard{ctx, po.slab};
+  const size_t R = po.R;
+  std::vector<uint32_t> unitOfContig(ctx->sizes.size(), 0);
+  for (size_t u = 0; u < po.units.size(); ++u) unitOfContig[po.units[u].contig] = (uint32_t)u;
+  out->n = R;
+  out->contig = alloc_arr<uint32_t>(R); out->left = alloc_arr<uint32_t>(R); out->len = alloc_arr<uint32_t>(R); out->sum = alloc_arr<uint32_t>(R);
+  out->replayed = alloc_arr<uint8_t>(R);
+  if (!out->contig || !out->left || !out->len || !out->sum || !out->replayed) { upb_free_shift_regions(out); return fail(ctx, UPB_ERR_NOMEM, "upb_shift_regions: out of host memory"); }
+  if (R) {
+    memcpy(out->contig, po.col<uint32_t>(po.layout.oContig), R * 4);
+    memcpy(out->left, po.col<uint32_t>(po.layout.oLeft), R * 4);
+    memcpy(out->len, po.col<uint32_t>(po.layout.oLen), R * 4);
+    memcpy(out->sum, po.col<uint32_t>(po.layout.oWsum), R * 4);
+    for (size_t i = 0; i < R; ++i) out->replayed[i] = out->left[i] <= po.unitEdgeStop[unitOfContig[out->contig[i]]] ? 1 : 0;
+  }
+  return UPB_OK;
+}
+
+extern "C" int upb_shift_examine_order (uint64_t n, const uint32_t* sums, uint64_t want, uint32_t* order_out, uint64_t* sorted_end) {
+  if ((n && (!sums || !order_out)) || !sorted_end || n > 0xFFFFFFFFull) return UPB_ERR_BAD_ARG;
+  std::vector<SumIdx> order((size_t)n);
+  for (size_t i = 0; i < (size_t)n; ++i) { order[i].sum = sums[i]; order[i].idx = (uint32_t)i; }
+  *sorted_end = sort_prefix_like_std_sort(order.begin(), order.end(), (size_t)std::min<uint64_t>(want, n), compareRegionCounts);
+  for (size_t i = 0; i < (size_t)n; ++i) order_out[i] = order[i].idx;
+  return UPB_OK;
+}
+
+extern "C" int upb_shift_sweep (upb_ctx* ctx, const upb_shift_params* p, uint64_t n, const uint32_t* contig, const uint32_t* left, const uint32_t* len,
+                                uint32_t* best_shift_out, double* best_corr_out) {
+  if (!ctx) return UPB_ERR_BAD_ARG;
+  if (!p || (n && (!contig || !left || !len || !best_shift_out || !best_corr_out))) return fail(ctx, UPB_ERR_BAD_ARG, "upb_shift_sweep: NULL argument");
+  if (n > 0x7FFFFFFFull) return fail(ctx, UPB_ERR_UNSUPPORTED, "upb_shift_sweep: too many regions in one batch");
+  if (!n) return UPB_OK;
+  CU(cudaSetDevice(ctx->device));
+  const PipeCfg cfg = shift_cfg(p);
+  Prep pr;
+  uint32_t launches = 0;
+  int r = prepare(ctx, cfg, pr, &launches, true);
+  if (r) return r;
+  const uint32_t C = (uint32_t)ctx->sizes.size();
+  std::vector<uint32_t> unitOfContig(C, 0xFFFFFFFFu);
+  for (size_t u = 0; u < pr.units.size(); ++u) unitOfContig[pr.units[u].contig] = (uint32_t)u;
+  for (uint64_t k = 0; k < n; ++k) {
+    if (contig[k] >= C || unitOfContig[contig[k]] == 0xFFFFFFFFu) return fail(ctx, UPB_ERR_BAD_ARG, "upb_shift_sweep: a region lies on a contig without tags on this context");
+    if (len[k] <= 2 * p->max_shift + 3) return fail(ctx, UPB_ERR_BAD_ARG, "upb_shift_sweep: a region is too short to try all shifts (src/strand_shift.cpp:206)");
+    if (left[k] < 1 || (uint64_t)left[k] + len[k] - 1 > (uint64_t)ctx->sizes[contig[k]] + p->bandwidth) return fail(ctx, UPB_ERR_BAD_ARG, "upb_shift_sweep: a region lies outside its contig");
+  }
+  r = shift_sweep_batch(ctx, pr.dens, unitOfContig, (uint32_t)n, contig, left, len, p->max_shift + 1, best_shift_out, best_corr_out, &launches);
+  ctx->stats.launches = launches;
+  return r;
+}
+
+extern "C" int upb_shift_mode (const uint64_t* shift_freq, uint32_t n_freq, uint32_t min_shift, uint32_t* best_out) {
+  if (!shift_freq || !best_out) return UPB_ERR_BAD_ARG;
+  *best_out = shift_mode(shift_freq, n_freq, min_shift);
   return UPB_OK;
 }
 

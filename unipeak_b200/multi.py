@@ -203,3 +203,96 @@ class HostGather:
         cols = slab_columns(self.host, R, self.n)
         cols.update(n_rows=R, unit_candidates=tot[C2:2 * C2], tags_in_regions=tot[2 * C2:])
         return cols
+
+
+# ------------------------------------------------------------------------------------------------
+# bin/strand_shift over contig-sharded ranks (include/unipeak_b200.h "upb_shift_*")
+# ------------------------------------------------------------------------------------------------
+def allgather_rows(mat: np.ndarray, *, dist, world: int, device) -> List[np.ndarray]:
+    """All-gather of int64 matrices with the same number of columns and any number of rows: [rank 0's, rank 1's, ...]."""
+    import torch
+    mat = np.ascontiguousarray(mat, dtype=np.int64)
+    if world == 1:
+        return [mat]
+    n = torch.tensor([mat.shape[0]], dtype=torch.int64, device=device)
+    alln = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(alln, n)
+    counts = [int(x.item()) for x in alln]
+    padded = np.zeros((max(counts + [1]), mat.shape[1]), dtype=np.int64)
+    padded[:mat.shape[0]] = mat
+    t = torch.from_numpy(padded).to(device)
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    return [p.cpu().numpy()[:k] for p, k in zip(parts, counts)]
+
+
+def strand_shift_sharded(ctx, *, dist, rank: int, world: int, device, bandwidth=50, region_threshold=25.0, kurtosis_threshold=50.0,
+                         corr_threshold=0.3, hit_threshold=10, min_shift=25, max_shift=150, n_regions_to_test=1000, background: float) -> Dict:
+    """src/strand_shift.cpp:139-259 with the contigs spread over the ranks; `background` comes from the genome-wide tag total
+    (one all-reduce by the caller, as for bin/regions).  Every rank returns the same report, in the format of Context.strand_shift;
+    with world == 1 it is that report.  `ctx` needs shift_regions() and shift_sweep() (capi.Context)."""
+    from .capi import UpbError, shift_examine_order, shift_mode
+    params = dict(bandwidth=bandwidth, region_threshold=region_threshold, kurtosis_threshold=kurtosis_threshold, corr_threshold=corr_threshold,
+                  hit_threshold=hit_threshold, min_shift=min_shift, max_shift=max_shift, n_regions_to_test=n_regions_to_test, background=background)
+    # 1 + 2: the reference's Region vector (one non-directional buffer: contig order, then position), known to every rank
+    loc = ctx.shift_regions(**params)
+    mat = np.stack([loc[k].astype(np.int64) for k in ("contig", "left", "len", "sum", "replayed")], axis=1) if loc["left"].shape[0] else np.zeros((0, 5), np.int64)
+    parts = allgather_rows(mat, dist=dist, world=world, device=device)
+    owner = np.concatenate([np.full(p.shape[0], r, dtype=np.int64) for r, p in enumerate(parts)])
+    glob = np.concatenate(parts, axis=0)
+    o = np.lexsort((glob[:, 1], glob[:, 0]))
+    glob, owner = glob[o], owner[o]
+    contig, left, length, rsum, replayed = (glob[:, j] for j in range(5))
+    R = int(glob.shape[0])
+    n_freq = max_shift + 1
+    freq = np.zeros(n_freq, dtype=np.uint64)
+    to_test = int(n_regions_to_test) & 0xFFFF                       # UShort (SURVEY Q12)
+    out = dict(status=0, n_regions_found=R, n_regions_tested=0, n_tags_in_regions=0, best_shift=0, shift_freq=[], tested=[])
+
+    # 3: examination order = the head of the reference's std::sort by Region::sum(), grown on demand exactly as upb_strand_shift grows it
+    order, sorted_end = shift_examine_order(rsum.astype(np.uint32), min(R, 2 * to_test + 256))
+    tested, cursor, tags = 0, 0, 0
+    while tested < to_test and cursor < R:
+        batch = []
+        want = (to_test - tested) + (to_test - tested) // 4 + 8
+        while cursor < R and len(batch) < want:
+            if cursor >= sorted_end:
+                order, sorted_end = shift_examine_order(rsum.astype(np.uint32), min(R, max(2 * sorted_end, cursor + 1024)))
+            i = int(order[cursor])
+            if length[i] > 2 * max_shift + 3:                         # :206 large enough to try all shifts
+                if replayed[i]:
+                    raise UpbError(-6, "a region within `bandwidth` of a contig start is long enough for the shift sweep: the reference's left-edge densities (SURVEY Q2) are not emulated there")
+                batch.append(i)
+            cursor += 1
+        if not batch:
+            break
+        # 4: every rank sweeps the regions of the batch that lie on its contigs; (batch slot, shift, corr bits) go round
+        b = np.asarray(batch, dtype=np.int64)
+        slots = np.nonzero(owner[b] == rank)[0]
+        mine = b[slots]
+        bs_m, bc_m = ctx.shift_sweep(contig[mine], left[mine], length[mine], **params)
+        res = np.stack([slots.astype(np.int64), bs_m.astype(np.int64), bc_m.view(np.int64)], axis=1) if slots.shape[0] else np.zeros((0, 3), np.int64)
+        allres = np.concatenate(allgather_rows(res, dist=dist, world=world, device=device), axis=0)
+        bs = np.zeros(b.shape[0], dtype=np.int64)
+        bc = np.zeros(b.shape[0], dtype=np.float64)
+        bs[allres[:, 0]] = allres[:, 1]
+        bc[allres[:, 0]] = allres[:, 2].copy().view(np.float64)
+        # 5: :220-225 in examination order
+        for k in range(b.shape[0]):
+            if tested >= to_test:
+                break
+            if bc[k] >= corr_threshold:                               # NaN fails, as in the reference
+                i = int(b[k])
+                freq[int(bs[k])] += 1
+                tags += int(rsum[i])
+                out["tested"].append(dict(contig=int(contig[i]), left=int(left[i]), len=int(length[i]), best_shift=int(bs[k]), best_corr=float(bc[k])))
+                tested += 1
+    out["n_regions_tested"] = tested
+    out["n_tags_in_regions"] = tags
+    out["shift_freq"] = [int(x) for x in freq]
+    if tested == 0:                                                   # :228-230 "no regions qualified with given settings"
+        out["status"] = -8
+        out["shift_freq"] = [0] * n_freq
+        return out
+    out["best_shift"] = shift_mode(freq, min_shift)
+    return out
