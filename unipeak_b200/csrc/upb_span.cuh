@@ -22,6 +22,8 @@
 // region_pool_kernel + region_moment_kernel then compute Region::exptSums and posKurtosis for the candidates that pass the hit filter.
 #pragma once
 
+#include <type_traits>
+
 #include "upb_device.cuh"
 #include "upb_edge.cuh"
 
@@ -124,11 +126,7 @@ __device__ __forceinline__ unsigned long long warp_sum_u64 (unsigned long long v
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ uint32_t warp_sum_u32 (uint32_t v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
+__device__ __forceinline__ uint32_t warp_sum_u32 (uint32_t v) { return __reduce_add_sync(0xffffffffu, v); }   // one REDUX instead of five SHFL + five IADD
 template <class T> __device__ __forceinline__ T warp_incl_scan (T v, uint32_t lane) {
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const T n = __shfl_up_sync(0xffffffffu, v, o); if (lane >= (uint32_t)o) v += n; }
@@ -484,15 +482,38 @@ __global__ void __launch_bounds__(HOT_THREADS, 6) hot_span_kernel (const __grid_
     }
     __syncwarp();
     uint32_t any = 0, mine = 0;
+    // the envelope sum with the number of neighbour blocks known at compile time for the usual bandwidths (J <= 4: bandwidth <= 129):
+    // the j loop unrolls and its coefficients stay in registers (the run-time loop made this kernel issue-bound: 377 instructions per span)
+    auto words = [&] (auto jt) {
+      constexpr int JT = decltype(jt)::value;
+      const int JJ = JT ? JT : J;
+      float hf[JT ? JT + 1 : 1];
+      if (JT) {
 #pragma unroll
-    for (uint32_t m = 0; m < (uint32_t)SPAN_WORDS; ++m) {
-      const uint32_t kblk = 32 * m + lane;
-      float bound = wb[kblk + J] * hotf[0];
-      for (int j = 1; j <= J; ++j) bound = fmaf(wb[kblk + J - j] + wb[kblk + J + j], hotf[j], bound);
-      const uint32_t msk = __ballot_sync(0xffffffffu, kblk < nBlk && !(bound < a.thrLow));   // a NaN would count as hot
-      any |= msk;
-      if (lane == m) mine = msk;
-      stHot += __popc(msk);
+        for (int j = 0; j <= JT; ++j) hf[j] = hotf[j];
+      }
+#pragma unroll
+      for (uint32_t m = 0; m < (uint32_t)SPAN_WORDS; ++m) {
+        const uint32_t kblk = 32 * m + lane;
+        float bound = wb[kblk + JJ] * (JT ? hf[0] : hotf[0]);
+        if (JT) {
+#pragma unroll
+          for (int j = 1; j <= JT; ++j) bound = fmaf(wb[kblk + JT - j] + wb[kblk + JT + j], hf[j], bound);
+        } else {
+          for (int j = 1; j <= JJ; ++j) bound = fmaf(wb[kblk + JJ - j] + wb[kblk + JJ + j], hotf[j], bound);
+        }
+        const uint32_t msk = __ballot_sync(0xffffffffu, kblk < nBlk && !(bound < a.thrLow));   // a NaN would count as hot
+        any |= msk;
+        if (lane == m) mine = msk;
+        stHot += __popc(msk);
+      }
+    };
+    switch (J) {
+      case 1: words(std::integral_constant<int, 1>()); break;
+      case 2: words(std::integral_constant<int, 2>()); break;
+      case 3: words(std::integral_constant<int, 3>()); break;
+      case 4: words(std::integral_constant<int, 4>()); break;
+      default: words(std::integral_constant<int, 0>()); break;
     }
     __syncwarp();
     if (any) {
@@ -702,7 +723,8 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : MINB) span_kernel (con
             const S w = (S)D[u] + (NONDIR ? (S)DR[u] : (S)0);
             c0 += w; c1 += w * (S)u; c2 += w * (S)u * (S)u;
           }
-          c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2);
+          if constexpr (sizeof(S) == 4) { c0 = warp_sum_u32(c0); c1 = warp_sum_u32(c1); c2 = warp_sum_u32(c2); }
+          else { c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2); }
           // B3: classify every position: moment form, exact order only inside the error band
           const double thrHi = a.thr + dPiece, thrLo = a.thr - dPiece;
           for (uint32_t b = 0; b < nbEff; ++b) {
@@ -808,11 +830,10 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : MINB) span_kernel (con
               if (oe > best || (oe == best && oi < bestI)) { best = oe; bestI = oi; }
             }
           } else {
-          float fmax_ = -1.0f;
+          float fmax_ = 0.0f;                                         // the fast values are >= 0: their bit patterns order like the values
           for (uint32_t i = r0 + lane; i < r1; i += 32) { wsum += D[bw + i] + (NONDIR ? DR[bw + i] : 0u); fmax_ = fmaxf(fmax_, scf[i]); }
           wsum = warp_sum_u32(wsum);
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) fmax_ = fmaxf(fmax_, __shfl_xor_sync(0xffffffffu, fmax_, o));
+          fmax_ = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmax_)));
 
           // peak: first strict maximum of the exact-order score (misc/data.cpp:97-101).  Candidates are the positions
           // whose fast value (kept as float) could still be the maximum; they alone are evaluated exactly:
