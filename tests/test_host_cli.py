@@ -128,12 +128,25 @@ needs_ref = pytest.mark.skipif(not refutil.have_ref(), reason="compiled referenc
 
 
 def both(tmp_path, tool, args, outputs, rc=0):
-    """Run the reference's and our binary with identical argv in sibling directories that hold the same inputs."""
-    res = []
-    for which, d in (("ref", REF_DIR), ("new", BIN)):
+    """Run the reference's and our binary with identical argv in sibling directories that hold the same inputs.
+
+    The reference binary is not perfectly repeatable: on the B200 box its `regions -D -s 80,90,100,-5 -e 2,4` run once (1 of ~10 runs
+    of the suite, r01 v32) wrote a table that differs from what the same binary writes for the same files every other time (sample 1
+    lost half of its tags — it reads something it never initialised).  A mismatch therefore re-runs the reference twice; the
+    comparison stands against a reference output that the reference itself reproduces."""
+    def once(which, d):
         cwd = tmp_path / which
+        for o in outputs:
+            if (cwd / o).exists():
+                (cwd / o).unlink()
         p = run(d, tool, args, str(cwd))
-        res.append((p.returncode, p.stderr.decode(), {o: (cwd / o).read_bytes() if (cwd / o).exists() else None for o in outputs}, p.stdout))
+        return (p.returncode, p.stderr.decode(), {o: (cwd / o).read_bytes() if (cwd / o).exists() else None for o in outputs}, p.stdout)
+    res = [once("ref", REF_DIR), once("new", BIN)]
+    if res[0] != res[1]:
+        again = [once("ref", REF_DIR) for _ in range(2)]
+        if again[0] == again[1] and again[0] != res[0]:               # the first reference run was the odd one out
+            print("reference binary disagreed with itself on %s %s: first run discarded" % (tool, " ".join(args)))
+            res[0] = again[0]
     (rca, erra, outa, soa), (rcb, errb, outb, sob) = res
     assert rca == rc, erra
     assert rcb == rc, errb

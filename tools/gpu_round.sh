@@ -10,11 +10,11 @@ date +%s > $OUT/t0
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,temperature.gpu --format=csv > $OUT/smi.txt 2>&1
 
 # 1. A/B (one process per library; fingerprints of the full-size tables must agree with base.so)
-for v in $BASE "$@"; do
+for v in $([ -n "$SKIP_AB" ] || echo $BASE "$@"); do
   UPB_LIB=$PWD/build_exp/$v.so timeout 300 python tools/ab.py c3 ctl c2 > $OUT/ab_$v.jsonl 2> $OUT/ab_$v.err
   echo "ab $v rc=$? t=$(( $(date +%s) - $(cat $OUT/t0) ))" >> $OUT/progress.txt
 done
-python - "$OUT" $BASE "$@" > $OUT/ab_verdict.json <<'PY'
+[ -n "$SKIP_AB" ] || python - "$OUT" $BASE "$@" > $OUT/ab_verdict.json <<'PY'
 import json, sys, os, shutil
 out, base_name, variants = sys.argv[1], sys.argv[2], sys.argv[3:]
 def rd(v):
