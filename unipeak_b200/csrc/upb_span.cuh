@@ -213,32 +213,9 @@ __device__ __forceinline__ double exact_dense_warp (const double* __restrict__ K
 }
 
 // Entries of (strand d, contig c) whose mini-tile overlaps positions [lo, hi] (1-based, inclusive; lo may be <= 0), visited by
-// the 32 lanes with four loads in flight each: f(position, entry).  Entries carry their offset inside a 4096-position span, so
-// the mini-tiles are walked span by span (a piece window touches at most two spans).
-template <class F>
-__device__ __forceinline__ void piece_entries (const Tags& T, uint32_t d, uint32_t c, int64_t lo, int64_t hi, uint32_t lane, F f) {
-  const uint32_t gb = __ldg(T.mtBase + d * T.C + c);
-  const uint32_t nMt = __ldg(T.mtBase + d * T.C + c + 1) - gb;
-  if (nMt == 0 || hi < 1) return;
-  if (lo < 1) lo = 1;
-  const uint32_t ma = (uint32_t)((lo - 1) >> MT_SHIFT);
-  if (ma >= nMt) return;
-  const uint32_t mb = min((uint32_t)((hi - 1) >> MT_SHIFT), nMt - 1);
-  for (uint32_t sp = ma / SPAN_MT; sp <= mb / SPAN_MT; ++sp) {
-    const uint32_t m0 = max(ma, sp * SPAN_MT), m1 = min(mb, sp * SPAN_MT + SPAN_MT - 1);
-    const unsigned long long e0 = __ldg(T.mtOff + gb + m0), e1 = __ldg(T.mtOff + gb + m1 + 1);
-    const uint32_t base = sp * SPAN_LEN + 1;
-    for (unsigned long long eb = e0 + lane; eb - lane < e1; eb += 128) {
-      uint2 en[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) en[q] = (eb + 32 * q < e1) ? __ldg(T.ment + eb + 32 * q) : make_uint2(0u, 0u);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) if (en[q].x) f(base + (en[q].y & (SPAN_LEN - 1)), en[q]);
-    }
-  }
-}
-
-// The same walk with the mini-tile offsets taken from a table the warp loaded once per span: tab[j] = mtOff[gb + min(mBase + j, nMt)]
+// the 32 lanes with four loads in flight each: f(position, entry); a slot beyond the end of the chunk arrives with count 0.
+// Entries carry their offset inside a 4096-position span, so the mini-tiles are walked span by span (a piece window touches at
+// most two spans).  The mini-tile offsets come from a table the warp loaded once per span: tab[j] = mtOff[gb + min(mBase + j, nMt)]
 // for j = 0 .. MO_N - 1 (the span's mini-tiles, HALO_MT of halo on either side, and the end) — no dependent global look-up per piece.
 template <class F>
 __device__ __forceinline__ void piece_entries_tab (const uint2* __restrict__ ment, const unsigned long long* __restrict__ tab, int mBase, uint32_t nMt,
@@ -260,7 +237,7 @@ __device__ __forceinline__ void piece_entries_tab (const uint2* __restrict__ men
 #pragma unroll
       for (int q = 0; q < 4; ++q) en[q] = (k + 32 * q < n) ? __ldg(src + 32 * q) : make_uint2(0u, 0u);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) if (en[q].x) f(base + (en[q].y & (SPAN_LEN - 1)), en[q]);
+      for (int q = 0; q < 4; ++q) f(base + (en[q].y & (SPAN_LEN - 1)), en[q]);   // a slot beyond the end has count 0: f skips it
     }
   }
 }
@@ -314,7 +291,7 @@ __device__ __forceinline__ void piece_entries_async (const uint2* __restrict__ m
       for (int q = 0; q < 4; ++q) en[q] = (eb + 32 * q < e1) ? src[32 * q] : make_uint2(0u, 0u);
       issue(b + STAGE_SLOTS);                                          // refills the slot just read (same lane, same addresses)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) if (en[q].x) f(base + (en[q].y & (SPAN_LEN - 1)), en[q]);
+      for (int q = 0; q < 4; ++q) f(base + (en[q].y & (SPAN_LEN - 1)), en[q]);   // a slot beyond the end has count 0: f skips it
     }
     cp_async_wait<0>();                                                // nothing of this walk is still on its way when the ring is reused
   }
@@ -597,6 +574,7 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : MINB) span_kernel (con
     __syncwarp();
     if ((lane >> 2) == tb) hm[lane & 3] = maskWord;
     if (lane == 0) hm[SPAN_WORDS] = 0;
+    const uint32_t nzWords = (__ballot_sync(0xffffffffu, maskWord != 0) >> (4 * tb)) & ((1u << SPAN_WORDS) - 1);   // which of the span's mask words hold a hot block
     const int mBase = (int)(k * SPAN_MT) - HALO_MT;
     uint32_t nMtS[2] = {0u, 0u};
 #pragma unroll
@@ -615,7 +593,12 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : MINB) span_kernel (con
     while (kb < nBlk) {
       // next maximal group of hot blocks [zs, ze) (uniform scalar code over the mask words)
       { uint32_t m = hm[kb >> 5] >> (kb & 31);
-        if (!m) { kb = ((kb >> 5) + 1) << 5; continue; }
+        if (!m) {                                                      // nothing left in this word: on to the next word that has a hot block
+          const uint32_t w1 = (kb >> 5) + 1, rest = w1 < (uint32_t)SPAN_WORDS ? nzWords >> w1 : 0u;
+          if (!rest) break;
+          kb = (w1 + (uint32_t)__ffs(rest) - 1) << 5;
+          continue;
+        }
         kb += __ffs(m) - 1; }
       const uint32_t zs = kb;
       for (;;) {
@@ -635,7 +618,8 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : MINB) span_kernel (con
         const uint32_t nbEff = (P + 31) >> 5;
 
         auto zeroCells = [&] () {
-          for (uint32_t u = lane; u < W + 2; u += 32) { D[u] = 0; if (NONDIR) DR[u] = 0; }
+          // cells 0 .. W+1, eight bytes per store (D and DR are 8-byte aligned and PIECE_LEN + 2 bw + 4 cells long: W + 3 fits)
+          for (uint32_t u = 2 * lane; u < W + 2; u += 64) { *(uint2*)(D + u) = make_uint2(0u, 0u); if (NONDIR) *(uint2*)(DR + u) = make_uint2(0u, 0u); }
           __syncwarp();
         };
 
@@ -653,7 +637,7 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : MINB) span_kernel (con
               uint32_t* dst = str ? DR : D;
               piece_entries_async(a.T.ment, mo + MO_STRIDE * str, mBase, nMtS[str], lo, hi, lane, (uint2*)stage, zeroed, zeroCells, [&] (uint32_t pos, const uint2& en) {
                 const uint32_t u = pos - cell0;
-                if (u < W && !(a.hasControl && isCtl[en.y >> SPAN_SHIFT])) { atomicAdd(&dst[u], en.x); tot += en.x; }
+                if ((en.x != 0) & (u < W) && !(a.hasControl && isCtl[en.y >> SPAN_SHIFT])) { atomicAdd(&dst[u], en.x); tot += en.x; }
               });
             }
             if (!zeroed) zeroCells();
@@ -666,7 +650,7 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : MINB) span_kernel (con
             uint32_t* dst = str ? DR : D;
             piece_entries_tab(a.T.ment, mo + MO_STRIDE * str, mBase, nMtS[str], lo, hi, lane, [&] (uint32_t pos, const uint2& en) {
               const uint32_t u = pos - cell0;
-              if (u < W && !(a.hasControl && isCtl[en.y >> SPAN_SHIFT])) { atomicAdd(&dst[u], en.x); tot += en.x; }
+              if ((en.x != 0) & (u < W) && !(a.hasControl && isCtl[en.y >> SPAN_SHIFT])) { atomicAdd(&dst[u], en.x); tot += en.x; }
             });
           }
           }
@@ -690,7 +674,7 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : MINB) span_kernel (con
                 double* dst = str ? Wr : Wf;
                 const uint32_t cell0 = q0 - bw;
                 piece_entries_tab(a.T.ment, mo + MO_STRIDE * str, mBase, nMtS[str], (int64_t)q0 - bw, (int64_t)q0 + 32 * nb - 1 + bw, lane, [&] (uint32_t pos, const uint2& en) {
-                  if ((en.y >> SPAN_SHIFT) != sm) return;
+                  if (en.x == 0 || (en.y >> SPAN_SHIFT) != sm) return;
                   const uint32_t u = pos - cell0;
                   if (u < W) dst[u] = __dadd_rn(dst[u], phase ? (double)en.x : __dmul_rn((double)en.x, cf));
                 });
