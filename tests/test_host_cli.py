@@ -132,7 +132,8 @@ def both(tmp_path, tool, args, outputs, rc=0):
 
     The reference binary is not perfectly repeatable: on the B200 box its `regions -D -s 80,90,100,-5 -e 2,4` run once (1 of ~10 runs
     of the suite, r01 v32) wrote a table that differs from what the same binary writes for the same files every other time (sample 1
-    lost half of its tags — it reads something it never initialised).  A mismatch therefore re-runs the reference twice; the
+    lost half of its tags; UBSan flags a read of the never-initialised Alignment::forward at misc/format.cpp:875 on that path, which may
+    or may not be the cause).  A mismatch therefore re-runs the reference twice; the
     comparison stands against a reference output that the reference itself reproduces."""
     def once(which, d):
         cwd = tmp_path / which
