@@ -30,6 +30,9 @@
 #ifndef UPB_EXP_EXACT
 #define UPB_EXP_EXACT 1
 #endif
+#ifndef UPB_EXP_PREFETCH
+#define UPB_EXP_PREFETCH 0                          // span_kernel<directional>: the mini-tile offset tables of a ticket's later spans fetched with cp.async at ticket time, and the
+#endif                                              //   entries of the next span's first hot group prefetched into L2 one span ahead (written after the r01 GPU budget was spent: never run)
 #ifndef UPB_EXP_ASYNC
 #define UPB_EXP_ASYNC 0                             // B1 of span_kernel: entries staged through shared memory with cp.async (0: register loads, v4-v24)
 #endif
@@ -110,7 +113,7 @@ __host__ __device__ inline SpanSmem span_smem_layout (uint32_t bw, uint32_t nSam
   L.oWf = w;   w += coeff ? W * 8 : 0;              // -z: per-position weights are doubles
   L.oWr = w;   w += (coeff && nondir) ? W * 8 : 0;
   w = (w + 15) & ~15u;
-  L.oMo = w;   w += 2 * MO_STRIDE * 8;              // mini-tile offsets of the span + its halo on either side, per strand
+  L.oMo = w;   w += (UPB_EXP_PREFETCH ? 4 : 2) * MO_STRIDE * 8;   // mini-tile offsets of the span + its halo on either side, per strand (UPB_EXP_PREFETCH: per span of a ticket)
   L.oSt = w;   w += 128 * 8;                        // products of 128 taps (exact_dense_warp)
   L.oSc = w;   w += coeff ? PIECE_LEN * 8 : PIECE_LEN * 4;   // oSt + oSc together (>= 3 KB, contiguous) double as the entry staging ring of B1
   L.oMw = w;   w += (PIECE_BLOCKS + 2) * 4;
@@ -563,6 +566,49 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : MINB) span_kernel (con
     uint32_t maskWord = 0;                                            // lane 4t+m holds word m of the t-th span's hot-block mask
     { const uint32_t sp = __shfl_sync(0xffffffffu, item.x, lane >> 2);
       if ((lane >> 2) < nIn) maskWord = __ldg(a.hotMask + (size_t)sp * SPAN_WORDS + (lane & 3)); }
+#if UPB_EXP_PREFETCH
+    static_assert(BATCH == 4, "UPB_EXP_PREFETCH: one offset table per span of a ticket");
+    // offset tables of the ticket's spans 1 .. nIn-1 straight into shared memory (no registers held): by the time span t is
+    // reached its table has long landed, and the entries of its first hot group can be prefetched into L2 a whole span ahead
+    auto tableOf = [&] (uint32_t t, uint32_t& kt, uint32_t& gbT, uint32_t& nMtT) {
+      const SpanUnit Ut = a.units[__shfl_sync(0xffffffffu, item.y, t)];
+      kt = __shfl_sync(0xffffffffu, item.x, t) - Ut.spanStart;
+      gbT = __ldg(a.T.mtBase + Ut.buffer * a.T.C + Ut.contig);
+      nMtT = __ldg(a.T.mtBase + Ut.buffer * a.T.C + Ut.contig + 1) - gbT;
+    };
+    if constexpr (!NONDIR) {
+      __syncwarp();                                                    // the tables of the previous ticket are no longer read
+      for (uint32_t t = 1; t < nIn; ++t) {
+        uint32_t kt, gbT, nMtT;
+        tableOf(t, kt, gbT, nMtT);
+        const int mBaseT = (int)(kt * SPAN_MT) - HALO_MT;
+        if (lane < (uint32_t)MO_N) cp_async8(mo + MO_STRIDE * t + lane, a.T.mtOff + gbT + (uint32_t)min(max(mBaseT + (int)lane, 0), (int)nMtT));
+      }
+      cp_async_commit();
+    }
+    auto prefetchFirstGroup = [&] (uint32_t t) {                       // span t of the ticket (its table is in shared memory): first hot group -> L2
+      const uint32_t wordsT = (__ballot_sync(0xffffffffu, maskWord != 0) >> (4 * t)) & ((1u << SPAN_WORDS) - 1);
+      if (!wordsT) return;
+      const uint32_t w0 = (uint32_t)__ffs(wordsT) - 1;
+      const uint32_t word = __shfl_sync(0xffffffffu, maskWord, 4 * t + w0);
+      const uint32_t b0 = (uint32_t)__ffs(word) - 1;                   // first hot block of that word
+      const uint32_t x = ~(word >> b0);
+      const uint32_t len = min((uint32_t)PIECE_BLOCKS, x ? (uint32_t)__ffs(x) - 1 : 32u - b0);
+      uint32_t kt, gbT, nMtT;
+      tableOf(t, kt, gbT, nMtT);
+      if (nMtT == 0) return;
+      const int mBaseT = (int)(kt * SPAN_MT) - HALO_MT;
+      const int64_t lo = (int64_t)kt * SPAN_LEN + 1 + 32 * (32 * w0 + b0) - bw, hi = lo + 32 * len - 1 + 2 * bw;
+      const uint32_t ma = lo < 1 ? 0u : (uint32_t)((lo - 1) >> MT_SHIFT);
+      const uint32_t mb = min((uint32_t)((hi - 1) >> MT_SHIFT), nMtT - 1);
+      if (ma > mb) return;
+      const unsigned long long* tabT = mo + MO_STRIDE * t;
+      const char* p0 = (const char*)(a.T.ment + tabT[(int)ma - mBaseT]);
+      const char* p1 = (const char*)(a.T.ment + tabT[(int)mb + 1 - mBaseT]);
+      const char* line = (const char*)((unsigned long long)p0 & ~127ull) + 128u * lane;   // up to 32 lines = 512 entries: a piece reads ~470
+      if (line < p1) asm volatile("prefetch.global.L2 [%0];" :: "l"(line));
+    };
+#endif
   for (uint32_t tb = 0; tb < nIn; ++tb) {
     const uint32_t work = __shfl_sync(0xffffffffu, item.x, tb);        // span index
     const SpanUnit U = a.units[__shfl_sync(0xffffffffu, item.y, tb)];
@@ -577,14 +623,26 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : MINB) span_kernel (con
     const uint32_t nzWords = (__ballot_sync(0xffffffffu, maskWord != 0) >> (4 * tb)) & ((1u << SPAN_WORDS) - 1);   // which of the span's mask words hold a hot block
     const int mBase = (int)(k * SPAN_MT) - HALO_MT;
     uint32_t nMtS[2] = {0u, 0u};
+#if UPB_EXP_PREFETCH
+    unsigned long long* const moSpan = NONDIR ? mo : mo + MO_STRIDE * tb;   // this span's table(s)
+#else
+    unsigned long long* const moSpan = mo;
+#endif
 #pragma unroll
     for (int str = 0; str < (NONDIR ? 2 : 1); ++str) {
       const uint32_t d = NONDIR ? (uint32_t)str : U.buffer;
       const uint32_t gb = __ldg(a.T.mtBase + d * a.T.C + U.contig);
       nMtS[str] = __ldg(a.T.mtBase + d * a.T.C + U.contig + 1) - gb;
-      if (lane < (uint32_t)MO_N) mo[MO_STRIDE * str + lane] = __ldg(a.T.mtOff + gb + (uint32_t)min(max(mBase + (int)lane, 0), (int)nMtS[str]));
+      if ((NONDIR || !UPB_EXP_PREFETCH || tb == 0) && lane < (uint32_t)MO_N)
+        moSpan[MO_STRIDE * str + lane] = __ldg(a.T.mtOff + gb + (uint32_t)min(max(mBase + (int)lane, 0), (int)nMtS[str]));
     }
+#if UPB_EXP_PREFETCH
+    if (!NONDIR && tb >= 1) cp_async_wait<0>();                        // issued at ticket time, at least one whole span ago
     __syncwarp();
+    if (!NONDIR && tb >= 1 && tb + 1 < nIn) prefetchFirstGroup(tb + 1);   // (after span 0 its successor's table may still be on its way: see below)
+#else
+    __syncwarp();
+#endif
     ++stSpans;
 
     // ---- B: pieces, in position order -------------------------------------------------------------------------------
@@ -635,7 +693,7 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : MINB) span_kernel (con
 #pragma unroll
             for (int str = 0; str < (NONDIR ? 2 : 1); ++str) {
               uint32_t* dst = str ? DR : D;
-              piece_entries_async(a.T.ment, mo + MO_STRIDE * str, mBase, nMtS[str], lo, hi, lane, (uint2*)stage, zeroed, zeroCells, [&] (uint32_t pos, const uint2& en) {
+              piece_entries_async(a.T.ment, moSpan + MO_STRIDE * str, mBase, nMtS[str], lo, hi, lane, (uint2*)stage, zeroed, zeroCells, [&] (uint32_t pos, const uint2& en) {
                 const uint32_t u = pos - cell0;
                 if ((en.x != 0) & (u < W) && !(a.hasControl && isCtl[en.y >> SPAN_SHIFT])) { atomicAdd(&dst[u], en.x); tot += en.x; }
               });
@@ -648,7 +706,7 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : MINB) span_kernel (con
 #pragma unroll
           for (int str = 0; str < (NONDIR ? 2 : 1); ++str) {
             uint32_t* dst = str ? DR : D;
-            piece_entries_tab(a.T.ment, mo + MO_STRIDE * str, mBase, nMtS[str], lo, hi, lane, [&] (uint32_t pos, const uint2& en) {
+            piece_entries_tab(a.T.ment, moSpan + MO_STRIDE * str, mBase, nMtS[str], lo, hi, lane, [&] (uint32_t pos, const uint2& en) {
               const uint32_t u = pos - cell0;
               if ((en.x != 0) & (u < W) && !(a.hasControl && isCtl[en.y >> SPAN_SHIFT])) { atomicAdd(&dst[u], en.x); tot += en.x; }
             });
@@ -673,7 +731,7 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : MINB) span_kernel (con
               for (int str = 0; str < (NONDIR ? 2 : 1); ++str) {
                 double* dst = str ? Wr : Wf;
                 const uint32_t cell0 = q0 - bw;
-                piece_entries_tab(a.T.ment, mo + MO_STRIDE * str, mBase, nMtS[str], (int64_t)q0 - bw, (int64_t)q0 + 32 * nb - 1 + bw, lane, [&] (uint32_t pos, const uint2& en) {
+                piece_entries_tab(a.T.ment, moSpan + MO_STRIDE * str, mBase, nMtS[str], (int64_t)q0 - bw, (int64_t)q0 + 32 * nb - 1 + bw, lane, [&] (uint32_t pos, const uint2& en) {
                   if (en.x == 0 || (en.y >> SPAN_SHIFT) != sm) return;
                   const uint32_t u = pos - cell0;
                   if (u < W) dst[u] = __dadd_rn(dst[u], phase ? (double)en.x : __dmul_rn((double)en.x, cf));
@@ -846,6 +904,9 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : MINB) span_kernel (con
       }
     }
     if (lane == 0) a.spanRunCount[work] = spanRuns;
+#if UPB_EXP_PREFETCH
+    if (!NONDIR && tb == 0 && nIn > 1) { cp_async_wait<0>(); __syncwarp(); prefetchFirstGroup(1); }   // span 1's table has landed by now
+#endif
   }
   }
   if (rRoom && rUsed + lane < RUN_CHUNK) a.runs[rBase + rUsed + lane].span = RUN_INVALID;
