@@ -291,6 +291,17 @@ def main():
     load, load_alt = (load_packed, load_plain) if args.host_format == "packed" else (load_plain, load_packed)
     h2d_bytes = {"packed": 3 * E + 16 * n_exc + 8 * int(data.off.shape[0]), "plain": 8 * E + 8 * int(data.off.shape[0])}
 
+    # the 2-byte host form (12-bit position delta + 4-bit count per entry: upb_load_tags_packed2) — reported beside the others as
+    # `e2e_packed2`, never as the headline, until its device side has been through the GPU tests (include/unipeak_b200.h)
+    h_w2 = torch.empty(max(E, 1), dtype=torch.int16).pin_memory()
+    _, exc2 = unipeak_b200.pack_tags2(n_samples, len(sizes), data.off, data.pos, data.cnt, out=h_w2.numpy().view(np.uint16))
+    h_exc2 = torch.from_numpy(exc2.view(np.uint8).copy()).pin_memory()
+    n_exc2 = int(exc2.shape[0])
+    h2d_bytes["packed2"] = 2 * E + 16 * n_exc2 + 8 * int(data.off.shape[0])
+
+    def load_packed2():
+        ctx.load_tags_packed2_ptr(n_samples, h_off.data_ptr(), h_w2.data_ptr(), n_exc2, h_exc2.data_ptr())
+
     C = len(sizes)
     gather = None
     if world > 1:
@@ -444,10 +455,23 @@ def main():
                                     "host_cores_available": os.cpu_count(), "rows_match_gpu": bool(same), "rows": len(theirs)}
         if per_rank is not None:
             line["result"]["per_rank_ms"] = per_rank
+        if world == 1:
+            # last of all, so that nothing above depends on it: the 2-byte host form as a side leg (see load_packed2)
+            try:
+                ctx.release_view()
+                p2_ms, p2_wall_ms, res2 = time_e2e(load_packed2)
+                line["e2e_packed2"] = {"host_format": "packed2 (u16 per entry: 12-bit position delta + 4-bit count, exception list; upb_load_tags_packed2)",
+                                       "value": genome / (p2_ms * 1e-3), "unit": "bp/s", "ms_per_step": p2_ms, "wall_ms_per_step": p2_wall_ms,
+                                       "h2d_bytes_per_step": h2d_bytes["packed2"], "rows_equal_headline_leg": bool(int(res2["n_rows"]) == n_rows)}
+            except Exception as e:                                    # noqa: BLE001 — must never take the line down with it
+                line["e2e_packed2"] = {"host_format": "packed2", "error": str(e)[:200]}
         print(json.dumps(line))
     if gather is not None and hasattr(gather, "close"):
         gather.close()
-    ctx.close()
+    try:
+        ctx.close()
+    except Exception:                                                 # noqa: BLE001
+        pass
     if world > 1:
         dist.destroy_process_group()
 

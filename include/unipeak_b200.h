@@ -85,6 +85,14 @@ int upb_load_tags_packed (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off,
                           uint64_t n_exceptions, const upb_packed_exception* exceptions);
 int upb_pack_tags (uint32_t n_samples, uint32_t n_contigs, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt,
                    uint16_t* dpos_out, uint8_t* cnt8_out, upb_packed_exception* exc_out, uint64_t exc_cap, uint64_t* n_exc_out);
+/* The 2-byte form: one u16 per entry, position delta in the low 12 bits (0xFFF = escape), count in the high 4 (0xF = escape);
+ * exceptions as above.  On RNA-seq / ChIP-seq-like data well under 1 % of the entries escape, so the load moves 2.1 instead of
+ * 3 bytes per entry.  Same decoder, same validation.  (Added at the end of round 1: encoder and a numpy decoder are tested on the
+ * CPU, the device side has one GPU test that has not run yet — upb_load_tags_packed stays the default of bench.py until it has.) */
+int upb_load_tags_packed2 (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off, const uint16_t* words,
+                           uint64_t n_exceptions, const upb_packed_exception* exceptions);
+int upb_pack_tags2 (uint32_t n_samples, uint32_t n_contigs, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt,
+                    uint16_t* words_out, upb_packed_exception* exc_out, uint64_t exc_cap, uint64_t* n_exc_out);
 
 /* ---- bin/regions --------------------------------------------------------------------------- */
 /* What src/regions.cpp:104-232 derives from its flags before the hot loop. */

@@ -81,6 +81,7 @@ EXPORTS = [
     "upb_load_tags", "upb_call_regions", "upb_free_region_table", "upb_reference_order", "upb_profile_contig", "upb_free_profile",
     "upb_strand_shift", "upb_free_shift_report", "upb_count_tags_in_regions", "upb_kernel_taps", "upb_last_stats",
     "upb_slab_layout", "upb_scatter_rows", "upb_table_from_slab", "upb_stream", "upb_host_register", "upb_host_unregister", "upb_load_tags_packed", "upb_pack_tags", "upb_aggregate_tags", "upb_free_tag_counts",
+    "upb_load_tags_packed2", "upb_pack_tags2",
     "upb_shift_regions", "upb_free_shift_regions", "upb_shift_examine_order", "upb_shift_sweep", "upb_shift_mode",
 ]
 SLAB_COLS = ("cand_index", "peak_score", "kurtosis", "corr", "contig", "left", "len", "peak", "hit_sum", "counts", "buffer", "end")
@@ -114,6 +115,24 @@ def pack_tags(n_samples: int, n_contigs: int, off, pos, cnt, out=None):
     if rc:
         raise UpbError(rc, "upb_pack_tags failed")
     return dpos, cnt8, exc[:int(n_exc.value)]
+
+
+def pack_tags2(n_samples: int, n_contigs: int, off, pos, cnt, out=None):
+    """upb_pack_tags2: (words u16 = 12-bit position delta | 4-bit count << 12, exceptions) of the plain arrays."""
+    L = lib()
+    off = np.ascontiguousarray(off, dtype=np.uint64)
+    pos = np.ascontiguousarray(pos, dtype=np.uint32)
+    cnt = np.ascontiguousarray(cnt, dtype=np.uint32)
+    E = int(pos.shape[0])
+    n_exc = C.c_uint64(0)
+    L.upb_pack_tags2(n_samples, n_contigs, off.ctypes.data, pos.ctypes.data, cnt.ctypes.data, None, None, 0, C.byref(n_exc))
+    words = out if out is not None else np.empty(max(E, 1), np.uint16)
+    exc = np.zeros(max(int(n_exc.value), 1), dtype=PACKED_EXC_DTYPE)
+    rc = L.upb_pack_tags2(n_samples, n_contigs, off.ctypes.data, pos.ctypes.data, cnt.ctypes.data, words.ctypes.data,
+                          exc.ctypes.data, int(n_exc.value), C.byref(n_exc))
+    if rc:
+        raise UpbError(rc, "upb_pack_tags2 failed")
+    return words, exc[:int(n_exc.value)]
 
 
 def host_register(ptr: int, nbytes: int) -> int:
@@ -168,6 +187,8 @@ def lib():
         L.upb_stream.argtypes = [C.c_void_p]
         L.upb_load_tags_packed.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.upb_pack_tags.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.upb_load_tags_packed2.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.upb_pack_tags2.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.upb_host_register.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
         L.upb_host_unregister.argtypes = [C.c_void_p]
         L.upb_host_unregister.restype = None
@@ -308,6 +329,18 @@ class Context:
         """upb_load_tags_packed from raw host addresses (see pack_tags)."""
         self._check(self._lib.upb_load_tags_packed(self._h, n_samples, C.c_void_p(off_ptr), C.c_void_p(dpos_ptr), C.c_void_p(cnt8_ptr), n_exc, C.c_void_p(exc_ptr)))
         self.n_samples = n_samples
+
+    def load_tags_packed2_ptr(self, n_samples: int, off_ptr: int, words_ptr: int, n_exc: int, exc_ptr: int):
+        """upb_load_tags_packed2 from raw host addresses (see pack_tags2)."""
+        self._check(self._lib.upb_load_tags_packed2(self._h, n_samples, C.c_void_p(off_ptr), C.c_void_p(words_ptr), n_exc, C.c_void_p(exc_ptr)))
+        self.n_samples = n_samples
+
+    def load_packed2(self, data) -> None:
+        """Load a TagData through the 2-byte host form."""
+        self.set_contigs(data.contig_sizes)
+        off = np.ascontiguousarray(data.off, dtype=np.uint64)
+        words, exc = pack_tags2(data.n_samples, self.n_contigs, off, data.pos, data.cnt)
+        self.load_tags_packed2_ptr(data.n_samples, off.ctypes.data, words.ctypes.data, exc.shape[0], exc.ctypes.data)
 
     def load_packed(self, data) -> None:
         """Load a TagData through the compact host form (encode on the host, decode on the device)."""

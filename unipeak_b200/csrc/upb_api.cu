@@ -246,7 +246,7 @@ static int scan_u32 (upb_ctx* ctx, const uint32_t* d_in, uint64_t n, unsigned lo
 // Both load paths: validate the offsets, bring pos[] / cnt[] to the device SAMPLE BY SAMPLE on the copy stream (plain: two
 // copies; packed: the 3-byte form, decoded by upb_pack.cuh) with the validation + histogram pass of the counting sort running
 // one sample behind on the compute stream, then the scan, the scatter pass and the zone maps.
-struct PackedSrc { const uint16_t* dpos; const uint8_t* cnt8; uint64_t nExc; const upb_packed_exception* exc; };
+struct PackedSrc { const uint16_t* dpos; const uint8_t* cnt8; uint64_t nExc; const upb_packed_exception* exc; bool twoByte; };   // twoByte: cnt8 unused
 
 static int load_tags_impl (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt, const PackedSrc* pk) {
   if (!ctx) return UPB_ERR_BAD_ARG;
@@ -273,7 +273,7 @@ static int load_tags_impl (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off
   const uint64_t E = expect;
   segStart[nSeg] = E;
   if (E && !pk && (!pos || !cnt)) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags: pos/cnt are NULL");
-  if (E && pk && (!pk->dpos || !pk->cnt8 || (pk->nExc && !pk->exc))) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags_packed: NULL argument");
+  if (E && pk && (!pk->dpos || (!pk->twoByte && !pk->cnt8) || (pk->nExc && !pk->exc))) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags_packed: NULL argument");
   if (n_samples > (1u << 20)) return fail(ctx, UPB_ERR_UNSUPPORTED, "more than 2^20 samples");
   ctx->loaded = false;
   ctx->nSamples = n_samples;
@@ -313,7 +313,7 @@ static int load_tags_impl (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off
   for (uint32_t s = 0; s < n_samples; ++s) maxChunk = std::max(maxChunk, segStart[(size_t)(s + 1) * 2 * C] - segStart[(size_t)s * 2 * C]);
   if (pk) {
     ENSURE(ctx->d_pk16, (E ? E : 1) * 2);
-    ENSURE(ctx->d_pk8, (E ? E : 1));
+    if (!pk->twoByte) ENSURE(ctx->d_pk8, (E ? E : 1));
     ENSURE(ctx->d_pkExc, (pk->nExc ? pk->nExc : 1) * sizeof(PkException));
     ENSURE(ctx->d_pkAgg, 2 * (maxChunk / PK_TILE + 2) * sizeof(PkAgg));
     ENSURE(ctx->d_segEnds, 2 * ((size_t)nSeg + 1) * 4);
@@ -347,13 +347,14 @@ static int load_tags_impl (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off
       CU(cudaMemcpyAsync(ctx->d_cnt.as<uint32_t>() + first, cnt + first, n * 4, cudaMemcpyHostToDevice, ctx->copyStream));
     } else {
       CU(cudaMemcpyAsync(ctx->d_pk16.as<uint16_t>() + first, pk->dpos + first, n * 2, cudaMemcpyHostToDevice, ctx->copyStream));
-      CU(cudaMemcpyAsync(ctx->d_pk8.as<uint8_t>() + first, pk->cnt8 + first, n, cudaMemcpyHostToDevice, ctx->copyStream));
+      if (!pk->twoByte) CU(cudaMemcpyAsync(ctx->d_pk8.as<uint8_t>() + first, pk->cnt8 + first, n, cudaMemcpyHostToDevice, ctx->copyStream));
     }
     CU(cudaEventRecord(ctx->copyEv, ctx->copyStream));
     CU(cudaStreamWaitEvent(ctx->stream, ctx->copyEv, 0));
     if (pk) {
       PkArgs pa;
-      pa.dpos = ctx->d_pk16.as<uint16_t>(); pa.cnt8 = ctx->d_pk8.as<uint8_t>(); pa.exc = ctx->d_pkExc.as<PkException>(); pa.nExc = pk->nExc;
+      pa.dpos = ctx->d_pk16.as<uint16_t>(); pa.cnt8 = pk->twoByte ? nullptr : ctx->d_pk8.as<uint8_t>(); pa.exc = ctx->d_pkExc.as<PkException>(); pa.nExc = pk->nExc;
+      pa.dposMask = pk->twoByte ? PK2_DPOS_MASK : 0xFFFFu; pa.dposEsc = pk->twoByte ? PK2_DPOS_ESC : PK_DPOS_ESC; pa.cntEsc = pk->twoByte ? PK2_CNT_ESC : PK_CNT_ESC;
       pa.first = first; pa.E = n; pa.pos = ctx->d_pos.as<uint32_t>(); pa.cnt = ctx->d_cnt.as<uint32_t>(); pa.flags = ctx->d_small.as<uint32_t>();
       const uint32_t nTiles = (uint32_t)((n + PK_TILE - 1) / PK_TILE);
       pa.agg = ctx->d_pkAgg.as<PkAgg>(); pa.carry = pa.agg + (maxChunk / PK_TILE + 2);
@@ -386,7 +387,7 @@ static int load_tags_impl (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->cntEffValid = false;
   ctx->tidxBuilt = false;
-  if (flags & FLAG_BAD_PACK) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags_packed: an escape code (0xFFFF / 0xFF) without its exception entry");
+  if (flags & FLAG_BAD_PACK) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags_packed: an escape code without its exception entry");
   if (flags & FLAG_UNSORTED) return fail(ctx, UPB_ERR_UNSORTED, "upb_load_tags: positions must be strictly ascending within each (sample, strand, contig) — the reference asserts on unsorted input (misc/peakcall.cpp:171)");
   if (flags & FLAG_BAD_POS) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags: position outside 1..contig size (the reference's parser drops those, misc/format.cpp:670-676)");
   if (flags & FLAG_ZERO_COUNT) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags: zero count (the reference's parser never delivers those, misc/format.cpp:710)");
@@ -401,13 +402,21 @@ extern "C" int upb_load_tags (upb_ctx* ctx, uint32_t n_samples, const uint64_t* 
 
 extern "C" int upb_load_tags_packed (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off, const uint16_t* dpos, const uint8_t* cnt8,
                                      uint64_t n_exceptions, const upb_packed_exception* exceptions) {
-  PackedSrc pk; pk.dpos = dpos; pk.cnt8 = cnt8; pk.nExc = n_exceptions; pk.exc = exceptions;
+  PackedSrc pk; pk.dpos = dpos; pk.cnt8 = cnt8; pk.nExc = n_exceptions; pk.exc = exceptions; pk.twoByte = false;
+  return load_tags_impl(ctx, n_samples, off, nullptr, nullptr, &pk);
+}
+
+extern "C" int upb_load_tags_packed2 (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off, const uint16_t* words,
+                                      uint64_t n_exceptions, const upb_packed_exception* exceptions) {
+  PackedSrc pk; pk.dpos = words; pk.cnt8 = nullptr; pk.nExc = n_exceptions; pk.exc = exceptions; pk.twoByte = true;
   return load_tags_impl(ctx, n_samples, off, nullptr, nullptr, &pk);
 }
 
 // host-only encoder of the packed form (what a front end does while it parses)
-extern "C" int upb_pack_tags (uint32_t n_samples, uint32_t n_contigs, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt,
-                              uint16_t* dpos_out, uint8_t* cnt8_out, upb_packed_exception* exc_out, uint64_t exc_cap, uint64_t* n_exc_out) {
+// one encoder for both packed forms: dposEsc / cntEsc are the escape codes, cntShift != 0 puts the count into the high bits of the u16
+static int pack_tags_impl (uint32_t n_samples, uint32_t n_contigs, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt,
+                           uint16_t* dpos_out, uint8_t* cnt8_out, upb_packed_exception* exc_out, uint64_t exc_cap, uint64_t* n_exc_out,
+                           uint32_t dposEsc, uint32_t cntEsc, uint32_t cntShift) {
   if (!off || !n_exc_out || (exc_cap && !exc_out)) return UPB_ERR_BAD_ARG;
   uint64_t nExc = 0;
   for (uint32_t sd = 0; sd < n_samples * 2; ++sd)
@@ -416,19 +425,33 @@ extern "C" int upb_pack_tags (uint32_t n_samples, uint32_t n_contigs, const uint
       uint32_t prev = 0;
       for (uint64_t e = a; e < b; ++e) {
         const uint32_t p = pos[e], k = cnt[e];
-        const bool escP = e == a || p < prev || p - prev >= PK_DPOS_ESC;   // unsorted input is kept verbatim: the load then reports it
-        const bool escC = k >= PK_CNT_ESC;
+        const bool escP = e == a || p < prev || p - prev >= dposEsc;   // unsorted input is kept verbatim: the load then reports it
+        const bool escC = k >= cntEsc;
         if (escP || escC) {
           if (nExc < exc_cap) { exc_out[nExc].index = e; exc_out[nExc].pos = escP ? p : 0u; exc_out[nExc].cnt = escC ? k : 0u; }
           ++nExc;
         }
-        if (dpos_out) dpos_out[e] = escP ? (uint16_t)PK_DPOS_ESC : (uint16_t)(p - prev);
-        if (cnt8_out) cnt8_out[e] = escC ? (uint8_t)PK_CNT_ESC : (uint8_t)k;
+        const uint32_t dv = escP ? dposEsc : p - prev, cv = escC ? cntEsc : k;
+        if (cntShift) { if (dpos_out) dpos_out[e] = (uint16_t)(dv | (cv << cntShift)); }
+        else {
+          if (dpos_out) dpos_out[e] = (uint16_t)dv;
+          if (cnt8_out) cnt8_out[e] = (uint8_t)cv;
+        }
         prev = p;
       }
     }
   *n_exc_out = nExc;
   return nExc <= exc_cap ? UPB_OK : UPB_ERR_NOMEM;
+}
+
+extern "C" int upb_pack_tags (uint32_t n_samples, uint32_t n_contigs, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt,
+                              uint16_t* dpos_out, uint8_t* cnt8_out, upb_packed_exception* exc_out, uint64_t exc_cap, uint64_t* n_exc_out) {
+  return pack_tags_impl(n_samples, n_contigs, off, pos, cnt, dpos_out, cnt8_out, exc_out, exc_cap, n_exc_out, PK_DPOS_ESC, PK_CNT_ESC, 0);
+}
+
+extern "C" int upb_pack_tags2 (uint32_t n_samples, uint32_t n_contigs, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt,
+                               uint16_t* words_out, upb_packed_exception* exc_out, uint64_t exc_cap, uint64_t* n_exc_out) {
+  return pack_tags_impl(n_samples, n_contigs, off, pos, cnt, words_out, nullptr, exc_out, exc_cap, n_exc_out, PK2_DPOS_ESC, PK2_CNT_ESC, PK2_CNT_SHIFT);
 }
 
 // ------------------------------------------------------------------------------------------------

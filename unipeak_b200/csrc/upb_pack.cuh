@@ -19,6 +19,8 @@ constexpr int PK_ITEMS = 8;
 constexpr int PK_TILE = PK_THREADS * PK_ITEMS;
 constexpr uint32_t PK_DPOS_ESC = 0xFFFFu;
 constexpr uint32_t PK_CNT_ESC = 0xFFu;
+// the 2-byte form (upb_pack_tags2 / upb_load_tags_packed2): one u16 per entry, position delta in the low 12 bits, count in the high 4
+constexpr uint32_t PK2_DPOS_MASK = 0x0FFFu, PK2_DPOS_ESC = 0x0FFFu, PK2_CNT_SHIFT = 12, PK2_CNT_ESC = 0xFu;
 constexpr uint32_t FLAG_BAD_PACK = 16u;             // an escape without its exception entry
 
 struct PkException { unsigned long long index; uint32_t pos; uint32_t cnt; };   // == upb_packed_exception
@@ -41,7 +43,8 @@ __device__ __forceinline__ const PkException* pk_find (const PkException* __rest
 
 struct PkArgs {
   const uint16_t* dpos;
-  const uint8_t* cnt8;
+  const uint8_t* cnt8;               // NULL: the 2-byte form, the count sits in the high bits of dpos
+  uint32_t dposMask, dposEsc, cntEsc;   // 0xFFFF / 0xFFFF / 0xFF for the 3-byte form
   const PkException* exc;
   unsigned long long nExc;
   unsigned long long first, E;       // entries [first, first + E) are decoded (one sample's chunk when the load is pipelined)
@@ -61,8 +64,8 @@ __device__ __forceinline__ PkAgg pk_thread_scan (const PkArgs& a, unsigned long 
   for (int q = 0; q < PK_ITEMS; ++q) {
     const unsigned long long e = e0 + q;
     if (e < end) {
-      uint32_t v = a.dpos[e], rs = 0;
-      if (v == PK_DPOS_ESC) {
+      uint32_t v = a.dpos[e] & a.dposMask, rs = 0;
+      if (v == a.dposEsc) {
         const PkException* x = pk_find(a.exc, a.nExc, e);
         if (x) { v = x->pos; rs = 1; } else { atomicOr(a.flags, FLAG_BAD_PACK); v = 0; }
       }
@@ -136,8 +139,8 @@ __global__ void __launch_bounds__(PK_THREADS) pk_final_kernel (PkArgs a) {
   for (int q = 0; q < n; ++q) {
     const unsigned long long e = e0 + q;
     a.pos[e] = resets[q] ? vals[q] : excl.sum + vals[q];
-    uint32_t c = a.cnt8[e];
-    if (c == PK_CNT_ESC) {
+    uint32_t c = a.cnt8 ? (uint32_t)a.cnt8[e] : (uint32_t)a.dpos[e] >> PK2_CNT_SHIFT;
+    if (c == a.cntEsc) {
       const PkException* x = pk_find(a.exc, a.nExc, e);
       if (x) c = x->cnt; else { atomicOr(a.flags, FLAG_BAD_PACK); c = 0; }
     }
