@@ -121,6 +121,52 @@ def test_wiggle_reader_errors(tmp_path):
         assert p.stdout.decode().strip() == "error\t" + msg, name
 
 
+def _selftest_wig(cwd, wig, threads, extra=()):
+    env = dict(os.environ, UPB_WIG_THREADS=str(threads))
+    p = subprocess.run([os.path.join(BIN, "host_selftest"), "wig", "c.txt", wig] + list(extra), cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+    assert p.returncode == 0, p.stderr.decode()[-1000:]
+    return p.stdout
+
+
+def test_wiggle_reader_parallel_equals_sequential(tmp_path):
+    """big files are tokenised by several threads and the tokens run through the same state machine; whatever is not
+    plainly fine goes back to the sequential path.  Both must deliver the same arrays, counters, names and error texts — with
+    ranges that cut lines anywhere (UPB_WIG_THREADS forces the number of ranges whatever the file size)."""
+    import gzip
+    d = make_synthetic([300000, 120000, 50000], 2, 20000, directional=True, seed=31, peak_spacing=4000, contig_names=["chrA", "chrB", "chrC"])
+    d.write_contig_table(str(tmp_path / "c.txt"))
+    d.write_wig(str(tmp_path / "a.wig"), 0, "a")
+    text = (tmp_path / "a.wig").read_text()
+    with gzip.open(str(tmp_path / "a.wig.gz"), "wt") as f:
+        f.write(text)
+    lines = text.split("\n")
+    nd = make_synthetic([300000, 120000, 50000], 1, 20000, directional=False, seed=32, peak_spacing=4000, contig_names=["chrA", "chrB", "chrC"])
+    nd.write_wig(str(tmp_path / "n.wig"), 0, "n")
+    variants = {
+        "a.wig": None, "a.wig.gz": None, "n.wig": None,
+        "crlf.wig": text.replace("\n", "\r\n"),                                            # every data line is of another shape: sequential path decides
+        "tabs.wig": "\n".join(l.replace(" ", "\t") if l[:1].isdigit() else l for l in lines),
+        "plus.wig": "\n".join(("+" + l) if (i == 4000 and l[:1].isdigit()) else l for i, l in enumerate(lines)),      # a '+' in front of a position: bad format
+        "order.wig": "\n".join(lines[:5000] + lines[4990:]),                                # positions go backwards: alignments out of order
+        "unknown.wig": text.replace("chrom=chrB", "chrom=chrZ"),                            # a contig that is not in the table: its lines are skipped
+        "noeol.wig": text.rstrip("\n"),
+        "blank.wig": "\n".join(lines[:3] + [""] + lines[3:]),
+        "dup.wig": "\n".join(lines[:10] + lines[9:]),                                       # one position twice: merged
+        "big.wig": "\n".join(lines[:8] + ["4294967295 1", "99999999999 1"] + lines[8:]),
+    }
+    for name, content in variants.items():
+        if content is not None:
+            (tmp_path / name).write_text(content)
+        for extra in ((), ("7", "30")):                                                     # -s 7 and -l 30 move the bounds tests
+            want = _selftest_wig(str(tmp_path), name, 1, extra)
+            for threads in (2, 5, 16):
+                got = _selftest_wig(str(tmp_path), name, threads, extra)
+                assert got == want, (name, extra, threads, want[:300], got[:300])
+    assert _selftest_wig(str(tmp_path), "a.wig", 1).count(b"\n") > 10000
+    assert _selftest_wig(str(tmp_path), "plus.wig", 5).startswith(b"error\tbad format in plus.wig line ")
+    assert _selftest_wig(str(tmp_path), "order.wig", 5).startswith(b"error\talignments out of order in order.wig line ")
+
+
 # ---------------------------------------------------------------------------------------------------------
 # GPU: whole programs against the reference's
 # ---------------------------------------------------------------------------------------------------------

@@ -1,5 +1,6 @@
 // bin/host_selftest — CPU-only checks of the host front end (no device call): the %g formatter against printf, and a dump
 // of what the wiggle reader hands to upb_load_tags, for tests/test_host_cli.py.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -73,6 +74,21 @@ int main (int argc, char** argv) {
         for (size_t i = 0; i < s.pos[d][c].size(); ++i) printf("%d\t%u\t%u\t%u\n", d, c, s.pos[d][c][i], s.cnt[d][c][i]);
     return 0;
   }
-  fprintf(stderr, "usage: host_selftest g6 [n] | wig <contig table> <wig> [offset] [length]\n");
+  if (argc >= 4 && !strcmp(argv[1], "wigtime")) {                  // parse only: seconds, entries, a checksum of what was read
+    const ContigTable contigs = parse_contig_table(argv[2]);
+    Sample s;
+    const auto t0 = std::chrono::steady_clock::now();
+    read_wig(argv[3], contigs, argc > 4 ? atoi(argv[4]) : 0, argc > 5 ? (unsigned)atoi(argv[5]) : 0, &s);
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (!s.error.empty()) { printf("error\t%s\n", s.error.c_str()); return 0; }
+    unsigned long long n = 0, h = 1469598103934665603ull;
+    for (int d = 0; d < 2; ++d)
+      for (uint32_t c = 0; c < contigs.size(); ++c)
+        for (size_t i = 0; i < s.pos[d][c].size(); ++i) { ++n; h = (h ^ s.pos[d][c][i]) * 1099511628211ull; h = (h ^ s.cnt[d][c][i]) * 1099511628211ull; h = (h ^ (unsigned)(d * 131 + c)) * 1099511628211ull; }
+    printf("seconds\t%.4f\nentries\t%llu\nchecksum\t%016llx\ntotal\t%llu\nconfident\t%llu\noob\t%llu\n", dt, n, h, (unsigned long long)s.totalTags,
+           (unsigned long long)s.confidentTags, (unsigned long long)s.outOfBoundsTags);
+    return 0;
+  }
+  fprintf(stderr, "usage: host_selftest g6 [n] | sort | wig <contig table> <wig> [offset] [length] | wigtime <contig table> <wig> [offset] [length]\n");
   return 2;
 }

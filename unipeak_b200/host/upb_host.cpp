@@ -8,6 +8,7 @@
 #include <cerrno>
 #include <climits>
 #include <cmath>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <sstream>
@@ -388,55 +389,96 @@ static std::string line_error (const std::string& msg, const std::string& shown,
   return msg + " in " + shown + " line " + std::to_string(lineNo);
 }
 
-void read_wig (const std::string& fname, const ContigTable& contigs, int offset, unsigned useLength, Sample* out) {
-  Sample& S = *out;
-  S = Sample();
-  S.fname = fname;
-  S.name = fname_prefix(fname);
-  const uint32_t C = contigs.size();
-  for (int d = 0; d < 2; ++d) { S.pos[d].assign(C, std::vector<uint32_t>()); S.cnt[d].assign(C, std::vector<uint32_t>()); }
-  std::vector<char> buf;
-  std::string shown;
-  if (!slurp(fname, &buf, &shown, &S.error)) return;
+namespace {
 
+// The state machine of the wiggle reader: one instance per file, fed line by line (sequential path) or with pre-tokenised data
+// lines (parallel path).  Every rule of the reference's parser that this front end reproduces lives here, once.
+struct WigParser {
+  Sample& S;
+  const ContigTable& contigs;
+  const int offset;
+  const unsigned useLength;
+  const std::string& fname;
+  const std::string& shown;
+  const uint32_t C;
   int format = 0;                   // 0 unknown, 6 directional wiggle, 7 non-directional wiggle
   bool forward = true;
   uint32_t contig = 0;              // ParseAlignStream::open resets the Alignment to contig 0 (misc/format.cpp:122-127)
   bool inHeader = true;             // getExpectedTags only looks at the '#' lines before the first other line
-  uint64_t lineNo = 0;
   long lastKey = -1;                // (strand, contig) blocks must come in stream order
   std::vector<uint32_t>* vp = nullptr;
   std::vector<uint32_t>* vc = nullptr;
-  const char* base = buf.data();
-  size_t p = 0;
-  const size_t N = buf.size();
-  // InStream::good() is still true after the last '\n', so the reference reads one more (empty) line; it changes nothing
-  while (p < N) {
-    const char* nl = (const char*)memchr(base + p, '\n', N - p);
-    const size_t e = nl ? (size_t)(nl - base) : N;
-    const char* s = base + p;
-    const size_t len = e - p;
-    p = e + 1;
-    ++lineNo;
-    if (len == 0) { inHeader = false; continue; }              // an empty line ends getExpectedTags' header scan too
+
+  WigParser (Sample& s, const ContigTable& c, int off, unsigned len, const std::string& f, const std::string& sh)
+    : S(s), contigs(c), offset(off), useLength(len), fname(f), shown(sh), C(c.size()) {}
+
+  bool not_a_wiggle () { S.error = fname + " is not a tag-frequency wiggle file; this build reads only the output of convert_align"; return false; }
+
+  // a data line whose two numbers are already parsed; false: S.error is set
+  bool entry (uint32_t first, uint32_t count, uint64_t lineNo) {
+    S.totalTags += count;
+    if (count == 0) return true;
+    uint32_t last = first;
+    if (useLength != 0) last = forward ? first + (useLength - 1) : first - (useLength - 1);
+    if (offset != 0) {
+      if ((forward && (int)first > -offset) || (!forward && (int)last > offset)) {
+        first += (uint32_t)(forward ? offset : -offset);
+        last += (uint32_t)(forward ? offset : -offset);
+      } else { S.outOfBoundsTags += count; return true; }
+    }
+    const uint32_t size = contigs.sizes[contig];
+    if (first == 0 || first > size || last == 0 || last > size) { S.outOfBoundsTags += count; return true; }
+    S.confidentTags += count;
+    if (!vp) {
+      const long key = (long)(forward ? 0 : 1) * (long)C + contig;
+      if (key <= lastKey) { S.error = "alignments out of order in " + shown + " line " + std::to_string(lineNo) + " (strand/contig blocks must follow the contig table, '+' track first)"; return false; }
+      lastKey = key;
+      vp = &S.pos[forward ? 0 : 1][contig];
+      vc = &S.cnt[forward ? 0 : 1][contig];
+    }
+    if (!vp->empty() && first <= vp->back()) {
+      if (first == vp->back()) { vc->back() += count; return true; }   // the merge loop adds up equal positions (src/regions.cpp:341-350)
+      S.error = line_error("alignments out of order", shown, lineNo);
+      return false;
+    }
+    vp->push_back(first);
+    vc->push_back(count);
+    return true;
+  }
+
+  // a data line as text (it starts with a digit and the format is known)
+  bool data_line (const char* s, size_t len, uint64_t lineNo) {
+    if (contig == C) return true;                                   // contig not in the table: skipped
+    size_t delim = len;
+    while (delim-- > 0) if (s[delim] == '\t' || s[delim] == ' ') break;
+    if (delim == (size_t)-1) { S.error = line_error("bad format", shown, lineNo); return false; }
+    uint32_t first, count;
+    const size_t cs = delim + ((delim + 1 < len && s[delim + 1] == '-') ? 2 : 1);
+    if (!lexical_u32(s, delim, &first) || cs > len || !lexical_u32(s + cs, len - cs, &count)) { S.error = line_error("bad format", shown, lineNo); return false; }
+    return entry(first, count, lineNo);
+  }
+
+  // any line; false: S.error is set and parsing stops
+  bool line (const char* s, size_t len, uint64_t lineNo) {
+    if (len == 0) { inHeader = false; return true; }               // an empty line ends getExpectedTags' header scan too
     if (s[0] == '#') {
       if (inHeader) {
         // TAG_COUNT_REGEX "# tags=(\d+)" anywhere in the line
-        const std::string line(s, len);
+        const std::string ln(s, len);
         size_t q = 0;
-        while ((q = line.find("# tags=", q)) != std::string::npos) {
+        while ((q = ln.find("# tags=", q)) != std::string::npos) {
           size_t k = q + 7;
-          while (k < line.size() && isdigit((unsigned char)line[k])) ++k;
+          while (k < ln.size() && isdigit((unsigned char)ln[k])) ++k;
           if (k > q + 7) {
-            if (S.expectedTags != 0) { S.error = line_error("multiple tag count headers", shown, lineNo); return; }
-            S.expectedTags = strtoull(line.c_str() + q + 7, nullptr, 10);
-            if (S.expectedTags == 0) { S.error = line_error("zero tag count", shown, lineNo); return; }
+            if (S.expectedTags != 0) { S.error = line_error("multiple tag count headers", shown, lineNo); return false; }
+            S.expectedTags = strtoull(ln.c_str() + q + 7, nullptr, 10);
+            if (S.expectedTags == 0) { S.error = line_error("zero tag count", shown, lineNo); return false; }
             break;
           }
           ++q;
         }
       }
-      continue;
+      return true;
     }
     inHeader = false;
     if (format == 0) {
@@ -444,61 +486,21 @@ void read_wig (const std::string& fname, const ContigTable& contigs, int offset,
         std::string nm;
         const bool named = match_name(s, len, "name=\"", '"', &nm) || match_name(s, len, "name=", ' ', &nm);
         if (named) S.name = nm;
-        const std::string line(s, len);
-        if (line.find("type=wiggle_0") == std::string::npos) {
-          S.error = fname + " is not a tag-frequency wiggle file; this build reads only the output of convert_align";
-          return;
-        }
+        const std::string ln(s, len);
+        if (ln.find("type=wiggle_0") == std::string::npos) return not_a_wiggle();
         std::string b;
         bool f;
         if (split_directional(S.name, &b, &f)) { format = 6; S.name = b; forward = f; }
         else { format = 7; S.name = named ? nm : std::string(); forward = true; }
-        continue;
+        return true;
       }
-      S.error = fname + " is not a tag-frequency wiggle file; this build reads only the output of convert_align";
-      return;
+      return not_a_wiggle();
     }
-    if (isdigit((unsigned char)s[0])) {
-      if (contig == C) continue;                                   // contig not in the table: skipped
-      size_t delim = len;
-      while (delim-- > 0) if (s[delim] == '\t' || s[delim] == ' ') break;
-      if (delim == (size_t)-1) { S.error = line_error("bad format", shown, lineNo); return; }
-      uint32_t first, count;
-      const size_t cs = delim + ((delim + 1 < len && s[delim + 1] == '-') ? 2 : 1);
-      if (!lexical_u32(s, delim, &first) || cs > len || !lexical_u32(s + cs, len - cs, &count)) { S.error = line_error("bad format", shown, lineNo); return; }
-      S.totalTags += count;
-      if (count == 0) continue;
-      uint32_t last = first;
-      if (useLength != 0) last = forward ? first + (useLength - 1) : first - (useLength - 1);
-      if (offset != 0) {
-        if ((forward && (int)first > -offset) || (!forward && (int)last > offset)) {
-          first += (uint32_t)(forward ? offset : -offset);
-          last += (uint32_t)(forward ? offset : -offset);
-        } else { S.outOfBoundsTags += count; continue; }
-      }
-      const uint32_t size = contigs.sizes[contig];
-      if (first == 0 || first > size || last == 0 || last > size) { S.outOfBoundsTags += count; continue; }
-      S.confidentTags += count;
-      if (!vp) {
-        const long key = (long)(forward ? 0 : 1) * (long)C + contig;
-        if (key <= lastKey) { S.error = "alignments out of order in " + shown + " line " + std::to_string(lineNo) + " (strand/contig blocks must follow the contig table, '+' track first)"; return; }
-        lastKey = key;
-        vp = &S.pos[forward ? 0 : 1][contig];
-        vc = &S.cnt[forward ? 0 : 1][contig];
-      }
-      if (!vp->empty() && first <= vp->back()) {
-        if (first == vp->back()) { vc->back() += count; continue; }   // the merge loop adds up equal positions (src/regions.cpp:341-350)
-        S.error = line_error("alignments out of order", shown, lineNo);
-        return;
-      }
-      vp->push_back(first);
-      vc->push_back(count);
-      continue;
-    }
+    if (isdigit((unsigned char)s[0])) return data_line(s, len, lineNo);
     if (len > 19 && memcmp(s, "variableStep chrom=", 19) == 0) {
       contig = contigs.find(std::string(s + 19, len - 19));
       vp = vc = nullptr;
-      continue;
+      return true;
     }
     if (len >= 5 && memcmp(s, "track", 5) == 0) {
       std::string nm;
@@ -508,19 +510,143 @@ void read_wig (const std::string& fname, const ContigTable& contigs, int offset,
         if (format == 6) {
           std::string b;
           bool f;
-          if (!split_directional(nm, &b, &f)) { S.error = line_error("strand not defined", shown, lineNo); return; }
+          if (!split_directional(nm, &b, &f)) { S.error = line_error("strand not defined", shown, lineNo); return false; }
           S.name = b;
           forward = f;
         } else {
           S.name = nm;
         }
-        continue;
+        return true;
       }
     }
     S.error = line_error("bad format", shown, lineNo);
-    return;
+    return false;
   }
-  if (S.expectedTags == 0) S.expectedTags = S.confidentTags;       // "count tags the hard way", misc/format.cpp:754-758
+};
+
+void reset_sample (Sample& S, const std::string& fname, uint32_t C) {
+  S = Sample();
+  S.fname = fname;
+  S.name = fname_prefix(fname);
+  for (int d = 0; d < 2; ++d) { S.pos[d].assign(C, std::vector<uint32_t>()); S.cnt[d].assign(C, std::vector<uint32_t>()); }
+}
+
+void parse_sequential (const std::vector<char>& buf, WigParser& P) {
+  const char* base = buf.data();
+  size_t p = 0;
+  const size_t N = buf.size();
+  uint64_t lineNo = 0;
+  // InStream::good() is still true after the last '\n', so the reference reads one more (empty) line; it changes nothing
+  while (p < N) {
+    const char* nl = (const char*)memchr(base + p, '\n', N - p);
+    const size_t e = nl ? (size_t)(nl - base) : N;
+    ++lineNo;
+    if (!P.line(base + p, e - p, lineNo)) return;
+    p = e + 1;
+  }
+}
+
+// Parallel path (at one or two big files the single parsing thread is the longest part of the program): the file is cut
+// into byte ranges, every range is tokenised by its own thread — a line of the canonical shape  digits (blank | tab) [-] digits
+// becomes a (position, count) token, every other line a reference to its text — and the tokens then run through the same state
+// machine in file order.  Anything that is not plainly fine (a data line of another shape, any error of the state machine) makes
+// the caller parse the file again sequentially, so error texts, line numbers and every corner of the sequential path stay what
+// they are.  Returns false when that second pass is needed.
+struct WigToken { uint32_t first, count; };                          // first == 0xFFFFFFFF: count indexes `special`
+struct WigChunk { std::vector<WigToken> tok; std::vector<std::pair<size_t, size_t> > special; bool odd = false; };
+
+void tokenise_range (const char* base, size_t N, size_t lo, size_t hi, WigChunk* out) {
+  size_t p = lo;
+  if (lo != 0) {                                                      // first line that STARTS inside [lo, hi)
+    const char* nl = (const char*)memchr(base + lo - 1, '\n', N - (lo - 1));
+    if (!nl) return;
+    p = (size_t)(nl - base) + 1;
+  }
+  out->tok.reserve((hi - lo) / 9 + 16);
+  while (p < hi && p < N) {
+    const char* s = base + p;
+    const char* nl = (const char*)memchr(s, '\n', N - p);
+    const size_t len = nl ? (size_t)(nl - s) : N - p;
+    p += len + 1;
+    size_t i = 0;
+    uint64_t a = 0, b = 0;
+    while (i < len && (unsigned)(s[i] - '0') <= 9 && i < 10) { a = a * 10 + (unsigned)(s[i] - '0'); ++i; }
+    if (i == 0) {                                                     // not a data line
+      WigToken t; t.first = 0xFFFFFFFFu; t.count = (uint32_t)out->special.size();
+      out->special.push_back(std::make_pair((size_t)(s - base), len));
+      out->tok.push_back(t);
+      continue;
+    }
+    if (i >= len || (s[i] != ' ' && s[i] != '\t') || a > 0xFFFFFFFEull) { out->odd = true; return; }
+    ++i;
+    if (i < len && s[i] == '-') ++i;
+    const size_t d0 = i;
+    while (i < len && (unsigned)(s[i] - '0') <= 9 && i - d0 < 10) { b = b * 10 + (unsigned)(s[i] - '0'); ++i; }
+    if (i == d0 || i != len || b > 0xFFFFFFFFull) { out->odd = true; return; }
+    WigToken t; t.first = (uint32_t)a; t.count = (uint32_t)b;
+    out->tok.push_back(t);
+  }
+}
+
+bool parse_parallel (const std::vector<char>& buf, WigParser& P, unsigned nThreads) {
+  const char* base = buf.data();
+  const size_t N = buf.size();
+  std::vector<WigChunk> chunks(nThreads);
+  std::vector<std::thread> pool;
+  const auto tB = std::chrono::steady_clock::now();
+  for (unsigned t = 0; t < nThreads; ++t)
+    pool.emplace_back(tokenise_range, base, N, N * t / nThreads, N * (t + 1) / nThreads, &chunks[t]);
+  for (std::thread& th : pool) th.join();
+  if (getenv("UPB_WIG_DEBUG")) fprintf(stderr, "[wig] tokenise %.4f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - tB).count());
+  if (getenv("UPB_WIG_DEBUG")) { size_t nt = 0, ns = 0, odd = 0; for (const WigChunk& c : chunks) { nt += c.tok.size(); ns += c.special.size(); odd += c.odd; } fprintf(stderr, "[wig] %u ranges, %zu tokens, %zu special, %zu odd\n", nThreads, nt, ns, odd); }
+  for (const WigChunk& c : chunks) if (c.odd) return false;
+  for (const WigChunk& c : chunks)
+    for (const WigToken& t : c.tok) {
+      if (t.first == 0xFFFFFFFFu) {
+        const std::pair<size_t, size_t>& sp = c.special[t.count];
+        if (!P.line(base + sp.first, sp.second, 0)) return false;
+      } else {
+        // what line() does for a line that starts with a digit, without the text
+        if (P.format == 0) return false;
+        P.inHeader = false;
+        if (P.contig == P.C) continue;
+        if (!P.entry(t.first, t.count, 0)) return false;
+      }
+    }
+  return true;
+}
+
+}  // namespace
+
+static unsigned g_wigBudget = 0;     // threads one file may use (0: the whole machine); read_samples divides the machine among its files
+
+void read_wig (const std::string& fname, const ContigTable& contigs, int offset, unsigned useLength, Sample* out) {
+  Sample& S = *out;
+  const uint32_t C = contigs.size();
+  reset_sample(S, fname, C);
+  std::vector<char> buf;
+  std::string shown;
+  const auto tA = std::chrono::steady_clock::now();
+  if (!slurp(fname, &buf, &shown, &S.error)) return;
+  if (getenv("UPB_WIG_DEBUG")) fprintf(stderr, "[wig] slurp %.4f s, %zu bytes\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - tA).count(), buf.size());
+  unsigned nThreads;
+  if (const char* forced = getenv("UPB_WIG_THREADS")) nThreads = std::max(1, atoi(forced));   // test hook: 1 = always sequential, n = n ranges whatever the size
+  else {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned budget = g_wigBudget ? g_wigBudget : hw;
+    nThreads = buf.size() < (8u << 20) ? 1u : std::min<unsigned>(budget, (unsigned)(buf.size() >> 22));   // at least 4 MB per thread
+  }
+  if (nThreads > 1) {
+    WigParser P(S, contigs, offset, useLength, fname, shown);
+    if (parse_parallel(buf, P, nThreads)) {
+      if (S.expectedTags == 0) S.expectedTags = S.confidentTags;   // "count tags the hard way", misc/format.cpp:754-758
+      return;
+    }
+    reset_sample(S, fname, C);                                       // something was not plainly fine: the sequential path decides
+  }
+  WigParser P(S, contigs, offset, useLength, fname, shown);
+  parse_sequential(buf, P);
+  if (S.error.empty() && S.expectedTags == 0) S.expectedTags = S.confidentTags;
 }
 
 std::vector<Sample> read_samples (const std::vector<std::string>& fnames, const ContigTable& contigs,
@@ -532,6 +658,7 @@ std::vector<Sample> read_samples (const std::vector<std::string>& fnames, const 
   int nStdin = 0;
   for (const std::string& f : fnames) nStdin += f == "stdin";
   if (nStdin) nThreads = 1;
+  g_wigBudget = std::max(1u, std::max(1u, std::thread::hardware_concurrency()) / std::max(1u, nThreads));   // what is left of the machine per file
   std::vector<std::thread> pool;
   for (unsigned t = 0; t < nThreads; ++t)
     pool.emplace_back([&, t] () {
