@@ -14,7 +14,9 @@ gather of the region rows to rank 0.
            bracketed by barrier + synchronize, max over ranks; the wall clock of the same region is reported beside it).
 `e2e`    : the same through the C-ABI from pinned HOST buffers every step: H2D copy + decode + counting sort + zone maps +
            call + table D2H.  Default host form: the compact one (upb_load_tags_packed: u16 position deltas + u8 counts +
-           exception list, 3 B per entry); `e2e_alt` is the plain form (upb_load_tags: u32 + u32, 8 B per entry).
+           exception list, 3 B per entry); `e2e_alt` is the plain form (upb_load_tags: u32 + u32, 8 B per entry); `e2e_packed2`
+           (N = 1 only, measured after everything else, guarded) is the 2-byte form (upb_load_tags_packed2), a side leg until its
+           device path has been through the GPU tests.
 `roofline`: the fused span kernel, algorithmic bytes (8 B per tag entry read once + 40+4n B per candidate written)
            over its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
 `cpu_baseline` / --impl reference: the reference's own Kernel/ProfileBuffer/Region objects
