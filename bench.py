@@ -7,22 +7,27 @@ A step is one pass of the hot path over the resident synthetic input: upb_call_r
 Epanechnikov KDE, thresholding, region extraction, hit/kurtosis(/correlation) filters, regions x samples
 count matrix — ending with the region table in host memory in the reference's emission order.
 N > 1 (torchrun, one process per GPU): contigs are sharded over the ranks (strong scaling: the genome is
-fixed); NCCL carries only the per-sample tag totals (background), the tags-in-regions totals and the
-gather of the region rows to rank 0.
+fixed).  NCCL carries the per-sample tag totals (background) at set-up; inside a step there is no collective:
+every rank's GPU writes its rows straight into ONE host table shared by the ranks after a device-side exchange
+of the per-unit row counts (upb_call_regions_shared).
 
-`value`  : genome bp / step time, inputs already resident in HBM (CUDA events on the library's stream around the K steps,
-           bracketed by barrier + synchronize, max over ranks; the wall clock of the same region is reported beside it).
-`e2e`    : the same through the C-ABI from pinned HOST buffers every step: H2D copy + decode + counting sort + zone maps +
-           call + table D2H.  Default host form: the compact one (upb_load_tags_packed: u16 position deltas + u8 counts +
-           exception list, 3 B per entry); `e2e_alt` is the plain form (upb_load_tags: u32 + u32, 8 B per entry); `e2e_packed2`
-           (N = 1 only, measured after everything else, guarded) is the 2-byte form (upb_load_tags_packed2), a side leg until its
-           device path has been through the GPU tests.
+`value`   : genome bp / step time, inputs already resident in HBM (CUDA events on the library's stream around the K steps,
+            bracketed by barrier + synchronize, max over ranks; the wall clock of the same region is reported beside it).
+`e2e`     : the same through the C-ABI from pinned HOST buffers every step: upb_load_tags_async (H2D copy, decode, counting
+            sort, zone maps — pipelined by (strand, contig range)) + upb_call_regions, which starts on the groups that have
+            arrived; ends with the table on the host.  Host form: the 2-byte one (u16 per entry + exception list), which is
+            what the shipped front ends load; `pack_ms` is what its host-side encoder took (outside the timed region: a
+            front end encodes while it parses).  `e2e_alt` is the plain form (u32 pos + u32 cnt, 8 B per entry).
+`t_hot_cold`: sample-major arrays resident -> index build (tile-major copy + zone maps: the k-way merge's replacement)
+            -> call -> table on the host (SURVEY 8d's t_hot taken literally), with its own bp/s and roofline fraction.
 `roofline`: the fused span kernel, algorithmic bytes (8 B per tag entry read once + 40+4n B per candidate written)
-           over its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
+            over its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs; `kernels` = every stage of the call the
+            same way; `sweep` = the span kernel at bandwidth 10 ... 200 (BASELINE config 5).
 `cpu_baseline` / --impl reference: the reference's own Kernel/ProfileBuffer/Region objects
-           (oracle/_ref/ref_replay, kind "reference") — or the C restatement (kind "port") when the
-           compiled reference is absent — single-threaded like the reference, on a bounded sample
-           (one contig of the same workload, same thresholds).
+            (oracle/_ref/ref_replay, kind "reference") — or the C restatement (kind "port") when the
+            compiled reference is absent — single-threaded like the reference, on a bounded sample
+            (two contigs of the same workload, same thresholds); the whole table is additionally compared with
+            the fingerprints of the reference's own full-size run (tests/golden/fullsize_*.json).
 """
 from __future__ import annotations
 
@@ -62,7 +67,7 @@ def env_int(name, default):
         return default
 
 
-from unipeak_b200.multi import DeviceGather, HostGather, shard_contigs  # noqa: E402
+from unipeak_b200.multi import SharedRegionTable, shard_contigs  # noqa: E402
 
 
 class ClockSampler:
@@ -183,6 +188,32 @@ def run_cpu_reference(sample: TagData, st: dict, steps: int, workdir: str):
     return best, "port", rows
 
 
+def pin_check(view, workload, args, directional):
+    """Compare the whole table with the fingerprints of the reference's own full-size run (tools/pin_fullsize.py)."""
+    if args.samples or args.tags or args.bandwidth != 50 or args.seed != SEEDS.get(workload):
+        return None
+    path = os.path.join(ROOT, "tests", "golden", "fullsize_%s.json" % workload)
+    if not os.path.exists(path):
+        return None
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from pin_fullsize import column_hashes
+    pin = json.load(open(path))["regions"]
+    c = view.columns()
+    keep = np.concatenate([np.nonzero(c["dropped"] == 0)[0], np.nonzero(c["dropped"] != 0)[0]])
+    cols = {k: np.ascontiguousarray(np.asarray(c[k])[keep]) for k in ("forward_label", "contig", "left", "len", "peak", "peak_score", "kurtosis", "corr", "counts")}
+    h = column_hashes(cols)
+    bad = [k for k, v in pin["columns"].items() if h[k] != v and not (k == "corr" and directional)]
+    ok = (not bad and view.n_rows == pin["n_rows"] + pin["n_dropped"] and view.n_rejected == pin["n_rejected"]
+          and [int(x) for x in c["tags_in_regions"]] == pin["tags_in_regions"])
+    return {"identical_to_reference": bool(ok), "columns_checked": sorted(k for k in pin["columns"] if not (k == "corr" and directional)),
+            "rows": pin["n_rows"] + pin["n_dropped"], "differing": bad,
+            "what": "every column of the whole table (SHA-256 of the raw values, doubles as bit patterns) against the compiled reference's own run over this whole workload (tests/golden/fullsize_%s.json)" % workload,
+            "reference_seconds_whole_workload_cpu_container": pin.get("reference_seconds")}
+
+
+SEEDS = {"c3": 20261018, "c2": 20261019, "c1": 20261020, "c4": 20261021, "tiny": 7}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -193,13 +224,11 @@ def main():
     ap.add_argument("--samples", type=int, default=0)
     ap.add_argument("--tags", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--seed", type=int, default=20261018)
+    ap.add_argument("--no-sweep", action="store_true", help="skip roofline.sweep (bandwidth 10 ... 200) and the per-stage kernels[]")
+    ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--bandwidth", type=int, default=50, help="-b (config 5 sweeps 10..200)")
-    ap.add_argument("--host-format", default="packed", choices=["packed", "plain"],
-                    help="host buffers of the e2e leg: the compact form (u16 position deltas + u8 counts + exception list, upb_load_tags_packed) or plain u32 pos / u32 cnt (upb_load_tags); the other one is reported as e2e_alt")
-    ap.add_argument("--gather", default="host", choices=["host", "nccl"],
-                    help="N > 1 region-list gather: every rank writes its rows into one shared, mapped host table (host), or one NCCL reduce of a device slab + D2H on rank 0 (nccl)")
     args = ap.parse_args()
+    args.seed = args.seed or SEEDS[args.workload]
 
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     desc, n_samples, tags_per_sample, directional, sizes, names, mappable = WORKLOADS[args.workload]
@@ -210,24 +239,23 @@ def main():
     config = {"workload": desc if not (args.samples or args.tags) else "%s [overridden: %d samples x %d tags]" % (desc, n_samples, tags_per_sample),
               "samples": n_samples, "tags_per_sample": tags_per_sample, "genome_bp": genome, "bandwidth": args.bandwidth,
               "l2": "inputs (GBs of tag entries) are far larger than the 126 MB L2; no explicit flush",
+              "generator": "unipeak_b200.synth_det (integer hash; bit-identical on CPU and GPU), seed %d" % args.seed,
               "parallelism": "contig-sharded x%d" % world if world > 1 else "single GPU"}
 
     import torch
+    from unipeak_b200.synth_det import make_synthetic_det
     if args.impl == "reference":
         # the reference's own CPU implementation of the path, rank 0 only
         if rank != 0:
             return
         cs = CPU_SAMPLE_CONTIGS[args.workload]
-        if torch.cuda.is_available():
-            from unipeak_b200.synth_gpu import make_synthetic_gpu
-            data = make_synthetic_gpu(sizes, n_samples, tags_per_sample, directional=directional, seed=args.seed, device="cuda:%d" % local_rank, bandwidth=max(50, args.bandwidth))
-        else:
-            from unipeak_b200.synth import make_synthetic
-            data = make_synthetic(sizes, n_samples, tags_per_sample, directional=directional, seed=args.seed, bandwidth=max(50, args.bandwidth))
-        # thresholds come from the whole workload's tag totals, exactly as in our arm
-        st = settings_from_totals([data.tags(s) for s in range(n_samples)], n_samples, directional, mappable, genome, args.bandwidth)
-        sample = cpu_sample(data, cs)
-        del data
+        dev = "cuda:%d" % local_rank if torch.cuda.is_available() else "cpu"
+        # only the sample's contigs are generated (they are exactly those of the whole workload); the thresholds need the whole
+        # workload's tag totals, which the generator gives without the arrays: every tag lands somewhere unless it falls off an edge
+        full = make_synthetic_det(sizes, n_samples, tags_per_sample, directional=directional, seed=args.seed, device=dev, bandwidth=max(50, args.bandwidth))
+        st = settings_from_totals([full.tags(s) for s in range(n_samples)], n_samples, directional, mappable, genome, args.bandwidth)
+        sample = cpu_sample(full, cs)
+        del full
         with tempfile.TemporaryDirectory() as wd:
             if args.warmup:
                 run_cpu_reference(sample, st, 1, wd)
@@ -238,8 +266,9 @@ def main():
                 "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config,
                 "cpu_baseline": {"value": val, "unit": "bp/s", "cores": 1, "kind": kind,
-                                 "sample": "contigs %s (%d bp, %d tag entries) of the workload, all samples, workload-wide thresholds; best of %d runs"
-                                           % ("+".join(names[c] for c in cs), bp, int(sample.pos.shape[0]), max(1, args.steps))},
+                                 "sample": "contigs %s (%d bp = %.1f %% of the genome, %d tag entries) of the workload, all samples, workload-wide thresholds; best of %d runs; "
+                                           "bp/s of this slice stands for the whole workload (EXTRAPOLATED: tag density is uniform across contigs in the synthetic data)"
+                                           % ("+".join(names[c] for c in cs), bp, 100.0 * bp / genome, int(sample.pos.shape[0]), max(1, args.steps))},
                 "e2e": {"value": val, "unit": "bp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -249,7 +278,6 @@ def main():
     # ------------------------------------------------------------------------------------------------
     import torch.distributed as dist
     import unipeak_b200
-    from unipeak_b200.synth_gpu import make_synthetic_gpu
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU path)")
     torch.cuda.set_device(local_rank)
@@ -259,16 +287,16 @@ def main():
 
     owner = shard_contigs(sizes, world)
     mine = [c for c in range(len(sizes)) if owner[c] == rank]
-    data = make_synthetic_gpu(sizes, n_samples, tags_per_sample, directional=directional, seed=args.seed, contigs=mine, device=str(dev), bandwidth=max(50, args.bandwidth))
+    data = make_synthetic_det(sizes, n_samples, tags_per_sample, directional=directional, seed=args.seed, contigs=mine, device=str(dev), bandwidth=max(50, args.bandwidth))
 
-    # pinned host copies (the e2e leg copies from these every step)
+    # pinned host copies (the e2e legs copy from these every step)
     h_off = torch.from_numpy(data.off.view(np.int64)).pin_memory()
     h_pos = torch.from_numpy(data.pos.view(np.int32)).pin_memory()
     h_cnt = torch.from_numpy(data.cnt.view(np.int32)).pin_memory()
     E = int(data.pos.shape[0])
-    import unipeak_b200
+    C = len(sizes)
 
-    # genome-wide tag totals -> background (src/regions.cpp:190-210): the one NCCL all-reduce the path needs up front
+    # genome-wide tag totals -> background (src/regions.cpp:190-210): the one NCCL all-reduce the path needs, at set-up
     tags = torch.tensor([data.tags(s) for s in range(n_samples)], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(tags)
@@ -277,45 +305,37 @@ def main():
     ctx = unipeak_b200.Context(local_rank)
     ctx.set_contigs(sizes)
 
-    # the same data in the compact host form (encoded once, outside every timed region — a front end produces it while parsing)
-    h_dpos = torch.empty(max(E, 1), dtype=torch.int16).pin_memory()
-    h_cnt8 = torch.empty(max(E, 1), dtype=torch.uint8).pin_memory()
-    _, _, exc = unipeak_b200.pack_tags(n_samples, len(sizes), data.off, data.pos, data.cnt, out=(h_dpos.numpy().view(np.uint16), h_cnt8.numpy()))
-    h_exc = torch.from_numpy(exc.view(np.uint8).copy()).pin_memory()
-    n_exc = int(exc.shape[0])
-
-    def load_plain():
-        ctx.load_tags_ptr(n_samples, h_off.data_ptr(), h_pos.data_ptr(), h_cnt.data_ptr())
-
-    def load_packed():
-        ctx.load_tags_packed_ptr(n_samples, h_off.data_ptr(), h_dpos.data_ptr(), h_cnt8.data_ptr(), n_exc, h_exc.data_ptr())
-
-    load, load_alt = (load_packed, load_plain) if args.host_format == "packed" else (load_plain, load_packed)
-    h2d_bytes = {"packed": 3 * E + 16 * n_exc + 8 * int(data.off.shape[0]), "plain": 8 * E + 8 * int(data.off.shape[0])}
-
-    # the 2-byte host form (12-bit position delta + 4-bit count per entry: upb_load_tags_packed2) — reported beside the others as
-    # `e2e_packed2`, never as the headline, until its device side has been through the GPU tests (include/unipeak_b200.h)
+    # the same data in the 2-byte host form; the encoder's time is reported (pack_ms), outside every timed region — a front end
+    # encodes while it parses (bin/regions does: unipeak_b200/host/upb_host.cpp)
     h_w2 = torch.empty(max(E, 1), dtype=torch.int16).pin_memory()
-    _, exc2 = unipeak_b200.pack_tags2(n_samples, len(sizes), data.off, data.pos, data.cnt, out=h_w2.numpy().view(np.uint16))
+    t0 = time.perf_counter()
+    _, exc2 = unipeak_b200.pack_tags2(n_samples, C, data.off, data.pos, data.cnt, out=h_w2.numpy().view(np.uint16))
+    pack_ms = (time.perf_counter() - t0) * 1e3
     h_exc2 = torch.from_numpy(exc2.view(np.uint8).copy()).pin_memory()
     n_exc2 = int(exc2.shape[0])
-    h2d_bytes["packed2"] = 2 * E + 16 * n_exc2 + 8 * int(data.off.shape[0])
+    h2d_bytes = {"packed2": 2 * E + 16 * n_exc2 + 8 * int(data.off.shape[0]), "plain": 8 * E + 8 * int(data.off.shape[0])}
+
+    def load_plain():
+        ctx.load_async_ptr(n_samples, h_off.data_ptr(), pos_ptr=h_pos.data_ptr(), cnt_ptr=h_cnt.data_ptr(), directional_hint=directional)
 
     def load_packed2():
-        ctx.load_tags_packed2_ptr(n_samples, h_off.data_ptr(), h_w2.data_ptr(), n_exc2, h_exc2.data_ptr())
+        ctx.load_async_ptr(n_samples, h_off.data_ptr(), words_ptr=h_w2.data_ptr(), n_exc=n_exc2, exc_ptr=h_exc2.data_ptr(), directional_hint=directional)
 
-    C = len(sizes)
-    gather = None
+    load_packed2()
+    ctx.load_wait()
+    first = ctx.call_regions_view(**dict(st, reference_order=True))       # sizes the context's arrays; its row count sizes the shared table
+    shared = None
     if world > 1:
-        gather = (HostGather if args.gather == "host" else DeviceGather)(ctx, n_samples, C, dist=dist, rank=rank, world=world, device=dev)
-        config["parallelism"] += ", region-list gather: " + ("rows written by every rank into one shared mapped host table, two small NCCL all-reduces" if args.gather == "host" else "one NCCL reduce of a device slab + D2H on rank 0")
+        rows = torch.tensor([first.n_rows], dtype=torch.int64, device=dev)
+        dist.all_reduce(rows)
+        ctx.release_view()
+        shared = SharedRegionTable(ctx, n_samples, C, rank=rank, world=world, row_capacity=int(rows.item()) * 3 // 2 + 4096, dist=dist)
+        config["parallelism"] += ", region-list gather: every rank's GPU writes its rows into one shared mapped host table after a device-side exchange of the per-unit row counts; no collective inside a step"
 
     def step():
-        res = ctx.call_regions_view(**dict(st, reference_order=(1 if world == 1 else 2)))   # ranks of a multi-GPU job keep their rows on the device
         if world == 1:
-            return res
-        # NCCL: one small all-reduce (rows / candidates per unit, tags in regions) + one reduce of the table-wide slab to rank 0
-        return gather(res)
+            return ctx.call_regions_view(**dict(st, reference_order=True))
+        return shared(**dict(st, reference_order=True))
 
     def barrier():
         if world > 1:
@@ -328,13 +348,10 @@ def main():
     lib_stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=dev)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    load()
     for _ in range(args.warmup):
         last = step()
     kde_ms, launches = [], 0
     barrier()
-    if gather is not None:
-        gather.times = [0.0, 0.0, 0.0, 0]                             # per-phase host clocks of the timed steps only
     call_ms = []
     try:
         gpu_uuid = torch.cuda.get_device_properties(dev).uuid
@@ -346,14 +363,11 @@ def main():
         for _ in range(args.steps):
             last = step()
             s = ctx.stats()
-            kde_ms.append(s["ms_kde"]); launches += s["launches"] + (2 if world > 1 else 0); call_ms.append(s["ms_call"])   # + the two scatter kernels of the gather
-        if world > 1:
-            lib_stream.wait_stream(torch.cuda.current_stream())      # the NCCL gather of the last step runs on torch's stream
+            kde_ms.append(s["ms_kde"]); launches += s["launches"]; call_ms.append(s["ms_call"])
         ev1.record(lib_stream)
         barrier()
         dt_wall = time.perf_counter() - t0
     stats = ctx.stats()
-    gather_times = list(gather.times) if gather is not None and getattr(gather, "times", None) else [0.0, 0.0, 0.0, 1]
     ev1.synchronize()
     dt = ev0.elapsed_time(ev1) * 1e-3
     tmax = torch.tensor([dt, dt_wall], dtype=torch.float64, device=dev)
@@ -362,34 +376,48 @@ def main():
     dt, dt_wall = float(tmax[0].item()), float(tmax[1].item())
     ms_per_step = dt / args.steps * 1e3
     wall_ms_per_step = dt_wall / args.steps * 1e3
+    n_rows = int(last.n_rows) if rank == 0 else 0
+    pin = pin_check(last, args.workload, args, directional) if rank == 0 else None
 
-    # e2e: pinned host arrays -> device every step (same two clocks); once per host format
-    e2e_steps = max(1, min(args.steps, 3))
-
-    def time_e2e(loader):
-        loader(); step()                                             # untimed: buffers of this path reach their size
+    def timed(fn, reps):
+        """reps x fn() between two events on the library's stream; (device ms, wall ms) per repetition, max over ranks."""
         barrier()
         t0 = time.perf_counter()
         ev0.record(lib_stream)
-        for _ in range(e2e_steps):
-            loader()
-            res = step()
-        if world > 1:
-            lib_stream.wait_stream(torch.cuda.current_stream())
+        for _ in range(reps):
+            res = fn()
         ev1.record(lib_stream)
         barrier()
         wall = time.perf_counter() - t0
         ev1.synchronize()
-        e2e = torch.tensor([ev0.elapsed_time(ev1) * 1e-3, wall], dtype=torch.float64, device=dev)
+        t = torch.tensor([ev0.elapsed_time(ev1) * 1e-3, wall], dtype=torch.float64, device=dev)
         if world > 1:
-            dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
-        return float(e2e[0].item()) / e2e_steps * 1e3, float(e2e[1].item()) / e2e_steps * 1e3, res
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0].item()) / reps * 1e3, float(t[1].item()) / reps * 1e3, res
 
-    alt_ms, alt_wall_ms, _ = time_e2e(load_alt)
-    e2e_ms, e2e_wall_ms, last = time_e2e(load)
-    alt_format = "plain" if args.host_format == "packed" else "packed"
-    n_rows = int(last["n_rows"]) if last else 0
+    # e2e: pinned host arrays -> device every step; the call starts on the load groups that have arrived
+    e2e_steps = max(1, min(args.steps, 5))
+
+    def e2e_leg(loader):
+        def one():
+            loader()
+            return step()
+        one()                                                        # untimed: buffers of this path reach their size
+        return timed(one, e2e_steps)
+
+    alt_ms, alt_wall_ms, _ = e2e_leg(load_plain)
+    e2e_ms, e2e_wall_ms, last = e2e_leg(load_packed2)
+    e2e_rows = int(last.n_rows) if rank == 0 else 0
     d2h = n_rows * (41 + 4 * n_samples)
+
+    # t_hot_cold: from sample-major arrays resident in HBM (SURVEY 8d's "sorted arrays resident") to the table on the host: the
+    # index build (tile-major counting sort + both zone maps — the device-side replacement of the reference's k-way merge, row a3)
+    # is inside
+    def cold():
+        ctx.reindex()
+        return step()
+    cold()
+    cold_ms, cold_wall_ms, _ = timed(cold, e2e_steps)
 
     # roofline of the fused KDE kernel (rank-local numbers; every rank runs the same kernel on its shard)
     peaks = {}
@@ -399,6 +427,7 @@ def main():
         pass
     peak_gbs, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
     traffic = None
+    tj = {}
     try:    # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on this workload (profiles/)
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         key = "%s_bw%d" % (args.workload, args.bandwidth)
@@ -407,69 +436,111 @@ def main():
     except Exception:
         pass
     kde_avg_ms = float(np.mean(kde_ms)) if kde_ms else float("nan")
-    n_runs_bytes = (40 + 4 * n_samples) * stats["n_candidates"]     # run record + kurtosis + per-sample hits
-    alg_bytes = 8 * E + n_runs_bytes
+    n_cand = stats["n_candidates"]
+    alg_bytes = 8 * E + (40 + 4 * n_samples) * n_cand                # every entry read once + run record, kurtosis, per-sample hits per candidate
     achieved = alg_bytes / (kde_avg_ms * 1e-3) / 1e9 if kde_avg_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "span_kernel<directional>" if directional else "span_kernel<nondirectional>", "achieved": achieved, "peak": peak_gbs,
                 "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
+                "traffic_source": tj.get("_source") if traffic else None,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kde_avg_ms, "kernel_share_of_step": kde_avg_ms / ms_per_step}
 
-    # where the step goes on every rank (host clocks of the last call and of the gather phases, averaged over the gather's calls)
+    # every stage of the call the same way (CUDA events between the stages, upb_set_profiling; separate steps, not the timed ones)
+    kernels, sweep = None, None
+    if world == 1 and not args.no_sweep:
+        ctx.set_profiling(True)
+        acc = {}
+        for _ in range(5):
+            step()
+            for name, ms in ctx.stage_times():
+                acc.setdefault(name, []).append(ms)
+        ctx.set_profiling(False)
+        R1 = max(n_rows, 1)
+        # algorithmic bytes per stage: zone maps for the two prefilters, the entries for the span kernel, the entries
+        # of the accepted candidates' mini-tiles for the pooling, pooled cells for the moments, rows for the emit
+        stage_bytes = {
+            "warm_span_kernel+hot_span_kernel": 8 * 2 * (genome >> 9) + 4 * stats["warm_spans"] * 160,
+            "span_kernel": alg_bytes,
+            "order+stitch+hit filter": 32 * n_cand * 4,
+            "region_pool_kernel": None,
+            "region_moment_kernel": None,
+            "place+emit rows (to host)+totals": R1 * (41 + 4 * n_samples),
+        }
+        kernels = []
+        for name, v in acc.items():
+            ms = float(np.mean(v))
+            b = stage_bytes.get(name)
+            kernels.append({"name": name, "ms": ms, "algorithmic_bytes": b, "frac": (b / (ms * 1e-3) / 1e9 / peak_gbs) if (b and ms > 0) else None})
+        if args.workload in ("c3", "tiny") and not (args.samples or args.tags):
+            sweep = []
+            for bw in (10, 20, 50, 100, 150, 200):
+                stb = dict(st, bandwidth=bw, reference_order=True)
+                ctx.call_regions_view(**stb)
+                ms_l = []
+                for _ in range(5):
+                    ctx.call_regions_view(**stb)
+                    s5 = ctx.stats()
+                    ms_l.append(s5["ms_kde"])
+                ab = 8 * E + (40 + 4 * n_samples) * s5["n_candidates"]
+                m = float(np.mean(ms_l))
+                sweep.append({"bandwidth": bw, "kernel_ms": m, "achieved": ab / (m * 1e-3) / 1e9, "frac": ab / (m * 1e-3) / 1e9 / peak_gbs, "candidates": s5["n_candidates"], "call_ms": s5["ms_call"]})
+            ctx.call_regions_view(**dict(st, reference_order=True))
+        roofline["sweep"] = sweep
+
     per_rank = None
     if world > 1:
-        gt = gather_times
-        k = max(1, gt[3])
-        mine = torch.tensor([float(np.mean(call_ms)) if call_ms else 0.0, stats["ms_total"], gt[0] / k * 1e3, gt[1] / k * 1e3, gt[2] / k * 1e3, float(E)], dtype=torch.float64, device=dev)
-        allr = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(allr, mine)
-        per_rank = {"columns": ["call_ms", "device_ms", "allreduce_counts_ms", "scatter_ms", "completion_ms", "tag_entries"],
+        minev = torch.tensor([float(np.mean(call_ms)) if call_ms else 0.0, stats["ms_total"], float(np.mean(kde_ms)) if kde_ms else 0.0, float(E)], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(minev) for _ in range(world)]
+        dist.all_gather(allr, minev)
+        per_rank = {"columns": ["call_ms", "device_ms", "span_kernel_ms", "tag_entries"],
                     "rows": [[round(float(x), 4) for x in t.cpu().tolist()] for t in allr]}
 
     if rank == 0:
+        cold_bytes = alg_bytes + 16 * E + 12 * 2 * (genome >> 9) + 4 * 2 * (genome >> 5)   # + sort: 8E read + 8E written, + both zone maps written
         line = {"metric": metric, "value": genome / (ms_per_step * 1e-3), "unit": "bp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "wall_ms_per_step": wall_ms_per_step, "timing": "CUDA events on the library's stream around the K steps (max over ranks); wall clock alongside",
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config, "clocks": clocks.summary(),
-                "e2e": {"value": genome / (e2e_ms * 1e-3), "unit": "bp/s", "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall_ms, "h2d_bytes_per_step": h2d_bytes[args.host_format], "d2h_bytes_per_step": d2h,
-                        "host_format": args.host_format + (" (u16 position deltas + u8 counts + exception list, decoded on the device: upb_load_tags_packed)" if args.host_format == "packed" else " (u32 pos + u32 cnt: upb_load_tags)")},
-                "e2e_alt": {"host_format": alt_format, "value": genome / (alt_ms * 1e-3), "unit": "bp/s", "ms_per_step": alt_ms, "wall_ms_per_step": alt_wall_ms, "h2d_bytes_per_step": h2d_bytes[alt_format]},
-                "gpu_launches": launches, "roofline": roofline,
-                "result": {"regions": n_rows, "candidates": stats["n_candidates"], "tag_entries_rank0": E, "spans": stats["kde_tiles"], "warm_spans": stats["warm_spans"], "pieces": stats["kde_hot_tiles"],
+                "e2e": {"value": genome / (e2e_ms * 1e-3), "unit": "bp/s", "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall_ms, "h2d_bytes_per_step": h2d_bytes["packed2"], "d2h_bytes_per_step": d2h,
+                        "host_format": "packed2 (u16 per entry: 12-bit position delta + 4-bit count, exception list; upb_load_tags_async — what bin/regions loads)",
+                        "pack_ms": pack_ms, "pack_note": "host-side encoder (upb_pack_tags2, one thread, from the plain arrays), outside the timed region: a front end encodes while it parses",
+                        "rows_equal_resident_leg": bool(e2e_rows == n_rows)},
+                "e2e_alt": {"host_format": "plain (u32 pos + u32 cnt: upb_load_tags_async)", "value": genome / (alt_ms * 1e-3), "unit": "bp/s", "ms_per_step": alt_ms, "wall_ms_per_step": alt_wall_ms, "h2d_bytes_per_step": h2d_bytes["plain"]},
+                "t_hot_cold": {"value": genome / (cold_ms * 1e-3), "unit": "bp/s", "ms_per_step": cold_ms, "wall_ms_per_step": cold_wall_ms,
+                               "what": "sample-major pos/cnt resident in HBM -> upb_reindex (tile-major counting sort + zone maps) -> upb_call_regions -> table on the host",
+                               "algorithmic_bytes": cold_bytes, "roofline_frac": cold_bytes / (cold_ms * 1e-3) / 1e9 / peak_gbs / world},
+                "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
+                "hot_path_roofline_frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak_gbs,
+                "result": {"regions": n_rows, "candidates": n_cand, "tag_entries_rank0": E, "spans": stats["kde_tiles"], "warm_spans": stats["warm_spans"], "pieces": stats["kde_hot_tiles"],
                            "hot_blocks": stats["hot_blocks"], "exact_evals": stats["exact_evals"], "stitched": stats["n_stitched"],
-                           "device_ms_per_step_rank0": stats["ms_total"], "call_ms_rank0": stats["ms_call"]}}
+                           "device_ms_per_step_rank0": stats["ms_total"], "call_ms_rank0": stats["ms_call"], "launches_per_call": stats["launches"]}}
+        if pin is not None:
+            line["parity_full_size"] = pin
         if world == 1 and not args.no_cpu:
             cs = CPU_SAMPLE_CONTIGS[args.workload]
             sample = cpu_sample(data, cs)
             with tempfile.TemporaryDirectory() as wd:
                 secs, kind, ref = run_cpu_reference(sample, st, 1, wd)
             bp = int(sum(sizes[c] for c in cs))
-            # parity spot-check on the sample: every region the CPU side finds on these contigs must equal ours
+            # parity spot-check on the sample: every region the CPU side finds on these contigs must equal ours, doubles bit for bit
             ctx.release_view()
             full = ctx.call_regions(**dict(st, reference_order=True, rows=True))
             ours = [r for r in full["rows"] + full["dropped"] if r["contig"] in cs]
             theirs = ref["rows"] + ref["dropped"]
-            key_o = lambda r: (cs.index(r["contig"]), r["left"], r["len"], r["peak"], tuple(r["counts"]), r["kurtosis"])
-            key_t = lambda r: (r["contig"], r["left"], r["len"], r["peak"], tuple(r["counts"]), r["kurtosis"])
+            bits = lambda x: np.float64(x).view(np.uint64).item() if x == x else -1
+            key_o = lambda r: (cs.index(r["contig"]), r["left"], r["len"], r["peak"], tuple(r["counts"]), bits(r["kurtosis"]), bits(r["peak_score"]))
+            key_t = lambda r: (r["contig"], r["left"], r["len"], r["peak"], tuple(r["counts"]), bits(r["kurtosis"]), bits(r["peak_score"]))
             same = sorted(key_o(r) for r in ours) == sorted(key_t(r) for r in theirs)
             line["cpu_baseline"] = {"value": bp / secs, "unit": "bp/s", "cores": 1, "kind": kind, "seconds": secs,
-                                    "sample": "contigs %s (%d bp, %d tag entries) of the workload, all samples, workload-wide thresholds"
-                                              % ("+".join(names[c] for c in cs), bp, int(sample.pos.shape[0])),
-                                    "host_cores_available": os.cpu_count(), "rows_match_gpu": bool(same), "rows": len(theirs)}
+                                    "sample": "contigs %s (%d bp = %.1f %% of the genome, %d tag entries) of the workload, all samples, workload-wide thresholds; bp/s of this slice stands for the whole workload (EXTRAPOLATED)"
+                                              % ("+".join(names[c] for c in cs), bp, 100.0 * bp / genome, int(sample.pos.shape[0])),
+                                    "host_cores_available": os.cpu_count(), "rows_match_gpu": bool(same), "rows": len(theirs),
+                                    "rows_key": "contig, left, len, peak, counts[], kurtosis bits, peak_score bits"}
         if per_rank is not None:
             line["result"]["per_rank_ms"] = per_rank
-        if world == 1:
-            # last of all, so that nothing above depends on it: the 2-byte host form as a side leg (see load_packed2)
-            try:
-                ctx.release_view()
-                p2_ms, p2_wall_ms, res2 = time_e2e(load_packed2)
-                line["e2e_packed2"] = {"host_format": "packed2 (u16 per entry: 12-bit position delta + 4-bit count, exception list; upb_load_tags_packed2)",
-                                       "value": genome / (p2_ms * 1e-3), "unit": "bp/s", "ms_per_step": p2_ms, "wall_ms_per_step": p2_wall_ms,
-                                       "h2d_bytes_per_step": h2d_bytes["packed2"], "rows_equal_headline_leg": bool(int(res2["n_rows"]) == n_rows)}
-            except Exception as e:                                    # noqa: BLE001 — must never take the line down with it
-                line["e2e_packed2"] = {"host_format": "packed2", "error": str(e)[:200]}
         print(json.dumps(line))
-    if gather is not None and hasattr(gather, "close"):
-        gather.close()
+    if shared is not None:
+        barrier()
+        shared.close()
     try:
         ctx.close()
     except Exception:                                                 # noqa: BLE001

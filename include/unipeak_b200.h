@@ -54,9 +54,8 @@ int upb_device_count (void);
 /* pinned host memory for the arrays handed to upb_load_tags (optional; any host memory works) */
 int upb_host_alloc (void** out, size_t bytes);
 void upb_host_free (void* p);
-/* page-lock and map host memory the caller owns — e.g. a POSIX shared-memory segment shared by the ranks of a multi-GPU job, so that
- * every rank's upb_scatter_rows writes its rows straight into ONE host table (the destination of the region-list gather);
- * *device_ptr is the address to hand to upb_scatter_rows */
+/* page-lock and map host memory the caller owns — e.g. a POSIX shared-memory segment shared by the ranks of a multi-GPU job
+ * (upb_shared_table); *device_ptr is its device address */
 int upb_host_register (void* p, size_t bytes, void** device_ptr);
 void upb_host_unregister (void* p);
 
@@ -74,25 +73,49 @@ int upb_set_contigs (upb_ctx* ctx, uint32_t n_contigs, const uint32_t* sizes);
  * A rank of a multi-GPU job loads only the contigs it owns (empty segments elsewhere). */
 int upb_load_tags (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt);
 
-/* The same tag streams in the compact host form (3 bytes per entry instead of 8 — the load is PCIe-bound): dpos[e] = position
- * minus the previous position of the same (sample, strand, contig) segment, cnt8[e] = count; 0xFFFF / 0xFF are escapes whose
- * absolute position / full count sit in `exceptions` (sorted by entry index; pos or cnt is 0 where that field is not escaped).
- * The FIRST entry of every segment must be a position escape.  Decoded on the device (segmented scan), validated exactly as
- * upb_load_tags validates.  upb_pack_tags is the host-only encoder a front end runs while it parses (pass exc_cap = 0 to
- * count the exceptions first; returns UPB_ERR_NOMEM with *n_exc_out set when exc_cap is too small). */
+/* The same tag streams in the compact host form (2 bytes per entry instead of 8 — the load is PCIe-bound): one u16 per entry,
+ * words[e] = (position minus the previous position of the same (sample, strand, contig) segment) in the low 12 bits | count << 12;
+ * 0xFFF / 0xF are escapes whose absolute position / full count sit in `exceptions` (sorted by entry index; pos or cnt is 0 where
+ * that field is not escaped).  The first entry of every segment, and every 2048th entry after it, MUST be a position escape, so
+ * that a tile of 2048 entries decodes on its own.  Decoded on the device, validated exactly as upb_load_tags validates (plus: every
+ * escape has its exception, every tile starts with one).  On RNA-seq / ChIP-seq-like data well under 1 % of the entries escape
+ * (2.1 bytes per entry); sparse tracks (mean gap > 4095) are better off plain — upb_pack_tags2 reports the exception count, so a
+ * front end can choose (2 E + 16 n_exc against 8 E).  upb_pack_tags2 is the host-only encoder a front end runs while it parses (pass
+ * exc_cap = 0 to count the exceptions first; returns UPB_ERR_NOMEM with *n_exc_out set when exc_cap is too small). */
 typedef struct { uint64_t index; uint32_t pos; uint32_t cnt; } upb_packed_exception;
-int upb_load_tags_packed (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off, const uint16_t* dpos, const uint8_t* cnt8,
-                          uint64_t n_exceptions, const upb_packed_exception* exceptions);
-int upb_pack_tags (uint32_t n_samples, uint32_t n_contigs, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt,
-                   uint16_t* dpos_out, uint8_t* cnt8_out, upb_packed_exception* exc_out, uint64_t exc_cap, uint64_t* n_exc_out);
-/* The 2-byte form: one u16 per entry, position delta in the low 12 bits (0xFFF = escape), count in the high 4 (0xF = escape);
- * exceptions as above.  On RNA-seq / ChIP-seq-like data well under 1 % of the entries escape, so the load moves 2.1 instead of
- * 3 bytes per entry.  Same decoder, same validation.  (Added at the end of round 1: encoder and a numpy decoder are tested on the
- * CPU, the device side has one GPU test that has not run yet — upb_load_tags_packed stays the default of bench.py until it has.) */
 int upb_load_tags_packed2 (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off, const uint16_t* words,
                            uint64_t n_exceptions, const upb_packed_exception* exceptions);
 int upb_pack_tags2 (uint32_t n_samples, uint32_t n_contigs, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt,
                     uint16_t* words_out, upb_packed_exception* exc_out, uint64_t exc_cap, uint64_t* n_exc_out);
+
+/* The general, asynchronous form of the two loads above.  The transfer is cut into groups — (strand, range of contigs) — and
+ * pipelined: while a group's bytes cross PCIe the previous group is decoded, validated and indexed; upb_load_tags_async returns as
+ * soon as everything is queued, and a upb_call_regions that follows starts calling regions on the groups that have arrived while
+ * the rest is still on its way (the reference overlaps nothing: src/regions.cpp:195-199 parses, then :309-391 computes).
+ * The host arrays must stay valid (and, to overlap at all, page-locked) until upb_load_wait or the next call that uses the data
+ * returns; what the synchronous loads report at once (unsorted / out-of-range input, a malformed packed form) is reported there.
+ *   pos/cnt     plain form, or NULL
+ *   words ...   2-byte form, or NULL
+ *   keep_contig [n_contigs] 1 = load this contig's segments, 0 = leave them out (a rank of a multi-GPU job keeps the contigs it
+ *               owns: the arrays describe all contigs, only the kept ones travel); NULL = all
+ *   directional_hint  order of the groups: 1 = strand-major, the order a directional upb_call_regions works through them;
+ *               0 = contig-major (both strands of a contig range together: -D, strand_shift).  Only the overlap depends on it. */
+typedef struct {
+  uint32_t n_samples;
+  const uint64_t* off;
+  const uint32_t* pos;
+  const uint32_t* cnt;
+  const uint16_t* words;
+  uint64_t n_exceptions;
+  const upb_packed_exception* exceptions;
+  const uint8_t* keep_contig;
+  int directional_hint;
+} upb_tag_source;
+int upb_load_tags_async (upb_ctx* ctx, const upb_tag_source* src);
+int upb_load_wait (upb_ctx* ctx);
+/* Rebuild the region-calling index (tile-major copy + zone maps: the device-side replacement of the k-way merge of
+ * src/regions.cpp:335-354) from the sample-major arrays already resident — what a cold call pays on top of upb_call_regions. */
+int upb_reindex (upb_ctx* ctx);
 
 /* ---- bin/regions --------------------------------------------------------------------------- */
 /* What src/regions.cpp:104-232 derives from its flags before the hot loop. */
@@ -109,10 +132,7 @@ typedef struct {
   double background;            /* tags per mappable position, halved if directional (src/regions.cpp:209-210) */
   int reference_order;          /* 1: rows come back in the reference's emission order with its labels and its
                                    dropped tail; needs every contig loaded in this context.
-                                   0: canonical order (buffer, contig, left), nothing dropped.
-                                   2: as 0, but the rows stay in device memory only — for a rank of a multi-GPU job that hands them
-                                      to upb_scatter_rows; n_rows, the totals and the unit_* arrays of the returned table are valid,
-                                      the per-row columns are not filled. */
+                                   0: canonical order (buffer, contig, left), nothing dropped. */
 } upb_region_params;
 
 /* One row per accepted region == one Region the reference pushes into regionsOut (misc/peakcall.cpp:45)
@@ -157,22 +177,27 @@ int upb_reference_order (uint32_t n_contigs, uint32_t n_samples, int directional
                          const uint32_t* first_pos, const uint32_t* last_pos,
                          upb_region_table* t, uint64_t* perm_out);
 
-/* ---- several GPUs: one table out of the ranks' tables ---------------------------------------- */
-/* Every rank calls upb_call_regions on the contigs it loaded (reference_order = 0), the ranks sum their unit_rows
- * (one small all-reduce), and each rank scatters its rows to their place in ONE table-wide device slab that the
- * caller zeroed (or, when every row is written by exactly one rank, simply allocated — device memory or mapped host memory from
- * upb_host_register): slab columns are laid out as upb_slab_layout says, rows in canonical order (buffer, contig, left).
- * Summing the slabs over the ranks (ncclReduce on 64-bit words; the row sets are disjoint) gives rank 0 the whole
- * table without a host round trip; upb_table_from_slab wraps a host copy of it. */
-enum { UPB_COL_CAND_INDEX = 0, UPB_COL_PEAK_SCORE, UPB_COL_KURTOSIS, UPB_COL_CORR, UPB_COL_CONTIG, UPB_COL_LEFT, UPB_COL_LEN,
-       UPB_COL_PEAK, UPB_COL_HIT_SUM, UPB_COL_COUNTS, UPB_COL_BUFFER, UPB_COL_END /* = bytes of the slab */, UPB_N_COLS };
-int upb_slab_layout (uint64_t n_rows, uint32_t n_samples, uint64_t* offsets_out /* [UPB_N_COLS] byte offsets */);
-int upb_scatter_rows (upb_ctx* ctx, uint64_t total_rows, const uint64_t* unit_rows_total /* [2 * n_contigs] summed over ranks */,
-                      const uint64_t* unit_rows_local /* [2 * n_contigs] of this rank's last upb_call_regions (its table's unit_rows) */,
-                      void* d_slab /* device, upb_slab_layout(total_rows) bytes, zeroed */);
-/* Host-only: column pointers of `out` into a host copy of the summed slab (the caller keeps the memory alive; do not
- * pass such a table to upb_free_region_table). forward_label / dropped / unit arrays are left NULL. */
-int upb_table_from_slab (void* h_slab, uint64_t n_rows, uint32_t n_samples, upb_region_table* out);
+/* ---- several GPUs: one table every rank writes its rows into ----------------------------------- */
+/* The reference is one thread on one core (README:60-61); its regions table is written by src/regions.cpp:361-368 as regions
+ * close.  Here one rank per GPU (a thread or a process each) loads the contigs it owns and calls upb_call_regions_shared with the
+ * same `step` (1, 2, 3 ...).  The table lives in ONE page-locked host segment mapped by every rank (upb_host_alloc + threads, or a
+ * POSIX shared-memory segment + upb_host_register per process): each rank's GPU publishes its per-(buffer, contig) row counts
+ * there, waits ON THE DEVICE for the other ranks' counts and writes its rows straight to their place in table order over its own
+ * PCIe link — no collective and no host round trip inside the call.  On rank 0 the call returns the whole table (columns point
+ * into the segment: valid until rank 0's next call; upb_free_region_table is a no-op for it), reference_order honoured; on the
+ * other ranks only n_rows (their own rows) is set.  Rank 0 zeroes the exchange area once with upb_shared_table_init before any
+ * rank calls.  A rank that owns no contig still calls. */
+typedef struct {
+  void* host;                   /* the segment as this process sees it */
+  void* device;                 /* its device address (upb_host_register; == host for upb_host_alloc memory) */
+  uint64_t bytes;               /* >= upb_shared_table_bytes(...) */
+  uint32_t rank, world;
+  uint32_t n_contigs, n_samples;
+  uint64_t row_capacity;        /* rows the table has room for (all ranks together) */
+} upb_shared_table;
+uint64_t upb_shared_table_bytes (uint32_t n_contigs, uint32_t n_samples, uint32_t world, uint64_t row_capacity);
+int upb_shared_table_init (const upb_shared_table* t);
+int upb_call_regions_shared (upb_ctx* ctx, const upb_region_params* params, const upb_shared_table* t, uint64_t step, upb_region_table* out);
 
 /* ---- bin/regions -w (profile) -------------------------------------------------------------- */
 /* Replaces the FormatOutStream::write(PosScore) calls of ProfileBuffer::processPosition
@@ -302,6 +327,11 @@ typedef struct {
   float ms_call;                /* host wall clock of the last upb_call_regions, entry to return */
 } upb_stats;
 int upb_last_stats (const upb_ctx* ctx, upb_stats* out);
+
+/* Per-stage device time of the last region-calling call (CUDA events between the stages of the pipeline, on the context's stream),
+ * for the per-kernel roofline entries of bench.py.  Off by default.  names_out[k] points at static strings. */
+int upb_set_profiling (upb_ctx* ctx, int on);
+int upb_last_stage_times (const upb_ctx* ctx, uint32_t cap, const char** names_out, float* ms_out, uint32_t* n_out);
 
 /* The CUDA stream (cudaStream_t) every kernel and copy of this context is issued on, so that a caller can bracket calls with
  * its own CUDA events (bench.py times the step this way).  No reference counterpart: instrumentation only. */

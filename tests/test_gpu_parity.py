@@ -358,57 +358,61 @@ def test_tags_in_regions_single_contig_plus_row_eats_minus_track(gpu_ctx):
     assert got[1, 0] > int(d.seg(0, 0, 0)[1][-1])
 
 
-def test_scatter_rows_rebuilds_the_single_gpu_table(gpu_ctx):
-    # two "ranks" emulated on one GPU: each loads half of the contigs, both scatter into one table-wide slab
-    import torch
+def test_shared_table_rebuilds_the_single_gpu_table(gpu_ctx):
+    # two "ranks" emulated on one GPU (two contexts, one host thread each): each loads half of the contigs, both write into one
+    # shared table after the device-side exchange of their row counts (upb_call_regions_shared)
+    import ctypes
+    import threading
     import unipeak_b200
-    from unipeak_b200.multi import shard_contigs
+    from unipeak_b200.capi import lib
+    from unipeak_b200.multi import SharedRegionTable, shard_contigs
     sizes = [400000, 300000, 200000, 100000]
     d = make_synthetic(sizes, 3, 60000, directional=True, seed=51, peak_spacing=5000)
     st = region_settings(d)
     gpu_ctx.load(d)
-    full = gpu_ctx.call_regions(**dict(st, reference_order=False))["columns"]
+    full = gpu_ctx.call_regions(**dict(st, reference_order=True))
+    fullc = full["columns"]
     owner = shard_contigs(sizes, 2)
-    ctxs, views = [], []
+    ctxs = []
     for r in range(2):
         keep = [c for c in range(4) if owner[c] == r]
         segs = [[[d.seg(s, dd, c) if c in keep else (np.zeros(0, np.uint32), np.zeros(0, np.uint32)) for c in range(4)] for dd in range(2)] for s in range(3)]
-        part = TagData.from_segments(sizes, segs)
         cx = unipeak_b200.Context(0)
-        cx.load(part)
-        views.append(cx.call_regions_view(**dict(st, reference_order=(2 if r else 0))))   # 2: rows stay on the device (what a rank of a multi-GPU job asks for)
+        cx.load(TagData.from_segments(sizes, segs))
         ctxs.append(cx)
-    unit_total = sum(np.asarray(v["unit_rows"], dtype=np.uint64) for v in views)
-    R = int(unit_total.sum())
-    assert R == full["left"].shape[0]
-    nbytes = unipeak_b200.slab_layout(R, 3)["end"]
-    slab = torch.zeros((nbytes + 7) // 8, dtype=torch.int64, device="cuda:0")
-    torch.cuda.synchronize()
-    for cx, v in zip(ctxs, views):
-        cx.scatter_rows(R, unit_total, np.asarray(v["unit_rows"], dtype=np.uint64), slab.data_ptr())
-    cols = unipeak_b200.slab_columns(slab.cpu().numpy().view(np.uint8), R, 3)
-    for k in ("buffer", "contig", "left", "len", "peak", "hit_sum", "counts", "cand_index"):
-        assert np.array_equal(cols[k], full[k]), k
-    for k in ("kurtosis", "peak_score"):
-        assert np.array_equal(cols[k].view(np.uint64), full[k].view(np.uint64)), k
-    # the same scatter straight into mapped host memory (what HostGather does with a segment shared by the ranks)
-    from unipeak_b200.capi import host_register, host_unregister
-    host = np.zeros(((nbytes + 4095) // 4096) * 4096 + 4096, dtype=np.uint8)
-    base = (-host.ctypes.data) % 4096
-    host = host[base:base + ((nbytes + 4095) // 4096) * 4096]
-    dev_ptr = host_register(host.ctypes.data, host.shape[0])
+    row_cap = 4096
+    nbytes = unipeak_b200.shared_table_bytes(4, 3, 2, row_cap)
+    ptr = ctypes.c_void_p()
+    assert lib().upb_host_alloc(ctypes.byref(ptr), nbytes) == 0
+    ctypes.memset(ptr.value, 0, nbytes)
+    tabs = [SharedRegionTable(ctxs[r], 3, 4, rank=r, world=2, row_capacity=row_cap, local_ptr=ptr.value) for r in range(2)]
     try:
-        for cx, v in zip(ctxs, views):
-            cx.scatter_rows(R, unit_total, np.asarray(v["unit_rows"], dtype=np.uint64), dev_ptr)
-        cols = unipeak_b200.slab_columns(host, R, 3)
-        for k in ("buffer", "contig", "left", "len", "peak", "hit_sum", "counts", "cand_index"):
-            assert np.array_equal(cols[k], full[k]), k
-        for k in ("kurtosis", "peak_score"):
-            assert np.array_equal(cols[k].view(np.uint64), full[k].view(np.uint64)), k
+        for step in range(3):                                           # the exchange area is reused step after step
+            res, err = [None, None], [None, None]
+
+            def work(r):
+                try:
+                    res[r] = tabs[r](**dict(st, reference_order=True))
+                except Exception as e:                                  # noqa: BLE001
+                    err[r] = e
+            th = [threading.Thread(target=work, args=(r,)) for r in range(2)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            assert err == [None, None], err
+            v = res[0]
+            assert v.n_rows == fullc["left"].shape[0] and res[1].n_rows < v.n_rows
+            cols = v.columns()
+            for k in ("buffer", "forward_label", "dropped", "contig", "left", "len", "peak", "hit_sum", "counts", "cand_index", "tags_in_regions", "unit_candidates", "unit_rows", "unit_last_tag"):
+                assert np.array_equal(cols[k], fullc[k]), (step, k)
+            for k in ("kurtosis", "peak_score"):
+                assert np.array_equal(cols[k].view(np.uint64), fullc[k].view(np.uint64)), (step, k)
+            assert v.n_rejected == full["n_rejected"]
     finally:
-        host_unregister(host.ctypes.data)
-    for cx in ctxs:
-        cx.close()
+        for cx in ctxs:
+            cx.close()
+        lib().upb_host_free(ptr)
 
 
 def test_load_validation(gpu_ctx):
@@ -436,47 +440,130 @@ def test_load_validation(gpu_ctx):
     check_regions(gpu_ctx, good)
 
 
-def test_packed_load_equals_plain_load(gpu_ctx):
-    # the compact host form (16-bit deltas, 8-bit counts, exception list) decodes to exactly the arrays of the plain path:
-    # large gaps (>= 65535), large counts (>= 255), empty segments, several samples
-    import unipeak_b200
-    rng = np.random.default_rng(5)
-    sizes = [3000000, 200000, 90000]
-    d = make_synthetic(sizes, 3, 40000, directional=True, seed=77, peak_spacing=6000)
+def _packed_fixture():
+    rng = np.random.default_rng(8)
+    sizes = [3000000, 500000, 200000]
+    d = make_synthetic(sizes, 3, 40000, directional=True, seed=78, peak_spacing=6000)
     pos, cnt = d.pos.copy(), d.cnt.copy()
-    big = rng.choice(pos.shape[0], size=50, replace=False)
-    cnt[big] = rng.integers(255, 100000, size=50).astype(np.uint32)
+    cnt[rng.choice(pos.shape[0], size=60, replace=False)] = rng.integers(14, 18, size=60).astype(np.uint32)      # around the 4-bit escape
+    cnt[rng.choice(pos.shape[0], size=20, replace=False)] = rng.integers(255, 100000, size=20).astype(np.uint32)
     segs = [[[None] * 3 for _ in range(2)] for _ in range(3)]
     for s in range(3):
         for dd in range(2):
             for c in range(3):
                 a, b = int(d.off[(s * 2 + dd) * 4 + c]), int(d.off[(s * 2 + dd) * 4 + c + 1])
                 p, k = pos[a:b], cnt[a:b]
-                if c == 0:                                        # thin chr0 out so that gaps exceed 65535
+                if c == 0:                                            # thin chr0 out: gaps far beyond 4095
                     keep = (p < 400000) | (p > 2500000)
                     p, k = p[keep], k[keep]
                 if s == 1 and c == 2:
-                    p, k = p[:0], k[:0]                           # an empty segment
+                    p, k = p[:0], k[:0]                               # an empty segment
                 segs[s][dd][c] = (p, k)
-    data = TagData.from_segments(sizes, segs)
-    dpos, cnt8, exc = unipeak_b200.pack_tags(3, 3, data.off, data.pos, data.cnt)
-    assert exc.shape[0] >= 3 * 2 * 3 - 2 + 5 and (dpos == 0xFFFF).sum() >= 16 + 6 and (cnt8 == 0xFF).sum() >= 5
+    return TagData.from_segments(sizes, segs)
+
+
+def test_packed_load_equals_plain_load(gpu_ctx):
+    # the 2-byte host form (12-bit deltas, 4-bit counts, exception list, self-contained tiles of 2048 entries) decodes to exactly the
+    # arrays of the plain path: large gaps, large counts, empty segments, segments longer than one tile, several samples
+    import unipeak_b200
+    data = _packed_fixture()
+    words, exc = unipeak_b200.pack_tags2(3, 3, data.off, data.pos, data.cnt)
+    assert ((words & 0xFFF) == 0xFFF).sum() >= 16 + 2 and ((words >> 12) == 0xF).sum() >= 20
+    assert max(int(data.off[k + 1] - data.off[k]) for k in range(len(data.off) - 1)) > 2 * 2048          # several tiles per segment
     st = region_settings(data)
     gpu_ctx.load(data)
     want = gpu_ctx.call_regions(**st)
-    tir_keys = [(r["contig"], r["left"], r["left"] + r["len"] - 1) for r in want["rows"] if r["forward_label"]][:50]
-    tir_want = gpu_ctx.count_tags_in_regions(tir_keys, directional=True, extension=0)
-    gpu_ctx.load_packed(data)
+    keys = [(r["contig"], r["left"], r["left"] + r["len"] - 1) for r in want["rows"] if r["forward_label"]][:50]
+    tir_want = gpu_ctx.count_tags_in_regions(keys, directional=True, extension=0)
+    gpu_ctx.load_packed2(data)
     got = gpu_ctx.call_regions(**st)
-    assert_rows_equal(got["rows"], want["rows"], "packed load")
-    assert_rows_equal(got["dropped"], want["dropped"], "packed load (dropped)")
+    assert_rows_equal(got["rows"], want["rows"], "2-byte load")
+    assert_rows_equal(got["dropped"], want["dropped"], "2-byte load (dropped)")
     assert got["tags_in_regions"] == want["tags_in_regions"] and len(got["rows"]) > 3
-    assert np.array_equal(gpu_ctx.count_tags_in_regions(tir_keys, directional=True, extension=0), tir_want)   # reads the decoded pos[] / cnt[] directly
-    # a broken stream is refused: an escape without its exception entry
-    with pytest.raises(unipeak_b200.UpbError):
-        off = np.ascontiguousarray(data.off, dtype=np.uint64)
-        gpu_ctx.load_tags_packed_ptr(3, off.ctypes.data, dpos.ctypes.data, cnt8.ctypes.data, exc.shape[0] - 1, exc.ctypes.data)
-    check_regions(gpu_ctx, d)
+    assert np.array_equal(gpu_ctx.count_tags_in_regions(keys, directional=True, extension=0), tir_want)   # reads the decoded pos[] / cnt[] directly
+    off = np.ascontiguousarray(data.off, dtype=np.uint64)
+    # broken streams are refused: an escape without its exception entry ...
+    with pytest.raises(unipeak_b200.UpbError) as ei:
+        gpu_ctx.load_tags_packed2_ptr(3, off.ctypes.data, words.ctypes.data, exc.shape[0] - 1, exc.ctypes.data)
+    assert ei.value.code == -2
+    # ... a segment whose first entry is not an absolute position, a tile (2048th entry) that is not ...
+    first = int(off[0])
+    for victim in (first, first + 2048):
+        bad = words.copy()
+        assert (int(bad[victim]) & 0xFFF) == 0xFFF
+        bad[victim] = (int(bad[victim]) & 0xF000) | 7
+        with pytest.raises(unipeak_b200.UpbError) as ei:
+            gpu_ctx.load_tags_packed2_ptr(3, off.ctypes.data, bad.ctypes.data, exc.shape[0], exc.ctypes.data)
+        assert ei.value.code == -2
+    # ... and positions that do not ascend across a tile seam
+    bad_exc = exc.copy()
+    k = int(np.nonzero(bad_exc["index"] == first + 2048)[0][0])
+    bad_exc["pos"][k] = 1
+    with pytest.raises(unipeak_b200.UpbError) as ei:
+        gpu_ctx.load_tags_packed2_ptr(3, off.ctypes.data, words.ctypes.data, bad_exc.shape[0], bad_exc.ctypes.data)
+    assert ei.value.code == -5
+    check_regions(gpu_ctx, make_synthetic([200000, 80000], 2, 30000, directional=True, seed=79, peak_spacing=5000))
+
+
+def test_async_load_pipelines_into_the_call(gpu_ctx):
+    # upb_load_tags_async + upb_call_regions: the call starts on the load groups that have arrived; same table as load-then-call.
+    # Also: a subset load (keep mask), upb_reindex, and a call whose numbers outgrow the arrays sized by an earlier, smaller one.
+    import torch
+    import unipeak_b200
+    small = make_synthetic([300000, 120000], 2, 20000, directional=True, seed=90, peak_spacing=5000)
+    check_regions(gpu_ctx, small)                                       # sizes the context's arrays for a small table
+    sizes = [6000000, 2500000, 1200000, 800000, 300000]
+    data = make_synthetic(sizes, 4, 900000, directional=True, seed=91, peak_spacing=4000)
+    st = region_settings(data)
+    gpu_ctx.load(data)
+    want = gpu_ctx.call_regions(**dict(st, rows=False))                 # far more rows than the small one: repeated with sizing
+    wc = want["columns"]
+    assert wc["left"].shape[0] > 2000
+    again = gpu_ctx.call_regions(**dict(st, rows=False))["columns"]      # now without a read-back
+    for k in wc:
+        assert np.array_equal(np.asarray(wc[k]).view(np.uint8), np.asarray(again[k]).view(np.uint8)), k
+    words, exc = unipeak_b200.pack_tags2(4, 5, data.off, data.pos, data.cnt)
+    h_off = torch.from_numpy(np.ascontiguousarray(data.off).view(np.int64)).pin_memory()
+    h_words = torch.from_numpy(words.view(np.int16)).pin_memory()
+    h_exc = torch.from_numpy(exc.view(np.uint8).copy()).pin_memory()
+    h_pos = torch.from_numpy(data.pos.view(np.int32)).pin_memory()
+    h_cnt = torch.from_numpy(data.cnt.view(np.int32)).pin_memory()
+    for hint in (True, False):
+        for rep in range(2):
+            gpu_ctx.load_async_ptr(4, h_off.data_ptr(), words_ptr=h_words.data_ptr(), n_exc=exc.shape[0], exc_ptr=h_exc.data_ptr(), directional_hint=hint)
+            got = gpu_ctx.call_regions(**dict(st, rows=False))["columns"]
+            for k in wc:
+                assert np.array_equal(np.asarray(wc[k]).view(np.uint8), np.asarray(got[k]).view(np.uint8)), (hint, rep, k)
+    gpu_ctx.load_async_ptr(4, h_off.data_ptr(), pos_ptr=h_pos.data_ptr(), cnt_ptr=h_cnt.data_ptr())
+    got = gpu_ctx.call_regions(**dict(st, rows=False))["columns"]
+    for k in wc:
+        assert np.array_equal(np.asarray(wc[k]).view(np.uint8), np.asarray(got[k]).view(np.uint8)), ("plain async", k)
+    gpu_ctx.reindex()
+    got = gpu_ctx.call_regions(**dict(st, rows=False))["columns"]
+    for k in wc:
+        assert np.array_equal(np.asarray(wc[k]).view(np.uint8), np.asarray(got[k]).view(np.uint8)), ("reindex", k)
+    # invalid input that arrives through the asynchronous load is reported by the call that consumes it, and nothing crashes
+    bad = data.pos.copy()
+    a = int(data.off[1])
+    bad[a + 5000] = bad[a + 4999]
+    h_bad = torch.from_numpy(bad.view(np.int32)).pin_memory()
+    gpu_ctx.load_async_ptr(4, h_off.data_ptr(), pos_ptr=h_bad.data_ptr(), cnt_ptr=h_cnt.data_ptr())
+    with pytest.raises(unipeak_b200.UpbError) as ei:
+        gpu_ctx.call_regions(**dict(st, rows=False))
+    assert ei.value.code == -5
+    # a rank of a multi-GPU job keeps only its contigs: exactly their rows of the whole table
+    keep = [1, 3]
+    for packed in (True, False):
+        gpu_ctx.load_subset(data, keep, packed=packed)
+        part = gpu_ctx.call_regions(**dict(st, reference_order=False, rows=False))["columns"]
+        sel = np.isin(wc["contig"], keep)
+        # the whole-table call above was in reference order; for this input that is the canonical order with the last rows flagged as dropped
+        assert int(sel.sum()) == part["left"].shape[0]
+        for k in ("buffer", "contig", "left", "len", "peak", "hit_sum", "counts"):
+            assert np.array_equal(part[k], wc[k][sel]), (packed, k)
+        for k in ("kurtosis", "peak_score"):
+            assert np.array_equal(part[k].view(np.uint64), wc[k][sel].view(np.uint64)), (packed, k)
+    check_regions(gpu_ctx, small)
 
 
 def test_many_samples_c4_shape(gpu_ctx):
@@ -531,11 +618,11 @@ def test_full_size_properties_config3():
     import torch
     import unipeak_b200
     from unipeak_b200.synth import HG19_SIZES
-    from unipeak_b200.synth_gpu import make_synthetic_gpu
+    from unipeak_b200.synth_det import make_synthetic_det
     if torch.cuda.mem_get_info()[0] < 40e9:
         pytest.skip("needs ~40 GB of free HBM")
     n, G = 16, int(sum(HG19_SIZES))
-    data = make_synthetic_gpu(HG19_SIZES, n, 30_000_000, directional=True, seed=20261018)
+    data = make_synthetic_det(HG19_SIZES, n, 30_000_000, directional=True, seed=20261018, device="cuda:0")
     total = sum(data.tags(s) for s in range(n))
     st = dict(bandwidth=50, region_threshold=25.0, kurtosis_threshold=50.0, corr_threshold=-1.0, hit_threshold=10.0 * n, directional=True,
               control=np.zeros(n, np.uint8), coeffs=[], background=total / G / 2)
@@ -560,7 +647,7 @@ def test_full_size_properties_config3():
         assert np.array_equal(a["counts"].astype(np.uint64).sum(axis=1) & 0xFFFFFFFF, a["hit_sum"].astype(np.uint64))   # no controls: sum() of the row
         assert np.array_equal(a["counts"].astype(np.uint64).sum(axis=0), np.asarray(a["tags_in_regions"], dtype=np.uint64))
         # the compact host form decodes to the same table
-        ctx.load_packed(data)
+        ctx.load_packed2(data)
         c = ctx.call_regions(**dict(st, reference_order=False, rows=False))["columns"]
         for k in a:
             assert np.array_equal(a[k].view(np.uint8), c[k].view(np.uint8)), k

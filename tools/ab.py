@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import unipeak_b200  # noqa: E402
 from unipeak_b200.synth import HG19_SIZES  # noqa: E402
-from unipeak_b200.synth_gpu import make_synthetic_gpu  # noqa: E402
+from unipeak_b200.synth_det import make_synthetic_det as make_synthetic_gpu  # noqa: E402
 
 G = int(sum(HG19_SIZES))
 COLS = ("buffer", "forward_label", "dropped", "contig", "left", "len", "peak", "hit_sum", "peak_score", "kurtosis", "corr", "counts",
@@ -49,7 +49,7 @@ def main():
     steps = int(os.environ.get("AB_STEPS", "20"))
     ctx = unipeak_b200.Context(0)
     if "c3" in which:
-        data = make_synthetic_gpu(HG19_SIZES, 16, 30_000_000, directional=True, seed=20261018, bandwidth=200)
+        data = make_synthetic_gpu(HG19_SIZES, 16, 30_000_000, directional=True, seed=20261018, bandwidth=200, device="cuda:0")
         ctx.load(data)
         bg = sum(data.tags(s) for s in range(16)) / G / 2
         for bw in ((50, 10, 20, 100, 150, 200) if "bw" in which else (50,)):
@@ -60,7 +60,7 @@ def main():
                                                control=ctl, background=bg * 14 / 16), max(3, steps // 4))
         del data
     if "c2" in which:
-        data = make_synthetic_gpu(HG19_SIZES, 2, 20_000_000, directional=False, seed=20261019)
+        data = make_synthetic_gpu(HG19_SIZES, 2, 20_000_000, directional=False, seed=20261019, device="cuda:0")
         ctx.load(data)
         total = sum(data.tags(s) for s in range(2))
         run(ctx, "c2 regions -D", dict(bandwidth=50, region_threshold=25.0, kurtosis_threshold=50.0, corr_threshold=0.3, hit_threshold=20.0, directional=False, background=total / G), max(3, steps // 4))

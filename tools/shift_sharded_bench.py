@@ -22,7 +22,7 @@ sys.path.insert(0, ROOT)
 import unipeak_b200  # noqa: E402
 from unipeak_b200.multi import shard_contigs, strand_shift_sharded  # noqa: E402
 from unipeak_b200.synth import HG19_SIZES  # noqa: E402
-from unipeak_b200.synth_gpu import make_synthetic_gpu  # noqa: E402
+from unipeak_b200.synth_det import make_synthetic_det as make_synthetic_gpu  # noqa: E402
 
 
 def main():

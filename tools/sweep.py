@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import unipeak_b200  # noqa: E402
 from unipeak_b200.synth import HG19_SIZES, MM9_SIZES  # noqa: E402
-from unipeak_b200.synth_gpu import make_synthetic_gpu  # noqa: E402
+from unipeak_b200.synth_det import make_synthetic_det as make_synthetic_gpu  # noqa: E402
 
 PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 G = int(sum(HG19_SIZES))
@@ -35,7 +35,7 @@ def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     ctx = unipeak_b200.Context(0)
     if which in ("all", "c5"):
-        data = make_synthetic_gpu(HG19_SIZES, 16, 30_000_000, directional=True, seed=20261018, bandwidth=200)
+        data = make_synthetic_gpu(HG19_SIZES, 16, 30_000_000, directional=True, seed=20261018, bandwidth=200, device="cuda:0")
         ctx.load(data)
         E = int(data.pos.shape[0])
         total = sum(data.tags(s) for s in range(16))
@@ -51,7 +51,7 @@ def main():
         ctx.release_view()
         del data
     if which in ("all", "c2"):
-        data = make_synthetic_gpu(HG19_SIZES, 2, 20_000_000, directional=False, seed=20261019)
+        data = make_synthetic_gpu(HG19_SIZES, 2, 20_000_000, directional=False, seed=20261019, device="cuda:0")
         shifts = []
         for smp in range(2):
             one = data.subset_samples([smp])
@@ -72,7 +72,7 @@ def main():
         # config 4 scaled to one GPU's comfortable size: 96 samples x 5 M tags (the full 96 x 50 M is ~77 GB resident), mm9, then
         # tags_in_regions of 32 held-out samples x 5 M tags over the resulting table
         Gm = int(sum(MM9_SIZES))
-        data = make_synthetic_gpu(MM9_SIZES, 96, 5_000_000, directional=True, seed=20261020)
+        data = make_synthetic_gpu(MM9_SIZES, 96, 5_000_000, directional=True, seed=20261020, device="cuda:0")
         ctx.load(data)
         total = sum(data.tags(s) for s in range(96))
         st = dict(bandwidth=50, region_threshold=25.0, kurtosis_threshold=50.0, corr_threshold=-1.0, hit_threshold=960.0, directional=True, background=total / Gm / 2)
@@ -86,7 +86,7 @@ def main():
                           "span_kernel_ms": s["ms_kde"], "tag_entries": int(data.pos.shape[0]), "regions": v.n_rows, "candidates": s["n_candidates"]}))
         ctx.release_view()
         del data
-        held = make_synthetic_gpu(MM9_SIZES, 32, 5_000_000, directional=True, seed=20261021)
+        held = make_synthetic_gpu(MM9_SIZES, 32, 5_000_000, directional=True, seed=20261021, device="cuda:0")
         ctx.load(held)
         ms, counts = timed(lambda: ctx.count_tags_in_regions_arr(keys, directional=True, extension=0), reps=3, warm=1)
         print(json.dumps({"config": "c4 scaled: tags_in_regions, 32 held-out samples x 5M tags over the table above", "ms": ms, "rows": int(keys.shape[0]),

@@ -80,13 +80,21 @@ EXPORTS = [
     "upb_create", "upb_destroy", "upb_last_error", "upb_device_count", "upb_host_alloc", "upb_host_free", "upb_set_contigs",
     "upb_load_tags", "upb_call_regions", "upb_free_region_table", "upb_reference_order", "upb_profile_contig", "upb_free_profile",
     "upb_strand_shift", "upb_free_shift_report", "upb_count_tags_in_regions", "upb_kernel_taps", "upb_last_stats",
-    "upb_slab_layout", "upb_scatter_rows", "upb_table_from_slab", "upb_stream", "upb_host_register", "upb_host_unregister", "upb_load_tags_packed", "upb_pack_tags", "upb_aggregate_tags", "upb_free_tag_counts",
+    "upb_shared_table_bytes", "upb_shared_table_init", "upb_call_regions_shared", "upb_set_profiling", "upb_last_stage_times", "upb_stream", "upb_host_register", "upb_host_unregister", "upb_load_tags_async", "upb_load_wait", "upb_reindex", "upb_aggregate_tags", "upb_free_tag_counts",
     "upb_load_tags_packed2", "upb_pack_tags2",
     "upb_shift_regions", "upb_free_shift_regions", "upb_shift_examine_order", "upb_shift_sweep", "upb_shift_mode",
 ]
-SLAB_COLS = ("cand_index", "peak_score", "kurtosis", "corr", "contig", "left", "len", "peak", "hit_sum", "counts", "buffer", "end")
-SLAB_DTYPES = dict(cand_index=np.uint64, peak_score=np.float64, kurtosis=np.float64, corr=np.float64, contig=np.uint32, left=np.uint32,
-                   len=np.uint32, peak=np.uint32, hit_sum=np.uint32, counts=np.uint32, buffer=np.uint8)
+
+
+class TagSource(C.Structure):
+    _fields_ = [("n_samples", C.c_uint32), ("off", C.c_void_p), ("pos", C.c_void_p), ("cnt", C.c_void_p), ("words", C.c_void_p),
+                ("n_exceptions", C.c_uint64), ("exceptions", C.c_void_p), ("keep_contig", C.c_void_p), ("directional_hint", C.c_int)]
+
+
+class SharedTable(C.Structure):
+    _fields_ = [("host", C.c_void_p), ("device", C.c_void_p), ("bytes", C.c_uint64), ("rank", C.c_uint32), ("world", C.c_uint32),
+                ("n_contigs", C.c_uint32), ("n_samples", C.c_uint32), ("row_capacity", C.c_uint64)]
+
 
 _lib = None
 
@@ -96,25 +104,6 @@ class TagCounts(C.Structure):
 
 
 PACKED_EXC_DTYPE = np.dtype([("index", np.uint64), ("pos", np.uint32), ("cnt", np.uint32)])
-
-
-def pack_tags(n_samples: int, n_contigs: int, off, pos, cnt, out=None):
-    """upb_pack_tags: (dpos u16, cnt8 u8, exceptions) of the plain arrays.  `out` may supply preallocated (dpos, cnt8) arrays
-    (e.g. pinned); the exception list is sized by a counting pass first."""
-    L = lib()
-    off = np.ascontiguousarray(off, dtype=np.uint64)
-    pos = np.ascontiguousarray(pos, dtype=np.uint32)
-    cnt = np.ascontiguousarray(cnt, dtype=np.uint32)
-    E = int(pos.shape[0])
-    n_exc = C.c_uint64(0)
-    L.upb_pack_tags(n_samples, n_contigs, off.ctypes.data, pos.ctypes.data, cnt.ctypes.data, None, None, None, 0, C.byref(n_exc))
-    dpos, cnt8 = out if out is not None else (np.empty(max(E, 1), np.uint16), np.empty(max(E, 1), np.uint8))
-    exc = np.zeros(max(int(n_exc.value), 1), dtype=PACKED_EXC_DTYPE)
-    rc = L.upb_pack_tags(n_samples, n_contigs, off.ctypes.data, pos.ctypes.data, cnt.ctypes.data, dpos.ctypes.data, cnt8.ctypes.data,
-                         exc.ctypes.data, int(n_exc.value), C.byref(n_exc))
-    if rc:
-        raise UpbError(rc, "upb_pack_tags failed")
-    return dpos, cnt8, exc[:int(n_exc.value)]
 
 
 def pack_tags2(n_samples: int, n_contigs: int, off, pos, cnt, out=None):
@@ -185,40 +174,28 @@ def lib():
         L.upb_kernel_taps.argtypes = [C.c_uint32, C.c_double, C.POINTER(C.c_double)]
         L.upb_last_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.upb_stream.argtypes = [C.c_void_p]
-        L.upb_load_tags_packed.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
-        L.upb_pack_tags.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.upb_load_tags_async.argtypes = [C.c_void_p, C.POINTER(TagSource)]
+        L.upb_load_wait.argtypes = [C.c_void_p]
+        L.upb_reindex.argtypes = [C.c_void_p]
         L.upb_load_tags_packed2.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.upb_pack_tags2.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.upb_host_register.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
         L.upb_host_unregister.argtypes = [C.c_void_p]
         L.upb_host_unregister.restype = None
         L.upb_stream.restype = C.c_void_p
-        L.upb_slab_layout.argtypes = [C.c_uint64, C.c_uint32, C.c_void_p]
-        L.upb_scatter_rows.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
-        L.upb_table_from_slab.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(RegionTable)]
+        L.upb_shared_table_bytes.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64]
+        L.upb_shared_table_bytes.restype = C.c_uint64
+        L.upb_shared_table_init.argtypes = [C.POINTER(SharedTable)]
+        L.upb_call_regions_shared.argtypes = [C.c_void_p, C.POINTER(RegionParams), C.POINTER(SharedTable), C.c_uint64, C.POINTER(RegionTable)]
+        L.upb_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.upb_last_stage_times.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
         L.upb_reference_order.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(RegionTable), C.c_void_p]
         _lib = L
     return _lib
 
 
-def slab_layout(n_rows: int, n_samples: int) -> Dict[str, int]:
-    """Byte offsets of the columns of a table-wide result slab (upb_slab_layout); 'end' = its size."""
-    off = np.zeros(len(SLAB_COLS), dtype=np.uint64)
-    rc = lib().upb_slab_layout(int(n_rows), int(n_samples), off.ctypes.data)
-    if rc:
-        raise UpbError(rc, "upb_slab_layout")
-    return {k: int(v) for k, v in zip(SLAB_COLS, off)}
-
-
-def slab_columns(buf: np.ndarray, n_rows: int, n_samples: int) -> Dict[str, np.ndarray]:
-    """numpy views of the columns of a host copy (uint8 array) of a table-wide slab."""
-    L = slab_layout(n_rows, n_samples)
-    out = {}
-    for k, dt in SLAB_DTYPES.items():
-        count = n_rows * (n_samples if k == "counts" else 1)
-        out[k] = buf[L[k]:L[k] + count * np.dtype(dt).itemsize].view(dt)
-    out["counts"] = out["counts"].reshape(n_rows, n_samples)
-    return out
+def shared_table_bytes(n_contigs: int, n_samples: int, world: int, row_capacity: int) -> int:
+    return int(lib().upb_shared_table_bytes(n_contigs, n_samples, world, row_capacity))
 
 
 def shift_examine_order(sums: np.ndarray, want: int):
@@ -325,11 +302,6 @@ class Context:
         self._check(self._lib.upb_load_tags(self._h, n_samples, C.c_void_p(off_ptr), C.c_void_p(pos_ptr), C.c_void_p(cnt_ptr)))
         self.n_samples = n_samples
 
-    def load_tags_packed_ptr(self, n_samples: int, off_ptr: int, dpos_ptr: int, cnt8_ptr: int, n_exc: int, exc_ptr: int):
-        """upb_load_tags_packed from raw host addresses (see pack_tags)."""
-        self._check(self._lib.upb_load_tags_packed(self._h, n_samples, C.c_void_p(off_ptr), C.c_void_p(dpos_ptr), C.c_void_p(cnt8_ptr), n_exc, C.c_void_p(exc_ptr)))
-        self.n_samples = n_samples
-
     def load_tags_packed2_ptr(self, n_samples: int, off_ptr: int, words_ptr: int, n_exc: int, exc_ptr: int):
         """upb_load_tags_packed2 from raw host addresses (see pack_tags2)."""
         self._check(self._lib.upb_load_tags_packed2(self._h, n_samples, C.c_void_p(off_ptr), C.c_void_p(words_ptr), n_exc, C.c_void_p(exc_ptr)))
@@ -342,12 +314,39 @@ class Context:
         words, exc = pack_tags2(data.n_samples, self.n_contigs, off, data.pos, data.cnt)
         self.load_tags_packed2_ptr(data.n_samples, off.ctypes.data, words.ctypes.data, exc.shape[0], exc.ctypes.data)
 
-    def load_packed(self, data) -> None:
-        """Load a TagData through the compact host form (encode on the host, decode on the device)."""
+    def load_async_ptr(self, n_samples: int, off_ptr: int, *, pos_ptr: int = 0, cnt_ptr: int = 0, words_ptr: int = 0, n_exc: int = 0, exc_ptr: int = 0,
+                       keep_contig: Optional[np.ndarray] = None, directional_hint: bool = True) -> None:
+        """upb_load_tags_async from raw host addresses: returns once the transfers are queued.  The buffers (and `keep_contig`) must stay
+        alive until load_wait() or the next call that uses the data returns."""
+        self._keep = None if keep_contig is None else np.ascontiguousarray(keep_contig, dtype=np.uint8)
+        src = TagSource(n_samples, off_ptr, pos_ptr or None, cnt_ptr or None, words_ptr or None, n_exc, exc_ptr or None,
+                        None if self._keep is None else self._keep.ctypes.data, 1 if directional_hint else 0)
+        self._check(self._lib.upb_load_tags_async(self._h, C.byref(src)))
+        self.n_samples = n_samples
+
+    def load_wait(self) -> None:
+        self._check(self._lib.upb_load_wait(self._h))
+
+    def reindex(self) -> None:
+        """upb_reindex: rebuild the tile-major copy and the zone maps from the resident sample-major arrays."""
+        self._check(self._lib.upb_reindex(self._h))
+
+    def load_subset(self, data, keep_contigs: Sequence[int], packed: bool = True) -> None:
+        """Load only the segments of the given contigs out of arrays that describe all of them (what a rank of a multi-GPU job does)."""
         self.set_contigs(data.contig_sizes)
+        keep = np.zeros(self.n_contigs, dtype=np.uint8)
+        keep[list(keep_contigs)] = 1
         off = np.ascontiguousarray(data.off, dtype=np.uint64)
-        dpos, cnt8, exc = pack_tags(data.n_samples, self.n_contigs, off, data.pos, data.cnt)
-        self.load_tags_packed_ptr(data.n_samples, off.ctypes.data, dpos.ctypes.data, cnt8.ctypes.data, exc.shape[0], exc.ctypes.data)
+        if packed:
+            words, exc = pack_tags2(data.n_samples, self.n_contigs, off, data.pos, data.cnt)
+            self._hold = (off, words, exc)
+            self.load_async_ptr(data.n_samples, off.ctypes.data, words_ptr=words.ctypes.data, n_exc=exc.shape[0], exc_ptr=exc.ctypes.data, keep_contig=keep)
+        else:
+            pos = np.ascontiguousarray(data.pos, dtype=np.uint32); cnt = np.ascontiguousarray(data.cnt, dtype=np.uint32)
+            self._hold = (off, pos, cnt)
+            self.load_async_ptr(data.n_samples, off.ctypes.data, pos_ptr=pos.ctypes.data, cnt_ptr=cnt.ctypes.data, keep_contig=keep)
+        self.load_wait()
+        self._hold = None
 
     def aggregate_tags(self, key, pos, cnt=None, combine_strands=False):
         """upb_aggregate_tags: (off[2C+1], pos, cnt, tag_count) — distinct 5' positions with their tag counts per (strand, contig)."""
@@ -378,7 +377,7 @@ class Context:
         cf = np.ascontiguousarray(coeffs if coeffs is not None else [], dtype=np.float64)
         p = RegionParams(bandwidth, region_threshold, kurtosis_threshold, corr_threshold, hit_threshold, 1 if directional else 0,
                          ctrl.ctypes.data_as(C.POINTER(C.c_uint8)), cf.shape[0], cf.ctypes.data_as(C.POINTER(C.c_double)),
-                         background, int(reference_order) if reference_order in (0, 1, 2) and not isinstance(reference_order, bool) else (1 if reference_order else 0))
+                         background, 1 if reference_order else 0)
         return p, (ctrl, cf)
 
     @staticmethod
@@ -518,11 +517,28 @@ class Context:
         self._check(self._lib.upb_count_tags_in_regions(self._h, 1 if directional else 0, extension, keys.shape[0], C.cast(keys.ctypes.data, C.POINTER(RegionKey)), out.ctypes.data))
         return out[:keys.shape[0] * self.n_samples].reshape(keys.shape[0], self.n_samples)
 
-    def scatter_rows(self, total_rows: int, unit_rows_total: np.ndarray, unit_rows_local: np.ndarray, d_slab_ptr: int):
-        """Scatter the rows of the last call_regions(_view) on this context into a table-wide device slab (see upb_scatter_rows)."""
-        tot = np.ascontiguousarray(unit_rows_total, dtype=np.uint64)
-        loc = np.ascontiguousarray(unit_rows_local, dtype=np.uint64)
-        self._check(self._lib.upb_scatter_rows(self._h, int(total_rows), tot.ctypes.data, loc.ctypes.data, C.c_void_p(d_slab_ptr)))
+    def call_regions_shared(self, table: "SharedTable", step: int, *, bandwidth=50, region_threshold=25.0, kurtosis_threshold=50.0, corr_threshold=-1.0,
+                            hit_threshold=10.0, directional=True, control: Optional[Sequence[int]] = None, coeffs: Optional[Sequence[float]] = None,
+                            background: float, reference_order=True, **_ignored) -> "RegionView":
+        """upb_call_regions_shared: this rank's part of one table-wide call; on rank 0 the view is the whole table (columns inside the
+        shared segment), on the other ranks only n_rows (their own rows) is meaningful."""
+        self.release_view()
+        p, keep = self._region_params(bandwidth, region_threshold, kurtosis_threshold, corr_threshold, hit_threshold, directional, control,
+                                      coeffs, background, reference_order)
+        t = RegionTable()
+        self._check(self._lib.upb_call_regions_shared(self._h, C.byref(p), C.byref(table), int(step), C.byref(t)))
+        return RegionView(t, self.n_contigs)
+
+    def set_profiling(self, on: bool) -> None:
+        self._check(self._lib.upb_set_profiling(self._h, 1 if on else 0))
+
+    def stage_times(self) -> List:
+        """[(stage name, device ms)] of the last region-calling call (set_profiling(True) first)."""
+        n = C.c_uint32(0)
+        names = (C.c_char_p * 32)()
+        ms = (C.c_float * 32)()
+        self._check(self._lib.upb_last_stage_times(self._h, 32, names, ms, C.byref(n)))
+        return [(names[k].decode(), float(ms[k])) for k in range(min(int(n.value), 32))]
 
     def stream_ptr(self) -> int:
         """cudaStream_t of this context (for CUDA-event timing by the caller)."""

@@ -34,12 +34,21 @@ struct DevBuf {
 
 struct HostSlab { void* p = nullptr; size_t cap = 0; };
 
+struct LoadGroup {                      // (strand d, contigs c0 .. c1-1): one unit of the pipelined load
+  uint32_t d, c0, c1;
+  uint64_t entries, mentBase;           // its entries and where they start in the tile-major copy
+  uint32_t m0, m1, w0, w1;              // its mini-tiles and scatter windows
+  uint32_t seg0, nSeg, tileTab0, nTiles;   // its non-empty segments / tile table (d_grpSeg, d_grpTile)
+};
+
 struct upb_ctx {
   int device = 0;
   int smCount = 148;
   cudaStream_t stream = nullptr;
-  cudaStream_t copyStream = nullptr;    // H2D copies of upb_load_tags run here, one sample ahead of the kernels that consume them
-  cudaEvent_t copyEv = nullptr, doneEv = nullptr;
+  cudaStream_t copyStream = nullptr;    // H2D copies of the load run here, one load group ahead of the kernels that consume them ...
+  cudaStream_t loadStream = nullptr;    // ... on this one (decode, validation, counting sort, zone maps), while `stream` may already run the region pipeline of earlier groups
+  cudaEvent_t loadDoneEv = nullptr;
+  std::vector<cudaEvent_t> groupEv, copyEvs;   // per load group: index built / bytes on the device
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::string err;
   // contigs
@@ -50,18 +59,33 @@ struct upb_ctx {
   uint32_t nSamples = 0;
   uint64_t nEntries = 0;
   bool loaded = false;
-  std::vector<uint64_t> off;            // host copy
+  std::vector<uint64_t> off;            // offsets of the RESIDENT arrays in the caller's layout [(s*2+d)*(C+1)+c]
+  std::vector<uint64_t> segStart, srcStart;   // [nSeg+1] / [nSeg] first entry of segment g on the device / in the caller's arrays
+  std::vector<uint8_t> keptContig;      // [C] contigs whose segments this context holds (a rank of a multi-GPU job keeps the ones it owns)
+  std::vector<LoadGroup> groups;        // load groups of the current data, in transfer order
+  bool loadPending = false;             // upb_load_tags_async returned, nobody has waited yet
+  bool loadStrandMajor = true;
+  bool lastPosKnown = false;            // packed loads learn the last position of a segment from the device
+  HostSlab h_ends;                      // pinned: first / last positions and the validation flags come back here
   std::vector<uint32_t> firstPos, lastPos;   // [(s*2+d)*C + c], 0 if empty
   DevBuf d_pos, d_cnt, d_off, d_segStart, d_tidx, d_tidxBase, d_sizes, d_nTilesIdx, d_small;
   DevBuf d_winBase, d_wEnt;                                          // per-sample window index of the scatter pass
-  DevBuf d_pk16, d_pk8, d_pkExc, d_pkAgg, d_segEnds;                  // packed load (upb_pack.cuh)
+  DevBuf d_pk16, d_pkExc, d_segEnds, d_srcStart, d_grpSeg, d_grpTile, d_loadFlags;   // load (upb_pack.cuh)
   DevBuf d_ment, d_mtOff, d_mtBase, d_mtCount, d_mEff, d_mtW, d_blkW;   // tile-major copy and its zone maps (upb_device.cuh)
   std::vector<uint32_t> mtBase;         // [2*C+1]
   std::map<std::string, DevBuf> scratch;     // grow-only device scratch, by name
   unsigned char* h_small = nullptr;          // 4 KB of pinned host memory for small read-backs
   std::vector<HostSlab> slabPool;            // pinned host slabs of freed region tables, reused by the next call
   upb_stats stats;
-  uint64_t lastRows = 0;                // rows of the last upb_call_regions still sitting in the device slab (scratch "slab")
+  // what the region pipeline remembers from call to call: capacities of its arrays (a call runs without reading a size back when
+  // the previous call's numbers, plus a quarter, still hold; otherwise it sizes them itself)
+  size_t needRunCap = 0, capN1 = 0, capCells = 0, capRows = 0;
+  HostSlab h_res;                            // pinned block the counters of a call come back in
+  bool profiling = false;                    // upb_set_profiling: one CUDA event between the stages of the pipeline
+  std::vector<cudaEvent_t> stageEv;
+  size_t stageUsed = 0;
+  std::vector<const char*> stageNames;
+  std::vector<float> stageMs;
   std::vector<uint8_t> lastControl;     // control set cntEff was built for
   bool cntEffValid = false;
   bool tidxBuilt = false;
@@ -116,8 +140,8 @@ extern "C" int upb_create (int device, upb_ctx** out) {
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return fail(nullptr, UPB_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
   for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
   cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking);
-  cudaEventCreateWithFlags(&ctx->copyEv, cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&ctx->doneEv, cudaEventDisableTiming);
+  cudaStreamCreateWithFlags(&ctx->loadStream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&ctx->loadDoneEv, cudaEventDisableTiming);
   if ((e = cudaMallocHost((void**)&ctx->h_small, 4096)) != cudaSuccess) { upb_destroy(ctx); return fail(nullptr, UPB_ERR_NOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e)); }
   memset(&ctx->stats, 0, sizeof ctx->stats);
   *out = ctx;
@@ -127,16 +151,21 @@ extern "C" int upb_create (int device, upb_ctx** out) {
 extern "C" void upb_destroy (upb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  DevBuf* all[] = {&ctx->d_winBase, &ctx->d_wEnt, &ctx->d_pk16, &ctx->d_pk8, &ctx->d_pkExc, &ctx->d_pkAgg, &ctx->d_segEnds, &ctx->d_mtW, &ctx->d_blkW, &ctx->d_ment, &ctx->d_mtOff, &ctx->d_mtBase, &ctx->d_mtCount, &ctx->d_mEff, &ctx->d_pos, &ctx->d_cnt, &ctx->d_off, &ctx->d_segStart, &ctx->d_tidx, &ctx->d_tidxBase, &ctx->d_sizes,
+  DevBuf* all[] = {&ctx->d_winBase, &ctx->d_wEnt, &ctx->d_pk16, &ctx->d_pkExc, &ctx->d_segEnds, &ctx->d_srcStart, &ctx->d_grpSeg, &ctx->d_grpTile, &ctx->d_loadFlags, &ctx->d_mtW, &ctx->d_blkW, &ctx->d_ment, &ctx->d_mtOff, &ctx->d_mtBase, &ctx->d_mtCount, &ctx->d_mEff, &ctx->d_pos, &ctx->d_cnt, &ctx->d_off, &ctx->d_segStart, &ctx->d_tidx, &ctx->d_tidxBase, &ctx->d_sizes,
     &ctx->d_nTilesIdx, &ctx->d_small};
   for (DevBuf* b : all) release(*b);
   for (auto& kv : ctx->scratch) release(kv.second);
   for (HostSlab& h : ctx->slabPool) if (h.p) cudaFreeHost(h.p);
   if (ctx->h_small) cudaFreeHost(ctx->h_small);
+  if (ctx->h_res.p) cudaFreeHost(ctx->h_res.p);
+  for (cudaEvent_t e : ctx->stageEv) cudaEventDestroy(e);
   for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
-  if (ctx->copyEv) cudaEventDestroy(ctx->copyEv);
-  if (ctx->doneEv) cudaEventDestroy(ctx->doneEv);
+  if (ctx->loadDoneEv) cudaEventDestroy(ctx->loadDoneEv);
+  for (cudaEvent_t e : ctx->groupEv) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->copyEvs) cudaEventDestroy(e);
+  if (ctx->h_ends.p) cudaFreeHost(ctx->h_ends.p);
   if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
+  if (ctx->loadStream) cudaStreamDestroy(ctx->loadStream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -243,53 +272,93 @@ static Tags make_tags (const upb_ctx* ctx, bool useEff) {
 
 static int scan_u32 (upb_ctx* ctx, const uint32_t* d_in, uint64_t n, unsigned long long* d_out, unsigned long long* d_total, uint32_t* launches);
 
-// Both load paths: validate the offsets, bring pos[] / cnt[] to the device SAMPLE BY SAMPLE on the copy stream (plain: two
-// copies; packed: the 3-byte form, decoded by upb_pack.cuh) with the validation + histogram pass of the counting sort running
-// one sample behind on the compute stream, then the scan, the scatter pass and the zone maps.
-struct PackedSrc { const uint16_t* dpos; const uint8_t* cnt8; uint64_t nExc; const upb_packed_exception* exc; bool twoByte; };   // twoByte: cnt8 unused
+static int ensure_host (upb_ctx* ctx, HostSlab& h, size_t bytes);
 
-static int load_tags_impl (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt, const PackedSrc* pk) {
-  if (!ctx) return UPB_ERR_BAD_ARG;
-  if (ctx->sizes.empty()) return fail(ctx, UPB_ERR_NOT_LOADED, "upb_load_tags: call upb_set_contigs first");
-  if (n_samples == 0 || !off) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags: no samples");
-  CU(cudaSetDevice(ctx->device));
+// ------------------------------------------------------------------------------------------------
+// the load: host arrays -> resident sample-major arrays + tile-major copy + zone maps
+//
+// Work is cut into LOAD GROUPS — (strand, range of consecutive contigs this context keeps), sized to ~1/8 of the entries of a
+// strand — and pipelined group by group over three streams: the H2D copies of group k+1 (copy stream) run while group k is
+// decoded, validated, histogrammed (load_tile_kernel), scanned and scattered into the tile-major copy with its zone maps
+// (mt_scatter_kernel) on the load stream, and — when the load was started with upb_load_tags_async — while the region pipeline
+// of an earlier group already runs on the context's main stream (run_pipeline_once waits on the groups' events, not on the host).
+// r01 pipelined sample by sample, which left the scatter, the call and the table copy (~5 ms) exposed after the last byte.
+// ------------------------------------------------------------------------------------------------
+static int scan_load (upb_ctx* ctx, const uint32_t* d_in, uint64_t n, unsigned long long* d_out, unsigned long long bias, unsigned long long* d_total) {
+  const uint64_t maxTiles = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  DevBuf& b = ctx->scratch["loadScanPartial"];                        // not the pipeline's: the two run on different streams
+  { int r = ensure(ctx, b, (maxTiles + 2) * 8); if (r) return r; }
+  unsigned long long* part = b.as<unsigned long long>();
+  const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(maxTiles, (uint64_t)ctx->smCount * 4));
+  const DevN nn = devn_imm(n);
+  scanv_partial_kernel<<<grid, SCAN_THREADS, 0, ctx->loadStream>>>(LoadU32{d_in}, nn, part);
+  scanv_top_kernel<<<1, SCAN_THREADS, 0, ctx->loadStream>>>(part, nn, d_total);
+  scanv_final_kernel<<<grid, SCAN_THREADS, 0, ctx->loadStream>>>(LoadU32{d_in}, nn, part, d_out, bias);
+  CU(cudaGetLastError());
+  return UPB_OK;
+}
+
+static int load_finish (upb_ctx* ctx);
+
+// enqueue the whole load (resident == false: copies from `src`; true: rebuild the index from the arrays already on the device)
+static int load_enqueue (upb_ctx* ctx, const upb_tag_source* src, bool resident) {
   const uint32_t C = (uint32_t)ctx->sizes.size();
-  const size_t nOff = (size_t)n_samples * 2 * (C + 1);
+  const uint32_t n_samples = resident ? ctx->nSamples : src->n_samples;
   const uint32_t nSeg = n_samples * 2 * C;
-  // offsets must describe one contiguous, monotone packing (what TagData / the CLI front end produce)
-  std::vector<uint64_t> segStart(nSeg + 1);
-  uint64_t expect = off[0];
-  if (expect != 0) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags: off[0] must be 0");
-  for (uint32_t sd = 0; sd < n_samples * 2; ++sd) {
-    const uint64_t* o = off + (size_t)sd * (C + 1);
-    if (o[0] != expect) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags: offset blocks must be contiguous");
-    for (uint32_t c = 0; c < C; ++c) {
-      if (o[c + 1] < o[c]) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags: offsets must be non-decreasing");
-      if (o[c + 1] - o[c] > 0xFFFFFFFFull) return fail(ctx, UPB_ERR_UNSUPPORTED, "upb_load_tags: more than 2^32 entries in one segment");
-      segStart[(size_t)sd * C + c] = o[c];
+  const bool packed = !resident && src->words != nullptr;
+  cudaStream_t ls = ctx->loadStream, cs = ctx->copyStream;
+  if (!resident) {
+    const uint64_t* off = src->off;
+    const size_t nOff = (size_t)n_samples * 2 * (C + 1);
+    // offsets must describe one contiguous, monotone packing (what TagData / the CLI front end produce)
+    ctx->srcStart.assign(nSeg, 0);
+    ctx->segStart.assign((size_t)nSeg + 1, 0);
+    uint64_t expect = off[0], run = 0;
+    if (expect != 0) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags: off[0] must be 0");
+    for (uint32_t sd = 0; sd < n_samples * 2; ++sd) {
+      const uint64_t* o = off + (size_t)sd * (C + 1);
+      if (o[0] != expect) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags: offset blocks must be contiguous");
+      for (uint32_t c = 0; c < C; ++c) {
+        if (o[c + 1] < o[c]) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags: offsets must be non-decreasing");
+        if (o[c + 1] - o[c] > 0xFFFFFFFFull) return fail(ctx, UPB_ERR_UNSUPPORTED, "upb_load_tags: more than 2^32 entries in one segment");
+        const size_t g = (size_t)sd * C + c;
+        ctx->srcStart[g] = o[c];
+        ctx->segStart[g] = run;
+        if (!src->keep_contig || src->keep_contig[c]) run += o[c + 1] - o[c];
+      }
+      expect = o[C];
     }
-    expect = o[C];
+    ctx->segStart[nSeg] = run;
+    const uint64_t Esrc = expect, E = run;
+    if (Esrc && !packed && (!src->pos || !src->cnt)) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags: pos/cnt are NULL");
+    if (packed && src->n_exceptions && !src->exceptions) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags_packed2: NULL exception list");
+    ctx->nSamples = n_samples;
+    ctx->nEntries = E;
+    // device-side offsets in the layout of the caller's `off` (density kernel, tags_in_regions)
+    ctx->off.assign(nOff, 0);
+    for (uint32_t sd = 0; sd < n_samples * 2; ++sd) {
+      for (uint32_t c = 0; c < C; ++c) ctx->off[(size_t)sd * (C + 1) + c] = ctx->segStart[(size_t)sd * C + c];
+      ctx->off[(size_t)sd * (C + 1) + C] = ctx->segStart[(size_t)(sd + 1) * C];
+    }
+    ctx->firstPos.assign(nSeg, 0);
+    ctx->lastPos.assign(nSeg, 0);
+    ctx->lastPosKnown = !packed;
+    for (uint32_t g = 0; g < nSeg; ++g) {
+      const uint64_t len = ctx->segStart[g + 1] - ctx->segStart[g];
+      if (!len) continue;
+      const uint64_t a = ctx->srcStart[g];
+      if (!packed) { ctx->firstPos[g] = src->pos[a]; ctx->lastPos[g] = src->pos[a + len - 1]; }
+      else {                                                            // the first entry of a segment is a position escape: its exception holds the position
+        const upb_packed_exception* x = std::lower_bound(src->exceptions, src->exceptions + src->n_exceptions, a,
+                                                         [] (const upb_packed_exception& e, uint64_t v) { return e.index < v; });
+        ctx->firstPos[g] = (x != src->exceptions + src->n_exceptions && x->index == a && x->pos) ? x->pos : 0xFFFFFFFFu;   // malformed: the device reports it
+      }
+    }
   }
-  const uint64_t E = expect;
-  segStart[nSeg] = E;
-  if (E && !pk && (!pos || !cnt)) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags: pos/cnt are NULL");
-  if (E && pk && (!pk->dpos || (!pk->twoByte && !pk->cnt8) || (pk->nExc && !pk->exc))) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags_packed: NULL argument");
-  if (n_samples > (1u << 20)) return fail(ctx, UPB_ERR_UNSUPPORTED, "more than 2^20 samples");
-  ctx->loaded = false;
-  ctx->nSamples = n_samples;
-  ctx->nEntries = E;
-  ctx->off.assign(off, off + nOff);
-  ctx->firstPos.assign(nSeg, 0);
-  ctx->lastPos.assign(nSeg, 0);
-  if (!pk)
-    for (uint32_t g = 0; g < nSeg; ++g)
-      if (segStart[g + 1] > segStart[g]) { ctx->firstPos[g] = pos[segStart[g]]; ctx->lastPos[g] = pos[segStart[g + 1] - 1]; }
+  const uint64_t E = ctx->nEntries;
+  const size_t nOff = (size_t)n_samples * 2 * (C + 1);
 
-  ENSURE(ctx->d_pos, (E ? E : 1) * 4);
-  ENSURE(ctx->d_cnt, (E ? E : 1) * 4);
-  ENSURE(ctx->d_off, nOff * 8);
-  ENSURE(ctx->d_segStart, ((size_t)nSeg + 1) * 8);
-  ENSURE(ctx->d_small, 4096);
+  // ---- index geometry ---------------------------------------------------------------------------------------------------
   ctx->mtBase.assign(2 * (size_t)C + 1, 0);
   { uint64_t run = 0;
     for (uint32_t d = 0; d < 2; ++d) for (uint32_t c = 0; c < C; ++c) { ctx->mtBase[(size_t)d * C + c] = (uint32_t)run; run += ((uint64_t)(ctx->sizes[c] - 1) >> MT_SHIFT) + 1; }
@@ -301,6 +370,79 @@ static int load_tags_impl (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off
     for (size_t dc = 0; dc < 2 * (size_t)C; ++dc) { winBase[dc] = run; run += (ctx->mtBase[dc + 1] - ctx->mtBase[dc] + WIN_MT - 1) / WIN_MT; }
     winBase[2 * (size_t)C] = run; }
   const uint32_t nWinTotal = winBase.back();
+
+  // ---- load groups: (strand, run of kept contigs), cut to ~1/8 of a strand's entries -----------------------------------------
+  std::vector<uint64_t> perDC(2 * (size_t)C, 0);
+  std::vector<uint8_t> kept(C, 0);
+  for (uint32_t c = 0; c < C; ++c) kept[c] = resident ? ctx->keptContig[c] : (uint8_t)(!src->keep_contig || src->keep_contig[c]);
+  ctx->keptContig = kept;
+  for (uint32_t s = 0; s < n_samples; ++s) for (uint32_t d = 0; d < 2; ++d) for (uint32_t c = 0; c < C; ++c) {
+    const size_t g = ((size_t)s * 2 + d) * C + c;
+    perDC[(size_t)d * C + c] += ctx->segStart[g + 1] - ctx->segStart[g];
+  }
+  const uint64_t target = std::max<uint64_t>(E / 16 + 1, 1u << 20);    // entries (both strands) per contig range
+  struct Range { uint32_t c0, c1; };
+  std::vector<Range> ranges;
+  { uint32_t c = 0;
+    while (c < C) {
+      if (!kept[c]) { ++c; continue; }
+      Range r; r.c0 = c;
+      uint64_t acc = 0;
+      while (c < C && kept[c] && (acc == 0 || acc < target)) { acc += perDC[c] + perDC[(size_t)C + c]; ++c; }
+      r.c1 = c;
+      ranges.push_back(r);
+    } }
+  const bool strandMajor = resident ? ctx->loadStrandMajor : src->directional_hint != 0;
+  ctx->loadStrandMajor = strandMajor;
+  ctx->groups.clear();
+  auto addGroup = [&] (uint32_t d, const Range& r) { LoadGroup g; memset(&g, 0, sizeof g); g.d = d; g.c0 = r.c0; g.c1 = r.c1; ctx->groups.push_back(g); };
+  if (strandMajor) { for (uint32_t d = 0; d < 2; ++d) for (const Range& r : ranges) addGroup(d, r); }
+  else { for (const Range& r : ranges) for (uint32_t d = 0; d < 2; ++d) addGroup(d, r); }
+  // position of every group in the tile-major copy (mini-tile order = strand, contig): entries of everything before it
+  { std::vector<uint64_t> before(2 * (size_t)C + 1, 0);
+    for (size_t dc = 0; dc < 2 * (size_t)C; ++dc) before[dc + 1] = before[dc] + perDC[dc];
+    for (LoadGroup& g : ctx->groups) {
+      g.mentBase = before[(size_t)g.d * C + g.c0];
+      g.entries = before[(size_t)g.d * C + g.c1] - g.mentBase;
+      g.m0 = ctx->mtBase[(size_t)g.d * C + g.c0]; g.m1 = ctx->mtBase[(size_t)g.d * C + g.c1];
+      g.w0 = winBase[(size_t)g.d * C + g.c0]; g.w1 = winBase[(size_t)g.d * C + g.c1];
+    } }
+  // tiles of every group: its segments in (sample, contig) order
+  std::vector<uint32_t> grpSeg, grpTile;
+  for (LoadGroup& g : ctx->groups) {
+    g.seg0 = (uint32_t)grpSeg.size();
+    uint32_t tiles = 0;
+    g.tileTab0 = (uint32_t)grpTile.size();
+    for (uint32_t s = 0; s < n_samples; ++s) for (uint32_t c = g.c0; c < g.c1; ++c) {
+      const uint32_t sg = (s * 2 + g.d) * C + c;
+      const uint64_t len = ctx->segStart[(size_t)sg + 1] - ctx->segStart[sg];
+      if (!len) continue;
+      grpSeg.push_back(sg); grpTile.push_back(tiles);
+      tiles += (uint32_t)((len + PK_TILE - 1) / PK_TILE);
+    }
+    grpTile.push_back(tiles);
+    g.nSeg = (uint32_t)grpSeg.size() - g.seg0;
+    g.nTiles = tiles;
+  }
+  while (ctx->groupEv.size() < ctx->groups.size()) {
+    cudaEvent_t e = nullptr;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->groupEv.push_back(e);
+  }
+  while (ctx->copyEvs.size() < ctx->groups.size()) {
+    cudaEvent_t e = nullptr;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->copyEvs.push_back(e);
+  }
+
+  // ---- device arrays ------------------------------------------------------------------------------------------------------
+  ENSURE(ctx->d_pos, (E ? E : 1) * 4);
+  ENSURE(ctx->d_cnt, (E ? E : 1) * 4);
+  ENSURE(ctx->d_off, nOff * 8);
+  ENSURE(ctx->d_segStart, ((size_t)nSeg + 1) * 8);
+  ENSURE(ctx->d_srcStart, ((size_t)nSeg + 1) * 8);
+  ENSURE(ctx->d_small, 4096);
+  ENSURE(ctx->d_loadFlags, 256);
   ENSURE(ctx->d_mtBase, (2 * (size_t)C + 1) * 4);
   ENSURE(ctx->d_winBase, (2 * (size_t)C + 1) * 4);
   ENSURE(ctx->d_wEnt, ((size_t)n_samples * nWinTotal + 2) * 4);
@@ -309,114 +451,165 @@ static int load_tags_impl (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off
   ENSURE(ctx->d_ment, (E ? E : 1) * 8);
   ENSURE(ctx->d_mtW, ((size_t)nMtTotal + 1) * 8);
   ENSURE(ctx->d_blkW, ((size_t)nMtTotal + 1) * BLK_PER_MT * 4);
-  uint64_t maxChunk = 0;
-  for (uint32_t s = 0; s < n_samples; ++s) maxChunk = std::max(maxChunk, segStart[(size_t)(s + 1) * 2 * C] - segStart[(size_t)s * 2 * C]);
-  if (pk) {
+  ENSURE(ctx->d_grpSeg, (grpSeg.size() + 1) * 4);
+  ENSURE(ctx->d_grpTile, (grpTile.size() + 1) * 4);
+  ENSURE(ctx->d_segEnds, 2 * ((size_t)nSeg + 1) * 4);
+  if (packed) {
     ENSURE(ctx->d_pk16, (E ? E : 1) * 2);
-    if (!pk->twoByte) ENSURE(ctx->d_pk8, (E ? E : 1));
-    ENSURE(ctx->d_pkExc, (pk->nExc ? pk->nExc : 1) * sizeof(PkException));
-    ENSURE(ctx->d_pkAgg, 2 * (maxChunk / PK_TILE + 2) * sizeof(PkAgg));
-    ENSURE(ctx->d_segEnds, 2 * ((size_t)nSeg + 1) * 4);
-    if (pk->nExc) CU(cudaMemcpyAsync(ctx->d_pkExc.p, pk->exc, pk->nExc * sizeof(PkException), cudaMemcpyHostToDevice, ctx->stream));
+    ENSURE(ctx->d_pkExc, (src->n_exceptions ? src->n_exceptions : 1) * sizeof(PkException));
   }
-  CU(cudaMemcpyAsync(ctx->d_off.p, off, nOff * 8, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->d_segStart.p, segStart.data(), ((size_t)nSeg + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemsetAsync(ctx->d_small.p, 0, 4096, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->d_mtBase.p, ctx->mtBase.data(), (2 * (size_t)C + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemsetAsync(ctx->d_mtCount.p, 0, ((size_t)nMtTotal + 1) * 4, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->d_winBase.p, winBase.data(), (2 * (size_t)C + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
-  // the copy stream starts after whatever still reads the old arrays on the compute stream
-  CU(cudaEventRecord(ctx->doneEv, ctx->stream));
-  CU(cudaStreamWaitEvent(ctx->copyStream, ctx->doneEv, 0));
+  { int r = ensure_host(ctx, ctx->h_ends, 2 * ((size_t)nSeg + 1) * 4 + 64); if (r) return r; }
+  // small tables: staged through pageable memory by the runtime before the call returns
+  CU(cudaMemcpyAsync(ctx->d_off.p, ctx->off.data(), nOff * 8, cudaMemcpyHostToDevice, ls));
+  CU(cudaMemcpyAsync(ctx->d_segStart.p, ctx->segStart.data(), ((size_t)nSeg + 1) * 8, cudaMemcpyHostToDevice, ls));
+  CU(cudaMemcpyAsync(ctx->d_srcStart.p, ctx->srcStart.data(), (size_t)nSeg * 8, cudaMemcpyHostToDevice, ls));
+  CU(cudaMemcpyAsync(ctx->d_mtBase.p, ctx->mtBase.data(), (2 * (size_t)C + 1) * 4, cudaMemcpyHostToDevice, ls));
+  CU(cudaMemcpyAsync(ctx->d_winBase.p, winBase.data(), (2 * (size_t)C + 1) * 4, cudaMemcpyHostToDevice, ls));
+  if (!grpSeg.empty()) CU(cudaMemcpyAsync(ctx->d_grpSeg.p, grpSeg.data(), grpSeg.size() * 4, cudaMemcpyHostToDevice, ls));
+  CU(cudaMemcpyAsync(ctx->d_grpTile.p, grpTile.data(), grpTile.size() * 4, cudaMemcpyHostToDevice, ls));
+  CU(cudaMemsetAsync(ctx->d_loadFlags.p, 0, 256, ls));
+  CU(cudaMemsetAsync(ctx->d_mtCount.p, 0, ((size_t)nMtTotal + 1) * 4, ls));
+  CU(cudaMemsetAsync(ctx->d_mtOff.p, 0, ((size_t)nMtTotal + 2) * 8, ls));   // ranges of contigs this context does not keep stay empty
+  CU(cudaStreamSynchronize(ls));                                       // the host vectors above go out of scope; nothing large has been queued yet
+  if (packed && src->n_exceptions) CU(cudaMemcpyAsync(ctx->d_pkExc.p, src->exceptions, src->n_exceptions * sizeof(PkException), cudaMemcpyHostToDevice, cs));
 
+  LoadArgs la;
+  memset(&la, 0, sizeof la);
+  la.words = packed ? ctx->d_pk16.as<uint16_t>() : nullptr;
+  la.exc = ctx->d_pkExc.as<PkException>(); la.nExc = packed ? src->n_exceptions : 0;
+  la.pos = ctx->d_pos.as<uint32_t>(); la.cnt = ctx->d_cnt.as<uint32_t>();
+  la.segStart = ctx->d_segStart.as<uint64_t>(); la.srcStart = ctx->d_srcStart.as<uint64_t>();
+  la.sizes = ctx->d_sizes.as<uint32_t>(); la.mtBase = ctx->d_mtBase.as<uint32_t>(); la.mtCount = ctx->d_mtCount.as<uint32_t>();
+  la.winBase = ctx->d_winBase.as<uint32_t>(); la.wEnt = ctx->d_wEnt.as<uint32_t>(); la.nWinTotal = nWinTotal; la.C = C;
+  la.flags = ctx->d_loadFlags.as<uint32_t>();
   MtArgs ma;
-  ma.pos = ctx->d_pos.as<uint32_t>(); ma.cnt = ctx->d_cnt.as<uint32_t>(); ma.segStart = ctx->d_segStart.as<uint64_t>(); ma.mtBase = ctx->d_mtBase.as<uint32_t>();
-  ma.mtCount = ctx->d_mtCount.as<uint32_t>(); ma.mtOff = ctx->d_mtOff.as<unsigned long long>(); ma.ment = ctx->d_ment.as<uint2>();
-  ma.sizes = ctx->d_sizes.as<uint32_t>(); ma.flags = ctx->d_small.as<uint32_t>();
-  ma.C = C; ma.nSeg = nSeg;
+  memset(&ma, 0, sizeof ma);
+  ma.pos = la.pos; ma.cnt = la.cnt; ma.segStart = la.segStart; ma.mtBase = la.mtBase;
+  ma.mtCount = la.mtCount; ma.mtOff = ctx->d_mtOff.as<unsigned long long>(); ma.ment = ctx->d_ment.as<uint2>();
+  ma.sizes = la.sizes; ma.flags = la.flags; ma.C = C; ma.nSeg = nSeg;
   ma.mtW = ctx->d_mtW.as<unsigned long long>(); ma.blkW = ctx->d_blkW.as<float>();
-  ma.winBase = ctx->d_winBase.as<uint32_t>(); ma.wEnt = ctx->d_wEnt.as<uint32_t>(); ma.nWinTotal = nWinTotal;
-  ma.first = 0; ma.nEntries = 0;
-  win_fill_kernel<<<(unsigned)(((uint64_t)n_samples * nWinTotal + 255) / 256), 256, 0, ctx->stream>>>(ma, n_samples);
-  // tile-major copy, pass 1 (validation + per-mini-tile histogram), one sample behind the copies
-  for (uint32_t s = 0; s < n_samples; ++s) {
-    const uint64_t first = segStart[(size_t)s * 2 * C], n = segStart[(size_t)(s + 1) * 2 * C] - first;
-    if (!n) continue;
-    if (!pk) {
-      CU(cudaMemcpyAsync(ctx->d_pos.as<uint32_t>() + first, pos + first, n * 4, cudaMemcpyHostToDevice, ctx->copyStream));
-      CU(cudaMemcpyAsync(ctx->d_cnt.as<uint32_t>() + first, cnt + first, n * 4, cudaMemcpyHostToDevice, ctx->copyStream));
-    } else {
-      CU(cudaMemcpyAsync(ctx->d_pk16.as<uint16_t>() + first, pk->dpos + first, n * 2, cudaMemcpyHostToDevice, ctx->copyStream));
-      if (!pk->twoByte) CU(cudaMemcpyAsync(ctx->d_pk8.as<uint8_t>() + first, pk->cnt8 + first, n, cudaMemcpyHostToDevice, ctx->copyStream));
+  ma.winBase = la.winBase; ma.wEnt = la.wEnt; ma.nWinTotal = nWinTotal;
+  unsigned long long* d_scanTot = (unsigned long long*)(ctx->d_loadFlags.as<unsigned char>() + 64);
+
+  for (size_t gi = 0; gi < ctx->groups.size(); ++gi) {
+    const LoadGroup& g = ctx->groups[gi];
+    if (!resident && g.entries) {
+      // one copy per (sample, array): the segments of contigs c0 .. c1-1 of one (sample, strand) are contiguous on both sides
+      for (uint32_t s = 0; s < n_samples; ++s) {
+        const size_t sg0 = ((size_t)s * 2 + g.d) * C + g.c0, sg1 = ((size_t)s * 2 + g.d) * C + g.c1;
+        const uint64_t dev0 = ctx->segStart[sg0], cntE = ctx->segStart[sg1] - dev0, src0 = ctx->srcStart[sg0];
+        if (!cntE) continue;
+        if (packed) CU(cudaMemcpyAsync(ctx->d_pk16.as<uint16_t>() + dev0, src->words + src0, cntE * 2, cudaMemcpyHostToDevice, cs));
+        else {
+          CU(cudaMemcpyAsync(ctx->d_pos.as<uint32_t>() + dev0, src->pos + src0, cntE * 4, cudaMemcpyHostToDevice, cs));
+          CU(cudaMemcpyAsync(ctx->d_cnt.as<uint32_t>() + dev0, src->cnt + src0, cntE * 4, cudaMemcpyHostToDevice, cs));
+        }
+      }
+      CU(cudaEventRecord(ctx->copyEvs[gi], cs));
+      CU(cudaStreamWaitEvent(ls, ctx->copyEvs[gi], 0));
     }
-    CU(cudaEventRecord(ctx->copyEv, ctx->copyStream));
-    CU(cudaStreamWaitEvent(ctx->stream, ctx->copyEv, 0));
-    if (pk) {
-      PkArgs pa;
-      pa.dpos = ctx->d_pk16.as<uint16_t>(); pa.cnt8 = pk->twoByte ? nullptr : ctx->d_pk8.as<uint8_t>(); pa.exc = ctx->d_pkExc.as<PkException>(); pa.nExc = pk->nExc;
-      pa.dposMask = pk->twoByte ? PK2_DPOS_MASK : 0xFFFFu; pa.dposEsc = pk->twoByte ? PK2_DPOS_ESC : PK_DPOS_ESC; pa.cntEsc = pk->twoByte ? PK2_CNT_ESC : PK_CNT_ESC;
-      pa.first = first; pa.E = n; pa.pos = ctx->d_pos.as<uint32_t>(); pa.cnt = ctx->d_cnt.as<uint32_t>(); pa.flags = ctx->d_small.as<uint32_t>();
-      const uint32_t nTiles = (uint32_t)((n + PK_TILE - 1) / PK_TILE);
-      pa.agg = ctx->d_pkAgg.as<PkAgg>(); pa.carry = pa.agg + (maxChunk / PK_TILE + 2);
-      pk_tile_kernel<<<nTiles, PK_THREADS, 0, ctx->stream>>>(pa);
-      pk_top_kernel<<<1, 1024, 0, ctx->stream>>>(pa.agg, nTiles, pa.carry);
-      pk_final_kernel<<<nTiles, PK_THREADS, 0, ctx->stream>>>(pa);
+    la.grpSeg = ctx->d_grpSeg.as<uint32_t>() + g.seg0; la.grpTile = ctx->d_grpTile.as<uint32_t>() + g.tileTab0; la.nGrpSeg = g.nSeg;
+    if (g.w1 > g.w0) load_win_fill_kernel<<<(unsigned)(((uint64_t)n_samples * (g.w1 - g.w0) + 255) / 256), 256, 0, ls>>>(la, n_samples, g.w0, g.w1);
+    if (g.nTiles) {
+      load_tile_kernel<<<g.nTiles, PK_THREADS, 0, ls>>>(la);
+      load_seam_kernel<<<(g.nTiles + 255) / 256, 256, 0, ls>>>(la, g.nTiles);
     }
-    ma.first = first; ma.nEntries = n;
-    mt_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ma);
+    if (g.m1 > g.m0) {
+      int r = scan_load(ctx, ma.mtCount + g.m0, g.m1 - g.m0, ctx->d_mtOff.as<unsigned long long>() + g.m0, g.mentBase, d_scanTot);
+      if (r) return r;
+      set_u64_kernel<<<1, 1, 0, ls>>>(ctx->d_mtOff.as<unsigned long long>() + g.m1, g.mentBase + g.entries);
+      mt_scatter_kernel<<<g.w1 - g.w0, 256, 0, ls>>>(ma, n_samples, g.w0);
+    }
     CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->groupEv[gi], ls));
   }
-  {
-    uint32_t l = 0;
-    unsigned long long* d_tot = ctx->d_small.as<unsigned long long>() + 16;
-    int r = scan_u32(ctx, ma.mtCount, nMtTotal, ctx->d_mtOff.as<unsigned long long>(), d_tot, &l);
-    if (r) return r;
-    CU(cudaMemcpyAsync(ctx->d_mtOff.as<unsigned long long>() + nMtTotal, d_tot, 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    ma.first = 0; ma.nEntries = E;
-    if (E) mt_scatter_kernel<<<nWinTotal, 256, 0, ctx->stream>>>(ma, n_samples);
-    CU(cudaGetLastError());
-  }
-  uint32_t flags = 0;
-  CU(cudaMemcpyAsync(&flags, ctx->d_small.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  if (pk) {   // first / last position of every segment come back from the decoded arrays
-    uint32_t* ends = ctx->d_segEnds.as<uint32_t>();
-    seg_ends_kernel<<<(nSeg + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_pos.as<uint32_t>(), ctx->d_segStart.as<uint64_t>(), nSeg, ends, ends + nSeg);
-    CU(cudaMemcpyAsync(ctx->firstPos.data(), ends, (size_t)nSeg * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->lastPos.data(), ends + nSeg, (size_t)nSeg * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  }
-  CU(cudaStreamSynchronize(ctx->stream));
+  // first / last position of every segment (the reference-order logic and the left-edge test want them) and the validation flags
+  uint32_t* ends = ctx->d_segEnds.as<uint32_t>();
+  seg_ends_kernel<<<(nSeg + 255) / 256, 256, 0, ls>>>(ctx->d_pos.as<uint32_t>(), ctx->d_segStart.as<uint64_t>(), nSeg, ends, ends + nSeg);
+  CU(cudaGetLastError());
+  uint32_t* hEnds = (uint32_t*)ctx->h_ends.p;
+  CU(cudaMemcpyAsync(hEnds, ends, 2 * (size_t)nSeg * 4, cudaMemcpyDeviceToHost, ls));
+  CU(cudaMemcpyAsync(hEnds + 2 * (size_t)nSeg, ctx->d_loadFlags.p, 4, cudaMemcpyDeviceToHost, ls));
+  CU(cudaEventRecord(ctx->loadDoneEv, ls));
+  ctx->loaded = false;
+  ctx->loadPending = true;
   ctx->cntEffValid = false;
   ctx->tidxBuilt = false;
-  if (flags & FLAG_BAD_PACK) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags_packed: an escape code without its exception entry");
-  if (flags & FLAG_UNSORTED) return fail(ctx, UPB_ERR_UNSORTED, "upb_load_tags: positions must be strictly ascending within each (sample, strand, contig) — the reference asserts on unsorted input (misc/peakcall.cpp:171)");
-  if (flags & FLAG_BAD_POS) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags: position outside 1..contig size (the reference's parser drops those, misc/format.cpp:670-676)");
-  if (flags & FLAG_ZERO_COUNT) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags: zero count (the reference's parser never delivers those, misc/format.cpp:710)");
-  ctx->loaded = true;
-  ctx->stats.n_entries = E;
   return UPB_OK;
 }
 
-extern "C" int upb_load_tags (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt) {
-  return load_tags_impl(ctx, n_samples, off, pos, cnt, nullptr);
+// wait for a pending load and take over what it reports; errors of the input surface here
+static int load_finish (upb_ctx* ctx) {
+  if (!ctx->loadPending) return UPB_OK;
+  CU(cudaSetDevice(ctx->device));
+  ctx->loadPending = false;
+  CU(cudaEventSynchronize(ctx->loadDoneEv));
+  const uint32_t nSeg = (uint32_t)ctx->firstPos.size();
+  const uint32_t* hEnds = (const uint32_t*)ctx->h_ends.p;
+  const uint32_t flags = hEnds[2 * (size_t)nSeg];
+  if (flags & FLAG_BAD_PACK) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags_packed2: an escape code without its exception entry, or a tile of a segment that does not start with a position escape");
+  if (flags & FLAG_UNSORTED) return fail(ctx, UPB_ERR_UNSORTED, "upb_load_tags: positions must be strictly ascending within each (sample, strand, contig) — the reference asserts on unsorted input (misc/peakcall.cpp:171)");
+  if (flags & FLAG_BAD_POS) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags: position outside 1..contig size (the reference's parser drops those, misc/format.cpp:670-676)");
+  if (flags & FLAG_ZERO_COUNT) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags: zero count (the reference's parser never delivers those, misc/format.cpp:710)");
+  for (uint32_t g = 0; g < nSeg; ++g) { ctx->firstPos[g] = hEnds[g]; ctx->lastPos[g] = hEnds[nSeg + g]; }
+  ctx->lastPosKnown = true;
+  ctx->loaded = true;
+  ctx->stats.n_entries = ctx->nEntries;
+  return UPB_OK;
 }
 
-extern "C" int upb_load_tags_packed (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off, const uint16_t* dpos, const uint8_t* cnt8,
-                                     uint64_t n_exceptions, const upb_packed_exception* exceptions) {
-  PackedSrc pk; pk.dpos = dpos; pk.cnt8 = cnt8; pk.nExc = n_exceptions; pk.exc = exceptions; pk.twoByte = false;
-  return load_tags_impl(ctx, n_samples, off, nullptr, nullptr, &pk);
+extern "C" int upb_load_tags_async (upb_ctx* ctx, const upb_tag_source* src) {
+  if (!ctx) return UPB_ERR_BAD_ARG;
+  if (ctx->sizes.empty()) return fail(ctx, UPB_ERR_NOT_LOADED, "upb_load_tags: call upb_set_contigs first");
+  if (!src || src->n_samples == 0 || !src->off) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags: no samples");
+  if (src->n_samples > (1u << 20) || (uint64_t)src->n_samples * 2 * ctx->sizes.size() > 0x7FFFFFF0ull) return fail(ctx, UPB_ERR_UNSUPPORTED, "too many (sample, strand, contig) segments");
+  CU(cudaSetDevice(ctx->device));
+  if (ctx->loadPending) { ctx->loadPending = false; cudaEventSynchronize(ctx->loadDoneEv); }   // a load nobody waited for is simply replaced
+  ctx->loaded = false;
+  const int r = load_enqueue(ctx, src, false);
+  if (r) { ctx->loadPending = false; cudaStreamSynchronize(ctx->copyStream); cudaStreamSynchronize(ctx->loadStream); }
+  return r;
+}
+
+extern "C" int upb_load_wait (upb_ctx* ctx) {
+  if (!ctx) return UPB_ERR_BAD_ARG;
+  if (!ctx->loadPending) return ctx->loaded ? UPB_OK : fail(ctx, UPB_ERR_NOT_LOADED, "no tags loaded (upb_set_contigs + upb_load_tags first)");
+  return load_finish(ctx);
+}
+
+extern "C" int upb_reindex (upb_ctx* ctx) {
+  if (!ctx) return UPB_ERR_BAD_ARG;
+  { int r = load_finish(ctx); if (r) return r; }
+  if (!ctx->loaded) return fail(ctx, UPB_ERR_NOT_LOADED, "no tags loaded (upb_set_contigs + upb_load_tags first)");
+  CU(cudaSetDevice(ctx->device));
+  int r = load_enqueue(ctx, nullptr, true);
+  if (r) return r;
+  return load_finish(ctx);
+}
+
+extern "C" int upb_load_tags (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt) {
+  upb_tag_source s;
+  memset(&s, 0, sizeof s);
+  s.n_samples = n_samples; s.off = off; s.pos = pos; s.cnt = cnt; s.directional_hint = 1;
+  const int r = upb_load_tags_async(ctx, &s);
+  return r ? r : load_finish(ctx);
 }
 
 extern "C" int upb_load_tags_packed2 (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off, const uint16_t* words,
                                       uint64_t n_exceptions, const upb_packed_exception* exceptions) {
-  PackedSrc pk; pk.dpos = words; pk.cnt8 = nullptr; pk.nExc = n_exceptions; pk.exc = exceptions; pk.twoByte = true;
-  return load_tags_impl(ctx, n_samples, off, nullptr, nullptr, &pk);
+  if (ctx && !words) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags_packed2: NULL argument");
+  upb_tag_source s;
+  memset(&s, 0, sizeof s);
+  s.n_samples = n_samples; s.off = off; s.words = words; s.n_exceptions = n_exceptions; s.exceptions = exceptions; s.directional_hint = 1;
+  const int r = upb_load_tags_async(ctx, &s);
+  return r ? r : load_finish(ctx);
 }
 
-// host-only encoder of the packed form (what a front end does while it parses)
-// one encoder for both packed forms: dposEsc / cntEsc are the escape codes, cntShift != 0 puts the count into the high bits of the u16
-static int pack_tags_impl (uint32_t n_samples, uint32_t n_contigs, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt,
-                           uint16_t* dpos_out, uint8_t* cnt8_out, upb_packed_exception* exc_out, uint64_t exc_cap, uint64_t* n_exc_out,
-                           uint32_t dposEsc, uint32_t cntEsc, uint32_t cntShift) {
+// host-only encoder of the 2-byte form (what a front end does while it parses): position delta in the low 12 bits, count in the
+// high 4, escapes 0xFFF / 0xF with the full values in the exception list.  A position escape opens every segment and every
+// PK_TILE-th entry of it (upb_pack.cuh).
+extern "C" int upb_pack_tags2 (uint32_t n_samples, uint32_t n_contigs, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt,
+                               uint16_t* words_out, upb_packed_exception* exc_out, uint64_t exc_cap, uint64_t* n_exc_out) {
   if (!off || !n_exc_out || (exc_cap && !exc_out)) return UPB_ERR_BAD_ARG;
   uint64_t nExc = 0;
   for (uint32_t sd = 0; sd < n_samples * 2; ++sd)
@@ -425,33 +618,18 @@ static int pack_tags_impl (uint32_t n_samples, uint32_t n_contigs, const uint64_
       uint32_t prev = 0;
       for (uint64_t e = a; e < b; ++e) {
         const uint32_t p = pos[e], k = cnt[e];
-        const bool escP = e == a || p < prev || p - prev >= dposEsc;   // unsorted input is kept verbatim: the load then reports it
-        const bool escC = k >= cntEsc;
+        const bool escP = ((e - a) & (PK_TILE - 1)) == 0 || p < prev || p - prev >= PK2_DPOS_ESC;   // unsorted input is kept verbatim: the load then reports it
+        const bool escC = k >= PK2_CNT_ESC;
         if (escP || escC) {
           if (nExc < exc_cap) { exc_out[nExc].index = e; exc_out[nExc].pos = escP ? p : 0u; exc_out[nExc].cnt = escC ? k : 0u; }
           ++nExc;
         }
-        const uint32_t dv = escP ? dposEsc : p - prev, cv = escC ? cntEsc : k;
-        if (cntShift) { if (dpos_out) dpos_out[e] = (uint16_t)(dv | (cv << cntShift)); }
-        else {
-          if (dpos_out) dpos_out[e] = (uint16_t)dv;
-          if (cnt8_out) cnt8_out[e] = (uint8_t)cv;
-        }
+        if (words_out) words_out[e] = (uint16_t)((escP ? PK2_DPOS_ESC : p - prev) | ((escC ? PK2_CNT_ESC : k) << PK2_CNT_SHIFT));
         prev = p;
       }
     }
   *n_exc_out = nExc;
   return nExc <= exc_cap ? UPB_OK : UPB_ERR_NOMEM;
-}
-
-extern "C" int upb_pack_tags (uint32_t n_samples, uint32_t n_contigs, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt,
-                              uint16_t* dpos_out, uint8_t* cnt8_out, upb_packed_exception* exc_out, uint64_t exc_cap, uint64_t* n_exc_out) {
-  return pack_tags_impl(n_samples, n_contigs, off, pos, cnt, dpos_out, cnt8_out, exc_out, exc_cap, n_exc_out, PK_DPOS_ESC, PK_CNT_ESC, 0);
-}
-
-extern "C" int upb_pack_tags2 (uint32_t n_samples, uint32_t n_contigs, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt,
-                               uint16_t* words_out, upb_packed_exception* exc_out, uint64_t exc_cap, uint64_t* n_exc_out) {
-  return pack_tags_impl(n_samples, n_contigs, off, pos, cnt, words_out, nullptr, exc_out, exc_cap, n_exc_out, PK2_DPOS_ESC, PK2_CNT_ESC, PK2_CNT_SHIFT);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -480,7 +658,6 @@ struct PipeCfg {
   bool nondir;
   bool needCorr;                     // compute strandCorr(0) for regions passing the earlier filters
   const uint8_t* control;            // may be NULL
-  bool deviceOnly = false;           // leave the rows in the device slab (multi-GPU ranks: upb_scatter_rows reads them there)
   bool allowLeftEdge = false;        // replay the reference's left-edge behaviour (Q2) instead of refusing such inputs
   uint32_t nCoeffs = 0;              // 0, or the number of non-control samples (-z)
   const double* coeffs = nullptr;    // already normalised as src/regions.cpp:216-229
@@ -524,6 +701,8 @@ struct PipeOut {
   uint64_t nCand = 0;
   uint64_t R = 0;                    // accepted regions, canonical order (buffer, contig, left)
   std::vector<uint32_t> unitEdgeStop; // [nUnits] last position the left-edge replay owns in this unit, 0 if none
+  std::vector<uint64_t> unitRows;    // [nUnits] accepted rows
+  std::vector<uint64_t> tir;         // [nSamples] tags in regions
   HostSlab slab;                     // pinned; columns per `layout`
   SlabLayout layout;
   template <class T> T* col (size_t off) const { return (T*)((unsigned char*)slab.p + off); }
@@ -567,10 +746,11 @@ struct Prep {
 };
 
 // common set-up: units, taps, source list, control filter
-static int prepare (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, uint32_t* launches, bool allowLeftEdge = false) {
+static int prepare (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, uint32_t* launches, bool allowLeftEdge = false, bool allowPending = false) {
   const uint32_t C = (uint32_t)ctx->sizes.size();
   const uint32_t n = ctx->nSamples;
-  if (!ctx->loaded) return fail(ctx, UPB_ERR_NOT_LOADED, "no tags loaded (upb_set_contigs + upb_load_tags first)");
+  if (ctx->loadPending && !allowPending) { const int rl = load_finish(ctx); if (rl) return rl; }
+  if (!ctx->loaded && !(allowPending && ctx->loadPending)) return fail(ctx, UPB_ERR_NOT_LOADED, "no tags loaded (upb_set_contigs + upb_load_tags first)");
   if (cfg.bw == 0 || cfg.bw > (uint32_t)MAX_BW_FAST) return fail(ctx, UPB_ERR_UNSUPPORTED, "bandwidth must be in 1..448");
   if (!(cfg.thr > 0)) return fail(ctx, UPB_ERR_BAD_ARG, "region threshold must be > 0 (the reference's leap handling relies on it, SURVEY Q10)");
   if (!(cfg.background > 0)) return fail(ctx, UPB_ERR_BAD_ARG, "background must be > 0");
@@ -795,19 +975,79 @@ static int launch_span (upb_ctx* ctx, const SpanArgs& sa, bool nondir, uint32_t*
   return UPB_OK;
 }
 
-static void finish_stats (upb_ctx* ctx, uint32_t launches) {
-  cudaEventRecord(ctx->ev[3], ctx->stream);
-  cudaEventSynchronize(ctx->ev[3]);
-  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]);
-  ctx->stats.ms_total = ms;
-  ctx->stats.launches = launches;
+// ---- per-stage device timing (upb_set_profiling): one event between the stages of the pipeline, read after the call ----------
+static void stage_reset (upb_ctx* ctx) { ctx->stageUsed = 0; ctx->stageNames.clear(); }
+static void stage_mark (upb_ctx* ctx, const char* name) {
+  if (!ctx->profiling) return;
+  if (ctx->stageUsed == ctx->stageEv.size()) { cudaEvent_t e = nullptr; if (cudaEventCreate(&e) != cudaSuccess) return; ctx->stageEv.push_back(e); }
+  cudaEventRecord(ctx->stageEv[ctx->stageUsed++], ctx->stream);
+  ctx->stageNames.push_back(name);
+}
+static void stage_collect (upb_ctx* ctx) {                            // after the stream has been synchronised
+  ctx->stageMs.clear();
+  for (size_t k = 0; k + 1 < ctx->stageUsed; ++k) { float ms = 0; cudaEventElapsedTime(&ms, ctx->stageEv[k], ctx->stageEv[k + 1]); ctx->stageMs.push_back(ms); }
 }
 
-static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& out) {
+extern "C" int upb_set_profiling (upb_ctx* ctx, int on) { if (!ctx) return UPB_ERR_BAD_ARG; ctx->profiling = on != 0; return UPB_OK; }
+
+extern "C" int upb_last_stage_times (const upb_ctx* ctx, uint32_t cap, const char** names_out, float* ms_out, uint32_t* n_out) {
+  if (!ctx || !n_out) return UPB_ERR_BAD_ARG;
+  const uint32_t n = (uint32_t)ctx->stageMs.size();
+  *n_out = n;
+  for (uint32_t k = 0; k < n && k < cap; ++k) { if (names_out) names_out[k] = ctx->stageNames[k + 1]; if (ms_out) ms_out[k] = ctx->stageMs[k]; }
+  return UPB_OK;
+}
+
+// device-wide exclusive scan whose element count may live on the device (upb_device.cuh: scanv_*); `cap` bounds it
+template <class Load>
+static int scan_dev (upb_ctx* ctx, Load ld, DevN n, uint64_t cap, unsigned long long* d_out, unsigned long long* d_total, uint32_t* launches) {
+  const uint64_t maxTiles = (cap + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  unsigned long long* part = SCR("scanPartial", unsigned long long, maxTiles + 1);
+  const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(maxTiles, (uint64_t)ctx->smCount * 4));
+  scanv_partial_kernel<<<grid, SCAN_THREADS, 0, ctx->stream>>>(ld, n, part);
+  scanv_top_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(part, n, d_total);
+  scanv_final_kernel<<<grid, SCAN_THREADS, 0, ctx->stream>>>(ld, n, part, d_out, 0ull);
+  CU(cudaGetLastError());
+  *launches += 3;
+  return UPB_OK;
+}
+
+static int ensure_host (upb_ctx* ctx, HostSlab& h, size_t bytes) {
+  if (bytes <= h.cap) return UPB_OK;
+  if (h.p) { cudaFreeHost(h.p); h.p = nullptr; h.cap = 0; }
+  const size_t want = bytes + bytes / 2 + 4096;
+  cudaError_t e = cudaMallocHost(&h.p, want);
+  if (e != cudaSuccess) { h.p = nullptr; return fail(ctx, UPB_ERR_NOMEM, std::string("cudaMallocHost(") + std::to_string(want) + "): " + cudaGetErrorString(e)); }
+  h.cap = want;
+  return UPB_OK;
+}
+
+// A table the ranks of a multi-GPU job share (upb_call_regions_shared): columns in mapped host memory every rank writes its rows
+// into, and the exchange area through which row_place_kernel learns the other ranks' row counts.
+struct SharedDst {
+  unsigned char* slab;              // table columns, laid out by slab_layout(rowCap, n, C)
+  uint64_t rowCap;
+  XchgArgs x;
+};
+
+// One pass over the units: every kernel of the region pipeline is enqueued without reading a size back (sizing == false), or with
+// two read-backs that size the per-survivor arrays and the table exactly (sizing == true: the first call of a context, and the
+// repeat of a call whose numbers outgrew what the previous call left behind).  *retry: run again with sizing.
+static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& out, bool sizing, bool* retry, const SharedDst* shared) {
   CU(cudaSetDevice(ctx->device));
+  *retry = false;
   uint32_t launches = 0;
+  stage_reset(ctx);
   CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-  int r = prepare(ctx, cfg, pr, &launches, cfg.allowLeftEdge);
+  // A load that is still on its way (upb_load_tags_async): work through its groups as they arrive — unless this call needs a
+  // read-back in the middle (sizing, -D correlation), every mini-tile at once (controls) or the first positions' neighbourhood
+  // (left-edge replay), in which case it simply waits for the load.
+  bool pipelined = ctx->loadPending && !sizing && !cfg.needCorr && !shared;
+  if (pipelined) {
+    if (cfg.control) for (uint32_t s = 0; s < ctx->nSamples; ++s) if (cfg.control[s]) pipelined = false;
+    for (uint32_t fp : ctx->firstPos) if (fp != 0 && fp <= cfg.bw) pipelined = false;
+  }
+  int r = prepare(ctx, cfg, pr, &launches, cfg.allowLeftEdge, pipelined);
   if (r) return r;
   const uint32_t n = ctx->nSamples, C = (uint32_t)ctx->sizes.size();
   const uint32_t nUnits = (uint32_t)pr.units.size();
@@ -815,23 +1055,26 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
   out.unitCand.assign(nUnits, 0);
   out.unitEdgeStop.assign(nUnits, 0);
   out.nCand = 0; out.R = 0;
-  ctx->lastRows = 0;
   memset(&ctx->stats, 0, sizeof ctx->stats);
   ctx->stats.n_entries = ctx->nEntries;
   ctx->stats.kde_tiles = pr.totalSpans;
-  out.layout = slab_layout(0, n, C);
-  if (nUnits == 0 || pr.nSrc == 0) {
+  cudaStream_t st_ = ctx->stream;
+  GroupCtr* g = (GroupCtr*)ctx->d_small.p;
+  CallCtr* call = (CallCtr*)((unsigned char*)ctx->d_small.p + CALLCTR_OFFSET);
+  const bool empty = nUnits == 0 || pr.nSrc == 0;
+  if (empty && !shared) {
+    out.layout = slab_layout(0, n, C);
     if ((r = acquire_slab(ctx, out.layout.totalBytes, out.slab))) return r;
     memset(out.slab.p, 0, out.layout.totalBytes);
-    finish_stats(ctx, launches);
+    cudaEventRecord(ctx->ev[3], st_); cudaEventSynchronize(ctx->ev[3]);
+    ctx->stats.launches = launches;
+    if (ctx->loadPending) return load_finish(ctx);
     return UPB_OK;
   }
-  uint32_t* small32 = ctx->d_small.as<uint32_t>();
-  unsigned long long* d_tot = ctx->d_small.as<unsigned long long>() + 16;
-  uint32_t* h32 = (uint32_t*)ctx->h_small;
   Unit* d_units = ctx->scratch["units"].as<Unit>();
+  stage_mark(ctx, "begin");
 
-  // ---- K1: the fused span kernel ---------------------------------------------------------------------
+  // ---- K1: the fused span kernel and the two zone-map passes in front of it --------------------------------
   SpanArgs sa;
   memset(&sa, 0, sizeof sa);
   sa.T = pr.T; sa.units = d_units; sa.nTilesIdx = ctx->d_nTilesIdx.as<uint32_t>();
@@ -846,14 +1089,14 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
     // cold-block bound: a tag j blocks (of 32 positions) away from block B is at least 32(|j|-1)+1 positions from every position of
     // B (0 for j = 0); blocks further than J = (bw-2)/32+1 away cannot reach it (the taps at +-bw are exactly 0, misc/kernel.cpp:12-14)
     const int bwI = (int)cfg.bw, J = bwI >= 2 ? (bwI - 2) / 32 + 1 : 0;
-    std::vector<float> hf(J + 1);
+    float* hf = (float*)ctx->h_small;                                   // pinned: the copy below is asynchronous
     for (int j = 0; j <= J; ++j) {
       const int m = j == 0 ? 0 : 32 * (j - 1) + 1;
       const double hc = pr.taps[bwI - m] * (1.0 + pr.maxCoeff) * (1.0 + 1e-9);   // -z: a count c weighs at most c*(coeff+1)
       hf[j] = std::nextafter((float)(hc * (1.0 + 1e-5)), INFINITY);              // float sum of <= 58 terms: 1e-5 covers its rounding
     }
     float* d_hf = SCR("hotCoefF", float, J + 1);
-    CU(cudaMemcpyAsync(d_hf, hf.data(), (size_t)(J + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));   // pageable source: staged before the call returns
+    CU(cudaMemcpyAsync(d_hf, hf, (size_t)(J + 1) * 4, cudaMemcpyHostToDevice, st_));
     ha.hotCoefF = d_hf; ha.hotJ = (uint32_t)J;
     ha.thrLow = std::nextafter((float)cfg.thr, -INFINITY);
   }
@@ -861,30 +1104,34 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
   sa.coeff = pr.d_coeffBySample;
   sa.cN = kmax / ((double)cfg.bw * (double)cfg.bw);
   sa.dS = kmax * 1e-11;                                               // >= 100x the worst-case rounding difference between the two forms
-  sa.flags = small32; sa.ticket = small32 + 1; sa.runCount = small32 + 2; sa.runReal = small32 + 3; sa.stat = (unsigned long long*)(small32 + 4);
+  sa.flags = &g->flags; sa.ticket = &g->ticket; sa.runCount = &g->runCount; sa.runReal = &g->runReal; sa.stat = call->stat;
   sa.spanRunCount = SCR("spanRunCount", uint32_t, pr.totalSpans);
   WarmRec* warmList = SCR("warmList", WarmRec, pr.totalSpans);
   uint2* hotList = SCR("hotList", uint2, pr.totalSpans);
   uint32_t* hotMask = SCR("hotMask", uint32_t, (size_t)pr.totalSpans * SPAN_WORDS);
-  sa.hotList = hotList; sa.nHot = small32 + 14; sa.hotMask = hotMask;
-  ha.T = pr.T; ha.units = d_units; ha.warmList = warmList; ha.nWarm = small32 + 12; ha.bw = cfg.bw; ha.nondir = cfg.nondir ? 1 : 0;
-  ha.hotMask = hotMask; ha.hotList = hotList; ha.nHot = small32 + 14; ha.spanRunCount = sa.spanRunCount; ha.stat = sa.stat;
+  sa.hotList = hotList; sa.nHot = &g->nHot; sa.hotMask = hotMask;
+  ha.T = pr.T; ha.units = d_units; ha.warmList = warmList; ha.nWarm = &g->nWarm; ha.bw = cfg.bw; ha.nondir = cfg.nondir ? 1 : 0;
+  ha.hotMask = hotMask; ha.hotList = hotList; ha.nHot = &g->nHot; ha.spanRunCount = sa.spanRunCount; ha.stat = call->stat;
   WarmArgs wa;
   wa.T = pr.T; wa.units = d_units; wa.nUnits = nUnits; wa.totalSpans = pr.totalSpans; wa.nondir = cfg.nondir ? 1 : 0;
   wa.nAdj = ((31 + 2 * cfg.bw) >> MT_SHIFT) + 2;
-  wa.warmList = warmList; wa.nWarm = small32 + 12; wa.spanRunCount = sa.spanRunCount; wa.bw = cfg.bw;
+  wa.warmList = warmList; wa.nWarm = &g->nWarm; wa.spanRunCount = sa.spanRunCount; wa.bw = cfg.bw;
+  wa.flatBound = flatBound; wa.thr = cfg.thr;
+  wa.loadFlags = pipelined ? ctx->d_loadFlags.as<uint32_t>() : nullptr;
 
-  // ---- K0: left-edge replay for the units that need it ------------------------------------
+  // ---- K0: left-edge replay for the units that need it (rare: one small kernel and one read-back) ------------
   const uint32_t nAff = (uint32_t)pr.affected.size();
   const uint32_t EDGE_REG_CAP = 1u << 18, EDGE_ROW_CAP = 1024;
   EdgeArgs eg;
   memset(&eg, 0, sizeof eg);
   uint32_t* d_affected = nullptr;
-  std::vector<uint32_t> edgeStop(nAff, 0), edgeCand(nAff, 0), edgeRows(nAff, 0);
+  std::vector<uint32_t> edgeCand(nAff, 0), edgeRows(nAff, 0);
+  uint32_t* d_edgeRowsOfUnit = nullptr; int32_t* d_affOfUnit = nullptr; uint32_t* d_drop = nullptr;
+  uint64_t edgeRowsTotal = 0;
   if (nAff) {
     const uint32_t w = 2 * cfg.bw + 1;
     d_affected = SCR("edgeAffected", uint32_t, nAff);
-    CU(cudaMemcpyAsync(d_affected, pr.affected.data(), (size_t)nAff * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_affected, pr.affected.data(), (size_t)nAff * 4, cudaMemcpyHostToDevice, st_));
     eg.T = pr.T; eg.units = d_units; eg.affected = d_affected; eg.nAffected = nAff; eg.control = ctx->scratch["control"].as<uint8_t>();
     eg.coeffBySample = pr.d_coeffBySample; eg.taps = ctx->scratch["taps"].as<double>(); eg.bw = cfg.bw; eg.nondir = cfg.nondir ? 1 : 0;
     eg.thr = cfg.thr; eg.kurtThr = cfg.kurtThr; eg.corrThr = cfg.nondir ? cfg.corrThr : -1.0; eg.hitThr = cfg.hitThr;
@@ -896,268 +1143,347 @@ static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& ou
     eg.regSums = SCR("edgeRegSums", uint32_t, (size_t)nAff * n); eg.callCounts = SCR("edgeCall", uint32_t, (size_t)nAff * n);
     eg.regCap = EDGE_REG_CAP; eg.rowCap = EDGE_ROW_CAP; eg.maxPositions = 1ull << 23;
     uint32_t* eo = SCR("edgeOut", uint32_t, (size_t)3 * nAff + 4);
-    CU(cudaMemsetAsync(eo, 0, ((size_t)3 * nAff + 4) * 4, ctx->stream));
+    CU(cudaMemsetAsync(eo, 0, ((size_t)3 * nAff + 4) * 4, st_));
     eg.stop = eo; eg.nCand = eo + nAff; eg.nRows = eo + 2 * nAff; eg.flags = eo + 3 * nAff;
     eg.rows = SCR("edgeRows", EdgeRow, (size_t)nAff * EDGE_ROW_CAP);
     eg.rowCounts = SCR("edgeRowCounts", uint32_t, (size_t)nAff * EDGE_ROW_CAP * n);
-    left_edge_kernel<<<nAff, 32, 0, ctx->stream>>>(eg);
+    left_edge_kernel<<<nAff, 32, 0, st_>>>(eg);
     CU(cudaGetLastError());
     launches += 1;
     std::vector<uint32_t> eoh((size_t)3 * nAff + 4);
-    CU(cudaMemcpyAsync(eoh.data(), eo, eoh.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpyAsync(eoh.data(), eo, eoh.size() * 4, cudaMemcpyDeviceToHost, st_));
+    CU(cudaStreamSynchronize(st_));
     if (eoh[3 * nAff]) return fail(ctx, UPB_ERR_UNSUPPORTED, "left-edge replay (SURVEY Q2) ran out of its scratch or position budget");
-    for (uint32_t k = 0; k < nAff; ++k) { edgeStop[k] = eoh[k]; edgeCand[k] = eoh[nAff + k]; edgeRows[k] = eoh[2 * nAff + k]; out.unitEdgeStop[pr.affected[k]] = eoh[k]; }
+    std::vector<uint32_t> rowsOfUnit(nUnits, 0);
+    std::vector<int32_t> affOfUnit(nUnits, -1);
+    for (uint32_t k = 0; k < nAff; ++k) {
+      edgeCand[k] = eoh[nAff + k]; edgeRows[k] = eoh[2 * nAff + k]; out.unitEdgeStop[pr.affected[k]] = eoh[k];
+      rowsOfUnit[pr.affected[k]] = edgeRows[k]; affOfUnit[pr.affected[k]] = (int32_t)k; edgeRowsTotal += edgeRows[k];
+    }
+    d_edgeRowsOfUnit = SCR("edgeRowsOfUnit", uint32_t, nUnits);
+    d_affOfUnit = SCR("edgeAffOfUnit", int32_t, nUnits);
+    d_drop = SCR("edgeDrop", uint32_t, nAff);
+    CU(cudaMemcpyAsync(d_edgeRowsOfUnit, rowsOfUnit.data(), (size_t)nUnits * 4, cudaMemcpyHostToDevice, st_));
+    CU(cudaMemcpyAsync(d_affOfUnit, affOfUnit.data(), (size_t)nUnits * 4, cudaMemcpyHostToDevice, st_));
+    CU(cudaMemsetAsync(d_drop, 0, (size_t)nAff * 4, st_));
+    CU(cudaStreamSynchronize(st_));                                   // the host vectors go out of scope
+    stage_mark(ctx, "left_edge_kernel");
   }
-  uint64_t edgeRowsTotal = 0;
-  for (uint32_t k = 0; k < nAff; ++k) edgeRowsTotal += edgeRows[k];
 
-  size_t runCap = std::max<size_t>(1u << 18, (size_t)(ctx->nEntries / 64));
+  // ---- arrays sized by capacity ----------------------------------------------------------------------------------
+  size_t runCap = std::max<size_t>(std::max<size_t>(1u << 18, (size_t)(ctx->nEntries / 64)), ctx->needRunCap);
   { const size_t have = ctx->scratch["runs"].cap / sizeof(SpanRun); if (have > runCap) runCap = have; }
-  uint32_t nRuns = 0, runSlots = 0;
-  for (int attempt = 0; attempt < 2; ++attempt) {
-    sa.runs = SCR("runs", SpanRun, runCap);
-    sa.runCap = (uint32_t)std::min<size_t>(runCap, 0xFFFFFFF0u);
-    CU(cudaMemsetAsync(ctx->d_small.p, 0, 256, ctx->stream));
-    wa.flatBound = flatBound; wa.thr = cfg.thr;
-    warm_span_kernel<<<(pr.totalSpans + 255) / 256, 256, 0, ctx->stream>>>(wa);
+  runCap = std::min<size_t>(runCap, 0xFFFFFFF0u);
+  sa.runs = SCR("runs", SpanRun, runCap);
+  sa.runCap = (uint32_t)runCap;
+  unsigned long long* spanOrd = SCR("spanOrd", unsigned long long, pr.totalSpans);
+  uint32_t* ordIdx = SCR("ordIdx", uint32_t, runCap);
+  uint32_t* head = SCR("head", uint32_t, runCap);
+  unsigned long long* headScan = SCR("headScan", unsigned long long, runCap);
+  Cand2* cand = SCR("cand", Cand2, runCap);
+  uint32_t* pass = SCR("pass", uint32_t, runCap);
+  uint32_t* candLen = SCR("candLen", uint32_t, runCap);
+  unsigned long long* pvScan = SCR("pvScan", unsigned long long, runCap);
+  uint32_t* list1 = SCR("list1", uint32_t, runCap);
+  unsigned long long* unitCand = SCR("unitCand", unsigned long long, 6 * (size_t)nUnits + 8);
+  unsigned long long* unitFirst = unitCand + nUnits;
+  unsigned long long* normalFirst = unitFirst + nUnits;               // nUnits + 1
+  unsigned long long* unitRowsDev = normalFirst + nUnits + 1;
+  unsigned long long* edgeRowBase = unitRowsDev + nUnits;
+  long long* rowShift = (long long*)(edgeRowBase + nUnits);
+  unsigned long long* d_tir = SCR("tir", unsigned long long, n);
+  CU(cudaMemsetAsync(unitCand, 0, (6 * (size_t)nUnits + 8) * 8, st_));
+  CU(cudaMemsetAsync(d_tir, 0, (size_t)n * 8, st_));
+  (void)SCR("scanPartial", unsigned long long, std::max<size_t>(runCap, pr.totalSpans) / SCAN_BLOCK + 2);   // largest scan of the call: no regrowth (= free + malloc) in between
+  const unsigned GS = (unsigned)ctx->smCount * 8;                     // grid of the grid-stride kernels
+
+  // pinned block the counters come back in: GroupCtr, CallCtr, tir[n], unitCand[nUnits], unitRows[nUnits], edgeDrop[nAff]
+  const size_t resBytes = 1024 + (size_t)n * 8 + 2 * (size_t)nUnits * 8 + (size_t)nAff * 4 + 64;
+  if ((r = ensure_host(ctx, ctx->h_res, resBytes))) return r;
+  unsigned char* hres = (unsigned char*)ctx->h_res.p;
+  GroupCtr* hg = (GroupCtr*)hres;
+  CallCtr* hcall = (CallCtr*)(hres + 512);
+  unsigned long long* hTir = (unsigned long long*)(hres + 1024);
+  unsigned long long* hUnitCand = hTir + n;
+  unsigned long long* hUnitRows = hUnitCand + nUnits;
+  uint32_t* hDrop = (uint32_t*)(hUnitRows + nUnits);
+  auto read_group = [&] () -> int {                                    // sizing read-back of the group counters
+    CU(cudaMemcpyAsync(hg, g, sizeof(GroupCtr), cudaMemcpyDeviceToHost, st_));
+    CU(cudaStreamSynchronize(st_));
+    return UPB_OK;
+  };
+
+  // ---- the groups of units: one group (all units), or one per load group of a pending load ------------------------------
+  struct PGroup { uint32_t u0, u1, s0, s1; int ev0, ev1; };
+  std::vector<PGroup> pgroups;
+  if (!pipelined) { PGroup pg; pg.u0 = 0; pg.u1 = nUnits; pg.s0 = 0; pg.s1 = pr.totalSpans; pg.ev0 = pg.ev1 = -1; pgroups.push_back(pg); }
+  else {
+    // units are sorted by (buffer, contig); a directional unit needs the load group (its strand, its contig range), a -D unit both strands'
+    std::vector<std::pair<uint32_t, uint32_t>> order;                  // (sort key, load group index), strand 0 groups only for -D
+    for (uint32_t k = 0; k < ctx->groups.size(); ++k) {
+      const LoadGroup& lg = ctx->groups[k];
+      if (cfg.nondir && lg.d != 0) continue;
+      order.push_back(std::make_pair((cfg.nondir ? 0u : lg.d) * C + lg.c0, k));
+    }
+    std::sort(order.begin(), order.end());
+    uint32_t u = 0;
+    for (const auto& ok : order) {
+      const LoadGroup& lg = ctx->groups[ok.second];
+      const uint32_t b = cfg.nondir ? 0u : lg.d;
+      PGroup pg;
+      while (u < nUnits && (pr.units[u].buffer < b || (pr.units[u].buffer == b && pr.units[u].contig < lg.c0))) ++u;   // (cannot skip any: every unit's contig is kept)
+      pg.u0 = u;
+      while (u < nUnits && pr.units[u].buffer == b && pr.units[u].contig < lg.c1) ++u;
+      pg.u1 = u;
+      if (pg.u1 == pg.u0) continue;
+      pg.s0 = pr.units[pg.u0].spanStart; pg.s1 = pr.units[pg.u1 - 1].spanStart + pr.units[pg.u1 - 1].nSpans;
+      pg.ev0 = (int)ok.second; pg.ev1 = -1;
+      if (cfg.nondir) for (uint32_t k = 0; k < ctx->groups.size(); ++k) if (ctx->groups[k].d == 1 && ctx->groups[k].c0 == lg.c0) pg.ev1 = (int)k;
+      pgroups.push_back(pg);
+    }
+    if (pgroups.empty() || pgroups.back().u1 != nUnits || pgroups.front().u0 != 0) {   // not expected; fall back to waiting for the whole load
+      pipelined = false;
+      const int rl = load_finish(ctx); if (rl) return rl;
+      pgroups.clear();
+      PGroup pg; pg.u0 = 0; pg.u1 = nUnits; pg.s0 = 0; pg.s1 = pr.totalSpans; pg.ev0 = pg.ev1 = -1; pgroups.push_back(pg);
+    }
+  }
+  uint64_t rowCap = 0;
+  unsigned char* hs = nullptr;                                         // table columns (mapped host memory)
+  if (!empty && !shared && !sizing) {                                  // the table: sized from the previous call (sizing: once this call's row count is known)
+    rowCap = ctx->capRows;
+    out.layout = slab_layout(rowCap, n, C);
+    if ((r = acquire_slab(ctx, out.layout.totalBytes, out.slab))) return r;
+    hs = (unsigned char*)out.slab.p;
+  }
+  if (shared) { rowCap = shared->rowCap; hs = shared->slab; out.layout = slab_layout(rowCap, n, C); }
+  if (!empty) for (size_t gi = 0; gi < pgroups.size(); ++gi) {
+    const uint32_t u0 = pgroups[gi].u0, u1 = pgroups[gi].u1, s0 = pgroups[gi].s0, s1 = pgroups[gi].s1;
+    if (pgroups[gi].ev0 >= 0) CU(cudaStreamWaitEvent(st_, ctx->groupEv[pgroups[gi].ev0], 0));
+    if (pgroups[gi].ev1 >= 0) CU(cudaStreamWaitEvent(st_, ctx->groupEv[pgroups[gi].ev1], 0));
+    CU(cudaMemsetAsync(g, 0, sizeof(GroupCtr), st_));
+    wa.spanBegin = s0; wa.spanEnd = s1;
+    warm_span_kernel<<<(s1 - s0 + 255) / 256, 256, 0, st_>>>(wa);
     { int perSm = 0;
       if ((r = cached_occupancy(ctx, hot_span_kernel, HOT_THREADS, 0, &perSm))) return r;
-      hot_span_kernel<<<ctx->smCount * perSm, HOT_THREADS, 0, ctx->stream>>>(ha); }
+      hot_span_kernel<<<ctx->smCount * perSm, HOT_THREADS, 0, st_>>>(ha); }
     launches += 2;
-    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    stage_mark(ctx, "warm_span_kernel+hot_span_kernel");
+    CU(cudaEventRecord(ctx->ev[1], st_));
     if ((r = launch_span(ctx, sa, cfg.nondir, &launches))) return r;
-    CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-    CU(cudaMemcpyAsync(h32, ctx->d_small.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    nRuns = h32[3];                                                   // runs written
-    runSlots = h32[2];                                                // slots handed out (a warp reserves RUN_CHUNK at a time)
-    if (!(h32[0] & FLAG_RUN_OVERFLOW)) break;
-    if (attempt == 1) return fail(ctx, UPB_ERR_NOMEM, "run buffer overflow after resize");
-    runCap = (size_t)runSlots + (1u << 20);                           // the counter holds the need; chunks may fall differently next time
-  }
-  ctx->stats.warm_spans = h32[12];
-  { unsigned long long st[4]; memcpy(st, h32 + 4, 32); ctx->stats.kde_hot_tiles = st[1]; ctx->stats.hot_blocks = st[0]; ctx->stats.exact_evals = st[2]; ctx->stats.spans_with_tags = st[3]; }
-  { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->stats.ms_kde = ms; }
-  if (nRuns == 0 && edgeRowsTotal == 0) {
-    for (uint32_t k = 0; k < nAff; ++k) { out.unitCand[pr.affected[k]] = edgeCand[k]; out.nCand += edgeCand[k]; }
-    if ((r = acquire_slab(ctx, out.layout.totalBytes, out.slab))) return r;
-    memset(out.slab.p, 0, out.layout.totalBytes);
-    finish_stats(ctx, launches);
-    return UPB_OK;
-  }
-  unsigned long long* h64 = (unsigned long long*)ctx->h_small;
-  uint32_t nCand = 0, n1 = 0;
-  uint64_t R = 0;
-  Cand2* cand = nullptr; uint32_t* list1 = nullptr; unsigned long long* unitFirst = nullptr;
-  uint32_t* statCounts = nullptr; double* statKurt = nullptr; uint32_t* pass2 = nullptr; unsigned long long* pass2Scan = nullptr; double* rowCorr = nullptr;
-  std::vector<uint32_t> edgeDrop(nAff, 0);
-  if (nRuns) {
-  // ---- K2: (span, rank) order, stitch runs cut by piece / span boundaries ------------------------------
-  unsigned long long* spanOrd = SCR("spanOrd", unsigned long long, pr.totalSpans);
-  if ((r = scan_u32(ctx, sa.spanRunCount, pr.totalSpans, spanOrd, d_tot, &launches))) return r;
-  uint32_t* ordIdx = SCR("ordIdx", uint32_t, nRuns);
-  uint32_t* head = SCR("head", uint32_t, nRuns);
-  unsigned long long* headScan = SCR("headScan", unsigned long long, nRuns);
-  const unsigned gRuns = (nRuns + 255) / 256;
-  run_order_kernel<<<(runSlots + 255) / 256, 256, 0, ctx->stream>>>(sa.runs, runSlots, spanOrd, ordIdx);
-  run_heads2_kernel<<<gRuns, 256, 0, ctx->stream>>>(sa.runs, ordIdx, nRuns, d_units, nUnits, head);
-  CU(cudaGetLastError());
-  launches += 2;
-  if ((r = scan_u32(ctx, head, nRuns, headScan, d_tot, &launches))) return r;
-  cand = SCR("cand", Cand2, nRuns);                                   // nCand <= nRuns
-  unsigned long long* unitCand = SCR("unitCand", unsigned long long, 2 * (size_t)nUnits + 2);
-  unitFirst = unitCand + nUnits + 1;
-  CU(cudaMemsetAsync(unitCand, 0, (2 * (size_t)nUnits + 2) * 8, ctx->stream));
-  merge_runs2_kernel<<<gRuns, 256, 0, ctx->stream>>>(sa.runs, ordIdx, head, headScan, nRuns, d_units, nUnits, cand, unitCand);
-  unit_first_kernel<<<1, 32, 0, ctx->stream>>>(unitCand, nUnits, unitFirst);
-  CU(cudaGetLastError());
-  launches += 2;
-  // the number of candidates stays on the device for now (one read-back fewer): what follows runs over nRuns >= nCand slots and
-  // looks the count up itself
-  const unsigned long long* d_nCand = d_tot + 5;
-  CU(cudaMemcpyAsync(d_tot + 5, d_tot, 8, cudaMemcpyDeviceToDevice, ctx->stream));
-  const unsigned gCand = gRuns;
+    CU(cudaEventRecord(ctx->ev[2], st_));
+    stage_mark(ctx, "span_kernel");
 
-  // ---- K3: hit filter (misc/peakcall.cpp:41), then per-region statistics for the survivors ------------------
-  uint32_t* pass = SCR("pass", uint32_t, nRuns);
-  unsigned long long* passScan = SCR("passScan", unsigned long long, nRuns);
-  list1 = SCR("list1", uint32_t, nRuns);
-  cand_hit_kernel<<<gCand, 256, 0, ctx->stream>>>(cand, d_nCand, nRuns, cfg.hitThr, pass);
-  launches += 1;
-  uint32_t* d_drop = nullptr;
-  if (nAff) {                                                         // what the replay owns is not a Region of the reference
-    d_drop = SCR("edgeDrop", uint32_t, nAff);
-    CU(cudaMemsetAsync(d_drop, 0, (size_t)nAff * 4, ctx->stream));
-    edge_drop_kernel<<<gCand, 256, 0, ctx->stream>>>(d_affected, eg.stop, nAff, cand, d_nCand, pass, d_drop);
-    launches += 1;
-  }
-  if ((r = scan_u32(ctx, pass, nRuns, passScan, d_tot, &launches))) return r;
-  compact_index_kernel<<<gCand, 256, 0, ctx->stream>>>(pass, passScan, nRuns, list1);
-  // pooled position cells of the survivors live back to back in one scratch array: offsets by a scan of their lengths
-  uint32_t* candLen = SCR("candLen", uint32_t, nRuns);
-  unsigned long long* cellOff = SCR("cellOff", unsigned long long, nRuns);
-  cand_len_kernel<<<gCand, 256, 0, ctx->stream>>>(cand, pass, nRuns, candLen);
-  if ((r = scan_u32(ctx, candLen, nRuns, cellOff, d_tot + 2, &launches))) return r;
-  CU(cudaGetLastError());
-  launches += 2;
-  CU(cudaMemcpyAsync(h64, d_tot, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaMemcpyAsync(h64 + 2, d_tot + 2, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaMemcpyAsync(h64 + 5, d_tot + 5, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaMemcpyAsync(h64 + 8, unitCand, std::min<size_t>((size_t)nUnits, 400) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  if (nAff) CU(cudaMemcpyAsync(edgeDrop.data(), d_drop, (size_t)nAff * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
-  nCand = (uint32_t)h64[5];
-  out.nCand = nCand;
-  ctx->stats.n_candidates = nCand;
-  ctx->stats.n_stitched = nRuns - nCand;
-  n1 = (uint32_t)h64[0];
-  const unsigned long long totalCells = h64[2];
-  if (nUnits <= 400) for (uint32_t u = 0; u < nUnits; ++u) out.unitCand[u] = h64[8 + u];
-  else { CU(cudaMemcpy(out.unitCand.data(), unitCand, (size_t)nUnits * 8, cudaMemcpyDeviceToHost)); }
-
-  if (n1) {
-    const unsigned g1 = (n1 + 255) / 256;
-    statCounts = SCR("statCounts", uint32_t, (size_t)n1 * n);
-    statKurt = SCR("statKurt", double, n1);
-    pass2 = SCR("pass2", uint32_t, n1);
-    pass2Scan = SCR("pass2Scan", unsigned long long, n1);
-    StatArgs st;
-    st.T = pr.T; st.units = d_units; st.cand = cand; st.list = list1; st.nList = n1;
-    st.nondir = cfg.nondir ? 1 : 0; st.kurtThr = cfg.kurtThr; st.counts = statCounts; st.kurt = statKurt; st.pass = pass2;
-    st.cellOff = cellOff; st.cells = SCR("statCells", uint32_t, (size_t)totalCells + 1);
-    const size_t groupBytes = ((size_t)(ST_CHUNK + n) * 4 + 15) / 16 * 16;
-    const size_t statSmem = (size_t)ST_WARPS * ST_PER_WARP * groupBytes;
-    if (statSmem > 200 * 1024) return fail(ctx, UPB_ERR_UNSUPPORTED, "too many samples for the region statistics kernel");
-    st.ticket = small32 + 13;
-    CU(cudaMemsetAsync(st.ticket, 0, 4, ctx->stream));
-    int perSm = 0;
-    if ((r = cached_occupancy(ctx, region_pool_kernel, ST_WARPS * 32, statSmem, &perSm))) return r;
-    const uint32_t perBlock = ST_WARPS * ST_PER_WARP;
-    const uint32_t gridS = std::min<uint32_t>((n1 + perBlock - 1) / perBlock, (uint32_t)(ctx->smCount * std::max(perSm, 1)));
-    region_pool_kernel<<<gridS, ST_WARPS * 32, statSmem, ctx->stream>>>(st);
-    region_moment_kernel<<<g1, 256, 0, ctx->stream>>>(st);
-    CU(cudaGetLastError());
-    launches += 2;
-
-    // strand correlation for the regions that got this far (misc/peakcall.cpp:41 evaluates it last)
-    if (cfg.needCorr) {
-      if ((r = scan_u32(ctx, pass2, n1, pass2Scan, d_tot, &launches))) return r;
-      uint32_t* list2 = SCR("list2", uint32_t, n1);
-      compact_index_kernel<<<g1, 256, 0, ctx->stream>>>(pass2, pass2Scan, n1, list2);
+    // ---- K2: (span, rank) order, stitch runs cut by piece / span boundaries, hit filter ------------------------------
+    if ((r = scan_dev(ctx, LoadU32{sa.spanRunCount + s0}, devn_imm(s1 - s0), s1 - s0, spanOrd + s0, &g->totSpanRuns, &launches))) return r;
+    run_order_kernel<<<GS, 256, 0, st_>>>(sa.runs, g, (uint32_t)runCap, spanOrd, ordIdx);
+    run_heads2_kernel<<<GS, 256, 0, st_>>>(sa.runs, ordIdx, g, d_units, nUnits, head);
+    if ((r = scan_dev(ctx, LoadU32{head}, devn_u32(&g->runReal), runCap, headScan, &g->nCand, &launches))) return r;
+    merge_runs2_kernel<<<GS, 256, 0, st_>>>(sa.runs, ordIdx, head, headScan, g, d_units, nUnits, cfg.hitThr, cand, pass, candLen, unitCand);
+    unit_first_kernel<<<1, 32, 0, st_>>>(unitCand, u0, u1, unitFirst);
+    launches += 4;
+    if (nAff) {                                                         // what the replay owns is not a Region of the reference
+      edge_drop_kernel<<<GS, 256, 0, st_>>>(d_affected, eg.stop, nAff, cand, g, pass, candLen, d_drop);
       launches += 1;
-      CU(cudaMemcpyAsync(h64, d_tot, 8, cudaMemcpyDeviceToHost, ctx->stream));
-      CU(cudaStreamSynchronize(ctx->stream));
-      const uint32_t n2 = (uint32_t)h64[0];
-      rowCorr = SCR("rowCorr", double, n1);
-      CU(cudaMemsetAsync(rowCorr, 0xFF, (size_t)n1 * 8, ctx->stream));   // NaN where not computed
-      if (n2) {
-        uint32_t* dUnit = SCR("dUnit", uint32_t, n2); uint32_t* dLeft = SCR("dLeft", uint32_t, n2);
-        uint32_t* dLen = SCR("dLen", uint32_t, n2); uint32_t* dChunks = SCR("dChunks", uint32_t, n2);
-        dump_desc2_kernel<<<(n2 + 255) / 256, 256, 0, ctx->stream>>>(cand, list1, list2, n2, dUnit, dLeft, dLen, dChunks);
-        CU(cudaGetLastError());
-        launches += 1;
-        if ((r = dump_and_corr(ctx, pr.dens, cfg.nondir, n2, 1, &launches))) return r;
-        cand_corr_kernel<<<(n2 + 255) / 256, 256, 0, ctx->stream>>>(list2, n2, ctx->scratch["corr"].as<double>(), cfg.corrThr, pass2, rowCorr);
-        CU(cudaGetLastError());
-        launches += 1;
-      }
     }
-    if ((r = scan_u32(ctx, pass2, n1, pass2Scan, d_tot, &launches))) return r;
-    CU(cudaMemcpyAsync(h64, d_tot, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    R = h64[0];
-  }
+    if ((r = scan_dev(ctx, LoadPacked{pass, candLen}, devn_u64(&g->nCand), runCap, pvScan, &g->pv, &launches))) return r;
+    // per-survivor arrays: sized from the previous call, or (sizing) from this one's numbers
+    if (sizing || cfg.needCorr || shared) {
+      compact_pv_kernel<<<GS, 256, 0, st_>>>(pass, pvScan, g, (uint32_t)runCap, ~0ull, list1);
+      launches += 1;
+      CU(cudaGetLastError());
+      if ((r = read_group())) return r;
+      if (hg->flags & FLAG_RUN_OVERFLOW) { ctx->needRunCap = (size_t)hg->runCount + (1u << 20); *retry = true; return UPB_OK; }
+      const size_t n1 = (size_t)(hg->pv >> PACK_SHIFT), cells = (size_t)(hg->pv & PACK_MASK);
+      ctx->capN1 = std::max(ctx->capN1, n1 + n1 / 4 + 1024);
+      ctx->capCells = std::max(ctx->capCells, cells + cells / 4 + 4096);
+    }
+    const size_t n1Cap = std::min<size_t>(ctx->capN1, runCap), cellCap = ctx->capCells;
+    uint32_t* statCounts = SCR("statCounts", uint32_t, n1Cap * n);
+    double* statKurt = SCR("statKurt", double, n1Cap);
+    uint32_t* pass2 = SCR("pass2", uint32_t, n1Cap);
+    unsigned long long* pass2Scan = SCR("pass2Scan", unsigned long long, n1Cap);
+    uint32_t* statCells = SCR("statCells", uint32_t, cellCap + 1);
+    if (!(sizing || cfg.needCorr || shared)) {
+      compact_pv_kernel<<<GS, 256, 0, st_>>>(pass, pvScan, g, (uint32_t)n1Cap, cellCap, list1);
+      launches += 1;
+    }
+    stage_mark(ctx, "order+stitch+hit filter");
 
-  }  // nRuns
+    // ---- K3: per-region statistics of the survivors ---------------------------------------------------------------------
+    StatArgs sg;
+    sg.T = pr.T; sg.units = d_units; sg.cand = cand; sg.list = list1; sg.g = g;
+    sg.nondir = cfg.nondir ? 1 : 0; sg.kurtThr = cfg.kurtThr; sg.counts = statCounts; sg.kurt = statKurt; sg.pass = pass2;
+    sg.pvScan = pvScan; sg.cells = statCells; sg.cellCap = cellCap; sg.ticket = &g->poolTicket;
+    {
+      const size_t groupBytes = ((size_t)(ST_CHUNK + n) * 4 + 15) / 16 * 16;
+      const size_t statSmem = (size_t)ST_WARPS * ST_PER_WARP * groupBytes;
+      if (statSmem > 200 * 1024) return fail(ctx, UPB_ERR_UNSUPPORTED, "too many samples for the region statistics kernel");
+      int perSm = 0;
+      if ((r = cached_occupancy(ctx, region_pool_kernel, ST_WARPS * 32, statSmem, &perSm))) return r;
+      region_pool_kernel<<<(unsigned)(ctx->smCount * std::max(perSm, 1)), ST_WARPS * 32, statSmem, st_>>>(sg);
+      stage_mark(ctx, "region_pool_kernel");
+      region_moment_kernel<<<GS, 256, 0, st_>>>(sg);
+      CU(cudaGetLastError());
+      launches += 2;
+      stage_mark(ctx, "region_moment_kernel");
+    }
 
-  // ---- accepted rows -> result slab -------------------------------------------------------------------------
-  const uint64_t Rnormal = R;
-  R += edgeRowsTotal;
-  out.R = R;
-  ctx->lastRows = R;
-  out.layout = slab_layout(R, n, C);
-  const SlabLayout& SL = out.layout;
-  if ((r = acquire_slab(ctx, SL.totalBytes, out.slab))) return r;
-  unsigned char* hs = (unsigned char*)out.slab.p;
-  memset(hs + SL.devBytes, 0, SL.totalBytes - SL.devBytes);
-  // replay bookkeeping: its candidates replace the dropped ones, its rows precede the unit's other rows
-  long long* d_shift = nullptr;
-  if (nAff) {
-    std::vector<long long> shift(2 * (size_t)nUnits, 0);
-    long long runRows = 0;
-    size_t k = 0;
-    for (uint32_t u = 0; u < nUnits; ++u) {
-      if (k < nAff && pr.affected[k] == u) { runRows += edgeRows[k]; shift[nUnits + u] = (long long)edgeCand[k] - (long long)edgeDrop[k]; ++k; }
-      shift[u] = runRows;
-    }
-    for (k = 0; k < nAff; ++k) {
-      const uint32_t u = pr.affected[k];
-      out.unitCand[u] = (uint64_t)((long long)out.unitCand[u] + shift[nUnits + u]);
-      out.nCand = (uint64_t)((long long)out.nCand + shift[nUnits + u]);
-    }
-    d_shift = SCR("edgeShift", long long, 2 * (size_t)nUnits);
-    CU(cudaMemcpyAsync(d_shift, shift.data(), shift.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-  }
-  if (R) {
-    unsigned char* ds = SCR("slab", unsigned char, SL.devBytes);
-    unsigned long long* d_tir = SCR("tir", unsigned long long, n);
-    CU(cudaMemsetAsync(d_tir, 0, (size_t)n * 8, ctx->stream));
-    EmitArgs ea;
-    ea.cand = cand; ea.list = list1; ea.pass = pass2; ea.passScan = pass2Scan; ea.nList = n1; ea.units = d_units; ea.unitFirst = unitFirst;
-    ea.unitRowShift = d_shift; ea.unitCandShift = d_shift ? d_shift + nUnits : nullptr;
-    ea.statCounts = statCounts; ea.statKurt = statKurt; ea.rowCorr = rowCorr; ea.nSamples = n;
-    ea.buffer = ds + SL.oBuffer; ea.contig = (uint32_t*)(ds + SL.oContig); ea.left = (uint32_t*)(ds + SL.oLeft); ea.len = (uint32_t*)(ds + SL.oLen);
-    ea.peak = (uint32_t*)(ds + SL.oPeak); ea.wsum = (uint32_t*)(ds + SL.oWsum); ea.candIndex = (unsigned long long*)(ds + SL.oCandIndex);
-    ea.peakScore = (double*)(ds + SL.oPeakScore); ea.kurt = (double*)(ds + SL.oKurt); ea.corr = (double*)(ds + SL.oCorr);
-    ea.counts = (uint32_t*)(ds + SL.oCounts);
-    if (n1) { emit_rows_kernel<<<(n1 + 255) / 256, 256, 0, ctx->stream>>>(ea); launches += 1; }
-    if (edgeRowsTotal) {
-      // first table row of each unit's replay rows = accepted rows of span_kernel in earlier units + replay rows of earlier units
-      std::vector<unsigned long long> rowBase(nAff, 0);
-      std::vector<uint32_t> l1(n1), p2(n1);
-      std::vector<Cand2> hc;                                          // rare path: a few small host look-ups are fine
-      unsigned long long before = 0;
+    // strand correlation for the regions that got this far (misc/peakcall.cpp:41 evaluates it last); -D only, sizes read back
+    double* rowCorr = nullptr;
+    if (cfg.needCorr) {
+      const uint32_t n1 = (uint32_t)(hg->pv >> PACK_SHIFT);
+      rowCorr = SCR("rowCorr", double, n1Cap);
       if (n1) {
-        CU(cudaMemcpyAsync(l1.data(), list1, (size_t)n1 * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaMemcpyAsync(p2.data(), pass2, (size_t)n1 * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        hc.resize(nCand);
-        CU(cudaMemcpyAsync(hc.data(), cand, (size_t)nCand * sizeof(Cand2), cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
+        unsigned long long* d_tot = ctx->d_small.as<unsigned long long>() + 16;
+        if ((r = scan_u32(ctx, pass2, n1, pass2Scan, d_tot, &launches))) return r;
+        uint32_t* list2 = SCR("list2", uint32_t, n1);
+        compact_index_kernel<<<(n1 + 255) / 256, 256, 0, st_>>>(pass2, pass2Scan, n1, list2);
+        launches += 1;
+        unsigned long long* h64 = (unsigned long long*)ctx->h_small;
+        CU(cudaMemcpyAsync(h64, d_tot, 8, cudaMemcpyDeviceToHost, st_));
+        CU(cudaStreamSynchronize(st_));
+        const uint32_t n2 = (uint32_t)h64[0];
+        CU(cudaMemsetAsync(rowCorr, 0xFF, (size_t)n1 * 8, st_));      // NaN where not computed
+        if (n2) {
+          uint32_t* dUnit = SCR("dUnit", uint32_t, n2); uint32_t* dLeft = SCR("dLeft", uint32_t, n2);
+          uint32_t* dLen = SCR("dLen", uint32_t, n2); uint32_t* dChunks = SCR("dChunks", uint32_t, n2);
+          dump_desc2_kernel<<<(n2 + 255) / 256, 256, 0, st_>>>(cand, list1, list2, n2, dUnit, dLeft, dLen, dChunks);
+          CU(cudaGetLastError());
+          launches += 1;
+          if ((r = dump_and_corr(ctx, pr.dens, cfg.nondir, n2, 1, &launches))) return r;
+          cand_corr_kernel<<<(n2 + 255) / 256, 256, 0, st_>>>(list2, n2, ctx->scratch["corr"].as<double>(), cfg.corrThr, pass2, rowCorr);
+          CU(cudaGetLastError());
+          launches += 1;
+        }
       }
-      size_t j = 0; unsigned long long acc = 0;
-      for (uint32_t k = 0; k < nAff; ++k) {
-        const uint32_t u = pr.affected[k];
-        while (j < n1 && hc[l1[j]].unit < u) { acc += p2[j]; ++j; }
-        rowBase[k] = acc + before;
-        before += edgeRows[k];
-      }
-      unsigned long long* d_rowBase = SCR("edgeRowBase", unsigned long long, nAff);
-      CU(cudaMemcpyAsync(d_rowBase, rowBase.data(), (size_t)nAff * 8, cudaMemcpyHostToDevice, ctx->stream));
-      CU(cudaStreamSynchronize(ctx->stream));
+      stage_mark(ctx, "strand correlation");
+    }
+    if ((r = scan_dev(ctx, LoadU32{pass2}, devn_u64(&g->n1), n1Cap, pass2Scan, &g->rows, &launches))) return r;
+
+    // ---- where the rows go, then the rows themselves, straight into the (mapped) host table ---------------------------------
+    PlaceArgs pa;
+    memset(&pa, 0, sizeof pa);
+    pa.cand = cand; pa.list = list1; pa.pass2Scan = pass2Scan; pa.g = g; pa.call = call; pa.units = d_units; pa.u0 = u0; pa.u1 = u1;
+    pa.edgeRows = d_edgeRowsOfUnit; pa.normalFirst = normalFirst; pa.rowShift = rowShift; pa.edgeRowBase = edgeRowBase; pa.unitRows = unitRowsDev;
+    pa.shared = shared ? 1 : 0;
+    if (shared) pa.x = shared->x;
+    row_place_kernel<<<1, 256, 0, st_>>>(pa);
+    launches += 1;
+    if (!shared && sizing) {
+      if ((r = read_group())) return r;
+      const size_t R = (size_t)hg->rows + edgeRowsTotal;
+      ctx->capRows = std::max(ctx->capRows, R + R / 4 + 1024);
+      rowCap = ctx->capRows;
+      out.layout = slab_layout(rowCap, n, C);
+      if ((r = acquire_slab(ctx, out.layout.totalBytes, out.slab))) return r;
+      hs = (unsigned char*)out.slab.p;
+    }
+    const SlabLayout& SL = out.layout;
+    EmitArgs ea;
+    memset(&ea, 0, sizeof ea);
+    ea.cand = cand; ea.list = list1; ea.pass = pass2; ea.passScan = pass2Scan; ea.g = g; ea.units = d_units; ea.unitFirst = unitFirst;
+    ea.rowShift = rowShift; ea.affOfUnit = d_affOfUnit; ea.edgeCand = eg.nCand; ea.edgeDrop = d_drop;
+    ea.statCounts = statCounts; ea.statKurt = statKurt; ea.rowCorr = rowCorr; ea.nSamples = n; ea.rowCap = rowCap;
+    ea.buffer = hs + SL.oBuffer; ea.contig = (uint32_t*)(hs + SL.oContig); ea.left = (uint32_t*)(hs + SL.oLeft); ea.len = (uint32_t*)(hs + SL.oLen);
+    ea.peak = (uint32_t*)(hs + SL.oPeak); ea.wsum = (uint32_t*)(hs + SL.oWsum); ea.candIndex = (unsigned long long*)(hs + SL.oCandIndex);
+    ea.peakScore = (double*)(hs + SL.oPeakScore); ea.kurt = (double*)(hs + SL.oKurt); ea.corr = (double*)(hs + SL.oCorr);
+    ea.counts = (uint32_t*)(hs + SL.oCounts);
+    emit_rows_kernel<<<GS, 256, 0, st_>>>(ea);
+    launches += 1;
+    if (edgeRowsTotal) {
       EdgeEmitArgs ee;
+      memset(&ee, 0, sizeof ee);
       ee.rows = eg.rows; ee.rowCounts = eg.rowCounts; ee.rowCap = EDGE_ROW_CAP; ee.nSamples = n; ee.nAffected = nAff; ee.affected = d_affected; ee.nRows = eg.nRows;
-      ee.rowBase = d_rowBase; ee.units = d_units;
+      ee.edgeRowBase = edgeRowBase; ee.units = d_units; ee.tableCap = rowCap; ee.g = g;
       ee.buffer = ea.buffer; ee.contig = ea.contig; ee.left = ea.left; ee.len = ea.len; ee.peak = ea.peak; ee.candIndex = ea.candIndex;
       ee.peakScore = ea.peakScore; ee.kurt = ea.kurt; ee.corr = ea.corr; ee.counts = ea.counts; ee.wsum = ea.wsum;
-      edge_emit_kernel<<<dim3((EDGE_ROW_CAP + 127) / 128, nAff), 128, 0, ctx->stream>>>(ee);
+      edge_emit_kernel<<<dim3((EDGE_ROW_CAP + 127) / 128, nAff), 128, 0, st_>>>(ee);
       launches += 1;
     }
-    tags_in_regions_kernel<<<std::min<unsigned>(ctx->smCount * 4, (unsigned)((R * n + 255) / 256)), 256, (size_t)n * 8, ctx->stream>>>(ea.counts, R, n, d_tir);
+    GroupEndArgs ge;
+    memset(&ge, 0, sizeof ge);
+    ge.statCounts = statCounts; ge.pass = pass2; ge.g = g; ge.call = call; ge.nSamples = n;
+    ge.edgeRowCounts = eg.rowCounts; ge.edgeNRows = eg.nRows; ge.edgeRowCap = EDGE_ROW_CAP; ge.nAffected = edgeRowsTotal ? nAff : 0; ge.edgeRowsTotal = edgeRowsTotal;
+    ge.tir = d_tir;
+    group_end_kernel<<<(unsigned)ctx->smCount * 2, 256, (size_t)n * 8, st_>>>(ge);
     CU(cudaGetLastError());
     launches += 1;
-    if (!cfg.deviceOnly) CU(cudaMemcpyAsync(hs, ds, SL.devBytes, cudaMemcpyDeviceToHost, ctx->stream));
-    else {                                                            // only what the per-unit row counts need (5 bytes per row)
-      const size_t Rp = (R + 7) & ~(size_t)7;
-      CU(cudaMemcpyAsync(hs + SL.oContig, ds + SL.oContig, Rp * 4, cudaMemcpyDeviceToHost, ctx->stream));
-      CU(cudaMemcpyAsync(hs + SL.oBuffer, ds + SL.oBuffer, Rp, cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    CU(cudaMemcpyAsync(hs + SL.oTags, d_tir, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    stage_mark(ctx, "place+emit rows (to host)+totals");
   }
-  (void)Rnormal;
-  finish_stats(ctx, launches);
+  if (empty) {                                                          // a rank of a shared table with nothing loaded still takes part in the exchange
+    CU(cudaMemsetAsync(g, 0, sizeof(GroupCtr), st_));
+    PlaceArgs pa;
+    memset(&pa, 0, sizeof pa);
+    pa.g = g; pa.call = call; pa.units = d_units; pa.normalFirst = normalFirst; pa.rowShift = rowShift; pa.edgeRowBase = edgeRowBase; pa.unitRows = unitRowsDev;
+    pa.shared = 1; pa.x = shared->x;
+    row_place_kernel<<<1, 256, 0, st_>>>(pa);
+    launches += 1;
+  }
+
+  // ---- the one read-back: counters, totals, per-unit numbers ----------------------------------------------------------
+  CU(cudaMemcpyAsync(hg, g, sizeof(GroupCtr), cudaMemcpyDeviceToHost, st_));
+  CU(cudaMemcpyAsync(hcall, call, sizeof(CallCtr), cudaMemcpyDeviceToHost, st_));
+  CU(cudaMemcpyAsync(hTir, d_tir, (size_t)n * 8, cudaMemcpyDeviceToHost, st_));
+  if (nUnits) {
+    CU(cudaMemcpyAsync(hUnitCand, unitCand, (size_t)nUnits * 8, cudaMemcpyDeviceToHost, st_));
+    CU(cudaMemcpyAsync(hUnitRows, unitRowsDev, (size_t)nUnits * 8, cudaMemcpyDeviceToHost, st_));
+  }
+  if (nAff) CU(cudaMemcpyAsync(hDrop, d_drop, (size_t)nAff * 4, cudaMemcpyDeviceToHost, st_));
+  CU(cudaEventRecord(ctx->ev[3], st_));
+  if (!shared) memset(hs + out.layout.devBytes, 0, out.layout.totalBytes - out.layout.devBytes);   // host-only tail of the slab, while the device works
+  CU(cudaEventSynchronize(ctx->ev[3]));
+  { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]); ctx->stats.ms_total = ms; }
+  if (!empty) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->stats.ms_kde = ms; }
+  stage_collect(ctx);
+  ctx->stats.launches = launches;
+  if (pipelined) { const int rl = load_finish(ctx); if (rl) return rl; }   // what the load had to say about the input
+  const uint32_t flags = hcall->flags | hg->flags;
+  if (flags & FLAG_XCHG_TIMEOUT) return fail(ctx, UPB_ERR_CUDA, "shared table: another rank never published its row counts (timeout)");
+  if (flags & (FLAG_RUN_OVERFLOW | FLAG_CAP_OVERFLOW)) {
+    if (shared) return fail(ctx, UPB_ERR_NOMEM, "shared table: this call needs more room than the table or the arrays sized by the previous call have (call upb_call_regions once per context before sharing)");
+    if (out.slab.p) { ctx->slabPool.push_back(out.slab); out.slab = HostSlab(); }
+    if (flags & FLAG_RUN_OVERFLOW) ctx->needRunCap = (size_t)std::max<unsigned long long>(hcall->needSlots, hg->runCount) + (1u << 20);
+    *retry = true;
+    return UPB_OK;
+  }
+  ctx->stats.warm_spans = hcall->warm;
+  ctx->stats.hot_blocks = hcall->stat[0]; ctx->stats.kde_hot_tiles = hcall->stat[1]; ctx->stats.exact_evals = hcall->stat[2]; ctx->stats.spans_with_tags = hcall->stat[3];
+  out.R = hcall->rows;
+  out.nCand = hcall->cands;
+  ctx->stats.n_stitched = hcall->runs - hcall->cands;
+  for (uint32_t u = 0; u < nUnits; ++u) out.unitCand[u] = hUnitCand[u];
+  out.unitRows.assign(hUnitRows, hUnitRows + nUnits);
+  for (uint32_t k = 0; k < nAff; ++k) {                                 // the replay's candidates replace the ones it dropped
+    const long long d = (long long)edgeCand[k] - (long long)hDrop[k];
+    out.unitCand[pr.affected[k]] = (uint64_t)((long long)out.unitCand[pr.affected[k]] + d);
+    out.nCand = (uint64_t)((long long)out.nCand + d);
+  }
+  ctx->stats.n_candidates = out.nCand;
+  if (!shared) {
+    memcpy(hs + out.layout.oTags, hTir, (size_t)n * 8);
+    // what the next call of this context may assume without asking
+    const size_t n1 = (size_t)hcall->n1, cells = (size_t)hcall->cells, R = (size_t)out.R;
+    ctx->capN1 = std::max(ctx->capN1, n1 + n1 / 4 + 1024);
+    ctx->capCells = std::max(ctx->capCells, cells + cells / 4 + 4096);
+    ctx->capRows = std::max(ctx->capRows, R + R / 4 + 1024);
+  }
+  out.tir.assign(hTir, hTir + n);
   return UPB_OK;
+}
+
+static int run_pipeline (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& out, const SharedDst* shared = nullptr) {
+  // the first call of a context sizes its arrays from its own numbers; later calls run without a read-back and are repeated with
+  // sizing only when the numbers outgrew the arrays
+  bool sizing = !shared && (ctx->capN1 == 0 || ctx->capRows == 0);
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    bool retry = false;
+    const int r = run_pipeline_once(ctx, cfg, pr, out, sizing, &retry, shared);
+    if (r) { if (out.slab.p) { ctx->slabPool.push_back(out.slab); out.slab = HostSlab(); } return r; }
+    if (!retry) return UPB_OK;
+    sizing = true;
+  }
+  return fail(ctx, UPB_ERR_NOMEM, "region pipeline: buffers still too small after resizing");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1315,6 +1641,19 @@ static void fill_table (upb_ctx* ctx, const PipeOut& po, upb_region_table* t) {
   t->n_rejected = po.nCand - po.R;
 }
 
+// rows of a table into the order `perm` gives (row k of the result = old row perm[k])
+static void permute_table (upb_region_table* out, const std::vector<uint64_t>& perm, uint32_t n) {
+  const uint64_t R = out->n_rows;
+  auto permute = [&] (auto* col, size_t width) {
+    typedef typename std::remove_pointer<decltype(col)>::type T;
+    std::vector<T> tmp(col, col + R * width);
+    for (uint64_t k = 0; k < R; ++k) for (size_t w = 0; w < width; ++w) col[k * width + w] = tmp[perm[k] * width + w];
+  };
+  permute(out->buffer, 1); permute(out->forward_label, 1); permute(out->dropped, 1); permute(out->contig, 1); permute(out->left, 1);
+  permute(out->len, 1); permute(out->peak, 1); permute(out->hit_sum, 1); permute(out->cand_index, 1); permute(out->peak_score, 1);
+  permute(out->kurtosis, 1); permute(out->corr, 1); permute(out->counts, n);
+}
+
 extern "C" int upb_call_regions (upb_ctx* ctx, const upb_region_params* p, upb_region_table* out) {
   if (!ctx) return UPB_ERR_BAD_ARG;
   if (!p || !out) return fail(ctx, UPB_ERR_BAD_ARG, "upb_call_regions: NULL argument");
@@ -1326,7 +1665,6 @@ extern "C" int upb_call_regions (upb_ctx* ctx, const upb_region_params* p, upb_r
   cfg.nCoeffs = p->n_coeffs; cfg.coeffs = p->coeffs;
   cfg.needCorr = cfg.nondir;        // -D: the filter (if corr_threshold > -1) and the optional correlation column
   cfg.allowLeftEdge = true;
-  cfg.deviceOnly = p->reference_order == 2;
   PipeOut po;
   Prep pr;
   int r = run_pipeline(ctx, cfg, pr, po);
@@ -1344,107 +1682,161 @@ extern "C" int upb_call_regions (upb_ctx* ctx, const upb_region_params* p, upb_r
     bool identity = true;
     r = reference_order_impl(C, n, p->directional, p->bandwidth, ctx->firstPos.data(), ctx->lastPos.data(), out, &perm, &identity);
     if (r) { upb_free_region_table(out); return fail(ctx, r, "the reference's merge loop would abort on this input (several directional samples whose '-' track is read during pass 1; SURVEY Q7)"); }
-    const uint64_t R = out->n_rows;
-    if (!identity) {
-      auto permute = [&] (auto* col, size_t width) {
-        typedef typename std::remove_pointer<decltype(col)>::type T;
-        std::vector<T> tmp(col, col + R * width);
-        for (uint64_t k = 0; k < R; ++k) for (size_t w = 0; w < width; ++w) col[k * width + w] = tmp[perm[k] * width + w];
-      };
-      permute(out->buffer, 1); permute(out->forward_label, 1); permute(out->dropped, 1); permute(out->contig, 1); permute(out->left, 1);
-      permute(out->len, 1); permute(out->peak, 1); permute(out->hit_sum, 1); permute(out->cand_index, 1); permute(out->peak_score, 1);
-      permute(out->kurtosis, 1); permute(out->corr, 1); permute(out->counts, n);
-    }
+    if (!identity) permute_table(out, perm, n);
   }
   ctx->stats.ms_call = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return UPB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
-// several GPUs: one table out of the ranks' tables
+// several GPUs: one table every rank writes its rows into ("final region list — gather rows to rank 0")
+//
+// One rank per GPU (threads of one process: upb_multi_*; or processes: bench.py under torchrun), contigs sharded, no data-path
+// exchange.  The table lives in ONE page-locked host segment that every rank maps.  Each rank's row_place_kernel publishes its
+// per-(buffer, contig) row counts there and waits — on the device — for the other ranks' counts, so its emit_rows_kernel can write
+// its rows straight to their place in the table-wide order over its own PCIe link.  Rank 0's host then only waits for the other
+// ranks' "done" words.  No collective and no host round trip inside a step (r01: NCCL all-reduce + .cpu() + scatter + all-reduce).
+//
+// segment layout:  ready[world] u64 | done[world] u64 | counts[2][world][2C] u64 | per-rank blocks | table slab (slab_layout)
+// per-rank block:  nCand u64 | unitCand[2C] u64 | tir[n] u64 | lastTag[2C] u32 | firstPos[n*2*C] u32 | lastPos[n*2*C] u32
 // ------------------------------------------------------------------------------------------------
-extern "C" int upb_slab_layout (uint64_t n_rows, uint32_t n_samples, uint64_t* off) {
-  if (!off) return UPB_ERR_BAD_ARG;
-  const SlabLayout L = slab_layout((size_t)n_rows, n_samples, 1);
-  off[UPB_COL_CAND_INDEX] = L.oCandIndex; off[UPB_COL_PEAK_SCORE] = L.oPeakScore; off[UPB_COL_KURTOSIS] = L.oKurt; off[UPB_COL_CORR] = L.oCorr;
-  off[UPB_COL_CONTIG] = L.oContig; off[UPB_COL_LEFT] = L.oLeft; off[UPB_COL_LEN] = L.oLen; off[UPB_COL_PEAK] = L.oPeak; off[UPB_COL_HIT_SUM] = L.oWsum;
-  off[UPB_COL_COUNTS] = L.oCounts; off[UPB_COL_BUFFER] = L.oBuffer; off[UPB_COL_END] = L.devBytes;
+struct SharedLayout { size_t oReady, oDone, oCounts, oRank, rankBytes, oSlab, total; };
+
+static SharedLayout shared_layout (uint32_t C, uint32_t n, uint32_t world, uint64_t rowCap) {
+  SharedLayout L;
+  size_t o = 0;
+  L.oReady = o; o += (size_t)world * 8;
+  L.oDone = o;  o += (size_t)world * 8;
+  o = (o + 255) & ~(size_t)255;
+  L.oCounts = o; o += 2 * (size_t)world * 2 * C * 8;
+  o = (o + 255) & ~(size_t)255;
+  L.rankBytes = ((1 + 2 * (size_t)C + n) * 8 + (2 * (size_t)C + 2 * (size_t)n * 2 * C) * 4 + 255) & ~(size_t)255;
+  L.oRank = o; o += (size_t)world * L.rankBytes;
+  o = (o + 4095) & ~(size_t)4095;
+  L.oSlab = o; o += slab_layout((size_t)rowCap, n, C).totalBytes;
+  L.total = (o + 4095) & ~(size_t)4095;
+  return L;
+}
+
+extern "C" uint64_t upb_shared_table_bytes (uint32_t n_contigs, uint32_t n_samples, uint32_t world, uint64_t row_capacity) {
+  return shared_layout(n_contigs, n_samples, world, row_capacity).total;
+}
+
+extern "C" int upb_shared_table_init (const upb_shared_table* t) {
+  if (!t || !t->host || !t->world) return UPB_ERR_BAD_ARG;
+  const SharedLayout L = shared_layout(t->n_contigs, t->n_samples, t->world, t->row_capacity);
+  if (t->bytes < L.total) return UPB_ERR_BAD_ARG;
+  memset(t->host, 0, L.oSlab);
   return UPB_OK;
 }
 
-struct ScatterArgs {
-  const unsigned char* src; unsigned char* dst;
-  SlabLayout ls, ld;
-  unsigned long long R;
-  uint32_t n, C;
-  const unsigned long long* unitDst;   // [2C] first table-wide row of each (buffer, contig)
-  const unsigned long long* unitSrc;   // [2C] first local row of each (buffer, contig)
-};
+static void fill_table (upb_ctx* ctx, const PipeOut& po, upb_region_table* t);
 
-__global__ void scatter_rows_kernel (ScatterArgs a) {
-  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.R) return;
-  const uint32_t b = a.src[a.ls.oBuffer + i];
-  const uint32_t c = ((const uint32_t*)(a.src + a.ls.oContig))[i];
-  const size_t u = (size_t)b * a.C + c;
-  const unsigned long long o = a.unitDst[u] + (i - a.unitSrc[u]);
-#define UPB_MOVE(T, off) ((T*)(a.dst + a.ld.off))[o] = ((const T*)(a.src + a.ls.off))[i]
-  UPB_MOVE(unsigned long long, oCandIndex); UPB_MOVE(double, oPeakScore); UPB_MOVE(double, oKurt); UPB_MOVE(double, oCorr);
-  UPB_MOVE(uint32_t, oContig); UPB_MOVE(uint32_t, oLeft); UPB_MOVE(uint32_t, oLen); UPB_MOVE(uint32_t, oPeak); UPB_MOVE(uint32_t, oWsum);
-  UPB_MOVE(uint8_t, oBuffer);
-#undef UPB_MOVE
-}
-
-// the counts matrix, one thread per element: consecutive threads write consecutive words (the destination may be mapped host
-// memory, where only coalesced stores travel well over PCIe)
-__global__ void scatter_counts_kernel (ScatterArgs a) {
-  const unsigned long long total = a.R * a.n;
-  const uint32_t* sc = (const uint32_t*)(a.src + a.ls.oCounts);
-  uint32_t* dc = (uint32_t*)(a.dst + a.ld.oCounts);
-  for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (unsigned long long)gridDim.x * blockDim.x) {
-    const unsigned long long i = g / a.n;
-    const uint32_t b = a.src[a.ls.oBuffer + i];
-    const uint32_t c = ((const uint32_t*)(a.src + a.ls.oContig))[i];
-    const size_t u = (size_t)b * a.C + c;
-    dc[(a.unitDst[u] + (i - a.unitSrc[u])) * a.n + (g - i * a.n)] = sc[g];
-  }
-}
-
-extern "C" int upb_scatter_rows (upb_ctx* ctx, uint64_t total_rows, const uint64_t* unit_rows_total, const uint64_t* unit_rows_local, void* d_slab) {
+extern "C" int upb_call_regions_shared (upb_ctx* ctx, const upb_region_params* p, const upb_shared_table* t, uint64_t step, upb_region_table* out) {
   if (!ctx) return UPB_ERR_BAD_ARG;
-  if (!unit_rows_total || !unit_rows_local || !d_slab) return fail(ctx, UPB_ERR_BAD_ARG, "upb_scatter_rows: NULL argument");
-  CU(cudaSetDevice(ctx->device));
+  if (!p || !t || !out || !t->host || !t->device || !t->world || t->rank >= t->world || step == 0) return fail(ctx, UPB_ERR_BAD_ARG, "upb_call_regions_shared: bad argument");
+  memset(out, 0, sizeof *out);
+  const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
   const uint32_t C = (uint32_t)ctx->sizes.size(), n = ctx->nSamples;
-  const uint64_t R = ctx->lastRows;
-  if (R == 0) return UPB_OK;
-  ScatterArgs sa;
-  sa.src = ctx->scratch["slab"].as<unsigned char>(); sa.dst = (unsigned char*)d_slab;
-  sa.ls = slab_layout(R, n, C); sa.ld = slab_layout(total_rows, n, C);
-  sa.R = R; sa.n = n; sa.C = C;
-  // local first row of each unit: rows are in canonical order, so count them from the buffer / contig columns
-  std::vector<unsigned long long> h(4 * (size_t)C, 0);
-  { unsigned long long run = 0; for (size_t u = 0; u < 2 * (size_t)C; ++u) { h[u] = run; run += unit_rows_total[u]; } if (run != total_rows) return fail(ctx, UPB_ERR_BAD_ARG, "upb_scatter_rows: unit_rows_total does not add up to total_rows"); }
-  { unsigned long long run = 0; for (size_t u = 0; u < 2 * (size_t)C; ++u) { h[2 * (size_t)C + u] = run; run += unit_rows_local[u]; } if (run != R) return fail(ctx, UPB_ERR_BAD_ARG, "upb_scatter_rows: unit_rows_local does not match the last upb_call_regions on this context"); }
-  unsigned long long* d_u = SCR("scatterUnits", unsigned long long, 4 * (size_t)C);
-  CU(cudaMemcpyAsync(d_u, h.data(), 4 * (size_t)C * 8, cudaMemcpyHostToDevice, ctx->stream));
-  sa.unitDst = d_u; sa.unitSrc = d_u + 2 * (size_t)C;
-  scatter_rows_kernel<<<(unsigned)((R + 255) / 256), 256, 0, ctx->stream>>>(sa);
-  scatter_counts_kernel<<<(unsigned)std::min<uint64_t>((R * n + 255) / 256, (uint64_t)ctx->smCount * 16), 256, 0, ctx->stream>>>(sa);
-  CU(cudaGetLastError());
-  CU(cudaStreamSynchronize(ctx->stream));
-  return UPB_OK;
-}
+  if (C != t->n_contigs || n != t->n_samples) return fail(ctx, UPB_ERR_BAD_ARG, "upb_call_regions_shared: the table was laid out for another contig table / sample count");
+  const SharedLayout L = shared_layout(C, n, t->world, t->row_capacity);
+  if (t->bytes < L.total) return fail(ctx, UPB_ERR_BAD_ARG, "upb_call_regions_shared: segment smaller than upb_shared_table_bytes()");
+  unsigned char* hb = (unsigned char*)t->host;
+  unsigned char* db = (unsigned char*)t->device;
+  PipeCfg cfg;
+  cfg.bw = p->bandwidth; cfg.thr = p->region_threshold; cfg.kurtThr = p->kurtosis_threshold; cfg.corrThr = p->corr_threshold;
+  cfg.hitThr = p->hit_threshold; cfg.background = p->background; cfg.nondir = !p->directional; cfg.control = p->control;
+  cfg.nCoeffs = p->n_coeffs; cfg.coeffs = p->coeffs;
+  cfg.needCorr = cfg.nondir;
+  cfg.allowLeftEdge = true;
+  SharedDst sd;
+  sd.slab = db + L.oSlab; sd.rowCap = t->row_capacity;
+  sd.x.counts = (volatile unsigned long long*)(db + L.oCounts + (size_t)(step & 1) * t->world * 2 * C * 8);
+  sd.x.ready = (volatile unsigned long long*)(db + L.oReady);
+  sd.x.rank = t->rank; sd.x.world = t->world; sd.x.C = C; sd.x.step = step;
+  PipeOut po;
+  Prep pr;
+  int r = run_pipeline(ctx, cfg, pr, po, &sd);
+  unsigned long long* done = (unsigned long long*)(hb + L.oDone);
+  if (r) { __atomic_store_n(&done[t->rank], ~0ull, __ATOMIC_RELEASE); return r; }   // poison: rank 0 reports the step as failed instead of waiting
+  // this rank's contribution to what rank 0 assembles
+  {
+    unsigned char* rb = hb + L.oRank + (size_t)t->rank * L.rankBytes;
+    unsigned long long* w = (unsigned long long*)rb;
+    w[0] = po.nCand;
+    unsigned long long* uc = w + 1; unsigned long long* tir = uc + 2 * (size_t)C;
+    uint32_t* lastTag = (uint32_t*)(tir + n); uint32_t* fp = lastTag + 2 * (size_t)C; uint32_t* lp = fp + (size_t)n * 2 * C;
+    memset(uc, 0, 2 * (size_t)C * 8);
+    for (size_t u = 0; u < po.units.size(); ++u) uc[(size_t)po.units[u].buffer * C + po.units[u].contig] = po.unitCand[u];
+    for (uint32_t s = 0; s < n; ++s) tir[s] = s < po.tir.size() ? po.tir[s] : 0;
+    memset(lastTag, 0, 2 * (size_t)C * 4);
+    for (uint32_t s = 0; s < n; ++s) for (uint32_t d = 0; d < 2; ++d) for (uint32_t c = 0; c < C; ++c) {
+      const uint32_t lpv = ctx->lastPos[((size_t)s * 2 + d) * C + c];
+      const uint32_t b = p->directional ? d : 0;
+      if (lpv > lastTag[(size_t)b * C + c]) lastTag[(size_t)b * C + c] = lpv;
+    }
+    memcpy(fp, ctx->firstPos.data(), (size_t)n * 2 * C * 4);
+    memcpy(lp, ctx->lastPos.data(), (size_t)n * 2 * C * 4);
+  }
+  out->n_samples = n;
+  out->n_rows = po.R;                                                  // this rank's rows
+  __atomic_store_n(&done[t->rank], step, __ATOMIC_RELEASE);
+  if (t->rank != 0) { ctx->stats.ms_call = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(); return UPB_OK; }
 
-extern "C" int upb_table_from_slab (void* h_slab, uint64_t n_rows, uint32_t n_samples, upb_region_table* t) {
-  if (!h_slab || !t) return UPB_ERR_BAD_ARG;
-  const SlabLayout L = slab_layout((size_t)n_rows, n_samples, 1);
-  unsigned char* b = (unsigned char*)h_slab;
-  memset(t, 0, sizeof *t);
-  t->n_rows = n_rows; t->n_samples = n_samples;
-  t->buffer = b + L.oBuffer; t->contig = (uint32_t*)(b + L.oContig); t->left = (uint32_t*)(b + L.oLeft); t->len = (uint32_t*)(b + L.oLen);
-  t->peak = (uint32_t*)(b + L.oPeak); t->hit_sum = (uint32_t*)(b + L.oWsum); t->cand_index = (uint64_t*)(b + L.oCandIndex);
-  t->peak_score = (double*)(b + L.oPeakScore); t->kurtosis = (double*)(b + L.oKurt); t->corr = (double*)(b + L.oCorr); t->counts = (uint32_t*)(b + L.oCounts);
-  t->n_passed = n_rows;
+  // rank 0: every rank's rows have landed once its `done` word says so
+  for (uint32_t rk = 0; rk < t->world; ++rk) {
+    const std::chrono::steady_clock::time_point w0 = std::chrono::steady_clock::now();
+    for (uint64_t spin = 0;; ++spin) {
+      const unsigned long long v = __atomic_load_n(&done[rk], __ATOMIC_ACQUIRE);
+      if (v == ~0ull) return fail(ctx, UPB_ERR_CUDA, "shared table: a rank reported a failed step");
+      if (v >= step) break;
+      if ((spin & 1023) == 1023 && std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count() > 30.0)
+        return fail(ctx, UPB_ERR_CUDA, "shared table: timed out waiting for a rank");
+    }
+  }
+  const SlabLayout SL = slab_layout((size_t)t->row_capacity, n, C);
+  unsigned char* hs = hb + L.oSlab;
+  const unsigned long long* counts = (const unsigned long long*)(hb + L.oCounts + (size_t)(step & 1) * t->world * 2 * C * 8);
+  uint64_t R = 0;
+  memset(hs + SL.devBytes, 0, SL.totalBytes - SL.devBytes);
+  memset(out, 0, sizeof *out);
+  out->n_samples = n;
+  out->buffer = hs + SL.oBuffer; out->forward_label = hs + SL.oLabel; out->dropped = hs + SL.oDropped;
+  out->contig = (uint32_t*)(hs + SL.oContig); out->left = (uint32_t*)(hs + SL.oLeft); out->len = (uint32_t*)(hs + SL.oLen); out->peak = (uint32_t*)(hs + SL.oPeak);
+  out->hit_sum = (uint32_t*)(hs + SL.oWsum); out->cand_index = (uint64_t*)(hs + SL.oCandIndex); out->peak_score = (double*)(hs + SL.oPeakScore);
+  out->kurtosis = (double*)(hs + SL.oKurt); out->corr = (double*)(hs + SL.oCorr); out->counts = (uint32_t*)(hs + SL.oCounts);
+  out->tags_in_regions = (uint64_t*)(hs + SL.oTags); out->unit_candidates = (uint64_t*)(hs + SL.oUnitCand);
+  out->unit_last_tag = (uint32_t*)(hs + SL.oUnitLast); out->unit_rows = (uint64_t*)(hs + SL.oUnitRows);
+  std::vector<uint32_t> firstPos((size_t)n * 2 * C, 0), lastPos((size_t)n * 2 * C, 0);
+  uint64_t nCand = 0;
+  for (uint32_t rk = 0; rk < t->world; ++rk) {
+    const unsigned char* rb = hb + L.oRank + (size_t)rk * L.rankBytes;
+    const unsigned long long* w = (const unsigned long long*)rb;
+    nCand += w[0];
+    const unsigned long long* uc = w + 1; const unsigned long long* tir = uc + 2 * (size_t)C;
+    const uint32_t* lastTag = (const uint32_t*)(tir + n); const uint32_t* fp = lastTag + 2 * (size_t)C; const uint32_t* lp = fp + (size_t)n * 2 * C;
+    for (size_t k = 0; k < 2 * (size_t)C; ++k) {
+      out->unit_candidates[k] += uc[k];
+      out->unit_rows[k] += counts[(size_t)rk * 2 * C + k];
+      if (lastTag[k] > out->unit_last_tag[k]) out->unit_last_tag[k] = lastTag[k];
+    }
+    for (uint32_t s = 0; s < n; ++s) out->tags_in_regions[s] += tir[s];
+    for (size_t k = 0; k < (size_t)n * 2 * C; ++k) { if (fp[k]) firstPos[k] = fp[k]; if (lp[k]) lastPos[k] = lp[k]; }
+  }
+  for (size_t k = 0; k < 2 * (size_t)C; ++k) R += out->unit_rows[k];
+  if (R > t->row_capacity) return fail(ctx, UPB_ERR_NOMEM, "shared table: more rows than the table has room for");
+  out->n_rows = R; out->n_passed = R; out->n_rejected = nCand - R;
+  { uint64_t firstRev = 0; for (size_t k = 0; k < C; ++k) firstRev += out->unit_rows[k];
+    if (!p->directional) firstRev = R;
+    memset(out->forward_label, 1, firstRev); memset(out->forward_label + firstRev, 0, R - firstRev); }
+  if (p->reference_order == 1) {
+    std::vector<uint64_t> perm;
+    bool identity = true;
+    r = reference_order_impl(C, n, p->directional, p->bandwidth, firstPos.data(), lastPos.data(), out, &perm, &identity);
+    if (r) return fail(ctx, r, "the reference's merge loop would abort on this input (several directional samples whose '-' track is read during pass 1; SURVEY Q7)");
+    if (!identity) permute_table(out, perm, n);
+  }
+  ctx->stats.ms_call = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return UPB_OK;
 }
 
@@ -1749,6 +2141,7 @@ extern "C" int upb_profile_contig (upb_ctx* ctx, const upb_region_params* p, int
 extern "C" int upb_count_tags_in_regions (upb_ctx* ctx, int directional, uint32_t extension, uint64_t n_regions,
                                           const upb_region_key* regions, uint32_t* counts_out) {
   if (!ctx) return UPB_ERR_BAD_ARG;
+  { const int rl = load_finish(ctx); if (rl) return rl; }
   if (!ctx->loaded) return fail(ctx, UPB_ERR_NOT_LOADED, "no tags loaded (upb_set_contigs + upb_load_tags first)");
   if (n_regions && (!regions || !counts_out)) return fail(ctx, UPB_ERR_BAD_ARG, "upb_count_tags_in_regions: NULL argument");
   CU(cudaSetDevice(ctx->device));

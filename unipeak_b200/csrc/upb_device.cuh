@@ -61,7 +61,9 @@ struct Tags {                       // resident tag-frequency data (see upb_load
 };
 
 // flags word (device -> host)
-enum : uint32_t { FLAG_RUN_OVERFLOW = 1u, FLAG_UNSORTED = 2u, FLAG_BAD_POS = 4u, FLAG_ZERO_COUNT = 8u };
+enum : uint32_t { FLAG_RUN_OVERFLOW = 1u, FLAG_UNSORTED = 2u, FLAG_BAD_POS = 4u, FLAG_ZERO_COUNT = 8u, /* 16: FLAG_BAD_PACK (upb_pack.cuh) */
+                  FLAG_CAP_OVERFLOW = 32u,    // more survivors / positions / rows than the arrays sized from the previous call hold: the call is repeated
+                  FLAG_XCHG_TIMEOUT = 64u };  // a rank of a shared-table job never published its row counts
 
 // ------------------------------------------------------------------------------------------------
 // small device helpers
@@ -182,63 +184,21 @@ __device__ __forceinline__ uint32_t seg_of_entry (const uint64_t* __restrict__ s
 constexpr int WIN_SHIFT = 16;       // scatter window: 65536 positions = 128 mini-tiles, one CTA of mt_scatter_kernel
 constexpr int WIN_MT = 1 << (WIN_SHIFT - MT_SHIFT);
 
-// Pass 1 validates what the reference's parser guarantees (positions inside the contig and strictly
-// ascending per (sample, strand, contig), non-zero counts: misc/format.cpp:654-710, misc/peakcall.cpp:171) and builds
-// the per-mini-tile histogram and the per-sample window index; pass 2 (mt_scatter_kernel) scatters and builds the zone maps.  Entries that fail validation are never used as indices.
-__global__ void mt_build_kernel (MtArgs a) {
-  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= a.nEntries) return;
-  const uint64_t i = a.first + k;
-  // consecutive entries almost always share their segment: one search per warp, the lanes only check
-  uint32_t g = 0;
-  { const uint64_t i0 = a.first + (k & ~(uint64_t)31);
-    g = seg_of_entry(a.segStart, a.nSeg, i0);
-    if (i >= a.segStart[g + 1]) g = seg_of_entry(a.segStart, a.nSeg, i); }
-  const uint32_t c = g % a.C, sd = g / a.C, d = sd & 1u, s = sd >> 1;
-  const uint32_t pos1 = a.pos[i];
-  const uint32_t p = pos1 - 1;
-  if (pos1 < 1 || pos1 > a.sizes[c]) { atomicOr(a.flags, FLAG_BAD_POS); return; }
-  const uint32_t mt = a.mtBase[d * a.C + c] + (p >> MT_SHIFT);
-  {
-    uint32_t f = 0;
-    if (a.cnt[i] == 0) f |= FLAG_ZERO_COUNT;
-    if (i > a.segStart[g] && a.pos[i - 1] >= pos1) f |= FLAG_UNSORTED;
-    if (f) atomicOr(a.flags, f);
-    atomicAdd(&a.mtCount[mt], 1u);
-    if (!(f & FLAG_UNSORTED)) {     // per-sample window index: the first entry of every window this entry opens
-      const int64_t w = (int64_t)(p >> WIN_SHIFT);
-      const int64_t pw = i > a.segStart[g] ? (int64_t)((a.pos[i - 1] - 1) >> WIN_SHIFT) : -1;
-      uint32_t* we = a.wEnt + (size_t)s * a.nWinTotal + a.winBase[d * a.C + c];
-      for (int64_t t = pw + 1; t <= w; ++t) we[t] = (uint32_t)(i - a.segStart[g]);
-    }
-    return;
-  }
-}
-
-// window index default: "no entry at or after this window" = the segment's length
-__global__ void win_fill_kernel (MtArgs a, uint32_t nSamples) {
-  const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= (uint64_t)nSamples * a.nWinTotal) return;
-  const uint32_t s = (uint32_t)(e / a.nWinTotal), gw = (uint32_t)(e % a.nWinTotal);
-  uint32_t lo = 0, hi = 2 * a.C;    // largest dc with winBase[dc] <= gw (empty ranges are skipped by taking the largest)
-  while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.winBase[mid] <= gw) lo = mid; else hi = mid; }
-  const uint32_t d = lo / a.C, c = lo % a.C;
-  const uint64_t g = (uint64_t)(s * 2 + d) * a.C + c;
-  a.wEnt[e] = (uint32_t)(a.segStart[g + 1] - a.segStart[g]);
-}
+// Pass 1 (validation, per-mini-tile histogram, per-sample window index) is load_tile_kernel / load_seam_kernel in upb_pack.cuh, fused
+// with the decoder of the compact host form; pass 2 (mt_scatter_kernel) scatters and builds the zone maps.
 
 // Pass 2 of the counting sort, window-major: one CTA per 65536-position window of one (strand, contig) moves the entries of
 // ALL samples that fall into it (one warp per sample at a time; each sample's entries of the window are one contiguous range of
 // its sorted segment, found through the window index) to their mini-tiles.  The CTA's output is one contiguous stretch of the
 // tile-major copy (~28 KB on C3), so the 8-byte stores merge into full sectors in L2, and the per-mini-tile cursors are
 // shared-memory atomics — the sample-major version (v1–v19) did 326 M global atomics and partial-sector writes: 5.3 ms.
-__global__ void __launch_bounds__(256) mt_scatter_kernel (MtArgs a, uint32_t nSamples) {
+__global__ void __launch_bounds__(256) mt_scatter_kernel (MtArgs a, uint32_t nSamples, uint32_t w0 /* first window of the load group */) {
   __shared__ uint32_t cursor[WIN_MT];
   __shared__ unsigned long long base[WIN_MT];
   __shared__ uint32_t big[WIN_MT];                                    // a count large enough that a 32-bit block sum could wrap
   __shared__ uint32_t blk[WIN_MT * (1 << (MT_SHIFT - 5))];            // zone map per 32-position block
   if (*a.flags & (FLAG_UNSORTED | FLAG_BAD_POS)) return;             // pass 1 found invalid input: its entries are never used as indices
-  const uint32_t gw = blockIdx.x;
+  const uint32_t gw = w0 + blockIdx.x;
   uint32_t lo = 0, hi = 2 * a.C;
   while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.winBase[mid] <= gw) lo = mid; else hi = mid; }
   const uint32_t d = lo / a.C, c = lo % a.C, w = gw - a.winBase[lo];
@@ -516,6 +476,89 @@ __global__ void scan_final_kernel (const uint32_t* __restrict__ in, uint64_t n, 
   unsigned long long run = partial[blockIdx.x] + scan_block_excl_u64(s, sh, &total);
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; ++k) { const uint64_t i = b0 + k; if (i < n) out[i] = run; run += v[k]; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same scan with the element count taken from DEVICE memory (or an immediate) and any grid: every kernel walks its tiles
+// with a grid stride, so the host can enqueue the whole region pipeline without reading a single size back
+// (four synchronising read-backs per call).  The input value comes from a functor: a plain u32 array,
+// or two arrays packed into one 64-bit word (flag << 40 | length) so that one scan yields both prefixes.
+// ------------------------------------------------------------------------------------------------
+struct DevN {                       // a count the host may not know: *p32, *p64, or imm
+  unsigned long long imm;
+  const uint32_t* p32;
+  const unsigned long long* p64;
+  __device__ __forceinline__ unsigned long long get () const { return p32 ? (unsigned long long)*p32 : (p64 ? *p64 : imm); }
+};
+static inline DevN devn_imm (unsigned long long v) { DevN n; n.imm = v; n.p32 = nullptr; n.p64 = nullptr; return n; }
+static inline DevN devn_u32 (const uint32_t* p) { DevN n; n.imm = 0; n.p32 = p; n.p64 = nullptr; return n; }
+static inline DevN devn_u64 (const unsigned long long* p) { DevN n; n.imm = 0; n.p32 = nullptr; n.p64 = p; return n; }
+
+constexpr int PACK_SHIFT = 40;      // packed scans: (flag << 40) | length; lengths sum to < 2^40 (a genome has < 2^33 positions per strand)
+constexpr unsigned long long PACK_MASK = (1ull << PACK_SHIFT) - 1;
+
+struct LoadU32 {
+  const uint32_t* a;
+  __device__ __forceinline__ unsigned long long operator() (unsigned long long i) const { return a[i]; }
+};
+struct LoadPacked {                 // flag[i] << 40 | len[i]
+  const uint32_t* flag; const uint32_t* len;
+  __device__ __forceinline__ unsigned long long operator() (unsigned long long i) const { return ((unsigned long long)flag[i] << PACK_SHIFT) | len[i]; }
+};
+
+template <class Load>
+__global__ void __launch_bounds__(SCAN_THREADS) scanv_partial_kernel (Load ld, DevN nn, unsigned long long* __restrict__ partial) {
+  __shared__ unsigned long long sh[SCAN_THREADS / 32 + 1];
+  const unsigned long long n = nn.get();
+  const unsigned long long nTiles = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  for (unsigned long long tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+    const unsigned long long b0 = tile * SCAN_BLOCK;
+    unsigned long long s = 0;
+    for (int k = 0; k < SCAN_ITEMS; ++k) { const unsigned long long i = b0 + (unsigned long long)k * SCAN_THREADS + threadIdx.x; if (i < n) s += ld(i); }
+    unsigned long long total;
+    scan_block_excl_u64(s, sh, &total);
+    if (threadIdx.x == 0) partial[tile] = total;
+  }
+}
+
+// one block; also publishes the grand total (0 when there is nothing to scan)
+__global__ void __launch_bounds__(SCAN_THREADS) scanv_top_kernel (unsigned long long* partial, DevN nn, unsigned long long* grandTotal) {
+  __shared__ unsigned long long sh[SCAN_THREADS / 32 + 1];
+  __shared__ unsigned long long carry;
+  const unsigned long long n = nn.get();
+  const unsigned long long nTiles = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (unsigned long long b0 = 0; b0 < nTiles; b0 += SCAN_THREADS) {
+    const unsigned long long i = b0 + threadIdx.x;
+    const unsigned long long v = i < nTiles ? partial[i] : 0ull;
+    unsigned long long total;
+    const unsigned long long ex = scan_block_excl_u64(v, sh, &total);
+    if (i < nTiles) partial[i] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *grandTotal = carry;
+}
+
+template <class Load>
+__global__ void __launch_bounds__(SCAN_THREADS) scanv_final_kernel (Load ld, DevN nn, const unsigned long long* __restrict__ partial, unsigned long long* __restrict__ out,
+                                                                    unsigned long long bias) {
+  __shared__ unsigned long long sh[SCAN_THREADS / 32 + 1];
+  const unsigned long long n = nn.get();
+  const unsigned long long nTiles = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  for (unsigned long long tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+    const unsigned long long b0 = tile * SCAN_BLOCK + (unsigned long long)threadIdx.x * SCAN_ITEMS;
+    unsigned long long v[SCAN_ITEMS];
+    unsigned long long s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { const unsigned long long i = b0 + k; v[k] = i < n ? ld(i) : 0ull; s += v[k]; }
+    unsigned long long total;
+    unsigned long long run = bias + partial[tile] + scan_block_excl_u64(s, sh, &total);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { const unsigned long long i = b0 + k; if (i < n) out[i] = run; run += v[k]; }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

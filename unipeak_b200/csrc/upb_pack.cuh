@@ -1,151 +1,193 @@
-// upb_pack.cuh — the compact host format of the tag arrays and its device-side decoder.
+// upb_pack.cuh — the compact host format of the tag arrays and the device side of the load (decode + validation + the
+// histogram pass of the tile-major counting sort, in one kernel).
 //
-// The load is PCIe-bound (8 bytes per entry: position u32 + count u32).  Sorted positions and small counts compress well with
-// no entropy coding at all: 16-bit position deltas inside a (sample, strand, contig) segment and 8-bit counts, with a sparse,
-// index-sorted exception list for what does not fit (the first position of every segment, gaps >= 65535, counts >= 255):
-// 3 bytes per entry.  The decoder is a segmented inclusive scan of the deltas (an exception restarts the running position) in
-// three kernels — per-tile aggregates, one block that scans the aggregates, per-tile final scan — that writes the same pos[] /
-// cnt[] arrays the plain path copies, so everything downstream is shared.  What the reference's parser guarantees (ascending
-// positions inside the contig, non-zero counts) is validated afterwards on the decoded arrays exactly as for the plain path.
+// The load is PCIe-bound (plain form: 8 bytes per entry, position u32 + count u32).  Sorted positions and small counts compress
+// well with no entropy coding at all: ONE u16 per entry — the position delta to the previous entry of the same
+// (sample, strand, contig) segment in the low 12 bits, the count in the high 4 — with a sparse, index-sorted exception list for
+// what does not fit (0xFFF / 0xF escapes: absolute position / full count).  Every entry whose index inside its segment is a
+// multiple of PK_TILE (2048) MUST be a position escape, so a tile of 2048 entries decodes on its own: one block, one
+// shared-memory scan, no second pass over the input and no carry between tiles (r01 decoded with three kernels and read the
+// packed words twice).  On RNA-seq / ChIP-seq-like data ~0.5 % of the entries escape: 2.1 bytes per entry.
+//
+// load_tile_kernel works on the tiles of one LOAD GROUP — the segments of all samples on one strand and a range of contigs —
+// so that a group's decode, histogram, scan and scatter run while the next group's bytes are still crossing PCIe
+// (upb_api.cu: load_enqueue).  It validates what the reference's parser and asserts guarantee (positions inside the contig and
+// strictly ascending, non-zero counts: misc/format.cpp:654-710, misc/peakcall.cpp:171) and what the format itself promises (an
+// escape has its exception, tiles start with a position escape); the seams between tiles are checked by load_seam_kernel.
 #pragma once
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include "upb_device.cuh"
 
 namespace upb {
 
 constexpr int PK_THREADS = 256;
 constexpr int PK_ITEMS = 8;
 constexpr int PK_TILE = PK_THREADS * PK_ITEMS;
-constexpr uint32_t PK_DPOS_ESC = 0xFFFFu;
-constexpr uint32_t PK_CNT_ESC = 0xFFu;
-// the 2-byte form (upb_pack_tags2 / upb_load_tags_packed2): one u16 per entry, position delta in the low 12 bits, count in the high 4
 constexpr uint32_t PK2_DPOS_MASK = 0x0FFFu, PK2_DPOS_ESC = 0x0FFFu, PK2_CNT_SHIFT = 12, PK2_CNT_ESC = 0xFu;
-constexpr uint32_t FLAG_BAD_PACK = 16u;             // an escape without its exception entry
+constexpr uint32_t FLAG_BAD_PACK = 16u;             // an escape without its exception entry, or a tile that does not start with a position escape
 
-struct PkException { unsigned long long index; uint32_t pos; uint32_t cnt; };   // == upb_packed_exception
+struct PkException { unsigned long long index; uint32_t pos; uint32_t cnt; };   // == upb_packed_exception; index = entry index in the caller's arrays
 
-struct PkAgg { uint32_t sum; uint32_t reset; };     // running position contributed by a range; reset: the range holds an absolute position
-
-__device__ __forceinline__ PkAgg pk_combine (const PkAgg a, const PkAgg b) {   // a then b
-  PkAgg r;
-  r.sum = b.reset ? b.sum : a.sum + b.sum;
-  r.reset = a.reset | b.reset;
-  return r;
-}
-
-// exception of entry e, or nullptr
+// exception of source entry e, or nullptr
 __device__ __forceinline__ const PkException* pk_find (const PkException* __restrict__ exc, unsigned long long nExc, unsigned long long e) {
   unsigned long long lo = 0, hi = nExc;
   while (lo < hi) { const unsigned long long mid = (lo + hi) >> 1; if (exc[mid].index < e) lo = mid + 1; else hi = mid; }
   return (lo < nExc && exc[lo].index == e) ? exc + lo : nullptr;
 }
 
-struct PkArgs {
-  const uint16_t* dpos;
-  const uint8_t* cnt8;               // NULL: the 2-byte form, the count sits in the high bits of dpos
-  uint32_t dposMask, dposEsc, cntEsc;   // 0xFFFF / 0xFFFF / 0xFF for the 3-byte form
+struct LoadArgs {
+  const uint16_t* words;            // packed form: device copy of the caller's words, indexed like the caller's arrays (NULL: plain form, pos / cnt already hold the entries)
   const PkException* exc;
   unsigned long long nExc;
-  unsigned long long first, E;       // entries [first, first + E) are decoded (one sample's chunk when the load is pipelined)
-  PkAgg* agg;                        // [nTiles]
-  PkAgg* carry;                      // [nTiles] running position entering each tile
-  uint32_t* pos;
+  uint32_t* pos;                    // resident sample-major arrays (compacted: only the segments this context keeps)
   uint32_t* cnt;
+  const uint64_t* segStart;         // [nSeg + 1] first resident entry of segment g = (s*2+d)*C + c
+  const uint64_t* srcStart;         // [nSeg] first entry of segment g in the caller's arrays
+  const uint32_t* grpSeg;           // [nGrpSeg] segments of this load group
+  const uint32_t* grpTile;          // [nGrpSeg + 1] tiles before each of them
+  uint32_t nGrpSeg;
+  const uint32_t* sizes;            // [C]
+  const uint32_t* mtBase;           // [2C + 1]
+  uint32_t* mtCount;                // [nMtTotal] histogram of the counting sort
+  const uint32_t* winBase;          // [2C + 1]
+  uint32_t* wEnt;                   // [nSamples * nWinTotal] first entry (relative to its segment) of sample s at or after each window
+  uint32_t nWinTotal;
+  uint32_t C;
   uint32_t* flags;
 };
 
-// the items of one thread: value and reset flag of up to PK_ITEMS consecutive entries
-__device__ __forceinline__ PkAgg pk_thread_scan (const PkArgs& a, unsigned long long e0, uint32_t vals[PK_ITEMS], uint32_t resets[PK_ITEMS], int* nOut) {
-  PkAgg t; t.sum = 0; t.reset = 0;
-  int n = 0;
-  const unsigned long long end = a.first + a.E;
-#pragma unroll
-  for (int q = 0; q < PK_ITEMS; ++q) {
-    const unsigned long long e = e0 + q;
-    if (e < end) {
-      uint32_t v = a.dpos[e] & a.dposMask, rs = 0;
-      if (v == a.dposEsc) {
-        const PkException* x = pk_find(a.exc, a.nExc, e);
-        if (x) { v = x->pos; rs = 1; } else { atomicOr(a.flags, FLAG_BAD_PACK); v = 0; }
-      }
-      PkAgg it; it.sum = v; it.reset = rs;
-      t = pk_combine(t, it);
-      vals[q] = t.sum; resets[q] = t.reset;
-      n = q + 1;
-    }
-  }
-  *nOut = n;
-  return t;
+// window index of sample s: every window (65536 positions) that starts after the previous entry and not after this one begins here
+__device__ __forceinline__ void load_open_windows (const LoadArgs& a, uint32_t s, uint32_t dc, int64_t prevWin, uint32_t p0 /* position - 1 */, uint32_t rel) {
+  const int64_t w = (int64_t)(p0 >> WIN_SHIFT);
+  if (w <= prevWin) return;
+  uint32_t* we = a.wEnt + (size_t)s * a.nWinTotal + a.winBase[dc];
+  for (int64_t t = prevWin + 1; t <= w; ++t) we[t] = rel;
 }
 
-// block-wide exclusive segmented scan of the per-thread aggregates; returns the aggregate of everything before this thread
-// and (to thread 0's *total) of the whole tile
-__device__ __forceinline__ PkAgg pk_block_exclusive (PkAgg mine, PkAgg* total) {
-  __shared__ PkAgg warpAgg[PK_THREADS / 32];
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  PkAgg incl = mine;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    PkAgg up; up.sum = __shfl_up_sync(0xffffffffu, incl.sum, o); up.reset = __shfl_up_sync(0xffffffffu, incl.reset, o);
-    if (lane >= (uint32_t)o) incl = pk_combine(up, incl);
-  }
-  if (lane == 31) warpAgg[warp] = incl;
-  __syncthreads();
-  PkAgg before; before.sum = 0; before.reset = 0;
-  for (uint32_t w = 0; w < warp; ++w) before = pk_combine(before, warpAgg[w]);
-  PkAgg prevLane; prevLane.sum = __shfl_up_sync(0xffffffffu, incl.sum, 1); prevLane.reset = __shfl_up_sync(0xffffffffu, incl.reset, 1);
-  PkAgg excl = before;
-  if (lane > 0) excl = pk_combine(before, prevLane);
-  if (total) { PkAgg tt; tt.sum = 0; tt.reset = 0; for (uint32_t w = 0; w < PK_THREADS / 32; ++w) tt = pk_combine(tt, warpAgg[w]); *total = tt; }
-  __syncthreads();
-  return excl;
-}
-
-__global__ void __launch_bounds__(PK_THREADS) pk_tile_kernel (PkArgs a) {
-  uint32_t vals[PK_ITEMS], resets[PK_ITEMS];
-  int n;
-  const unsigned long long e0 = a.first + (unsigned long long)blockIdx.x * PK_TILE + (unsigned long long)threadIdx.x * PK_ITEMS;
-  const PkAgg mine = pk_thread_scan(a, e0, vals, resets, &n);
-  PkAgg total;
-  pk_block_exclusive(mine, &total);
-  if (threadIdx.x == 0) a.agg[blockIdx.x] = total;
-}
-
-// one block: exclusive segmented scan of the tile aggregates
-__global__ void __launch_bounds__(1024) pk_top_kernel (const PkAgg* __restrict__ agg, uint32_t nTiles, PkAgg* __restrict__ carry) {
-  __shared__ PkAgg part[1024];
-  const uint32_t per = (nTiles + 1023) / 1024;
-  const uint32_t t0 = threadIdx.x * per, t1 = min(t0 + per, nTiles);
-  PkAgg mine; mine.sum = 0; mine.reset = 0;
-  for (uint32_t t = t0; t < t1; ++t) mine = pk_combine(mine, agg[t]);
-  part[threadIdx.x] = mine;
-  __syncthreads();
+__global__ void __launch_bounds__(PK_THREADS) load_tile_kernel (const LoadArgs a) {
+  __shared__ uint32_t warpSum[PK_THREADS / 32], warpReset[PK_THREADS / 32];
+  __shared__ uint32_t lastOf[PK_THREADS];           // last decoded position of every thread (0: the thread holds no entry)
+  __shared__ uint32_t s_seg, s_tile;
   if (threadIdx.x == 0) {
-    PkAgg run; run.sum = 0; run.reset = 0;
-    for (uint32_t i = 0; i < 1024; ++i) { const PkAgg p = part[i]; part[i] = run; run = pk_combine(run, p); }
+    uint32_t lo = 0, hi = a.nGrpSeg;                // largest j with grpTile[j] <= blockIdx.x (segments without entries have no tile and are skipped)
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.grpTile[mid] <= blockIdx.x) lo = mid; else hi = mid; }
+    s_seg = a.grpSeg[lo]; s_tile = blockIdx.x - a.grpTile[lo];
   }
   __syncthreads();
-  PkAgg run = part[threadIdx.x];
-  for (uint32_t t = t0; t < t1; ++t) { carry[t] = run; run = pk_combine(run, agg[t]); }
+  const uint32_t g = s_seg, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t c = g % a.C, sd = g / a.C, d = sd & 1u, s = sd >> 1, dc = d * a.C + c;
+  const uint64_t seg0 = a.segStart[g], segN = a.segStart[g + 1] - seg0;
+  const uint64_t t0 = (uint64_t)s_tile * PK_TILE;                      // first entry of the tile, relative to the segment
+  const uint32_t nHere = (uint32_t)min((uint64_t)PK_TILE, segN - t0);
+  const uint32_t i0 = threadIdx.x * PK_ITEMS;
+  const uint32_t size = a.sizes[c];
+  uint32_t vals[PK_ITEMS], cnts[PK_ITEMS];
+  uint32_t flags = 0, run = 0, reset = 0, escMask = 0;
+  int n = 0;
+  if (a.words) {
+    const unsigned long long src0 = a.srcStart[g] + t0;
+#pragma unroll
+    for (int q = 0; q < PK_ITEMS; ++q) {
+      const uint32_t i = i0 + q;
+      if (i < nHere) {
+        const uint32_t w = a.words[src0 + i];
+        uint32_t v = w & PK2_DPOS_MASK, k = w >> PK2_CNT_SHIFT;
+        const bool escP = v == PK2_DPOS_ESC, escC = k == PK2_CNT_ESC;
+        if (escP || escC) {
+          const PkException* x = pk_find(a.exc, a.nExc, src0 + i);
+          if (!x) { flags |= FLAG_BAD_PACK; if (escP) v = 0; if (escC) k = 0; }
+          else { if (escP) v = x->pos; if (escC) k = x->cnt; }
+        }
+        if (i == 0 && !escP) flags |= FLAG_BAD_PACK;                   // a tile starts with an absolute position
+        if (escP) { run = v; reset = 1; escMask |= 1u << q; } else run += v;
+        vals[q] = run; cnts[q] = k;
+        n = q + 1;
+      }
+    }
+    // block-wide segmented scan of (run, reset): a thread without a reset adds the running position of the threads before it
+    uint32_t isum = run, ires = reset;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t us = __shfl_up_sync(0xffffffffu, isum, o), ur = __shfl_up_sync(0xffffffffu, ires, o);
+      if (lane >= (uint32_t)o) { if (!ires) isum += us; ires |= ur; }
+    }
+    if (lane == 31) { warpSum[warp] = isum; warpReset[warp] = ires; }
+    __syncthreads();
+    uint32_t bs = 0, br = 0;                                           // everything before this warp
+    for (uint32_t w2 = 0; w2 < warp; ++w2) { if (warpReset[w2]) { bs = warpSum[w2]; br = 1; } else bs += warpSum[w2]; }
+    uint32_t ps = __shfl_up_sync(0xffffffffu, isum, 1), pr = __shfl_up_sync(0xffffffffu, ires, 1);
+    if (lane == 0) { ps = 0; pr = 0; }
+    const uint32_t before = pr ? ps : bs + ps;                         // running position entering this thread
+    (void)br;
+    const int firstEsc = escMask ? __ffs(escMask) - 1 : PK_ITEMS;      // entries before this thread's first escape continue the position entering the thread
+#pragma unroll
+    for (int q = 0; q < PK_ITEMS; ++q) if (q < n && q < firstEsc) vals[q] += before;
+  } else {
+#pragma unroll
+    for (int q = 0; q < PK_ITEMS; ++q) {
+      const uint32_t i = i0 + q;
+      if (i < nHere) { vals[q] = a.pos[seg0 + t0 + i]; cnts[q] = a.cnt[seg0 + t0 + i]; n = q + 1; }
+    }
+  }
+  lastOf[threadIdx.x] = n ? vals[n - 1] : 0u;
+  __syncthreads();
+  // validation, histogram, window index, and (packed form) the decoded arrays
+  uint32_t prev = 0;                                                   // position of the entry before this thread's first one, 0 at the start of the tile (the seam kernel looks at that one)
+  if (threadIdx.x > 0 && n) prev = lastOf[threadIdx.x - 1];
+  const uint32_t gb = a.mtBase[dc];
+#pragma unroll
+  for (int q = 0; q < PK_ITEMS; ++q) if (q < n) {
+    const uint32_t p = vals[q], k = cnts[q];
+    const uint64_t rel = t0 + i0 + q;
+    if (a.words) { a.pos[seg0 + rel] = p; a.cnt[seg0 + rel] = k; }
+    if (p < 1 || p > size) { flags |= FLAG_BAD_POS; prev = p; continue; }
+    if (k == 0) flags |= FLAG_ZERO_COUNT;
+    const bool first = i0 + q == 0;
+    if (!first && prev >= p) flags |= FLAG_UNSORTED;
+    else {
+      atomicAdd(&a.mtCount[gb + ((p - 1) >> MT_SHIFT)], 1u);
+      if (!first) load_open_windows(a, s, dc, (int64_t)((prev - 1) >> WIN_SHIFT), p - 1, (uint32_t)rel);
+    }
+    prev = p;
+  }
+  if (flags) atomicOr(a.flags, flags);
 }
 
-__global__ void __launch_bounds__(PK_THREADS) pk_final_kernel (PkArgs a) {
-  uint32_t vals[PK_ITEMS], resets[PK_ITEMS];
-  int n;
-  const unsigned long long e0 = a.first + (unsigned long long)blockIdx.x * PK_TILE + (unsigned long long)threadIdx.x * PK_ITEMS;
-  const PkAgg mine = pk_thread_scan(a, e0, vals, resets, &n);
-  const PkAgg excl = pk_combine(a.carry[blockIdx.x], pk_block_exclusive(mine, nullptr));
-  for (int q = 0; q < n; ++q) {
-    const unsigned long long e = e0 + q;
-    a.pos[e] = resets[q] ? vals[q] : excl.sum + vals[q];
-    uint32_t c = a.cnt8 ? (uint32_t)a.cnt8[e] : (uint32_t)a.dpos[e] >> PK2_CNT_SHIFT;
-    if (c == a.cntEsc) {
-      const PkException* x = pk_find(a.exc, a.nExc, e);
-      if (x) c = x->cnt; else { atomicOr(a.flags, FLAG_BAD_PACK); c = 0; }
-    }
-    a.cnt[e] = c;
+// the first entry of every tile against the entry before it (the last one of the previous tile of the same segment)
+__global__ void load_seam_kernel (const LoadArgs a, uint32_t nTiles) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nTiles) return;
+  uint32_t lo = 0, hi = a.nGrpSeg;
+  while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.grpTile[mid] <= t) lo = mid; else hi = mid; }
+  const uint32_t g = a.grpSeg[lo], k = t - a.grpTile[lo];
+  const uint32_t c = g % a.C, sd = g / a.C, d = sd & 1u, s = sd >> 1, dc = d * a.C + c;
+  const uint64_t seg0 = a.segStart[g];
+  const uint64_t rel = (uint64_t)k * PK_TILE;
+  const uint32_t p = a.pos[seg0 + rel];
+  if (p < 1 || p > a.sizes[c]) return;                                 // already reported
+  int64_t prevWin = -1;
+  if (k > 0) {
+    const uint32_t q = a.pos[seg0 + rel - 1];
+    if (q >= p) { atomicOr(a.flags, FLAG_UNSORTED); return; }          // its histogram entry was counted by the tile kernel; the scatter pass does not run on invalid input
+    if (q >= 1) prevWin = (int64_t)((q - 1) >> WIN_SHIFT);
   }
+  load_open_windows(a, s, dc, prevWin, p - 1, (uint32_t)rel);
+}
+
+// window index default of the windows [w0, w1) of one (strand, contig range): "no entry at or after this window" = the segment's length
+__global__ void load_win_fill_kernel (const LoadArgs a, uint32_t nSamples, uint32_t w0, uint32_t w1) {
+  const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t nw = w1 - w0;
+  if (e >= (uint64_t)nSamples * nw) return;
+  const uint32_t s = (uint32_t)(e / nw), gw = w0 + (uint32_t)(e % nw);
+  uint32_t lo = 0, hi = 2 * a.C;    // largest dc with winBase[dc] <= gw (empty ranges are skipped by taking the largest)
+  while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.winBase[mid] <= gw) lo = mid; else hi = mid; }
+  const uint32_t d = lo / a.C, c = lo % a.C;
+  const uint64_t g = (uint64_t)(s * 2 + d) * a.C + c;
+  a.wEnt[(size_t)s * a.nWinTotal + gw] = (uint32_t)(a.segStart[g + 1] - a.segStart[g]);
 }
 
 // first / last position of every segment (the host keeps them for the reference-order logic)
@@ -156,5 +198,7 @@ __global__ void seg_ends_kernel (const uint32_t* __restrict__ pos, const uint64_
   firstPos[g] = e > s ? pos[s] : 0u;
   lastPos[g] = e > s ? pos[e - 1] : 0u;
 }
+
+__global__ void set_u64_kernel (unsigned long long* p, unsigned long long v) { if (blockIdx.x == 0 && threadIdx.x == 0) *p = v; }
 
 }  // namespace upb

@@ -317,6 +317,7 @@ struct WarmArgs {
   Tags T;
   const SpanUnit* units;
   uint32_t nUnits, totalSpans;
+  uint32_t spanBegin, spanEnd;      // spans of the group of units this launch covers
   int nondir;
   uint32_t nAdj;
   double flatBound, thr;
@@ -324,15 +325,19 @@ struct WarmArgs {
   uint32_t bw;
   uint32_t* nWarm;
   uint32_t* spanRunCount;           // zeroed here for the spans that are skipped
+  const uint32_t* loadFlags;        // validation flags of a load that is still being waited for group by group (NULL: the load was checked before the call):
+                                    //   once it has reported invalid input nothing is evaluated any more — the entries may be anything
 };
 
 constexpr int WARM_ADJ_MAX = ((31 + 2 * MAX_BW_SPAN) >> MT_SHIFT) + 2;   // upb_api.cu: nAdj = ((31 + 2 bw) >> MT_SHIFT) + 2
 
 __global__ void warm_span_kernel (WarmArgs a) {
-  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t w = a.spanBegin + blockIdx.x * blockDim.x + threadIdx.x;
   bool warm = false;
   uint32_t unit = 0;
-  if (w < a.totalSpans) {
+  const bool badInput = a.loadFlags && (*a.loadFlags & (2u | 4u | 8u | 16u)) != 0;   // FLAG_UNSORTED | FLAG_BAD_POS | FLAG_ZERO_COUNT | FLAG_BAD_PACK
+  if (w < a.spanEnd && badInput) a.spanRunCount[w] = 0;
+  if (w < a.spanEnd && !badInput) {
     uint32_t lo = 0, hi = a.nUnits;
     while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.units[mid].spanStart <= w) lo = mid; else hi = mid; }
     const SpanUnit U = a.units[lo];
@@ -920,20 +925,56 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : MINB) span_kernel (con
 }
 
 // ------------------------------------------------------------------------------------------------
+// counters of the region pipeline.  They live in device memory (upb_ctx::d_small) and the host reads them ONCE, when the call
+// is over: every kernel below takes its element counts from here and walks them with a grid stride, so the whole pipeline is
+// enqueued without a single synchronising read-back (r01 had four per call).
+// ------------------------------------------------------------------------------------------------
+struct GroupCtr {                   // zeroed before every group of units (a call works through its units in one or more groups)
+  uint32_t flags;                   // FLAG_RUN_OVERFLOW / FLAG_CAP_OVERFLOW of this group
+  uint32_t ticket;                  // span_kernel work ticket
+  uint32_t runCount;                // run slots handed out
+  uint32_t runReal;                 // runs written
+  uint32_t nWarm, poolTicket, nHot, pad0;
+  unsigned long long totSpanRuns;   // scan totals: runs by span order,
+  unsigned long long nCand;         //   candidate regions (= Region objects of the reference),
+  unsigned long long pv;            //   hit-filter survivors << PACK_SHIFT | their positions,
+  unsigned long long n1, cells;     //   the same two unpacked (n1 clamped to the capacity of the per-survivor arrays),
+  unsigned long long rows;          //   accepted rows of span_kernel's candidates
+  unsigned long long pad1[4];
+};
+static_assert(sizeof(GroupCtr) <= 128, "GroupCtr: the scan totals of dump_and_corr start at byte 128 of d_small");
+
+struct CallCtr {                    // zeroed once per call; accumulated over the groups
+  unsigned long long stat[4];       // hot blocks, pieces, exact evaluations, spans with a hot block
+  unsigned long long rows;          // table rows so far (left-edge replay rows included)
+  unsigned long long cands, runs, n1, cells, warm;
+  unsigned long long needSlots;     // largest runCount of a group (what runCap has to be when a group overflowed)
+  uint32_t flags, pad;
+};
+constexpr size_t CALLCTR_OFFSET = 512;   // byte offset of CallCtr inside d_small
+
+__device__ __forceinline__ bool pipe_dead (const GroupCtr* g) { return (g->flags & FLAG_RUN_OVERFLOW) != 0; }   // runs are incomplete: nothing downstream may index through them
+
+// ------------------------------------------------------------------------------------------------
 // ordering, stitching, filtering
 // ------------------------------------------------------------------------------------------------
 struct Cand2 {                      // a candidate region == one Region object of the reference
   uint32_t unit, left, len, peak, wsum;
-  uint32_t slot;                    // run slot of the first piece (row of runCounts / runKurt)
+  uint32_t slot;                    // run slot of the first piece
   uint32_t nPieces, pad;
   double score;
 };
 
-// position of every run in (span, rank) order
-__global__ void run_order_kernel (const SpanRun* __restrict__ runs, uint32_t nRuns, const unsigned long long* __restrict__ spanOrd, uint32_t* __restrict__ ordIdx) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nRuns || runs[i].span == RUN_INVALID) return;              // nRuns = slots handed out; unfilled ones are skipped
-  ordIdx[spanOrd[runs[i].span] + runs[i].rank] = i;
+// position of every run in (span, rank) order; spanOrd = exclusive scan of spanRunCount over the group's spans
+__global__ void run_order_kernel (const SpanRun* __restrict__ runs, const GroupCtr* __restrict__ g, uint32_t cap, const unsigned long long* __restrict__ spanOrd,
+                                  uint32_t* __restrict__ ordIdx) {
+  if (pipe_dead(g)) return;
+  const uint32_t n = min(g->runCount, cap);                           // slots handed out; unfilled ones are skipped
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t sp = runs[i].span;
+    if (sp == RUN_INVALID) continue;
+    ordIdx[spanOrd[sp] + runs[i].rank] = i;
+  }
 }
 
 __device__ __forceinline__ uint32_t unit_of_span (const SpanUnit* __restrict__ units, uint32_t nUnits, uint32_t span) {
@@ -942,61 +983,90 @@ __device__ __forceinline__ uint32_t unit_of_span (const SpanUnit* __restrict__ u
   return lo;
 }
 
-__global__ void run_heads2_kernel (const SpanRun* __restrict__ runs, const uint32_t* __restrict__ ordIdx, uint32_t nRuns,
+__global__ void run_heads2_kernel (const SpanRun* __restrict__ runs, const uint32_t* __restrict__ ordIdx, const GroupCtr* __restrict__ g,
                                    const SpanUnit* __restrict__ units, uint32_t nUnits, uint32_t* __restrict__ head) {
-  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= nRuns) return;
-  bool cont = false;
-  if (j > 0) {
-    const SpanRun a = runs[ordIdx[j]], p = runs[ordIdx[j - 1]];
-    cont = a.left == p.left + p.len && unit_of_span(units, nUnits, a.span) == unit_of_span(units, nUnits, p.span);
+  if (pipe_dead(g)) return;
+  const uint32_t n = g->runReal;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    bool cont = false;
+    if (j > 0) {
+      const SpanRun a = runs[ordIdx[j]], p = runs[ordIdx[j - 1]];
+      cont = a.left == p.left + p.len && unit_of_span(units, nUnits, a.span) == unit_of_span(units, nUnits, p.span);
+    }
+    head[j] = cont ? 0u : 1u;
   }
-  head[j] = cont ? 0u : 1u;
 }
 
+// runs -> candidates (stitching what a piece or span boundary cut), with the hit filter (misc/peakcall.cpp:41, first clause) and
+// the length of the survivors (the size of their pooled position cells) written alongside: pass[i], candLen[i]
 __global__ void merge_runs2_kernel (const SpanRun* __restrict__ runs, const uint32_t* __restrict__ ordIdx, const uint32_t* __restrict__ head,
-                                    const unsigned long long* __restrict__ headScan, uint32_t nRuns, const SpanUnit* __restrict__ units, uint32_t nUnits,
-                                    Cand2* __restrict__ cand, unsigned long long* __restrict__ unitCand) {
-  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool isHead = j < nRuns && head[j];
-  uint32_t myUnit = 0xFFFFFFFFu;
-  if (isHead) myUnit = unit_of_span(units, nUnits, runs[ordIdx[j]].span);
-  {                                                                   // candidates per unit: one atomic per (warp, unit) instead of one per candidate
-    const uint32_t peers = __match_any_sync(0xffffffffu, myUnit);
-    if (isHead && (threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&unitCand[myUnit], (unsigned long long)__popc(peers));
+                                    const unsigned long long* __restrict__ headScan, const GroupCtr* __restrict__ g, const SpanUnit* __restrict__ units, uint32_t nUnits,
+                                    double hitThr, Cand2* __restrict__ cand, uint32_t* __restrict__ pass, uint32_t* __restrict__ candLen,
+                                    unsigned long long* __restrict__ unitCand) {
+  if (pipe_dead(g)) return;
+  const uint32_t n = g->runReal;
+  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {   // whole warps stay together (match_any below)
+    const uint32_t j = base + threadIdx.x;
+    const bool isHead = j < n && head[j];
+    uint32_t myUnit = 0xFFFFFFFFu;
+    if (isHead) myUnit = unit_of_span(units, nUnits, runs[ordIdx[j]].span);
+    {                                                                 // candidates per unit: one atomic per (warp, unit) instead of one per candidate
+      const uint32_t peers = __match_any_sync(0xffffffffu, myUnit);
+      if (isHead && (threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&unitCand[myUnit], (unsigned long long)__popc(peers));
+    }
+    if (!isHead) continue;
+    const SpanRun f = runs[ordIdx[j]];
+    Cand2 c;
+    c.unit = myUnit; c.left = f.left; c.len = f.len; c.peak = f.peak; c.wsum = f.wsum; c.score = f.score;
+    c.slot = ordIdx[j]; c.nPieces = 1; c.pad = 0;
+    for (uint32_t q = j + 1; q < n && !head[q]; ++q) {
+      const SpanRun r = runs[ordIdx[q]];
+      c.len += r.len;
+      c.wsum += r.wsum;                                               // HitCount wraps mod 2^32 (misc/peakcall.cpp:36-40)
+      if (r.score > c.score) { c.score = r.score; c.peak = r.peak; }  // first strict maximum (misc/data.cpp:97-101)
+      ++c.nPieces;
+    }
+    const unsigned long long i = headScan[j];
+    cand[i] = c;
+    const bool hit = (double)c.wsum >= hitThr;
+    pass[i] = hit ? 1u : 0u;
+    candLen[i] = hit ? c.len : 0u;
   }
-  if (!isHead) return;
-  const SpanRun f = runs[ordIdx[j]];
-  Cand2 c;
-  c.unit = myUnit; c.left = f.left; c.len = f.len; c.peak = f.peak; c.wsum = f.wsum; c.score = f.score;
-  c.slot = ordIdx[j]; c.nPieces = 1; c.pad = 0;
-  for (uint32_t q = j + 1; q < nRuns && !head[q]; ++q) {
-    const SpanRun r = runs[ordIdx[q]];
-    c.len += r.len;
-    c.wsum += r.wsum;                                                 // HitCount wraps mod 2^32 (misc/peakcall.cpp:36-40)
-    if (r.score > c.score) { c.score = r.score; c.peak = r.peak; }    // first strict maximum (misc/data.cpp:97-101)
-    ++c.nPieces;
-  }
-  cand[headScan[j]] = c;
+}
+
+// ordinal of the first candidate of every unit of the group [u0, u1) among the group's candidates
+__global__ void unit_first_kernel (const unsigned long long* __restrict__ unitCand, uint32_t u0, uint32_t u1, unsigned long long* __restrict__ unitFirst) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long run = 0; for (uint32_t u = u0; u < u1; ++u) { unitFirst[u] = run; run += unitCand[u]; } }
 }
 
 // candidates of span_kernel that lie in the stretch the left-edge replay owns (upb_edge.cuh) are not Region objects of the
 // reference: they are dropped and counted per affected unit
 __global__ void edge_drop_kernel (const uint32_t* __restrict__ affected, const uint32_t* __restrict__ stop, uint32_t nAffected,
-                                  const Cand2* __restrict__ cand, const unsigned long long* __restrict__ nCand, uint32_t* __restrict__ pass, uint32_t* __restrict__ dropCount) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= *nCand) return;
-  const uint32_t unit = cand[i].unit;
-  for (uint32_t k = 0; k < nAffected; ++k)
-    if (affected[k] == unit) { if (cand[i].left <= stop[k]) { pass[i] = 0; atomicAdd(&dropCount[k], 1u); } break; }
+                                  const Cand2* __restrict__ cand, const GroupCtr* __restrict__ g, uint32_t* __restrict__ pass, uint32_t* __restrict__ candLen,
+                                  uint32_t* __restrict__ dropCount) {
+  if (pipe_dead(g)) return;
+  const unsigned long long n = g->nCand;
+  for (unsigned long long i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t unit = cand[i].unit;
+    for (uint32_t k = 0; k < nAffected; ++k)
+      if (affected[k] == unit) { if (cand[i].left <= stop[k]) { pass[i] = 0; candLen[i] = 0; atomicAdd(&dropCount[k], 1u); } break; }
+  }
 }
 
-// hit filter (misc/peakcall.cpp:41 first clause)
-// n = the number of candidates (still on the device), bound = slots to fill: slots beyond the candidates get 0
-__global__ void cand_hit_kernel (const Cand2* __restrict__ cand, const unsigned long long* __restrict__ n, uint32_t bound, double hitThr, uint32_t* __restrict__ pass) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= bound) return;
-  pass[i] = (i < *n && (double)cand[i].wsum >= hitThr) ? 1u : 0u;
+// hit-filter survivors -> list (candidate indices, ascending); pvScan = exclusive scan of (pass << PACK_SHIFT | candLen).
+// Also unpacks the scan total and checks it against the capacities of the per-survivor arrays.
+__global__ void compact_pv_kernel (const uint32_t* __restrict__ pass, const unsigned long long* __restrict__ pvScan, GroupCtr* __restrict__ g,
+                                   uint32_t n1Cap, unsigned long long cellCap, uint32_t* __restrict__ list) {
+  if (pipe_dead(g)) { if (blockIdx.x == 0 && threadIdx.x == 0) { g->n1 = 0; g->cells = 0; } return; }
+  const unsigned long long n = g->nCand;
+  for (unsigned long long i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (pass[i]) { const unsigned long long k = pvScan[i] >> PACK_SHIFT; if (k < n1Cap) list[k] = (uint32_t)i; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const unsigned long long n1 = g->pv >> PACK_SHIFT, cells = g->pv & PACK_MASK;
+    g->n1 = n1 < n1Cap ? n1 : n1Cap;
+    g->cells = cells;
+    if (n1 > n1Cap || cells > cellCap) atomicOr(&g->flags, FLAG_CAP_OVERFLOW);
+  }
 }
 
 // Region::exptSums (misc/data.cpp:116-131) and Region::posKurtosis (misc/data.cpp:133-182) of the candidates that passed the
@@ -1016,14 +1086,15 @@ struct StatArgs {
   const SpanUnit* units;
   const Cand2* cand;
   const uint32_t* list;             // hit-filter survivors (candidate indices, ascending)
-  uint32_t nList;
+  const GroupCtr* g;                // g->n1 survivors
   int nondir;
   double kurtThr;
-  const unsigned long long* cellOff;   // [nCand] first pooled cell of every surviving candidate (exclusive scan of len over the survivors)
+  const unsigned long long* pvScan; // [nCand] low PACK_SHIFT bits: first pooled cell of every surviving candidate
+  unsigned long long cellCap;       // capacity of `cells`
   uint32_t* cells;                  // pooled counts per position of every surviving candidate
-  uint32_t* counts;                 // [nList * nSamples]
-  double* kurt;                     // [nList]
-  uint32_t* pass;                   // [nList] kurtosis filter (misc/peakcall.cpp:41 second clause)
+  uint32_t* counts;                 // [n1 * nSamples]
+  double* kurt;                     // [n1]
+  uint32_t* pass;                   // [n1] kurtosis filter (misc/peakcall.cpp:41 second clause)
   uint32_t* ticket;
 };
 
@@ -1038,6 +1109,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32) region_pool_kernel (StatArgs a)
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
   const uint32_t g = lane / ST_GROUP, gl = lane % ST_GROUP, leader = lane & ~(uint32_t)(ST_GROUP - 1);
   const uint32_t n = a.T.nSamples;
+  const uint32_t nList = (uint32_t)a.g->n1;
   const size_t groupBytes = ((size_t)(ST_CHUNK + n) * 4 + 15) / 16 * 16;   // per group: cell[ST_CHUNK] u32, cnts[n] u32
   unsigned char* gbase = stat_smem_raw + ((size_t)warp * ST_PER_WARP + g) * groupBytes;
   uint32_t* cell = (uint32_t*)gbase;
@@ -1047,7 +1119,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32) region_pool_kernel (StatArgs a)
   bool active = false, exhausted = false;
   uint32_t tkNext = 0, tkEnd = 0;
   uint32_t i = 0, left = 1, right = 0, contig = 0;
-  bool single = true;
+  bool single = true, cellsOk = true;
   uint32_t d = 0, dEnd = 0, sp = 0, spEnd = 0, ma = 0, mb = 0, gb = 0;
   unsigned long long eb = 0, e1 = 0, cellBase = 0;
 
@@ -1057,7 +1129,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32) region_pool_kernel (StatArgs a)
     const bool wantTicket = !active && !exhausted && tkNext == tkEnd;
     if (wantTicket && gl == 0) t = atomicAdd(a.ticket, ST_TICKET);
     t = __shfl_sync(0xffffffffu, t, leader);
-    if (wantTicket) { tkNext = t; tkEnd = min(t + ST_TICKET, a.nList); if (t >= a.nList) { exhausted = true; tkEnd = tkNext; } }
+    if (wantTicket) { tkNext = t; tkEnd = min(t + ST_TICKET, nList); if (t >= nList) { exhausted = true; tkEnd = tkNext; } }
     bool needSeg = false;                                             // (re)load the entry range of segment (d, sp)
     if (!active && tkNext < tkEnd) {
       i = tkNext++;
@@ -1066,11 +1138,12 @@ __global__ void __launch_bounds__(ST_WARPS * 32) region_pool_kernel (StatArgs a)
       const SpanUnit U = a.units[c.unit];
       left = c.left; right = c.left + c.len - 1; contig = U.contig;
       single = c.len <= (uint32_t)ST_CHUNK;
-      cellBase = a.cellOff[ci];
+      cellBase = a.pvScan[ci] & PACK_MASK;
+      cellsOk = cellBase + c.len <= a.cellCap;                        // beyond the capacity: the call is repeated with a larger array (FLAG_CAP_OVERFLOW)
       d = a.nondir ? 0u : U.buffer; dEnd = a.nondir ? 1u : U.buffer;
       for (uint32_t s2 = gl; s2 < n; s2 += ST_GROUP) cnts[s2] = 0;
       if (single) { for (uint32_t k = gl; k < (uint32_t)ST_CHUNK; k += ST_GROUP) cell[k] = 0; }
-      else { for (unsigned long long k = gl; k < c.len; k += ST_GROUP) a.cells[cellBase + k] = 0; }
+      else if (cellsOk) { for (unsigned long long k = gl; k < c.len; k += ST_GROUP) a.cells[cellBase + k] = 0; }
       active = true;
       needSeg = true;
       sp = 0xFFFFFFFFu;                                               // "strand d not opened yet"
@@ -1107,7 +1180,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32) region_pool_kernel (StatArgs a)
         const uint32_t p = sp * SPAN_LEN + (en[q].y & (SPAN_LEN - 1)) + 1;
         if (eff[q] && p >= left && p <= right) {
           atomicAdd(&cnts[en[q].y >> SPAN_SHIFT], eff[q]);
-          if (single) atomicAdd(&cell[p - left], eff[q]); else atomicAdd(&a.cells[cellBase + (p - left)], eff[q]);
+          if (single) atomicAdd(&cell[p - left], eff[q]); else if (cellsOk) atomicAdd(&a.cells[cellBase + (p - left)], eff[q]);
         }
       }
       eb += 8 * ST_GROUP;
@@ -1136,7 +1209,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32) region_pool_kernel (StatArgs a)
       }
       if (done) {                                                     // write the region out: matrix row and (short regions) the pooled cells
         for (uint32_t s2 = gl; s2 < n; s2 += ST_GROUP) a.counts[(uint64_t)i * n + s2] = cnts[s2];
-        if (single) { const uint32_t len = right - left + 1; for (uint32_t k = gl; k < len; k += ST_GROUP) a.cells[cellBase + k] = cell[k]; }
+        if (single && cellsOk) { const uint32_t len = right - left + 1; for (uint32_t k = gl; k < len; k += ST_GROUP) a.cells[cellBase + k] = cell[k]; }
         active = false;
       }
     }
@@ -1145,34 +1218,30 @@ __global__ void __launch_bounds__(ST_WARPS * 32) region_pool_kernel (StatArgs a)
 }
 
 __global__ void region_moment_kernel (StatArgs a) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.nList) return;
-  const uint32_t ci = a.list[i];
-  const uint32_t len = a.cand[ci].len;
-  const uint32_t* __restrict__ cells = a.cells + a.cellOff[ci];
-  uint32_t count = 0, sum = 0;                                        // HitCount arithmetic (wraps), offsets as UShort (Q8)
-  for (uint32_t o = 0; o < len; ++o) { const uint32_t k = cells[o]; count += k; sum += k * (o & 0xFFFFu); }
-  const double xbar = (double)sum / (double)count;                   // misc/data.cpp:147
-  double sum2 = 0.0, sum4 = 0.0;
-  for (uint32_t o = 0; o < len; ++o) {
-    const uint32_t pc = cells[o];
-    if (!pc) continue;                                                // positions without a stored hit vector are not visited (misc/data.cpp:171-173)
-    const double dd = __dsub_rn((double)(o & 0xFFFFu), xbar);
-    const double d2 = __dmul_rn(dd, dd);
-    const double d4 = __dmul_rn(d2, d2);                              // pow(x,4) == (x*x)*(x*x) in the reference build (Q9)
-    sum2 = __dadd_rn(sum2, __dmul_rn((double)pc, d2));
-    sum4 = __dadd_rn(sum4, __dmul_rn((double)pc, d4));
+  const uint32_t nList = (uint32_t)a.g->n1;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nList; i += gridDim.x * blockDim.x) {
+    const uint32_t ci = a.list[i];
+    const uint32_t len = a.cand[ci].len;
+    const unsigned long long cb = a.pvScan[ci] & PACK_MASK;
+    if (cb + len > a.cellCap) { a.kurt[i] = 0.0; a.pass[i] = 0; continue; }   // capacity overflow: the call is repeated
+    const uint32_t* __restrict__ cells = a.cells + cb;
+    uint32_t count = 0, sum = 0;                                        // HitCount arithmetic (wraps), offsets as UShort (Q8)
+    for (uint32_t o = 0; o < len; ++o) { const uint32_t k = cells[o]; count += k; sum += k * (o & 0xFFFFu); }
+    const double xbar = (double)sum / (double)count;                   // misc/data.cpp:147
+    double sum2 = 0.0, sum4 = 0.0;
+    for (uint32_t o = 0; o < len; ++o) {
+      const uint32_t pc = cells[o];
+      if (!pc) continue;                                                // positions without a stored hit vector are not visited (misc/data.cpp:171-173)
+      const double dd = __dsub_rn((double)(o & 0xFFFFu), xbar);
+      const double d2 = __dmul_rn(dd, dd);
+      const double d4 = __dmul_rn(d2, d2);                              // pow(x,4) == (x*x)*(x*x) in the reference build (Q9)
+      sum2 = __dadd_rn(sum2, __dmul_rn((double)pc, d2));
+      sum4 = __dadd_rn(sum4, __dmul_rn((double)pc, d4));
+    }
+    const double k = __ddiv_rn(__dmul_rn(__dsub_rn((double)count, 1.0), sum4), __dmul_rn(sum2, sum2));   // misc/data.cpp:181
+    a.kurt[i] = k;
+    a.pass[i] = (a.kurtThr == 0.0 || (len > 1 && k <= a.kurtThr)) ? 1u : 0u;
   }
-  const double k = __ddiv_rn(__dmul_rn(__dsub_rn((double)count, 1.0), sum4), __dmul_rn(sum2, sum2));   // misc/data.cpp:181
-  a.kurt[i] = k;
-  a.pass[i] = (a.kurtThr == 0.0 || (len > 1 && k <= a.kurtThr)) ? 1u : 0u;
-}
-
-// len of the candidates that passed the hit filter, 0 for the others (scanned into StatArgs::cellOff)
-__global__ void cand_len_kernel (const Cand2* __restrict__ cand, const uint32_t* __restrict__ pass, uint32_t n, uint32_t* __restrict__ lenOut) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  lenOut[i] = pass[i] ? cand[i].len : 0u;
 }
 
 // strand-correlation filter (third clause); list2 holds positions in list1 space, corr[k] belongs to list2[k]
@@ -1193,40 +1262,148 @@ __global__ void dump_desc2_kernel (const Cand2* __restrict__ cand, const uint32_
   dUnit[i] = c.unit; dLeft[i] = c.left; dLen[i] = c.len; dChunks[i] = (c.len + TILE - 1) / TILE;
 }
 
-// accepted candidates -> the column arrays of the result table (canonical order: buffer, contig, left)
+// ------------------------------------------------------------------------------------------------
+// where the rows go.  A table row has the place (buffer, contig, left) gives it: the rows of unit u follow those of all units
+// before it.  row_place_kernel (one block) counts the group's accepted rows per unit and turns that into the table row of each
+// unit's first row.  With several GPUs (one rank per GPU, contigs sharded, upb_call_regions_shared) the per-unit counts of ALL
+// ranks are needed for that: every rank publishes its counts in one host segment all ranks map and waits — on the device, inside
+// this kernel — until the others have published theirs.  No collective, no host round trip (r01: an NCCL all-reduce + .cpu()).
+// ------------------------------------------------------------------------------------------------
+struct XchgArgs {                   // the exchange area of a shared table (mapped host memory, one per job)
+  volatile unsigned long long* counts;   // [world][2*C] accepted rows per (buffer, contig), written by the rank that owns the contig
+  volatile unsigned long long* ready;    // [world] step number once counts[rank][] of that step are complete
+  uint32_t rank, world, C;
+  unsigned long long step;          // 1, 2, 3 ... (all ranks call in lock step)
+};
+
+struct PlaceArgs {
+  const Cand2* cand;
+  const uint32_t* list;             // survivors
+  const unsigned long long* pass2Scan;   // [n1] exclusive scan of the final pass flags
+  GroupCtr* g;
+  CallCtr* call;
+  const SpanUnit* units;
+  uint32_t u0, u1;                  // units of this group
+  const uint32_t* edgeRows;         // [nUnits] rows the left-edge replay contributes to each unit (NULL: none)
+  unsigned long long* normalFirst;  // [nUnits + 1] scratch
+  long long* rowShift;              // [nUnits] out: table row of a unit's candidate i = rowShift[u] + pass2Scan[i]
+  unsigned long long* edgeRowBase;  // [nUnits] out: table row of the unit's first replay row
+  unsigned long long* unitRows;     // [nUnits] out: rows of the unit (replay rows included)
+  int shared;                       // 0: one GPU (rows follow the earlier groups' rows); 1: exchange
+  XchgArgs x;
+};
+
+__global__ void __launch_bounds__(256) row_place_kernel (PlaceArgs a) {
+  const uint32_t nu = a.u1 - a.u0;
+  const uint32_t n1 = (uint32_t)a.g->n1;
+  const unsigned long long rows = a.g->rows;
+  // first survivor of every unit (survivors are in unit order): rows of span_kernel's candidates before the unit
+  for (uint32_t t = threadIdx.x; t <= nu; t += blockDim.x) {
+    const uint32_t u = a.u0 + t;
+    uint32_t lo = 0, hi = n1;
+    if (t == nu) lo = n1;
+    else while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (a.cand[a.list[mid]].unit < u) lo = mid + 1; else hi = mid; }
+    a.normalFirst[u] = lo < n1 ? a.pass2Scan[lo] : rows;
+  }
+  __syncthreads();
+  for (uint32_t t = threadIdx.x; t < nu; t += blockDim.x) {
+    const uint32_t u = a.u0 + t;
+    a.unitRows[u] = a.normalFirst[u + 1] - a.normalFirst[u] + (a.edgeRows ? a.edgeRows[u] : 0u);
+  }
+  __syncthreads();
+  if (!a.shared) {
+    if (threadIdx.x == 0) {
+      unsigned long long base = a.call->rows;
+      for (uint32_t u = a.u0; u < a.u1; ++u) {
+        const unsigned long long er = a.edgeRows ? a.edgeRows[u] : 0u;
+        a.edgeRowBase[u] = base;
+        a.rowShift[u] = (long long)(base + er) - (long long)a.normalFirst[u];
+        base += a.unitRows[u];
+      }
+    }
+    return;
+  }
+  // shared table: publish this rank's counts, wait for the others, place by (buffer, contig) over all ranks
+  const uint32_t C2 = 2 * a.x.C;
+  volatile unsigned long long* mine = a.x.counts + (size_t)a.x.rank * C2;
+  for (uint32_t k = threadIdx.x; k < C2; k += blockDim.x) mine[k] = 0;
+  __syncthreads();
+  for (uint32_t t = threadIdx.x; t < nu; t += blockDim.x) { const SpanUnit U = a.units[a.u0 + t]; mine[U.buffer * a.x.C + U.contig] = a.unitRows[a.u0 + t]; }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) { a.x.ready[a.x.rank] = a.x.step; __threadfence_system(); }
+  for (uint32_t r = threadIdx.x; r < a.x.world; r += blockDim.x) {
+    uint32_t spins = 0;                                               // bounded (a few seconds): a rank that died must not hang the others' GPUs
+    while (a.x.ready[r] < a.x.step) { __nanosleep(256); if (++spins > (1u << 24)) { atomicOr(&a.g->flags, FLAG_XCHG_TIMEOUT); break; } }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // table row of the first row of every (buffer, contig), summed over the ranks in table order; this rank's units pick theirs
+    uint32_t t = 0;
+    unsigned long long base = 0;
+    for (uint32_t k = 0; k < C2 && t < nu; ++k) {
+      const SpanUnit U = a.units[a.u0 + t];
+      if (U.buffer * a.x.C + U.contig == k) {
+        const uint32_t u = a.u0 + t;
+        const unsigned long long er = a.edgeRows ? a.edgeRows[u] : 0u;
+        a.edgeRowBase[u] = base;
+        a.rowShift[u] = (long long)(base + er) - (long long)a.normalFirst[u];
+        ++t;
+      }
+      for (uint32_t r = 0; r < a.x.world; ++r) base += a.x.counts[(size_t)r * C2 + k];
+    }
+  }
+}
+
+// accepted candidates -> the column arrays of the result table (canonical order: buffer, contig, left).  The columns are MAPPED
+// HOST memory: the rows cross PCIe as they are written (coalesced 4- and 8-byte stores), there is no device copy of the table
+// and no D2H copy whose size the host would have to know.
 struct EmitArgs {
   const Cand2* cand;
   const uint32_t* list;                  // hit-filter survivors
-  const uint32_t* pass;                  // [nList] after the kurtosis (and correlation) filters
+  const uint32_t* pass;                  // [n1] after the kurtosis (and correlation) filters
   const unsigned long long* passScan;
-  uint32_t nList;
+  GroupCtr* g;
   const SpanUnit* units;
-  const unsigned long long* unitFirst;   // [nUnits] ordinal of the first candidate of each unit
-  const long long* unitRowShift;         // [nUnits] left-edge replay: rows it contributes to this and earlier units (NULL if none)
-  const long long* unitCandShift;        // [nUnits] left-edge replay: its candidates minus the dropped ones of this unit
-  const uint32_t* statCounts;            // [nList * nSamples]
-  const double* statKurt;                // [nList]
-  const double* rowCorr;                 // [nList] or NULL
+  const unsigned long long* unitFirst;   // [nUnits] ordinal of the first candidate of each unit among the group's candidates
+  const long long* rowShift;             // [nUnits] row_place_kernel
+  const int32_t* affOfUnit;              // [nUnits] index into the left-edge replay's arrays, -1 if the unit is not replayed (NULL: no replay)
+  const uint32_t* edgeCand;              // [nAffected] candidates the replay produced
+  const uint32_t* edgeDrop;              // [nAffected] candidates of span_kernel it replaced
+  const uint32_t* statCounts;            // [n1 * nSamples]
+  const double* statKurt;                // [n1]
+  const double* rowCorr;                 // [n1] or NULL
   uint32_t nSamples;
-  // outputs (device slab)
+  unsigned long long rowCap;             // rows the table has room for
+  // outputs (mapped host memory)
   uint8_t* buffer; uint32_t* contig; uint32_t* left; uint32_t* len; uint32_t* peak; unsigned long long* candIndex;
   double* peakScore; double* kurt; double* corr; uint32_t* counts; uint32_t* wsum;
 };
 
 __global__ void emit_rows_kernel (EmitArgs a) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.nList || !a.pass[i]) return;
-  const uint32_t ci = a.list[i];
-  const Cand2 c = a.cand[ci];
-  const unsigned long long o = a.passScan[i] + (a.unitRowShift ? (unsigned long long)a.unitRowShift[c.unit] : 0ull);
-  a.buffer[o] = (uint8_t)a.units[c.unit].buffer;
-  a.contig[o] = a.units[c.unit].contig;
-  a.left[o] = c.left; a.len[o] = c.len; a.peak[o] = c.peak; a.wsum[o] = c.wsum;
-  a.candIndex[o] = (unsigned long long)((long long)((unsigned long long)ci - a.unitFirst[c.unit]) + (a.unitCandShift ? a.unitCandShift[c.unit] : 0ll));
-  a.peakScore[o] = c.score;
-  a.kurt[o] = a.statKurt[i];
-  a.corr[o] = a.rowCorr ? a.rowCorr[i] : __longlong_as_double(0x7ff8000000000000ll);
-  for (uint32_t s = 0; s < a.nSamples; ++s) a.counts[o * a.nSamples + s] = a.statCounts[(uint64_t)i * a.nSamples + s];
+  const uint32_t n1 = (uint32_t)a.g->n1;
+  bool over = false;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n1; i += gridDim.x * blockDim.x) {
+    if (!a.pass[i]) continue;
+    const uint32_t ci = a.list[i];
+    const Cand2 c = a.cand[ci];
+    const unsigned long long o = (unsigned long long)(a.rowShift[c.unit] + (long long)a.passScan[i]);
+    if (o >= a.rowCap) { over = true; continue; }
+    long long candShift = 0;
+    if (a.affOfUnit) { const int32_t k = a.affOfUnit[c.unit]; if (k >= 0) candShift = (long long)a.edgeCand[k] - (long long)a.edgeDrop[k]; }
+    a.buffer[o] = (uint8_t)a.units[c.unit].buffer;
+    a.contig[o] = a.units[c.unit].contig;
+    a.left[o] = c.left; a.len[o] = c.len; a.peak[o] = c.peak; a.wsum[o] = c.wsum;
+    a.candIndex[o] = (unsigned long long)((long long)((unsigned long long)ci - a.unitFirst[c.unit]) + candShift);
+    a.peakScore[o] = c.score;
+    a.kurt[o] = a.statKurt[i];
+    a.corr[o] = a.rowCorr ? a.rowCorr[i] : __longlong_as_double(0x7ff8000000000000ll);
+    const uint32_t* __restrict__ src = a.statCounts + (uint64_t)i * a.nSamples;
+    uint32_t* dst = a.counts + o * a.nSamples;
+    for (uint32_t s = 0; s < a.nSamples; ++s) dst[s] = src[s];
+  }
+  if (over) atomicOr(&a.g->flags, FLAG_CAP_OVERFLOW);
 }
 
 // rows of the left-edge replay -> their slots in the table (they precede span_kernel's rows of the same unit)
@@ -1234,8 +1411,10 @@ struct EdgeEmitArgs {
   const EdgeRow* rows; const uint32_t* rowCounts;
   uint32_t rowCap, nSamples, nAffected;
   const uint32_t* affected; const uint32_t* nRows;
-  const unsigned long long* rowBase;     // [nAffected] first table row of the unit's replay rows
+  const unsigned long long* edgeRowBase;   // [nUnits] first table row of the unit's replay rows (row_place_kernel)
   const SpanUnit* units;
+  unsigned long long tableCap;
+  GroupCtr* g;
   uint8_t* buffer; uint32_t* contig; uint32_t* left; uint32_t* len; uint32_t* peak; unsigned long long* candIndex;
   double* peakScore; double* kurt; double* corr; uint32_t* counts; uint32_t* wsum;
 };
@@ -1244,28 +1423,51 @@ __global__ void edge_emit_kernel (EdgeEmitArgs a) {
   const uint32_t ai = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
   if (ai >= a.nAffected || k >= a.nRows[ai]) return;
   const EdgeRow r = a.rows[(size_t)ai * a.rowCap + k];
-  const SpanUnit U = a.units[a.affected[ai]];
-  const unsigned long long o = a.rowBase[ai] + k;
+  const uint32_t u = a.affected[ai];
+  const SpanUnit U = a.units[u];
+  const unsigned long long o = a.edgeRowBase[u] + k;
+  if (o >= a.tableCap) { atomicOr(&a.g->flags, FLAG_CAP_OVERFLOW); return; }
   a.buffer[o] = (uint8_t)U.buffer; a.contig[o] = U.contig;
   a.left[o] = r.left; a.len[o] = r.len; a.peak[o] = r.peak; a.wsum[o] = r.wsum; a.candIndex[o] = r.candIndex;
   a.peakScore[o] = r.score; a.kurt[o] = r.kurt; a.corr[o] = r.corr;
   for (uint32_t s = 0; s < a.nSamples; ++s) a.counts[o * a.nSamples + s] = a.rowCounts[((size_t)ai * a.rowCap + k) * a.nSamples + s];
 }
 
-// per-sample totals of the accepted rows (ProfileBuffer::nTagsInRegions, misc/peakcall.cpp:44)
-__global__ void tags_in_regions_kernel (const uint32_t* __restrict__ counts, unsigned long long nRows, uint32_t nSamples, unsigned long long* __restrict__ out) {
-  extern __shared__ unsigned long long sh[];
-  for (uint32_t s = threadIdx.x; s < nSamples; s += blockDim.x) sh[s] = 0;
-  __syncthreads();
-  const unsigned long long total = nRows * nSamples;
-  for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (unsigned long long)gridDim.x * blockDim.x)
-    atomicAdd(&sh[g % nSamples], (unsigned long long)counts[g]);
-  __syncthreads();
-  for (uint32_t s = threadIdx.x; s < nSamples; s += blockDim.x) if (sh[s]) atomicAdd(&out[s], sh[s]);
-}
+// per-sample totals of the accepted rows (ProfileBuffer::nTagsInRegions, misc/peakcall.cpp:44) from the per-survivor matrix rows,
+// plus the end-of-group bookkeeping: the call-wide counters take this group's numbers (one thread; the next group's kernels,
+// later in the stream, read them)
+struct GroupEndArgs {
+  const uint32_t* statCounts; const uint32_t* pass; GroupCtr* g; CallCtr* call;
+  uint32_t nSamples;
+  const uint32_t* edgeRowCounts; const uint32_t* edgeNRows; uint32_t edgeRowCap, nAffected;   // left-edge replay rows count too
+  unsigned long long edgeRowsTotal;
+  unsigned long long* tir;          // [nSamples]
+};
 
-__global__ void unit_first_kernel (const unsigned long long* __restrict__ unitCand, uint32_t nUnits, unsigned long long* __restrict__ unitFirst) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long run = 0; for (uint32_t u = 0; u < nUnits; ++u) { unitFirst[u] = run; run += unitCand[u]; } }
+__global__ void group_end_kernel (GroupEndArgs a) {
+  extern __shared__ unsigned long long sh[];
+  const uint32_t n = a.nSamples;
+  for (uint32_t s = threadIdx.x; s < n; s += blockDim.x) sh[s] = 0;
+  __syncthreads();
+  const unsigned long long total = (unsigned long long)a.g->n1 * n;
+  for (unsigned long long gI = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; gI < total; gI += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long i = gI / n;
+    if (a.pass[i]) { const uint32_t v = a.statCounts[gI]; if (v) atomicAdd(&sh[gI - i * n], (unsigned long long)v); }
+  }
+  if (blockIdx.x == 0)
+    for (uint32_t ai = 0; ai < a.nAffected; ++ai) {
+      const unsigned long long tot2 = (unsigned long long)a.edgeNRows[ai] * n;
+      for (unsigned long long q = threadIdx.x; q < tot2; q += blockDim.x) atomicAdd(&sh[q % n], (unsigned long long)a.edgeRowCounts[(size_t)ai * a.edgeRowCap * n + q]);
+    }
+  __syncthreads();
+  for (uint32_t s = threadIdx.x; s < n; s += blockDim.x) if (sh[s]) atomicAdd(&a.tir[s], sh[s]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    GroupCtr* g = a.g; CallCtr* c = a.call;
+    c->rows += g->rows + a.edgeRowsTotal;
+    c->cands += g->nCand; c->runs += g->runReal; c->n1 += g->pv >> PACK_SHIFT; c->cells += g->pv & PACK_MASK; c->warm += g->nWarm;
+    if (g->runCount > c->needSlots) c->needSlots = g->runCount;
+    c->flags |= g->flags;
+  }
 }
 
 }  // namespace upb

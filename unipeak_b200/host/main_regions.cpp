@@ -248,11 +248,8 @@ int main (int argc, char* argv[]) {
       if (firstMinus >= 0 && firstMinus >= lastPlus) early = true;
     }
   }
-  {
-    Flat flat;
-    flatten(samples, C, &flat);
-    if ((rc = upb_load_tags(ctx, (uint32_t)n, flat.off.data(), flat.pos, flat.cnt))) die_upb(ctx, rc);
-  }
+  TagLoader loader;                                                  // 2-byte host form, queued asynchronously: the call below starts on what has arrived
+  if ((rc = loader.start(ctx, samples, C, directional))) die_upb(ctx, rc);
   upb_region_params prm;
   memset(&prm, 0, sizeof prm);
   prm.bandwidth = bandwidth;

@@ -66,11 +66,8 @@ int main (int argc, char* argv[]) {
   int rc = upb_create(0, &ctx);
   if (rc) die_upb(nullptr, rc);
   if ((rc = upb_set_contigs(ctx, C, contigs.sizes.data()))) die_upb(ctx, rc);
-  {
-    Flat flat;
-    flatten(samples, C, &flat);
-    if ((rc = upb_load_tags(ctx, (uint32_t)samples.size(), flat.off.data(), flat.pos, flat.cnt))) die_upb(ctx, rc);
-  }
+  TagLoader loader;
+  if ((rc = loader.start(ctx, samples, C, false)) || (rc = loader.wait(ctx))) die_upb(ctx, rc);
   upb_shift_params prm;
   memset(&prm, 0, sizeof prm);
   prm.bandwidth = bandwidth;

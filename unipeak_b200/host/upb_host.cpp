@@ -903,6 +903,83 @@ void flatten (const std::vector<Sample>& samples, uint32_t C, Flat* out) {
     }
 }
 
+// the 2-byte form of one (sample, strand, contig) segment: include/unipeak_b200.h (upb_pack_tags2 is the same encoder over flat arrays)
+static void pack_segment (const uint32_t* pos, const uint32_t* cnt, size_t n, uint64_t first, uint16_t* words, std::vector<upb_packed_exception>* exc) {
+  uint32_t prev = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const uint32_t p = pos[i], k = cnt[i];
+    const bool escP = (i & 2047) == 0 || p < prev || p - prev >= 0xFFFu;
+    const bool escC = k >= 0xFu;
+    if (escP || escC) { upb_packed_exception x; x.index = first + i; x.pos = escP ? p : 0u; x.cnt = escC ? k : 0u; exc->push_back(x); }
+    words[first + i] = (uint16_t)((escP ? 0xFFFu : p - prev) | ((escC ? 0xFu : k) << 12));
+    prev = p;
+  }
+}
+
+TagLoader::~TagLoader () { if (words_) { if (wordsPinned_) upb_host_free(words_); else free(words_); } }
+
+int TagLoader::start (upb_ctx* ctx, const std::vector<Sample>& samples, uint32_t C, bool directionalHint) {
+  const size_t n = samples.size();
+  off_.assign(n * 2 * ((size_t)C + 1), 0);
+  uint64_t run = 0;
+  for (size_t s = 0; s < n; ++s)
+    for (int d = 0; d < 2; ++d) {
+      uint64_t* o = &off_[(s * 2 + d) * ((size_t)C + 1)];
+      for (uint32_t c = 0; c < C; ++c) { o[c] = run; run += samples[s].pos[d][c].size(); }
+      o[C] = run;
+    }
+  n_ = run;
+  // escapes without encoding anything: a first pass over the gaps decides the form (16 bytes per exception against 6 saved per entry)
+  const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  std::vector<uint64_t> nEsc(n, 0);
+  {
+    std::vector<std::thread> th;
+    for (size_t s = 0; s < n; ++s) th.emplace_back([&, s] {
+      uint64_t e = 0;
+      for (int d = 0; d < 2; ++d) for (uint32_t c = 0; c < C; ++c) {
+        const std::vector<uint32_t>& vp = samples[s].pos[d][c]; const std::vector<uint32_t>& vc = samples[s].cnt[d][c];
+        uint32_t prev = 0;
+        for (size_t i = 0; i < vp.size(); ++i) { e += ((i & 2047) == 0 || vp[i] < prev || vp[i] - prev >= 0xFFFu || vc[i] >= 0xFu) ? 1 : 0; prev = vp[i]; }
+      }
+      nEsc[s] = e;
+    });
+    for (std::thread& t : th) t.join();
+  }
+  uint64_t escTotal = 0;
+  for (uint64_t e : nEsc) escTotal += e;
+  upb_tag_source src;
+  memset(&src, 0, sizeof src);
+  src.n_samples = (uint32_t)n; src.off = off_.data(); src.directional_hint = directionalHint ? 1 : 0;
+  if (2 * run + 16 * escTotal < 6 * run) {
+    void* pw = nullptr;
+    const size_t bytes = (size_t)(run ? run : 1) * 2;
+    if (upb_host_alloc(&pw, bytes) == UPB_OK) wordsPinned_ = true; else { pw = malloc(bytes); wordsPinned_ = false; }
+    if (!pw) die("out of host memory");
+    words_ = (uint16_t*)pw;
+    std::vector<std::vector<upb_packed_exception> > per(n);
+    std::vector<std::thread> th;
+    for (size_t s = 0; s < n; ++s) th.emplace_back([&, s] {
+      per[s].reserve((size_t)nEsc[s]);
+      for (int d = 0; d < 2; ++d) {
+        const uint64_t* o = &off_[(s * 2 + d) * ((size_t)C + 1)];
+        for (uint32_t c = 0; c < C; ++c) {
+          const std::vector<uint32_t>& vp = samples[s].pos[d][c];
+          if (!vp.empty()) pack_segment(vp.data(), samples[s].cnt[d][c].data(), vp.size(), o[c], words_, &per[s]);
+        }
+      }
+    });
+    for (std::thread& t : th) t.join();
+    exc_.reserve((size_t)escTotal);
+    for (size_t s = 0; s < n; ++s) exc_.insert(exc_.end(), per[s].begin(), per[s].end());   // samples are laid out one after the other: sorted by index
+    src.words = words_; src.n_exceptions = exc_.size(); src.exceptions = exc_.empty() ? nullptr : exc_.data();
+  } else {
+    flatten(samples, C, &flat_);
+    src.pos = flat_.pos; src.cnt = flat_.cnt;
+  }
+  packSeconds_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return upb_load_tags_async(ctx, &src);
+}
+
 // ---------------------------------------------------------------------------------------------------------------------------
 // number formatting
 // ---------------------------------------------------------------------------------------------------------------------------

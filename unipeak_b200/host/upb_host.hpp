@@ -98,6 +98,32 @@ std::string align_summary (const AlignBatch& b, double probThreshold);   // Pars
 struct Flat { std::vector<uint64_t> off; uint32_t* pos = nullptr; uint32_t* cnt = nullptr; uint64_t n = 0; bool pinned = false; ~Flat (); };
 void flatten (const std::vector<Sample>& samples, uint32_t nContigs, Flat* out);
 
+// What the three drivers do with the samples they parsed: hand them to the device in the 2-byte host form (one u16 per entry +
+// exception list, include/unipeak_b200.h) — encoded here, one thread per sample, straight from the per-segment vectors the wiggle
+// reader filled — or in the plain form where the 2-byte form would be larger (sparse tracks: mean gap > 4095 positions).  start()
+// returns as soon as the transfers are queued (upb_load_tags_async): a upb_call_regions that follows works on the groups that have
+// arrived while the rest is still crossing PCIe.  The buffers live until the loader is destroyed: keep it until the first call
+// that uses the data has returned (or call wait()).
+class TagLoader {
+ public:
+  TagLoader () {}
+  ~TagLoader ();
+  int start (upb_ctx* ctx, const std::vector<Sample>& samples, uint32_t nContigs, bool directionalHint);
+  int wait (upb_ctx* ctx) { return upb_load_wait(ctx); }
+  bool packed () const { return words_ != nullptr; }
+  uint64_t entries () const { return n_; }
+  uint64_t exceptions () const { return exc_.size(); }
+  double packSeconds () const { return packSeconds_; }
+ private:
+  TagLoader (const TagLoader&);
+  std::vector<uint64_t> off_;
+  uint16_t* words_ = nullptr; bool wordsPinned_ = false;
+  std::vector<upb_packed_exception> exc_;
+  Flat flat_;
+  uint64_t n_ = 0;
+  double packSeconds_ = 0;
+};
+
 // ---- formatting ----------------------------------------------------------------------------------------------------------------
 std::string fmt_lexical (double x);        // OutStream << double == boost::lexical_cast<string>(double): 17 significant digits
 std::string fmt_g (double x);              // std::ostream << double

@@ -7,9 +7,9 @@ calls only its own contigs.  Three small, latency-bound collectives remain:
   * the gather of the region rows to rank 0, which puts them in canonical order (buffer, contig, left).
 Works on any backend (NCCL on the GPUs; gloo in the CPU tests).
 
-Two device-side gathers: DeviceGather (one NCCL reduce of a table-wide device slab, then rank 0 copies it to the host) and
-HostGather (the table lives in ONE host segment shared by the ranks and mapped into every GPU; each rank's scatter kernel
-writes its rows there directly over its own PCIe link — the destination is host memory either way, and eight links beat one).
+The gather on GPUs is SharedRegionTable: the table lives in ONE host segment shared by the ranks and mapped into every GPU; each
+rank's emit kernel writes its rows there directly over its own PCIe link after a device-side exchange of the per-unit row counts
+(upb_call_regions_shared) — the destination is host memory either way, eight links beat one, and no collective runs in a step.
 """
 from __future__ import annotations
 
@@ -86,123 +86,71 @@ def gather_region_rows(cols, n_samples: int, tags_in_regions, unit_candidates, *
     return out
 
 
-class DeviceGather:
-    """The fast path on GPUs: every rank scatters its rows into ONE table-wide device slab (rows in canonical
-    order), the slabs are summed over the ranks with a single NCCL reduce (disjoint rows, so the sum is the union),
-    and rank 0 copies the result into pinned host memory.  No host staging, no sort."""
+class SharedRegionTable:
+    """The table-wide host segment of upb_call_regions_shared, for ranks that are PROCESSES (torchrun): a POSIX shared-memory file
+    created exclusively (O_CREAT | O_EXCL, mode 0600) under a random name that rank 0 broadcasts, mapped and page-locked by every rank
+    (upb_host_register) and unlinked as soon as all ranks hold it — nothing is left behind when a job dies, and two jobs on one host
+    cannot meet.  Each rank's GPU writes its rows straight to their place in table order; there is no collective in a step.
+    `dist` is only used here, at set-up.  Ranks that are threads of one process can pass `local=True` (pinned memory from
+    upb_host_alloc, shared by address)."""
 
-    def __init__(self, ctx, n_samples: int, n_contigs: int, *, dist, rank: int, world: int, device):
-        import torch
-        self.ctx, self.n, self.C, self.dist, self.rank, self.world, self.device = ctx, n_samples, n_contigs, dist, rank, world, device
-        self.torch = torch
-        self._slab = None
-        self._host = None
-        self._small = torch.zeros(2 * n_contigs * 2 + n_samples, dtype=torch.int64, device=device)
-
-    def _ensure(self, nbytes: int):
-        torch = self.torch
-        words = (nbytes + 7) // 8 + 1
-        if self._slab is None or self._slab.shape[0] < words:
-            words = int(words * 1.25) + 1024
-            self._slab = torch.zeros(words, dtype=torch.int64, device=self.device)
-            self._host = torch.zeros(words, dtype=torch.int64).pin_memory() if self.rank == 0 else None
-        return self._slab
-
-    def __call__(self, view):
-        """`view`: the RegionView of this rank's call_regions_view(reference_order=False).  Returns the table-wide
-        columns on rank 0, None elsewhere."""
-        torch, dist = self.torch, self.dist
-        C2 = 2 * self.C
-        local_rows = np.asarray(view["unit_rows"], dtype=np.int64)
-        small = np.concatenate([local_rows, np.asarray(view["unit_candidates"], dtype=np.int64), np.asarray(view["tags_in_regions"], dtype=np.int64)])
-        self._small.copy_(torch.from_numpy(small))
-        dist.all_reduce(self._small)                                   # unit rows, unit candidates, tags in regions: one small all-reduce
-        tot = self._small.cpu().numpy()
-        unit_rows_total = tot[:C2].astype(np.uint64)
-        R = int(unit_rows_total.sum())
-        from .capi import slab_columns, slab_layout
-        nbytes = slab_layout(R, self.n)["end"]
-        slab = self._ensure(nbytes)
-        words = (nbytes + 7) // 8
-        slab[:words].zero_()
-        torch.cuda.current_stream().synchronize()
-        self.ctx.scatter_rows(R, unit_rows_total, local_rows.astype(np.uint64), slab.data_ptr())
-        dist.reduce(slab[:words], dst=0)                               # region-list gather (NCCL over NVLink)
-        if self.rank != 0:
-            return None
-        self._host[:words].copy_(slab[:words], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        cols = slab_columns(self._host.numpy().view(np.uint8), R, self.n)
-        cols.update(n_rows=R, unit_candidates=tot[C2:2 * C2], tags_in_regions=tot[2 * C2:])
-        return cols
-
-
-class HostGather:
-    """Region-list gather without the detour through GPU 0: the table-wide slab is a POSIX shared-memory segment that every
-    rank page-locks and maps (upb_host_register); after one small all-reduce (rows per unit, candidates per unit, tags in
-    regions) each rank's upb_scatter_rows kernel writes its rows to their canonical place over its own PCIe link, and a
-    second small all-reduce tells rank 0 that every rank is done."""
-
-    def __init__(self, ctx, n_samples: int, n_contigs: int, *, dist, rank: int, world: int, device, capacity_bytes: int = 256 << 20, name: str = None):
+    def __init__(self, ctx, n_samples: int, n_contigs: int, *, rank: int, world: int, row_capacity: int, dist=None, local_ptr: int = 0):
+        import mmap
         import os
-        import torch
-        from .capi import host_register
-        self.ctx, self.n, self.C, self.dist, self.rank, self.world, self.device = ctx, n_samples, n_contigs, dist, rank, world, device
-        self.torch = torch
-        self.cap = int(capacity_bytes)
-        name = name or "upb_gather_%s" % os.environ.get("MASTER_PORT", "0")
-        self.path = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp", name)
-        if rank == 0:
-            with open(self.path, "wb") as f:
-                f.truncate(self.cap)
-        dist.barrier()
-        self.host = np.memmap(self.path, dtype=np.uint8, mode="r+", shape=(self.cap,))
-        self.host_ptr = self.host.ctypes.data
-        self.dev_ptr = host_register(self.host_ptr, self.cap)
-        self._small = torch.zeros(2 * n_contigs * 2 + n_samples, dtype=torch.int64, device=device)
-        self._done = torch.zeros(1, dtype=torch.int64, device=device)
-        dist.barrier()
+        import uuid
+        from .capi import SharedTable, UpbError, host_register, lib, shared_table_bytes
+        self.ctx, self.rank, self.world, self.dist = ctx, rank, world, dist
+        self.nbytes = shared_table_bytes(n_contigs, n_samples, world, row_capacity)
+        self._mm = None
+        self._registered = False
+        if local_ptr:
+            self.host_ptr = self.dev_ptr = int(local_ptr)
+        else:
+            names = [None]
+            if rank == 0:
+                names[0] = "/dev/shm/upb_%s" % uuid.uuid4().hex
+                fd = os.open(names[0], os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+                os.ftruncate(fd, self.nbytes)
+            if world > 1:
+                dist.broadcast_object_list(names, src=0)
+            if rank != 0:
+                fd = os.open(names[0], os.O_RDWR)
+            self._mm = mmap.mmap(fd, self.nbytes)
+            os.close(fd)
+            self._arr = np.frombuffer(self._mm, dtype=np.uint8)
+            self.host_ptr = self._arr.ctypes.data
+            if world > 1:
+                dist.barrier()
+            if rank == 0:
+                os.unlink(names[0])                                    # the mappings keep the memory alive
+            self.dev_ptr = host_register(self.host_ptr, self.nbytes)
+            self._registered = True
+        self.table = SharedTable(self.host_ptr, self.dev_ptr, self.nbytes, rank, world, n_contigs, n_samples, row_capacity)
+        if rank == 0 and not local_ptr:
+            rc = lib().upb_shared_table_init(self.table)
+            if rc:
+                raise UpbError(rc, "upb_shared_table_init")
+        if world > 1 and dist is not None and not local_ptr:
+            dist.barrier()
+        self.step = 0
+
+    def __call__(self, **settings):
+        """One table-wide call; every rank calls with the same settings.  Rank 0 gets the whole table, the others their row count."""
+        self.step += 1
+        return self.ctx.call_regions_shared(self.table, self.step, **settings)
 
     def close(self):
         from .capi import host_unregister
-        import os
-        if self.host is not None:
+        if self._registered:
             host_unregister(self.host_ptr)
-            self.host = None
-            self.dist.barrier()
-            if self.rank == 0 and os.path.exists(self.path):
-                os.unlink(self.path)
-
-    def __call__(self, view):
-        import time
-        torch, dist = self.torch, self.dist
-        C2 = 2 * self.C
-        t0 = time.perf_counter()
-        local_rows = np.asarray(view["unit_rows"], dtype=np.int64)
-        small = np.concatenate([local_rows, np.asarray(view["unit_candidates"], dtype=np.int64), np.asarray(view["tags_in_regions"], dtype=np.int64)])
-        self._small.copy_(torch.from_numpy(small))
-        dist.all_reduce(self._small)                                   # unit rows, unit candidates, tags in regions
-        tot = self._small.cpu().numpy()
-        t1 = time.perf_counter()
-        unit_rows_total = tot[:C2].astype(np.uint64)
-        R = int(unit_rows_total.sum())
-        from .capi import slab_columns, slab_layout
-        nbytes = slab_layout(R, self.n)["end"]
-        if nbytes > self.cap:
-            raise RuntimeError("region table (%d bytes) exceeds the shared gather segment (%d bytes)" % (nbytes, self.cap))
-        self.ctx.scatter_rows(R, unit_rows_total, local_rows.astype(np.uint64), self.dev_ptr)   # returns when this rank's rows are in host memory
-        t2 = time.perf_counter()
-        dist.all_reduce(self._done)                                    # completion: every rank's rows have landed
-        torch.cuda.current_stream().synchronize()
-        t3 = time.perf_counter()
-        if getattr(self, "times", None) is None:
-            self.times = [0.0, 0.0, 0.0, 0]
-        self.times[0] += t1 - t0; self.times[1] += t2 - t1; self.times[2] += t3 - t2; self.times[3] += 1
-        if self.rank != 0:
-            return None
-        cols = slab_columns(self.host, R, self.n)
-        cols.update(n_rows=R, unit_candidates=tot[C2:2 * C2], tags_in_regions=tot[2 * C2:])
-        return cols
+            self._registered = False
+        self._arr = None
+        if self._mm is not None:
+            try:
+                self._mm.close()
+            except BufferError:
+                pass
+            self._mm = None
 
 
 # ------------------------------------------------------------------------------------------------
