@@ -224,7 +224,7 @@ def main():
     ap.add_argument("--samples", type=int, default=0)
     ap.add_argument("--tags", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-sweep", action="store_true", help="skip roofline.sweep (bandwidth 10 ... 200) and the per-stage kernels[]")
+    ap.add_argument("--no-sweep", action="store_true", help="skip roofline.sweep (bandwidth 10 ... 200)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--bandwidth", type=int, default=50, help="-b (config 5 sweeps 10..200)")
     args = ap.parse_args()
@@ -446,7 +446,7 @@ def main():
 
     # every stage of the call the same way (CUDA events between the stages, upb_set_profiling; separate steps, not the timed ones)
     kernels, sweep = None, None
-    if world == 1 and not args.no_sweep:
+    if world == 1:
         ctx.set_profiling(True)
         acc = {}
         for _ in range(5):
@@ -470,7 +470,7 @@ def main():
             ms = float(np.mean(v))
             b = stage_bytes.get(name)
             kernels.append({"name": name, "ms": ms, "algorithmic_bytes": b, "frac": (b / (ms * 1e-3) / 1e9 / peak_gbs) if (b and ms > 0) else None})
-        if args.workload in ("c3", "tiny") and not (args.samples or args.tags):
+        if args.workload in ("c3", "tiny") and not (args.samples or args.tags) and not args.no_sweep:
             sweep = []
             for bw in (10, 20, 50, 100, 150, 200):
                 stb = dict(st, bandwidth=bw, reference_order=True)

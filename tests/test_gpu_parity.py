@@ -513,8 +513,8 @@ def test_async_load_pipelines_into_the_call(gpu_ctx):
     small = make_synthetic([300000, 120000], 2, 20000, directional=True, seed=90, peak_spacing=5000)
     check_regions(gpu_ctx, small)                                       # sizes the context's arrays for a small table
     sizes = [6000000, 2500000, 1200000, 800000, 300000]
-    data = make_synthetic(sizes, 4, 900000, directional=True, seed=91, peak_spacing=4000)
-    st = region_settings(data)
+    data = make_synthetic(sizes, 4, 900000, directional=True, seed=91, peak_spacing=1500)
+    st = region_settings(data, hit_threshold=2.0, kurtosis_threshold=0.0, region_threshold=5.0)
     gpu_ctx.load(data)
     want = gpu_ctx.call_regions(**dict(st, rows=False))                 # far more rows than the small one: repeated with sizing
     wc = want["columns"]

@@ -39,7 +39,7 @@ __device__ __forceinline__ const PkException* pk_find (const PkException* __rest
 }
 
 struct LoadArgs {
-  const uint16_t* words;            // packed form: device copy of the caller's words, indexed like the caller's arrays (NULL: plain form, pos / cnt already hold the entries)
+  const uint16_t* words;            // packed form: device copy of the kept segments' words, laid out like pos / cnt (NULL: plain form, pos / cnt already hold the entries)
   const PkException* exc;
   unsigned long long nExc;
   uint32_t* pos;                    // resident sample-major arrays (compacted: only the segments this context keeps)
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(PK_THREADS) load_tile_kernel (const LoadArgs a
     for (int q = 0; q < PK_ITEMS; ++q) {
       const uint32_t i = i0 + q;
       if (i < nHere) {
-        const uint32_t w = a.words[src0 + i];
+        const uint32_t w = a.words[seg0 + t0 + i];                     // the device copy is laid out like the resident arrays; exceptions are indexed like the caller's
         uint32_t v = w & PK2_DPOS_MASK, k = w >> PK2_CNT_SHIFT;
         const bool escP = v == PK2_DPOS_ESC, escC = k == PK2_CNT_ESC;
         if (escP || escC) {
@@ -116,12 +116,11 @@ __global__ void __launch_bounds__(PK_THREADS) load_tile_kernel (const LoadArgs a
     }
     if (lane == 31) { warpSum[warp] = isum; warpReset[warp] = ires; }
     __syncthreads();
-    uint32_t bs = 0, br = 0;                                           // everything before this warp
-    for (uint32_t w2 = 0; w2 < warp; ++w2) { if (warpReset[w2]) { bs = warpSum[w2]; br = 1; } else bs += warpSum[w2]; }
+    uint32_t bs = 0;                                                   // everything before this warp
+    for (uint32_t w2 = 0; w2 < warp; ++w2) { if (warpReset[w2]) bs = warpSum[w2]; else bs += warpSum[w2]; }
     uint32_t ps = __shfl_up_sync(0xffffffffu, isum, 1), pr = __shfl_up_sync(0xffffffffu, ires, 1);
     if (lane == 0) { ps = 0; pr = 0; }
     const uint32_t before = pr ? ps : bs + ps;                         // running position entering this thread
-    (void)br;
     const int firstEsc = escMask ? __ffs(escMask) - 1 : PK_ITEMS;      // entries before this thread's first escape continue the position entering the thread
 #pragma unroll
     for (int q = 0; q < PK_ITEMS; ++q) if (q < n && q < firstEsc) vals[q] += before;
