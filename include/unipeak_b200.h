@@ -32,9 +32,9 @@ enum {
   UPB_ERR_NO_DEVICE = -3,       /* no CUDA device: there is deliberately no CPU path */
   UPB_ERR_NOT_LOADED = -4,      /* contigs / tags not set before a call that needs them */
   UPB_ERR_UNSORTED = -5,        /* reference would assert: misc/peakcall.cpp:171 */
-  UPB_ERR_LEFT_EDGE = -6,       /* a tag lies within `bandwidth` of a contig start and the call is one for which the
-                                   reference's left-edge behaviour (misc/peakcall.cpp:176-184) is not replayed:
-                                   the -w profile, a strand-shift sweep over a replayed region, a contig with nothing else */
+  UPB_ERR_LEFT_EDGE = -6,       /* no longer returned (kept for ABI stability): every shape of the reference's left-edge behaviour
+                                   (misc/peakcall.cpp:176-184,224-231) is replayed - regions, the -w profile, the shift
+                                   sweep, and contigs whose every tag lies within `bandwidth` of the start */
   UPB_ERR_REFERENCE_ABORTS = -7,/* the reference's merge loop would trip its own assert on this input
                                    (several directional samples whose '-' track is read in pass 1) */
   UPB_ERR_NO_REGIONS = -8,      /* src/strand_shift.cpp:228-230 "no regions qualified" */

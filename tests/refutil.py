@@ -407,3 +407,81 @@ def assert_rows_equal(got, want, what, fp_keys=("peak_score", "kurtosis", "corr"
             assert g[k] == w[k], "%s row %d field %s: got %r, expected %r (%r)" % (what, i, k, g[k], w[k], w)
         for k in fp_keys:
             assert same_fp(g[k], w[k]), "%s row %d field %s: got %r, expected %r" % (what, i, k, g[k], w[k])
+
+
+# ---- fixtures for the reference's left-edge quirk in its rarer shapes ------------------------------------
+def chain_leak_data(variant: int, seed: int = 5):
+    """Contigs whose EVERY tag lies within `bandwidth` (50) of the contig start: the reference's flush cannot drain the
+    window (misc/peakcall.cpp:176-184,224-231), so stale cells - and sometimes an open region - travel into the next
+    contig the same ProfileBuffer sees.  Returns (TagData, control list).
+
+    variant 0: normal contig, all-early contig, contig whose first tag is far from the start, normal contig
+    variant 1: all-early contig followed by a contig that only the CONTROL sample touches, then a normal one
+    variant 2: two all-early contigs in a row, then one whose own first tags are early as well (but not all of them)
+    variant 3: the all-early contig is the last one (nothing inherits the window)"""
+    rng = np.random.default_rng(seed + 100 * variant)
+    n = 3 if variant == 1 else 2
+
+    def normal(size, first=60):
+        centres = rng.integers(first + 200, size - 300, size=max(2, size // 4000))
+        pos = np.unique(np.clip(np.concatenate([c + rng.integers(-60, 60, size=40) for c in centres]), first, size - 60)).astype(np.uint32)
+        return pos, rng.integers(1, 7, size=pos.shape[0]).astype(np.uint32)
+
+    def early(lo=2, hi=48, k=14, heavy=True):
+        pos = np.sort(rng.choice(np.arange(lo, hi + 1), size=k, replace=False)).astype(np.uint32)
+        return pos, rng.integers(3 if heavy else 1, 12 if heavy else 3, size=k).astype(np.uint32)
+
+    def none():
+        return np.zeros(0, np.uint32), np.zeros(0, np.uint32)
+
+    shapes = {
+        0: ["normal", "early", "far", "normal"],
+        1: ["normal", "early", "control_only", "normal"],
+        2: ["early", "early", "early_then_normal", "normal"],
+        3: ["normal", "normal", "early"],
+    }[variant]
+    sizes = [30000, 20000, 25000, 30000][:len(shapes)]
+    segs = []
+    for s in range(n):
+        per = [[None] * len(shapes), [None] * len(shapes)]
+        is_control = variant == 1 and s == 2
+        for d in range(2):
+            for c, shape in enumerate(shapes):
+                size = sizes[c]
+                if shape == "control_only":
+                    per[d][c] = normal(size, first=70 + 40 * d) if is_control else none()
+                elif is_control:
+                    per[d][c] = normal(size) if shape == "normal" else none()
+                elif shape == "normal":
+                    per[d][c] = normal(size)
+                elif shape == "early":
+                    per[d][c] = early(k=10 + 3 * s + d)
+                elif shape == "far":
+                    p, k = normal(size, first=4000)
+                    per[d][c] = (p, k)
+                elif shape == "early_then_normal":
+                    p0, k0 = early(lo=5, hi=40, k=8)
+                    p1, k1 = normal(size, first=200)
+                    per[d][c] = (np.concatenate([p0, p1]), np.concatenate([k0, k1]))
+        segs.append(per)
+    data = TagData.from_segments(sizes, segs, ["chr%s" % "ABCD"[c] for c in range(len(shapes))])
+    return data, ([2] if variant == 1 else [])
+
+
+def long_start_region_data(seed: int = 9):
+    """Non-directional sample with a chrM-like contig: dense from position 1 on, reverse tags displaced by ~80, so the region that
+    starts at the contig start is long enough for the shift sweep of bin/strand_shift (src/strand_shift.cpp:206)."""
+    rng = np.random.default_rng(seed)
+    sizes = [16000, 600000]
+    per = [[None, None], [None, None]]
+    base = np.arange(1, 2400, dtype=np.uint32)
+    base = base[rng.random(base.shape[0]) < 0.7]
+    per[0][0] = (base, rng.integers(1, 5, size=base.shape[0]).astype(np.uint32))
+    rev = np.unique(np.clip(base.astype(np.int64) + 80 + rng.integers(-3, 4, size=base.shape[0]), 1, sizes[0])).astype(np.uint32)
+    per[1][0] = (rev, rng.integers(1, 5, size=rev.shape[0]).astype(np.uint32))
+    # ordinary peaks on the second contig
+    centres = rng.integers(2000, sizes[1] - 2000, size=60)
+    for d in range(2):
+        pos = np.unique(np.concatenate([c + 90 * d + rng.integers(-150, 150, size=260) for c in centres])).astype(np.uint32)
+        per[d][1] = (pos, rng.integers(1, 4, size=pos.shape[0]).astype(np.uint32))
+    return TagData.from_segments(sizes, [per], ["chrM", "chr1"])

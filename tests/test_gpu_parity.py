@@ -683,3 +683,70 @@ def test_strand_shift_with_left_edge_tags(gpu_ctx):
     for g, w in zip(got["tested"], want["tested"]):
         assert (g["contig"], g["left"], g["len"], g["best_shift"]) == (w["contig"], w["left"], w["len"], w["best_shift"])
         assert g["best_corr"] == w["best_corr"]
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+def test_left_edge_window_inherited_by_the_next_contig(gpu_ctx, variant):
+    # every tag of a contig within `bandwidth` of its start: the reference's flush leaves stale cells (and sometimes an open region)
+    # for the next contig of the same buffer, also one that only the control sample touches (misc/peakcall.cpp:176-184,224-231)
+    import refutil
+    d, ctrl = refutil.chain_leak_data(variant)
+    kw = dict(region_threshold=3.0, hit_threshold=2.0, kurtosis_threshold=0.0, mappable=20 * d.genome_size())
+    if ctrl:
+        kw["control"] = ctrl
+    got, want = check_regions(gpu_ctx, d, **kw)
+    if variant in (0, 1, 2):
+        assert any(r["contig"] == 2 and r["left"] == 2 for r in want["rows"])
+    check_regions(gpu_ctx, d, directional=False, corr_threshold=-1.0, **kw)
+    check_regions(gpu_ctx, d, directional=False, corr_threshold=0.0, **kw)
+
+
+def _check_profile(ctx, d, **kw):
+    st = region_settings(d, **kw)
+    want = oracle_regions(d, st, want_profile=True)
+    assert want["status"] == 0
+    ctx.load(d)
+    n_buf = 2 if st["directional"] else 1
+    got = []
+    for b in range(n_buf):
+        for c in range(d.n_contigs):
+            pos, score = ctx.profile_contig(b, c, **st)
+            got += [(b, c, int(p), float(s)) for p, s in zip(pos, score)]
+    key = lambda t: (t[0], t[1], t[2])
+    assert sorted(got, key=key) == sorted(want["profile"], key=key)
+    return want
+
+
+def test_profile_at_the_left_edge(gpu_ctx):
+    # -w with tags inside the first `bandwidth` positions (chrM-like data): the points written for the first positions are the displaced
+    # scores of the reference's unshifted window (misc/peakcall.cpp:81-84,176-184)
+    import refutil
+    d = make_synthetic([60000, 30000], 2, 30000, directional=True, seed=21, peak_spacing=2000, keep_clear_of_edges=False)
+    want = _check_profile(gpu_ctx, d)
+    assert min(p[2] for p in want["profile"]) <= 2                     # the window reports from the first positions of the contig on
+    _check_profile(gpu_ctx, d, directional=False)
+    for variant in (0, 1, 2, 3):
+        d, ctrl = refutil.chain_leak_data(variant)
+        kw = dict(region_threshold=3.0, mappable=20 * d.genome_size())
+        if ctrl:
+            kw["control"] = ctrl
+        _check_profile(gpu_ctx, d, **kw)
+        _check_profile(gpu_ctx, d, directional=False, **kw)
+
+
+def test_strand_shift_sweeps_a_region_at_a_contig_start(gpu_ctx):
+    # a chrM-like contig, dense from position 1: its first region comes from the left-edge replay and is long enough for the sweep, which
+    # then runs over the replay's own forward / reverse score vectors (src/strand_shift.cpp:206-219)
+    import refutil
+    d = refutil.long_start_region_data()
+    kw = dict(n_regions_to_test=30, region_threshold=4.0, corr_threshold=0.05, hit_threshold=5)
+    want = oracle_strand_shift(d, **kw)
+    assert want["status"] == 0 and any(t["contig"] == 0 and t["left"] <= 50 for t in want["tested"])
+    gpu_ctx.load(d)
+    got = gpu_ctx.strand_shift(background=want["background"], **kw)
+    assert got["status"] == 0
+    for k in ("n_regions_found", "n_regions_tested", "n_tags_in_regions", "best_shift", "shift_freq"):
+        assert got[k] == want[k], k
+    for g, w in zip(got["tested"], want["tested"]):
+        assert (g["contig"], g["left"], g["len"], g["best_shift"]) == (w["contig"], w["left"], w["len"], w["best_shift"])
+        assert g["best_corr"] == w["best_corr"]

@@ -266,6 +266,30 @@ def test_cli_regions_left_edge_q2(tmp_path):
 
 @pytest.mark.gpu
 @needs_ref
+def test_cli_left_edge_profile_shift_and_inherited_window(tmp_path):
+    # what round 1 refused with UPB_ERR_LEFT_EDGE: the -w profile of chrM-like input, a region at a contig start that enters the
+    # shift sweep, and contigs whose every tag lies within `bandwidth` of the start (the next contig inherits the window)
+    d = make_synthetic([60000, 30000], 2, 30000, directional=True, seed=21, peak_spacing=2000, keep_clear_of_edges=False, contig_names=["chrM", "chrB"])
+    f = stage(tmp_path, d)
+    out = both(tmp_path, "regions", ["-f", "-o", "r.txt", "-w", "p.wig", "-c", f["contigs"]] + f["wigs"], ["r.txt", "p.wig"])
+    assert out["p.wig"].count(b"\n") > 1000
+    both(tmp_path, "regions", ["-D", "-q", "-o", "rd.txt", "-w", "pd.wig", "-c", f["contigs"]] + f["wigs"], ["rd.txt", "pd.wig"])
+    for variant in (0, 1, 2, 3):
+        dv, ctrl = refutil.chain_leak_data(variant)
+        fv = stage(tmp_path, dv, prefix="v%d_" % variant, sub="v%d" % variant)
+        extra = (["-e", ",".join(str(c + 1) for c in ctrl)] if ctrl else [])
+        m = str(20 * dv.genome_size())
+        both(tmp_path, "regions", ["-f", "-r", "3", "-t", "2", "-k", "0", "-m", m, "-o", "v%d.txt" % variant, "-w", "v%d.wig" % variant, "-c", fv["contigs"]] + extra + fv["wigs"],
+             ["v%d.txt" % variant, "v%d.wig" % variant])
+        both(tmp_path, "regions", ["-D", "-y", "-r", "3", "-t", "2", "-k", "0", "-u", "-1", "-m", m, "-o", "w%d.txt" % variant, "-w", "w%d.wig" % variant, "-c", fv["contigs"]] + extra + fv["wigs"],
+             ["w%d.txt" % variant, "w%d.wig" % variant])
+    dl = refutil.long_start_region_data()
+    fl = stage(tmp_path, dl, prefix="l", sub="long")
+    both(tmp_path, "strand_shift", ["-o", "shift.txt", "-c", fl["contigs"], "-g", "30", "-r", "4", "-u", "0.05", "-t", "5"] + fl["wigs"], ["shift.txt"])
+
+
+@pytest.mark.gpu
+@needs_ref
 def test_cli_regions_header_mismatch_warning(tmp_path):
     d = make_synthetic([200000], 2, 20000, directional=True, seed=6, peak_spacing=5000, contig_names=["chrA"])
     for which in ("ref", "new"):

@@ -85,6 +85,35 @@ def test_replay_left_edge_q2(tmp_path):
     check_replay(d, tmp_path, directional=False)
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+def test_replay_left_edge_window_inherited_by_the_next_contig(tmp_path, variant):
+    # every tag of a contig within `bandwidth` of its start: the flush leaves stale cells (and sometimes an open region) for the
+    # next contig of the same buffer - also when that contig is touched by the control sample only (variant 1)
+    d, ctrl = refutil.chain_leak_data(variant)
+    kw = dict(region_threshold=3.0, hit_threshold=2.0, kurtosis_threshold=0.0, mappable=20 * d.genome_size())
+    if ctrl:
+        kw["control"] = ctrl
+    ours = check_replay(d, tmp_path, **kw)
+    if variant in (0, 1, 2):
+        assert any(r["contig"] == 2 and r["left"] == 2 for r in ours["rows"])       # opened on contig 1, written with contig 2
+    check_replay(d, tmp_path, directional=False, corr_threshold=-1.0, **kw)
+    check_replay(d, tmp_path, directional=False, corr_threshold=0.0, **kw)
+
+
+def test_replay_strand_shift_long_region_at_contig_start(tmp_path):
+    d = refutil.long_start_region_data()
+    kw = dict(n_regions_to_test=30, region_threshold=4.0, corr_threshold=0.05, hit_threshold=5)
+    ours = oracle_strand_shift(d, **kw)
+    ref = run_ref_replay_shift(d, str(tmp_path), **kw)
+    assert ours["status"] == 0
+    assert any(t["contig"] == 0 and t["left"] <= 50 for t in ours["tested"])       # the region at the contig start is swept
+    for k in ("n_regions_found", "n_regions_tested", "n_tags_in_regions", "best_shift", "shift_freq"):
+        assert ours[k] == ref[k], k
+    for g, w in zip(ours["tested"], ref["tested"]):
+        assert (g["contig"], g["left"], g["len"], g["best_shift"]) == (w["contig"], w["left"], w["len"], w["best_shift"])
+        assert g["best_corr"] == w["best_corr"]
+
+
 def test_replay_single_sample_single_contig_q7(tmp_path):
     d = make_synthetic([2000000], 1, 60000, directional=True, seed=3, peak_spacing=10000)
     check_replay(d, tmp_path, mappable=300000000)

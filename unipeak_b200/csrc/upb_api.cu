@@ -740,7 +740,6 @@ struct PipeCfg {
   bool nondir;
   bool needCorr;                     // compute strandCorr(0) for regions passing the earlier filters
   const uint8_t* control;            // may be NULL
-  bool allowLeftEdge = false;        // replay the reference's left-edge behaviour (Q2) instead of refusing such inputs
   uint32_t nCoeffs = 0;              // 0, or the number of non-control samples (-z)
   const double* coeffs = nullptr;    // already normalised as src/regions.cpp:216-229
 };
@@ -805,19 +804,12 @@ static int acquire_slab (upb_ctx* ctx, size_t bytes, HostSlab& out) {
   return UPB_OK;
 }
 
-static int check_left_edge (upb_ctx* ctx, uint32_t bw) {
-  // every add() call moves the window, control samples included (src/regions.cpp:356-359)
-  const uint32_t nSeg = (uint32_t)ctx->firstPos.size();
-  for (uint32_t g = 0; g < nSeg; ++g)
-    if (ctx->firstPos[g] != 0 && ctx->firstPos[g] <= bw)
-      return fail(ctx, UPB_ERR_LEFT_EDGE, "a tag lies within `bandwidth` positions of a contig start: the reference's left-edge path (misc/peakcall.cpp:176-184, SURVEY Q2) is not emulated");
-  return UPB_OK;
-}
-
 struct Prep {
   std::vector<Unit> units;
   std::vector<double> taps;
-  std::vector<uint32_t> affected;    // units with a tag within `bandwidth` of the contig start: replayed by left_edge_kernel
+  std::vector<uint32_t> affected;    // units with a tag within `bandwidth` of the contig start, or inheriting stale window cells: replayed by left_edge_kernel
+  std::vector<uint32_t> chainNext;   // [affected] the affected unit that inherits this one's window (every tag of this one lies within `bandwidth`), else 0xFFFFFFFF
+  std::vector<uint8_t> chainHead;    // [affected] 0: replayed by its predecessor's thread
   double maxCoeff = 0;               // -z: largest coefficient (bounds the weight of a position)
   const float* d_hotCoefF = nullptr; // hot_span_kernel's envelope coefficients
   uint32_t hotJ = 0;
@@ -830,7 +822,7 @@ struct Prep {
 };
 
 // common set-up: units, taps, source list, control filter
-static int prepare (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, uint32_t* launches, bool allowLeftEdge = false, bool allowPending = false) {
+static int prepare (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, uint32_t* launches, bool allowPending = false) {
   const uint32_t C = (uint32_t)ctx->sizes.size();
   const uint32_t n = ctx->nSamples;
   if (ctx->loadPending && !allowPending) { const int rl = load_finish(ctx); if (rl) return rl; }
@@ -839,7 +831,6 @@ static int prepare (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, uint32_t* launch
   if (!(cfg.thr > 0)) return fail(ctx, UPB_ERR_BAD_ARG, "region threshold must be > 0 (the reference's leap handling relies on it, SURVEY Q10)");
   if (!(cfg.background > 0)) return fail(ctx, UPB_ERR_BAD_ARG, "background must be > 0");
   int r;
-  if (!allowLeftEdge && (r = check_left_edge(ctx, cfg.bw))) return r;
 
   std::vector<uint32_t> src;
   std::vector<uint8_t> control(n, 0);
@@ -863,32 +854,41 @@ static int prepare (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, uint32_t* launch
   pr.affected.clear();
   uint64_t spanStart = 0;
   const uint32_t nBuf = cfg.nondir ? 1u : 2u;
-  for (uint32_t b = 0; b < nBuf; ++b)
+  pr.chainNext.clear(); pr.chainHead.clear();
+  for (uint32_t b = 0; b < nBuf; ++b) {
+    int32_t leakFrom = -1;                                            // affected index of the unit whose flush leaves stale cells in this buffer's window
     for (uint32_t c = 0; c < C; ++c) {
       bool any = false;
       for (uint32_t s : src) {
         if (cfg.nondir) any = any || ctx->firstPos[(size_t)(s * 2 + 0) * C + c] || ctx->firstPos[(size_t)(s * 2 + 1) * C + c];
         else any = any || ctx->firstPos[(size_t)(s * 2 + b) * C + c];
       }
-      if (!any) continue;
-      Unit u;
-      u.contig = c; u.buffer = b; u.size = ctx->sizes[c];
-      u.nSpans = (uint32_t)(((uint64_t)ctx->sizes[c] + cfg.bw + SPAN_LEN - 1) / SPAN_LEN);
-      u.spanStart = (uint32_t)spanStart;
-      spanStart += u.nSpans;
-      if (spanStart > 0xFFFFFFF0ull) return fail(ctx, UPB_ERR_UNSUPPORTED, "too many spans");
       // Q2: every add() moves the window, control samples included (src/regions.cpp:356-359)
       uint32_t first = 0xFFFFFFFFu, last = 0;
       for (uint32_t s = 0; s < n; ++s) for (uint32_t d = (cfg.nondir ? 0u : b); d <= (cfg.nondir ? 1u : b); ++d) {
         const uint32_t fp = ctx->firstPos[(size_t)(s * 2 + d) * C + c], lp = ctx->lastPos[(size_t)(s * 2 + d) * C + c];
         if (fp) { first = std::min(first, fp); last = std::max(last, lp); }
       }
-      if (first <= cfg.bw) {
-        if (last <= cfg.bw) return fail(ctx, UPB_ERR_LEFT_EDGE, "every tag of a contig lies within `bandwidth` of its start: the reference then leaks window cells into the next contig (misc/peakcall.cpp:176-184,224-231), which is not emulated");
+      // a contig that only control samples touch makes no unit — unless the buffer arrives with stale cells, which its add() calls then report
+      if (!any && !(leakFrom >= 0 && first != 0xFFFFFFFFu)) continue;
+      Unit u;
+      u.contig = c; u.buffer = b; u.size = ctx->sizes[c];
+      u.nSpans = (uint32_t)(((uint64_t)ctx->sizes[c] + cfg.bw + SPAN_LEN - 1) / SPAN_LEN);
+      u.spanStart = (uint32_t)spanStart;
+      spanStart += u.nSpans;
+      if (spanStart > 0xFFFFFFF0ull) return fail(ctx, UPB_ERR_UNSUPPORTED, "too many spans");
+      if (first <= cfg.bw || leakFrom >= 0) {
+        const int32_t k = (int32_t)pr.affected.size();
         pr.affected.push_back((uint32_t)pr.units.size());
+        pr.chainNext.push_back(0xFFFFFFFFu);
+        pr.chainHead.push_back(leakFrom < 0 ? 1 : 0);
+        if (leakFrom >= 0) pr.chainNext[leakFrom] = (uint32_t)k;
+        // every tag within `bandwidth` of the start: the flush cannot drain the window (misc/peakcall.cpp:176-184,224-231) and the next contig inherits it
+        leakFrom = last <= cfg.bw ? k : -1;
       }
       pr.units.push_back(u);
     }
+  }
   pr.totalSpans = (uint32_t)spanStart;
 
   pr.taps.assign(2 * (size_t)cfg.bw + 1, 0.0);
@@ -1017,7 +1017,16 @@ static int launch_density (upb_ctx* ctx, DensArgs& da, bool nondir, uint32_t tot
 
 // exact F/R densities for `n` position ranges (descriptor arrays dUnit/dLeft/dLen/dChunks already filled on the
 // device) and, if asked, strandCorr(shift) for shifts 0..nShifts-1 into scratch "corr"
-static int dump_and_corr (upb_ctx* ctx, const DensArgs& base, bool nondir, uint32_t n, uint32_t nShifts, uint32_t* launches) {
+struct VecPatch { uint32_t k, src, len; };     // range k of the dump takes its scores from the replay's vector pool at `src`
+__global__ void vec_patch_kernel (const VecPatch* __restrict__ patches, const unsigned long long* __restrict__ dOff, const double* __restrict__ srcF, const double* __restrict__ srcR,
+                                  double* __restrict__ F, double* __restrict__ R) {
+  const VecPatch q = patches[blockIdx.x];
+  const unsigned long long at = dOff[q.k];
+  for (uint32_t i = threadIdx.x; i < q.len; i += blockDim.x) { F[at + i] = srcF[q.src + i]; R[at + i] = srcR[q.src + i]; }
+}
+
+static int dump_and_corr (upb_ctx* ctx, const DensArgs& base, bool nondir, uint32_t n, uint32_t nShifts, uint32_t* launches,
+                          const std::vector<VecPatch>* patches = nullptr, const double* patchF = nullptr, const double* patchR = nullptr) {
   unsigned long long* dOff = SCR("dOff", unsigned long long, (size_t)n + 1);
   unsigned long long* dChunkStart = SCR("dChunkStart", unsigned long long, (size_t)n + 1);
   uint32_t* dUnit = ctx->scratch["dUnit"].as<uint32_t>(); uint32_t* dLeft = ctx->scratch["dLeft"].as<uint32_t>();
@@ -1042,6 +1051,14 @@ static int dump_and_corr (upb_ctx* ctx, const DensArgs& base, bool nondir, uint3
   da.dumpF = F; da.dumpR = R;
   CU(cudaMemsetAsync(da.ticket, 0, 4, ctx->stream));
   if ((r = launch_density(ctx, da, nondir, (uint32_t)totChunks, launches))) return r;
+  if (patches && !patches->empty()) {                                 // regions of the left-edge replay: the reference's displaced scores, not the density
+    VecPatch* d_p = SCR("vecPatches", VecPatch, patches->size());
+    CU(cudaMemcpyAsync(d_p, patches->data(), patches->size() * sizeof(VecPatch), cudaMemcpyHostToDevice, ctx->stream));
+    vec_patch_kernel<<<(unsigned)patches->size(), 256, 0, ctx->stream>>>(d_p, dOff, patchF, patchR, F, R);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));                           // `patches` is the caller's
+    *launches += 1;
+  }
   if (nShifts) {
     double* corr = SCR("corr", double, (size_t)n * nShifts);
     CorrArgs ca;
@@ -1067,6 +1084,13 @@ static int launch_span (upb_ctx* ctx, const SpanArgs& sa, bool nondir, uint32_t*
     kern = nondir ? span_kernel<true, false, SP_MIN_BLOCKS - 1> : span_kernel<false, false, SP_MIN_BLOCKS - 1>;
     int rr = cached_occupancy(ctx, kern, SP_THREADS, smem, &perSm); if (rr) return rr;
   }
+  // B1 through the bulk-copy engine (cp.async.bulk + mbarrier, SASS UBLKCP) where it was measured to win: directional calls at bandwidth >= 100, whose
+  // chunks (piece + 2 x bandwidth of halo, all samples) are long enough to amortise arming a barrier (profiles/r02_b1_bulk_ab.txt: 0.539 -> 0.497 ms at
+  // bandwidth 200, level at 50, behind at 10 / 20 and on the two-sample -D workload).  UPB_B1=bulk|ldg overrides (A/B runs)
+  bool bulk = !coeff && !nondir && sa.bw >= 100;
+  if (const char* e = getenv("UPB_B1")) { if (!strcmp(e, "bulk")) bulk = !coeff && !nondir; else if (!strcmp(e, "ldg")) bulk = false; }
+  if (bulk) kern = perSm < SP_MIN_BLOCKS ? span_kernel<false, false, SP_MIN_BLOCKS - 1, true> : span_kernel<false, false, SP_MIN_BLOCKS, true>;
+  if (bulk) { int rr = cached_occupancy(ctx, kern, SP_THREADS, smem, &perSm); if (rr) return rr; }
   const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)ctx->smCount * perSm, std::max<uint32_t>(sa.totalSpans, 1u));
   kern<<<grid, SP_THREADS, smem, ctx->stream>>>(sa);
   CU(cudaGetLastError());
@@ -1132,6 +1156,66 @@ struct SharedDst {
 // One pass over the units: every kernel of the region pipeline is enqueued without reading a size back (sizing == false), or with
 // two read-backs that size the per-survivor arrays and the table exactly (sizing == true: the first call of a context, and the
 // repeat of a call whose numbers outgrew what the previous call left behind).  *retry: run again with sizing.
+// ---- left-edge replay (upb_edge.cuh): one launch and one read-back; rare (a tag within `bandwidth` of a contig start) -------------
+constexpr uint32_t EDGE_REG_CAP = 1u << 18, EDGE_ROW_CAP = 1024;
+struct EdgeRec {                     // optional recordings
+  int profUnit = -1;                 // unit whose -w profile points are wanted
+  uint32_t vecMinLen = 0xFFFFFFFFu;  // accepted rows longer than this keep their forward / reverse score vectors (the shift sweep)
+};
+struct EdgeRun {
+  EdgeArgs eg;                       // device side, valid until the scratch arrays are reused
+  uint32_t* d_affected = nullptr;
+  std::vector<uint32_t> out;         // [3 * nAff + 8]: stop, nCand, nRows per affected unit; flags; profile points; vector pool use
+  uint32_t profN = 0;
+};
+static int run_edge_replay (upb_ctx* ctx, const PipeCfg& cfg, const Prep& pr, cudaStream_t st_, const EdgeRec& rec, EdgeRun& er, uint32_t* launches) {
+  const uint32_t nAff = (uint32_t)pr.affected.size(), n = ctx->nSamples, w = 2 * cfg.bw + 1;
+  EdgeArgs& eg = er.eg;
+  memset(&eg, 0, sizeof eg);
+  er.d_affected = SCR("edgeAffected", uint32_t, nAff);
+  uint32_t* d_chainNext = SCR("edgeChainNext", uint32_t, nAff);
+  uint8_t* d_chainHead = SCR("edgeChainHead", uint8_t, nAff);
+  CU(cudaMemcpyAsync(er.d_affected, pr.affected.data(), (size_t)nAff * 4, cudaMemcpyHostToDevice, st_));
+  CU(cudaMemcpyAsync(d_chainNext, pr.chainNext.data(), (size_t)nAff * 4, cudaMemcpyHostToDevice, st_));
+  CU(cudaMemcpyAsync(d_chainHead, pr.chainHead.data(), (size_t)nAff, cudaMemcpyHostToDevice, st_));
+  eg.T = pr.T; eg.units = ctx->scratch["units"].as<Unit>(); eg.affected = er.d_affected; eg.chainNext = d_chainNext; eg.chainHead = d_chainHead;
+  eg.nAffected = nAff; eg.control = ctx->scratch["control"].as<uint8_t>();
+  eg.coeffBySample = pr.d_coeffBySample; eg.taps = ctx->scratch["taps"].as<double>(); eg.bw = cfg.bw; eg.nondir = cfg.nondir ? 1 : 0;
+  eg.thr = cfg.thr; eg.kurtThr = cfg.kurtThr; eg.corrThr = cfg.nondir ? cfg.corrThr : -1.0; eg.hitThr = cfg.hitThr;
+  eg.cursors = SCR("edgeCursors", unsigned long long, (size_t)nAff * 2 * n);
+  eg.ringF = SCR("edgeRingF", double, (size_t)nAff * w); eg.ringR = SCR("edgeRingR", double, (size_t)nAff * w);
+  eg.ringHits = SCR("edgeRingHits", uint32_t, (size_t)nAff * w * n); eg.ringHas = SCR("edgeRingHas", uint8_t, (size_t)nAff * w);
+  eg.regPc = SCR("edgeRegPc", uint32_t, (size_t)nAff * EDGE_REG_CAP); eg.regHas = SCR("edgeRegHas", uint8_t, (size_t)nAff * EDGE_REG_CAP);
+  eg.regF = SCR("edgeRegF", double, (size_t)nAff * EDGE_REG_CAP); eg.regR = SCR("edgeRegR", double, (size_t)nAff * EDGE_REG_CAP);
+  eg.regSums = SCR("edgeRegSums", uint32_t, (size_t)nAff * n); eg.callCounts = SCR("edgeCall", uint32_t, (size_t)nAff * n);
+  eg.regCap = EDGE_REG_CAP; eg.rowCap = EDGE_ROW_CAP; eg.maxPositions = 1ull << 23;
+  uint32_t* eo = SCR("edgeOut", uint32_t, (size_t)3 * nAff + 8);
+  CU(cudaMemsetAsync(eo, 0, ((size_t)3 * nAff + 8) * 4, st_));
+  eg.stop = eo; eg.nCand = eo + nAff; eg.nRows = eo + 2 * nAff; eg.flags = eo + 3 * nAff;
+  eg.profN = eo + 3 * nAff + 1; eg.vecUsed = eo + 3 * nAff + 2;
+  eg.rows = SCR("edgeRows", EdgeRow, (size_t)nAff * EDGE_ROW_CAP);
+  eg.rowCounts = SCR("edgeRowCounts", uint32_t, (size_t)nAff * EDGE_ROW_CAP * n);
+  eg.profAff = 0xFFFFFFFFu; eg.vecMinLen = rec.vecMinLen;
+  if (rec.profUnit >= 0) {
+    for (uint32_t k = 0; k < nAff; ++k) if (pr.affected[k] == (uint32_t)rec.profUnit) eg.profAff = k;
+    eg.profCap = (uint32_t)eg.maxPositions + 4 * w;                   // the budget bounds the positions a replay processes
+    eg.profPos = SCR("edgeProfPos", uint32_t, eg.profCap); eg.profScore = SCR("edgeProfScore", double, eg.profCap);
+  }
+  if (rec.vecMinLen != 0xFFFFFFFFu) {
+    eg.vecCap = nAff * EDGE_REG_CAP > (1u << 24) ? (1u << 24) : nAff * EDGE_REG_CAP;
+    eg.vecF = SCR("edgeVecF", double, eg.vecCap); eg.vecR = SCR("edgeVecR", double, eg.vecCap);
+  }
+  left_edge_kernel<<<nAff, 32, 0, st_>>>(eg);
+  CU(cudaGetLastError());
+  *launches += 1;
+  er.out.resize((size_t)3 * nAff + 8);
+  CU(cudaMemcpyAsync(er.out.data(), eo, er.out.size() * 4, cudaMemcpyDeviceToHost, st_));
+  CU(cudaStreamSynchronize(st_));
+  if (er.out[3 * nAff]) return fail(ctx, UPB_ERR_UNSUPPORTED, "left-edge replay (SURVEY Q2) ran out of its scratch or position budget");
+  er.profN = er.out[3 * nAff + 1];
+  return UPB_OK;
+}
+
 static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOut& out, bool sizing, bool* retry, const SharedDst* shared) {
   CU(cudaSetDevice(ctx->device));
   *retry = false;
@@ -1146,7 +1230,7 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
     if (cfg.control) for (uint32_t s = 0; s < ctx->nSamples; ++s) if (cfg.control[s]) pipelined = false;
     for (uint32_t fp : ctx->firstPos) if (fp != 0 && fp <= cfg.bw) pipelined = false;
   }
-  int r = prepare(ctx, cfg, pr, &launches, cfg.allowLeftEdge, pipelined);
+  int r = prepare(ctx, cfg, pr, &launches, pipelined);
   if (r) return r;
   const uint32_t n = ctx->nSamples, C = (uint32_t)ctx->sizes.size();
   const uint32_t nUnits = (uint32_t)pr.units.size();
@@ -1207,7 +1291,6 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
 
   // ---- K0: left-edge replay for the units that need it (rare: one small kernel and one read-back) ------------
   const uint32_t nAff = (uint32_t)pr.affected.size();
-  const uint32_t EDGE_REG_CAP = 1u << 18, EDGE_ROW_CAP = 1024;
   EdgeArgs eg;
   memset(&eg, 0, sizeof eg);
   uint32_t* d_affected = nullptr;
@@ -1215,31 +1298,10 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
   uint32_t* d_edgeRowsOfUnit = nullptr; int32_t* d_affOfUnit = nullptr; uint32_t* d_drop = nullptr;
   uint64_t edgeRowsTotal = 0;
   if (nAff) {
-    const uint32_t w = 2 * cfg.bw + 1;
-    d_affected = SCR("edgeAffected", uint32_t, nAff);
-    CU(cudaMemcpyAsync(d_affected, pr.affected.data(), (size_t)nAff * 4, cudaMemcpyHostToDevice, st_));
-    eg.T = pr.T; eg.units = d_units; eg.affected = d_affected; eg.nAffected = nAff; eg.control = ctx->scratch["control"].as<uint8_t>();
-    eg.coeffBySample = pr.d_coeffBySample; eg.taps = ctx->scratch["taps"].as<double>(); eg.bw = cfg.bw; eg.nondir = cfg.nondir ? 1 : 0;
-    eg.thr = cfg.thr; eg.kurtThr = cfg.kurtThr; eg.corrThr = cfg.nondir ? cfg.corrThr : -1.0; eg.hitThr = cfg.hitThr;
-    eg.cursors = SCR("edgeCursors", unsigned long long, (size_t)nAff * 2 * n);
-    eg.ringF = SCR("edgeRingF", double, (size_t)nAff * w); eg.ringR = SCR("edgeRingR", double, (size_t)nAff * w);
-    eg.ringHits = SCR("edgeRingHits", uint32_t, (size_t)nAff * w * n); eg.ringHas = SCR("edgeRingHas", uint8_t, (size_t)nAff * w);
-    eg.regPc = SCR("edgeRegPc", uint32_t, (size_t)nAff * EDGE_REG_CAP); eg.regHas = SCR("edgeRegHas", uint8_t, (size_t)nAff * EDGE_REG_CAP);
-    eg.regF = SCR("edgeRegF", double, (size_t)nAff * EDGE_REG_CAP); eg.regR = SCR("edgeRegR", double, (size_t)nAff * EDGE_REG_CAP);
-    eg.regSums = SCR("edgeRegSums", uint32_t, (size_t)nAff * n); eg.callCounts = SCR("edgeCall", uint32_t, (size_t)nAff * n);
-    eg.regCap = EDGE_REG_CAP; eg.rowCap = EDGE_ROW_CAP; eg.maxPositions = 1ull << 23;
-    uint32_t* eo = SCR("edgeOut", uint32_t, (size_t)3 * nAff + 4);
-    CU(cudaMemsetAsync(eo, 0, ((size_t)3 * nAff + 4) * 4, st_));
-    eg.stop = eo; eg.nCand = eo + nAff; eg.nRows = eo + 2 * nAff; eg.flags = eo + 3 * nAff;
-    eg.rows = SCR("edgeRows", EdgeRow, (size_t)nAff * EDGE_ROW_CAP);
-    eg.rowCounts = SCR("edgeRowCounts", uint32_t, (size_t)nAff * EDGE_ROW_CAP * n);
-    left_edge_kernel<<<nAff, 32, 0, st_>>>(eg);
-    CU(cudaGetLastError());
-    launches += 1;
-    std::vector<uint32_t> eoh((size_t)3 * nAff + 4);
-    CU(cudaMemcpyAsync(eoh.data(), eo, eoh.size() * 4, cudaMemcpyDeviceToHost, st_));
-    CU(cudaStreamSynchronize(st_));
-    if (eoh[3 * nAff]) return fail(ctx, UPB_ERR_UNSUPPORTED, "left-edge replay (SURVEY Q2) ran out of its scratch or position budget");
+    EdgeRun er;
+    if ((r = run_edge_replay(ctx, cfg, pr, st_, EdgeRec(), er, &launches))) return r;
+    eg = er.eg; d_affected = er.d_affected;
+    const std::vector<uint32_t>& eoh = er.out;
     std::vector<uint32_t> rowsOfUnit(nUnits, 0);
     std::vector<int32_t> affOfUnit(nUnits, -1);
     for (uint32_t k = 0; k < nAff; ++k) {
@@ -1790,7 +1852,6 @@ extern "C" int upb_call_regions (upb_ctx* ctx, const upb_region_params* p, upb_r
   cfg.hitThr = p->hit_threshold; cfg.background = p->background; cfg.nondir = !p->directional; cfg.control = p->control;
   cfg.nCoeffs = p->n_coeffs; cfg.coeffs = p->coeffs;
   cfg.needCorr = cfg.nondir;        // -D: the filter (if corr_threshold > -1) and the optional correlation column
-  cfg.allowLeftEdge = true;
   PipeOut po;
   Prep pr;
   int r = run_pipeline(ctx, cfg, pr, po);
@@ -1874,7 +1935,6 @@ extern "C" int upb_call_regions_shared (upb_ctx* ctx, const upb_region_params* p
   cfg.hitThr = p->hit_threshold; cfg.background = p->background; cfg.nondir = !p->directional; cfg.control = p->control;
   cfg.nCoeffs = p->n_coeffs; cfg.coeffs = p->coeffs;
   cfg.needCorr = cfg.nondir;
-  cfg.allowLeftEdge = true;
   SharedDst sd;
   sd.slab = db + L.oSlab; sd.rowCap = t->row_capacity;
   sd.x.counts = (volatile unsigned long long*)(db + L.oCounts + (size_t)(step & 1) * t->world * 2 * C * 8);
@@ -1985,15 +2045,43 @@ static PipeCfg shift_cfg (const upb_shift_params* p) {
   PipeCfg cfg;
   cfg.bw = p->bandwidth; cfg.thr = p->region_threshold; cfg.kurtThr = p->kurtosis_threshold; cfg.corrThr = -1;   // :142
   cfg.hitThr = (double)p->hit_threshold; cfg.background = p->background; cfg.nondir = true; cfg.control = nullptr; cfg.needCorr = false;
-  cfg.allowLeftEdge = true;          // regions at a contig start come from the replay of the reference's left-edge behaviour (Q2)
   return cfg;
 }
 
 // :206-219 for a batch of regions that are long enough: strandCorr(shift) for every shift 0..max_shift on the device, then the
 // first strict maximum per region.  `dens` is the density template of a prepare() / run_pipeline() with shift_cfg.
-static int shift_sweep_batch (upb_ctx* ctx, const DensArgs& dens, const std::vector<uint32_t>& unitOfContig, uint32_t nb, const uint32_t* contig,
+static int shift_sweep_batch (upb_ctx* ctx, const PipeCfg& cfg, const Prep& pr, const std::vector<uint32_t>& unitOfContig, uint32_t nb, const uint32_t* contig,
                               const uint32_t* left, const uint32_t* len, uint32_t nShifts, uint32_t* bestShift, double* bestCorr, uint32_t* launches) {
   if (!nb) return UPB_OK;
+  const DensArgs& dens = pr.dens;
+  // regions that the left-edge replay produced are swept over the score vectors the reference's Region holds for them —
+  // the displaced contents of its unshifted window — which only the replay knows: run it again, keeping the vectors of the long rows
+  std::vector<VecPatch> patches;
+  EdgeRun er;
+  {
+    std::vector<int32_t> affOfUnit(pr.units.size(), -1);
+    for (size_t k = 0; k < pr.affected.size(); ++k) affOfUnit[pr.affected[k]] = (int32_t)k;
+    bool any = false;
+    for (uint32_t k = 0; k < nb && !any; ++k) any = affOfUnit[unitOfContig[contig[k]]] >= 0;
+    if (any) {
+      EdgeRec rec; rec.vecMinLen = 2 * (nShifts - 1) + 3;
+      int r = run_edge_replay(ctx, cfg, pr, ctx->stream, rec, er, launches);
+      if (r) return r;
+      const uint32_t nAff = (uint32_t)pr.affected.size();
+      if (er.out[3 * nAff + 2] > er.eg.vecCap) return fail(ctx, UPB_ERR_UNSUPPORTED, "left-edge replay (SURVEY Q2): score-vector pool too small");
+      std::vector<EdgeRow> rows;
+      for (uint32_t k = 0; k < nb; ++k) {
+        const int32_t a = affOfUnit[unitOfContig[contig[k]]];
+        if (a < 0 || left[k] > er.out[a]) continue;                   // beyond the position the replay hands over at
+        const uint32_t nRows = std::min<uint32_t>(er.out[2 * nAff + a], EDGE_ROW_CAP);
+        rows.resize(nRows);
+        if (nRows) CU(cudaMemcpy(rows.data(), er.eg.rows + (size_t)a * EDGE_ROW_CAP, (size_t)nRows * sizeof(EdgeRow), cudaMemcpyDeviceToHost));
+        bool found = false;
+        for (const EdgeRow& row : rows) if (row.left == left[k] && row.len == len[k] && row.vecOff) { patches.push_back(VecPatch{k, row.vecOff - 1, len[k]}); found = true; break; }
+        if (!found) return fail(ctx, UPB_ERR_BAD_ARG, "shift sweep: a region at a contig start is not one the left-edge replay (SURVEY Q2) produces");
+      }
+    }
+  }
   std::vector<uint32_t> hUnit(nb), hChunks(nb);
   for (uint32_t k = 0; k < nb; ++k) { hUnit[k] = unitOfContig[contig[k]]; hChunks[k] = (len[k] + TILE - 1) / TILE; }
   uint32_t* dUnit = SCR("dUnit", uint32_t, nb); uint32_t* dLeft = SCR("dLeft", uint32_t, nb);
@@ -2004,7 +2092,7 @@ static int shift_sweep_batch (upb_ctx* ctx, const DensArgs& dens, const std::vec
   CU(cudaMemcpyAsync(dChunks, hChunks.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));                           // the host vectors go out of scope below
   int r;
-  if ((r = dump_and_corr(ctx, dens, true, nb, nShifts, launches))) return r;
+  if ((r = dump_and_corr(ctx, dens, true, nb, nShifts, launches, &patches, er.eg.vecF, er.eg.vecR))) return r;
   uint32_t* dBestShift = SCR("bestShift", uint32_t, nb);
   double* dBestCorr = SCR("bestCorr", double, nb);
   best_shift_kernel<<<(nb + 255) / 256, 256, 0, ctx->stream>>>(ctx->scratch["corr"].as<double>(), nb, nShifts, dBestShift, dBestCorr);
@@ -2080,10 +2168,7 @@ extern "C" int upb_strand_shift (upb_ctx* ctx, const upb_shift_params* p, upb_sh
       if (cursor >= sortedEnd) sort_more(std::min<size_t>(R, std::max<size_t>(2 * sortedEnd, cursor + 1024)));
       const uint32_t i = order[cursor].idx;
       if (rLen[i] > 2 * p->max_shift + 3) {                            // :206 large enough to try all shifts
-        // a region the left-edge replay produced has displaced densities (Q2); its shift sweep is not replayed
-        if (rLeft[i] <= po.unitEdgeStop[unitOfContig[rContig[i]]])
-          return fail(ctx, UPB_ERR_LEFT_EDGE, "a region within `bandwidth` of a contig start is long enough for the shift sweep: the reference's left-edge densities (SURVEY Q2) are not emulated there");
-        batch.push_back(i);
+        batch.push_back(i);                                            // (a region of the left-edge replay is swept over the replay's own score vectors, shift_sweep_batch)
       }
       ++cursor;
     }
@@ -2092,7 +2177,7 @@ extern "C" int upb_strand_shift (upb_ctx* ctx, const upb_shift_params* p, upb_sh
     std::vector<uint32_t> hContig(nb), hLeft(nb), hLen(nb), bs(nb);
     std::vector<double> bc(nb);
     for (uint32_t k = 0; k < nb; ++k) { const uint32_t i = batch[k]; hContig[k] = rContig[i]; hLeft[k] = rLeft[i]; hLen[k] = rLen[i]; }
-    if ((r = shift_sweep_batch(ctx, pr.dens, unitOfContig, nb, hContig.data(), hLeft.data(), hLen.data(), nShifts, bs.data(), bc.data(), &launches))) return r;
+    if ((r = shift_sweep_batch(ctx, cfg, pr, unitOfContig, nb, hContig.data(), hLeft.data(), hLen.data(), nShifts, bs.data(), bc.data(), &launches))) return r;
     for (uint32_t k = 0; k < nb && tested < toTest; ++k) {
       if (bc[k] >= p->corr_threshold) {                              // :220 disqualify regions under threshold
         const uint32_t i = batch[k];
@@ -2172,7 +2257,7 @@ extern "C" int upb_shift_sweep (upb_ctx* ctx, const upb_shift_params* p, uint64_
   const PipeCfg cfg = shift_cfg(p);
   Prep pr;
   uint32_t launches = 0;
-  int r = prepare(ctx, cfg, pr, &launches, true);
+  int r = prepare(ctx, cfg, pr, &launches);
   if (r) return r;
   const uint32_t C = (uint32_t)ctx->sizes.size();
   std::vector<uint32_t> unitOfContig(C, 0xFFFFFFFFu);
@@ -2182,7 +2267,7 @@ extern "C" int upb_shift_sweep (upb_ctx* ctx, const upb_shift_params* p, uint64_
     if (len[k] <= 2 * p->max_shift + 3) return fail(ctx, UPB_ERR_BAD_ARG, "upb_shift_sweep: a region is too short to try all shifts (src/strand_shift.cpp:206)");
     if (left[k] < 1 || (uint64_t)left[k] + len[k] - 1 > (uint64_t)ctx->sizes[contig[k]] + p->bandwidth) return fail(ctx, UPB_ERR_BAD_ARG, "upb_shift_sweep: a region lies outside its contig");
   }
-  r = shift_sweep_batch(ctx, pr.dens, unitOfContig, (uint32_t)n, contig, left, len, p->max_shift + 1, best_shift_out, best_corr_out, &launches);
+  r = shift_sweep_batch(ctx, cfg, pr, unitOfContig, (uint32_t)n, contig, left, len, p->max_shift + 1, best_shift_out, best_corr_out, &launches);
   ctx->stats.launches = launches;
   return r;
 }
@@ -2216,12 +2301,27 @@ extern "C" int upb_profile_contig (upb_ctx* ctx, const upb_region_params* p, int
   int unit = -1;
   for (size_t u = 0; u < pr.units.size(); ++u) if (pr.units[u].contig == contig && pr.units[u].buffer == (uint32_t)buffer) unit = (int)u;
   if (unit < 0) return UPB_OK;      // no non-control tags: the reference writes nothing for it
+  std::vector<uint32_t> posOut;
+  std::vector<double> scoreOut;
+  // a unit with a tag within `bandwidth` of the contig start (or one that inherits stale window cells): what the reference writes for its first
+  // positions are the displaced scores of its unshifted window — they come from the replay, up to the position it hands over at
+  uint64_t first = 1;
+  for (size_t k = 0; k < pr.affected.size(); ++k) if (pr.affected[k] == (uint32_t)unit) {
+    EdgeRec rec; rec.profUnit = unit;
+    EdgeRun er;
+    if ((r = run_edge_replay(ctx, cfg, pr, ctx->stream, rec, er, &launches))) return r;
+    if (er.profN) {
+      posOut.resize(er.profN); scoreOut.resize(er.profN);
+      CU(cudaMemcpyAsync(posOut.data(), er.eg.profPos, (size_t)er.profN * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaMemcpyAsync(scoreOut.data(), er.eg.profScore, (size_t)er.profN * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+    }
+    first = (uint64_t)er.out[k] + 1;                                  // 2^32 if the replay owns the whole unit
+  }
   // evaluate the contig in slabs of 8M positions; the reference evaluates firstTag-bw .. lastTag+bw (Q20)
   const uint64_t last = (uint64_t)ctx->sizes[contig] + cfg.bw;
   const uint32_t SLAB = 8u << 20;
-  std::vector<uint32_t> posOut;
-  std::vector<double> scoreOut;
-  for (uint64_t start = 1; start <= last; start += SLAB) {
+  for (uint64_t start = first; start <= last; start += SLAB) {
     const uint32_t len = (uint32_t)std::min<uint64_t>(SLAB, last - start + 1);
     const uint32_t desc[4] = {(uint32_t)unit, (uint32_t)start, len, (len + TILE - 1) / TILE};
     uint32_t* dUnit = SCR("dUnit", uint32_t, 1); uint32_t* dLeft = SCR("dLeft", uint32_t, 1);

@@ -13,6 +13,17 @@
 // the region statistics, statement by statement — from the first tag until the first position beyond X at which no
 // region is open (Xstop).  Its regions replace whatever span_kernel finds at or before Xstop.  The replay is strictly
 // sequential, as the reference is; it touches a few hundred positions per affected unit in practice.
+//
+// Chains.  A unit whose EVERY tag lies within `bandwidth` of the contig start never shifts the window far enough for the flush
+// (flushContig, misc/peakcall.cpp:224-231) to drain it: bandwidth + 1 - lastTag cells survive at the front of the deque — and a
+// region may stay open — when the buffer moves on to its next contig, where the stale cells are reported at the first positions
+// processed.  The thread that replays such a unit therefore carries its window and its open Region into the next unit of the same
+// ProfileBuffer (the next contig on which any sample, controls included, has a tag) and replays that one as well, until the
+// stale cells are gone; `chainNext` links the affected units in that order and only chain heads start a thread.
+//
+// Two optional recordings, for the callers that need more than the region rows: the -w profile points of one unit
+// (processPosition's profileOut_->write, misc/peakcall.cpp:81-84) and the forward / reverse score vectors of the accepted regions
+// long enough for the shift sweep of bin/strand_shift (Region::forwardScores / reverseScores, src/strand_shift.cpp:206-219).
 #pragma once
 
 #include "upb_device.cuh"
@@ -21,7 +32,7 @@ namespace upb {
 
 struct EdgeRow {
   uint32_t left, len, peak, wsum;
-  uint32_t candIndex, pad;
+  uint32_t candIndex, vecOff;       // vecOff: 1 + offset of the row's score vectors in vecF / vecR, 0 if not recorded
   double score, kurt, corr;
 };
 
@@ -29,6 +40,8 @@ struct EdgeArgs {
   Tags T;
   const Unit* units;
   const uint32_t* affected;         // [nAffected] unit indices
+  const uint32_t* chainNext;        // [nAffected] affected index of the unit that inherits this one's window if it leaves stale cells, 0xFFFFFFFF if none
+  const uint8_t* chainHead;         // [nAffected] 1: a thread starts here; 0: reached through chainNext
   uint32_t nAffected;
   const uint8_t* control;           // [nSamples]
   const double* coeffBySample;      // [nSamples] or NULL
@@ -54,7 +67,12 @@ struct EdgeArgs {
   uint32_t* nRows;                  // [nAffected] accepted
   EdgeRow* rows;                    // [nAffected * rowCap]
   uint32_t* rowCounts;              // [nAffected * rowCap * nSamples]
-  uint32_t* flags;                  // bit 0: row buffer full, bit 1: region scratch full, bit 2: replay budget exceeded
+  uint32_t* flags;                  // bit 0: row buffer full, bit 1: region scratch full, bit 2: replay budget exceeded, bit 3: profile buffer full, bit 4: vector pool full
+  // optional recordings
+  uint32_t profAff;                 // affected index whose profile points are recorded, 0xFFFFFFFF: none
+  uint32_t* profPos; double* profScore; uint32_t profCap; uint32_t* profN;
+  uint32_t vecMinLen;               // accepted rows with len > vecMinLen keep their score vectors; 0xFFFFFFFF: none
+  double* vecF; double* vecR; uint32_t vecCap; uint32_t* vecUsed;
 };
 
 struct EdgeState {
@@ -70,16 +88,18 @@ struct EdgeState {
   unsigned long long processed;
   bool done;
   uint32_t stop;
+  uint32_t ri;                      // scratch slot of the chain (the head's affected index): window, open region, per-sample sums
+  bool carried;                     // this unit started on the window its predecessor left behind
 };
 
 __device__ inline void edge_process_region (const EdgeArgs& a, uint32_t ai, EdgeState& st) {
   // misc/peakcall.cpp:33-53 over misc/data.cpp:104-193
   const uint32_t n = a.T.nSamples;
-  uint32_t* sums = a.regSums + (size_t)ai * n;
-  const uint32_t* pc = a.regPc + (size_t)ai * a.regCap;
-  const uint8_t* has = a.regHas + (size_t)ai * a.regCap;
-  const double* f = a.regF + (size_t)ai * a.regCap;
-  const double* r = a.regR + (size_t)ai * a.regCap;
+  uint32_t* sums = a.regSums + (size_t)st.ri * n;
+  const uint32_t* pc = a.regPc + (size_t)st.ri * a.regCap;
+  const uint8_t* has = a.regHas + (size_t)st.ri * a.regCap;
+  const double* f = a.regF + (size_t)st.ri * a.regCap;
+  const double* r = a.regR + (size_t)st.ri * a.regCap;
   uint32_t nonControl = 0;
   for (uint32_t e = 0; e < n; ++e) if (!a.control[e]) nonControl += sums[e];
   // posMean / posKurtosis: offsets are UShort, count and sum HitCount
@@ -116,8 +136,15 @@ __device__ inline void edge_process_region (const EdgeArgs& a, uint32_t ai, Edge
   if (pass) {
     if (st.nRows < a.rowCap) {
       EdgeRow row;
-      row.left = st.left; row.len = st.len; row.peak = st.peakPos; row.wsum = nonControl; row.candIndex = st.nCand; row.pad = 0;
+      row.left = st.left; row.len = st.len; row.peak = st.peakPos; row.wsum = nonControl; row.candIndex = st.nCand; row.vecOff = 0;
       row.score = st.peakScore; row.kurt = kurt; row.corr = corr;
+      if (st.len > a.vecMinLen) {
+        const uint32_t at = atomicAdd(a.vecUsed, st.len);
+        if (at <= a.vecCap && st.len <= a.vecCap - at) {
+          for (uint32_t i = 0; i < st.len; ++i) { a.vecF[at + i] = f[i]; a.vecR[at + i] = r[i]; }
+          row.vecOff = at + 1;
+        } else atomicOr(a.flags, 16u);
+      }
       a.rows[(size_t)ai * a.rowCap + st.nRows] = row;
       uint32_t* rc = a.rowCounts + ((size_t)ai * a.rowCap + st.nRows) * n;
       for (uint32_t e = 0; e < n; ++e) rc[e] = sums[e];
@@ -135,8 +162,8 @@ __device__ inline void edge_add_pos (const EdgeArgs& a, uint32_t ai, EdgeState& 
   const uint32_t n = a.T.nSamples;
   if (st.len >= a.regCap) { atomicOr(a.flags, 2u); return; }
   uint32_t pc = 0;
-  if (hasHits) { uint32_t* sums = a.regSums + (size_t)ai * n; for (uint32_t e = 0; e < n; ++e) { pc += hits[e]; sums[e] += hits[e]; } }
-  const size_t o = (size_t)ai * a.regCap + st.len;
+  if (hasHits) { uint32_t* sums = a.regSums + (size_t)st.ri * n; for (uint32_t e = 0; e < n; ++e) { pc += hits[e]; sums[e] += hits[e]; } }
+  const size_t o = (size_t)st.ri * a.regCap + st.len;
   a.regPc[o] = pc; a.regHas[o] = hasHits ? 1 : 0; a.regF[o] = fs; a.regR[o] = rs;
   ++st.len;
   const double score = __dadd_rn(fs, rs);
@@ -155,6 +182,11 @@ __device__ inline void edge_process_position (const EdgeArgs& a, uint32_t ai, Ed
     if (st.left != 0) edge_process_region(a, ai, st);
     if (score >= a.thr) edge_add_pos(a, ai, st, hasHits, hits, fs, rs);
   }
+  if (score != 0.0 && ai == a.profAff) {                             // profileOut_->write(PosScore(forward_, contig_, pos, score)), :81-84
+    const uint32_t k = *a.profN;
+    if (k < a.profCap) { a.profPos[k] = pos; a.profScore[k] = score; } else atomicOr(a.flags, 8u);
+    *a.profN = k + 1;
+  }
   st.lastPos = pos;
   ++st.processed;
   // hand over to span_kernel at the first position beyond the displaced cells with no region open
@@ -165,8 +197,8 @@ __device__ inline void edge_process_position (const EdgeArgs& a, uint32_t ai, Ed
 // ProfileBuffer::add, misc/peakcall.cpp:161-222.  counts == NULL stands for the empty vector flushContig passes.
 __device__ inline void edge_add (const EdgeArgs& a, uint32_t ai, EdgeState& st, const uint32_t* counts, uint32_t pos, bool forward) {
   const uint32_t n = a.T.nSamples, w = st.w;
-  double* F = a.ringF + (size_t)ai * w; double* R = a.ringR + (size_t)ai * w;
-  uint32_t* H = a.ringHits + (size_t)ai * w * n; uint8_t* has = a.ringHas + (size_t)ai * w;
+  double* F = a.ringF + (size_t)st.ri * w; double* R = a.ringR + (size_t)st.ri * w;
+  uint32_t* H = a.ringHits + (size_t)st.ri * w * n; uint8_t* has = a.ringHas + (size_t)st.ri * w;
   uint32_t nStatic = w;
   if ((unsigned long long)pos <= (unsigned long long)st.bufferPos + 2ull * st.bw) nStatic = pos - st.bufferPos;
   if (st.bufferPos != 0) {
@@ -180,6 +212,7 @@ __device__ inline void edge_add (const EdgeArgs& a, uint32_t ai, EdgeState& st, 
     }
   }
   if (st.done) return;
+  if (st.carried && st.bufferPos == 0) { st.skipped = true; st.lastSkipAdd = pos; }   // stale cells sit in front of this first tag's window
   double countSum = 0.0;
   if (counts) {
     if (!a.coeffBySample) { for (uint32_t e = 0; e < n; ++e) if (!a.control[e]) countSum = __dadd_rn(countSum, (double)counts[e]); }
@@ -203,47 +236,58 @@ __device__ inline void edge_add (const EdgeArgs& a, uint32_t ai, EdgeState& st, 
 }
 
 __global__ void left_edge_kernel (EdgeArgs a) {
-  const uint32_t ai = blockIdx.x;
-  if (ai >= a.nAffected || threadIdx.x != 0) return;
-  const Unit U = a.units[a.affected[ai]];
+  if (blockIdx.x >= a.nAffected || threadIdx.x != 0 || !a.chainHead[blockIdx.x]) return;
   const uint32_t n = a.T.nSamples, C = a.T.C, w = 2 * a.bw + 1;
   EdgeState st;
-  st.w = w; st.head = 0; st.bw = a.bw; st.bufferPos = 0; st.lastPos = 0;
+  st.ri = blockIdx.x;
+  st.w = w; st.head = 0; st.bw = a.bw;
   st.left = 0; st.len = 0; st.peakPos = 0; st.peakScore = 0.0;
-  st.lastSkipAdd = 0; st.skipped = false; st.nCand = 0; st.nRows = 0; st.processed = 0; st.done = false; st.stop = 0;
-  for (uint32_t j = 0; j < w; ++j) { a.ringF[(size_t)ai * w + j] = 0.0; a.ringR[(size_t)ai * w + j] = 0.0; a.ringHas[(size_t)ai * w + j] = 0; }
-  uint32_t* sums = a.regSums + (size_t)ai * n;
+  st.processed = 0;
+  for (uint32_t j = 0; j < w; ++j) { a.ringF[(size_t)st.ri * w + j] = 0.0; a.ringR[(size_t)st.ri * w + j] = 0.0; a.ringHas[(size_t)st.ri * w + j] = 0; }
+  uint32_t* sums = a.regSums + (size_t)st.ri * n;
   for (uint32_t e = 0; e < n; ++e) sums[e] = 0;
-  // stream cursors of every sample (and strand) on this contig: src/regions.cpp:335-354
-  unsigned long long* cur = a.cursors + (size_t)ai * 2 * n;
-  const uint32_t d0 = a.nondir ? 0u : U.buffer, d1 = a.nondir ? 1u : U.buffer;
-  for (uint32_t s = 0; s < n; ++s) for (uint32_t d = 0; d < 2; ++d) cur[s * 2 + d] = a.T.off[(uint64_t)(s * 2 + d) * (C + 1) + U.contig];
-  uint32_t* counts = a.callCounts + (size_t)ai * n;
-  while (!st.done) {
-    // next position carrying a tag of any sample on the strands this buffer sees
-    uint32_t pos = 0xFFFFFFFFu;
-    for (uint32_t s = 0; s < n; ++s) for (uint32_t d = d0; d <= d1; ++d) {
-      const unsigned long long e = cur[s * 2 + d];
-      if (e < a.T.off[(uint64_t)(s * 2 + d) * (C + 1) + U.contig + 1]) pos = min(pos, a.T.pos[e]);
-    }
-    if (pos == 0xFFFFFFFFu) break;
-    for (uint32_t d = d0; d <= d1 && !st.done; ++d) {                // forward call first, then reverse (src/regions.cpp:356-359)
-      bool any = false;
-      for (uint32_t s = 0; s < n; ++s) {
-        counts[s] = 0;
+  unsigned long long* cur = a.cursors + (size_t)st.ri * 2 * n;
+  uint32_t* counts = a.callCounts + (size_t)st.ri * n;
+  bool carried = false;
+  for (uint32_t ai = blockIdx.x; ai != 0xFFFFFFFFu; ai = a.chainNext[ai]) {
+    const Unit U = a.units[a.affected[ai]];
+    // what flushContig leaves behind for the next contig: bufferPos_ = 0, lastPos_ = 0 (misc/peakcall.cpp:226-227); window and Region stay
+    st.bufferPos = 0; st.lastPos = 0;
+    st.lastSkipAdd = 0; st.skipped = false; st.nCand = 0; st.nRows = 0; st.done = false; st.stop = 0; st.carried = carried;
+    // stream cursors of every sample (and strand) on this contig: src/regions.cpp:335-354
+    const uint32_t d0 = a.nondir ? 0u : U.buffer, d1 = a.nondir ? 1u : U.buffer;
+    for (uint32_t s = 0; s < n; ++s) for (uint32_t d = 0; d < 2; ++d) cur[s * 2 + d] = a.T.off[(uint64_t)(s * 2 + d) * (C + 1) + U.contig];
+    while (!st.done) {
+      // next position carrying a tag of any sample on the strands this buffer sees
+      uint32_t pos = 0xFFFFFFFFu;
+      for (uint32_t s = 0; s < n; ++s) for (uint32_t d = d0; d <= d1; ++d) {
         const unsigned long long e = cur[s * 2 + d];
-        if (e < a.T.off[(uint64_t)(s * 2 + d) * (C + 1) + U.contig + 1] && a.T.pos[e] == pos) { counts[s] = a.T.cnt[e]; cur[s * 2 + d] = e + 1; any = true; }
+        if (e < a.T.off[(uint64_t)(s * 2 + d) * (C + 1) + U.contig + 1]) pos = min(pos, a.T.pos[e]);
       }
-      if (any) edge_add(a, ai, st, counts, pos, d == 0);
+      if (pos == 0xFFFFFFFFu) break;
+      for (uint32_t d = d0; d <= d1 && !st.done; ++d) {              // forward call first, then reverse (src/regions.cpp:356-359)
+        bool any = false;
+        for (uint32_t s = 0; s < n; ++s) {
+          counts[s] = 0;
+          const unsigned long long e = cur[s * 2 + d];
+          if (e < a.T.off[(uint64_t)(s * 2 + d) * (C + 1) + U.contig + 1] && a.T.pos[e] == pos) { counts[s] = a.T.cnt[e]; cur[s * 2 + d] = e + 1; any = true; }
+        }
+        if (any) edge_add(a, ai, st, counts, pos, d == 0);
+      }
     }
+    bool leaks = false;
+    if (!st.done) {
+      // flushContig (misc/peakcall.cpp:224-231).  If the last tag lies beyond `bandwidth` every cell is shifted out: the last one is an end
+      // tap (exactly 0), so any open region is closed by the flush itself and the window is clean.  Otherwise bandwidth + 1 - lastTag cells
+      // (and possibly an open region) stay for the next contig of this buffer
+      leaks = st.bufferPos != 0 && st.bufferPos <= st.bw;
+      edge_add(a, ai, st, nullptr, st.bufferPos + w, true);
+      if (!st.done) st.stop = 0xFFFFFFFFu;                            // the replay owns the whole unit
+    }
+    a.stop[ai] = st.stop; a.nCand[ai] = st.nCand; a.nRows[ai] = st.nRows;
+    if (!leaks) break;                                                // prepare() links a successor exactly when the last tag lies within `bandwidth`
+    carried = true;
   }
-  if (!st.done) {
-    // flushContig (misc/peakcall.cpp:224-231): the window is drained.  Its last cell is an end tap (exactly 0), so any
-    // open region is closed by the flush itself; the replay owns the whole unit
-    edge_add(a, ai, st, nullptr, st.bufferPos + w, true);
-    if (!st.done) st.stop = 0xFFFFFFFFu;
-  }
-  a.stop[ai] = st.stop; a.nCand[ai] = st.nCand; a.nRows[ai] = st.nRows;
 }
 
 }  // namespace upb

@@ -33,9 +33,6 @@
 #ifndef UPB_EXP_PREFETCH
 #define UPB_EXP_PREFETCH 0                          // span_kernel<directional>: the mini-tile offset tables of a ticket's later spans fetched with cp.async at ticket time, and the
 #endif                                              //   entries of the next span's first hot group prefetched into L2 one span ahead (written after the r01 GPU budget was spent: never run)
-#ifndef UPB_EXP_ASYNC
-#define UPB_EXP_ASYNC 0                             // B1 of span_kernel: entries staged through shared memory with cp.async (0: register loads, v4-v24)
-#endif
 
 namespace upb {
 
@@ -94,7 +91,7 @@ struct SpanArgs {
   unsigned long long* stat;                         // [0] hot blocks, [1] pieces, [2] exact evaluations, [3] spans with tags
 };
 
-struct SpanSmem { uint32_t taps, ctl, coef, warp0, warpStride, oD, oDR, oWf, oWr, oSt, oMo, oSc, oMw, oHm, total; };
+struct SpanSmem { uint32_t taps, ctl, coef, warp0, warpStride, oD, oDR, oWf, oWr, oSt, oMo, oSc, oMw, oHm, oBar, total; };
 
 __host__ __device__ inline SpanSmem span_smem_layout (uint32_t bw, uint32_t nSamples, bool nondir, bool coeff) {
   SpanSmem L;
@@ -119,6 +116,7 @@ __host__ __device__ inline SpanSmem span_smem_layout (uint32_t bw, uint32_t nSam
   L.oMw = w;   w += (PIECE_BLOCKS + 2) * 4;
   L.oHm = w;   w += (SPAN_WORDS + 2) * 4;
   w = (w + 15) & ~15u;
+  L.oBar = w;  w += 16;                             // two mbarriers: one per slot of B1's bulk-copy ring
   L.warpStride = w;
   L.total = o + w * SP_WARPS;
   return L;
@@ -245,24 +243,40 @@ __device__ __forceinline__ void piece_entries_tab (const uint2* __restrict__ men
   }
 }
 
-// The same walk with the entries staged through shared memory: every lane copies its own entries (8 bytes each, cp.async) into a
-// ring of STAGE_SLOTS batches of 128 and consumes them STAGE_SLOTS - 1 batches later, so up to 12 loads per lane are in flight with no
-// registers held, instead of four that are waited for before the next four are issued.  A lane reads back only what it copied
-// itself: cp.async.wait_group is all the ordering this needs.  `pre` runs once, after the first batches are on their way (the
-// caller zeroes the piece's cells there, behind the loads).
-constexpr uint32_t STAGE_SLOTS = 3;
-static_assert(128 * 8 + PIECE_LEN * 4 >= STAGE_SLOTS * 128 * 8, "SpanSmem: oSt + oSc must hold the staging ring");
+// B1 with the entries staged by the bulk-copy engine (cp.async.bulk, SASS UBLKCP — the 1-D form of TMA: the chunk is contiguous,
+// no tensor map is needed).  One elected lane posts the copy of a sub-chunk of BULK_ENTRIES entries into one of two ring slots and
+// arms that slot's mbarrier with the byte count; the warp waits on the barrier's phase, pulls the slot into registers with conflict-
+// free LDS.64, hands the slot back (the next sub-chunk is posted before the current one is pooled) and pools from registers.  Against
+// the per-lane LDG walk above (r01: 17 instructions per entry, 20 % of the kernel's stall samples on the loads' scoreboard) the lanes
+// issue no global load, no address arithmetic and no bounds predicate per load.  Copies are 16-byte granular: the chunk is widened
+// to even entry indices at both ends and the odd entry is masked by index.
+#ifndef UPB_PREFETCH_L2
+#define UPB_PREFETCH_L2 1                         // span_kernel: the entries of the next piece are prefetched into L2 while the current one is worked on
+#endif
+constexpr uint32_t BULK_ENTRIES = 192;                                // per ring slot: 1536 bytes; two slots = SpanSmem oSt + oSc (3 KB, contiguous)
+static_assert(128 * 8 + PIECE_LEN * 4 >= 2 * BULK_ENTRIES * 8, "SpanSmem: oSt + oSc must hold the bulk ring");
 
 __device__ __forceinline__ void cp_async8 (void* smemDst, const void* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((uint32_t)__cvta_generic_to_shared(smemDst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit () { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait () { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ uint32_t smem_u32 (const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init (uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx (uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_g2s (uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait (uint32_t bar, uint32_t parity) {
+  asm volatile("{\n .reg .pred P1;\n LAB_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n @P1 bra DONE;\n bra LAB_WAIT;\n DONE:\n }" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async () { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// seq: sub-chunks this warp has posted so far (slot = seq & 1, phase parity = (seq >> 1) & 1); persists across pieces
 template <class P, class F>
-__device__ __forceinline__ void piece_entries_async (const uint2* __restrict__ ment, const unsigned long long* __restrict__ tab, int mBase, uint32_t nMt,
-                                                     int64_t lo, int64_t hi, uint32_t lane, uint2* ring /* [STAGE_SLOTS * 128], 8-byte aligned, this warp's */,
-                                                     bool& preDone, P pre, F f) {
+__device__ __forceinline__ void piece_entries_bulk (const uint2* __restrict__ ment, const unsigned long long* __restrict__ tab, int mBase, uint32_t nMt,
+                                                    int64_t lo, int64_t hi, uint32_t lane, const uint2* ring, uint32_t ringAddr, uint32_t barAddr, uint32_t& seq,
+                                                    bool& preDone, P pre, F f) {
   if (nMt == 0 || hi < 1) return;
   if (lo < 1) lo = 1;
   const uint32_t ma = (uint32_t)((lo - 1) >> MT_SHIFT);
@@ -271,32 +285,43 @@ __device__ __forceinline__ void piece_entries_async (const uint2* __restrict__ m
   for (uint32_t sp = ma / SPAN_MT; sp <= mb / SPAN_MT; ++sp) {
     const uint32_t m0 = max(ma, sp * SPAN_MT), m1 = min(mb, sp * SPAN_MT + SPAN_MT - 1);
     const unsigned long long e0 = tab[(int)m0 - mBase], e1 = tab[(int)m1 + 1 - mBase];
+    if (e1 <= e0) continue;
     const uint32_t base = sp * SPAN_LEN + 1;
-    const uint32_t nB = (uint32_t)((e1 - e0 + 127) >> 7);             // batches of 128 entries
-    auto issue = [&] (uint32_t b) {                                    // batch b -> slot b % STAGE_SLOTS; always one group, empty beyond the end
-      if (b < nB) {
-        const unsigned long long eb = e0 + ((unsigned long long)b << 7) + lane;
-        uint2* dst = ring + (b % STAGE_SLOTS) * 128 + lane;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) if (eb + 32 * q < e1) cp_async8(dst + 32 * q, ment + eb + 32 * q);
+    const unsigned long long eA = e0 & ~1ull;                          // 16-byte granules: even entry indices
+    const uint32_t nAll = (uint32_t)(((e1 + 1) & ~1ull) - eA);          // entries copied (the chunk of a piece fits 32 bits)
+    const uint32_t skip = (uint32_t)(e0 - eA), nEnd = (uint32_t)(e1 - eA);   // entries [skip, nEnd) of the copy are the chunk
+    const uint32_t nSub = (nAll + BULK_ENTRIES - 1) / BULK_ENTRIES;
+    auto post = [&] (uint32_t j) {                                     // sub-chunk j -> slot (seq + j) & 1
+      if (lane == 0) {
+        const uint32_t g = seq + j, slot = g & 1u;
+        const uint32_t cnt = min(BULK_ENTRIES, nAll - j * BULK_ENTRIES);
+        fence_proxy_async();                                           // the slot was read (or written as stage / scf) through the generic proxy
+        mbar_expect_tx(barAddr + 8 * slot, cnt * 8);
+        bulk_g2s(ringAddr + slot * (BULK_ENTRIES * 8), ment + eA + (unsigned long long)j * BULK_ENTRIES, cnt * 8, barAddr + 8 * slot);
       }
-      cp_async_commit();
     };
-#pragma unroll
-    for (uint32_t b = 0; b < STAGE_SLOTS; ++b) issue(b);
+    post(0);
+    if (nSub > 1) post(1);
     if (!preDone) { pre(); preDone = true; }
-    for (uint32_t b = 0; b < nB; ++b) {
-      cp_async_wait<STAGE_SLOTS - 1>();                                // all but the newest STAGE_SLOTS - 1 groups have landed: batch b is here
-      const unsigned long long eb = e0 + ((unsigned long long)b << 7) + lane;
-      const uint2* src = ring + (b % STAGE_SLOTS) * 128 + lane;
-      uint2 en[4];
+    for (uint32_t j = 0; j < nSub; ++j) {
+      const uint32_t g = seq + j, slot = g & 1u;
+      mbar_wait(barAddr + 8 * slot, (g >> 1) & 1u);
+      const uint2* src = ring + slot * BULK_ENTRIES + lane;
+      const uint32_t i0 = j * BULK_ENTRIES + lane;
+      constexpr int HALF = (int)(BULK_ENTRIES / 64);                   // two batches per slot: half the registers held across the pooling
+      uint2 en[HALF];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) en[q] = (eb + 32 * q < e1) ? src[32 * q] : make_uint2(0u, 0u);
-      issue(b + STAGE_SLOTS);                                          // refills the slot just read (same lane, same addresses)
+      for (int q = 0; q < HALF; ++q) { const uint32_t i = i0 + 32 * q; en[q] = (i >= skip && i < nEnd) ? src[32 * q] : make_uint2(0u, 0u); }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) f(base + (en[q].y & (SPAN_LEN - 1)), en[q]);   // a slot beyond the end has count 0: f skips it
+      for (int q = 0; q < HALF; ++q) f(base + (en[q].y & (SPAN_LEN - 1)), en[q]);   // a masked slot has count 0: f skips it
+#pragma unroll
+      for (int q = 0; q < HALF; ++q) { const uint32_t i = i0 + 32 * (q + HALF); en[q] = (i >= skip && i < nEnd) ? src[32 * (q + HALF)] : make_uint2(0u, 0u); }
+      __syncwarp();                                                    // every lane holds the rest of its entries: the slot can be refilled
+      if (j + 2 < nSub) post(j + 2);
+#pragma unroll
+      for (int q = 0; q < HALF; ++q) f(base + (en[q].y & (SPAN_LEN - 1)), en[q]);
     }
-    cp_async_wait<0>();                                                // nothing of this walk is still on its way when the ring is reused
+    seq += nSub;
   }
 }
 
@@ -528,7 +553,7 @@ __global__ void __launch_bounds__(HOT_THREADS, 6) hot_span_kernel (const __grid_
 // MINB: CTAs per SM the register budget is sized for.  Four (64 registers) when the shared memory of four CTAs fits; where it
 // does not (bandwidth > ~150, or -D with its second cell array) the kernel is built for three (no spills, 78 registers): measured
 // on C3 at bandwidth 200 0.69 -> 0.60 ms, C2 0.57 -> 0.47 ms, while at bandwidth <= 150 four CTAs win (profiles/r01_v26_ab.txt).
-template <bool NONDIR, bool COEFF, int MINB = SP_MIN_BLOCKS>
+template <bool NONDIR, bool COEFF, int MINB = SP_MIN_BLOCKS, bool BULK = false>
 __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : MINB) span_kernel (const __grid_constant__ SpanArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const uint32_t bw = a.bw;
@@ -548,6 +573,12 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : MINB) span_kernel (con
   double* Wr = (double*)(wbase + L.oWr);
   uint32_t* mw = (uint32_t*)(wbase + L.oMw);
   uint32_t* hm = (uint32_t*)(wbase + L.oHm);
+  const uint32_t barAddr = smem_u32(wbase + L.oBar), ringAddr = smem_u32(stage);
+  uint32_t bulkSeq = 0;
+  if (BULK) {
+    if (lane == 0) { mbar_init(barAddr, 1); mbar_init(barAddr + 8, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncwarp();
+  }
 
   for (uint32_t i = tid; i < 2 * bw + 1; i += SP_THREADS) Ks[i] = a.taps[i];
   for (uint32_t i = tid; i < a.nSamples; i += SP_THREADS) isCtl[i] = a.control[i];
@@ -652,28 +683,64 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : MINB) span_kernel (con
 
     // ---- B: pieces, in position order -------------------------------------------------------------------------------
     uint32_t spanRuns = 0;
-    uint32_t kb = 0;
-    while (kb < nBlk) {
-      // next maximal group of hot blocks [zs, ze) (uniform scalar code over the mask words)
-      { uint32_t m = hm[kb >> 5] >> (kb & 31);
-        if (!m) {                                                      // nothing left in this word: on to the next word that has a hot block
-          const uint32_t w1 = (kb >> 5) + 1, rest = w1 < (uint32_t)SPAN_WORDS ? nzWords >> w1 : 0u;
-          if (!rest) break;
-          kb = (w1 + (uint32_t)__ffs(rest) - 1) << 5;
-          continue;
+    // the pieces of the span come from a small scanner over the hot-block mask that runs ONE PIECE AHEAD of the work: while piece k is
+    // pooled, classified and cut into runs (~10 us of a warp's time), the entries of piece k+1 are already on their way into L2
+    // (cp.async.bulk.prefetch.L2, one instruction of one lane) — its loads then pay an L2 round trip instead of a DRAM one
+    uint32_t kb = 0, gEnd = 0, gNext = 0;                              // scanner state: current group of hot blocks is [.., gEnd), next piece starts at gNext
+    auto nextPiece = [&] (uint32_t& pbOut, uint32_t& nbOut) -> bool {
+      if (gNext >= gEnd) {                                             // next maximal group of hot blocks (uniform scalar code over the mask words)
+        for (;;) {
+          if (kb >= nBlk) return false;
+          const uint32_t m = hm[kb >> 5] >> (kb & 31);
+          if (!m) {                                                    // nothing left in this word: on to the next word that has a hot block
+            const uint32_t w1 = (kb >> 5) + 1, rest = w1 < (uint32_t)SPAN_WORDS ? nzWords >> w1 : 0u;
+            if (!rest) { kb = nBlk; return false; }
+            kb = (w1 + (uint32_t)__ffs(rest) - 1) << 5;
+            continue;
+          }
+          kb += __ffs(m) - 1;
+          break;
         }
-        kb += __ffs(m) - 1; }
-      const uint32_t zs = kb;
-      for (;;) {
-        const uint32_t x = ~(hm[kb >> 5] >> (kb & 31));
-        kb += x ? (uint32_t)(__ffs(x) - 1) : 32u;
-        if ((kb & 31) != 0 || kb >= nBlk || !(hm[kb >> 5] & 1u)) break;
+        gNext = kb;
+        for (;;) {
+          const uint32_t x = ~(hm[kb >> 5] >> (kb & 31));
+          kb += x ? (uint32_t)(__ffs(x) - 1) : 32u;
+          if ((kb & 31) != 0 || kb >= nBlk || !(hm[kb >> 5] & 1u)) break;
+        }
+        if (kb > nBlk) kb = nBlk;
+        gEnd = kb;
       }
-      if (kb > nBlk) kb = nBlk;
-      const uint32_t ze = kb;
-
-      for (uint32_t pb = zs; pb < ze; pb += PIECE_BLOCKS) {
-        const uint32_t nb = min((uint32_t)PIECE_BLOCKS, ze - pb);
+      pbOut = gNext;
+      nbOut = min((uint32_t)PIECE_BLOCKS, gEnd - gNext);
+      gNext += nbOut;
+      return true;
+    };
+#if UPB_PREFETCH_L2
+    auto prefetchPiece = [&] (uint32_t pbN, uint32_t nbN) {
+      if (lane != 0) return;
+      const int64_t lo = (int64_t)ts + 32 * pbN - bw, hi = (int64_t)ts + 32 * pbN + 32 * nbN - 1 + bw;
+#pragma unroll
+      for (int str = 0; str < (NONDIR ? 2 : 1); ++str) {
+        const uint32_t nMt = nMtS[str];
+        if (nMt == 0 || hi < 1) continue;
+        const uint32_t ma = lo < 1 ? 0u : (uint32_t)((lo - 1) >> MT_SHIFT);
+        if (ma >= nMt) continue;
+        const uint32_t mb = min((uint32_t)((hi - 1) >> MT_SHIFT), nMt - 1);
+        const unsigned long long* tab = moSpan + MO_STRIDE * str;
+        const unsigned long long e0 = tab[(int)ma - mBase] & ~1ull, e1 = (tab[(int)mb + 1 - mBase] + 1) & ~1ull;   // the chunk is contiguous across a span boundary too
+        if (e1 > e0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a.T.ment + e0), "r"((uint32_t)min(e1 - e0, 8192ull) * 8u) : "memory");
+      }
+    };
+#endif
+    uint32_t pb = 0, nb = 0;
+    bool havePiece = nextPiece(pb, nb);
+    while (havePiece) {
+      uint32_t pbNext = 0, nbNext = 0;
+      const bool haveNext = nextPiece(pbNext, nbNext);
+#if UPB_PREFETCH_L2
+      if (haveNext) prefetchPiece(pbNext, nbNext);
+#endif
+      do {                                                             // `continue` below leaves the piece
         ++stPieces;
         const uint32_t P = min(32 * nb, np - 32 * pb);                // positions of this piece
         const uint32_t q0 = ts + 32 * pb;                             // first position
@@ -691,21 +758,20 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : MINB) span_kernel (con
         {
           const int64_t lo = (int64_t)q0 - bw, hi = (int64_t)q0 + 32 * nb - 1 + bw;
           const uint32_t cell0 = q0 - bw;                              // may wrap below 0: the unsigned difference below is still right
-#if UPB_EXP_ASYNC
-          bool zeroed = false;                                         // the cells are zeroed behind the first batches of loads
-          if (!COEFF) {
+          if (BULK && !COEFF) {
+            bool zeroed = false;                                       // the cells are zeroed behind the first bulk copies
             __syncwarp();                                              // the ring (stage + scf) was read by other lanes in B4 of the previous piece
 #pragma unroll
             for (int str = 0; str < (NONDIR ? 2 : 1); ++str) {
               uint32_t* dst = str ? DR : D;
-              piece_entries_async(a.T.ment, moSpan + MO_STRIDE * str, mBase, nMtS[str], lo, hi, lane, (uint2*)stage, zeroed, zeroCells, [&] (uint32_t pos, const uint2& en) {
+              piece_entries_bulk(a.T.ment, moSpan + MO_STRIDE * str, mBase, nMtS[str], lo, hi, lane, (const uint2*)stage, ringAddr, barAddr, bulkSeq, zeroed, zeroCells,
+                                 [&] (uint32_t pos, const uint2& en) {
                 const uint32_t u = pos - cell0;
                 if ((en.x != 0) & (u < W) && !(a.hasControl && isCtl[en.y >> SPAN_SHIFT])) { atomicAdd(&dst[u], en.x); tot += en.x; }
               });
             }
             if (!zeroed) zeroCells();
           } else
-#endif
           {
           zeroCells();
 #pragma unroll
@@ -906,7 +972,8 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : MINB) span_kernel (con
           }
         }
         spanRuns += nRuns;
-      }
+      } while (0);
+      pb = pbNext; nb = nbNext; havePiece = haveNext;
     }
     if (lane == 0) a.spanRunCount[work] = spanRuns;
 #if UPB_EXP_PREFETCH
