@@ -262,7 +262,7 @@ typedef struct {
   uint32_t* left;
   uint32_t* len;
   uint32_t* sum;                /* Region::sum() (no controls in strand_shift: the pooled hit sum) */
-  uint8_t* replayed;            /* 1: produced by the left-edge replay (Q2); upb_strand_shift refuses to sweep such a region */
+  uint8_t* replayed;            /* 1: produced by the left-edge replay (Q2): swept over the replay's own score vectors */
 } upb_shift_region_list;
 
 int upb_shift_regions (upb_ctx* ctx, const upb_shift_params* params, upb_shift_region_list* out);
@@ -336,6 +336,36 @@ int upb_last_stage_times (const upb_ctx* ctx, uint32_t cap, const char** names_o
 /* The CUDA stream (cudaStream_t) every kernel and copy of this context is issued on, so that a caller can bracket calls with
  * its own CUDA events (bench.py times the step this way).  No reference counterpart: instrumentation only. */
 void* upb_stream (const upb_ctx* ctx);
+
+/* ---- several GPUs of one box behind one handle ------------------------------------------------------------------------------
+ * The three drivers' loops (src/regions.cpp:304-393, src/strand_shift.cpp:139-259, src/tags_in_regions.cpp:131-199) run on one core
+ * in the reference.  A upb_multi owns one context and one worker thread per GPU and shards them the way SURVEY 8e describes: whole
+ * contigs per GPU for region calling and the shift calibration (no halo crosses a contig), whole samples per GPU for
+ * tags_in_regions.  Results are what the one-GPU entry points return, bit for bit.  The region table is ONE pinned host table
+ * every GPU writes its rows into (upb_call_regions_shared); there is no collective on the path.  bin/regions, bin/strand_shift and
+ * bin/tags_in_regions use it when UPB_GPUS=N is set. */
+typedef struct upb_multi upb_multi;
+int upb_multi_create (int n_gpus, const int* devices /* NULL: 0 .. n_gpus-1 */, upb_multi** out);
+void upb_multi_destroy (upb_multi* m);
+const char* upb_multi_last_error (const upb_multi* m);
+int upb_multi_gpus (const upb_multi* m);
+upb_ctx* upb_multi_context (upb_multi* m, int rank);                  /* statistics, profiling */
+int upb_multi_set_contigs (upb_multi* m, uint32_t n_contigs, const uint32_t* sizes);
+int upb_multi_owner (const upb_multi* m, uint32_t* owner_out);        /* [n_contigs] rank that holds each contig */
+/* Contig-sharded load: the arrays describe every contig (as for upb_load_tags_async; src->keep_contig is ignored), each GPU takes
+ * the segments of the contigs it owns.  Asynchronous like upb_load_tags_async; upb_multi_load_wait reports load errors. */
+int upb_multi_load_tags (upb_multi* m, const upb_tag_source* src);
+int upb_multi_load_wait (upb_multi* m);
+/* upb_call_regions over all GPUs.  `out` points into the handle's shared table: valid until the next call on the handle,
+ * upb_free_region_table on it is a no-op. */
+int upb_multi_call_regions (upb_multi* m, const upb_region_params* params, upb_region_table* out);
+int upb_multi_profile_contig (upb_multi* m, const upb_region_params* params, int buffer, uint32_t contig, upb_profile* out);
+/* upb_strand_shift over all GPUs (after upb_multi_load_tags): the report of the one-GPU call; free with upb_free_shift_report. */
+int upb_multi_strand_shift (upb_multi* m, const upb_shift_params* params, upb_shift_report* out);
+/* Sample-sharded load (plain form) and upb_count_tags_in_regions over all GPUs: counts_out is [n_regions * n_samples]. */
+int upb_multi_load_tags_by_sample (upb_multi* m, uint32_t n_samples, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt);
+int upb_multi_count_tags_in_regions (upb_multi* m, int directional, uint32_t extension, uint64_t n_regions,
+                                     const upb_region_key* regions, uint32_t* counts_out);
 
 #ifdef __cplusplus
 }

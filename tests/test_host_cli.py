@@ -28,8 +28,9 @@ def _built():
     assert have_bins()
 
 
-def run(tool_dir, tool, args, cwd, check=None):
-    p = subprocess.run([os.path.join(tool_dir, tool)] + list(args), cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+def run(tool_dir, tool, args, cwd, check=None, env=None):
+    p = subprocess.run([os.path.join(tool_dir, tool)] + list(args), cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                       env=None if env is None else dict(os.environ, **env))
     if check is not None:
         assert p.returncode == check, (tool, args, p.returncode, p.stderr.decode()[-2000:])
     return p
@@ -173,7 +174,7 @@ def test_wiggle_reader_parallel_equals_sequential(tmp_path):
 needs_ref = pytest.mark.skipif(not refutil.have_ref(), reason="compiled reference (oracle/_ref) not present")
 
 
-def both(tmp_path, tool, args, outputs, rc=0):
+def both(tmp_path, tool, args, outputs, rc=0, new_env=None):
     """Run the reference's and our binary with identical argv in sibling directories that hold the same inputs.
 
     The reference binary is not perfectly repeatable: on the B200 box its `regions -D -s 80,90,100,-5 -e 2,4` run once (1 of ~10 runs
@@ -186,7 +187,7 @@ def both(tmp_path, tool, args, outputs, rc=0):
         for o in outputs:
             if (cwd / o).exists():
                 (cwd / o).unlink()
-        p = run(d, tool, args, str(cwd))
+        p = run(d, tool, args, str(cwd), env=new_env if which == "new" else None)
         return (p.returncode, p.stderr.decode(), {o: (cwd / o).read_bytes() if (cwd / o).exists() else None for o in outputs}, p.stdout)
     res = [once("ref", REF_DIR), once("new", BIN)]
     if res[0] != res[1]:
@@ -286,6 +287,32 @@ def test_cli_left_edge_profile_shift_and_inherited_window(tmp_path):
     dl = refutil.long_start_region_data()
     fl = stage(tmp_path, dl, prefix="l", sub="long")
     both(tmp_path, "strand_shift", ["-o", "shift.txt", "-c", fl["contigs"], "-g", "30", "-r", "4", "-u", "0.05", "-t", "5"] + fl["wigs"], ["shift.txt"])
+
+
+def _n_gpus():
+    try:
+        from unipeak_b200.capi import lib
+        return lib().upb_device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs")
+def test_cli_with_two_gpus_writes_the_same_bytes(tmp_path):
+    # UPB_GPUS=2: contigs spread over two GPUs (regions, strand_shift), samples over two GPUs (tags_in_regions); files and stderr
+    # must still be byte-identical to the reference binaries'
+    env = {"UPB_GPUS": "2"}
+    d = make_synthetic([200000, 100000, 50000], 3, 20000, directional=True, seed=1, peak_spacing=5000, contig_names=["chrA", "chrB", "chrC"])
+    f = stage(tmp_path, d)
+    both(tmp_path, "regions", ["-f", "-o", "r.txt", "-w", "p.wig", "-c", f["contigs"]] + f["wigs"], ["r.txt", "p.wig"], new_env=env)
+    both(tmp_path, "regions", ["-D", "-y", "-q", "-o", "rd.txt", "-c", f["contigs"], "-e", "2"] + f["wigs"], ["rd.txt"], new_env=env)
+    both(tmp_path, "regions", ["-q", "-o", "plain.txt", "-c", f["contigs"]] + f["wigs"][:1], ["plain.txt"], new_env=env)
+    both(tmp_path, "tags_in_regions", ["-f", "plain.txt", "-o", "more.txt", "-c", f["contigs"]] + f["wigs"][1:], ["more.txt"], new_env=env)
+    ds = make_synthetic([1500000, 900000, 600000], 1, 400000, directional=False, seed=11, peak_spacing=10000, contig_names=["chrA", "chrB", "chrC"])
+    fs = stage(tmp_path, ds, prefix="n", sub="shift")
+    both(tmp_path, "strand_shift", ["-o", "shift.txt", "-c", fs["contigs"], "-g", "30", "-r", "8", "-u", "0.1"] + fs["wigs"], ["shift.txt"], new_env=env)
 
 
 @pytest.mark.gpu

@@ -83,6 +83,9 @@ EXPORTS = [
     "upb_shared_table_bytes", "upb_shared_table_init", "upb_call_regions_shared", "upb_set_profiling", "upb_last_stage_times", "upb_stream", "upb_host_register", "upb_host_unregister", "upb_load_tags_async", "upb_load_wait", "upb_reindex", "upb_aggregate_tags", "upb_free_tag_counts",
     "upb_load_tags_packed2", "upb_pack_tags2",
     "upb_shift_regions", "upb_free_shift_regions", "upb_shift_examine_order", "upb_shift_sweep", "upb_shift_mode",
+    "upb_multi_create", "upb_multi_destroy", "upb_multi_last_error", "upb_multi_gpus", "upb_multi_context", "upb_multi_set_contigs", "upb_multi_owner",
+    "upb_multi_load_tags", "upb_multi_load_wait", "upb_multi_call_regions", "upb_multi_profile_contig", "upb_multi_strand_shift",
+    "upb_multi_load_tags_by_sample", "upb_multi_count_tags_in_regions",
 ]
 
 
@@ -190,6 +193,23 @@ def lib():
         L.upb_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.upb_last_stage_times.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
         L.upb_reference_order.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(RegionTable), C.c_void_p]
+        L.upb_multi_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.upb_multi_destroy.argtypes = [C.c_void_p]
+        L.upb_multi_destroy.restype = None
+        L.upb_multi_last_error.argtypes = [C.c_void_p]
+        L.upb_multi_last_error.restype = C.c_char_p
+        L.upb_multi_gpus.argtypes = [C.c_void_p]
+        L.upb_multi_context.argtypes = [C.c_void_p, C.c_int]
+        L.upb_multi_context.restype = C.c_void_p
+        L.upb_multi_set_contigs.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        L.upb_multi_owner.argtypes = [C.c_void_p, C.c_void_p]
+        L.upb_multi_load_tags.argtypes = [C.c_void_p, C.POINTER(TagSource)]
+        L.upb_multi_load_wait.argtypes = [C.c_void_p]
+        L.upb_multi_call_regions.argtypes = [C.c_void_p, C.POINTER(RegionParams), C.POINTER(RegionTable)]
+        L.upb_multi_profile_contig.argtypes = [C.c_void_p, C.POINTER(RegionParams), C.c_int, C.c_uint32, C.POINTER(Profile)]
+        L.upb_multi_strand_shift.argtypes = [C.c_void_p, C.POINTER(ShiftParams), C.POINTER(ShiftReport)]
+        L.upb_multi_load_tags_by_sample.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.upb_multi_count_tags_in_regions.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint64, C.POINTER(RegionKey), C.c_void_p]
         _lib = L
     return _lib
 
@@ -397,6 +417,30 @@ class Context:
                     tags_in_regions=v(t.tags_in_regions, n, np.uint64), unit_candidates=v(t.unit_candidates, 2 * n_contigs, np.uint64),
                     unit_last_tag=v(t.unit_last_tag, 2 * n_contigs, np.uint32), unit_rows=v(t.unit_rows, 2 * n_contigs, np.uint64))
 
+    @staticmethod
+    def _table_dict(t, n_contigs, want_rows=True) -> Dict:
+        R = int(t.n_rows)
+        cols = {k: np.array(v, copy=True) for k, v in Context._views(t, n_contigs).items()}
+        rows, dropped = [], []
+        for i in range(R if want_rows else 0):
+            row = dict(forward_label=int(cols["forward_label"][i]), buffer=int(cols["buffer"][i]), contig=int(cols["contig"][i]),
+                       left=int(cols["left"][i]), len=int(cols["len"][i]), peak=int(cols["peak"][i]),
+                       peak_score=float(cols["peak_score"][i]), kurtosis=float(cols["kurtosis"][i]), corr=float(cols["corr"][i]),
+                       counts=[int(x) for x in cols["counts"][i]])
+            (dropped if cols["dropped"][i] else rows).append(row)
+        return dict(rows=rows, dropped=dropped, n_passed=int(t.n_passed), n_rejected=int(t.n_rejected),
+                    tags_in_regions=[int(x) for x in cols["tags_in_regions"]], columns=cols,
+                    unit_candidates=cols["unit_candidates"], unit_last_tag=cols["unit_last_tag"])
+
+    @staticmethod
+    def _shift_dict(rc, r) -> Dict:
+        return dict(status=rc, n_regions_found=int(r.n_regions_found), n_regions_tested=int(r.n_regions_tested),
+                    n_tags_in_regions=int(r.n_tags_in_regions), best_shift=int(r.best_shift),
+                    shift_freq=[int(r.shift_freq[i]) for i in range(int(r.n_freq))] if r.shift_freq else [],
+                    tested=[dict(contig=int(r.tested_contig[i]), left=int(r.tested_left[i]), len=int(r.tested_len[i]),
+                                 best_shift=int(r.tested_best_shift[i]), best_corr=float(r.tested_best_corr[i]))
+                            for i in range(int(r.n_regions_tested))])
+
     def call_regions_view(self, *, bandwidth=50, region_threshold=25.0, kurtosis_threshold=50.0, corr_threshold=-1.0, hit_threshold=10.0,
                           directional=True, control: Optional[Sequence[int]] = None, coeffs: Optional[Sequence[float]] = None,
                           background: float, reference_order=True, **_ignored) -> "RegionView":
@@ -425,19 +469,7 @@ class Context:
         t = RegionTable()
         self._check(self._lib.upb_call_regions(self._h, C.byref(p), C.byref(t)))
         try:
-            R, n = int(t.n_rows), int(t.n_samples)
-            cols = {k: np.array(v, copy=True) for k, v in self._views(t, self.n_contigs).items()}
-            want_rows = rows
-            rows, dropped = [], []
-            for i in range(R if want_rows else 0):
-                row = dict(forward_label=int(cols["forward_label"][i]), buffer=int(cols["buffer"][i]), contig=int(cols["contig"][i]),
-                           left=int(cols["left"][i]), len=int(cols["len"][i]), peak=int(cols["peak"][i]),
-                           peak_score=float(cols["peak_score"][i]), kurtosis=float(cols["kurtosis"][i]), corr=float(cols["corr"][i]),
-                           counts=[int(x) for x in cols["counts"][i]])
-                (dropped if cols["dropped"][i] else rows).append(row)
-            return dict(rows=rows, dropped=dropped, n_passed=int(t.n_passed), n_rejected=int(t.n_rejected),
-                        tags_in_regions=[int(x) for x in cols["tags_in_regions"]], columns=cols,
-                        unit_candidates=cols["unit_candidates"], unit_last_tag=cols["unit_last_tag"])
+            return self._table_dict(t, self.n_contigs, rows)
         finally:
             self._lib.upb_free_region_table(C.byref(t))
 
@@ -460,12 +492,7 @@ class Context:
         r = ShiftReport()
         rc = self._lib.upb_strand_shift(self._h, C.byref(p), C.byref(r))
         try:
-            out = dict(status=rc, n_regions_found=int(r.n_regions_found), n_regions_tested=int(r.n_regions_tested),
-                       n_tags_in_regions=int(r.n_tags_in_regions), best_shift=int(r.best_shift),
-                       shift_freq=[int(r.shift_freq[i]) for i in range(int(r.n_freq))] if r.shift_freq else [],
-                       tested=[dict(contig=int(r.tested_contig[i]), left=int(r.tested_left[i]), len=int(r.tested_len[i]),
-                                    best_shift=int(r.tested_best_shift[i]), best_corr=float(r.tested_best_corr[i]))
-                               for i in range(int(r.n_regions_tested))])
+            out = self._shift_dict(rc, r)
         finally:
             self._lib.upb_free_shift_report(C.byref(r))
         if rc and rc != -8:
@@ -551,3 +578,111 @@ class Context:
                     kde_hot_tiles=int(s.kde_hot_tiles), n_candidates=int(s.n_candidates), n_entries=int(s.n_entries),
                     hot_blocks=int(s.hot_blocks), exact_evals=int(s.exact_evals), spans_with_tags=int(s.spans_with_tags),
                     n_stitched=int(s.n_stitched), warm_spans=int(s.warm_spans), ms_call=float(s.ms_call))
+
+
+class MultiContext:
+    """upb_multi: the GPUs of one box behind one handle (one context and one worker thread per GPU inside the library).  Same calls and
+    same results as Context; contigs are spread over the GPUs for regions / strand_shift, samples for tags_in_regions."""
+
+    def __init__(self, n_gpus: int, devices: Optional[Sequence[int]] = None):
+        self._lib = lib()
+        self._h = C.c_void_p()
+        dev = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
+        rc = self._lib.upb_multi_create(n_gpus, None if dev is None else dev.ctypes.data, C.byref(self._h))
+        if rc:
+            raise UpbError(rc, "upb_multi_create(%d) failed" % n_gpus)
+        self.n_gpus, self.n_contigs, self.n_samples = n_gpus, 0, 0
+        self._hold = None
+
+    def close(self):
+        if self._h:
+            self._lib.upb_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc:
+            raise UpbError(rc, self._lib.upb_multi_last_error(self._h).decode())
+
+    def set_contigs(self, sizes: Sequence[int]):
+        arr = np.ascontiguousarray(sizes, dtype=np.uint32)
+        self._check(self._lib.upb_multi_set_contigs(self._h, arr.shape[0], arr.ctypes.data))
+        self.n_contigs = int(arr.shape[0])
+
+    def owner(self) -> np.ndarray:
+        out = np.zeros(self.n_contigs, dtype=np.uint32)
+        self._check(self._lib.upb_multi_owner(self._h, out.ctypes.data))
+        return out
+
+    def load(self, data, packed: bool = False) -> None:
+        self.set_contigs(data.contig_sizes)
+        off = np.ascontiguousarray(data.off, dtype=np.uint64)
+        if packed:
+            words, exc = pack_tags2(data.n_samples, self.n_contigs, off, data.pos, data.cnt)
+            self._hold = (off, words, exc)
+            src = TagSource(data.n_samples, off.ctypes.data, None, None, words.ctypes.data, exc.shape[0], exc.ctypes.data, None, 1)
+        else:
+            pos = np.ascontiguousarray(data.pos, dtype=np.uint32); cnt = np.ascontiguousarray(data.cnt, dtype=np.uint32)
+            self._hold = (off, pos, cnt)
+            src = TagSource(data.n_samples, off.ctypes.data, pos.ctypes.data, cnt.ctypes.data, None, 0, None, None, 1)
+        self._check(self._lib.upb_multi_load_tags(self._h, C.byref(src)))
+        self._check(self._lib.upb_multi_load_wait(self._h))
+        self._hold = None
+        self.n_samples = data.n_samples
+
+    def load_by_sample(self, data) -> None:
+        self.set_contigs(data.contig_sizes)
+        off = np.ascontiguousarray(data.off, dtype=np.uint64)
+        pos = np.ascontiguousarray(data.pos, dtype=np.uint32); cnt = np.ascontiguousarray(data.cnt, dtype=np.uint32)
+        self._check(self._lib.upb_multi_load_tags_by_sample(self._h, data.n_samples, off.ctypes.data, pos.ctypes.data, cnt.ctypes.data))
+        self.n_samples = data.n_samples
+
+    def call_regions(self, *, bandwidth=50, region_threshold=25.0, kurtosis_threshold=50.0, corr_threshold=-1.0, hit_threshold=10.0,
+                     directional=True, control: Optional[Sequence[int]] = None, coeffs: Optional[Sequence[float]] = None,
+                     background: float, reference_order=True, rows=True, **_ignored) -> Dict:
+        ctrl = np.ascontiguousarray(control if control is not None else np.zeros(self.n_samples, np.uint8), dtype=np.uint8)
+        cf = np.ascontiguousarray(coeffs if coeffs is not None else [], dtype=np.float64)
+        p = RegionParams(bandwidth, region_threshold, kurtosis_threshold, corr_threshold, hit_threshold, 1 if directional else 0,
+                         ctrl.ctypes.data_as(C.POINTER(C.c_uint8)), cf.shape[0], cf.ctypes.data_as(C.POINTER(C.c_double)),
+                         background, 1 if reference_order else 0)
+        t = RegionTable()
+        self._check(self._lib.upb_multi_call_regions(self._h, C.byref(p), C.byref(t)))
+        return Context._table_dict(t, self.n_contigs, rows)
+
+    def profile_contig(self, buffer: int, contig: int, *, bandwidth=50, region_threshold=25.0, directional=True,
+                       control: Optional[Sequence[int]] = None, background: float, **_ignored):
+        ctrl = np.ascontiguousarray(control if control is not None else np.zeros(self.n_samples, np.uint8), dtype=np.uint8)
+        p = RegionParams(bandwidth, region_threshold, 0.0, -1.0, 0.0, 1 if directional else 0, ctrl.ctypes.data_as(C.POINTER(C.c_uint8)),
+                         0, None, background, 0)
+        pr = Profile()
+        self._check(self._lib.upb_multi_profile_contig(self._h, C.byref(p), buffer, contig, C.byref(pr)))
+        try:
+            return _np(pr.pos, int(pr.n), np.uint32), _np(pr.score, int(pr.n), np.float64)
+        finally:
+            self._lib.upb_free_profile(C.byref(pr))
+
+    def strand_shift(self, *, bandwidth=50, region_threshold=25.0, kurtosis_threshold=50.0, corr_threshold=0.3, hit_threshold=10,
+                     min_shift=25, max_shift=150, n_regions_to_test=1000, background: float) -> Dict:
+        p = ShiftParams(bandwidth, region_threshold, kurtosis_threshold, corr_threshold, hit_threshold, min_shift, max_shift,
+                        n_regions_to_test, background)
+        r = ShiftReport()
+        rc = self._lib.upb_multi_strand_shift(self._h, C.byref(p), C.byref(r))
+        try:
+            out = Context._shift_dict(rc, r)
+        finally:
+            self._lib.upb_free_shift_report(C.byref(r))
+        if rc and rc != -8:
+            self._check(rc)
+        return out
+
+    def count_tags_in_regions(self, keys: Sequence[Sequence[int]], *, directional=True, extension=0) -> np.ndarray:
+        keys = np.ascontiguousarray(keys, dtype=np.uint32).reshape(-1, 3)
+        out = np.zeros(max(1, keys.shape[0] * self.n_samples), dtype=np.uint32)
+        self._check(self._lib.upb_multi_count_tags_in_regions(self._h, 1 if directional else 0, extension, keys.shape[0],
+                                                              C.cast(keys.ctypes.data, C.POINTER(RegionKey)), out.ctypes.data))
+        return out[:keys.shape[0] * self.n_samples].reshape(keys.shape[0], self.n_samples)

@@ -480,7 +480,16 @@ static int load_enqueue (upb_ctx* ctx, const upb_tag_source* src, bool resident)
   CU(cudaMemcpyAsync(ctx->d_grpTile.p, grpTile.data(), grpTile.size() * 4, cudaMemcpyHostToDevice, ls));
   CU(cudaMemsetAsync(ctx->d_loadFlags.p, 0, 256, ls));
   CU(cudaMemsetAsync(ctx->d_mtCount.p, 0, ((size_t)nMtTotal + 1) * 4, ls));
-  CU(cudaMemsetAsync(ctx->d_mtOff.p, 0, ((size_t)nMtTotal + 2) * 8, ls));   // ranges of contigs this context does not keep stay empty
+  CU(cudaMemsetAsync(ctx->d_mtOff.p, 0, ((size_t)nMtTotal + 2) * 8, ls));
+  // ranges of contigs this context does not keep stay empty, but mtOff stays a prefix array over ALL mini-tiles (mtOff[m + 1] - mtOff[m] is a count
+  // for every m: mt_control_kernel walks them all): a range that is not kept repeats the number of entries before it
+  { uint64_t before = 0;
+    for (size_t dc = 0; dc < 2 * (size_t)C; ++dc) {
+      const uint32_t m0 = ctx->mtBase[dc], m1 = ctx->mtBase[dc + 1];
+      if (!kept[dc % C] && m1 > m0) fill_u64_kernel<<<(m1 - m0 + 255) / 256, 256, 0, ls>>>(ctx->d_mtOff.as<unsigned long long>() + m0, m1 - m0, before);
+      before += perDC[dc];
+    }
+    fill_u64_kernel<<<1, 32, 0, ls>>>(ctx->d_mtOff.as<unsigned long long>() + nMtTotal, 2, before); }
   CU(cudaStreamSynchronize(ls));                                       // the host vectors above go out of scope; nothing large has been queued yet
   CU(cudaEventRecord(ctx->copyEvs[ctx->groups.size()], cs));
   ctx->loadCopied = !resident;
@@ -2011,6 +2020,26 @@ extern "C" int upb_call_regions_shared (upb_ctx* ctx, const upb_region_params* p
   }
   for (size_t k = 0; k < 2 * (size_t)C; ++k) R += out->unit_rows[k];
   if (R > t->row_capacity) return fail(ctx, UPB_ERR_NOMEM, "shared table: more rows than the table has room for");
+  // A contig whose every tag lies within `bandwidth` of its start hands its window to the next contig of the buffer (SURVEY Q2,
+  // upb_edge.cuh "Chains"): a rank replays that only if it holds both contigs
+  for (uint32_t b = 0; b < (p->directional ? 2u : 1u); ++b) {
+    int leakRank = -1;
+    for (uint32_t c = 0; c < C; ++c) {
+      uint32_t last = 0; int rankOf = -1;
+      for (uint32_t rk = 0; rk < t->world; ++rk) {
+        const unsigned char* rb = hb + L.oRank + (size_t)rk * L.rankBytes;
+        const uint32_t* lp = (const uint32_t*)((const unsigned long long*)rb + 1 + 2 * (size_t)C + n) + 2 * (size_t)C + (size_t)n * 2 * C;
+        for (uint32_t s = 0; s < n; ++s) for (uint32_t d = (p->directional ? b : 0u); d <= (p->directional ? b : 1u); ++d) {
+          const uint32_t v = lp[((size_t)s * 2 + d) * C + c];
+          if (v) { last = std::max(last, v); rankOf = (int)rk; }
+        }
+      }
+      if (rankOf < 0) continue;
+      if (leakRank >= 0 && leakRank != rankOf)
+        return fail(ctx, UPB_ERR_UNSUPPORTED, "every tag of a contig lies within `bandwidth` of its start and the next contig of that buffer is loaded on another rank: the reference's window travels between them (SURVEY Q2); load both on one rank");
+      leakRank = last <= p->bandwidth ? rankOf : -1;
+    }
+  }
   out->n_rows = R; out->n_passed = R; out->n_rejected = nCand - R;
   { uint64_t firstRev = 0; for (size_t k = 0; k < C; ++k) firstRev += out->unit_rows[k];
     if (!p->directional) firstRev = R;

@@ -199,5 +199,6 @@ __global__ void seg_ends_kernel (const uint32_t* __restrict__ pos, const uint64_
 }
 
 __global__ void set_u64_kernel (unsigned long long* p, unsigned long long v) { if (blockIdx.x == 0 && threadIdx.x == 0) *p = v; }
+__global__ void fill_u64_kernel (unsigned long long* p, uint32_t n, unsigned long long v) { const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
 
 }  // namespace upb

@@ -233,10 +233,8 @@ int main (int argc, char* argv[]) {
 
   // the hot path (:304-391), on the device
   fprintf(stderr, "calling enriched regions...\n");
-  upb_ctx* ctx = nullptr;
-  int rc = upb_create(0, &ctx);
-  if (rc) die_upb(nullptr, rc);
-  if ((rc = upb_set_contigs(ctx, C, contigs.sizes.data()))) die_upb(ctx, rc);
+  Device dev;                                                        // one GPU, or UPB_GPUS=N of them with the contigs spread over them
+  dev.setContigs(C, contigs.sizes.data());
   // which strand/contig units does the merge loop read in pass 1?  (single sample whose '-' track starts at or after its
   // last '+' contig: src/regions.cpp:341 consumes it there) — needed for the progress lines and the profile order
   bool early = false;
@@ -249,7 +247,7 @@ int main (int argc, char* argv[]) {
     }
   }
   TagLoader loader;                                                  // 2-byte host form, queued asynchronously: the call below starts on what has arrived
-  if ((rc = loader.start(ctx, samples, C, directional))) die_upb(ctx, rc);
+  dev.load(loader, samples, C, directional, false);
   upb_region_params prm;
   memset(&prm, 0, sizeof prm);
   prm.bandwidth = bandwidth;
@@ -264,7 +262,7 @@ int main (int argc, char* argv[]) {
   prm.background = background;
   prm.reference_order = 1;
   upb_region_table tab;
-  if ((rc = upb_call_regions(ctx, &prm, &tab))) die_upb(ctx, rc);
+  dev.callRegions(&prm, &tab);
 
   // rows (FormatOutStream::write(Region), misc/format.cpp:1141-1162); the rows the reference's last flush loses stay lost
   {
@@ -310,8 +308,7 @@ int main (int argc, char* argv[]) {
   if (profile) {
     auto unit = [&] (int buffer, uint32_t c, int part /* 0 all, 1 before the flush, 2 the flush */) {
       upb_profile pf;
-      const int r = upb_profile_contig(ctx, &prm, buffer, c, &pf);
-      if (r) die_upb(ctx, r);
+      dev.profileContig(&prm, buffer, c, &pf);
       uint64_t lo = 0, hi = pf.n;
       if (part) {
         // add() has processed every position < lastTag - bw when flushContig() takes over (misc/peakcall.cpp:172-184)
@@ -342,8 +339,7 @@ int main (int argc, char* argv[]) {
     const unsigned long long t = tab.tags_in_regions[i];
     fprintf(stderr, "  %s: %llu (%s%%)\n", s.name.c_str(), t, fmt_fixed(100 * (double)t / (double)s.confidentTags, 1).c_str());
   }
-  upb_free_region_table(&tab);
-  upb_destroy(ctx);
+  if (dev.gpus() == 1) upb_free_region_table(&tab);                  // (several GPUs: the table is the handle's)
   fprintf(stderr, "\nAll done!\n\n");
   return 0;
 }

@@ -62,12 +62,10 @@ int main (int argc, char* argv[]) {
 
   fprintf(stderr, "calling enriched regions for shift calibration... ");
   fflush(stderr);
-  upb_ctx* ctx = nullptr;
-  int rc = upb_create(0, &ctx);
-  if (rc) die_upb(nullptr, rc);
-  if ((rc = upb_set_contigs(ctx, C, contigs.sizes.data()))) die_upb(ctx, rc);
+  Device dev;                                                        // one GPU, or UPB_GPUS=N of them with the contigs spread over them
+  dev.setContigs(C, contigs.sizes.data());
   TagLoader loader;
-  if ((rc = loader.start(ctx, samples, C, false)) || (rc = loader.wait(ctx))) die_upb(ctx, rc);
+  dev.load(loader, samples, C, false, true);
   upb_shift_params prm;
   memset(&prm, 0, sizeof prm);
   prm.bandwidth = bandwidth;
@@ -80,8 +78,7 @@ int main (int argc, char* argv[]) {
   prm.n_regions_to_test = nRegionsToTest;
   prm.background = background;
   upb_shift_report rep;
-  rc = upb_strand_shift(ctx, &prm, &rep);
-  if (rc && rc != UPB_ERR_NO_REGIONS) { fprintf(stderr, "\n"); die_upb(ctx, rc); }
+  const int rc = dev.strandShift(&prm, &rep);
   fprintf(stderr, "%llu found\n", (unsigned long long)rep.n_regions_found);
   if (rc == UPB_ERR_NO_REGIONS || rep.n_regions_tested == 0) {      // :231-233
     fprintf(stderr, "error: no regions qualified with given settings\n\n");
@@ -127,7 +124,6 @@ int main (int argc, char* argv[]) {
     out.close();
   }
   upb_free_shift_report(&rep);
-  upb_destroy(ctx);
   fprintf(stderr, "done!\n\n");
   return 0;
 }

@@ -131,14 +131,10 @@ int main (int argc, char* argv[]) {
 
   std::vector<uint32_t> counts(keys.size() * n + 1, 0);
   if (!keys.empty()) {
-    upb_ctx* ctx = nullptr;
-    int rc = upb_create(0, &ctx);
-    if (rc) die_upb(nullptr, rc);
-    if ((rc = upb_set_contigs(ctx, C, contigs.sizes.data()))) die_upb(ctx, rc);
-    TagLoader loader;
-    if ((rc = loader.start(ctx, samples, C, directional)) || (rc = loader.wait(ctx))) die_upb(ctx, rc);
-    if ((rc = upb_count_tags_in_regions(ctx, directional ? 1 : 0, extension, keys.size(), keys.data(), counts.data()))) die_upb(ctx, rc);
-    upb_destroy(ctx);
+    Device dev;                                                      // one GPU, or UPB_GPUS=N of them with the samples spread over them
+    dev.setContigs(C, contigs.sizes.data());
+    dev.loadBySample(samples, C, directional);
+    dev.countTagsInRegions(directional ? 1 : 0, extension, keys.size(), keys.data(), counts.data());
   }
   std::vector<uint64_t> tagsInRegions(n, 0);
   {

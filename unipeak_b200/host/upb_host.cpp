@@ -918,7 +918,7 @@ static void pack_segment (const uint32_t* pos, const uint32_t* cnt, size_t n, ui
 
 TagLoader::~TagLoader () { if (words_) { if (wordsPinned_) upb_host_free(words_); else free(words_); } }
 
-int TagLoader::start (upb_ctx* ctx, const std::vector<Sample>& samples, uint32_t C, bool directionalHint) {
+void TagLoader::encode (const std::vector<Sample>& samples, uint32_t C, bool directionalHint, upb_tag_source* srcOut) {
   const size_t n = samples.size();
   off_.assign(n * 2 * ((size_t)C + 1), 0);
   uint64_t run = 0;
@@ -977,7 +977,80 @@ int TagLoader::start (upb_ctx* ctx, const std::vector<Sample>& samples, uint32_t
     src.pos = flat_.pos; src.cnt = flat_.cnt;
   }
   packSeconds_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  *srcOut = src;
+}
+
+int TagLoader::start (upb_ctx* ctx, const std::vector<Sample>& samples, uint32_t C, bool directionalHint) {
+  upb_tag_source src;
+  encode(samples, C, directionalHint, &src);
   return upb_load_tags_async(ctx, &src);
+}
+
+int TagLoader::start (upb_multi* multi, const std::vector<Sample>& samples, uint32_t C, bool directionalHint) {
+  upb_tag_source src;
+  encode(samples, C, directionalHint, &src);
+  return upb_multi_load_tags(multi, &src);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Device: one GPU, or UPB_GPUS=N of them
+// ---------------------------------------------------------------------------------------------------------------------------
+Device::Device () {
+  int want = 1;
+  if (const char* e = getenv("UPB_GPUS")) want = atoi(e);
+  if (want > 1) {
+    const int have = upb_device_count();
+    if (want > have) die("UPB_GPUS=" + std::to_string(want) + " but only " + std::to_string(have) + " CUDA device(s) are visible");
+    const int rc = upb_multi_create(want, nullptr, &multi_);
+    if (rc) die_upb(nullptr, rc);
+  } else {
+    const int rc = upb_create(0, &ctx_);
+    if (rc) die_upb(nullptr, rc);
+  }
+}
+Device::~Device () { if (multi_) upb_multi_destroy(multi_); if (ctx_) upb_destroy(ctx_); }
+void Device::fail (int rc) {
+  if (!multi_) die_upb(ctx_, rc);
+  const char* m = upb_multi_last_error(multi_);
+  die(std::string((m && *m) ? m : "device call failed") + " (unipeak_b200 error " + std::to_string(rc) + ")");
+}
+void Device::setContigs (uint32_t C, const uint32_t* sizes) {
+  const int rc = multi_ ? upb_multi_set_contigs(multi_, C, sizes) : upb_set_contigs(ctx_, C, sizes);
+  if (rc) fail(rc);
+}
+void Device::load (TagLoader& loader, const std::vector<Sample>& samples, uint32_t C, bool directionalHint, bool wait) {
+  int rc = multi_ ? loader.start(multi_, samples, C, directionalHint) : loader.start(ctx_, samples, C, directionalHint);
+  if (!rc && wait) rc = multi_ ? upb_multi_load_wait(multi_) : upb_load_wait(ctx_);
+  if (rc) fail(rc);
+}
+void Device::loadBySample (const std::vector<Sample>& samples, uint32_t C, bool directionalHint) {
+  int rc;
+  if (multi_) {
+    flatten(samples, C, &flat_);
+    rc = upb_multi_load_tags_by_sample(multi_, (uint32_t)samples.size(), flat_.off.data(), flat_.pos, flat_.cnt);
+  } else {
+    rc = sampleLoader_.start(ctx_, samples, C, directionalHint);
+    if (!rc) rc = upb_load_wait(ctx_);
+  }
+  if (rc) fail(rc);
+}
+void Device::callRegions (const upb_region_params* p, upb_region_table* out) {
+  const int rc = multi_ ? upb_multi_call_regions(multi_, p, out) : upb_call_regions(ctx_, p, out);
+  if (rc) fail(rc);
+}
+void Device::profileContig (const upb_region_params* p, int buffer, uint32_t contig, upb_profile* out) {
+  const int rc = multi_ ? upb_multi_profile_contig(multi_, p, buffer, contig, out) : upb_profile_contig(ctx_, p, buffer, contig, out);
+  if (rc) fail(rc);
+}
+int Device::strandShift (const upb_shift_params* p, upb_shift_report* out) {
+  const int rc = multi_ ? upb_multi_strand_shift(multi_, p, out) : upb_strand_shift(ctx_, p, out);
+  if (rc && rc != UPB_ERR_NO_REGIONS) { fprintf(stderr, "\n"); fail(rc); }
+  return rc;
+}
+void Device::countTagsInRegions (int directional, uint32_t extension, uint64_t nRegions, const upb_region_key* regions, uint32_t* countsOut) {
+  const int rc = multi_ ? upb_multi_count_tags_in_regions(multi_, directional, extension, nRegions, regions, countsOut)
+                        : upb_count_tags_in_regions(ctx_, directional, extension, nRegions, regions, countsOut);
+  if (rc) fail(rc);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------

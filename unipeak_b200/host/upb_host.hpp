@@ -109,6 +109,7 @@ class TagLoader {
   TagLoader () {}
   ~TagLoader ();
   int start (upb_ctx* ctx, const std::vector<Sample>& samples, uint32_t nContigs, bool directionalHint);
+  int start (upb_multi* multi, const std::vector<Sample>& samples, uint32_t nContigs, bool directionalHint);   // contig-sharded over the GPUs of the handle
   int wait (upb_ctx* ctx) { return upb_load_wait(ctx); }
   bool packed () const { return words_ != nullptr; }
   uint64_t entries () const { return n_; }
@@ -116,6 +117,7 @@ class TagLoader {
   double packSeconds () const { return packSeconds_; }
  private:
   TagLoader (const TagLoader&);
+  void encode (const std::vector<Sample>& samples, uint32_t nContigs, bool directionalHint, upb_tag_source* src);
   std::vector<uint64_t> off_;
   uint16_t* words_ = nullptr; bool wordsPinned_ = false;
   std::vector<upb_packed_exception> exc_;
@@ -147,5 +149,29 @@ class Out {
 
 [[noreturn]] void die (const std::string& msg);                    // "error: <msg>\n\n", exit(1)
 [[noreturn]] void die_upb (upb_ctx* ctx, int code);
+
+// The device side of a driver: one GPU (upb_ctx), or — with UPB_GPUS=N in the environment — N GPUs of the box behind a upb_multi
+// (contigs spread over the GPUs for regions / strand_shift, samples for tags_in_regions).  Output is byte-identical either way.
+// Every method dies with the library's message on failure, as the drivers did with die_upb.
+class Device {
+ public:
+  Device ();
+  ~Device ();
+  int gpus () const { return multi_ ? upb_multi_gpus(multi_) : 1; }
+  void setContigs (uint32_t nContigs, const uint32_t* sizes);
+  void load (TagLoader& loader, const std::vector<Sample>& samples, uint32_t nContigs, bool directionalHint, bool wait);   // by contig
+  void loadBySample (const std::vector<Sample>& samples, uint32_t nContigs, bool directionalHint);                       // tags_in_regions
+  void callRegions (const upb_region_params* p, upb_region_table* out);
+  void profileContig (const upb_region_params* p, int buffer, uint32_t contig, upb_profile* out);
+  int strandShift (const upb_shift_params* p, upb_shift_report* out);       // returns UPB_OK or UPB_ERR_NO_REGIONS
+  void countTagsInRegions (int directional, uint32_t extension, uint64_t nRegions, const upb_region_key* regions, uint32_t* countsOut);
+ private:
+  Device (const Device&);
+  [[noreturn]] void fail (int rc);
+  upb_ctx* ctx_ = nullptr;
+  upb_multi* multi_ = nullptr;
+  TagLoader sampleLoader_;
+  Flat flat_;
+};
 
 }  // namespace upbhost

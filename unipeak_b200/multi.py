@@ -208,9 +208,7 @@ def strand_shift_sharded(ctx, *, dist, rank: int, world: int, device, bandwidth=
                 order, sorted_end = shift_examine_order(rsum.astype(np.uint32), min(R, max(2 * sorted_end, cursor + 1024)))
             i = int(order[cursor])
             if length[i] > 2 * max_shift + 3:                         # :206 large enough to try all shifts
-                if replayed[i]:
-                    raise UpbError(-6, "a region within `bandwidth` of a contig start is long enough for the shift sweep: the reference's left-edge densities (SURVEY Q2) are not emulated there")
-                batch.append(i)
+                batch.append(i)                                       # (a region of the left-edge replay is swept over the replay's own score vectors)
             cursor += 1
         if not batch:
             break
