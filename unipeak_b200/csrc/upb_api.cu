@@ -75,6 +75,7 @@ struct upb_ctx {
   DevBuf d_pos, d_cnt, d_off, d_segStart, d_tidx, d_tidxBase, d_sizes, d_nTilesIdx, d_small;
   DevBuf d_winBase, d_wEnt;                                          // per-sample window index of the scatter pass
   DevBuf d_pk16, d_pkExc, d_segEnds, d_srcStart, d_grpSeg, d_grpTile, d_loadFlags;   // load (upb_pack.cuh)
+  DevBuf d_tileExc;                    // packed load: first exception of every tile of the load group being decoded
   DevBuf d_ment, d_mtOff, d_mtBase, d_mtCount, d_mEff, d_mtW, d_blkW;   // tile-major copy and its zone maps (upb_device.cuh)
   std::vector<uint32_t> mtBase;         // [2*C+1]
   std::map<std::string, DevBuf> scratch;     // grow-only device scratch, by name
@@ -142,10 +143,16 @@ extern "C" int upb_create (int device, upb_ctx** out) {
   cudaDeviceProp prop;
   if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { delete ctx; return fail(nullptr, UPB_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e)); }
   ctx->smCount = prop.multiProcessorCount;
-  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return fail(nullptr, UPB_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
+  // The region pipeline is a chain of ~27 small dependent kernels per group of units; when it runs behind a load (upb_load_tags_async) the
+  // index build of the groups still arriving keeps the device full of blocks, and every link of the chain then queues behind them.  Priority
+  // UPB_PRIO: 0 none, 1 (default) the call stream above the load stream, 2 the other way round
+  int prLo = 0, prHi = 0;
+  cudaDeviceGetStreamPriorityRange(&prLo, &prHi);                     // lowest, highest (numerically smaller = higher)
+  const int mode = getenv("UPB_PRIO") ? atoi(getenv("UPB_PRIO")) : 1;
+  if ((e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, mode == 1 ? prHi : prLo)) != cudaSuccess) { delete ctx; return fail(nullptr, UPB_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
   for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
   cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking);
-  cudaStreamCreateWithFlags(&ctx->loadStream, cudaStreamNonBlocking);
+  cudaStreamCreateWithPriority(&ctx->loadStream, cudaStreamNonBlocking, mode == 2 ? prHi : prLo);
   cudaStreamCreateWithFlags(&ctx->copyStream2, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&ctx->loadDoneEv, cudaEventDisableTiming);
   if ((e = cudaMallocHost((void**)&ctx->h_small, 4096)) != cudaSuccess) { upb_destroy(ctx); return fail(nullptr, UPB_ERR_NOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e)); }
@@ -157,7 +164,7 @@ extern "C" int upb_create (int device, upb_ctx** out) {
 extern "C" void upb_destroy (upb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  DevBuf* all[] = {&ctx->d_winBase, &ctx->d_wEnt, &ctx->d_pk16, &ctx->d_pkExc, &ctx->d_segEnds, &ctx->d_srcStart, &ctx->d_grpSeg, &ctx->d_grpTile, &ctx->d_loadFlags, &ctx->d_mtW, &ctx->d_blkW, &ctx->d_ment, &ctx->d_mtOff, &ctx->d_mtBase, &ctx->d_mtCount, &ctx->d_mEff, &ctx->d_pos, &ctx->d_cnt, &ctx->d_off, &ctx->d_segStart, &ctx->d_tidx, &ctx->d_tidxBase, &ctx->d_sizes,
+  DevBuf* all[] = {&ctx->d_tileExc, &ctx->d_winBase, &ctx->d_wEnt, &ctx->d_pk16, &ctx->d_pkExc, &ctx->d_segEnds, &ctx->d_srcStart, &ctx->d_grpSeg, &ctx->d_grpTile, &ctx->d_loadFlags, &ctx->d_mtW, &ctx->d_blkW, &ctx->d_ment, &ctx->d_mtOff, &ctx->d_mtBase, &ctx->d_mtCount, &ctx->d_mEff, &ctx->d_pos, &ctx->d_cnt, &ctx->d_off, &ctx->d_segStart, &ctx->d_tidx, &ctx->d_tidxBase, &ctx->d_sizes,
     &ctx->d_nTilesIdx, &ctx->d_small};
   for (DevBuf* b : all) release(*b);
   for (auto& kv : ctx->scratch) release(kv.second);
@@ -237,6 +244,7 @@ extern "C" int upb_kernel_taps (uint32_t bandwidth, double sum, double* taps) {
 extern "C" int upb_set_contigs (upb_ctx* ctx, uint32_t n_contigs, const uint32_t* sizes) {
   if (!ctx) return UPB_ERR_BAD_ARG;
   if (n_contigs == 0 || !sizes) return fail(ctx, UPB_ERR_BAD_ARG, "upb_set_contigs: empty contig table");
+  for (uint32_t c = 0; c < n_contigs; ++c) if (sizes[c] == 0) return fail(ctx, UPB_ERR_BAD_ARG, "upb_set_contigs: a contig of size 0 (it cannot hold a tag; the index arithmetic assumes size >= 1)");
   CU(cudaSetDevice(ctx->device));
   ctx->sizes.assign(sizes, sizes + n_contigs);
   ctx->nTilesIdx.resize(n_contigs);
@@ -389,10 +397,14 @@ static int load_enqueue (upb_ctx* ctx, const upb_tag_source* src, bool resident)
     const size_t g = ((size_t)s * 2 + d) * C + c;
     perDC[(size_t)d * C + c] += ctx->segStart[g + 1] - ctx->segStart[g];
   }
-  const uint64_t target = std::max<uint64_t>(E / 16 + 1, 1u << 20);    // entries (both strands) per contig range
+  // Contig ranges of decreasing size: every (sample, range) is one copy, and a copy costs ~5 us on top of its bytes (r02: 416 copies of
+  // 1.5 MB reached 46 GB/s), so the ranges are large where it does not matter — early, while the device has nothing else to do — and
+  // small at the end, where the last range's index build and region calls trail the last byte.  UPB_LOAD_GROUPS=uniform: 13 equal ranges
   struct Range { uint32_t c0, c1; };
   std::vector<Range> ranges;
-  { uint32_t c = 0;
+  if (getenv("UPB_LOAD_GROUPS") && !strcmp(getenv("UPB_LOAD_GROUPS"), "uniform")) {
+    const uint64_t target = std::max<uint64_t>(E / 16 + 1, 1u << 20);  // entries (both strands) per contig range
+    uint32_t c = 0;
     while (c < C) {
       if (!kept[c]) { ++c; continue; }
       Range r; r.c0 = c;
@@ -400,7 +412,27 @@ static int load_enqueue (upb_ctx* ctx, const upb_tag_source* src, bool resident)
       while (c < C && kept[c] && (acc == 0 || acc < target)) { acc += perDC[c] + perDC[(size_t)C + c]; ++c; }
       r.c1 = c;
       ranges.push_back(r);
-    } }
+    }
+  } else {
+    static const double cum[] = {0.26, 0.48, 0.66, 0.80, 0.90, 0.96, 1.0};
+    const int nCut = (int)(sizeof cum / sizeof cum[0]);
+    int part = 0;
+    uint64_t acc = 0, inRange = 0;
+    uint32_t c = 0;
+    while (c < C) {
+      if (!kept[c]) { ++c; continue; }
+      Range r; r.c0 = c;
+      inRange = 0;
+      // a range ends at a contig that is not kept (its segments are not contiguous across it), or when the running total reaches its share
+      while (c < C && kept[c]) {
+        const uint64_t e = perDC[c] + perDC[(size_t)C + c];
+        acc += e; inRange += e; ++c;
+        if ((double)acc >= cum[part] * (double)E && inRange >= (1u << 20)) { while (part < nCut - 1 && (double)acc >= cum[part] * (double)E) ++part; break; }
+      }
+      r.c1 = c;
+      ranges.push_back(r);
+    }
+  }
   const bool strandMajor = resident ? ctx->loadStrandMajor : src->directional_hint != 0;
   ctx->loadStrandMajor = strandMajor;
   ctx->groups.clear();
@@ -466,6 +498,9 @@ static int load_enqueue (upb_ctx* ctx, const upb_tag_source* src, bool resident)
   ENSURE(ctx->d_grpTile, (grpTile.size() + 1) * 4);
   ENSURE(ctx->d_segEnds, 2 * ((size_t)nSeg + 1) * 4);
   if (packed) {
+    uint32_t maxTiles = 0;
+    for (const LoadGroup& g : ctx->groups) maxTiles = std::max(maxTiles, g.nTiles);
+    ENSURE(ctx->d_tileExc, ((size_t)maxTiles + 2) * 8);
     ENSURE(ctx->d_pk16, (E ? E : 1) * 2);
     ENSURE(ctx->d_pkExc, (src->n_exceptions ? src->n_exceptions : 1) * sizeof(PkException));
   }
@@ -504,6 +539,7 @@ static int load_enqueue (upb_ctx* ctx, const upb_tag_source* src, bool resident)
   la.sizes = ctx->d_sizes.as<uint32_t>(); la.mtBase = ctx->d_mtBase.as<uint32_t>(); la.mtCount = ctx->d_mtCount.as<uint32_t>();
   la.winBase = ctx->d_winBase.as<uint32_t>(); la.wEnt = ctx->d_wEnt.as<uint32_t>(); la.nWinTotal = nWinTotal; la.C = C;
   la.flags = ctx->d_loadFlags.as<uint32_t>();
+  la.tileExc = packed ? ctx->d_tileExc.as<unsigned long long>() : nullptr;
   MtArgs ma;
   memset(&ma, 0, sizeof ma);
   ma.pos = la.pos; ma.cnt = la.cnt; ma.segStart = la.segStart; ma.mtBase = la.mtBase;
@@ -521,7 +557,7 @@ static int load_enqueue (upb_ctx* ctx, const upb_tag_source* src, bool resident)
         const size_t sg0 = ((size_t)s * 2 + g.d) * C + g.c0, sg1 = ((size_t)s * 2 + g.d) * C + g.c1;
         const uint64_t dev0 = ctx->segStart[sg0], cntE = ctx->segStart[sg1] - dev0, src0 = ctx->srcStart[sg0];
         if (!cntE) continue;
-        cudaStream_t q = cs;
+        cudaStream_t q = cs;                                             // one queue: alternating the copies of a group over two queues was slower (r02: 18.5 vs 16.7 ms per load + call)
         if (packed) CU(cudaMemcpyAsync(ctx->d_pk16.as<uint16_t>() + dev0, src->words + src0, cntE * 2, cudaMemcpyHostToDevice, q));
         else {
           CU(cudaMemcpyAsync(ctx->d_pos.as<uint32_t>() + dev0, src->pos + src0, cntE * 4, cudaMemcpyHostToDevice, q));
@@ -534,6 +570,7 @@ static int load_enqueue (upb_ctx* ctx, const upb_tag_source* src, bool resident)
     la.grpSeg = ctx->d_grpSeg.as<uint32_t>() + g.seg0; la.grpTile = ctx->d_grpTile.as<uint32_t>() + g.tileTab0; la.nGrpSeg = g.nSeg;
     if (g.w1 > g.w0) load_win_fill_kernel<<<(unsigned)(((uint64_t)n_samples * (g.w1 - g.w0) + 255) / 256), 256, 0, ls>>>(la, n_samples, g.w0, g.w1);
     if (g.nTiles) {
+      if (packed) load_tile_exc_kernel<<<g.nTiles / 256 + 1, 256, 0, ls>>>(la, g.nTiles);
       load_tile_kernel<<<g.nTiles, PK_THREADS, 0, ls>>>(la);
       load_seam_kernel<<<(g.nTiles + 255) / 256, 256, 0, ls>>>(la, g.nTiles);
     }
@@ -541,7 +578,7 @@ static int load_enqueue (upb_ctx* ctx, const upb_tag_source* src, bool resident)
       int r = scan_load(ctx, ma.mtCount + g.m0, g.m1 - g.m0, ctx->d_mtOff.as<unsigned long long>() + g.m0, g.mentBase, d_scanTot);
       if (r) return r;
       set_u64_kernel<<<1, 1, 0, ls>>>(ctx->d_mtOff.as<unsigned long long>() + g.m1, g.mentBase + g.entries);
-      mt_scatter_kernel<<<g.w1 - g.w0, 256, 0, ls>>>(ma, n_samples, g.w0);
+      mt_scatter_kernel<<<g.w1 - g.w0, n_samples > 8 ? 512 : 256, 0, ls>>>(ma, n_samples, g.w0);   // one warp per sample at a time
     }
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->groupEv[gi], ls));
@@ -2173,6 +2210,10 @@ extern "C" int upb_strand_shift (upb_ctx* ctx, const upb_shift_params* p, upb_sh
   const size_t cap = toTest ? toTest : 1;
   out->tested_contig = alloc_arr<uint32_t>(cap); out->tested_left = alloc_arr<uint32_t>(cap); out->tested_len = alloc_arr<uint32_t>(cap);
   out->tested_best_shift = alloc_arr<uint32_t>(cap); out->tested_best_corr = alloc_arr<double>(cap);
+  if (!out->shift_freq || !out->tested_contig || !out->tested_left || !out->tested_len || !out->tested_best_shift || !out->tested_best_corr) {
+    upb_free_shift_report(out);
+    return fail(ctx, UPB_ERR_NOMEM, "upb_strand_shift: out of host memory");
+  }
 
   // :198 std::sort by Region::sum() descending — same comparator outcomes, same libstdc++ algorithm, hence the same
   // permutation as the reference's sort of Region pointers; only as much of it as the examination below needs (upb_introsort.hpp)
@@ -2206,7 +2247,7 @@ extern "C" int upb_strand_shift (upb_ctx* ctx, const upb_shift_params* p, upb_sh
     std::vector<uint32_t> hContig(nb), hLeft(nb), hLen(nb), bs(nb);
     std::vector<double> bc(nb);
     for (uint32_t k = 0; k < nb; ++k) { const uint32_t i = batch[k]; hContig[k] = rContig[i]; hLeft[k] = rLeft[i]; hLen[k] = rLen[i]; }
-    if ((r = shift_sweep_batch(ctx, cfg, pr, unitOfContig, nb, hContig.data(), hLeft.data(), hLen.data(), nShifts, bs.data(), bc.data(), &launches))) return r;
+    if ((r = shift_sweep_batch(ctx, cfg, pr, unitOfContig, nb, hContig.data(), hLeft.data(), hLen.data(), nShifts, bs.data(), bc.data(), &launches))) { upb_free_shift_report(out); return r; }
     for (uint32_t k = 0; k < nb && tested < toTest; ++k) {
       if (bc[k] >= p->corr_threshold) {                              // :220 disqualify regions under threshold
         const uint32_t i = batch[k];
@@ -2503,7 +2544,7 @@ extern "C" int upb_aggregate_tags (upb_ctx* ctx, uint64_t n, const uint32_t* key
   CU(cudaMemcpyAsync(h64, d_tot, 64, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(h64 + 8, ctx->d_small.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  if (((uint32_t*)(h64 + 8))[0] & FLAG_BAD_POS) return fail(ctx, UPB_ERR_BAD_ARG, "upb_aggregate_tags: strand/contig key or position out of range");
+  if (((uint32_t*)(h64 + 8))[0] & FLAG_BAD_POS) { upb_free_tag_counts(out); return fail(ctx, UPB_ERR_BAD_ARG, "upb_aggregate_tags: strand/contig key or position out of range"); }
   const uint64_t nOut = h64[1];
   out->n = nOut; out->tag_count = h64[4];
   out->pos = (uint32_t*)malloc((nOut ? nOut : 1) * 4); out->cnt = (uint32_t*)malloc((nOut ? nOut : 1) * 4);

@@ -192,7 +192,7 @@ constexpr int WIN_MT = 1 << (WIN_SHIFT - MT_SHIFT);
 // its sorted segment, found through the window index) to their mini-tiles.  The CTA's output is one contiguous stretch of the
 // tile-major copy (~28 KB on C3), so the 8-byte stores merge into full sectors in L2, and the per-mini-tile cursors are
 // shared-memory atomics — the sample-major version (v1–v19) did 326 M global atomics and partial-sector writes: 5.3 ms.
-__global__ void __launch_bounds__(256) mt_scatter_kernel (MtArgs a, uint32_t nSamples, uint32_t w0 /* first window of the load group */) {
+__global__ void __launch_bounds__(512) mt_scatter_kernel (MtArgs a, uint32_t nSamples, uint32_t w0 /* first window of the load group */) {
   __shared__ uint32_t cursor[WIN_MT];
   __shared__ unsigned long long base[WIN_MT];
   __shared__ uint32_t big[WIN_MT];                                    // a count large enough that a 32-bit block sum could wrap
@@ -215,15 +215,21 @@ __global__ void __launch_bounds__(256) mt_scatter_kernel (MtArgs a, uint32_t nSa
     const uint64_t seg = a.segStart[g];
     const uint32_t* we = a.wEnt + (size_t)s * a.nWinTotal + gw;
     const uint64_t e0 = seg + we[0], e1 = lastWin ? a.segStart[g + 1] : seg + we[1];
-    for (uint64_t e = e0 + lane; e < e1; e += 32) {
-      const uint32_t p = a.pos[e] - 1;
-      const uint32_t lm = (p >> MT_SHIFT) - m0;
-      if (lm >= nHere) continue;                                      // cannot happen on validated input
-      const unsigned long long slot = base[lm] + atomicAdd(&cursor[lm], 1u);
-      const uint32_t k = a.cnt[e];
-      a.ment[slot] = make_uint2(k, (s << SPAN_SHIFT) | (p & (SPAN_LEN - 1)));
-      if (k >= kBig) big[lm] = 1;
-      atomicAdd(&blk[(lm << (MT_SHIFT - 5)) | ((p >> 5) & ((1u << (MT_SHIFT - 5)) - 1))], k);
+    for (uint64_t eb = e0; eb < e1; eb += 128) {                      // four loads of each array in flight per lane (one at a time: 64 % of the stall samples on them, r02)
+      uint32_t pp[4], kk[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const uint64_t e = eb + lane + 32 * q; const bool ok = e < e1; pp[q] = ok ? __ldg(a.pos + e) : 0u; kk[q] = ok ? __ldg(a.cnt + e) : 0u; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (!pp[q]) continue;                                         // beyond the range (validated positions are >= 1)
+        const uint32_t p = pp[q] - 1, k = kk[q];
+        const uint32_t lm = (p >> MT_SHIFT) - m0;
+        if (lm >= nHere) continue;                                    // cannot happen on validated input
+        const unsigned long long slot = base[lm] + atomicAdd(&cursor[lm], 1u);
+        a.ment[slot] = make_uint2(k, (s << SPAN_SHIFT) | (p & (SPAN_LEN - 1)));
+        if (k >= kBig) big[lm] = 1;
+        atomicAdd(&blk[(lm << (MT_SHIFT - 5)) | ((p >> 5) & ((1u << (MT_SHIFT - 5)) - 1))], k);
+      }
     }
   }
   // zone maps of the window: mtW[m] = total count of the mini-tile, blkW[16m + j] = total count of its j-th 32-position block as a

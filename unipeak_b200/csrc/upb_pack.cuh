@@ -32,8 +32,9 @@ constexpr uint32_t FLAG_BAD_PACK = 16u;             // an escape without its exc
 struct PkException { unsigned long long index; uint32_t pos; uint32_t cnt; };   // == upb_packed_exception; index = entry index in the caller's arrays
 
 // exception of source entry e, or nullptr
-__device__ __forceinline__ const PkException* pk_find (const PkException* __restrict__ exc, unsigned long long nExc, unsigned long long e) {
-  unsigned long long lo = 0, hi = nExc;
+__device__ __forceinline__ const PkException* pk_find (const PkException* __restrict__ exc, unsigned long long nExc, unsigned long long e,
+                                                      unsigned long long lo = 0, unsigned long long hi = ~0ull) {
+  if (hi > nExc) hi = nExc;
   while (lo < hi) { const unsigned long long mid = (lo + hi) >> 1; if (exc[mid].index < e) lo = mid + 1; else hi = mid; }
   return (lo < nExc && exc[lo].index == e) ? exc + lo : nullptr;
 }
@@ -57,6 +58,7 @@ struct LoadArgs {
   uint32_t nWinTotal;
   uint32_t C;
   uint32_t* flags;
+  unsigned long long* tileExc;      // [tiles of the group + 1] packed form: index of the first exception at or after each tile's first entry (load_tile_exc_kernel)
 };
 
 // window index of sample s: every window (65536 positions) that starts after the previous entry and not after this one begins here
@@ -65,6 +67,23 @@ __device__ __forceinline__ void load_open_windows (const LoadArgs& a, uint32_t s
   if (w <= prevWin) return;
   uint32_t* we = a.wEnt + (size_t)s * a.nWinTotal + a.winBase[dc];
   for (int64_t t = prevWin + 1; t <= w; ++t) we[t] = rel;
+}
+
+// Packed form: where the exceptions of every tile start.  A tile's first entry is a position escape, so every tile has at least one
+// exception and its exceptions are consecutive in the index-sorted list: one binary search per tile HERE (one thread per tile, all
+// tiles of the group in flight at once) instead of a 22-step chain of dependent loads inside load_tile_kernel, where a whole block
+// waited at its barrier for the threads that hold an escape (r02 capture: 44 % of the kernel's stall samples on that barrier).
+__global__ void load_tile_exc_kernel (const LoadArgs a, uint32_t nTiles) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > nTiles) return;
+  if (t == nTiles) { a.tileExc[t] = a.nExc; return; }                  // (only an upper bound of the last tile's window)
+  uint32_t lo = 0, hi = a.nGrpSeg;
+  while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.grpTile[mid] <= t) lo = mid; else hi = mid; }
+  const uint32_t g = a.grpSeg[lo];
+  const unsigned long long e = a.srcStart[g] + (unsigned long long)(t - a.grpTile[lo]) * PK_TILE;
+  unsigned long long xl = 0, xh = a.nExc;
+  while (xl < xh) { const unsigned long long mid = (xl + xh) >> 1; if (a.exc[mid].index < e) xl = mid + 1; else xh = mid; }
+  a.tileExc[t] = xl;
 }
 
 __global__ void __launch_bounds__(PK_THREADS) load_tile_kernel (const LoadArgs a) {
@@ -89,6 +108,7 @@ __global__ void __launch_bounds__(PK_THREADS) load_tile_kernel (const LoadArgs a
   int n = 0;
   if (a.words) {
     const unsigned long long src0 = a.srcStart[g] + t0;
+    const unsigned long long x0 = a.tileExc[blockIdx.x], x1 = x0 + nHere;   // the tile's exceptions: at most one per entry, from x0 on
 #pragma unroll
     for (int q = 0; q < PK_ITEMS; ++q) {
       const uint32_t i = i0 + q;
@@ -97,7 +117,7 @@ __global__ void __launch_bounds__(PK_THREADS) load_tile_kernel (const LoadArgs a
         uint32_t v = w & PK2_DPOS_MASK, k = w >> PK2_CNT_SHIFT;
         const bool escP = v == PK2_DPOS_ESC, escC = k == PK2_CNT_ESC;
         if (escP || escC) {
-          const PkException* x = pk_find(a.exc, a.nExc, src0 + i);
+          const PkException* x = pk_find(a.exc, a.nExc, src0 + i, x0, x1);
           if (!x) { flags |= FLAG_BAD_PACK; if (escP) v = 0; if (escC) k = 0; }
           else { if (escP) v = x->pos; if (escC) k = x->cnt; }
         }
