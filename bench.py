@@ -314,6 +314,10 @@ def main():
     h_exc2 = torch.from_numpy(exc2.view(np.uint8).copy()).pin_memory()
     n_exc2 = int(exc2.shape[0])
     h2d_bytes = {"packed2": 2 * E + 16 * n_exc2 + 8 * int(data.off.shape[0]), "plain": 8 * E + 8 * int(data.off.shape[0])}
+    if world > 1:                                                     # whole job: the ranks' loads together
+        hb = torch.tensor([h2d_bytes["packed2"], h2d_bytes["plain"]], dtype=torch.int64, device=dev)
+        dist.all_reduce(hb)
+        h2d_bytes = {"packed2": int(hb[0].item()), "plain": int(hb[1].item())}
 
     def load_plain():
         ctx.load_async_ptr(n_samples, h_off.data_ptr(), pos_ptr=h_pos.data_ptr(), cnt_ptr=h_cnt.data_ptr(), directional_hint=directional)
@@ -351,19 +355,24 @@ def main():
     for _ in range(args.warmup):
         last = step()
     kde_ms, launches = [], 0
-    barrier()
-    call_ms = []
+    call_ms, host_ms, dev_ms, step_wall = [], [], [], []
     try:
         gpu_uuid = torch.cuda.get_device_properties(dev).uuid
     except Exception:
         gpu_uuid = None
-    with (ClockSampler(local_rank, gpu_uuid) if rank == 0 else NoSampler()) as clocks:   # rank 0's GPU stands for the box
+    # the sampler is built (NVML initialised: ~0.1 s) BEFORE the barrier: built after it, rank 0 entered the timed region that much later than
+    # the other ranks, whose first step then waited for its row counts on the device — 20 steps read 9.3 ms instead of 2.1 (r02, N = 2)
+    sampler = ClockSampler(local_rank, gpu_uuid) if rank == 0 else NoSampler()      # rank 0's GPU stands for the box
+    barrier()
+    with sampler as clocks:
         t0 = time.perf_counter()
         ev0.record(lib_stream)
         for _ in range(args.steps):
+            ts = time.perf_counter()
             last = step()
+            step_wall.append((time.perf_counter() - ts) * 1e3)
             s = ctx.stats()
-            kde_ms.append(s["ms_kde"]); launches += s["launches"]; call_ms.append(s["ms_call"])
+            kde_ms.append(s["ms_kde"]); launches += s["launches"]; call_ms.append(s["ms_call"]); host_ms.append(s["host_ms"]); dev_ms.append(s["ms_total"])
         ev1.record(lib_stream)
         barrier()
         dt_wall = time.perf_counter() - t0
@@ -398,15 +407,29 @@ def main():
     # e2e: pinned host arrays -> device every step; the call starts on the load groups that have arrived
     e2e_steps = max(1, min(args.steps, 5))
 
+    load_phases = []                                                 # (copied_ms, indexed_ms) of this rank's loads in the e2e legs
+
     def e2e_leg(loader):
         def one():
             loader()
-            return step()
+            res = step()
+            load_phases.append(ctx.last_load_ms())
+            return res
         one()                                                        # untimed: buffers of this path reach their size
+        del load_phases[:]
         return timed(one, e2e_steps)
 
     alt_ms, alt_wall_ms, _ = e2e_leg(load_plain)
     e2e_ms, e2e_wall_ms, last = e2e_leg(load_packed2)
+    # per-rank phases of the packed2 leg: bytes this rank moves, when its last byte was on the device, when its index was complete (library events)
+    ph = np.asarray(load_phases, dtype=np.float64).reshape(-1, 2) if load_phases else np.full((1, 2), -1.0)
+    e2e_phase = torch.tensor([float(ph[:, 0].mean()), float(ph[:, 1].mean()), float(E)], dtype=torch.float64, device=dev)
+    e2e_phase_all = [torch.zeros_like(e2e_phase) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(e2e_phase_all, e2e_phase)
+    else:
+        e2e_phase_all = [e2e_phase]
+    e2e_per_rank = {"columns": ["h2d_done_ms", "index_done_ms", "tag_entries"], "rows": [[round(float(x), 3) for x in t.tolist()] for t in e2e_phase_all]}
     e2e_rows = int(last.n_rows) if rank == 0 else 0
     d2h = n_rows * (41 + 4 * n_samples)
 
@@ -446,7 +469,7 @@ def main():
 
     # every stage of the call the same way (CUDA events between the stages, upb_set_profiling; separate steps, not the timed ones)
     kernels, sweep = None, None
-    if world == 1:
+    if True:                                                            # (N > 1: every rank steps, rank 0's stage times are reported, without byte counts)
         ctx.set_profiling(True)
         acc = {}
         for _ in range(5):
@@ -465,12 +488,14 @@ def main():
             "region_moment_kernel": None,
             "place+emit rows (to host)+totals": R1 * (41 + 4 * n_samples),
         }
+        if world > 1:
+            stage_bytes = {}
         kernels = []
         for name, v in acc.items():
             ms = float(np.mean(v))
             b = stage_bytes.get(name)
             kernels.append({"name": name, "ms": ms, "algorithmic_bytes": b, "frac": (b / (ms * 1e-3) / 1e9 / peak_gbs) if (b and ms > 0) else None})
-        if args.workload in ("c3", "tiny") and not (args.samples or args.tags) and not args.no_sweep:
+        if world == 1 and args.workload in ("c3", "tiny") and not (args.samples or args.tags) and not args.no_sweep:
             sweep = []
             for bw in (10, 20, 50, 100, 150, 200):
                 stb = dict(st, bandwidth=bw, reference_order=True)
@@ -488,10 +513,14 @@ def main():
 
     per_rank = None
     if world > 1:
-        minev = torch.tensor([float(np.mean(call_ms)) if call_ms else 0.0, stats["ms_total"], float(np.mean(kde_ms)) if kde_ms else 0.0, float(E)], dtype=torch.float64, device=dev)
+        hm = np.asarray(host_ms, dtype=np.float64).reshape(-1, 5).mean(axis=0) if host_ms else np.zeros(5)
+        minev = torch.tensor([float(np.mean(step_wall)) if step_wall else 0.0, float(np.mean(call_ms)) if call_ms else 0.0, float(np.mean(dev_ms)) if dev_ms else 0.0,
+                              float(np.mean(kde_ms)) if kde_ms else 0.0] + [float(x) for x in hm] + [float(E)] +
+                             [float(np.median(np.asarray(host_ms)[:, 1])) if host_ms else 0.0, float(np.max(np.asarray(host_ms)[:, 1])) if host_ms else 0.0], dtype=torch.float64, device=dev)
         allr = [torch.zeros_like(minev) for _ in range(world)]
         dist.all_gather(allr, minev)
-        per_rank = {"columns": ["call_ms", "device_ms", "span_kernel_ms", "tag_entries"],
+        per_rank = {"columns": ["python_step_ms", "call_ms", "device_ms", "span_kernel_ms", "host_prepare_ms", "host_enqueue_ms", "host_wait_ms", "host_post_ms", "host_assemble_ms", "tag_entries", "host_enqueue_median_ms", "host_enqueue_max_ms"],
+                    "note": "means over the timed steps; python_step_ms: wall clock around the binding's call; call_ms: inside the library; device_ms: first event to last event on the call's stream; host_*: where the library's host thread was",
                     "rows": [[round(float(x), 4) for x in t.cpu().tolist()] for t in allr]}
 
     if rank == 0:
@@ -502,7 +531,8 @@ def main():
                 "config": config, "clocks": clocks.summary(),
                 "e2e": {"value": genome / (e2e_ms * 1e-3), "unit": "bp/s", "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall_ms, "h2d_bytes_per_step": h2d_bytes["packed2"], "d2h_bytes_per_step": d2h,
                         "host_format": "packed2 (u16 per entry: 12-bit position delta + 4-bit count, exception list; upb_load_tags_async — what bin/regions loads)",
-                        "pack_ms": pack_ms, "pack_note": "host-side encoder (upb_pack_tags2, one thread, from the plain arrays), outside the timed region: a front end encodes while it parses",
+                        "pack_ms": pack_ms, "pack_note": "host-side encoder (upb_pack_tags2, one thread per (sample, strand), from the plain arrays), outside the timed region: a front end encodes while it parses (bin/regions: TagLoader)",
+                        "per_rank_ms": e2e_per_rank, "per_rank_note": "from the first queued copy of a rank's load: last byte on the device, index complete (library CUDA events)",
                         "rows_equal_resident_leg": bool(e2e_rows == n_rows)},
                 "e2e_alt": {"host_format": "plain (u32 pos + u32 cnt: upb_load_tags_async)", "value": genome / (alt_ms * 1e-3), "unit": "bp/s", "ms_per_step": alt_ms, "wall_ms_per_step": alt_wall_ms, "h2d_bytes_per_step": h2d_bytes["plain"]},
                 "t_hot_cold": {"value": genome / (cold_ms * 1e-3), "unit": "bp/s", "ms_per_step": cold_ms, "wall_ms_per_step": cold_wall_ms,

@@ -113,6 +113,9 @@ typedef struct {
 } upb_tag_source;
 int upb_load_tags_async (upb_ctx* ctx, const upb_tag_source* src);
 int upb_load_wait (upb_ctx* ctx);
+/* Instrumentation: when the last byte of the last (completed) load was on the device and when its index was complete, in ms after the
+ * first copy was queued. */
+int upb_last_load_ms (const upb_ctx* ctx, float* copied_ms, float* indexed_ms);
 /* Rebuild the region-calling index (tile-major copy + zone maps: the device-side replacement of the k-way merge of
  * src/regions.cpp:335-354) from the sample-major arrays already resident — what a cold call pays on top of upb_call_regions. */
 int upb_reindex (upb_ctx* ctx);
@@ -325,6 +328,11 @@ typedef struct {
   uint64_t n_stitched;          /* run pieces merged into a neighbour (runs cut by a piece / span boundary) */
   uint64_t warm_spans;          /* spans that survived the zone-map prefilter */
   float ms_call;                /* host wall clock of the last upb_call_regions, entry to return */
+  float ms_host_prepare;        /* host side of the last region call: set-up before the first launch (units, taps, small tables) */
+  float ms_host_enqueue;        /*   issuing the launches (excluding the waits below) */
+  float ms_host_wait;           /*   blocked on the device (the mid-call read-back of a sizing / shared call, and the final one) */
+  float ms_host_post;           /*   after the last read-back (counters, per-unit numbers) */
+  float ms_host_assemble;       /*   upb_call_regions_shared on rank 0: waiting for the other ranks' rows + totals + emission order */
 } upb_stats;
 int upb_last_stats (const upb_ctx* ctx, upb_stats* out);
 

@@ -73,7 +73,8 @@ class RegionKey(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("ms_total", C.c_float), ("ms_kde", C.c_float), ("launches", C.c_uint32), ("kde_tiles", C.c_uint64),
                 ("kde_hot_tiles", C.c_uint64), ("n_candidates", C.c_uint64), ("n_entries", C.c_uint64), ("hot_blocks", C.c_uint64),
-                ("exact_evals", C.c_uint64), ("spans_with_tags", C.c_uint64), ("n_stitched", C.c_uint64), ("warm_spans", C.c_uint64), ("ms_call", C.c_float)]
+                ("exact_evals", C.c_uint64), ("spans_with_tags", C.c_uint64), ("n_stitched", C.c_uint64), ("warm_spans", C.c_uint64), ("ms_call", C.c_float),
+                ("ms_host_prepare", C.c_float), ("ms_host_enqueue", C.c_float), ("ms_host_wait", C.c_float), ("ms_host_post", C.c_float), ("ms_host_assemble", C.c_float)]
 
 
 EXPORTS = [
@@ -81,7 +82,7 @@ EXPORTS = [
     "upb_load_tags", "upb_call_regions", "upb_free_region_table", "upb_reference_order", "upb_profile_contig", "upb_free_profile",
     "upb_strand_shift", "upb_free_shift_report", "upb_count_tags_in_regions", "upb_kernel_taps", "upb_last_stats",
     "upb_shared_table_bytes", "upb_shared_table_init", "upb_call_regions_shared", "upb_set_profiling", "upb_last_stage_times", "upb_stream", "upb_host_register", "upb_host_unregister", "upb_load_tags_async", "upb_load_wait", "upb_reindex", "upb_aggregate_tags", "upb_free_tag_counts",
-    "upb_load_tags_packed2", "upb_pack_tags2",
+    "upb_load_tags_packed2", "upb_pack_tags2", "upb_last_load_ms",
     "upb_shift_regions", "upb_free_shift_regions", "upb_shift_examine_order", "upb_shift_sweep", "upb_shift_mode",
     "upb_multi_create", "upb_multi_destroy", "upb_multi_last_error", "upb_multi_gpus", "upb_multi_context", "upb_multi_set_contigs", "upb_multi_owner",
     "upb_multi_load_tags", "upb_multi_load_wait", "upb_multi_call_regions", "upb_multi_profile_contig", "upb_multi_strand_shift",
@@ -179,6 +180,7 @@ def lib():
         L.upb_stream.argtypes = [C.c_void_p]
         L.upb_load_tags_async.argtypes = [C.c_void_p, C.POINTER(TagSource)]
         L.upb_load_wait.argtypes = [C.c_void_p]
+        L.upb_last_load_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.upb_reindex.argtypes = [C.c_void_p]
         L.upb_load_tags_packed2.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.upb_pack_tags2.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
@@ -346,6 +348,12 @@ class Context:
 
     def load_wait(self) -> None:
         self._check(self._lib.upb_load_wait(self._h))
+
+    def last_load_ms(self):
+        """(ms until the last byte of the last load was on the device, ms until its index was complete), from the first queued copy."""
+        a, b = C.c_float(-1), C.c_float(-1)
+        rc = self._lib.upb_last_load_ms(self._h, C.byref(a), C.byref(b))
+        return (float(a.value), float(b.value)) if rc == 0 else (-1.0, -1.0)
 
     def reindex(self) -> None:
         """upb_reindex: rebuild the tile-major copy and the zone maps from the resident sample-major arrays."""
@@ -577,7 +585,8 @@ class Context:
         return dict(ms_total=float(s.ms_total), ms_kde=float(s.ms_kde), launches=int(s.launches), kde_tiles=int(s.kde_tiles),
                     kde_hot_tiles=int(s.kde_hot_tiles), n_candidates=int(s.n_candidates), n_entries=int(s.n_entries),
                     hot_blocks=int(s.hot_blocks), exact_evals=int(s.exact_evals), spans_with_tags=int(s.spans_with_tags),
-                    n_stitched=int(s.n_stitched), warm_spans=int(s.warm_spans), ms_call=float(s.ms_call))
+                    n_stitched=int(s.n_stitched), warm_spans=int(s.warm_spans), ms_call=float(s.ms_call),
+                    host_ms=[float(s.ms_host_prepare), float(s.ms_host_enqueue), float(s.ms_host_wait), float(s.ms_host_post), float(s.ms_host_assemble)])
 
 
 class MultiContext:

@@ -93,6 +93,8 @@ struct upb_ctx {
   std::vector<const char*> stageNames;
   std::vector<float> stageMs;
   std::vector<uint8_t> lastControl;     // control set cntEff was built for
+  uint64_t callNo = 0;                  // region calls of this context so far (trace output)
+  std::vector<std::pair<const char*, std::chrono::steady_clock::time_point>> hostMarks;   // when the host passed the stage marks of the last call
   bool cntEffValid = false;
   bool tidxBuilt = false;
   std::map<std::pair<const void*, size_t>, int> occCache;   // resident CTAs per SM of (kernel, dynamic shared memory)               // per-2048-tile entry offsets of the sample-major arrays: built on first use (density kernel only)
@@ -642,6 +644,18 @@ extern "C" int upb_load_tags_async (upb_ctx* ctx, const upb_tag_source* src) {
   return r;
 }
 
+// when the last byte of the last load was on the device and when its index was complete, in ms after the first copy was queued
+// (CUDA events of the load; valid once the load has been waited for).  Instrumentation only (bench.py: per-rank load phases).
+extern "C" int upb_last_load_ms (const upb_ctx* ctx, float* copied_ms, float* indexed_ms) {
+  if (!ctx || !copied_ms || !indexed_ms) return UPB_ERR_BAD_ARG;
+  *copied_ms = *indexed_ms = -1.f;
+  const size_t G = ctx->groups.size();
+  if (ctx->loadPending || !G || ctx->copyEvs.size() <= G || ctx->groupEv.size() < G) return UPB_ERR_NOT_LOADED;
+  if (ctx->loadCopied) for (size_t k = G; k-- > 0;) if (ctx->groups[k].entries) { cudaEventElapsedTime(copied_ms, ctx->copyEvs[G], ctx->copyEvs[k]); break; }
+  cudaEventElapsedTime(indexed_ms, ctx->copyEvs[G], ctx->groupEv[G - 1]);
+  return UPB_OK;
+}
+
 extern "C" int upb_load_wait (upb_ctx* ctx) {
   if (!ctx) return UPB_ERR_BAD_ARG;
   if (!ctx->loadPending) return ctx->loaded ? UPB_OK : fail(ctx, UPB_ERR_NOT_LOADED, "no tags loaded (upb_set_contigs + upb_load_tags first)");
@@ -1145,8 +1159,9 @@ static int launch_span (upb_ctx* ctx, const SpanArgs& sa, bool nondir, uint32_t*
 }
 
 // ---- per-stage device timing (upb_set_profiling): one event between the stages of the pipeline, read after the call ----------
-static void stage_reset (upb_ctx* ctx) { ctx->stageUsed = 0; ctx->stageNames.clear(); }
+static void stage_reset (upb_ctx* ctx) { ctx->stageUsed = 0; ctx->stageNames.clear(); ctx->hostMarks.clear(); }
 static void stage_mark (upb_ctx* ctx, const char* name) {
+  ctx->hostMarks.push_back(std::make_pair(name, std::chrono::steady_clock::now()));   // host side of the same points (UPB_TRACE_SLOW)
   if (!ctx->profiling) return;
   if (ctx->stageUsed == ctx->stageEv.size()) { cudaEvent_t e = nullptr; if (cudaEventCreate(&e) != cudaSuccess) return; ctx->stageEv.push_back(e); }
   cudaEventRecord(ctx->stageEv[ctx->stageUsed++], ctx->stream);
@@ -1266,6 +1281,10 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
   CU(cudaSetDevice(ctx->device));
   *retry = false;
   uint32_t launches = 0;
+  typedef std::chrono::steady_clock Clk;
+  const Clk::time_point tA = Clk::now();
+  ++ctx->callNo;
+  double waitMid = 0;                                                 // ms the host spent blocked on the device before the final read-back
   stage_reset(ctx);
   CU(cudaEventRecord(ctx->ev[0], ctx->stream));
   // A load that is still on its way (upb_load_tags_async): work through its groups as they arrive — unless this call needs a
@@ -1278,6 +1297,7 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
   }
   int r = prepare(ctx, cfg, pr, &launches, pipelined);
   if (r) return r;
+  const Clk::time_point tB = Clk::now();
   const uint32_t n = ctx->nSamples, C = (uint32_t)ctx->sizes.size();
   const uint32_t nUnits = (uint32_t)pr.units.size();
   out.units = pr.units;
@@ -1364,9 +1384,14 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
     stage_mark(ctx, "left_edge_kernel");
   }
 
+  auto hmark = [&] (const char* name) { ctx->hostMarks.push_back(std::make_pair(name, Clk::now())); };
+  hmark("h:setup");
   // ---- arrays sized by capacity ----------------------------------------------------------------------------------
   size_t runCap = std::max<size_t>(std::max<size_t>(1u << 18, (size_t)(ctx->nEntries / 64)), ctx->needRunCap);
-  { const size_t have = ctx->scratch["runs"].cap / sizeof(SpanRun); if (have > runCap) runCap = have; }
+  // (what the array already holds — minus SCR's 16 bytes of slack: counting them as room made the request outgrow the array whenever
+  //  cap mod sizeof(SpanRun) < 16, and every run-sized array was then freed and reallocated 25 % larger, call after call, until a
+  //  capacity happened to leave more than 16 bytes over: 2 - 20 ms stalls in the first calls of a context, r02 N = 4 trace)
+  { const size_t cap = ctx->scratch["runs"].cap; const size_t have = cap > 16 ? (cap - 16) / sizeof(SpanRun) : 0; if (have > runCap) runCap = have; }
   runCap = std::min<size_t>(runCap, 0xFFFFFFF0u);
   sa.runs = SCR("runs", SpanRun, runCap);
   sa.runCap = (uint32_t)runCap;
@@ -1402,11 +1427,14 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
   unsigned long long* hUnitRows = hUnitCand + nUnits;
   uint32_t* hDrop = (uint32_t*)(hUnitRows + nUnits);
   auto read_group = [&] () -> int {                                    // sizing read-back of the group counters
+    const Clk::time_point w0 = Clk::now();
     CU(cudaMemcpyAsync(hg, g, sizeof(GroupCtr), cudaMemcpyDeviceToHost, st_));
     CU(cudaStreamSynchronize(st_));
+    waitMid += std::chrono::duration<double, std::milli>(Clk::now() - w0).count();
     return UPB_OK;
   };
 
+  hmark("h:scratch");
   // ---- the groups of units: one group (all units), or one per load group of a pending load ------------------------------
   struct PGroup { uint32_t u0, u1, s0, s1; int ev0, ev1; };
   std::vector<PGroup> pgroups;
@@ -1487,12 +1515,16 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
     const uint32_t u0 = pgroups[gi].u0, u1 = pgroups[gi].u1, s0 = pgroups[gi].s0, s1 = pgroups[gi].s1;
     if (pgroups[gi].ev0 >= 0) CU(cudaStreamWaitEvent(st_, ctx->groupEv[pgroups[gi].ev0], 0));
     if (pgroups[gi].ev1 >= 0) CU(cudaStreamWaitEvent(st_, ctx->groupEv[pgroups[gi].ev1], 0));
+    hmark("h:events");
     CU(cudaMemsetAsync(g, 0, sizeof(GroupCtr), st_));
+    hmark("h:memset g");
     wa.spanBegin = s0; wa.spanEnd = s1;
     warm_span_kernel<<<(s1 - s0 + 255) / 256, 256, 0, st_>>>(wa);
+    hmark("h:warm launch");
     { int perSm = 0;
       if ((r = cached_occupancy(ctx, hot_span_kernel, HOT_THREADS, 0, &perSm))) return r;
       hot_span_kernel<<<ctx->smCount * perSm, HOT_THREADS, 0, st_>>>(ha); }
+    hmark("h:hot launch");
     launches += 2;
     stage_mark(ctx, "warm_span_kernel+hot_span_kernel");
     CU(cudaEventRecord(ctx->ev[1], st_));
@@ -1660,8 +1692,18 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
   if (nAff) CU(cudaMemcpyAsync(hDrop, d_drop, (size_t)nAff * 4, cudaMemcpyDeviceToHost, st_));
   CU(cudaEventRecord(ctx->ev[3], st_));
   if (!shared) memset(hs + out.layout.devBytes, 0, out.layout.totalBytes - out.layout.devBytes);   // host-only tail of the slab, while the device works
+  const Clk::time_point tC = Clk::now();
   CU(cudaEventSynchronize(ctx->ev[3]));
+  const Clk::time_point tD = Clk::now();
   { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]); ctx->stats.ms_total = ms; }
+  { auto ms = [] (Clk::time_point a, Clk::time_point b) { return std::chrono::duration<float, std::milli>(b - a).count(); };
+    ctx->stats.ms_host_prepare = ms(tA, tB); ctx->stats.ms_host_enqueue = ms(tB, tC) - (float)waitMid; ctx->stats.ms_host_wait = (float)waitMid + ms(tC, tD);
+    if (ctx->stats.ms_host_enqueue > 2.f && getenv("UPB_TRACE_SLOW")) {   // a call whose launches took unusually long to issue: where
+      fprintf(stderr, "[upb] slow enqueue on device %d, call %llu%s: %.3f ms (mid-call waits %.3f ms);", ctx->device, (unsigned long long)ctx->callNo, shared ? " (shared)" : "", ctx->stats.ms_host_enqueue, waitMid);
+      Clk::time_point prev = tB;
+      for (const auto& hm : ctx->hostMarks) { fprintf(stderr, " %s +%.3f", hm.first, ms(prev, hm.second)); prev = hm.second; }
+      fprintf(stderr, " end +%.3f\n", ms(prev, tC));
+    } }
   if (!empty) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->stats.ms_kde = ms; }
   stage_collect(ctx);
   ctx->stats.launches = launches;
@@ -1703,6 +1745,7 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
     ctx->capRows = std::max(ctx->capRows, R + R / 4 + 1024);
   }
   out.tir.assign(hTir, hTir + n);
+  ctx->stats.ms_host_post = std::chrono::duration<float, std::milli>(Clk::now() - tD).count();
   return UPB_OK;
 }
 
@@ -1989,6 +2032,7 @@ extern "C" int upb_call_regions_shared (upb_ctx* ctx, const upb_region_params* p
   PipeOut po;
   Prep pr;
   int r = run_pipeline(ctx, cfg, pr, po, &sd);
+  const std::chrono::steady_clock::time_point tAsm = std::chrono::steady_clock::now();
   unsigned long long* done = (unsigned long long*)(hb + L.oDone);
   if (r) { __atomic_store_n(&done[t->rank], ~0ull, __ATOMIC_RELEASE); return r; }   // poison: rank 0 reports the step as failed instead of waiting
   // this rank's contribution to what rank 0 assembles
@@ -2089,6 +2133,7 @@ extern "C" int upb_call_regions_shared (upb_ctx* ctx, const upb_region_params* p
     if (!identity) permute_table(out, perm, n);
   }
   ctx->stats.ms_call = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  ctx->stats.ms_host_assemble = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - tAsm).count();
   return UPB_OK;
 }
 

@@ -93,9 +93,11 @@ def _peak_set(seed: int, which: int, G: int, npk: int, dev):
 
 def make_synthetic_det(contig_sizes: Sequence[int], n_samples: int, tags_per_sample: int, *, directional: bool = True,
                        seed: int = 1234, bandwidth: int = 50, peak_fraction: float = 0.7, peak_spacing: int = 10000,
-                       contigs: Sequence[int] | None = None, device: str = "cpu", contig_names=None) -> TagData:
+                       contigs: Sequence[int] | None = None, device: str = "cpu", contig_names=None, first_sample: int = 0) -> TagData:
     """Returns host (numpy) arrays.  `contigs`: keep only these contigs' tags (a rank's shard); the other segments are left
-    empty so contig indices stay global — the kept segments are exactly those of the unsharded call."""
+    empty so contig indices stay global — the kept segments are exactly those of the unsharded call.  `first_sample`: the
+    samples generated are numbers first_sample .. first_sample + n_samples - 1 of the (unbounded) series this seed defines — the
+    same arrays a larger call would hold for them (a rank that holds a block of samples)."""
     dev = torch.device(device)
     sizes = torch.tensor(list(contig_sizes), dtype=torch.int64, device=dev)
     C = int(sizes.shape[0])
@@ -111,7 +113,8 @@ def make_synthetic_det(contig_sizes: Sequence[int], n_samples: int, tags_per_sam
     off = np.zeros(n_samples * 2 * (C + 1), dtype=np.uint64)
     total = 0
     n_peak = int(round(tags_per_sample * peak_fraction))
-    for s in range(n_samples):
+    for s_local in range(n_samples):
+        s = s_local + first_sample                                      # sample number in the seed's series (keys); s_local: slot in the arrays
         glob = [[], []]
         n_bg = tags_per_sample - n_peak
         if directional:
@@ -148,7 +151,7 @@ def make_synthetic_det(contig_sizes: Sequence[int], n_samples: int, tags_per_sam
             del key
             uc = uk >> 32
             bounds = torch.searchsorted(uc, torch.arange(C + 1, device=dev, dtype=torch.int64)).cpu().numpy().astype(np.uint64)
-            base = (s * 2 + d) * (C + 1)
+            base = (s_local * 2 + d) * (C + 1)
             off[base:base + C + 1] = bounds + np.uint64(total)
             pos_parts.append((uk & 0xFFFFFFFF).cpu().numpy().astype(np.uint32))
             cnt_parts.append(k.cpu().numpy().astype(np.uint32))
