@@ -33,6 +33,10 @@ for step in "$@"; do
         python bench.py --steps 2 --warmup 1 --no-cpu --no-sweep > $OUT/ncu_full.log 2>&1; note ncu-full $?
       timeout 300 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:upb::region_pool_kernel -c 1 -f -o $OUT/pool \
         python bench.py --steps 2 --warmup 1 --no-cpu --no-sweep > $OUT/ncu_full_pool.log 2>&1; note ncu-full-pool $? ;;
+    cli)
+      timeout 600 python tools/cli_bench.py > $OUT/cli_bench.jsonl 2> $OUT/cli_bench.err; note cli $? ;;
+    wig)
+      timeout 600 python tools/wig_bench.py > $OUT/wig_bench.json 2> $OUT/wig_bench.err; note wig $? ;;
     refarm)
       timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > $OUT/reference_arm.json 2> $OUT/reference_arm.err; note refarm $? ;;
     ab:*)
@@ -46,5 +50,6 @@ for step in "$@"; do
 done
 cat $OUT/progress.txt
 for f in smoke.txt sanitize.txt pytest_gpu.txt pytest_gpu_fast.txt pytest_gpu_all.txt; do [ -f $OUT/$f ] && { echo "== $f"; tail -25 $OUT/$f; }; done
+for f in cli_bench.jsonl wig_bench.json reference_arm.json; do [ -f $OUT/$f ] && { echo "== $f"; cut -c1-1500 $OUT/$f; }; done
 for f in bench_c3 bench_quick; do [ -f $OUT/$f.json ] && { echo "== $f"; cut -c1-1500 $OUT/$f.json; tail -5 $OUT/$f.err; }; done
 exit 0

@@ -19,6 +19,13 @@ for step in "$@"; do
       timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29703 bench.py --gpus $N --steps 20 --warmup 3 > $OUT/bench_n$N.json 2> $OUT/bench_n$N.err; note bench $? ;;
     bench4)
       timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29704 bench.py --gpus 4 --steps 20 --warmup 3 --no-cpu > $OUT/bench_n4.json 2> $OUT/bench_n4.err; note bench4 $? ;;
+    scale)
+      for k in 1 2 4 8; do
+        [ $k -le $N ] || continue
+        if [ $k -eq 1 ]; then timeout 400 python bench.py --steps 20 --warmup 3 --no-cpu --no-sweep > $OUT/scale_n$k.json 2> $OUT/scale_n$k.err
+        else timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $k --master-addr 127.0.0.1 --master-port 2980$k bench.py --gpus $k --steps 20 --warmup 3 --no-cpu --no-sweep > $OUT/scale_n$k.json 2> $OUT/scale_n$k.err; fi
+        note scale$k $?
+      done ;;
     benchc4)
       timeout 700 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29705 bench.py --gpus $N --workload c4 --steps 5 --warmup 3 --no-cpu --no-sweep > $OUT/bench_c4_n$N.json 2> $OUT/bench_c4_n$N.err; note benchc4 $? ;;
     multi)

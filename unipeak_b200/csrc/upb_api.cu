@@ -141,6 +141,7 @@ extern "C" int upb_create (int device, upb_ctx** out) {
   if (device < 0 || device >= n) return fail(nullptr, UPB_ERR_BAD_ARG, "upb_create: device index out of range");
   upb_ctx* ctx = new upb_ctx;
   ctx->device = device;
+  const std::chrono::steady_clock::time_point tc0 = std::chrono::steady_clock::now();
   if ((e = cudaSetDevice(device)) != cudaSuccess) { delete ctx; return fail(nullptr, UPB_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e)); }
   cudaDeviceProp prop;
   if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { delete ctx; return fail(nullptr, UPB_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e)); }
@@ -159,6 +160,8 @@ extern "C" int upb_create (int device, upb_ctx** out) {
   cudaEventCreateWithFlags(&ctx->loadDoneEv, cudaEventDisableTiming);
   if ((e = cudaMallocHost((void**)&ctx->h_small, 4096)) != cudaSuccess) { upb_destroy(ctx); return fail(nullptr, UPB_ERR_NOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e)); }
   memset(&ctx->stats, 0, sizeof ctx->stats);
+  if (getenv("UPB_TRACE") && *getenv("UPB_TRACE"))
+    fprintf(stderr, "[upb] create: device %d, CUDA context + streams + pinned block in %.1f ms\n", device, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count());
   *out = ctx;
   return UPB_OK;
 }

@@ -30,9 +30,6 @@
 #ifndef UPB_EXP_EXACT
 #define UPB_EXP_EXACT 1
 #endif
-#ifndef UPB_EXP_PREFETCH
-#define UPB_EXP_PREFETCH 0                          // span_kernel<directional>: the mini-tile offset tables of a ticket's later spans fetched with cp.async at ticket time, and the
-#endif                                              //   entries of the next span's first hot group prefetched into L2 one span ahead (written after the r01 GPU budget was spent: never run)
 
 namespace upb {
 
@@ -110,7 +107,7 @@ __host__ __device__ inline SpanSmem span_smem_layout (uint32_t bw, uint32_t nSam
   L.oWf = w;   w += coeff ? W * 8 : 0;              // -z: per-position weights are doubles
   L.oWr = w;   w += (coeff && nondir) ? W * 8 : 0;
   w = (w + 15) & ~15u;
-  L.oMo = w;   w += (UPB_EXP_PREFETCH ? 4 : 2) * MO_STRIDE * 8;   // mini-tile offsets of the span + its halo on either side, per strand (UPB_EXP_PREFETCH: per span of a ticket)
+  L.oMo = w;   w += 2 * MO_STRIDE * 8;                   // mini-tile offsets of the span + its halo on either side, per strand
   L.oSt = w;   w += 128 * 8;                        // products of 128 taps (exact_dense_warp)
   L.oSc = w;   w += coeff ? PIECE_LEN * 8 : PIECE_LEN * 4;   // oSt + oSc together (>= 3 KB, contiguous) double as the entry staging ring of B1
   L.oMw = w;   w += (PIECE_BLOCKS + 2) * 4;
@@ -256,11 +253,6 @@ __device__ __forceinline__ void piece_entries_tab (const uint2* __restrict__ men
 constexpr uint32_t BULK_ENTRIES = 192;                                // per ring slot: 1536 bytes; two slots = SpanSmem oSt + oSc (3 KB, contiguous)
 static_assert(128 * 8 + PIECE_LEN * 4 >= 2 * BULK_ENTRIES * 8, "SpanSmem: oSt + oSc must hold the bulk ring");
 
-__device__ __forceinline__ void cp_async8 (void* smemDst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((uint32_t)__cvta_generic_to_shared(smemDst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit () { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait () { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 __device__ __forceinline__ uint32_t smem_u32 (const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init (uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_expect_tx (uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory"); }
@@ -589,62 +581,20 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : MINB) span_kernel (con
   const uint32_t nHot = *a.nHot;
   uint32_t rBase = 0, rUsed = RUN_CHUNK, rTotal = 0;                   // current chunk of run slots: [rBase, rBase + RUN_CHUNK), rUsed taken
   bool rRoom = true;
-  constexpr uint32_t BATCH = 4;                                        // hot spans per ticket: one atomic and two dependent loads per four spans
+  constexpr uint32_t BATCH = 4;                                        // hot spans per ticket: one atomic and two dependent loads per four spans ...
+  const uint32_t batch = nHot > gridDim.x * (uint32_t)SP_WARPS * 16u ? BATCH : (nHot > gridDim.x * (uint32_t)SP_WARPS * 4u ? 2u : 1u);   // ... fewer where a rank's shard leaves a warp only a handful (N = 8)
 
   for (;;) {
     uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(a.ticket, BATCH);
+    if (lane == 0) base = atomicAdd(a.ticket, batch);
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base >= nHot) break;
-    const uint32_t nIn = min(BATCH, nHot - base);
+    const uint32_t nIn = min(batch, nHot - base);
     uint2 item = make_uint2(0u, 0u);
     if (lane < nIn) item = __ldg(a.hotList + base + lane);
     uint32_t maskWord = 0;                                            // lane 4t+m holds word m of the t-th span's hot-block mask
     { const uint32_t sp = __shfl_sync(0xffffffffu, item.x, lane >> 2);
       if ((lane >> 2) < nIn) maskWord = __ldg(a.hotMask + (size_t)sp * SPAN_WORDS + (lane & 3)); }
-#if UPB_EXP_PREFETCH
-    static_assert(BATCH == 4, "UPB_EXP_PREFETCH: one offset table per span of a ticket");
-    // offset tables of the ticket's spans 1 .. nIn-1 straight into shared memory (no registers held): by the time span t is
-    // reached its table has long landed, and the entries of its first hot group can be prefetched into L2 a whole span ahead
-    auto tableOf = [&] (uint32_t t, uint32_t& kt, uint32_t& gbT, uint32_t& nMtT) {
-      const SpanUnit Ut = a.units[__shfl_sync(0xffffffffu, item.y, t)];
-      kt = __shfl_sync(0xffffffffu, item.x, t) - Ut.spanStart;
-      gbT = __ldg(a.T.mtBase + Ut.buffer * a.T.C + Ut.contig);
-      nMtT = __ldg(a.T.mtBase + Ut.buffer * a.T.C + Ut.contig + 1) - gbT;
-    };
-    if constexpr (!NONDIR) {
-      __syncwarp();                                                    // the tables of the previous ticket are no longer read
-      for (uint32_t t = 1; t < nIn; ++t) {
-        uint32_t kt, gbT, nMtT;
-        tableOf(t, kt, gbT, nMtT);
-        const int mBaseT = (int)(kt * SPAN_MT) - HALO_MT;
-        if (lane < (uint32_t)MO_N) cp_async8(mo + MO_STRIDE * t + lane, a.T.mtOff + gbT + (uint32_t)min(max(mBaseT + (int)lane, 0), (int)nMtT));
-      }
-      cp_async_commit();
-    }
-    auto prefetchFirstGroup = [&] (uint32_t t) {                       // span t of the ticket (its table is in shared memory): first hot group -> L2
-      const uint32_t wordsT = (__ballot_sync(0xffffffffu, maskWord != 0) >> (4 * t)) & ((1u << SPAN_WORDS) - 1);
-      if (!wordsT) return;
-      const uint32_t w0 = (uint32_t)__ffs(wordsT) - 1;
-      const uint32_t word = __shfl_sync(0xffffffffu, maskWord, 4 * t + w0);
-      const uint32_t b0 = (uint32_t)__ffs(word) - 1;                   // first hot block of that word
-      const uint32_t x = ~(word >> b0);
-      const uint32_t len = min((uint32_t)PIECE_BLOCKS, x ? (uint32_t)__ffs(x) - 1 : 32u - b0);
-      uint32_t kt, gbT, nMtT;
-      tableOf(t, kt, gbT, nMtT);
-      if (nMtT == 0) return;
-      const int mBaseT = (int)(kt * SPAN_MT) - HALO_MT;
-      const int64_t lo = (int64_t)kt * SPAN_LEN + 1 + 32 * (32 * w0 + b0) - bw, hi = lo + 32 * len - 1 + 2 * bw;
-      const uint32_t ma = lo < 1 ? 0u : (uint32_t)((lo - 1) >> MT_SHIFT);
-      const uint32_t mb = min((uint32_t)((hi - 1) >> MT_SHIFT), nMtT - 1);
-      if (ma > mb) return;
-      const unsigned long long* tabT = mo + MO_STRIDE * t;
-      const char* p0 = (const char*)(a.T.ment + tabT[(int)ma - mBaseT]);
-      const char* p1 = (const char*)(a.T.ment + tabT[(int)mb + 1 - mBaseT]);
-      const char* line = (const char*)((unsigned long long)p0 & ~127ull) + 128u * lane;   // up to 32 lines = 512 entries: a piece reads ~470
-      if (line < p1) asm volatile("prefetch.global.L2 [%0];" :: "l"(line));
-    };
-#endif
   for (uint32_t tb = 0; tb < nIn; ++tb) {
     const uint32_t work = __shfl_sync(0xffffffffu, item.x, tb);        // span index
     const SpanUnit U = a.units[__shfl_sync(0xffffffffu, item.y, tb)];
@@ -659,26 +609,16 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : MINB) span_kernel (con
     const uint32_t nzWords = (__ballot_sync(0xffffffffu, maskWord != 0) >> (4 * tb)) & ((1u << SPAN_WORDS) - 1);   // which of the span's mask words hold a hot block
     const int mBase = (int)(k * SPAN_MT) - HALO_MT;
     uint32_t nMtS[2] = {0u, 0u};
-#if UPB_EXP_PREFETCH
-    unsigned long long* const moSpan = NONDIR ? mo : mo + MO_STRIDE * tb;   // this span's table(s)
-#else
     unsigned long long* const moSpan = mo;
-#endif
 #pragma unroll
     for (int str = 0; str < (NONDIR ? 2 : 1); ++str) {
       const uint32_t d = NONDIR ? (uint32_t)str : U.buffer;
       const uint32_t gb = __ldg(a.T.mtBase + d * a.T.C + U.contig);
       nMtS[str] = __ldg(a.T.mtBase + d * a.T.C + U.contig + 1) - gb;
-      if ((NONDIR || !UPB_EXP_PREFETCH || tb == 0) && lane < (uint32_t)MO_N)
+      if (lane < (uint32_t)MO_N)
         moSpan[MO_STRIDE * str + lane] = __ldg(a.T.mtOff + gb + (uint32_t)min(max(mBase + (int)lane, 0), (int)nMtS[str]));
     }
-#if UPB_EXP_PREFETCH
-    if (!NONDIR && tb >= 1) cp_async_wait<0>();                        // issued at ticket time, at least one whole span ago
     __syncwarp();
-    if (!NONDIR && tb >= 1 && tb + 1 < nIn) prefetchFirstGroup(tb + 1);   // (after span 0 its successor's table may still be on its way: see below)
-#else
-    __syncwarp();
-#endif
     ++stSpans;
 
     // ---- B: pieces, in position order -------------------------------------------------------------------------------
@@ -976,9 +916,6 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : MINB) span_kernel (con
       pb = pbNext; nb = nbNext; havePiece = haveNext;
     }
     if (lane == 0) a.spanRunCount[work] = spanRuns;
-#if UPB_EXP_PREFETCH
-    if (!NONDIR && tb == 0 && nIn > 1) { cp_async_wait<0>(); __syncwarp(); prefetchFirstGroup(1); }   // span 1's table has landed by now
-#endif
   }
   }
   if (rRoom && rUsed + lane < RUN_CHUNK) a.runs[rBase + rUsed + lane].span = RUN_INVALID;
@@ -1177,6 +1114,9 @@ __global__ void __launch_bounds__(ST_WARPS * 32) region_pool_kernel (StatArgs a)
   const uint32_t g = lane / ST_GROUP, gl = lane % ST_GROUP, leader = lane & ~(uint32_t)(ST_GROUP - 1);
   const uint32_t n = a.T.nSamples;
   const uint32_t nList = (uint32_t)a.g->n1;
+  // regions a group takes per atomic: four where there are many per group (one same-address atomic per region serialises), one where a rank's
+  // shard leaves a group fewer than eight (N = 8 on C3: 1.6 regions per group — with tickets of four, 60 % of the groups got none)
+  const uint32_t tkSize = nList > gridDim.x * (uint32_t)(ST_WARPS * ST_PER_WARP) * 8u ? ST_TICKET : 1u;
   const size_t groupBytes = ((size_t)(ST_CHUNK + n) * 4 + 15) / 16 * 16;   // per group: cell[ST_CHUNK] u32, cnts[n] u32
   unsigned char* gbase = stat_smem_raw + ((size_t)warp * ST_PER_WARP + g) * groupBytes;
   uint32_t* cell = (uint32_t*)gbase;
@@ -1194,9 +1134,9 @@ __global__ void __launch_bounds__(ST_WARPS * 32) region_pool_kernel (StatArgs a)
     // ---- fetch: a group without a region takes the next one -------------------------------------------------------------------
     uint32_t t = 0;
     const bool wantTicket = !active && !exhausted && tkNext == tkEnd;
-    if (wantTicket && gl == 0) t = atomicAdd(a.ticket, ST_TICKET);
+    if (wantTicket && gl == 0) t = atomicAdd(a.ticket, tkSize);
     t = __shfl_sync(0xffffffffu, t, leader);
-    if (wantTicket) { tkNext = t; tkEnd = min(t + ST_TICKET, nList); if (t >= nList) { exhausted = true; tkEnd = tkNext; } }
+    if (wantTicket) { tkNext = t; tkEnd = min(t + tkSize, nList); if (t >= nList) { exhausted = true; tkEnd = tkNext; } }
     bool needSeg = false;                                             // (re)load the entry range of segment (d, sp)
     if (!active && tkNext < tkEnd) {
       i = tkNext++;
