@@ -35,8 +35,12 @@ enum {
   UPB_ERR_LEFT_EDGE = -6,       /* no longer returned (kept for ABI stability): every shape of the reference's left-edge behaviour
                                    (misc/peakcall.cpp:176-184,224-231) is replayed - regions, the -w profile, the shift
                                    sweep, and contigs whose every tag lies within `bandwidth` of the start */
-  UPB_ERR_REFERENCE_ABORTS = -7,/* the reference's merge loop would trip its own assert on this input
-                                   (several directional samples whose '-' track is read in pass 1) */
+  UPB_ERR_REFERENCE_ABORTS = -7,/* reference_order == 1 only: several directional samples, and the reference's merge loop reads the
+                                   '-' track of at least one of them during pass 1 (it starts at or after the last contig of that
+                                   sample's '+' track: one-contig tables, toy inputs).  Depending on the tag positions the
+                                   reference then trips its own assert (misc/peakcall.cpp:171) or sweeps that sample's '-' tags
+                                   through reverseBuffer separately from the other samples'; neither is reproduced.
+                                   reference_order == 0 still returns the canonical, pooled table. */
   UPB_ERR_NO_REGIONS = -8,      /* src/strand_shift.cpp:228-230 "no regions qualified" */
   UPB_ERR_REVERSE_NONDIR = -9,  /* src/tags_in_regions.cpp:167-170 */
   UPB_ERR_NOMEM = -10,

@@ -1138,14 +1138,19 @@ static int dump_and_corr (upb_ctx* ctx, const DensArgs& base, bool nondir, uint3
 static int launch_span (upb_ctx* ctx, const SpanArgs& sa, bool nondir, uint32_t* launches) {
   const bool coeff = sa.coeff != nullptr;
   const SpanSmem L = span_smem_layout(sa.bw, sa.nSamples, nondir, coeff);
-  const size_t smem = L.total;
-  if (smem > 227 * 1024) return fail(ctx, UPB_ERR_UNSUPPORTED, "bandwidth / sample count need more shared memory than one SM has");
+  // eight warps per CTA where their private windows fit one SM's shared memory; fewer where they do not (-z with -D at bandwidth
+  // >= ~290: two u32 and two f64 windows of 512 + 2 bandwidth cells per warp)
+  const size_t smemMax = 227 * 1024;
+  if (L.warp0 + L.warpStride > smemMax) return fail(ctx, UPB_ERR_UNSUPPORTED, "bandwidth / sample count need more shared memory than one SM has");
+  const uint32_t nWarps = (uint32_t)std::min<size_t>(SP_WARPS, (smemMax - L.warp0) / L.warpStride);
+  const int threads = (int)nWarps * 32;
+  const size_t smem = (size_t)L.warp0 + (size_t)L.warpStride * nWarps;
   void (*kern)(const SpanArgs) = coeff ? (nondir ? span_kernel<true, true> : span_kernel<false, true>) : (nondir ? span_kernel<true, false> : span_kernel<false, false>);
   int perSm = 0;
-  { int rr = cached_occupancy(ctx, kern, SP_THREADS, smem, &perSm); if (rr) return rr; }
+  { int rr = cached_occupancy(ctx, kern, threads, smem, &perSm); if (rr) return rr; }
   if (!coeff && perSm < SP_MIN_BLOCKS) {                              // shared memory admits fewer CTAs than the 64-register build is sized for: take the build without that cap
     kern = nondir ? span_kernel<true, false, SP_MIN_BLOCKS - 1> : span_kernel<false, false, SP_MIN_BLOCKS - 1>;
-    int rr = cached_occupancy(ctx, kern, SP_THREADS, smem, &perSm); if (rr) return rr;
+    int rr = cached_occupancy(ctx, kern, threads, smem, &perSm); if (rr) return rr;
   }
   // B1 through the bulk-copy engine (cp.async.bulk + mbarrier, SASS UBLKCP) where it was measured to win: directional calls at bandwidth >= 100, whose
   // chunks (piece + 2 x bandwidth of halo, all samples) are long enough to amortise arming a barrier (profiles/r02_b1_bulk_ab.txt: 0.539 -> 0.497 ms at
@@ -1153,9 +1158,9 @@ static int launch_span (upb_ctx* ctx, const SpanArgs& sa, bool nondir, uint32_t*
   bool bulk = !coeff && !nondir && sa.bw >= 100;
   if (const char* e = getenv("UPB_B1")) { if (!strcmp(e, "bulk")) bulk = !coeff && !nondir; else if (!strcmp(e, "ldg")) bulk = false; }
   if (bulk) kern = perSm < SP_MIN_BLOCKS ? span_kernel<false, false, SP_MIN_BLOCKS - 1, true> : span_kernel<false, false, SP_MIN_BLOCKS, true>;
-  if (bulk) { int rr = cached_occupancy(ctx, kern, SP_THREADS, smem, &perSm); if (rr) return rr; }
+  if (bulk) { int rr = cached_occupancy(ctx, kern, threads, smem, &perSm); if (rr) return rr; }
   const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)ctx->smCount * perSm, std::max<uint32_t>(sa.totalSpans, 1u));
-  kern<<<grid, SP_THREADS, smem, ctx->stream>>>(sa);
+  kern<<<grid, threads, smem, ctx->stream>>>(sa);
   CU(cudaGetLastError());
   *launches += 1;
   return UPB_OK;
@@ -1960,7 +1965,7 @@ extern "C" int upb_call_regions (upb_ctx* ctx, const upb_region_params* p, upb_r
     std::vector<uint64_t> perm;
     bool identity = true;
     r = reference_order_impl(C, n, p->directional, p->bandwidth, ctx->firstPos.data(), ctx->lastPos.data(), out, &perm, &identity);
-    if (r) { upb_free_region_table(out); return fail(ctx, r, "the reference's merge loop would abort on this input (several directional samples whose '-' track is read during pass 1; SURVEY Q7)"); }
+    if (r) { upb_free_region_table(out); return fail(ctx, r, "several directional samples and a '-' track that the reference's merge loop reads during pass 1: it then aborts (assert) or pools that sample's '-' tags separately, neither is reproduced (SURVEY Q7); reference_order = 0 returns the canonical table"); }
     if (!identity) permute_table(out, perm, n);
   }
   ctx->stats.ms_call = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -2132,7 +2137,7 @@ extern "C" int upb_call_regions_shared (upb_ctx* ctx, const upb_region_params* p
     std::vector<uint64_t> perm;
     bool identity = true;
     r = reference_order_impl(C, n, p->directional, p->bandwidth, firstPos.data(), lastPos.data(), out, &perm, &identity);
-    if (r) return fail(ctx, r, "the reference's merge loop would abort on this input (several directional samples whose '-' track is read during pass 1; SURVEY Q7)");
+    if (r) return fail(ctx, r, "several directional samples and a '-' track that the reference's merge loop reads during pass 1: it then aborts (assert) or pools that sample's '-' tags separately, neither is reproduced (SURVEY Q7); reference_order = 0 returns the canonical table");
     if (!identity) permute_table(out, perm, n);
   }
   ctx->stats.ms_call = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();

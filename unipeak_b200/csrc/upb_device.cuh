@@ -710,10 +710,14 @@ __device__ __forceinline__ void tir_eval (const Tags& T, bool directional, uint3
     if (r.strand == 0 && a1 == o[C]) {                                // ran off the end of the '+' track: the '-' track follows in the stream
       const uint64_t* om = T.off + (uint64_t)(s * 2 + 1) * (C + 1);
       const uint64_t b0 = om[0];
-      if (b0 < om[C] && tir_contig_of(T, s, 1, b0) == r.contig && T.pos[b0] <= r.right) {
-        const uint64_t b1 = upper_bound_u32(T.pos, b0, om[r.contig + 1], r.right);
-        hits += tir_sum(T, b0, b1);
-        E = tir_key(true, 1, r.contig, (uint64_t)r.right + 1);
+      if (b0 >= om[C]) E = TIR_END;                                    // no '-' track: the stream has ended
+      else {
+        const uint32_t c0 = tir_contig_of(T, s, 1, b0);
+        if (c0 == r.contig && T.pos[b0] <= r.right) {
+          const uint64_t b1 = upper_bound_u32(T.pos, b0, om[r.contig + 1], r.right);
+          hits += tir_sum(T, b0, b1);
+          E = tir_key(true, 1, r.contig, (uint64_t)r.right + 1);
+        } else E = tir_key(true, 1, c0, T.pos[b0]);                     // the cursor rests on the first '-' entry: a later '+' row skips the whole '-' track (Q13 i)
       }
     }
   } else {

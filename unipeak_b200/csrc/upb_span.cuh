@@ -572,9 +572,9 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : MINB) span_kernel (con
     __syncwarp();
   }
 
-  for (uint32_t i = tid; i < 2 * bw + 1; i += SP_THREADS) Ks[i] = a.taps[i];
-  for (uint32_t i = tid; i < a.nSamples; i += SP_THREADS) isCtl[i] = a.control[i];
-  if (COEFF) for (uint32_t i = tid; i < a.nSamples; i += SP_THREADS) coef[i] = a.coeff[i];
+  for (uint32_t i = tid; i < 2 * bw + 1; i += blockDim.x) Ks[i] = a.taps[i];      // (blockDim.x: a launch may bring fewer than SP_WARPS warps, launch_span)
+  for (uint32_t i = tid; i < a.nSamples; i += blockDim.x) isCtl[i] = a.control[i];
+  if (COEFF) for (uint32_t i = tid; i < a.nSamples; i += blockDim.x) coef[i] = a.coeff[i];
   __syncthreads();                                                    // the only block-level barrier
   const unsigned long long bw2 = (unsigned long long)bw * bw;
   unsigned long long stPieces = 0, stExact = 0, stSpans = 0;
@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(SP_THREADS, COEFF ? 2 : MINB) span_kernel (con
   uint32_t rBase = 0, rUsed = RUN_CHUNK, rTotal = 0;                   // current chunk of run slots: [rBase, rBase + RUN_CHUNK), rUsed taken
   bool rRoom = true;
   constexpr uint32_t BATCH = 4;                                        // hot spans per ticket: one atomic and two dependent loads per four spans ...
-  const uint32_t batch = nHot > gridDim.x * (uint32_t)SP_WARPS * 16u ? BATCH : (nHot > gridDim.x * (uint32_t)SP_WARPS * 4u ? 2u : 1u);   // ... fewer where a rank's shard leaves a warp only a handful (N = 8)
+  const uint32_t batch = nHot > gridDim.x * (blockDim.x >> 5) * 16u ? BATCH : (nHot > gridDim.x * (blockDim.x >> 5) * 4u ? 2u : 1u);   // ... fewer where a rank's shard leaves a warp only a handful (N = 8)
 
   for (;;) {
     uint32_t base = 0;
