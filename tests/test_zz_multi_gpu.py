@@ -2,6 +2,7 @@
 strand_shift, samples for tags_in_regions — against the one-context entry points, which test_gpu_parity.py pins to the oracle.
 Every comparison is bit for bit.  devices=[0, 0] puts both ranks on one GPU (runs anywhere); [0, 1] needs two GPUs."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -116,5 +117,37 @@ def test_multi_profile_comes_from_the_owner(gpu_ctx):
                 p0, s0 = gpu_ctx.profile_contig(b, c, **st)
                 p1, s1 = m.profile_contig(b, c, **st)
                 assert np.array_equal(p0, p1) and np.array_equal(s0, s1)
+    finally:
+        m.close()
+
+
+@pytest.mark.parametrize("seed", list(range(int(os.environ.get("UPB_FUZZ_MULTI_SEEDS", "8")))))   # ~4 s each: ranks that share a GPU stall each other when scratch grows (upb_multi.cu); 24 were green in r02
+def test_multi_random_workloads_equal_one_context(gpu_ctx, seed):
+    # the randomised workloads of test_zz_fuzz_gpu.py (controls, -z, -D, left-edge tags, tiny and empty contigs), two and three ranks on one GPU
+    from test_zz_fuzz_gpu import _case, _pass1_reads_a_minus_track
+    from unipeak_b200.capi import UpbError
+    d, kw = _case(seed)
+    if sum(d.tags(s) for s in range(d.n_samples) if s not in kw.get("control", [])) == 0:
+        pytest.skip("no non-control tags left")
+    st = region_settings(d, **kw)
+    if _pass1_reads_a_minus_track(d, st):
+        st = dict(st, reference_order=False)                           # (the emission-order emulation refuses these by name, Q7)
+    gpu_ctx.load(d)
+    try:
+        want = gpu_ctx.call_regions(**st)
+    except UpbError as e:
+        pytest.skip("one context refuses this input too: %s" % e)
+    m = MultiContext(2 + seed % 2, [0] * (2 + seed % 2))
+    try:
+        m.load(d, packed=bool(seed & 2))
+        try:
+            got = m.call_regions(**st)
+        except UpbError as e:
+            assert "another rank" in str(e), e                         # a window inherited across ranks: refused, not guessed
+            return
+        _same_rows(got["rows"], want["rows"])
+        _same_rows(got["dropped"], want["dropped"])
+        for k in ("n_passed", "n_rejected", "tags_in_regions"):
+            assert got[k] == want[k], k
     finally:
         m.close()

@@ -1,7 +1,7 @@
 #!/bin/bash
-# One gpurun call of round 2: smoke (optionally under compute-sanitizer), the GPU test suite, the bench line, the ncu launch list and
+# One gpurun call of round 2: smoke, the GPU test suite, the bench line, the ncu launch list and
 # one full capture of span_kernel.  Everything lands in gpurun_out/$TAG/.  Steps are chosen by name:
-#   bash tools/gpu_session.sh <tag> [smoke] [sanitize] [tests] [tests-fast] [bench] [bench-quick] [ncu] [ncufull] [refarm] [ab:<workloads>]
+#   bash tools/gpu_session.sh <tag> [smoke] [tests] [tests-fast] [bench] [bench-quick] [ncu] [ncufull] [refarm] [ab:<workloads>]
 set +e
 TAG=${1:-r02}; shift
 OUT=gpurun_out/$TAG
@@ -13,8 +13,6 @@ for step in "$@"; do
   case $step in
     smoke)
       timeout 300 python __graft_entry__.py --smoke > $OUT/smoke.txt 2>&1; note smoke $? ;;
-    sanitize)
-      timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python __graft_entry__.py --smoke > $OUT/sanitize.txt 2>&1; note sanitize $? ;;
     tests)
       timeout 1500 python -m pytest tests -x -q -m gpu > $OUT/pytest_gpu.txt 2>&1; note pytest $? ;;
     tests-fast)
@@ -49,7 +47,7 @@ for step in "$@"; do
   esac
 done
 cat $OUT/progress.txt
-for f in smoke.txt sanitize.txt pytest_gpu.txt pytest_gpu_fast.txt pytest_gpu_all.txt; do [ -f $OUT/$f ] && { echo "== $f"; tail -25 $OUT/$f; }; done
+for f in smoke.txt pytest_gpu.txt pytest_gpu_fast.txt pytest_gpu_all.txt; do [ -f $OUT/$f ] && { echo "== $f"; tail -25 $OUT/$f; }; done
 for f in cli_bench.jsonl wig_bench.json reference_arm.json; do [ -f $OUT/$f ] && { echo "== $f"; cut -c1-1500 $OUT/$f; }; done
 for f in bench_c3 bench_quick; do [ -f $OUT/$f.json ] && { echo "== $f"; cut -c1-1500 $OUT/$f.json; tail -5 $OUT/$f.err; }; done
 exit 0
