@@ -502,6 +502,15 @@ def test_packed_load_equals_plain_load(gpu_ctx):
     with pytest.raises(unipeak_b200.UpbError) as ei:
         gpu_ctx.load_tags_packed2_ptr(3, off.ctypes.data, words.ctypes.data, bad_exc.shape[0], bad_exc.ctypes.data)
     assert ei.value.code == -5
+    # ... an exception list that is not strictly increasing in its entry index, or points beyond the arrays
+    swapped = exc.copy()
+    swapped[[3, 4]] = swapped[[4, 3]]
+    beyond = exc.copy()
+    beyond["index"][-1] = int(off[-1]) + 5
+    for bad_list in (swapped, beyond):
+        with pytest.raises(unipeak_b200.UpbError) as ei:
+            gpu_ctx.load_tags_packed2_ptr(3, off.ctypes.data, words.ctypes.data, bad_list.shape[0], bad_list.ctypes.data)
+        assert ei.value.code == -2
     check_regions(gpu_ctx, make_synthetic([200000, 80000], 2, 30000, directional=True, seed=79, peak_spacing=5000))
 
 

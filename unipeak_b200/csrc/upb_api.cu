@@ -533,7 +533,10 @@ static int load_enqueue (upb_ctx* ctx, const upb_tag_source* src, bool resident)
   CU(cudaStreamSynchronize(ls));                                       // the host vectors above go out of scope; nothing large has been queued yet
   CU(cudaEventRecord(ctx->copyEvs[ctx->groups.size()], cs));
   ctx->loadCopied = !resident;
-  if (packed && src->n_exceptions) CU(cudaMemcpyAsync(ctx->d_pkExc.p, src->exceptions, src->n_exceptions * sizeof(PkException), cudaMemcpyHostToDevice, cs));
+  if (packed && src->n_exceptions) {
+    CU(cudaMemcpyAsync(ctx->d_pkExc.p, src->exceptions, src->n_exceptions * sizeof(PkException), cudaMemcpyHostToDevice, cs));
+    load_check_exc_kernel<<<(unsigned)((src->n_exceptions + 255) / 256), 256, 0, cs>>>(ctx->d_pkExc.as<PkException>(), src->n_exceptions, src->off[(size_t)n_samples * 2 * (C + 1) - 1], ctx->d_loadFlags.as<uint32_t>());
+  }
 
   LoadArgs la;
   memset(&la, 0, sizeof la);

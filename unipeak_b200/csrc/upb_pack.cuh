@@ -69,6 +69,14 @@ __device__ __forceinline__ void load_open_windows (const LoadArgs& a, uint32_t s
   for (int64_t t = prevWin + 1; t <= w; ++t) we[t] = rel;
 }
 
+// Packed form: the exception list must be strictly increasing in its entry index and stay inside the caller's arrays — the look-ups are
+// binary searches, which would otherwise miss (or find) an exception by accident.
+__global__ void load_check_exc_kernel (const PkException* __restrict__ exc, unsigned long long nExc, unsigned long long nSrcEntries, uint32_t* __restrict__ flags) {
+  const unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nExc) return;
+  if (exc[j].index >= nSrcEntries || (j > 0 && exc[j - 1].index >= exc[j].index)) atomicOr(flags, FLAG_BAD_PACK);
+}
+
 // Packed form: where the exceptions of every tile start.  A tile's first entry is a position escape, so every tile has at least one
 // exception and its exceptions are consecutive in the index-sorted list: one binary search per tile HERE (one thread per tile, all
 // tiles of the group in flight at once) instead of a 22-step chain of dependent loads inside load_tile_kernel, where a whole block
