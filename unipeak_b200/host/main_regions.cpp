@@ -143,6 +143,7 @@ int main (int argc, char* argv[]) {
     }
   }
 
+  Device dev;                                                        // one GPU, or UPB_GPUS=N of them; its CUDA context is created in the background while the inputs are parsed
   const ContigTable contigs = parse_contig_table(contigFname);
   const uint32_t C = contigs.size();
 
@@ -233,7 +234,6 @@ int main (int argc, char* argv[]) {
 
   // the hot path (:304-391), on the device
   fprintf(stderr, "calling enriched regions...\n");
-  Device dev;                                                        // one GPU, or UPB_GPUS=N of them with the contigs spread over them
   dev.setContigs(C, contigs.sizes.data());
   // which strand/contig units does the merge loop read in pass 1?  (single sample whose '-' track starts at or after its
   // last '+' contig: src/regions.cpp:341 consumes it there) — needed for the progress lines and the profile order

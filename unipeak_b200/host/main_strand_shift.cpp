@@ -41,6 +41,7 @@ int main (int argc, char* argv[]) {
   const std::vector<std::string>& alignFnames = cmd.unlabeled();
 
   const std::vector<short> offsets = parse_offsets(offsetString, alignFnames.size());
+  Device dev;                                                        // one GPU, or UPB_GPUS=N of them; its CUDA context is created in the background while the inputs are parsed
   const ContigTable contigs = parse_contig_table(contigFname);
   const uint32_t C = contigs.size();
 
@@ -62,7 +63,6 @@ int main (int argc, char* argv[]) {
 
   fprintf(stderr, "calling enriched regions for shift calibration... ");
   fflush(stderr);
-  Device dev;                                                        // one GPU, or UPB_GPUS=N of them with the contigs spread over them
   dev.setContigs(C, contigs.sizes.data());
   TagLoader loader;
   dev.load(loader, samples, C, false, true);

@@ -66,6 +66,7 @@ int main (int argc, char* argv[]) {
   const bool directional = !cmd.sw('D');
 
   const std::vector<short> offsets = parse_offsets(offsetString, alignFnames.size());
+  Device dev;                                                        // one GPU, or UPB_GPUS=N of them; its CUDA context is created in the background while the inputs are parsed
   const ContigTable contigs = parse_contig_table(contigFname);
   const uint32_t C = contigs.size();
 
@@ -131,7 +132,6 @@ int main (int argc, char* argv[]) {
 
   std::vector<uint32_t> counts(keys.size() * n + 1, 0);
   if (!keys.empty()) {
-    Device dev;                                                      // one GPU, or UPB_GPUS=N of them with the samples spread over them
     dev.setContigs(C, contigs.sizes.data());
     dev.loadBySample(samples, C, directional);
     dev.countTagsInRegions(directional ? 1 : 0, extension, keys.size(), keys.data(), counts.data());

@@ -995,35 +995,58 @@ int TagLoader::start (upb_multi* multi, const std::vector<Sample>& samples, uint
 // ---------------------------------------------------------------------------------------------------------------------------
 // Device: one GPU, or UPB_GPUS=N of them
 // ---------------------------------------------------------------------------------------------------------------------------
+static Device* g_pendingDevice = nullptr;      // a device whose creation may still be running
+static void join_pending_device () { if (g_pendingDevice) g_pendingDevice->join(); }   // exit() (die, usage errors) must not tear the process down under a thread inside the driver
+
 Device::Device () {
-  int want = 1;
-  if (const char* e = getenv("UPB_GPUS")) want = atoi(e);
-  if (want > 1) {
-    const int have = upb_device_count();
-    if (want > have) die("UPB_GPUS=" + std::to_string(want) + " but only " + std::to_string(have) + " CUDA device(s) are visible");
-    const int rc = upb_multi_create(want, nullptr, &multi_);
-    if (rc) die_upb(nullptr, rc);
-  } else {
-    const int rc = upb_create(0, &ctx_);
-    if (rc) die_upb(nullptr, rc);
-  }
+  if (const char* e = getenv("UPB_GPUS")) want_ = atoi(e);
+  if (want_ < 1) want_ = 1;
+  // Driver initialisation + context creation take 0.3 - 2 s (more than the reference's whole run on a small input): they run here, on a thread
+  // of their own, while the caller parses contig table and wiggle files — nothing in the reference's front end waits for a device
+  static const bool registered = (atexit(join_pending_device), true);
+  (void)registered;
+  g_pendingDevice = this;
+  init_ = new std::thread([this] {
+    if (want_ > 1) {
+      const int have = upb_device_count();
+      if (want_ > have) { initRc_ = UPB_ERR_NO_DEVICE; initMsg_ = "UPB_GPUS=" + std::to_string(want_) + " but only " + std::to_string(have) + " CUDA device(s) are visible"; return; }
+      initRc_ = upb_multi_create(want_, nullptr, &multi_);
+    } else initRc_ = upb_create(0, &ctx_);
+    if (initRc_) { const char* m = upb_last_error(nullptr); initMsg_ = (m && *m) ? m : "device call failed"; }
+  });
+  if (getenv("UPB_SYNC_INIT")) join();                               // (A/B of the overlap: create the context before parsing, as r01 did in effect)
 }
-Device::~Device () { if (multi_) upb_multi_destroy(multi_); if (ctx_) upb_destroy(ctx_); }
+void Device::join () {
+  if (!init_) return;
+  std::thread* t = (std::thread*)init_;
+  init_ = nullptr;
+  t->join();
+  delete t;
+  if (g_pendingDevice == this) g_pendingDevice = nullptr;
+}
+void Device::ready () {
+  join();
+  if (initRc_) { const int rc = initRc_; initRc_ = 0; die(initMsg_ + " (unipeak_b200 error " + std::to_string(rc) + ")"); }
+}
+Device::~Device () { join(); if (multi_) upb_multi_destroy(multi_); if (ctx_) upb_destroy(ctx_); }
 void Device::fail (int rc) {
   if (!multi_) die_upb(ctx_, rc);
   const char* m = upb_multi_last_error(multi_);
   die(std::string((m && *m) ? m : "device call failed") + " (unipeak_b200 error " + std::to_string(rc) + ")");
 }
 void Device::setContigs (uint32_t C, const uint32_t* sizes) {
+  ready();
   const int rc = multi_ ? upb_multi_set_contigs(multi_, C, sizes) : upb_set_contigs(ctx_, C, sizes);
   if (rc) fail(rc);
 }
 void Device::load (TagLoader& loader, const std::vector<Sample>& samples, uint32_t C, bool directionalHint, bool wait) {
+  ready();
   int rc = multi_ ? loader.start(multi_, samples, C, directionalHint) : loader.start(ctx_, samples, C, directionalHint);
   if (!rc && wait) rc = multi_ ? upb_multi_load_wait(multi_) : upb_load_wait(ctx_);
   if (rc) fail(rc);
 }
 void Device::loadBySample (const std::vector<Sample>& samples, uint32_t C, bool directionalHint) {
+  ready();
   int rc;
   if (multi_) {
     flatten(samples, C, &flat_);
@@ -1035,19 +1058,23 @@ void Device::loadBySample (const std::vector<Sample>& samples, uint32_t C, bool 
   if (rc) fail(rc);
 }
 void Device::callRegions (const upb_region_params* p, upb_region_table* out) {
+  ready();
   const int rc = multi_ ? upb_multi_call_regions(multi_, p, out) : upb_call_regions(ctx_, p, out);
   if (rc) fail(rc);
 }
 void Device::profileContig (const upb_region_params* p, int buffer, uint32_t contig, upb_profile* out) {
+  ready();
   const int rc = multi_ ? upb_multi_profile_contig(multi_, p, buffer, contig, out) : upb_profile_contig(ctx_, p, buffer, contig, out);
   if (rc) fail(rc);
 }
 int Device::strandShift (const upb_shift_params* p, upb_shift_report* out) {
+  ready();
   const int rc = multi_ ? upb_multi_strand_shift(multi_, p, out) : upb_strand_shift(ctx_, p, out);
   if (rc && rc != UPB_ERR_NO_REGIONS) { fprintf(stderr, "\n"); fail(rc); }
   return rc;
 }
 void Device::countTagsInRegions (int directional, uint32_t extension, uint64_t nRegions, const upb_region_key* regions, uint32_t* countsOut) {
+  ready();
   const int rc = multi_ ? upb_multi_count_tags_in_regions(multi_, directional, extension, nRegions, regions, countsOut)
                         : upb_count_tags_in_regions(ctx_, directional, extension, nRegions, regions, countsOut);
   if (rc) fail(rc);

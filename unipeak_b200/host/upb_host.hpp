@@ -155,9 +155,10 @@ class Out {
 // Every method dies with the library's message on failure, as the drivers did with die_upb.
 class Device {
  public:
-  Device ();
+  Device ();                                   // returns at once: the CUDA context(s) are created by a background thread while the caller parses its inputs
   ~Device ();
-  int gpus () const { return multi_ ? upb_multi_gpus(multi_) : 1; }
+  int gpus () const { return want_ > 1 ? want_ : 1; }
+  void join ();                                // (die() calls this so that the process does not exit under a thread that is inside the driver)
   void setContigs (uint32_t nContigs, const uint32_t* sizes);
   void load (TagLoader& loader, const std::vector<Sample>& samples, uint32_t nContigs, bool directionalHint, bool wait);   // by contig
   void loadBySample (const std::vector<Sample>& samples, uint32_t nContigs, bool directionalHint);                       // tags_in_regions
@@ -168,6 +169,10 @@ class Device {
  private:
   Device (const Device&);
   [[noreturn]] void fail (int rc);
+  void ready ();                               // joins the background creation; dies with the library's message if it failed
+  void* init_ = nullptr;                       // std::thread
+  int initRc_ = 0, want_ = 1;
+  std::string initMsg_;
   upb_ctx* ctx_ = nullptr;
   upb_multi* multi_ = nullptr;
   TagLoader sampleLoader_;
