@@ -3,5 +3,5 @@
 set -e
 NAME=$1; shift
 mkdir -p build_exp
-nvcc -shared -std=c++17 -O3 -lineinfo -fmad=false -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC "$@" -o build_exp/$NAME.so unipeak_b200/csrc/upb_api.cu
+nvcc -shared -std=c++17 -O3 -lineinfo -fmad=false -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC "$@" -o build_exp/$NAME.so unipeak_b200/csrc/upb_api.cu unipeak_b200/csrc/upb_multi.cu
 echo build_exp/$NAME.so
