@@ -602,6 +602,10 @@ def test_aggregate_tags_equals_a_map(gpu_ctx):
     pos = np.minimum(pos, np.array(sizes, dtype=np.uint32)[contig])
     cnt = rng.integers(1, 5, size=n).astype(np.uint32)
     cnt[::1000] = 0xFFFFFFF0                                                                           # HitCount arithmetic wraps
+    # a count that wraps to exactly 0 mod 2^32 keeps its key in the reference's map (i->second += hit.count), an alignment with count 0 never makes one
+    contig[:4] = 0; strand[:4] = 1; pos[:4] = [123457, 123457, 654321, 654321]; cnt[:4] = [0xFFFFFFFF, 1, 0, 0]
+    keep_out = (contig == 0) & ((pos == 654321) | (pos == 123457)); keep_out[:4] = False
+    pos[keep_out] -= 1
     key = (strand * 4 + contig).astype(np.uint32)
     for combine in (False, True):
         off, opos, ocnt, total = gpu_ctx.aggregate_tags(key, pos, cnt, combine_strands=combine)
@@ -610,7 +614,9 @@ def test_aggregate_tags_equals_a_map(gpu_ctx):
         order = np.argsort(full, kind="stable")
         u, start = np.unique(full[order], return_index=True)
         sums = np.add.reduceat(cnt[order].astype(np.uint64), start) & 0xFFFFFFFF
-        u, sums = u[sums != 0], sums[sums != 0]                        # a count that wraps to exactly 0 (mod 2^32) is an empty cell on the device
+        made = np.add.reduceat((cnt[order] != 0).astype(np.int64), start) > 0
+        u, sums = u[made], sums[made]
+        assert 0 in sums.tolist()                                      # the planted wrapped key is there, with count 0
         assert np.array_equal(opos, (u & 0xFFFFFFFF).astype(np.uint32)) and np.array_equal(ocnt, sums.astype(np.uint32))
         assert total == int(cnt.astype(np.uint64).sum())
         want_off = np.searchsorted(u >> 32, np.arange(9), side="left")

@@ -3,7 +3,9 @@
 //
 // Same two-level layout as the tag loader: a counting sort of the alignments by (strand, contig, 512-position mini-tile)
 // (histogram, scan, scatter), then one warp per non-empty mini-tile pools its alignments into 512 shared-memory cells and
-// writes the non-zero cells out in ascending position — first pass counts them, a scan places them, second pass emits.
+// writes the cells that received an alignment out in ascending position — first pass counts them, a scan places them, second
+// pass emits.  "Received an alignment" is a bit per cell, not "count != 0": the map keeps a key whose count wrapped to exactly
+// 0 mod 2^32 (i->second += hit.count), and never creates one for an alignment with count 0 (misc/data.cpp:302).
 #pragma once
 
 #include "upb_device.cuh"
@@ -54,16 +56,22 @@ constexpr int AG_CELLS = 1 << MT_SHIFT;
 template <bool EMIT>
 __global__ void __launch_bounds__(AG_WARPS * 32) aggr_reduce_kernel (AggrArgs a) {
   __shared__ uint32_t cells[AG_WARPS][AG_CELLS];
+  __shared__ uint32_t present[AG_WARPS][AG_CELLS / 32];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t m = blockIdx.x * AG_WARPS + warp;
   if (m >= a.nMt) return;
   const unsigned long long e0 = a.mtOff[m], e1 = a.mtOff[m + 1];
   if (e0 == e1) { if (!EMIT && lane == 0) a.uniq[m] = 0; return; }
   uint32_t* cell = cells[warp];
+  uint32_t* seen = present[warp];
   for (uint32_t k = lane; k < (uint32_t)AG_CELLS; k += 32) cell[k] = 0;
+  if (lane < (uint32_t)AG_CELLS / 32) seen[lane] = 0;
   __syncwarp();
   unsigned long long tot = 0;
-  for (unsigned long long e = e0 + lane; e < e1; e += 32) { const uint2 x = a.ent[e]; atomicAdd(&cell[x.y], x.x); tot += x.x; }   // HitCount arithmetic wraps like the map's +=
+  for (unsigned long long e = e0 + lane; e < e1; e += 32) {
+    const uint2 x = a.ent[e];
+    if (x.x) { atomicAdd(&cell[x.y], x.x); atomicOr(&seen[x.y >> 5], 1u << (x.y & 31)); tot += x.x; }   // HitCount arithmetic wraps like the map's +=
+  }
   __syncwarp();
   // position of mini-tile m inside its (strand, contig): largest dc with mtBase[dc] <= m
   uint32_t lo = 0, hi = 2 * a.C;
@@ -72,8 +80,8 @@ __global__ void __launch_bounds__(AG_WARPS * 32) aggr_reduce_kernel (AggrArgs a)
   uint32_t run = 0;
   for (uint32_t k0 = 0; k0 < (uint32_t)AG_CELLS; k0 += 32) {
     const uint32_t v = cell[k0 + lane];
-    const uint32_t msk = __ballot_sync(0xffffffffu, v != 0);
-    if (EMIT && v) {
+    const uint32_t msk = seen[k0 >> 5];
+    if (EMIT && ((msk >> lane) & 1u)) {
       const unsigned long long o = a.outOff[m] + run + __popc(msk & ((1u << lane) - 1));
       a.outPos[o] = p0 + k0 + lane;
       a.outCnt[o] = v;

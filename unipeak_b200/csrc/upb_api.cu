@@ -47,6 +47,15 @@ struct upb_ctx {
   int device = 0;
   int smCount = 148;
   cudaStream_t stream = nullptr;
+  // A region call works through its units in groups; consecutive groups alternate between two LANES — `stream` and `laneStream`, each with its
+  // own set of per-group scratch arrays and its own GroupCtr — so that one group's latency-bound tail (order / stitch / pooling / rows over PCIe)
+  // runs beside the next group's span kernel.  `cur` / `lane` are what the helpers (scan_dev, launch_span, SCR) enqueue on / allocate for.
+  cudaStream_t laneStream = nullptr;
+  cudaStream_t cur = nullptr;
+  int lane = 0;
+  cudaEvent_t laneSetupEv = nullptr, laneDoneEv = nullptr;
+  std::vector<cudaEvent_t> placeEv;     // per group: its rows have their place (row_place_kernel done)
+  std::vector<cudaEvent_t> spanEv;      // per group: before / after its span kernel
   cudaStream_t copyStream = nullptr;    // H2D copies of the load run here, one load group ahead of the kernels that consume them ...
   cudaStream_t copyStream2 = nullptr;   // second H2D queue: the copies of a group alternate between the two, so the next descriptor is always ready
   cudaStream_t loadStream = nullptr;    // ... on this one (decode, validation, counting sort, zone maps), while `stream` may already run the region pipeline of earlier groups
@@ -153,6 +162,10 @@ extern "C" int upb_create (int device, upb_ctx** out) {
   cudaDeviceGetStreamPriorityRange(&prLo, &prHi);                     // lowest, highest (numerically smaller = higher)
   const int mode = getenv("UPB_PRIO") ? atoi(getenv("UPB_PRIO")) : 1;
   if ((e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, mode == 1 ? prHi : prLo)) != cudaSuccess) { delete ctx; return fail(nullptr, UPB_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
+  ctx->cur = ctx->stream;
+  cudaStreamCreateWithPriority(&ctx->laneStream, cudaStreamNonBlocking, mode == 1 ? prHi : prLo);
+  cudaEventCreateWithFlags(&ctx->laneSetupEv, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->laneDoneEv, cudaEventDisableTiming);
   for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
   cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking);
   cudaStreamCreateWithPriority(&ctx->loadStream, cudaStreamNonBlocking, mode == 2 ? prHi : prLo);
@@ -183,6 +196,11 @@ extern "C" void upb_destroy (upb_ctx* ctx) {
   for (cudaEvent_t e : ctx->groupEv) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->copyEvs) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->copyEvs2) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->placeEv) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->spanEv) cudaEventDestroy(e);
+  if (ctx->laneSetupEv) cudaEventDestroy(ctx->laneSetupEv);
+  if (ctx->laneDoneEv) cudaEventDestroy(ctx->laneDoneEv);
+  if (ctx->laneStream) cudaStreamDestroy(ctx->laneStream);
   if (ctx->copyStream2) cudaStreamDestroy(ctx->copyStream2);
   if (ctx->h_ends.p) cudaFreeHost(ctx->h_ends.p);
   if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
@@ -744,7 +762,7 @@ extern "C" int upb_pack_tags2 (uint32_t n_samples, uint32_t n_contigs, const uin
 // ------------------------------------------------------------------------------------------------
 // device-wide exclusive scan (uint32 in, uint64 out); total -> *d_total
 // ------------------------------------------------------------------------------------------------
-#define SCR(name, T, count) ({ DevBuf& b__ = ctx->scratch[name]; int r__ = ensure(ctx, b__, (size_t)(count) * sizeof(T) + 16); if (r__) return r__; (T*)b__.p; })
+#define SCR(name, T, count) ({ DevBuf& b__ = ctx->scratch[ctx->lane ? std::string(name) + "~lane1" : std::string(name)]; int r__ = ensure(ctx, b__, (size_t)(count) * sizeof(T) + 16); if (r__) return r__; (T*)b__.p; })
 
 static int scan_u32 (upb_ctx* ctx, const uint32_t* d_in, uint64_t n, unsigned long long* d_out, unsigned long long* d_total, uint32_t* launches) {
   const uint32_t nBlocks = (uint32_t)((n + SCAN_BLOCK - 1) / SCAN_BLOCK);
@@ -1163,7 +1181,7 @@ static int launch_span (upb_ctx* ctx, const SpanArgs& sa, bool nondir, uint32_t*
   if (bulk) kern = perSm < SP_MIN_BLOCKS ? span_kernel<false, false, SP_MIN_BLOCKS - 1, true> : span_kernel<false, false, SP_MIN_BLOCKS, true>;
   if (bulk) { int rr = cached_occupancy(ctx, kern, threads, smem, &perSm); if (rr) return rr; }
   const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)ctx->smCount * perSm, std::max<uint32_t>(sa.totalSpans, 1u));
-  kern<<<grid, threads, smem, ctx->stream>>>(sa);
+  kern<<<grid, threads, smem, ctx->cur>>>(sa);
   CU(cudaGetLastError());
   *launches += 1;
   return UPB_OK;
@@ -1175,7 +1193,7 @@ static void stage_mark (upb_ctx* ctx, const char* name) {
   ctx->hostMarks.push_back(std::make_pair(name, std::chrono::steady_clock::now()));   // host side of the same points (UPB_TRACE_SLOW)
   if (!ctx->profiling) return;
   if (ctx->stageUsed == ctx->stageEv.size()) { cudaEvent_t e = nullptr; if (cudaEventCreate(&e) != cudaSuccess) return; ctx->stageEv.push_back(e); }
-  cudaEventRecord(ctx->stageEv[ctx->stageUsed++], ctx->stream);
+  cudaEventRecord(ctx->stageEv[ctx->stageUsed++], ctx->cur);
   ctx->stageNames.push_back(name);
 }
 static void stage_collect (upb_ctx* ctx) {                            // after the stream has been synchronised
@@ -1199,9 +1217,9 @@ static int scan_dev (upb_ctx* ctx, Load ld, DevN n, uint64_t cap, unsigned long 
   const uint64_t maxTiles = (cap + SCAN_BLOCK - 1) / SCAN_BLOCK;
   unsigned long long* part = SCR("scanPartial", unsigned long long, maxTiles + 1);
   const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(maxTiles, (uint64_t)ctx->smCount * 4));
-  scanv_partial_kernel<<<grid, SCAN_THREADS, 0, ctx->stream>>>(ld, n, part);
-  scanv_top_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(part, n, d_total);
-  scanv_final_kernel<<<grid, SCAN_THREADS, 0, ctx->stream>>>(ld, n, part, d_out, 0ull);
+  scanv_partial_kernel<<<grid, SCAN_THREADS, 0, ctx->cur>>>(ld, n, part);
+  scanv_top_kernel<<<1, SCAN_THREADS, 0, ctx->cur>>>(part, n, d_total);
+  scanv_final_kernel<<<grid, SCAN_THREADS, 0, ctx->cur>>>(ld, n, part, d_out, 0ull);
   CU(cudaGetLastError());
   *launches += 3;
   return UPB_OK;
@@ -1404,17 +1422,8 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
   //  capacity happened to leave more than 16 bytes over: 2 - 20 ms stalls in the first calls of a context, r02 N = 4 trace)
   { const size_t cap = ctx->scratch["runs"].cap; const size_t have = cap > 16 ? (cap - 16) / sizeof(SpanRun) : 0; if (have > runCap) runCap = have; }
   runCap = std::min<size_t>(runCap, 0xFFFFFFF0u);
-  sa.runs = SCR("runs", SpanRun, runCap);
-  sa.runCap = (uint32_t)runCap;
+  sa.runCap = (uint32_t)runCap;                                        // (the run-sized arrays are per lane: allocated at the head of the group loop)
   unsigned long long* spanOrd = SCR("spanOrd", unsigned long long, pr.totalSpans);
-  uint32_t* ordIdx = SCR("ordIdx", uint32_t, runCap);
-  uint32_t* head = SCR("head", uint32_t, runCap);
-  unsigned long long* headScan = SCR("headScan", unsigned long long, runCap);
-  Cand2* cand = SCR("cand", Cand2, runCap);
-  uint32_t* pass = SCR("pass", uint32_t, runCap);
-  uint32_t* candLen = SCR("candLen", uint32_t, runCap);
-  unsigned long long* pvScan = SCR("pvScan", unsigned long long, runCap);
-  uint32_t* list1 = SCR("list1", uint32_t, runCap);
   unsigned long long* unitCand = SCR("unitCand", unsigned long long, 6 * (size_t)nUnits + 8);
   unsigned long long* unitFirst = unitCand + nUnits;
   unsigned long long* normalFirst = unitFirst + nUnits;               // nUnits + 1
@@ -1511,8 +1520,39 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
       PGroup pg; pg.u0 = 0; pg.u1 = nUnits; pg.s0 = 0; pg.s1 = pr.totalSpans; pg.ev0 = pg.ev1 = -1; pgroups.push_back(pg);
     }
   }
+  // Two lanes (see upb_ctx::laneStream).  A resident call is cut into `wantGroups` groups of units of about equal span counts, dealt to the lanes in
+  // turn; a call behind a load deals the groups it already has.  Not for calls with a read-back in the middle (sizing, -D correlation), the
+  // left-edge replay or per-stage profiling (events on one stream).  With a shared table the groups before the last only COUNT their rows
+  // (row_place_kernel, countOnly); the last group's launch publishes the rank's counts once, waits for the other ranks and places every
+  // unit, and the earlier groups' rows are emitted behind it.
+  int wantGroups = 2;
+  if (const char* e = getenv("UPB_CALL_GROUPS")) wantGroups = std::max(1, std::min(16, atoi(e)));
+  bool twoLanes = wantGroups > 1 && !sizing && !cfg.needCorr && nAff == 0 && !ctx->profiling && !empty && ctx->laneStream != nullptr;
+  if (shared && (ctx->capN1 == 0 || ctx->capCells == 0)) twoLanes = false;   // (reads its sizes back in the middle of the call)
+  if (shared && getenv("UPB_SHARED_LANES") && !atoi(getenv("UPB_SHARED_LANES"))) twoLanes = false;
+  if (twoLanes && !pipelined) {
+    if (nUnits < 2 || pr.totalSpans < (1u << 16)) twoLanes = false;    // small inputs: one chain of launches is all there is to wait for
+    else {
+      pgroups.clear();
+      uint32_t u = 0;
+      for (int k = 0; k < wantGroups && u < nUnits; ++k) {
+        const uint64_t upTo = (uint64_t)pr.totalSpans * (uint64_t)(k + 1) / (uint64_t)wantGroups;
+        PGroup pg; pg.u0 = u; pg.ev0 = pg.ev1 = -1;
+        while (u < nUnits && (u == pg.u0 || k + 1 == wantGroups || (uint64_t)pr.units[u].spanStart + pr.units[u].nSpans / 2 < upTo)) ++u;
+        pg.u1 = u; pg.s0 = pr.units[pg.u0].spanStart; pg.s1 = pr.units[pg.u1 - 1].spanStart + pr.units[pg.u1 - 1].nSpans;
+        pgroups.push_back(pg);
+      }
+      if (pgroups.size() < 2) twoLanes = false;
+    }
+  }
+  if (twoLanes && pgroups.size() < 2) twoLanes = false;
+  struct LaneReset { upb_ctx* c; ~LaneReset () { c->lane = 0; c->cur = c->stream; } } laneReset{ctx};
+  while (ctx->placeEv.size() < pgroups.size()) { cudaEvent_t e = nullptr; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->placeEv.push_back(e); }
+  while (ctx->spanEv.size() < 2 * pgroups.size()) { cudaEvent_t e = nullptr; CU(cudaEventCreate(&e)); ctx->spanEv.push_back(e); }
+  GroupCtr* const gLane[2] = {g, (GroupCtr*)((unsigned char*)ctx->d_small.p + LANE1_GROUPCTR_OFFSET)};
+  if (twoLanes) { CU(cudaEventRecord(ctx->laneSetupEv, ctx->stream)); CU(cudaStreamWaitEvent(ctx->laneStream, ctx->laneSetupEv, 0)); }
   const bool trace = getenv("UPB_TRACE") && *getenv("UPB_TRACE");
-  if (trace) fprintf(stderr, "[upb] call: %s, %zu group(s) of units, sizing %d\n", pipelined ? "pipelined behind the load" : "resident", pgroups.size(), (int)sizing);
+  if (trace) fprintf(stderr, "[upb] call: %s, %zu group(s) of units on %d lane(s), sizing %d\n", pipelined ? "pipelined behind the load" : "resident", pgroups.size(), twoLanes ? 2 : 1, (int)sizing);
   uint64_t rowCap = 0;
   unsigned char* hs = nullptr;                                         // table columns (mapped host memory)
   if (!empty && !shared && !sizing) {                                  // the table: sized from the previous call (sizing: once this call's row count is known)
@@ -1522,8 +1562,29 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
     hs = (unsigned char*)out.slab.p;
   }
   if (shared) { rowCap = shared->rowCap; hs = shared->slab; out.layout = slab_layout(rowCap, n, C); }
+  struct Deferred { EmitArgs ea; GroupEndArgs ge; cudaStream_t st; };
+  std::vector<Deferred> deferred;
   if (!empty) for (size_t gi = 0; gi < pgroups.size(); ++gi) {
     const uint32_t u0 = pgroups[gi].u0, u1 = pgroups[gi].u1, s0 = pgroups[gi].s0, s1 = pgroups[gi].s1;
+    const int lane = twoLanes ? (int)(gi & 1) : 0;
+    ctx->lane = lane; ctx->cur = lane ? ctx->laneStream : ctx->stream;
+    cudaStream_t st_ = ctx->cur;                                         // (shadows: everything below is this lane's)
+    GroupCtr* g = gLane[lane];
+    sa.flags = &g->flags; sa.ticket = &g->ticket; sa.runCount = &g->runCount; sa.runReal = &g->runReal; sa.nHot = &g->nHot;
+    ha.nWarm = &g->nWarm; ha.nHot = &g->nHot; wa.nWarm = &g->nWarm;
+    WarmRec* warmList = SCR("warmList", WarmRec, pr.totalSpans);
+    uint2* hotList = SCR("hotList", uint2, pr.totalSpans);
+    sa.hotList = hotList; ha.warmList = warmList; ha.hotList = hotList; wa.warmList = warmList;
+    sa.runs = SCR("runs", SpanRun, runCap);
+    uint32_t* ordIdx = SCR("ordIdx", uint32_t, runCap);
+    uint32_t* head = SCR("head", uint32_t, runCap);
+    unsigned long long* headScan = SCR("headScan", unsigned long long, runCap);
+    Cand2* cand = SCR("cand", Cand2, runCap);
+    uint32_t* pass = SCR("pass", uint32_t, runCap);
+    uint32_t* candLen = SCR("candLen", uint32_t, runCap);
+    unsigned long long* pvScan = SCR("pvScan", unsigned long long, runCap);
+    uint32_t* list1 = SCR("list1", uint32_t, runCap);
+    (void)SCR("scanPartial", unsigned long long, std::max<size_t>(runCap, pr.totalSpans) / SCAN_BLOCK + 2);
     if (pgroups[gi].ev0 >= 0) CU(cudaStreamWaitEvent(st_, ctx->groupEv[pgroups[gi].ev0], 0));
     if (pgroups[gi].ev1 >= 0) CU(cudaStreamWaitEvent(st_, ctx->groupEv[pgroups[gi].ev1], 0));
     hmark("h:events");
@@ -1538,9 +1599,9 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
     hmark("h:hot launch");
     launches += 2;
     stage_mark(ctx, "warm_span_kernel+hot_span_kernel");
-    CU(cudaEventRecord(ctx->ev[1], st_));
+    CU(cudaEventRecord(ctx->spanEv[2 * gi], st_));
     if ((r = launch_span(ctx, sa, cfg.nondir, &launches))) return r;
-    CU(cudaEventRecord(ctx->ev[2], st_));
+    CU(cudaEventRecord(ctx->spanEv[2 * gi + 1], st_));
     stage_mark(ctx, "span_kernel");
 
     // ---- K2: (span, rank) order, stitch runs cut by piece / span boundaries, hit filter ------------------------------
@@ -1557,7 +1618,10 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
     }
     if ((r = scan_dev(ctx, LoadPacked{pass, candLen}, devn_u64(&g->nCand), runCap, pvScan, &g->pv, &launches))) return r;
     // per-survivor arrays: sized from the previous call, or (sizing) from this one's numbers
-    if (sizing || cfg.needCorr || shared) {
+    // (a shared call cannot be repeated with larger arrays — the other ranks would wait for it — so it reads its sizes back unless an earlier
+    //  call of this context has already sized the per-survivor arrays, margin included; outgrowing those is then an error, like outgrowing the table)
+    const bool readSizes = sizing || cfg.needCorr || (shared && (ctx->capN1 == 0 || ctx->capCells == 0));
+    if (readSizes) {
       compact_pv_kernel<<<GS, 256, 0, st_>>>(pass, pvScan, g, (uint32_t)runCap, ~0ull, list1);
       launches += 1;
       CU(cudaGetLastError());
@@ -1573,7 +1637,7 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
     uint32_t* pass2 = SCR("pass2", uint32_t, n1Cap);
     unsigned long long* pass2Scan = SCR("pass2Scan", unsigned long long, n1Cap);
     uint32_t* statCells = SCR("statCells", uint32_t, cellCap + 1);
-    if (!(sizing || cfg.needCorr || shared)) {
+    if (!readSizes) {
       compact_pv_kernel<<<GS, 256, 0, st_>>>(pass, pvScan, g, (uint32_t)n1Cap, cellCap, list1);
       launches += 1;
     }
@@ -1636,8 +1700,11 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
     pa.cand = cand; pa.list = list1; pa.pass2Scan = pass2Scan; pa.g = g; pa.call = call; pa.units = d_units; pa.u0 = u0; pa.u1 = u1;
     pa.edgeRows = d_edgeRowsOfUnit; pa.normalFirst = normalFirst; pa.rowShift = rowShift; pa.edgeRowBase = edgeRowBase; pa.unitRows = unitRowsDev;
     pa.shared = shared ? 1 : 0;
-    if (shared) pa.x = shared->x;
+    const bool lastGroup = gi + 1 == pgroups.size();
+    if (shared) { pa.x = shared->x; pa.countOnly = (twoLanes && !lastGroup) ? 1 : 0; pa.allU0 = twoLanes ? 0u : u0; pa.allU1 = twoLanes ? nUnits : u1; }
+    if (twoLanes && gi > 0) CU(cudaStreamWaitEvent(st_, ctx->placeEv[gi - 1], 0));   // rows of a group follow the rows of the groups before it
     row_place_kernel<<<1, 256, 0, st_>>>(pa);
+    if (twoLanes) CU(cudaEventRecord(ctx->placeEv[gi], st_));
     launches += 1;
     if (!shared && sizing) {
       if ((r = read_group())) return r;
@@ -1658,6 +1725,16 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
     ea.peak = (uint32_t*)(hs + SL.oPeak); ea.wsum = (uint32_t*)(hs + SL.oWsum); ea.candIndex = (unsigned long long*)(hs + SL.oCandIndex);
     ea.peakScore = (double*)(hs + SL.oPeakScore); ea.kurt = (double*)(hs + SL.oKurt); ea.corr = (double*)(hs + SL.oCorr);
     ea.counts = (uint32_t*)(hs + SL.oCounts);
+    GroupEndArgs ge;
+    memset(&ge, 0, sizeof ge);
+    ge.statCounts = statCounts; ge.pass = pass2; ge.g = g; ge.call = call; ge.nSamples = n;
+    ge.edgeRowCounts = eg.rowCounts; ge.edgeNRows = eg.nRows; ge.edgeRowCap = EDGE_ROW_CAP; ge.nAffected = edgeRowsTotal ? nAff : 0; ge.edgeRowsTotal = edgeRowsTotal;
+    ge.tir = d_tir;
+    if (shared && twoLanes && !lastGroup) {                              // its rows have no place yet: emitted behind the last group's row_place_kernel
+      Deferred df; df.ea = ea; df.ge = ge; df.st = st_;
+      deferred.push_back(df);
+      continue;
+    }
     emit_rows_kernel<<<GS, 256, 0, st_>>>(ea);
     emit_counts_kernel<<<GS, 256, 0, st_>>>(ea);
     launches += 2;
@@ -1671,17 +1748,22 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
       edge_emit_kernel<<<dim3((EDGE_ROW_CAP + 127) / 128, nAff), 128, 0, st_>>>(ee);
       launches += 1;
     }
-    GroupEndArgs ge;
-    memset(&ge, 0, sizeof ge);
-    ge.statCounts = statCounts; ge.pass = pass2; ge.g = g; ge.call = call; ge.nSamples = n;
-    ge.edgeRowCounts = eg.rowCounts; ge.edgeNRows = eg.nRows; ge.edgeRowCap = EDGE_ROW_CAP; ge.nAffected = edgeRowsTotal ? nAff : 0; ge.edgeRowsTotal = edgeRowsTotal;
-    ge.tir = d_tir;
     group_end_kernel<<<(unsigned)ctx->smCount * 2, 256, (size_t)n * 8, st_>>>(ge);
     CU(cudaGetLastError());
     launches += 1;
     stage_mark(ctx, "place+emit rows (to host)+totals");
     if (trace && gi < ctx->copyEvs2.size()) cudaEventRecord(ctx->copyEvs2[gi], st_);
   }
+  for (const Deferred& df : deferred) {
+    CU(cudaStreamWaitEvent(df.st, ctx->placeEv[pgroups.size() - 1], 0));
+    emit_rows_kernel<<<GS, 256, 0, df.st>>>(df.ea);
+    emit_counts_kernel<<<GS, 256, 0, df.st>>>(df.ea);
+    group_end_kernel<<<(unsigned)ctx->smCount * 2, 256, (size_t)n * 8, df.st>>>(df.ge);
+    CU(cudaGetLastError());
+    launches += 3;
+  }
+  ctx->lane = 0; ctx->cur = ctx->stream;
+  if (twoLanes) { CU(cudaEventRecord(ctx->laneDoneEv, ctx->laneStream)); CU(cudaStreamWaitEvent(ctx->stream, ctx->laneDoneEv, 0)); }
   if (empty) {                                                          // a rank of a shared table with nothing loaded still takes part in the exchange
     CU(cudaMemsetAsync(g, 0, sizeof(GroupCtr), st_));
     PlaceArgs pa;
@@ -1715,7 +1797,11 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
       for (const auto& hm : ctx->hostMarks) { fprintf(stderr, " %s +%.3f", hm.first, ms(prev, hm.second)); prev = hm.second; }
       fprintf(stderr, " end +%.3f\n", ms(prev, tC));
     } }
-  if (!empty) { float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->stats.ms_kde = ms; }
+  if (!empty) {                                                          // span kernel time: the groups' launches added up (two lanes: each bracket may hold a share of the other lane's kernels)
+    float sum = 0;
+    for (size_t gi = 0; gi < pgroups.size(); ++gi) { float ms = 0; cudaEventElapsedTime(&ms, ctx->spanEv[2 * gi], ctx->spanEv[2 * gi + 1]); sum += ms; }
+    ctx->stats.ms_kde = sum;
+  }
   stage_collect(ctx);
   ctx->stats.launches = launches;
   if (pipelined) { const int rl = load_finish(ctx); if (rl) return rl; }   // what the load had to say about the input
@@ -1728,7 +1814,10 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
   const uint32_t flags = hcall->flags | hg->flags;
   if (flags & FLAG_XCHG_TIMEOUT) return fail(ctx, UPB_ERR_CUDA, "shared table: another rank never published its row counts (timeout)");
   if (flags & (FLAG_RUN_OVERFLOW | FLAG_CAP_OVERFLOW)) {
-    if (shared) return fail(ctx, UPB_ERR_NOMEM, "shared table: this call needs more room than the table or the arrays sized by the previous call have (call upb_call_regions once per context before sharing)");
+    if (shared) {
+      ctx->capN1 = 0; ctx->capCells = 0;                                // the next shared call of this context reads its sizes back instead of trusting the old ones
+      return fail(ctx, UPB_ERR_NOMEM, "shared table: this call needs more room than the table or the arrays sized by the previous call have (call upb_call_regions once per context before sharing)");
+    }
     if (out.slab.p) { ctx->slabPool.push_back(out.slab); out.slab = HostSlab(); }
     if (flags & FLAG_RUN_OVERFLOW) ctx->needRunCap = (size_t)std::max<unsigned long long>(hcall->needSlots, hg->runCount) + (1u << 20);
     *retry = true;
@@ -1747,13 +1836,15 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
     out.nCand = (uint64_t)((long long)out.nCand + d);
   }
   ctx->stats.n_candidates = out.nCand;
-  if (!shared) {
-    memcpy(hs + out.layout.oTags, hTir, (size_t)n * 8);
+  {
     // what the next call of this context may assume without asking
     const size_t n1 = (size_t)hcall->n1, cells = (size_t)hcall->cells, R = (size_t)out.R;
     ctx->capN1 = std::max(ctx->capN1, n1 + n1 / 4 + 1024);
     ctx->capCells = std::max(ctx->capCells, cells + cells / 4 + 4096);
-    ctx->capRows = std::max(ctx->capRows, R + R / 4 + 1024);
+    if (!shared) {
+      memcpy(hs + out.layout.oTags, hTir, (size_t)n * 8);
+      ctx->capRows = std::max(ctx->capRows, R + R / 4 + 1024);
+    }
   }
   out.tir.assign(hTir, hTir + n);
   ctx->stats.ms_host_post = std::chrono::duration<float, std::milli>(Clk::now() - tD).count();

@@ -956,6 +956,7 @@ struct CallCtr {                    // zeroed once per call; accumulated over th
   uint32_t flags, pad;
 };
 constexpr size_t CALLCTR_OFFSET = 512;   // byte offset of CallCtr inside d_small
+constexpr size_t LANE1_GROUPCTR_OFFSET = 1024;   // the second lane's GroupCtr (upb_ctx::laneStream); lane 0's is at byte 0
 
 __device__ __forceinline__ bool pipe_dead (const GroupCtr* g) { return (g->flags & FLAG_RUN_OVERFLOW) != 0; }   // runs are incomplete: nothing downstream may index through them
 
@@ -1297,6 +1298,9 @@ struct PlaceArgs {
   unsigned long long* edgeRowBase;  // [nUnits] out: table row of the unit's first replay row
   unsigned long long* unitRows;     // [nUnits] out: rows of the unit (replay rows included)
   int shared;                       // 0: one GPU (rows follow the earlier groups' rows); 1: exchange
+  int countOnly;                    // shared table, a group that is not the call's last: count this group's rows per unit and leave; the last group's
+                                    // launch (ordered behind the others) publishes and places the units [allU0, allU1) of all groups
+  uint32_t allU0, allU1;
   XchgArgs x;
 };
 
@@ -1327,15 +1331,18 @@ __global__ void __launch_bounds__(256) row_place_kernel (PlaceArgs a) {
         a.rowShift[u] = (long long)(base + er) - (long long)a.normalFirst[u];
         base += a.unitRows[u];
       }
+      a.call->rows = base;                                               // the next group's rows follow (its row_place_kernel is ordered behind this one)
     }
     return;
   }
+  if (a.countOnly) return;
   // shared table: publish this rank's counts, wait for the others, place by (buffer, contig) over all ranks
   const uint32_t C2 = 2 * a.x.C;
+  const uint32_t nAll = a.allU1 - a.allU0;
   volatile unsigned long long* mine = a.x.counts + (size_t)a.x.rank * C2;
   for (uint32_t k = threadIdx.x; k < C2; k += blockDim.x) mine[k] = 0;
   __syncthreads();
-  for (uint32_t t = threadIdx.x; t < nu; t += blockDim.x) { const SpanUnit U = a.units[a.u0 + t]; mine[U.buffer * a.x.C + U.contig] = a.unitRows[a.u0 + t]; }
+  for (uint32_t t = threadIdx.x; t < nAll; t += blockDim.x) { const SpanUnit U = a.units[a.allU0 + t]; mine[U.buffer * a.x.C + U.contig] = a.unitRows[a.allU0 + t]; }
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) { a.x.ready[a.x.rank] = a.x.step; __threadfence_system(); }
@@ -1349,10 +1356,10 @@ __global__ void __launch_bounds__(256) row_place_kernel (PlaceArgs a) {
     // table row of the first row of every (buffer, contig), summed over the ranks in table order; this rank's units pick theirs
     uint32_t t = 0;
     unsigned long long base = 0;
-    for (uint32_t k = 0; k < C2 && t < nu; ++k) {
-      const SpanUnit U = a.units[a.u0 + t];
+    for (uint32_t k = 0; k < C2 && t < nAll; ++k) {
+      const SpanUnit U = a.units[a.allU0 + t];
       if (U.buffer * a.x.C + U.contig == k) {
-        const uint32_t u = a.u0 + t;
+        const uint32_t u = a.allU0 + t;
         const unsigned long long er = a.edgeRows ? a.edgeRows[u] : 0u;
         a.edgeRowBase[u] = base;
         a.rowShift[u] = (long long)(base + er) - (long long)a.normalFirst[u];
@@ -1360,6 +1367,9 @@ __global__ void __launch_bounds__(256) row_place_kernel (PlaceArgs a) {
       }
       for (uint32_t r = 0; r < a.x.world; ++r) base += a.x.counts[(size_t)r * C2 + k];
     }
+    unsigned long long mineRows = 0;                                   // this rank's rows of the call
+    for (uint32_t u = a.allU0; u < a.allU1; ++u) mineRows += a.unitRows[u];
+    a.call->rows += mineRows;
   }
 }
 
@@ -1452,8 +1462,7 @@ __global__ void edge_emit_kernel (EdgeEmitArgs a) {
 }
 
 // per-sample totals of the accepted rows (ProfileBuffer::nTagsInRegions, misc/peakcall.cpp:44) from the per-survivor matrix rows,
-// plus the end-of-group bookkeeping: the call-wide counters take this group's numbers (one thread; the next group's kernels,
-// later in the stream, read them)
+// plus the end-of-group bookkeeping: the call-wide counters take this group's numbers
 struct GroupEndArgs {
   const uint32_t* statCounts; const uint32_t* pass; GroupCtr* g; CallCtr* call;
   uint32_t nSamples;
@@ -1480,11 +1489,12 @@ __global__ void group_end_kernel (GroupEndArgs a) {
   __syncthreads();
   for (uint32_t s = threadIdx.x; s < n; s += blockDim.x) if (sh[s]) atomicAdd(&a.tir[s], sh[s]);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
+    // (atomics: the groups of the two lanes of a call end independently of each other; CallCtr::rows is row_place_kernel's)
     GroupCtr* g = a.g; CallCtr* c = a.call;
-    c->rows += g->rows + a.edgeRowsTotal;
-    c->cands += g->nCand; c->runs += g->runReal; c->n1 += g->pv >> PACK_SHIFT; c->cells += g->pv & PACK_MASK; c->warm += g->nWarm;
-    if (g->runCount > c->needSlots) c->needSlots = g->runCount;
-    c->flags |= g->flags;
+    atomicAdd(&c->cands, g->nCand); atomicAdd(&c->runs, (unsigned long long)g->runReal);
+    atomicAdd(&c->n1, g->pv >> PACK_SHIFT); atomicAdd(&c->cells, g->pv & PACK_MASK); atomicAdd(&c->warm, (unsigned long long)g->nWarm);
+    atomicMax(&c->needSlots, (unsigned long long)g->runCount);
+    atomicOr(&c->flags, g->flags);
   }
 }
 
