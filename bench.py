@@ -214,6 +214,14 @@ def pin_check(view, workload, args, directional):
 SEEDS = {"c3": 20261018, "c2": 20261019, "c1": 20261020, "c4": 20261021, "tiny": 7}
 
 
+FORM_TEXT = {
+    "vbyte": "vbyte (variable-length byte code, ~1.5 B per entry: marker bit + 6 + 7k-bit position delta, optional count byte, exception list for counts > 127; "
+             "upb_load_tags_async — what bin/regions loads)",
+    "packed2": "packed2 (u16 per entry: 12-bit position delta + 4-bit count, exception list; upb_load_tags_async)",
+    "plain": "plain (u32 pos + u32 cnt: upb_load_tags_async)",
+}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -227,6 +235,8 @@ def main():
     ap.add_argument("--no-sweep", action="store_true", help="skip roofline.sweep (bandwidth 10 ... 200)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--bandwidth", type=int, default=50, help="-b (config 5 sweeps 10..200)")
+    ap.add_argument("--host-form", default=os.environ.get("UPB_HOST_FORM", "vbyte"), choices=["vbyte", "packed2", "plain"],
+                    help="host form of the tag arrays in the headline e2e leg (the other packed form is reported as e2e_alt2, the plain one as e2e_alt)")
     args = ap.parse_args()
     args.seed = args.seed or SEEDS[args.workload]
 
@@ -313,11 +323,20 @@ def main():
     pack_ms = (time.perf_counter() - t0) * 1e3
     h_exc2 = torch.from_numpy(exc2.view(np.uint8).copy()).pin_memory()
     n_exc2 = int(exc2.shape[0])
-    h2d_bytes = {"packed2": 2 * E + 16 * n_exc2 + 8 * int(data.off.shape[0]), "plain": 8 * E + 8 * int(data.off.shape[0])}
+    # ... and in the variable-length byte form (upb_vbyte.hpp: ~1.5 bytes per entry)
+    h_vb = torch.empty(max(6 * E, 1) if E < (1 << 24) else max(3 * E, 1), dtype=torch.uint8).pin_memory()
+    t0 = time.perf_counter()
+    vb, vb_off, vb_tiles, exc_v = unipeak_b200.pack_tags_vbyte(n_samples, C, data.off, data.pos, data.cnt, out=h_vb.numpy())
+    pack_vbyte_ms = (time.perf_counter() - t0) * 1e3
+    n_vb = int(vb.shape[0])
+    h_excv = torch.from_numpy(exc_v.view(np.uint8).copy()).pin_memory()
+    n_excv = int(exc_v.shape[0])
+    h2d_bytes = {"packed2": 2 * E + 16 * n_exc2 + 8 * int(data.off.shape[0]), "plain": 8 * E + 8 * int(data.off.shape[0]),
+                 "vbyte": n_vb + 16 * n_excv + 8 * int(vb_tiles.shape[0]) + 16 * int(data.off.shape[0])}
     if world > 1:                                                     # whole job: the ranks' loads together
-        hb = torch.tensor([h2d_bytes["packed2"], h2d_bytes["plain"]], dtype=torch.int64, device=dev)
+        hb = torch.tensor([h2d_bytes["packed2"], h2d_bytes["plain"], h2d_bytes["vbyte"]], dtype=torch.int64, device=dev)
         dist.all_reduce(hb)
-        h2d_bytes = {"packed2": int(hb[0].item()), "plain": int(hb[1].item())}
+        h2d_bytes = {"packed2": int(hb[0].item()), "plain": int(hb[1].item()), "vbyte": int(hb[2].item())}
 
     def load_plain():
         ctx.load_async_ptr(n_samples, h_off.data_ptr(), pos_ptr=h_pos.data_ptr(), cnt_ptr=h_cnt.data_ptr(), directional_hint=directional)
@@ -325,7 +344,12 @@ def main():
     def load_packed2():
         ctx.load_async_ptr(n_samples, h_off.data_ptr(), words_ptr=h_w2.data_ptr(), n_exc=n_exc2, exc_ptr=h_exc2.data_ptr(), directional_hint=directional)
 
-    load_packed2()
+    def load_vbyte():
+        ctx.load_async_ptr(n_samples, h_off.data_ptr(), vbytes_ptr=h_vb.data_ptr(), vbyte_off_ptr=vb_off.ctypes.data, vtile_off_ptr=vb_tiles.ctypes.data,
+                           n_vtiles=int(vb_tiles.shape[0]) - 1, n_exc=n_excv, exc_ptr=h_excv.data_ptr(), directional_hint=directional)
+
+    loaders = {"vbyte": load_vbyte, "packed2": load_packed2, "plain": load_plain}
+    loaders[args.host_form]()
     ctx.load_wait()
     first = ctx.call_regions_view(**dict(st, reference_order=True))       # sizes the context's arrays; its row count sizes the shared table
     shared = None
@@ -420,8 +444,11 @@ def main():
         return timed(one, e2e_steps)
 
     alt_ms, alt_wall_ms, _ = e2e_leg(load_plain)
-    e2e_ms, e2e_wall_ms, last = e2e_leg(load_packed2)
-    # per-rank phases of the packed2 leg: bytes this rank moves, when its last byte was on the device, when its index was complete (library events)
+    other_form = "packed2" if args.host_form == "vbyte" else "vbyte"
+    alt2_ms, alt2_wall_ms, alt2_last = e2e_leg(loaders[other_form])
+    alt2_rows = int(alt2_last.n_rows) if rank == 0 else 0
+    e2e_ms, e2e_wall_ms, last = e2e_leg(loaders[args.host_form])
+    # per-rank phases of the headline leg: bytes this rank moves, when its last byte was on the device, when its index was complete (library events)
     ph = np.asarray(load_phases, dtype=np.float64).reshape(-1, 2) if load_phases else np.full((1, 2), -1.0)
     e2e_phase = torch.tensor([float(ph[:, 0].mean()), float(ph[:, 1].mean()), float(E)], dtype=torch.float64, device=dev)
     e2e_phase_all = [torch.zeros_like(e2e_phase) for _ in range(world)]
@@ -431,6 +458,7 @@ def main():
         e2e_phase_all = [e2e_phase]
     e2e_per_rank = {"columns": ["h2d_done_ms", "index_done_ms", "tag_entries"], "rows": [[round(float(x), 3) for x in t.tolist()] for t in e2e_phase_all]}
     e2e_rows = int(last.n_rows) if rank == 0 else 0
+    E_all = int(sum(float(t[2].item()) for t in e2e_phase_all))
     d2h = n_rows * (41 + 4 * n_samples)
 
     # t_hot_cold: from sample-major arrays resident in HBM (SURVEY 8d's "sorted arrays resident") to the table on the host: the
@@ -529,12 +557,16 @@ def main():
                 "ms_per_step": ms_per_step, "wall_ms_per_step": wall_ms_per_step, "timing": "CUDA events on the library's stream around the K steps (max over ranks); wall clock alongside",
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config, "clocks": clocks.summary(),
-                "e2e": {"value": genome / (e2e_ms * 1e-3), "unit": "bp/s", "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall_ms, "h2d_bytes_per_step": h2d_bytes["packed2"], "d2h_bytes_per_step": d2h,
-                        "host_format": "packed2 (u16 per entry: 12-bit position delta + 4-bit count, exception list; upb_load_tags_async — what bin/regions loads)",
-                        "pack_ms": pack_ms, "pack_note": "host-side encoder (upb_pack_tags2, one thread per (sample, strand), from the plain arrays), outside the timed region: a front end encodes while it parses (bin/regions: TagLoader)",
+                "e2e": {"value": genome / (e2e_ms * 1e-3), "unit": "bp/s", "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall_ms, "h2d_bytes_per_step": h2d_bytes[args.host_form], "d2h_bytes_per_step": d2h,
+                        "host_format": FORM_TEXT[args.host_form],
+                        "bytes_per_entry": h2d_bytes[args.host_form] / max(E_all, 1),
+                        "pack_ms": {"vbyte": pack_vbyte_ms, "packed2": pack_ms, "plain": 0.0}[args.host_form],
+                        "pack_note": "host-side encoder (upb_pack_tags_vbyte / upb_pack_tags2, one thread per (sample, strand), from the plain arrays), outside the timed region: a front end encodes while it parses (bin/regions: TagLoader)",
                         "per_rank_ms": e2e_per_rank, "per_rank_note": "from the first queued copy of a rank's load: last byte on the device, index complete (library CUDA events)",
                         "rows_equal_resident_leg": bool(e2e_rows == n_rows)},
                 "e2e_alt": {"host_format": "plain (u32 pos + u32 cnt: upb_load_tags_async)", "value": genome / (alt_ms * 1e-3), "unit": "bp/s", "ms_per_step": alt_ms, "wall_ms_per_step": alt_wall_ms, "h2d_bytes_per_step": h2d_bytes["plain"]},
+                "e2e_alt2": {"host_format": FORM_TEXT[other_form], "value": genome / (alt2_ms * 1e-3), "unit": "bp/s", "ms_per_step": alt2_ms, "wall_ms_per_step": alt2_wall_ms,
+                             "h2d_bytes_per_step": h2d_bytes[other_form], "pack_ms": {"vbyte": pack_vbyte_ms, "packed2": pack_ms}[other_form], "rows_equal_resident_leg": bool(alt2_rows == n_rows)},
                 "t_hot_cold": {"value": genome / (cold_ms * 1e-3), "unit": "bp/s", "ms_per_step": cold_ms, "wall_ms_per_step": cold_wall_ms,
                                "what": "sample-major pos/cnt resident in HBM -> upb_reindex (tile-major counting sort + zone maps) -> upb_call_regions -> table on the host",
                                "algorithmic_bytes": cold_bytes, "roofline_frac": cold_bytes / (cold_ms * 1e-3) / 1e9 / peak_gbs / world},

@@ -92,7 +92,28 @@ int upb_load_tags_packed2 (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off
 int upb_pack_tags2 (uint32_t n_samples, uint32_t n_contigs, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt,
                     uint16_t* words_out, upb_packed_exception* exc_out, uint64_t exc_cap, uint64_t* n_exc_out);
 
-/* The general, asynchronous form of the two loads above.  The transfer is cut into groups — (strand, range of contigs) — and
+/* The densest host form: a self-synchronising variable-length byte code, ~1.5 bytes per entry on RNA-seq / ChIP-seq-like data (the
+ * load is PCIe-bound, so bytes are time).  Per entry, in segment order:
+ *   first byte   1 c v5..v0        bit 7 marks the start of an entry; v = position minus the previous position of the same
+ *                                  (sample, strand, contig) segment — the ABSOLUTE position for the first entry of every tile of 2048
+ *                                  entries of a segment, so that a tile decodes on its own; c = 1: a count byte closes the entry
+ *   then         0 xxxxxxx ...     0 - 4 bytes with the higher bits of v, 7 per byte, low to high
+ *   then (c = 1) 0 kkkkkkk         the count, 2 - 127; 0 = the count sits in `exceptions` (index = entry index, pos = 0).  c = 0: count 1
+ * Entry starts are found from bit 7 alone (a prefix count over the bytes), so a tile is decoded by a whole thread block at once.
+ * byte_off has the layout of `off` (n_samples * 2 * (n_contigs + 1) entries): the bytes of segment (s, d, c) are
+ * bytes[byte_off[(s*2+d)*(n_contigs+1)+c] .. byte_off[.. + c + 1]); tile_off[t] is the first byte of tile t, tiles numbered through the
+ * segments in order (a segment of n entries has (n + 2047) / 2048 tiles), tile_off[n_tiles] = total bytes.  Validated on the device
+ * like the other forms (plus: the byte code is well formed and every tile holds exactly its entries).
+ * upb_pack_tags_vbyte is the host-only encoder (one task per (sample, strand)); call it with bytes_cap = 0 to learn the sizes
+ * (*n_bytes_out, *n_tiles_out, *n_exc_out; returns UPB_ERR_NOMEM), then with buffers of those sizes. */
+int upb_load_tags_vbyte (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off, const uint8_t* bytes, const uint64_t* byte_off,
+                         uint64_t n_tiles, const uint64_t* tile_off, uint64_t n_exceptions, const upb_packed_exception* exceptions);
+int upb_pack_tags_vbyte (uint32_t n_samples, uint32_t n_contigs, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt,
+                         uint8_t* bytes_out, uint64_t bytes_cap, uint64_t* n_bytes_out, uint64_t* byte_off_out,
+                         uint64_t* tile_off_out, uint64_t tile_cap, uint64_t* n_tiles_out,
+                         upb_packed_exception* exc_out, uint64_t exc_cap, uint64_t* n_exc_out);
+
+/* The general, asynchronous form of the loads above.  The transfer is cut into groups — (strand, range of contigs) — and
  * pipelined: while a group's bytes cross PCIe the previous group is decoded, validated and indexed; upb_load_tags_async returns as
  * soon as everything is queued, and a upb_call_regions that follows starts calling regions on the groups that have arrived while
  * the rest is still on its way (the reference overlaps nothing: src/regions.cpp:195-199 parses, then :309-391 computes).
@@ -100,6 +121,7 @@ int upb_pack_tags2 (uint32_t n_samples, uint32_t n_contigs, const uint64_t* off,
  * returns; what the synchronous loads report at once (unsorted / out-of-range input, a malformed packed form) is reported there.
  *   pos/cnt     plain form, or NULL
  *   words ...   2-byte form, or NULL
+ *   vbytes ...  variable-length byte form, or NULL
  *   keep_contig [n_contigs] 1 = load this contig's segments, 0 = leave them out (a rank of a multi-GPU job keeps the contigs it
  *               owns: the arrays describe all contigs, only the kept ones travel); NULL = all
  *   directional_hint  order of the groups: 1 = strand-major, the order a directional upb_call_regions works through them;
@@ -114,6 +136,11 @@ typedef struct {
   const upb_packed_exception* exceptions;
   const uint8_t* keep_contig;
   int directional_hint;
+  /* variable-length byte form (upb_load_tags_vbyte), or NULL; uses n_exceptions / exceptions for the counts that do not fit */
+  const uint8_t* vbytes;
+  const uint64_t* vbyte_off;
+  const uint64_t* vtile_off;
+  uint64_t n_vtiles;
 } upb_tag_source;
 int upb_load_tags_async (upb_ctx* ctx, const upb_tag_source* src);
 int upb_load_wait (upb_ctx* ctx);

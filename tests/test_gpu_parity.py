@@ -514,6 +514,89 @@ def test_packed_load_equals_plain_load(gpu_ctx):
     check_regions(gpu_ctx, make_synthetic([200000, 80000], 2, 30000, directional=True, seed=79, peak_spacing=5000))
 
 
+def test_vbyte_load_equals_plain_load(gpu_ctx):
+    # the variable-length byte form (upb_vbyte.hpp: marker bit, 6 + 7k-bit values, count byte, count exceptions, self-contained tiles of 2048
+    # entries) decodes to exactly the arrays of the plain path: large gaps, large counts, empty segments, several tiles per segment; a subset
+    # load (a rank's contigs) and the asynchronous load behind which the call starts
+    import torch
+    import unipeak_b200
+    data = _packed_fixture()
+    vb, boff, toff, exc = unipeak_b200.pack_tags_vbyte(3, 3, data.off, data.pos, data.cnt)
+    assert exc.shape[0] >= 10 and vb.shape[0] < 2 * data.pos.shape[0]
+    st = region_settings(data)
+    gpu_ctx.load(data)
+    want = gpu_ctx.call_regions(**st)
+    wc = gpu_ctx.call_regions(**dict(st, reference_order=False, rows=False))["columns"]
+    keys = [(r["contig"], r["left"], r["left"] + r["len"] - 1) for r in want["rows"] if r["forward_label"]][:50]
+    tir_want = gpu_ctx.count_tags_in_regions(keys, directional=True, extension=0)
+    gpu_ctx.load_vbyte(data)
+    got = gpu_ctx.call_regions(**st)
+    assert_rows_equal(got["rows"], want["rows"], "byte-form load")
+    assert_rows_equal(got["dropped"], want["dropped"], "byte-form load (dropped)")
+    assert got["tags_in_regions"] == want["tags_in_regions"] and len(got["rows"]) > 3
+    assert np.array_equal(gpu_ctx.count_tags_in_regions(keys, directional=True, extension=0), tir_want)   # reads the decoded pos[] / cnt[] directly
+    # a rank's contigs only
+    keep = [0, 2]
+    gpu_ctx.load_vbyte(data, keep_contigs=keep)
+    part = gpu_ctx.call_regions(**dict(st, reference_order=False, rows=False))["columns"]
+    sel = np.isin(wc["contig"], keep)
+    assert int(sel.sum()) == part["left"].shape[0] and int(sel.sum()) > 0
+    for k in ("buffer", "contig", "left", "len", "peak", "hit_sum", "counts"):
+        assert np.array_equal(part[k], wc[k][sel]), k
+    for k in ("kurtosis", "peak_score"):
+        assert np.array_equal(part[k].view(np.uint64), wc[k][sel].view(np.uint64)), k
+    # asynchronous, from pinned memory: the call works through the groups as they arrive
+    off = np.ascontiguousarray(data.off, dtype=np.uint64)
+    h_vb = torch.from_numpy(vb.copy()).pin_memory()
+    gpu_ctx.load_async_ptr(3, off.ctypes.data, vbytes_ptr=h_vb.data_ptr(), vbyte_off_ptr=boff.ctypes.data, vtile_off_ptr=toff.ctypes.data, n_vtiles=toff.shape[0] - 1,
+                           n_exc=exc.shape[0], exc_ptr=exc.ctypes.data)
+    got = gpu_ctx.call_regions(**dict(st, reference_order=False, rows=False))["columns"]
+    for k in wc:
+        assert np.array_equal(np.asarray(wc[k]).view(np.uint8), np.asarray(got[k]).view(np.uint8)), ("async", k)
+
+    def load(vb_, boff_=boff, toff_=toff, exc_=exc):
+        gpu_ctx._check(gpu_ctx._lib.upb_load_tags_vbyte(gpu_ctx._h, 3, off.ctypes.data, vb_.ctypes.data, boff_.ctypes.data, toff_.shape[0] - 1, toff_.ctypes.data,
+                                                        exc_.shape[0], exc_.ctypes.data if exc_.shape[0] else None))
+    load(vb)                                                               # (the synchronous entry point)
+    # broken streams are refused: a count escape without its exception entry ...
+    with pytest.raises(unipeak_b200.UpbError) as ei:
+        load(vb, exc_=exc[:-1])
+    assert ei.value.code == -2
+    # ... a tile that does not start with an entry, an entry with too many value bytes, a missing entry (marker bit cleared) ...
+    first = int(boff[0])
+    second_tile = int(toff[1])
+    for victim, value in ((first, 0x05), (second_tile, 0x05), (first + 1, None)):
+        bad = vb.copy()
+        if value is None:                                                  # turn the first byte of the SECOND entry into a continuation byte
+            at = first + 1
+            while not (int(bad[at]) & 0x80):
+                at += 1
+            bad[at] = int(bad[at]) & 0x7F
+        else:
+            bad[victim] = value
+        with pytest.raises(unipeak_b200.UpbError) as ei:
+            load(bad)
+        assert ei.value.code == -2
+    # ... a tile table that does not match the segments, positions that do not ascend (a zero delta)
+    bad_t = toff.copy(); bad_t[1] += 1
+    with pytest.raises(unipeak_b200.UpbError) as ei:
+        load(vb, toff_=bad_t)
+    assert ei.value.code == -2
+    bad = vb.copy()
+    at = first + 1
+    while not (int(bad[at]) & 0x80):
+        at += 1
+    nxt = at + 1
+    while not (int(bad[nxt]) & 0x80):
+        nxt += 1
+    if nxt - at == 1 and not (int(bad[at]) & 0x40):                        # a one-byte entry: make its delta 0
+        bad[at] = 0x80
+        with pytest.raises(unipeak_b200.UpbError) as ei:
+            load(bad)
+        assert ei.value.code == -5
+    check_regions(gpu_ctx, make_synthetic([200000, 80000], 2, 30000, directional=True, seed=79, peak_spacing=5000))
+
+
 def test_async_load_pipelines_into_the_call(gpu_ctx):
     # upb_load_tags_async + upb_call_regions: the call starts on the load groups that have arrived; same table as load-then-call.
     # Also: a subset load (keep mask), upb_reindex, and a call whose numbers outgrow the arrays sized by an earlier, smaller one.

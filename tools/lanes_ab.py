@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Groups-per-call sweep of the two-lane region call (UPB_CALL_GROUPS, read by the library at every call): C3 resident, call time
-(wall inside the library, device first-to-last event) per setting and the table fingerprint, which must not move."""
+"""Groups-per-call sweep of the two-lane region call (UPB_CALL_GROUPS, read by the library at every call): C3 resident — whole, and the
+shard rank 0 of a contig-sharded job of 2 / 4 / 8 ranks would hold — call time (wall inside the library, device first-to-last event)
+per setting and the table fingerprint, which must not move within a workload."""
 import json
 import os
 import sys
@@ -12,31 +13,38 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 import unipeak_b200  # noqa: E402
 from ab import fingerprint, G  # noqa: E402
+from unipeak_b200.multi import shard_contigs  # noqa: E402
 from unipeak_b200.synth import HG19_SIZES  # noqa: E402
 from unipeak_b200.synth_det import make_synthetic_det  # noqa: E402
 
 
 def main():
-    groups = [int(x) for x in (sys.argv[1:] or ["1", "2", "3", "4", "6", "8", "1", "2"])]
-    steps = int(os.environ.get("AB_STEPS", "20"))
+    groups = [int(x) for x in (sys.argv[1:] or ["1", "2", "3", "4", "6", "1", "2"])]
+    steps = int(os.environ.get("AB_STEPS", "15"))
+    worlds = [int(x) for x in os.environ.get("AB_WORLDS", "1,2,4,8").split(",")]
     ctx = unipeak_b200.Context(0)
-    data = make_synthetic_det(HG19_SIZES, 16, 30_000_000, directional=True, seed=20261018, bandwidth=200, device="cuda:0")
-    ctx.load(data)
-    bg = sum(data.tags(s) for s in range(16)) / G / 2
-    for bw in (50, 10, 200):
-        st = dict(bandwidth=bw, region_threshold=25.0, kurtosis_threshold=50.0, corr_threshold=-1.0, hit_threshold=160.0, directional=True, background=bg)
-        for g in groups:
-            os.environ["UPB_CALL_GROUPS"] = str(g)
-            for _ in range(3):
-                ctx.call_regions_view(**st)
-            call, dev, kde = [], [], []
-            for _ in range(steps):
-                v = ctx.call_regions_view(**st)
-                s = ctx.stats()
-                call.append(s["ms_call"]); dev.append(s["ms_total"]); kde.append(s["ms_kde"])
-            print(json.dumps({"bandwidth": bw, "groups": g, "call_ms": float(np.mean(call)), "call_ms_min": float(np.min(call)), "device_ms": float(np.mean(dev)),
-                              "span_brackets_ms": float(np.mean(kde)), "launches": s["launches"], "regions": v.n_rows, "sha": fingerprint(v)}), flush=True)
-            ctx.release_view()
+    bg = 16 * 30_000_000 / G / 2
+    for world in worlds:
+        owner = shard_contigs(HG19_SIZES, world)
+        mine = [c for c in range(len(HG19_SIZES)) if owner[c] == 0]
+        data = make_synthetic_det(HG19_SIZES, 16, 30_000_000, directional=True, seed=20261018, bandwidth=200, device="cuda:0", contigs=mine if world > 1 else None)
+        ctx.load(data)
+        for bw in ((50, 10, 200) if world == 1 else (50,)):
+            st = dict(bandwidth=bw, region_threshold=25.0, kurtosis_threshold=50.0, corr_threshold=-1.0, hit_threshold=160.0, directional=True, background=bg)
+            for g in (groups if world == 1 else [x for x in (1, 2, 4) if x in groups]):
+                os.environ["UPB_CALL_GROUPS"] = str(g)
+                for _ in range(3):
+                    ctx.call_regions_view(**st)
+                call, dev, kde = [], [], []
+                for _ in range(steps):
+                    v = ctx.call_regions_view(**st)
+                    s = ctx.stats()
+                    call.append(s["ms_call"]); dev.append(s["ms_total"]); kde.append(s["ms_kde"])
+                print(json.dumps({"shard_of": world, "bandwidth": bw, "groups": g, "call_ms": round(float(np.mean(call)), 4), "call_ms_min": round(float(np.min(call)), 4),
+                                  "device_ms": round(float(np.mean(dev)), 4), "span_brackets_ms": round(float(np.mean(kde)), 4), "launches": s["launches"], "regions": v.n_rows,
+                                  "sha": fingerprint(v)}), flush=True)
+                ctx.release_view()
+        del data
     ctx.close()
 
 

@@ -82,7 +82,7 @@ EXPORTS = [
     "upb_load_tags", "upb_call_regions", "upb_free_region_table", "upb_reference_order", "upb_profile_contig", "upb_free_profile",
     "upb_strand_shift", "upb_free_shift_report", "upb_count_tags_in_regions", "upb_kernel_taps", "upb_last_stats",
     "upb_shared_table_bytes", "upb_shared_table_init", "upb_call_regions_shared", "upb_set_profiling", "upb_last_stage_times", "upb_stream", "upb_host_register", "upb_host_unregister", "upb_load_tags_async", "upb_load_wait", "upb_reindex", "upb_aggregate_tags", "upb_free_tag_counts",
-    "upb_load_tags_packed2", "upb_pack_tags2", "upb_last_load_ms",
+    "upb_load_tags_packed2", "upb_pack_tags2", "upb_load_tags_vbyte", "upb_pack_tags_vbyte", "upb_last_load_ms",
     "upb_shift_regions", "upb_free_shift_regions", "upb_shift_examine_order", "upb_shift_sweep", "upb_shift_mode",
     "upb_multi_create", "upb_multi_destroy", "upb_multi_last_error", "upb_multi_gpus", "upb_multi_context", "upb_multi_set_contigs", "upb_multi_owner",
     "upb_multi_load_tags", "upb_multi_load_wait", "upb_multi_call_regions", "upb_multi_profile_contig", "upb_multi_strand_shift",
@@ -92,7 +92,8 @@ EXPORTS = [
 
 class TagSource(C.Structure):
     _fields_ = [("n_samples", C.c_uint32), ("off", C.c_void_p), ("pos", C.c_void_p), ("cnt", C.c_void_p), ("words", C.c_void_p),
-                ("n_exceptions", C.c_uint64), ("exceptions", C.c_void_p), ("keep_contig", C.c_void_p), ("directional_hint", C.c_int)]
+                ("n_exceptions", C.c_uint64), ("exceptions", C.c_void_p), ("keep_contig", C.c_void_p), ("directional_hint", C.c_int),
+                ("vbytes", C.c_void_p), ("vbyte_off", C.c_void_p), ("vtile_off", C.c_void_p), ("n_vtiles", C.c_uint64)]
 
 
 class SharedTable(C.Structure):
@@ -126,6 +127,30 @@ def pack_tags2(n_samples: int, n_contigs: int, off, pos, cnt, out=None):
     if rc:
         raise UpbError(rc, "upb_pack_tags2 failed")
     return words, exc[:int(n_exc.value)]
+
+
+def pack_tags_vbyte(n_samples: int, n_contigs: int, off, pos, cnt, out=None):
+    """upb_pack_tags_vbyte: the variable-length byte form of the plain arrays -> (bytes u8, byte_off u64 [layout of off], tile_off u64
+    [tiles + 1], exceptions).  `out`: a u8 array to encode into (e.g. pinned), at least 6 bytes per entry or the size a first call reported."""
+    L = lib()
+    off = np.ascontiguousarray(off, dtype=np.uint64)
+    pos = np.ascontiguousarray(pos, dtype=np.uint32)
+    cnt = np.ascontiguousarray(cnt, dtype=np.uint32)
+    nb, nt, nx = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    args = (n_samples, n_contigs, off.ctypes.data, pos.ctypes.data, cnt.ctypes.data)
+    L.upb_pack_tags_vbyte(*args, None, 0, C.byref(nb), None, None, 0, C.byref(nt), None, 0, C.byref(nx))
+    n_bytes, n_tiles, n_exc = int(nb.value), int(nt.value), int(nx.value)
+    buf = out if out is not None else np.empty(max(n_bytes, 1), np.uint8)
+    if buf.shape[0] < n_bytes:
+        raise ValueError("pack_tags_vbyte: `out` holds %d bytes, %d needed" % (buf.shape[0], n_bytes))
+    byte_off = np.zeros(max(off.shape[0], 1), np.uint64)
+    tile_off = np.zeros(n_tiles + 1, np.uint64)
+    exc = np.zeros(max(n_exc, 1), dtype=PACKED_EXC_DTYPE)
+    rc = L.upb_pack_tags_vbyte(*args, buf.ctypes.data, int(buf.shape[0]), C.byref(nb), byte_off.ctypes.data, tile_off.ctypes.data, n_tiles + 1, C.byref(nt),
+                               exc.ctypes.data, n_exc, C.byref(nx))
+    if rc:
+        raise UpbError(rc, "upb_pack_tags_vbyte failed")
+    return buf[:n_bytes], byte_off, tile_off, exc[:n_exc]
 
 
 def host_register(ptr: int, nbytes: int) -> int:
@@ -183,6 +208,9 @@ def lib():
         L.upb_last_load_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.upb_reindex.argtypes = [C.c_void_p]
         L.upb_load_tags_packed2.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.upb_load_tags_vbyte.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.upb_pack_tags_vbyte.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p,
+                                          C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.upb_pack_tags2.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.upb_host_register.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
         L.upb_host_unregister.argtypes = [C.c_void_p]
@@ -336,13 +364,30 @@ class Context:
         words, exc = pack_tags2(data.n_samples, self.n_contigs, off, data.pos, data.cnt)
         self.load_tags_packed2_ptr(data.n_samples, off.ctypes.data, words.ctypes.data, exc.shape[0], exc.ctypes.data)
 
+    def load_vbyte(self, data, keep_contigs: Optional[Sequence[int]] = None) -> None:
+        """Load a TagData through the variable-length byte form (all contigs, or — what a rank of a multi-GPU job does — only the given ones)."""
+        self.set_contigs(data.contig_sizes)
+        off = np.ascontiguousarray(data.off, dtype=np.uint64)
+        vb, boff, toff, exc = pack_tags_vbyte(data.n_samples, self.n_contigs, off, data.pos, data.cnt)
+        keep = None
+        if keep_contigs is not None:
+            keep = np.zeros(self.n_contigs, dtype=np.uint8)
+            keep[list(keep_contigs)] = 1
+        self._hold = (off, vb, boff, toff, exc)
+        self.load_async_ptr(data.n_samples, off.ctypes.data, vbytes_ptr=vb.ctypes.data, vbyte_off_ptr=boff.ctypes.data, vtile_off_ptr=toff.ctypes.data,
+                            n_vtiles=toff.shape[0] - 1, n_exc=exc.shape[0], exc_ptr=exc.ctypes.data, keep_contig=keep)
+        self.load_wait()
+        self._hold = None
+
     def load_async_ptr(self, n_samples: int, off_ptr: int, *, pos_ptr: int = 0, cnt_ptr: int = 0, words_ptr: int = 0, n_exc: int = 0, exc_ptr: int = 0,
-                       keep_contig: Optional[np.ndarray] = None, directional_hint: bool = True) -> None:
+                       keep_contig: Optional[np.ndarray] = None, directional_hint: bool = True,
+                       vbytes_ptr: int = 0, vbyte_off_ptr: int = 0, vtile_off_ptr: int = 0, n_vtiles: int = 0) -> None:
         """upb_load_tags_async from raw host addresses: returns once the transfers are queued.  The buffers (and `keep_contig`) must stay
         alive until load_wait() or the next call that uses the data returns."""
         self._keep = None if keep_contig is None else np.ascontiguousarray(keep_contig, dtype=np.uint8)
         src = TagSource(n_samples, off_ptr, pos_ptr or None, cnt_ptr or None, words_ptr or None, n_exc, exc_ptr or None,
-                        None if self._keep is None else self._keep.ctypes.data, 1 if directional_hint else 0)
+                        None if self._keep is None else self._keep.ctypes.data, 1 if directional_hint else 0,
+                        vbytes_ptr or None, vbyte_off_ptr or None, vtile_off_ptr or None, n_vtiles)
         self._check(self._lib.upb_load_tags_async(self._h, C.byref(src)))
         self.n_samples = n_samples
 

@@ -7,6 +7,7 @@
 #include "upb_device.cuh"
 #include "upb_span.cuh"
 #include "upb_pack.cuh"
+#include "upb_vbyte.hpp"
 #include "upb_aggr.cuh"
 #include "upb_introsort.hpp"
 
@@ -85,6 +86,7 @@ struct upb_ctx {
   DevBuf d_winBase, d_wEnt;                                          // per-sample window index of the scatter pass
   DevBuf d_pk16, d_pkExc, d_segEnds, d_srcStart, d_grpSeg, d_grpTile, d_loadFlags;   // load (upb_pack.cuh)
   DevBuf d_tileExc;                    // packed load: first exception of every tile of the load group being decoded
+  DevBuf d_vbytes, d_vSrcByte, d_vDevByte, d_vSrcTile, d_vTileOff;   // variable-length byte form (upb_vbyte.hpp)
   DevBuf d_ment, d_mtOff, d_mtBase, d_mtCount, d_mEff, d_mtW, d_blkW;   // tile-major copy and its zone maps (upb_device.cuh)
   std::vector<uint32_t> mtBase;         // [2*C+1]
   std::map<std::string, DevBuf> scratch;     // grow-only device scratch, by name
@@ -182,7 +184,7 @@ extern "C" int upb_create (int device, upb_ctx** out) {
 extern "C" void upb_destroy (upb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  DevBuf* all[] = {&ctx->d_tileExc, &ctx->d_winBase, &ctx->d_wEnt, &ctx->d_pk16, &ctx->d_pkExc, &ctx->d_segEnds, &ctx->d_srcStart, &ctx->d_grpSeg, &ctx->d_grpTile, &ctx->d_loadFlags, &ctx->d_mtW, &ctx->d_blkW, &ctx->d_ment, &ctx->d_mtOff, &ctx->d_mtBase, &ctx->d_mtCount, &ctx->d_mEff, &ctx->d_pos, &ctx->d_cnt, &ctx->d_off, &ctx->d_segStart, &ctx->d_tidx, &ctx->d_tidxBase, &ctx->d_sizes,
+  DevBuf* all[] = {&ctx->d_vbytes, &ctx->d_vSrcByte, &ctx->d_vDevByte, &ctx->d_vSrcTile, &ctx->d_vTileOff, &ctx->d_tileExc, &ctx->d_winBase, &ctx->d_wEnt, &ctx->d_pk16, &ctx->d_pkExc, &ctx->d_segEnds, &ctx->d_srcStart, &ctx->d_grpSeg, &ctx->d_grpTile, &ctx->d_loadFlags, &ctx->d_mtW, &ctx->d_blkW, &ctx->d_ment, &ctx->d_mtOff, &ctx->d_mtBase, &ctx->d_mtCount, &ctx->d_mEff, &ctx->d_pos, &ctx->d_cnt, &ctx->d_off, &ctx->d_segStart, &ctx->d_tidx, &ctx->d_tidxBase, &ctx->d_sizes,
     &ctx->d_nTilesIdx, &ctx->d_small};
   for (DevBuf* b : all) release(*b);
   for (auto& kv : ctx->scratch) release(kv.second);
@@ -345,8 +347,33 @@ static int load_enqueue (upb_ctx* ctx, const upb_tag_source* src, bool resident)
   const uint32_t C = (uint32_t)ctx->sizes.size();
   const uint32_t n_samples = resident ? ctx->nSamples : src->n_samples;
   const uint32_t nSeg = n_samples * 2 * C;
-  const bool packed = !resident && src->words != nullptr;
+  const bool vbyte = !resident && src->vbytes != nullptr;
+  const bool packed = !resident && !vbyte && src->words != nullptr;
   cudaStream_t ls = ctx->loadStream, cs = ctx->copyStream;
+  std::vector<uint64_t> vSrcByte, vDevByte, vSrcTile;                  // vbyte form: per segment
+  if (vbyte) {
+    if (src->words || !src->vbyte_off || !src->vtile_off) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags_vbyte: byte_off / tile_off are NULL (or two packed forms at once)");
+    vSrcByte.assign((size_t)nSeg + 1, 0); vDevByte.assign((size_t)nSeg + 1, 0); vSrcTile.assign((size_t)nSeg + 1, 0);
+    uint64_t tiles = 0, devAt = 0, expectB = 0;
+    for (uint32_t sd = 0; sd < n_samples * 2; ++sd) {
+      const uint64_t* o = src->off + (size_t)sd * (C + 1);
+      const uint64_t* bo = src->vbyte_off + (size_t)sd * (C + 1);
+      if (bo[0] != expectB) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags_vbyte: byte offset blocks must be contiguous and start at 0");
+      for (uint32_t c = 0; c < C; ++c) {
+        if (o[c + 1] < o[c] || bo[c + 1] < bo[c]) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags_vbyte: offsets must be non-decreasing");
+        const uint64_t len = o[c + 1] - o[c], nb = bo[c + 1] - bo[c], nt = (len + PK_TILE - 1) / PK_TILE;
+        if (nb < len || nb > len * upb_vb::VB_MAX_ENTRY) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags_vbyte: a segment's bytes cannot hold its entries");
+        const size_t g = (size_t)sd * C + c;
+        vSrcByte[g] = bo[c]; vDevByte[g] = devAt; vSrcTile[g] = tiles;
+        if (nt && (tiles + nt > src->n_vtiles || src->vtile_off[tiles] != bo[c])) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags_vbyte: the tile table does not match the segments");
+        tiles += nt;
+        if (!src->keep_contig || src->keep_contig[c]) devAt += nb;
+      }
+      expectB = bo[C];
+    }
+    vSrcByte[nSeg] = expectB; vDevByte[nSeg] = devAt; vSrcTile[nSeg] = tiles;
+    if (tiles != src->n_vtiles || src->vtile_off[tiles] != expectB) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags_vbyte: the tile table does not match the segments");
+  }
   if (!resident) {
     const uint64_t* off = src->off;
     const size_t nOff = (size_t)n_samples * 2 * (C + 1);
@@ -370,8 +397,8 @@ static int load_enqueue (upb_ctx* ctx, const upb_tag_source* src, bool resident)
     }
     ctx->segStart[nSeg] = run;
     const uint64_t Esrc = expect, E = run;
-    if (Esrc && !packed && (!src->pos || !src->cnt)) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags: pos/cnt are NULL");
-    if (packed && src->n_exceptions && !src->exceptions) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags_packed2: NULL exception list");
+    if (Esrc && !packed && !vbyte && (!src->pos || !src->cnt)) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags: pos/cnt are NULL");
+    if ((packed || vbyte) && src->n_exceptions && !src->exceptions) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags_packed2 / _vbyte: NULL exception list");
     ctx->nSamples = n_samples;
     ctx->nEntries = E;
     // device-side offsets in the layout of the caller's `off` (density kernel, tags_in_regions)
@@ -382,12 +409,19 @@ static int load_enqueue (upb_ctx* ctx, const upb_tag_source* src, bool resident)
     }
     ctx->firstPos.assign(nSeg, 0);
     ctx->lastPos.assign(nSeg, 0);
-    ctx->lastPosKnown = !packed;
+    ctx->lastPosKnown = !packed && !vbyte;
     for (uint32_t g = 0; g < nSeg; ++g) {
       const uint64_t len = ctx->segStart[g + 1] - ctx->segStart[g];
       if (!len) continue;
       const uint64_t a = ctx->srcStart[g];
-      if (!packed) { ctx->firstPos[g] = src->pos[a]; ctx->lastPos[g] = src->pos[a + len - 1]; }
+      if (vbyte) {                                                      // the first entry of a segment opens a tile: its value is the position itself
+        const uint8_t* b = src->vbytes + vSrcByte[g];
+        const uint64_t nb = vSrcByte[g + 1] - vSrcByte[g];
+        uint32_t nCont = 0, v = 0, k = 0;
+        while (nCont <= upb_vb::VB_MAX_ENTRY && 1 + nCont < nb && !(b[1 + nCont] & 0x80u)) ++nCont;
+        ctx->firstPos[g] = ((b[0] & 0x80u) && upb_vb::vb_get(b, nCont, &v, &k) && v) ? v : 0xFFFFFFFFu;   // malformed: the device reports it
+      }
+      else if (!packed) { ctx->firstPos[g] = src->pos[a]; ctx->lastPos[g] = src->pos[a + len - 1]; }
       else {                                                            // the first entry of a segment is a position escape: its exception holds the position
         const upb_packed_exception* x = std::lower_bound(src->exceptions, src->exceptions + src->n_exceptions, a,
                                                          [] (const upb_packed_exception& e, uint64_t v) { return e.index < v; });
@@ -520,12 +554,19 @@ static int load_enqueue (upb_ctx* ctx, const upb_tag_source* src, bool resident)
   ENSURE(ctx->d_grpSeg, (grpSeg.size() + 1) * 4);
   ENSURE(ctx->d_grpTile, (grpTile.size() + 1) * 4);
   ENSURE(ctx->d_segEnds, 2 * ((size_t)nSeg + 1) * 4);
-  if (packed) {
+  if (packed || vbyte) {
     uint32_t maxTiles = 0;
     for (const LoadGroup& g : ctx->groups) maxTiles = std::max(maxTiles, g.nTiles);
     ENSURE(ctx->d_tileExc, ((size_t)maxTiles + 2) * 8);
-    ENSURE(ctx->d_pk16, (E ? E : 1) * 2);
+    if (packed) ENSURE(ctx->d_pk16, (E ? E : 1) * 2);
     ENSURE(ctx->d_pkExc, (src->n_exceptions ? src->n_exceptions : 1) * sizeof(PkException));
+  }
+  if (vbyte) {
+    ENSURE(ctx->d_vbytes, vDevByte[nSeg] + 64);                         // (+ slack: the decoder moves whole 16-byte words)
+    ENSURE(ctx->d_vSrcByte, ((size_t)nSeg + 1) * 8);
+    ENSURE(ctx->d_vDevByte, ((size_t)nSeg + 1) * 8);
+    ENSURE(ctx->d_vSrcTile, ((size_t)nSeg + 1) * 8);
+    ENSURE(ctx->d_vTileOff, (src->n_vtiles + 1) * 8);
   }
   { int r = ensure_host(ctx, ctx->h_ends, 2 * ((size_t)nSeg + 1) * 4 + 64); if (r) return r; }
   // small tables: staged through pageable memory by the runtime before the call returns
@@ -536,6 +577,12 @@ static int load_enqueue (upb_ctx* ctx, const upb_tag_source* src, bool resident)
   CU(cudaMemcpyAsync(ctx->d_winBase.p, winBase.data(), (2 * (size_t)C + 1) * 4, cudaMemcpyHostToDevice, ls));
   if (!grpSeg.empty()) CU(cudaMemcpyAsync(ctx->d_grpSeg.p, grpSeg.data(), grpSeg.size() * 4, cudaMemcpyHostToDevice, ls));
   CU(cudaMemcpyAsync(ctx->d_grpTile.p, grpTile.data(), grpTile.size() * 4, cudaMemcpyHostToDevice, ls));
+  if (vbyte) {
+    CU(cudaMemcpyAsync(ctx->d_vSrcByte.p, vSrcByte.data(), ((size_t)nSeg + 1) * 8, cudaMemcpyHostToDevice, ls));
+    CU(cudaMemcpyAsync(ctx->d_vDevByte.p, vDevByte.data(), ((size_t)nSeg + 1) * 8, cudaMemcpyHostToDevice, ls));
+    CU(cudaMemcpyAsync(ctx->d_vSrcTile.p, vSrcTile.data(), ((size_t)nSeg + 1) * 8, cudaMemcpyHostToDevice, ls));
+    CU(cudaMemcpyAsync(ctx->d_vTileOff.p, src->vtile_off, (src->n_vtiles + 1) * 8, cudaMemcpyHostToDevice, ls));
+  }
   CU(cudaMemsetAsync(ctx->d_loadFlags.p, 0, 256, ls));
   CU(cudaMemsetAsync(ctx->d_mtCount.p, 0, ((size_t)nMtTotal + 1) * 4, ls));
   CU(cudaMemsetAsync(ctx->d_mtOff.p, 0, ((size_t)nMtTotal + 2) * 8, ls));
@@ -551,7 +598,7 @@ static int load_enqueue (upb_ctx* ctx, const upb_tag_source* src, bool resident)
   CU(cudaStreamSynchronize(ls));                                       // the host vectors above go out of scope; nothing large has been queued yet
   CU(cudaEventRecord(ctx->copyEvs[ctx->groups.size()], cs));
   ctx->loadCopied = !resident;
-  if (packed && src->n_exceptions) {
+  if ((packed || vbyte) && src->n_exceptions) {
     CU(cudaMemcpyAsync(ctx->d_pkExc.p, src->exceptions, src->n_exceptions * sizeof(PkException), cudaMemcpyHostToDevice, cs));
     load_check_exc_kernel<<<(unsigned)((src->n_exceptions + 255) / 256), 256, 0, cs>>>(ctx->d_pkExc.as<PkException>(), src->n_exceptions, src->off[(size_t)n_samples * 2 * (C + 1) - 1], ctx->d_loadFlags.as<uint32_t>());
   }
@@ -559,13 +606,17 @@ static int load_enqueue (upb_ctx* ctx, const upb_tag_source* src, bool resident)
   LoadArgs la;
   memset(&la, 0, sizeof la);
   la.words = packed ? ctx->d_pk16.as<uint16_t>() : nullptr;
-  la.exc = ctx->d_pkExc.as<PkException>(); la.nExc = packed ? src->n_exceptions : 0;
+  la.exc = ctx->d_pkExc.as<PkException>(); la.nExc = (packed || vbyte) ? src->n_exceptions : 0;
+  if (vbyte) {
+    la.vbytes = ctx->d_vbytes.as<uint8_t>(); la.vSrcByte = ctx->d_vSrcByte.as<uint64_t>(); la.vDevByte = ctx->d_vDevByte.as<uint64_t>();
+    la.vSrcTile = ctx->d_vSrcTile.as<uint64_t>(); la.vTileOff = ctx->d_vTileOff.as<uint64_t>(); la.vTiles = src->n_vtiles;
+  }
   la.pos = ctx->d_pos.as<uint32_t>(); la.cnt = ctx->d_cnt.as<uint32_t>();
   la.segStart = ctx->d_segStart.as<uint64_t>(); la.srcStart = ctx->d_srcStart.as<uint64_t>();
   la.sizes = ctx->d_sizes.as<uint32_t>(); la.mtBase = ctx->d_mtBase.as<uint32_t>(); la.mtCount = ctx->d_mtCount.as<uint32_t>();
   la.winBase = ctx->d_winBase.as<uint32_t>(); la.wEnt = ctx->d_wEnt.as<uint32_t>(); la.nWinTotal = nWinTotal; la.C = C;
   la.flags = ctx->d_loadFlags.as<uint32_t>();
-  la.tileExc = packed ? ctx->d_tileExc.as<unsigned long long>() : nullptr;
+  la.tileExc = (packed || vbyte) ? ctx->d_tileExc.as<unsigned long long>() : nullptr;
   MtArgs ma;
   memset(&ma, 0, sizeof ma);
   ma.pos = la.pos; ma.cnt = la.cnt; ma.segStart = la.segStart; ma.mtBase = la.mtBase;
@@ -584,7 +635,8 @@ static int load_enqueue (upb_ctx* ctx, const upb_tag_source* src, bool resident)
         const uint64_t dev0 = ctx->segStart[sg0], cntE = ctx->segStart[sg1] - dev0, src0 = ctx->srcStart[sg0];
         if (!cntE) continue;
         cudaStream_t q = cs;                                             // one queue: alternating the copies of a group over two queues was slower (r02: 18.5 vs 16.7 ms per load + call)
-        if (packed) CU(cudaMemcpyAsync(ctx->d_pk16.as<uint16_t>() + dev0, src->words + src0, cntE * 2, cudaMemcpyHostToDevice, q));
+        if (vbyte) CU(cudaMemcpyAsync(ctx->d_vbytes.as<uint8_t>() + vDevByte[sg0], src->vbytes + vSrcByte[sg0], vSrcByte[sg1] - vSrcByte[sg0], cudaMemcpyHostToDevice, q));
+        else if (packed) CU(cudaMemcpyAsync(ctx->d_pk16.as<uint16_t>() + dev0, src->words + src0, cntE * 2, cudaMemcpyHostToDevice, q));
         else {
           CU(cudaMemcpyAsync(ctx->d_pos.as<uint32_t>() + dev0, src->pos + src0, cntE * 4, cudaMemcpyHostToDevice, q));
           CU(cudaMemcpyAsync(ctx->d_cnt.as<uint32_t>() + dev0, src->cnt + src0, cntE * 4, cudaMemcpyHostToDevice, q));
@@ -596,8 +648,10 @@ static int load_enqueue (upb_ctx* ctx, const upb_tag_source* src, bool resident)
     la.grpSeg = ctx->d_grpSeg.as<uint32_t>() + g.seg0; la.grpTile = ctx->d_grpTile.as<uint32_t>() + g.tileTab0; la.nGrpSeg = g.nSeg;
     if (g.w1 > g.w0) load_win_fill_kernel<<<(unsigned)(((uint64_t)n_samples * (g.w1 - g.w0) + 255) / 256), 256, 0, ls>>>(la, n_samples, g.w0, g.w1);
     if (g.nTiles) {
-      if (packed) load_tile_exc_kernel<<<g.nTiles / 256 + 1, 256, 0, ls>>>(la, g.nTiles);
-      load_tile_kernel<<<g.nTiles, PK_THREADS, 0, ls>>>(la);
+      if (packed || vbyte) load_tile_exc_kernel<<<g.nTiles / 256 + 1, 256, 0, ls>>>(la, g.nTiles);
+      if (vbyte) load_tile_kernel<LOAD_VBYTE><<<g.nTiles, PK_THREADS, 0, ls>>>(la);
+      else if (packed) load_tile_kernel<LOAD_WORDS><<<g.nTiles, PK_THREADS, 0, ls>>>(la);
+      else load_tile_kernel<LOAD_PLAIN><<<g.nTiles, PK_THREADS, 0, ls>>>(la);
       load_seam_kernel<<<(g.nTiles + 255) / 256, 256, 0, ls>>>(la, g.nTiles);
     }
     if (g.m1 > g.m0) {
@@ -644,7 +698,7 @@ static int load_finish (upb_ctx* ctx) {
   const uint32_t nSeg = (uint32_t)ctx->firstPos.size();
   const uint32_t* hEnds = (const uint32_t*)ctx->h_ends.p;
   const uint32_t flags = hEnds[2 * (size_t)nSeg];
-  if (flags & FLAG_BAD_PACK) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags_packed2: an escape code without its exception entry, or a tile of a segment that does not start with a position escape");
+  if (flags & FLAG_BAD_PACK) return fail(ctx, UPB_ERR_BAD_ARG, "packed load: malformed input (2-byte form: an escape code without its exception entry, or a tile of a segment that does not start with a position escape; byte form: a malformed entry, a tile that does not hold exactly its entries, or a count escape without its exception entry)");
   if (flags & FLAG_UNSORTED) return fail(ctx, UPB_ERR_UNSORTED, "upb_load_tags: positions must be strictly ascending within each (sample, strand, contig) — the reference asserts on unsorted input (misc/peakcall.cpp:171)");
   if (flags & FLAG_BAD_POS) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags: position outside 1..contig size (the reference's parser drops those, misc/format.cpp:670-676)");
   if (flags & FLAG_ZERO_COUNT) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags: zero count (the reference's parser never delivers those, misc/format.cpp:710)");
@@ -717,6 +771,17 @@ extern "C" int upb_load_tags_packed2 (upb_ctx* ctx, uint32_t n_samples, const ui
 // host-only encoder of the 2-byte form (what a front end does while it parses): position delta in the low 12 bits, count in the
 // high 4, escapes 0xFFF / 0xF with the full values in the exception list.  A position escape opens every segment and every
 // PK_TILE-th entry of it (upb_pack.cuh).
+extern "C" int upb_load_tags_vbyte (upb_ctx* ctx, uint32_t n_samples, const uint64_t* off, const uint8_t* bytes, const uint64_t* byte_off,
+                                    uint64_t n_tiles, const uint64_t* tile_off, uint64_t n_exceptions, const upb_packed_exception* exceptions) {
+  if (ctx && (!bytes || !byte_off || !tile_off)) return fail(ctx, UPB_ERR_BAD_ARG, "upb_load_tags_vbyte: NULL argument");
+  upb_tag_source s;
+  memset(&s, 0, sizeof s);
+  s.n_samples = n_samples; s.off = off; s.vbytes = bytes; s.vbyte_off = byte_off; s.vtile_off = tile_off; s.n_vtiles = n_tiles;
+  s.n_exceptions = n_exceptions; s.exceptions = exceptions; s.directional_hint = 1;
+  const int r = upb_load_tags_async(ctx, &s);
+  return r ? r : load_finish(ctx);
+}
+
 extern "C" int upb_pack_tags2 (uint32_t n_samples, uint32_t n_contigs, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt,
                                uint16_t* words_out, upb_packed_exception* exc_out, uint64_t exc_cap, uint64_t* n_exc_out) {
   if (!off || !n_exc_out || (exc_cap && !exc_out)) return UPB_ERR_BAD_ARG;
@@ -756,6 +821,70 @@ extern "C" int upb_pack_tags2 (uint32_t n_samples, uint32_t n_contigs, const uin
   *n_exc_out = total;
   if (total > exc_cap || (!words_out && !exc_cap)) return total <= exc_cap ? UPB_OK : UPB_ERR_NOMEM;
   parallel(true, base);
+  return UPB_OK;
+}
+
+// host-only encoder of the variable-length byte form (upb_vbyte.hpp): one task per (sample, strand) — sizes first (every task then
+// knows where its bytes, tiles and exceptions go), then the bytes
+extern "C" int upb_pack_tags_vbyte (uint32_t n_samples, uint32_t n_contigs, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt,
+                                    uint8_t* bytes_out, uint64_t bytes_cap, uint64_t* n_bytes_out, uint64_t* byte_off_out,
+                                    uint64_t* tile_off_out, uint64_t tile_cap, uint64_t* n_tiles_out,
+                                    upb_packed_exception* exc_out, uint64_t exc_cap, uint64_t* n_exc_out) {
+  using namespace upb_vb;
+  if (!off || !n_bytes_out || !n_tiles_out || !n_exc_out) return UPB_ERR_BAD_ARG;
+  const uint32_t nTasks = n_samples * 2, C1 = n_contigs + 1;
+  std::vector<uint64_t> segBytes((size_t)nTasks * n_contigs, 0), nExcOf(nTasks, 0), tilesOf(nTasks, 0);
+  auto run = [&] (uint32_t sd, bool write, uint64_t byteBase, uint64_t tileBase, uint64_t excBase) {
+    uint64_t nExc = 0, at = byteBase, tile = tileBase;
+    for (uint32_t c = 0; c < n_contigs; ++c) {
+      const uint64_t a = off[(size_t)sd * C1 + c], b = off[(size_t)sd * C1 + c + 1];
+      const uint64_t at0 = at;
+      uint32_t prev = 0;
+      for (uint64_t e = a; e < b; ++e) {
+        const uint32_t p = pos[e], k = cnt[e];
+        const bool head = ((e - a) & (VB_TILE - 1)) == 0;
+        const uint32_t v = head ? p : (p > prev ? p - prev : 0u);       // unsorted input decodes to a repeated position: the load then reports it
+        bool esc = false;
+        const uint32_t nb = vb_size(v, k, &esc);
+        if (write) {
+          if (head) tile_off_out[tile] = at;
+          vb_put(bytes_out + at, v, k);
+          if (esc) { upb_packed_exception& x = exc_out[excBase + nExc]; x.index = e; x.pos = 0u; x.cnt = k; }
+        }
+        if (head) ++tile;
+        if (esc) ++nExc;
+        at += nb;
+        prev = p;
+      }
+      if (!write) segBytes[(size_t)sd * n_contigs + c] = at - at0;
+    }
+    if (!write) { nExcOf[sd] = nExc; tilesOf[sd] = tile - tileBase; }
+  };
+  const unsigned nThreads = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), nTasks));
+  std::vector<uint64_t> byteBase(nTasks, 0), tileBase(nTasks, 0), excBase(nTasks, 0);
+  auto parallel = [&] (bool write) {
+    std::vector<std::thread> th;
+    std::atomic<uint32_t> next(0);
+    for (unsigned t = 0; t < nThreads; ++t) th.emplace_back([&] { for (uint32_t sd; (sd = next.fetch_add(1)) < nTasks;) run(sd, write, byteBase[sd], tileBase[sd], excBase[sd]); });
+    for (std::thread& t : th) t.join();
+  };
+  parallel(false);
+  uint64_t nBytes = 0, nTiles = 0, nExc = 0;
+  for (uint32_t sd = 0; sd < nTasks; ++sd) {
+    byteBase[sd] = nBytes; tileBase[sd] = nTiles; excBase[sd] = nExc;
+    for (uint32_t c = 0; c < n_contigs; ++c) nBytes += segBytes[(size_t)sd * n_contigs + c];
+    nTiles += tilesOf[sd]; nExc += nExcOf[sd];
+  }
+  *n_bytes_out = nBytes; *n_tiles_out = nTiles; *n_exc_out = nExc;
+  if (nBytes > bytes_cap || nTiles + 1 > tile_cap || nExc > exc_cap) return UPB_ERR_NOMEM;
+  if (!bytes_out || !byte_off_out || !tile_off_out || (nExc && !exc_out)) return UPB_ERR_BAD_ARG;
+  { uint64_t at = 0;
+    for (uint32_t sd = 0; sd < nTasks; ++sd) {
+      for (uint32_t c = 0; c < n_contigs; ++c) { byte_off_out[(size_t)sd * C1 + c] = at; at += segBytes[(size_t)sd * n_contigs + c]; }
+      byte_off_out[(size_t)sd * C1 + n_contigs] = at;
+    } }
+  tile_off_out[nTiles] = nBytes;
+  parallel(true);
   return UPB_OK;
 }
 
@@ -1525,11 +1654,14 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
   // left-edge replay or per-stage profiling (events on one stream).  With a shared table the groups before the last only COUNT their rows
   // (row_place_kernel, countOnly); the last group's launch publishes the rank's counts once, waits for the other ranks and places every
   // unit, and the earlier groups' rows are emitted behind it.
-  int wantGroups = 2;
+  // Measured on C3 (tools/lanes_ab.py, gpurun_out/r02_lanes1): two groups 2.32 -> 2.22 ms on the whole workload (326 M entries), level at bandwidth 200,
+  // three and more groups slower (every group pays the chain's ~27 launches), and on a rank's shard of a 2 / 4 / 8-GPU job (163 / 81 / 40 M entries)
+  // two groups LOSE 4 - 7 %: the pooling kernels of two groups share the SMs and the emits share the PCIe link, so only launch gaps and one
+  // group's emit hide behind the other group's kernels.  Hence: two lanes for large calls only.  UPB_CALL_GROUPS=n forces n groups.
+  int wantGroups = ctx->nEntries >= (pipelined ? 50000000ull : 250000000ull) ? 2 : 1;
   if (const char* e = getenv("UPB_CALL_GROUPS")) wantGroups = std::max(1, std::min(16, atoi(e)));
   bool twoLanes = wantGroups > 1 && !sizing && !cfg.needCorr && nAff == 0 && !ctx->profiling && !empty && ctx->laneStream != nullptr;
   if (shared && (ctx->capN1 == 0 || ctx->capCells == 0)) twoLanes = false;   // (reads its sizes back in the middle of the call)
-  if (shared && getenv("UPB_SHARED_LANES") && !atoi(getenv("UPB_SHARED_LANES"))) twoLanes = false;
   if (twoLanes && !pipelined) {
     if (nUnits < 2 || pr.totalSpans < (1u << 16)) twoLanes = false;    // small inputs: one chain of launches is all there is to wait for
     else {
@@ -1546,7 +1678,8 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
     }
   }
   if (twoLanes && pgroups.size() < 2) twoLanes = false;
-  struct LaneReset { upb_ctx* c; ~LaneReset () { c->lane = 0; c->cur = c->stream; } } laneReset{ctx};
+  // (on every way out: the helpers are back on lane 0, and — an error may leave in the middle of the groups — `stream` is behind whatever the other lane still runs)
+  struct LaneReset { upb_ctx* c; bool two; ~LaneReset () { c->lane = 0; c->cur = c->stream; if (two && cudaEventRecord(c->laneDoneEv, c->laneStream) == cudaSuccess) cudaStreamWaitEvent(c->stream, c->laneDoneEv, 0); } } laneReset{ctx, twoLanes};
   while (ctx->placeEv.size() < pgroups.size()) { cudaEvent_t e = nullptr; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->placeEv.push_back(e); }
   while (ctx->spanEv.size() < 2 * pgroups.size()) { cudaEvent_t e = nullptr; CU(cudaEventCreate(&e)); ctx->spanEv.push_back(e); }
   GroupCtr* const gLane[2] = {g, (GroupCtr*)((unsigned char*)ctx->d_small.p + LANE1_GROUPCTR_OFFSET)};

@@ -20,12 +20,14 @@
 #include <stdint.h>
 
 #include "upb_device.cuh"
+#include "upb_vbyte.hpp"
 
 namespace upb {
 
 constexpr int PK_THREADS = 256;
 constexpr int PK_ITEMS = 8;
 constexpr int PK_TILE = PK_THREADS * PK_ITEMS;
+static_assert(PK_TILE == (int)upb_vb::VB_TILE, "the variable-length byte form restarts its positions at the tiles of the load");
 constexpr uint32_t PK2_DPOS_MASK = 0x0FFFu, PK2_DPOS_ESC = 0x0FFFu, PK2_CNT_SHIFT = 12, PK2_CNT_ESC = 0xFu;
 constexpr uint32_t FLAG_BAD_PACK = 16u;             // an escape without its exception entry, or a tile that does not start with a position escape
 
@@ -59,7 +61,16 @@ struct LoadArgs {
   uint32_t C;
   uint32_t* flags;
   unsigned long long* tileExc;      // [tiles of the group + 1] packed form: index of the first exception at or after each tile's first entry (load_tile_exc_kernel)
+  // variable-length byte form (upb_vbyte.hpp)
+  const uint8_t* vbytes;            // device copy of the kept segments' bytes, in segment order
+  const uint64_t* vSrcByte;         // [nSeg + 1] first byte of segment g in the caller's byte array
+  const uint64_t* vDevByte;         // [nSeg] first byte of segment g in the device copy
+  const uint64_t* vSrcTile;         // [nSeg] number of segment g's first tile in the caller's tile table
+  const uint64_t* vTileOff;         // [caller's tiles + 1] first byte of every tile in the caller's byte array
+  unsigned long long vTiles;        // tiles in the caller's table
 };
+
+enum { LOAD_PLAIN = 0, LOAD_WORDS = 1, LOAD_VBYTE = 2 };
 
 // window index of sample s: every window (65536 positions) that starts after the previous entry and not after this one begins here
 __device__ __forceinline__ void load_open_windows (const LoadArgs& a, uint32_t s, uint32_t dc, int64_t prevWin, uint32_t p0 /* position - 1 */, uint32_t rel) {
@@ -94,6 +105,7 @@ __global__ void load_tile_exc_kernel (const LoadArgs a, uint32_t nTiles) {
   a.tileExc[t] = xl;
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(PK_THREADS) load_tile_kernel (const LoadArgs a) {
   __shared__ uint32_t warpSum[PK_THREADS / 32], warpReset[PK_THREADS / 32];
   __shared__ uint32_t lastOf[PK_THREADS];           // last decoded position of every thread (0: the thread holds no entry)
@@ -114,7 +126,64 @@ __global__ void __launch_bounds__(PK_THREADS) load_tile_kernel (const LoadArgs a
   uint32_t vals[PK_ITEMS], cnts[PK_ITEMS];
   uint32_t flags = 0, run = 0, reset = 0, escMask = 0;
   int n = 0;
-  if (a.words) {
+  if constexpr (MODE == LOAD_VBYTE) {
+    // ---- the tile's bytes -> (value, count) per entry, by the whole block: bit 7 marks the first byte of an entry, so a prefix count of
+    // the marked bytes numbers the entries; the thread that holds an entry's first byte decodes it (upb_vbyte.hpp)
+    using namespace upb_vb;
+    __shared__ __align__(16) uint8_t sb[VB_MAX_TILE_BYTES + 32];
+    __shared__ uint32_t eVal[PK_TILE];
+    __shared__ uint8_t eCnt[PK_TILE];
+    __shared__ uint32_t vbWarp[PK_THREADS / 32];
+    __shared__ uint32_t s_len, s_shift, s_bad;
+    __shared__ const uint8_t* s_src;
+    if (threadIdx.x == 0) {
+      const unsigned long long T = a.vSrcTile[g] + s_tile;
+      unsigned long long bs = 0, be = 0;
+      bool ok = T < a.vTiles;
+      if (ok) { bs = a.vTileOff[T]; be = a.vTileOff[T + 1]; ok = be >= bs && be - bs <= VB_MAX_TILE_BYTES && bs >= a.vSrcByte[g] && be <= a.vSrcByte[g + 1]; }
+      const uint8_t* p = a.vbytes + a.vDevByte[g] + (ok ? bs - a.vSrcByte[g] : 0ull);
+      s_len = ok ? (uint32_t)(be - bs) : 0u; s_bad = ok ? 0u : 1u;
+      s_shift = (uint32_t)((unsigned long long)p & 15ull); s_src = p - s_shift;
+    }
+    for (uint32_t i = threadIdx.x; i < (uint32_t)PK_TILE; i += PK_THREADS) { eVal[i] = 0; eCnt[i] = 1; }
+    __syncthreads();
+    const uint32_t len = s_len, shift = s_shift;
+    { const uint4* src = (const uint4*)s_src; uint4* dst = (uint4*)sb;
+      for (uint32_t i = threadIdx.x; i < (shift + len + 15) >> 4; i += PK_THREADS) dst[i] = src[i]; }
+    __syncthreads();
+    const uint8_t* tb = sb + shift;                                    // the tile's bytes 0 .. len-1
+    uint32_t b0, b1;
+    vb_chunk(len, PK_THREADS, threadIdx.x, &b0, &b1);
+    const uint32_t mine = vb_count_starts(tb, b0, b1);
+    uint32_t inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (uint32_t)o) inc += u; }
+    if (lane == 31) vbWarp[warp] = inc;
+    __syncthreads();
+    uint32_t j = inc - mine, total = 0;                                   // entries that start before this thread's bytes
+    for (uint32_t w2 = 0; w2 < (uint32_t)PK_THREADS / 32; ++w2) { if (w2 < warp) j += vbWarp[w2]; total += vbWarp[w2]; }
+    if (s_bad || total != nHere || (len && !(tb[0] & 0x80u))) flags |= FLAG_BAD_PACK;   // the tile holds exactly its entries and starts with one
+    if (!vb_decode_chunk(tb, len, b0, b1, j, nHere, eVal, eCnt)) flags |= FLAG_BAD_PACK;
+    __syncthreads();
+    const unsigned long long src0 = a.srcStart[g] + t0;
+    const unsigned long long x0 = a.tileExc[blockIdx.x], x1 = x0 + nHere;   // the tile's exceptions: at most one per entry, from x0 on
+#pragma unroll
+    for (int q = 0; q < PK_ITEMS; ++q) {
+      const uint32_t i = i0 + q;
+      if (i < nHere) {
+        const uint32_t v = eVal[i];
+        uint32_t k = eCnt[i];
+        if (k == 0) {                                                  // the count did not fit its byte
+          const PkException* x = pk_find(a.exc, a.nExc, src0 + i, x0, x1);
+          if (!x) flags |= FLAG_BAD_PACK; else k = x->cnt;
+        }
+        if (i == 0) { run = v; reset = 1; escMask |= 1u << q; } else run += v;   // a tile starts with an absolute position
+        vals[q] = run; cnts[q] = k;
+        n = q + 1;
+      }
+    }
+  }
+  if constexpr (MODE == LOAD_WORDS) {
     const unsigned long long src0 = a.srcStart[g] + t0;
     const unsigned long long x0 = a.tileExc[blockIdx.x], x1 = x0 + nHere;   // the tile's exceptions: at most one per entry, from x0 on
 #pragma unroll
@@ -135,6 +204,8 @@ __global__ void __launch_bounds__(PK_THREADS) load_tile_kernel (const LoadArgs a
         n = q + 1;
       }
     }
+  }
+  if constexpr (MODE != LOAD_PLAIN) {
     // block-wide segmented scan of (run, reset): a thread without a reset adds the running position of the threads before it
     uint32_t isum = run, ires = reset;
 #pragma unroll
@@ -169,7 +240,7 @@ __global__ void __launch_bounds__(PK_THREADS) load_tile_kernel (const LoadArgs a
   for (int q = 0; q < PK_ITEMS; ++q) if (q < n) {
     const uint32_t p = vals[q], k = cnts[q];
     const uint64_t rel = t0 + i0 + q;
-    if (a.words) { a.pos[seg0 + rel] = p; a.cnt[seg0 + rel] = k; }
+    if (MODE != LOAD_PLAIN) { a.pos[seg0 + rel] = p; a.cnt[seg0 + rel] = k; }
     if (p < 1 || p > size) { flags |= FLAG_BAD_POS; prev = p; continue; }
     if (k == 0) flags |= FLAG_ZERO_COUNT;
     const bool first = i0 + q == 0;

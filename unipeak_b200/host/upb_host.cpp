@@ -916,7 +916,19 @@ static void pack_segment (const uint32_t* pos, const uint32_t* cnt, size_t n, ui
   }
 }
 
-TagLoader::~TagLoader () { if (words_) { if (wordsPinned_) upb_host_free(words_); else free(words_); } }
+TagLoader::~TagLoader () {
+  if (words_) { if (wordsPinned_) upb_host_free(words_); else free(words_); }
+  if (vbytes_) { if (vbytesPinned_) upb_host_free(vbytes_); else free(vbytes_); }
+}
+
+// which host form the drivers load: the variable-length byte form (1 - 6 bytes per entry, ~1.5 on real tracks: never more than the plain
+// form's 8); UPB_HOST_FORM = packed2 (the 2-byte form where it pays, else plain) | plain | vbyte
+static int host_form () {
+  const char* e = getenv("UPB_HOST_FORM");
+  if (e && !strcmp(e, "packed2")) return 1;
+  if (e && !strcmp(e, "plain")) return 0;
+  return 2;
+}
 
 void TagLoader::encode (const std::vector<Sample>& samples, uint32_t C, bool directionalHint, upb_tag_source* srcOut) {
   const size_t n = samples.size();
@@ -950,7 +962,23 @@ void TagLoader::encode (const std::vector<Sample>& samples, uint32_t C, bool dir
   upb_tag_source src;
   memset(&src, 0, sizeof src);
   src.n_samples = (uint32_t)n; src.off = off_.data(); src.directional_hint = directionalHint ? 1 : 0;
-  if (2 * run + 16 * escTotal < 6 * run) {
+  const int form = host_form();
+  if (form == 2) {
+    // the variable-length byte form, by the library's encoder over the flat arrays (one task per (sample, strand))
+    flatten(samples, C, &flat_);
+    uint64_t nb = 0, nt = 0, nx = 0;
+    upb_pack_tags_vbyte((uint32_t)n, C, off_.data(), flat_.pos, flat_.cnt, nullptr, 0, &nb, nullptr, nullptr, 0, &nt, nullptr, 0, &nx);
+    void* pb = nullptr;
+    const size_t bytes = (size_t)(nb ? nb : 1);
+    if (upb_host_alloc(&pb, bytes) == UPB_OK) vbytesPinned_ = true; else { pb = malloc(bytes); vbytesPinned_ = false; }
+    if (!pb) die("out of host memory");
+    vbytes_ = (uint8_t*)pb;
+    vbyteOff_.assign(off_.size(), 0); vtileOff_.assign((size_t)nt + 1, 0); exc_.resize((size_t)nx);
+    if (upb_pack_tags_vbyte((uint32_t)n, C, off_.data(), flat_.pos, flat_.cnt, vbytes_, nb, &nb, vbyteOff_.data(), vtileOff_.data(), nt + 1, &nt,
+                            exc_.empty() ? nullptr : exc_.data(), nx, &nx) != UPB_OK) die("encoding the tag arrays failed");
+    src.vbytes = vbytes_; src.vbyte_off = vbyteOff_.data(); src.vtile_off = vtileOff_.data(); src.n_vtiles = nt;
+    src.n_exceptions = exc_.size(); src.exceptions = exc_.empty() ? nullptr : exc_.data();
+  } else if (form == 1 && 2 * run + 16 * escTotal < 6 * run) {
     void* pw = nullptr;
     const size_t bytes = (size_t)(run ? run : 1) * 2;
     if (upb_host_alloc(&pw, bytes) == UPB_OK) wordsPinned_ = true; else { pw = malloc(bytes); wordsPinned_ = false; }

@@ -111,7 +111,7 @@ class TagLoader {
   int start (upb_ctx* ctx, const std::vector<Sample>& samples, uint32_t nContigs, bool directionalHint);
   int start (upb_multi* multi, const std::vector<Sample>& samples, uint32_t nContigs, bool directionalHint);   // contig-sharded over the GPUs of the handle
   int wait (upb_ctx* ctx) { return upb_load_wait(ctx); }
-  bool packed () const { return words_ != nullptr; }
+  bool packed () const { return words_ != nullptr || vbytes_ != nullptr; }
   uint64_t entries () const { return n_; }
   uint64_t exceptions () const { return exc_.size(); }
   double packSeconds () const { return packSeconds_; }
@@ -120,6 +120,8 @@ class TagLoader {
   void encode (const std::vector<Sample>& samples, uint32_t nContigs, bool directionalHint, upb_tag_source* src);
   std::vector<uint64_t> off_;
   uint16_t* words_ = nullptr; bool wordsPinned_ = false;
+  uint8_t* vbytes_ = nullptr; bool vbytesPinned_ = false;             // variable-length byte form (UPB_HOST_FORM=vbyte)
+  std::vector<uint64_t> vbyteOff_, vtileOff_;
   std::vector<upb_packed_exception> exc_;
   Flat flat_;
   uint64_t n_ = 0;
