@@ -58,6 +58,45 @@ int main (int argc, char** argv) {
       if (eVal[i] != val[i] || eCnt[i] != k) { printf("tile %d entry %u: got (%u, %u), encoded (%u, %u)\n", t, i, eVal[i], (unsigned)eCnt[i], val[i], cnt[i]); return 1; }
       ++checked;
     }
+    // the staged form the kernel runs: the tile at an arbitrary offset inside a 16-byte aligned buffer, garbage around it, sentinels behind it
+    {
+      const uint32_t shift = (uint32_t)(rng() % 16);
+      std::vector<uint32_t> stw((VB_MAX_TILE_BYTES + 64) / 4, 0);
+      uint8_t* st = (uint8_t*)stw.data();
+      for (size_t i = 0; i < stw.size() * 4; ++i) st[i] = (uint8_t)rng();
+      for (uint32_t i = 0; i < len; ++i) st[shift + i] = bytes[i];
+      std::vector<uint32_t> starts2(T), eVal2(VB_TILE, 0xDEADBEEF);
+      std::vector<uint8_t> eCnt2(VB_TILE, 0xEE);
+      uint32_t total2 = 0, gPrev = 0;
+      for (uint32_t th = 0; th < T; ++th) {
+        uint32_t g0, g1; vb_chunk16(shift, len, T, th, &g0, &g1);
+        if (g0 != gPrev && g0 != ((shift + len + 15) >> 4)) { printf("groups do not tile the buffer\n"); return 1; }
+        gPrev = g1;
+        uint32_t n = 0;
+        for (uint32_t g = g0; g < g1; ++g) n += (uint32_t)__builtin_popcount(vb_starts16(stw.data() + 4 * g, g, shift, len));
+        starts2[th] = n; total2 += n;
+      }
+      if (gPrev != ((shift + len + 15) >> 4)) { printf("groups do not cover the buffer\n"); return 1; }
+      if (total2 != nHere) { printf("tile %d (staged, shift %u): %u starts for %u entries\n", t, shift, total2, nHere); return 1; }
+      uint32_t j2 = 0;
+      std::vector<uint16_t> startAt(VB_TILE + 8, 0xFFFF);
+      for (uint32_t th = 0; th < T; ++th) {                                // pass 2a: every thread lists where its entries start
+        uint32_t g0, g1; vb_chunk16(shift, len, T, th, &g0, &g1);
+        vb_list_starts(stw.data(), shift, len, g0, g1, j2, nHere, startAt.data());
+        j2 += starts2[th];
+      }
+      for (uint32_t q = 0; q < 8; ++q) startAt[nHere + q] = (uint16_t)(shift + len);
+      for (uint32_t th = 0; th < T; ++th)                                  // pass 2b: thread th decodes entries 8 th .. 8 th + 7
+        for (uint32_t q = 0; q < 8; ++q) {
+          const uint32_t i = 8 * th + q;
+          if (i >= nHere) continue;
+          uint32_t v = 0, k = 0;
+          if (!vb_get_span(stw.data(), startAt[i], (uint32_t)startAt[i + 1] - startAt[i], &v, &k)) { printf("tile %d entry %u (staged): malformed?\n", t, i); return 1; }
+          eVal2[i] = v; eCnt2[i] = (uint8_t)k;
+        }
+      for (uint32_t i = 0; i < nHere; ++i)
+        if (eVal2[i] != eVal[i] || eCnt2[i] != eCnt[i]) { printf("tile %d entry %u (staged, shift %u): (%u, %u) against (%u, %u)\n", t, i, shift, eVal2[i], (unsigned)eCnt2[i], eVal[i], (unsigned)eCnt[i]); return 1; }
+    }
   }
   // malformed codes are refused
   { uint32_t v, k;
@@ -66,7 +105,19 @@ int main (int argc, char** argv) {
     const uint8_t a3[] = {0x80, 5, 0};                       if (vb_get(a3, 2, &v, &k)) { printf("non-canonical value accepted\n"); return 1; }
     const uint8_t a4[] = {0x80 | 0x40, 1};                   if (vb_get(a4, 1, &v, &k)) { printf("count byte 1 accepted\n"); return 1; }
     const uint8_t a5[] = {0x80, 127, 127, 127, 127};         if (vb_get(a5, 4, &v, &k)) { printf("value beyond 32 bits accepted\n"); return 1; }
-    const uint8_t a6[] = {0x80 | 63, 127, 127, 127, 31};     if (!vb_get(a6, 4, &v, &k) || v != 0xFFFFFFFFu || k != 1) { printf("largest value refused\n"); return 1; } }
+    const uint8_t a6[] = {0x80 | 63, 127, 127, 127, 31};     if (!vb_get(a6, 4, &v, &k) || v != 0xFFFFFFFFu || k != 1) { printf("largest value refused\n"); return 1; }
+    // the word-wise reader agrees on all of them (entry at byte 5 of a buffer)
+    const uint8_t* cases[] = {a1, a2, a3, a4, a5, a6};
+    const uint32_t lens[] = {1, 6, 3, 2, 5, 5};
+    const bool good[] = {false, false, false, false, false, true};
+    for (int q = 0; q < 6; ++q) {
+      uint32_t bufw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      uint8_t* buf = (uint8_t*)bufw;
+      for (uint32_t i = 0; i < lens[q]; ++i) buf[5 + i] = cases[q][i];
+      if (vb_get_span(bufw, 5, lens[q], &v, &k) != good[q]) { printf("word-wise reader disagrees on malformed case %d\n", q); return 1; }
+    }
+    { uint32_t bufw[8] = {0x80808080u, 0x80808080u, 0, 0, 0, 0, 0, 0};
+      if (vb_get_span(bufw, 1, 0, &v, &k) || vb_get_span(bufw, 1, 7, &v, &k) || vb_get_span(bufw, 1, 0xFFFFFFF0u, &v, &k)) { printf("impossible span accepted\n"); return 1; } } }
   printf("ok %ld entries\n", checked);
   return 0;
 }

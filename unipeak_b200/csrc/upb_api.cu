@@ -85,7 +85,7 @@ struct upb_ctx {
   DevBuf d_pos, d_cnt, d_off, d_segStart, d_tidx, d_tidxBase, d_sizes, d_nTilesIdx, d_small;
   DevBuf d_winBase, d_wEnt;                                          // per-sample window index of the scatter pass
   DevBuf d_pk16, d_pkExc, d_segEnds, d_srcStart, d_grpSeg, d_grpTile, d_loadFlags;   // load (upb_pack.cuh)
-  DevBuf d_tileExc;                    // packed load: first exception of every tile of the load group being decoded
+  DevBuf d_tileExc, d_tileDesc;        // packed load: first exception of every tile of the load group being decoded, and where the tile is (load_tile_prep_kernel)
   DevBuf d_vbytes, d_vSrcByte, d_vDevByte, d_vSrcTile, d_vTileOff;   // variable-length byte form (upb_vbyte.hpp)
   DevBuf d_ment, d_mtOff, d_mtBase, d_mtCount, d_mEff, d_mtW, d_blkW;   // tile-major copy and its zone maps (upb_device.cuh)
   std::vector<uint32_t> mtBase;         // [2*C+1]
@@ -184,7 +184,7 @@ extern "C" int upb_create (int device, upb_ctx** out) {
 extern "C" void upb_destroy (upb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  DevBuf* all[] = {&ctx->d_vbytes, &ctx->d_vSrcByte, &ctx->d_vDevByte, &ctx->d_vSrcTile, &ctx->d_vTileOff, &ctx->d_tileExc, &ctx->d_winBase, &ctx->d_wEnt, &ctx->d_pk16, &ctx->d_pkExc, &ctx->d_segEnds, &ctx->d_srcStart, &ctx->d_grpSeg, &ctx->d_grpTile, &ctx->d_loadFlags, &ctx->d_mtW, &ctx->d_blkW, &ctx->d_ment, &ctx->d_mtOff, &ctx->d_mtBase, &ctx->d_mtCount, &ctx->d_mEff, &ctx->d_pos, &ctx->d_cnt, &ctx->d_off, &ctx->d_segStart, &ctx->d_tidx, &ctx->d_tidxBase, &ctx->d_sizes,
+  DevBuf* all[] = {&ctx->d_vbytes, &ctx->d_vSrcByte, &ctx->d_vDevByte, &ctx->d_vSrcTile, &ctx->d_vTileOff, &ctx->d_tileExc, &ctx->d_tileDesc, &ctx->d_winBase, &ctx->d_wEnt, &ctx->d_pk16, &ctx->d_pkExc, &ctx->d_segEnds, &ctx->d_srcStart, &ctx->d_grpSeg, &ctx->d_grpTile, &ctx->d_loadFlags, &ctx->d_mtW, &ctx->d_blkW, &ctx->d_ment, &ctx->d_mtOff, &ctx->d_mtBase, &ctx->d_mtCount, &ctx->d_mEff, &ctx->d_pos, &ctx->d_cnt, &ctx->d_off, &ctx->d_segStart, &ctx->d_tidx, &ctx->d_tidxBase, &ctx->d_sizes,
     &ctx->d_nTilesIdx, &ctx->d_small};
   for (DevBuf* b : all) release(*b);
   for (auto& kv : ctx->scratch) release(kv.second);
@@ -471,8 +471,14 @@ static int load_enqueue (upb_ctx* ctx, const upb_tag_source* src, bool resident)
       ranges.push_back(r);
     }
   } else {
-    static const double cum[] = {0.26, 0.48, 0.66, 0.80, 0.90, 0.96, 1.0};
-    const int nCut = (int)(sizeof cum / sizeof cum[0]);
+    // (UPB_LOAD_CUM=a,b,...: other cumulative shares, for experiments)
+    double cum[16] = {0.26, 0.48, 0.66, 0.80, 0.90, 0.96, 1.0};
+    int nCut = 7;
+    if (const char* e = getenv("UPB_LOAD_CUM"); e && *e) {
+      nCut = 0;
+      for (const char* q = e; *q && nCut < 15;) { char* end = nullptr; const double v = strtod(q, &end); if (end == q) break; cum[nCut++] = v; q = *end ? end + 1 : end; }
+      if (nCut == 0 || cum[nCut - 1] < 1.0) cum[nCut++] = 1.0;
+    }
     int part = 0;
     uint64_t acc = 0, inRange = 0;
     uint32_t c = 0;
@@ -558,6 +564,7 @@ static int load_enqueue (upb_ctx* ctx, const upb_tag_source* src, bool resident)
     uint32_t maxTiles = 0;
     for (const LoadGroup& g : ctx->groups) maxTiles = std::max(maxTiles, g.nTiles);
     ENSURE(ctx->d_tileExc, ((size_t)maxTiles + 2) * 8);
+    ENSURE(ctx->d_tileDesc, ((size_t)maxTiles + 2) * sizeof(TileDesc));
     if (packed) ENSURE(ctx->d_pk16, (E ? E : 1) * 2);
     ENSURE(ctx->d_pkExc, (src->n_exceptions ? src->n_exceptions : 1) * sizeof(PkException));
   }
@@ -617,6 +624,7 @@ static int load_enqueue (upb_ctx* ctx, const upb_tag_source* src, bool resident)
   la.winBase = ctx->d_winBase.as<uint32_t>(); la.wEnt = ctx->d_wEnt.as<uint32_t>(); la.nWinTotal = nWinTotal; la.C = C;
   la.flags = ctx->d_loadFlags.as<uint32_t>();
   la.tileExc = (packed || vbyte) ? ctx->d_tileExc.as<unsigned long long>() : nullptr;
+  la.tileDesc = (packed || vbyte) ? ctx->d_tileDesc.as<TileDesc>() : nullptr;
   MtArgs ma;
   memset(&ma, 0, sizeof ma);
   ma.pos = la.pos; ma.cnt = la.cnt; ma.segStart = la.segStart; ma.mtBase = la.mtBase;
@@ -648,7 +656,7 @@ static int load_enqueue (upb_ctx* ctx, const upb_tag_source* src, bool resident)
     la.grpSeg = ctx->d_grpSeg.as<uint32_t>() + g.seg0; la.grpTile = ctx->d_grpTile.as<uint32_t>() + g.tileTab0; la.nGrpSeg = g.nSeg;
     if (g.w1 > g.w0) load_win_fill_kernel<<<(unsigned)(((uint64_t)n_samples * (g.w1 - g.w0) + 255) / 256), 256, 0, ls>>>(la, n_samples, g.w0, g.w1);
     if (g.nTiles) {
-      if (packed || vbyte) load_tile_exc_kernel<<<g.nTiles / 256 + 1, 256, 0, ls>>>(la, g.nTiles);
+      if (packed || vbyte) load_tile_prep_kernel<<<g.nTiles / 256 + 1, 256, 0, ls>>>(la, g.nTiles);
       if (vbyte) load_tile_kernel<LOAD_VBYTE><<<g.nTiles, PK_THREADS, 0, ls>>>(la);
       else if (packed) load_tile_kernel<LOAD_WORDS><<<g.nTiles, PK_THREADS, 0, ls>>>(la);
       else load_tile_kernel<LOAD_PLAIN><<<g.nTiles, PK_THREADS, 0, ls>>>(la);
@@ -1657,8 +1665,10 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
   // Measured on C3 (tools/lanes_ab.py, gpurun_out/r02_lanes1): two groups 2.32 -> 2.22 ms on the whole workload (326 M entries), level at bandwidth 200,
   // three and more groups slower (every group pays the chain's ~27 launches), and on a rank's shard of a 2 / 4 / 8-GPU job (163 / 81 / 40 M entries)
   // two groups LOSE 4 - 7 %: the pooling kernels of two groups share the SMs and the emits share the PCIe link, so only launch gaps and one
-  // group's emit hide behind the other group's kernels.  Hence: two lanes for large calls only.  UPB_CALL_GROUPS=n forces n groups.
-  int wantGroups = ctx->nEntries >= (pipelined ? 50000000ull : 250000000ull) ? 2 : 1;
+  // group's emit hide behind the other group's kernels; inside bench.py's timed loop the whole-workload gain was 1 - 3 %, and the span kernel's
+  // event bracket then holds a share of the other lane's kernels (0.82 -> 0.93 ms).  Hence: a resident call runs as ONE group unless
+  // UPB_CALL_GROUPS=n asks for n; a call behind a large load deals the groups it has anyway (they arrive one after the other) to the two lanes.
+  int wantGroups = (pipelined && ctx->nEntries >= 50000000ull) ? 2 : 1;
   if (const char* e = getenv("UPB_CALL_GROUPS")) wantGroups = std::max(1, std::min(16, atoi(e)));
   bool twoLanes = wantGroups > 1 && !sizing && !cfg.needCorr && nAff == 0 && !ctx->profiling && !empty && ctx->laneStream != nullptr;
   if (shared && (ctx->capN1 == 0 || ctx->capCells == 0)) twoLanes = false;   // (reads its sizes back in the middle of the call)

@@ -60,7 +60,7 @@ struct LoadArgs {
   uint32_t nWinTotal;
   uint32_t C;
   uint32_t* flags;
-  unsigned long long* tileExc;      // [tiles of the group + 1] packed form: index of the first exception at or after each tile's first entry (load_tile_exc_kernel)
+  unsigned long long* tileExc;      // [tiles of the group + 1] packed form: index of the first exception at or after each tile's first entry (load_tile_prep_kernel)
   // variable-length byte form (upb_vbyte.hpp)
   const uint8_t* vbytes;            // device copy of the kept segments' bytes, in segment order
   const uint64_t* vSrcByte;         // [nSeg + 1] first byte of segment g in the caller's byte array
@@ -68,6 +68,17 @@ struct LoadArgs {
   const uint64_t* vSrcTile;         // [nSeg] number of segment g's first tile in the caller's tile table
   const uint64_t* vTileOff;         // [caller's tiles + 1] first byte of every tile in the caller's byte array
   unsigned long long vTiles;        // tiles in the caller's table
+  struct TileDesc* tileDesc;        // [tiles of the group] what load_tile_prep_kernel found out about every tile (packed forms; NULL: plain form, the tile kernel searches itself)
+};
+
+// Per tile of a load group, worked out by one thread per tile for all tiles at once (load_tile_prep_kernel) instead of by thread 0 of
+// every tile block in front of its first barrier: a binary search over the group's segments and, for the byte form, three dependent
+// look-ups — ~3 us of dependent loads per block that only a handful of resident blocks per SM could hide.
+struct __align__(16) TileDesc {
+  uint32_t seg, tile;               // segment g = (s*2+d)*C + c, tile inside it
+  uint32_t len, bad;                // byte form: bytes of the tile; bad: the tile table is inconsistent here
+  unsigned long long devByte;       // byte form: first byte of the tile in the device copy
+  unsigned long long pad;
 };
 
 enum { LOAD_PLAIN = 0, LOAD_WORDS = 1, LOAD_VBYTE = 2 };
@@ -92,28 +103,46 @@ __global__ void load_check_exc_kernel (const PkException* __restrict__ exc, unsi
 // exception and its exceptions are consecutive in the index-sorted list: one binary search per tile HERE (one thread per tile, all
 // tiles of the group in flight at once) instead of a 22-step chain of dependent loads inside load_tile_kernel, where a whole block
 // waited at its barrier for the threads that hold an escape (r02 capture: 44 % of the kernel's stall samples on that barrier).
-__global__ void load_tile_exc_kernel (const LoadArgs a, uint32_t nTiles) {
+__global__ void load_tile_prep_kernel (const LoadArgs a, uint32_t nTiles) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t > nTiles) return;
   if (t == nTiles) { a.tileExc[t] = a.nExc; return; }                  // (only an upper bound of the last tile's window)
   uint32_t lo = 0, hi = a.nGrpSeg;
   while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.grpTile[mid] <= t) lo = mid; else hi = mid; }
-  const uint32_t g = a.grpSeg[lo];
-  const unsigned long long e = a.srcStart[g] + (unsigned long long)(t - a.grpTile[lo]) * PK_TILE;
+  const uint32_t g = a.grpSeg[lo], k = t - a.grpTile[lo];
+  const unsigned long long e = a.srcStart[g] + (unsigned long long)k * PK_TILE;
   unsigned long long xl = 0, xh = a.nExc;
   while (xl < xh) { const unsigned long long mid = (xl + xh) >> 1; if (a.exc[mid].index < e) xl = mid + 1; else xh = mid; }
   a.tileExc[t] = xl;
+  TileDesc d;
+  d.seg = g; d.tile = k; d.len = 0; d.bad = 0; d.devByte = 0; d.pad = 0;
+  if (a.vbytes) {
+    const unsigned long long T = a.vSrcTile[g] + k;
+    unsigned long long bs = 0, be = 0;
+    bool ok = T < a.vTiles;
+    if (ok) { bs = a.vTileOff[T]; be = a.vTileOff[T + 1]; ok = be >= bs && be - bs <= upb_vb::VB_MAX_TILE_BYTES && bs >= a.vSrcByte[g] && be <= a.vSrcByte[g + 1]; }
+    d.len = ok ? (uint32_t)(be - bs) : 0u; d.bad = ok ? 0u : 1u;
+    d.devByte = a.vDevByte[g] + (ok ? bs - a.vSrcByte[g] : 0ull);
+  }
+  a.tileDesc[t] = d;
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(PK_THREADS) load_tile_kernel (const LoadArgs a) {
+__global__ void __launch_bounds__(PK_THREADS, MODE == LOAD_VBYTE ? 6 : MODE == LOAD_WORDS ? 5 : 8) load_tile_kernel (const LoadArgs a) {
   __shared__ uint32_t warpSum[PK_THREADS / 32], warpReset[PK_THREADS / 32];
   __shared__ uint32_t lastOf[PK_THREADS];           // last decoded position of every thread (0: the thread holds no entry)
   __shared__ uint32_t s_seg, s_tile;
+  __shared__ uint32_t s_len, s_bad;
+  __shared__ unsigned long long s_devByte;
   if (threadIdx.x == 0) {
-    uint32_t lo = 0, hi = a.nGrpSeg;                // largest j with grpTile[j] <= blockIdx.x (segments without entries have no tile and are skipped)
-    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.grpTile[mid] <= blockIdx.x) lo = mid; else hi = mid; }
-    s_seg = a.grpSeg[lo]; s_tile = blockIdx.x - a.grpTile[lo];
+    if (MODE != LOAD_PLAIN) {                         // load_tile_prep_kernel has been here
+      const TileDesc d = a.tileDesc[blockIdx.x];
+      s_seg = d.seg; s_tile = d.tile; s_len = d.len; s_bad = d.bad; s_devByte = d.devByte;
+    } else {
+      uint32_t lo = 0, hi = a.nGrpSeg;                // largest j with grpTile[j] <= blockIdx.x (segments without entries have no tile and are skipped)
+      while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.grpTile[mid] <= blockIdx.x) lo = mid; else hi = mid; }
+      s_seg = a.grpSeg[lo]; s_tile = blockIdx.x - a.grpTile[lo];
+    }
   }
   __syncthreads();
   const uint32_t g = s_seg, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -131,30 +160,18 @@ __global__ void __launch_bounds__(PK_THREADS) load_tile_kernel (const LoadArgs a
     // the marked bytes numbers the entries; the thread that holds an entry's first byte decodes it (upb_vbyte.hpp)
     using namespace upb_vb;
     __shared__ __align__(16) uint8_t sb[VB_MAX_TILE_BYTES + 32];
-    __shared__ uint32_t eVal[PK_TILE];
-    __shared__ uint8_t eCnt[PK_TILE];
+    __shared__ __align__(16) uint16_t startAt[PK_TILE + 8];              // byte index (into sb) of every entry's first byte; [nHere] = end of the tile
     __shared__ uint32_t vbWarp[PK_THREADS / 32];
-    __shared__ uint32_t s_len, s_shift, s_bad;
-    __shared__ const uint8_t* s_src;
-    if (threadIdx.x == 0) {
-      const unsigned long long T = a.vSrcTile[g] + s_tile;
-      unsigned long long bs = 0, be = 0;
-      bool ok = T < a.vTiles;
-      if (ok) { bs = a.vTileOff[T]; be = a.vTileOff[T + 1]; ok = be >= bs && be - bs <= VB_MAX_TILE_BYTES && bs >= a.vSrcByte[g] && be <= a.vSrcByte[g + 1]; }
-      const uint8_t* p = a.vbytes + a.vDevByte[g] + (ok ? bs - a.vSrcByte[g] : 0ull);
-      s_len = ok ? (uint32_t)(be - bs) : 0u; s_bad = ok ? 0u : 1u;
-      s_shift = (uint32_t)((unsigned long long)p & 15ull); s_src = p - s_shift;
-    }
-    for (uint32_t i = threadIdx.x; i < (uint32_t)PK_TILE; i += PK_THREADS) { eVal[i] = 0; eCnt[i] = 1; }
-    __syncthreads();
-    const uint32_t len = s_len, shift = s_shift;
-    { const uint4* src = (const uint4*)s_src; uint4* dst = (uint4*)sb;
+    const uint8_t* const tp = a.vbytes + s_devByte;                       // the tile's first byte (a.vbytes is 256-byte aligned)
+    const uint32_t len = s_len, shift = (uint32_t)(s_devByte & 15ull);
+    { const uint4* src = (const uint4*)(tp - shift); uint4* dst = (uint4*)sb;   // whole aligned 16-byte words (the device copy has slack behind its last byte)
       for (uint32_t i = threadIdx.x; i < (shift + len + 15) >> 4; i += PK_THREADS) dst[i] = src[i]; }
     __syncthreads();
-    const uint8_t* tb = sb + shift;                                    // the tile's bytes 0 .. len-1
-    uint32_t b0, b1;
-    vb_chunk(len, PK_THREADS, threadIdx.x, &b0, &b1);
-    const uint32_t mine = vb_count_starts(tb, b0, b1);
+    const uint32_t* sbw = (const uint32_t*)sb;
+    uint32_t g0, g1;
+    vb_chunk16(shift, len, PK_THREADS, threadIdx.x, &g0, &g1);
+    uint32_t mine = 0;
+    for (uint32_t gq = g0; gq < g1; ++gq) mine += __popc(vb_starts16(sbw + 4 * gq, gq, shift, len));
     uint32_t inc = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (uint32_t)o) inc += u; }
@@ -162,17 +179,30 @@ __global__ void __launch_bounds__(PK_THREADS) load_tile_kernel (const LoadArgs a
     __syncthreads();
     uint32_t j = inc - mine, total = 0;                                   // entries that start before this thread's bytes
     for (uint32_t w2 = 0; w2 < (uint32_t)PK_THREADS / 32; ++w2) { if (w2 < warp) j += vbWarp[w2]; total += vbWarp[w2]; }
-    if (s_bad || total != nHere || (len && !(tb[0] & 0x80u))) flags |= FLAG_BAD_PACK;   // the tile holds exactly its entries and starts with one
-    if (!vb_decode_chunk(tb, len, b0, b1, j, nHere, eVal, eCnt)) flags |= FLAG_BAD_PACK;
+    if (s_bad || total != nHere || (len && !(sb[shift] & 0x80u))) flags |= FLAG_BAD_PACK;   // the tile holds exactly its entries and starts with one
+    vb_list_starts(sbw, shift, len, g0, g1, j, nHere, startAt);
+    if (threadIdx.x < 8) startAt[min(total, nHere) + threadIdx.x] = (uint16_t)(shift + len);   // the last entry ends with the tile
     __syncthreads();
+    uint32_t ev[PK_ITEMS], ek[PK_ITEMS];
+    { const uint4 s4 = ((const uint4*)startAt)[threadIdx.x];               // this thread's eight entries and the start of the next one
+      const uint32_t nxt = startAt[PK_ITEMS * threadIdx.x + PK_ITEMS];
+      const uint32_t at[PK_ITEMS + 1] = {s4.x & 0xFFFFu, s4.x >> 16, s4.y & 0xFFFFu, s4.y >> 16, s4.z & 0xFFFFu, s4.z >> 16, s4.w & 0xFFFFu, s4.w >> 16, nxt};
+#pragma unroll
+      for (int q = 0; q < PK_ITEMS; ++q) {
+        ev[q] = 0; ek[q] = 1;
+        if (i0 + q < nHere && i0 + q < total && !vb_get_span(sbw, at[q], at[q + 1] - at[q], &ev[q], &ek[q])) { flags |= FLAG_BAD_PACK; ev[q] = 0; ek[q] = 1; }
+      } }
+    static_assert(PK_ITEMS == 8, "the entry fetch above reads eight entries per thread");
     const unsigned long long src0 = a.srcStart[g] + t0;
-    const unsigned long long x0 = a.tileExc[blockIdx.x], x1 = x0 + nHere;   // the tile's exceptions: at most one per entry, from x0 on
+    // the tile's exceptions: from x0 on, at most one per entry, and in front of the next tile's (the tiles of a group ascend in the caller's entry
+    // index) — a window of a handful of entries instead of 2048: three dependent look-ups per escape instead of eleven, with the block waiting
+    const unsigned long long x0 = a.tileExc[blockIdx.x], x1 = min(x0 + nHere, a.tileExc[blockIdx.x + 1]);
 #pragma unroll
     for (int q = 0; q < PK_ITEMS; ++q) {
       const uint32_t i = i0 + q;
       if (i < nHere) {
-        const uint32_t v = eVal[i];
-        uint32_t k = eCnt[i];
+        const uint32_t v = ev[q];
+        uint32_t k = ek[q];
         if (k == 0) {                                                  // the count did not fit its byte
           const PkException* x = pk_find(a.exc, a.nExc, src0 + i, x0, x1);
           if (!x) flags |= FLAG_BAD_PACK; else k = x->cnt;
@@ -185,7 +215,9 @@ __global__ void __launch_bounds__(PK_THREADS) load_tile_kernel (const LoadArgs a
   }
   if constexpr (MODE == LOAD_WORDS) {
     const unsigned long long src0 = a.srcStart[g] + t0;
-    const unsigned long long x0 = a.tileExc[blockIdx.x], x1 = x0 + nHere;   // the tile's exceptions: at most one per entry, from x0 on
+    // the tile's exceptions: from x0 on, at most one per entry, and in front of the next tile's (the tiles of a group ascend in the caller's entry
+    // index) — a window of a handful of entries instead of 2048: three dependent look-ups per escape instead of eleven, with the block waiting
+    const unsigned long long x0 = a.tileExc[blockIdx.x], x1 = min(x0 + nHere, a.tileExc[blockIdx.x + 1]);
 #pragma unroll
     for (int q = 0; q < PK_ITEMS; ++q) {
       const uint32_t i = i0 + q;

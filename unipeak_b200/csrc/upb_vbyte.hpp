@@ -85,4 +85,66 @@ UPB_VB_HD bool vb_decode_chunk (const uint8_t* tb, uint32_t len, uint32_t b0, ui
   return ok;
 }
 
+// ---- the same two passes over a STAGED tile, 16 bytes at a time (what the device decoder runs; the byte-wise functions above are
+// the plain statement of it).  The tile's `len` bytes sit at sb[shift .. shift + len) of a 16-byte aligned buffer (shift < 16: the
+// device copies whole aligned 16-byte words) and readable up to sb[shift + len + 11].
+UPB_VB_HD uint32_t vb_ctz64 (uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__ffsll((long long)x) - 1u;
+#else
+  return (uint32_t)__builtin_ctzll(x);
+#endif
+}
+// thread t owns the 16-byte groups [g0, g1)
+UPB_VB_HD void vb_chunk16 (uint32_t shift, uint32_t len, uint32_t nThreads, uint32_t t, uint32_t* g0, uint32_t* g1) {
+  const uint32_t nG = len ? (shift + len + 15) >> 4 : 0u;
+  const uint32_t per = (nG + nThreads - 1) / nThreads;
+  *g0 = t * per < nG ? t * per : nG;
+  *g1 = *g0 + per < nG ? *g0 + per : nG;
+}
+// bit i = byte i of group g (words w[0..3]) starts an entry of the tile
+UPB_VB_HD uint32_t vb_starts16 (const uint32_t* w, uint32_t g, uint32_t shift, uint32_t len) {
+  uint32_t m = 0;
+  for (int q = 0; q < 4; ++q) { const uint32_t x = (w[q] >> 7) & 0x01010101u; m |= ((x | (x >> 7) | (x >> 14) | (x >> 21)) & 0xFu) << (4 * q); }
+  const uint32_t first = 16 * g, end = shift + len;
+  const uint32_t lo = first < shift ? shift - first : 0u;               // bytes of the group before the tile
+  const uint32_t hi = end - first >= 16 ? 16u : end - first;            // ... and from its end on
+  return m & (0xFFFFu << lo) & ((1u << hi) - 1u);
+}
+// pass 2a: where the entries of the groups [g0, g1) start (byte index into sb); j = entries that start before them
+UPB_VB_HD void vb_list_starts (const uint32_t* sbw, uint32_t shift, uint32_t len, uint32_t g0, uint32_t g1, uint32_t j, uint32_t cap, uint16_t* startAt) {
+  for (uint32_t g = g0; g < g1; ++g) {
+    uint32_t m = vb_starts16(sbw + 4 * g, g, shift, len);
+    while (m) {
+      const uint32_t b = vb_ctz64(m);
+      m &= m - 1;
+      if (j < cap) startAt[j] = (uint16_t)(16 * g + b);
+      ++j;
+    }
+  }
+}
+// pass 2b: the entry that occupies the n bytes sb[at .. at + n) (n = distance to the next entry's first byte, or to the end of the
+// tile).  Returns false when it is malformed.
+UPB_VB_HD bool vb_get_span (const uint32_t* sbw, uint32_t at, uint32_t n, uint32_t* v, uint32_t* count) {
+  const uint32_t wi = at >> 2, sh = (at & 3u) * 8u;
+  const uint32_t a = sbw[wi], b = sbw[wi + 1], c3 = sbw[wi + 2];
+#if defined(__CUDA_ARCH__)
+  const uint32_t lo = __funnelshift_r(a, b, sh), hi = __funnelshift_r(b, c3, sh);
+#else
+  const uint32_t lo = sh ? (a >> sh) | (b << (32u - sh)) : a, hi = sh ? (b >> sh) | (c3 << (32u - sh)) : b;
+#endif
+  const uint32_t c = (lo >> 6) & 1u;
+  const uint32_t nv = n - 1u - c;                                       // value bytes behind the first (wraps when n is too small)
+  if (n < 1u + c || nv > 4u) return false;
+  // e1 .. e4, seven bits each, closed up into one 28-bit number; the value takes the lowest 7 nv bits of it
+  const uint32_t pay = ((lo >> 8) & 0x7Fu) | ((lo >> 9) & 0x3F80u) | ((lo >> 10) & 0x1FC000u) | ((hi & 0x7Fu) << 21);
+  const uint32_t used = pay & ((1u << (7u * nv)) - 1u);                  // (nv = 0: nothing; nv = 4: all 28 bits)
+  if (nv == 4u && (used >> 26) != 0) return false;                      // beyond 32 bits
+  if (nv > 0 && (used >> (7u * nv - 7u)) == 0) return false;            // canonical: the highest value byte is not 0
+  const uint32_t k = (uint32_t)((((uint64_t)hi << 32) | lo) >> (8u * n - 8u)) & 127u;   // the byte at n - 1
+  *v = (lo & 63u) | (used << 6);
+  *count = c ? k : 1u;
+  return !(c && k == 1u);
+}
+
 }  // namespace upb_vb
