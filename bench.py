@@ -15,9 +15,10 @@ of the per-unit row counts (upb_call_regions_shared).
             bracketed by barrier + synchronize, max over ranks; the wall clock of the same region is reported beside it).
 `e2e`     : the same through the C-ABI from pinned HOST buffers every step: upb_load_tags_async (H2D copy, decode, counting
             sort, zone maps — pipelined by (strand, contig range)) + upb_call_regions, which starts on the groups that have
-            arrived; ends with the table on the host.  Host form: the 2-byte one (u16 per entry + exception list), which is
-            what the shipped front ends load; `pack_ms` is what its host-side encoder took (outside the timed region: a
-            front end encodes while it parses).  `e2e_alt` is the plain form (u32 pos + u32 cnt, 8 B per entry).
+            arrived; ends with the table on the host.  Host form (--host-form): the variable-length byte one (~1.5 B per
+            entry + count exceptions), which is what the shipped front ends load; `pack_ms` is what its host-side encoder
+            took (outside the timed region: a front end encodes while it parses).  `e2e_alt2` is the other compact form
+            (u16 per entry + exception list), `e2e_alt` the plain one (u32 pos + u32 cnt, 8 B per entry).
 `t_hot_cold`: sample-major arrays resident -> index build (tile-major copy + zone maps: the k-way merge's replacement)
             -> call -> table on the host (SURVEY 8d's t_hot taken literally), with its own bp/s and roofline fraction.
 `roofline`: the fused span kernel, algorithmic bytes (8 B per tag entry read once + 40+4n B per candidate written)

@@ -1,7 +1,7 @@
 #!/bin/bash
 # One gpurun call of round 2: smoke, the GPU test suite, the bench line, the ncu launch list and
 # one full capture of span_kernel.  Everything lands in gpurun_out/$TAG/.  Steps are chosen by name:
-#   bash tools/gpu_session.sh <tag> [smoke] [tests] [tests-fast] [bench] [bench-quick] [ncu] [ncufull] [refarm] [ab:<workloads>]
+#   bash tools/gpu_session.sh <tag> [smoke] [tests] [tests-fast] [bench] [bench-quick] [onelane] [trace] [ncu] [ncufull] [ncutile] [refarm] [cli] [ab:<workloads>]
 set +e
 TAG=${1:-r02}; shift
 OUT=gpurun_out/$TAG
@@ -31,6 +31,13 @@ for step in "$@"; do
         python bench.py --steps 2 --warmup 1 --no-cpu --no-sweep > $OUT/ncu_full.log 2>&1; note ncu-full $?
       timeout 300 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:upb::region_pool_kernel -c 1 -f -o $OUT/pool \
         python bench.py --steps 2 --warmup 1 --no-cpu --no-sweep > $OUT/ncu_full_pool.log 2>&1; note ncu-full-pool $? ;;
+    ncutile)
+      timeout 400 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:upb::load_tile_kernel -s 14 -c 1 -f -o $OUT/tile \
+        python tools/e2e_trace.py > $OUT/ncu_full_tile.log 2>&1; note ncu-full-tile $? ;;
+    onelane)
+      UPB_CALL_GROUPS=1 timeout 400 python bench.py --steps 5 --warmup 3 --no-cpu --no-sweep > $OUT/bench_quick_onelane.json 2> $OUT/bench_quick_onelane.err; note bench-quick-onelane $? ;;
+    trace)
+      UPB_TRACE=1 timeout 300 python tools/e2e_trace.py > $OUT/e2e_trace.txt 2>&1; note trace $? ;;
     cli)
       timeout 600 python tools/cli_bench.py > $OUT/cli_bench.jsonl 2> $OUT/cli_bench.err; note cli $? ;;
     wig)
@@ -49,5 +56,5 @@ done
 cat $OUT/progress.txt
 for f in smoke.txt pytest_gpu.txt pytest_gpu_fast.txt pytest_gpu_all.txt; do [ -f $OUT/$f ] && { echo "== $f"; tail -25 $OUT/$f; }; done
 for f in cli_bench.jsonl wig_bench.json reference_arm.json; do [ -f $OUT/$f ] && { echo "== $f"; cut -c1-1500 $OUT/$f; }; done
-for f in bench_c3 bench_quick; do [ -f $OUT/$f.json ] && { echo "== $f"; cut -c1-1500 $OUT/$f.json; tail -5 $OUT/$f.err; }; done
+for f in bench_c3 bench_quick bench_quick_onelane; do [ -f $OUT/$f.json ] && { echo "== $f"; cut -c1-1500 $OUT/$f.json; tail -5 $OUT/$f.err; }; done
 exit 0

@@ -1456,7 +1456,10 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
   // A load that is still on its way (upb_load_tags_async): work through its groups as they arrive — unless this call needs a
   // read-back in the middle (sizing, -D correlation), every mini-tile at once (controls) or the first positions' neighbourhood
   // (left-edge replay), in which case it simply waits for the load.
-  bool pipelined = ctx->loadPending && !sizing && !cfg.needCorr && !shared;
+  // (a shared-table call too, once the context's arrays are sized: its groups count their rows as they go, the last one publishes and places
+  //  them all — row_place_kernel, countOnly — and the rows of the earlier groups are emitted behind it)
+  bool pipelined = ctx->loadPending && !sizing && !cfg.needCorr && (!shared || (ctx->capN1 != 0 && ctx->capCells != 0));
+  if (pipelined && shared && getenv("UPB_SHARED_PIPELINE") && !atoi(getenv("UPB_SHARED_PIPELINE"))) pipelined = false;
   if (pipelined) {
     if (cfg.control) for (uint32_t s = 0; s < ctx->nSamples; ++s) if (cfg.control[s]) pipelined = false;
     for (uint32_t fp : ctx->firstPos) if (fp != 0 && fp <= cfg.bw) pipelined = false;
@@ -1662,13 +1665,13 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
   // left-edge replay or per-stage profiling (events on one stream).  With a shared table the groups before the last only COUNT their rows
   // (row_place_kernel, countOnly); the last group's launch publishes the rank's counts once, waits for the other ranks and places every
   // unit, and the earlier groups' rows are emitted behind it.
-  // Measured on C3 (tools/lanes_ab.py, gpurun_out/r02_lanes1): two groups 2.32 -> 2.22 ms on the whole workload (326 M entries), level at bandwidth 200,
-  // three and more groups slower (every group pays the chain's ~27 launches), and on a rank's shard of a 2 / 4 / 8-GPU job (163 / 81 / 40 M entries)
-  // two groups LOSE 4 - 7 %: the pooling kernels of two groups share the SMs and the emits share the PCIe link, so only launch gaps and one
-  // group's emit hide behind the other group's kernels; inside bench.py's timed loop the whole-workload gain was 1 - 3 %, and the span kernel's
-  // event bracket then holds a share of the other lane's kernels (0.82 -> 0.93 ms).  Hence: a resident call runs as ONE group unless
-  // UPB_CALL_GROUPS=n asks for n; a call behind a large load deals the groups it has anyway (they arrive one after the other) to the two lanes.
-  int wantGroups = (pipelined && ctx->nEntries >= 50000000ull) ? 2 : 1;
+  // OFF by default — measured on C3 (tools/lanes_ab.py, profiles/r02_lanes_ab.jsonl): two groups 2.32 -> 2.22 ms on the whole workload (326 M
+  // entries) in a tight loop of calls, 1 - 3 % inside bench.py's timed loop, level at bandwidth 200, three and more groups slower (every group
+  // pays the chain's ~27 launches); on a rank's shard of a 2 / 4 / 8-GPU job (163 / 81 / 40 M entries) two groups LOSE 4 - 7 %; behind a load
+  // (e2e) 12.51 ms with two lanes against 12.45 with one.  The pooling kernels of two groups share the SMs and the emits share the PCIe link,
+  // so only launch gaps and one group's emit hide behind the other group's kernels — and the span kernel's event bracket then holds a share of
+  // the other lane's kernels (0.82 -> 0.93 ms).  UPB_CALL_GROUPS=n (n >= 2) turns the lanes on with n groups per resident call.
+  int wantGroups = 1;
   if (const char* e = getenv("UPB_CALL_GROUPS")) wantGroups = std::max(1, std::min(16, atoi(e)));
   bool twoLanes = wantGroups > 1 && !sizing && !cfg.needCorr && nAff == 0 && !ctx->profiling && !empty && ctx->laneStream != nullptr;
   if (shared && (ctx->capN1 == 0 || ctx->capCells == 0)) twoLanes = false;   // (reads its sizes back in the middle of the call)
@@ -1844,10 +1847,11 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
     pa.edgeRows = d_edgeRowsOfUnit; pa.normalFirst = normalFirst; pa.rowShift = rowShift; pa.edgeRowBase = edgeRowBase; pa.unitRows = unitRowsDev;
     pa.shared = shared ? 1 : 0;
     const bool lastGroup = gi + 1 == pgroups.size();
-    if (shared) { pa.x = shared->x; pa.countOnly = (twoLanes && !lastGroup) ? 1 : 0; pa.allU0 = twoLanes ? 0u : u0; pa.allU1 = twoLanes ? nUnits : u1; }
+    const bool sharedGroups = shared && pgroups.size() > 1;             // several groups into a shared table: only the last one publishes and places
+    if (shared) { pa.x = shared->x; pa.countOnly = (sharedGroups && !lastGroup) ? 1 : 0; pa.allU0 = sharedGroups ? 0u : u0; pa.allU1 = sharedGroups ? nUnits : u1; }
     if (twoLanes && gi > 0) CU(cudaStreamWaitEvent(st_, ctx->placeEv[gi - 1], 0));   // rows of a group follow the rows of the groups before it
     row_place_kernel<<<1, 256, 0, st_>>>(pa);
-    if (twoLanes) CU(cudaEventRecord(ctx->placeEv[gi], st_));
+    if (twoLanes || sharedGroups) CU(cudaEventRecord(ctx->placeEv[gi], st_));
     launches += 1;
     if (!shared && sizing) {
       if ((r = read_group())) return r;
@@ -1873,7 +1877,7 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
     ge.statCounts = statCounts; ge.pass = pass2; ge.g = g; ge.call = call; ge.nSamples = n;
     ge.edgeRowCounts = eg.rowCounts; ge.edgeNRows = eg.nRows; ge.edgeRowCap = EDGE_ROW_CAP; ge.nAffected = edgeRowsTotal ? nAff : 0; ge.edgeRowsTotal = edgeRowsTotal;
     ge.tir = d_tir;
-    if (shared && twoLanes && !lastGroup) {                              // its rows have no place yet: emitted behind the last group's row_place_kernel
+    if (sharedGroups && !lastGroup) {                              // its rows have no place yet: emitted behind the last group's row_place_kernel
       Deferred df; df.ea = ea; df.ge = ge; df.st = st_;
       deferred.push_back(df);
       continue;
