@@ -83,7 +83,8 @@ def test_random_workload_matches_the_oracle(gpu_ctx, seed):
         with pytest.raises(Exception):
             gpu_ctx.call_regions(**st)
         return
-    gpu_ctx.load(d)
+    # the same arrays through the three host forms in turn: plain, the variable-length byte form (what the drivers load), the 2-byte form
+    (gpu_ctx.load, gpu_ctx.load_vbyte, gpu_ctx.load_packed2)[seed % 3](d)
     what = "seed %d %r" % (seed, {k: v for k, v in kw.items() if k != "mappable"})
     if _pass1_reads_a_minus_track(d, st):
         # several directional samples and a '-' track the reference's merge loop reads in pass 1: it aborts or, as here, pools that sample's
@@ -132,7 +133,7 @@ def test_random_strand_shift_matches_the_oracle(gpu_ctx, seed):
     from refutil import oracle_strand_shift
     d, kw = _shift_case(seed)
     want = oracle_strand_shift(d, **kw)
-    gpu_ctx.load(d)
+    (gpu_ctx.load_vbyte if seed % 2 else gpu_ctx.load)(d)
     got = gpu_ctx.strand_shift(background=want["background"], **kw)
     what = "seed %d %r" % (seed, kw)
     assert (got["status"] != 0) == (want["status"] != 0), what
