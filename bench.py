@@ -327,7 +327,12 @@ def main():
     # ... and in the variable-length byte form (upb_vbyte.hpp: ~1.5 bytes per entry)
     h_vb = torch.empty(max(6 * E, 1) if E < (1 << 24) else max(3 * E, 1), dtype=torch.uint8).pin_memory()
     t0 = time.perf_counter()
-    vb, vb_off, vb_tiles, exc_v = unipeak_b200.pack_tags_vbyte(n_samples, C, data.off, data.pos, data.cnt, out=h_vb.numpy())
+    try:
+        vb, vb_off, vb_tiles, exc_v = unipeak_b200.pack_tags_vbyte(n_samples, C, data.off, data.pos, data.cnt, out=h_vb.numpy())
+    except ValueError:                                                # a track so sparse that it needs more than 3 bytes per entry: the worst case is 6
+        h_vb = torch.empty(6 * E, dtype=torch.uint8).pin_memory()
+        t0 = time.perf_counter()
+        vb, vb_off, vb_tiles, exc_v = unipeak_b200.pack_tags_vbyte(n_samples, C, data.off, data.pos, data.cnt, out=h_vb.numpy())
     pack_vbyte_ms = (time.perf_counter() - t0) * 1e3
     n_vb = int(vb.shape[0])
     h_excv = torch.from_numpy(exc_v.view(np.uint8).copy()).pin_memory()
