@@ -514,6 +514,26 @@ def test_packed_load_equals_plain_load(gpu_ctx):
     check_regions(gpu_ctx, make_synthetic([200000, 80000], 2, 30000, directional=True, seed=79, peak_spacing=5000))
 
 
+def test_split_tail_equals_one_pass(gpu_ctx, monkeypatch):
+    # a large call runs its statistics + emit tail in two halves of the units on two streams (upb_api.cu: split tail; by default only when the
+    # previous call had >= 150 K survivors): forced here, the table must be the one-pass table bit for bit, and the oracle's
+    d = make_synthetic([600000, 250000, 90000, 40000], 4, 60000, directional=True, seed=83, peak_spacing=4000)
+    st = region_settings(d)
+    gpu_ctx.load(d)
+    monkeypatch.setenv("UPB_SPLIT_TAIL", "0")
+    gpu_ctx.call_regions(**dict(st, rows=False))                       # (sizes the context's arrays)
+    one = gpu_ctx.call_regions(**dict(st, rows=False))["columns"]
+    launches_one = gpu_ctx.stats()["launches"]
+    monkeypatch.setenv("UPB_SPLIT_TAIL", "2")
+    two = gpu_ctx.call_regions(**dict(st, rows=False))["columns"]
+    assert gpu_ctx.stats()["launches"] > launches_one                  # the split ran: its second half's kernels are extra launches
+    assert one["left"].shape[0] > 50
+    for k in one:
+        assert np.array_equal(np.asarray(one[k]).view(np.uint8), np.asarray(two[k]).view(np.uint8)), k
+    check_regions(gpu_ctx, d)                                          # against the oracle, split still forced
+    check_regions(gpu_ctx, make_synthetic([300000, 100000], 6, 20000, directional=True, seed=84, peak_spacing=5000), control=[1])   # controls: statistics on mEff
+
+
 def test_vbyte_load_equals_plain_load(gpu_ctx):
     # the variable-length byte form (upb_vbyte.hpp: marker bit, 6 + 7k-bit values, count byte, count exceptions, self-contained tiles of 2048
     # entries) decodes to exactly the arrays of the plain path: large gaps, large counts, empty segments, several tiles per segment; a subset

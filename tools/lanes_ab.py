@@ -19,7 +19,7 @@ from unipeak_b200.synth_det import make_synthetic_det  # noqa: E402
 
 
 def main():
-    groups = [int(x) for x in (sys.argv[1:] or ["1", "2", "3", "4", "6", "1", "2"])]
+    groups = [int(x) for x in (sys.argv[1:] or ["1", "0", "2", "1", "0"])]
     steps = int(os.environ.get("AB_STEPS", "15"))
     worlds = [int(x) for x in os.environ.get("AB_WORLDS", "1,2,4,8").split(",")]
     ctx = unipeak_b200.Context(0)
@@ -31,8 +31,10 @@ def main():
         ctx.load(data)
         for bw in ((50, 10, 200) if world == 1 else (50,)):
             st = dict(bandwidth=bw, region_threshold=25.0, kurtosis_threshold=50.0, corr_threshold=-1.0, hit_threshold=160.0, directional=True, background=bg)
-            for g in (groups if world == 1 else [x for x in (1, 2, 4) if x in groups]):
-                os.environ["UPB_CALL_GROUPS"] = str(g)
+            for g in (groups if world == 1 else [x for x in (1, 0, 2) if x in groups]):
+                # g = 0: one group, its statistics + emit tail in two halves (UPB_SPLIT_TAIL); g >= 1: that many groups of the whole call, tail not split
+                os.environ["UPB_CALL_GROUPS"] = str(max(g, 1))
+                os.environ["UPB_SPLIT_TAIL"] = "2" if g == 0 else "0"
                 for _ in range(3):
                     ctx.call_regions_view(**st)
                 call, dev, kde = [], [], []

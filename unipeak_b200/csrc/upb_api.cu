@@ -54,7 +54,8 @@ struct upb_ctx {
   cudaStream_t laneStream = nullptr;
   cudaStream_t cur = nullptr;
   int lane = 0;
-  cudaEvent_t laneSetupEv = nullptr, laneDoneEv = nullptr;
+  cudaEvent_t laneSetupEv = nullptr, laneDoneEv = nullptr, lanePoolEv = nullptr;
+  size_t lastN1 = 0;                    // hit-filter survivors of the last region call (decides whether the next call splits its tail)
   std::vector<cudaEvent_t> placeEv;     // per group: its rows have their place (row_place_kernel done)
   std::vector<cudaEvent_t> spanEv;      // per group: before / after its span kernel
   cudaStream_t copyStream = nullptr;    // H2D copies of the load run here, one load group ahead of the kernels that consume them ...
@@ -168,6 +169,7 @@ extern "C" int upb_create (int device, upb_ctx** out) {
   cudaStreamCreateWithPriority(&ctx->laneStream, cudaStreamNonBlocking, mode == 1 ? prHi : prLo);
   cudaEventCreateWithFlags(&ctx->laneSetupEv, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->laneDoneEv, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->lanePoolEv, cudaEventDisableTiming);
   for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
   cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking);
   cudaStreamCreateWithPriority(&ctx->loadStream, cudaStreamNonBlocking, mode == 2 ? prHi : prLo);
@@ -202,6 +204,7 @@ extern "C" void upb_destroy (upb_ctx* ctx) {
   for (cudaEvent_t e : ctx->spanEv) cudaEventDestroy(e);
   if (ctx->laneSetupEv) cudaEventDestroy(ctx->laneSetupEv);
   if (ctx->laneDoneEv) cudaEventDestroy(ctx->laneDoneEv);
+  if (ctx->lanePoolEv) cudaEventDestroy(ctx->lanePoolEv);
   if (ctx->laneStream) cudaStreamDestroy(ctx->laneStream);
   if (ctx->copyStream2) cudaStreamDestroy(ctx->copyStream2);
   if (ctx->h_ends.p) cudaFreeHost(ctx->h_ends.p);
@@ -1692,7 +1695,17 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
   }
   if (twoLanes && pgroups.size() < 2) twoLanes = false;
   // (on every way out: the helpers are back on lane 0, and — an error may leave in the middle of the groups — `stream` is behind whatever the other lane still runs)
-  struct LaneReset { upb_ctx* c; bool two; ~LaneReset () { c->lane = 0; c->cur = c->stream; if (two && cudaEventRecord(c->laneDoneEv, c->laneStream) == cudaSuccess) cudaStreamWaitEvent(c->stream, c->laneDoneEv, 0); } } laneReset{ctx, twoLanes};
+  bool laneBusy = twoLanes;                                              // the second stream has been given work in this call
+  struct LaneReset { upb_ctx* c; const bool* two; ~LaneReset () { c->lane = 0; c->cur = c->stream; if (*two && cudaEventRecord(c->laneDoneEv, c->laneStream) == cudaSuccess) cudaStreamWaitEvent(c->stream, c->laneDoneEv, 0); } } laneReset{ctx, &laneBusy};
+  // Split tail: the statistics + emit half of a large resident call (pooling, moments, final scan, row placement, rows over PCIe) runs in two halves of
+  // the units on the two streams — the second half's pooling starts when the first half's is through, so the first half's moments, scan and 9 MB of
+  // rows crossing PCIe run beside it.  Unlike the two lanes above the front of the call (prefilters, span kernel, order / stitch / filter) runs once.
+  // Measured (tools/lanes_ab.py, groups = 0; profiles/r02_split_tail_ab.jsonl): C3 at bandwidth 50 2.34 -> 2.22 ms, at 10 2.80 -> 2.74, but 1.52 -> 1.59
+  // at bandwidth 200 (82 K regions) and 3 - 10 % slower on a 2 / 4 / 8-GPU rank's shard: nine more launches against half of a shorter emit.  Hence
+  // only for calls whose predecessor had >= 150 K hit-filter survivors.  UPB_SPLIT_TAIL=0 never, =2 whenever possible (the GPU tests force it).
+  const int splitMode = getenv("UPB_SPLIT_TAIL") ? atoi(getenv("UPB_SPLIT_TAIL")) : 1;   // 0 never, 1 large calls (by the last call's survivors), 2 whenever possible (tests)
+  const bool splitTail = splitMode != 0 && !twoLanes && !pipelined && !sizing && !cfg.needCorr && !shared && nAff == 0 && !ctx->profiling && !empty &&
+                         ctx->laneStream != nullptr && pgroups.size() == 1 && nUnits >= 2 && (splitMode == 2 || ctx->lastN1 >= 150000);
   while (ctx->placeEv.size() < pgroups.size()) { cudaEvent_t e = nullptr; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->placeEv.push_back(e); }
   while (ctx->spanEv.size() < 2 * pgroups.size()) { cudaEvent_t e = nullptr; CU(cudaEventCreate(&e)); ctx->spanEv.push_back(e); }
   GroupCtr* const gLane[2] = {g, (GroupCtr*)((unsigned char*)ctx->d_small.p + LANE1_GROUPCTR_OFFSET)};
@@ -1763,6 +1776,77 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
       launches += 1;
     }
     if ((r = scan_dev(ctx, LoadPacked{pass, candLen}, devn_u64(&g->nCand), runCap, pvScan, &g->pv, &launches))) return r;
+    if (splitTail) {
+      uint32_t uMid = u0 + 1;
+      while (uMid + 1 < u1 && (uint64_t)pr.units[uMid].spanStart < (uint64_t)s0 + (s1 - s0) / 2) ++uMid;
+      const size_t n1Cap = std::min<size_t>(ctx->capN1, runCap), cellCap = ctx->capCells;
+      uint32_t* statCells = SCR("statCells", uint32_t, cellCap + 1);   // (pooled cells: one array, the halves own disjoint stretches of it)
+      GroupCtr* gT[2] = {(GroupCtr*)((unsigned char*)ctx->d_small.p + TAIL_GROUPCTR_OFFSET), (GroupCtr*)((unsigned char*)ctx->d_small.p + TAIL_GROUPCTR_OFFSET + 256)};
+      uint32_t* listT[2] = {list1, nullptr};
+      ctx->lane = 1; listT[1] = SCR("list1", uint32_t, runCap); ctx->lane = 0;
+      compact_pv_split_kernel<<<GS, 256, 0, st_>>>(pass, pvScan, g, gT[0], gT[1], unitFirst, uMid, (uint32_t)n1Cap, cellCap, listT[0], listT[1]);
+      launches += 1;
+      CU(cudaEventRecord(ctx->laneSetupEv, st_));
+      CU(cudaStreamWaitEvent(ctx->laneStream, ctx->laneSetupEv, 0));
+      laneBusy = true;
+      const size_t groupBytes = ((size_t)(ST_CHUNK + n) * 4 + 15) / 16 * 16;
+      const size_t statSmem = (size_t)ST_WARPS * ST_PER_WARP * groupBytes;
+      if (statSmem > 200 * 1024) return fail(ctx, UPB_ERR_UNSUPPORTED, "too many samples for the region statistics kernel");
+      int poolPerSm = 0;
+      if ((r = cached_occupancy(ctx, region_pool_kernel, ST_WARPS * 32, statSmem, &poolPerSm))) return r;
+      const SlabLayout& SL = out.layout;
+      for (int t = 0; t < 2; ++t) {
+        ctx->lane = t; ctx->cur = t ? ctx->laneStream : ctx->stream;
+        cudaStream_t ts = ctx->cur;
+        uint32_t* statCounts = SCR("statCounts", uint32_t, n1Cap * n);
+        double* statKurt = SCR("statKurt", double, n1Cap);
+        uint32_t* pass2 = SCR("pass2", uint32_t, n1Cap);
+        unsigned long long* pass2Scan = SCR("pass2Scan", unsigned long long, n1Cap);
+        (void)SCR("scanPartial", unsigned long long, std::max<size_t>(runCap, pr.totalSpans) / SCAN_BLOCK + 2);
+        StatArgs sg;
+        sg.T = pr.T; sg.units = d_units; sg.cand = cand; sg.list = listT[t]; sg.g = gT[t];
+        sg.nondir = cfg.nondir ? 1 : 0; sg.kurtThr = cfg.kurtThr; sg.counts = statCounts; sg.kurt = statKurt; sg.pass = pass2;
+        sg.pvScan = pvScan; sg.cells = statCells; sg.cellCap = cellCap; sg.ticket = &gT[t]->poolTicket;
+        if (t == 1) CU(cudaStreamWaitEvent(ts, ctx->lanePoolEv, 0));     // the halves' pooling kernels one after the other: side by side they only share the SMs
+        // (the pooling kernel at full occupancy owns every register of an SM: the second half runs one CTA per SM short, so that the first half's
+        //  emit kernels get on the SMs beside it instead of behind it)
+        const int less = (t == 1 && poolPerSm > 1) ? (getenv("UPB_SPLIT_POOL_LESS") ? atoi(getenv("UPB_SPLIT_POOL_LESS")) : 1) : 0;
+        region_pool_kernel<<<(unsigned)(ctx->smCount * std::max(poolPerSm - less, 1)), ST_WARPS * 32, statSmem, ts>>>(sg);
+        if (t == 0) CU(cudaEventRecord(ctx->lanePoolEv, ts));
+        region_moment_kernel<<<GS, 256, 0, ts>>>(sg);
+        CU(cudaGetLastError());
+        launches += 2;
+        if ((r = scan_dev(ctx, LoadU32{pass2}, devn_u64(&gT[t]->n1), n1Cap, pass2Scan, &gT[t]->rows, &launches))) return r;
+        PlaceArgs pa;
+        memset(&pa, 0, sizeof pa);
+        pa.cand = cand; pa.list = listT[t]; pa.pass2Scan = pass2Scan; pa.g = gT[t]; pa.call = call; pa.units = d_units;
+        pa.u0 = t ? uMid : u0; pa.u1 = t ? u1 : uMid;
+        pa.normalFirst = normalFirst; pa.rowShift = rowShift; pa.edgeRowBase = edgeRowBase; pa.unitRows = unitRowsDev;
+        if (t == 1) CU(cudaStreamWaitEvent(ts, ctx->placeEv[0], 0));      // the second half's rows follow the first half's
+        row_place_kernel<<<1, 256, 0, ts>>>(pa);
+        if (t == 0) CU(cudaEventRecord(ctx->placeEv[0], ts));
+        EmitArgs ea;
+        memset(&ea, 0, sizeof ea);
+        ea.cand = cand; ea.list = listT[t]; ea.pass = pass2; ea.passScan = pass2Scan; ea.g = gT[t]; ea.units = d_units; ea.unitFirst = unitFirst;
+        ea.rowShift = rowShift; ea.statCounts = statCounts; ea.statKurt = statKurt; ea.nSamples = n; ea.rowCap = rowCap;
+        ea.buffer = hs + SL.oBuffer; ea.contig = (uint32_t*)(hs + SL.oContig); ea.left = (uint32_t*)(hs + SL.oLeft); ea.len = (uint32_t*)(hs + SL.oLen);
+        ea.peak = (uint32_t*)(hs + SL.oPeak); ea.wsum = (uint32_t*)(hs + SL.oWsum); ea.candIndex = (unsigned long long*)(hs + SL.oCandIndex);
+        ea.peakScore = (double*)(hs + SL.oPeakScore); ea.kurt = (double*)(hs + SL.oKurt); ea.corr = (double*)(hs + SL.oCorr);
+        ea.counts = (uint32_t*)(hs + SL.oCounts);
+        emit_rows_kernel<<<GS, 256, 0, ts>>>(ea);
+        emit_counts_kernel<<<GS, 256, 0, ts>>>(ea);
+        GroupEndArgs ge;
+        memset(&ge, 0, sizeof ge);
+        ge.statCounts = statCounts; ge.pass = pass2; ge.g = gT[t]; ge.call = call; ge.nSamples = n; ge.tir = d_tir;
+        group_end_kernel<<<(unsigned)ctx->smCount * 2, 256, (size_t)n * 8, ts>>>(ge);
+        CU(cudaGetLastError());
+        launches += 4;
+      }
+      ctx->lane = 0; ctx->cur = ctx->stream;
+      CU(cudaEventRecord(ctx->laneDoneEv, ctx->laneStream));
+      CU(cudaStreamWaitEvent(ctx->stream, ctx->laneDoneEv, 0));
+      continue;
+    }
     // per-survivor arrays: sized from the previous call, or (sizing) from this one's numbers
     // (a shared call cannot be repeated with larger arrays — the other ranks would wait for it — so it reads its sizes back unless an earlier
     //  call of this context has already sized the per-survivor arrays, margin included; outgrowing those is then an error, like outgrowing the table)
@@ -1986,6 +2070,7 @@ static int run_pipeline_once (upb_ctx* ctx, const PipeCfg& cfg, Prep& pr, PipeOu
   {
     // what the next call of this context may assume without asking
     const size_t n1 = (size_t)hcall->n1, cells = (size_t)hcall->cells, R = (size_t)out.R;
+    ctx->lastN1 = n1;
     ctx->capN1 = std::max(ctx->capN1, n1 + n1 / 4 + 1024);
     ctx->capCells = std::max(ctx->capCells, cells + cells / 4 + 4096);
     if (!shared) {

@@ -957,6 +957,7 @@ struct CallCtr {                    // zeroed once per call; accumulated over th
 };
 constexpr size_t CALLCTR_OFFSET = 512;   // byte offset of CallCtr inside d_small
 constexpr size_t LANE1_GROUPCTR_OFFSET = 1024;   // the second lane's GroupCtr (upb_ctx::laneStream); lane 0's is at byte 0
+constexpr size_t TAIL_GROUPCTR_OFFSET = 1536;    // two more: the halves of a split statistics + emit tail (compact_pv_split_kernel), 256 bytes apart
 
 __device__ __forceinline__ bool pipe_dead (const GroupCtr* g) { return (g->flags & FLAG_RUN_OVERFLOW) != 0; }   // runs are incomplete: nothing downstream may index through them
 
@@ -1071,6 +1072,36 @@ __global__ void compact_pv_kernel (const uint32_t* __restrict__ pass, const unsi
     g->n1 = n1 < n1Cap ? n1 : n1Cap;
     g->cells = cells;
     if (n1 > n1Cap || cells > cellCap) atomicOr(&g->flags, FLAG_CAP_OVERFLOW);
+  }
+}
+
+// The same for a call whose statistics + emit tail runs in two halves (upb_api.cu: split tail): survivors of the units before uMid go to
+// listA, the others to listB, each half with its own counters — gA takes over the group's totals (so that group_end_kernel adds them to the
+// call's once), gB starts from zero.
+__global__ void compact_pv_split_kernel (const uint32_t* __restrict__ pass, const unsigned long long* __restrict__ pvScan, const GroupCtr* g, GroupCtr* gA, GroupCtr* gB,
+                                         const unsigned long long* __restrict__ unitFirst, uint32_t uMid, uint32_t n1Cap, unsigned long long cellCap,
+                                         uint32_t* __restrict__ listA, uint32_t* __restrict__ listB) {
+  const bool dead = pipe_dead(g);
+  const unsigned long long n = dead ? 0ull : g->nCand;
+  const unsigned long long cMid = dead ? 0ull : unitFirst[uMid];       // ordinal of the first candidate of unit uMid among the group's candidates
+  const unsigned long long n1 = dead ? 0ull : g->pv >> PACK_SHIFT;
+  const unsigned long long nA = cMid < n ? pvScan[cMid] >> PACK_SHIFT : n1;
+  for (unsigned long long i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (pass[i]) {
+      const unsigned long long k = pvScan[i] >> PACK_SHIFT;
+      if (i < cMid) { if (k < n1Cap) listA[k] = (uint32_t)i; }
+      else if (k - nA < n1Cap) listB[k - nA] = (uint32_t)i;
+    }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const unsigned long long cells = dead ? 0ull : g->pv & PACK_MASK, nB = n1 - nA;
+    GroupCtr a = *g;
+    a.poolTicket = 0; a.n1 = nA < n1Cap ? nA : n1Cap; a.cells = cells; a.rows = 0;
+    if (nA > n1Cap || nB > n1Cap || cells > cellCap) a.flags |= FLAG_CAP_OVERFLOW;
+    *gA = a;
+    GroupCtr b;
+    memset(&b, 0, sizeof b);
+    b.n1 = nB < n1Cap ? nB : n1Cap; b.cells = cells;
+    *gB = b;
   }
 }
 
