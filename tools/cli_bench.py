@@ -46,8 +46,14 @@ def case(name, sizes, names, n_samples, tags, extra_args, wd, reps=3):
     if out["reference"] is not None and out["ours"] is not None:
         same = open(os.path.join(wd, "reference.txt"), "rb").read() == open(os.path.join(wd, "ours.txt"), "rb").read()
     rows = sum(1 for l in open(os.path.join(wd, "ours.txt")) if l[:1] not in "#\t\n")
+    trace = None
+    if out["ours"] is not None:                                        # where our program's time goes: the library's and the driver's own timeline
+        t0 = time.perf_counter()
+        p = subprocess.run([os.path.join(NEW, "regions")] + args + ["-o", "ours_trace.txt"] + wigs, cwd=wd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE,
+                           env=dict(os.environ, UPB_TRACE="1"))
+        trace = {"seconds": time.perf_counter() - t0, "lines": [l for l in p.stderr.decode().splitlines() if l.startswith("[upb]")][:40]}
     print(json.dumps({"case": name, "samples": n_samples, "tags_per_sample": tags, "genome_bp": int(sum(sizes)), "wig_bytes": wig_bytes,
-                      "seconds_reference_cli": out["reference"], "seconds_ours_cli": out["ours"], "regions": rows, "identical_output": same,
+                      "seconds_reference_cli": out["reference"], "seconds_ours_cli": out["ours"], "regions": rows, "identical_output": same, "trace_ours": trace,
                       "note": "wall clock of the whole program (process start, CUDA context creation ~0.3 s, parse, call, write); best of %d" % reps}))
     sys.stdout.flush()
 
