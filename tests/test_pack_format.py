@@ -141,3 +141,19 @@ def test_vbyte_device_decoder_logic_on_the_host(tmp_path):
     for seed in (1, 2, 3):
         out = subprocess.run([exe, str(seed), "120"], capture_output=True, text=True)
         assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr
+
+
+def test_vbyte_encoder_into_a_caller_buffer():
+    # with `out` the binding encodes in one call (tile count from `off`, exception list sized by guess, repeated when the guess was short)
+    d = make_synthetic([900000, 200000], 3, 40000, directional=True, seed=21, peak_spacing=3000)
+    want = unipeak_b200.pack_tags_vbyte(3, 2, d.off, d.pos, d.cnt)
+    got = unipeak_b200.pack_tags_vbyte(3, 2, d.off, d.pos, d.cnt, out=np.empty(3 * d.pos.shape[0], np.uint8))
+    assert all(np.array_equal(a, b) for a, b in zip(want, got))
+    big = d.cnt.copy()
+    big[:] = 500                                                               # every count escapes: far more exceptions than the guess
+    want = unipeak_b200.pack_tags_vbyte(3, 2, d.off, d.pos, big)
+    got = unipeak_b200.pack_tags_vbyte(3, 2, d.off, d.pos, big, out=np.empty(6 * d.pos.shape[0], np.uint8))
+    assert got[3].shape[0] == d.pos.shape[0] and all(np.array_equal(a, b) for a, b in zip(want, got))
+    import pytest
+    with pytest.raises(ValueError):
+        unipeak_b200.pack_tags_vbyte(3, 2, d.off, d.pos, d.cnt, out=np.empty(d.pos.shape[0] // 2, np.uint8))

@@ -131,26 +131,36 @@ def pack_tags2(n_samples: int, n_contigs: int, off, pos, cnt, out=None):
 
 def pack_tags_vbyte(n_samples: int, n_contigs: int, off, pos, cnt, out=None):
     """upb_pack_tags_vbyte: the variable-length byte form of the plain arrays -> (bytes u8, byte_off u64 [layout of off], tile_off u64
-    [tiles + 1], exceptions).  `out`: a u8 array to encode into (e.g. pinned), at least 6 bytes per entry or the size a first call reported."""
+    [tiles + 1], exceptions).  `out`: a u8 array to encode into (e.g. pinned); with it the encoder runs once (the tile count follows from `off`,
+    the exception list is sized by guess and the call repeated if the guess was short), without it a first call reports the sizes."""
     L = lib()
     off = np.ascontiguousarray(off, dtype=np.uint64)
     pos = np.ascontiguousarray(pos, dtype=np.uint32)
     cnt = np.ascontiguousarray(cnt, dtype=np.uint32)
     nb, nt, nx = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
     args = (n_samples, n_contigs, off.ctypes.data, pos.ctypes.data, cnt.ctypes.data)
-    L.upb_pack_tags_vbyte(*args, None, 0, C.byref(nb), None, None, 0, C.byref(nt), None, 0, C.byref(nx))
-    n_bytes, n_tiles, n_exc = int(nb.value), int(nt.value), int(nx.value)
-    buf = out if out is not None else np.empty(max(n_bytes, 1), np.uint8)
-    if buf.shape[0] < n_bytes:
-        raise ValueError("pack_tags_vbyte: `out` holds %d bytes, %d needed" % (buf.shape[0], n_bytes))
+    E = int(pos.shape[0])
+    if out is None:
+        L.upb_pack_tags_vbyte(*args, None, 0, C.byref(nb), None, None, 0, C.byref(nt), None, 0, C.byref(nx))
+        n_bytes, n_tiles, exc_cap = int(nb.value), int(nt.value), int(nx.value)
+        buf = np.empty(max(n_bytes, 1), np.uint8)
+    else:
+        lens = np.diff(off.reshape(n_samples * 2, n_contigs + 1).astype(np.int64), axis=1)
+        n_tiles = int(((lens + 2047) // 2048).sum())
+        exc_cap = max(4096, E // 64)
+        buf = out
     byte_off = np.zeros(max(off.shape[0], 1), np.uint64)
-    tile_off = np.zeros(n_tiles + 1, np.uint64)
-    exc = np.zeros(max(n_exc, 1), dtype=PACKED_EXC_DTYPE)
-    rc = L.upb_pack_tags_vbyte(*args, buf.ctypes.data, int(buf.shape[0]), C.byref(nb), byte_off.ctypes.data, tile_off.ctypes.data, n_tiles + 1, C.byref(nt),
-                               exc.ctypes.data, n_exc, C.byref(nx))
-    if rc:
-        raise UpbError(rc, "upb_pack_tags_vbyte failed")
-    return buf[:n_bytes], byte_off, tile_off, exc[:n_exc]
+    for _ in range(2):
+        tile_off = np.zeros(n_tiles + 1, np.uint64)
+        exc = np.zeros(max(exc_cap, 1), dtype=PACKED_EXC_DTYPE)
+        rc = L.upb_pack_tags_vbyte(*args, buf.ctypes.data, int(buf.shape[0]), C.byref(nb), byte_off.ctypes.data, tile_off.ctypes.data, n_tiles + 1, C.byref(nt),
+                                   exc.ctypes.data, exc_cap, C.byref(nx))
+        if rc == 0:
+            return buf[:int(nb.value)], byte_off, tile_off, exc[:int(nx.value)]
+        if int(nb.value) > buf.shape[0]:
+            raise ValueError("pack_tags_vbyte: `out` holds %d bytes, %d needed" % (buf.shape[0], int(nb.value)))
+        n_tiles, exc_cap = int(nt.value), int(nx.value)                    # the sizes the encoder reported: once more with those
+    raise UpbError(rc, "upb_pack_tags_vbyte failed")
 
 
 def host_register(ptr: int, nbytes: int) -> int:
