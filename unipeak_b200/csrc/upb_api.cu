@@ -17,7 +17,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <atomic>
 #include <string>
@@ -835,8 +837,9 @@ extern "C" int upb_pack_tags2 (uint32_t n_samples, uint32_t n_contigs, const uin
   return UPB_OK;
 }
 
-// host-only encoder of the variable-length byte form (upb_vbyte.hpp): one task per (sample, strand) — sizes first (every task then
-// knows where its bytes, tiles and exceptions go), then the bytes
+// host-only encoder of the variable-length byte form (upb_vbyte.hpp): one task per (sample, strand).  A call without buffers only adds up
+// the sizes; a call with buffers encodes every task ONCE into a buffer of its own and then moves the tasks' bytes, tile offsets and exceptions
+// to their places (a second pass of plain copies: the sizes that place them are only known when every task is through)
 extern "C" int upb_pack_tags_vbyte (uint32_t n_samples, uint32_t n_contigs, const uint64_t* off, const uint32_t* pos, const uint32_t* cnt,
                                     uint8_t* bytes_out, uint64_t bytes_cap, uint64_t* n_bytes_out, uint64_t* byte_off_out,
                                     uint64_t* tile_off_out, uint64_t tile_cap, uint64_t* n_tiles_out,
@@ -844,9 +847,16 @@ extern "C" int upb_pack_tags_vbyte (uint32_t n_samples, uint32_t n_contigs, cons
   using namespace upb_vb;
   if (!off || !n_bytes_out || !n_tiles_out || !n_exc_out) return UPB_ERR_BAD_ARG;
   const uint32_t nTasks = n_samples * 2, C1 = n_contigs + 1;
-  std::vector<uint64_t> segBytes((size_t)nTasks * n_contigs, 0), nExcOf(nTasks, 0), tilesOf(nTasks, 0);
-  auto run = [&] (uint32_t sd, bool write, uint64_t byteBase, uint64_t tileBase, uint64_t excBase) {
-    uint64_t nExc = 0, at = byteBase, tile = tileBase;
+  const bool encode = bytes_out && byte_off_out && tile_off_out && bytes_cap > 0;
+  // (bytes: worst-case sized but never initialised — only the pages the code really fills are ever touched)
+  struct Task { std::unique_ptr<uint8_t[]> bytes; std::vector<uint64_t> tileRel, segBytes; std::vector<upb_packed_exception> exc; uint64_t nBytes = 0, nTiles = 0, nExc = 0; };
+  std::vector<Task> tasks(nTasks);
+  auto run = [&] (uint32_t sd) {
+    Task& T = tasks[sd];
+    const uint64_t a0 = off[(size_t)sd * C1], b0 = off[(size_t)sd * C1 + n_contigs];
+    T.segBytes.assign(n_contigs, 0);
+    if (encode) { T.bytes.reset(new uint8_t[(size_t)(b0 - a0) * VB_MAX_ENTRY + 8]); T.tileRel.reserve((size_t)((b0 - a0) / VB_TILE) + n_contigs + 1); }
+    uint64_t at = 0;
     for (uint32_t c = 0; c < n_contigs; ++c) {
       const uint64_t a = off[(size_t)sd * C1 + c], b = off[(size_t)sd * C1 + c + 1];
       const uint64_t at0 = at;
@@ -857,45 +867,44 @@ extern "C" int upb_pack_tags_vbyte (uint32_t n_samples, uint32_t n_contigs, cons
         const uint32_t v = head ? p : (p > prev ? p - prev : 0u);       // unsorted input decodes to a repeated position: the load then reports it
         bool esc = false;
         const uint32_t nb = vb_size(v, k, &esc);
-        if (write) {
-          if (head) tile_off_out[tile] = at;
-          vb_put(bytes_out + at, v, k);
-          if (esc) { upb_packed_exception& x = exc_out[excBase + nExc]; x.index = e; x.pos = 0u; x.cnt = k; }
+        if (encode) {
+          if (head) T.tileRel.push_back(at);
+          vb_put(T.bytes.get() + at, v, k);
+          if (esc) { upb_packed_exception x; x.index = e; x.pos = 0u; x.cnt = k; T.exc.push_back(x); }
         }
-        if (head) ++tile;
-        if (esc) ++nExc;
+        if (head) ++T.nTiles;
+        if (esc) ++T.nExc;
         at += nb;
         prev = p;
       }
-      if (!write) segBytes[(size_t)sd * n_contigs + c] = at - at0;
+      T.segBytes[c] = at - at0;
     }
-    if (!write) { nExcOf[sd] = nExc; tilesOf[sd] = tile - tileBase; }
+    T.nBytes = at;
   };
   const unsigned nThreads = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), nTasks));
-  std::vector<uint64_t> byteBase(nTasks, 0), tileBase(nTasks, 0), excBase(nTasks, 0);
-  auto parallel = [&] (bool write) {
+  auto parallel = [&] (const std::function<void(uint32_t)>& f) {
     std::vector<std::thread> th;
     std::atomic<uint32_t> next(0);
-    for (unsigned t = 0; t < nThreads; ++t) th.emplace_back([&] { for (uint32_t sd; (sd = next.fetch_add(1)) < nTasks;) run(sd, write, byteBase[sd], tileBase[sd], excBase[sd]); });
+    for (unsigned t = 0; t < nThreads; ++t) th.emplace_back([&] { for (uint32_t sd; (sd = next.fetch_add(1)) < nTasks;) f(sd); });
     for (std::thread& t : th) t.join();
   };
-  parallel(false);
+  parallel(run);
+  std::vector<uint64_t> byteBase(nTasks, 0), tileBase(nTasks, 0), excBase(nTasks, 0);
   uint64_t nBytes = 0, nTiles = 0, nExc = 0;
-  for (uint32_t sd = 0; sd < nTasks; ++sd) {
-    byteBase[sd] = nBytes; tileBase[sd] = nTiles; excBase[sd] = nExc;
-    for (uint32_t c = 0; c < n_contigs; ++c) nBytes += segBytes[(size_t)sd * n_contigs + c];
-    nTiles += tilesOf[sd]; nExc += nExcOf[sd];
-  }
+  for (uint32_t sd = 0; sd < nTasks; ++sd) { byteBase[sd] = nBytes; tileBase[sd] = nTiles; excBase[sd] = nExc; nBytes += tasks[sd].nBytes; nTiles += tasks[sd].nTiles; nExc += tasks[sd].nExc; }
   *n_bytes_out = nBytes; *n_tiles_out = nTiles; *n_exc_out = nExc;
   if (nBytes > bytes_cap || nTiles + 1 > tile_cap || nExc > exc_cap) return UPB_ERR_NOMEM;
-  if (!bytes_out || !byte_off_out || !tile_off_out || (nExc && !exc_out)) return UPB_ERR_BAD_ARG;
-  { uint64_t at = 0;
-    for (uint32_t sd = 0; sd < nTasks; ++sd) {
-      for (uint32_t c = 0; c < n_contigs; ++c) { byte_off_out[(size_t)sd * C1 + c] = at; at += segBytes[(size_t)sd * n_contigs + c]; }
-      byte_off_out[(size_t)sd * C1 + n_contigs] = at;
-    } }
+  if (!encode || (nExc && !exc_out)) return UPB_ERR_BAD_ARG;
+  parallel([&] (uint32_t sd) {
+    const Task& T = tasks[sd];
+    if (T.nBytes) memcpy(bytes_out + byteBase[sd], T.bytes.get(), (size_t)T.nBytes);
+    for (size_t i = 0; i < T.tileRel.size(); ++i) tile_off_out[tileBase[sd] + i] = byteBase[sd] + T.tileRel[i];
+    for (size_t i = 0; i < T.exc.size(); ++i) exc_out[excBase[sd] + i] = T.exc[i];
+    uint64_t at = byteBase[sd];
+    for (uint32_t c = 0; c < n_contigs; ++c) { byte_off_out[(size_t)sd * C1 + c] = at; at += T.segBytes[c]; }
+    byte_off_out[(size_t)sd * C1 + n_contigs] = at;
+  });
   tile_off_out[nTiles] = nBytes;
-  parallel(true);
   return UPB_OK;
 }
 
