@@ -228,6 +228,27 @@ def test_cli_regions_directional(tmp_path):
 
 @pytest.mark.gpu
 @needs_ref
+def test_cli_regions_without_tags(tmp_path):
+    # wiggle files that hold no tag at all (one of them, or all of them): the reference runs through (0 usable tags, background 0, -nan%)
+    d = make_synthetic([200000, 100000], 2, 15000, directional=True, seed=5, peak_spacing=5000, contig_names=["chrA", "chrB"])
+    f = stage(tmp_path, d)
+    for which in ("ref", "new"):
+        (tmp_path / which / "none.wig").write_text("track type=wiggle_0 name=none\n")
+        (tmp_path / which / "none2.wig").write_text("track type=wiggle_0 name=none2\n")
+    both(tmp_path, "regions", ["-f", "-o", "e.txt", "-c", f["contigs"], "none.wig"], ["e.txt"])
+    both(tmp_path, "regions", ["-f", "-o", "e2.txt", "-c", f["contigs"], "none.wig", "none2.wig"], ["e2.txt"])
+    both(tmp_path, "regions", ["-f", "-o", "e3.txt", "-c", f["contigs"], f["wigs"][0], "none.wig"], ["e3.txt"])
+    for form in ("packed2", "plain"):
+        both(tmp_path, "regions", ["-f", "-o", "e4.txt", "-c", f["contigs"], "none.wig", f["wigs"][1]], ["e4.txt"], new_env={"UPB_HOST_FORM": form})
+    # the other two programs on an empty track: strand_shift finds nothing to calibrate on, tags_in_regions counts zeros
+    both(tmp_path, "strand_shift", ["-c", f["contigs"], "-o", "shift.txt", "none.wig"], [], rc=1)
+    both(tmp_path, "regions", ["-q", "-o", "regions.txt", "-c", f["contigs"]] + f["wigs"], ["regions.txt"])
+    both(tmp_path, "tags_in_regions", ["-f", "regions.txt", "-o", "more.txt", "-c", f["contigs"], "none.wig"], ["more.txt"])
+    both(tmp_path, "tags_in_regions", ["-f", "regions.txt", "-o", "more2.txt", "-c", f["contigs"], "none.wig", f["wigs"][0]], ["more2.txt"])
+
+
+@pytest.mark.gpu
+@needs_ref
 def test_cli_regions_nondirectional_shifts_controls_coeffs(tmp_path):
     d = make_synthetic([200000, 100000], 4, 30000, directional=False, seed=2, peak_spacing=5000, contig_names=["chrA", "chrB"])
     f = stage(tmp_path, d)

@@ -246,8 +246,13 @@ int main (int argc, char* argv[]) {
       if (firstMinus >= 0 && firstMinus >= lastPlus) early = true;
     }
   }
-  TagLoader loader;                                                  // 2-byte host form, queued asynchronously: the call below starts on what has arrived
-  dev.load(loader, samples, C, directional, false);
+  // No usable tag at all (empty tracks, or tags in control samples only): the reference runs through — its Kernel(bandwidth, 1 / 0) is all
+  // inf / NaN, no score compares >= the threshold — and writes headers, zero counts and "-nan%".  Nothing to ask a device for.
+  const bool noTags = !(background > 0);
+  std::vector<uint64_t> zero64(std::max<size_t>(2 * (size_t)C, n) + 1, 0);
+  std::vector<uint32_t> zero32(2 * (size_t)C + 1, 0);
+  TagLoader loader;                                                  // compact host form, queued asynchronously: the call below starts on what has arrived
+  if (!noTags) dev.load(loader, samples, C, directional, false);
   upb_region_params prm;
   memset(&prm, 0, sizeof prm);
   prm.bandwidth = bandwidth;
@@ -262,7 +267,9 @@ int main (int argc, char* argv[]) {
   prm.background = background;
   prm.reference_order = 1;
   upb_region_table tab;
-  dev.callRegions(&prm, &tab);
+  memset(&tab, 0, sizeof tab);
+  if (noTags) { tab.tags_in_regions = zero64.data(); tab.unit_rows = zero64.data(); tab.unit_last_tag = zero32.data(); }
+  else dev.callRegions(&prm, &tab);
 
   // rows (FormatOutStream::write(Region), misc/format.cpp:1141-1162); the rows the reference's last flush loses stay lost
   {
@@ -305,6 +312,7 @@ int main (int argc, char* argv[]) {
   }
 
   // profile (-w): positions with score != 0 in the order ProfileBuffer::processPosition writes them
+  if (profile && noTags) { profile->out.close(); delete profile; profile = nullptr; }
   if (profile) {
     auto unit = [&] (int buffer, uint32_t c, int part /* 0 all, 1 before the flush, 2 the flush */) {
       upb_profile pf;
@@ -339,7 +347,7 @@ int main (int argc, char* argv[]) {
     const unsigned long long t = tab.tags_in_regions[i];
     fprintf(stderr, "  %s: %llu (%s%%)\n", s.name.c_str(), t, fmt_fixed(100 * (double)t / (double)s.confidentTags, 1).c_str());
   }
-  if (dev.gpus() == 1) upb_free_region_table(&tab);                  // (several GPUs: the table is the handle's)
+  if (!noTags && dev.gpus() == 1) upb_free_region_table(&tab);       // (several GPUs: the table is the handle's)
   fprintf(stderr, "\nAll done!\n\n");
   return 0;
 }

@@ -63,6 +63,11 @@ int main (int argc, char* argv[]) {
 
   fprintf(stderr, "calling enriched regions for shift calibration... ");
   fflush(stderr);
+  if (!(background > 0)) {                                             // no tag at all: the reference's loop finds no region (:143-233) and says so
+    fprintf(stderr, "0 found\n");
+    fprintf(stderr, "error: no regions qualified with given settings\n\n");
+    exit(1);
+  }
   dev.setContigs(C, contigs.sizes.data());
   TagLoader loader;
   dev.load(loader, samples, C, false, true);

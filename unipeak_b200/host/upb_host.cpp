@@ -974,7 +974,7 @@ void TagLoader::encode (const std::vector<Sample>& samples, uint32_t C, bool dir
     if (!pb) die("out of host memory");
     vbytes_ = (uint8_t*)pb;
     vbyteOff_.assign(off_.size(), 0); vtileOff_.assign((size_t)nt + 1, 0); exc_.resize((size_t)nx);
-    if (upb_pack_tags_vbyte((uint32_t)n, C, off_.data(), flat_.pos, flat_.cnt, vbytes_, nb, &nb, vbyteOff_.data(), vtileOff_.data(), nt + 1, &nt,
+    if (upb_pack_tags_vbyte((uint32_t)n, C, off_.data(), flat_.pos, flat_.cnt, vbytes_, bytes, &nb, vbyteOff_.data(), vtileOff_.data(), nt + 1, &nt,
                             exc_.empty() ? nullptr : exc_.data(), nx, &nx) != UPB_OK) die("encoding the tag arrays failed");
     src.vbytes = vbytes_; src.vbyte_off = vbyteOff_.data(); src.vtile_off = vtileOff_.data(); src.n_vtiles = nt;
     src.n_exceptions = exc_.size(); src.exceptions = exc_.empty() ? nullptr : exc_.data();
