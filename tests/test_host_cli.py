@@ -237,6 +237,8 @@ def test_cli_regions_without_tags(tmp_path):
         (tmp_path / which / "none2.wig").write_text("track type=wiggle_0 name=none2\n")
     both(tmp_path, "regions", ["-f", "-o", "e.txt", "-c", f["contigs"], "none.wig"], ["e.txt"])
     both(tmp_path, "regions", ["-f", "-o", "e2.txt", "-c", f["contigs"], "none.wig", "none2.wig"], ["e2.txt"])
+    both(tmp_path, "regions", ["-f", "-o", "e2w.txt", "-w", "e2w.wig", "-c", f["contigs"], "none.wig"], ["e2w.txt", "e2w.wig"])
+    both(tmp_path, "regions", ["-D", "-f", "-o", "e2d.txt", "-w", "e2d.wig", "-c", f["contigs"], "none.wig", "none2.wig"], ["e2d.txt", "e2d.wig"])
     both(tmp_path, "regions", ["-f", "-o", "e3.txt", "-c", f["contigs"], f["wigs"][0], "none.wig"], ["e3.txt"])
     for form in ("packed2", "plain"):
         both(tmp_path, "regions", ["-f", "-o", "e4.txt", "-c", f["contigs"], "none.wig", f["wigs"][1]], ["e4.txt"], new_env={"UPB_HOST_FORM": form})
